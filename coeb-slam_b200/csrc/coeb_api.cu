@@ -1,0 +1,577 @@
+// coeb_api.cu -- C ABI of the extractor (include/coeb_frontend.h): handle, geometry, device arenas,
+// launch sequence. Host side of ORBextractor (reference src/ORBextractor.cc:418-477, 1088-1367).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/coeb_frontend.h"
+#include "coeb_device.cuh"
+#include "coeb_host.hpp"
+
+namespace coeb {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+int check_device(int device) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(COEB_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU fallback");
+    }
+    if (device < 0 || device >= n) return fail(COEB_ERR_INVALID_ARG, "device %d out of range (%d devices)", device, n);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(COEB_ERR_NO_DEVICE, "device %d is sm_%d%d; the kernels are built for sm_100a only", device, prop.major,
+                    prop.minor);
+    return COEB_OK;
+}
+
+static inline int round_half_even(float v) { return (int)lrintf(v); }  // cvRound(float)
+
+}  // namespace coeb
+
+using namespace coeb;
+
+struct coeb_extractor {
+    coeb_orb_params params;
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    // tables of the reference constructor
+    std::vector<float> scale, inv_scale, sigma2, inv_sigma2;
+    std::vector<int> per_level;
+    int umax[16];
+    // geometry for the current image size
+    Geometry geom{};
+    bool geom_valid = false;
+    std::vector<int2> h_tabs;
+    int2* d_tabs = nullptr;
+    size_t pyr_bytes_per_frame = 0;
+    // arenas
+    int cap_B = 0;
+    int last_B = 0;
+    uint8_t *d_pyr = nullptr, *d_blur = nullptr;
+    uint32_t* d_cand = nullptr;
+    uint16_t* d_knode = nullptr;
+    int *d_cand_count = nullptr, *d_key_count = nullptr;
+    LevelKey* d_keys = nullptr;
+    DynState* d_dyn = nullptr;
+    // staging for the host entry points
+    uint8_t* d_in_gray = nullptr; size_t in_gray_bytes = 0; int in_pitch = 0;
+    float *d_in_boxes = nullptr, *d_in_tm = nullptr;
+    int *d_in_nbox = nullptr, *d_in_ntm = nullptr, *d_in_blur = nullptr;
+    size_t in_dyn_cap[5] = {0, 0, 0, 0, 0};
+    coeb_keypoint* d_out_kps = nullptr; uint8_t* d_out_desc = nullptr; int *d_out_count = nullptr, *d_out_status = nullptr;
+    size_t out_cap_elems = 0; int out_cap_B = 0;
+    BatchView last_view{};
+};
+
+namespace {
+
+// ORBextractor::ORBextractor tables (src/ORBextractor.cc:418-477)
+void build_tables(coeb_extractor* ex) {
+    const int nl = ex->params.nlevels;
+    const double scaleFactor = (double)ex->params.scale_factor;  // double member initialised from a float
+    ex->scale.assign(nl, 1.f);
+    ex->sigma2.assign(nl, 1.f);
+    for (int i = 1; i < nl; i++) {
+        ex->scale[i] = (float)(ex->scale[i - 1] * scaleFactor);
+        ex->sigma2[i] = ex->scale[i] * ex->scale[i];
+    }
+    ex->inv_scale.resize(nl);
+    ex->inv_sigma2.resize(nl);
+    for (int i = 0; i < nl; i++) {
+        ex->inv_scale[i] = 1.0f / ex->scale[i];
+        ex->inv_sigma2[i] = 1.0f / ex->sigma2[i];
+    }
+    ex->per_level.assign(nl, 0);
+    const float factor = (float)(1.0f / scaleFactor);
+    float desired = ex->params.nfeatures * (1 - factor) / (1 - (float)std::pow((double)factor, (double)nl));
+    int sum = 0;
+    for (int l = 0; l < nl - 1; l++) {
+        ex->per_level[l] = round_half_even(desired);
+        sum += ex->per_level[l];
+        desired *= factor;
+    }
+    ex->per_level[nl - 1] = std::max(ex->params.nfeatures - sum, 0);
+    // circular patch row ends (:461-476)
+    const int hp = kHalfPatch;
+    int vmax = (int)std::floor(hp * std::sqrt(2.f) / 2 + 1);
+    int vmin = (int)std::ceil(hp * std::sqrt(2.f) / 2);
+    for (int v = 0; v <= hp; v++) ex->umax[v] = 0;
+    for (int v = 0; v <= vmax; v++) ex->umax[v] = (int)lrint(std::sqrt((double)hp * hp - (double)v * v));
+    for (int v = hp, v0 = 0; v >= vmin; --v) {
+        while (ex->umax[v0] == ex->umax[v0 + 1]) ++v0;
+        ex->umax[v] = v0;
+        ++v0;
+    }
+}
+
+// cv::resize INTER_LINEAR coefficient tables (imgproc/resize.cpp), one (offset, a0 | a1<<16) per
+// destination column and row.
+void build_resize_tables(int sw, int sh, int dw, int dh, std::vector<int2>& out) {
+    const double scale_x = (double)sw / dw, scale_y = (double)sh / dh;
+    for (int dx = 0; dx < dw; dx++) {
+        float fx = (float)((dx + 0.5) * scale_x - 0.5);
+        int sx = (int)std::floor(fx);
+        fx -= sx;
+        if (sx < 0) { fx = 0; sx = 0; }
+        if (sx >= sw - 1) { fx = 0; sx = sw - 1; }
+        const int a0 = (int)lrintf((1.f - fx) * 2048.f), a1 = (int)lrintf(fx * 2048.f);
+        out.push_back(make_int2(sx, (a0 & 0xFFFF) | (a1 << 16)));
+    }
+    for (int dy = 0; dy < dh; dy++) {
+        float fy = (float)((dy + 0.5) * scale_y - 0.5);
+        int sy = (int)std::floor(fy);
+        fy -= sy;
+        const int b0 = (int)lrintf((1.f - fy) * 2048.f), b1 = (int)lrintf(fy * 2048.f);
+        out.push_back(make_int2(sy, (b0 & 0xFFFF) | (b1 << 16)));
+    }
+}
+
+int build_geometry(coeb_extractor* ex, int w, int h) {
+    Geometry& g = ex->geom;
+    if (ex->geom_valid && g.w0 == w && g.h0 == h) return COEB_OK;
+    const int nl = ex->params.nlevels;
+    std::memset(&g, 0, sizeof(g));
+    g.nlevels = nl;
+    g.w0 = w;
+    g.h0 = h;
+    for (int i = 0; i < 16; i++) g.umax[i] = ex->umax[i];
+    ex->h_tabs.clear();
+    unsigned long long img_off = 0;
+    int cells = 0, cand = 0, keys = 0, max_nodes = 8;
+    for (int l = 0; l < nl; l++) {
+        LevelGeom& L = g.lv[l];
+        // level size (src/ORBextractor.cc:1348-1349): both from the level-0 size
+        L.w = round_half_even((float)w * ex->inv_scale[l]);
+        L.h = round_half_even((float)h * ex->inv_scale[l]);
+        if (L.w > 4095 + 32 || L.h > 4095 + 32) return fail(COEB_ERR_UNSUPPORTED, "level %d is %dx%d; at most 4127 px per side", l, L.w, L.h);
+        L.pitch = (L.w + 63) & ~63;
+        L.maxBX = L.w - kEdge + 3;
+        L.maxBY = L.h - kEdge + 3;
+        const float width = (float)(L.maxBX - kMinBorder), height = (float)(L.maxBY - kMinBorder);
+        L.nCols = (int)(width / (float)kCellW);
+        L.nRows = (int)(height / (float)kCellW);
+        if (L.nCols < 1 || L.nRows < 1)
+            return fail(COEB_ERR_UNSUPPORTED, "level %d (%dx%d) is smaller than one 30-px FAST cell", l, L.w, L.h);
+        L.wCell = (int)std::ceil(width / L.nCols);
+        L.hCell = (int)std::ceil(height / L.nRows);
+        if (L.wCell + 6 > 72 || L.hCell + 6 > 72) return fail(COEB_ERR_UNSUPPORTED, "cell larger than the staged ROI");
+        if (L.nCols > 4095 || L.nRows > 4095) return fail(COEB_ERR_UNSUPPORTED, "too many cells");
+        L.cell_base = cells;
+        cells += L.nCols * L.nRows;
+        L.n_target = ex->per_level[l];
+        L.n_ini = (int)std::round((float)(L.maxBX - kMinBorder) / (float)(L.maxBY - kMinBorder));  // :550
+        if (L.n_ini < 1) return fail(COEB_ERR_UNSUPPORTED, "image taller than wide by more than 2:1 (no octree root)");
+        L.hX = (float)(L.maxBX - kMinBorder) / L.n_ini;  // :552
+        // candidate capacity = 3x3-NMS upper bound summed over the cells of this level
+        int cap = 0;
+        for (int i = 0; i < L.nRows; i++) {
+            const int iniY = kMinBorder + i * L.hCell;
+            if (iniY >= L.maxBY - 3) continue;
+            const int rh = std::min(iniY + L.hCell + 6, L.maxBY) - iniY;
+            for (int j = 0; j < L.nCols; j++) {
+                const int iniX = kMinBorder + j * L.wCell;
+                if (iniX >= L.maxBX - 6) continue;
+                const int rw = std::min(iniX + L.wCell + 6, L.maxBX) - iniX;
+                if (rw < 7 || rh < 7) continue;
+                cap += ((rw - 6 + 1) / 2) * ((rh - 6 + 1) / 2);
+            }
+        }
+        L.cand_cap = (cap + 31) & ~31;
+        L.cand_base = cand;
+        cand += L.cand_cap;
+        L.key_cap = std::max(L.n_target + 3, 4 * L.n_ini) + 1;
+        L.key_base = keys;
+        keys += L.key_cap;
+        max_nodes = std::max(max_nodes, L.key_cap + 3);
+        L.scale = ex->scale[l];
+        L.scaled_patch = (int)(kPatch * ex->scale[l]);  // :877
+        L.img_base = img_off;
+        L.img_stride = (unsigned long long)L.pitch * L.h;
+        L.img_stride = (L.img_stride + 255) & ~255ull;
+        L.tab_base = ex->h_tabs.size();
+        if (l > 0) build_resize_tables(g.lv[l - 1].w, g.lv[l - 1].h, L.w, L.h, ex->h_tabs);
+        img_off += L.img_stride;  // per-frame offset; scaled by the batch capacity when the arena is laid out
+    }
+    g.cells_per_frame = cells;
+    g.cand_per_frame = cand;
+    g.keys_per_frame = keys;
+    g.max_nodes = max_nodes;
+    ex->pyr_bytes_per_frame = img_off;
+    if (select_smem_bytes(max_nodes) > 200 * 1024)
+        return fail(COEB_ERR_UNSUPPORTED, "nfeatures too large for the shared-memory octree (%d nodes)", max_nodes);
+    if (ex->d_tabs) cudaFree(ex->d_tabs);
+    ex->d_tabs = nullptr;
+    if (!ex->h_tabs.empty()) {
+        CUDA_TRY(cudaMalloc(&ex->d_tabs, ex->h_tabs.size() * sizeof(int2)));
+        CUDA_TRY(cudaMemcpy(ex->d_tabs, ex->h_tabs.data(), ex->h_tabs.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    }
+    ex->geom_valid = true;
+    ex->cap_B = 0;  // arenas must be re-laid out for the new geometry
+    return COEB_OK;
+}
+
+void free_arenas(coeb_extractor* ex) {
+    cudaFree(ex->d_pyr); cudaFree(ex->d_blur); cudaFree(ex->d_cand); cudaFree(ex->d_knode); cudaFree(ex->d_cand_count);
+    cudaFree(ex->d_key_count); cudaFree(ex->d_keys); cudaFree(ex->d_dyn);
+    ex->d_pyr = ex->d_blur = nullptr; ex->d_cand = nullptr; ex->d_knode = nullptr; ex->d_cand_count = ex->d_key_count = nullptr;
+    ex->d_keys = nullptr; ex->d_dyn = nullptr;
+    ex->cap_B = 0;
+}
+
+// Arena layout: level blocks back to back, each [cap_B] frames. img_base in the geometry is finalised here.
+int ensure_arenas(coeb_extractor* ex, int B) {
+    Geometry& g = ex->geom;
+    if (B <= ex->cap_B) return COEB_OK;
+    free_arenas(ex);
+    unsigned long long off = 0;
+    for (int l = 0; l < g.nlevels; l++) {
+        g.lv[l].img_base = off;
+        off += g.lv[l].img_stride * (unsigned long long)B;
+    }
+    CUDA_TRY(cudaMalloc(&ex->d_pyr, off));
+    CUDA_TRY(cudaMalloc(&ex->d_blur, off));
+    CUDA_TRY(cudaMalloc(&ex->d_cand, (size_t)B * g.cand_per_frame * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&ex->d_knode, (size_t)B * g.cand_per_frame * sizeof(uint16_t)));
+    CUDA_TRY(cudaMalloc(&ex->d_cand_count, (size_t)B * g.nlevels * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&ex->d_key_count, (size_t)B * g.nlevels * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&ex->d_keys, (size_t)B * g.keys_per_frame * sizeof(LevelKey)));
+    CUDA_TRY(cudaMalloc(&ex->d_dyn, (size_t)B * sizeof(DynState)));
+    ex->cap_B = B;
+    return COEB_OK;
+}
+
+template <typename T>
+int ensure_buf(T** p, size_t* cap, size_t n) {
+    if (n <= *cap && *p) return COEB_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    CUDA_TRY(cudaMalloc(p, std::max<size_t>(n, 1) * sizeof(T)));
+    *cap = n;
+    return COEB_OK;
+}
+
+int enqueue(coeb_extractor* ex, const BatchView& v) {
+    const Geometry& g = ex->geom;
+    launch_classify(g, v, ex->stream);
+    launch_pyramid(g, v, ex->stream);
+    launch_blur(g, v, ex->stream);
+    launch_fast(g, v, ex->stream);
+    launch_select(g, v, ex->stream);
+    launch_describe(g, v, ex->stream);
+    CUDA_TRY(cudaGetLastError());
+    ex->last_view = v;
+    ex->last_B = v.B;
+    return COEB_OK;
+}
+
+int validate_common(coeb_extractor* ex, int B, const uint8_t* gray, int w, int h, int stride, int cap) {
+    if (!ex) return fail(COEB_ERR_INVALID_ARG, "null extractor");
+    if (B < 1) return fail(COEB_ERR_INVALID_ARG, "batch size %d", B);
+    if (!gray || w <= 0 || h <= 0 || stride < w) return fail(COEB_ERR_INVALID_ARG, "bad image arguments (w=%d h=%d stride=%d)", w, h, stride);
+    if (cap < 1) return fail(COEB_ERR_INVALID_ARG, "output capacity %d", cap);
+    return COEB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* coeb_last_error(void) { return g_last_error.c_str(); }
+const char* coeb_version(void) { return "coeb-frontend-b200 0.1 (sm_100a)"; }
+
+int coeb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int i = 0; i < n; i++) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major >= 10) ok++;
+    }
+    return ok;
+}
+
+int coeb_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return fail(COEB_ERR_INVALID_ARG, "null pointer");
+    CUDA_TRY(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+    return COEB_OK;
+}
+int coeb_host_free(void* ptr) {
+    CUDA_TRY(cudaFreeHost(ptr));
+    return COEB_OK;
+}
+
+int coeb_extractor_create(const coeb_orb_params* params, int device, coeb_extractor** out) {
+    if (!params || !out) return fail(COEB_ERR_INVALID_ARG, "null argument");
+    if (params->nlevels < 1 || params->nlevels > COEB_MAX_LEVELS) return fail(COEB_ERR_INVALID_ARG, "nlevels %d not in [1,%d]", params->nlevels, COEB_MAX_LEVELS);
+    if (params->nfeatures < 1 || !(params->scale_factor > 1.0f)) return fail(COEB_ERR_INVALID_ARG, "nfeatures=%d scale_factor=%f", params->nfeatures, params->scale_factor);
+    int st = check_device(device);
+    if (st != COEB_OK) return st;
+    CUDA_TRY(cudaSetDevice(device));
+    coeb_extractor* ex = new coeb_extractor();
+    ex->params = *params;
+    ex->device = device;
+    build_tables(ex);
+    if (cudaStreamCreateWithFlags(&ex->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ex;
+        return fail(COEB_ERR_CUDA, "cudaStreamCreate failed");
+    }
+    ex->stream = ex->own_stream;
+    *out = ex;
+    return COEB_OK;
+}
+
+void coeb_extractor_destroy(coeb_extractor* ex) {
+    if (!ex) return;
+    cudaSetDevice(ex->device);
+    cudaStreamSynchronize(ex->stream);
+    free_arenas(ex);
+    cudaFree(ex->d_tabs);
+    cudaFree(ex->d_in_gray); cudaFree(ex->d_in_boxes); cudaFree(ex->d_in_tm); cudaFree(ex->d_in_nbox); cudaFree(ex->d_in_ntm);
+    cudaFree(ex->d_in_blur); cudaFree(ex->d_out_kps); cudaFree(ex->d_out_desc); cudaFree(ex->d_out_count); cudaFree(ex->d_out_status);
+    cudaStreamDestroy(ex->own_stream);
+    delete ex;
+}
+
+int coeb_extractor_set_stream(coeb_extractor* ex, void* cuda_stream) {
+    if (!ex) return fail(COEB_ERR_INVALID_ARG, "null extractor");
+    ex->stream = cuda_stream ? (cudaStream_t)cuda_stream : ex->own_stream;
+    return COEB_OK;
+}
+
+int coeb_extractor_reserve(coeb_extractor* ex, int width, int height, int max_batch) {
+    if (!ex || max_batch < 1) return fail(COEB_ERR_INVALID_ARG, "bad argument");
+    CUDA_TRY(cudaSetDevice(ex->device));
+    int st = build_geometry(ex, width, height);
+    if (st != COEB_OK) return st;
+    return ensure_arenas(ex, max_batch);
+}
+
+int coeb_extractor_tables(const coeb_extractor* ex, int* nlevels, float* scale, float* inv_scale, float* sigma2,
+                          float* inv_sigma2, int* features_per_level) {
+    if (!ex) return fail(COEB_ERR_INVALID_ARG, "null extractor");
+    const int nl = ex->params.nlevels;
+    if (nlevels) *nlevels = nl;
+    for (int i = 0; i < nl; i++) {
+        if (scale) scale[i] = ex->scale[i];
+        if (inv_scale) inv_scale[i] = ex->inv_scale[i];
+        if (sigma2) sigma2[i] = ex->sigma2[i];
+        if (inv_sigma2) inv_sigma2[i] = ex->inv_sigma2[i];
+        if (features_per_level) features_per_level[i] = ex->per_level[i];
+    }
+    return COEB_OK;
+}
+
+int coeb_extractor_launches_per_call(const coeb_extractor* ex) {
+    if (!ex) return 0;
+    // classify + (nlevels-1) resizes + blur + zero-counts + FAST + select + describe
+    return 1 + (ex->params.nlevels - 1) + 1 + 2 + 1 + 1;
+}
+
+int coeb_extract_batch_device(coeb_extractor* ex, int B, const uint8_t* gray, int width, int height, int stride,
+                              size_t frame_stride, const float* boxes, const int* nbox, int max_box, const float* tm,
+                              const int* ntm, int max_tm, const int* blur_flag, coeb_keypoint* kps_out,
+                              uint8_t* desc_out, int* counts_out, int* status_out, int cap) {
+    int st = validate_common(ex, B, gray, width, height, stride, cap);
+    if (st != COEB_OK) return st;
+    if (!kps_out || !desc_out || !counts_out || !status_out) return fail(COEB_ERR_INVALID_ARG, "null output pointer");
+    if (nbox && (!boxes || !blur_flag || max_box < 1)) return fail(COEB_ERR_INVALID_ARG, "nbox given without boxes/blur_flag");
+    if (ntm && (!tm || max_tm < 1)) return fail(COEB_ERR_INVALID_ARG, "ntm given without tm");
+    CUDA_TRY(cudaSetDevice(ex->device));
+    st = build_geometry(ex, width, height);
+    if (st != COEB_OK) return st;
+    st = ensure_arenas(ex, B);
+    if (st != COEB_OK) return st;
+    ex->geom.out_cap = cap;
+    BatchView v{};
+    v.B = B;
+    v.l0 = gray; v.l0_pitch = stride; v.l0_stride = frame_stride;
+    v.pyr = ex->d_pyr; v.blur = ex->d_blur; v.tabs = ex->d_tabs;
+    v.cand = ex->d_cand; v.cand_count = ex->d_cand_count; v.keys = ex->d_keys; v.key_count = ex->d_key_count;
+    v.dyn = ex->d_dyn; v.knode = ex->d_knode;
+    v.boxes = boxes; v.nbox = nbox; v.max_box = max_box; v.tm = tm; v.ntm = ntm; v.max_tm = max_tm; v.blur_flag = blur_flag;
+    v.out_kps = kps_out; v.out_desc = desc_out; v.out_count = counts_out; v.status = status_out;
+    return enqueue(ex, v);
+}
+
+int coeb_extract_batch_host(coeb_extractor* ex, int B, const uint8_t* gray, int width, int height, int stride,
+                            size_t frame_stride, const float* boxes, const int* nbox, int max_box, const float* tm,
+                            const int* ntm, int max_tm, const int* blur_flag, coeb_keypoint* kps_out,
+                            uint8_t* desc_out, int* counts_out, int* status_out, int cap) {
+    int st = validate_common(ex, B, gray, width, height, stride, cap);
+    if (st != COEB_OK) return st;
+    if (!counts_out) return fail(COEB_ERR_INVALID_ARG, "null counts_out");
+    if (nbox && (!boxes || !blur_flag || max_box < 1)) return fail(COEB_ERR_INVALID_ARG, "nbox given without boxes/blur_flag");
+    if (ntm && (!tm || max_tm < 1)) return fail(COEB_ERR_INVALID_ARG, "ntm given without tm");
+    if (nbox) for (int i = 0; i < B; i++) if (nbox[i] < 0 || nbox[i] > max_box || nbox[i] > COEB_MAX_BOXES)
+        return fail(COEB_ERR_INVALID_ARG, "frame %d: nbox=%d (max_box=%d, at most %d boxes per frame)", i, nbox[i], max_box, COEB_MAX_BOXES);
+    if (ntm) for (int i = 0; i < B; i++) if (ntm[i] < 0 || ntm[i] > max_tm) return fail(COEB_ERR_INVALID_ARG, "frame %d: ntm=%d > max_tm=%d", i, ntm[i], max_tm);
+    CUDA_TRY(cudaSetDevice(ex->device));
+    cudaStream_t s = ex->stream;
+    // stage inputs: level 0 goes into a pitch-aligned device buffer
+    const int pitch = (width + 63) & ~63;
+    const size_t fstride = (size_t)pitch * height;
+    st = ensure_buf(&ex->d_in_gray, &ex->in_gray_bytes, fstride * B);
+    if (st != COEB_OK) return st;
+    if (frame_stride == (size_t)stride * height) {
+        CUDA_TRY(cudaMemcpy2DAsync(ex->d_in_gray, pitch, gray, stride, width, (size_t)height * B, cudaMemcpyHostToDevice, s));
+    } else {
+        for (int i = 0; i < B; i++)
+            CUDA_TRY(cudaMemcpy2DAsync(ex->d_in_gray + fstride * i, pitch, gray + frame_stride * i, stride, width, height, cudaMemcpyHostToDevice, s));
+    }
+    const float *dboxes = nullptr, *dtm = nullptr;
+    const int *dnbox = nullptr, *dntm = nullptr, *dblur = nullptr;
+    if (nbox) {
+        if ((st = ensure_buf(&ex->d_in_boxes, &ex->in_dyn_cap[0], (size_t)B * max_box * 4)) != COEB_OK) return st;
+        if ((st = ensure_buf(&ex->d_in_nbox, &ex->in_dyn_cap[1], (size_t)B)) != COEB_OK) return st;
+        if ((st = ensure_buf(&ex->d_in_blur, &ex->in_dyn_cap[2], (size_t)B * max_box)) != COEB_OK) return st;
+        CUDA_TRY(cudaMemcpyAsync(ex->d_in_boxes, boxes, sizeof(float) * B * max_box * 4, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(ex->d_in_nbox, nbox, sizeof(int) * B, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(ex->d_in_blur, blur_flag, sizeof(int) * B * max_box, cudaMemcpyHostToDevice, s));
+        dboxes = ex->d_in_boxes; dnbox = ex->d_in_nbox; dblur = ex->d_in_blur;
+    }
+    if (ntm) {
+        if ((st = ensure_buf(&ex->d_in_tm, &ex->in_dyn_cap[3], (size_t)B * max_tm * 2)) != COEB_OK) return st;
+        if ((st = ensure_buf(&ex->d_in_ntm, &ex->in_dyn_cap[4], (size_t)B)) != COEB_OK) return st;
+        CUDA_TRY(cudaMemcpyAsync(ex->d_in_tm, tm, sizeof(float) * B * max_tm * 2, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(ex->d_in_ntm, ntm, sizeof(int) * B, cudaMemcpyHostToDevice, s));
+        dtm = ex->d_in_tm; dntm = ex->d_in_ntm;
+    }
+    // output staging
+    if ((size_t)B * cap > ex->out_cap_elems || B > ex->out_cap_B) {
+        cudaFree(ex->d_out_kps); cudaFree(ex->d_out_desc); cudaFree(ex->d_out_count); cudaFree(ex->d_out_status);
+        ex->d_out_kps = nullptr; ex->d_out_desc = nullptr; ex->d_out_count = ex->d_out_status = nullptr;
+        CUDA_TRY(cudaMalloc(&ex->d_out_kps, (size_t)B * cap * sizeof(coeb_keypoint)));
+        CUDA_TRY(cudaMalloc(&ex->d_out_desc, (size_t)B * cap * 32));
+        CUDA_TRY(cudaMalloc(&ex->d_out_count, (size_t)B * sizeof(int)));
+        CUDA_TRY(cudaMalloc(&ex->d_out_status, (size_t)B * sizeof(int)));
+        ex->out_cap_elems = (size_t)B * cap;
+        ex->out_cap_B = B;
+    }
+    st = coeb_extract_batch_device(ex, B, ex->d_in_gray, width, height, pitch, fstride, dboxes, dnbox, max_box, dtm, dntm, max_tm,
+                                   dblur, ex->d_out_kps, ex->d_out_desc, ex->d_out_count, ex->d_out_status, cap);
+    if (st != COEB_OK) return st;
+    std::vector<int> status_local;
+    int* hstatus = status_out;
+    if (!hstatus) { status_local.resize(B); hstatus = status_local.data(); }
+    CUDA_TRY(cudaMemcpyAsync(counts_out, ex->d_out_count, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(hstatus, ex->d_out_status, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
+    if (kps_out) CUDA_TRY(cudaMemcpyAsync(kps_out, ex->d_out_kps, sizeof(coeb_keypoint) * B * cap, cudaMemcpyDeviceToHost, s));
+    if (desc_out) CUDA_TRY(cudaMemcpyAsync(desc_out, ex->d_out_desc, (size_t)32 * B * cap, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    int worst = COEB_OK;
+    for (int i = 0; i < B; i++)
+        if (hstatus[i] != COEB_OK && worst == COEB_OK) {
+            worst = hstatus[i];
+            fail(worst, "frame %d: %s", i,
+                 worst == COEB_ERR_BAD_BOX ? "a box lies outside the image (the reference's cv::Mat ROI would throw)"
+                 : worst == COEB_ERR_CAPACITY ? "output capacity too small" : "device-side failure");
+        }
+    return worst;
+}
+
+int coeb_extract(coeb_extractor* ex, const uint8_t* gray, int width, int height, int stride, const float* boxes_xyxy,
+                 int nbox, const float* tm_xy, int ntm, const int* blur_flag, int nblur, coeb_keypoint* kps_out,
+                 uint8_t* desc_out, int cap, int* n_out) {
+    if (n_out) *n_out = 0;
+    if (!ex) return fail(COEB_ERR_INVALID_ARG, "null extractor");
+    if (!gray || width <= 0 || height <= 0) return COEB_OK;  // `if (_image.empty()) return;` (src/ORBextractor.cc:1096)
+    if (nbox < 0 || ntm < 0 || nblur < 0) return fail(COEB_ERR_INVALID_ARG, "negative count");
+    if (nbox > COEB_MAX_BOXES) return fail(COEB_ERR_INVALID_ARG, "at most %d boxes per frame", COEB_MAX_BOXES);
+    // blur_flag is indexed by box id in the reference (:1168); missing entries count as 0
+    std::vector<int> blur(std::max(nbox, 1), 0);
+    for (int i = 0; i < nbox && i < nblur; i++) blur[i] = blur_flag[i];
+    int count = 0, status = 0;
+    const int nb = nbox, nt = ntm;
+    int st = coeb_extract_batch_host(ex, 1, gray, width, height, stride, (size_t)stride * height, nbox ? boxes_xyxy : nullptr,
+                                     nbox ? &nb : nullptr, std::max(nbox, 1), ntm ? tm_xy : nullptr, ntm ? &nt : nullptr,
+                                     std::max(ntm, 1), nbox ? blur.data() : nullptr, kps_out, desc_out, &count, &status, cap);
+    if (n_out) *n_out = count;
+    return st;
+}
+
+int coeb_extractor_dyn_info(coeb_extractor* ex, int frame, coeb_dyn_info* out) {
+    if (!ex || !out || frame < 0 || frame >= ex->last_B) return fail(COEB_ERR_INVALID_ARG, "bad argument");
+    CUDA_TRY(cudaSetDevice(ex->device));
+    CUDA_TRY(cudaStreamSynchronize(ex->stream));
+    DynState d;
+    CUDA_TRY(cudaMemcpy(&d, ex->d_dyn + frame, sizeof(d), cudaMemcpyDeviceToHost));
+    out->area_flag = d.area_flag;
+    out->n_dynamic = d.n_dynamic;
+    std::memcpy(out->rect, d.rect, sizeof(d.rect));
+    out->area = d.area;
+    return COEB_OK;
+}
+
+int coeb_pyramid_level(coeb_extractor* ex, int frame, int level, int blurred, const uint8_t** dev_ptr, int* width,
+                       int* height, int* pitch) {
+    if (!ex || !ex->geom_valid || frame < 0 || frame >= ex->last_B || level < 0 || level >= ex->geom.nlevels)
+        return fail(COEB_ERR_INVALID_ARG, "bad argument");
+    const Geometry& g = ex->geom;
+    const BatchView& v = ex->last_view;
+    if (dev_ptr) *dev_ptr = blurred ? blur_ptr(g, v, level, frame) : level_ptr(g, v, level, frame);
+    if (width) *width = g.lv[level].w;
+    if (height) *height = g.lv[level].h;
+    if (pitch) *pitch = blurred ? g.lv[level].pitch : level_pitch(g, v, level);
+    return COEB_OK;
+}
+
+int coeb_pyramid_level_copy(coeb_extractor* ex, int frame, int level, int blurred, uint8_t* host_dst) {
+    const uint8_t* p = nullptr;
+    int w = 0, h = 0, pitch = 0;
+    int st = coeb_pyramid_level(ex, frame, level, blurred, &p, &w, &h, &pitch);
+    if (st != COEB_OK) return st;
+    CUDA_TRY(cudaSetDevice(ex->device));
+    CUDA_TRY(cudaStreamSynchronize(ex->stream));
+    CUDA_TRY(cudaMemcpy2D(host_dst, w, p, pitch, w, h, cudaMemcpyDeviceToHost));
+    return COEB_OK;
+}
+
+int coeb_debug_candidates(coeb_extractor* ex, int frame, int level, uint32_t* host_out, int cap, int* n_out) {
+    if (!ex || !ex->geom_valid || frame < 0 || frame >= ex->last_B || level < 0 || level >= ex->geom.nlevels || !n_out)
+        return fail(COEB_ERR_INVALID_ARG, "bad argument");
+    CUDA_TRY(cudaSetDevice(ex->device));
+    CUDA_TRY(cudaStreamSynchronize(ex->stream));
+    const Geometry& g = ex->geom;
+    int n = 0;
+    CUDA_TRY(cudaMemcpy(&n, ex->d_cand_count + frame * g.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+    *n_out = n;
+    if (n > cap) return fail(COEB_ERR_CAPACITY, "need %d entries", n);
+    if (n > 0 && host_out)
+        CUDA_TRY(cudaMemcpy(host_out, ex->d_cand + (size_t)frame * g.cand_per_frame + g.lv[level].cand_base, sizeof(uint32_t) * n,
+                            cudaMemcpyDeviceToHost));
+    return COEB_OK;
+}
+
+int coeb_debug_level_keys(coeb_extractor* ex, int frame, int level, float* host_out, int cap, int* n_out) {
+    if (!ex || !ex->geom_valid || frame < 0 || frame >= ex->last_B || level < 0 || level >= ex->geom.nlevels || !n_out)
+        return fail(COEB_ERR_INVALID_ARG, "bad argument");
+    CUDA_TRY(cudaSetDevice(ex->device));
+    CUDA_TRY(cudaStreamSynchronize(ex->stream));
+    const Geometry& g = ex->geom;
+    int n = 0;
+    CUDA_TRY(cudaMemcpy(&n, ex->d_key_count + frame * g.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+    *n_out = n;
+    if (n > cap) return fail(COEB_ERR_CAPACITY, "need %d entries", n);
+    if (n > 0 && host_out)
+        CUDA_TRY(cudaMemcpy(host_out, ex->d_keys + (size_t)frame * g.keys_per_frame + g.lv[level].key_base, sizeof(LevelKey) * n,
+                            cudaMemcpyDeviceToHost));
+    return COEB_OK;
+}
+
+}  // extern "C"

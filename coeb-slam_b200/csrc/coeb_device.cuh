@@ -1,0 +1,134 @@
+// coeb_device.cuh -- shared host/device declarations of the B200 front end (internal; the public
+// boundary is include/coeb_frontend.h).
+//
+// HBM layout:
+//   pyramid arena : for each level l a [B][h_l][pitch_l] uint8 block (pitch_l = w_l rounded up to 64 B),
+//                   levels back to back; level 0 may alias the caller's device input instead.
+//   blurred arena : same shape, the 7x7 sigma=2 fixed-point Gaussian of every level.
+//   candidates    : per (frame, level) a uint32 array (x:12 | y:12 | response:8, minBorder-relative)
+//                   sized to the 3x3-NMS upper bound, plus one counter per (frame, level).
+//   level keys    : per (frame, level) up to key_cap selected keypoints {x,y (level coords), response,
+//                   angle}, list order, after culling; plus one counter per (frame, level).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/coeb_types.h"
+
+namespace coeb {
+
+constexpr int kEdge = 19;        // EDGE_THRESHOLD, reference src/ORBextractor.cc:76
+constexpr int kHalfPatch = 15;   // HALF_PATCH_SIZE, :75
+constexpr int kPatch = 31;       // PATCH_SIZE, :74
+constexpr int kMinBorder = 16;   // EDGE_THRESHOLD - 3, :795
+constexpr int kCellW = 30;       // W, :789
+
+struct LevelGeom {
+    int w, h, pitch;             // level image size and row pitch (bytes)
+    int maxBX, maxBY;            // w - 16, h - 16
+    int nCols, nRows, wCell, hCell;
+    int cell_base;               // index of this level's first cell in the per-frame cell list
+    int n_target;                // mnFeaturesPerLevel[l]
+    int n_ini;                   // octree root count, round(W/H)
+    int cand_cap, cand_base;     // per-frame candidate capacity / offset (uint32 units)
+    int key_cap, key_base;       // per-frame selected-key capacity / offset
+    int scaled_patch;            // (int)(31 * scale)
+    float hX;                    // (float)(maxX-minX)/nIni
+    float scale;                 // mvScaleFactor[l]
+    unsigned long long img_base;   // byte offset of this level's [B] block inside the pyramid arena
+    unsigned long long img_stride; // bytes between consecutive frames of this level
+    unsigned long long tab_base;   // offset (int2 units) of this level's resize tables: dw x-entries then dh y-entries
+};
+
+struct Geometry {
+    int nlevels;
+    int w0, h0;
+    int cells_per_frame;
+    int cand_per_frame;          // sum of cand_cap
+    int keys_per_frame;          // sum of key_cap
+    int out_cap;                 // per-frame capacity of the caller's keypoint/descriptor arrays
+    int max_nodes;               // octree node-table capacity (per generation)
+    LevelGeom lv[COEB_MAX_LEVELS];
+    int umax[16];
+};
+
+// One selected keypoint of a level before the final rescale (16 bytes).
+struct LevelKey {
+    float x, y;      // level coordinates including the +16 border offset
+    float response;
+    float angle;
+};
+
+// Per-frame dynamic-object decision kept on the device (mirrors coeb_dyn_info).
+struct DynState {
+    int area_flag;
+    int n_dynamic;
+    int rect[COEB_MAX_BOXES][4];
+    float area;
+    int bad_box;     // a box lay outside the image: the frame is reported as COEB_ERR_BAD_BOX
+};
+
+// Device pointers of one batch launch.
+struct BatchView {
+    int B;
+    const uint8_t* l0;                 // level-0 images
+    int l0_pitch;
+    unsigned long long l0_stride;      // bytes between level-0 frames
+    uint8_t* pyr;                      // pyramid arena (levels >= 1; level 0 too unless aliased)
+    uint8_t* blur;                     // blurred arena
+    const int2* tabs;                  // resize tables
+    uint32_t* cand;                    // [B][cand_per_frame]
+    int* cand_count;                   // [B][nlevels]
+    LevelKey* keys;                    // [B][keys_per_frame]
+    int* key_count;                    // [B][nlevels]
+    DynState* dyn;                     // [B]
+    uint16_t* knode;                   // [B][cand_per_frame] octree scratch: node id per candidate
+    // dynamic-object inputs
+    const float* boxes; const int* nbox; int max_box;
+    const float* tm; const int* ntm; int max_tm;
+    const int* blur_flag;
+    // outputs
+    coeb_keypoint* out_kps;            // [B][out_cap]
+    uint8_t* out_desc;                 // [B][out_cap][32]
+    int* out_count;                    // [B]
+    int* status;                       // [B] per-frame coeb_status
+};
+
+__host__ __device__ inline const uint8_t* level_ptr(const Geometry& g, const BatchView& v, int level, int frame) {
+    if (level == 0) return v.l0 + (unsigned long long)frame * v.l0_stride;
+    return v.pyr + g.lv[level].img_base + (unsigned long long)frame * g.lv[level].img_stride;
+}
+__host__ __device__ inline int level_pitch(const Geometry& g, const BatchView& v, int level) {
+    return level == 0 ? v.l0_pitch : g.lv[level].pitch;
+}
+__host__ __device__ inline uint8_t* blur_ptr(const Geometry& g, const BatchView& v, int level, int frame) {
+    return v.blur + g.lv[level].img_base + (unsigned long long)frame * g.lv[level].img_stride;
+}
+
+// `*mask.ptr<uchar>(y, x) == 0` of the reference (src/ORBextractor.cc:1397,1440): the mask is the union
+// of the zero-filled dynamic rectangles, so it is evaluated from the rectangle list.
+__device__ inline bool mask_is_zero(const DynState& d, int x, int y) {
+    for (int i = 0; i < d.n_dynamic; i++) {
+        if (x >= d.rect[i][0] && x < d.rect[i][2] && y >= d.rect[i][1] && y < d.rect[i][3]) return true;
+    }
+    return false;
+}
+
+// CheckMovingKeyPoints / CheckMovingKeyPoints_finall predicate (src/ORBextractor.cc:1391-1397, 1426-1440).
+__device__ inline bool is_moving(const DynState& d, float ptx, float pty, int level, float scale_l, int w0, int h0) {
+    const float s = level != 0 ? scale_l : 1.f;
+    float sx = __fmul_rn(ptx, s), sy = __fmul_rn(pty, s);
+    if (sx >= (float)(w0 - 1)) sx = (float)(w0 - 1);
+    if (sy >= (float)(h0 - 1)) sy = (float)(h0 - 1);
+    return mask_is_zero(d, (int)sx, (int)sy);
+}
+
+// kernel launchers (each enqueues on `stream`, no synchronisation)
+void launch_classify(const Geometry& g, const BatchView& v, cudaStream_t stream);
+void launch_pyramid(const Geometry& g, const BatchView& v, cudaStream_t stream);
+void launch_blur(const Geometry& g, const BatchView& v, cudaStream_t stream);
+void launch_fast(const Geometry& g, const BatchView& v, cudaStream_t stream);
+void launch_select(const Geometry& g, const BatchView& v, cudaStream_t stream);
+void launch_describe(const Geometry& g, const BatchView& v, cudaStream_t stream);
+
+}  // namespace coeb

@@ -1,0 +1,430 @@
+// octree.cu -- DistributeOctTree (E6), border/scale fix-up (E7), IC_Angle (E8) and the post-octree
+// cull (E9), one CTA per (level, frame).
+//
+// Reference: ExtractorNode::DivideNode + ORBextractor::DistributeOctTree (src/ORBextractor.cc:489-769),
+// IC_Angle (:80-107), CheckMovingKeyPoints_finall (:1371-1408).
+//
+// The reference grows a std::list of nodes by repeatedly splitting every multi-key node ("full
+// pass"), and, once one more pass could overshoot N, by splitting nodes in descending size order
+// until the list holds N nodes ("careful phase"). Its result depends on (a) which keys share a node
+// and (b) the list order, which fixes the output order and therefore descriptor row indices.
+// Both are reproduced exactly, but with data-parallel steps:
+//   * a node is a rectangle; a key's quadrant under a node depends only on the key and the node, so
+//     every key finds its child independently and children are counted with shared-memory atomics;
+//   * node ids ARE list positions. A round (full or careful) turns the list L into
+//         reverse(children created this round, in creation order) ++ (L minus the split nodes)
+//     (children are push_front'ed as created, :630-667 / :698-733), which is two prefix sums;
+//   * the careful phase's sort of (size, pointer) pairs (:691) uses the creation index as the second
+//     key (documented tie-break, identical to the CPU oracle) and is done by rank counting;
+//   * the per-node "best response, first key wins" (:748-766) is a 64-bit atomicMax on
+//     (response, reversed candidate order), the candidate order being re-derived from (x, y).
+#include "coeb_device.cuh"
+
+namespace coeb {
+
+constexpr int kSelThreads = 512;
+constexpr unsigned long long kOrdMask = 0xFFFFFFFFFFFFull;  // 48-bit candidate-order field
+
+struct QNode {
+    unsigned short x0, x1, y0, y1;
+    int count;
+};
+
+// In-place exclusive prefix sum of data[0..n) in shared memory; returns the total. All threads call.
+__device__ int block_exclusive_scan(int* data, int n, int* s_warp) {
+    const int T = blockDim.x, tid = threadIdx.x;
+    const int chunk = (n + T - 1) / T;
+    const int lo = min(tid * chunk, n), hi = min(lo + chunk, n);
+    int sum = 0;
+    for (int i = lo; i < hi; i++) sum += data[i];
+    // block scan of per-thread sums
+    const int lane = tid & 31, wid = tid >> 5;
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int wv = lane < (T >> 5) ? s_warp[lane] : 0;
+        int winc = wv;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        s_warp[lane] = winc - wv;       // exclusive warp offsets
+        if (lane == 31) s_warp[32] = winc;  // total
+    }
+    __syncthreads();
+    int run = s_warp[wid] + inc - sum;
+    for (int i = lo; i < hi; i++) {
+        const int t = data[i];
+        data[i] = run;
+        run += t;
+    }
+    const int total = s_warp[32];
+    __syncthreads();
+    return total;
+}
+
+// cv::fastAtan2 (degrees), scalar fp32 path; explicit rn intrinsics keep the compiler from fusing
+// multiply-adds (the CPU build is -ffp-contract=off).
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+    const float scale = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = __fmul_rn(0.9997878412794807f, scale);
+    const float p3 = __fmul_rn(-0.3258083974640975f, scale);
+    const float p5 = __fmul_rn(0.1555786518463281f, scale);
+    const float p7 = __fmul_rn(-0.04432655554792128f, scale);
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float eps = (float)2.2204460492503131e-16;
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+// Candidate order of the reference's vToDistributeKeys: cells row-major, raster inside a cell
+// (src/ORBextractor.cc:811-848). A cell detects x in [j*wCell+3, (j+1)*wCell+3) (minBorder-relative),
+// the last cell of a row/column absorbing the clamped remainder, so (x, y) identifies the cell.
+__device__ __forceinline__ unsigned long long order_key(const LevelGeom& L, int x, int y, int lastI, int lastJ) {
+    const int j = min((x - 3) / L.wCell, lastJ), i = min((y - 3) / L.hCell, lastI);
+    const unsigned long long ord = ((((unsigned long long)i << 12 | (unsigned long long)j) << 12 | (unsigned long long)y) << 12) |
+                                   (unsigned long long)x;
+    return ord;  // < 2^48
+}
+
+extern __shared__ unsigned char s_dyn_raw[];
+
+__global__ void __launch_bounds__(kSelThreads) select_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v) {
+    const int level = blockIdx.x, frame = blockIdx.y;
+    const LevelGeom& L = g.lv[level];
+    const DynState& dyn = v.dyn[frame];
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int LC = g.max_nodes;
+
+    // ---- shared memory carve-up -----------------------------------------------------------------
+    unsigned char* sp = s_dyn_raw;
+    unsigned long long* s_best = reinterpret_cast<unsigned long long*>(sp); sp += sizeof(unsigned long long) * LC;
+    QNode* s_nodeA = reinterpret_cast<QNode*>(sp); sp += sizeof(QNode) * LC;
+    QNode* s_nodeB = reinterpret_cast<QNode*>(sp); sp += sizeof(QNode) * LC;
+    int* s_cc = reinterpret_cast<int*>(sp); sp += sizeof(int) * 4 * LC;      // tentative child counts [slot][4]
+    int* s_scanA = reinterpret_cast<int*>(sp); sp += sizeof(int) * 4 * LC;   // scratch for scans (up to 4*LC entries)
+    int* s_scanB = reinterpret_cast<int*>(sp); sp += sizeof(int) * LC;
+    unsigned short* s_childpos = reinterpret_cast<unsigned short*>(sp); sp += sizeof(unsigned short) * 4 * LC;
+    unsigned short* s_oldpos = reinterpret_cast<unsigned short*>(sp); sp += sizeof(unsigned short) * LC;
+    unsigned short* s_slot = reinterpret_cast<unsigned short*>(sp); sp += sizeof(unsigned short) * LC;
+    unsigned short* s_P = reinterpret_cast<unsigned short*>(sp); sp += sizeof(unsigned short) * LC;
+    unsigned short* s_E = reinterpret_cast<unsigned short*>(sp); sp += sizeof(unsigned short) * LC;
+    unsigned short* s_E2 = reinterpret_cast<unsigned short*>(sp); sp += sizeof(unsigned short) * LC;
+    __shared__ int s_warp[33];
+    __shared__ int s_misc[8];
+
+    int nkeys = v.cand_count[frame * g.nlevels + level];
+    int* key_count = v.key_count + frame * g.nlevels + level;
+    if (nkeys > L.cand_cap) {  // cannot happen (capacity is the NMS bound); fail loudly rather than truncate
+        if (tid == 0) { *key_count = 0; atomicMin(&v.status[frame], (int)COEB_ERR_CAPACITY); }
+        return;
+    }
+    if (nkeys == 0 || dyn.bad_box) {
+        if (tid == 0) *key_count = 0;
+        return;
+    }
+    const uint32_t* __restrict__ keys = v.cand + (size_t)frame * g.cand_per_frame + L.cand_base;
+    unsigned short* knode = v.knode + (size_t)frame * g.cand_per_frame + L.cand_base;
+
+    int N = L.n_target;
+    if (dyn.area_flag) N = (int)((double)N * 0.7);  // (int)(mnFeaturesPerLevel[level])*0.7 -> const int& (:869)
+    const int H = L.maxBY - kMinBorder;
+    const int nIni = L.n_ini;
+    const float hX = L.hX;
+
+    // ---- roots (:550-592) ------------------------------------------------------------------------
+    QNode* cur = s_nodeA;
+    QNode* nxt = s_nodeB;
+    for (int i = tid; i < nIni; i += T) {
+        QNode n;
+        n.x0 = (unsigned short)(int)__fmul_rn(hX, (float)i);
+        n.x1 = (unsigned short)(int)__fmul_rn(hX, (float)(i + 1));
+        n.y0 = 0;
+        n.y1 = (unsigned short)H;
+        n.count = 0;
+        nxt[i] = n;
+    }
+    __syncthreads();
+    for (int k = tid; k < nkeys; k += T) {
+        const int x = keys[k] & 0xFFF;
+        int r = (int)__fdiv_rn((float)x, hX);
+        r = min(max(r, 0), nIni - 1);
+        knode[k] = (unsigned short)r;
+        atomicAdd(&nxt[r].count, 1);
+    }
+    __syncthreads();
+    for (int i = tid; i < nIni; i += T) s_scanA[i] = nxt[i].count > 0;
+    __syncthreads();
+    int nList = block_exclusive_scan(s_scanA, nIni, s_warp);
+    for (int i = tid; i < nIni; i += T)
+        if (nxt[i].count > 0) cur[s_scanA[i]] = nxt[i];
+    __syncthreads();
+    if (nList != nIni) {
+        for (int k = tid; k < nkeys; k += T) knode[k] = (unsigned short)s_scanA[knode[k]];
+    }
+    __syncthreads();
+
+    // ---- rounds (:601-745) -------------------------------------------------------------------------
+    bool careful = false;
+    int nE = 0;  // expandable nodes created in the previous round, creation order, in s_E
+    for (int round = 0; round < 64; round++) {
+        const int prevSize = nList;
+        int nP;
+        if (!careful) {
+            // full pass: every multi-key node, in list order (:613-672)
+            for (int i = tid; i < nList; i += T) s_scanA[i] = cur[i].count > 1;
+            __syncthreads();
+            nP = block_exclusive_scan(s_scanA, nList, s_warp);
+            for (int i = tid; i < nList; i += T) {
+                if (cur[i].count > 1) { s_P[s_scanA[i]] = (unsigned short)i; s_slot[i] = (unsigned short)s_scanA[i]; }
+                else s_slot[i] = 0xFFFF;
+            }
+        } else {
+            // careful phase: previous round's multi-key children, largest first, later-created first on ties (:688-692)
+            nP = nE;
+            for (int i = tid; i < nList; i += T) s_slot[i] = 0xFFFF;
+            __syncthreads();
+            for (int e = tid; e < nE; e += T) {
+                const int ce = cur[s_E[e]].count;
+                int rank = 0;
+                for (int f = 0; f < nE; f++) {
+                    const int cf = cur[s_E[f]].count;
+                    rank += (cf > ce) || (cf == ce && f > e);
+                }
+                s_P[rank] = s_E[e];
+                s_slot[s_E[e]] = (unsigned short)rank;
+            }
+        }
+        __syncthreads();
+        if (nP == 0) break;  // nothing left to split: list size cannot change (:676)
+
+        // tentative children of every node in P
+        for (int i = tid; i < 4 * nP; i += T) s_cc[i] = 0;
+        __syncthreads();
+        for (int k = tid; k < nkeys; k += T) {
+            const int nd = knode[k];
+            const int p = s_slot[nd];
+            if (p != 0xFFFF) {
+                const QNode n = cur[nd];
+                const int xm = n.x0 + ((n.x1 - n.x0 + 1) >> 1), ym = n.y0 + ((n.y1 - n.y0 + 1) >> 1);  // ceil(w/2) (:491-492)
+                const uint32_t key = keys[k];
+                const int x = key & 0xFFF, y = (key >> 12) & 0xFFF;
+                const int q = (x < xm ? 0 : 1) + (y < ym ? 0 : 2);
+                atomicAdd(&s_cc[4 * p + q], 1);
+            }
+        }
+        __syncthreads();
+
+        // how many nodes get split this round
+        int nProc = nP;
+        if (careful) {
+            for (int p = tid; p < nP; p += T) {
+                const int* c = &s_cc[4 * p];
+                s_scanA[p] = (c[0] > 0) + (c[1] > 0) + (c[2] > 0) + (c[3] > 0) - 1;
+            }
+            __syncthreads();
+            block_exclusive_scan(s_scanA, nP, s_warp);
+            if (tid == 0) s_misc[0] = nP;
+            __syncthreads();
+            for (int p = tid; p < nP; p += T) {
+                const int* c = &s_cc[4 * p];
+                const int after = nList + s_scanA[p] + (c[0] > 0) + (c[1] > 0) + (c[2] > 0) + (c[3] > 0) - 1;
+                if (after >= N) atomicMin(&s_misc[0], p + 1);  // break after the first split reaching N (:737-738)
+            }
+            __syncthreads();
+            nProc = s_misc[0];
+            __syncthreads();
+        }
+
+        // creation sequence: for p in processing order, children q = 0..3 that hold keys
+        for (int i = tid; i < 4 * nProc; i += T) s_scanA[i] = s_cc[i] > 0;
+        __syncthreads();
+        const int totalNew = block_exclusive_scan(s_scanA, 4 * nProc, s_warp);
+        // surviving old nodes keep their relative order behind the new ones
+        for (int i = tid; i < nList; i += T) {
+            const int p = s_slot[i];
+            s_scanB[i] = !(p != 0xFFFF && p < nProc);
+        }
+        __syncthreads();
+        const int nKeep = block_exclusive_scan(s_scanB, nList, s_warp);
+        const int newSize = totalNew + nKeep;
+        if (newSize > LC) {  // cannot happen for max_nodes >= max(N + 3, 4 * nIni); fail loudly
+            if (tid == 0) { *key_count = 0; atomicMin(&v.status[frame], (int)COEB_ERR_CAPACITY); }
+            return;
+        }
+        for (int i = tid; i < nList; i += T) {
+            const int p = s_slot[i];
+            if (!(p != 0xFFFF && p < nProc)) {
+                const int pos = totalNew + s_scanB[i];
+                s_oldpos[i] = (unsigned short)pos;
+                nxt[pos] = cur[i];
+            }
+        }
+        for (int i = tid; i < 4 * nProc; i += T) {
+            const int cnt = s_cc[i];
+            if (cnt > 0) {
+                const int p = i >> 2, q = i & 3;
+                const QNode n = cur[s_P[p]];
+                const int xm = n.x0 + ((n.x1 - n.x0 + 1) >> 1), ym = n.y0 + ((n.y1 - n.y0 + 1) >> 1);
+                QNode c;
+                c.x0 = (q & 1) ? xm : n.x0;
+                c.x1 = (q & 1) ? n.x1 : xm;
+                c.y0 = (q & 2) ? ym : n.y0;
+                c.y1 = (q & 2) ? n.y1 : ym;
+                c.count = cnt;
+                const int pos = totalNew - 1 - s_scanA[i];  // push_front in creation order
+                nxt[pos] = c;
+                s_childpos[i] = (unsigned short)pos;
+            }
+        }
+        __syncthreads();
+        // next round's expandable list: multi-key children in creation order
+        // creation index c = s_scanA[i] for children with keys; flag multi-key ones, indexed by creation index
+        int* s_flag = s_scanB;  // size LC >= totalNew
+        for (int i = tid; i < totalNew; i += T) s_flag[i] = 0;
+        __syncthreads();
+        for (int i = tid; i < 4 * nProc; i += T)
+            if (s_cc[i] > 1) s_flag[s_scanA[i]] = 1;
+        __syncthreads();
+        // s_E2[rank among multi-key children] = list position of that child
+        // (position of creation index c is totalNew-1-c)
+        for (int i = tid; i < totalNew; i += T) s_cc[i] = s_flag[i];  // s_cc is free now (4*LC >= totalNew)
+        __syncthreads();
+        const int nE2 = block_exclusive_scan(s_cc, totalNew, s_warp);
+        for (int i = tid; i < totalNew; i += T)
+            if (s_flag[i]) s_E2[s_cc[i]] = (unsigned short)(totalNew - 1 - i);
+        __syncthreads();
+
+        // move the keys
+        for (int k = tid; k < nkeys; k += T) {
+            const int nd = knode[k];
+            const int p = s_slot[nd];
+            if (p != 0xFFFF && p < nProc) {
+                const QNode n = cur[nd];
+                const int xm = n.x0 + ((n.x1 - n.x0 + 1) >> 1), ym = n.y0 + ((n.y1 - n.y0 + 1) >> 1);
+                const uint32_t key = keys[k];
+                const int x = key & 0xFFF, y = (key >> 12) & 0xFFF;
+                const int q = (x < xm ? 0 : 1) + (y < ym ? 0 : 2);
+                knode[k] = s_childpos[4 * p + q];
+            } else {
+                knode[k] = s_oldpos[nd];
+            }
+        }
+        __syncthreads();
+        { QNode* t = cur; cur = nxt; nxt = t; }
+        { unsigned short* t = s_E; s_E = s_E2; s_E2 = t; }
+        nE = nE2;
+        nList = newSize;
+        if (nList >= N || nList == prevSize) break;               // :676, :741
+        if (!careful && nList + 3 * nE > N) careful = true;        // :680
+    }
+
+    // ---- best key per node (:748-766) -------------------------------------------------------------
+    for (int i = tid; i < nList; i += T) s_best[i] = 0ull;
+    __syncthreads();
+    {
+        const int lastJ = max(min(L.nCols - 1, (L.maxBX - 6 - kMinBorder - 1) / L.wCell), 0);
+        const int lastI = max(min(L.nRows - 1, (L.maxBY - 3 - kMinBorder - 1) / L.hCell), 0);
+        for (int k = tid; k < nkeys; k += T) {
+            const uint32_t key = keys[k];
+            const int x = key & 0xFFF, y = (key >> 12) & 0xFFF;
+            const unsigned long long ord = order_key(L, x, y, lastI, lastJ);
+            const unsigned long long pri = ((unsigned long long)(key >> 24) << 48) | (kOrdMask - ord);
+            atomicMax(&s_best[knode[k]], pri);
+        }
+    }
+    __syncthreads();
+
+    // ---- fix-up (:877-890), orientation (:902-903), post cull (:1204-1207), ordered compaction -----
+    // s_scanA: keep flag / position; keys are written level-relative + 16.
+    for (int i = tid; i < nList; i += T) {
+        const unsigned long long ord = kOrdMask - (s_best[i] & kOrdMask);
+        const int x = (int)(ord & 0xFFF), y = (int)((ord >> 12) & 0xFFF);
+        const float fx = (float)(x + kMinBorder), fy = (float)(y + kMinBorder);
+        int keep = 1;
+        if (!dyn.area_flag && level < 8 && is_moving(dyn, fx, fy, level, L.scale, g.w0, g.h0)) keep = 0;
+        s_scanA[i] = keep;
+    }
+    __syncthreads();
+    const int nOut = block_exclusive_scan(s_scanA, nList, s_warp);
+    LevelKey* out = v.keys + (size_t)frame * g.keys_per_frame + L.key_base;
+    if (nOut > L.key_cap) {
+        if (tid == 0) { *key_count = 0; atomicMin(&v.status[frame], (int)COEB_ERR_CAPACITY); }
+        return;
+    }
+    if (tid == 0) *key_count = nOut;
+
+    const uint8_t* __restrict__ img = level_ptr(g, v, level, frame);
+    const int pitch = level_pitch(g, v, level);
+    const int lane = tid & 31, wid = tid >> 5, nwarps = T >> 5;
+    for (int i = wid; i < nList; i += nwarps) {
+        const unsigned long long best = s_best[i];
+        const unsigned long long ord = kOrdMask - (best & kOrdMask);
+        const int x = (int)(ord & 0xFFF) + kMinBorder, y = (int)((ord >> 12) & 0xFFF) + kMinBorder;
+        const bool keep = (i + 1 < nList ? s_scanA[i + 1] : nOut) != s_scanA[i];
+        if (!keep) continue;
+        // IC_Angle: lanes span u = -15..15 of each patch row
+        int m10 = 0, m01 = 0;
+        const int u = lane - kHalfPatch;
+        if (lane < 31) {
+            const uint8_t* c = img + (size_t)y * pitch + x + u;
+            const int au = u < 0 ? -u : u;
+#pragma unroll 1
+            for (int vv = -kHalfPatch; vv <= kHalfPatch; vv++) {
+                const int d = g.umax[vv < 0 ? -vv : vv];
+                if (au <= d) {
+                    const int val = __ldg(c + (ptrdiff_t)vv * pitch);
+                    m10 += u * val;
+                    m01 += vv * val;
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+            m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+        }
+        if (lane == 0) {
+            LevelKey k;
+            k.x = (float)x;
+            k.y = (float)y;
+            k.response = (float)(int)(best >> 48);
+            k.angle = fast_atan2_deg((float)m01, (float)m10);
+            out[s_scanA[i]] = k;
+        }
+    }
+}
+
+size_t select_smem_bytes(int LC) {
+    return (size_t)LC * (sizeof(unsigned long long) + 2 * sizeof(QNode) + 4 * 4 + 4 * 4 + 4 + 4 * 2 + 2 * 5);
+}
+
+void launch_select(const Geometry& g, const BatchView& v, cudaStream_t stream) {
+    const size_t smem = select_smem_bytes(g.max_nodes);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    select_kernel<<<dim3(g.nlevels, v.B), kSelThreads, smem, stream>>>(g, v);
+}
+
+}  // namespace coeb

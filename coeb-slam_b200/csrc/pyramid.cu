@@ -1,0 +1,204 @@
+// pyramid.cu -- image pyramid (E2), per-level Gaussian blur (E10) and the dynamic-box decision (E3).
+//
+// Replaces, bit for bit, what the reference obtains from OpenCV:
+//   cv::resize(prev, level, sz, 0, 0, INTER_LINEAR)             src/ORBextractor.cc:1356
+//   cv::GaussianBlur(level, level, Size(7,7), 2, 2, REFLECT_101) src/ORBextractor.cc:1318
+// and the box -> mask logic of src/ORBextractor.cc:1101-1195.
+#include "coeb_device.cuh"
+
+namespace coeb {
+
+// ------------------------------------------------------------------------------------------------
+// Resize: OpenCV's 8-bit INTER_LINEAR is an 11-bit fixed-point separable filter:
+//   h(dx)  = S[sx]*a0 + S[sx+1]*a1                       (a0,a1 = rint((1-fx)*2048), rint(fx*2048))
+//   out    = (((b0*(h0>>4))>>16) + ((b1*(h1>>4))>>16) + 2) >> 2
+// The per-column / per-row (offset, a0|a1<<16) tables are built on the host (coeb_api.cu) with the
+// exact double/float arithmetic of cv::resize and kept resident.
+// Each thread produces 4 adjacent output pixels and stores them as one 32-bit word.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) resize_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v,
+                                                     int level) {
+    const LevelGeom& D = g.lv[level];
+    const LevelGeom& S = g.lv[level - 1];
+    const int frame = blockIdx.z;
+    const int dx0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int dy = blockIdx.y * 8 + threadIdx.y;
+    if (dx0 >= D.w || dy >= D.h) return;
+    const uint8_t* __restrict__ src = level_ptr(g, v, level - 1, frame);
+    const int spitch = level_pitch(g, v, level - 1);
+    uint8_t* dst = v.pyr + D.img_base + (unsigned long long)frame * D.img_stride;
+    const int2* xt = v.tabs + D.tab_base;
+    const int2* yt = xt + D.w;
+    const int2 ye = __ldg(&yt[dy]);
+    const int sy0 = min(max(ye.x, 0), S.h - 1), sy1 = min(max(ye.x + 1, 0), S.h - 1);
+    const int b0 = ye.y & 0xFFFF, b1 = ye.y >> 16;
+    const uint8_t* r0 = src + (size_t)sy0 * spitch;
+    const uint8_t* r1 = src + (size_t)sy1 * spitch;
+    uint32_t packed = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int dx = dx0 + i;
+        if (dx < D.w) {
+            const int2 xe = __ldg(&xt[dx]);
+            const int sx = xe.x, sx1 = min(sx + 1, S.w - 1);
+            const int a0 = xe.y & 0xFFFF, a1 = xe.y >> 16;
+            const int h0 = __ldg(r0 + sx) * a0 + __ldg(r0 + sx1) * a1;
+            const int h1 = __ldg(r1 + sx) * a0 + __ldg(r1 + sx1) * a1;
+            int o = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+            o = min(max(o, 0), 255);
+            packed |= (uint32_t)o << (8 * i);
+        }
+    }
+    uint8_t* drow = dst + (size_t)dy * D.pitch;
+    *reinterpret_cast<uint32_t*>(drow + dx0) = packed;  // pitch is a multiple of 64, so padding absorbs the tail
+}
+
+void launch_pyramid(const Geometry& g, const BatchView& v, cudaStream_t stream) {
+    for (int l = 1; l < g.nlevels; l++) {
+        dim3 block(32, 8);
+        dim3 grid((g.lv[l].w + 127) / 128, (g.lv[l].h + 7) / 8, v.B);
+        resize_kernel<<<grid, block, 0, stream>>>(g, v, l);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gaussian 7x7 sigma=2, OpenCV bit-exact fixed point: Q8 kernel {18,34,48,56,48,34,18};
+// horizontal pass -> Q8.8 (uint16), vertical pass -> Q16.16, (v + 32768) >> 16. BORDER_REFLECT_101
+// on the level itself (the reference blurs a clone of the ROI, so the pyramid border is not seen).
+// One CTA = 128 x 16 output tile of one level of one frame; all levels in one launch.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBlurTW = 128, kBlurTH = 16;
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;
+    return i;
+}
+
+struct BlurTileMap {          // first tile index of every level inside one frame's tile list
+    int tile_base[COEB_MAX_LEVELS + 1];
+    int tiles_x[COEB_MAX_LEVELS];
+};
+
+__global__ void __launch_bounds__(256) blur_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v,
+                                                   const __grid_constant__ BlurTileMap tm) {
+    __shared__ uint8_t s_in[kBlurTH + 6][kBlurTW + 8];
+    __shared__ uint16_t s_h[kBlurTH + 6][kBlurTW];
+    const int frame = blockIdx.y;
+    int level = 0;
+    while (level + 1 < g.nlevels && (int)blockIdx.x >= tm.tile_base[level + 1]) level++;
+    const LevelGeom& L = g.lv[level];
+    const int t = blockIdx.x - tm.tile_base[level];
+    const int tx0 = (t % tm.tiles_x[level]) * kBlurTW, ty0 = (t / tm.tiles_x[level]) * kBlurTH;
+    const uint8_t* __restrict__ src = level_ptr(g, v, level, frame);
+    const int spitch = level_pitch(g, v, level);
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+
+    for (int i = tid; i < (kBlurTH + 6) * (kBlurTW + 6); i += 256) {
+        const int ry = i / (kBlurTW + 6), rx = i - ry * (kBlurTW + 6);
+        const int gy = reflect101(min(ty0 + ry - 3, L.h + 2), L.h);
+        const int gx = reflect101(min(tx0 + rx - 3, L.w + 2), L.w);
+        s_in[ry][rx] = __ldg(src + (size_t)gy * spitch + gx);
+    }
+    __syncthreads();
+    for (int i = tid; i < (kBlurTH + 6) * kBlurTW; i += 256) {
+        const int ry = i / kBlurTW, rx = i - ry * kBlurTW;
+        const uint8_t* p = &s_in[ry][rx];
+        const int acc = 18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3];
+        s_h[ry][rx] = (uint16_t)acc;
+    }
+    __syncthreads();
+    uint8_t* dst = blur_ptr(g, v, level, frame);
+    for (int i = tid; i < kBlurTH * (kBlurTW / 4); i += 256) {
+        const int ry = i / (kBlurTW / 4), rx = (i - ry * (kBlurTW / 4)) * 4;
+        const int gy = ty0 + ry, gx = tx0 + rx;
+        if (gy >= L.h || gx >= L.w) continue;
+        uint32_t packed = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t acc = 18u * (s_h[ry][rx + k] + s_h[ry + 6][rx + k]) + 34u * (s_h[ry + 1][rx + k] + s_h[ry + 5][rx + k]) +
+                                 48u * (s_h[ry + 2][rx + k] + s_h[ry + 4][rx + k]) + 56u * s_h[ry + 3][rx + k];
+            packed |= ((acc + 32768u) >> 16) << (8 * k);
+        }
+        *reinterpret_cast<uint32_t*>(dst + (size_t)gy * L.pitch + gx) = packed;  // tail lands in row padding
+    }
+}
+
+void launch_blur(const Geometry& g, const BatchView& v, cudaStream_t stream) {
+    BlurTileMap tm;
+    int total = 0;
+    for (int l = 0; l < g.nlevels; l++) {
+        tm.tile_base[l] = total;
+        tm.tiles_x[l] = (g.lv[l].w + kBlurTW - 1) / kBlurTW;
+        total += tm.tiles_x[l] * ((g.lv[l].h + kBlurTH - 1) / kBlurTH);
+    }
+    tm.tile_base[g.nlevels] = total;
+    blur_kernel<<<dim3(total, v.B), dim3(32, 8), 0, stream>>>(g, v, tm);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dynamic-object decision (src/ORBextractor.cc:1101-1195). One warp per frame.
+//   count  = #T_M points whose truncated coordinates fall in Rect(int(xmin), int(ymin), int(xmax-xmin), int(ymax-ymin))
+//   layer1 = T_M not empty && count*10000 > area_box   (the reference tests after every point with an
+//            early break; the count is monotone, so this equals the test on the final count)
+//   layer2 = blur_flag[b]==1 && count>0
+// Dynamic boxes are recorded as the rectangle [(int)xmin,(int)xmax) x [(int)ymin,(int)ymax) that the
+// reference zero-fills in its 480x640 mask; area accumulates in box order (fp32).
+// ------------------------------------------------------------------------------------------------
+__global__ void classify_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v) {
+    const int frame = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x & 31;
+    if (frame >= v.B) return;
+    DynState* out = &v.dyn[frame];
+    const int nbox = v.nbox ? v.nbox[frame] : 0;
+    const int ntm = v.ntm ? v.ntm[frame] : 0;
+    const float* boxes = v.boxes + (size_t)frame * v.max_box * 4;
+    const float* tm = v.tm + (size_t)frame * v.max_tm * 2;
+    const int* blur = v.blur_flag + (size_t)frame * v.max_box;
+    float area = 0.f;
+    int ndyn = 0, bad = 0;
+    if (nbox > v.max_box || nbox > COEB_MAX_BOXES || ntm > v.max_tm) bad = 1;
+    for (int b = 0; b < nbox && !bad; b++) {
+        const float xmin = boxes[4 * b], ymin = boxes[4 * b + 1], xmax = boxes[4 * b + 2], ymax = boxes[4 * b + 3];
+        const int rx = (int)xmin, ry = (int)ymin, rw = (int)(xmax - xmin), rh = (int)(ymax - ymin);
+        if (rx < 0 || ry < 0 || rw < 0 || rh < 0 || rx + rw > g.w0 || ry + rh > g.h0 || (int)xmax > g.w0 || (int)ymax > g.h0) {
+            bad = 1;
+            break;
+        }
+        const float area_box = __fmul_rn(xmax - xmin, ymax - ymin);
+        int count = 0;
+        for (int t0 = 0; t0 < ntm; t0 += 32) {
+            const int t = t0 + lane;
+            bool in = false;
+            if (t < ntm) {
+                const int tx = (int)tm[2 * t], ty = (int)tm[2 * t + 1];
+                in = tx >= rx && tx < rx + rw && ty >= ry && ty < ry + rh;
+            }
+            count += __popc(__ballot_sync(0xffffffffu, in));
+        }
+        bool mark = ntm > 0 && (float)((unsigned long long)count * 10000ull) > area_box;
+        if (!mark && blur[b] == 1 && count > 0) mark = true;
+        if (mark) {
+            area = __fadd_rn(area, area_box);
+            if (lane == 0) {
+                out->rect[ndyn][0] = (int)xmin; out->rect[ndyn][1] = (int)ymin;
+                out->rect[ndyn][2] = (int)xmax; out->rect[ndyn][3] = (int)ymax;
+            }
+            ndyn++;
+        }
+    }
+    if (lane == 0) {
+        out->n_dynamic = bad ? 0 : ndyn;
+        out->area = area;
+        out->area_flag = (!bad && area > 200000.f) ? 1 : 0;
+        out->bad_box = bad;
+        v.status[frame] = bad ? COEB_ERR_BAD_BOX : COEB_OK;
+    }
+}
+
+void launch_classify(const Geometry& g, const BatchView& v, cudaStream_t stream) {
+    const int warps = 4;
+    classify_kernel<<<(v.B + warps - 1) / warps, warps * 32, 0, stream>>>(g, v);
+}
+
+}  // namespace coeb

@@ -1,0 +1,214 @@
+"""coeb_b200 -- thin ctypes binding of libcoeb_frontend.so (the C ABI in include/coeb_frontend.h).
+
+This is test/bench plumbing around the C boundary; the reference-facing host API is the C++ drop-in
+in include/ORBextractor.h / include/ORBmatcher.h. Nothing here computes: every call goes to the
+hand-written sm_100a kernels, and loading fails loudly if the library is missing. There is no CPU
+fallback and this package never imports the oracle.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PKG_ROOT = os.path.normpath(os.path.join(_HERE, "..", ".."))
+LIB_PATH = os.path.join(PKG_ROOT, "lib", "libcoeb_frontend.so")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+MAX_BOXES = 32
+OK, ERR_INVALID_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_CAPACITY, ERR_BAD_BOX, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
+
+
+class OrbParams(C.Structure):
+    _fields_ = [("nfeatures", C.c_int32), ("scale_factor", C.c_float), ("nlevels", C.c_int32),
+                ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32)]
+
+
+class DynInfo(C.Structure):
+    _fields_ = [("area_flag", C.c_int32), ("n_dynamic", C.c_int32), ("rect", (C.c_int32 * 4) * MAX_BOXES),
+                ("area", C.c_float)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("bf", C.c_float),
+                ("b", C.c_float), ("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float),
+                ("max_y", C.c_float)]
+
+
+class CoebError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("coeb status %d: %s" % (status, msg))
+        self.status = status
+
+
+_lib = None
+
+
+def lib():
+    """Loads the CUDA library; raises if it has not been built (no fallback of any kind)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("%s not built: run `make -C coeb-slam_b200` (or __graft_entry__.build())" % LIB_PATH)
+        _lib = C.CDLL(LIB_PATH)
+        _lib.coeb_last_error.restype = C.c_char_p
+        _lib.coeb_version.restype = C.c_char_p
+    return _lib
+
+
+def _check(st):
+    if st != 0:
+        raise CoebError(st, lib().coeb_last_error().decode())
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(int(a))  # raw device pointer
+
+
+def device_count():
+    return int(lib().coeb_device_count())
+
+
+def _c(a, dt):
+    return None if a is None else np.ascontiguousarray(a, dtype=dt)
+
+
+class Extractor:
+    """ORB_SLAM2::ORBextractor over the C ABI."""
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, device=0):
+        self.params = OrbParams(nfeatures, scale_factor, nlevels, ini_th, min_th)
+        self.nlevels = nlevels
+        self.nfeatures = nfeatures
+        h = C.c_void_p()
+        _check(lib().coeb_extractor_create(C.byref(self.params), int(device), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().coeb_extractor_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def default_cap(self):
+        return self.nfeatures + 4 * self.nlevels + 32
+
+    def set_stream(self, stream_ptr):
+        _check(lib().coeb_extractor_set_stream(self.h, C.c_void_p(int(stream_ptr) if stream_ptr else 0)))
+
+    def reserve(self, w, h, max_batch):
+        _check(lib().coeb_extractor_reserve(self.h, int(w), int(h), int(max_batch)))
+
+    def launches_per_call(self):
+        return int(lib().coeb_extractor_launches_per_call(self.h))
+
+    def tables(self):
+        n = self.nlevels
+        nl = C.c_int()
+        sc, isc, s2, is2 = (np.empty(n, np.float32) for _ in range(4))
+        per = np.empty(n, np.int32)
+        _check(lib().coeb_extractor_tables(self.h, C.byref(nl), _p(sc), _p(isc), _p(s2), _p(is2), _p(per)))
+        return dict(nlevels=nl.value, scale=sc, inv_scale=isc, sigma2=s2, inv_sigma2=is2, per_level=per)
+
+    def extract(self, gray, boxes=None, tm=None, blur_flag=None, cap=None):
+        """Single frame, host buffers (ORBextractor::operator())."""
+        gray = np.ascontiguousarray(gray, dtype=np.uint8)
+        h, w = gray.shape
+        boxes = _c(boxes if boxes is not None else np.zeros((0, 4)), np.float32).reshape(-1, 4)
+        tm = _c(tm if tm is not None else np.zeros((0, 2)), np.float32).reshape(-1, 2)
+        blur = _c(blur_flag if blur_flag is not None else np.zeros(len(boxes)), np.int32)
+        cap = cap or self.default_cap()
+        kps = np.empty(cap, KP_DTYPE)
+        desc = np.empty((cap, 32), np.uint8)
+        n = C.c_int(0)
+        _check(lib().coeb_extract(self.h, _p(gray), w, h, gray.strides[0], _p(boxes), len(boxes), _p(tm), len(tm),
+                                  _p(blur), len(blur), _p(kps), _p(desc), cap, C.byref(n)))
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    def extract_batch_host(self, gray, boxes=None, nbox=None, tm=None, ntm=None, blur=None, cap=None, out=None,
+                           check=True):
+        """gray [B,h,w] u8 (host). Returns (kps [B,cap], desc [B,cap,32], counts [B], status [B])."""
+        assert gray.dtype == np.uint8 and gray.ndim == 3 and gray.flags.c_contiguous
+        B, h, w = gray.shape
+        cap = cap or self.default_cap()
+        if out is None:
+            out = (np.empty((B, cap), KP_DTYPE), np.empty((B, cap, 32), np.uint8), np.empty(B, np.int32),
+                   np.empty(B, np.int32))
+        kps, desc, counts, status = out
+        max_box = boxes.shape[1] if boxes is not None else 0
+        max_tm = tm.shape[1] if tm is not None else 0
+        st = lib().coeb_extract_batch_host(self.h, B, _p(gray), w, h, w, C.c_size_t(w * h), _p(boxes), _p(nbox), max_box,
+                                           _p(tm), _p(ntm), max_tm, _p(blur), _p(kps), _p(desc), _p(counts), _p(status),
+                                           cap)
+        if check:
+            _check(st)
+        return kps, desc, counts, status
+
+    def extract_batch_device(self, B, d_gray, w, h, stride, frame_stride, d_boxes, d_nbox, max_box, d_tm, d_ntm, max_tm,
+                             d_blur, d_kps, d_desc, d_counts, d_status, cap):
+        """All pointers are raw device addresses (ints). Enqueues on the extractor's stream."""
+        _check(lib().coeb_extract_batch_device(self.h, int(B), _p(d_gray), int(w), int(h), int(stride),
+                                               C.c_size_t(frame_stride), _p(d_boxes), _p(d_nbox), int(max_box), _p(d_tm),
+                                               _p(d_ntm), int(max_tm), _p(d_blur), _p(d_kps), _p(d_desc), _p(d_counts),
+                                               _p(d_status), int(cap)))
+
+    def dyn_info(self, frame=0):
+        d = DynInfo()
+        _check(lib().coeb_extractor_dyn_info(self.h, frame, C.byref(d)))
+        rects = np.array([[d.rect[i][k] for k in range(4)] for i in range(min(d.n_dynamic, MAX_BOXES))],
+                         np.int32).reshape(-1, 4)
+        return dict(area_flag=bool(d.area_flag), n_dynamic=d.n_dynamic, rects=rects, area=d.area)
+
+    def level_image(self, level, frame=0, blurred=False):
+        w, h, pitch = C.c_int(), C.c_int(), C.c_int()
+        ptr = C.c_void_p()
+        _check(lib().coeb_pyramid_level(self.h, frame, level, int(blurred), C.byref(ptr), C.byref(w), C.byref(h),
+                                        C.byref(pitch)))
+        img = np.empty((h.value, w.value), np.uint8)
+        _check(lib().coeb_pyramid_level_copy(self.h, frame, level, int(blurred), _p(img)))
+        return img
+
+    def level_candidates(self, level, frame=0, cap=400000):
+        """FAST candidates (x, y, response) as an (n,3) int array sorted into the reference's vector order
+        is NOT guaranteed; callers sort."""
+        out = np.empty(cap, np.uint32)
+        n = C.c_int()
+        _check(lib().coeb_debug_candidates(self.h, frame, level, _p(out), cap, C.byref(n)))
+        p = out[:n.value]
+        return np.stack([p & 0xFFF, (p >> 12) & 0xFFF, p >> 24], axis=1).astype(np.int64)
+
+    def level_keys(self, level, frame=0, cap=20000):
+        out = np.empty((cap, 4), np.float32)
+        n = C.c_int()
+        _check(lib().coeb_debug_level_keys(self.h, frame, level, _p(out), cap, C.byref(n)))
+        return out[:n.value].copy()
+
+
+def host_alloc(nbytes):
+    p = C.c_void_p()
+    _check(lib().coeb_host_alloc(C.byref(p), C.c_size_t(nbytes)))
+    return p
+
+
+def host_free(p):
+    _check(lib().coeb_host_free(p))
+
+
+def pinned_array(shape, dtype):
+    """numpy array backed by cudaHostAlloc'ed (pinned) memory; keep the returned owner alive."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = host_alloc(max(n, 1))
+    buf = (C.c_char * max(n, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    return arr, p

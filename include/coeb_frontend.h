@@ -1,0 +1,186 @@
+/*
+ * coeb_frontend.h -- C ABI of the B200-native COEB-SLAM front end (libcoeb_frontend.so).
+ *
+ * Drop-in boundary for the reference's data-parallel hot path. Every entry point names the reference
+ * interface it replaces (paths relative to the COEB-SLAM tree). Plain pointers and sizes only; no
+ * C++, OpenCV or torch types. All functions return COEB_OK (0) or a negative coeb_status;
+ * coeb_last_error() gives the message for the calling thread. There is no CPU fallback: without an
+ * sm_100 device creation fails with COEB_ERR_NO_DEVICE.
+ *
+ * Threading: a coeb_extractor / coeb_matcher is owned by one thread at a time, like the reference's
+ * ORBextractor (non re-entrant: it mutates mvImagePyramid, include/ORBextractor.h:99). Use one
+ * handle per stream / per GPU. Handles are cheap to re-create (COEB's frame-loss logic does
+ * `new ORBextractor(nFeatures+500, ...)`, src/Tracking.cc:434-465): device arenas are pooled per device.
+ */
+#ifndef COEB_FRONTEND_H
+#define COEB_FRONTEND_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "coeb_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct coeb_extractor coeb_extractor;
+typedef struct coeb_frame coeb_frame;
+typedef struct coeb_matcher coeb_matcher;
+
+const char* coeb_last_error(void);
+const char* coeb_version(void);
+/* Number of usable sm_100 devices (0 if none). */
+int coeb_device_count(void);
+
+/* Pinned host memory for the host-buffer entry points (cudaHostAlloc / cudaFreeHost). */
+int coeb_host_alloc(void** ptr, size_t bytes);
+int coeb_host_free(void* ptr);
+
+/* ---------------------------------------------------------------------------------------------
+ * ORBextractor
+ * ------------------------------------------------------------------------------------------- */
+
+/* ORBextractor::ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)
+ * (include/ORBextractor.h:50-51, src/ORBextractor.cc:418-477). `device` is the CUDA ordinal. */
+int coeb_extractor_create(const coeb_orb_params* params, int device, coeb_extractor** out);
+void coeb_extractor_destroy(coeb_extractor* ex);
+
+/* Run on a caller-owned CUDA stream (cudaStream_t passed as void*); NULL restores the handle's own
+ * stream. The *_device entry point only enqueues work on it. */
+int coeb_extractor_set_stream(coeb_extractor* ex, void* cuda_stream);
+
+/* Pre-size the device arenas for `max_batch` frames of width x height so that later calls do not
+ * allocate (replaces the per-call pyramid reallocation of src/ORBextractor.cc:1351). */
+int coeb_extractor_reserve(coeb_extractor* ex, int width, int height, int max_batch);
+
+/* GetLevels / GetScaleFactor(s) / GetInverseScaleFactors / GetScaleSigmaSquares /
+ * GetInverseScaleSigmaSquares (include/ORBextractor.h:77-97) and mnFeaturesPerLevel.
+ * Any pointer may be NULL; arrays hold nlevels entries. */
+int coeb_extractor_tables(const coeb_extractor* ex, int* nlevels, float* scale, float* inv_scale, float* sigma2,
+                          float* inv_sigma2, int* features_per_level);
+
+/* ORBextractor::operator()(image, mask, img, imD, keypoints, descriptors, box, T_M, mask_result, blur_flag)
+ * (include/ORBextractor.h:73-75, src/ORBextractor.cc:1088-1342) for one 8-bit gray frame in HOST memory.
+ * `mask`, `img`, `imD`, `mask_result` of the reference are never read and have no counterpart here.
+ *   boxes_xyxy : nbox x 4 floats (xmin, ymin, xmax, ymax), person boxes from YOLO
+ *   tm_xy      : ntm x 2 floats, the moving points T_M (Frame::ProcessMovingObject)
+ *   blur_flag  : nblur ints (missing entries count as 0)
+ *   kps_out / desc_out : caller arrays of `cap` keypoints / cap x 32 bytes; *n_out = keypoints produced.
+ * nbox == 0 gives the classic 4-argument ORB-SLAM2 operator()(image, mask, keypoints, descriptors).
+ * Blocking. COEB_ERR_CAPACITY if cap is too small (*n_out still holds the required size). */
+int coeb_extract(coeb_extractor* ex, const uint8_t* gray, int width, int height, int stride, const float* boxes_xyxy,
+                 int nbox, const float* tm_xy, int ntm, const int* blur_flag, int nblur, coeb_keypoint* kps_out,
+                 uint8_t* desc_out, int cap, int* n_out);
+
+/* Batched form of the same call for B independent frames. Packed layouts:
+ *   gray [B] frames `frame_stride` bytes apart, rows `stride` bytes apart
+ *   boxes [B][max_box][4], nbox [B], tm [B][max_tm][2], ntm [B], blur_flag [B][max_box]
+ *   kps_out [B][cap], desc_out [B][cap][32], counts_out [B], status_out [B] (per-frame coeb_status)
+ * boxes/nbox/tm/ntm/blur_flag may all be NULL (no dynamic objects).
+ * _host: all pointers are host memory; copies in, runs, copies out, blocks until done.
+ * _device: all pointers are device memory on the extractor's device; enqueues on the stream and returns. */
+int coeb_extract_batch_host(coeb_extractor* ex, int B, const uint8_t* gray, int width, int height, int stride,
+                            size_t frame_stride, const float* boxes, const int* nbox, int max_box, const float* tm,
+                            const int* ntm, int max_tm, const int* blur_flag, coeb_keypoint* kps_out,
+                            uint8_t* desc_out, int* counts_out, int* status_out, int cap);
+int coeb_extract_batch_device(coeb_extractor* ex, int B, const uint8_t* gray, int width, int height, int stride,
+                              size_t frame_stride, const float* boxes, const int* nbox, int max_box, const float* tm,
+                              const int* ntm, int max_tm, const int* blur_flag, coeb_keypoint* kps_out,
+                              uint8_t* desc_out, int* counts_out, int* status_out, int cap);
+
+/* Kernel launches one coeb_extract_batch_* call enqueues (for benchmark accounting). */
+int coeb_extractor_launches_per_call(const coeb_extractor* ex);
+
+/* Dynamic-object decision of frame `frame` of the last call (area_flag, zero-filled mask rectangles;
+ * src/ORBextractor.cc:1101-1195). Blocking. */
+int coeb_extractor_dyn_info(coeb_extractor* ex, int frame, coeb_dyn_info* out);
+
+/* ORBextractor::mvImagePyramid[level] (include/ORBextractor.h:99) of frame `frame` of the last call:
+ * device pointer + geometry, or a tight host copy. blurred != 0 selects the 7x7 sigma=2 blurred level
+ * used for descriptors. The 19-px border of the reference's buffers is never read on this path and
+ * is not materialised. */
+int coeb_pyramid_level(coeb_extractor* ex, int frame, int level, int blurred, const uint8_t** dev_ptr, int* width,
+                       int* height, int* pitch);
+int coeb_pyramid_level_copy(coeb_extractor* ex, int frame, int level, int blurred, uint8_t* host_dst);
+
+/* Stage outputs of the last call for parity tests (blocking host copies).
+ * candidates: FAST keypoints handed to the octree (vToDistributeKeys, src/ORBextractor.cc:846) as
+ *   packed uint32 x | y<<12 | response<<24, minBorder-relative, in unspecified order.
+ * level keys: per-level keypoints after octree, orientation and culling, as float4 {x, y, response, angle}
+ *   in level coordinates, reference list order. */
+int coeb_debug_candidates(coeb_extractor* ex, int frame, int level, uint32_t* host_out, int cap, int* n_out);
+int coeb_debug_level_keys(coeb_extractor* ex, int frame, int level, float* host_out, int cap, int* n_out);
+
+/* ---------------------------------------------------------------------------------------------
+ * Frame keypoint grid + ORBmatcher (declared here, implemented in match.cu)
+ * ------------------------------------------------------------------------------------------- */
+
+/* Matcher context: device scratch + stream for one GPU. */
+int coeb_matcher_create(int device, coeb_matcher** out);
+void coeb_matcher_destroy(coeb_matcher* m);
+int coeb_matcher_set_stream(coeb_matcher* m, void* cuda_stream);
+
+/* The part of ORB_SLAM2::Frame the matchers read, resident on the device: mvKeysUn, mDescriptors,
+ * mvuRight (NULL: all -1), image bounds and mvScaleFactors, plus the 64x48 grid of
+ * Frame::AssignFeaturesToGrid / PosInGrid (src/Frame.cc:396-411, 558-568). Host pointers. */
+int coeb_frame_create(coeb_matcher* m, const coeb_keypoint* kps_un, const uint8_t* desc, int n, const float* uright,
+                      const coeb_camera* cam, const float* scale_factors, int nlevels, coeb_frame** out);
+void coeb_frame_destroy(coeb_frame* f);
+
+/* Frame::GetFeaturesInArea(x, y, r, minLevel, maxLevel) (src/Frame.cc:503-556): indices in the
+ * reference's traversal order (ix outer, iy inner, insertion order). */
+int coeb_frame_features_in_area(coeb_frame* f, float x, float y, float r, int min_level, int max_level, int* idx_out,
+                                int cap, int* n_out);
+
+/* ORBmatcher::DescriptorDistance for n pairs (src/ORBmatcher.cc:1648-1664). Host pointers, n x 32 bytes each. */
+int coeb_hamming256_batch(coeb_matcher* m, const uint8_t* a, const uint8_t* b, int n, int* dist_out);
+
+/* ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>&, th) (src/ORBmatcher.cc:45-129), with the
+ * MapPoint fields flattened (set by Frame::isInFrustum, src/Frame.cc:492-498):
+ *   track_in_view, bad, has_obs (Observations()>0): n bytes each; proj_x, proj_y, proj_xr, view_cos: n floats;
+ *   level: n ints (mnTrackScaleLevel); desc: n x 32 bytes (GetDescriptor()).
+ * kp_match (in/out, F.n ints) encodes F.mvpMapPoints: -1 empty, -2 holds a MapPoint with observations,
+ * -3 holds one without; on return >= 0 is the index of the map point assigned by this call.
+ * nnratio is the matcher's mfNNratio. *nmatches_out = return value of the reference function. */
+int coeb_match_projection(coeb_matcher* m, coeb_frame* F, int n, const uint8_t* track_in_view, const uint8_t* bad,
+                          const uint8_t* has_obs, const float* proj_x, const float* proj_y, const float* proj_xr,
+                          const int* level, const float* view_cos, const uint8_t* desc, float th, float nnratio,
+                          int* kp_match, int* nmatches_out);
+
+/* ORBmatcher::SearchByProjection(Frame& cur, const Frame& last, th, bMono) (src/ORBmatcher.cc:1329-1471).
+ * Per last-frame keypoint i: valid (mvpMapPoints[i] && !mvbOutlier[i]), has_obs, xyz (GetWorldPos),
+ * octave (LastFrame.mvKeys[i].octave), angle (LastFrame.mvKeysUn[i].angle), desc (pMP->GetDescriptor()).
+ * Tcw_cur / Tcw_last: 3x4 row-major [R|t]. check_ori is the matcher's mbCheckOrientation. */
+int coeb_match_lastframe(coeb_matcher* m, coeb_frame* cur, int n, const uint8_t* valid, const uint8_t* has_obs,
+                         const float* xyz, const int* octave, const float* angle, const uint8_t* desc,
+                         const float* Tcw_cur, const float* Tcw_last, float th, int mono, int check_ori,
+                         int* kp_match, int* nmatches_out);
+
+/* ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize)
+ * (src/ORBmatcher.cc:405-520). prev_matched: F1.n x 2 floats in/out; matches12: F1.n ints out. */
+int coeb_match_init(coeb_matcher* m, coeb_frame* f1, coeb_frame* f2, float* prev_matched, int* matches12,
+                    int window_size, float nnratio, int check_ori, int* nmatches_out);
+
+/* Frame::ComputeStereoMatches (src/Frame.cc:644-818). Keypoints/descriptors are host arrays; the two
+ * pyramids are taken from the extractors that produced them (their last call, frame 0).
+ * uright_out / depth_out: N floats (mvuRight, mvDepth; -1 = none). */
+int coeb_stereo_match(coeb_matcher* m, coeb_extractor* left, coeb_extractor* right, int N,
+                      const coeb_keypoint* keys_left, const uint8_t* desc_left, int Nr,
+                      const coeb_keypoint* keys_right, const uint8_t* desc_right, float bf, float b,
+                      float* uright_out, float* depth_out, int* nmatched_out);
+
+/* Brute-force k=2 Hamming search with ratio test over a whole train set (BASELINE.json config 5;
+ * semantics of the SearchByBoW inner loop, src/ORBmatcher.cc:201-231: strict '<', first index wins
+ * ties, accept if best <= TH_LOW and best < nnratio * second). Host pointers.
+ * best_idx: nq ints (-1 if rejected); d1/d2: best and second-best distances (may be NULL). */
+int coeb_knn2(coeb_matcher* m, const uint8_t* query, int nq, const uint8_t* train, int nt, float nnratio,
+              int* best_idx, int* d1, int* d2, int* naccepted_out);
+/* Same with device-resident descriptors/outputs, enqueued on the matcher's stream. */
+int coeb_knn2_device(coeb_matcher* m, const uint8_t* d_query, int nq, const uint8_t* d_train, int nt, float nnratio,
+                     int* d_best_idx, int* d_d1, int* d_d2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COEB_FRONTEND_H */
