@@ -1,0 +1,162 @@
+"""GPU parity: the CUDA extractor (through the C ABI) against the CPU oracle, stage by stage and on the
+final keypoints/descriptors. Bit-exact for everything integer; angles must be bit-identical floats
+(same fp32 polynomial, no FMA), which is stricter than the 1e-3 rad the north star allows."""
+import numpy as np
+import pytest
+
+import orc
+from coeb_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import coeb_b200
+    if coeb_b200.device_count() < 1:
+        pytest.fail("no sm_100 device visible: GPU tests need the CUDA library to run for real")
+    return coeb_b200
+
+
+def _inputs(seed, w=640, h=480, dynamic=True):
+    gray = synth.make_frame(seed, w, h)
+    if dynamic:
+        boxes, tm, blur = synth.make_dynamic(seed, w, h, force_area=(seed % 8 == 3))
+    else:
+        boxes, tm, blur = np.zeros((0, 4), np.float32), np.zeros((0, 2), np.float32), np.zeros(0, np.int32)
+    return gray, boxes, tm, blur
+
+
+def compare_frame(gpu_ex, cpu_ex, gray, boxes, tm, blur, stages=True, frame=0, kps=None, desc=None):
+    kb, db = cpu_ex.extract(gray, boxes, tm, blur)
+    if kps is None:
+        kps, desc = gpu_ex.extract(gray, boxes, tm, blur)
+    if stages:
+        info_c, info_g = cpu_ex.dyn_info(), gpu_ex.dyn_info(frame)
+        assert info_c["area_flag"] == info_g["area_flag"]
+        assert np.array_equal(info_c["rects"], info_g["rects"])
+        assert info_c["area"] == info_g["area"]
+        for l in range(cpu_ex.nlevels):
+            assert np.array_equal(cpu_ex.level_image(l), gpu_ex.level_image(l, frame)), "pyramid level %d" % l
+            cb = cpu_ex.level_image(l, blurred=True)
+            if cb is not None:
+                assert np.array_equal(cb, gpu_ex.level_image(l, frame, blurred=True)), "blurred level %d" % l
+            cc = cpu_ex.level_candidates(l).astype(np.int64)
+            gc = gpu_ex.level_candidates(l, frame)
+            cs = cc[np.lexsort((cc[:, 0], cc[:, 1]))] if len(cc) else cc.reshape(0, 3)
+            gs = gc[np.lexsort((gc[:, 0], gc[:, 1]))] if len(gc) else gc.reshape(0, 3)
+            assert len(cs) == len(gs), "level %d: %d vs %d FAST candidates" % (l, len(cs), len(gs))
+            assert np.array_equal(cs, gs), "FAST candidate set, level %d" % l
+            ck = cpu_ex.level_keypoints(l)
+            gk = gpu_ex.level_keys(l, frame)
+            assert len(ck) == len(gk), "level %d: %d vs %d selected keys" % (l, len(ck), len(gk))
+            assert np.array_equal(ck["x"], gk[:, 0]) and np.array_equal(ck["y"], gk[:, 1]), \
+                "octree selection/order, level %d" % l
+            assert np.array_equal(ck["response"], gk[:, 2])
+            assert np.array_equal(ck["angle"], gk[:, 3]), "IC angle, level %d (max diff %g deg)" % (
+                l, np.abs(ck["angle"] - gk[:, 3]).max())
+    assert len(kb) == len(kps)
+    for f in ("x", "y", "size", "angle", "response", "octave", "class_id"):
+        assert np.array_equal(kb[f], kps[f]), f
+    bits = np.unpackbits(np.bitwise_xor(db, desc)).sum()
+    assert bits == 0, "descriptor bit agreement %.6f" % (1 - bits / max(db.size * 8, 1))
+    return len(kb)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 11])
+def test_single_frame_640x480_bit_exact(gpu, seed):
+    gray, boxes, tm, blur = _inputs(seed)
+    n = compare_frame(gpu.Extractor(), orc.Extractor(), gray, boxes, tm, blur)
+    assert n > 300
+
+
+def test_tables_match_oracle(gpu):
+    for nf in (1000, 1500, 2000, 4000):
+        g, c = gpu.Extractor(nfeatures=nf).tables(), orc.Extractor(nfeatures=nf).tables()
+        for k in ("scale", "inv_scale", "sigma2", "inv_sigma2", "per_level"):
+            assert np.array_equal(g[k], c[k]), (nf, k)
+
+
+def test_no_boxes_equals_classic_operator(gpu):
+    gray = synth.make_frame(21)
+    compare_frame(gpu.Extractor(), orc.Extractor(), gray, None, None, None)
+
+
+def test_blur_flag_layer_and_short_blur_array(gpu):
+    # layer 2: few T_M points inside a box, blur flag set -> dynamic; blur_flag shorter than the box list
+    gray = synth.make_frame(5)
+    boxes = np.array([[100, 60, 300, 400], [350, 100, 500, 380]], np.float32)
+    tm = np.array([[150.5, 100.2], [400.7, 200.9], [20.0, 20.0]], np.float32)
+    g, c = gpu.Extractor(), orc.Extractor()
+    compare_frame(g, c, gray, boxes, tm, np.array([1], np.int32))
+    assert g.dyn_info()["n_dynamic"] == 1
+    compare_frame(g, c, gray, boxes, tm, np.array([1, 1], np.int32))
+    assert g.dyn_info()["n_dynamic"] == 2
+    compare_frame(g, c, gray, boxes, tm, np.array([0, 0], np.int32))
+    assert g.dyn_info()["n_dynamic"] == 0
+
+
+def test_nfeatures_bump_1500_2000(gpu):
+    # COEB's frame-loss logic re-creates the extractor with nFeatures += 500 (src/Tracking.cc:434-465)
+    gray, boxes, tm, blur = _inputs(6)
+    for nf in (1500, 2000):
+        compare_frame(gpu.Extractor(nfeatures=nf), orc.Extractor(nfeatures=nf), gray, boxes, tm, blur)
+
+
+def test_flat_and_noise_images(gpu):
+    g, c = gpu.Extractor(), orc.Extractor()
+    flat = np.full((480, 640), 127, np.uint8)
+    k, d = g.extract(flat)
+    assert len(k) == 0 and len(c.extract(flat)[0]) == 0
+    rng = np.random.default_rng(3)
+    noise = rng.integers(0, 256, size=(480, 640), dtype=np.uint8)
+    compare_frame(g, c, noise, None, None, None)
+
+
+def test_clustered_features_deep_octree(gpu):
+    # all texture in one corner: deep quadtree, many single-key nodes, careful phase with ties
+    rng = np.random.default_rng(8)
+    img = np.full((480, 640), 90, np.uint8)
+    img[40:160, 60:220] = rng.integers(0, 256, size=(120, 160), dtype=np.uint8)
+    img[300:330, 500:560] = synth.make_frame(9)[300:330, 500:560]
+    compare_frame(gpu.Extractor(), orc.Extractor(), img, None, None, None)
+
+
+def test_bad_box_is_rejected(gpu):
+    gray = synth.make_frame(1)
+    g = gpu.Extractor()
+    with pytest.raises(gpu.CoebError) as e:
+        g.extract(gray, np.array([[600, 400, 700, 500]], np.float32), np.array([[610., 410.]], np.float32), [1])
+    assert e.value.status == gpu.ERR_BAD_BOX
+
+
+@pytest.mark.parametrize("w,h,nf", [(1241, 376, 2000), (1920, 1080, 4000), (752, 480, 1200), (333, 257, 500)])
+def test_other_resolutions(gpu, w, h, nf):
+    gray = synth.make_frame(31, w, h)
+    compare_frame(gpu.Extractor(nfeatures=nf), orc.Extractor(nfeatures=nf), gray, None, None, None)
+
+
+def test_batch_host_matches_per_frame_oracle(gpu):
+    B = 12
+    batch = synth.make_batch(B, base_seed=40)
+    g = gpu.Extractor()
+    kps, desc, counts, status = g.extract_batch_host(batch["gray"], batch["boxes"], batch["nbox"], batch["tm"],
+                                                     batch["ntm"], batch["blur"])
+    assert (status == 0).all()
+    c = orc.Extractor()
+    flags = 0
+    for i in range(B):
+        nb, nt = batch["nbox"][i], batch["ntm"][i]
+        compare_frame(g, c, batch["gray"][i], batch["boxes"][i, :nb], batch["tm"][i, :nt], batch["blur"][i, :nb],
+                      stages=True, frame=i, kps=kps[i, :counts[i]], desc=desc[i, :counts[i]])
+        flags += c.dyn_info()["area_flag"]
+    assert flags >= 1  # the area_flag path (30/10 thresholds, x0.7 quota, pre-octree cull) was exercised
+
+
+def test_repeat_call_is_deterministic(gpu):
+    gray, boxes, tm, blur = _inputs(2)
+    g = gpu.Extractor()
+    k1, d1 = g.extract(gray, boxes, tm, blur)
+    for _ in range(3):
+        k2, d2 = g.extract(gray, boxes, tm, blur)
+        assert k1.tobytes() == k2.tobytes() and d1.tobytes() == d2.tobytes()
