@@ -1,0 +1,382 @@
+#!/usr/bin/env python3
+"""bench.py -- frames/s of ORB extract + dynamic-keypoint filter on B200 (BASELINE.json metric).
+
+Workload (BASELINE.json configs[1]): 256 synthetic 640x480 frames per GPU, nFeatures=1000, 8 levels x1.2,
+FAST 20/7 (30/10 on the area_flag path), YOLO person boxes + moving points injected per frame; frames are
+sharded across ranks with no collective (weak scaling). A "step" is one pass of the hot path over the
+rank's 256-frame shard.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]           # CUDA arm (default N=1)
+  python bench.py --impl reference ...                           # the reference's CPU algorithm (oracle port)
+
+Prints ONE JSON line on rank 0. torch is used only for device buffers, the timing events on the launch
+stream and the (gloo) barrier / max-over-ranks; the hot path is libcoeb_frontend.so.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [os.path.join(ROOT, "coeb-slam_b200", "python")]
+
+import numpy as np  # noqa: E402
+
+W, H, NFEAT, NLEVELS = 640, 480, 1000, 8
+FRAMES_PER_GPU = 256
+LEVELS = [(640, 480), (533, 400), (444, 333), (370, 278), (309, 231), (257, 193), (214, 161), (179, 134)]
+SIGMA_P = sum(w * h for w, h in LEVELS)
+
+
+def stage_bytes(n_kp, n_cand):
+    """ALGORITHMIC bytes per frame of each stage."""
+    p0, p7 = LEVELS[0][0] * LEVELS[0][1], LEVELS[-1][0] * LEVELS[-1][1]
+    return {
+        "classify": 0.0,
+        "pyramid": float((SIGMA_P - p7) + (SIGMA_P - p0)),      # read resize sources + write L1..L7
+        "blur": float(2 * SIGMA_P),                               # read + write every level
+        "fast": float(SIGMA_P + 4 * n_cand),                      # read every level + candidate words out
+        "select": float(n_kp * 749 + 4 * n_cand + 16 * n_kp),     # IC patches + candidates in + level keys out
+        "describe": float(n_kp * (512 + 60 + 16)),                # pattern samples + 28 B kp + 32 B desc (+ keys in)
+    }
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled while the timed region runs."""
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile(prefix="clocks", suffix=".csv", delete=False)
+            self.path = f.name
+            q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        try:
+            rows = [r.split(",") for r in open(self.path).read().strip().splitlines() if r.strip()]
+            sm = [float(r[0]) for r in rows]
+            out["sm_mhz"] = float(np.median(sm)) if sm else None
+            out["sm_max_mhz"] = float(rows[0][1]) if rows else None
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            out["reasons"] = [n for i, n in enumerate(names) if any("Active" in r[3 + i] and "Not" not in r[3 + i] for r in rows)]
+            out["samples"] = len(rows)
+        except Exception:
+            pass
+        finally:
+            try:
+                os.unlink(self.path)
+            except Exception:
+                pass
+        return out
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist_mod.init_process_group(backend="gloo", rank=rank, world_size=world)
+        dist = dist_mod
+    return rank, world, local, dist
+
+
+def reduce_max(dist, value):
+    if dist is None:
+        return value
+    import torch
+    t = torch.tensor([value], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def reduce_sum(dist, value):
+    if dist is None:
+        return value
+    import torch
+    t = torch.tensor([value], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def base_config(n_gpus):
+    return {"workload": "configs[1]: batched ORB extract + dynamic filter, %d synthetic 640x480 frames per GPU, "
+                        "nFeatures=1000, 8 levels x1.2, FAST 20/7, YOLO boxes + T_M per frame" % FRAMES_PER_GPU,
+            "frames_per_gpu": FRAMES_PER_GPU, "width": W, "height": H, "nfeatures": NFEAT, "nlevels": NLEVELS,
+            "sharding": "independent frame shards, no collective", "n_gpus": n_gpus}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU algorithm (oracle port; the reference itself cannot be built
+# here: no OpenCV C++ headers, DBoW2/g2o absent -- DESIGN.md section 7)
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orc
+    from coeb_b200 import synth
+    threads = orc.hardware_threads()
+    sample = int(args.ref_frames)
+    batch = synth.make_batch(sample, base_seed=0, w=W, h=H, unique=min(sample, 32))
+    params = orc.OrbParams(NFEAT, 1.2, NLEVELS, 20, 7)
+
+    def step():
+        secs, counts, _, _ = orc.extract_batch_mt(params, batch["gray"], batch["boxes"], batch["nbox"], batch["tm"],
+                                                  batch["ntm"], batch["blur"], threads)
+        return secs, counts
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t = 0.0
+    for _ in range(args.steps):
+        s, counts = step()
+        t += s
+    fps = sample * args.steps / t
+    line = {"impl": "reference", "metric": "frames/s ORB extract+dyn-filter (640x480,1k kps)", "value": fps, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": base_config(args.gpus),
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                             "sample": "%d frames of the same workload per step, one oracle extractor per thread" % sample},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "mean_keypoints": float(np.mean(counts))}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# CUDA arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import coeb_b200 as cb
+    from coeb_b200 import synth
+
+    rank, world, local, dist = dist_setup(args.gpus)
+    if not torch.cuda.is_available() or cb.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; the CUDA arm has no CPU fallback (use --impl reference for the CPU arm)")
+    dev = local % torch.cuda.device_count()
+    torch.cuda.set_device(dev)
+    B = FRAMES_PER_GPU
+    # seeds 0..255 are the frame ids within a shard, the rank is added x1000
+    batch = synth.make_batch(B, base_seed=rank * 1000, w=W, h=H, unique=args.unique)
+    ex = cb.Extractor(NFEAT, 1.2, NLEVELS, 20, 7, device=dev)
+    cap = ex.default_cap()
+    ex.reserve(W, H, B)
+    stream = torch.cuda.current_stream(dev)
+    ex.set_stream(stream.cuda_stream)
+
+    def to_dev(a):
+        return torch.from_numpy(a).to("cuda:%d" % dev)
+    d_gray, d_boxes, d_nbox = to_dev(batch["gray"]), to_dev(batch["boxes"]), to_dev(batch["nbox"])
+    d_tm, d_ntm, d_blur = to_dev(batch["tm"]), to_dev(batch["ntm"]), to_dev(batch["blur"])
+    d_kps = torch.empty((B, cap, 28), dtype=torch.uint8, device=d_gray.device)
+    d_desc = torch.empty((B, cap, 32), dtype=torch.uint8, device=d_gray.device)
+    d_counts = torch.zeros(B, dtype=torch.int32, device=d_gray.device)
+    d_status = torch.zeros(B, dtype=torch.int32, device=d_gray.device)
+
+    def step_device():
+        ex.extract_batch_device(B, d_gray.data_ptr(), W, H, W, W * H, d_boxes.data_ptr(), d_nbox.data_ptr(), synth.MAX_BOX,
+                                d_tm.data_ptr(), d_ntm.data_ptr(), synth.MAX_TM, d_blur.data_ptr(), d_kps.data_ptr(),
+                                d_desc.data_ptr(), d_counts.data_ptr(), d_status.data_ptr(), cap)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value") + per-stage times for the roofline ------------------
+    ex.set_profiling(True)
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(dev)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage_acc = {k: 0.0 for k in ex.STAGES}
+    stage_events = []
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+        if args.stage_sync:  # read the stage events of this step (blocks on the step's end; off by default)
+            for k, v in ex.stage_ms().items():
+                stage_acc[k] += v
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    counts = d_counts.cpu().numpy()
+    status = d_status.cpu().numpy()
+    assert (status == 0).all(), "device reported per-frame failures: %s" % status[status != 0][:8]
+    # stage breakdown: a second, identical pass with a sync per step (not part of `value`)
+    if not args.stage_sync:
+        for _ in range(args.steps):
+            step_device()
+            for k, v in ex.stage_ms().items():
+                stage_acc[k] += v
+    stage_ms = {k: v / args.steps for k, v in stage_acc.items()}
+    ex.set_profiling(False)
+    ms_total = reduce_max(dist, ms_total)
+    frames_total = reduce_sum(dist, float(B * args.steps))
+    value = frames_total / (ms_total * 1e-3)
+
+    # ---- end to end through the host-buffer C ABI call (pinned host memory in, host results out) ----
+    pin = {}
+    owners = []
+    for k in ("gray", "boxes", "nbox", "tm", "ntm", "blur"):
+        arr, own = cb.pinned_array(batch[k].shape, batch[k].dtype)
+        arr[...] = batch[k]
+        pin[k] = arr
+        owners.append(own)
+    o_kps, p1 = cb.pinned_array((B, cap), cb.KP_DTYPE)
+    o_desc, p2 = cb.pinned_array((B, cap, 32), np.uint8)
+    o_cnt, p3 = cb.pinned_array((B,), np.int32)
+    o_st, p4 = cb.pinned_array((B,), np.int32)
+    owners += [p1, p2, p3, p4]
+
+    def step_host():
+        ex.extract_batch_host(pin["gray"], pin["boxes"], pin["nbox"], pin["tm"], pin["ntm"], pin["blur"], cap=cap,
+                              out=(o_kps, o_desc, o_cnt, o_st))
+    for _ in range(max(1, min(args.warmup, 3))):
+        step_host()
+    barrier()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    t0 = time.perf_counter()
+    h0.record(stream)
+    for _ in range(e2e_steps):
+        step_host()
+    h1.record(stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    e2e_ms = reduce_max(dist, h0.elapsed_time(h1))  # device time between the bracketing events, max over ranks
+    e2e_wall_ms = reduce_max(dist, wall * 1e3)
+    e2e_frames = reduce_sum(dist, float(B * e2e_steps))
+    assert np.array_equal(o_cnt, counts), "host-path and device-path keypoint counts differ"
+    h2d = sum(int(pin[k].nbytes) for k in pin)
+    d2h = int(o_kps.nbytes + o_desc.nbytes + o_cnt.nbytes + o_st.nbytes)
+
+    # ---- single-frame latency (the tracking thread consumes one frame at a time) -------------------
+    lat = None
+    if rank == 0:
+        ex1 = cb.Extractor(NFEAT, 1.2, NLEVELS, 20, 7, device=dev)
+        f = 0
+        nb, nt = int(batch["nbox"][f]), int(batch["ntm"][f])
+        args1 = (batch["gray"][f], batch["boxes"][f, :nb], batch["tm"][f, :nt], batch["blur"][f, :nb])
+        for _ in range(5):
+            ex1.extract(*args1)
+        ts = []
+        for i in range(50):
+            f = i % 16
+            nb, nt = int(batch["nbox"][f]), int(batch["ntm"][f])
+            a = (batch["gray"][f], batch["boxes"][f, :nb], batch["tm"][f, :nt], batch["blur"][f, :nb])
+            t = time.perf_counter()
+            ex1.extract(*a)
+            ts.append(time.perf_counter() - t)
+        lat = {"extract_filter_us_median": 1e6 * float(np.median(ts)), "extract_filter_us_p90": 1e6 * float(np.percentile(ts, 90)),
+               "note": "host buffers in, host results out, one 640x480 frame per call (wall clock around the blocking C call)"}
+        ex1.close()
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) --------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import orc
+        threads = orc.hardware_threads()
+        sample = int(args.cpu_frames)
+        params = orc.OrbParams(NFEAT, 1.2, NLEVELS, 20, 7)
+        sub = {k: np.ascontiguousarray(batch[k][:sample]) for k in batch}
+        secs, ccounts, ckps, cdesc = orc.extract_batch_mt(params, sub["gray"], sub["boxes"], sub["nbox"], sub["tm"], sub["ntm"],
+                                                          sub["blur"], threads, cap=cap, want_outputs=True)
+        # the CPU sample doubles as a parity check of the timed GPU run
+        same = all(ccounts[i] == o_cnt[i] and ckps[i, :ccounts[i]].tobytes() == o_kps[i, :o_cnt[i]].tobytes()
+                   and cdesc[i, :ccounts[i]].tobytes() == o_desc[i, :o_cnt[i]].tobytes() for i in range(sample))
+        cpu = {"value": sample / secs, "unit": "frames/s", "cores": threads, "kind": "port",
+               "sample": "first %d frames of the rank-0 shard, one oracle extractor per thread, %d threads" % (sample, threads),
+               "bit_exact_vs_gpu": bool(same)}
+
+    if rank != 0:
+        return 0
+    n_kp = float(np.mean(counts))
+    n_cand = float(args.cand_estimate)
+    sb = stage_bytes(n_kp, n_cand)
+    dom = max(stage_ms, key=lambda k: stage_ms[k])
+    peak, peak_kind = measured_peak_gbs()
+    achieved = sb[dom] * B / (stage_ms[dom] * 1e-3) / 1e9
+    pipeline_bytes = 6049674.0
+    line = {
+        "metric": "frames/s ORB extract+dyn-filter (640x480,1k kps)", "value": value, "unit": "frames/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": dict(base_config(world), l2="inputs + pyramid arenas (~0.6 GB per shard) exceed the 126 MB L2; no explicit flush",
+                       mean_keypoints=n_kp),
+        "e2e": {"value": e2e_frames / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "wall_frames_per_s": e2e_frames / (e2e_wall_ms * 1e-3)},
+        "gpu_launches": args.steps * ex.launches_per_call(),
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None,
+                     "algorithmic_bytes_per_launch": sb[dom] * B,
+                     "stage_ms": stage_ms,
+                     "pipeline": {"bytes_per_frame": pipeline_bytes, "achieved_gbs": pipeline_bytes * value / world / 1e9,
+                                  "frac": pipeline_bytes * value / world / 1e9 / peak}},
+        "cpu_baseline": cpu, "clocks": clocks, "latency": lat,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--unique", type=int, default=64, help="distinct generated images per shard (the rest are shifted copies)")
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--cpu-frames", type=int, default=128, help="frames of the shard timed on the host cores (CPU baseline)")
+    ap.add_argument("--ref-frames", type=int, default=64, help="--impl reference: frames per step")
+    ap.add_argument("--cand-estimate", type=float, default=16000.0, help="FAST candidates per frame used for algorithmic bytes")
+    ap.add_argument("--stage-sync", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

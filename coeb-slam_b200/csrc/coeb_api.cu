@@ -77,6 +77,9 @@ struct coeb_extractor {
     coeb_keypoint* d_out_kps = nullptr; uint8_t* d_out_desc = nullptr; int *d_out_count = nullptr, *d_out_status = nullptr;
     size_t out_cap_elems = 0; int out_cap_B = 0;
     BatchView last_view{};
+    // optional per-stage CUDA events (benchmark accounting)
+    bool profiling = false;
+    cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -268,12 +271,20 @@ int ensure_buf(T** p, size_t* cap, size_t n) {
 
 int enqueue(coeb_extractor* ex, const BatchView& v) {
     const Geometry& g = ex->geom;
+    const bool prof = ex->profiling;
+    if (prof) cudaEventRecord(ex->ev[0], ex->stream);
     launch_classify(g, v, ex->stream);
+    if (prof) cudaEventRecord(ex->ev[1], ex->stream);
     launch_pyramid(g, v, ex->stream);
+    if (prof) cudaEventRecord(ex->ev[2], ex->stream);
     launch_blur(g, v, ex->stream);
+    if (prof) cudaEventRecord(ex->ev[3], ex->stream);
     launch_fast(g, v, ex->stream);
+    if (prof) cudaEventRecord(ex->ev[4], ex->stream);
     launch_select(g, v, ex->stream);
+    if (prof) cudaEventRecord(ex->ev[5], ex->stream);
     launch_describe(g, v, ex->stream);
+    if (prof) cudaEventRecord(ex->ev[6], ex->stream);
     CUDA_TRY(cudaGetLastError());
     ex->last_view = v;
     ex->last_B = v.B;
@@ -344,6 +355,7 @@ void coeb_extractor_destroy(coeb_extractor* ex) {
     cudaFree(ex->d_tabs);
     cudaFree(ex->d_in_gray); cudaFree(ex->d_in_boxes); cudaFree(ex->d_in_tm); cudaFree(ex->d_in_nbox); cudaFree(ex->d_in_ntm);
     cudaFree(ex->d_in_blur); cudaFree(ex->d_out_kps); cudaFree(ex->d_out_desc); cudaFree(ex->d_out_count); cudaFree(ex->d_out_status);
+    for (int i = 0; i < 7; i++) if (ex->ev[i]) cudaEventDestroy(ex->ev[i]);
     cudaStreamDestroy(ex->own_stream);
     delete ex;
 }
@@ -381,6 +393,23 @@ int coeb_extractor_launches_per_call(const coeb_extractor* ex) {
     if (!ex) return 0;
     // classify + (nlevels-1) resizes + blur + zero-counts + FAST + select + describe
     return 1 + (ex->params.nlevels - 1) + 1 + 2 + 1 + 1;
+}
+
+int coeb_extractor_set_profiling(coeb_extractor* ex, int on) {
+    if (!ex) return fail(COEB_ERR_INVALID_ARG, "null extractor");
+    CUDA_TRY(cudaSetDevice(ex->device));
+    if (on && !ex->ev[0])
+        for (int i = 0; i < 7; i++) CUDA_TRY(cudaEventCreate(&ex->ev[i]));
+    ex->profiling = on != 0;
+    return COEB_OK;
+}
+
+int coeb_extractor_stage_ms(coeb_extractor* ex, float* ms6) {
+    if (!ex || !ms6 || !ex->ev[0]) return fail(COEB_ERR_INVALID_ARG, "profiling not enabled");
+    CUDA_TRY(cudaSetDevice(ex->device));
+    CUDA_TRY(cudaEventSynchronize(ex->ev[6]));
+    for (int i = 0; i < 6; i++) CUDA_TRY(cudaEventElapsedTime(&ms6[i], ex->ev[i], ex->ev[i + 1]));
+    return COEB_OK;
 }
 
 int coeb_extract_batch_device(coeb_extractor* ex, int B, const uint8_t* gray, int width, int height, int stride,

@@ -112,6 +112,16 @@ class Extractor:
     def launches_per_call(self):
         return int(lib().coeb_extractor_launches_per_call(self.h))
 
+    STAGES = ("classify", "pyramid", "blur", "fast", "select", "describe")
+
+    def set_profiling(self, on=True):
+        _check(lib().coeb_extractor_set_profiling(self.h, int(bool(on))))
+
+    def stage_ms(self):
+        ms = (C.c_float * 6)()
+        _check(lib().coeb_extractor_stage_ms(self.h, ms))
+        return {k: float(ms[i]) for i, k in enumerate(self.STAGES)}
+
     def tables(self):
         n = self.nlevels
         nl = C.c_int()

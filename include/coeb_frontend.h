@@ -92,6 +92,12 @@ int coeb_extract_batch_device(coeb_extractor* ex, int B, const uint8_t* gray, in
 /* Kernel launches one coeb_extract_batch_* call enqueues (for benchmark accounting). */
 int coeb_extractor_launches_per_call(const coeb_extractor* ex);
 
+/* Benchmark accounting: with profiling on, every coeb_extract_batch_* call brackets its six stages
+ * (classify, pyramid, blur, FAST, octree-select, describe) with CUDA events on the launch stream;
+ * coeb_extractor_stage_ms returns the device time of each stage of the last call (blocks on its end). */
+int coeb_extractor_set_profiling(coeb_extractor* ex, int on);
+int coeb_extractor_stage_ms(coeb_extractor* ex, float* ms6);
+
 /* Dynamic-object decision of frame `frame` of the last call (area_flag, zero-filled mask rectangles;
  * src/ORBextractor.cc:1101-1195). Blocking. */
 int coeb_extractor_dyn_info(coeb_extractor* ex, int frame, coeb_dyn_info* out);
