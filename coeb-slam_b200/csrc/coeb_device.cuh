@@ -123,6 +123,50 @@ __device__ inline bool is_moving(const DynState& d, float ptx, float pty, int le
     return mask_is_zero(d, (int)sx, (int)sy);
 }
 
+#ifdef __CUDACC__
+// In-place exclusive prefix sum of data[0..n) (shared or global memory) by the whole CTA; returns the total.
+// All threads must call; s_warp is a 33-int shared scratch array.
+__device__ inline int block_exclusive_scan(int* data, int n, int* s_warp) {
+    const int T = blockDim.x, tid = threadIdx.x;
+    const int chunk = (n + T - 1) / T;
+    const int lo = min(tid * chunk, n), hi = min(lo + chunk, n);
+    int sum = 0;
+    for (int i = lo; i < hi; i++) sum += data[i];
+    // block scan of per-thread sums
+    const int lane = tid & 31, wid = tid >> 5;
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int wv = lane < (T >> 5) ? s_warp[lane] : 0;
+        int winc = wv;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        s_warp[lane] = winc - wv;       // exclusive warp offsets
+        if (lane == 31) s_warp[32] = winc;  // total
+    }
+    __syncthreads();
+    int run = s_warp[wid] + inc - sum;
+    for (int i = lo; i < hi; i++) {
+        const int t = data[i];
+        data[i] = run;
+        run += t;
+    }
+    const int total = s_warp[32];
+    __syncthreads();
+    return total;
+}
+
+#endif
+
 // kernel launchers (each enqueues on `stream`, no synchronisation)
 void launch_classify(const Geometry& g, const BatchView& v, cudaStream_t stream);
 void launch_pyramid(const Geometry& g, const BatchView& v, cudaStream_t stream);

@@ -1,0 +1,1045 @@
+// match.cu -- Frame keypoint grid (F2, F3), Hamming matchers (M1-M6), stereo matcher (F4) and the
+// brute-force k=2 matcher (config 5) behind the C ABI of include/coeb_frontend.h.
+//
+// Reference: Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea (src/Frame.cc:396-411, 503-568),
+// ORBmatcher (src/ORBmatcher.cc:37-137, 405-520, 1329-1471, 1602-1664), Frame::ComputeStereoMatches
+// (src/Frame.cc:644-818).
+//
+// Loop-carried state. The reference matchers are sequential: a query skips keypoints that EARLIER
+// queries of the same call already claimed (:87-89 with :123; :1404-1406 with :1429), and
+// SearchForInitialization carries vMatchedDistance / vnMatches21 (:444, :463-471). The result of
+// query i is a function F(i, results of queries j < i). The kernels evaluate all queries in
+// parallel and iterate R <- F(R) to a fixed point; any fixed point equals the sequential result
+// (induction on i), and the iteration reaches it after at most n rounds (round t fixes queries < t);
+// in practice 2-4 rounds, since conflicts are rare and local.
+//
+// Tie-breaks follow the grid traversal order of GetFeaturesInArea (ix outer, iy inner, insertion
+// order inside a cell): the device grid stores cells ix-major, items in ascending keypoint index, so
+// one query walks, per ix, one contiguous item range, and "first candidate wins" (strict '<') is the
+// natural outcome of the per-thread sequential scan.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "../../include/coeb_frontend.h"
+#include "coeb_device.cuh"
+#include "coeb_host.hpp"
+
+namespace coeb {
+
+constexpr int kGridCells = COEB_GRID_COLS * COEB_GRID_ROWS;
+constexpr int kInf = 0x7fffffff;
+
+struct FrameDev {
+    int n;
+    const float* x; const float* y; const float* angle; const int* octave;
+    const uint32_t* desc;       // n x 8 words
+    const float* uright;        // n floats, or nullptr (all -1)
+    const int* cell_start;      // [kGridCells + 1], cell = ix * ROWS + iy
+    const int* cell_items;      // [n_in_grid] keypoint indices, ascending inside a cell
+    float min_x, min_y, max_x, max_y, gw_inv, gh_inv;
+    float fx, fy, cx, cy, bf, b;
+    float scale[COEB_MAX_LEVELS];
+};
+
+__device__ __forceinline__ int hamming256(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b) {
+    const uint4 a0 = *reinterpret_cast<const uint4*>(a), a1 = *reinterpret_cast<const uint4*>(a + 4);
+    const uint4 b0 = *reinterpret_cast<const uint4*>(b), b1 = *reinterpret_cast<const uint4*>(b + 4);
+    return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) + __popc(a1.x ^ b1.x) +
+           __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+// Frame::GetFeaturesInArea (src/Frame.cc:503-556): calls fn(idx) for every keypoint of the window in the
+// reference's order.
+template <class F>
+__device__ __forceinline__ void for_each_in_area(const FrameDev& f, float x, float y, float r, int minLevel, int maxLevel, F&& fn) {
+    const int nMinCellX = max(0, (int)floorf((x - f.min_x - r) * f.gw_inv));
+    if (nMinCellX >= COEB_GRID_COLS) return;
+    const int nMaxCellX = min(COEB_GRID_COLS - 1, (int)ceilf((x - f.min_x + r) * f.gw_inv));
+    if (nMaxCellX < 0) return;
+    const int nMinCellY = max(0, (int)floorf((y - f.min_y - r) * f.gh_inv));
+    if (nMinCellY >= COEB_GRID_ROWS) return;
+    const int nMaxCellY = min(COEB_GRID_ROWS - 1, (int)ceilf((y - f.min_y + r) * f.gh_inv));
+    if (nMaxCellY < 0) return;
+    const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+    for (int ix = nMinCellX; ix <= nMaxCellX; ix++) {
+        const int lo = f.cell_start[ix * COEB_GRID_ROWS + nMinCellY], hi = f.cell_start[ix * COEB_GRID_ROWS + nMaxCellY + 1];
+        for (int p = lo; p < hi; p++) {
+            const int idx = f.cell_items[p];
+            if (bCheckLevels) {
+                const int o = f.octave[idx];
+                if (o < minLevel) continue;
+                if (maxLevel >= 0 && o > maxLevel) continue;
+            }
+            const float dx = f.x[idx] - x, dy = f.y[idx] - y;
+            if (fabsf(dx) < r && fabsf(dy) < r) fn(idx);
+        }
+    }
+}
+
+// ---- grid build (Frame::AssignFeaturesToGrid, src/Frame.cc:396-411) -------------------------------------
+// One CTA. Cells ix-major; items ascending by keypoint index (the reference pushes in index order).
+__global__ void __launch_bounds__(1024) grid_build_kernel(FrameDev f, int* cell_start, int* cell_items, int* kp_cell) {
+    __shared__ int s_cnt[kGridCells + 1];
+    __shared__ int s_warp[33];
+    const int tid = threadIdx.x, T = blockDim.x;
+    for (int i = tid; i <= kGridCells; i += T) s_cnt[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < f.n; i += T) {
+        // PosInGrid: round() half away from zero (src/Frame.cc:560-561)
+        const int px = (int)roundf((f.x[i] - f.min_x) * f.gw_inv), py = (int)roundf((f.y[i] - f.min_y) * f.gh_inv);
+        int c = -1;
+        if (!(px < 0 || px >= COEB_GRID_COLS || py < 0 || py >= COEB_GRID_ROWS)) {
+            c = px * COEB_GRID_ROWS + py;
+            atomicAdd(&s_cnt[c], 1);
+        }
+        kp_cell[i] = c;
+    }
+    __syncthreads();
+    const int total = block_exclusive_scan(s_cnt, kGridCells, s_warp);
+    if (tid == 0) s_cnt[kGridCells] = total;
+    __syncthreads();
+    for (int i = tid; i <= kGridCells; i += T) cell_start[i] = s_cnt[i];
+    __syncthreads();
+    // fill with atomic slots, then sort each (tiny) cell: items end up ascending by keypoint index,
+    // the order in which the reference pushes them.
+    for (int i = tid; i < f.n; i += T) {
+        const int c = kp_cell[i];
+        if (c >= 0) cell_items[atomicAdd(&s_cnt[c], 1)] = i;
+    }
+    __syncthreads();
+    for (int c = tid; c < kGridCells; c += T) {
+        const int a = cell_start[c], b = cell_start[c + 1];
+        for (int i = a + 1; i < b; i++) {  // insertion sort, ascending keypoint index
+            const int v = cell_items[i];
+            int j = i - 1;
+            while (j >= a && cell_items[j] > v) { cell_items[j + 1] = cell_items[j]; j--; }
+            cell_items[j + 1] = v;
+        }
+    }
+}
+
+__global__ void features_in_area_kernel(FrameDev f, float x, float y, float r, int minLevel, int maxLevel, int* out, int cap, int* n_out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int n = 0;
+    for_each_in_area(f, x, y, r, minLevel, maxLevel, [&](int idx) { if (n < cap) out[n] = idx; n++; });
+    *n_out = n;
+}
+
+__global__ void hamming_pairs_kernel(const uint32_t* a, const uint32_t* b, int n, int* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = hamming256(a + 8 * (size_t)i, b + 8 * (size_t)i);
+}
+
+// ---- M2: SearchByProjection(Frame&, vector<MapPoint*>&, th) (src/ORBmatcher.cc:45-129) -------------------
+struct MapDev {
+    int n;
+    const uint8_t *track_in_view, *bad, *has_obs;
+    const float *proj_x, *proj_y, *proj_xr, *view_cos;
+    const int* level;
+    const uint32_t* desc;
+};
+
+// One CTA iterates to the fixed point. res[i] = keypoint claimed by map point i or -1.
+// claim_min[idx] = smallest i (with Observations()>0) that currently claims idx.
+__global__ void __launch_bounds__(1024) match_projection_kernel(FrameDev F, MapDev M, float th, float nnratio, int* kp_match /*in/out*/,
+                                                                int* res, int* claim_min, int* out_info) {
+    __shared__ int s_changed, s_count;
+    const int tid = threadIdx.x, T = blockDim.x;
+    const bool bFactor = th != 1.0f;
+    for (int i = tid; i < M.n; i += T) res[i] = -1;
+    for (int round = 0; round <= M.n; round++) {
+        for (int k = tid; k < F.n; k += T) claim_min[k] = kInf;
+        if (tid == 0) s_changed = 0;
+        __syncthreads();
+        for (int i = tid; i < M.n; i += T) {
+            const int k = res[i];
+            if (k >= 0 && M.has_obs[i]) atomicMin(&claim_min[k], i);
+        }
+        __syncthreads();
+        for (int i = tid; i < M.n; i += T) {
+            int out = -1;
+            if (M.track_in_view[i] && !M.bad[i]) {
+                const int lvl = M.level[i];
+                float r = ((double)M.view_cos[i] > 0.998) ? 2.5f : 4.0f;  // RadiusByViewingCos (:131-137)
+                if (bFactor) r *= th;
+                const float rs = r * F.scale[lvl];
+                const uint32_t* d = M.desc + 8 * (size_t)i;
+                const float pxr = M.proj_xr[i];
+                int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+                for_each_in_area(F, M.proj_x[i], M.proj_y[i], rs, lvl - 1, lvl, [&](int idx) {
+                    const int cur = kp_match[idx];
+                    if (cur == -2 || claim_min[idx] < i) return;            // already holds a MapPoint with observations
+                    if (F.uright) {
+                        const float ur = F.uright[idx];
+                        if (ur > 0) { const float er = fabsf(pxr - ur); if (er > rs) return; }
+                    }
+                    const int dist = hamming256(d, F.desc + 8 * (size_t)idx);
+                    if (dist < bestDist) {
+                        bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = F.octave[idx]; bestIdx = idx;
+                    } else if (dist < bestDist2) {
+                        bestLevel2 = F.octave[idx]; bestDist2 = dist;
+                    }
+                });
+                if (bestDist <= COEB_TH_HIGH && !(bestLevel == bestLevel2 && (float)bestDist > nnratio * (float)bestDist2)) out = bestIdx;
+            }
+            if (out != res[i]) { res[i] = out; s_changed = 1; }
+        }
+        __syncthreads();
+        const int changed = s_changed;
+        __syncthreads();
+        if (!changed) { if (tid == 0) out_info[1] = round + 1; break; }
+    }
+    // F.mvpMapPoints[bestIdx] = pMP in query order: the last writer wins; every success counts (:123-124)
+    if (tid == 0) s_count = 0;
+    for (int k = tid; k < F.n; k += T) claim_min[k] = -1;  // reuse as "last claimant"
+    __syncthreads();
+    int mine = 0;
+    for (int i = tid; i < M.n; i += T)
+        if (res[i] >= 0) { atomicMax(&claim_min[res[i]], i); mine++; }
+    if (mine) atomicAdd(&s_count, mine);
+    __syncthreads();
+    for (int k = tid; k < F.n; k += T)
+        if (claim_min[k] >= 0) kp_match[k] = claim_min[k];
+    if (tid == 0) out_info[0] = s_count;
+}
+
+// ---- M5: ComputeThreeMaxima (src/ORBmatcher.cc:1602-1643) ------------------------------------------------------
+__device__ void three_maxima(const int* histo, int L, int& ind1, int& ind2, int& ind3) {
+    int max1 = 0, max2 = 0, max3 = 0;
+    ind1 = ind2 = ind3 = -1;
+    for (int i = 0; i < L; i++) {
+        const int s = histo[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if ((float)max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if ((float)max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+
+__device__ __forceinline__ int rot_bin(float a1, float a2) {  // :1434-1439
+    const float factor = 1.0f / COEB_HISTO_LENGTH;
+    float rot = a1 - a2;
+    if (rot < 0.0f) rot += 360.0f;
+    int bin = (int)roundf(rot * factor);
+    if (bin == COEB_HISTO_LENGTH) bin = 0;
+    return bin;
+}
+
+// ---- M3: SearchByProjection(Frame& cur, const Frame& last, th, bMono) (src/ORBmatcher.cc:1329-1471) ------------
+struct LastDev {
+    int n;
+    const uint8_t *valid, *has_obs;
+    const float* xyz;
+    const int* octave;
+    const float* angle;
+    const uint32_t* desc;
+    float T[12];       // Tcw of the current frame, 3x4 row-major
+    int forward, backward;
+};
+
+__global__ void __launch_bounds__(1024) match_lastframe_kernel(FrameDev C, LastDev L, float th, int check_ori, int* kp_match, int* res,
+                                                               int* claim_min, int* out_info) {
+    __shared__ int s_changed, s_count;
+    __shared__ int s_hist[COEB_HISTO_LENGTH];
+    __shared__ int s_ind[3];
+    const int tid = threadIdx.x, T = blockDim.x;
+    for (int i = tid; i < L.n; i += T) res[i] = -1;
+    for (int round = 0; round <= L.n; round++) {
+        for (int k = tid; k < C.n; k += T) claim_min[k] = kInf;
+        if (tid == 0) s_changed = 0;
+        __syncthreads();
+        for (int i = tid; i < L.n; i += T) {
+            const int k = res[i];
+            if (k >= 0 && L.has_obs[i]) atomicMin(&claim_min[k], i);
+        }
+        __syncthreads();
+        for (int i = tid; i < L.n; i += T) {
+            int out = -1;
+            if (L.valid[i]) {
+                const float X = L.xyz[3 * i], Y = L.xyz[3 * i + 1], Z = L.xyz[3 * i + 2];
+                // x3Dc = Rcw*x3Dw + tcw (:1362), fp32 left to right (no FMA: the file is built with -fmad=false)
+                const float xc = L.T[0] * X + L.T[1] * Y + L.T[2] * Z + L.T[3];
+                const float yc = L.T[4] * X + L.T[5] * Y + L.T[6] * Z + L.T[7];
+                const float zc = L.T[8] * X + L.T[9] * Y + L.T[10] * Z + L.T[11];
+                const float invzc = (float)(1.0 / (double)zc);
+                bool ok = !(invzc < 0);
+                const float u = C.fx * xc * invzc + C.cx, v = C.fy * yc * invzc + C.cy;
+                if (u < C.min_x || u > C.max_x) ok = false;
+                if (v < C.min_y || v > C.max_y) ok = false;
+                if (ok) {
+                    const int oct = L.octave[i];
+                    const float radius = th * C.scale[oct];
+                    int minL, maxL;
+                    if (L.forward) { minL = oct; maxL = -1; }
+                    else if (L.backward) { minL = 0; maxL = oct; }
+                    else { minL = oct - 1; maxL = oct + 1; }
+                    const uint32_t* d = L.desc + 8 * (size_t)i;
+                    const float ur_proj = u - C.bf * invzc;
+                    int bestDist = 256, bestIdx2 = -1;
+                    for_each_in_area(C, u, v, radius, minL, maxL, [&](int i2) {
+                        const int cur = kp_match[i2];
+                        if (cur == -2 || claim_min[i2] < i) return;
+                        if (C.uright) {
+                            const float ur = C.uright[i2];
+                            if (ur > 0) { const float er = fabsf(ur_proj - ur); if (er > radius) return; }
+                        }
+                        const int dist = hamming256(d, C.desc + 8 * (size_t)i2);
+                        if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+                    });
+                    if (bestDist <= COEB_TH_HIGH) out = bestIdx2;
+                }
+            }
+            if (out != res[i]) { res[i] = out; s_changed = 1; }
+        }
+        __syncthreads();
+        const int changed = s_changed;
+        __syncthreads();
+        if (!changed) { if (tid == 0) out_info[1] = round + 1; break; }
+    }
+    if (tid == 0) s_count = 0;
+    for (int k = tid; k < COEB_HISTO_LENGTH; k += T) s_hist[k] = 0;
+    for (int k = tid; k < C.n; k += T) claim_min[k] = -1;
+    __syncthreads();
+    int mine = 0;
+    for (int i = tid; i < L.n; i += T)
+        if (res[i] >= 0) {
+            atomicMax(&claim_min[res[i]], i);
+            mine++;
+            if (check_ori) atomicAdd(&s_hist[rot_bin(L.angle[i], C.angle[res[i]])], 1);
+        }
+    if (mine) atomicAdd(&s_count, mine);
+    __syncthreads();
+    for (int k = tid; k < C.n; k += T)
+        if (claim_min[k] >= 0) kp_match[k] = claim_min[k];
+    if (tid == 0 && check_ori) {
+        int a, b, c;
+        three_maxima(s_hist, COEB_HISTO_LENGTH, a, b, c);
+        s_ind[0] = a; s_ind[1] = b; s_ind[2] = c;
+    }
+    __syncthreads();
+    if (check_ori) {  // rotation consistency (:1449-1468): entries of the losing bins are cleared, each decrements
+        int removed = 0;
+        for (int i = tid; i < L.n; i += T)
+            if (res[i] >= 0) {
+                const int bin = rot_bin(L.angle[i], C.angle[res[i]]);
+                if (bin != s_ind[0] && bin != s_ind[1] && bin != s_ind[2]) { kp_match[res[i]] = -1; removed++; }
+            }
+        if (removed) atomicSub(&s_count, removed);
+    }
+    __syncthreads();
+    if (tid == 0) out_info[0] = s_count;
+}
+
+// ---- M4: SearchForInitialization (src/ORBmatcher.cc:405-520) -----------------------------------------------------
+// res[i1] = claimed F2 keypoint or -1, rdist[i1] = its distance. vMatchedDistance seen by query i1 at keypoint k is
+// min{rdist[j] : j < i1, res[j] == k}; claimants of every k are gathered into CSR lists each round.
+__global__ void __launch_bounds__(1024) match_init_kernel(FrameDev F1, FrameDev F2, const float* prev_in, float window, float nnratio,
+                                                          int check_ori, int* res, int* rdist, int* cl_start, int* cl_fill,
+                                                          int2* cl_items, int* matches12, float* prev_out, int* out_info) {
+    __shared__ int s_changed, s_count;
+    __shared__ int s_hist[COEB_HISTO_LENGTH];
+    __shared__ int s_ind[3];
+    __shared__ int s_warp[33];
+    const int tid = threadIdx.x, T = blockDim.x;
+    for (int i = tid; i < F1.n; i += T) { res[i] = -1; rdist[i] = kInf; }
+    for (int round = 0; round <= F1.n; round++) {
+        for (int k = tid; k <= F2.n; k += T) cl_start[k] = 0;
+        if (tid == 0) s_changed = 0;
+        __syncthreads();
+        for (int i = tid; i < F1.n; i += T)
+            if (res[i] >= 0) atomicAdd(&cl_start[res[i]], 1);
+        __syncthreads();
+        block_exclusive_scan(cl_start, F2.n + 1, s_warp);
+        for (int k = tid; k < F2.n; k += T) cl_fill[k] = cl_start[k];
+        __syncthreads();
+        for (int i = tid; i < F1.n; i += T)
+            if (res[i] >= 0) cl_items[atomicAdd(&cl_fill[res[i]], 1)] = make_int2(i, rdist[i]);
+        __syncthreads();
+        for (int i1 = tid; i1 < F1.n; i1 += T) {
+            int out = -1, outd = kInf;
+            if (F1.octave[i1] <= 0) {  // level1 > 0 -> continue (:421-423)
+                const uint32_t* d1 = F1.desc + 8 * (size_t)i1;
+                int bestDist = kInf, bestDist2 = kInf, bestIdx2 = -1;
+                for_each_in_area(F2, prev_in[2 * i1], prev_in[2 * i1 + 1], window, 0, 0, [&](int i2) {
+                    const int dist = hamming256(d1, F2.desc + 8 * (size_t)i2);
+                    int md = kInf;
+                    for (int p = cl_start[i2]; p < cl_start[i2 + 1]; p++) {
+                        const int2 c = cl_items[p];
+                        if (c.x < i1) md = min(md, c.y);
+                    }
+                    if (md <= dist) return;   // vMatchedDistance[i2] <= dist (:444)
+                    if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                });
+                if (bestDist <= COEB_TH_LOW && (float)bestDist < (float)bestDist2 * nnratio) { out = bestIdx2; outd = bestDist; }
+            }
+            if (out != res[i1] || outd != rdist[i1]) { res[i1] = out; rdist[i1] = outd; s_changed = 1; }
+        }
+        __syncthreads();
+        const int changed = s_changed;
+        __syncthreads();
+        if (!changed) { if (tid == 0) out_info[1] = round + 1; break; }
+    }
+    // vnMatches12[i1] survives iff i1 is the last claimant of its keypoint (steal-back, :463-469);
+    // nmatches = keypoints with at least one claimant.
+    for (int k = tid; k < F2.n; k += T) cl_fill[k] = -1;
+    for (int k = tid; k < COEB_HISTO_LENGTH; k += T) s_hist[k] = 0;
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    for (int i = tid; i < F1.n; i += T)
+        if (res[i] >= 0) {
+            atomicMax(&cl_fill[res[i]], i);
+            if (check_ori) atomicAdd(&s_hist[rot_bin(F1.angle[i], F2.angle[res[i]])], 1);  // every success is binned (:482)
+        }
+    __syncthreads();
+    int mine = 0;
+    for (int i = tid; i < F1.n; i += T) {
+        const int k = res[i];
+        const bool keep = k >= 0 && cl_fill[k] == i;
+        matches12[i] = keep ? k : -1;
+        mine += keep;
+    }
+    if (mine) atomicAdd(&s_count, mine);
+    if (tid == 0 && check_ori) {
+        int a, b, c;
+        three_maxima(s_hist, COEB_HISTO_LENGTH, a, b, c);
+        s_ind[0] = a; s_ind[1] = b; s_ind[2] = c;
+    }
+    __syncthreads();
+    if (check_ori) {
+        int removed = 0;
+        for (int i = tid; i < F1.n; i += T)
+            if (res[i] >= 0) {
+                const int bin = rot_bin(F1.angle[i], F2.angle[res[i]]);
+                if (bin != s_ind[0] && bin != s_ind[1] && bin != s_ind[2] && matches12[i] >= 0) { matches12[i] = -1; removed++; }
+            }
+        if (removed) atomicSub(&s_count, removed);
+    }
+    __syncthreads();
+    for (int i = tid; i < F1.n; i += T) {  // update prev matched (:515-517)
+        const int k = matches12[i];
+        prev_out[2 * i] = k >= 0 ? F2.x[k] : prev_in[2 * i];
+        prev_out[2 * i + 1] = k >= 0 ? F2.y[k] : prev_in[2 * i + 1];
+    }
+    if (tid == 0) out_info[0] = s_count;
+}
+
+// ---- F4: Frame::ComputeStereoMatches (src/Frame.cc:644-818) -------------------------------------------------------
+struct StereoDev {
+    int N, Nr;
+    const float *xl, *yl; const int* octl; const uint32_t* descl;
+    const float *xr, *yr; const int* octr; const uint32_t* descr;
+    float scale[COEB_MAX_LEVELS], inv_scale[COEB_MAX_LEVELS];
+    const uint8_t* pyrL[COEB_MAX_LEVELS]; const uint8_t* pyrR[COEB_MAX_LEVELS];
+    int pitchL[COEB_MAX_LEVELS], pitchR[COEB_MAX_LEVELS], lw[COEB_MAX_LEVELS], lh[COEB_MAX_LEVELS];
+    int nRows;
+    float bf, b;
+};
+
+// One warp per left keypoint. The reference's row table (vRowIndices) lists, for image row (int)vL, the right
+// keypoints iR (ascending) with floor(yR - r) <= row <= ceil(yR + r), r = 2*scale[octR]; membership is tested directly.
+// Best Hamming: strict '<' from TH_HIGH, first iR wins -> argmin over (dist, iR). Then the 11x11 SAD search over 11
+// shifts at the left keypoint's level, parabola refinement and the disparity test.
+__global__ void __launch_bounds__(256) stereo_match_kernel(StereoDev S, float* uright, float* depth, int* sad_out) {
+    const int lane = threadIdx.x & 31;
+    const int iL = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (iL >= S.N) return;
+    float out_u = -1.f, out_d = -1.f;
+    int out_sad = -1;
+    const float uL = S.xl[iL], vL = S.yl[iL];
+    const int levelL = S.octl[iL];
+    const int row = (int)vL;
+    const float minZ = S.b, minD = 0.f, maxD = S.bf / minZ;
+    const float minU = uL - maxD, maxU = uL - minD;
+    unsigned long long best = ((unsigned long long)COEB_TH_HIGH << 32) | 0xFFFFFFFFull;
+    bool any = false;
+    if (row >= 0 && row < S.nRows && !(maxU < 0)) {
+        const uint32_t* dL = S.descl + 8 * (size_t)iL;
+        for (int iR = lane; iR < S.Nr; iR += 32) {
+            const float kpY = S.yr[iR];
+            const int oR = S.octr[iR];
+            const float r = 2.0f * S.scale[oR];
+            const int maxr = (int)ceilf(kpY + r), minr = (int)floorf(kpY - r);
+            if (row < minr || row > maxr) continue;
+            any = true;
+            if (oR < levelL - 1 || oR > levelL + 1) continue;
+            const float uR = S.xr[iR];
+            if (uR >= minU && uR <= maxU) {
+                const int dist = hamming256(dL, S.descr + 8 * (size_t)iR);
+                if (dist < COEB_TH_HIGH) {
+                    const unsigned long long key = ((unsigned long long)dist << 32) | (unsigned)iR;
+                    best = key < best ? key : best;
+                }
+            }
+        }
+    }
+    any = __any_sync(0xffffffffu, any);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other < best ? other : best;
+    }
+    const int bestDist = (int)(best >> 32);
+    const int thOrbDist = (COEB_TH_HIGH + COEB_TH_LOW) / 2;
+    if (any && bestDist < thOrbDist) {
+        const int bestIdxR = (int)(best & 0xFFFFFFFFu);
+        const float uR0 = S.xr[bestIdxR];
+        const float sf = S.inv_scale[levelL];
+        const float scaleduL = roundf(uL * sf), scaledvL = roundf(vL * sf), scaleduR0 = roundf(uR0 * sf);
+        const int w = 5, L = 5;
+        const int yl = (int)(scaledvL - w), xl = (int)(scaleduL - w);
+        const float iniu = scaleduR0 + L - w, endu = scaleduR0 + L + w + 1;
+        const int W = S.lw[levelL], H = S.lh[levelL];
+        bool ok = !(iniu < 0 || endu >= (float)W);
+        // the reference's rowRange/colRange would throw outside the image; such points are dropped
+        if (yl < 0 || yl + 2 * w + 1 > H || xl < 0 || xl + 2 * w + 1 > W) ok = false;
+        if (ok) {
+            const uint8_t* IL = S.pyrL[levelL];
+            const uint8_t* IR = S.pyrR[levelL];
+            const int pL = S.pitchL[levelL], pR = S.pitchR[levelL];
+            const int cL = IL[(size_t)(yl + w) * pL + xl + w];
+            // each lane owns up to 4 of the 121 patch pixels
+            int lv[4], py[4], px[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int p = lane + 32 * k;
+                py[k] = p / 11; px[k] = p - py[k] * 11;
+                lv[k] = p < 121 ? (int)IL[(size_t)(yl + py[k]) * pL + xl + px[k]] - cL : 0;
+            }
+            int bestSad = 0x7fffffff, bestinc = 0;
+            float vd[11];
+#pragma unroll
+            for (int inc = -5; inc <= 5; inc++) {
+                const int xr = (int)(scaleduR0 + (float)inc - w);
+                const int cR = IR[(size_t)(yl + w) * pR + xr + w];
+                int acc = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int p = lane + 32 * k;
+                    if (p < 121) acc += abs(lv[k] - ((int)IR[(size_t)(yl + py[k]) * pR + xr + px[k]] - cR));
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                vd[inc + 5] = (float)acc;   // exact: the L1 norm of integer differences
+                if (acc < bestSad) { bestSad = acc; bestinc = inc; }
+            }
+            if (!(bestinc == -L || bestinc == L)) {
+                float d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+                for (int k = 1; k < 10; k++)
+                    if (k == bestinc + 5) { d1 = vd[k - 1]; d2 = vd[k]; d3 = vd[k + 1]; }
+                const float deltaR = (d1 - d3) / (2.0f * (d1 + d3 - 2.0f * d2));
+                if (!(deltaR < -1 || deltaR > 1)) {
+                    float bestuR = S.scale[levelL] * (scaleduR0 + (float)bestinc + deltaR);
+                    float disparity = uL - bestuR;
+                    if (disparity >= minD && disparity < maxD) {
+                        if (disparity <= 0) { disparity = 0.01f; bestuR = (float)((double)uL - 0.01); }
+                        out_d = S.bf / disparity;
+                        out_u = bestuR;
+                        out_sad = bestSad;
+                    }
+                }
+            }
+        }
+    }
+    if (lane == 0) { uright[iL] = out_u; depth[iL] = out_d; sad_out[iL] = out_sad; }
+}
+
+// Outlier cut (:804-817): median = SAD at sorted position size/2; entries with SAD >= 1.5*1.4*median are removed.
+__global__ void __launch_bounds__(1024) stereo_outlier_kernel(int N, float* uright, float* depth, const int* sad, int* out_info) {
+    __shared__ int s_cnt, s_lo, s_hi;
+    const int tid = threadIdx.x, T = blockDim.x;
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    int mine = 0;
+    for (int i = tid; i < N; i += T) mine += sad[i] >= 0;
+    if (mine) atomicAdd(&s_cnt, mine);
+    __syncthreads();
+    const int M = s_cnt;
+    if (M == 0) { if (tid == 0) out_info[0] = 0; return; }
+    const int target = M / 2;  // 0-based rank in ascending order
+    // smallest v with #(sad <= v) >= target + 1, by bisection on the value range
+    int lo = 0, hi = 121 * 510;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        __syncthreads();
+        if (tid == 0) s_lo = 0;
+        __syncthreads();
+        int c = 0;
+        for (int i = tid; i < N; i += T) c += (sad[i] >= 0 && sad[i] <= mid);
+        if (c) atomicAdd(&s_lo, c);
+        __syncthreads();
+        if (s_lo >= target + 1) hi = mid; else lo = mid + 1;
+    }
+    const float median = (float)lo;
+    const float thDist = 1.5f * 1.4f * median;
+    __syncthreads();
+    if (tid == 0) s_hi = 0;
+    __syncthreads();
+    int kept = 0;
+    for (int i = tid; i < N; i += T)
+        if (sad[i] >= 0) {
+            if ((float)sad[i] < thDist) kept++;
+            else { uright[i] = -1.f; depth[i] = -1.f; }
+        }
+    if (kept) atomicAdd(&s_hi, kept);
+    __syncthreads();
+    if (tid == 0) out_info[0] = s_hi;
+}
+
+// ---- config 5: brute-force k=2 Hamming search + ratio test -----------------------------------------------------------
+// Integer-pipe bound: 8 XOR + 8 POPC + adds per pair. Each thread keeps kKnnQ query descriptors in registers and
+// walks a train chunk staged in shared memory (all lanes read the same train word: broadcast). Partial (d1, idx, d2)
+// per (query, chunk) are merged by a second kernel; the strict-'<' / first-index-wins rule is order independent once
+// ties are broken on the index, and d2 is the second smallest distance with multiplicity.
+constexpr int kKnnQ = 2;         // queries per thread
+constexpr int kKnnThreads = 128;
+constexpr int kKnnTile = 256;    // train descriptors per shared-memory stage
+
+__global__ void __launch_bounds__(kKnnThreads) knn2_partial_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __restrict__ t, int nt,
+                                                                    int chunk, int* p_d1, int* p_idx, int* p_d2) {
+    __shared__ uint4 s_t[kKnnTile * 2];
+    const int q0 = (blockIdx.x * kKnnThreads + threadIdx.x) * kKnnQ;
+    const int c = blockIdx.y;
+    const int t_lo = c * chunk, t_hi = min(t_lo + chunk, nt);
+    uint4 qa[kKnnQ], qb[kKnnQ];
+    int d1[kKnnQ], d2[kKnnQ], bi[kKnnQ];
+#pragma unroll
+    for (int k = 0; k < kKnnQ; k++) {
+        const int qi = min(q0 + k, nq - 1);
+        qa[k] = *reinterpret_cast<const uint4*>(q + 8 * (size_t)qi);
+        qb[k] = *reinterpret_cast<const uint4*>(q + 8 * (size_t)qi + 4);
+        d1[k] = 256; d2[k] = 256; bi[k] = -1;
+    }
+    for (int base = t_lo; base < t_hi; base += kKnnTile) {
+        const int m = min(kKnnTile, t_hi - base);
+        __syncthreads();
+        for (int i = threadIdx.x; i < m * 2; i += kKnnThreads) s_t[i] = *reinterpret_cast<const uint4*>(t + 8 * (size_t)base + 4 * (size_t)i);
+        __syncthreads();
+#pragma unroll 4
+        for (int j = 0; j < m; j++) {
+            const uint4 ta = s_t[2 * j], tb = s_t[2 * j + 1];
+#pragma unroll
+            for (int k = 0; k < kKnnQ; k++) {
+                const int dist = __popc(qa[k].x ^ ta.x) + __popc(qa[k].y ^ ta.y) + __popc(qa[k].z ^ ta.z) + __popc(qa[k].w ^ ta.w) +
+                                 __popc(qb[k].x ^ tb.x) + __popc(qb[k].y ^ tb.y) + __popc(qb[k].z ^ tb.z) + __popc(qb[k].w ^ tb.w);
+                if (dist < d1[k]) { d2[k] = d1[k]; d1[k] = dist; bi[k] = base + j; }
+                else if (dist < d2[k]) d2[k] = dist;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kKnnQ; k++)
+        if (q0 + k < nq) {
+            const size_t o = (size_t)c * nq + q0 + k;
+            p_d1[o] = d1[k]; p_idx[o] = bi[k]; p_d2[o] = d2[k];
+        }
+}
+
+__global__ void knn2_merge_kernel(int nq, int nchunks, const int* p_d1, const int* p_idx, const int* p_d2, float nnratio, int* best_idx,
+                                  int* out_d1, int* out_d2, int* accepted) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    int d1 = 256, d2 = 256, idx = -1;
+    for (int c = 0; c < nchunks; c++) {  // chunks in ascending train order, so an equal distance never replaces the earlier index
+        const size_t o = (size_t)c * nq + i;
+        const int a = p_d1[o], b = p_d2[o];
+        if (a < d1) { d2 = min(d1, b); d1 = a; idx = p_idx[o]; }
+        else { d2 = min(d2, a); }
+    }
+    const bool ok = d1 <= COEB_TH_LOW && (float)d1 < nnratio * (float)d2;
+    best_idx[i] = ok ? idx : -1;
+    if (out_d1) out_d1[i] = d1;
+    if (out_d2) out_d2[i] = d2;
+    if (ok && accepted) atomicAdd(accepted, 1);
+}
+
+}  // namespace coeb
+
+// =====================================================================================================================
+// C ABI (host side)
+// =====================================================================================================================
+using namespace coeb;
+
+struct coeb_matcher {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    // scratch, grown on demand
+    void* d_scratch = nullptr; size_t scratch_bytes = 0;
+    void* d_in = nullptr; size_t in_bytes = 0;
+};
+
+struct coeb_frame {
+    coeb_matcher* m = nullptr;
+    int n = 0, nlevels = 0;
+    float *d_x = nullptr, *d_y = nullptr, *d_angle = nullptr, *d_uright = nullptr;
+    int *d_octave = nullptr, *d_cell_start = nullptr, *d_cell_items = nullptr, *d_kp_cell = nullptr;
+    uint32_t* d_desc = nullptr;
+    FrameDev dev{};
+};
+
+// The extractor handle is opaque here; coeb_api.cu exports the pyramid accessor used by the stereo matcher.
+extern "C" int coeb_pyramid_level(coeb_extractor* ex, int frame, int level, int blurred, const uint8_t** dev_ptr, int* width,
+                                  int* height, int* pitch);
+extern "C" int coeb_extractor_tables(const coeb_extractor* ex, int* nlevels, float* scale, float* inv_scale, float* sigma2,
+                                     float* inv_sigma2, int* features_per_level);
+
+namespace {
+
+int grow(void** p, size_t* cap, size_t bytes) {
+    if (bytes <= *cap && *p) return COEB_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    CUDA_TRY(cudaMalloc(p, std::max<size_t>(bytes, 256)));
+    *cap = bytes;
+    return COEB_OK;
+}
+
+// Bump allocator over one device block; every piece 256-byte aligned.
+struct Carver {
+    char* base; size_t off = 0;
+    explicit Carver(void* b) : base((char*)b) {}
+    template <typename T> T* take(size_t n) { T* p = (T*)(base + off); off += (n * sizeof(T) + 255) & ~(size_t)255; return p; }
+    static size_t need(std::initializer_list<size_t> bytes) { size_t s = 0; for (size_t b : bytes) s += (b + 255) & ~(size_t)255; return s; }
+};
+
+template <typename T>
+int upload(cudaStream_t s, T* dst, const T* src, size_t n) {
+    if (n) CUDA_TRY(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, s));
+    return COEB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int coeb_matcher_create(int device, coeb_matcher** out) {
+    if (!out) return fail(COEB_ERR_INVALID_ARG, "null argument");
+    int st = check_device(device);
+    if (st != COEB_OK) return st;
+    CUDA_TRY(cudaSetDevice(device));
+    coeb_matcher* m = new coeb_matcher();
+    m->device = device;
+    if (cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete m; return fail(COEB_ERR_CUDA, "cudaStreamCreate failed"); }
+    m->stream = m->own_stream;
+    *out = m;
+    return COEB_OK;
+}
+
+void coeb_matcher_destroy(coeb_matcher* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    cudaStreamSynchronize(m->stream);
+    cudaFree(m->d_scratch);
+    cudaFree(m->d_in);
+    cudaStreamDestroy(m->own_stream);
+    delete m;
+}
+
+int coeb_matcher_set_stream(coeb_matcher* m, void* cuda_stream) {
+    if (!m) return fail(COEB_ERR_INVALID_ARG, "null matcher");
+    m->stream = cuda_stream ? (cudaStream_t)cuda_stream : m->own_stream;
+    return COEB_OK;
+}
+
+int coeb_frame_create(coeb_matcher* m, const coeb_keypoint* kps, const uint8_t* desc, int n, const float* uright,
+                      const coeb_camera* cam, const float* scale_factors, int nlevels, coeb_frame** out) {
+    if (!m || !out || !cam || !scale_factors || n < 0 || (n > 0 && (!kps || !desc))) return fail(COEB_ERR_INVALID_ARG, "bad argument");
+    if (nlevels < 1 || nlevels > COEB_MAX_LEVELS) return fail(COEB_ERR_INVALID_ARG, "nlevels %d", nlevels);
+    CUDA_TRY(cudaSetDevice(m->device));
+    coeb_frame* f = new coeb_frame();
+    f->m = m; f->n = n; f->nlevels = nlevels;
+    const size_t nn = std::max(n, 1);
+    cudaError_t e = cudaSuccess;
+    e = e ? e : cudaMalloc(&f->d_x, nn * 4); e = e ? e : cudaMalloc(&f->d_y, nn * 4); e = e ? e : cudaMalloc(&f->d_angle, nn * 4);
+    e = e ? e : cudaMalloc(&f->d_octave, nn * 4); e = e ? e : cudaMalloc(&f->d_desc, nn * 32);
+    e = e ? e : cudaMalloc(&f->d_cell_start, (kGridCells + 1) * 4); e = e ? e : cudaMalloc(&f->d_cell_items, nn * 4);
+    e = e ? e : cudaMalloc(&f->d_kp_cell, nn * 4);
+    if (uright) e = e ? e : cudaMalloc(&f->d_uright, nn * 4);
+    if (e != cudaSuccess) { coeb_frame_destroy(f); return fail(COEB_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e)); }
+    std::vector<float> hx(nn), hy(nn), ha(nn);
+    std::vector<int> ho(nn);
+    for (int i = 0; i < n; i++) { hx[i] = kps[i].x; hy[i] = kps[i].y; ha[i] = kps[i].angle; ho[i] = kps[i].octave; }
+    cudaStream_t s = m->stream;
+    int st;
+    if ((st = upload(s, f->d_x, hx.data(), n)) || (st = upload(s, f->d_y, hy.data(), n)) || (st = upload(s, f->d_angle, ha.data(), n)) ||
+        (st = upload(s, f->d_octave, ho.data(), n)) || (st = upload(s, (uint8_t*)f->d_desc, desc, (size_t)n * 32)) ||
+        (uright && (st = upload(s, f->d_uright, uright, n)))) { coeb_frame_destroy(f); return st; }
+    FrameDev& d = f->dev;
+    d.n = n; d.x = f->d_x; d.y = f->d_y; d.angle = f->d_angle; d.octave = f->d_octave; d.desc = f->d_desc; d.uright = f->d_uright;
+    d.cell_start = f->d_cell_start; d.cell_items = f->d_cell_items;
+    d.min_x = cam->min_x; d.min_y = cam->min_y; d.max_x = cam->max_x; d.max_y = cam->max_y;
+    d.gw_inv = (float)COEB_GRID_COLS / (cam->max_x - cam->min_x);   // mfGridElementWidthInv (src/Frame.cc:233)
+    d.gh_inv = (float)COEB_GRID_ROWS / (cam->max_y - cam->min_y);
+    d.fx = cam->fx; d.fy = cam->fy; d.cx = cam->cx; d.cy = cam->cy; d.bf = cam->bf; d.b = cam->b;
+    for (int i = 0; i < COEB_MAX_LEVELS; i++) d.scale[i] = i < nlevels ? scale_factors[i] : 0.f;
+    grid_build_kernel<<<1, 1024, 0, s>>>(d, f->d_cell_start, f->d_cell_items, f->d_kp_cell);
+    cudaError_t le = cudaGetLastError();
+    if (le == cudaSuccess) le = cudaStreamSynchronize(s);  // host staging vectors go out of scope
+    if (le != cudaSuccess) { coeb_frame_destroy(f); return fail(COEB_ERR_CUDA, "grid build failed: %s", cudaGetErrorString(le)); }
+    *out = f;
+    return COEB_OK;
+}
+
+void coeb_frame_destroy(coeb_frame* f) {
+    if (!f) return;
+    cudaSetDevice(f->m->device);
+    cudaFree(f->d_x); cudaFree(f->d_y); cudaFree(f->d_angle); cudaFree(f->d_uright); cudaFree(f->d_octave);
+    cudaFree(f->d_cell_start); cudaFree(f->d_cell_items); cudaFree(f->d_kp_cell); cudaFree(f->d_desc);
+    delete f;
+}
+
+int coeb_frame_features_in_area(coeb_frame* f, float x, float y, float r, int min_level, int max_level, int* idx_out, int cap,
+                                int* n_out) {
+    if (!f || !n_out || cap < 0) return fail(COEB_ERR_INVALID_ARG, "bad argument");
+    coeb_matcher* m = f->m;
+    CUDA_TRY(cudaSetDevice(m->device));
+    int st = grow(&m->d_scratch, &m->scratch_bytes, (size_t)(cap + 1) * 4 + 256);
+    if (st != COEB_OK) return st;
+    int* d_out = (int*)m->d_scratch;
+    int* d_n = d_out + cap;
+    features_in_area_kernel<<<1, 32, 0, m->stream>>>(f->dev, x, y, r, min_level, max_level, d_out, cap, d_n);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(n_out, d_n, 4, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    const int n = std::min(*n_out, cap);
+    if (n > 0 && idx_out) CUDA_TRY(cudaMemcpy(idx_out, d_out, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return *n_out > cap ? fail(COEB_ERR_CAPACITY, "need %d entries", *n_out) : COEB_OK;
+}
+
+int coeb_hamming256_batch(coeb_matcher* m, const uint8_t* a, const uint8_t* b, int n, int* dist_out) {
+    if (!m || !a || !b || !dist_out || n < 0) return fail(COEB_ERR_INVALID_ARG, "bad argument");
+    if (n == 0) return COEB_OK;
+    CUDA_TRY(cudaSetDevice(m->device));
+    int st = grow(&m->d_scratch, &m->scratch_bytes, Carver::need({(size_t)n * 32, (size_t)n * 32, (size_t)n * 4}));
+    if (st != COEB_OK) return st;
+    Carver c(m->d_scratch);
+    uint32_t* da = c.take<uint32_t>((size_t)n * 8);
+    uint32_t* db = c.take<uint32_t>((size_t)n * 8);
+    int* dd = c.take<int>(n);
+    CUDA_TRY(cudaMemcpyAsync(da, a, (size_t)n * 32, cudaMemcpyHostToDevice, m->stream));
+    CUDA_TRY(cudaMemcpyAsync(db, b, (size_t)n * 32, cudaMemcpyHostToDevice, m->stream));
+    hamming_pairs_kernel<<<(n + 255) / 256, 256, 0, m->stream>>>(da, db, n, dd);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(dist_out, dd, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    return COEB_OK;
+}
+
+int coeb_match_projection(coeb_matcher* m, coeb_frame* F, int n, const uint8_t* track_in_view, const uint8_t* bad,
+                          const uint8_t* has_obs, const float* proj_x, const float* proj_y, const float* proj_xr,
+                          const int* level, const float* view_cos, const uint8_t* desc, float th, float nnratio,
+                          int* kp_match, int* nmatches_out) {
+    if (!m || !F || n < 0 || !kp_match) return fail(COEB_ERR_INVALID_ARG, "bad argument");
+    if (nmatches_out) *nmatches_out = 0;
+    if (n == 0 || F->n == 0) return COEB_OK;
+    if (!track_in_view || !bad || !has_obs || !proj_x || !proj_y || !proj_xr || !level || !view_cos || !desc)
+        return fail(COEB_ERR_INVALID_ARG, "null map-point array");
+    for (int i = 0; i < n; i++)
+        if (track_in_view[i] && !bad[i] && (level[i] < 0 || level[i] >= F->nlevels)) return fail(COEB_ERR_INVALID_ARG, "map point %d: level %d", i, level[i]);
+    CUDA_TRY(cudaSetDevice(m->device));
+    const size_t N = n, K = F->n;
+    int st = grow(&m->d_scratch, &m->scratch_bytes,
+                  Carver::need({N, N, N, N * 4, N * 4, N * 4, N * 4, N * 4, N * 32, K * 4, N * 4, K * 4, 64}));
+    if (st != COEB_OK) return st;
+    Carver c(m->d_scratch);
+    uint8_t *d_tiv = c.take<uint8_t>(N), *d_bad = c.take<uint8_t>(N), *d_obs = c.take<uint8_t>(N);
+    float *d_px = c.take<float>(N), *d_py = c.take<float>(N), *d_pxr = c.take<float>(N), *d_vc = c.take<float>(N);
+    int* d_lvl = c.take<int>(N);
+    uint32_t* d_desc = c.take<uint32_t>(N * 8);
+    int *d_kpm = c.take<int>(K), *d_res = c.take<int>(N), *d_claim = c.take<int>(K), *d_info = c.take<int>(16);
+    cudaStream_t s = m->stream;
+    if ((st = upload(s, d_tiv, track_in_view, N)) || (st = upload(s, d_bad, bad, N)) || (st = upload(s, d_obs, has_obs, N)) ||
+        (st = upload(s, d_px, proj_x, N)) || (st = upload(s, d_py, proj_y, N)) || (st = upload(s, d_pxr, proj_xr, N)) ||
+        (st = upload(s, d_vc, view_cos, N)) || (st = upload(s, d_lvl, level, N)) || (st = upload(s, (uint8_t*)d_desc, desc, N * 32)) ||
+        (st = upload(s, d_kpm, kp_match, K)))
+        return st;
+    MapDev M{n, d_tiv, d_bad, d_obs, d_px, d_py, d_pxr, d_vc, d_lvl, d_desc};
+    match_projection_kernel<<<1, 1024, 0, s>>>(F->dev, M, th, nnratio, d_kpm, d_res, d_claim, d_info);
+    CUDA_TRY(cudaGetLastError());
+    int info[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(kp_match, d_kpm, K * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(info, d_info, 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (nmatches_out) *nmatches_out = info[0];
+    return COEB_OK;
+}
+
+int coeb_match_lastframe(coeb_matcher* m, coeb_frame* cur, int n, const uint8_t* valid, const uint8_t* has_obs,
+                         const float* xyz, const int* octave, const float* angle, const uint8_t* desc,
+                         const float* Tcw_cur, const float* Tcw_last, float th, int mono, int check_ori,
+                         int* kp_match, int* nmatches_out) {
+    if (!m || !cur || n < 0 || !kp_match || !Tcw_cur || !Tcw_last) return fail(COEB_ERR_INVALID_ARG, "bad argument");
+    if (nmatches_out) *nmatches_out = 0;
+    if (n == 0 || cur->n == 0) return COEB_OK;
+    if (!valid || !has_obs || !xyz || !octave || !angle || !desc) return fail(COEB_ERR_INVALID_ARG, "null last-frame array");
+    for (int i = 0; i < n; i++)
+        if (valid[i] && (octave[i] < 0 || octave[i] >= cur->nlevels)) return fail(COEB_ERR_INVALID_ARG, "last-frame point %d: octave %d", i, octave[i]);
+    CUDA_TRY(cudaSetDevice(m->device));
+    const size_t N = n, K = cur->n;
+    int st = grow(&m->d_scratch, &m->scratch_bytes, Carver::need({N, N, N * 12, N * 4, N * 4, N * 32, K * 4, N * 4, K * 4, 64}));
+    if (st != COEB_OK) return st;
+    Carver c(m->d_scratch);
+    uint8_t *d_valid = c.take<uint8_t>(N), *d_obs = c.take<uint8_t>(N);
+    float* d_xyz = c.take<float>(N * 3);
+    int* d_oct = c.take<int>(N);
+    float* d_ang = c.take<float>(N);
+    uint32_t* d_desc = c.take<uint32_t>(N * 8);
+    int *d_kpm = c.take<int>(K), *d_res = c.take<int>(N), *d_claim = c.take<int>(K), *d_info = c.take<int>(16);
+    cudaStream_t s = m->stream;
+    if ((st = upload(s, d_valid, valid, N)) || (st = upload(s, d_obs, has_obs, N)) || (st = upload(s, d_xyz, xyz, N * 3)) ||
+        (st = upload(s, d_oct, octave, N)) || (st = upload(s, d_ang, angle, N)) || (st = upload(s, (uint8_t*)d_desc, desc, N * 32)) ||
+        (st = upload(s, d_kpm, kp_match, K)))
+        return st;
+    LastDev L{};
+    L.n = n; L.valid = d_valid; L.has_obs = d_obs; L.xyz = d_xyz; L.octave = d_oct; L.angle = d_ang; L.desc = d_desc;
+    for (int i = 0; i < 12; i++) L.T[i] = Tcw_cur[i];
+    // tlc = Rlw * twc + tlw with twc = -Rcw^T tcw (src/ORBmatcher.cc:1339-1350); only its z component is used. fp32, fixed order.
+    float twc[3];
+    for (int k = 0; k < 3; k++) twc[k] = -(Tcw_cur[0 * 4 + k] * Tcw_cur[3] + Tcw_cur[1 * 4 + k] * Tcw_cur[7] + Tcw_cur[2 * 4 + k] * Tcw_cur[11]);
+    const float tz = Tcw_last[8] * twc[0] + Tcw_last[9] * twc[1] + Tcw_last[10] * twc[2] + Tcw_last[11];
+    L.forward = (tz > cur->dev.b && !mono) ? 1 : 0;
+    L.backward = (-tz > cur->dev.b && !mono) ? 1 : 0;
+    match_lastframe_kernel<<<1, 1024, 0, s>>>(cur->dev, L, th, check_ori, d_kpm, d_res, d_claim, d_info);
+    CUDA_TRY(cudaGetLastError());
+    int info[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(kp_match, d_kpm, K * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(info, d_info, 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (nmatches_out) *nmatches_out = info[0];
+    return COEB_OK;
+}
+
+int coeb_match_init(coeb_matcher* m, coeb_frame* f1, coeb_frame* f2, float* prev_matched, int* matches12, int window_size,
+                    float nnratio, int check_ori, int* nmatches_out) {
+    if (!m || !f1 || !f2 || !prev_matched || !matches12) return fail(COEB_ERR_INVALID_ARG, "bad argument");
+    if (nmatches_out) *nmatches_out = 0;
+    if (f1->n == 0) return COEB_OK;
+    if (f2->n == 0) { for (int i = 0; i < f1->n; i++) matches12[i] = -1; return COEB_OK; }
+    CUDA_TRY(cudaSetDevice(m->device));
+    const size_t N1 = f1->n, N2 = f2->n;
+    int st = grow(&m->d_scratch, &m->scratch_bytes,
+                  Carver::need({N1 * 8, N1 * 8, N1 * 4, N1 * 4, (N2 + 1) * 4, (N2 + 1) * 4, N1 * 8, N1 * 4, 64}));
+    if (st != COEB_OK) return st;
+    Carver c(m->d_scratch);
+    float *d_prev = c.take<float>(N1 * 2), *d_prev_out = c.take<float>(N1 * 2);
+    int *d_res = c.take<int>(N1), *d_rdist = c.take<int>(N1), *d_cls = c.take<int>(N2 + 1), *d_clf = c.take<int>(N2 + 1);
+    int2* d_items = c.take<int2>(N1);
+    int *d_m12 = c.take<int>(N1), *d_info = c.take<int>(16);
+    cudaStream_t s = m->stream;
+    if ((st = upload(s, d_prev, prev_matched, N1 * 2))) return st;
+    match_init_kernel<<<1, 1024, 0, s>>>(f1->dev, f2->dev, d_prev, (float)window_size, nnratio, check_ori, d_res, d_rdist, d_cls, d_clf,
+                                         d_items, d_m12, d_prev_out, d_info);
+    CUDA_TRY(cudaGetLastError());
+    int info[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(matches12, d_m12, N1 * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(prev_matched, d_prev_out, N1 * 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(info, d_info, 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (nmatches_out) *nmatches_out = info[0];
+    return COEB_OK;
+}
+
+int coeb_stereo_match(coeb_matcher* m, coeb_extractor* left, coeb_extractor* right, int N, const coeb_keypoint* keys_left,
+                      const uint8_t* desc_left, int Nr, const coeb_keypoint* keys_right, const uint8_t* desc_right, float bf,
+                      float b, float* uright_out, float* depth_out, int* nmatched_out) {
+    if (!m || !left || !right || N < 0 || Nr < 0 || !uright_out || !depth_out) return fail(COEB_ERR_INVALID_ARG, "bad argument");
+    if (nmatched_out) *nmatched_out = 0;
+    for (int i = 0; i < N; i++) { uright_out[i] = -1.f; depth_out[i] = -1.f; }
+    if (N == 0 || Nr == 0) return COEB_OK;
+    CUDA_TRY(cudaSetDevice(m->device));
+    StereoDev S{};
+    int nl = 0;
+    int st = coeb_extractor_tables(left, &nl, S.scale, S.inv_scale, nullptr, nullptr, nullptr);
+    if (st != COEB_OK) return st;
+    for (int l = 0; l < nl; l++) {
+        int w2 = 0, h2 = 0;
+        if ((st = coeb_pyramid_level(left, 0, l, 0, &S.pyrL[l], &S.lw[l], &S.lh[l], &S.pitchL[l])) != COEB_OK) return st;
+        if ((st = coeb_pyramid_level(right, 0, l, 0, &S.pyrR[l], &w2, &h2, &S.pitchR[l])) != COEB_OK) return st;
+        if (w2 != S.lw[l] || h2 != S.lh[l]) return fail(COEB_ERR_INVALID_ARG, "left/right pyramids differ in size at level %d", l);
+    }
+    for (int i = 0; i < N; i++) if (keys_left[i].octave < 0 || keys_left[i].octave >= nl) return fail(COEB_ERR_INVALID_ARG, "left keypoint %d: octave", i);
+    for (int i = 0; i < Nr; i++) if (keys_right[i].octave < 0 || keys_right[i].octave >= nl) return fail(COEB_ERR_INVALID_ARG, "right keypoint %d: octave", i);
+    S.nRows = S.lh[0];
+    S.N = N; S.Nr = Nr; S.bf = bf; S.b = b;
+    const size_t NL = N, NR = Nr;
+    st = grow(&m->d_scratch, &m->scratch_bytes,
+              Carver::need({NL * 4, NL * 4, NL * 4, NL * 32, NR * 4, NR * 4, NR * 4, NR * 32, NL * 4, NL * 4, NL * 4, 64}));
+    if (st != COEB_OK) return st;
+    Carver c(m->d_scratch);
+    float *dxl = c.take<float>(NL), *dyl = c.take<float>(NL); int* dol = c.take<int>(NL); uint32_t* ddl = c.take<uint32_t>(NL * 8);
+    float *dxr = c.take<float>(NR), *dyr = c.take<float>(NR); int* dor_ = c.take<int>(NR); uint32_t* ddr = c.take<uint32_t>(NR * 8);
+    float *dur = c.take<float>(NL), *ddp = c.take<float>(NL); int *dsad = c.take<int>(NL), *dinfo = c.take<int>(16);
+    std::vector<float> hx(NL), hy(NL), rx(NR), ry(NR);
+    std::vector<int> ho(NL), ro(NR);
+    for (int i = 0; i < N; i++) { hx[i] = keys_left[i].x; hy[i] = keys_left[i].y; ho[i] = keys_left[i].octave; }
+    for (int i = 0; i < Nr; i++) { rx[i] = keys_right[i].x; ry[i] = keys_right[i].y; ro[i] = keys_right[i].octave; }
+    cudaStream_t s = m->stream;
+    if ((st = upload(s, dxl, hx.data(), NL)) || (st = upload(s, dyl, hy.data(), NL)) || (st = upload(s, dol, ho.data(), NL)) ||
+        (st = upload(s, (uint8_t*)ddl, desc_left, NL * 32)) || (st = upload(s, dxr, rx.data(), NR)) || (st = upload(s, dyr, ry.data(), NR)) ||
+        (st = upload(s, dor_, ro.data(), NR)) || (st = upload(s, (uint8_t*)ddr, desc_right, NR * 32)))
+        return st;
+    S.xl = dxl; S.yl = dyl; S.octl = dol; S.descl = ddl; S.xr = dxr; S.yr = dyr; S.octr = dor_; S.descr = ddr;
+    stereo_match_kernel<<<(N + 7) / 8, 256, 0, s>>>(S, dur, ddp, dsad);
+    stereo_outlier_kernel<<<1, 1024, 0, s>>>(N, dur, ddp, dsad, dinfo);
+    CUDA_TRY(cudaGetLastError());
+    int info = 0;
+    CUDA_TRY(cudaMemcpyAsync(uright_out, dur, NL * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(depth_out, ddp, NL * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(&info, dinfo, 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (nmatched_out) *nmatched_out = info;
+    return COEB_OK;
+}
+
+int coeb_knn2_device(coeb_matcher* m, const uint8_t* d_query, int nq, const uint8_t* d_train, int nt, float nnratio,
+                     int* d_best_idx, int* d_d1, int* d_d2) {
+    if (!m || !d_query || !d_train || nq < 1 || nt < 1 || !d_best_idx) return fail(COEB_ERR_INVALID_ARG, "bad argument");
+    CUDA_TRY(cudaSetDevice(m->device));
+    const int qblocks = (nq + kKnnThreads * kKnnQ - 1) / (kKnnThreads * kKnnQ);
+    int nchunks = std::max(1, (148 * 4 + qblocks - 1) / qblocks);          // ~4 CTAs per SM overall
+    nchunks = std::min(nchunks, std::max(1, nt / 64));
+    int chunk = (nt + nchunks - 1) / nchunks;
+    nchunks = (nt + chunk - 1) / chunk;
+    int st = grow(&m->d_in, &m->in_bytes, Carver::need({(size_t)nchunks * nq * 4, (size_t)nchunks * nq * 4, (size_t)nchunks * nq * 4}));
+    if (st != COEB_OK) return st;
+    Carver c(m->d_in);
+    int *p1 = c.take<int>((size_t)nchunks * nq), *pi = c.take<int>((size_t)nchunks * nq), *p2 = c.take<int>((size_t)nchunks * nq);
+    knn2_partial_kernel<<<dim3(qblocks, nchunks), kKnnThreads, 0, m->stream>>>((const uint32_t*)d_query, nq, (const uint32_t*)d_train, nt, chunk,
+                                                                              p1, pi, p2);
+    knn2_merge_kernel<<<(nq + 255) / 256, 256, 0, m->stream>>>(nq, nchunks, p1, pi, p2, nnratio, d_best_idx, d_d1, d_d2, nullptr);
+    CUDA_TRY(cudaGetLastError());
+    return COEB_OK;
+}
+
+int coeb_knn2(coeb_matcher* m, const uint8_t* query, int nq, const uint8_t* train, int nt, float nnratio, int* best_idx,
+              int* d1, int* d2, int* naccepted_out) {
+    if (!m || !query || !train || nq < 0 || nt < 0 || !best_idx) return fail(COEB_ERR_INVALID_ARG, "bad argument");
+    if (naccepted_out) *naccepted_out = 0;
+    if (nq == 0) return COEB_OK;
+    if (nt == 0) { for (int i = 0; i < nq; i++) { best_idx[i] = -1; if (d1) d1[i] = 256; if (d2) d2[i] = 256; } return COEB_OK; }
+    CUDA_TRY(cudaSetDevice(m->device));
+    const size_t NQ = nq, NT = nt;
+    int st = grow(&m->d_scratch, &m->scratch_bytes, Carver::need({NQ * 32, NT * 32, NQ * 4, NQ * 4, NQ * 4}));
+    if (st != COEB_OK) return st;
+    Carver c(m->d_scratch);
+    uint8_t *dq = c.take<uint8_t>(NQ * 32), *dt = c.take<uint8_t>(NT * 32);
+    int *di = c.take<int>(NQ), *dd1 = c.take<int>(NQ), *dd2 = c.take<int>(NQ);
+    cudaStream_t s = m->stream;
+    CUDA_TRY(cudaMemcpyAsync(dq, query, NQ * 32, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(dt, train, NT * 32, cudaMemcpyHostToDevice, s));
+    st = coeb_knn2_device(m, dq, nq, dt, nt, nnratio, di, dd1, dd2);
+    if (st != COEB_OK) return st;
+    CUDA_TRY(cudaMemcpyAsync(best_idx, di, NQ * 4, cudaMemcpyDeviceToHost, s));
+    if (d1) CUDA_TRY(cudaMemcpyAsync(d1, dd1, NQ * 4, cudaMemcpyDeviceToHost, s));
+    if (d2) CUDA_TRY(cudaMemcpyAsync(d2, dd2, NQ * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (naccepted_out) { int a = 0; for (int i = 0; i < nq; i++) a += best_idx[i] >= 0; *naccepted_out = a; }
+    return COEB_OK;
+}
+
+}  // extern "C"

@@ -30,46 +30,6 @@ struct QNode {
     int count;
 };
 
-// In-place exclusive prefix sum of data[0..n) in shared memory; returns the total. All threads call.
-__device__ int block_exclusive_scan(int* data, int n, int* s_warp) {
-    const int T = blockDim.x, tid = threadIdx.x;
-    const int chunk = (n + T - 1) / T;
-    const int lo = min(tid * chunk, n), hi = min(lo + chunk, n);
-    int sum = 0;
-    for (int i = lo; i < hi; i++) sum += data[i];
-    // block scan of per-thread sums
-    const int lane = tid & 31, wid = tid >> 5;
-    int inc = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) s_warp[wid] = inc;
-    __syncthreads();
-    if (wid == 0) {
-        int wv = lane < (T >> 5) ? s_warp[lane] : 0;
-        int winc = wv;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, winc, o);
-            if (lane >= o) winc += t;
-        }
-        s_warp[lane] = winc - wv;       // exclusive warp offsets
-        if (lane == 31) s_warp[32] = winc;  // total
-    }
-    __syncthreads();
-    int run = s_warp[wid] + inc - sum;
-    for (int i = lo; i < hi; i++) {
-        const int t = data[i];
-        data[i] = run;
-        run += t;
-    }
-    const int total = s_warp[32];
-    __syncthreads();
-    return total;
-}
-
 // cv::fastAtan2 (degrees), scalar fp32 path; explicit rn intrinsics keep the compiler from fusing
 // multiply-adds (the CPU build is -ffp-contract=off).
 __device__ __forceinline__ float fast_atan2_deg(float y, float x) {

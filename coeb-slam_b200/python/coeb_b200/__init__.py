@@ -222,3 +222,138 @@ def pinned_array(shape, dtype):
     buf = (C.c_char * max(n, 1)).from_address(p.value)
     arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
     return arr, p
+
+
+# ---------------------------------------------------------------------------------------------------
+# Frame grid + ORBmatcher over the C ABI
+# ---------------------------------------------------------------------------------------------------
+def _u8(a):
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class Matcher:
+    """Device context (stream + scratch) of the ORBmatcher kernels."""
+
+    def __init__(self, device=0):
+        h = C.c_void_p()
+        _check(lib().coeb_matcher_create(int(device), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().coeb_matcher_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, stream_ptr):
+        _check(lib().coeb_matcher_set_stream(self.h, C.c_void_p(int(stream_ptr) if stream_ptr else 0)))
+
+    def hamming(self, a, b):
+        a, b = _u8(a).reshape(-1, 32), _u8(b).reshape(-1, 32)
+        out = np.empty(len(a), np.int32)
+        _check(lib().coeb_hamming256_batch(self.h, _p(a), _p(b), len(a), _p(out)))
+        return out
+
+    def frame(self, kps, desc, cam, scale, uright=None):
+        return Frame(self, kps, desc, cam, scale, uright)
+
+    def match_projection(self, frame, mp, th, nnratio, kp_match):
+        kp_match = _i32(kp_match).copy()
+        a = dict(track_in_view=_u8(mp["track_in_view"]), bad=_u8(mp["bad"]), has_obs=_u8(mp["has_obs"]),
+                 proj_x=_f32(mp["proj_x"]), proj_y=_f32(mp["proj_y"]), proj_xr=_f32(mp["proj_xr"]),
+                 level=_i32(mp["level"]), view_cos=_f32(mp["view_cos"]), desc=_u8(mp["desc"]))
+        n = C.c_int()
+        _check(lib().coeb_match_projection(self.h, frame.h, len(a["proj_x"]), _p(a["track_in_view"]), _p(a["bad"]),
+                                           _p(a["has_obs"]), _p(a["proj_x"]), _p(a["proj_y"]), _p(a["proj_xr"]),
+                                           _p(a["level"]), _p(a["view_cos"]), _p(a["desc"]), C.c_float(th),
+                                           C.c_float(nnratio), _p(kp_match), C.byref(n)))
+        return n.value, kp_match
+
+    def match_lastframe(self, cur, last, Tcw_cur, Tcw_last, th, mono, check_ori, kp_match):
+        kp_match = _i32(kp_match).copy()
+        a = dict(valid=_u8(last["valid"]), has_obs=_u8(last["has_obs"]), xyz=_f32(last["xyz"]),
+                 octave=_i32(last["octave"]), angle=_f32(last["angle"]), desc=_u8(last["desc"]))
+        tc, tl = _f32(Tcw_cur).reshape(12), _f32(Tcw_last).reshape(12)
+        n = C.c_int()
+        _check(lib().coeb_match_lastframe(self.h, cur.h, len(a["valid"]), _p(a["valid"]), _p(a["has_obs"]), _p(a["xyz"]),
+                                          _p(a["octave"]), _p(a["angle"]), _p(a["desc"]), _p(tc), _p(tl), C.c_float(th),
+                                          int(mono), int(check_ori), _p(kp_match), C.byref(n)))
+        return n.value, kp_match
+
+    def match_init(self, f1, f2, prev_matched, window, nnratio, check_ori=True):
+        prev = _f32(prev_matched).reshape(-1, 2).copy()
+        m12 = np.empty(f1.n, np.int32)
+        n = C.c_int()
+        _check(lib().coeb_match_init(self.h, f1.h, f2.h, _p(prev), _p(m12), int(window), C.c_float(nnratio),
+                                     int(check_ori), C.byref(n)))
+        return n.value, m12, prev
+
+    def stereo_match(self, exL, exR, kpsL, descL, kpsR, descR, bf, b):
+        kpsL = np.ascontiguousarray(kpsL, dtype=KP_DTYPE)
+        kpsR = np.ascontiguousarray(kpsR, dtype=KP_DTYPE)
+        descL, descR = _u8(descL), _u8(descR)
+        ur = np.empty(len(kpsL), np.float32)
+        dp = np.empty(len(kpsL), np.float32)
+        n = C.c_int()
+        _check(lib().coeb_stereo_match(self.h, exL.h, exR.h, len(kpsL), _p(kpsL), _p(descL), len(kpsR), _p(kpsR),
+                                       _p(descR), C.c_float(bf), C.c_float(b), _p(ur), _p(dp), C.byref(n)))
+        return n.value, ur, dp
+
+    def knn2(self, q, t, nnratio):
+        q, t = _u8(q).reshape(-1, 32), _u8(t).reshape(-1, 32)
+        idx, d1, d2 = (np.empty(len(q), np.int32) for _ in range(3))
+        n = C.c_int()
+        _check(lib().coeb_knn2(self.h, _p(q), len(q), _p(t), len(t), C.c_float(nnratio), _p(idx), _p(d1), _p(d2),
+                               C.byref(n)))
+        return idx, d1, d2, n.value
+
+    def knn2_device(self, d_q, nq, d_t, nt, nnratio, d_idx, d_d1, d_d2):
+        _check(lib().coeb_knn2_device(self.h, _p(d_q), int(nq), _p(d_t), int(nt), C.c_float(nnratio), _p(d_idx),
+                                      _p(d_d1), _p(d_d2)))
+
+
+class Frame:
+    """Device-resident view of ORB_SLAM2::Frame for the matchers (undistorted keypoints + 64x48 grid)."""
+
+    def __init__(self, matcher, kps, desc, cam, scale, uright=None):
+        self.kps = np.ascontiguousarray(kps, dtype=KP_DTYPE)
+        self.desc = _u8(desc).reshape(-1, 32)
+        self.n = len(self.kps)
+        self.scale = _f32(scale)
+        self.uright = None if uright is None else _f32(uright)
+        self.matcher = matcher
+        h = C.c_void_p()
+        _check(lib().coeb_frame_create(matcher.h, _p(self.kps), _p(self.desc), self.n, _p(self.uright), C.byref(cam),
+                                       _p(self.scale), len(self.scale), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().coeb_frame_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def features_in_area(self, x, y, r, min_level=-1, max_level=-1):
+        out = np.empty(self.n + 1, np.int32)
+        n = C.c_int()
+        _check(lib().coeb_frame_features_in_area(self.h, C.c_float(x), C.c_float(y), C.c_float(r), int(min_level),
+                                                 int(max_level), _p(out), len(out), C.byref(n)))
+        return out[:n.value].copy()

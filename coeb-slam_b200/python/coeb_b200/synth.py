@@ -159,3 +159,101 @@ def flip_bits(desc, rng, max_flips):
             for p in pos:
                 out[i, p >> 3] ^= np.uint8(1 << (p & 7))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# Matching workloads
+# ---------------------------------------------------------------------------------------------------
+def make_map_points(kps, desc, scale, seed=0, n_map=5000, n_true=800, w=640, h=480, bf=40.0):
+    """Config 3: `n_true` true correspondences (a frame descriptor with 0..40 bit flips, projected at the
+    keypoint + N(0, 3 px), predicted level = octave or octave + 1) and distractors with random descriptors
+    at uniform positions. Returns the SoA dict of coeb_match_projection plus a uRight array for the frame."""
+    rng = np.random.default_rng(seed + 91)
+    n = len(kps)
+    nlevels = len(scale)
+    n_true = min(n_true, n)
+    src = rng.choice(n, size=n_true, replace=False)
+    d = np.empty((n_map, 32), np.uint8)
+    d[:n_true] = flip_bits(desc[src], rng, 40)
+    d[n_true:] = rng.integers(0, 256, size=(n_map - n_true, 32), dtype=np.uint8)
+    px = np.empty(n_map, np.float32)
+    py = np.empty(n_map, np.float32)
+    px[:n_true] = kps["x"][src] + rng.normal(0, 3, n_true)
+    py[:n_true] = kps["y"][src] + rng.normal(0, 3, n_true)
+    px[n_true:] = rng.uniform(0, w, n_map - n_true)
+    py[n_true:] = rng.uniform(0, h, n_map - n_true)
+    level = np.empty(n_map, np.int32)
+    level[:n_true] = np.minimum(kps["octave"][src] + rng.integers(0, 2, n_true), nlevels - 1)
+    level[n_true:] = rng.integers(0, nlevels, n_map - n_true)
+    perm = rng.permutation(n_map)
+    depth = rng.uniform(0.5, 5.0, n_map).astype(np.float32)
+    mp = dict(track_in_view=(rng.random(n_map) < 0.95).astype(np.uint8), bad=(rng.random(n_map) < 0.02).astype(np.uint8),
+              has_obs=(rng.random(n_map) < 0.97).astype(np.uint8), proj_x=px, proj_y=py,
+              proj_xr=(px - np.float32(bf) / depth).astype(np.float32), level=level,
+              view_cos=rng.uniform(0.9, 1.0, n_map).astype(np.float32), desc=d)
+    mp = {k: np.ascontiguousarray(v[perm]) for k, v in mp.items()}
+    uright = np.where(rng.random(n) < 0.3, kps["x"] - np.float32(bf) / rng.uniform(0.5, 5.0, n).astype(np.float32),
+                      np.float32(-1)).astype(np.float32)
+    return mp, uright
+
+
+def make_last_frame(kps, desc, seed=0, fx=535.4, fy=539.2, cx=320.1, cy=247.6, shift=(0.02, -0.01, 0.03)):
+    """Config 3 (frame to frame): every keypoint of a 'last frame' gets a 3-D point that projects, under the
+    current pose, near a keypoint of the current frame. Returns (last SoA dict, Tcw_cur, Tcw_last)."""
+    rng = np.random.default_rng(seed + 17)
+    n = len(kps)
+    z = rng.uniform(0.8, 6.0, n).astype(np.float32)
+    # small rotation about y plus a translation
+    a = 0.01
+    R = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]], np.float32)
+    t = np.array(shift, np.float32)
+    Tc = np.concatenate([R, t[:, None]], axis=1).astype(np.float32)
+    Tl = np.concatenate([np.eye(3, dtype=np.float32), np.zeros((3, 1), np.float32)], axis=1)
+    # camera-frame points that project onto the keypoints (+ noise), moved back to the world frame
+    u = kps["x"] + rng.normal(0, 2.0, n).astype(np.float32)
+    v = kps["y"] + rng.normal(0, 2.0, n).astype(np.float32)
+    pc = np.stack([(u - cx) * z / fx, (v - cy) * z / fy, z], axis=1).astype(np.float32)
+    pw = ((pc - t) @ R).astype(np.float32)  # R^T (pc - t)
+    last = dict(valid=(rng.random(n) < 0.8).astype(np.uint8), has_obs=(rng.random(n) < 0.97).astype(np.uint8), xyz=pw,
+                octave=np.clip(kps["octave"] + rng.integers(-1, 2, n), 0, 7).astype(np.int32), angle=(kps["angle"] + rng.normal(0, 4.0, n)).astype(np.float32) % 360,
+                desc=flip_bits(desc, rng, 30))
+    return last, Tc, Tl
+
+
+def shift_image(gray, dx, dy):
+    """Second view for the initialisation matcher: the frame shifted by (dx, dy), edges replicated."""
+    h, w = gray.shape
+    ys = np.clip(np.arange(h) - dy, 0, h - 1)
+    xs = np.clip(np.arange(w) - dx, 0, w - 1)
+    return np.ascontiguousarray(gray[ys][:, xs])
+
+
+def make_stereo_right(left, seed=0, dmin=2, dmax=80, band=24):
+    """Config 4: right image = left image with a per-row-band horizontal disparity in [dmin, dmax] px."""
+    rng = np.random.default_rng(seed + 33)
+    h, w = left.shape
+    right = np.empty_like(left)
+    for y0 in range(0, h, band):
+        d = int(rng.integers(dmin, dmax + 1))
+        xs = np.clip(np.arange(w) + d, 0, w - 1)
+        right[y0:y0 + band] = left[y0:y0 + band][:, xs]
+    return right
+
+
+def make_knn_sets(nq=4000, nt=100000, seed=0):
+    """Config 5: random query descriptors; 10% of the train set are noisy copies of queries."""
+    rng = np.random.default_rng(seed + 55)
+    q = rng.integers(0, 256, size=(nq, 32), dtype=np.uint8)
+    t = rng.integers(0, 256, size=(nt, 32), dtype=np.uint8)
+    ncopy = nt // 10
+    src = rng.integers(0, nq, ncopy)
+    pos = rng.choice(nt, size=ncopy, replace=False)
+    noisy = q[src].copy()
+    flips = rng.integers(0, 60, ncopy)
+    for i in range(ncopy):
+        k = int(flips[i])
+        if k:
+            p = rng.choice(256, size=k, replace=False)
+            np.bitwise_xor.at(noisy[i], p >> 3, (1 << (p & 7)).astype(np.uint8))
+    t[pos] = noisy
+    return q, t
