@@ -66,6 +66,8 @@ struct coeb_extractor {
     uint8_t *d_pyr = nullptr, *d_blur = nullptr;
     uint32_t* d_cand = nullptr;
     uint16_t* d_knode = nullptr;
+    uint32_t* d_lmax = nullptr;
+    int *d_lmax_count = nullptr, *d_cell_count = nullptr;
     int *d_cand_count = nullptr, *d_key_count = nullptr;
     LevelKey* d_keys = nullptr;
     DynState* d_dyn = nullptr;
@@ -230,6 +232,8 @@ int build_geometry(coeb_extractor* ex, int w, int h) {
 }
 
 void free_arenas(coeb_extractor* ex) {
+    cudaFree(ex->d_lmax); cudaFree(ex->d_lmax_count); cudaFree(ex->d_cell_count);
+    ex->d_lmax = nullptr; ex->d_lmax_count = ex->d_cell_count = nullptr;
     cudaFree(ex->d_pyr); cudaFree(ex->d_blur); cudaFree(ex->d_cand); cudaFree(ex->d_knode); cudaFree(ex->d_cand_count);
     cudaFree(ex->d_key_count); cudaFree(ex->d_keys); cudaFree(ex->d_dyn);
     ex->d_pyr = ex->d_blur = nullptr; ex->d_cand = nullptr; ex->d_knode = nullptr; ex->d_cand_count = ex->d_key_count = nullptr;
@@ -251,6 +255,9 @@ int ensure_arenas(coeb_extractor* ex, int B) {
     CUDA_TRY(cudaMalloc(&ex->d_blur, off));
     CUDA_TRY(cudaMalloc(&ex->d_cand, (size_t)B * g.cand_per_frame * sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc(&ex->d_knode, (size_t)B * g.cand_per_frame * sizeof(uint16_t)));
+    CUDA_TRY(cudaMalloc(&ex->d_lmax, (size_t)B * g.cand_per_frame * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&ex->d_lmax_count, (size_t)B * g.nlevels * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&ex->d_cell_count, (size_t)B * g.cells_per_frame * sizeof(int)));
     CUDA_TRY(cudaMalloc(&ex->d_cand_count, (size_t)B * g.nlevels * sizeof(int)));
     CUDA_TRY(cudaMalloc(&ex->d_key_count, (size_t)B * g.nlevels * sizeof(int)));
     CUDA_TRY(cudaMalloc(&ex->d_keys, (size_t)B * g.keys_per_frame * sizeof(LevelKey)));
@@ -391,8 +398,8 @@ int coeb_extractor_tables(const coeb_extractor* ex, int* nlevels, float* scale, 
 
 int coeb_extractor_launches_per_call(const coeb_extractor* ex) {
     if (!ex) return 0;
-    // classify + (nlevels-1) resizes + blur + zero-counts + FAST + select + describe
-    return 1 + (ex->params.nlevels - 1) + 1 + 2 + 1 + 1;
+    // classify + (nlevels-1) resizes + blur + FAST + select + describe (the two counter memsets are not kernels of ours)
+    return 1 + (ex->params.nlevels - 1) + 1 + 1 + 1 + 1;
 }
 
 int coeb_extractor_set_profiling(coeb_extractor* ex, int on) {
@@ -430,9 +437,20 @@ int coeb_extract_batch_device(coeb_extractor* ex, int B, const uint8_t* gray, in
     BatchView v{};
     v.B = B;
     v.l0 = gray; v.l0_pitch = stride; v.l0_stride = frame_stride;
+    if (((uintptr_t)gray | (uintptr_t)stride | (uintptr_t)frame_stride) & 3) {
+        // The tile loaders read aligned 32-bit words. A caller buffer that is not 4-byte aligned in base, row pitch and
+        // frame stride (e.g. tightly packed 1241-px rows) is first copied into the arena's pitch-aligned level-0 block.
+        const LevelGeom& L0 = ex->geom.lv[0];
+        uint8_t* dst = ex->d_pyr + L0.img_base;
+        for (int i = 0; i < B; i++)
+            CUDA_TRY(cudaMemcpy2DAsync(dst + (size_t)i * L0.img_stride, L0.pitch, gray + (size_t)i * frame_stride, stride, width, height,
+                                       cudaMemcpyDeviceToDevice, ex->stream));
+        v.l0 = dst; v.l0_pitch = L0.pitch; v.l0_stride = L0.img_stride;
+    }
     v.pyr = ex->d_pyr; v.blur = ex->d_blur; v.tabs = ex->d_tabs;
     v.cand = ex->d_cand; v.cand_count = ex->d_cand_count; v.keys = ex->d_keys; v.key_count = ex->d_key_count;
     v.dyn = ex->d_dyn; v.knode = ex->d_knode;
+    v.lmax = ex->d_lmax; v.lmax_count = ex->d_lmax_count; v.cell_count = ex->d_cell_count;
     v.boxes = boxes; v.nbox = nbox; v.max_box = max_box; v.tm = tm; v.ntm = ntm; v.max_tm = max_tm; v.blur_flag = blur_flag;
     v.out_kps = kps_out; v.out_desc = desc_out; v.out_count = counts_out; v.status = status_out;
     return enqueue(ex, v);

@@ -13,6 +13,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
+
 #include "../../include/coeb_types.h"
 
 namespace coeb {
@@ -68,6 +70,12 @@ struct DynState {
     int bad_box;     // a box lay outside the image: the frame is reported as COEB_ERR_BAD_BOX
 };
 
+// First tile index of every level inside one frame's tile list (kernels that walk all levels in one launch).
+struct TileMap {
+    int tile_base[COEB_MAX_LEVELS + 1];
+    int tiles_x[COEB_MAX_LEVELS];
+};
+
 // Device pointers of one batch launch.
 struct BatchView {
     int B;
@@ -83,6 +91,9 @@ struct BatchView {
     int* key_count;                    // [B][nlevels]
     DynState* dyn;                     // [B]
     uint16_t* knode;                   // [B][cand_per_frame] octree scratch: node id per candidate
+    uint32_t* lmax;                    // [B][cand_per_frame] FAST cell-local maxima above minTh (same packing as cand)
+    int* lmax_count;                   // [B][nlevels]
+    int* cell_count;                   // [B][cells_per_frame] local maxima above iniTh per FAST cell
     // dynamic-object inputs
     const float* boxes; const int* nbox; int max_box;
     const float* tm; const int* ntm; int max_tm;

@@ -91,18 +91,40 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const __grid_consta
     __shared__ int s_warp[33];
     __shared__ int s_misc[8];
 
-    int nkeys = v.cand_count[frame * g.nlevels + level];
     int* key_count = v.key_count + frame * g.nlevels + level;
-    if (nkeys > L.cand_cap) {  // cannot happen (capacity is the NMS bound); fail loudly rather than truncate
-        if (tid == 0) { *key_count = 0; atomicMin(&v.status[frame], (int)COEB_ERR_CAPACITY); }
+    const int nl = v.lmax_count[frame * g.nlevels + level];
+    if (nl > L.cand_cap) {  // cannot happen (capacity is the NMS bound); fail loudly rather than truncate
+        if (tid == 0) { *key_count = 0; v.cand_count[frame * g.nlevels + level] = 0; atomicMin(&v.status[frame], (int)COEB_ERR_CAPACITY); }
         return;
     }
+    // ---- gather: apply each FAST cell's threshold (iniTh, or minTh if the cell has nothing above iniTh,
+    //      src/ORBextractor.cc:831-838) and, on the area_flag path, CheckMovingKeyPoints (:854-858) ----
+    uint32_t* keys = v.cand + (size_t)frame * g.cand_per_frame + L.cand_base;
+    unsigned short* knode = v.knode + (size_t)frame * g.cand_per_frame + L.cand_base;
+    const int lastJ = max(min(L.nCols - 1, (L.maxBX - 6 - kMinBorder - 1) / L.wCell), 0);
+    const int lastI = max(min(L.nRows - 1, (L.maxBY - 3 - kMinBorder - 1) / L.hCell), 0);
+    {
+        const uint32_t* __restrict__ lm = v.lmax + (size_t)frame * g.cand_per_frame + L.cand_base;
+        const int* __restrict__ cellcnt = v.cell_count + (size_t)frame * g.cells_per_frame + L.cell_base;
+        const int thIni = dyn.area_flag ? 30 : 20, thMin = dyn.area_flag ? 10 : 7;   // :775-784
+        if (tid == 0) s_misc[1] = 0;
+        __syncthreads();
+        for (int k = tid; k < nl; k += T) {
+            const uint32_t key = lm[k];
+            const int x = key & 0xFFF, y = (key >> 12) & 0xFFF, A = (int)(key >> 24) + 1;
+            const int j = min((x - 3) / L.wCell, lastJ), i = min((y - 3) / L.hCell, lastI);
+            const int th = cellcnt[i * L.nCols + j] > 0 ? thIni : thMin;
+            if (A > th && !(dyn.area_flag && is_moving(dyn, (float)x, (float)y, level, L.scale, g.w0, g.h0)))
+                keys[atomicAdd(&s_misc[1], 1)] = key;
+        }
+        __syncthreads();
+    }
+    const int nkeys = s_misc[1];
+    if (tid == 0) v.cand_count[frame * g.nlevels + level] = nkeys;
     if (nkeys == 0 || dyn.bad_box) {
         if (tid == 0) *key_count = 0;
         return;
     }
-    const uint32_t* __restrict__ keys = v.cand + (size_t)frame * g.cand_per_frame + L.cand_base;
-    unsigned short* knode = v.knode + (size_t)frame * g.cand_per_frame + L.cand_base;
 
     int N = L.n_target;
     if (dyn.area_flag) N = (int)((double)N * 0.7);  // (int)(mnFeaturesPerLevel[level])*0.7 -> const int& (:869)
@@ -301,8 +323,6 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const __grid_consta
     for (int i = tid; i < nList; i += T) s_best[i] = 0ull;
     __syncthreads();
     {
-        const int lastJ = max(min(L.nCols - 1, (L.maxBX - 6 - kMinBorder - 1) / L.wCell), 0);
-        const int lastI = max(min(L.nRows - 1, (L.maxBY - 3 - kMinBorder - 1) / L.hCell), 0);
         for (int k = tid; k < nkeys; k += T) {
             const uint32_t key = keys[k];
             const int x = key & 0xFFF, y = (key >> 12) & 0xFFF;

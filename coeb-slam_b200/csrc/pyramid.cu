@@ -65,9 +65,16 @@ void launch_pyramid(const Geometry& g, const BatchView& v, cudaStream_t stream) 
 // Gaussian 7x7 sigma=2, OpenCV bit-exact fixed point: Q8 kernel {18,34,48,56,48,34,18};
 // horizontal pass -> Q8.8 (uint16), vertical pass -> Q16.16, (v + 32768) >> 16. BORDER_REFLECT_101
 // on the level itself (the reference blurs a clone of the ROI, so the pyramid border is not seen).
-// One CTA = 128 x 16 output tile of one level of one frame; all levels in one launch.
+// One CTA = 128 x 32 output tile of one level of one frame; all levels in one launch.
+//   stage : aligned 32-bit words into shared memory (rows reflected by index, the <= 3 reflected
+//           columns at the image's left/right edge patched in place)
+//   H pass: 4 px per thread; the 10 source bytes become nine s16x2 pairs (funnel shift + PRMT) and
+//           the taps are packed 16-bit multiply-adds (no lane can overflow: 255*256 < 65536)
+//   V pass: 4 px x 4 rows per thread from the uint16 intermediate, 32-bit accumulation, one 32-bit store per row
 // ------------------------------------------------------------------------------------------------
-constexpr int kBlurTW = 128, kBlurTH = 16;
+constexpr int kBlurTW = 128, kBlurTH = 32, kBlurThreads = 256;
+constexpr int kBlurInWords = kBlurTW / 4 + 2 + 1;   // 34 words (x from tx0-4) + 1 pad
+constexpr int kBlurRows = kBlurTH + 6;
 
 __device__ __forceinline__ int reflect101(int i, int n) {
     if (n == 1) return 0;
@@ -75,15 +82,10 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return i;
 }
 
-struct BlurTileMap {          // first tile index of every level inside one frame's tile list
-    int tile_base[COEB_MAX_LEVELS + 1];
-    int tiles_x[COEB_MAX_LEVELS];
-};
-
-__global__ void __launch_bounds__(256) blur_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v,
-                                                   const __grid_constant__ BlurTileMap tm) {
-    __shared__ uint8_t s_in[kBlurTH + 6][kBlurTW + 8];
-    __shared__ uint16_t s_h[kBlurTH + 6][kBlurTW];
+__global__ void __launch_bounds__(kBlurThreads) blur_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v,
+                                                            const __grid_constant__ TileMap tm) {
+    __shared__ uint32_t s_in[kBlurRows * kBlurInWords];
+    __shared__ uint2 s_h[kBlurRows * (kBlurTW / 4 + 1)];
     const int frame = blockIdx.y;
     int level = 0;
     while (level + 1 < g.nlevels && (int)blockIdx.x >= tm.tile_base[level + 1]) level++;
@@ -92,40 +94,83 @@ __global__ void __launch_bounds__(256) blur_kernel(const __grid_constant__ Geome
     const int tx0 = (t % tm.tiles_x[level]) * kBlurTW, ty0 = (t / tm.tiles_x[level]) * kBlurTH;
     const uint8_t* __restrict__ src = level_ptr(g, v, level, frame);
     const int spitch = level_pitch(g, v, level);
-    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int tid = threadIdx.x;
+    const int wwords = (L.w + 3) >> 2;
 
-    for (int i = tid; i < (kBlurTH + 6) * (kBlurTW + 6); i += 256) {
-        const int ry = i / (kBlurTW + 6), rx = i - ry * (kBlurTW + 6);
+    for (int i = tid; i < kBlurRows * (kBlurInWords - 1); i += kBlurThreads) {
+        const int ry = i / (kBlurInWords - 1), rw = i - ry * (kBlurInWords - 1);
         const int gy = reflect101(min(ty0 + ry - 3, L.h + 2), L.h);
-        const int gx = reflect101(min(tx0 + rx - 3, L.w + 2), L.w);
-        s_in[ry][rx] = __ldg(src + (size_t)gy * spitch + gx);
+        const int gw = (tx0 >> 2) - 1 + rw;
+        uint32_t w = 0;
+        if (gw >= 0 && gw < wwords) w = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)gy * spitch) + gw);
+        s_in[ry * kBlurInWords + rw] = w;
     }
     __syncthreads();
-    for (int i = tid; i < (kBlurTH + 6) * kBlurTW; i += 256) {
-        const int ry = i / kBlurTW, rx = i - ry * kBlurTW;
-        const uint8_t* p = &s_in[ry][rx];
-        const int acc = 18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3];
-        s_h[ry][rx] = (uint16_t)acc;
-    }
-    __syncthreads();
-    uint8_t* dst = blur_ptr(g, v, level, frame);
-    for (int i = tid; i < kBlurTH * (kBlurTW / 4); i += 256) {
-        const int ry = i / (kBlurTW / 4), rx = (i - ry * (kBlurTW / 4)) * 4;
-        const int gy = ty0 + ry, gx = tx0 + rx;
-        if (gy >= L.h || gx >= L.w) continue;
-        uint32_t packed = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint32_t acc = 18u * (s_h[ry][rx + k] + s_h[ry + 6][rx + k]) + 34u * (s_h[ry + 1][rx + k] + s_h[ry + 5][rx + k]) +
-                                 48u * (s_h[ry + 2][rx + k] + s_h[ry + 4][rx + k]) + 56u * s_h[ry + 3][rx + k];
-            packed |= ((acc + 32768u) >> 16) << (8 * k);
+    uint8_t* s_b = reinterpret_cast<uint8_t*>(s_in);   // byte view: column c <-> x = tx0 - 4 + c
+    constexpr int kRowBytes = kBlurInWords * 4;
+    if (tx0 == 0) {   // x = -1,-2,-3  <-  x = 1,2,3
+        for (int i = tid; i < kBlurRows * 3; i += kBlurThreads) {
+            const int ry = i / 3, k = i - ry * 3 + 1;
+            s_b[ry * kRowBytes + 4 - k] = s_b[ry * kRowBytes + 4 + k];
         }
-        *reinterpret_cast<uint32_t*>(dst + (size_t)gy * L.pitch + gx) = packed;  // tail lands in row padding
+    }
+    if (tx0 + kBlurTW + 3 > L.w - 1) {   // x = w, w+1, w+2  <-  x = w-2, w-3, w-4
+        for (int i = tid; i < kBlurRows * 3; i += kBlurThreads) {
+            const int ry = i / 3, k = i - ry * 3;
+            const int c = L.w + k - tx0 + 4, cs = L.w - 2 - k - tx0 + 4;
+            if (c < kRowBytes - 4 && cs >= 0) s_b[ry * kRowBytes + c] = s_b[ry * kRowBytes + cs];
+        }
+    }
+    __syncthreads();
+
+    for (int i = tid; i < kBlurRows * (kBlurTW / 4); i += kBlurThreads) {
+        const int ry = i >> 5, gx = i & 31;
+        const uint32_t* w = &s_in[ry * kBlurInWords + gx];     // w[0]: x-4.., w[1]: the 4 output pixels, w[2]: x+4..
+        const uint32_t wm = w[0], w0 = w[1], wp = w[2];
+        // B[i] = byte i of (wm, w0, wp); pair P_i = (B[i], B[i+1]) widened to 16 bits
+        const uint32_t Sa = __funnelshift_r(wm, w0, 8), Sb = __funnelshift_r(wm, w0, 16), Sc = __funnelshift_r(wm, w0, 24);
+        const uint32_t Sd = __funnelshift_r(w0, wp, 8), Se = __funnelshift_r(w0, wp, 16), Sf = __funnelshift_r(w0, wp, 24);
+        const uint32_t P1 = __byte_perm(Sa, 0u, 0x4140), P2 = __byte_perm(Sb, 0u, 0x4140), P3 = __byte_perm(Sa, 0u, 0x4342),
+                       P4 = __byte_perm(Sb, 0u, 0x4342), P5 = __byte_perm(Sc, 0u, 0x4342), P6 = __byte_perm(w0, 0u, 0x4342),
+                       P7 = __byte_perm(Sd, 0u, 0x4342), P8 = __byte_perm(Se, 0u, 0x4342), P9 = __byte_perm(Sf, 0u, 0x4342);
+        uint2 o;
+        o.x = 18u * (P1 + P7) + 34u * (P2 + P6) + 48u * (P3 + P5) + 56u * P4;   // outputs x, x+1 (Q8.8 each)
+        o.y = 18u * (P3 + P9) + 34u * (P4 + P8) + 48u * (P5 + P7) + 56u * P6;   // outputs x+2, x+3
+        s_h[ry * (kBlurTW / 4 + 1) + gx] = o;
+    }
+    __syncthreads();
+
+    uint8_t* dst = blur_ptr(g, v, level, frame);
+    {
+        const int gx = tid & 31, strip = tid >> 5;           // 32 column groups x 8 strips of 4 rows
+        const int x = tx0 + 4 * gx;
+        if (x < L.w) {
+            uint32_t hv[10][4];
+#pragma unroll
+            for (int r = 0; r < 10; r++) {
+                const uint2 q = s_h[(strip * 4 + r) * (kBlurTW / 4 + 1) + gx];
+                hv[r][0] = q.x & 0xFFFFu; hv[r][1] = q.x >> 16; hv[r][2] = q.y & 0xFFFFu; hv[r][3] = q.y >> 16;
+            }
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const int y = ty0 + strip * 4 + r;
+                if (y < L.h) {
+                    uint32_t packed = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t acc = 18u * (hv[r][k] + hv[r + 6][k]) + 34u * (hv[r + 1][k] + hv[r + 5][k]) +
+                                             48u * (hv[r + 2][k] + hv[r + 4][k]) + 56u * hv[r + 3][k];
+                        packed |= ((acc + 32768u) >> 16) << (8 * k);
+                    }
+                    *reinterpret_cast<uint32_t*>(dst + (size_t)y * L.pitch + x) = packed;   // tail lands in row padding
+                }
+            }
+        }
     }
 }
 
 void launch_blur(const Geometry& g, const BatchView& v, cudaStream_t stream) {
-    BlurTileMap tm;
+    TileMap tm;
     int total = 0;
     for (int l = 0; l < g.nlevels; l++) {
         tm.tile_base[l] = total;
@@ -133,7 +178,7 @@ void launch_blur(const Geometry& g, const BatchView& v, cudaStream_t stream) {
         total += tm.tiles_x[l] * ((g.lv[l].h + kBlurTH - 1) / kBlurTH);
     }
     tm.tile_base[g.nlevels] = total;
-    blur_kernel<<<dim3(total, v.B), dim3(32, 8), 0, stream>>>(g, v, tm);
+    blur_kernel<<<dim3(total, v.B), kBlurThreads, 0, stream>>>(g, v, tm);
 }
 
 // ------------------------------------------------------------------------------------------------
