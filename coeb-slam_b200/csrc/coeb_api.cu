@@ -79,12 +79,19 @@ struct coeb_extractor {
     coeb_keypoint* d_out_kps = nullptr; uint8_t* d_out_desc = nullptr; int *d_out_count = nullptr, *d_out_status = nullptr;
     size_t out_cap_elems = 0; int out_cap_B = 0;
     BatchView last_view{};
+    // copy/compute pipelining of the host entry point
+    cudaStream_t pipe_stream[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t pipe_done[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t pipe_ready = nullptr;
     // optional per-stage CUDA events (benchmark accounting)
     bool profiling = false;
     cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace {
+
+constexpr int kPipeStreams = 3;
+constexpr int kPipeChunk = 32;
 
 // ORBextractor::ORBextractor tables (src/ORBextractor.cc:418-477)
 void build_tables(coeb_extractor* ex) {
@@ -206,13 +213,12 @@ int build_geometry(coeb_extractor* ex, int w, int h) {
         max_nodes = std::max(max_nodes, L.key_cap + 3);
         L.scale = ex->scale[l];
         L.scaled_patch = (int)(kPatch * ex->scale[l]);  // :877
-        L.img_base = img_off;
-        L.img_stride = (unsigned long long)L.pitch * L.h;
-        L.img_stride = (L.img_stride + 255) & ~255ull;
+        L.img_base = img_off;   // frame-major arena: every frame holds its whole pyramid, levels back to back
         L.tab_base = ex->h_tabs.size();
         if (l > 0) build_resize_tables(g.lv[l - 1].w, g.lv[l - 1].h, L.w, L.h, ex->h_tabs);
-        img_off += L.img_stride;  // per-frame offset; scaled by the batch capacity when the arena is laid out
+        img_off += ((unsigned long long)L.pitch * L.h + 255) & ~255ull;
     }
+    for (int l = 0; l < nl; l++) g.lv[l].img_stride = img_off;   // bytes between consecutive frames
     g.cells_per_frame = cells;
     g.cand_per_frame = cand;
     g.keys_per_frame = keys;
@@ -241,16 +247,12 @@ void free_arenas(coeb_extractor* ex) {
     ex->cap_B = 0;
 }
 
-// Arena layout: level blocks back to back, each [cap_B] frames. img_base in the geometry is finalised here.
+// Arena layout: frame-major ([B] frames, each a whole pyramid), so a sub-batch is a pointer offset.
 int ensure_arenas(coeb_extractor* ex, int B) {
     Geometry& g = ex->geom;
     if (B <= ex->cap_B) return COEB_OK;
     free_arenas(ex);
-    unsigned long long off = 0;
-    for (int l = 0; l < g.nlevels; l++) {
-        g.lv[l].img_base = off;
-        off += g.lv[l].img_stride * (unsigned long long)B;
-    }
+    const unsigned long long off = (unsigned long long)ex->pyr_bytes_per_frame * B;
     CUDA_TRY(cudaMalloc(&ex->d_pyr, off));
     CUDA_TRY(cudaMalloc(&ex->d_blur, off));
     CUDA_TRY(cudaMalloc(&ex->d_cand, (size_t)B * g.cand_per_frame * sizeof(uint32_t)));
@@ -276,26 +278,51 @@ int ensure_buf(T** p, size_t* cap, size_t n) {
     return COEB_OK;
 }
 
-int enqueue(coeb_extractor* ex, const BatchView& v) {
+int enqueue(coeb_extractor* ex, const BatchView& v, cudaStream_t s, bool prof) {
     const Geometry& g = ex->geom;
-    const bool prof = ex->profiling;
-    if (prof) cudaEventRecord(ex->ev[0], ex->stream);
-    launch_classify(g, v, ex->stream);
-    if (prof) cudaEventRecord(ex->ev[1], ex->stream);
-    launch_pyramid(g, v, ex->stream);
-    if (prof) cudaEventRecord(ex->ev[2], ex->stream);
-    launch_blur(g, v, ex->stream);
-    if (prof) cudaEventRecord(ex->ev[3], ex->stream);
-    launch_fast(g, v, ex->stream);
-    if (prof) cudaEventRecord(ex->ev[4], ex->stream);
-    launch_select(g, v, ex->stream);
-    if (prof) cudaEventRecord(ex->ev[5], ex->stream);
-    launch_describe(g, v, ex->stream);
-    if (prof) cudaEventRecord(ex->ev[6], ex->stream);
+    if (prof) cudaEventRecord(ex->ev[0], s);
+    launch_classify(g, v, s);
+    if (prof) cudaEventRecord(ex->ev[1], s);
+    launch_pyramid(g, v, s);
+    if (prof) cudaEventRecord(ex->ev[2], s);
+    launch_blur(g, v, s);
+    if (prof) cudaEventRecord(ex->ev[3], s);
+    launch_fast(g, v, s);
+    if (prof) cudaEventRecord(ex->ev[4], s);
+    launch_select(g, v, s);
+    if (prof) cudaEventRecord(ex->ev[5], s);
+    launch_describe(g, v, s);
+    if (prof) cudaEventRecord(ex->ev[6], s);
     CUDA_TRY(cudaGetLastError());
-    ex->last_view = v;
-    ex->last_B = v.B;
     return COEB_OK;
+}
+
+// View of frames [f0, f0 + n) of a full-batch view: every per-frame array is [B][...], so this is pointer arithmetic.
+BatchView sub_view(const Geometry& g, const BatchView& v, int f0, int n, size_t pyr_frame_bytes) {
+    BatchView s = v;
+    s.B = n;
+    s.l0 = v.l0 + (size_t)f0 * v.l0_stride;
+    s.pyr = v.pyr + (size_t)f0 * pyr_frame_bytes;
+    s.blur = v.blur + (size_t)f0 * pyr_frame_bytes;
+    s.cand = v.cand + (size_t)f0 * g.cand_per_frame;
+    s.knode = v.knode + (size_t)f0 * g.cand_per_frame;
+    s.lmax = v.lmax + (size_t)f0 * g.cand_per_frame;
+    s.cand_count = v.cand_count + (size_t)f0 * g.nlevels;
+    s.lmax_count = v.lmax_count + (size_t)f0 * g.nlevels;
+    s.key_count = v.key_count + (size_t)f0 * g.nlevels;
+    s.cell_count = v.cell_count + (size_t)f0 * g.cells_per_frame;
+    s.keys = v.keys + (size_t)f0 * g.keys_per_frame;
+    s.dyn = v.dyn + f0;
+    if (v.boxes) s.boxes = v.boxes + (size_t)f0 * v.max_box * 4;
+    if (v.nbox) s.nbox = v.nbox + f0;
+    if (v.tm) s.tm = v.tm + (size_t)f0 * v.max_tm * 2;
+    if (v.ntm) s.ntm = v.ntm + f0;
+    if (v.blur_flag) s.blur_flag = v.blur_flag + (size_t)f0 * v.max_box;
+    s.out_kps = v.out_kps + (size_t)f0 * g.out_cap;
+    s.out_desc = v.out_desc + (size_t)f0 * g.out_cap * 32;
+    s.out_count = v.out_count + f0;
+    s.status = v.status + f0;
+    return s;
 }
 
 int validate_common(coeb_extractor* ex, int B, const uint8_t* gray, int w, int h, int stride, int cap) {
@@ -363,6 +390,11 @@ void coeb_extractor_destroy(coeb_extractor* ex) {
     cudaFree(ex->d_in_gray); cudaFree(ex->d_in_boxes); cudaFree(ex->d_in_tm); cudaFree(ex->d_in_nbox); cudaFree(ex->d_in_ntm);
     cudaFree(ex->d_in_blur); cudaFree(ex->d_out_kps); cudaFree(ex->d_out_desc); cudaFree(ex->d_out_count); cudaFree(ex->d_out_status);
     for (int i = 0; i < 7; i++) if (ex->ev[i]) cudaEventDestroy(ex->ev[i]);
+    for (int i = 0; i < 3; i++) {
+        if (ex->pipe_stream[i]) cudaStreamDestroy(ex->pipe_stream[i]);
+        if (ex->pipe_done[i]) cudaEventDestroy(ex->pipe_done[i]);
+    }
+    if (ex->pipe_ready) cudaEventDestroy(ex->pipe_ready);
     cudaStreamDestroy(ex->own_stream);
     delete ex;
 }
@@ -419,10 +451,10 @@ int coeb_extractor_stage_ms(coeb_extractor* ex, float* ms6) {
     return COEB_OK;
 }
 
-int coeb_extract_batch_device(coeb_extractor* ex, int B, const uint8_t* gray, int width, int height, int stride,
-                              size_t frame_stride, const float* boxes, const int* nbox, int max_box, const float* tm,
-                              const int* ntm, int max_tm, const int* blur_flag, coeb_keypoint* kps_out,
-                              uint8_t* desc_out, int* counts_out, int* status_out, int cap) {
+// Validates, sizes the arenas and fills the full-batch view (no launch).
+static int prepare_view(coeb_extractor* ex, int B, const uint8_t* gray, int width, int height, int stride, size_t frame_stride,
+                        const float* boxes, const int* nbox, int max_box, const float* tm, const int* ntm, int max_tm, const int* blur_flag,
+                        coeb_keypoint* kps_out, uint8_t* desc_out, int* counts_out, int* status_out, int cap, BatchView* out) {
     int st = validate_common(ex, B, gray, width, height, stride, cap);
     if (st != COEB_OK) return st;
     if (!kps_out || !desc_out || !counts_out || !status_out) return fail(COEB_ERR_INVALID_ARG, "null output pointer");
@@ -437,6 +469,24 @@ int coeb_extract_batch_device(coeb_extractor* ex, int B, const uint8_t* gray, in
     BatchView v{};
     v.B = B;
     v.l0 = gray; v.l0_pitch = stride; v.l0_stride = frame_stride;
+    v.pyr = ex->d_pyr; v.blur = ex->d_blur; v.tabs = ex->d_tabs;
+    v.cand = ex->d_cand; v.cand_count = ex->d_cand_count; v.keys = ex->d_keys; v.key_count = ex->d_key_count;
+    v.dyn = ex->d_dyn; v.knode = ex->d_knode;
+    v.lmax = ex->d_lmax; v.lmax_count = ex->d_lmax_count; v.cell_count = ex->d_cell_count;
+    v.boxes = boxes; v.nbox = nbox; v.max_box = max_box; v.tm = tm; v.ntm = ntm; v.max_tm = max_tm; v.blur_flag = blur_flag;
+    v.out_kps = kps_out; v.out_desc = desc_out; v.out_count = counts_out; v.status = status_out;
+    *out = v;
+    return COEB_OK;
+}
+
+int coeb_extract_batch_device(coeb_extractor* ex, int B, const uint8_t* gray, int width, int height, int stride,
+                              size_t frame_stride, const float* boxes, const int* nbox, int max_box, const float* tm,
+                              const int* ntm, int max_tm, const int* blur_flag, coeb_keypoint* kps_out,
+                              uint8_t* desc_out, int* counts_out, int* status_out, int cap) {
+    BatchView v;
+    int st = prepare_view(ex, B, gray, width, height, stride, frame_stride, boxes, nbox, max_box, tm, ntm, max_tm, blur_flag, kps_out,
+                          desc_out, counts_out, status_out, cap, &v);
+    if (st != COEB_OK) return st;
     if (((uintptr_t)gray | (uintptr_t)stride | (uintptr_t)frame_stride) & 3) {
         // The tile loaders read aligned 32-bit words. A caller buffer that is not 4-byte aligned in base, row pitch and
         // frame stride (e.g. tightly packed 1241-px rows) is first copied into the arena's pitch-aligned level-0 block.
@@ -447,13 +497,9 @@ int coeb_extract_batch_device(coeb_extractor* ex, int B, const uint8_t* gray, in
                                        cudaMemcpyDeviceToDevice, ex->stream));
         v.l0 = dst; v.l0_pitch = L0.pitch; v.l0_stride = L0.img_stride;
     }
-    v.pyr = ex->d_pyr; v.blur = ex->d_blur; v.tabs = ex->d_tabs;
-    v.cand = ex->d_cand; v.cand_count = ex->d_cand_count; v.keys = ex->d_keys; v.key_count = ex->d_key_count;
-    v.dyn = ex->d_dyn; v.knode = ex->d_knode;
-    v.lmax = ex->d_lmax; v.lmax_count = ex->d_lmax_count; v.cell_count = ex->d_cell_count;
-    v.boxes = boxes; v.nbox = nbox; v.max_box = max_box; v.tm = tm; v.ntm = ntm; v.max_tm = max_tm; v.blur_flag = blur_flag;
-    v.out_kps = kps_out; v.out_desc = desc_out; v.out_count = counts_out; v.status = status_out;
-    return enqueue(ex, v);
+    ex->last_view = v;
+    ex->last_B = B;
+    return enqueue(ex, v, ex->stream, ex->profiling);
 }
 
 int coeb_extract_batch_host(coeb_extractor* ex, int B, const uint8_t* gray, int width, int height, int stride,
@@ -470,20 +516,14 @@ int coeb_extract_batch_host(coeb_extractor* ex, int B, const uint8_t* gray, int 
     if (ntm) for (int i = 0; i < B; i++) if (ntm[i] < 0 || ntm[i] > max_tm) return fail(COEB_ERR_INVALID_ARG, "frame %d: ntm=%d > max_tm=%d", i, ntm[i], max_tm);
     CUDA_TRY(cudaSetDevice(ex->device));
     cudaStream_t s = ex->stream;
-    // stage inputs: level 0 goes into a pitch-aligned device buffer
+    // device staging: level 0 goes into a pitch-aligned buffer; outputs into [B][cap] arrays
     const int pitch = (width + 63) & ~63;
     const size_t fstride = (size_t)pitch * height;
     st = ensure_buf(&ex->d_in_gray, &ex->in_gray_bytes, fstride * B);
     if (st != COEB_OK) return st;
-    if (frame_stride == (size_t)stride * height) {
-        CUDA_TRY(cudaMemcpy2DAsync(ex->d_in_gray, pitch, gray, stride, width, (size_t)height * B, cudaMemcpyHostToDevice, s));
-    } else {
-        for (int i = 0; i < B; i++)
-            CUDA_TRY(cudaMemcpy2DAsync(ex->d_in_gray + fstride * i, pitch, gray + frame_stride * i, stride, width, height, cudaMemcpyHostToDevice, s));
-    }
     const float *dboxes = nullptr, *dtm = nullptr;
     const int *dnbox = nullptr, *dntm = nullptr, *dblur = nullptr;
-    if (nbox) {
+    if (nbox) {  // the per-frame box / T_M arrays are tiny: one copy up front
         if ((st = ensure_buf(&ex->d_in_boxes, &ex->in_dyn_cap[0], (size_t)B * max_box * 4)) != COEB_OK) return st;
         if ((st = ensure_buf(&ex->d_in_nbox, &ex->in_dyn_cap[1], (size_t)B)) != COEB_OK) return st;
         if ((st = ensure_buf(&ex->d_in_blur, &ex->in_dyn_cap[2], (size_t)B * max_box)) != COEB_OK) return st;
@@ -499,7 +539,6 @@ int coeb_extract_batch_host(coeb_extractor* ex, int B, const uint8_t* gray, int 
         CUDA_TRY(cudaMemcpyAsync(ex->d_in_ntm, ntm, sizeof(int) * B, cudaMemcpyHostToDevice, s));
         dtm = ex->d_in_tm; dntm = ex->d_in_ntm;
     }
-    // output staging
     if ((size_t)B * cap > ex->out_cap_elems || B > ex->out_cap_B) {
         cudaFree(ex->d_out_kps); cudaFree(ex->d_out_desc); cudaFree(ex->d_out_count); cudaFree(ex->d_out_status);
         ex->d_out_kps = nullptr; ex->d_out_desc = nullptr; ex->d_out_count = ex->d_out_status = nullptr;
@@ -510,16 +549,59 @@ int coeb_extract_batch_host(coeb_extractor* ex, int B, const uint8_t* gray, int 
         ex->out_cap_elems = (size_t)B * cap;
         ex->out_cap_B = B;
     }
-    st = coeb_extract_batch_device(ex, B, ex->d_in_gray, width, height, pitch, fstride, dboxes, dnbox, max_box, dtm, dntm, max_tm,
-                                   dblur, ex->d_out_kps, ex->d_out_desc, ex->d_out_count, ex->d_out_status, cap);
+    BatchView v;
+    st = prepare_view(ex, B, ex->d_in_gray, width, height, pitch, fstride, dboxes, dnbox, max_box, dtm, dntm, max_tm, dblur, ex->d_out_kps,
+                      ex->d_out_desc, ex->d_out_count, ex->d_out_status, cap, &v);
     if (st != COEB_OK) return st;
+    ex->last_view = v;
+    ex->last_B = B;
     std::vector<int> status_local;
     int* hstatus = status_out;
     if (!hstatus) { status_local.resize(B); hstatus = status_local.data(); }
-    CUDA_TRY(cudaMemcpyAsync(counts_out, ex->d_out_count, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(hstatus, ex->d_out_status, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
-    if (kps_out) CUDA_TRY(cudaMemcpyAsync(kps_out, ex->d_out_kps, sizeof(coeb_keypoint) * B * cap, cudaMemcpyDeviceToHost, s));
-    if (desc_out) CUDA_TRY(cudaMemcpyAsync(desc_out, ex->d_out_desc, (size_t)32 * B * cap, cudaMemcpyDeviceToHost, s));
+
+    // Sub-batches of kPipeChunk frames round-robin over kPipeStreams streams: the H2D copy of chunk c+1 and the D2H
+    // copy of chunk c-1 overlap the kernels of chunk c (the arenas are frame-major, so a chunk is a pointer offset).
+    const int chunk = B <= 2 * kPipeChunk ? B : kPipeChunk;
+    const int nchunks = (B + chunk - 1) / chunk;
+    const bool piped = nchunks > 1;
+    if (piped && !ex->pipe_stream[0]) {
+        for (int i = 0; i < kPipeStreams; i++) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&ex->pipe_stream[i], cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&ex->pipe_done[i], cudaEventDisableTiming));
+        }
+        CUDA_TRY(cudaEventCreateWithFlags(&ex->pipe_ready, cudaEventDisableTiming));
+    }
+    if (piped) {
+        CUDA_TRY(cudaEventRecord(ex->pipe_ready, s));
+        for (int i = 0; i < kPipeStreams; i++) CUDA_TRY(cudaStreamWaitEvent(ex->pipe_stream[i], ex->pipe_ready, 0));
+    }
+    for (int c = 0; c < nchunks; c++) {
+        cudaStream_t ps = piped ? ex->pipe_stream[c % kPipeStreams] : s;
+        const int f0 = c * chunk, n = std::min(chunk, B - f0);
+        if (frame_stride == (size_t)stride * height) {
+            CUDA_TRY(cudaMemcpy2DAsync(ex->d_in_gray + fstride * f0, pitch, gray + frame_stride * f0, stride, width, (size_t)height * n,
+                                       cudaMemcpyHostToDevice, ps));
+        } else {
+            for (int i = f0; i < f0 + n; i++)
+                CUDA_TRY(cudaMemcpy2DAsync(ex->d_in_gray + fstride * i, pitch, gray + frame_stride * i, stride, width, height,
+                                           cudaMemcpyHostToDevice, ps));
+        }
+        st = enqueue(ex, sub_view(ex->geom, v, f0, n, ex->pyr_bytes_per_frame), ps, !piped && ex->profiling);
+        if (st != COEB_OK) return st;
+        CUDA_TRY(cudaMemcpyAsync(counts_out + f0, ex->d_out_count + f0, sizeof(int) * n, cudaMemcpyDeviceToHost, ps));
+        CUDA_TRY(cudaMemcpyAsync(hstatus + f0, ex->d_out_status + f0, sizeof(int) * n, cudaMemcpyDeviceToHost, ps));
+        if (kps_out)
+            CUDA_TRY(cudaMemcpyAsync(kps_out + (size_t)f0 * cap, ex->d_out_kps + (size_t)f0 * cap, sizeof(coeb_keypoint) * n * cap,
+                                     cudaMemcpyDeviceToHost, ps));
+        if (desc_out)
+            CUDA_TRY(cudaMemcpyAsync(desc_out + (size_t)f0 * cap * 32, ex->d_out_desc + (size_t)f0 * cap * 32, (size_t)32 * n * cap,
+                                     cudaMemcpyDeviceToHost, ps));
+    }
+    if (piped)
+        for (int i = 0; i < kPipeStreams; i++) {
+            CUDA_TRY(cudaEventRecord(ex->pipe_done[i], ex->pipe_stream[i]));
+            CUDA_TRY(cudaStreamWaitEvent(s, ex->pipe_done[i], 0));
+        }
     CUDA_TRY(cudaStreamSynchronize(s));
     int worst = COEB_OK;
     for (int i = 0; i < B; i++)

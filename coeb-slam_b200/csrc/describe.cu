@@ -12,11 +12,12 @@ __constant__ signed char c_pattern[1024] = {
 };
 
 __global__ void __launch_bounds__(256) describe_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v) {
-    __shared__ signed char s_pat[1024];
+    __shared__ signed char s_pat[1024];   // transposed: [4*bit + component][lane], conflict-free per-lane reads
+    __shared__ float2 s_cs[256];          // (cos, sin) of the keypoints of the current chunk
     const int level = blockIdx.x, frame = blockIdx.y;
     const LevelGeom& L = g.lv[level];
     const int tid = threadIdx.x;
-    for (int i = tid; i < 1024; i += 256) s_pat[i] = c_pattern[i];
+    for (int i = tid; i < 1024; i += 256) s_pat[(i & 31) * 32 + (i >> 5)] = c_pattern[i];   // byte `i>>5` uses ints [32*(i>>5), +32)
 
     // row offset of this level in the frame's output = keypoints of the lower levels (:1307-1324)
     const int* kc = v.key_count + frame * g.nlevels;
@@ -44,39 +45,47 @@ __global__ void __launch_bounds__(256) describe_kernel(const __grid_constant__ G
     uint8_t* odesc = v.out_desc + ((size_t)frame * g.out_cap + offset) * 32;
     const int lane = tid & 31, wid = tid >> 5;
     const float factorPI = (float)(3.14159265358979323846 / 180.0);  // (float)(CV_PI/180.f), :109
-    for (int i = wid; i < n; i += 8) {
-        const LevelKey k = keys[i];
-        const float angle = __fmul_rn(k.angle, factorPI);
-        // (float)cos(angle), (float)sin(angle) with a float argument promoted to double (:115)
-        const float a = (float)cos((double)angle), b = (float)sin((double)angle);
-        const int cx = __float2int_rn(k.x), cy = __float2int_rn(k.y);
-        const uint8_t* center = img + (size_t)cy * pitch + cx;
-        const signed char* pat = s_pat + lane * 32;
-        int val = 0;
-#pragma unroll
-        for (int bit = 0; bit < 8; bit++) {
-            const float x0 = (float)pat[4 * bit], y0 = (float)pat[4 * bit + 1];
-            const float x1 = (float)pat[4 * bit + 2], y1 = (float)pat[4 * bit + 3];
-            // cvRound(x*b + y*a) rows, cvRound(x*a - y*b) cols: separate roundings, half-to-even (:121-122)
-            const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
-            const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
-            const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
-            const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-            const int t0 = __ldg(center + (ptrdiff_t)r0 * pitch + c0);
-            const int t1 = __ldg(center + (ptrdiff_t)r1 * pitch + c1);
-            val |= (t0 < t1) << bit;
+    for (int base = 0; base < n; base += 256) {
+        __syncthreads();
+        if (base + tid < n) {
+            // (float)cos(angle), (float)sin(angle) with the float argument promoted to double (:114-115); once per keypoint
+            const float angle = __fmul_rn(keys[base + tid].angle, factorPI);
+            s_cs[tid] = make_float2((float)cos((double)angle), (float)sin((double)angle));
         }
-        odesc[(size_t)i * 32 + lane] = (uint8_t)val;
-        if (lane == 0) {
-            coeb_keypoint o;
-            o.x = level != 0 ? __fmul_rn(k.x, L.scale) : k.x;   // keypoint->pt *= scale (:1327-1334)
-            o.y = level != 0 ? __fmul_rn(k.y, L.scale) : k.y;
-            o.size = (float)L.scaled_patch;
-            o.angle = k.angle;
-            o.response = k.response;
-            o.octave = level;
-            o.class_id = -1;
-            okp[i] = o;
+        __syncthreads();
+        const int m = min(256, n - base);
+        for (int j = wid; j < m; j += 8) {
+            const int i = base + j;
+            const LevelKey k = keys[i];
+            const float a = s_cs[j].x, b = s_cs[j].y;
+            const int cx = __float2int_rn(k.x), cy = __float2int_rn(k.y);
+            const uint8_t* center = img + (size_t)cy * pitch + cx;
+            int val = 0;
+#pragma unroll
+            for (int bit = 0; bit < 8; bit++) {
+                const float x0 = (float)s_pat[(4 * bit) * 32 + lane], y0 = (float)s_pat[(4 * bit + 1) * 32 + lane];
+                const float x1 = (float)s_pat[(4 * bit + 2) * 32 + lane], y1 = (float)s_pat[(4 * bit + 3) * 32 + lane];
+                // cvRound(x*b + y*a) rows, cvRound(x*a - y*b) cols: separate roundings, half-to-even (:121-122)
+                const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+                const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+                const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+                const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+                const int t0 = __ldg(center + (ptrdiff_t)r0 * pitch + c0);
+                const int t1 = __ldg(center + (ptrdiff_t)r1 * pitch + c1);
+                val |= (t0 < t1) << bit;
+            }
+            odesc[(size_t)i * 32 + lane] = (uint8_t)val;
+            if (lane == 0) {
+                coeb_keypoint o;
+                o.x = level != 0 ? __fmul_rn(k.x, L.scale) : k.x;   // keypoint->pt *= scale (:1327-1334)
+                o.y = level != 0 ? __fmul_rn(k.y, L.scale) : k.y;
+                o.size = (float)L.scaled_patch;
+                o.angle = k.angle;
+                o.response = k.response;
+                o.octave = level;
+                o.class_id = -1;
+                okp[i] = o;
+            }
         }
     }
 }

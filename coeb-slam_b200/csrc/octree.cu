@@ -23,6 +23,7 @@
 namespace coeb {
 
 constexpr int kSelThreads = 512;
+constexpr int kKeyCache = 4096;   // candidates per (level, frame) kept in shared memory (4 + 2 bytes each)
 constexpr unsigned long long kOrdMask = 0xFFFFFFFFFFFFull;  // 48-bit candidate-order field
 
 struct QNode {
@@ -88,6 +89,9 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const __grid_consta
     unsigned short* s_P = reinterpret_cast<unsigned short*>(sp); sp += sizeof(unsigned short) * LC;
     unsigned short* s_E = reinterpret_cast<unsigned short*>(sp); sp += sizeof(unsigned short) * LC;
     unsigned short* s_E2 = reinterpret_cast<unsigned short*>(sp); sp += sizeof(unsigned short) * LC;
+    sp = s_dyn_raw + ((sp - s_dyn_raw + 15) & ~(size_t)15);
+    uint32_t* s_keys = reinterpret_cast<uint32_t*>(sp); sp += sizeof(uint32_t) * kKeyCache;          // candidate cache
+    unsigned short* s_knode = reinterpret_cast<unsigned short*>(sp); sp += sizeof(unsigned short) * kKeyCache;
     __shared__ int s_warp[33];
     __shared__ int s_misc[8];
 
@@ -99,8 +103,12 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const __grid_consta
     }
     // ---- gather: apply each FAST cell's threshold (iniTh, or minTh if the cell has nothing above iniTh,
     //      src/ORBextractor.cc:831-838) and, on the area_flag path, CheckMovingKeyPoints (:854-858) ----
-    uint32_t* keys = v.cand + (size_t)frame * g.cand_per_frame + L.cand_base;
-    unsigned short* knode = v.knode + (size_t)frame * g.cand_per_frame + L.cand_base;
+    // Candidates and their node ids live in shared memory when the level's local maxima fit the cache (the usual
+    // case); otherwise the passes below run on the global arrays. The candidate list is always written to global too.
+    uint32_t* gkeys = v.cand + (size_t)frame * g.cand_per_frame + L.cand_base;
+    const bool cached = nl <= kKeyCache;
+    uint32_t* keys = cached ? s_keys : gkeys;
+    unsigned short* knode = cached ? s_knode : v.knode + (size_t)frame * g.cand_per_frame + L.cand_base;
     const int lastJ = max(min(L.nCols - 1, (L.maxBX - 6 - kMinBorder - 1) / L.wCell), 0);
     const int lastI = max(min(L.nRows - 1, (L.maxBY - 3 - kMinBorder - 1) / L.hCell), 0);
     {
@@ -115,7 +123,11 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const __grid_consta
             const int j = min((x - 3) / L.wCell, lastJ), i = min((y - 3) / L.hCell, lastI);
             const int th = cellcnt[i * L.nCols + j] > 0 ? thIni : thMin;
             if (A > th && !(dyn.area_flag && is_moving(dyn, (float)x, (float)y, level, L.scale, g.w0, g.h0)))
-                keys[atomicAdd(&s_misc[1], 1)] = key;
+            {
+                const int pos = atomicAdd(&s_misc[1], 1);
+                gkeys[pos] = key;
+                if (cached) s_keys[pos] = key;
+            }
         }
         __syncthreads();
     }
@@ -367,15 +379,19 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const __grid_consta
         if (lane < 31) {
             const uint8_t* c = img + (size_t)y * pitch + x + u;
             const int au = u < 0 ? -u : u;
-#pragma unroll 1
+            // all 31 row loads are issued before any is consumed (they are independent; a rolled loop would
+            // serialise 31 L2 round trips per keypoint)
+            int val[2 * kHalfPatch + 1];
+#pragma unroll
+            for (int vv = -kHalfPatch; vv <= kHalfPatch; vv++)
+                val[vv + kHalfPatch] = (au <= g.umax[vv < 0 ? -vv : vv]) ? (int)__ldg(c + (ptrdiff_t)vv * pitch) : 0;
+            int colsum = 0;
+#pragma unroll
             for (int vv = -kHalfPatch; vv <= kHalfPatch; vv++) {
-                const int d = g.umax[vv < 0 ? -vv : vv];
-                if (au <= d) {
-                    const int val = __ldg(c + (ptrdiff_t)vv * pitch);
-                    m10 += u * val;
-                    m01 += vv * val;
-                }
+                colsum += val[vv + kHalfPatch];
+                m01 += vv * val[vv + kHalfPatch];
             }
+            m10 = u * colsum;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -394,7 +410,7 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const __grid_consta
 }
 
 size_t select_smem_bytes(int LC) {
-    return (size_t)LC * (sizeof(unsigned long long) + 2 * sizeof(QNode) + 4 * 4 + 4 * 4 + 4 + 4 * 2 + 2 * 5);
+    return (size_t)LC * (sizeof(unsigned long long) + 2 * sizeof(QNode) + 4 * 4 + 4 * 4 + 4 + 4 * 2 + 2 * 5) + 16 + (size_t)kKeyCache * 6;
 }
 
 void launch_select(const Geometry& g, const BatchView& v, cudaStream_t stream) {
