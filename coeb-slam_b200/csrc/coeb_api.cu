@@ -487,8 +487,8 @@ int coeb_extract_batch_device(coeb_extractor* ex, int B, const uint8_t* gray, in
     int st = prepare_view(ex, B, gray, width, height, stride, frame_stride, boxes, nbox, max_box, tm, ntm, max_tm, blur_flag, kps_out,
                           desc_out, counts_out, status_out, cap, &v);
     if (st != COEB_OK) return st;
-    if (((uintptr_t)gray | (uintptr_t)stride | (uintptr_t)frame_stride) & 3) {
-        // The tile loaders read aligned 32-bit words. A caller buffer that is not 4-byte aligned in base, row pitch and
+    if (((uintptr_t)gray | (uintptr_t)stride | (uintptr_t)frame_stride) & 15) {
+        // The tile loaders read aligned 16-byte vectors. A caller buffer that is not 16-byte aligned in base, row pitch and
         // frame stride (e.g. tightly packed 1241-px rows) is first copied into the arena's pitch-aligned level-0 block.
         const LevelGeom& L0 = ex->geom.lv[0];
         uint8_t* dst = ex->d_pyr + L0.img_base;

@@ -26,7 +26,7 @@ namespace coeb {
 
 constexpr int kFtW = 64, kFtH = 30;            // output tile
 constexpr int kFtThreads = 288;                // 18 four-pixel groups x 32 rows of A = 576 = 2 per thread
-constexpr int kImgWords = 21;                  // 20 words (80 px: tile + 8 each side) + 1 pad
+constexpr int kImgWords = 28;                  // 24 words (96 px from x = tx0-16, six 16-byte loads) + pad to a 16-byte multiple
 constexpr int kImgRows = kFtH + 8;             // 3 (ring) + 1 (NMS halo) each side
 constexpr int kAW = 72, kARows = kFtH + 2;     // A tile: x from tx0-4 (18 groups), y from ty0-1
 
@@ -61,9 +61,9 @@ __device__ __forceinline__ uint32_t corner_strength2(uint32_t c, const uint32_t 
     return __vimax3_s16x2(ab, ad, 0u);
 }
 
-__global__ void __launch_bounds__(kFtThreads) fast_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v,
+__global__ void __launch_bounds__(kFtThreads, 4) fast_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v,
                                                           const __grid_constant__ TileMap tm) {
-    __shared__ uint32_t s_img[kImgRows * kImgWords];
+    __shared__ __align__(16) uint32_t s_img[kImgRows * kImgWords];
     __shared__ __align__(4) uint8_t s_A[kARows * kAW];
     __shared__ __align__(8) short s_colcell[kAW];
     __shared__ short s_rowcell[kARows];
@@ -79,15 +79,15 @@ __global__ void __launch_bounds__(kFtThreads) fast_kernel(const __grid_constant_
     const int tid = threadIdx.x;
     const uint8_t* __restrict__ img = level_ptr(g, v, level, frame);
     const int pitch = level_pitch(g, v, level);
-    const int wwords = (L.w + 3) >> 2;   // readable words per row (the row pitch is padded beyond w)
 
-    // ---- stage the tile: rows ty0-4 .. ty0+33, words from x = tx0-8; outside the image -> 0 ----
-    for (int i = tid; i < kImgRows * 20; i += kFtThreads) {
-        const int ry = i / 20, rw = i - ry * 20;
-        const int gy = ty0 - 4 + ry, gw = ((tx0 - 8) >> 2) + rw;
-        uint32_t w = 0;
-        if (gy >= 0 && gy < L.h && gw >= 0 && gw < wwords) w = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)gy * pitch) + gw);
-        s_img[ry * kImgWords + rw] = w;
+    // ---- stage the tile: rows ty0-4 .. ty0+33, 96 bytes from x = tx0-16 as six 16-byte loads per row (228 loads per
+    //      CTA); outside the image -> 0. Bytes between w and the row pitch are padding and never reach an in-domain pixel.
+    for (int i = tid; i < kImgRows * 6; i += kFtThreads) {
+        const int ry = i / 6, q = i - ry * 6;
+        const int gy = ty0 - 4 + ry, gx = tx0 - 16 + 16 * q;
+        uint4 w = make_uint4(0u, 0u, 0u, 0u);
+        if (gy >= 0 && gy < L.h && gx + 16 <= pitch) w = __ldg(reinterpret_cast<const uint4*>(img + (size_t)gy * pitch + gx));
+        *reinterpret_cast<uint4*>(&s_img[ry * kImgWords + 4 * q]) = w;
     }
     // cell index of every column / row of the A tile (minBorder-relative detection coordinates, src/ORBextractor.cc:813-828)
     const int lastJ = max(min(L.nCols - 1, (L.maxBX - 6 - kMinBorder - 1) / L.wCell), 0);
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(kFtThreads) fast_kernel(const __grid_constant_
     for (int it = 0; it < 2; it++) {
         const int grp = tid + it * kFtThreads;          // 0..575
         const int ay = grp / 18, gxi = grp - ay * 18;   // A row (y = ty0-1+ay), group (x = tx0-4+4*gxi)
-        const uint32_t* row = &s_img[(ay + 3) * kImgWords + gxi + 1];   // word holding the 4 centre pixels
+        const uint32_t* row = &s_img[(ay + 3) * kImgWords + gxi + 3];   // word holding the 4 centre pixels
         uint32_t S[16];
         {   // ring words: 4 consecutive bytes starting at x+dx on row y+dy (FAST circle, OpenCV order)
             const uint32_t *r3 = row + 3 * kImgWords, *rm3 = row - 3 * kImgWords, *r2 = row + 2 * kImgWords, *rm2 = row - 2 * kImgWords,
@@ -156,30 +156,36 @@ __global__ void __launch_bounds__(kFtThreads) fast_kernel(const __grid_constant_
     const int thIni = dyn.area_flag ? 30 : 20;   // threshold override, src/ORBextractor.cc:775-784
     const int thMin = dyn.area_flag ? 10 : 7;
     int* cellcnt = v.cell_count + (size_t)frame * g.cells_per_frame + L.cell_base;
-    for (int i = tid; i < kFtW * kFtH; i += kFtThreads) {
-        const int py = i >> 6, px = i & 63;
-        const uint8_t* a = &s_A[(py + 1) * kAW + px + 4];
-        const int A = a[0];
-        if (A <= thMin) continue;
-        const int n_l = a[-1], n_r = a[1], n_ul = a[-kAW - 1], n_u = a[-kAW], n_ur = a[-kAW + 1], n_dl = a[kAW - 1], n_d = a[kAW], n_dr = a[kAW + 1];
-        bool keep = A > max(max(max(n_l, n_r), max(n_ul, n_u)), max(max(n_ur, n_dl), max(n_d, n_dr)));
-        const int cj = s_colcell[px + 4], ci = s_rowcell[py + 1];
-        if (!keep) {
-            // a larger neighbour only counts if it belongs to the same cell (each cell is an independent cv::FAST call)
-            const bool sl = s_colcell[px + 3] == cj, sr = s_colcell[px + 5] == cj, su = s_rowcell[py] == ci, sd = s_rowcell[py + 2] == ci;
-            if (!(sl && sr && su && sd)) {
-                int m = 0;
-                if (sl) m = max(m, n_l);
-                if (sr) m = max(m, n_r);
-                if (su) { m = max(m, n_u); if (sl) m = max(m, n_ul); if (sr) m = max(m, n_ur); }
-                if (sd) { m = max(m, n_d); if (sl) m = max(m, n_dl); if (sr) m = max(m, n_dr); }
-                keep = A > m;
+    for (int i = tid; i < (kFtW / 4) * kFtH; i += kFtThreads) {
+        const int py = i >> 4, px0 = (i & 15) * 4;
+        const uint32_t a4 = *reinterpret_cast<const uint32_t*>(&s_A[(py + 1) * kAW + px0 + 4]);
+        if ((a4 & 0xF8F8F8F8u) == 0u) continue;   // all four strengths < 8 <= minTh + 1: nothing to do (minTh is 7 or 10)
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int A = (a4 >> (8 * k)) & 0xFF;
+            if (A <= thMin) continue;
+            const int px = px0 + k;
+            const uint8_t* a = &s_A[(py + 1) * kAW + px + 4];
+            const int n_l = a[-1], n_r = a[1], n_ul = a[-kAW - 1], n_u = a[-kAW], n_ur = a[-kAW + 1], n_dl = a[kAW - 1], n_d = a[kAW], n_dr = a[kAW + 1];
+            bool keep = A > max(max(max(n_l, n_r), max(n_ul, n_u)), max(max(n_ur, n_dl), max(n_d, n_dr)));
+            const int cj = s_colcell[px + 4], ci = s_rowcell[py + 1];
+            if (!keep) {
+                // a larger neighbour only counts if it belongs to the same cell (each cell is an independent cv::FAST call)
+                const bool sl = s_colcell[px + 3] == cj, sr = s_colcell[px + 5] == cj, su = s_rowcell[py] == ci, sd = s_rowcell[py + 2] == ci;
+                if (!(sl && sr && su && sd)) {
+                    int m = 0;
+                    if (sl) m = max(m, n_l);
+                    if (sr) m = max(m, n_r);
+                    if (su) { m = max(m, n_u); if (sl) m = max(m, n_ul); if (sr) m = max(m, n_ur); }
+                    if (sd) { m = max(m, n_d); if (sl) m = max(m, n_dl); if (sr) m = max(m, n_dr); }
+                    keep = A > m;
+                }
             }
-        }
-        if (keep) {
-            const int x = tx0 + px - kMinBorder, y = ty0 + py - kMinBorder;   // minBorder-relative (:844-845)
-            s_list[atomicAdd(&s_n, 1)] = (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)(A - 1) << 24);
-            if (A > thIni) atomicAdd(&cellcnt[ci * L.nCols + cj], 1);
+            if (keep) {
+                const int x = tx0 + px - kMinBorder, y = ty0 + py - kMinBorder;   // minBorder-relative (:844-845)
+                s_list[atomicAdd(&s_n, 1)] = (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)(A - 1) << 24);
+                if (A > thIni) atomicAdd(&cellcnt[ci * L.nCols + cj], 1);
+            }
         }
     }
     __syncthreads();
