@@ -317,6 +317,11 @@ def run_b200(args):
                "note": "host buffers in, host results out, one 640x480 frame per call (wall clock around the blocking C call)"}
         ex1.close()
 
+    # ---- matching: us per call through the C ABI (host arrays in, results out), CPU oracle beside it ----------------
+    match = None
+    if rank == 0 and not args.no_match:
+        match = bench_matching(cb, dev, batch, o_kps, o_desc, o_cnt, ex, args)
+
     # ---- CPU baseline beside it (rank 0, N=1 only) --------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -359,10 +364,111 @@ def run_b200(args):
                      "stage_ms": stage_ms,
                      "pipeline": {"bytes_per_frame": pipeline_bytes, "achieved_gbs": pipeline_bytes * value / world / 1e9,
                                   "frac": pipeline_bytes * value / world / 1e9 / peak}},
-        "cpu_baseline": cpu, "clocks": clocks, "latency": lat,
+        "cpu_baseline": cpu, "clocks": clocks, "latency": lat, "match": match,
     }
     print(json.dumps(line))
     return 0
+
+
+def _median_us(fn, reps):
+    ts = []
+    for _ in range(reps):
+        t = time.perf_counter()
+        fn()
+        ts.append(time.perf_counter() - t)
+    return 1e6 * float(np.median(ts))
+
+
+def bench_matching(cb, dev, batch, o_kps, o_desc, o_cnt, ex, args):
+    """BASELINE.json configs[2] (1000 keypoints vs a 5k-point local map; frame-to-frame; initialisation) and configs[4]
+    (4000 x 100k brute-force k=2). Wall time around the blocking C calls (host arrays in, host results out); the kNN is
+    also timed device-resident with CUDA events. The CPU oracle is timed on the same inputs when available."""
+    import torch
+    from coeb_b200 import synth
+    out = {}
+    kps = np.ascontiguousarray(o_kps[0, :o_cnt[0]])
+    desc = np.ascontiguousarray(o_desc[0, :o_cnt[0]])
+    scale = ex.tables()["scale"]
+    cam_args = (535.4, 539.2, 320.1, 247.6, 40.0, 40.0 / 535.4, 0.0, 640.0, 0.0, 480.0)
+    m = cb.Matcher(device=dev)
+    mp, uright = synth.make_map_points(kps, desc, scale, seed=1)
+    last, Tc, Tl = synth.make_last_frame(kps, desc, seed=2)
+    state = np.full(len(kps), -1, np.int32)
+    f = m.frame(kps, desc, cb.Camera(*cam_args), scale, uright)
+    out["n_keypoints"] = int(len(kps))
+    out["frame_upload_grid_us"] = _median_us(lambda: m.frame(kps, desc, cb.Camera(*cam_args), scale, uright).close(), 20)
+    # pre-marshalled ctypes calls: the timed region is the blocking C-ABI call itself, not numpy conversions
+    import ctypes as C
+    L = cb.lib()
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    nm = C.c_int()
+    a2 = [u8(mp["track_in_view"]), u8(mp["bad"]), u8(mp["has_obs"]), f32(mp["proj_x"]), f32(mp["proj_y"]), f32(mp["proj_xr"]),
+          i32(mp["level"]), f32(mp["view_cos"]), u8(mp["desc"])]
+    km = state.copy()
+
+    def call_m2():
+        km[:] = state
+        L.coeb_match_projection(m.h, f.h, len(a2[3]), *[P(a) for a in a2], C.c_float(3.0), C.c_float(0.8), P(km), C.byref(nm))
+    a3 = [u8(last["valid"]), u8(last["has_obs"]), f32(last["xyz"]), i32(last["octave"]), f32(last["angle"]), u8(last["desc"])]
+    tc, tl = f32(Tc).reshape(12), f32(Tl).reshape(12)
+
+    def call_m3():
+        km[:] = state
+        L.coeb_match_lastframe(m.h, f.h, len(a3[0]), *[P(a) for a in a3], P(tc), P(tl), C.c_float(15.0), 0, 1, P(km), C.byref(nm))
+    out["search_by_projection_map5k_us"] = _median_us(call_m2, 50)
+    out["search_by_projection_lastframe_us"] = _median_us(call_m3, 50)
+    k2 = np.ascontiguousarray(o_kps[1, :o_cnt[1]])
+    d2 = np.ascontiguousarray(o_desc[1, :o_cnt[1]])
+    f2 = m.frame(k2, d2, cb.Camera(*cam_args), scale, None)
+    prev = np.stack([kps["x"], kps["y"]], axis=1).astype(np.float32)
+    pv, m12 = prev.copy(), np.empty(len(kps), np.int32)
+
+    def call_m4():
+        pv[:] = prev
+        L.coeb_match_init(m.h, f.h, f2.h, P(pv), P(m12), 100, C.c_float(0.9), 1, C.byref(nm))
+    out["search_for_initialization_us"] = _median_us(call_m4, 50)
+    # kNN 4000 x 100k, device resident
+    q, t = synth.make_knn_sets(4000, 100000, seed=3)
+    dq, dt = torch.from_numpy(q).cuda(dev), torch.from_numpy(t).cuda(dev)
+    di, d1, d2_ = (torch.empty(4000, dtype=torch.int32, device=dq.device) for _ in range(3))
+    stream = torch.cuda.current_stream(dev)
+    m.set_stream(stream.cuda_stream)
+    for _ in range(3):
+        m.knn2_device(dq.data_ptr(), 4000, dt.data_ptr(), 100000, 0.7, di.data_ptr(), d1.data_ptr(), d2_.data_ptr())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    reps = 10
+    for _ in range(reps):
+        m.knn2_device(dq.data_ptr(), 4000, dt.data_ptr(), 100000, 0.7, di.data_ptr(), d1.data_ptr(), d2_.data_ptr())
+    e1.record(stream)
+    torch.cuda.synchronize()
+    knn_ms = e0.elapsed_time(e1) / reps
+    popc = 4000 * 100000 * 8
+    n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    out["knn2_4000x100k_ms"] = knn_ms
+    out["knn2_popc_per_s"] = popc / (knn_ms * 1e-3)
+    # POPC issues at 16 lanes/clk/SM on CC 10.0 (CUDA programming guide, arithmetic instruction throughput table)
+    out["knn2_int_pipe_frac_at_max_clock"] = popc / (knn_ms * 1e-3) / (n_sm * 16 * 1.965e9)
+    m.set_stream(0)
+    if not args.no_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import orc
+        fc = orc.Frame(kps, desc, orc.Camera(*cam_args), scale, uright)
+        f2c = orc.Frame(k2, d2, orc.Camera(*cam_args), scale, None)
+        out["cpu_search_by_projection_map5k_us"] = _median_us(lambda: orc.match_projection(fc, mp, 3.0, 0.8, state), 10)
+        out["cpu_search_by_projection_lastframe_us"] = _median_us(lambda: orc.match_lastframe(fc, last, Tc, Tl, 15.0, False, True, state), 10)
+        out["cpu_search_for_initialization_us"] = _median_us(lambda: orc.match_init(fc, f2c, prev, 100, 0.9, True), 10)
+        th = orc.hardware_threads()
+        _, _, _, secs = orc.knn2(q[:1000], t, 0.7, nthreads=th)
+        out["cpu_knn2_4000x100k_ms_extrapolated"] = 4e3 * secs
+        out["cpu_threads"] = th
+        n_g, km_g = m.match_projection(f, mp, 3.0, 0.8, state)
+        n_c, km_c = orc.match_projection(fc, mp, 3.0, 0.8, state)
+        out["bit_exact_vs_cpu"] = bool(n_g == n_c and np.array_equal(km_g, km_c))
+    return out
 
 
 def main():
@@ -378,6 +484,7 @@ def main():
     ap.add_argument("--cand-estimate", type=float, default=16000.0, help="FAST candidates per frame used for algorithmic bytes")
     ap.add_argument("--stage-sync", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-match", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: device-resident part only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -132,6 +132,21 @@ __global__ void hamming_pairs_kernel(const uint32_t* a, const uint32_t* b, int n
     if (i < n) out[i] = hamming256(a + 8 * (size_t)i, b + 8 * (size_t)i);
 }
 
+// =====================================================================================================================
+// Windowed matchers. Each has
+//   * a static visitor  xx_visit(i, fn): walks query i's grid window in the reference's traversal order, applies the
+//     filters that do not depend on other queries of the call, computes the Hamming distance and calls
+//     fn(idx, dist, octave) per surviving candidate;
+//   * a collect kernel (one thread per query, many CTAs) that stores those candidates as per-query lists;
+//   * a resolve kernel (one CTA) that iterates R <- F(R) to the fixed point over the stored lists -- or, when
+//     kLists == false, by re-walking the windows (fallback used only if some list overflowed its capacity).
+// =====================================================================================================================
+struct CandLists {
+    int2* items;   // [n][cap]: x = idx | octave << 24, y = distance
+    int* count;    // [n] candidates found (may exceed cap: overflow)
+    int cap;
+};
+
 // ---- M2: SearchByProjection(Frame&, vector<MapPoint*>&, th) (src/ORBmatcher.cc:45-129) -------------------
 struct MapDev {
     int n;
@@ -141,13 +156,49 @@ struct MapDev {
     const uint32_t* desc;
 };
 
+template <class Fn>
+__device__ __forceinline__ void m2_visit(const FrameDev& F, const MapDev& M, float th, const int* __restrict__ kp_state, int i, Fn&& fn) {
+    if (!M.track_in_view[i] || M.bad[i]) return;
+    const int lvl = M.level[i];
+    float r = ((double)M.view_cos[i] > 0.998) ? 2.5f : 4.0f;  // RadiusByViewingCos (:131-137)
+    if (th != 1.0f) r *= th;                                   // bFactor (:49, :65-66)
+    const float rs = r * F.scale[lvl];
+    const uint32_t* d = M.desc + 8 * (size_t)i;
+    const float pxr = M.proj_xr[i];
+    for_each_in_area(F, M.proj_x[i], M.proj_y[i], rs, lvl - 1, lvl, [&](int idx) {
+        if (kp_state[idx] == -2) return;                       // already holds a MapPoint with observations (:87-89)
+        if (F.uright) {
+            const float ur = F.uright[idx];
+            if (ur > 0) { const float er = fabsf(pxr - ur); if (er > rs) return; }   // :91-96
+        }
+        fn(idx, hamming256(d, F.desc + 8 * (size_t)idx), F.octave[idx]);
+    });
+}
+
+__global__ void __launch_bounds__(128) m2_collect_kernel(FrameDev F, MapDev M, float th, const int* kp_state, CandLists C) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M.n) return;
+    int cnt = 0;
+    int2* out = C.items + (size_t)i * C.cap;
+    m2_visit(F, M, th, kp_state, i, [&](int idx, int dist, int oct) {
+        if (cnt < C.cap) out[cnt] = make_int2(idx | (oct << 24), dist);
+        cnt++;
+    });
+    C.count[i] = cnt;
+}
+
 // One CTA iterates to the fixed point. res[i] = keypoint claimed by map point i or -1.
 // claim_min[idx] = smallest i (with Observations()>0) that currently claims idx.
-__global__ void __launch_bounds__(1024) match_projection_kernel(FrameDev F, MapDev M, float th, float nnratio, int* kp_match /*in/out*/,
-                                                                int* res, int* claim_min, int* out_info) {
+template <bool kLists>
+__global__ void __launch_bounds__(1024) m2_resolve_kernel(FrameDev F, MapDev M, float th, float nnratio, const int* kp_state, CandLists C,
+                                                          int* kp_match /*out, pre-filled with kp_state*/, int* res, int* claim_min, int* out_info) {
     __shared__ int s_changed, s_count;
     const int tid = threadIdx.x, T = blockDim.x;
-    const bool bFactor = th != 1.0f;
+    if (kLists) {   // a list overflowed: report and let the host rerun the window-walking variant
+        int over = 0;
+        for (int i = tid; i < M.n; i += T) over |= C.count[i] > C.cap;
+        if (__syncthreads_or(over)) { if (tid == 0) { out_info[0] = 0; out_info[1] = 0; out_info[2] = 1; } return; }
+    }
     for (int i = tid; i < M.n; i += T) res[i] = -1;
     for (int round = 0; round <= M.n; round++) {
         for (int k = tid; k < F.n; k += T) claim_min[k] = kInf;
@@ -159,31 +210,21 @@ __global__ void __launch_bounds__(1024) match_projection_kernel(FrameDev F, MapD
         }
         __syncthreads();
         for (int i = tid; i < M.n; i += T) {
-            int out = -1;
-            if (M.track_in_view[i] && !M.bad[i]) {
-                const int lvl = M.level[i];
-                float r = ((double)M.view_cos[i] > 0.998) ? 2.5f : 4.0f;  // RadiusByViewingCos (:131-137)
-                if (bFactor) r *= th;
-                const float rs = r * F.scale[lvl];
-                const uint32_t* d = M.desc + 8 * (size_t)i;
-                const float pxr = M.proj_xr[i];
-                int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
-                for_each_in_area(F, M.proj_x[i], M.proj_y[i], rs, lvl - 1, lvl, [&](int idx) {
-                    const int cur = kp_match[idx];
-                    if (cur == -2 || claim_min[idx] < i) return;            // already holds a MapPoint with observations
-                    if (F.uright) {
-                        const float ur = F.uright[idx];
-                        if (ur > 0) { const float er = fabsf(pxr - ur); if (er > rs) return; }
-                    }
-                    const int dist = hamming256(d, F.desc + 8 * (size_t)idx);
-                    if (dist < bestDist) {
-                        bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = F.octave[idx]; bestIdx = idx;
-                    } else if (dist < bestDist2) {
-                        bestLevel2 = F.octave[idx]; bestDist2 = dist;
-                    }
-                });
-                if (bestDist <= COEB_TH_HIGH && !(bestLevel == bestLevel2 && (float)bestDist > nnratio * (float)bestDist2)) out = bestIdx;
+            int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+            auto consider = [&](int idx, int dist, int oct) {
+                if (claim_min[idx] < i) return;   // claimed earlier in this call by a MapPoint with observations (:87-89, :123)
+                if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = oct; bestIdx = idx; }
+                else if (dist < bestDist2) { bestLevel2 = oct; bestDist2 = dist; }
+            };
+            if (kLists) {
+                const int2* it = C.items + (size_t)i * C.cap;
+                const int n = C.count[i];
+                for (int c = 0; c < n; c++) { const int2 e = it[c]; consider(e.x & 0xFFFFFF, e.y, e.x >> 24); }
+            } else {
+                m2_visit(F, M, th, kp_state, i, consider);
             }
+            int out = -1;
+            if (bestDist <= COEB_TH_HIGH && !(bestLevel == bestLevel2 && (float)bestDist > nnratio * (float)bestDist2)) out = bestIdx;
             if (out != res[i]) { res[i] = out; s_changed = 1; }
         }
         __syncthreads();
@@ -202,7 +243,7 @@ __global__ void __launch_bounds__(1024) match_projection_kernel(FrameDev F, MapD
     __syncthreads();
     for (int k = tid; k < F.n; k += T)
         if (claim_min[k] >= 0) kp_match[k] = claim_min[k];
-    if (tid == 0) out_info[0] = s_count;
+    if (tid == 0) { out_info[0] = s_count; out_info[2] = 0; }
 }
 
 // ---- M5: ComputeThreeMaxima (src/ORBmatcher.cc:1602-1643) ------------------------------------------------------
@@ -240,12 +281,61 @@ struct LastDev {
     int forward, backward;
 };
 
-__global__ void __launch_bounds__(1024) match_lastframe_kernel(FrameDev C, LastDev L, float th, int check_ori, int* kp_match, int* res,
-                                                               int* claim_min, int* out_info) {
+template <class Fn>
+__device__ __forceinline__ void m3_visit(const FrameDev& C, const LastDev& L, float th, const int* __restrict__ kp_state, int i, Fn&& fn) {
+    if (!L.valid[i]) return;
+    const float X = L.xyz[3 * i], Y = L.xyz[3 * i + 1], Z = L.xyz[3 * i + 2];
+    // x3Dc = Rcw*x3Dw + tcw (:1362), fp32 left to right (no FMA: the file is built with -fmad=false)
+    const float xc = L.T[0] * X + L.T[1] * Y + L.T[2] * Z + L.T[3];
+    const float yc = L.T[4] * X + L.T[5] * Y + L.T[6] * Z + L.T[7];
+    const float zc = L.T[8] * X + L.T[9] * Y + L.T[10] * Z + L.T[11];
+    const float invzc = (float)(1.0 / (double)zc);
+    if (invzc < 0) return;
+    const float u = C.fx * xc * invzc + C.cx, v = C.fy * yc * invzc + C.cy;
+    if (u < C.min_x || u > C.max_x) return;
+    if (v < C.min_y || v > C.max_y) return;
+    const int oct = L.octave[i];
+    const float radius = th * C.scale[oct];
+    int minL, maxL;
+    if (L.forward) { minL = oct; maxL = -1; }           // :1386-1391
+    else if (L.backward) { minL = 0; maxL = oct; }
+    else { minL = oct - 1; maxL = oct + 1; }
+    const uint32_t* d = L.desc + 8 * (size_t)i;
+    const float ur_proj = u - C.bf * invzc;
+    for_each_in_area(C, u, v, radius, minL, maxL, [&](int i2) {
+        if (kp_state[i2] == -2) return;
+        if (C.uright) {
+            const float ur = C.uright[i2];
+            if (ur > 0) { const float er = fabsf(ur_proj - ur); if (er > radius) return; }   // :1408-1414
+        }
+        fn(i2, hamming256(d, C.desc + 8 * (size_t)i2), 0);
+    });
+}
+
+__global__ void __launch_bounds__(128) m3_collect_kernel(FrameDev Cf, LastDev L, float th, const int* kp_state, CandLists C) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L.n) return;
+    int cnt = 0;
+    int2* out = C.items + (size_t)i * C.cap;
+    m3_visit(Cf, L, th, kp_state, i, [&](int idx, int dist, int) {
+        if (cnt < C.cap) out[cnt] = make_int2(idx, dist);
+        cnt++;
+    });
+    C.count[i] = cnt;
+}
+
+template <bool kLists>
+__global__ void __launch_bounds__(1024) m3_resolve_kernel(FrameDev C, LastDev L, float th, int check_ori, const int* kp_state, CandLists Cl,
+                                                          int* kp_match, int* res, int* claim_min, int* out_info) {
     __shared__ int s_changed, s_count;
     __shared__ int s_hist[COEB_HISTO_LENGTH];
     __shared__ int s_ind[3];
     const int tid = threadIdx.x, T = blockDim.x;
+    if (kLists) {
+        int over = 0;
+        for (int i = tid; i < L.n; i += T) over |= Cl.count[i] > Cl.cap;
+        if (__syncthreads_or(over)) { if (tid == 0) { out_info[0] = 0; out_info[1] = 0; out_info[2] = 1; } return; }
+    }
     for (int i = tid; i < L.n; i += T) res[i] = -1;
     for (int round = 0; round <= L.n; round++) {
         for (int k = tid; k < C.n; k += T) claim_min[k] = kInf;
@@ -257,41 +347,19 @@ __global__ void __launch_bounds__(1024) match_lastframe_kernel(FrameDev C, LastD
         }
         __syncthreads();
         for (int i = tid; i < L.n; i += T) {
-            int out = -1;
-            if (L.valid[i]) {
-                const float X = L.xyz[3 * i], Y = L.xyz[3 * i + 1], Z = L.xyz[3 * i + 2];
-                // x3Dc = Rcw*x3Dw + tcw (:1362), fp32 left to right (no FMA: the file is built with -fmad=false)
-                const float xc = L.T[0] * X + L.T[1] * Y + L.T[2] * Z + L.T[3];
-                const float yc = L.T[4] * X + L.T[5] * Y + L.T[6] * Z + L.T[7];
-                const float zc = L.T[8] * X + L.T[9] * Y + L.T[10] * Z + L.T[11];
-                const float invzc = (float)(1.0 / (double)zc);
-                bool ok = !(invzc < 0);
-                const float u = C.fx * xc * invzc + C.cx, v = C.fy * yc * invzc + C.cy;
-                if (u < C.min_x || u > C.max_x) ok = false;
-                if (v < C.min_y || v > C.max_y) ok = false;
-                if (ok) {
-                    const int oct = L.octave[i];
-                    const float radius = th * C.scale[oct];
-                    int minL, maxL;
-                    if (L.forward) { minL = oct; maxL = -1; }
-                    else if (L.backward) { minL = 0; maxL = oct; }
-                    else { minL = oct - 1; maxL = oct + 1; }
-                    const uint32_t* d = L.desc + 8 * (size_t)i;
-                    const float ur_proj = u - C.bf * invzc;
-                    int bestDist = 256, bestIdx2 = -1;
-                    for_each_in_area(C, u, v, radius, minL, maxL, [&](int i2) {
-                        const int cur = kp_match[i2];
-                        if (cur == -2 || claim_min[i2] < i) return;
-                        if (C.uright) {
-                            const float ur = C.uright[i2];
-                            if (ur > 0) { const float er = fabsf(ur_proj - ur); if (er > radius) return; }
-                        }
-                        const int dist = hamming256(d, C.desc + 8 * (size_t)i2);
-                        if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
-                    });
-                    if (bestDist <= COEB_TH_HIGH) out = bestIdx2;
-                }
+            int bestDist = 256, bestIdx2 = -1;
+            auto consider = [&](int i2, int dist, int) {
+                if (claim_min[i2] < i) return;                           // :1404-1406 with :1429
+                if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+            };
+            if (kLists) {
+                const int2* it = Cl.items + (size_t)i * Cl.cap;
+                const int n = Cl.count[i];
+                for (int c = 0; c < n; c++) { const int2 e = it[c]; consider(e.x, e.y, 0); }
+            } else {
+                m3_visit(C, L, th, kp_state, i, consider);
             }
+            const int out = bestDist <= COEB_TH_HIGH ? bestIdx2 : -1;
             if (out != res[i]) { res[i] = out; s_changed = 1; }
         }
         __syncthreads();
@@ -330,20 +398,46 @@ __global__ void __launch_bounds__(1024) match_lastframe_kernel(FrameDev C, LastD
         if (removed) atomicSub(&s_count, removed);
     }
     __syncthreads();
-    if (tid == 0) out_info[0] = s_count;
+    if (tid == 0) { out_info[0] = s_count; out_info[2] = 0; }
 }
 
 // ---- M4: SearchForInitialization (src/ORBmatcher.cc:405-520) -----------------------------------------------------
+template <class Fn>
+__device__ __forceinline__ void m4_visit(const FrameDev& F1, const FrameDev& F2, const float* __restrict__ prev_in, float window, int i1, Fn&& fn) {
+    if (F1.octave[i1] > 0) return;   // level1 > 0 -> continue (:421-423)
+    const uint32_t* d1 = F1.desc + 8 * (size_t)i1;
+    for_each_in_area(F2, prev_in[2 * i1], prev_in[2 * i1 + 1], window, 0, 0,
+                     [&](int i2) { fn(i2, hamming256(d1, F2.desc + 8 * (size_t)i2), 0); });
+}
+
+__global__ void __launch_bounds__(128) m4_collect_kernel(FrameDev F1, FrameDev F2, const float* prev_in, float window, CandLists C) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= F1.n) return;
+    int cnt = 0;
+    int2* out = C.items + (size_t)i * C.cap;
+    m4_visit(F1, F2, prev_in, window, i, [&](int idx, int dist, int) {
+        if (cnt < C.cap) out[cnt] = make_int2(idx, dist);
+        cnt++;
+    });
+    C.count[i] = cnt;
+}
+
 // res[i1] = claimed F2 keypoint or -1, rdist[i1] = its distance. vMatchedDistance seen by query i1 at keypoint k is
 // min{rdist[j] : j < i1, res[j] == k}; claimants of every k are gathered into CSR lists each round.
-__global__ void __launch_bounds__(1024) match_init_kernel(FrameDev F1, FrameDev F2, const float* prev_in, float window, float nnratio,
-                                                          int check_ori, int* res, int* rdist, int* cl_start, int* cl_fill,
+template <bool kLists>
+__global__ void __launch_bounds__(1024) m4_resolve_kernel(FrameDev F1, FrameDev F2, const float* prev_in, float window, float nnratio,
+                                                          int check_ori, CandLists C, int* res, int* rdist, int* cl_start, int* cl_fill,
                                                           int2* cl_items, int* matches12, float* prev_out, int* out_info) {
     __shared__ int s_changed, s_count;
     __shared__ int s_hist[COEB_HISTO_LENGTH];
     __shared__ int s_ind[3];
     __shared__ int s_warp[33];
     const int tid = threadIdx.x, T = blockDim.x;
+    if (kLists) {
+        int over = 0;
+        for (int i = tid; i < F1.n; i += T) over |= C.count[i] > C.cap;
+        if (__syncthreads_or(over)) { if (tid == 0) { out_info[0] = 0; out_info[1] = 0; out_info[2] = 1; } return; }
+    }
     for (int i = tid; i < F1.n; i += T) { res[i] = -1; rdist[i] = kInf; }
     for (int round = 0; round <= F1.n; round++) {
         for (int k = tid; k <= F2.n; k += T) cl_start[k] = 0;
@@ -359,23 +453,26 @@ __global__ void __launch_bounds__(1024) match_init_kernel(FrameDev F1, FrameDev 
             if (res[i] >= 0) cl_items[atomicAdd(&cl_fill[res[i]], 1)] = make_int2(i, rdist[i]);
         __syncthreads();
         for (int i1 = tid; i1 < F1.n; i1 += T) {
-            int out = -1, outd = kInf;
-            if (F1.octave[i1] <= 0) {  // level1 > 0 -> continue (:421-423)
-                const uint32_t* d1 = F1.desc + 8 * (size_t)i1;
-                int bestDist = kInf, bestDist2 = kInf, bestIdx2 = -1;
-                for_each_in_area(F2, prev_in[2 * i1], prev_in[2 * i1 + 1], window, 0, 0, [&](int i2) {
-                    const int dist = hamming256(d1, F2.desc + 8 * (size_t)i2);
-                    int md = kInf;
-                    for (int p = cl_start[i2]; p < cl_start[i2 + 1]; p++) {
-                        const int2 c = cl_items[p];
-                        if (c.x < i1) md = min(md, c.y);
-                    }
-                    if (md <= dist) return;   // vMatchedDistance[i2] <= dist (:444)
-                    if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
-                    else if (dist < bestDist2) bestDist2 = dist;
-                });
-                if (bestDist <= COEB_TH_LOW && (float)bestDist < (float)bestDist2 * nnratio) { out = bestIdx2; outd = bestDist; }
+            int bestDist = kInf, bestDist2 = kInf, bestIdx2 = -1;
+            auto consider = [&](int i2, int dist, int) {
+                int md = kInf;
+                for (int p = cl_start[i2]; p < cl_start[i2 + 1]; p++) {
+                    const int2 c = cl_items[p];
+                    if (c.x < i1) md = min(md, c.y);
+                }
+                if (md <= dist) return;   // vMatchedDistance[i2] <= dist (:444)
+                if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+                else if (dist < bestDist2) bestDist2 = dist;
+            };
+            if (kLists) {
+                const int2* it = C.items + (size_t)i1 * C.cap;
+                const int n = C.count[i1];
+                for (int c = 0; c < n; c++) { const int2 e = it[c]; consider(e.x, e.y, 0); }
+            } else {
+                m4_visit(F1, F2, prev_in, window, i1, consider);
             }
+            int out = -1, outd = kInf;
+            if (bestDist <= COEB_TH_LOW && (float)bestDist < (float)bestDist2 * nnratio) { out = bestIdx2; outd = bestDist; }
             if (out != res[i1] || outd != rdist[i1]) { res[i1] = out; rdist[i1] = outd; s_changed = 1; }
         }
         __syncthreads();
@@ -424,7 +521,7 @@ __global__ void __launch_bounds__(1024) match_init_kernel(FrameDev F1, FrameDev 
         prev_out[2 * i] = k >= 0 ? F2.x[k] : prev_in[2 * i];
         prev_out[2 * i + 1] = k >= 0 ? F2.y[k] : prev_in[2 * i + 1];
     }
-    if (tid == 0) out_info[0] = s_count;
+    if (tid == 0) { out_info[0] = s_count; out_info[2] = 0; }
 }
 
 // ---- F4: Frame::ComputeStereoMatches (src/Frame.cc:644-818) -------------------------------------------------------
@@ -661,23 +758,77 @@ __global__ void knn2_merge_kernel(int nq, int nchunks, const int* p_d1, const in
 
 // =====================================================================================================================
 // C ABI (host side)
+//
+// Every call packs its inputs into ONE pinned staging block, issues one host->device copy, the kernel(s) and one
+// device->host copy of the packed results: the tracking thread calls these once per frame, so the fixed cost per
+// call (copies, launches, one synchronisation) is what matters, not bandwidth.
 // =====================================================================================================================
 using namespace coeb;
+
+namespace {
+
+// Pinned host block with a device mirror, grown geometrically.
+struct Stage {
+    char* h = nullptr;
+    char* d = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return COEB_OK;
+        size_t want = std::max<size_t>(bytes + bytes / 2, 1 << 16);
+        if (h) cudaFreeHost(h);
+        if (d) cudaFree(d);
+        h = d = nullptr;
+        cap = 0;
+        CUDA_TRY(cudaHostAlloc((void**)&h, want, cudaHostAllocDefault));
+        CUDA_TRY(cudaMalloc((void**)&d, want));
+        cap = want;
+        return COEB_OK;
+    }
+    void release() {
+        if (h) cudaFreeHost(h);
+        if (d) cudaFree(d);
+        h = d = nullptr;
+        cap = 0;
+    }
+};
+
+inline size_t al(size_t b) { return (b + 255) & ~(size_t)255; }
+
+// Lays arrays out in a Stage: place() copies host data in and returns the device address it will have.
+struct Packer {
+    Stage& st;
+    size_t off = 0;
+    explicit Packer(Stage& s) : st(s) {}
+    template <typename T> T* place(const T* src, size_t n) {
+        T* dev = reinterpret_cast<T*>(st.d + off);
+        if (n && src) std::memcpy(st.h + off, src, n * sizeof(T));
+        off += al(n * sizeof(T));
+        return dev;
+    }
+    template <typename T> T* host_at(const T* dev) { return reinterpret_cast<T*>(st.h + (reinterpret_cast<const char*>(dev) - st.d)); }
+    template <typename T> T* room(size_t n) {   // uninitialised device space (outputs / scratch)
+        T* dev = reinterpret_cast<T*>(st.d + off);
+        off += al(n * sizeof(T));
+        return dev;
+    }
+};
+
+}  // namespace
 
 struct coeb_matcher {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    // scratch, grown on demand
+    Stage in, out;                                   // inputs (H2D) and results (D2H)
     void* d_scratch = nullptr; size_t scratch_bytes = 0;
-    void* d_in = nullptr; size_t in_bytes = 0;
+    void* d_in = nullptr; size_t in_bytes = 0;        // kNN partials
+    std::vector<std::pair<size_t, void*>> frame_pool;  // device blocks of destroyed frames, reused by the next ones
 };
 
 struct coeb_frame {
     coeb_matcher* m = nullptr;
     int n = 0, nlevels = 0;
-    float *d_x = nullptr, *d_y = nullptr, *d_angle = nullptr, *d_uright = nullptr;
-    int *d_octave = nullptr, *d_cell_start = nullptr, *d_cell_items = nullptr, *d_kp_cell = nullptr;
-    uint32_t* d_desc = nullptr;
+    void* block = nullptr;
+    size_t block_bytes = 0;
     FrameDev dev{};
 };
 
@@ -694,22 +845,18 @@ int grow(void** p, size_t* cap, size_t bytes) {
     if (*p) cudaFree(*p);
     *p = nullptr;
     *cap = 0;
-    CUDA_TRY(cudaMalloc(p, std::max<size_t>(bytes, 256)));
-    *cap = bytes;
+    CUDA_TRY(cudaMalloc(p, std::max<size_t>(bytes + bytes / 2, 1 << 16)));
+    *cap = std::max<size_t>(bytes + bytes / 2, 1 << 16);
     return COEB_OK;
 }
 
-// Bump allocator over one device block; every piece 256-byte aligned.
-struct Carver {
-    char* base; size_t off = 0;
-    explicit Carver(void* b) : base((char*)b) {}
-    template <typename T> T* take(size_t n) { T* p = (T*)(base + off); off += (n * sizeof(T) + 255) & ~(size_t)255; return p; }
-    static size_t need(std::initializer_list<size_t> bytes) { size_t s = 0; for (size_t b : bytes) s += (b + 255) & ~(size_t)255; return s; }
-};
-
-template <typename T>
-int upload(cudaStream_t s, T* dst, const T* src, size_t n) {
-    if (n) CUDA_TRY(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, s));
+int push_inputs(coeb_matcher* m, const Packer& p) {
+    if (p.off) CUDA_TRY(cudaMemcpyAsync(m->in.d, m->in.h, p.off, cudaMemcpyHostToDevice, m->stream));
+    return COEB_OK;
+}
+int pull_outputs(coeb_matcher* m, size_t bytes) {
+    if (bytes) CUDA_TRY(cudaMemcpyAsync(m->out.h, m->out.d, bytes, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
     return COEB_OK;
 }
 
@@ -734,8 +881,11 @@ void coeb_matcher_destroy(coeb_matcher* m) {
     if (!m) return;
     cudaSetDevice(m->device);
     cudaStreamSynchronize(m->stream);
+    m->in.release();
+    m->out.release();
     cudaFree(m->d_scratch);
     cudaFree(m->d_in);
+    for (auto& b : m->frame_pool) cudaFree(b.second);
     cudaStreamDestroy(m->own_stream);
     delete m;
 }
@@ -751,45 +901,64 @@ int coeb_frame_create(coeb_matcher* m, const coeb_keypoint* kps, const uint8_t* 
     if (!m || !out || !cam || !scale_factors || n < 0 || (n > 0 && (!kps || !desc))) return fail(COEB_ERR_INVALID_ARG, "bad argument");
     if (nlevels < 1 || nlevels > COEB_MAX_LEVELS) return fail(COEB_ERR_INVALID_ARG, "nlevels %d", nlevels);
     CUDA_TRY(cudaSetDevice(m->device));
+    const size_t nn = std::max(n, 1);
+    // one device block per frame: x, y, angle, octave, uright, desc, cell_start, cell_items, kp_cell
+    const size_t need = 5 * al(nn * 4) + al(nn * 32) + al((kGridCells + 1) * 4) + 2 * al(nn * 4);
     coeb_frame* f = new coeb_frame();
     f->m = m; f->n = n; f->nlevels = nlevels;
-    const size_t nn = std::max(n, 1);
-    cudaError_t e = cudaSuccess;
-    e = e ? e : cudaMalloc(&f->d_x, nn * 4); e = e ? e : cudaMalloc(&f->d_y, nn * 4); e = e ? e : cudaMalloc(&f->d_angle, nn * 4);
-    e = e ? e : cudaMalloc(&f->d_octave, nn * 4); e = e ? e : cudaMalloc(&f->d_desc, nn * 32);
-    e = e ? e : cudaMalloc(&f->d_cell_start, (kGridCells + 1) * 4); e = e ? e : cudaMalloc(&f->d_cell_items, nn * 4);
-    e = e ? e : cudaMalloc(&f->d_kp_cell, nn * 4);
-    if (uright) e = e ? e : cudaMalloc(&f->d_uright, nn * 4);
-    if (e != cudaSuccess) { coeb_frame_destroy(f); return fail(COEB_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e)); }
-    std::vector<float> hx(nn), hy(nn), ha(nn);
-    std::vector<int> ho(nn);
-    for (int i = 0; i < n; i++) { hx[i] = kps[i].x; hy[i] = kps[i].y; ha[i] = kps[i].angle; ho[i] = kps[i].octave; }
+    for (size_t i = 0; i < m->frame_pool.size(); i++)
+        if (m->frame_pool[i].first >= need) {
+            f->block_bytes = m->frame_pool[i].first;
+            f->block = m->frame_pool[i].second;
+            m->frame_pool.erase(m->frame_pool.begin() + i);
+            break;
+        }
+    if (!f->block) {
+        const size_t want = std::max<size_t>(need + need / 4, 1 << 17);
+        if (cudaMalloc(&f->block, want) != cudaSuccess) { delete f; return fail(COEB_ERR_CUDA, "cudaMalloc(%zu) failed", want); }
+        f->block_bytes = want;
+    }
+    int st = m->in.reserve(4 * al(nn * 4) + al(nn * 4) + al(nn * 32));
+    if (st != COEB_OK) { coeb_frame_destroy(f); return st; }
+    // pack SoA in pinned memory in the same order as the device block, then one copy
+    char* base = (char*)f->block;
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { char* p = base + off; off += al(bytes); return p; };
+    float* d_x = (float*)carve(nn * 4); float* d_y = (float*)carve(nn * 4); float* d_angle = (float*)carve(nn * 4);
+    int* d_octave = (int*)carve(nn * 4); float* d_uright = (float*)carve(nn * 4); uint32_t* d_desc = (uint32_t*)carve(nn * 32);
+    const size_t upload_bytes = off;
+    int* d_cell_start = (int*)carve((kGridCells + 1) * 4); int* d_cell_items = (int*)carve(nn * 4); int* d_kp_cell = (int*)carve(nn * 4);
+    {
+        char* h = m->in.h;
+        float* hx = (float*)h; float* hy = (float*)(h + al(nn * 4)); float* ha = (float*)(h + 2 * al(nn * 4));
+        int* ho = (int*)(h + 3 * al(nn * 4)); float* hu = (float*)(h + 4 * al(nn * 4)); uint8_t* hd = (uint8_t*)(h + 5 * al(nn * 4));
+        for (int i = 0; i < n; i++) { hx[i] = kps[i].x; hy[i] = kps[i].y; ha[i] = kps[i].angle; ho[i] = kps[i].octave; hu[i] = uright ? uright[i] : -1.f; }
+        if (n) std::memcpy(hd, desc, (size_t)n * 32);
+    }
     cudaStream_t s = m->stream;
-    int st;
-    if ((st = upload(s, f->d_x, hx.data(), n)) || (st = upload(s, f->d_y, hy.data(), n)) || (st = upload(s, f->d_angle, ha.data(), n)) ||
-        (st = upload(s, f->d_octave, ho.data(), n)) || (st = upload(s, (uint8_t*)f->d_desc, desc, (size_t)n * 32)) ||
-        (uright && (st = upload(s, f->d_uright, uright, n)))) { coeb_frame_destroy(f); return st; }
+    cudaError_t e = cudaMemcpyAsync(base, m->in.h, upload_bytes, cudaMemcpyHostToDevice, s);
     FrameDev& d = f->dev;
-    d.n = n; d.x = f->d_x; d.y = f->d_y; d.angle = f->d_angle; d.octave = f->d_octave; d.desc = f->d_desc; d.uright = f->d_uright;
-    d.cell_start = f->d_cell_start; d.cell_items = f->d_cell_items;
+    d.n = n; d.x = d_x; d.y = d_y; d.angle = d_angle; d.octave = d_octave; d.desc = d_desc; d.uright = uright ? d_uright : nullptr;
+    d.cell_start = d_cell_start; d.cell_items = d_cell_items;
     d.min_x = cam->min_x; d.min_y = cam->min_y; d.max_x = cam->max_x; d.max_y = cam->max_y;
     d.gw_inv = (float)COEB_GRID_COLS / (cam->max_x - cam->min_x);   // mfGridElementWidthInv (src/Frame.cc:233)
     d.gh_inv = (float)COEB_GRID_ROWS / (cam->max_y - cam->min_y);
     d.fx = cam->fx; d.fy = cam->fy; d.cx = cam->cx; d.cy = cam->cy; d.bf = cam->bf; d.b = cam->b;
     for (int i = 0; i < COEB_MAX_LEVELS; i++) d.scale[i] = i < nlevels ? scale_factors[i] : 0.f;
-    grid_build_kernel<<<1, 1024, 0, s>>>(d, f->d_cell_start, f->d_cell_items, f->d_kp_cell);
-    cudaError_t le = cudaGetLastError();
-    if (le == cudaSuccess) le = cudaStreamSynchronize(s);  // host staging vectors go out of scope
-    if (le != cudaSuccess) { coeb_frame_destroy(f); return fail(COEB_ERR_CUDA, "grid build failed: %s", cudaGetErrorString(le)); }
+    grid_build_kernel<<<1, 1024, 0, s>>>(d, d_cell_start, d_cell_items, d_kp_cell);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);  // the pinned staging block is reused by the next call
+    if (e != cudaSuccess) { coeb_frame_destroy(f); return fail(COEB_ERR_CUDA, "frame upload / grid build failed: %s", cudaGetErrorString(e)); }
     *out = f;
     return COEB_OK;
 }
 
 void coeb_frame_destroy(coeb_frame* f) {
     if (!f) return;
-    cudaSetDevice(f->m->device);
-    cudaFree(f->d_x); cudaFree(f->d_y); cudaFree(f->d_angle); cudaFree(f->d_uright); cudaFree(f->d_octave);
-    cudaFree(f->d_cell_start); cudaFree(f->d_cell_items); cudaFree(f->d_kp_cell); cudaFree(f->d_desc);
+    if (f->block) {
+        if (f->m->frame_pool.size() < 8) f->m->frame_pool.push_back({f->block_bytes, f->block});
+        else { cudaSetDevice(f->m->device); cudaFree(f->block); }
+    }
     delete f;
 }
 
@@ -798,16 +967,17 @@ int coeb_frame_features_in_area(coeb_frame* f, float x, float y, float r, int mi
     if (!f || !n_out || cap < 0) return fail(COEB_ERR_INVALID_ARG, "bad argument");
     coeb_matcher* m = f->m;
     CUDA_TRY(cudaSetDevice(m->device));
-    int st = grow(&m->d_scratch, &m->scratch_bytes, (size_t)(cap + 1) * 4 + 256);
+    int st = m->out.reserve((size_t)(cap + 1) * 4 + 256);
     if (st != COEB_OK) return st;
-    int* d_out = (int*)m->d_scratch;
-    int* d_n = d_out + cap;
+    int* d_n = (int*)m->out.d;
+    int* d_out = d_n + 1;
     features_in_area_kernel<<<1, 32, 0, m->stream>>>(f->dev, x, y, r, min_level, max_level, d_out, cap, d_n);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(n_out, d_n, 4, cudaMemcpyDeviceToHost, m->stream));
-    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    if ((st = pull_outputs(m, (size_t)(cap + 1) * 4)) != COEB_OK) return st;
+    const int* h = (const int*)m->out.h;
+    *n_out = h[0];
     const int n = std::min(*n_out, cap);
-    if (n > 0 && idx_out) CUDA_TRY(cudaMemcpy(idx_out, d_out, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    if (n > 0 && idx_out) std::memcpy(idx_out, h + 1, (size_t)n * 4);
     return *n_out > cap ? fail(COEB_ERR_CAPACITY, "need %d entries", *n_out) : COEB_OK;
 }
 
@@ -815,18 +985,16 @@ int coeb_hamming256_batch(coeb_matcher* m, const uint8_t* a, const uint8_t* b, i
     if (!m || !a || !b || !dist_out || n < 0) return fail(COEB_ERR_INVALID_ARG, "bad argument");
     if (n == 0) return COEB_OK;
     CUDA_TRY(cudaSetDevice(m->device));
-    int st = grow(&m->d_scratch, &m->scratch_bytes, Carver::need({(size_t)n * 32, (size_t)n * 32, (size_t)n * 4}));
-    if (st != COEB_OK) return st;
-    Carver c(m->d_scratch);
-    uint32_t* da = c.take<uint32_t>((size_t)n * 8);
-    uint32_t* db = c.take<uint32_t>((size_t)n * 8);
-    int* dd = c.take<int>(n);
-    CUDA_TRY(cudaMemcpyAsync(da, a, (size_t)n * 32, cudaMemcpyHostToDevice, m->stream));
-    CUDA_TRY(cudaMemcpyAsync(db, b, (size_t)n * 32, cudaMemcpyHostToDevice, m->stream));
-    hamming_pairs_kernel<<<(n + 255) / 256, 256, 0, m->stream>>>(da, db, n, dd);
+    int st;
+    if ((st = m->in.reserve(2 * al((size_t)n * 32))) != COEB_OK || (st = m->out.reserve((size_t)n * 4)) != COEB_OK) return st;
+    Packer p(m->in);
+    const uint32_t* da = (const uint32_t*)p.place(a, (size_t)n * 32);
+    const uint32_t* db = (const uint32_t*)p.place(b, (size_t)n * 32);
+    if ((st = push_inputs(m, p)) != COEB_OK) return st;
+    hamming_pairs_kernel<<<(n + 255) / 256, 256, 0, m->stream>>>(da, db, n, (int*)m->out.d);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(dist_out, dd, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
-    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    if ((st = pull_outputs(m, (size_t)n * 4)) != COEB_OK) return st;
+    std::memcpy(dist_out, m->out.h, (size_t)n * 4);
     return COEB_OK;
 }
 
@@ -843,29 +1011,38 @@ int coeb_match_projection(coeb_matcher* m, coeb_frame* F, int n, const uint8_t* 
         if (track_in_view[i] && !bad[i] && (level[i] < 0 || level[i] >= F->nlevels)) return fail(COEB_ERR_INVALID_ARG, "map point %d: level %d", i, level[i]);
     CUDA_TRY(cudaSetDevice(m->device));
     const size_t N = n, K = F->n;
-    int st = grow(&m->d_scratch, &m->scratch_bytes,
-                  Carver::need({N, N, N, N * 4, N * 4, N * 4, N * 4, N * 4, N * 32, K * 4, N * 4, K * 4, 64}));
-    if (st != COEB_OK) return st;
-    Carver c(m->d_scratch);
-    uint8_t *d_tiv = c.take<uint8_t>(N), *d_bad = c.take<uint8_t>(N), *d_obs = c.take<uint8_t>(N);
-    float *d_px = c.take<float>(N), *d_py = c.take<float>(N), *d_pxr = c.take<float>(N), *d_vc = c.take<float>(N);
-    int* d_lvl = c.take<int>(N);
-    uint32_t* d_desc = c.take<uint32_t>(N * 8);
-    int *d_kpm = c.take<int>(K), *d_res = c.take<int>(N), *d_claim = c.take<int>(K), *d_info = c.take<int>(16);
-    cudaStream_t s = m->stream;
-    if ((st = upload(s, d_tiv, track_in_view, N)) || (st = upload(s, d_bad, bad, N)) || (st = upload(s, d_obs, has_obs, N)) ||
-        (st = upload(s, d_px, proj_x, N)) || (st = upload(s, d_py, proj_y, N)) || (st = upload(s, d_pxr, proj_xr, N)) ||
-        (st = upload(s, d_vc, view_cos, N)) || (st = upload(s, d_lvl, level, N)) || (st = upload(s, (uint8_t*)d_desc, desc, N * 32)) ||
-        (st = upload(s, d_kpm, kp_match, K)))
-        return st;
-    MapDev M{n, d_tiv, d_bad, d_obs, d_px, d_py, d_pxr, d_vc, d_lvl, d_desc};
-    match_projection_kernel<<<1, 1024, 0, s>>>(F->dev, M, th, nnratio, d_kpm, d_res, d_claim, d_info);
+    int st;
+    if ((st = m->in.reserve(3 * al(N) + 5 * al(N * 4) + al(N * 32) + al(K * 4))) != COEB_OK) return st;
+    if ((st = m->out.reserve(al(K * 4) + 256)) != COEB_OK) return st;
+    const int cap = 32;   // candidates kept per map point; a fuller window falls back to the window-walking kernel
+    if ((st = grow(&m->d_scratch, &m->scratch_bytes, al(N * 4) + al(K * 4) + al(N * 4) + al(N * cap * 8))) != COEB_OK) return st;
+    Packer p(m->in);
+    MapDev M{};
+    M.n = n;
+    M.track_in_view = p.place(track_in_view, N); M.bad = p.place(bad, N); M.has_obs = p.place(has_obs, N);
+    M.proj_x = p.place(proj_x, N); M.proj_y = p.place(proj_y, N); M.proj_xr = p.place(proj_xr, N); M.view_cos = p.place(view_cos, N);
+    M.level = p.place(level, N);
+    M.desc = (const uint32_t*)p.place(desc, N * 32);
+    const int* d_state = p.place(kp_match, K);
+    if ((st = push_inputs(m, p)) != COEB_OK) return st;
+    int* d_kpm = (int*)m->out.d;                       // [K] then info[2]
+    int* d_info = (int*)(m->out.d + al(K * 4));
+    int* d_res = (int*)m->d_scratch;
+    int* d_claim = (int*)((char*)m->d_scratch + al(N * 4));
+    CandLists C{(int2*)((char*)m->d_scratch + 2 * al(N * 4) + al(K * 4)), (int*)((char*)m->d_scratch + al(N * 4) + al(K * 4)), cap};
+    CUDA_TRY(cudaMemcpyAsync(d_kpm, d_state, K * 4, cudaMemcpyDeviceToDevice, m->stream));
+    m2_collect_kernel<<<(n + 127) / 128, 128, 0, m->stream>>>(F->dev, M, th, d_state, C);
+    m2_resolve_kernel<true><<<1, 1024, 0, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info);
     CUDA_TRY(cudaGetLastError());
-    int info[2] = {0, 0};
-    CUDA_TRY(cudaMemcpyAsync(kp_match, d_kpm, K * 4, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(info, d_info, 8, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
-    if (nmatches_out) *nmatches_out = info[0];
+    if ((st = pull_outputs(m, al(K * 4) + 12)) != COEB_OK) return st;
+    if (((const int*)(m->out.h + al(K * 4)))[2]) {   // a candidate list overflowed: exact window-walking variant
+        CUDA_TRY(cudaMemcpyAsync(d_kpm, d_state, K * 4, cudaMemcpyDeviceToDevice, m->stream));
+        m2_resolve_kernel<false><<<1, 1024, 0, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info);
+        CUDA_TRY(cudaGetLastError());
+        if ((st = pull_outputs(m, al(K * 4) + 12)) != COEB_OK) return st;
+    }
+    std::memcpy(kp_match, m->out.h, K * 4);
+    if (nmatches_out) *nmatches_out = ((const int*)(m->out.h + al(K * 4)))[0];
     return COEB_OK;
 }
 
@@ -881,22 +1058,18 @@ int coeb_match_lastframe(coeb_matcher* m, coeb_frame* cur, int n, const uint8_t*
         if (valid[i] && (octave[i] < 0 || octave[i] >= cur->nlevels)) return fail(COEB_ERR_INVALID_ARG, "last-frame point %d: octave %d", i, octave[i]);
     CUDA_TRY(cudaSetDevice(m->device));
     const size_t N = n, K = cur->n;
-    int st = grow(&m->d_scratch, &m->scratch_bytes, Carver::need({N, N, N * 12, N * 4, N * 4, N * 32, K * 4, N * 4, K * 4, 64}));
-    if (st != COEB_OK) return st;
-    Carver c(m->d_scratch);
-    uint8_t *d_valid = c.take<uint8_t>(N), *d_obs = c.take<uint8_t>(N);
-    float* d_xyz = c.take<float>(N * 3);
-    int* d_oct = c.take<int>(N);
-    float* d_ang = c.take<float>(N);
-    uint32_t* d_desc = c.take<uint32_t>(N * 8);
-    int *d_kpm = c.take<int>(K), *d_res = c.take<int>(N), *d_claim = c.take<int>(K), *d_info = c.take<int>(16);
-    cudaStream_t s = m->stream;
-    if ((st = upload(s, d_valid, valid, N)) || (st = upload(s, d_obs, has_obs, N)) || (st = upload(s, d_xyz, xyz, N * 3)) ||
-        (st = upload(s, d_oct, octave, N)) || (st = upload(s, d_ang, angle, N)) || (st = upload(s, (uint8_t*)d_desc, desc, N * 32)) ||
-        (st = upload(s, d_kpm, kp_match, K)))
-        return st;
+    int st;
+    if ((st = m->in.reserve(2 * al(N) + al(N * 12) + 2 * al(N * 4) + al(N * 32) + al(K * 4))) != COEB_OK) return st;
+    if ((st = m->out.reserve(al(K * 4) + 256)) != COEB_OK) return st;
+    const int cap = 64;
+    if ((st = grow(&m->d_scratch, &m->scratch_bytes, al(N * 4) + al(K * 4) + al(N * 4) + al(N * cap * 8))) != COEB_OK) return st;
+    Packer p(m->in);
     LastDev L{};
-    L.n = n; L.valid = d_valid; L.has_obs = d_obs; L.xyz = d_xyz; L.octave = d_oct; L.angle = d_ang; L.desc = d_desc;
+    L.n = n;
+    L.valid = p.place(valid, N); L.has_obs = p.place(has_obs, N); L.xyz = p.place(xyz, N * 3); L.octave = p.place(octave, N);
+    L.angle = p.place(angle, N); L.desc = (const uint32_t*)p.place(desc, N * 32);
+    const int* d_state = p.place(kp_match, K);
+    if ((st = push_inputs(m, p)) != COEB_OK) return st;
     for (int i = 0; i < 12; i++) L.T[i] = Tcw_cur[i];
     // tlc = Rlw * twc + tlw with twc = -Rcw^T tcw (src/ORBmatcher.cc:1339-1350); only its z component is used. fp32, fixed order.
     float twc[3];
@@ -904,13 +1077,24 @@ int coeb_match_lastframe(coeb_matcher* m, coeb_frame* cur, int n, const uint8_t*
     const float tz = Tcw_last[8] * twc[0] + Tcw_last[9] * twc[1] + Tcw_last[10] * twc[2] + Tcw_last[11];
     L.forward = (tz > cur->dev.b && !mono) ? 1 : 0;
     L.backward = (-tz > cur->dev.b && !mono) ? 1 : 0;
-    match_lastframe_kernel<<<1, 1024, 0, s>>>(cur->dev, L, th, check_ori, d_kpm, d_res, d_claim, d_info);
+    int* d_kpm = (int*)m->out.d;
+    int* d_info = (int*)(m->out.d + al(K * 4));
+    int* d_res = (int*)m->d_scratch;
+    int* d_claim = (int*)((char*)m->d_scratch + al(N * 4));
+    CandLists C{(int2*)((char*)m->d_scratch + 2 * al(N * 4) + al(K * 4)), (int*)((char*)m->d_scratch + al(N * 4) + al(K * 4)), cap};
+    CUDA_TRY(cudaMemcpyAsync(d_kpm, d_state, K * 4, cudaMemcpyDeviceToDevice, m->stream));
+    m3_collect_kernel<<<(n + 127) / 128, 128, 0, m->stream>>>(cur->dev, L, th, d_state, C);
+    m3_resolve_kernel<true><<<1, 1024, 0, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info);
     CUDA_TRY(cudaGetLastError());
-    int info[2] = {0, 0};
-    CUDA_TRY(cudaMemcpyAsync(kp_match, d_kpm, K * 4, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(info, d_info, 8, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
-    if (nmatches_out) *nmatches_out = info[0];
+    if ((st = pull_outputs(m, al(K * 4) + 12)) != COEB_OK) return st;
+    if (((const int*)(m->out.h + al(K * 4)))[2]) {
+        CUDA_TRY(cudaMemcpyAsync(d_kpm, d_state, K * 4, cudaMemcpyDeviceToDevice, m->stream));
+        m3_resolve_kernel<false><<<1, 1024, 0, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info);
+        CUDA_TRY(cudaGetLastError());
+        if ((st = pull_outputs(m, al(K * 4) + 12)) != COEB_OK) return st;
+    }
+    std::memcpy(kp_match, m->out.h, K * 4);
+    if (nmatches_out) *nmatches_out = ((const int*)(m->out.h + al(K * 4)))[0];
     return COEB_OK;
 }
 
@@ -922,25 +1106,39 @@ int coeb_match_init(coeb_matcher* m, coeb_frame* f1, coeb_frame* f2, float* prev
     if (f2->n == 0) { for (int i = 0; i < f1->n; i++) matches12[i] = -1; return COEB_OK; }
     CUDA_TRY(cudaSetDevice(m->device));
     const size_t N1 = f1->n, N2 = f2->n;
-    int st = grow(&m->d_scratch, &m->scratch_bytes,
-                  Carver::need({N1 * 8, N1 * 8, N1 * 4, N1 * 4, (N2 + 1) * 4, (N2 + 1) * 4, N1 * 8, N1 * 4, 64}));
-    if (st != COEB_OK) return st;
-    Carver c(m->d_scratch);
-    float *d_prev = c.take<float>(N1 * 2), *d_prev_out = c.take<float>(N1 * 2);
-    int *d_res = c.take<int>(N1), *d_rdist = c.take<int>(N1), *d_cls = c.take<int>(N2 + 1), *d_clf = c.take<int>(N2 + 1);
-    int2* d_items = c.take<int2>(N1);
-    int *d_m12 = c.take<int>(N1), *d_info = c.take<int>(16);
-    cudaStream_t s = m->stream;
-    if ((st = upload(s, d_prev, prev_matched, N1 * 2))) return st;
-    match_init_kernel<<<1, 1024, 0, s>>>(f1->dev, f2->dev, d_prev, (float)window_size, nnratio, check_ori, d_res, d_rdist, d_cls, d_clf,
-                                         d_items, d_m12, d_prev_out, d_info);
+    int st;
+    if ((st = m->in.reserve(al(N1 * 8))) != COEB_OK) return st;
+    if ((st = m->out.reserve(al(N1 * 4) + al(N1 * 8) + 256)) != COEB_OK) return st;
+    const int cap = 256;
+    if ((st = grow(&m->d_scratch, &m->scratch_bytes, 2 * al(N1 * 4) + 2 * al((N2 + 1) * 4) + al(N1 * 8) + al(N1 * 4) + al(N1 * cap * 8))) != COEB_OK) return st;
+    Packer p(m->in);
+    const float* d_prev = p.place(prev_matched, N1 * 2);
+    if ((st = push_inputs(m, p)) != COEB_OK) return st;
+    char* sc = (char*)m->d_scratch;
+    int* d_res = (int*)sc; sc += al(N1 * 4);
+    int* d_rdist = (int*)sc; sc += al(N1 * 4);
+    int* d_cls = (int*)sc; sc += al((N2 + 1) * 4);
+    int* d_clf = (int*)sc; sc += al((N2 + 1) * 4);
+    int2* d_items = (int2*)sc; sc += al(N1 * 8);
+    CandLists C{nullptr, (int*)sc, cap}; sc += al(N1 * 4);
+    C.items = (int2*)sc;
+    int* d_m12 = (int*)m->out.d;
+    float* d_prev_out = (float*)(m->out.d + al(N1 * 4));
+    int* d_info = (int*)(m->out.d + al(N1 * 4) + al(N1 * 8));
+    m4_collect_kernel<<<(f1->n + 127) / 128, 128, 0, m->stream>>>(f1->dev, f2->dev, d_prev, (float)window_size, C);
+    m4_resolve_kernel<true><<<1, 1024, 0, m->stream>>>(f1->dev, f2->dev, d_prev, (float)window_size, nnratio, check_ori, C, d_res, d_rdist, d_cls,
+                                                       d_clf, d_items, d_m12, d_prev_out, d_info);
     CUDA_TRY(cudaGetLastError());
-    int info[2] = {0, 0};
-    CUDA_TRY(cudaMemcpyAsync(matches12, d_m12, N1 * 4, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(prev_matched, d_prev_out, N1 * 8, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(info, d_info, 8, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
-    if (nmatches_out) *nmatches_out = info[0];
+    if ((st = pull_outputs(m, al(N1 * 4) + al(N1 * 8) + 12)) != COEB_OK) return st;
+    if (((const int*)(m->out.h + al(N1 * 4) + al(N1 * 8)))[2]) {
+        m4_resolve_kernel<false><<<1, 1024, 0, m->stream>>>(f1->dev, f2->dev, d_prev, (float)window_size, nnratio, check_ori, C, d_res, d_rdist,
+                                                            d_cls, d_clf, d_items, d_m12, d_prev_out, d_info);
+        CUDA_TRY(cudaGetLastError());
+        if ((st = pull_outputs(m, al(N1 * 4) + al(N1 * 8) + 12)) != COEB_OK) return st;
+    }
+    std::memcpy(matches12, m->out.h, N1 * 4);
+    std::memcpy(prev_matched, m->out.h + al(N1 * 4), N1 * 8);
+    if (nmatches_out) *nmatches_out = ((const int*)(m->out.h + al(N1 * 4) + al(N1 * 8)))[0];
     return COEB_OK;
 }
 
@@ -967,32 +1165,33 @@ int coeb_stereo_match(coeb_matcher* m, coeb_extractor* left, coeb_extractor* rig
     S.nRows = S.lh[0];
     S.N = N; S.Nr = Nr; S.bf = bf; S.b = b;
     const size_t NL = N, NR = Nr;
-    st = grow(&m->d_scratch, &m->scratch_bytes,
-              Carver::need({NL * 4, NL * 4, NL * 4, NL * 32, NR * 4, NR * 4, NR * 4, NR * 32, NL * 4, NL * 4, NL * 4, 64}));
-    if (st != COEB_OK) return st;
-    Carver c(m->d_scratch);
-    float *dxl = c.take<float>(NL), *dyl = c.take<float>(NL); int* dol = c.take<int>(NL); uint32_t* ddl = c.take<uint32_t>(NL * 8);
-    float *dxr = c.take<float>(NR), *dyr = c.take<float>(NR); int* dor_ = c.take<int>(NR); uint32_t* ddr = c.take<uint32_t>(NR * 8);
-    float *dur = c.take<float>(NL), *ddp = c.take<float>(NL); int *dsad = c.take<int>(NL), *dinfo = c.take<int>(16);
-    std::vector<float> hx(NL), hy(NL), rx(NR), ry(NR);
-    std::vector<int> ho(NL), ro(NR);
-    for (int i = 0; i < N; i++) { hx[i] = keys_left[i].x; hy[i] = keys_left[i].y; ho[i] = keys_left[i].octave; }
-    for (int i = 0; i < Nr; i++) { rx[i] = keys_right[i].x; ry[i] = keys_right[i].y; ro[i] = keys_right[i].octave; }
-    cudaStream_t s = m->stream;
-    if ((st = upload(s, dxl, hx.data(), NL)) || (st = upload(s, dyl, hy.data(), NL)) || (st = upload(s, dol, ho.data(), NL)) ||
-        (st = upload(s, (uint8_t*)ddl, desc_left, NL * 32)) || (st = upload(s, dxr, rx.data(), NR)) || (st = upload(s, dyr, ry.data(), NR)) ||
-        (st = upload(s, dor_, ro.data(), NR)) || (st = upload(s, (uint8_t*)ddr, desc_right, NR * 32)))
-        return st;
+    if ((st = m->in.reserve(3 * al(NL * 4) + al(NL * 32) + 3 * al(NR * 4) + al(NR * 32))) != COEB_OK) return st;
+    if ((st = m->out.reserve(2 * al(NL * 4) + 256)) != COEB_OK) return st;
+    if ((st = grow(&m->d_scratch, &m->scratch_bytes, al(NL * 4))) != COEB_OK) return st;
+    Packer p(m->in);
+    float *dxl = p.room<float>(NL), *dyl = p.room<float>(NL); int* dol = p.room<int>(NL);
+    const uint32_t* ddl = (const uint32_t*)p.place(desc_left, NL * 32);
+    float *dxr = p.room<float>(NR), *dyr = p.room<float>(NR); int* dor_ = p.room<int>(NR);
+    const uint32_t* ddr = (const uint32_t*)p.place(desc_right, NR * 32);
+    {
+        float *hx = p.host_at(dxl), *hy = p.host_at(dyl); int* ho = p.host_at(dol);
+        for (int i = 0; i < N; i++) { hx[i] = keys_left[i].x; hy[i] = keys_left[i].y; ho[i] = keys_left[i].octave; }
+        float *rx = p.host_at(dxr), *ry = p.host_at(dyr); int* ro = p.host_at(dor_);
+        for (int i = 0; i < Nr; i++) { rx[i] = keys_right[i].x; ry[i] = keys_right[i].y; ro[i] = keys_right[i].octave; }
+    }
+    if ((st = push_inputs(m, p)) != COEB_OK) return st;
     S.xl = dxl; S.yl = dyl; S.octl = dol; S.descl = ddl; S.xr = dxr; S.yr = dyr; S.octr = dor_; S.descr = ddr;
-    stereo_match_kernel<<<(N + 7) / 8, 256, 0, s>>>(S, dur, ddp, dsad);
-    stereo_outlier_kernel<<<1, 1024, 0, s>>>(N, dur, ddp, dsad, dinfo);
+    float* dur = (float*)m->out.d;
+    float* ddp = (float*)(m->out.d + al(NL * 4));
+    int* dinfo = (int*)(m->out.d + 2 * al(NL * 4));
+    int* dsad = (int*)m->d_scratch;
+    stereo_match_kernel<<<(N + 7) / 8, 256, 0, m->stream>>>(S, dur, ddp, dsad);
+    stereo_outlier_kernel<<<1, 1024, 0, m->stream>>>(N, dur, ddp, dsad, dinfo);
     CUDA_TRY(cudaGetLastError());
-    int info = 0;
-    CUDA_TRY(cudaMemcpyAsync(uright_out, dur, NL * 4, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(depth_out, ddp, NL * 4, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(&info, dinfo, 4, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
-    if (nmatched_out) *nmatched_out = info;
+    if ((st = pull_outputs(m, 2 * al(NL * 4) + 8)) != COEB_OK) return st;
+    std::memcpy(uright_out, m->out.h, NL * 4);
+    std::memcpy(depth_out, m->out.h + al(NL * 4), NL * 4);
+    if (nmatched_out) *nmatched_out = ((const int*)(m->out.h + 2 * al(NL * 4)))[0];
     return COEB_OK;
 }
 
@@ -1005,10 +1204,11 @@ int coeb_knn2_device(coeb_matcher* m, const uint8_t* d_query, int nq, const uint
     nchunks = std::min(nchunks, std::max(1, nt / 64));
     int chunk = (nt + nchunks - 1) / nchunks;
     nchunks = (nt + chunk - 1) / chunk;
-    int st = grow(&m->d_in, &m->in_bytes, Carver::need({(size_t)nchunks * nq * 4, (size_t)nchunks * nq * 4, (size_t)nchunks * nq * 4}));
+    int st = grow(&m->d_in, &m->in_bytes, 3 * al((size_t)nchunks * nq * 4));
     if (st != COEB_OK) return st;
-    Carver c(m->d_in);
-    int *p1 = c.take<int>((size_t)nchunks * nq), *pi = c.take<int>((size_t)nchunks * nq), *p2 = c.take<int>((size_t)nchunks * nq);
+    int* p1 = (int*)m->d_in;
+    int* pi = (int*)((char*)m->d_in + al((size_t)nchunks * nq * 4));
+    int* p2 = (int*)((char*)m->d_in + 2 * al((size_t)nchunks * nq * 4));
     knn2_partial_kernel<<<dim3(qblocks, nchunks), kKnnThreads, 0, m->stream>>>((const uint32_t*)d_query, nq, (const uint32_t*)d_train, nt, chunk,
                                                                               p1, pi, p2);
     knn2_merge_kernel<<<(nq + 255) / 256, 256, 0, m->stream>>>(nq, nchunks, p1, pi, p2, nnratio, d_best_idx, d_d1, d_d2, nullptr);
@@ -1024,20 +1224,21 @@ int coeb_knn2(coeb_matcher* m, const uint8_t* query, int nq, const uint8_t* trai
     if (nt == 0) { for (int i = 0; i < nq; i++) { best_idx[i] = -1; if (d1) d1[i] = 256; if (d2) d2[i] = 256; } return COEB_OK; }
     CUDA_TRY(cudaSetDevice(m->device));
     const size_t NQ = nq, NT = nt;
-    int st = grow(&m->d_scratch, &m->scratch_bytes, Carver::need({NQ * 32, NT * 32, NQ * 4, NQ * 4, NQ * 4}));
-    if (st != COEB_OK) return st;
-    Carver c(m->d_scratch);
-    uint8_t *dq = c.take<uint8_t>(NQ * 32), *dt = c.take<uint8_t>(NT * 32);
-    int *di = c.take<int>(NQ), *dd1 = c.take<int>(NQ), *dd2 = c.take<int>(NQ);
-    cudaStream_t s = m->stream;
-    CUDA_TRY(cudaMemcpyAsync(dq, query, NQ * 32, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(dt, train, NT * 32, cudaMemcpyHostToDevice, s));
+    int st;
+    if ((st = m->in.reserve(al(NQ * 32) + al(NT * 32))) != COEB_OK || (st = m->out.reserve(3 * al(NQ * 4))) != COEB_OK) return st;
+    Packer p(m->in);
+    const uint8_t* dq = p.place(query, NQ * 32);
+    const uint8_t* dt = p.place(train, NT * 32);
+    if ((st = push_inputs(m, p)) != COEB_OK) return st;
+    int* di = (int*)m->out.d;
+    int* dd1 = (int*)(m->out.d + al(NQ * 4));
+    int* dd2 = (int*)(m->out.d + 2 * al(NQ * 4));
     st = coeb_knn2_device(m, dq, nq, dt, nt, nnratio, di, dd1, dd2);
     if (st != COEB_OK) return st;
-    CUDA_TRY(cudaMemcpyAsync(best_idx, di, NQ * 4, cudaMemcpyDeviceToHost, s));
-    if (d1) CUDA_TRY(cudaMemcpyAsync(d1, dd1, NQ * 4, cudaMemcpyDeviceToHost, s));
-    if (d2) CUDA_TRY(cudaMemcpyAsync(d2, dd2, NQ * 4, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
+    if ((st = pull_outputs(m, 3 * al(NQ * 4))) != COEB_OK) return st;
+    std::memcpy(best_idx, m->out.h, NQ * 4);
+    if (d1) std::memcpy(d1, m->out.h + al(NQ * 4), NQ * 4);
+    if (d2) std::memcpy(d2, m->out.h + 2 * al(NQ * 4), NQ * 4);
     if (naccepted_out) { int a = 0; for (int i = 0; i < nq; i++) a += best_idx[i] >= 0; *naccepted_out = a; }
     return COEB_OK;
 }

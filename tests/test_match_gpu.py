@@ -190,3 +190,29 @@ def test_knn2_full_size_properties_and_sample(gpu):
     # exact comparison with the oracle on a 256-query sample against the whole train set
     ic, d1c, d2c, _ = orc.knn2(q[:256], t, 0.7, nthreads=orc.hardware_threads())
     assert np.array_equal(ig[:256], ic) and np.array_equal(d1g[:256], d1c) and np.array_equal(d2g[:256], d2c)
+
+
+def test_wide_windows_take_the_overflow_fallback(gpu, tum):
+    """Windows with more candidates than the per-query list capacity (32 / 64 / 256) must fall back to the
+    window-walking kernels and still match the oracle exactly."""
+    mp, uright = synth.make_map_points(tum["kps"], tum["desc"], tum["scale"], seed=77, n_map=600, n_true=300)
+    m, fg, fc = _frames(gpu, tum, uright=uright)
+    state = np.full(len(tum["kps"]), -1, np.int32)
+    n_c, km_c = orc.match_projection(fc, mp, 40.0, 0.8, state)
+    n_g, km_g = m.match_projection(fg, mp, 40.0, 0.8, state)
+    assert (n_c, km_c.tolist()) == (n_g, km_g.tolist()) and n_c > 20
+    last, Tc, Tl = synth.make_last_frame(tum["kps"], tum["desc"], seed=78)
+    n_c, km_c = orc.match_lastframe(fc, last, Tc, Tl, 120.0, False, True, state)
+    n_g, km_g = m.match_lastframe(fg, last, Tc, Tl, 120.0, False, True, state)
+    assert (n_c, km_c.tolist()) == (n_g, km_g.tolist()) and n_c > 20
+    ex = orc.Extractor(nfeatures=2000)
+    g1 = synth.make_frame(210)
+    k1, d1 = ex.extract(g1)
+    k2, d2 = ex.extract(synth.shift_image(g1, 8, 4))
+    cam_args = tum["cam_args"]
+    f1g, f2g = m.frame(k1, d1, gpu.Camera(*cam_args), tum["scale"]), m.frame(k2, d2, gpu.Camera(*cam_args), tum["scale"])
+    f1c, f2c = orc.Frame(k1, d1, orc.Camera(*cam_args), tum["scale"]), orc.Frame(k2, d2, orc.Camera(*cam_args), tum["scale"])
+    prev = np.stack([k1["x"], k1["y"]], axis=1).astype(np.float32)
+    n_c, m_c, p_c = orc.match_init(f1c, f2c, prev, 400, 0.9, True)
+    n_g, m_g, p_g = m.match_init(f1g, f2g, prev, 400, 0.9, True)
+    assert n_c == n_g and np.array_equal(m_c, m_g) and np.array_equal(p_c, p_g)
