@@ -83,6 +83,10 @@ struct coeb_extractor {
     cudaStream_t pipe_stream[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t pipe_done[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t pipe_ready = nullptr;
+    // CUDA graphs of the kernel sequence for small non-pipelined host calls (single-frame latency path)
+    struct GraphEntry { BatchView view; int w, h, cap; cudaGraphExec_t exec; };
+    std::vector<GraphEntry> graphs;
+    int graph_warm = 0;
     // optional per-stage CUDA events (benchmark accounting)
     bool profiling = false;
     cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -92,6 +96,7 @@ namespace {
 
 constexpr int kPipeStreams = 3;
 constexpr int kPipeChunk = 32;
+constexpr int kGraphMaxBatch = 8;
 
 // ORBextractor::ORBextractor tables (src/ORBextractor.cc:418-477)
 void build_tables(coeb_extractor* ex) {
@@ -234,6 +239,8 @@ int build_geometry(coeb_extractor* ex, int w, int h) {
     }
     ex->geom_valid = true;
     ex->cap_B = 0;  // arenas must be re-laid out for the new geometry
+    for (auto& e : ex->graphs) cudaGraphExecDestroy(e.exec);
+    ex->graphs.clear();
     return COEB_OK;
 }
 
@@ -389,6 +396,7 @@ void coeb_extractor_destroy(coeb_extractor* ex) {
     cudaFree(ex->d_tabs);
     cudaFree(ex->d_in_gray); cudaFree(ex->d_in_boxes); cudaFree(ex->d_in_tm); cudaFree(ex->d_in_nbox); cudaFree(ex->d_in_ntm);
     cudaFree(ex->d_in_blur); cudaFree(ex->d_out_kps); cudaFree(ex->d_out_desc); cudaFree(ex->d_out_count); cudaFree(ex->d_out_status);
+    for (auto& e : ex->graphs) cudaGraphExecDestroy(e.exec);
     for (int i = 0; i < 7; i++) if (ex->ev[i]) cudaEventDestroy(ex->ev[i]);
     for (int i = 0; i < 3; i++) {
         if (ex->pipe_stream[i]) cudaStreamDestroy(ex->pipe_stream[i]);
@@ -448,6 +456,47 @@ int coeb_extractor_stage_ms(coeb_extractor* ex, float* ms6) {
     CUDA_TRY(cudaSetDevice(ex->device));
     CUDA_TRY(cudaEventSynchronize(ex->ev[6]));
     for (int i = 0; i < 6; i++) CUDA_TRY(cudaEventElapsedTime(&ms6[i], ex->ev[i], ex->ev[i + 1]));
+    return COEB_OK;
+}
+
+// Replays the kernel sequence of `v` as a CUDA graph (captured on first use for this exact view). All pointers in the
+// view are the handle's own staging buffers and arenas, so the same graph serves every later call of the same shape.
+static bool same_view(const BatchView& a, const BatchView& b) {
+    return a.B == b.B && a.l0 == b.l0 && a.l0_pitch == b.l0_pitch && a.l0_stride == b.l0_stride && a.pyr == b.pyr && a.blur == b.blur &&
+           a.tabs == b.tabs && a.cand == b.cand && a.keys == b.keys && a.dyn == b.dyn && a.boxes == b.boxes && a.nbox == b.nbox &&
+           a.max_box == b.max_box && a.tm == b.tm && a.ntm == b.ntm && a.max_tm == b.max_tm && a.blur_flag == b.blur_flag &&
+           a.out_kps == b.out_kps && a.out_desc == b.out_desc && a.out_count == b.out_count && a.status == b.status;
+}
+
+static int launch_graphed(coeb_extractor* ex, const BatchView& v, cudaStream_t s) {
+    const Geometry& g = ex->geom;
+    for (auto& e : ex->graphs)
+        if (e.w == g.w0 && e.h == g.h0 && e.cap == g.out_cap && same_view(e.view, v)) {
+            CUDA_TRY(cudaGraphLaunch(e.exec, s));
+            return COEB_OK;
+        }
+    if (ex->graph_warm < 2) {   // first calls run eagerly (lazy module loading, function attributes) before anything is captured
+        ex->graph_warm++;
+        return enqueue(ex, v, s, false);
+    }
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    int st = enqueue(ex, v, s, false);
+    cudaError_t e = cudaStreamEndCapture(s, &graph);
+    if (st != COEB_OK || e != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        return enqueue(ex, v, s, false);   // capture not possible here: plain launches
+    }
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { cudaGetLastError(); return enqueue(ex, v, s, false); }
+    if (ex->graphs.size() >= 8) { cudaGraphExecDestroy(ex->graphs.front().exec); ex->graphs.erase(ex->graphs.begin()); }
+    coeb_extractor::GraphEntry ge;
+    ge.view = v; ge.w = g.w0; ge.h = g.h0; ge.cap = g.out_cap; ge.exec = exec;
+    ex->graphs.push_back(ge);
+    CUDA_TRY(cudaGraphLaunch(exec, s));
     return COEB_OK;
 }
 
@@ -586,7 +635,11 @@ int coeb_extract_batch_host(coeb_extractor* ex, int B, const uint8_t* gray, int 
                 CUDA_TRY(cudaMemcpy2DAsync(ex->d_in_gray + fstride * i, pitch, gray + frame_stride * i, stride, width, height,
                                            cudaMemcpyHostToDevice, ps));
         }
-        st = enqueue(ex, sub_view(ex->geom, v, f0, n, ex->pyr_bytes_per_frame), ps, !piped && ex->profiling);
+        if (!piped && !ex->profiling && B <= kGraphMaxBatch) {
+            st = launch_graphed(ex, v, ps);   // one graph launch instead of ~14 stream operations
+        } else {
+            st = enqueue(ex, sub_view(ex->geom, v, f0, n, ex->pyr_bytes_per_frame), ps, !piped && ex->profiling);
+        }
         if (st != COEB_OK) return st;
         CUDA_TRY(cudaMemcpyAsync(counts_out + f0, ex->d_out_count + f0, sizeof(int) * n, cudaMemcpyDeviceToHost, ps));
         CUDA_TRY(cudaMemcpyAsync(hstatus + f0, ex->d_out_status + f0, sizeof(int) * n, cudaMemcpyDeviceToHost, ps));
@@ -622,14 +675,20 @@ int coeb_extract(coeb_extractor* ex, const uint8_t* gray, int width, int height,
     if (!gray || width <= 0 || height <= 0) return COEB_OK;  // `if (_image.empty()) return;` (src/ORBextractor.cc:1096)
     if (nbox < 0 || ntm < 0 || nblur < 0) return fail(COEB_ERR_INVALID_ARG, "negative count");
     if (nbox > COEB_MAX_BOXES) return fail(COEB_ERR_INVALID_ARG, "at most %d boxes per frame", COEB_MAX_BOXES);
-    // blur_flag is indexed by box id in the reference (:1168); missing entries count as 0
-    std::vector<int> blur(std::max(nbox, 1), 0);
+    // Fixed-shape staging (COEB_MAX_BOXES boxes, T_M capacity rounded up to 64) so that every call of this handle has the
+    // same device view and replays the same CUDA graph. blur_flag is indexed by box id in the reference (:1168);
+    // missing entries count as 0.
+    float boxes[COEB_MAX_BOXES * 4] = {0};
+    int blur[COEB_MAX_BOXES] = {0};
+    for (int i = 0; i < nbox * 4; i++) boxes[i] = boxes_xyxy[i];
     for (int i = 0; i < nbox && i < nblur; i++) blur[i] = blur_flag[i];
+    const int max_tm = std::max(64, (ntm + 63) & ~63);
+    std::vector<float> tm((size_t)max_tm * 2, 0.f);
+    if (ntm) std::memcpy(tm.data(), tm_xy, sizeof(float) * 2 * ntm);
     int count = 0, status = 0;
     const int nb = nbox, nt = ntm;
-    int st = coeb_extract_batch_host(ex, 1, gray, width, height, stride, (size_t)stride * height, nbox ? boxes_xyxy : nullptr,
-                                     nbox ? &nb : nullptr, std::max(nbox, 1), ntm ? tm_xy : nullptr, ntm ? &nt : nullptr,
-                                     std::max(ntm, 1), nbox ? blur.data() : nullptr, kps_out, desc_out, &count, &status, cap);
+    int st = coeb_extract_batch_host(ex, 1, gray, width, height, stride, (size_t)stride * height, boxes, &nb, COEB_MAX_BOXES, tm.data(), &nt,
+                                     max_tm, blur, kps_out, desc_out, &count, &status, cap);
     if (n_out) *n_out = count;
     return st;
 }

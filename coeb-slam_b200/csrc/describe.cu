@@ -11,6 +11,8 @@ __constant__ signed char c_pattern[1024] = {
 #include "../../include/coeb_orb_pattern.inc"
 };
 
+constexpr int kDescChunk = 64;   // keypoints per CTA: several CTAs per level keep a single frame's latency low
+
 __global__ void __launch_bounds__(256) describe_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v) {
     __shared__ signed char s_pat[1024];   // transposed: [4*bit + component][lane], conflict-free per-lane reads
     __shared__ float2 s_cs[256];          // (cos, sin) of the keypoints of the current chunk
@@ -29,14 +31,15 @@ __global__ void __launch_bounds__(256) describe_kernel(const __grid_constant__ G
     }
     const int n = kc[level];
     const int status = v.status[frame];
-    if (level == 0 && tid == 0) {
+    const int chunk0 = blockIdx.z * kDescChunk;   // this CTA describes keypoints [chunk0, chunk0 + kDescChunk) of the level
+    if (level == 0 && blockIdx.z == 0 && tid == 0) {
         int cnt = total;
         if (status != COEB_OK) cnt = 0;
         else if (total > g.out_cap) { v.status[frame] = COEB_ERR_CAPACITY; }
         v.out_count[frame] = cnt;
     }
     __syncthreads();
-    if (n == 0 || status != COEB_OK || total > g.out_cap) return;
+    if (chunk0 >= n || status != COEB_OK || total > g.out_cap) return;
 
     const uint8_t* __restrict__ img = blur_ptr(g, v, level, frame);
     const int pitch = L.pitch;
@@ -45,15 +48,16 @@ __global__ void __launch_bounds__(256) describe_kernel(const __grid_constant__ G
     uint8_t* odesc = v.out_desc + ((size_t)frame * g.out_cap + offset) * 32;
     const int lane = tid & 31, wid = tid >> 5;
     const float factorPI = (float)(3.14159265358979323846 / 180.0);  // (float)(CV_PI/180.f), :109
-    for (int base = 0; base < n; base += 256) {
+    const int nend = min(n, chunk0 + kDescChunk);
+    for (int base = chunk0; base < nend; base += 256) {
         __syncthreads();
-        if (base + tid < n) {
+        if (base + tid < nend) {
             // (float)cos(angle), (float)sin(angle) with the float argument promoted to double (:114-115); once per keypoint
             const float angle = __fmul_rn(keys[base + tid].angle, factorPI);
             s_cs[tid] = make_float2((float)cos((double)angle), (float)sin((double)angle));
         }
         __syncthreads();
-        const int m = min(256, n - base);
+        const int m = min(256, nend - base);
         for (int j = wid; j < m; j += 8) {
             const int i = base + j;
             const LevelKey k = keys[i];
@@ -91,7 +95,9 @@ __global__ void __launch_bounds__(256) describe_kernel(const __grid_constant__ G
 }
 
 void launch_describe(const Geometry& g, const BatchView& v, cudaStream_t stream) {
-    describe_kernel<<<dim3(g.nlevels, v.B), 256, 0, stream>>>(g, v);
+    int max_keys = 1;
+    for (int l = 0; l < g.nlevels; l++) max_keys = std::max(max_keys, g.lv[l].key_cap);
+    describe_kernel<<<dim3(g.nlevels, v.B, (max_keys + kDescChunk - 1) / kDescChunk), 256, 0, stream>>>(g, v);
 }
 
 }  // namespace coeb
