@@ -59,6 +59,7 @@ struct coeb_extractor {
     bool geom_valid = false;
     std::vector<int2> h_tabs;
     int2* d_tabs = nullptr;
+    int4* d_fast_tiles = nullptr;
     size_t pyr_bytes_per_frame = 0;
     // arenas
     int cap_B = 0;
@@ -233,6 +234,15 @@ int build_geometry(coeb_extractor* ex, int w, int h) {
         return fail(COEB_ERR_UNSUPPORTED, "nfeatures too large for the shared-memory octree (%d nodes)", max_nodes);
     if (ex->d_tabs) cudaFree(ex->d_tabs);
     ex->d_tabs = nullptr;
+    if (ex->d_fast_tiles) cudaFree(ex->d_fast_tiles);
+    ex->d_fast_tiles = nullptr;
+    {
+        g.fast_tiles_per_frame = build_fast_tiles(g, nullptr);
+        std::vector<int4> tiles(g.fast_tiles_per_frame);
+        build_fast_tiles(g, tiles.data());
+        CUDA_TRY(cudaMalloc(&ex->d_fast_tiles, tiles.size() * sizeof(int4)));
+        CUDA_TRY(cudaMemcpy(ex->d_fast_tiles, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    }
     if (!ex->h_tabs.empty()) {
         CUDA_TRY(cudaMalloc(&ex->d_tabs, ex->h_tabs.size() * sizeof(int2)));
         CUDA_TRY(cudaMemcpy(ex->d_tabs, ex->h_tabs.data(), ex->h_tabs.size() * sizeof(int2), cudaMemcpyHostToDevice));
@@ -394,6 +404,7 @@ void coeb_extractor_destroy(coeb_extractor* ex) {
     cudaStreamSynchronize(ex->stream);
     free_arenas(ex);
     cudaFree(ex->d_tabs);
+    cudaFree(ex->d_fast_tiles);
     cudaFree(ex->d_in_gray); cudaFree(ex->d_in_boxes); cudaFree(ex->d_in_tm); cudaFree(ex->d_in_nbox); cudaFree(ex->d_in_ntm);
     cudaFree(ex->d_in_blur); cudaFree(ex->d_out_kps); cudaFree(ex->d_out_desc); cudaFree(ex->d_out_count); cudaFree(ex->d_out_status);
     for (auto& e : ex->graphs) cudaGraphExecDestroy(e.exec);
@@ -438,8 +449,8 @@ int coeb_extractor_tables(const coeb_extractor* ex, int* nlevels, float* scale, 
 
 int coeb_extractor_launches_per_call(const coeb_extractor* ex) {
     if (!ex) return 0;
-    // classify + (nlevels-1) resizes + blur + FAST + select + describe (the two counter memsets are not kernels of ours)
-    return 1 + (ex->params.nlevels - 1) + 1 + 1 + 1 + 1;
+    // classify + (nlevels-1) resizes + blur + FAST + FAST fallback + select + describe (the two counter memsets are not kernels of ours)
+    return 1 + (ex->params.nlevels - 1) + 1 + 2 + 1 + 1;
 }
 
 int coeb_extractor_set_profiling(coeb_extractor* ex, int on) {
@@ -518,7 +529,7 @@ static int prepare_view(coeb_extractor* ex, int B, const uint8_t* gray, int widt
     BatchView v{};
     v.B = B;
     v.l0 = gray; v.l0_pitch = stride; v.l0_stride = frame_stride;
-    v.pyr = ex->d_pyr; v.blur = ex->d_blur; v.tabs = ex->d_tabs;
+    v.pyr = ex->d_pyr; v.blur = ex->d_blur; v.tabs = ex->d_tabs; v.fast_tiles = ex->d_fast_tiles;
     v.cand = ex->d_cand; v.cand_count = ex->d_cand_count; v.keys = ex->d_keys; v.key_count = ex->d_key_count;
     v.dyn = ex->d_dyn; v.knode = ex->d_knode;
     v.lmax = ex->d_lmax; v.lmax_count = ex->d_lmax_count; v.cell_count = ex->d_cell_count;
