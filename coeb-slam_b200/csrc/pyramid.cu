@@ -73,7 +73,7 @@ void launch_pyramid(const Geometry& g, const BatchView& v, cudaStream_t stream) 
 //   V pass: 4 px x 4 rows per thread from the uint16 intermediate, 32-bit accumulation, one 32-bit store per row
 // ------------------------------------------------------------------------------------------------
 constexpr int kBlurTW = 128, kBlurTH = 32, kBlurThreads = 256;
-constexpr int kBlurInWords = kBlurTW / 4 + 2 + 1;   // 34 words (x from tx0-4) + 1 pad
+constexpr int kBlurInWords = kBlurTW / 4 + 8;       // 40 words = ten 16-byte vectors per row, x from tx0-16
 constexpr int kBlurRows = kBlurTH + 6;
 
 __device__ __forceinline__ int reflect101(int i, int n) {
@@ -84,7 +84,7 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 
 __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v,
                                                             const __grid_constant__ TileMap tm) {
-    __shared__ uint32_t s_in[kBlurRows * kBlurInWords];
+    __shared__ __align__(16) uint32_t s_in[kBlurRows * kBlurInWords];
     __shared__ uint2 s_h[kBlurRows * (kBlurTW / 4 + 1)];
     const int frame = blockIdx.y;
     int level = 0;
@@ -95,37 +95,37 @@ __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const __grid_constan
     const uint8_t* __restrict__ src = level_ptr(g, v, level, frame);
     const int spitch = level_pitch(g, v, level);
     const int tid = threadIdx.x;
-    const int wwords = (L.w + 3) >> 2;
 
-    for (int i = tid; i < kBlurRows * (kBlurInWords - 1); i += kBlurThreads) {
-        const int ry = i / (kBlurInWords - 1), rw = i - ry * (kBlurInWords - 1);
+    // stage rows ty0-3 .. ty0+34 (reflected by index), 160 bytes from x = tx0-16 as ten 16-byte loads per row
+    for (int i = tid; i < kBlurRows * 10; i += kBlurThreads) {
+        const int ry = i / 10, q = i - ry * 10;
         const int gy = reflect101(min(ty0 + ry - 3, L.h + 2), L.h);
-        const int gw = (tx0 >> 2) - 1 + rw;
-        uint32_t w = 0;
-        if (gw >= 0 && gw < wwords) w = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)gy * spitch) + gw);
-        s_in[ry * kBlurInWords + rw] = w;
+        const int gx = tx0 - 16 + 16 * q;
+        uint4 w = make_uint4(0u, 0u, 0u, 0u);
+        if (gx >= 0 && gx + 16 <= spitch) w = __ldg(reinterpret_cast<const uint4*>(src + (size_t)gy * spitch + gx));
+        *reinterpret_cast<uint4*>(&s_in[ry * kBlurInWords + 4 * q]) = w;
     }
     __syncthreads();
-    uint8_t* s_b = reinterpret_cast<uint8_t*>(s_in);   // byte view: column c <-> x = tx0 - 4 + c
+    uint8_t* s_b = reinterpret_cast<uint8_t*>(s_in);   // byte view: column c <-> x = tx0 - 16 + c
     constexpr int kRowBytes = kBlurInWords * 4;
     if (tx0 == 0) {   // x = -1,-2,-3  <-  x = 1,2,3
         for (int i = tid; i < kBlurRows * 3; i += kBlurThreads) {
             const int ry = i / 3, k = i - ry * 3 + 1;
-            s_b[ry * kRowBytes + 4 - k] = s_b[ry * kRowBytes + 4 + k];
+            s_b[ry * kRowBytes + 16 - k] = s_b[ry * kRowBytes + 16 + k];
         }
     }
     if (tx0 + kBlurTW + 3 > L.w - 1) {   // x = w, w+1, w+2  <-  x = w-2, w-3, w-4
         for (int i = tid; i < kBlurRows * 3; i += kBlurThreads) {
             const int ry = i / 3, k = i - ry * 3;
-            const int c = L.w + k - tx0 + 4, cs = L.w - 2 - k - tx0 + 4;
-            if (c < kRowBytes - 4 && cs >= 0) s_b[ry * kRowBytes + c] = s_b[ry * kRowBytes + cs];
+            const int c = L.w + k - tx0 + 16, cs = L.w - 2 - k - tx0 + 16;
+            if (c < kRowBytes && cs >= 0) s_b[ry * kRowBytes + c] = s_b[ry * kRowBytes + cs];
         }
     }
     __syncthreads();
 
     for (int i = tid; i < kBlurRows * (kBlurTW / 4); i += kBlurThreads) {
         const int ry = i >> 5, gx = i & 31;
-        const uint32_t* w = &s_in[ry * kBlurInWords + gx];     // w[0]: x-4.., w[1]: the 4 output pixels, w[2]: x+4..
+        const uint32_t* w = &s_in[ry * kBlurInWords + gx + 3]; // w[0]: x-4.., w[1]: the 4 output pixels, w[2]: x+4..
         const uint32_t wm = w[0], w0 = w[1], wp = w[2];
         // B[i] = byte i of (wm, w0, wp); pair P_i = (B[i], B[i+1]) widened to 16 bits
         const uint32_t Sa = __funnelshift_r(wm, w0, 8), Sb = __funnelshift_r(wm, w0, 16), Sc = __funnelshift_r(wm, w0, 24);
