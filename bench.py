@@ -45,6 +45,20 @@ def stage_bytes(n_kp, n_cand):
     }
 
 
+STAGE_KERNELS = {"classify": ["classify_kernel"], "pyramid": ["resize_kernel"], "blur": ["blur_kernel"],
+                 "fast": ["fast_kernel", "fast_fallback_kernel"], "select": ["select_kernel"], "describe": ["describe_kernel"]}
+
+
+def profiled_traffic(stage):
+    """dram__bytes_read.sum + dram__bytes_write.sum per step of the stage's kernels, from the committed `ncu --set full`
+    capture of this same command (profiles/r01d_traffic.json); None if the capture is missing."""
+    try:
+        k = json.load(open(os.path.join(ROOT, "profiles", "r01d_traffic.json")))["kernels"]
+        return float(sum(k[n]["dram_bytes"] for n in STAGE_KERNELS[stage])), {n: k[n]["alu_pipe_pct"] for n in STAGE_KERNELS[stage]}
+    except Exception:
+        return None, None
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -356,6 +370,7 @@ def run_b200(args):
     dom = max(stage_ms, key=lambda k: stage_ms[k])
     peak, peak_kind = measured_peak_gbs()
     achieved = sb[dom] * B / (stage_ms[dom] * 1e-3) / 1e9
+    traffic, alu_pct = profiled_traffic(dom)
     pipeline_bytes = 6049674.0
     line = {
         "metric": "frames/s ORB extract+dyn-filter (640x480,1k kps)", "value": value, "unit": "frames/s", "n_gpus": world,
@@ -367,7 +382,9 @@ def run_b200(args):
                 "steps": e2e_steps, "wall_frames_per_s": e2e_frames / (e2e_wall_ms * 1e-3)},
         "gpu_launches": args.steps * ex.launches_per_call(),
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None,
+                     "frac": achieved / peak, "traffic": traffic, "traffic_source": "profiles/r01d_traffic.json (ncu --set full, per 256-frame step)",
+                     "alu_pipe_pct_ncu": alu_pct,
+                     "note": "the stage is integer-ALU bound (packed 16-bit min/max), not HBM bound: see DESIGN.md section 5",
                      "algorithmic_bytes_per_launch": sb[dom] * B,
                      "stage_ms": stage_ms,
                      "pipeline": {"bytes_per_frame": pipeline_bytes, "achieved_gbs": pipeline_bytes * value / world / 1e9,

@@ -2,6 +2,7 @@
 // launch sequence. Host side of ORBextractor (reference src/ORBextractor.cc:418-477, 1088-1367).
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -621,7 +622,8 @@ int coeb_extract_batch_host(coeb_extractor* ex, int B, const uint8_t* gray, int 
 
     // Sub-batches of kPipeChunk frames round-robin over kPipeStreams streams: the H2D copy of chunk c+1 and the D2H
     // copy of chunk c-1 overlap the kernels of chunk c (the arenas are frame-major, so a chunk is a pointer offset).
-    const int chunk = B <= 2 * kPipeChunk ? B : kPipeChunk;
+    static const int pipe_chunk = [] { const char* e = getenv("COEB_PIPE_CHUNK"); int v = e ? atoi(e) : 0; return v > 0 ? v : kPipeChunk; }();
+    const int chunk = B <= 2 * pipe_chunk ? B : pipe_chunk;
     const int nchunks = (B + chunk - 1) / chunk;
     const bool piped = nchunks > 1;
     if (piped && !ex->pipe_stream[0]) {
