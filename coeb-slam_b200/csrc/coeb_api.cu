@@ -69,7 +69,7 @@ struct coeb_extractor {
     uint32_t* d_cand = nullptr;
     uint16_t* d_knode = nullptr;
     uint32_t* d_lmax = nullptr;
-    int *d_lmax_count = nullptr, *d_cell_count = nullptr;
+    int *d_lmax_count = nullptr, *d_cell_count = nullptr, *d_empty_cells = nullptr, *d_empty_count = nullptr;
     int *d_cand_count = nullptr, *d_key_count = nullptr;
     LevelKey* d_keys = nullptr;
     DynState* d_dyn = nullptr;
@@ -256,8 +256,8 @@ int build_geometry(coeb_extractor* ex, int w, int h) {
 }
 
 void free_arenas(coeb_extractor* ex) {
-    cudaFree(ex->d_lmax); cudaFree(ex->d_lmax_count); cudaFree(ex->d_cell_count);
-    ex->d_lmax = nullptr; ex->d_lmax_count = ex->d_cell_count = nullptr;
+    cudaFree(ex->d_lmax); cudaFree(ex->d_lmax_count); cudaFree(ex->d_cell_count); cudaFree(ex->d_empty_cells); cudaFree(ex->d_empty_count);
+    ex->d_lmax = nullptr; ex->d_lmax_count = ex->d_cell_count = ex->d_empty_cells = ex->d_empty_count = nullptr;
     cudaFree(ex->d_pyr); cudaFree(ex->d_blur); cudaFree(ex->d_cand); cudaFree(ex->d_knode); cudaFree(ex->d_cand_count);
     cudaFree(ex->d_key_count); cudaFree(ex->d_keys); cudaFree(ex->d_dyn);
     ex->d_pyr = ex->d_blur = nullptr; ex->d_cand = nullptr; ex->d_knode = nullptr; ex->d_cand_count = ex->d_key_count = nullptr;
@@ -278,6 +278,8 @@ int ensure_arenas(coeb_extractor* ex, int B) {
     CUDA_TRY(cudaMalloc(&ex->d_lmax, (size_t)B * g.cand_per_frame * sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc(&ex->d_lmax_count, (size_t)B * g.nlevels * sizeof(int)));
     CUDA_TRY(cudaMalloc(&ex->d_cell_count, (size_t)B * g.cells_per_frame * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&ex->d_empty_cells, (size_t)B * g.cells_per_frame * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&ex->d_empty_count, (size_t)B * sizeof(int)));   // one counter per possible sub-batch start
     CUDA_TRY(cudaMalloc(&ex->d_cand_count, (size_t)B * g.nlevels * sizeof(int)));
     CUDA_TRY(cudaMalloc(&ex->d_key_count, (size_t)B * g.nlevels * sizeof(int)));
     CUDA_TRY(cudaMalloc(&ex->d_keys, (size_t)B * g.keys_per_frame * sizeof(LevelKey)));
@@ -329,6 +331,8 @@ BatchView sub_view(const Geometry& g, const BatchView& v, int f0, int n, size_t 
     s.lmax_count = v.lmax_count + (size_t)f0 * g.nlevels;
     s.key_count = v.key_count + (size_t)f0 * g.nlevels;
     s.cell_count = v.cell_count + (size_t)f0 * g.cells_per_frame;
+    s.empty_cells = v.empty_cells + (size_t)f0 * g.cells_per_frame;
+    s.empty_count = v.empty_count + f0;
     s.keys = v.keys + (size_t)f0 * g.keys_per_frame;
     s.dyn = v.dyn + f0;
     if (v.boxes) s.boxes = v.boxes + (size_t)f0 * v.max_box * 4;
@@ -450,8 +454,8 @@ int coeb_extractor_tables(const coeb_extractor* ex, int* nlevels, float* scale, 
 
 int coeb_extractor_launches_per_call(const coeb_extractor* ex) {
     if (!ex) return 0;
-    // classify + (nlevels-1) resizes + blur + FAST + FAST fallback + select + describe (the two counter memsets are not kernels of ours)
-    return 1 + (ex->params.nlevels - 1) + 1 + 2 + 1 + 1;
+    // classify + (nlevels-1) resizes + blur + FAST + empty-cell list + FAST fallback + select + describe (the two counter memsets are not kernels of ours)
+    return 1 + (ex->params.nlevels - 1) + 1 + 3 + 1 + 1;
 }
 
 int coeb_extractor_set_profiling(coeb_extractor* ex, int on) {
@@ -534,6 +538,7 @@ static int prepare_view(coeb_extractor* ex, int B, const uint8_t* gray, int widt
     v.cand = ex->d_cand; v.cand_count = ex->d_cand_count; v.keys = ex->d_keys; v.key_count = ex->d_key_count;
     v.dyn = ex->d_dyn; v.knode = ex->d_knode;
     v.lmax = ex->d_lmax; v.lmax_count = ex->d_lmax_count; v.cell_count = ex->d_cell_count;
+    v.empty_cells = ex->d_empty_cells; v.empty_count = ex->d_empty_count;
     v.boxes = boxes; v.nbox = nbox; v.max_box = max_box; v.tm = tm; v.ntm = ntm; v.max_tm = max_tm; v.blur_flag = blur_flag;
     v.out_kps = kps_out; v.out_desc = desc_out; v.out_count = counts_out; v.status = status_out;
     *out = v;

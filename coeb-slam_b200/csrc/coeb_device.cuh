@@ -96,6 +96,8 @@ struct BatchView {
     uint32_t* lmax;                    // [B][cand_per_frame] FAST cell-local maxima above minTh (same packing as cand)
     int* lmax_count;                   // [B][nlevels]
     int* cell_count;                   // [B][cells_per_frame] local maxima above iniTh per FAST cell
+    int* empty_cells;                  // [B * cells_per_frame] cells that need the minTh fallback (frame * cells_per_frame + cell)
+    int* empty_count;                  // [1] (one per batch view)
     // dynamic-object inputs
     const float* boxes; const int* nbox; int max_box;
     const float* tm; const int* ntm; int max_tm;

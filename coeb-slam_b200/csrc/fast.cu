@@ -241,16 +241,44 @@ __global__ void __launch_bounds__(kFtThreads, 4) fast_kernel(const __grid_consta
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kMaxRoi = 72;   // ROI side bound: wCell + 6 <= 66 (checked on the host)
 
+// Lists the FAST cells that exist (src/ORBextractor.cc:816-826) and produced nothing at iniTh. One thread per cell.
+__global__ void __launch_bounds__(256) fast_empty_cells_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int total = v.B * g.cells_per_frame;
+    bool empty = false;
+    if (c < total && v.cell_count[c] == 0) {
+        const int cf = c % g.cells_per_frame;
+        int level = 0;
+        while (level + 1 < g.nlevels && cf >= g.lv[level + 1].cell_base) level++;
+        const LevelGeom& L = g.lv[level];
+        const int cell = cf - L.cell_base;
+        const int ci = cell / L.nCols, cj = cell - ci * L.nCols;
+        const int iniX = kMinBorder + cj * L.wCell, iniY = kMinBorder + ci * L.hCell;
+        if (!(iniY >= L.maxBY - 3 || iniX >= L.maxBX - 6)) {
+            const int rw = min(iniX + L.wCell + 6, L.maxBX) - iniX, rh = min(iniY + L.hCell + 6, L.maxBY) - iniY;
+            empty = rw >= 7 && rh >= 7;
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, empty);
+    if (m) {
+        const int lane = threadIdx.x & 31;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(v.empty_count, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (empty) v.empty_cells[base + __popc(m & ((1u << lane) - 1))] = c;
+    }
+}
+
 __global__ void __launch_bounds__(128) fast_fallback_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v) {
     __shared__ uint8_t s_img[kMaxRoi * kMaxRoi];
     __shared__ uint8_t s_A[(kMaxRoi - 4) * (kMaxRoi - 4)];
     __shared__ uint32_t s_list[(kMaxRoi - 6) * (kMaxRoi - 6) / 2];
     __shared__ int s_n, s_base;
-    const int tid = threadIdx.x;
-    const int total = v.B * g.cells_per_frame;
-    for (int c = blockIdx.x; c < total; c += gridDim.x) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_empty = *v.empty_count;
+    for (int e = blockIdx.x; e < n_empty; e += gridDim.x) {
+        const int c = v.empty_cells[e];
         const int frame = c / g.cells_per_frame, cf = c - frame * g.cells_per_frame;
-        if (v.cell_count[c] != 0) continue;
         int level = 0;
         while (level + 1 < g.nlevels && cf >= g.lv[level + 1].cell_base) level++;
         const LevelGeom& L = g.lv[level];
@@ -258,64 +286,59 @@ __global__ void __launch_bounds__(128) fast_fallback_kernel(const __grid_constan
         const int ci = cell / L.nCols, cj = cell - ci * L.nCols;
         // cell ROI (src/ORBextractor.cc:813-828), level coordinates
         const int iniX = kMinBorder + cj * L.wCell, iniY = kMinBorder + ci * L.hCell;
-        if (iniY >= L.maxBY - 3 || iniX >= L.maxBX - 6) continue;
         const int maxX = min(iniX + L.wCell + 6, L.maxBX), maxY = min(iniY + L.hCell + 6, L.maxBY);
         const int rw = maxX - iniX, rh = maxY - iniY;
-        if (rw < 7 || rh < 7) continue;
         const int dw = rw - 6, dh = rh - 6;          // detection area: ROI rows/cols [3, dim-3)
         const int aw = dw + 2;                       // s_A row pitch (1 px zero border each side)
         const int thMin = v.dyn[frame].area_flag ? 10 : 7;
         const int pitch = level_pitch(g, v, level);
         const uint8_t* __restrict__ img = level_ptr(g, v, level, frame) + (size_t)iniY * pitch + iniX;
         __syncthreads();   // previous cell's shared data fully consumed
-        for (int i = tid; i < rw * rh; i += 128) {
-            const int y = i / rw, x = i - y * rw;
-            s_img[y * kMaxRoi + x] = __ldg(img + (size_t)y * pitch + x);
-        }
+        for (int y = warp; y < rh; y += 4)
+            for (int x = lane; x < rw; x += 32) s_img[y * kMaxRoi + x] = __ldg(img + (size_t)y * pitch + x);
         for (int i = tid; i < aw * (dh + 2); i += 128) s_A[i] = 0;
         if (tid == 0) s_n = 0;
         __syncthreads();
         const int off[16] = {3 * kMaxRoi,      3 * kMaxRoi + 1,  2 * kMaxRoi + 2,  kMaxRoi + 3,      3,                -kMaxRoi + 3,
                              -2 * kMaxRoi + 2, -3 * kMaxRoi + 1, -3 * kMaxRoi,     -3 * kMaxRoi - 1, -2 * kMaxRoi - 2, -kMaxRoi - 3,
                              -3,               kMaxRoi - 3,      2 * kMaxRoi - 2,  3 * kMaxRoi - 1};
-        for (int i = tid; i < dw * dh; i += 128) {
-            const int y = i / dw, x = i - y * dw;
-            const uint8_t* p = &s_img[(y + 3) * kMaxRoi + (x + 3)];
-            const int cc = p[0];
-            {   // compass bound (see fast_kernel 1a): in flat cells almost every pixel stops here
-                const int e0 = cc - (int)p[off[0]], e4 = cc - (int)p[off[4]], e8 = cc - (int)p[off[8]], e12 = cc - (int)p[off[12]];
-                const int ub = max(max(min(e0, e4), min(e4, e8)), max(min(e8, e12), min(e12, e0)));
-                const int ud = min(min(max(e0, e4), max(e4, e8)), min(max(e8, e12), max(e12, e0)));
-                if (ub <= thMin && -ud <= thMin) continue;   // s_A stays 0
+        for (int y = warp; y < dh; y += 4)
+            for (int x = lane; x < dw; x += 32) {
+                const uint8_t* p = &s_img[(y + 3) * kMaxRoi + (x + 3)];
+                const int cc = p[0];
+                {   // compass bound (see fast_kernel 1a): in flat cells almost every pixel stops here
+                    const int e0 = cc - (int)p[off[0]], e4 = cc - (int)p[off[4]], e8 = cc - (int)p[off[8]], e12 = cc - (int)p[off[12]];
+                    const int ub = max(max(min(e0, e4), min(e4, e8)), max(min(e8, e12), min(e12, e0)));
+                    const int ud = min(min(max(e0, e4), max(e4, e8)), min(max(e8, e12), max(e12, e0)));
+                    if (ub <= thMin && -ud <= thMin) continue;   // s_A stays 0
+                }
+                int d[16];
+#pragma unroll
+                for (int k = 0; k < 16; k++) d[k] = cc - (int)p[off[k]];
+                int mn[16], mx[16];
+#pragma unroll
+                for (int k = 0; k < 16; k++) { mn[k] = min(d[k], min(d[(k + 1) & 15], d[(k + 2) & 15])); mx[k] = max(d[k], max(d[(k + 1) & 15], d[(k + 2) & 15])); }
+                int best_b = -256, best_d = 256;
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    best_b = max(best_b, min(mn[k], min(mn[(k + 3) & 15], mn[(k + 6) & 15])));
+                    best_d = min(best_d, max(mx[k], max(mx[(k + 3) & 15], mx[(k + 6) & 15])));
+                }
+                s_A[(y + 1) * aw + (x + 1)] = (uint8_t)max(max(best_b, -best_d), 0);
             }
-            int d[16];
-#pragma unroll
-            for (int k = 0; k < 16; k++) d[k] = cc - (int)p[off[k]];
-            int mn[16], mx[16];
-#pragma unroll
-            for (int k = 0; k < 16; k++) { mn[k] = min(d[k], min(d[(k + 1) & 15], d[(k + 2) & 15])); mx[k] = max(d[k], max(d[(k + 1) & 15], d[(k + 2) & 15])); }
-            int best_b = -256, best_d = 256;
-#pragma unroll
-            for (int k = 0; k < 16; k++) {
-                best_b = max(best_b, min(mn[k], min(mn[(k + 3) & 15], mn[(k + 6) & 15])));
-                best_d = min(best_d, max(mx[k], max(mx[(k + 3) & 15], mx[(k + 6) & 15])));
-            }
-            const int A = max(max(best_b, -best_d), 0);
-            s_A[(y + 1) * aw + (x + 1)] = (uint8_t)A;
-        }
         __syncthreads();
-        for (int i = tid; i < dw * dh; i += 128) {
-            const int y = i / dw, x = i - y * dw;
-            const uint8_t* a = &s_A[(y + 1) * aw + (x + 1)];
-            const int A = a[0];
-            if (A > thMin) {
-                const int nb = max(max(max(a[-1], a[1]), max(a[-aw - 1], a[-aw])), max(max(a[-aw + 1], a[aw - 1]), max(a[aw], a[aw + 1])));
-                if (A > nb) {
-                    const int px = x + 3 + cj * L.wCell, py = y + 3 + ci * L.hCell;  // minBorder-relative (:844-845)
-                    s_list[atomicAdd(&s_n, 1)] = (uint32_t)px | ((uint32_t)py << 12) | ((uint32_t)(A - 1) << 24);
+        for (int y = warp; y < dh; y += 4)
+            for (int x = lane; x < dw; x += 32) {
+                const uint8_t* a = &s_A[(y + 1) * aw + (x + 1)];
+                const int A = a[0];
+                if (A > thMin) {
+                    const int nb = max(max(max(a[-1], a[1]), max(a[-aw - 1], a[-aw])), max(max(a[-aw + 1], a[aw - 1]), max(a[aw], a[aw + 1])));
+                    if (A > nb) {
+                        const int px = x + 3 + cj * L.wCell, py = y + 3 + ci * L.hCell;  // minBorder-relative (:844-845)
+                        s_list[atomicAdd(&s_n, 1)] = (uint32_t)px | ((uint32_t)py << 12) | ((uint32_t)(A - 1) << 24);
+                    }
                 }
             }
-        }
         __syncthreads();
         const int n = s_n;
         if (n > 0) {
@@ -346,6 +369,8 @@ void launch_fast(const Geometry& g, const BatchView& v, cudaStream_t stream) {
     cudaMemsetAsync(v.cell_count, 0, sizeof(int) * (size_t)v.B * g.cells_per_frame, stream);
     fast_kernel<<<dim3(g.fast_tiles_per_frame, v.B), kFtThreads, 0, stream>>>(g, v, v.fast_tiles);
     const int cells = v.B * g.cells_per_frame;
+    cudaMemsetAsync(v.empty_count, 0, sizeof(int), stream);
+    fast_empty_cells_kernel<<<(cells + 255) / 256, 256, 0, stream>>>(g, v);
     fast_fallback_kernel<<<std::min(cells, 148 * 8), 128, 0, stream>>>(g, v);
 }
 
