@@ -232,8 +232,8 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput ("value") + per-stage times for the roofline ------------------
-    ex.set_profiling(True)
+    # ---- device-resident throughput ("value"); per-stage times for the roofline come from a second pass ------------
+    ex.set_profiling(bool(args.stage_sync))
     for _ in range(args.warmup):
         step_device()
     barrier()
@@ -256,8 +256,10 @@ def run_b200(args):
     counts = d_counts.cpu().numpy()
     status = d_status.cpu().numpy()
     assert (status == 0).all(), "device reported per-frame failures: %s" % status[status != 0][:8]
-    # stage breakdown: a second, identical pass with a sync per step (not part of `value`)
+    # stage breakdown: a second, identical pass with per-stage events (serialises blur with FAST) and a sync per step;
+    # not part of `value`
     if not args.stage_sync:
+        ex.set_profiling(True)
         for _ in range(args.steps):
             step_device()
             for k, v in ex.stage_ms().items():

@@ -85,6 +85,9 @@ struct coeb_extractor {
     cudaStream_t pipe_stream[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t pipe_done[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t pipe_ready = nullptr;
+    // blur runs beside FAST + octree on a side stream (both only need the pyramid); one lane per launching stream
+    struct Lane { cudaStream_t main; cudaStream_t aux; cudaEvent_t fork, join; };
+    std::vector<Lane> lanes;
     // CUDA graphs of the kernel sequence for small non-pipelined host calls (single-frame latency path)
     struct GraphEntry { BatchView view; int w, h, cap; cudaGraphExec_t exec; };
     std::vector<GraphEntry> graphs;
@@ -298,8 +301,35 @@ int ensure_buf(T** p, size_t* cap, size_t n) {
     return COEB_OK;
 }
 
+coeb_extractor::Lane* lane_for(coeb_extractor* ex, cudaStream_t s) {
+    for (auto& l : ex->lanes)
+        if (l.main == s) return &l;
+    coeb_extractor::Lane l{s, nullptr, nullptr, nullptr};
+    if (cudaStreamCreateWithFlags(&l.aux, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    ex->lanes.push_back(l);
+    return &ex->lanes.back();
+}
+
 int enqueue(coeb_extractor* ex, const BatchView& v, cudaStream_t s, bool prof) {
     const Geometry& g = ex->geom;
+    coeb_extractor::Lane* lane = prof ? nullptr : lane_for(ex, s);
+    if (lane) {
+        // classify, pyramid | fork: blur on the side stream, FAST + octree on the main one | join | describe
+        launch_classify(g, v, s);
+        launch_pyramid(g, v, s);
+        CUDA_TRY(cudaEventRecord(lane->fork, s));
+        CUDA_TRY(cudaStreamWaitEvent(lane->aux, lane->fork, 0));
+        launch_blur(g, v, lane->aux);
+        CUDA_TRY(cudaEventRecord(lane->join, lane->aux));
+        launch_fast(g, v, s);
+        launch_select(g, v, s);
+        CUDA_TRY(cudaStreamWaitEvent(s, lane->join, 0));
+        launch_describe(g, v, s);
+        CUDA_TRY(cudaGetLastError());
+        return COEB_OK;
+    }
     if (prof) cudaEventRecord(ex->ev[0], s);
     launch_classify(g, v, s);
     if (prof) cudaEventRecord(ex->ev[1], s);
@@ -413,6 +443,7 @@ void coeb_extractor_destroy(coeb_extractor* ex) {
     cudaFree(ex->d_in_gray); cudaFree(ex->d_in_boxes); cudaFree(ex->d_in_tm); cudaFree(ex->d_in_nbox); cudaFree(ex->d_in_ntm);
     cudaFree(ex->d_in_blur); cudaFree(ex->d_out_kps); cudaFree(ex->d_out_desc); cudaFree(ex->d_out_count); cudaFree(ex->d_out_status);
     for (auto& e : ex->graphs) cudaGraphExecDestroy(e.exec);
+    for (auto& l : ex->lanes) { cudaStreamDestroy(l.aux); cudaEventDestroy(l.fork); cudaEventDestroy(l.join); }
     for (int i = 0; i < 7; i++) if (ex->ev[i]) cudaEventDestroy(ex->ev[i]);
     for (int i = 0; i < 3; i++) {
         if (ex->pipe_stream[i]) cudaStreamDestroy(ex->pipe_stream[i]);
