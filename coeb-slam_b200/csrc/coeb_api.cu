@@ -483,6 +483,14 @@ int coeb_extractor_tables(const coeb_extractor* ex, int* nlevels, float* scale, 
     return COEB_OK;
 }
 
+// Internal: device ordinal and launch stream of a handle, for the translation units that hold other kernels.
+int coeb_extractor_device_stream(coeb_extractor* ex, int* device, void** stream) {
+    if (!ex || !device || !stream) return fail(COEB_ERR_INVALID_ARG, "null argument");
+    *device = ex->device;
+    *stream = (void*)ex->stream;
+    return COEB_OK;
+}
+
 int coeb_extractor_launches_per_call(const coeb_extractor* ex) {
     if (!ex) return 0;
     // classify + (nlevels-1) resizes + blur + FAST + empty-cell list + FAST fallback + select + describe (the two counter memsets are not kernels of ours)

@@ -119,6 +119,30 @@ int coeb_debug_candidates(coeb_extractor* ex, int frame, int level, uint32_t* ho
 int coeb_debug_level_keys(coeb_extractor* ex, int frame, int level, float* host_out, int cap, int* n_out);
 
 /* ---------------------------------------------------------------------------------------------
+ * Producers directly in front of the extractor (run on the extractor's device and stream)
+ * ------------------------------------------------------------------------------------------- */
+
+/* cv::cvtColor(im, gray, CV_RGB2GRAY | CV_BGR2GRAY | CV_RGBA2GRAY | CV_BGRA2GRAY) of Tracking::GrabImageRGBD
+ * (src/Tracking.cc:212-224): 8-bit, channels = 3 or 4, bgr != 0 for the BGR orders. OpenCV's fixed-point weights,
+ * bit-exact. _batch_device: device pointers, enqueued on the stream; the host form is blocking. */
+int coeb_rgb_to_gray_batch_device(coeb_extractor* ex, int B, const uint8_t* d_rgb, int width, int height, int stride,
+                                  size_t frame_stride, int channels, int bgr, uint8_t* d_gray, int gray_stride,
+                                  size_t gray_frame_stride);
+int coeb_rgb_to_gray(coeb_extractor* ex, const uint8_t* rgb, int width, int height, int stride, int channels, int bgr,
+                     uint8_t* gray_out, int gray_stride);
+
+/* blur_flag producer of the RGB-D Frame constructor (src/Frame.cc:171-202 with Frame::detect_laplacian, :905-913):
+ * per YOLO box, mean of abs(cv::Laplacian(box.clone(), CV_16U)); flag = 1 if the mean is < 4.2. Boxes are
+ * [B][max_box][4] (xmin, ymin, xmax, ymax), nbox [B] (NULL: max_box boxes in every frame); flags [B][max_box] are
+ * exactly the blur_flag array coeb_extract_batch_* takes; means (optional) [B][max_box] doubles, -1 for an unused or
+ * out-of-image box. The reference's first-frame rule (no previous image: blur_flag = {0, 0}, :205-209) is the caller's. */
+int coeb_blur_flags_batch_device(coeb_extractor* ex, int B, const uint8_t* d_gray, int width, int height, int stride,
+                                 size_t frame_stride, const float* d_boxes, const int* d_nbox, int max_box, int* d_flags,
+                                 double* d_means);
+int coeb_blur_flags(coeb_extractor* ex, const uint8_t* gray, int width, int height, int stride, const float* boxes_xyxy,
+                    int nbox, int* flags_out, double* means_out);
+
+/* ---------------------------------------------------------------------------------------------
  * Frame keypoint grid + ORBmatcher (declared here, implemented in match.cu)
  * ------------------------------------------------------------------------------------------- */
 

@@ -148,6 +148,38 @@ static inline void gaussian7x7_8u(const uint8_t* src, int w, int h, int sstride,
     }
 }
 
+// cv::cvtColor(src, dst, CV_RGB2GRAY / CV_BGR2GRAY / CV_RGBA2GRAY / CV_BGRA2GRAY) for 8-bit images (imgproc
+// color_rgb: RGB2Gray<uchar>, 15-bit BT.601 weights 9798/19235/3735, round to nearest). Called by the reference at
+// src/Tracking.cc:212-224 ("next" row 3 of SURVEY.md section 8f).
+static inline void rgb_to_gray_8u(const uint8_t* src, int w, int h, int sstride, int channels, bool bgr, uint8_t* dst, int dstride) {
+    for (int y = 0; y < h; y++) {
+        const uint8_t* S = src + (size_t)y * sstride;
+        uint8_t* D = dst + (size_t)y * dstride;
+        for (int x = 0; x < w; x++) {
+            const int c0 = S[x * channels], c1 = S[x * channels + 1], c2 = S[x * channels + 2];
+            const int r = bgr ? c2 : c0, b = bgr ? c0 : c2;
+            D[x] = (uint8_t)((r * 9798 + c1 * 19235 + b * 3735 + (1 << 14)) >> 15);
+        }
+    }
+}
+
+// Frame::detect_laplacian on a box of the gray image (src/Frame.cc:173-202, 905-913): cv::Laplacian(roi.clone(), CV_16U)
+// (3x3 cross, BORDER_REFLECT_101 on the cloned ROI, negative responses saturate to 0), cv::abs, cv::mean. The box is
+// blurred (blur_flag = 1) if the mean is < 4.2. "next" row 2 of SURVEY.md section 8f. Returns the mean; -1 if the box is
+// empty or leaves the image (the reference's cv::Mat ROI would throw).
+static inline double laplacian_box_mean(const uint8_t* gray, int w, int h, int stride, const float* box) {
+    const int x0 = (int)box[0], y0 = (int)box[1], bw = (int)(box[2] - box[0]), bh = (int)(box[3] - box[1]);
+    if (x0 < 0 || y0 < 0 || bw <= 0 || bh <= 0 || x0 + bw > w || y0 + bh > h) return -1.0;
+    unsigned long long sum = 0;
+    for (int y = 0; y < bh; y++)
+        for (int x = 0; x < bw; x++) {
+            auto px = [&](int xx, int yy) { return (int)gray[(size_t)(y0 + reflect101(yy, bh)) * stride + x0 + reflect101(xx, bw)]; };
+            const int lap = px(x, y - 1) + px(x, y + 1) + px(x - 1, y) + px(x + 1, y) - 4 * px(x, y);
+            sum += (unsigned)std::max(lap, 0);
+        }
+    return (double)sum / ((double)bw * (double)bh);
+}
+
 // ---------------------------------------------------------------------------------------------
 // cv::FAST(roi, keypoints, threshold, nonmaxSuppression=true) == FAST_t<16> (features2d/fast.cpp,
 // fast_score.cpp). Called per cell by the reference at src/ORBextractor.cc:831,836.

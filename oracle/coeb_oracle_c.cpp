@@ -21,6 +21,17 @@ void orc_gaussian7(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, 
     gaussian7x7_8u(src, w, h, sstride, dst, dstride);
 }
 float orc_fast_atan2(float y, float x) { return fast_atan2(y, x); }
+void orc_rgb_to_gray(const uint8_t* src, int w, int h, int sstride, int channels, int bgr, uint8_t* dst, int dstride) {
+    rgb_to_gray_8u(src, w, h, sstride, channels, bgr != 0, dst, dstride);
+}
+// blur_flag producer: means[b] = Laplacian mean of box b (-1 if invalid), flags[b] = mean in [0, 4.2)
+void orc_blur_flags(const uint8_t* gray, int w, int h, int stride, const float* boxes, int nbox, int* flags, double* means) {
+    for (int b = 0; b < nbox; b++) {
+        const double m = laplacian_box_mean(gray, w, h, stride, boxes + 4 * b);
+        if (means) means[b] = m;
+        flags[b] = (m >= 0 && m < 4.2) ? 1 : 0;
+    }
+}
 int orc_cv_round_f(float v) { return cv_round(v); }
 
 // FAST-9/16 + NMS on a ROI; out is n x 3 int32 (x, y, score). Returns the count (may exceed cap).

@@ -90,6 +90,23 @@ def gaussian7(src):
     return dst
 
 
+def rgb_to_gray(img, bgr=False):
+    img = _u8(img)
+    h, w, c = img.shape
+    out = np.empty((h, w), np.uint8)
+    lib().orc_rgb_to_gray(_p(img), w, h, img.strides[0], c, int(bgr), _p(out), w)
+    return out
+
+
+def blur_flags(gray, boxes):
+    gray = _u8(gray)
+    boxes = _f32(boxes).reshape(-1, 4)
+    flags = np.zeros(len(boxes), np.int32)
+    means = np.zeros(len(boxes), np.float64)
+    lib().orc_blur_flags(_p(gray), gray.shape[1], gray.shape[0], gray.strides[0], _p(boxes), len(boxes), _p(flags), _p(means))
+    return flags, means
+
+
 def fast_atan2(y, x):
     return float(lib().orc_fast_atan2(C.c_float(y), C.c_float(x)))
 

@@ -122,3 +122,25 @@ def test_full_extraction_oracle_b_equals_oracle_a(seed, dynamic, orb_pattern):
     assert np.array_equal(da, db)
     if dynamic:
         assert info["n_dynamic"] >= 1
+
+
+@pytest.mark.parametrize("code,ch,bgr", [(cv2.COLOR_RGB2GRAY, 3, False), (cv2.COLOR_BGR2GRAY, 3, True), (cv2.COLOR_RGBA2GRAY, 4, False),
+                                         (cv2.COLOR_BGRA2GRAY, 4, True)])
+def test_rgb_to_gray_bit_exact(code, ch, bgr):
+    rng = np.random.default_rng(ch)
+    img = rng.integers(0, 256, size=(123, 217, ch), dtype=np.uint8)
+    img[:4, :4] = [[0] * ch, [255] * ch, [1] * ch, [254] * ch]
+    assert np.array_equal(orc.rgb_to_gray(img, bgr), cv2.cvtColor(img, code))
+
+
+def test_laplacian_blur_flag_model():
+    gray = synth.make_frame(12)
+    gray[50:200, 300:520] = 90   # flat box -> mean 0 -> blurred
+    boxes = np.array([[300, 50, 520, 200], [20, 30, 200, 400], [5, 5, 6, 6], [0, 0, 640, 480], [100.7, 80.2, 300.9, 333.3]], np.float32)
+    flags, means = orc.blur_flags(gray, boxes)
+    for b, f, m in zip(boxes, flags, means):
+        x0, y0, bw, bh = int(b[0]), int(b[1]), int(b[2] - b[0]), int(b[3] - b[1])
+        roi = gray[y0:y0 + bh, x0:x0 + bw].copy()
+        ref = cv2.mean(np.abs(cv2.Laplacian(roi, cv2.CV_16U)))[0]
+        assert m == ref and f == int(ref < 4.2)
+    assert flags[0] == 1 and flags[1] == 0
