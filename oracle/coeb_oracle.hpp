@@ -128,21 +128,27 @@ static inline void resize_linear_8u(const uint8_t* src, int sw, int sh, int sstr
 static inline void gaussian7x7_8u(const uint8_t* src, int w, int h, int sstride, uint8_t* dst,
                                   int dstride) {
     static const int K[7] = {18, 34, 48, 56, 48, 34, 18};
+    // The CPU baseline times this function, so it is written the way a tuned CPU filter is: each row is first copied
+    // into a padded buffer with its 3 reflected pixels per side (no index arithmetic in the inner loops, which the
+    // compiler then vectorises); the arithmetic is unchanged.
     std::vector<uint16_t> hbuf((size_t)w * h);
+    std::vector<uint8_t> prow((size_t)w + 6);
     for (int y = 0; y < h; y++) {
         const uint8_t* S = src + (size_t)y * sstride;
-        for (int x = 0; x < w; x++) {
-            int acc = 0;
-            for (int k = 0; k < 7; k++) acc += K[k] * S[reflect101(x + k - 3, w)];
-            hbuf[(size_t)y * w + x] = (uint16_t)acc;
-        }
+        for (int k = 0; k < 3; k++) { prow[k] = S[reflect101(k - 3, w)]; prow[w + 3 + k] = S[reflect101(w + k, w)]; }
+        std::memcpy(prow.data() + 3, S, w);
+        const uint8_t* p = prow.data();
+        uint16_t* H = &hbuf[(size_t)y * w];
+        for (int x = 0; x < w; x++)
+            H[x] = (uint16_t)(18 * (p[x] + p[x + 6]) + 34 * (p[x + 1] + p[x + 5]) + 48 * (p[x + 2] + p[x + 4]) + 56 * p[x + 3]);
     }
     for (int y = 0; y < h; y++) {
         uint8_t* D = dst + (size_t)y * dstride;
+        const uint16_t* r[7];
+        for (int k = 0; k < 7; k++) r[k] = &hbuf[(size_t)reflect101(y + k - 3, h) * w];
         for (int x = 0; x < w; x++) {
-            uint32_t acc = 0;
-            for (int k = 0; k < 7; k++)
-                acc += (uint32_t)K[k] * hbuf[(size_t)reflect101(y + k - 3, h) * w + x];
+            const uint32_t acc = (uint32_t)K[0] * ((uint32_t)r[0][x] + r[6][x]) + (uint32_t)K[1] * ((uint32_t)r[1][x] + r[5][x]) +
+                                 (uint32_t)K[2] * ((uint32_t)r[2][x] + r[4][x]) + (uint32_t)K[3] * r[3][x];
             D[x] = (uint8_t)((acc + 32768u) >> 16);
         }
     }
@@ -228,26 +234,48 @@ static inline void fast9_nms(const uint8_t* img, int w, int h, int stride, int t
     if (w < 7 || h < 7) return;
     std::vector<uint8_t> score((size_t)w * h, 0);
     std::vector<uint8_t> corner((size_t)w * h, 0);
+    int off[16];
+    for (int k = 0; k < 16; k++) off[k] = kFastDy[k] * stride + kFastDx[k];
+    uint8_t thr_tab[511];
+    for (int i = -255; i <= 255; i++) thr_tab[i + 255] = (uint8_t)(i < -threshold ? 1 : (i > threshold ? 2 : 0));
     for (int y = 3; y < h - 3; y++) {
         for (int x = 3; x < w - 3; x++) {
             const uint8_t* p = img + (size_t)y * stride + x;
             const int v = p[0];
+            {   // FAST_t's early rejection: a 9-arc contains one pixel of every opposite pair (k, k+8), all of one sign.
+                // Like OpenCV, the darker(1)/brighter(2) class comes from a 511-entry table indexed by q - v.
+                const uint8_t* tab = &thr_tab[255 - v];
+                auto cls = [&](int k) { return (int)tab[p[off[k]]]; };
+                int dd = cls(0) | cls(8);
+                if (!dd) continue;
+                dd &= cls(2) | cls(10);
+                dd &= cls(4) | cls(12);
+                dd &= cls(6) | cls(14);
+                if (!dd) continue;
+                dd &= cls(1) | cls(9);
+                dd &= cls(3) | cls(11);
+                dd &= cls(5) | cls(13);
+                dd &= cls(7) | cls(15);
+                if (!dd) continue;
+            }
             int d[25];
             uint32_t brighter = 0, darker = 0;  // ring pixel brighter / darker than centre by > th
             for (int k = 0; k < 16; k++) {
-                int q = p[kFastDy[k] * stride + kFastDx[k]];
+                const int q = p[off[k]];
                 d[k] = v - q;
                 if (q > v + threshold) brighter |= 1u << k;
                 if (q < v - threshold) darker |= 1u << k;
             }
-            for (int k = 16; k < 25; k++) d[k] = d[k - 16];
-            auto has_arc9 = [](uint32_t m) {
+            auto has_arc9 = [](uint32_t m) {   // 9 contiguous set bits in a circular 16-bit mask
                 m |= m << 16;
-                for (int s = 0; s < 16; s++)
-                    if (((m >> s) & 0x1FFu) == 0x1FFu) return true;
-                return false;
+                uint32_t a = m & (m >> 1);
+                a &= a >> 2;
+                a &= a >> 4;
+                a &= m >> 8;
+                return (a & 0xFFFFu) != 0;
             };
             if (has_arc9(brighter) || has_arc9(darker)) {
+                for (int k = 16; k < 25; k++) d[k] = d[k - 16];
                 corner[(size_t)y * w + x] = 1;
                 score[(size_t)y * w + x] = (uint8_t)fast_corner_score(d, threshold);
             }
