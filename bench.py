@@ -81,7 +81,7 @@ class ClockSampler:
                  "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
                  "clocks_event_reasons.sw_power_cap")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=f, stderr=subprocess.DEVNULL)
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -501,11 +501,11 @@ def bench_matching(cb, dev, batch, o_kps, o_desc, o_cnt, ex, args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--unique", type=int, default=64, help="distinct generated images per shard (the rest are shifted copies)")
-    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-frames", type=int, default=128, help="frames of the shard timed on the host cores (CPU baseline)")
     ap.add_argument("--ref-frames", type=int, default=64, help="--impl reference: frames per step")
     ap.add_argument("--cand-estimate", type=float, default=16000.0, help="FAST candidates per frame used for algorithmic bytes")
