@@ -16,47 +16,57 @@ namespace coeb {
 // exact double/float arithmetic of cv::resize and kept resident.
 // Each thread produces 4 adjacent output pixels and stores them as one 32-bit word.
 // ------------------------------------------------------------------------------------------------
+constexpr int kResizeRows = 4;   // destination rows per thread (rows dy, dy+8, dy+16, dy+24 of a 128x32 tile)
+
 __global__ void __launch_bounds__(256) resize_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v,
                                                      int level) {
     const LevelGeom& D = g.lv[level];
     const LevelGeom& S = g.lv[level - 1];
     const int frame = blockIdx.z;
     const int dx0 = (blockIdx.x * 32 + threadIdx.x) * 4;
-    const int dy = blockIdx.y * 8 + threadIdx.y;
-    if (dx0 >= D.w || dy >= D.h) return;
+    if (dx0 >= D.w) return;
     const uint8_t* __restrict__ src = level_ptr(g, v, level - 1, frame);
     const int spitch = level_pitch(g, v, level - 1);
     uint8_t* dst = v.pyr + D.img_base + (unsigned long long)frame * D.img_stride;
-    const int2* xt = v.tabs + D.tab_base;
-    const int2* yt = xt + D.w;
-    const int2 ye = __ldg(&yt[dy]);
-    const int sy0 = min(max(ye.x, 0), S.h - 1), sy1 = min(max(ye.x + 1, 0), S.h - 1);
-    const int b0 = ye.y & 0xFFFF, b1 = ye.y >> 16;
-    const uint8_t* r0 = src + (size_t)sy0 * spitch;
-    const uint8_t* r1 = src + (size_t)sy1 * spitch;
-    uint32_t packed = 0;
+    const int2* __restrict__ xt = v.tabs + D.tab_base;
+    const int2* __restrict__ yt = xt + D.w;
+    // the column entries (source offsets and weights) are the same for every row: fetch them once, then walk
+    // kResizeRows destination rows
+    int sx[4], sx1[4], a0[4], a1[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        const int dx = dx0 + i;
-        if (dx < D.w) {
-            const int2 xe = __ldg(&xt[dx]);
-            const int sx = xe.x, sx1 = min(sx + 1, S.w - 1);
-            const int a0 = xe.y & 0xFFFF, a1 = xe.y >> 16;
-            const int h0 = __ldg(r0 + sx) * a0 + __ldg(r0 + sx1) * a1;
-            const int h1 = __ldg(r1 + sx) * a0 + __ldg(r1 + sx1) * a1;
+        const int2 xe = __ldg(&xt[min(dx0 + i, D.w - 1)]);   // the tail of the last word lands in row padding
+        sx[i] = xe.x;
+        sx1[i] = min(xe.x + 1, S.w - 1);
+        a0[i] = xe.y & 0xFFFF;
+        a1[i] = xe.y >> 16;
+    }
+#pragma unroll
+    for (int j = 0; j < kResizeRows; j++) {
+        const int dy = blockIdx.y * (8 * kResizeRows) + threadIdx.y + 8 * j;
+        if (dy >= D.h) break;
+        const int2 ye = __ldg(&yt[dy]);
+        const int sy0 = min(max(ye.x, 0), S.h - 1), sy1 = min(max(ye.x + 1, 0), S.h - 1);
+        const int b0 = ye.y & 0xFFFF, b1 = ye.y >> 16;
+        const uint8_t* r0 = src + (size_t)sy0 * spitch;
+        const uint8_t* r1 = src + (size_t)sy1 * spitch;
+        uint32_t packed = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int h0 = __ldg(r0 + sx[i]) * a0[i] + __ldg(r0 + sx1[i]) * a1[i];
+            const int h1 = __ldg(r1 + sx[i]) * a0[i] + __ldg(r1 + sx1[i]) * a1[i];
             int o = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
             o = min(max(o, 0), 255);
             packed |= (uint32_t)o << (8 * i);
         }
+        *reinterpret_cast<uint32_t*>(dst + (size_t)dy * D.pitch + dx0) = packed;  // pitch is a multiple of 64: padding absorbs the tail
     }
-    uint8_t* drow = dst + (size_t)dy * D.pitch;
-    *reinterpret_cast<uint32_t*>(drow + dx0) = packed;  // pitch is a multiple of 64, so padding absorbs the tail
 }
 
 void launch_pyramid(const Geometry& g, const BatchView& v, cudaStream_t stream) {
     for (int l = 1; l < g.nlevels; l++) {
         dim3 block(32, 8);
-        dim3 grid((g.lv[l].w + 127) / 128, (g.lv[l].h + 7) / 8, v.B);
+        dim3 grid((g.lv[l].w + 127) / 128, (g.lv[l].h + 8 * kResizeRows - 1) / (8 * kResizeRows), v.B);
         resize_kernel<<<grid, block, 0, stream>>>(g, v, l);
     }
 }
