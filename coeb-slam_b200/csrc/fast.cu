@@ -77,7 +77,7 @@ __device__ __forceinline__ uint32_t compass_bound2(uint32_t c, uint32_t r0, uint
     return __vimax3_s16x2(__vsub2(bb, 0x01000100u), __vsub2(0x01000100u, bd), 0u);
 }
 
-__global__ void __launch_bounds__(kFtThreads, 4) fast_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v,
+__global__ void __launch_bounds__(kFtThreads, 6) fast_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v,
                                                              const int4* __restrict__ tiles) {
     __shared__ __align__(16) uint32_t s_img[kImgRows * kImgWords];
     __shared__ __align__(4) uint8_t s_A[kARows * kAW];

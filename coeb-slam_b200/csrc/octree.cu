@@ -22,7 +22,7 @@
 
 namespace coeb {
 
-constexpr int kSelThreads = 512;
+constexpr int kSelThreads = 384;
 constexpr int kKeyCache = 4096;   // candidates per (level, frame) kept in shared memory (4 + 2 bytes each)
 constexpr unsigned long long kOrdMask = 0xFFFFFFFFFFFFull;  // 48-bit candidate-order field
 

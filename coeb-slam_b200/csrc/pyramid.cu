@@ -16,8 +16,9 @@ namespace coeb {
 // exact double/float arithmetic of cv::resize and kept resident.
 // Each thread produces 4 adjacent output pixels and stores them as one 32-bit word.
 // ------------------------------------------------------------------------------------------------
-constexpr int kResizeRows = 4;   // destination rows per thread (rows dy, dy+8, dy+16, dy+24 of a 128x32 tile)
-
+// kResizeRows = destination rows per thread (rows dy, dy+8, ... of a 128 x 8*kResizeRows tile): 4 for batches, 1 when the
+// grid would otherwise be too small to fill the GPU (single-frame latency path).
+template <int kResizeRows>
 __global__ void __launch_bounds__(256) resize_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v,
                                                      int level) {
     const LevelGeom& D = g.lv[level];
@@ -66,8 +67,12 @@ __global__ void __launch_bounds__(256) resize_kernel(const __grid_constant__ Geo
 void launch_pyramid(const Geometry& g, const BatchView& v, cudaStream_t stream) {
     for (int l = 1; l < g.nlevels; l++) {
         dim3 block(32, 8);
-        dim3 grid((g.lv[l].w + 127) / 128, (g.lv[l].h + 8 * kResizeRows - 1) / (8 * kResizeRows), v.B);
-        resize_kernel<<<grid, block, 0, stream>>>(g, v, l);
+        const int tiles_x = (g.lv[l].w + 127) / 128;
+        if ((long long)tiles_x * ((g.lv[l].h + 31) / 32) * v.B >= 2 * 148) {
+            resize_kernel<4><<<dim3(tiles_x, (g.lv[l].h + 31) / 32, v.B), block, 0, stream>>>(g, v, l);
+        } else {
+            resize_kernel<1><<<dim3(tiles_x, (g.lv[l].h + 7) / 8, v.B), block, 0, stream>>>(g, v, l);
+        }
     }
 }
 
@@ -92,7 +97,7 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return i;
 }
 
-__global__ void __launch_bounds__(kBlurThreads) blur_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v,
+__global__ void __launch_bounds__(kBlurThreads, 6) blur_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v,
                                                             const __grid_constant__ TileMap tm) {
     __shared__ __align__(16) uint32_t s_in[kBlurRows * kBlurInWords];
     __shared__ uint2 s_h[kBlurRows * (kBlurTW / 4 + 1)];
