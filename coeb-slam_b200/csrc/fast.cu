@@ -26,6 +26,8 @@
 //   2   cell-aware NMS over A > iniTh, local maxima appended to the level's list, one count per FAST cell.
 // Fallback kernel: persistent CTAs scan the cell counters; a cell with count 0 is recomputed alone (plain scalar code,
 // it is rare) and its local maxima above minTh are appended to the same list.
+#include <type_traits>
+
 #include "coeb_device.cuh"
 
 namespace coeb {
@@ -41,40 +43,53 @@ __device__ __forceinline__ uint32_t pair_lo(uint32_t w) { return __byte_perm(w, 
 __device__ __forceinline__ uint32_t pair_hi(uint32_t w) { return __byte_perm(w, 0u, 0x4342); }
 
 // A for the two pixels packed in `c` (centre, s16x2) given their 16 ring pairs r[k] (s16x2), all unbiased bytes.
+// kBright / kDark select which arc polarity is evaluated: a pair whose compass bound rules one polarity out (for both
+// of its pixels) only needs the other half of the min/max network.
+template <bool kBright, bool kDark>
 __device__ __forceinline__ uint32_t corner_strength2(uint32_t c, const uint32_t (&r)[16]) {
     const uint32_t cb = c + 0x01000100u;  // +256 per lane: d' = d + 256 in [1, 511], no borrow between lanes
     uint32_t d[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) d[k] = cb - r[k];
-    uint32_t mn[16], mx[16];
+    uint32_t ab = 0u, ad = 0u;
+    if (kBright) {
+        uint32_t mn[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
-        mn[k] = __vimin3_s16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
-        mx[k] = __vimax3_s16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
-    }
-    uint32_t best_b = 0u, best_d = 0x7fff7fffu;
+        for (int k = 0; k < 16; k++) mn[k] = __vimin3_s16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+        uint32_t best_b = 0u;
 #pragma unroll
-    for (int k = 0; k < 16; k += 2) {
-        const uint32_t a0 = __vimin3_s16x2(mn[k], mn[(k + 3) & 15], mn[(k + 6) & 15]);
-        const uint32_t a1 = __vimin3_s16x2(mn[k + 1], mn[(k + 4) & 15], mn[(k + 7) & 15]);
-        best_b = __vimax3_s16x2(best_b, a0, a1);
-        const uint32_t b0 = __vimax3_s16x2(mx[k], mx[(k + 3) & 15], mx[(k + 6) & 15]);
-        const uint32_t b1 = __vimax3_s16x2(mx[k + 1], mx[(k + 4) & 15], mx[(k + 7) & 15]);
-        best_d = __vimin3_s16x2(best_d, b0, b1);
+        for (int k = 0; k < 16; k += 2) {
+            const uint32_t a0 = __vimin3_s16x2(mn[k], mn[(k + 3) & 15], mn[(k + 6) & 15]);
+            const uint32_t a1 = __vimin3_s16x2(mn[k + 1], mn[(k + 4) & 15], mn[(k + 7) & 15]);
+            best_b = __vimax3_s16x2(best_b, a0, a1);
+        }
+        ab = __vsub2(best_b, 0x01000100u);   // best_b - 256
     }
-    // A = max(best_b - 256, 256 - best_d), clamped at 0
-    const uint32_t ab = __vsub2(best_b, 0x01000100u);
-    const uint32_t ad = __vsub2(0x01000100u, best_d);
-    return __vimax3_s16x2(ab, ad, 0u);
+    if (kDark) {
+        uint32_t mx[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) mx[k] = __vimax3_s16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+        uint32_t best_d = 0x7fff7fffu;
+#pragma unroll
+        for (int k = 0; k < 16; k += 2) {
+            const uint32_t b0 = __vimax3_s16x2(mx[k], mx[(k + 3) & 15], mx[(k + 6) & 15]);
+            const uint32_t b1 = __vimax3_s16x2(mx[k + 1], mx[(k + 4) & 15], mx[(k + 7) & 15]);
+            best_d = __vimin3_s16x2(best_d, b0, b1);
+        }
+        ad = __vsub2(0x01000100u, best_d);   // 256 - best_d
+    }
+    return __vimax3_s16x2(ab, ad, 0u);       // A = max(bright, dark), clamped at 0
 }
 
-// Upper bound of A for the two pixels packed in `c` from the four compass ring pairs (ring 0, 4, 8, 12).
-__device__ __forceinline__ uint32_t compass_bound2(uint32_t c, uint32_t r0, uint32_t r4, uint32_t r8, uint32_t r12) {
+// Upper bounds of the bright and dark arc strengths of the two pixels packed in `c`, from the four compass ring pairs
+// (ring 0, 4, 8, 12). Returns bit 0: some lane's bright bound exceeds th; bit 1: same for dark.
+__device__ __forceinline__ int compass_bound2(uint32_t c, uint32_t r0, uint32_t r4, uint32_t r8, uint32_t r12, uint32_t th2) {
     const uint32_t cb = c + 0x01000100u;
     const uint32_t d0 = cb - r0, d4 = cb - r4, d8 = cb - r8, d12 = cb - r12;
     const uint32_t bb = __vimax3_s16x2(__vimax3_s16x2(__vmins2(d0, d4), __vmins2(d4, d8), __vmins2(d8, d12)), __vmins2(d12, d0), 0u);
     const uint32_t bd = __vimin3_s16x2(__vimin3_s16x2(__vmaxs2(d0, d4), __vmaxs2(d4, d8), __vmaxs2(d8, d12)), __vmaxs2(d12, d0), 0x7fff7fffu);
-    return __vimax3_s16x2(__vsub2(bb, 0x01000100u), __vsub2(0x01000100u, bd), 0u);
+    const uint32_t ub = __vimax3_s16x2(__vsub2(bb, 0x01000100u), th2, 0u), ud = __vimax3_s16x2(__vsub2(0x01000100u, bd), th2, 0u);
+    return (int)(ub != th2) | ((int)(ud != th2) << 1);
 }
 
 __global__ void __launch_bounds__(kFtThreads, 6) fast_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v,
@@ -84,9 +99,9 @@ __global__ void __launch_bounds__(kFtThreads, 6) fast_kernel(const __grid_consta
     __shared__ __align__(8) short s_colcell[kAW];
     __shared__ short s_rowcell[kARows];
     __shared__ uint32_t s_list[kFtW * kFtH / 2];
-    __shared__ unsigned short s_queue[2 * kGroups];
+    __shared__ unsigned short s_queue[3][2 * kGroups];   // pairs needing the bright network, the dark one, both
     __shared__ unsigned short s_cq[kFtW * kFtH];   // interior pixels with A > iniTh, to be checked by the NMS
-    __shared__ int s_n, s_base, s_nq, s_nc;
+    __shared__ int s_n, s_base, s_nq[3], s_nc;
 
     const int frame = blockIdx.y;
     const int4 ti = __ldg(&tiles[blockIdx.x]);   // {level, tx0, ty0, -} built on the host: no per-thread div/mod or level search
@@ -118,7 +133,7 @@ __global__ void __launch_bounds__(kFtThreads, 6) fast_kernel(const __grid_consta
         const int y = ty0 - 1 + (tid - 96);
         s_rowcell[tid - 96] = (y >= kEdge && y < L.h - kEdge) ? (short)min((y - kEdge) / L.hCell, lastI) : (short)-1;
     }
-    if (tid == 0) { s_n = 0; s_nq = 0; s_nc = 0; }
+    if (tid == 0) { s_n = 0; s_nq[0] = s_nq[1] = s_nq[2] = 0; s_nc = 0; }
     __syncthreads();
 
     // ---- 1a: compass bound for every pixel pair of the tile + 1 px halo; survivors go to the queue ----
@@ -130,69 +145,68 @@ __global__ void __launch_bounds__(kFtThreads, 6) fast_kernel(const __grid_consta
         const uint32_t c = row[0];
         const uint32_t S0 = row[3 * kImgWords], S8 = row[-3 * kImgWords];
         const uint32_t S4 = __funnelshift_r(c, row[1], 24), S12 = __funnelshift_r(row[-1], c, 8);
-        const uint32_t u01 = compass_bound2(pair_lo(c), pair_lo(S0), pair_lo(S4), pair_lo(S8), pair_lo(S12));
-        const uint32_t u23 = compass_bound2(pair_hi(c), pair_hi(S0), pair_hi(S4), pair_hi(S8), pair_hi(S12));
         const uint32_t th2 = (uint32_t)thIni * 0x00010001u;
-        const bool p01 = __vmaxs2(u01, th2) != th2, p23 = __vmaxs2(u23, th2) != th2;   // some lane's bound exceeds iniTh
-        const int np = (int)p01 + (int)p23;
-        if (np) {
-            const int pos = atomicAdd(&s_nq, np);
-            if (p01) s_queue[pos] = (unsigned short)(2 * grp);
-            if (p23) s_queue[pos + (int)p01] = (unsigned short)(2 * grp + 1);
-        }
+        const int f01 = compass_bound2(pair_lo(c), pair_lo(S0), pair_lo(S4), pair_lo(S8), pair_lo(S12), th2);
+        const int f23 = compass_bound2(pair_hi(c), pair_hi(S0), pair_hi(S4), pair_hi(S8), pair_hi(S12), th2);
+        if (f01) s_queue[f01 - 1][atomicAdd(&s_nq[f01 - 1], 1)] = (unsigned short)(2 * grp);
+        if (f23) s_queue[f23 - 1][atomicAdd(&s_nq[f23 - 1], 1)] = (unsigned short)(2 * grp + 1);
     }
     __syncthreads();
 
-    // ---- 1b: exact corner strength of the queued pairs ----
-    const int nq = s_nq;
+    // ---- 1b: exact corner strength of the queued pairs, one dense pass per class (no divergence inside a pass) ----
+    auto exact_pass = [&](auto bright, auto dark, const unsigned short* queue, int nq) {
 #pragma unroll 1
-    for (int qi = tid; qi < nq; qi += kFtThreads) {
-        const int e = s_queue[qi];
-        const int grp = e >> 1, half = e & 1;
-        const int ay = grp / 18, gxi = grp - ay * 18;
-        const uint32_t* row = &s_img[(ay + 3) * kImgWords + gxi + 3];
-        uint32_t S[16];
-        {   // ring words: 4 consecutive bytes starting at x+dx on row y+dy (FAST circle, OpenCV order)
-            const uint32_t *r3 = row + 3 * kImgWords, *rm3 = row - 3 * kImgWords, *r2 = row + 2 * kImgWords, *rm2 = row - 2 * kImgWords,
-                           *r1 = row + kImgWords, *rm1 = row - kImgWords;
-            S[0] = r3[0];                                   // ( 0, 3)
-            S[1] = __funnelshift_r(r3[0], r3[1], 8);        // ( 1, 3)
-            S[2] = __funnelshift_r(r2[0], r2[1], 16);       // ( 2, 2)
-            S[3] = __funnelshift_r(r1[0], r1[1], 24);       // ( 3, 1)
-            S[4] = __funnelshift_r(row[0], row[1], 24);     // ( 3, 0)
-            S[5] = __funnelshift_r(rm1[0], rm1[1], 24);     // ( 3,-1)
-            S[6] = __funnelshift_r(rm2[0], rm2[1], 16);     // ( 2,-2)
-            S[7] = __funnelshift_r(rm3[0], rm3[1], 8);      // ( 1,-3)
-            S[8] = rm3[0];                                  // ( 0,-3)
-            S[9] = __funnelshift_r(rm3[-1], rm3[0], 24);    // (-1,-3)
-            S[10] = __funnelshift_r(rm2[-1], rm2[0], 16);   // (-2,-2)
-            S[11] = __funnelshift_r(rm1[-1], rm1[0], 8);    // (-3,-1)
-            S[12] = __funnelshift_r(row[-1], row[0], 8);    // (-3, 0)
-            S[13] = __funnelshift_r(r1[-1], r1[0], 8);      // (-3, 1)
-            S[14] = __funnelshift_r(r2[-1], r2[0], 16);     // (-2, 2)
-            S[15] = __funnelshift_r(r3[-1], r3[0], 24);     // (-1, 3)
-        }
-        const uint32_t sel = half ? 0x4342u : 0x4140u;
-        uint32_t r[16];
+        for (int qi = tid; qi < nq; qi += kFtThreads) {
+            const int e = queue[qi];
+            const int grp = e >> 1, half = e & 1;
+            const int ay = grp / 18, gxi = grp - ay * 18;
+            const uint32_t* row = &s_img[(ay + 3) * kImgWords + gxi + 3];
+            uint32_t S[16];
+            {   // ring words: 4 consecutive bytes starting at x+dx on row y+dy (FAST circle, OpenCV order)
+                const uint32_t *r3 = row + 3 * kImgWords, *rm3 = row - 3 * kImgWords, *r2 = row + 2 * kImgWords, *rm2 = row - 2 * kImgWords,
+                               *r1 = row + kImgWords, *rm1 = row - kImgWords;
+                S[0] = r3[0];                                   // ( 0, 3)
+                S[1] = __funnelshift_r(r3[0], r3[1], 8);        // ( 1, 3)
+                S[2] = __funnelshift_r(r2[0], r2[1], 16);       // ( 2, 2)
+                S[3] = __funnelshift_r(r1[0], r1[1], 24);       // ( 3, 1)
+                S[4] = __funnelshift_r(row[0], row[1], 24);     // ( 3, 0)
+                S[5] = __funnelshift_r(rm1[0], rm1[1], 24);     // ( 3,-1)
+                S[6] = __funnelshift_r(rm2[0], rm2[1], 16);     // ( 2,-2)
+                S[7] = __funnelshift_r(rm3[0], rm3[1], 8);      // ( 1,-3)
+                S[8] = rm3[0];                                  // ( 0,-3)
+                S[9] = __funnelshift_r(rm3[-1], rm3[0], 24);    // (-1,-3)
+                S[10] = __funnelshift_r(rm2[-1], rm2[0], 16);   // (-2,-2)
+                S[11] = __funnelshift_r(rm1[-1], rm1[0], 8);    // (-3,-1)
+                S[12] = __funnelshift_r(row[-1], row[0], 8);    // (-3, 0)
+                S[13] = __funnelshift_r(r1[-1], r1[0], 8);      // (-3, 1)
+                S[14] = __funnelshift_r(r2[-1], r2[0], 16);     // (-2, 2)
+                S[15] = __funnelshift_r(r3[-1], r3[0], 24);     // (-1, 3)
+            }
+            const uint32_t sel = half ? 0x4342u : 0x4140u;
+            uint32_t r[16];
 #pragma unroll
-        for (int k = 0; k < 16; k++) r[k] = __byte_perm(S[k], 0u, sel);
-        const uint32_t a2 = corner_strength2(__byte_perm(row[0], 0u, sel), r);   // two strengths, one per 16-bit lane
-        // blank pixels outside the detection domain of the level, store the two bytes
-        const int rc = s_rowcell[ay];
-        const int c0 = s_colcell[4 * gxi + 2 * half], c1 = s_colcell[4 * gxi + 2 * half + 1];
-        const uint32_t lo = (rc >= 0 && c0 >= 0) ? (a2 & 0xFFu) : 0u, hi = (rc >= 0 && c1 >= 0) ? ((a2 >> 16) & 0xFFu) : 0u;
-        *reinterpret_cast<unsigned short*>(&s_A[ay * kAW + 4 * gxi + 2 * half]) = (unsigned short)(lo | (hi << 8));
-        // tile-interior pixels above iniTh are the NMS candidates (few per tile): queue them for a dense second pass
-        const int py = ay - 1, px = 4 * gxi - 4 + 2 * half;
-        if (py >= 0 && py < kFtH) {
-            const bool q0 = (int)lo > thIni && px >= 0 && px < kFtW, q1 = (int)hi > thIni && px + 1 >= 0 && px + 1 < kFtW;
-            if (q0 || q1) {
-                const int pos = atomicAdd(&s_nc, (int)q0 + (int)q1);
-                if (q0) s_cq[pos] = (unsigned short)(py * kFtW + px);
-                if (q1) s_cq[pos + (int)q0] = (unsigned short)(py * kFtW + px + 1);
+            for (int k = 0; k < 16; k++) r[k] = __byte_perm(S[k], 0u, sel);
+            const uint32_t a2 = corner_strength2<decltype(bright)::value, decltype(dark)::value>(__byte_perm(row[0], 0u, sel), r);
+            // blank pixels outside the detection domain of the level, store the two bytes (one strength per 16-bit lane)
+            const int rc = s_rowcell[ay];
+            const int c0 = s_colcell[4 * gxi + 2 * half], c1 = s_colcell[4 * gxi + 2 * half + 1];
+            const uint32_t lo = (rc >= 0 && c0 >= 0) ? (a2 & 0xFFu) : 0u, hi = (rc >= 0 && c1 >= 0) ? ((a2 >> 16) & 0xFFu) : 0u;
+            *reinterpret_cast<unsigned short*>(&s_A[ay * kAW + 4 * gxi + 2 * half]) = (unsigned short)(lo | (hi << 8));
+            // tile-interior pixels above iniTh are the NMS candidates (few per tile): queue them for a dense second pass
+            const int py = ay - 1, px = 4 * gxi - 4 + 2 * half;
+            if (py >= 0 && py < kFtH) {
+                const bool q0 = (int)lo > thIni && px >= 0 && px < kFtW, q1 = (int)hi > thIni && px + 1 >= 0 && px + 1 < kFtW;
+                if (q0 || q1) {
+                    const int pos = atomicAdd(&s_nc, (int)q0 + (int)q1);
+                    if (q0) s_cq[pos] = (unsigned short)(py * kFtW + px);
+                    if (q1) s_cq[pos + (int)q0] = (unsigned short)(py * kFtW + px + 1);
+                }
             }
         }
-    }
+    };
+    exact_pass(std::true_type{}, std::false_type{}, s_queue[0], s_nq[0]);
+    exact_pass(std::false_type{}, std::true_type{}, s_queue[1], s_nq[1]);
+    exact_pass(std::true_type{}, std::true_type{}, s_queue[2], s_nq[2]);
     __syncthreads();
 
     // ---- 2: cell-aware NMS over the tile interior at iniTh; local maxima are emitted, each FAST cell counts its own ----
