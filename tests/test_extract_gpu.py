@@ -160,3 +160,45 @@ def test_repeat_call_is_deterministic(gpu):
     for _ in range(3):
         k2, d2 = g.extract(gray, boxes, tm, blur)
         assert k1.tobytes() == k2.tobytes() and d1.tobytes() == d2.tobytes()
+
+
+@pytest.mark.parametrize("nlevels,sf,nf", [(4, 1.5, 800), (6, 1.2, 600), (8, 1.1, 1000), (1, 1.2, 300)])
+def test_other_pyramid_parameters(gpu, nlevels, sf, nf):
+    gray = synth.make_frame(33)
+    g = gpu.Extractor(nfeatures=nf, scale_factor=sf, nlevels=nlevels)
+    c = orc.Extractor(nfeatures=nf, scale_factor=sf, nlevels=nlevels)
+    kb, db = c.extract(gray)
+    kg, dg = g.extract(gray)
+    assert len(kb) == len(kg) and kb.tobytes() == kg.tobytes() and np.array_equal(db, dg)
+
+
+def test_one_handle_many_shapes_and_capacities(gpu):
+    # geometry is rebuilt (and the cached CUDA graphs dropped) when the image size changes; a too-small output capacity
+    # is reported, not truncated
+    g, c = gpu.Extractor(), orc.Extractor()
+    for (w, h) in [(640, 480), (400, 300), (640, 480), (752, 480), (400, 300)]:
+        gray = synth.make_frame(w + h, w, h)
+        for _ in range(3):   # 3 calls per shape: eager, eager, graph replay
+            kg, dg = g.extract(gray)
+        kb, db = c.extract(gray)
+        assert kb.tobytes() == kg.tobytes() and np.array_equal(db, dg), (w, h)
+    gray = synth.make_frame(1)
+    with pytest.raises(gpu.CoebError) as e:
+        g.extract(gray, cap=100)
+    assert e.value.status == gpu.ERR_CAPACITY
+    kg, dg = g.extract(gray, cap=5000)
+    kb, db = c.extract(gray)
+    assert kb.tobytes() == kg.tobytes()
+
+
+def test_large_host_batch_takes_the_pipelined_path(gpu):
+    B = 80   # > 64 frames: 32-frame sub-batches over three streams
+    batch = synth.make_batch(B, base_seed=500, unique=10)
+    g = gpu.Extractor()
+    kps, desc, counts, status = g.extract_batch_host(batch["gray"], batch["boxes"], batch["nbox"], batch["tm"], batch["ntm"], batch["blur"])
+    assert (status == 0).all()
+    c = orc.Extractor()
+    for i in list(range(0, B, 7)) + [31, 32, 63, 64, B - 1]:
+        nb, nt = batch["nbox"][i], batch["ntm"][i]
+        kb, db = c.extract(batch["gray"][i], batch["boxes"][i, :nb], batch["tm"][i, :nt], batch["blur"][i, :nb])
+        assert counts[i] == len(kb) and kps[i, :counts[i]].tobytes() == kb.tobytes() and np.array_equal(desc[i, :counts[i]], db), i
