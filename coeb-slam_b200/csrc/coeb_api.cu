@@ -194,6 +194,13 @@ int build_geometry(coeb_extractor* ex, int w, int h) {
         L.hCell = (int)std::ceil(height / L.nRows);
         if (L.wCell + 6 > 72 || L.hCell + 6 > 72) return fail(COEB_ERR_UNSUPPORTED, "cell larger than the staged ROI");
         if (L.nCols > 4095 || L.nRows > 4095) return fail(COEB_ERR_UNSUPPORTED, "too many cells");
+        L.lastJ = std::max(std::min(L.nCols - 1, (L.maxBX - 6 - kMinBorder - 1) / L.wCell), 0);
+        L.lastI = std::max(std::min(L.nRows - 1, (L.maxBY - 3 - kMinBorder - 1) / L.hCell), 0);
+        L.rcpW = ((1 << 20) + L.wCell - 1) / L.wCell;
+        L.rcpH = ((1 << 20) + L.hCell - 1) / L.hCell;
+        for (int n = 0; n < 4128; n++)
+            if ((int)(((unsigned)n * (unsigned)L.rcpW) >> 20) != n / L.wCell || (int)(((unsigned)n * (unsigned)L.rcpH) >> 20) != n / L.hCell)
+                return fail(COEB_ERR_UNSUPPORTED, "internal: reciprocal cell division is inexact at level %d", l);
         L.cell_base = cells;
         cells += L.nCols * L.nRows;
         L.n_target = ex->per_level[l];

@@ -29,6 +29,8 @@ struct LevelGeom {
     int w, h, pitch;             // level image size and row pitch (bytes)
     int maxBX, maxBY;            // w - 16, h - 16
     int nCols, nRows, wCell, hCell;
+    int lastJ, lastI;            // last cell column / row that exists (:816-826); detection pixels beyond it belong to it
+    int rcpW, rcpH;              // ceil(2^20 / wCell), ceil(2^20 / hCell): (n * rcp) >> 20 == n / cell for n < 4128
     int cell_base;               // index of this level's first cell in the per-frame cell list
     int n_target;                // mnFeaturesPerLevel[l]
     int n_ini;                   // octree root count, round(W/H)

@@ -26,141 +26,201 @@
 //   2   cell-aware NMS over A > iniTh, local maxima appended to the level's list, one count per FAST cell.
 // Fallback kernel: persistent CTAs scan the cell counters; a cell with count 0 is recomputed alone (plain scalar code,
 // it is rare) and its local maxima above minTh are appended to the same list.
-#include <type_traits>
-
 #include "coeb_device.cuh"
 
 namespace coeb {
 
-constexpr int kFtW = 64, kFtH = 30;            // output tile
-constexpr int kFtThreads = 288;                // 18 four-pixel groups x 32 rows of A = 576 = 2 per thread
-constexpr int kImgWords = 28;                  // 24 words (96 px from x = tx0-16, six 16-byte loads) + pad to a 16-byte multiple
+constexpr int kFtW = 64, kFtH = 32;            // output tile: 16 four-pixel groups x kFtH rows
+constexpr int kFtThreads = 256;
+constexpr int kImgWords = 24;                  // 96 staged bytes per row from x = tx0-16: six 16-byte loads
+constexpr int kImgPitch = 4 * kImgWords;
 constexpr int kImgRows = kFtH + 8;             // 3 (ring) + 1 (NMS halo) each side
-constexpr int kAW = 72, kARows = kFtH + 2;     // A tile: x from tx0-4 (18 groups), y from ty0-1
-constexpr int kGroups = 18 * kARows;           // 576 four-pixel groups = 1152 pixel pairs
+constexpr int kAW = 72, kARows = kFtH + 2;     // A tile: x from tx0-4 (alignment), y from ty0-1
+constexpr int kPairIters = kFtH / 16;          // 1a iterations: a warp covers 2 rows x 16 groups per iteration
+constexpr int kRingPairs = 2 * (kFtW / 2 + 2) + 2 * kFtH;   // pixel pairs holding the 1 px ring around the tile
+constexpr int kPairCap = kFtW * kFtH / 2 + kRingPairs;
+static_assert(kFtH % 16 == 0 && kFtH <= 64 && kRingPairs <= kFtThreads, "tile shape");
+// one shared arena (a single base register for every access), byte offsets
+constexpr int oImg = 0;
+constexpr int oA = oImg + kImgRows * kImgPitch;
+constexpr int oQueue = oA + kARows * kAW;                 // ushort[kPairCap]     pixel pairs that pass the compass bound
+constexpr int oCq = (oQueue + 2 * kPairCap + 15) & ~15;   // ushort[kFtW*kFtH]    pixels with A > iniTh (NMS candidates)
+constexpr int oList = oCq + 2 * kFtW * kFtH;              // uint32[kFtW*kFtH/2]  emitted local maxima
+constexpr int oEdge = oList + 2 * kFtW * kFtH;            // uint32[8]: cell-boundary masks (columns L/R, rows U/D), 64 bit each
+constexpr int oCtr = oEdge + 32;                          // int[8]: nq, nc, n, base
+constexpr int kFastSmem = oCtr + 32;
+static_assert(oA % 16 == 0 && oQueue % 16 == 0 && (kARows * kAW) % 16 == 0, "16-byte stores");
 
 __device__ __forceinline__ uint32_t pair_lo(uint32_t w) { return __byte_perm(w, 0u, 0x4140); }
 __device__ __forceinline__ uint32_t pair_hi(uint32_t w) { return __byte_perm(w, 0u, 0x4342); }
+__device__ __forceinline__ int smem_add(uint32_t addr, int val) {
+    int old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(val) : "memory");
+    return old;
+}
 
 // A for the two pixels packed in `c` (centre, s16x2) given their 16 ring pairs r[k] (s16x2), all unbiased bytes.
-// kBright / kDark select which arc polarity is evaluated: a pair whose compass bound rules one polarity out (for both
-// of its pixels) only needs the other half of the min/max network.
-template <bool kBright, bool kDark>
 __device__ __forceinline__ uint32_t corner_strength2(uint32_t c, const uint32_t (&r)[16]) {
     const uint32_t cb = c + 0x01000100u;  // +256 per lane: d' = d + 256 in [1, 511], no borrow between lanes
     uint32_t d[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) d[k] = cb - r[k];
-    uint32_t ab = 0u, ad = 0u;
-    if (kBright) {
-        uint32_t mn[16];
+    uint32_t mn[16], mx[16];
 #pragma unroll
-        for (int k = 0; k < 16; k++) mn[k] = __vimin3_s16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
-        uint32_t best_b = 0u;
-#pragma unroll
-        for (int k = 0; k < 16; k += 2) {
-            const uint32_t a0 = __vimin3_s16x2(mn[k], mn[(k + 3) & 15], mn[(k + 6) & 15]);
-            const uint32_t a1 = __vimin3_s16x2(mn[k + 1], mn[(k + 4) & 15], mn[(k + 7) & 15]);
-            best_b = __vimax3_s16x2(best_b, a0, a1);
-        }
-        ab = __vsub2(best_b, 0x01000100u);   // best_b - 256
+    for (int k = 0; k < 16; k++) {
+        mn[k] = __vimin3_s16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+        mx[k] = __vimax3_s16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
     }
-    if (kDark) {
-        uint32_t mx[16];
+    uint32_t best_b = 0u, best_d = 0x7fff7fffu;
 #pragma unroll
-        for (int k = 0; k < 16; k++) mx[k] = __vimax3_s16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
-        uint32_t best_d = 0x7fff7fffu;
-#pragma unroll
-        for (int k = 0; k < 16; k += 2) {
-            const uint32_t b0 = __vimax3_s16x2(mx[k], mx[(k + 3) & 15], mx[(k + 6) & 15]);
-            const uint32_t b1 = __vimax3_s16x2(mx[k + 1], mx[(k + 4) & 15], mx[(k + 7) & 15]);
-            best_d = __vimin3_s16x2(best_d, b0, b1);
-        }
-        ad = __vsub2(0x01000100u, best_d);   // 256 - best_d
+    for (int k = 0; k < 16; k += 2) {
+        const uint32_t a0 = __vimin3_s16x2(mn[k], mn[(k + 3) & 15], mn[(k + 6) & 15]);
+        const uint32_t a1 = __vimin3_s16x2(mn[k + 1], mn[(k + 4) & 15], mn[(k + 7) & 15]);
+        best_b = __vimax3_s16x2(best_b, a0, a1);
+        const uint32_t b0 = __vimax3_s16x2(mx[k], mx[(k + 3) & 15], mx[(k + 6) & 15]);
+        const uint32_t b1 = __vimax3_s16x2(mx[k + 1], mx[(k + 4) & 15], mx[(k + 7) & 15]);
+        best_d = __vimin3_s16x2(best_d, b0, b1);
     }
-    return __vimax3_s16x2(ab, ad, 0u);       // A = max(bright, dark), clamped at 0
+    // A = max(bright, dark), clamped at 0
+    return __vimax3_s16x2(__vsub2(best_b, 0x01000100u), __vsub2(0x01000100u, best_d), 0u);
 }
 
-// Upper bounds of the bright and dark arc strengths of the two pixels packed in `c`, from the four compass ring pairs
-// (ring 0, 4, 8, 12). Returns bit 0: some lane's bright bound exceeds th; bit 1: same for dark.
-__device__ __forceinline__ int compass_bound2(uint32_t c, uint32_t r0, uint32_t r4, uint32_t r8, uint32_t r12, uint32_t th2) {
+// Can either pixel packed in `c` be a corner at the threshold? Every 9-arc holds two neighbouring compass points
+// (ring 0, 4, 8, 12), so the arc strength is bounded by max_k min(d_k, d_k+4) (mirrored for dark arcs).
+// thb / tdb = 256 + th / 256 - th per lane.
+__device__ __forceinline__ bool compass_bound2(uint32_t c, uint32_t r0, uint32_t r4, uint32_t r8, uint32_t r12, uint32_t thb, uint32_t tdb) {
     const uint32_t cb = c + 0x01000100u;
     const uint32_t d0 = cb - r0, d4 = cb - r4, d8 = cb - r8, d12 = cb - r12;
-    const uint32_t bb = __vimax3_s16x2(__vimax3_s16x2(__vmins2(d0, d4), __vmins2(d4, d8), __vmins2(d8, d12)), __vmins2(d12, d0), 0u);
-    const uint32_t bd = __vimin3_s16x2(__vimin3_s16x2(__vmaxs2(d0, d4), __vmaxs2(d4, d8), __vmaxs2(d8, d12)), __vmaxs2(d12, d0), 0x7fff7fffu);
-    const uint32_t ub = __vimax3_s16x2(__vsub2(bb, 0x01000100u), th2, 0u), ud = __vimax3_s16x2(__vsub2(0x01000100u, bd), th2, 0u);
-    return (int)(ub != th2) | ((int)(ud != th2) << 1);
+    const uint32_t bb = __vimax3_s16x2(__vimax3_s16x2(__vmins2(d0, d4), __vmins2(d4, d8), __vmins2(d8, d12)), __vmins2(d12, d0), thb);
+    const uint32_t bd = __vimin3_s16x2(__vimin3_s16x2(__vmaxs2(d0, d4), __vmaxs2(d4, d8), __vmaxs2(d8, d12)), __vmaxs2(d12, d0), tdb);
+    return (bb != thb) | (bd != tdb);
+}
+
+// FAST cell of a level coordinate (minBorder-relative detection coordinates, src/ORBextractor.cc:813-828); -1 outside the
+// detection domain. rcp = ceil(2^20 / cell size): exact quotient for coordinates below 4128 (checked on the host).
+__device__ __forceinline__ int cell_of(int x, int size, int rcp, int last) {
+    return (x >= kEdge && x < size - kEdge) ? min((int)(((unsigned)(x - kEdge) * (unsigned)rcp) >> 20), last) : -1;
 }
 
 __global__ void __launch_bounds__(kFtThreads, 6) fast_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v,
                                                              const int4* __restrict__ tiles) {
-    __shared__ __align__(16) uint32_t s_img[kImgRows * kImgWords];
-    __shared__ __align__(4) uint8_t s_A[kARows * kAW];
-    __shared__ __align__(8) short s_colcell[kAW];
-    __shared__ short s_rowcell[kARows];
-    __shared__ uint32_t s_list[kFtW * kFtH / 2];
-    __shared__ unsigned short s_queue[3][2 * kGroups];   // pairs needing the bright network, the dark one, both
-    __shared__ unsigned short s_cq[kFtW * kFtH];   // interior pixels with A > iniTh, to be checked by the NMS
-    __shared__ int s_n, s_base, s_nq[3], s_nc;
+    __shared__ __align__(16) uint8_t smem[kFastSmem];
+    uint32_t* const s_img = reinterpret_cast<uint32_t*>(smem + oImg);
+    uint8_t* const s_A = smem + oA;
+    unsigned short* const s_queue = reinterpret_cast<unsigned short*>(smem + oQueue);
+    unsigned short* const s_cq = reinterpret_cast<unsigned short*>(smem + oCq);
+    uint32_t* const s_list = reinterpret_cast<uint32_t*>(smem + oList);
+    uint32_t* const s_edge = reinterpret_cast<uint32_t*>(smem + oEdge);
+    int* const s_ctr = reinterpret_cast<int*>(smem + oCtr);   // 0 nq, 1 nc, 2 n, 3 base
+    const uint32_t a_ctr = (uint32_t)__cvta_generic_to_shared(s_ctr);
 
     const int frame = blockIdx.y;
     const int4 ti = __ldg(&tiles[blockIdx.x]);   // {level, tx0, ty0, -} built on the host: no per-thread div/mod or level search
     const int level = ti.x, tx0 = ti.y, ty0 = ti.z;
     const LevelGeom& L = g.lv[level];
-    const int tid = threadIdx.x;
-    const uint8_t* __restrict__ img = level_ptr(g, v, level, frame);
-    const int pitch = level_pitch(g, v, level);
-    const DynState& dyn = v.dyn[frame];
-    const int thIni = dyn.area_flag ? 30 : 20;   // threshold override, src/ORBextractor.cc:775-784
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int thIni = v.dyn[frame].area_flag ? 30 : 20;   // threshold override, src/ORBextractor.cc:775-784
 
-    // ---- stage the tile: rows ty0-4 .. ty0+33, 96 bytes from x = tx0-16 as six 16-byte loads per row (228 loads per
-    //      CTA); outside the image -> 0. Bytes between w and the row pitch are padding and never reach an in-domain pixel.
-    for (int i = tid; i < kImgRows * 6; i += kFtThreads) {
-        const int ry = i / 6, q = i - ry * 6;
-        const int gy = ty0 - 4 + ry, gx = tx0 - 16 + 16 * q;
-        uint4 w = make_uint4(0u, 0u, 0u, 0u);
-        if (gy >= 0 && gy < L.h && gx + 16 <= pitch) w = __ldg(reinterpret_cast<const uint4*>(img + (size_t)gy * pitch + gx));
-        *reinterpret_cast<uint4*>(&s_img[ry * kImgWords + 4 * q]) = w;
+    // ---- stage the tile: rows ty0-4 .. ty0+kFtH+3, 96 bytes from x = tx0-16 as six 16-byte loads per row. Rows below the
+    //      image and columns beyond the row pitch are clamped: only pixels outside the detection domain (whose strength is
+    //      never used) can see them, as can the padding bytes between w and the pitch.
+    {
+        const int pitch = level_pitch(g, v, level);
+        const int q = tid & 7, r0 = tid >> 3;
+        const uint8_t* __restrict__ src = level_ptr(g, v, level, frame) + min(tx0 - 16 + 16 * q, pitch - 16);
+        if (q < 6) {
+#pragma unroll
+            for (int ry = r0; ry < kImgRows; ry += kFtThreads / 8)
+                reinterpret_cast<uint4*>(s_img)[ry * 6 + q] = __ldg(reinterpret_cast<const uint4*>(src + (long long)min(ty0 - 4 + ry, L.h - 1) * pitch));
+        }
     }
-    for (int i = tid; i < kARows * kAW / 4; i += kFtThreads) reinterpret_cast<uint32_t*>(s_A)[i] = 0u;
-    // cell index of every column / row of the A tile (minBorder-relative detection coordinates, src/ORBextractor.cc:813-828)
-    const int lastJ = max(min(L.nCols - 1, (L.maxBX - 6 - kMinBorder - 1) / L.wCell), 0);
-    const int lastI = max(min(L.nRows - 1, (L.maxBY - 3 - kMinBorder - 1) / L.hCell), 0);
-    if (tid < kAW) {
-        const int x = tx0 - 4 + tid;   // level coordinate
-        s_colcell[tid] = (x >= kEdge && x < L.w - kEdge) ? (short)min((x - kEdge) / L.wCell, lastJ) : (short)-1;
-    } else if (tid >= 96 && tid < 96 + kARows) {
-        const int y = ty0 - 1 + (tid - 96);
-        s_rowcell[tid - 96] = (y >= kEdge && y < L.h - kEdge) ? (short)min((y - kEdge) / L.hCell, lastI) : (short)-1;
+    for (int i = tid; i < kARows * kAW / 16; i += kFtThreads) reinterpret_cast<uint4*>(s_A)[i] = make_uint4(0u, 0u, 0u, 0u);
+    // cell-boundary masks: bit i of word pair 0/1 = the left/right neighbour of column tx0+i lies in another FAST cell (or
+    // outside the detection domain) and so cannot suppress it; word pairs 2/3 = same for the rows above/below
+    if (tid < 128) {
+        const bool rows = tid >= 64;
+        const int i = tid & 63;
+        const int x = (rows ? ty0 : tx0) + i, size = rows ? L.h : L.w, rcp = rows ? L.rcpH : L.rcpW, last = rows ? L.lastI : L.lastJ;
+        const int c = cell_of(x, size, rcp, last);
+        const unsigned ml = __ballot_sync(0xffffffffu, cell_of(x - 1, size, rcp, last) != c);
+        const unsigned mr = __ballot_sync(0xffffffffu, cell_of(x + 1, size, rcp, last) != c);
+        if (lane == 0) { s_edge[(tid >> 5) & 1 | (rows ? 4 : 0)] = ml; s_edge[((tid >> 5) & 1 | (rows ? 4 : 0)) + 2] = mr; }
     }
-    if (tid == 0) { s_n = 0; s_nq[0] = s_nq[1] = s_nq[2] = 0; s_nc = 0; }
+    if (tid < 4) s_ctr[tid] = 0;
     __syncthreads();
 
-    // ---- 1a: compass bound for every pixel pair of the tile + 1 px halo; survivors go to the queue ----
-#pragma unroll 1
-    for (int it = 0; it < 2; it++) {
-        const int grp = tid + it * kFtThreads;          // 0..575
-        const int ay = grp / 18, gxi = grp - ay * 18;   // A row (y = ty0-1+ay), group (x = tx0-4+4*gxi)
-        const uint32_t* row = &s_img[(ay + 3) * kImgWords + gxi + 3];   // word holding the 4 centre pixels
-        const uint32_t c = row[0];
-        const uint32_t S0 = row[3 * kImgWords], S8 = row[-3 * kImgWords];
-        const uint32_t S4 = __funnelshift_r(c, row[1], 24), S12 = __funnelshift_r(row[-1], c, 8);
-        const uint32_t th2 = (uint32_t)thIni * 0x00010001u;
-        const int f01 = compass_bound2(pair_lo(c), pair_lo(S0), pair_lo(S4), pair_lo(S8), pair_lo(S12), th2);
-        const int f23 = compass_bound2(pair_hi(c), pair_hi(S0), pair_hi(S4), pair_hi(S8), pair_hi(S12), th2);
-        if (f01) s_queue[f01 - 1][atomicAdd(&s_nq[f01 - 1], 1)] = (unsigned short)(2 * grp);
-        if (f23) s_queue[f23 - 1][atomicAdd(&s_nq[f23 - 1], 1)] = (unsigned short)(2 * grp + 1);
+    // detection domain [19, w-19) x [19, h-19) in tile coordinates, cut to the A tile [-2, kFtW+2) x [-1, kFtH+1)
+    const int xlo = max(kEdge - tx0, -2), xspan = max(min(L.w - kEdge - tx0, kFtW + 2) - xlo, 0);
+    const int ylo = max(kEdge - ty0, -1), yspan = max(min(L.h - kEdge - ty0, kFtH + 1) - ylo, 0);
+
+    // ---- 1a: compass bound of every pixel pair; survivors are queued, which re-packs them densely over the threads.
+    //      A warp takes 16 groups of rows y and y+2 (24-word row pitch: the two half-warps hit disjoint banks); the 1 px
+    //      ring the NMS needs around the tile is one more pass of single pairs.
+    {
+        const uint32_t th2 = (uint32_t)thIni * 0x00010001u, thb = 0x01000100u + th2, tdb = 0x01000100u - th2;
+        const int gxi = lane & 15, px = 4 * gxi;
+        const int ay0 = 4 * (tid >> 6) + ((tid >> 5) & 1) + ((lane >> 4) << 1);   // + 16 per iteration
+        const bool x01 = (unsigned)(px + 1 - xlo) < (unsigned)(xspan + 1), x23 = (unsigned)(px + 3 - xlo) < (unsigned)(xspan + 1);
+        const uint32_t* row = &s_img[(ay0 + 4) * kImgWords + gxi + 4];   // word holding the 4 centre pixels
+        unsigned flags = 0u;
+#pragma unroll
+        for (int it = 0; it < kPairIters; it++, row += 16 * kImgWords) {
+            const uint32_t c = row[0];
+            const uint32_t S0 = row[3 * kImgWords], S8 = row[-3 * kImgWords];
+            const uint32_t S4 = __funnelshift_r(c, row[1], 24), S12 = __funnelshift_r(row[-1], c, 8);
+            const bool yok = (unsigned)(ay0 + 16 * it - ylo) < (unsigned)yspan;
+            const bool f01 = compass_bound2(pair_lo(c), pair_lo(S0), pair_lo(S4), pair_lo(S8), pair_lo(S12), thb, tdb) & yok & x01;
+            const bool f23 = compass_bound2(pair_hi(c), pair_hi(S0), pair_hi(S4), pair_hi(S8), pair_hi(S12), thb, tdb) & yok & x23;
+            flags |= ((unsigned)f01 << (2 * it)) | ((unsigned)f23 << (2 * it + 1));
+        }
+        // ring pairs: rows -1 and kFtH over x = -2 .. kFtW+1, columns (-2,-1) and (kFtW, kFtW+1) over the tile rows
+        int re = 0;
+        if (tid < kRingPairs) {   // whole warps except the last one
+            int ray, rpi;   // A row, pair index (first pixel x = 2 * rpi)
+            if (tid < kFtW / 2 + 2) { ray = -1; rpi = tid - 1; }
+            else if (tid < kFtW + 4) { ray = kFtH; rpi = tid - (kFtW / 2 + 2) - 1; }
+            else if (tid < kFtW + 4 + kFtH) { ray = tid - (kFtW + 4); rpi = -1; }
+            else { ray = tid - (kFtW + 4 + kFtH); rpi = kFtW / 2; }
+            const uint32_t* rr = &s_img[(ray + 4) * kImgWords + 4 + (rpi >> 1)];
+            const uint32_t sel = (rpi & 1) ? 0x4342u : 0x4140u;
+            const uint32_t c = rr[0];
+            const uint32_t S4 = __funnelshift_r(c, rr[1], 24), S12 = __funnelshift_r(rr[-1], c, 8);
+            const bool ok = (unsigned)(ray - ylo) < (unsigned)yspan && (unsigned)(2 * rpi + 1 - xlo) < (unsigned)(xspan + 1);
+            const bool f = compass_bound2(__byte_perm(c, 0u, sel), __byte_perm(rr[3 * kImgWords], 0u, sel), __byte_perm(S4, 0u, sel),
+                                          __byte_perm(rr[-3 * kImgWords], 0u, sel), __byte_perm(S12, 0u, sel), thb, tdb) & ok;
+            re = ((ray + 1) << 6) | (rpi + 1);
+            flags |= (unsigned)f << (2 * kPairIters);
+        }
+        // one queue reservation per warp: ballots give every set flag its slot
+        unsigned m[2 * kPairIters + 1];
+        int n = 0;
+#pragma unroll
+        for (int j = 0; j <= 2 * kPairIters; j++) { m[j] = __ballot_sync(0xffffffffu, (flags >> j) & 1u); n += __popc(m[j]); }
+        if (n > 0) {
+            int base = 0;
+            if (lane == 0) base = smem_add(a_ctr, n);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const unsigned lt = (1u << lane) - 1u;
+            const int e0 = ((ay0 + 1) << 6) | (2 * gxi + 1);   // A row + 1, pair index + 1
+#pragma unroll
+            for (int j = 0; j < 2 * kPairIters; j++) {
+                if ((flags >> j) & 1u) s_queue[base + __popc(m[j] & lt)] = (unsigned short)(e0 + ((j >> 1) << 10) + (j & 1));
+                base += __popc(m[j]);
+            }
+            if ((flags >> (2 * kPairIters)) & 1u) s_queue[base + __popc(m[2 * kPairIters] & lt)] = (unsigned short)re;
+        }
     }
     __syncthreads();
 
-    // ---- 1b: exact corner strength of the queued pairs, one dense pass per class (no divergence inside a pass) ----
-    auto exact_pass = [&](auto bright, auto dark, const unsigned short* queue, int nq) {
+    // ---- 1b: exact corner strength of the queued pairs, branch-free ----
+    {
+        const int nq = s_ctr[0];
 #pragma unroll 1
         for (int qi = tid; qi < nq; qi += kFtThreads) {
-            const int e = queue[qi];
-            const int grp = e >> 1, half = e & 1;
-            const int ay = grp / 18, gxi = grp - ay * 18;
-            const uint32_t* row = &s_img[(ay + 3) * kImgWords + gxi + 3];
+            const int e = s_queue[qi];
+            const int er = e >> 6, ep = e & 63;                 // A row + 1, pair index + 1
+            const int px = 2 * ep - 2;                          // first pixel of the pair, tile coordinate
+            const uint32_t* row = &s_img[(er + 3) * kImgWords + 4 + ((ep - 1) >> 1)];
             uint32_t S[16];
             {   // ring words: 4 consecutive bytes starting at x+dx on row y+dy (FAST circle, OpenCV order)
                 const uint32_t *r3 = row + 3 * kImgWords, *rm3 = row - 3 * kImgWords, *r2 = row + 2 * kImgWords, *rm2 = row - 2 * kImgWords,
@@ -182,36 +242,33 @@ __global__ void __launch_bounds__(kFtThreads, 6) fast_kernel(const __grid_consta
                 S[14] = __funnelshift_r(r2[-1], r2[0], 16);     // (-2, 2)
                 S[15] = __funnelshift_r(r3[-1], r3[0], 24);     // (-1, 3)
             }
-            const uint32_t sel = half ? 0x4342u : 0x4140u;
+            const uint32_t sel = (ep & 1) ? 0x4140u : 0x4342u;   // odd ep = even pair index = low half of the word
             uint32_t r[16];
 #pragma unroll
             for (int k = 0; k < 16; k++) r[k] = __byte_perm(S[k], 0u, sel);
-            const uint32_t a2 = corner_strength2<decltype(bright)::value, decltype(dark)::value>(__byte_perm(row[0], 0u, sel), r);
-            // blank pixels outside the detection domain of the level, store the two bytes (one strength per 16-bit lane)
-            const int rc = s_rowcell[ay];
-            const int c0 = s_colcell[4 * gxi + 2 * half], c1 = s_colcell[4 * gxi + 2 * half + 1];
-            const uint32_t lo = (rc >= 0 && c0 >= 0) ? (a2 & 0xFFu) : 0u, hi = (rc >= 0 && c1 >= 0) ? ((a2 >> 16) & 0xFFu) : 0u;
-            *reinterpret_cast<unsigned short*>(&s_A[ay * kAW + 4 * gxi + 2 * half]) = (unsigned short)(lo | (hi << 8));
-            // tile-interior pixels above iniTh are the NMS candidates (few per tile): queue them for a dense second pass
-            const int py = ay - 1, px = 4 * gxi - 4 + 2 * half;
-            if (py >= 0 && py < kFtH) {
-                const bool q0 = (int)lo > thIni && px >= 0 && px < kFtW, q1 = (int)hi > thIni && px + 1 >= 0 && px + 1 < kFtW;
-                if (q0 || q1) {
-                    const int pos = atomicAdd(&s_nc, (int)q0 + (int)q1);
-                    if (q0) s_cq[pos] = (unsigned short)(py * kFtW + px);
-                    if (q1) s_cq[pos + (int)q0] = (unsigned short)(py * kFtW + px + 1);
-                }
+            const uint32_t a2 = corner_strength2(__byte_perm(row[0], 0u, sel), r);
+            // blank the pixel of a straddling pair that lies outside the detection domain; one strength per byte
+            const uint32_t lo = (unsigned)(px - xlo) < (unsigned)xspan ? (a2 & 0xFFu) : 0u;
+            const uint32_t hi = (unsigned)(px + 1 - xlo) < (unsigned)xspan ? (a2 >> 16) : 0u;
+            *reinterpret_cast<unsigned short*>(&s_A[er * kAW + px + 4]) = (unsigned short)(lo | (hi << 8));
+            // tile pixels above iniTh are the NMS candidates: queue them for a dense second pass
+            const bool in = (unsigned)(er - 1) < (unsigned)kFtH && (unsigned)px < (unsigned)kFtW;
+            const bool q0 = in && (int)lo > thIni, q1 = in && (int)hi > thIni;
+            if (q0 || q1) {
+                const int id = ((er - 1) << 6) | px;
+                const int pos = smem_add(a_ctr + 4, (int)q0 + (int)q1);
+                if (q0) s_cq[pos] = (unsigned short)id;
+                if (q1) s_cq[pos + (int)q0] = (unsigned short)(id + 1);
             }
         }
-    };
-    exact_pass(std::true_type{}, std::false_type{}, s_queue[0], s_nq[0]);
-    exact_pass(std::false_type{}, std::true_type{}, s_queue[1], s_nq[1]);
-    exact_pass(std::true_type{}, std::true_type{}, s_queue[2], s_nq[2]);
+    }
     __syncthreads();
 
-    // ---- 2: cell-aware NMS over the tile interior at iniTh; local maxima are emitted, each FAST cell counts its own ----
+    // ---- 2: cell-aware NMS at iniTh; local maxima are emitted, each FAST cell counts its own ----
+    const int nc = s_ctr[1];
+    const unsigned long long eL = *reinterpret_cast<const unsigned long long*>(s_edge), eR = *reinterpret_cast<const unsigned long long*>(s_edge + 2);
+    const unsigned long long eU = *reinterpret_cast<const unsigned long long*>(s_edge + 4), eD = *reinterpret_cast<const unsigned long long*>(s_edge + 6);
     int* cellcnt = v.cell_count + (size_t)frame * g.cells_per_frame + L.cell_base;
-    const int nc = s_nc;
     for (int i = tid; i < nc; i += kFtThreads) {
         const int e = s_cq[i];
         const int py = e >> 6, px = e & 63;
@@ -219,10 +276,9 @@ __global__ void __launch_bounds__(kFtThreads, 6) fast_kernel(const __grid_consta
         const int A = a[0];
         const int n_l = a[-1], n_r = a[1], n_ul = a[-kAW - 1], n_u = a[-kAW], n_ur = a[-kAW + 1], n_dl = a[kAW - 1], n_d = a[kAW], n_dr = a[kAW + 1];
         bool keep = A > max(max(max(n_l, n_r), max(n_ul, n_u)), max(max(n_ur, n_dl), max(n_d, n_dr)));
-        const int cj = s_colcell[px + 4], ci = s_rowcell[py + 1];
         if (!keep) {
             // a larger neighbour only counts if it belongs to the same cell (each cell is an independent cv::FAST call)
-            const bool sl = s_colcell[px + 3] == cj, sr = s_colcell[px + 5] == cj, su = s_rowcell[py] == ci, sd = s_rowcell[py + 2] == ci;
+            const bool sl = !((eL >> px) & 1ull), sr = !((eR >> px) & 1ull), su = !((eU >> py) & 1ull), sd = !((eD >> py) & 1ull);
             if (!(sl && sr && su && sd)) {
                 int m = 0;
                 if (sl) m = max(m, n_l);
@@ -233,18 +289,20 @@ __global__ void __launch_bounds__(kFtThreads, 6) fast_kernel(const __grid_consta
             }
         }
         if (keep) {
-            const int x = tx0 + px - kMinBorder, y = ty0 + py - kMinBorder;   // minBorder-relative (:844-845)
-            s_list[atomicAdd(&s_n, 1)] = (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)(A - 1) << 24);
+            const int x = tx0 + px, y = ty0 + py;   // level coordinates; emitted minBorder-relative (:844-845)
+            const int cj = cell_of(x, L.w, L.rcpW, L.lastJ), ci = cell_of(y, L.h, L.rcpH, L.lastI);
+            s_list[smem_add(a_ctr + 8, 1)] = (uint32_t)(x - kMinBorder) | ((uint32_t)(y - kMinBorder) << 12) | ((uint32_t)(A - 1) << 24);
             atomicAdd(&cellcnt[ci * L.nCols + cj], 1);
         }
     }
     __syncthreads();
-    const int n = s_n;
+    const int n = s_ctr[2];
     if (n == 0) return;
-    if (tid == 0) s_base = atomicAdd(v.lmax_count + frame * g.nlevels + level, n);
+    if (tid == 0) s_ctr[3] = atomicAdd(v.lmax_count + frame * g.nlevels + level, n);
     __syncthreads();
-    uint32_t* out = v.lmax + (size_t)frame * g.cand_per_frame + L.cand_base + s_base;
-    const int room = L.cand_cap - s_base;
+    const int base = s_ctr[3];
+    uint32_t* out = v.lmax + (size_t)frame * g.cand_per_frame + L.cand_base + base;
+    const int room = L.cand_cap - base;
     for (int i = tid; i < n && i < room; i += kFtThreads) out[i] = s_list[i];
 }
 

@@ -109,8 +109,7 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const __grid_consta
     const bool cached = nl <= kKeyCache;
     uint32_t* keys = cached ? s_keys : gkeys;
     unsigned short* knode = cached ? s_knode : v.knode + (size_t)frame * g.cand_per_frame + L.cand_base;
-    const int lastJ = max(min(L.nCols - 1, (L.maxBX - 6 - kMinBorder - 1) / L.wCell), 0);
-    const int lastI = max(min(L.nRows - 1, (L.maxBY - 3 - kMinBorder - 1) / L.hCell), 0);
+    const int lastJ = L.lastJ, lastI = L.lastI;
     {
         const uint32_t* __restrict__ lm = v.lmax + (size_t)frame * g.cand_per_frame + L.cand_base;
         const int* __restrict__ cellcnt = v.cell_count + (size_t)frame * g.cells_per_frame + L.cell_base;
