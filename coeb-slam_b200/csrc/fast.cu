@@ -30,7 +30,13 @@
 
 namespace coeb {
 
-constexpr int kFtW = 64, kFtH = 32;            // output tile: 16 four-pixel groups x kFtH rows
+#ifndef COEB_FT_H
+#define COEB_FT_H 64
+#endif
+#ifndef COEB_FT_MINB
+#define COEB_FT_MINB 6
+#endif
+constexpr int kFtW = 64, kFtH = COEB_FT_H;     // output tile: 16 four-pixel groups x kFtH rows
 constexpr int kFtThreads = 256;
 constexpr int kImgWords = 24;                  // 96 staged bytes per row from x = tx0-16: six 16-byte loads
 constexpr int kImgPitch = 4 * kImgWords;
@@ -102,7 +108,7 @@ __device__ __forceinline__ int cell_of(int x, int size, int rcp, int last) {
     return (x >= kEdge && x < size - kEdge) ? min((int)(((unsigned)(x - kEdge) * (unsigned)rcp) >> 20), last) : -1;
 }
 
-__global__ void __launch_bounds__(kFtThreads, 6) fast_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v,
+__global__ void __launch_bounds__(kFtThreads, COEB_FT_MINB) fast_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v,
                                                              const int4* __restrict__ tiles) {
     __shared__ __align__(16) uint8_t smem[kFastSmem];
     uint32_t* const s_img = reinterpret_cast<uint32_t*>(smem + oImg);

@@ -68,7 +68,7 @@ __device__ __forceinline__ unsigned long long order_key(const LevelGeom& L, int 
 
 extern __shared__ unsigned char s_dyn_raw[];
 
-__global__ void __launch_bounds__(kSelThreads) select_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v) {
+__global__ void __launch_bounds__(kSelThreads, 3) select_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v) {
     const int level = blockIdx.x, frame = blockIdx.y;
     const LevelGeom& L = g.lv[level];
     const DynState& dyn = v.dyn[frame];

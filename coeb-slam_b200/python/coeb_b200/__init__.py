@@ -12,7 +12,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 PKG_ROOT = os.path.normpath(os.path.join(_HERE, "..", ".."))
-LIB_PATH = os.path.join(PKG_ROOT, "lib", "libcoeb_frontend.so")
+LIB_PATH = os.environ.get("COEB_B200_LIB") or os.path.join(PKG_ROOT, "lib", "libcoeb_frontend.so")   # override: development builds only
 
 KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
                      ("octave", "<i4"), ("class_id", "<i4")])
