@@ -53,6 +53,7 @@ struct Geometry {
     int out_cap;                 // per-frame capacity of the caller's keypoint/descriptor arrays
     int max_nodes;               // octree node-table capacity (per generation)
     int fast_tiles_per_frame;    // entries of the FAST tile table
+    int blur_tiles_per_frame;    // entries of the blur tile table
     LevelGeom lv[COEB_MAX_LEVELS];
     int umax[16];
 };
@@ -88,7 +89,8 @@ struct BatchView {
     uint8_t* pyr;                      // pyramid arena (levels >= 1; level 0 too unless aliased)
     uint8_t* blur;                     // blurred arena
     const int2* tabs;                  // resize tables
-    const int4* fast_tiles;            // FAST tile table {level, tx0, ty0, 0}, one entry per 64x30 tile of one frame
+    const int4* fast_tiles;            // FAST tile table {level, tx0, ty0, 0}, one entry per tile of one frame
+    const int4* blur_tiles;            // blur tile table, same layout
     uint32_t* cand;                    // [B][cand_per_frame]
     int* cand_count;                   // [B][nlevels]
     LevelKey* keys;                    // [B][keys_per_frame]
@@ -191,6 +193,7 @@ void launch_blur(const Geometry& g, const BatchView& v, cudaStream_t stream);
 void launch_fast(const Geometry& g, const BatchView& v, cudaStream_t stream);
 // Host-side FAST tile table of one frame (level, tx0, ty0 per 64x30 tile), uploaded once per geometry.
 int build_fast_tiles(const Geometry& g, int4* out_or_null);
+int build_blur_tiles(const Geometry& g, int4* out_or_null);
 void launch_select(const Geometry& g, const BatchView& v, cudaStream_t stream);
 void launch_describe(const Geometry& g, const BatchView& v, cudaStream_t stream);
 

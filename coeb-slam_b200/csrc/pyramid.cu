@@ -80,16 +80,23 @@ void launch_pyramid(const Geometry& g, const BatchView& v, cudaStream_t stream) 
 // Gaussian 7x7 sigma=2, OpenCV bit-exact fixed point: Q8 kernel {18,34,48,56,48,34,18};
 // horizontal pass -> Q8.8 (uint16), vertical pass -> Q16.16, (v + 32768) >> 16. BORDER_REFLECT_101
 // on the level itself (the reference blurs a clone of the ROI, so the pyramid border is not seen).
-// One CTA = 128 x 32 output tile of one level of one frame; all levels in one launch.
-//   stage : aligned 32-bit words into shared memory (rows reflected by index, the <= 3 reflected
-//           columns at the image's left/right edge patched in place)
-//   H pass: 4 px per thread; the 10 source bytes become nine s16x2 pairs (funnel shift + PRMT) and
-//           the taps are packed 16-bit multiply-adds (no lane can overflow: 255*256 < 65536)
-//   V pass: 4 px x 4 rows per thread from the uint16 intermediate, 32-bit accumulation, one 32-bit store per row
+// Both passes are exact integer sums (no intermediate rounding, no saturation: 255*256 < 65536), and both are
+// byte / halfword dot products, which is what IDP.4A / IDP.2A compute on the multiply pipe (the integer ALU pipe,
+// which bounds FAST, stays free):
+//   stage : aligned 16-byte vectors into shared memory (rows reflected by index, the <= 3 reflected columns at the
+//           image's left/right edge patched in place)
+//   H pass: 4 px x 2 rows per thread. With the three aligned words around the 4 pixels, output x+i is
+//           dp4a(wm, Km[i]) + dp4a(w0, K0[i]) + dp4a(wp, Kp[i]) with the taps shifted inside the weight words
+//           (10 IDP.4A per 4 px, no byte shuffling). Rows 2m and 2m+1 are stored as one (lo, hi) 16-bit pair.
+//   V pass: 4 px x 4 rows per thread: an output row is 4 IDP.2A over four row pairs; even and odd rows use the same
+//           pairs with the tap pattern moved by one row.
+// One CTA = 64 x 32 output tile of one level of one frame (host-built tile table); all levels in one launch.
 // ------------------------------------------------------------------------------------------------
-constexpr int kBlurTW = 128, kBlurTH = 32, kBlurThreads = 256;
-constexpr int kBlurInWords = kBlurTW / 4 + 8;       // 40 words = ten 16-byte vectors per row, x from tx0-16
-constexpr int kBlurRows = kBlurTH + 6;
+constexpr int kBlurTW = 64, kBlurTH = 32, kBlurThreads = 128;
+constexpr int kBlurInWords = 24;                    // 96 staged bytes per row from x = tx0-16: six 16-byte vectors
+constexpr int kBlurRows = kBlurTH + 6;              // staged row r <-> y = ty0 - 3 + r
+constexpr int kBlurPairRows = kBlurRows / 2;        // 19
+constexpr int kBlurVPitch = kBlurTW + 4;            // words per pair row (+4: rows of 16-byte vectors on distinct banks)
 
 __device__ __forceinline__ int reflect101(int i, int n) {
     if (n == 1) return 0;
@@ -97,103 +104,128 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return i;
 }
 
-__global__ void __launch_bounds__(kBlurThreads, 6) blur_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v,
-                                                            const __grid_constant__ TileMap tm) {
+__device__ __forceinline__ uint32_t blur_h(uint32_t wm, uint32_t w0, uint32_t wp, int i) {
+    // taps {18,34,48,56,48,34,18} centred on byte i of w0, laid over the bytes of (wm, w0, wp)
+    switch (i) {
+        case 0: return __dp4a(wm, 0x30221200u, __dp4a(w0, 0x12223038u, 0u));
+        case 1: return __dp4a(wm, 0x22120000u, __dp4a(w0, 0x22303830u, __dp4a(wp, 0x00000012u, 0u)));
+        case 2: return __dp4a(wm, 0x12000000u, __dp4a(w0, 0x30383022u, __dp4a(wp, 0x00001222u, 0u)));
+        default: return __dp4a(w0, 0x38302212u, __dp4a(wp, 0x00122230u, 0u));
+    }
+}
+
+__global__ void __launch_bounds__(kBlurThreads) blur_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v,
+                                                            const int4* __restrict__ tiles) {
     __shared__ __align__(16) uint32_t s_in[kBlurRows * kBlurInWords];
-    __shared__ uint2 s_h[kBlurRows * (kBlurTW / 4 + 1)];
+    __shared__ __align__(16) uint32_t s_v[kBlurPairRows * kBlurVPitch];   // [pair row][x]: H(row 2m) | H(row 2m+1) << 16
     const int frame = blockIdx.y;
-    int level = 0;
-    while (level + 1 < g.nlevels && (int)blockIdx.x >= tm.tile_base[level + 1]) level++;
+    const int4 ti = __ldg(&tiles[blockIdx.x]);   // {level, tx0, ty0, -}
+    const int level = ti.x, tx0 = ti.y, ty0 = ti.z;
     const LevelGeom& L = g.lv[level];
-    const int t = blockIdx.x - tm.tile_base[level];
-    const int tx0 = (t % tm.tiles_x[level]) * kBlurTW, ty0 = (t / tm.tiles_x[level]) * kBlurTH;
-    const uint8_t* __restrict__ src = level_ptr(g, v, level, frame);
-    const int spitch = level_pitch(g, v, level);
     const int tid = threadIdx.x;
 
-    // stage rows ty0-3 .. ty0+34 (reflected by index), 160 bytes from x = tx0-16 as ten 16-byte loads per row
-    for (int i = tid; i < kBlurRows * 10; i += kBlurThreads) {
-        const int ry = i / 10, q = i - ry * 10;
-        const int gy = reflect101(min(ty0 + ry - 3, L.h + 2), L.h);
-        const int gx = tx0 - 16 + 16 * q;
-        uint4 w = make_uint4(0u, 0u, 0u, 0u);
-        if (gx >= 0 && gx + 16 <= spitch) w = __ldg(reinterpret_cast<const uint4*>(src + (size_t)gy * spitch + gx));
-        *reinterpret_cast<uint4*>(&s_in[ry * kBlurInWords + 4 * q]) = w;
-    }
-    __syncthreads();
-    uint8_t* s_b = reinterpret_cast<uint8_t*>(s_in);   // byte view: column c <-> x = tx0 - 16 + c
-    constexpr int kRowBytes = kBlurInWords * 4;
-    if (tx0 == 0) {   // x = -1,-2,-3  <-  x = 1,2,3
-        for (int i = tid; i < kBlurRows * 3; i += kBlurThreads) {
-            const int ry = i / 3, k = i - ry * 3 + 1;
-            s_b[ry * kRowBytes + 16 - k] = s_b[ry * kRowBytes + 16 + k];
-        }
-    }
-    if (tx0 + kBlurTW + 3 > L.w - 1) {   // x = w, w+1, w+2  <-  x = w-2, w-3, w-4
-        for (int i = tid; i < kBlurRows * 3; i += kBlurThreads) {
-            const int ry = i / 3, k = i - ry * 3;
-            const int c = L.w + k - tx0 + 16, cs = L.w - 2 - k - tx0 + 16;
-            if (c < kRowBytes && cs >= 0) s_b[ry * kRowBytes + c] = s_b[ry * kRowBytes + cs];
-        }
-    }
-    __syncthreads();
-
-    for (int i = tid; i < kBlurRows * (kBlurTW / 4); i += kBlurThreads) {
-        const int ry = i >> 5, gx = i & 31;
-        const uint32_t* w = &s_in[ry * kBlurInWords + gx + 3]; // w[0]: x-4.., w[1]: the 4 output pixels, w[2]: x+4..
-        const uint32_t wm = w[0], w0 = w[1], wp = w[2];
-        // B[i] = byte i of (wm, w0, wp); pair P_i = (B[i], B[i+1]) widened to 16 bits
-        const uint32_t Sa = __funnelshift_r(wm, w0, 8), Sb = __funnelshift_r(wm, w0, 16), Sc = __funnelshift_r(wm, w0, 24);
-        const uint32_t Sd = __funnelshift_r(w0, wp, 8), Se = __funnelshift_r(w0, wp, 16), Sf = __funnelshift_r(w0, wp, 24);
-        const uint32_t P1 = __byte_perm(Sa, 0u, 0x4140), P2 = __byte_perm(Sb, 0u, 0x4140), P3 = __byte_perm(Sa, 0u, 0x4342),
-                       P4 = __byte_perm(Sb, 0u, 0x4342), P5 = __byte_perm(Sc, 0u, 0x4342), P6 = __byte_perm(w0, 0u, 0x4342),
-                       P7 = __byte_perm(Sd, 0u, 0x4342), P8 = __byte_perm(Se, 0u, 0x4342), P9 = __byte_perm(Sf, 0u, 0x4342);
-        uint2 o;
-        o.x = 18u * (P1 + P7) + 34u * (P2 + P6) + 48u * (P3 + P5) + 56u * P4;   // outputs x, x+1 (Q8.8 each)
-        o.y = 18u * (P3 + P9) + 34u * (P4 + P8) + 48u * (P5 + P7) + 56u * P6;   // outputs x+2, x+3
-        s_h[ry * (kBlurTW / 4 + 1) + gx] = o;
-    }
-    __syncthreads();
-
-    uint8_t* dst = blur_ptr(g, v, level, frame);
+    // stage rows ty0-3 .. ty0+34 (reflected by index), 96 bytes from x = tx0-16 as six 16-byte loads per row
     {
-        const int gx = tid & 31, strip = tid >> 5;           // 32 column groups x 8 strips of 4 rows
+        const uint8_t* __restrict__ src = level_ptr(g, v, level, frame);
+        const int spitch = level_pitch(g, v, level);
+        const int q = tid & 7, r0 = tid >> 3;
+        const int gx = tx0 - 16 + 16 * q;
+        const bool xok = gx >= 0 && gx + 16 <= spitch;
+        if (q < 6) {
+#pragma unroll
+            for (int ry = r0; ry < kBlurRows; ry += kBlurThreads / 8) {
+                int gy = ty0 + ry - 3;
+                gy = gy < 0 ? -gy : gy;
+                gy = gy >= L.h ? 2 * L.h - 2 - gy : gy;
+                gy = min(max(gy, 0), L.h - 1);   // rows far below a short level: never used by an output row
+                uint4 w = make_uint4(0u, 0u, 0u, 0u);
+                if (xok) w = __ldg(reinterpret_cast<const uint4*>(src + (size_t)gy * spitch + gx));
+                reinterpret_cast<uint4*>(s_in)[ry * 6 + q] = w;
+            }
+        }
+    }
+    __syncthreads();
+    constexpr int kRowBytes = kBlurInWords * 4;
+    if (tx0 == 0 || tx0 + kBlurTW + 3 > L.w - 1) {   // uniform: tiles touching the left / right image edge
+        uint8_t* s_b = reinterpret_cast<uint8_t*>(s_in);   // byte view: column c <-> x = tx0 - 16 + c
+        if (tx0 == 0) {   // x = -1,-2,-3  <-  x = 1,2,3
+            for (int i = tid; i < kBlurRows * 3; i += kBlurThreads) {
+                const int ry = i / 3, k = i - ry * 3 + 1;
+                s_b[ry * kRowBytes + 16 - k] = s_b[ry * kRowBytes + 16 + reflect101(k, L.w)];
+            }
+        }
+        if (tx0 + kBlurTW + 3 > L.w - 1) {   // x = w, w+1, w+2  <-  x = w-2, w-3, w-4
+            for (int i = tid; i < kBlurRows * 3; i += kBlurThreads) {
+                const int ry = i / 3, k = i - ry * 3;
+                const int c = L.w + k - tx0 + 16, cs = reflect101(L.w + k, L.w) - tx0 + 16;
+                if (c < kRowBytes && cs >= 0) s_b[ry * kRowBytes + c] = s_b[ry * kRowBytes + cs];
+            }
+        }
+        __syncthreads();
+    }
+
+    // H pass: (pair row, 4-pixel group) tasks
+    for (int i = tid; i < kBlurPairRows * (kBlurTW / 4); i += kBlurThreads) {
+        const int pr = i >> 4, gx = i & 15;
+        const uint32_t* w = &s_in[(2 * pr) * kBlurInWords + gx + 3];   // w[0]: x-4.., w[1]: the 4 output pixels, w[2]: x+4..
+        const uint32_t am = w[0], a0 = w[1], ap = w[2];
+        const uint32_t bm = w[kBlurInWords], b0 = w[kBlurInWords + 1], bp = w[kBlurInWords + 2];
+        uint4 o;
+        o.x = blur_h(am, a0, ap, 0) | (blur_h(bm, b0, bp, 0) << 16);
+        o.y = blur_h(am, a0, ap, 1) | (blur_h(bm, b0, bp, 1) << 16);
+        o.z = blur_h(am, a0, ap, 2) | (blur_h(bm, b0, bp, 2) << 16);
+        o.w = blur_h(am, a0, ap, 3) | (blur_h(bm, b0, bp, 3) << 16);
+        *reinterpret_cast<uint4*>(&s_v[pr * kBlurVPitch + 4 * gx]) = o;
+    }
+    __syncthreads();
+
+    // V pass: 16 column groups x 8 strips of 4 rows; strip s reads pair rows 2s .. 2s+4
+    {
+        const int gx = tid & 15, strip = tid >> 4;
         const int x = tx0 + 4 * gx;
         if (x < L.w) {
-            uint32_t hv[10][4];
+            uint4 p[5];
 #pragma unroll
-            for (int r = 0; r < 10; r++) {
-                const uint2 q = s_h[(strip * 4 + r) * (kBlurTW / 4 + 1) + gx];
-                hv[r][0] = q.x & 0xFFFFu; hv[r][1] = q.x >> 16; hv[r][2] = q.y & 0xFFFFu; hv[r][3] = q.y >> 16;
-            }
+            for (int m = 0; m < 5; m++) p[m] = *reinterpret_cast<const uint4*>(&s_v[(2 * strip + m) * kBlurVPitch + 4 * gx]);
+            uint8_t* dst = blur_ptr(g, v, level, frame) + (size_t)(ty0 + 4 * strip) * L.pitch + x;
+            // taps over rows r..r+6 as (lo, hi) weights of four row pairs: an even row starts on a pair, an odd row one
+            // halfword later
+            constexpr uint32_t E0 = 18u | (34u << 8), E1 = 48u | (56u << 8), E2 = 48u | (34u << 8), E3 = 18u;
+            constexpr uint32_t O0 = 18u << 8, O1 = 34u | (48u << 8), O2 = 56u | (48u << 8), O3 = 34u | (18u << 8);
 #pragma unroll
             for (int r = 0; r < 4; r++) {
-                const int y = ty0 + strip * 4 + r;
-                if (y < L.h) {
-                    uint32_t packed = 0;
+                if (ty0 + 4 * strip + r < L.h) {
+                    const int m = r >> 1;
+                    const uint32_t k0 = (r & 1) ? O0 : E0, k1 = (r & 1) ? O1 : E1, k2 = (r & 1) ? O2 : E2, k3 = (r & 1) ? O3 : E3;
+                    uint32_t acc[4];
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const uint32_t acc = 18u * (hv[r][k] + hv[r + 6][k]) + 34u * (hv[r + 1][k] + hv[r + 5][k]) +
-                                             48u * (hv[r + 2][k] + hv[r + 4][k]) + 56u * hv[r + 3][k];
-                        packed |= ((acc + 32768u) >> 16) << (8 * k);
+                    for (int c = 0; c < 4; c++) {
+                        const uint32_t q0 = c == 0 ? p[m].x : c == 1 ? p[m].y : c == 2 ? p[m].z : p[m].w;
+                        const uint32_t q1 = c == 0 ? p[m + 1].x : c == 1 ? p[m + 1].y : c == 2 ? p[m + 1].z : p[m + 1].w;
+                        const uint32_t q2 = c == 0 ? p[m + 2].x : c == 1 ? p[m + 2].y : c == 2 ? p[m + 2].z : p[m + 2].w;
+                        const uint32_t q3 = c == 0 ? p[m + 3].x : c == 1 ? p[m + 3].y : c == 2 ? p[m + 3].z : p[m + 3].w;
+                        acc[c] = __dp2a_lo(q0, k0, __dp2a_lo(q1, k1, __dp2a_lo(q2, k2, __dp2a_lo(q3, k3, 32768u))));
                     }
-                    *reinterpret_cast<uint32_t*>(dst + (size_t)y * L.pitch + x) = packed;   // tail lands in row padding
+                    // (acc >> 16) is the output byte: gather byte 2 of the four accumulators
+                    const uint32_t lo = __byte_perm(acc[0], acc[1], 0x0062), hi = __byte_perm(acc[2], acc[3], 0x0062);
+                    *reinterpret_cast<uint32_t*>(dst + (size_t)r * L.pitch) = __byte_perm(lo, hi, 0x5410);   // tail lands in row padding
                 }
             }
         }
     }
 }
 
-void launch_blur(const Geometry& g, const BatchView& v, cudaStream_t stream) {
-    TileMap tm;
+int build_blur_tiles(const Geometry& g, int4* out) {
     int total = 0;
-    for (int l = 0; l < g.nlevels; l++) {
-        tm.tile_base[l] = total;
-        tm.tiles_x[l] = (g.lv[l].w + kBlurTW - 1) / kBlurTW;
-        total += tm.tiles_x[l] * ((g.lv[l].h + kBlurTH - 1) / kBlurTH);
-    }
-    tm.tile_base[g.nlevels] = total;
-    blur_kernel<<<dim3(total, v.B), kBlurThreads, 0, stream>>>(g, v, tm);
+    for (int l = 0; l < g.nlevels; l++)
+        for (int ty = 0; ty < g.lv[l].h; ty += kBlurTH)
+            for (int tx = 0; tx < g.lv[l].w; tx += kBlurTW, total++)
+                if (out) out[total] = make_int4(l, tx, ty, 0);
+    return total;
+}
+
+void launch_blur(const Geometry& g, const BatchView& v, cudaStream_t stream) {
+    blur_kernel<<<dim3(g.blur_tiles_per_frame, v.B), kBlurThreads, 0, stream>>>(g, v, v.blur_tiles);
 }
 
 // ------------------------------------------------------------------------------------------------
