@@ -18,6 +18,11 @@ namespace coeb {
 // ------------------------------------------------------------------------------------------------
 // kResizeRows = destination rows per thread (rows dy, dy+8, ... of a 128 x 8*kResizeRows tile): 4 for batches, 1 when the
 // grid would otherwise be too small to fill the GPU (single-frame latency path).
+//
+// Fast path (scale factors up to 2, i.e. every ORB pyramid in practice): the two source pixels of an output pixel are
+// cut out of two aligned source words with one PRMT whose selector depends only on the column (computed once per
+// thread), and h = a0*S[sx] + a1*S[sx+1] is one IDP.2A with the table's packed (a0, a1) halfwords as they are. Output
+// pixels 0,1 and 2,3 of a thread each share one pair of source words per source row.
 template <int kResizeRows>
 __global__ void __launch_bounds__(256) resize_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v,
                                                      int level) {
@@ -31,16 +36,18 @@ __global__ void __launch_bounds__(256) resize_kernel(const __grid_constant__ Geo
     uint8_t* dst = v.pyr + D.img_base + (unsigned long long)frame * D.img_stride;
     const int2* __restrict__ xt = v.tabs + D.tab_base;
     const int2* __restrict__ yt = xt + D.w;
-    // the column entries (source offsets and weights) are the same for every row: fetch them once, then walk
-    // kResizeRows destination rows
-    int sx[4], sx1[4], a0[4], a1[4];
+    // column entries (source offset, packed weights) are the same for every row: fetch them once
+    uint32_t wgt[4], sel[4];
+    int wb[2];
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int2 xe = __ldg(&xt[min(dx0 + i, D.w - 1)]);   // the tail of the last word lands in row padding
-        sx[i] = xe.x;
-        sx1[i] = min(xe.x + 1, S.w - 1);
-        a0[i] = xe.y & 0xFFFF;
-        a1[i] = xe.y >> 16;
+    for (int u = 0; u < 2; u++) {
+        const int2 e0 = __ldg(&xt[min(dx0 + 2 * u, D.w - 1)]), e1 = __ldg(&xt[min(dx0 + 2 * u + 1, D.w - 1)]);   // tail -> row padding
+        wb[u] = min(e0.x & ~3, spitch - 8);          // two aligned words from here hold both pixels' source pairs
+        const int o0 = e0.x - wb[u], o1 = e1.x - wb[u];
+        sel[2 * u] = (uint32_t)(o0 | (min(o0 + 1, 7) << 4));       // beyond byte 7 only when sx is the last column: weight 0
+        sel[2 * u + 1] = (uint32_t)(o1 | (min(o1 + 1, 7) << 4));
+        wgt[2 * u] = (uint32_t)e0.y;
+        wgt[2 * u + 1] = (uint32_t)e1.y;
     }
 #pragma unroll
     for (int j = 0; j < kResizeRows; j++) {
@@ -48,27 +55,65 @@ __global__ void __launch_bounds__(256) resize_kernel(const __grid_constant__ Geo
         if (dy >= D.h) break;
         const int2 ye = __ldg(&yt[dy]);
         const int sy0 = min(max(ye.x, 0), S.h - 1), sy1 = min(max(ye.x + 1, 0), S.h - 1);
-        const int b0 = ye.y & 0xFFFF, b1 = ye.y >> 16;
+        const uint32_t b0 = ye.y & 0xFFFF, b1 = (uint32_t)ye.y >> 16;
         const uint8_t* r0 = src + (size_t)sy0 * spitch;
         const uint8_t* r1 = src + (size_t)sy1 * spitch;
-        uint32_t packed = 0;
+        uint32_t o[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int h0 = __ldg(r0 + sx[i]) * a0[i] + __ldg(r0 + sx1[i]) * a1[i];
-            const int h1 = __ldg(r1 + sx[i]) * a0[i] + __ldg(r1 + sx1[i]) * a1[i];
-            int o = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
-            o = min(max(o, 0), 255);
-            packed |= (uint32_t)o << (8 * i);
+        for (int u = 0; u < 2; u++) {
+            const uint32_t t0 = __ldg(reinterpret_cast<const uint32_t*>(r0 + wb[u])), t1 = __ldg(reinterpret_cast<const uint32_t*>(r0 + wb[u] + 4));
+            const uint32_t q0 = __ldg(reinterpret_cast<const uint32_t*>(r1 + wb[u])), q1 = __ldg(reinterpret_cast<const uint32_t*>(r1 + wb[u] + 4));
+#pragma unroll
+            for (int i = 2 * u; i < 2 * u + 2; i++) {
+                const uint32_t h0 = __dp2a_lo(wgt[i], __byte_perm(t0, t1, sel[i]), 0u);
+                const uint32_t h1 = __dp2a_lo(wgt[i], __byte_perm(q0, q1, sel[i]), 0u);
+                o[i] = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2u) >> 2;   // <= 255 by construction
+            }
         }
-        *reinterpret_cast<uint32_t*>(dst + (size_t)dy * D.pitch + dx0) = packed;  // pitch is a multiple of 64: padding absorbs the tail
+        *reinterpret_cast<uint32_t*>(dst + (size_t)dy * D.pitch + dx0) = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);  // padding absorbs the tail
     }
+}
+
+// Any scale factor: four byte loads per output pixel.
+__global__ void __launch_bounds__(256) resize_generic_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v,
+                                                             int level) {
+    const LevelGeom& D = g.lv[level];
+    const LevelGeom& S = g.lv[level - 1];
+    const int frame = blockIdx.z;
+    const int dx0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int dy = blockIdx.y * 8 + threadIdx.y;
+    if (dx0 >= D.w || dy >= D.h) return;
+    const uint8_t* __restrict__ src = level_ptr(g, v, level - 1, frame);
+    const int spitch = level_pitch(g, v, level - 1);
+    uint8_t* dst = v.pyr + D.img_base + (unsigned long long)frame * D.img_stride;
+    const int2* __restrict__ xt = v.tabs + D.tab_base;
+    const int2 ye = __ldg(&xt[D.w + dy]);
+    const int sy0 = min(max(ye.x, 0), S.h - 1), sy1 = min(max(ye.x + 1, 0), S.h - 1);
+    const int b0 = ye.y & 0xFFFF, b1 = ye.y >> 16;
+    const uint8_t* r0 = src + (size_t)sy0 * spitch;
+    const uint8_t* r1 = src + (size_t)sy1 * spitch;
+    uint32_t packed = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int2 xe = __ldg(&xt[min(dx0 + i, D.w - 1)]);
+        const int sx = xe.x, sx1 = min(xe.x + 1, S.w - 1), a0 = xe.y & 0xFFFF, a1 = xe.y >> 16;
+        const int h0 = __ldg(r0 + sx) * a0 + __ldg(r0 + sx1) * a1;
+        const int h1 = __ldg(r1 + sx) * a0 + __ldg(r1 + sx1) * a1;
+        const int o = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+        packed |= (uint32_t)min(max(o, 0), 255) << (8 * i);
+    }
+    *reinterpret_cast<uint32_t*>(dst + (size_t)dy * D.pitch + dx0) = packed;
 }
 
 void launch_pyramid(const Geometry& g, const BatchView& v, cudaStream_t stream) {
     for (int l = 1; l < g.nlevels; l++) {
         dim3 block(32, 8);
         const int tiles_x = (g.lv[l].w + 127) / 128;
-        if ((long long)tiles_x * ((g.lv[l].h + 31) / 32) * v.B >= 2 * 148) {
+        // consecutive output columns are at most 2 source columns apart up to a 2:1 reduction: the paired-word path applies
+        const bool paired = 2LL * g.lv[l].w >= g.lv[l - 1].w && g.lv[l - 1].w >= 8;
+        if (!paired) {
+            resize_generic_kernel<<<dim3(tiles_x, (g.lv[l].h + 7) / 8, v.B), block, 0, stream>>>(g, v, l);
+        } else if ((long long)tiles_x * ((g.lv[l].h + 31) / 32) * v.B >= 2 * 148) {
             resize_kernel<4><<<dim3(tiles_x, (g.lv[l].h + 31) / 32, v.B), block, 0, stream>>>(g, v, l);
         } else {
             resize_kernel<1><<<dim3(tiles_x, (g.lv[l].h + 7) / 8, v.B), block, 0, stream>>>(g, v, l);

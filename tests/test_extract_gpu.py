@@ -162,7 +162,7 @@ def test_repeat_call_is_deterministic(gpu):
         assert k1.tobytes() == k2.tobytes() and d1.tobytes() == d2.tobytes()
 
 
-@pytest.mark.parametrize("nlevels,sf,nf", [(4, 1.5, 800), (6, 1.2, 600), (8, 1.1, 1000), (1, 1.2, 300)])
+@pytest.mark.parametrize("nlevels,sf,nf", [(4, 1.5, 800), (6, 1.2, 600), (8, 1.1, 1000), (1, 1.2, 300), (3, 2.5, 300), (3, 2.0, 500)])
 def test_other_pyramid_parameters(gpu, nlevels, sf, nf):
     gray = synth.make_frame(33)
     g = gpu.Extractor(nfeatures=nf, scale_factor=sf, nlevels=nlevels)
