@@ -317,7 +317,8 @@ __global__ void __launch_bounds__(kFtThreads, COEB_FT_MINB) fast_kernel(const __
 // scan the per-cell counters written by fast_kernel; an empty cell is processed alone, exactly like one cv::FAST call
 // on its ROI: scalar sliding-window A, NMS inside the cell, local maxima above minTh appended to the level's list.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kMaxRoi = 72;   // ROI side bound: wCell + 6 <= 66 (checked on the host)
+constexpr int kMaxRoi = 72;   // ROI side bound: wCell + 6 <= 72 (checked on the host)
+constexpr int kRoiPitch = kMaxRoi + 4;   // staged with aligned word loads: up to 3 bytes of lead-in per row
 
 // Lists the FAST cells that exist (src/ORBextractor.cc:816-826) and produced nothing at iniTh. One thread per cell.
 __global__ void __launch_bounds__(256) fast_empty_cells_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v) {
@@ -348,7 +349,7 @@ __global__ void __launch_bounds__(256) fast_empty_cells_kernel(const __grid_cons
 }
 
 __global__ void __launch_bounds__(128) fast_fallback_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v) {
-    __shared__ uint8_t s_img[kMaxRoi * kMaxRoi];
+    __shared__ __align__(4) uint8_t s_img[kMaxRoi * kRoiPitch];
     __shared__ uint8_t s_A[(kMaxRoi - 4) * (kMaxRoi - 4)];
     __shared__ uint32_t s_list[(kMaxRoi - 6) * (kMaxRoi - 6) / 2];
     __shared__ int s_n, s_base;
@@ -370,19 +371,21 @@ __global__ void __launch_bounds__(128) fast_fallback_kernel(const __grid_constan
         const int aw = dw + 2;                       // s_A row pitch (1 px zero border each side)
         const int thMin = v.dyn[frame].area_flag ? 10 : 7;
         const int pitch = level_pitch(g, v, level);
-        const uint8_t* __restrict__ img = level_ptr(g, v, level, frame) + (size_t)iniY * pitch + iniX;
+        const int ax = iniX & 3, nw = (ax + rw + 3) >> 2;   // aligned words per ROI row (the ROI ends 16 px before the row does)
+        const uint8_t* __restrict__ img = level_ptr(g, v, level, frame) + (size_t)iniY * pitch + (iniX - ax);
         __syncthreads();   // previous cell's shared data fully consumed
-        for (int y = warp; y < rh; y += 4)
-            for (int x = lane; x < rw; x += 32) s_img[y * kMaxRoi + x] = __ldg(img + (size_t)y * pitch + x);
+        for (int i = tid; i < rh * nw; i += 128) {
+            const int y = i / nw, wi = i - y * nw;
+            reinterpret_cast<uint32_t*>(s_img)[y * (kRoiPitch / 4) + wi] = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)y * pitch) + wi);
+        }
         for (int i = tid; i < aw * (dh + 2); i += 128) s_A[i] = 0;
         if (tid == 0) s_n = 0;
         __syncthreads();
-        const int off[16] = {3 * kMaxRoi,      3 * kMaxRoi + 1,  2 * kMaxRoi + 2,  kMaxRoi + 3,      3,                -kMaxRoi + 3,
-                             -2 * kMaxRoi + 2, -3 * kMaxRoi + 1, -3 * kMaxRoi,     -3 * kMaxRoi - 1, -2 * kMaxRoi - 2, -kMaxRoi - 3,
-                             -3,               kMaxRoi - 3,      2 * kMaxRoi - 2,  3 * kMaxRoi - 1};
+        constexpr int P = kRoiPitch;
+        const int off[16] = {3 * P, 3 * P + 1, 2 * P + 2, P + 3, 3, -P + 3, -2 * P + 2, -3 * P + 1, -3 * P, -3 * P - 1, -2 * P - 2, -P - 3, -3, P - 3, 2 * P - 2, 3 * P - 1};
         for (int y = warp; y < dh; y += 4)
             for (int x = lane; x < dw; x += 32) {
-                const uint8_t* p = &s_img[(y + 3) * kMaxRoi + (x + 3)];
+                const uint8_t* p = &s_img[(y + 3) * kRoiPitch + ax + (x + 3)];
                 const int cc = p[0];
                 {   // compass bound (see fast_kernel 1a): in flat cells almost every pixel stops here
                     const int e0 = cc - (int)p[off[0]], e4 = cc - (int)p[off[4]], e8 = cc - (int)p[off[8]], e12 = cc - (int)p[off[12]];

@@ -3,7 +3,8 @@
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
-#define ITER 512
+#include <cuda_fp16.h>
+#define ITER 4096
 template <int OP>
 __global__ void __launch_bounds__(256) k(uint32_t* out, uint32_t seed) {
     uint32_t a[8];
@@ -29,6 +30,13 @@ __global__ void __launch_bounds__(256) k(uint32_t* out, uint32_t seed) {
             if (OP == 12) { a[i] = a[i] * b + c; a[i] = __vimin3_s16x2(a[i], b, c); }   // IMAD + VIMNMX3 pair (dual pipe?)
             if (OP == 13) { a[i] = __dp4a(a[i], b, c); a[i] = __vimin3_s16x2(a[i], b, c); }   // IDP + VIMNMX3
             if (OP == 14) { a[i] = __dp4a(a[i], b, c); a[i] = a[i] * b + c; }      // IDP + IMAD
+            if (OP == 15) { __half2 h = __hmin2(*reinterpret_cast<__half2*>(&a[i]), *reinterpret_cast<__half2*>(&b)); a[i] = *reinterpret_cast<uint32_t*>(&h); }   // HMNMX2
+            if (OP == 16) { __half2 h = __hmin2(*reinterpret_cast<__half2*>(&a[i]), *reinterpret_cast<__half2*>(&b)); a[i] = __vimin3_s16x2(*reinterpret_cast<uint32_t*>(&h), b, c); }
+            if (OP == 17) a[i] = __float_as_uint(fminf(__uint_as_float(a[i]), __uint_as_float(b)));   // FMNMX
+            if (OP == 18) a[i] = __umulhi(a[i], b) + c;                            // IMAD.HI
+            if (OP == 19) { __half2 h = __hfma2(*reinterpret_cast<__half2*>(&a[i]), *reinterpret_cast<__half2*>(&b), *reinterpret_cast<__half2*>(&c)); a[i] = *reinterpret_cast<uint32_t*>(&h); }   // HFMA2
+            if (OP == 20) { __half2 h = __hfma2(*reinterpret_cast<__half2*>(&a[i]), *reinterpret_cast<__half2*>(&b), *reinterpret_cast<__half2*>(&c)); a[i] = __vimin3_s16x2(*reinterpret_cast<uint32_t*>(&h), b, c); }
+            if (OP == 21) { a[i] = __viaddmin_s16x2(a[i], b, c); }                 // VIADDMNMX.S16x2
         }
     }
     uint32_t s = 0;
@@ -53,5 +61,6 @@ int main() {
     run<0>("IMAD", 1); run<1>("VIMNMX3.S16x2", 1); run<2>("PRMT", 1); run<3>("SHF", 1); run<4>("IDP.4A", 1); run<5>("IDP.2A", 1);
     run<6>("LOP3", 1); run<7>("IADD3", 1); run<8>("VIMNMX.S16x2", 1); run<9>("VIMNMX.U32", 1); run<10>("VABSDIFF4", 1); run<11>("POPC+IADD", 2);
     run<12>("IMAD+VIMNMX3", 2); run<13>("IDP4A+VIMNMX3", 2); run<14>("IDP4A+IMAD", 2);
+    run<15>("HMNMX2", 1); run<16>("HMNMX2+VIMNMX3", 2); run<17>("FMNMX", 1); run<18>("IMAD.HI+IADD", 2); run<19>("HFMA2", 1); run<20>("HFMA2+VIMNMX3", 2); run<21>("VIADDMNMX.S16x2", 1);
     return 0;
 }
