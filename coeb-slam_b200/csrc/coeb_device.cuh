@@ -91,6 +91,7 @@ struct BatchView {
     const int2* tabs;                  // resize tables
     const int4* fast_tiles;            // FAST tile table {level, tx0, ty0, 0}, one entry per tile of one frame
     const int4* blur_tiles;            // blur tile table, same layout
+    const uint32_t* ic_mask;           // [4 alignments][16 |v|][9 words]: 0xFF per patch byte inside the circular IC_Angle patch
     uint32_t* cand;                    // [B][cand_per_frame]
     int* cand_count;                   // [B][nlevels]
     LevelKey* keys;                    // [B][keys_per_frame]
@@ -194,6 +195,8 @@ void launch_fast(const Geometry& g, const BatchView& v, cudaStream_t stream);
 // Host-side FAST tile table of one frame (level, tx0, ty0 per 64x30 tile), uploaded once per geometry.
 int build_fast_tiles(const Geometry& g, int4* out_or_null);
 int build_blur_tiles(const Geometry& g, int4* out_or_null);
+constexpr int kIcMaskWords = 4 * 16 * 9;
+void build_ic_masks(const Geometry& g, uint32_t* out);
 void launch_select(const Geometry& g, const BatchView& v, cudaStream_t stream);
 void launch_describe(const Geometry& g, const BatchView& v, cudaStream_t stream);
 

@@ -1,8 +1,13 @@
-// describe.cu -- steered rBRIEF descriptors (E11) and output assembly (E12).
+// describe.cu -- IC_Angle orientation (E8), steered rBRIEF descriptors (E11) and output assembly (E12).
 //
-// Reference: computeOrbDescriptor / computeDescriptors (src/ORBextractor.cc:109-156, 1078-1085) and the
-// assembly loop of ORBextractor::operator() (:1291-1337). One CTA per (level, frame); one warp per
-// keypoint, lane i producing descriptor byte i from pattern pairs 8i..8i+7 on the blurred level.
+// Reference: IC_Angle / computeOrientation (src/ORBextractor.cc:80-107, 902-903), computeOrbDescriptor /
+// computeDescriptors (:109-156, 1078-1085) and the assembly loop of ORBextractor::operator() (:1291-1337).
+// One CTA per (level, frame, 64-keypoint chunk); one warp per keypoint.
+//   orientation: lane v+15 owns patch row v. The row's 31 pixels are 9 aligned words funnel-shifted to start at the
+//                patch's first column; m10 and the row sum are byte dot products (IDP.4A) with per-lane constant
+//                weight words (u inside the circular patch, 0 outside), m01 = v * row sum; a warp reduction and
+//                cv::fastAtan2 finish it.
+//   descriptor : lane i produces descriptor byte i from pattern pairs 8i..8i+7 on the blurred level.
 #include "coeb_device.cuh"
 
 namespace coeb {
@@ -11,15 +16,49 @@ __constant__ signed char c_pattern[1024] = {
 #include "../../include/coeb_orb_pattern.inc"
 };
 
+// cv::fastAtan2 (degrees), scalar fp32 path; explicit rn intrinsics keep the compiler from fusing
+// multiply-adds (the CPU build is -ffp-contract=off).
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+    const float scale = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = __fmul_rn(0.9997878412794807f, scale);
+    const float p3 = __fmul_rn(-0.3258083974640975f, scale);
+    const float p5 = __fmul_rn(0.1555786518463281f, scale);
+    const float p7 = __fmul_rn(-0.04432655554792128f, scale);
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float eps = (float)2.2204460492503131e-16;
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+// cvRound for |x| < 2^22: adding 1.5 * 2^23 rounds to the nearest integer, ties to even, and leaves that integer in the low
+// mantissa bits; no F2I (a quarter-rate conversion) on the descriptor's 512 coordinates per keypoint.
+__device__ __forceinline__ int round_even(float x) { return __float_as_int(__fadd_rn(x, 12582912.f)) - 0x4B400000; }
+
+#ifndef COEB_DESC_MINB
+#define COEB_DESC_MINB 3
+#endif
 constexpr int kDescChunk = 64;   // keypoints per CTA: several CTAs per level keep a single frame's latency low
 
-__global__ void __launch_bounds__(256) describe_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v) {
-    __shared__ signed char s_pat[1024];   // transposed: [4*bit + component][lane], conflict-free per-lane reads
+__global__ void __launch_bounds__(256, COEB_DESC_MINB) describe_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v) {
+    __shared__ float s_pat[1024];         // pattern as floats, transposed: [4*bit + component][lane], conflict-free per-lane reads
     __shared__ float2 s_cs[256];          // (cos, sin) of the keypoints of the current chunk
+    __shared__ float s_angle[256];
+    __shared__ int s_ioff[279], s_ipk[279];
+    __shared__ uint32_t s_imask[kIcMaskWords];
     const int level = blockIdx.x, frame = blockIdx.y;
     const LevelGeom& L = g.lv[level];
     const int tid = threadIdx.x;
-    for (int i = tid; i < 1024; i += 256) s_pat[(i & 31) * 32 + (i >> 5)] = c_pattern[i];   // byte `i>>5` uses ints [32*(i>>5), +32)
 
     // row offset of this level in the frame's output = keypoints of the lower levels (:1307-1324)
     const int* kc = v.key_count + frame * g.nlevels;
@@ -38,26 +77,78 @@ __global__ void __launch_bounds__(256) describe_kernel(const __grid_constant__ G
         else if (total > g.out_cap) { v.status[frame] = COEB_ERR_CAPACITY; }
         v.out_count[frame] = cnt;
     }
-    __syncthreads();
-    if (chunk0 >= n || status != COEB_OK || total > g.out_cap) return;
+    if (chunk0 >= n || status != COEB_OK || total > g.out_cap) return;   // uniform; most chunks of the coarse levels are empty
+    for (int i = tid; i < 1024; i += 256) s_pat[(i & 31) * 32 + (i >> 5)] = (float)c_pattern[i];   // byte `i>>5` uses ints [32*(i>>5), +32)
 
     const uint8_t* __restrict__ img = blur_ptr(g, v, level, frame);
     const int pitch = L.pitch;
-    const LevelKey* keys = v.keys + (size_t)frame * g.keys_per_frame + L.key_base;
+    const uint8_t* __restrict__ raw = level_ptr(g, v, level, frame);   // IC_Angle runs on the unblurred level
+    const int rpitch = level_pitch(g, v, level);
+    LevelKey* keys = v.keys + (size_t)frame * g.keys_per_frame + L.key_base;
     coeb_keypoint* okp = v.out_kps + (size_t)frame * g.out_cap + offset;
     uint8_t* odesc = v.out_desc + ((size_t)frame * g.out_cap + offset) * 32;
     const int lane = tid & 31, wid = tid >> 5;
     const float factorPI = (float)(3.14159265358979323846 / 180.0);  // (float)(CV_PI/180.f), :109
     const int nend = min(n, chunk0 + kDescChunk);
+    // IC_Angle tables: the patch rows are fetched as aligned words, (row r, word q) -> task r*9 + q; a warp takes the 279
+    // tasks of a keypoint in 9 coalesced steps. Per task: byte offset from the patch's aligned origin and
+    // v | (4q - 15 + 32) << 8 | mask index << 16.
+    for (int i = tid; i < 279; i += 256) {
+        const int r = i / 9, q = i - 9 * r, vv = r - kHalfPatch;
+        s_ioff[i] = r * rpitch + 4 * q;
+        s_ipk[i] = (vv & 0xFF) | ((4 * q - kHalfPatch + 32) << 8) | ((abs(vv) * 9 + q) << 16);   // column weights are biased by +32
+    }
+    for (int i = tid; i < kIcMaskWords; i += 256) s_imask[i] = __ldg(v.ic_mask + i);
     for (int base = chunk0; base < nend; base += 256) {
+        __syncthreads();
+        const int m = min(256, nend - base);
+        for (int j = wid; j < m; j += 8) {   // IC_Angle: m10 = sum u*I, m01 = sum v*I over the circular patch
+            const LevelKey k = keys[base + j];
+            const int x0 = (int)k.x - kHalfPatch, y0 = (int)k.y - kHalfPatch;   // coordinates are integers here
+            const int al = x0 & 3;
+            const uint8_t* org = raw + (size_t)y0 * rpitch + (x0 - al);
+            uint32_t w[9];
+            int pk[9];
+#pragma unroll
+            for (int t = 0; t < 9; t++) {
+                const int i = lane + 32 * t;
+                const bool on = t < 8 || i < 279;
+                pk[t] = on ? s_ipk[i] : 0;
+                w[t] = on ? __ldg(reinterpret_cast<const uint32_t*>(org + s_ioff[on ? i : 0])) : 0u;
+            }
+            int m10 = 0, m01 = 0;
+            {
+                uint32_t m10b = 0u, sum = 0u;   // sum of (u + 32) * I and of I over this lane's words
+#pragma unroll
+                for (int t = 0; t < 9; t++) {
+                    const uint32_t mk = s_imask[al * 144 + (pk[t] >> 16)];
+                    const uint32_t u0 = ((uint32_t)(pk[t] >> 8) & 0xFFu) - (uint32_t)al;      // biased column of the word's first byte: 14..49
+                    const uint32_t u4 = u0 * 0x01010101u + 0x03020100u;                       // u0 .. u0+3, one per byte, no carries
+                    m10b = __dp4a(w[t], u4 & mk, m10b);
+                    const uint32_t rs = __dp4a(w[t], mk & 0x01010101u, 0u);
+                    sum += rs;
+                    m01 += (int)(signed char)pk[t] * (int)rs;
+                }
+                m10 = (int)m10b - 32 * (int)sum;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+                m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+            }
+            if (lane == 0) {
+                const float ang = fast_atan2_deg((float)m01, (float)m10);
+                s_angle[j] = ang;
+                keys[base + j].angle = ang;
+            }
+        }
         __syncthreads();
         if (base + tid < nend) {
             // (float)cos(angle), (float)sin(angle) with the float argument promoted to double (:114-115); once per keypoint
-            const float angle = __fmul_rn(keys[base + tid].angle, factorPI);
+            const float angle = __fmul_rn(s_angle[tid], factorPI);
             s_cs[tid] = make_float2((float)cos((double)angle), (float)sin((double)angle));
         }
         __syncthreads();
-        const int m = min(256, nend - base);
         for (int j = wid; j < m; j += 8) {
             const int i = base + j;
             const LevelKey k = keys[i];
@@ -67,13 +158,13 @@ __global__ void __launch_bounds__(256) describe_kernel(const __grid_constant__ G
             int val = 0;
 #pragma unroll
             for (int bit = 0; bit < 8; bit++) {
-                const float x0 = (float)s_pat[(4 * bit) * 32 + lane], y0 = (float)s_pat[(4 * bit + 1) * 32 + lane];
-                const float x1 = (float)s_pat[(4 * bit + 2) * 32 + lane], y1 = (float)s_pat[(4 * bit + 3) * 32 + lane];
+                const float x0 = s_pat[(4 * bit) * 32 + lane], y0 = s_pat[(4 * bit + 1) * 32 + lane];
+                const float x1 = s_pat[(4 * bit + 2) * 32 + lane], y1 = s_pat[(4 * bit + 3) * 32 + lane];
                 // cvRound(x*b + y*a) rows, cvRound(x*a - y*b) cols: separate roundings, half-to-even (:121-122)
-                const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
-                const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
-                const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
-                const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+                const int r0 = round_even(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+                const int c0 = round_even(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+                const int r1 = round_even(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+                const int c1 = round_even(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
                 const int t0 = __ldg(center + (ptrdiff_t)r0 * pitch + c0);
                 const int t1 = __ldg(center + (ptrdiff_t)r1 * pitch + c1);
                 val |= (t0 < t1) << bit;
@@ -84,7 +175,7 @@ __global__ void __launch_bounds__(256) describe_kernel(const __grid_constant__ G
                 o.x = level != 0 ? __fmul_rn(k.x, L.scale) : k.x;   // keypoint->pt *= scale (:1327-1334)
                 o.y = level != 0 ? __fmul_rn(k.y, L.scale) : k.y;
                 o.size = (float)L.scaled_patch;
-                o.angle = k.angle;
+                o.angle = s_angle[j];
                 o.response = k.response;
                 o.octave = level;
                 o.class_id = -1;
@@ -92,6 +183,21 @@ __global__ void __launch_bounds__(256) describe_kernel(const __grid_constant__ G
             }
         }
     }
+}
+
+// 0xFF for every byte of aligned word q of a patch row |v| that lies inside the circular patch, for the four alignments
+// of the patch's first column (byte j of word q is column u = 4q + j - al - 15).
+void build_ic_masks(const Geometry& g, uint32_t* out) {
+    for (int al = 0; al < 4; al++)
+        for (int av = 0; av < 16; av++)
+            for (int q = 0; q < 9; q++) {
+                uint32_t m = 0;
+                for (int j = 0; j < 4; j++) {
+                    const int u = 4 * q + j - al - kHalfPatch;
+                    if (std::abs(u) <= g.umax[av]) m |= 0xFFu << (8 * j);
+                }
+                out[(al * 16 + av) * 9 + q] = m;
+            }
 }
 
 void launch_describe(const Geometry& g, const BatchView& v, cudaStream_t stream) {

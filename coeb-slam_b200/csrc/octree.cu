@@ -1,8 +1,8 @@
-// octree.cu -- DistributeOctTree (E6), border/scale fix-up (E7), IC_Angle (E8) and the post-octree
-// cull (E9), one CTA per (level, frame).
+// octree.cu -- DistributeOctTree (E6), border/scale fix-up (E7) and the post-octree cull (E9), one CTA per
+// (level, frame). IC_Angle (E8) lives in describe.cu.
 //
 // Reference: ExtractorNode::DivideNode + ORBextractor::DistributeOctTree (src/ORBextractor.cc:489-769),
-// IC_Angle (:80-107), CheckMovingKeyPoints_finall (:1371-1408).
+// CheckMovingKeyPoints_finall (:1371-1408).
 //
 // The reference grows a std::list of nodes by repeatedly splitting every multi-key node ("full
 // pass"), and, once one more pass could overshoot N, by splitting nodes in descending size order
@@ -30,31 +30,6 @@ struct QNode {
     unsigned short x0, x1, y0, y1;
     int count;
 };
-
-// cv::fastAtan2 (degrees), scalar fp32 path; explicit rn intrinsics keep the compiler from fusing
-// multiply-adds (the CPU build is -ffp-contract=off).
-__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
-    const float scale = (float)(180.0 / 3.14159265358979323846);
-    const float p1 = __fmul_rn(0.9997878412794807f, scale);
-    const float p3 = __fmul_rn(-0.3258083974640975f, scale);
-    const float p5 = __fmul_rn(0.1555786518463281f, scale);
-    const float p7 = __fmul_rn(-0.04432655554792128f, scale);
-    const float ax = fabsf(x), ay = fabsf(y);
-    const float eps = (float)2.2204460492503131e-16;
-    float a, c, c2;
-    if (ax >= ay) {
-        c = __fdiv_rn(ay, __fadd_rn(ax, eps));
-        c2 = __fmul_rn(c, c);
-        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
-    } else {
-        c = __fdiv_rn(ax, __fadd_rn(ay, eps));
-        c2 = __fmul_rn(c, c);
-        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
-    }
-    if (x < 0) a = __fsub_rn(180.f, a);
-    if (y < 0) a = __fsub_rn(360.f, a);
-    return a;
-}
 
 // Candidate order of the reference's vToDistributeKeys: cells row-major, raster inside a cell
 // (src/ORBextractor.cc:811-848). A cell detects x in [j*wCell+3, (j+1)*wCell+3) (minBorder-relative),
@@ -363,48 +338,18 @@ __global__ void __launch_bounds__(kSelThreads, 3) select_kernel(const __grid_con
     }
     if (tid == 0) *key_count = nOut;
 
-    const uint8_t* __restrict__ img = level_ptr(g, v, level, frame);
-    const int pitch = level_pitch(g, v, level);
-    const int lane = tid & 31, wid = tid >> 5, nwarps = T >> 5;
-    for (int i = wid; i < nList; i += nwarps) {
-        const unsigned long long best = s_best[i];
-        const unsigned long long ord = kOrdMask - (best & kOrdMask);
-        const int x = (int)(ord & 0xFFF) + kMinBorder, y = (int)((ord >> 12) & 0xFFF) + kMinBorder;
+    // orientation (:902-903) is computed by describe_kernel, which has the keypoint-parallel shape for it
+    for (int i = tid; i < nList; i += T) {
         const bool keep = (i + 1 < nList ? s_scanA[i + 1] : nOut) != s_scanA[i];
         if (!keep) continue;
-        // IC_Angle: lanes span u = -15..15 of each patch row
-        int m10 = 0, m01 = 0;
-        const int u = lane - kHalfPatch;
-        if (lane < 31) {
-            const uint8_t* c = img + (size_t)y * pitch + x + u;
-            const int au = u < 0 ? -u : u;
-            // all 31 row loads are issued before any is consumed (they are independent; a rolled loop would
-            // serialise 31 L2 round trips per keypoint)
-            int val[2 * kHalfPatch + 1];
-#pragma unroll
-            for (int vv = -kHalfPatch; vv <= kHalfPatch; vv++)
-                val[vv + kHalfPatch] = (au <= g.umax[vv < 0 ? -vv : vv]) ? (int)__ldg(c + (ptrdiff_t)vv * pitch) : 0;
-            int colsum = 0;
-#pragma unroll
-            for (int vv = -kHalfPatch; vv <= kHalfPatch; vv++) {
-                colsum += val[vv + kHalfPatch];
-                m01 += vv * val[vv + kHalfPatch];
-            }
-            m10 = u * colsum;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            m10 += __shfl_xor_sync(0xffffffffu, m10, o);
-            m01 += __shfl_xor_sync(0xffffffffu, m01, o);
-        }
-        if (lane == 0) {
-            LevelKey k;
-            k.x = (float)x;
-            k.y = (float)y;
-            k.response = (float)(int)(best >> 48);
-            k.angle = fast_atan2_deg((float)m01, (float)m10);
-            out[s_scanA[i]] = k;
-        }
+        const unsigned long long best = s_best[i];
+        const unsigned long long ord = kOrdMask - (best & kOrdMask);
+        LevelKey k;
+        k.x = (float)((int)(ord & 0xFFF) + kMinBorder);
+        k.y = (float)((int)((ord >> 12) & 0xFFF) + kMinBorder);
+        k.response = (float)(int)(best >> 48);
+        k.angle = 0.f;
+        out[s_scanA[i]] = k;
     }
 }
 

@@ -11,4 +11,4 @@ nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=fals
 objs=""
 for o in build/*.o; do if [ "$(basename $o .o)" = "$base" ]; then objs="$objs build/variants/$name.$base.o"; else objs="$objs $o"; fi; done
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o build/variants/$name.so $objs -cudart static
-grep -A2 "${3:-fast_kernel}" build/variants/$name.ptxas.log | grep -E "Used|spill" | tr '\n' ' '; echo
+grep -A2 "${KERNEL:-fast_kernel}" build/variants/$name.ptxas.log | grep -E "Used|spill" | tr '\n' ' '; echo
