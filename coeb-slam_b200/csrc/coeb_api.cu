@@ -89,9 +89,10 @@ struct coeb_extractor {
     struct Lane { cudaStream_t main; cudaStream_t aux; cudaEvent_t fork, join; };
     std::vector<Lane> lanes;
     // CUDA graphs of the kernel sequence for small non-pipelined host calls (single-frame latency path)
-    struct GraphEntry { BatchView view; int w, h, cap; cudaGraphExec_t exec; };
+    struct GraphEntry { BatchView view; int w, h, cap, chunk; cudaGraphExec_t exec; };
     std::vector<GraphEntry> graphs;
     int graph_warm = 0;
+    int last_passes = 1;   // sub-batches the last batch call was split into (launch accounting)
     // optional per-stage CUDA events (benchmark accounting)
     bool profiling = false;
     cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -101,6 +102,7 @@ namespace {
 
 constexpr int kPipeStreams = 3;
 constexpr int kPipeChunk = 32;
+constexpr int kDevChunk = 128; // sub-batch of the device-resident batch call: batches of 2 * kDevChunk and more are split (0 = never)
 constexpr int kGraphMaxBatch = 8;
 
 // ORBextractor::ORBextractor tables (src/ORBextractor.cc:418-477)
@@ -388,6 +390,16 @@ BatchView sub_view(const Geometry& g, const BatchView& v, int f0, int n, size_t 
     return s;
 }
 
+int ensure_pipe_streams(coeb_extractor* ex) {
+    if (ex->pipe_stream[0]) return COEB_OK;
+    for (int i = 0; i < kPipeStreams; i++) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&ex->pipe_stream[i], cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&ex->pipe_done[i], cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventCreateWithFlags(&ex->pipe_ready, cudaEventDisableTiming));
+    return COEB_OK;
+}
+
 int validate_common(coeb_extractor* ex, int B, const uint8_t* gray, int w, int h, int stride, int cap) {
     if (!ex) return fail(COEB_ERR_INVALID_ARG, "null extractor");
     if (B < 1) return fail(COEB_ERR_INVALID_ARG, "batch size %d", B);
@@ -505,7 +517,7 @@ int coeb_extractor_device_stream(coeb_extractor* ex, int* device, void** stream)
 int coeb_extractor_launches_per_call(const coeb_extractor* ex) {
     if (!ex) return 0;
     // classify + (nlevels-1) resizes + blur + FAST + empty-cell list + FAST fallback + select + describe (the two counter memsets are not kernels of ours)
-    return 1 + (ex->params.nlevels - 1) + 1 + 3 + 1 + 1;
+    return (1 + (ex->params.nlevels - 1) + 1 + 3 + 1 + 1) * ex->last_passes;
 }
 
 int coeb_extractor_set_profiling(coeb_extractor* ex, int on) {
@@ -534,33 +546,52 @@ static bool same_view(const BatchView& a, const BatchView& b) {
            a.out_kps == b.out_kps && a.out_desc == b.out_desc && a.out_count == b.out_count && a.status == b.status;
 }
 
-static int launch_graphed(coeb_extractor* ex, const BatchView& v, cudaStream_t s) {
+// Large resident batches run as sub-batches round-robin over the pipeline streams: kernel tails of one sub-batch overlap
+// the next one's kernels, and a sub-batch's pyramid is more likely still in L2 when the later stages read it.
+static int enqueue_chunked(coeb_extractor* ex, const BatchView& v, cudaStream_t s, int chunk) {
+    if (chunk <= 0 || v.B < 2 * chunk) return enqueue(ex, v, s, false);
+    int st = ensure_pipe_streams(ex);
+    if (st != COEB_OK) return st;
+    CUDA_TRY(cudaEventRecord(ex->pipe_ready, s));
+    for (int i = 0; i < kPipeStreams; i++) CUDA_TRY(cudaStreamWaitEvent(ex->pipe_stream[i], ex->pipe_ready, 0));
+    for (int f0 = 0, c = 0; f0 < v.B; f0 += chunk, c++) {
+        st = enqueue(ex, sub_view(ex->geom, v, f0, std::min(chunk, v.B - f0), ex->pyr_bytes_per_frame), ex->pipe_stream[c % kPipeStreams], false);
+        if (st != COEB_OK) return st;
+    }
+    for (int i = 0; i < kPipeStreams; i++) {
+        CUDA_TRY(cudaEventRecord(ex->pipe_done[i], ex->pipe_stream[i]));
+        CUDA_TRY(cudaStreamWaitEvent(s, ex->pipe_done[i], 0));
+    }
+    return COEB_OK;
+}
+
+static int launch_graphed(coeb_extractor* ex, const BatchView& v, cudaStream_t s, int chunk = 0) {
     const Geometry& g = ex->geom;
     for (auto& e : ex->graphs)
-        if (e.w == g.w0 && e.h == g.h0 && e.cap == g.out_cap && same_view(e.view, v)) {
+        if (e.w == g.w0 && e.h == g.h0 && e.cap == g.out_cap && e.chunk == chunk && same_view(e.view, v)) {
             CUDA_TRY(cudaGraphLaunch(e.exec, s));
             return COEB_OK;
         }
     if (ex->graph_warm < 2) {   // first calls run eagerly (lazy module loading, function attributes) before anything is captured
         ex->graph_warm++;
-        return enqueue(ex, v, s, false);
+        return enqueue_chunked(ex, v, s, chunk);
     }
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    int st = enqueue(ex, v, s, false);
+    int st = enqueue_chunked(ex, v, s, chunk);
     cudaError_t e = cudaStreamEndCapture(s, &graph);
     if (st != COEB_OK || e != cudaSuccess || !graph) {
         if (graph) cudaGraphDestroy(graph);
         cudaGetLastError();
-        return enqueue(ex, v, s, false);   // capture not possible here: plain launches
+        return enqueue_chunked(ex, v, s, chunk);   // capture not possible here: plain launches
     }
     e = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
-    if (e != cudaSuccess) { cudaGetLastError(); return enqueue(ex, v, s, false); }
+    if (e != cudaSuccess) { cudaGetLastError(); return enqueue_chunked(ex, v, s, chunk); }
     if (ex->graphs.size() >= 8) { cudaGraphExecDestroy(ex->graphs.front().exec); ex->graphs.erase(ex->graphs.begin()); }
     coeb_extractor::GraphEntry ge;
-    ge.view = v; ge.w = g.w0; ge.h = g.h0; ge.cap = g.out_cap; ge.exec = exec;
+    ge.view = v; ge.w = g.w0; ge.h = g.h0; ge.cap = g.out_cap; ge.chunk = chunk; ge.exec = exec;
     ex->graphs.push_back(ge);
     CUDA_TRY(cudaGraphLaunch(exec, s));
     return COEB_OK;
@@ -616,7 +647,11 @@ int coeb_extract_batch_device(coeb_extractor* ex, int B, const uint8_t* gray, in
     }
     ex->last_view = v;
     ex->last_B = B;
-    return enqueue(ex, v, ex->stream, ex->profiling);
+    ex->last_passes = 1;
+    if (ex->profiling) return enqueue(ex, v, ex->stream, true);
+    static const int dev_chunk = [] { const char* e = getenv("COEB_DEV_CHUNK"); return e ? atoi(e) : kDevChunk; }();
+    if (dev_chunk > 0 && B >= 2 * dev_chunk) ex->last_passes = (B + dev_chunk - 1) / dev_chunk;
+    return launch_graphed(ex, v, ex->stream, dev_chunk);
 }
 
 int coeb_extract_batch_host(coeb_extractor* ex, int B, const uint8_t* gray, int width, int height, int stride,
@@ -682,12 +717,10 @@ int coeb_extract_batch_host(coeb_extractor* ex, int B, const uint8_t* gray, int 
     const int chunk = B <= 2 * pipe_chunk ? B : pipe_chunk;
     const int nchunks = (B + chunk - 1) / chunk;
     const bool piped = nchunks > 1;
-    if (piped && !ex->pipe_stream[0]) {
-        for (int i = 0; i < kPipeStreams; i++) {
-            CUDA_TRY(cudaStreamCreateWithFlags(&ex->pipe_stream[i], cudaStreamNonBlocking));
-            CUDA_TRY(cudaEventCreateWithFlags(&ex->pipe_done[i], cudaEventDisableTiming));
-        }
-        CUDA_TRY(cudaEventCreateWithFlags(&ex->pipe_ready, cudaEventDisableTiming));
+    ex->last_passes = nchunks;
+    if (piped) {
+        st = ensure_pipe_streams(ex);
+        if (st != COEB_OK) return st;
     }
     if (piped) {
         CUDA_TRY(cudaEventRecord(ex->pipe_ready, s));

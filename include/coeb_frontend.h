@@ -89,7 +89,8 @@ int coeb_extract_batch_device(coeb_extractor* ex, int B, const uint8_t* gray, in
                               const int* ntm, int max_tm, const int* blur_flag, coeb_keypoint* kps_out,
                               uint8_t* desc_out, int* counts_out, int* status_out, int cap);
 
-/* Kernel launches one coeb_extract_batch_* call enqueues (for benchmark accounting). */
+/* Kernel launches the last coeb_extract_batch_* call enqueued (for benchmark accounting; large batches run as several
+ * sub-batches, each with its own launches). */
 int coeb_extractor_launches_per_call(const coeb_extractor* ex);
 
 /* Benchmark accounting: with profiling on, every coeb_extract_batch_* call brackets its six stages
