@@ -149,15 +149,21 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return i;
 }
 
-__device__ __forceinline__ uint32_t blur_h(uint32_t wm, uint32_t w0, uint32_t wp, int i) {
-    // taps {18,34,48,56,48,34,18} centred on byte i of w0, laid over the bytes of (wm, w0, wp)
-    switch (i) {
-        case 0: return __dp4a(wm, 0x30221200u, __dp4a(w0, 0x12223038u, 0u));
-        case 1: return __dp4a(wm, 0x22120000u, __dp4a(w0, 0x22303830u, __dp4a(wp, 0x00000012u, 0u)));
-        case 2: return __dp4a(wm, 0x12000000u, __dp4a(w0, 0x30383022u, __dp4a(wp, 0x00001222u, 0u)));
-        default: return __dp4a(w0, 0x38302212u, __dp4a(wp, 0x00122230u, 0u));
+// Taps {18,34,48,56,48,34,18} centred on byte i of w0, laid over the bytes of (wm, w0, wp): weight words per output byte,
+// kept in constant memory so that they are instruction operands (as immediates the compiler re-materialises them in
+// uniform registers on every trip of the loop).
+__constant__ uint32_t c_blur_taps[10] = {0x30221200u, 0x12223038u, 0x22120000u, 0x22303830u, 0x00000012u,
+                                         0x12000000u, 0x30383022u, 0x00001222u, 0x38302212u, 0x00122230u};
+struct BlurTaps {
+    __device__ __forceinline__ uint32_t h0(uint32_t wm, uint32_t w0) const { return __dp4a(wm, c_blur_taps[0], __dp4a(w0, c_blur_taps[1], 0u)); }
+    __device__ __forceinline__ uint32_t h1(uint32_t wm, uint32_t w0, uint32_t wp) const {
+        return __dp4a(wm, c_blur_taps[2], __dp4a(w0, c_blur_taps[3], __dp4a(wp, c_blur_taps[4], 0u)));
     }
-}
+    __device__ __forceinline__ uint32_t h2(uint32_t wm, uint32_t w0, uint32_t wp) const {
+        return __dp4a(wm, c_blur_taps[5], __dp4a(w0, c_blur_taps[6], __dp4a(wp, c_blur_taps[7], 0u)));
+    }
+    __device__ __forceinline__ uint32_t h3(uint32_t w0, uint32_t wp) const { return __dp4a(w0, c_blur_taps[8], __dp4a(wp, c_blur_taps[9], 0u)); }
+};
 
 __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v,
                                                             const int4* __restrict__ tiles) {
@@ -174,8 +180,9 @@ __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const __grid_constan
         const uint8_t* __restrict__ src = level_ptr(g, v, level, frame);
         const int spitch = level_pitch(g, v, level);
         const int q = tid & 7, r0 = tid >> 3;
-        const int gx = tx0 - 16 + 16 * q;
-        const bool xok = gx >= 0 && gx + 16 <= spitch;
+        // vectors left of the image or beyond the row pitch (always whole vectors: both are multiples of 16) are clamped: the
+        // only bytes of them an in-image output can see are the 3 reflected columns patched below
+        const uint8_t* __restrict__ col = src + min(max(tx0 - 16 + 16 * q, 0), spitch - 16);
         if (q < 6) {
 #pragma unroll
             for (int ry = r0; ry < kBlurRows; ry += kBlurThreads / 8) {
@@ -183,9 +190,7 @@ __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const __grid_constan
                 gy = gy < 0 ? -gy : gy;
                 gy = gy >= L.h ? 2 * L.h - 2 - gy : gy;
                 gy = min(max(gy, 0), L.h - 1);   // rows far below a short level: never used by an output row
-                uint4 w = make_uint4(0u, 0u, 0u, 0u);
-                if (xok) w = __ldg(reinterpret_cast<const uint4*>(src + (size_t)gy * spitch + gx));
-                reinterpret_cast<uint4*>(s_in)[ry * 6 + q] = w;
+                reinterpret_cast<uint4*>(s_in)[ry * 6 + q] = __ldg(reinterpret_cast<const uint4*>(col + (size_t)gy * spitch));
             }
         }
     }
@@ -210,16 +215,17 @@ __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const __grid_constan
     }
 
     // H pass: (pair row, 4-pixel group) tasks
+    const BlurTaps tp;
     for (int i = tid; i < kBlurPairRows * (kBlurTW / 4); i += kBlurThreads) {
         const int pr = i >> 4, gx = i & 15;
         const uint32_t* w = &s_in[(2 * pr) * kBlurInWords + gx + 3];   // w[0]: x-4.., w[1]: the 4 output pixels, w[2]: x+4..
         const uint32_t am = w[0], a0 = w[1], ap = w[2];
         const uint32_t bm = w[kBlurInWords], b0 = w[kBlurInWords + 1], bp = w[kBlurInWords + 2];
         uint4 o;
-        o.x = blur_h(am, a0, ap, 0) | (blur_h(bm, b0, bp, 0) << 16);
-        o.y = blur_h(am, a0, ap, 1) | (blur_h(bm, b0, bp, 1) << 16);
-        o.z = blur_h(am, a0, ap, 2) | (blur_h(bm, b0, bp, 2) << 16);
-        o.w = blur_h(am, a0, ap, 3) | (blur_h(bm, b0, bp, 3) << 16);
+        o.x = tp.h0(am, a0) | (tp.h0(bm, b0) << 16);
+        o.y = tp.h1(am, a0, ap) | (tp.h1(bm, b0, bp) << 16);
+        o.z = tp.h2(am, a0, ap) | (tp.h2(bm, b0, bp) << 16);
+        o.w = tp.h3(a0, ap) | (tp.h3(b0, bp) << 16);
         *reinterpret_cast<uint4*>(&s_v[pr * kBlurVPitch + 4 * gx]) = o;
     }
     __syncthreads();
@@ -237,9 +243,10 @@ __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const __grid_constan
             // halfword later
             constexpr uint32_t E0 = 18u | (34u << 8), E1 = 48u | (56u << 8), E2 = 48u | (34u << 8), E3 = 18u;
             constexpr uint32_t O0 = 18u << 8, O1 = 34u | (48u << 8), O2 = 56u | (48u << 8), O3 = 34u | (18u << 8);
+            const int rows = min(4, L.h - (ty0 + 4 * strip));   // rows of this strip inside the image (may be <= 0)
 #pragma unroll
             for (int r = 0; r < 4; r++) {
-                if (ty0 + 4 * strip + r < L.h) {
+                if (r < rows) {
                     const int m = r >> 1;
                     const uint32_t k0 = (r & 1) ? O0 : E0, k1 = (r & 1) ? O1 : E1, k2 = (r & 1) ? O2 : E2, k3 = (r & 1) ? O3 : E3;
                     uint32_t acc[4];
@@ -253,7 +260,8 @@ __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const __grid_constan
                     }
                     // (acc >> 16) is the output byte: gather byte 2 of the four accumulators
                     const uint32_t lo = __byte_perm(acc[0], acc[1], 0x0062), hi = __byte_perm(acc[2], acc[3], 0x0062);
-                    *reinterpret_cast<uint32_t*>(dst + (size_t)r * L.pitch) = __byte_perm(lo, hi, 0x5410);   // tail lands in row padding
+                    *reinterpret_cast<uint32_t*>(dst) = __byte_perm(lo, hi, 0x5410);   // tail lands in row padding
+                    dst += L.pitch;
                 }
             }
         }
