@@ -162,7 +162,8 @@ void build_resize_tables(int sw, int sh, int dw, int dh, std::vector<int2>& out)
         int sy = (int)std::floor(fy);
         fy -= sy;
         const int b0 = (int)lrintf((1.f - fy) * 2048.f), b1 = (int)lrintf(fy * 2048.f);
-        out.push_back(make_int2(sy, (b0 & 0xFFFF) | (b1 << 16)));
+        const int sy0 = std::min(std::max(sy, 0), sh - 1), sy1 = std::min(std::max(sy + 1, 0), sh - 1);   // rows clamped here, once
+        out.push_back(make_int2(sy0 | (sy1 << 16), (b0 & 0xFFFF) | (b1 << 16)));
     }
 }
 

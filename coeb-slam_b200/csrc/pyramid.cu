@@ -12,7 +12,7 @@ namespace coeb {
 // Resize: OpenCV's 8-bit INTER_LINEAR is an 11-bit fixed-point separable filter:
 //   h(dx)  = S[sx]*a0 + S[sx+1]*a1                       (a0,a1 = rint((1-fx)*2048), rint(fx*2048))
 //   out    = (((b0*(h0>>4))>>16) + ((b1*(h1>>4))>>16) + 2) >> 2
-// The per-column / per-row (offset, a0|a1<<16) tables are built on the host (coeb_api.cu) with the
+// The per-column (offset, a0|a1<<16) and per-row (row0|row1<<16, b0|b1<<16) tables are built on the host (coeb_api.cu) with the
 // exact double/float arithmetic of cv::resize and kept resident.
 // Each thread produces 4 adjacent output pixels and stores them as one 32-bit word.
 // ------------------------------------------------------------------------------------------------
@@ -38,31 +38,32 @@ __global__ void __launch_bounds__(256) resize_kernel(const __grid_constant__ Geo
     const int2* __restrict__ yt = xt + D.w;
     // column entries (source offset, packed weights) are the same for every row: fetch them once
     uint32_t wgt[4], sel[4];
-    int wb[2];
+    const uint8_t* colp[2];   // source column of each pixel pair's two aligned words (row 0)
 #pragma unroll
     for (int u = 0; u < 2; u++) {
         const int2 e0 = __ldg(&xt[min(dx0 + 2 * u, D.w - 1)]), e1 = __ldg(&xt[min(dx0 + 2 * u + 1, D.w - 1)]);   // tail -> row padding
-        wb[u] = min(e0.x & ~3, spitch - 8);          // two aligned words from here hold both pixels' source pairs
-        const int o0 = e0.x - wb[u], o1 = e1.x - wb[u];
+        const int wb = min(e0.x & ~3, spitch - 8);   // two aligned words from here hold both pixels' source pairs
+        const int o0 = e0.x - wb, o1 = e1.x - wb;
         sel[2 * u] = (uint32_t)(o0 | (min(o0 + 1, 7) << 4));       // beyond byte 7 only when sx is the last column: weight 0
         sel[2 * u + 1] = (uint32_t)(o1 | (min(o1 + 1, 7) << 4));
         wgt[2 * u] = (uint32_t)e0.y;
         wgt[2 * u + 1] = (uint32_t)e1.y;
+        colp[u] = src + wb;
     }
+    uint8_t* out = dst + dx0;
 #pragma unroll
     for (int j = 0; j < kResizeRows; j++) {
         const int dy = blockIdx.y * (8 * kResizeRows) + threadIdx.y + 8 * j;
         if (dy >= D.h) break;
         const int2 ye = __ldg(&yt[dy]);
-        const int sy0 = min(max(ye.x, 0), S.h - 1), sy1 = min(max(ye.x + 1, 0), S.h - 1);
+        const int sy0 = ye.x & 0xFFFF, sy1 = (int)((uint32_t)ye.x >> 16);   // clamped on the host
         const uint32_t b0 = ye.y & 0xFFFF, b1 = (uint32_t)ye.y >> 16;
-        const uint8_t* r0 = src + (size_t)sy0 * spitch;
-        const uint8_t* r1 = src + (size_t)sy1 * spitch;
         uint32_t o[4];
 #pragma unroll
         for (int u = 0; u < 2; u++) {
-            const uint32_t t0 = __ldg(reinterpret_cast<const uint32_t*>(r0 + wb[u])), t1 = __ldg(reinterpret_cast<const uint32_t*>(r0 + wb[u] + 4));
-            const uint32_t q0 = __ldg(reinterpret_cast<const uint32_t*>(r1 + wb[u])), q1 = __ldg(reinterpret_cast<const uint32_t*>(r1 + wb[u] + 4));
+            const uint32_t* t = reinterpret_cast<const uint32_t*>(colp[u] + (long long)sy0 * spitch);
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(colp[u] + (long long)sy1 * spitch);
+            const uint32_t t0 = __ldg(t), t1 = __ldg(t + 1), q0 = __ldg(q), q1 = __ldg(q + 1);
 #pragma unroll
             for (int i = 2 * u; i < 2 * u + 2; i++) {
                 const uint32_t h0 = __dp2a_lo(wgt[i], __byte_perm(t0, t1, sel[i]), 0u);
@@ -70,7 +71,8 @@ __global__ void __launch_bounds__(256) resize_kernel(const __grid_constant__ Geo
                 o[i] = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2u) >> 2;   // <= 255 by construction
             }
         }
-        *reinterpret_cast<uint32_t*>(dst + (size_t)dy * D.pitch + dx0) = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);  // padding absorbs the tail
+        // pitch is a multiple of 64: padding absorbs the tail
+        *reinterpret_cast<uint32_t*>(out + (long long)dy * D.pitch) = __byte_perm(__byte_perm(o[0], o[1], 0x0040), __byte_perm(o[2], o[3], 0x0040), 0x5410);
     }
 }
 
@@ -88,7 +90,7 @@ __global__ void __launch_bounds__(256) resize_generic_kernel(const __grid_consta
     uint8_t* dst = v.pyr + D.img_base + (unsigned long long)frame * D.img_stride;
     const int2* __restrict__ xt = v.tabs + D.tab_base;
     const int2 ye = __ldg(&xt[D.w + dy]);
-    const int sy0 = min(max(ye.x, 0), S.h - 1), sy1 = min(max(ye.x + 1, 0), S.h - 1);
+    const int sy0 = ye.x & 0xFFFF, sy1 = (int)((uint32_t)ye.x >> 16);   // clamped on the host
     const int b0 = ye.y & 0xFFFF, b1 = ye.y >> 16;
     const uint8_t* r0 = src + (size_t)sy0 * spitch;
     const uint8_t* r1 = src + (size_t)sy1 * spitch;
