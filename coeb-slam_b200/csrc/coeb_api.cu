@@ -590,7 +590,7 @@ static int launch_graphed(coeb_extractor* ex, const BatchView& v, cudaStream_t s
     e = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) { cudaGetLastError(); return enqueue_chunked(ex, v, s, chunk); }
-    if (ex->graphs.size() >= 8) { cudaGraphExecDestroy(ex->graphs.front().exec); ex->graphs.erase(ex->graphs.begin()); }
+    if (ex->graphs.size() >= 32) { cudaGraphExecDestroy(ex->graphs.front().exec); ex->graphs.erase(ex->graphs.begin()); }
     coeb_extractor::GraphEntry ge;
     ge.view = v; ge.w = g.w0; ge.h = g.h0; ge.cap = g.out_cap; ge.chunk = chunk; ge.exec = exec;
     ex->graphs.push_back(ge);
@@ -730,7 +730,10 @@ int coeb_extract_batch_host(coeb_extractor* ex, int B, const uint8_t* gray, int 
     for (int c = 0; c < nchunks; c++) {
         cudaStream_t ps = piped ? ex->pipe_stream[c % kPipeStreams] : s;
         const int f0 = c * chunk, n = std::min(chunk, B - f0);
-        if (frame_stride == (size_t)stride * height) {
+        if (frame_stride == (size_t)stride * height && stride == pitch && stride == width) {
+            // tightly packed frames whose width is already the arena pitch: one linear DMA (2D copies go row by row)
+            CUDA_TRY(cudaMemcpyAsync(ex->d_in_gray + fstride * f0, gray + frame_stride * f0, fstride * n, cudaMemcpyHostToDevice, ps));
+        } else if (frame_stride == (size_t)stride * height) {
             CUDA_TRY(cudaMemcpy2DAsync(ex->d_in_gray + fstride * f0, pitch, gray + frame_stride * f0, stride, width, (size_t)height * n,
                                        cudaMemcpyHostToDevice, ps));
         } else {
@@ -738,10 +741,12 @@ int coeb_extract_batch_host(coeb_extractor* ex, int B, const uint8_t* gray, int 
                 CUDA_TRY(cudaMemcpy2DAsync(ex->d_in_gray + fstride * i, pitch, gray + frame_stride * i, stride, width, height,
                                            cudaMemcpyHostToDevice, ps));
         }
-        if (!piped && !ex->profiling && B <= kGraphMaxBatch) {
-            st = launch_graphed(ex, v, ps);   // one graph launch instead of ~14 stream operations
+        if (ex->profiling) {
+            st = enqueue(ex, sub_view(ex->geom, v, f0, n, ex->pyr_bytes_per_frame), ps, !piped);
         } else {
-            st = enqueue(ex, sub_view(ex->geom, v, f0, n, ex->pyr_bytes_per_frame), ps, !piped && ex->profiling);
+            // one graph launch instead of ~20 stream operations; the staging buffers and arenas are the handle's own, so a
+            // (sub-)view recurs call after call
+            st = launch_graphed(ex, piped ? sub_view(ex->geom, v, f0, n, ex->pyr_bytes_per_frame) : v, ps);
         }
         if (st != COEB_OK) return st;
         CUDA_TRY(cudaMemcpyAsync(counts_out + f0, ex->d_out_count + f0, sizeof(int) * n, cudaMemcpyDeviceToHost, ps));
