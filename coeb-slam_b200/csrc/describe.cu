@@ -46,9 +46,12 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 __device__ __forceinline__ int round_even(float x) { return __float_as_int(__fadd_rn(x, 12582912.f)) - 0x4B400000; }
 
 #ifndef COEB_DESC_MINB
-#define COEB_DESC_MINB 3
+#define COEB_DESC_MINB 4
 #endif
-constexpr int kDescChunk = 64;   // keypoints per CTA: several CTAs per level keep a single frame's latency low
+#ifndef COEB_DESC_CHUNK
+#define COEB_DESC_CHUNK 64
+#endif
+constexpr int kDescChunk = COEB_DESC_CHUNK;   // keypoints per CTA: several CTAs per level keep a single frame's latency low
 
 __global__ void __launch_bounds__(256, COEB_DESC_MINB) describe_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v) {
     __shared__ float s_pat[1024];         // pattern as floats, transposed: [4*bit + component][lane], conflict-free per-lane reads
