@@ -515,6 +515,20 @@ int coeb_extractor_device_stream(coeb_extractor* ex, int* device, void** stream)
     return COEB_OK;
 }
 
+/* Device-resident results of the last coeb_extract* call (the handle's own output arrays for the host entry points, the
+ * caller's for coeb_extract_batch_device): keypoints [cap], descriptors [cap][32] and the count of frame `frame`. */
+int coeb_extractor_device_outputs(coeb_extractor* ex, int frame, const coeb_keypoint** d_kps, const uint8_t** d_desc,
+                                  const int** d_count, int* cap) {
+    if (!ex || !ex->geom_valid || frame < 0 || frame >= ex->last_B) return fail(COEB_ERR_INVALID_ARG, "bad argument");
+    const BatchView& v = ex->last_view;
+    const int c = ex->geom.out_cap;
+    if (d_kps) *d_kps = v.out_kps + (size_t)frame * c;
+    if (d_desc) *d_desc = v.out_desc + (size_t)frame * c * 32;
+    if (d_count) *d_count = v.out_count + frame;
+    if (cap) *cap = c;
+    return COEB_OK;
+}
+
 int coeb_extractor_launches_per_call(const coeb_extractor* ex) {
     if (!ex) return 0;
     // classify + (nlevels-1) resizes + blur + FAST + empty-cell list + FAST fallback + select + describe (the two counter memsets are not kernels of ours)

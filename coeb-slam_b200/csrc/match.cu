@@ -754,6 +754,166 @@ __global__ void knn2_merge_kernel(int nq, int nchunks, const int* p_d1, const in
     if (ok && accepted) atomicAdd(accepted, 1);
 }
 
+
+// =====================================================================================================================
+// Either side of the extractor and the matchers ("next" rows): the tail of the RGB-D Frame constructor and the
+// visibility test of Tracking::SearchLocalPoints, so that keypoints, descriptors and projected map points never make a
+// host round trip between the extractor and the matcher.
+// =====================================================================================================================
+
+// cv::undistortPoints(src, dst, K, D, noArray(), K) for one point (Frame::UndistortKeyPoints, src/Frame.cc:579-609):
+// double precision, 5 fixed-point iterations, no FMA (-fmad=false). dist = {k1, k2, p1, p2, k3}.
+__device__ __forceinline__ void undistort_point(float u, float v, float fx, float fy, float cx, float cy, const float* dist, float& xo, float& yo) {
+    const double dfx = fx, dfy = fy, dcx = cx, dcy = cy;
+    const double k0 = dist[0], k1 = dist[1], k2 = dist[2], k3 = dist[3], k4 = dist[4];
+    const double ifx = 1. / dfx, ify = 1. / dfy;
+    double x = ((double)u - dcx) * ifx, y = ((double)v - dcy) * ify;
+    const double x0 = x, y0 = y;
+    for (int j = 0; j < 5; j++) {
+        const double r2 = x * x + y * y;
+        const double icdist = 1. / (1 + ((k4 * r2 + k1) * r2 + k0) * r2);
+        if (icdist < 0) { x = x0; y = y0; break; }
+        const double deltaX = 2 * k2 * x * y + k3 * (r2 + 2 * x * x);
+        const double deltaY = k2 * (r2 + 2 * y * y) + 2 * k3 * x * y;
+        x = (x0 - deltaX) * icdist;
+        y = (y0 - deltaY) * icdist;
+    }
+    xo = (float)(dfx * x + dcx);
+    yo = (float)(dfy * y + dcy);
+}
+
+struct TailArgs {
+    const coeb_keypoint* kps;    // mvKeys (extractor output, device)
+    const uint32_t* desc;        // mDescriptors, n x 8 words
+    int n;
+    float fx, fy, cx, cy, bf;
+    float dist[5];
+    int undistort;
+    const void* depth; int depth_kind, depth_stride, depth_w, depth_h; float depth_factor;
+    // frame block
+    float *x, *y, *angle; int* octave; float* uright; uint32_t* desc_out;
+    coeb_keypoint* keys_un; float* depth_out;
+};
+
+// UndistortKeyPoints + ComputeStereoFromRGBD (src/Frame.cc:579-609, 820-842): one thread per keypoint writes the SoA
+// the matchers read and the AoS the host downloads; the descriptor rows are copied as words.
+__global__ void __launch_bounds__(128) frame_tail_kernel(TailArgs a) {
+    const int n = a.n;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int w = i; w < n * 8; w += gridDim.x * blockDim.x) a.desc_out[w] = a.desc[w];
+    if (i >= n) return;
+    coeb_keypoint kp = a.kps[i];
+    const float u = kp.x, v = kp.y;
+    if (a.undistort) undistort_point(u, v, a.fx, a.fy, a.cx, a.cy, a.dist, kp.x, kp.y);
+    float ur = -1.f, dp = -1.f;
+    if (a.depth_kind) {
+        const int row = (int)v, col = (int)u;   // imDepth.at<float>(v, u): float -> int truncation
+        float d = 0.f;
+        if ((unsigned)row < (unsigned)a.depth_h && (unsigned)col < (unsigned)a.depth_w) {
+            const char* p = (const char*)a.depth + (size_t)row * a.depth_stride;
+            d = a.depth_kind == 1 ? ((const float*)p)[col] : __fmul_rn((float)((const unsigned short*)p)[col], a.depth_factor);
+        }
+        if (d > 0) { dp = d; ur = __fsub_rn(kp.x, __fdiv_rn(a.bf, d)); }
+    }
+    a.x[i] = kp.x; a.y[i] = kp.y; a.angle[i] = kp.angle; a.octave[i] = kp.octave; a.uright[i] = ur;
+    a.keys_un[i] = kp; a.depth_out[i] = dp;
+}
+
+// glibc 2.39 logf (sysdeps/ieee754/flt-32/e_logf.c: 16-entry table, degree-3 polynomial in double), restated so that
+// MapPoint::PredictScale's `ceil(log(ratio) / mfLogScaleFactor)` (src/MapPoint.cc:402-417, float overloads) is the same
+// float on the device as on the reference's host; the oracle carries the same restatement and pins it against libm.
+__constant__ double kLogfTab[16][2] = {
+    {0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2}, {0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2},
+    {0x1.49539f0f010bp+0, -0x1.01eae7f513a67p-2},  {0x1.3c995b0b80385p+0, -0x1.b31d8a68224e9p-3},
+    {0x1.30d190c8864a5p+0, -0x1.6574f0ac07758p-3}, {0x1.25e227b0b8eap+0, -0x1.1aa2bc79c81p-3},
+    {0x1.1bb4a4a1a343fp+0, -0x1.a4e76ce8c0e5ep-4}, {0x1.12358f08ae5bap+0, -0x1.1973c5a611cccp-4},
+    {0x1.0953f419900a7p+0, -0x1.252f438e10c1ep-5}, {0x1p+0, 0x0p+0},
+    {0x1.e608cfd9a47acp-1, 0x1.aa5aa5df25984p-5},  {0x1.ca4b31f026aap-1, 0x1.c5e53aa362eb4p-4},
+    {0x1.b2036576afce6p-1, 0x1.526e57720db08p-3},  {0x1.9c2d163a1aa2dp-1, 0x1.bc2860d22477p-3},
+    {0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2},  {0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2}};
+
+__device__ __forceinline__ float glibc_logf(float x) {   // normal positive x only (the caller guarantees it)
+    const uint32_t ix = __float_as_uint(x);
+    if (ix == 0x3f800000u) return 0.f;
+    const uint32_t tmp = ix - 0x3f330000u;
+    const int i = (tmp >> 19) & 15;
+    const int k = (int)tmp >> 23;
+    const double z = (double)__uint_as_float(ix - (tmp & 0xff800000u));
+    const double r = z * kLogfTab[i][0] - 1, y0 = kLogfTab[i][1] + (double)k * 0x1.62e42fefa39efp-1, r2 = r * r;
+    double y = 0x1.5575b0be00b6ap-2 * r + -0x1.ffffef20a4123p-2;
+    y = -0x1.00ea348b88334p-2 * r2 + y;
+    y = y * r2 + (y0 + r);
+    return (float)y;
+}
+
+struct LocalMapDev {
+    int n;
+    const float *xyz, *normal, *min_dist, *max_dist;
+    const uint32_t* desc;
+};
+struct PoseArgs { float T[12]; float Ow[3]; float cos_limit; int nlevels; };
+struct MapFields {   // the MapPoint members isInFrustum writes, as device arrays (they are MapDev's inputs)
+    uint8_t* track_in_view; float *proj_x, *proj_y, *proj_xr, *view_cos; int* level;
+};
+
+// Frame::isInFrustum (src/Frame.cc:445-501) + the candidate collection of SearchByProjection for the same map point.
+// fp32 projection left to right without FMA (cv::gemm on 3x3 . 3x1, pinned in tests/test_oracle_vs_cv2.py); cv::norm and
+// Mat::dot accumulate in double.
+__global__ void __launch_bounds__(128) frustum_collect_kernel(FrameDev F, LocalMapDev LM, PoseArgs P, const uint8_t* __restrict__ skip,
+                                                              MapFields out, MapDev M, float th, const int* kp_state, CandLists C, float* proj_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= LM.n) return;
+    bool in = false;
+    float u = 0.f, v = 0.f, ur = 0.f, viewCos = 0.f;
+    int lvl = 0;
+    const float log_scale = P.nlevels > 1 ? glibc_logf(F.scale[1]) : 1.f;   // mfLogScaleFactor = log(mfScaleFactor) (src/Frame.cc:151)
+    if (!skip[i]) {
+        const float X = LM.xyz[3 * i], Y = LM.xyz[3 * i + 1], Z = LM.xyz[3 * i + 2];
+        const float* T = P.T;
+        const float PcX = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[0], X), __fmul_rn(T[1], Y)), __fmul_rn(T[2], Z)), T[3]);
+        const float PcY = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[4], X), __fmul_rn(T[5], Y)), __fmul_rn(T[6], Z)), T[7]);
+        const float PcZ = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[8], X), __fmul_rn(T[9], Y)), __fmul_rn(T[10], Z)), T[11]);
+        if (!(PcZ < 0.0f)) {
+            const float invz = __fdiv_rn(1.0f, PcZ);
+            u = __fadd_rn(__fmul_rn(__fmul_rn(F.fx, PcX), invz), F.cx);
+            v = __fadd_rn(__fmul_rn(__fmul_rn(F.fy, PcY), invz), F.cy);
+            if (!(u < F.min_x || u > F.max_x) && !(v < F.min_y || v > F.max_y)) {
+                const float maxD = __fmul_rn(1.2f, LM.max_dist[i]), minD = __fmul_rn(0.8f, LM.min_dist[i]);
+                const float ox = __fsub_rn(X, P.Ow[0]), oy = __fsub_rn(Y, P.Ow[1]), oz = __fsub_rn(Z, P.Ow[2]);
+                const double s = __dadd_rn(__dadd_rn(__dmul_rn((double)ox, (double)ox), __dmul_rn((double)oy, (double)oy)), __dmul_rn((double)oz, (double)oz));
+                const float dist = (float)sqrt(s);
+                if (!(dist < minD || dist > maxD)) {
+                    const float nx = LM.normal[3 * i], ny = LM.normal[3 * i + 1], nz = LM.normal[3 * i + 2];
+                    const double dot = __dadd_rn(__dadd_rn(__dmul_rn((double)ox, (double)nx), __dmul_rn((double)oy, (double)ny)), __dmul_rn((double)oz, (double)nz));
+                    viewCos = (float)(dot / (double)dist);
+                    if (!(viewCos < P.cos_limit)) {
+                        const float ratio = __fdiv_rn(LM.max_dist[i], dist);
+                        int nScale = 0;
+                        if (ratio >= 1.17549435e-38f && ratio <= 3.402823466e+38f) nScale = (int)ceilf(__fdiv_rn(glibc_logf(ratio), log_scale));
+                        lvl = nScale < 0 ? 0 : (nScale >= P.nlevels ? P.nlevels - 1 : nScale);
+                        ur = __fsub_rn(u, __fmul_rn(F.bf, invz));
+                        in = true;
+                    }
+                }
+            }
+        }
+    }
+    if (!in) { u = v = ur = viewCos = 0.f; lvl = 0; }
+    out.track_in_view[i] = in ? 1 : 0;
+    out.proj_x[i] = u; out.proj_y[i] = v; out.proj_xr[i] = ur; out.view_cos[i] = viewCos; out.level[i] = lvl;
+    if (proj_out) { float* q = proj_out + 5 * (size_t)i; q[0] = u; q[1] = v; q[2] = ur; q[3] = viewCos; q[4] = (float)lvl; }
+    // candidate collection of SearchByProjection for this map point (same thread: it reads back its own stores)
+    int cnt = 0;
+    if (in) {
+        int2* lst = C.items + (size_t)i * C.cap;
+        m2_visit(F, M, th, kp_state, i, [&](int idx, int dist, int oct) {
+            if (cnt < C.cap) lst[cnt] = make_int2(idx | (oct << 24), dist);
+            cnt++;
+        });
+    }
+    C.count[i] = cnt;
+}
+
 }  // namespace coeb
 
 // =====================================================================================================================
@@ -821,6 +981,8 @@ struct coeb_matcher {
     Stage in, out;                                   // inputs (H2D) and results (D2H)
     void* d_scratch = nullptr; size_t scratch_bytes = 0;
     void* d_in = nullptr; size_t in_bytes = 0;        // kNN partials
+    void* d_depth = nullptr; size_t depth_bytes = 0;  // uploaded depth map of coeb_frame_from_extractor
+    cudaEvent_t ev_ex = nullptr;                       // orders the matcher's stream after an extractor's
     std::vector<std::pair<size_t, void*>> frame_pool;  // device blocks of destroyed frames, reused by the next ones
 };
 
@@ -832,11 +994,19 @@ struct coeb_frame {
     FrameDev dev{};
 };
 
+struct coeb_local_map {
+    coeb_matcher* m = nullptr;
+    int n = 0;
+    void* block = nullptr;
+    coeb::LocalMapDev dev{};
+};
+
 // The extractor handle is opaque here; coeb_api.cu exports the pyramid accessor used by the stereo matcher.
 extern "C" int coeb_pyramid_level(coeb_extractor* ex, int frame, int level, int blurred, const uint8_t** dev_ptr, int* width,
                                   int* height, int* pitch);
 extern "C" int coeb_extractor_tables(const coeb_extractor* ex, int* nlevels, float* scale, float* inv_scale, float* sigma2,
                                      float* inv_sigma2, int* features_per_level);
+extern "C" int coeb_extractor_device_stream(coeb_extractor* ex, int* device, void** stream);
 
 namespace {
 
@@ -885,6 +1055,8 @@ void coeb_matcher_destroy(coeb_matcher* m) {
     m->out.release();
     cudaFree(m->d_scratch);
     cudaFree(m->d_in);
+    cudaFree(m->d_depth);
+    if (m->ev_ex) cudaEventDestroy(m->ev_ex);
     for (auto& b : m->frame_pool) cudaFree(b.second);
     cudaStreamDestroy(m->own_stream);
     delete m;
@@ -1240,6 +1412,232 @@ int coeb_knn2(coeb_matcher* m, const uint8_t* query, int nq, const uint8_t* trai
     if (d1) std::memcpy(d1, m->out.h + al(NQ * 4), NQ * 4);
     if (d2) std::memcpy(d2, m->out.h + 2 * al(NQ * 4), NQ * 4);
     if (naccepted_out) { int a = 0; for (int i = 0; i < nq; i++) a += best_idx[i] >= 0; *naccepted_out = a; }
+    return COEB_OK;
+}
+
+// ---- Frame constructor tail from the extractor's device output ------------------------------------------------------------
+int coeb_frame_from_extractor(coeb_matcher* m, coeb_extractor* ex, int frame_index, int n, const coeb_camera* cam,
+                              const float* dist_coef5, const coeb_depth_image* depth, coeb_keypoint* keys_un_out,
+                              float* uright_out, float* depth_out, int* n_out, coeb_frame** out) {
+    if (!m || !ex || !cam || !out) return fail(COEB_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    if (n_out) *n_out = 0;
+    int ex_dev = 0;
+    void* ex_stream = nullptr;
+    int st = coeb_extractor_device_stream(ex, &ex_dev, &ex_stream);
+    if (st != COEB_OK) return st;
+    if (ex_dev != m->device) return fail(COEB_ERR_INVALID_ARG, "extractor on device %d, matcher on device %d", ex_dev, m->device);
+    const coeb_keypoint* d_kps = nullptr;
+    const uint8_t* d_desc = nullptr;
+    const int* d_count = nullptr;
+    int cap = 0;
+    if ((st = coeb_extractor_device_outputs(ex, frame_index, &d_kps, &d_desc, &d_count, &cap)) != COEB_OK) return st;
+    CUDA_TRY(cudaSetDevice(m->device));
+    cudaStream_t s = m->stream;
+    if (n < 0) {   // count unknown to the caller: one 4-byte read behind the extractor's stream
+        CUDA_TRY(cudaStreamSynchronize((cudaStream_t)ex_stream));
+        CUDA_TRY(cudaMemcpy(&n, d_count, sizeof(int), cudaMemcpyDeviceToHost));
+    } else if ((cudaStream_t)ex_stream != s) {
+        if (!m->ev_ex) CUDA_TRY(cudaEventCreateWithFlags(&m->ev_ex, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventRecord(m->ev_ex, (cudaStream_t)ex_stream));
+        CUDA_TRY(cudaStreamWaitEvent(s, m->ev_ex, 0));
+    }
+    if (n < 0 || n > cap) return fail(COEB_ERR_INVALID_ARG, "n = %d outside the extractor's capacity %d", n, cap);
+    int nlevels = 0;
+    float scale[COEB_MAX_LEVELS] = {0};
+    if ((st = coeb_extractor_tables(ex, &nlevels, scale, nullptr, nullptr, nullptr, nullptr)) != COEB_OK) return st;
+    const int kind = depth ? depth->kind : 0;
+    if (kind < 0 || kind > 2) return fail(COEB_ERR_INVALID_ARG, "depth kind %d", kind);
+    if (kind && (!depth->data || depth->width < 1 || depth->height < 1 || depth->stride_bytes < depth->width * (kind == 1 ? 4 : 2)))
+        return fail(COEB_ERR_INVALID_ARG, "bad depth image");
+
+    const size_t nn = std::max(n, 1);
+    // device block: x, y, angle, octave, uright, desc | cell_start, cell_items, kp_cell | keys_un (AoS), depth: the last two
+    // are contiguous so that the host copy is one transfer
+    const size_t need = 5 * al(nn * 4) + al(nn * 32) + al((kGridCells + 1) * 4) + 2 * al(nn * 4) + al(nn * sizeof(coeb_keypoint)) + 2 * al(nn * 4);
+    coeb_frame* f = new coeb_frame();
+    f->m = m; f->n = n; f->nlevels = nlevels;
+    for (size_t i = 0; i < m->frame_pool.size(); i++)
+        if (m->frame_pool[i].first >= need) {
+            f->block_bytes = m->frame_pool[i].first;
+            f->block = m->frame_pool[i].second;
+            m->frame_pool.erase(m->frame_pool.begin() + i);
+            break;
+        }
+    if (!f->block) {
+        const size_t want = std::max<size_t>(need + need / 4, 1 << 17);
+        if (cudaMalloc(&f->block, want) != cudaSuccess) { delete f; return fail(COEB_ERR_CUDA, "cudaMalloc(%zu) failed", want); }
+        f->block_bytes = want;
+    }
+    char* base = (char*)f->block;
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { char* p = base + off; off += al(bytes); return p; };
+    TailArgs a{};
+    a.kps = d_kps; a.desc = (const uint32_t*)d_desc; a.n = n;
+    a.fx = cam->fx; a.fy = cam->fy; a.cx = cam->cx; a.cy = cam->cy; a.bf = cam->bf;
+    a.undistort = (dist_coef5 && dist_coef5[0] != 0.0f) ? 1 : 0;   // `if (mDistCoef.at<float>(0) == 0.0)` (src/Frame.cc:581)
+    for (int i = 0; i < 5; i++) a.dist[i] = dist_coef5 ? dist_coef5[i] : 0.f;
+    a.x = (float*)carve(nn * 4); a.y = (float*)carve(nn * 4); a.angle = (float*)carve(nn * 4); a.octave = (int*)carve(nn * 4);
+    a.uright = (float*)carve(nn * 4); a.desc_out = (uint32_t*)carve(nn * 32);
+    int* d_cell_start = (int*)carve((kGridCells + 1) * 4); int* d_cell_items = (int*)carve(nn * 4); int* d_kp_cell = (int*)carve(nn * 4);
+    a.keys_un = (coeb_keypoint*)carve(nn * sizeof(coeb_keypoint));
+    float* d_uright_copy = (float*)carve(nn * 4);
+    a.depth_out = (float*)carve(nn * 4);
+    const size_t dl_bytes = (size_t)((char*)a.depth_out - (char*)a.keys_un) + nn * 4;
+
+    auto bail = [&](int code) { coeb_frame_destroy(f); return code; };
+    a.depth_kind = kind;
+    if (kind) {
+        a.depth_w = depth->width; a.depth_h = depth->height; a.depth_factor = depth->factor;
+        if (depth->on_device) { a.depth = depth->data; a.depth_stride = depth->stride_bytes; }
+        else {
+            const size_t row = (size_t)depth->width * (kind == 1 ? 4 : 2);
+            const size_t pitch = (row + 15) & ~(size_t)15;
+            if ((st = grow(&m->d_depth, &m->depth_bytes, pitch * depth->height)) != COEB_OK) return bail(st);
+            cudaError_t e = (size_t)depth->stride_bytes == row && pitch == row
+                                ? cudaMemcpyAsync(m->d_depth, depth->data, row * depth->height, cudaMemcpyHostToDevice, s)
+                                : cudaMemcpy2DAsync(m->d_depth, pitch, depth->data, depth->stride_bytes, row, depth->height, cudaMemcpyHostToDevice, s);
+            if (e != cudaSuccess) return bail(fail(COEB_ERR_CUDA, "depth upload failed: %s", cudaGetErrorString(e)));
+            a.depth = m->d_depth; a.depth_stride = (int)pitch;
+        }
+    }
+    FrameDev& d = f->dev;
+    d.n = n; d.x = a.x; d.y = a.y; d.angle = a.angle; d.octave = a.octave; d.desc = a.desc_out; d.uright = kind ? a.uright : nullptr;
+    d.cell_start = d_cell_start; d.cell_items = d_cell_items;
+    d.min_x = cam->min_x; d.min_y = cam->min_y; d.max_x = cam->max_x; d.max_y = cam->max_y;
+    d.gw_inv = (float)COEB_GRID_COLS / (cam->max_x - cam->min_x);
+    d.gh_inv = (float)COEB_GRID_ROWS / (cam->max_y - cam->min_y);
+    d.fx = cam->fx; d.fy = cam->fy; d.cx = cam->cx; d.cy = cam->cy; d.bf = cam->bf; d.b = cam->b;
+    for (int i = 0; i < COEB_MAX_LEVELS; i++) d.scale[i] = i < nlevels ? scale[i] : 0.f;
+    if (n > 0) frame_tail_kernel<<<(n + 127) / 128, 128, 0, s>>>(a);
+    grid_build_kernel<<<1, 1024, 0, s>>>(d, d_cell_start, d_cell_items, d_kp_cell);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return bail(fail(COEB_ERR_CUDA, "frame tail launch failed: %s", cudaGetErrorString(e)));
+    const bool want = n > 0 && (keys_un_out || uright_out || depth_out);
+    if (want) {
+        // uright lives in the SoA part; a copy next to keys_un / depth makes the download one block
+        if ((e = cudaMemcpyAsync(d_uright_copy, a.uright, nn * 4, cudaMemcpyDeviceToDevice, s)) != cudaSuccess)
+            return bail(fail(COEB_ERR_CUDA, "%s", cudaGetErrorString(e)));
+        if ((st = m->out.reserve(dl_bytes)) != COEB_OK) return bail(st);
+        if ((e = cudaMemcpyAsync(m->out.h, a.keys_un, dl_bytes, cudaMemcpyDeviceToHost, s)) != cudaSuccess)
+            return bail(fail(COEB_ERR_CUDA, "%s", cudaGetErrorString(e)));
+    }
+    // blocking like every Frame-building call: the caller may reuse its depth buffer and the extractor
+    if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return bail(fail(COEB_ERR_CUDA, "frame tail failed: %s", cudaGetErrorString(e)));
+    if (want) {
+        const char* h = m->out.h;
+        if (keys_un_out) std::memcpy(keys_un_out, h, (size_t)n * sizeof(coeb_keypoint));
+        if (uright_out) std::memcpy(uright_out, h + ((char*)d_uright_copy - (char*)a.keys_un), (size_t)n * 4);
+        if (depth_out) std::memcpy(depth_out, h + ((char*)a.depth_out - (char*)a.keys_un), (size_t)n * 4);
+    }
+    if (n_out) *n_out = n;
+    *out = f;
+    return COEB_OK;
+}
+
+// ---- resident local map + SearchLocalPoints -------------------------------------------------------------------------------
+int coeb_local_map_create(coeb_matcher* m, int n, const float* xyz, const float* normal, const float* min_dist, const float* max_dist,
+                          const uint8_t* desc, coeb_local_map** out) {
+    if (!m || !out || n < 0 || (n > 0 && (!xyz || !normal || !min_dist || !max_dist || !desc))) return fail(COEB_ERR_INVALID_ARG, "bad argument");
+    CUDA_TRY(cudaSetDevice(m->device));
+    const size_t N = std::max(n, 1);
+    const size_t bytes = 2 * al(N * 12) + 2 * al(N * 4) + al(N * 32);
+    int st = m->in.reserve(bytes);
+    if (st != COEB_OK) return st;
+    coeb_local_map* lm = new coeb_local_map();
+    lm->m = m; lm->n = n;
+    if (cudaMalloc(&lm->block, bytes) != cudaSuccess) { delete lm; return fail(COEB_ERR_CUDA, "cudaMalloc(%zu) failed", bytes); }
+    size_t off = 0;
+    auto put = [&](const void* src, size_t elem_bytes) {   // stages one array, returns its device address
+        char* d = (char*)lm->block + off;
+        if (n) std::memcpy(m->in.h + off, src, (size_t)n * elem_bytes);
+        off += al(N * elem_bytes);
+        return d;
+    };
+    lm->dev.n = n;
+    lm->dev.xyz = (const float*)put(xyz, 12);
+    lm->dev.normal = (const float*)put(normal, 12);
+    lm->dev.min_dist = (const float*)put(min_dist, 4);
+    lm->dev.max_dist = (const float*)put(max_dist, 4);
+    lm->dev.desc = (const uint32_t*)put(desc, 32);
+    cudaError_t e = cudaMemcpyAsync(lm->block, m->in.h, bytes, cudaMemcpyHostToDevice, m->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+    if (e != cudaSuccess) { cudaFree(lm->block); delete lm; return fail(COEB_ERR_CUDA, "local map upload failed: %s", cudaGetErrorString(e)); }
+    *out = lm;
+    return COEB_OK;
+}
+
+void coeb_local_map_destroy(coeb_local_map* lm) {
+    if (!lm) return;
+    cudaSetDevice(lm->m->device);
+    cudaFree(lm->block);
+    delete lm;
+}
+
+int coeb_search_local_points(coeb_matcher* m, coeb_frame* F, coeb_local_map* lm, const uint8_t* skip, const uint8_t* has_obs,
+                             const float* Tcw, const float* Ow, float viewing_cos_limit, float th, float nnratio, int* kp_match,
+                             uint8_t* in_view_out, float* proj_out, int* nmatches_out) {
+    if (!m || !F || !lm || !Tcw || !Ow || !kp_match) return fail(COEB_ERR_INVALID_ARG, "bad argument");
+    if (nmatches_out) *nmatches_out = 0;
+    const int n = lm->n;
+    if (n == 0) return COEB_OK;
+    if (!skip || !has_obs) return fail(COEB_ERR_INVALID_ARG, "null map-point flags");
+    // an empty frame still gets its visibility flags: every window is empty, nothing matches
+    CUDA_TRY(cudaSetDevice(m->device));
+    const size_t N = n, K = std::max(F->n, 1);
+    int st;
+    if ((st = m->in.reserve(2 * al(N) + al(K * 4))) != COEB_OK) return st;
+    const size_t out_bytes = al(K * 4) + 256 + al(N) + (proj_out ? al(N * 20) : 0);
+    if ((st = m->out.reserve(out_bytes)) != COEB_OK) return st;
+    const int cap = 32;
+    // scratch: res, claim, list counts, lists | MapPoint fields written by the frustum pass
+    const size_t sc_bytes = al(N * 4) + al(K * 4) + al(N * 4) + al(N * cap * 8) + 5 * al(N * 4) + 2 * al(N);
+    if ((st = grow(&m->d_scratch, &m->scratch_bytes, sc_bytes)) != COEB_OK) return st;
+    Packer p(m->in);
+    const uint8_t* d_skip = p.place(skip, N);
+    const uint8_t* d_obs = p.place(has_obs, N);
+    const int* d_state = p.place(kp_match, (size_t)F->n);
+    if ((st = push_inputs(m, p)) != COEB_OK) return st;
+    char* sc = (char*)m->d_scratch;
+    int* d_res = (int*)sc; sc += al(N * 4);
+    int* d_claim = (int*)sc; sc += al(K * 4);
+    CandLists C{nullptr, (int*)sc, cap}; sc += al(N * 4);
+    C.items = (int2*)sc; sc += al(N * cap * 8);
+    MapFields mf{};
+    mf.proj_x = (float*)sc; sc += al(N * 4);
+    mf.proj_y = (float*)sc; sc += al(N * 4);
+    mf.proj_xr = (float*)sc; sc += al(N * 4);
+    mf.view_cos = (float*)sc; sc += al(N * 4);
+    mf.level = (int*)sc; sc += al(N * 4);
+    uint8_t* d_zero = (uint8_t*)sc; sc += al(N);   // isBad(): bad points arrive as skip
+    int* d_kpm = (int*)m->out.d;
+    int* d_info = (int*)(m->out.d + al(K * 4));
+    mf.track_in_view = (uint8_t*)(m->out.d + al(K * 4) + 256);
+    float* d_proj = proj_out ? (float*)(m->out.d + al(K * 4) + 256 + al(N)) : nullptr;
+    MapDev M{};
+    M.n = n; M.track_in_view = mf.track_in_view; M.bad = d_zero; M.has_obs = d_obs;
+    M.proj_x = mf.proj_x; M.proj_y = mf.proj_y; M.proj_xr = mf.proj_xr; M.view_cos = mf.view_cos; M.level = mf.level; M.desc = lm->dev.desc;
+    PoseArgs P{};
+    for (int i = 0; i < 12; i++) P.T[i] = Tcw[i];
+    for (int i = 0; i < 3; i++) P.Ow[i] = Ow[i];
+    P.cos_limit = viewing_cos_limit;
+    P.nlevels = F->nlevels;
+    CUDA_TRY(cudaMemsetAsync(d_zero, 0, N, m->stream));
+    if (F->n) CUDA_TRY(cudaMemcpyAsync(d_kpm, d_state, (size_t)F->n * 4, cudaMemcpyDeviceToDevice, m->stream));
+    frustum_collect_kernel<<<(n + 127) / 128, 128, 0, m->stream>>>(F->dev, lm->dev, P, d_skip, mf, M, th, d_state, C, d_proj);
+    m2_resolve_kernel<true><<<1, 1024, 0, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info);
+    CUDA_TRY(cudaGetLastError());
+    if ((st = pull_outputs(m, out_bytes)) != COEB_OK) return st;
+    if (((const int*)(m->out.h + al(K * 4)))[2]) {   // a candidate list overflowed: exact window-walking variant
+        if (F->n) CUDA_TRY(cudaMemcpyAsync(d_kpm, d_state, (size_t)F->n * 4, cudaMemcpyDeviceToDevice, m->stream));
+        m2_resolve_kernel<false><<<1, 1024, 0, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info);
+        CUDA_TRY(cudaGetLastError());
+        if ((st = pull_outputs(m, al(K * 4) + 12)) != COEB_OK) return st;
+    }
+    if (F->n) std::memcpy(kp_match, m->out.h, (size_t)F->n * 4);
+    if (in_view_out) std::memcpy(in_view_out, m->out.h + al(K * 4) + 256, N);
+    if (proj_out) std::memcpy(proj_out, m->out.h + al(K * 4) + 256 + al(N), N * 20);
+    if (nmatches_out) *nmatches_out = ((const int*)(m->out.h + al(K * 4)))[0];
     return COEB_OK;
 }
 

@@ -36,6 +36,11 @@ class Camera(C.Structure):
                 ("max_y", C.c_float)]
 
 
+class DepthImage(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("kind", C.c_int32), ("stride_bytes", C.c_int32), ("factor", C.c_float),
+                ("on_device", C.c_int32), ("width", C.c_int32), ("height", C.c_int32)]
+
+
 class CoebError(RuntimeError):
     def __init__(self, status, msg):
         super().__init__("coeb status %d: %s" % (status, msg))
@@ -270,6 +275,27 @@ class Matcher:
     def frame(self, kps, desc, cam, scale, uright=None):
         return Frame(self, kps, desc, cam, scale, uright)
 
+    def frame_from_extractor(self, ex, cam, n=-1, frame_index=0, dist5=None, depth=None, depth_factor=1.0, download=True):
+        """Frame constructor tail on the device (UndistortKeyPoints + ComputeStereoFromRGBD + grid) from the extractor's
+        resident output. depth: None, a float32 map or a uint16 map (scaled by depth_factor), host numpy arrays.
+        Returns (frame, keys_un, uright, depth) (the arrays are None when download is False)."""
+        return ExtractedFrame.build(self, ex, cam, n, frame_index, dist5, depth, depth_factor, download)
+
+    def local_map(self, lm):
+        return LocalMap(self, lm)
+
+    def search_local_points(self, frame, local_map, skip, has_obs, Tcw, Ow, th, nnratio, kp_match, cos_limit=0.5, want_proj=True):
+        kp_match = _i32(kp_match).copy()
+        skip, has_obs = _u8(skip), _u8(has_obs)
+        tc, ow = _f32(Tcw).reshape(12), _f32(Ow).reshape(3)
+        in_view = np.zeros(local_map.n, np.uint8)
+        proj = np.zeros((local_map.n, 5), np.float32) if want_proj else None
+        n = C.c_int()
+        _check(lib().coeb_search_local_points(self.h, frame.h, local_map.h, _p(skip), _p(has_obs), _p(tc), _p(ow),
+                                              C.c_float(cos_limit), C.c_float(th), C.c_float(nnratio), _p(kp_match),
+                                              _p(in_view), _p(proj), C.byref(n)))
+        return n.value, kp_match, in_view, proj
+
     def match_projection(self, frame, mp, th, nnratio, kp_match):
         kp_match = _i32(kp_match).copy()
         a = dict(track_in_view=_u8(mp["track_in_view"]), bad=_u8(mp["bad"]), has_obs=_u8(mp["has_obs"]),
@@ -357,3 +383,61 @@ class Frame:
         _check(lib().coeb_frame_features_in_area(self.h, C.c_float(x), C.c_float(y), C.c_float(r), int(min_level),
                                                  int(max_level), _p(out), len(out), C.byref(n)))
         return out[:n.value].copy()
+
+
+class ExtractedFrame(Frame):
+    """A Frame built on the device from an Extractor's last call (coeb_frame_from_extractor)."""
+
+    def __init__(self):   # use build()
+        self.h = None
+
+    @classmethod
+    def build(cls, matcher, ex, cam, n, frame_index, dist5, depth, depth_factor, download):
+        f = cls()
+        f.matcher = matcher
+        d5 = None if dist5 is None else _f32(dist5).reshape(5)
+        dimg = None
+        if depth is not None:
+            depth = np.ascontiguousarray(depth)   # the call is blocking, so this temporary outlives the upload
+            assert depth.dtype in (np.float32, np.uint16) and depth.ndim == 2
+            dimg = DepthImage(depth.ctypes.data, 1 if depth.dtype == np.float32 else 2, depth.strides[0], float(depth_factor), 0,
+                              depth.shape[1], depth.shape[0])
+        cap = ex.default_cap() if n < 0 else max(n, 1)
+        keys_un = np.empty(cap, KP_DTYPE) if download else None
+        ur = np.empty(cap, np.float32) if download else None
+        dp = np.empty(cap, np.float32) if download else None
+        h = C.c_void_p()
+        nn = C.c_int()
+        _check(lib().coeb_frame_from_extractor(matcher.h, ex.h, int(frame_index), int(n), C.byref(cam), _p(d5),
+                                               C.byref(dimg) if dimg is not None else None, _p(keys_un), _p(ur), _p(dp),
+                                               C.byref(nn), C.byref(h)))
+        f.h = h
+        f.n = nn.value
+        if download:
+            keys_un, ur, dp = keys_un[:f.n].copy(), ur[:f.n].copy(), dp[:f.n].copy()
+        return f, keys_un, ur, dp
+
+
+class LocalMap:
+    """Tracking::mvpLocalMapPoints resident on the device. lm: dict of arrays (xyz, normal, min_dist, max_dist, desc)."""
+
+    def __init__(self, matcher, lm):
+        a = dict(xyz=_f32(lm["xyz"]).reshape(-1, 3), normal=_f32(lm["normal"]).reshape(-1, 3), min_dist=_f32(lm["min_dist"]),
+                 max_dist=_f32(lm["max_dist"]), desc=_u8(lm["desc"]).reshape(-1, 32))
+        self.n = len(a["min_dist"])
+        self.matcher = matcher
+        h = C.c_void_p()
+        _check(lib().coeb_local_map_create(matcher.h, self.n, _p(a["xyz"]), _p(a["normal"]), _p(a["min_dist"]), _p(a["max_dist"]),
+                                           _p(a["desc"]), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().coeb_local_map_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

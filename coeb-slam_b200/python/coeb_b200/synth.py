@@ -257,3 +257,78 @@ def make_knn_sets(nq=4000, nt=100000, seed=0):
             np.bitwise_xor.at(noisy[i], p >> 3, (1 << (p & 7)).astype(np.uint8))
     t[pos] = noisy
     return q, t
+
+
+def make_pose(seed=0):
+    """A small camera motion: Tcw (3x4 row-major, float32) and the camera centre Ow = -Rcw^T tcw (float32)."""
+    rng = np.random.default_rng(seed + 301)
+    ax, ay, az = rng.uniform(-0.05, 0.05, 3)
+    Rx = np.array([[1, 0, 0], [0, np.cos(ax), -np.sin(ax)], [0, np.sin(ax), np.cos(ax)]])
+    Ry = np.array([[np.cos(ay), 0, np.sin(ay)], [0, 1, 0], [-np.sin(ay), 0, np.cos(ay)]])
+    Rz = np.array([[np.cos(az), -np.sin(az), 0], [np.sin(az), np.cos(az), 0], [0, 0, 1]])
+    R = (Rz @ Ry @ Rx).astype(np.float32)
+    t = rng.uniform(-0.2, 0.2, 3).astype(np.float32)
+    Tcw = np.concatenate([R, t[:, None]], axis=1).astype(np.float32)
+    Ow = (-(R.T.astype(np.float32) @ t)).astype(np.float32)
+    return Tcw, Ow
+
+
+def make_local_map(kps, desc, scale, Tcw, seed=0, n_map=5000, n_true=800, fx=535.4, fy=539.2, cx=320.1, cy=247.6):
+    """Config 3 with the visibility test in front (Tracking::SearchLocalPoints): world points, normals and scale-invariance
+    distances of a local map. `n_true` points project (under Tcw) within a few pixels of a frame keypoint, carry its
+    descriptor with 0..40 bit flips and a distance range that predicts the keypoint's octave or the next one; the rest are
+    distractors spread so that every rejection of Frame::isInFrustum fires (behind the camera, outside the image, outside
+    the distance range, grazing view). Returns (local-map SoA dict, skip, has_obs)."""
+    rng = np.random.default_rng(seed + 57)
+    n = len(kps)
+    nlevels = len(scale)
+    sf = float(scale[1]) if nlevels > 1 else 1.2
+    n_true = min(n_true, n)
+    R, t = Tcw[:, :3].astype(np.float64), Tcw[:, 3].astype(np.float64)
+    Ow = -R.T @ t
+    src = rng.choice(n, size=n_true, replace=False)
+    u = np.empty(n_map)
+    v = np.empty(n_map)
+    u[:n_true] = kps["x"][src] + rng.normal(0, 3, n_true)
+    v[:n_true] = kps["y"][src] + rng.normal(0, 3, n_true)
+    u[n_true:] = rng.uniform(-120, 760, n_map - n_true)    # some outside the image
+    v[n_true:] = rng.uniform(-90, 570, n_map - n_true)
+    z = rng.uniform(0.6, 6.0, n_map)
+    z[n_true:][rng.random(n_map - n_true) < 0.1] *= -1      # behind the camera
+    pc = np.stack([(u - cx) * z / fx, (v - cy) * z / fy, z], axis=1)
+    pw = (pc - t) @ R                                       # R^T (pc - t)
+    po = pw - Ow
+    dist = np.linalg.norm(po, axis=1)
+    # normals: towards the camera, tilted; distractors include grazing / back-facing ones
+    tilt = rng.normal(0, 0.25, (n_map, 3))
+    tilt[n_true:] = rng.normal(0, 1.2, (n_map - n_true, 3))
+    nrm = po / dist[:, None] + tilt
+    nrm /= np.linalg.norm(nrm, axis=1)[:, None]
+    level = np.empty(n_map, np.int64)
+    level[:n_true] = np.minimum(kps["octave"][src] + rng.integers(0, 2, n_true), nlevels - 1)
+    level[n_true:] = rng.integers(0, nlevels, n_map - n_true)
+    max_dist = dist * sf ** (level - rng.uniform(0.05, 0.95, n_map))     # PredictScale -> level
+    far = rng.random(n_map) < 0.05
+    far[:n_true] = False
+    max_dist[far] *= rng.choice([0.05, 40.0], size=int(far.sum()))       # outside [0.8 min, 1.2 max] either way
+    min_dist = max_dist / float(scale[-1])
+    d = np.empty((n_map, 32), np.uint8)
+    d[:n_true] = flip_bits(desc[src], rng, 40)
+    d[n_true:] = rng.integers(0, 256, size=(n_map - n_true, 32), dtype=np.uint8)
+    perm = rng.permutation(n_map)
+    lm = dict(xyz=pw.astype(np.float32)[perm], normal=nrm.astype(np.float32)[perm], min_dist=min_dist.astype(np.float32)[perm],
+              max_dist=max_dist.astype(np.float32)[perm], desc=d[perm])
+    lm = {k: np.ascontiguousarray(a) for k, a in lm.items()}
+    skip = (rng.random(n_map) < 0.04).astype(np.uint8)
+    has_obs = (rng.random(n_map) < 0.97).astype(np.uint8)
+    return lm, skip, has_obs
+
+
+def make_depth(seed=0, w=640, h=480, factor=5000.0):
+    """TUM-style raw depth map: uint16, metres x `factor`, smooth 0.5-5 m surface with ~15 % invalid (0) pixels."""
+    rng = np.random.default_rng(seed + 411)
+    base = _upsample_bilinear(rng.uniform(0.5, 5.0, (h // 32 + 2, w // 32 + 2)), h, w)
+    d = np.clip(base * factor, 1, 65535).astype(np.uint16)
+    holes = _upsample_bilinear(rng.random((h // 16 + 2, w // 16 + 2)), h, w) < 0.3
+    d[holes] = 0
+    return np.ascontiguousarray(d)

@@ -89,6 +89,13 @@ int coeb_extract_batch_device(coeb_extractor* ex, int B, const uint8_t* gray, in
                               const int* ntm, int max_tm, const int* blur_flag, coeb_keypoint* kps_out,
                               uint8_t* desc_out, int* counts_out, int* status_out, int cap);
 
+/* Device-resident results of the last coeb_extract* call: keypoints [cap], descriptors [cap][32] and the count of
+ * frame `frame` (the handle's own output arrays for the host entry points, the caller's arrays for
+ * coeb_extract_batch_device). Valid until the next call on the handle. Consumers on another stream must order
+ * themselves after the extractor's stream (coeb_frame_from_extractor does). */
+int coeb_extractor_device_outputs(coeb_extractor* ex, int frame, const coeb_keypoint** d_kps, const uint8_t** d_desc,
+                                  const int** d_count, int* cap);
+
 /* Kernel launches the last coeb_extract_batch_* call enqueued (for benchmark accounting; large batches run as several
  * sub-batches, each with its own launches). */
 int coeb_extractor_launches_per_call(const coeb_extractor* ex);
@@ -159,6 +166,31 @@ int coeb_frame_create(coeb_matcher* m, const coeb_keypoint* kps_un, const uint8_
                       const coeb_camera* cam, const float* scale_factors, int nlevels, coeb_frame** out);
 void coeb_frame_destroy(coeb_frame* f);
 
+/* Tail of the RGB-D Frame constructor (src/Frame.cc:213-240) straight from the extractor's device-resident output, with
+ * no host round trip of keypoints or descriptors: UndistortKeyPoints (:579-609, cv::undistortPoints in double, 5
+ * iterations; skipped when dist_coef5 is NULL or k1 == 0 like the reference), ComputeStereoFromRGBD (:820-842, depth
+ * read at the truncated distorted coordinates, uRight = xUn - bf / d) and AssignFeaturesToGrid (:396-411).
+ *   frame_index : frame of the extractor's last call;  n : its keypoint count (< 0: read it from the device)
+ *   dist_coef5  : k1, k2, p1, p2, k3 (mDistCoef)
+ *   depth       : NULL or kind 0 = none (mvuRight = mvDepth = -1); kind 1 = float32 metres as Tracking::GrabImageRGBD
+ *                 hands it over; kind 2 = raw uint16 with `factor` = mDepthMapFactor, i.e. the reference's
+ *                 imDepth.convertTo(CV_32F, factor) (src/Tracking.cc:226-229) folded into the gather. Host memory
+ *                 (uploaded by the call; pinned memory from coeb_host_alloc makes that copy asynchronous) unless
+ *                 on_device != 0.
+ *   keys_un_out / uright_out / depth_out : optional host arrays of n entries (mvKeysUn, mvuRight, mvDepth).
+ * The frame is usable by every matcher entry point below. */
+typedef struct coeb_depth_image {
+    const void* data;
+    int32_t kind;          /* 0 none, 1 float32, 2 uint16 */
+    int32_t stride_bytes;
+    float factor;          /* kind 2 only */
+    int32_t on_device;
+    int32_t width, height;
+} coeb_depth_image;
+int coeb_frame_from_extractor(coeb_matcher* m, coeb_extractor* ex, int frame_index, int n, const coeb_camera* cam,
+                              const float* dist_coef5, const coeb_depth_image* depth, coeb_keypoint* keys_un_out,
+                              float* uright_out, float* depth_out, int* n_out, coeb_frame** out);
+
 /* Frame::GetFeaturesInArea(x, y, r, minLevel, maxLevel) (src/Frame.cc:503-556): indices in the
  * reference's traversal order (ix outer, iy inner, insertion order). */
 int coeb_frame_features_in_area(coeb_frame* f, float x, float y, float r, int min_level, int max_level, int* idx_out,
@@ -178,6 +210,28 @@ int coeb_match_projection(coeb_matcher* m, coeb_frame* F, int n, const uint8_t* 
                           const uint8_t* has_obs, const float* proj_x, const float* proj_y, const float* proj_xr,
                           const int* level, const float* view_cos, const uint8_t* desc, float th, float nnratio,
                           int* kp_match, int* nmatches_out);
+
+/* Tracking::mvpLocalMapPoints resident on the device (src/Tracking.cc:1284-1311 rebuilds it per keyframe change, not per
+ * frame): GetWorldPos() n x 3, GetNormal() n x 3, mfMinDistance / mfMaxDistance (the 0.8 / 1.2 invariance factors of
+ * src/MapPoint.cc:373-383 are applied on the device), GetDescriptor() n x 32. Host pointers. */
+typedef struct coeb_local_map coeb_local_map;
+int coeb_local_map_create(coeb_matcher* m, int n, const float* xyz, const float* normal, const float* min_dist,
+                          const float* max_dist, const uint8_t* desc, coeb_local_map** out);
+void coeb_local_map_destroy(coeb_local_map* lm);
+
+/* Tracking::SearchLocalPoints (src/Tracking.cc:1222-1272), second loop + matcher call, as one device pass:
+ * Frame::isInFrustum(pMP, viewing_cos_limit) (src/Frame.cc:445-501) with MapPoint::PredictScale (src/MapPoint.cc:402-417)
+ * for every map point with skip[i] == 0, then ORBmatcher::SearchByProjection(F, mvpLocalMapPoints, th) (:45-129).
+ *   skip    : n bytes, 1 = mnLastFrameSeen == current frame id or isBad() (the caller's first loop)
+ *   has_obs : n bytes, Observations() > 0
+ *   Tcw     : 3x4 row-major [mRcw | mtcw];  Ow : mOw
+ *   kp_match: as coeb_match_projection
+ *   in_view_out : n bytes, isInFrustum's return value (the points IncreaseVisible() applies to; their sum is nToMatch)
+ *   proj_out    : optional n x 5 floats {mTrackProjX, mTrackProjY, mTrackProjXR, mTrackViewCos, mnTrackScaleLevel}
+ * The only per-frame upload is skip/has_obs/kp_match; the projected fields never leave the device. */
+int coeb_search_local_points(coeb_matcher* m, coeb_frame* F, coeb_local_map* lm, const uint8_t* skip,
+                             const uint8_t* has_obs, const float* Tcw, const float* Ow, float viewing_cos_limit, float th,
+                             float nnratio, int* kp_match, uint8_t* in_view_out, float* proj_out, int* nmatches_out);
 
 /* ORBmatcher::SearchByProjection(Frame& cur, const Frame& last, th, bMono) (src/ORBmatcher.cc:1329-1471).
  * Per last-frame keypoint i: valid (mvpMapPoints[i] && !mvbOutlier[i]), has_obs, xyz (GetWorldPos),

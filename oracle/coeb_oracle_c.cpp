@@ -7,6 +7,7 @@
 
 #include "coeb_oracle.hpp"
 #include "coeb_oracle_match.hpp"
+#include "coeb_oracle_frame.hpp"
 
 using namespace orc;
 
@@ -261,6 +262,41 @@ double orc_knn2_mt(int nq, const uint8_t* q, int nt, const uint8_t* t, float nnr
     work(0, std::min(nq, per));
     for (auto& x : th) x.join();
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// ---- Frame constructor tail + SearchLocalPoints (coeb_oracle_frame.hpp) -----------------------------------
+void orc_undistort_keypoints(const coeb_keypoint* keys, int n, const coeb_camera* cam, const float* dist5,
+                             coeb_keypoint* keys_un) {
+    undistort_keypoints(keys, n, *cam, dist5, keys_un);
+}
+
+void orc_stereo_from_rgbd(const coeb_keypoint* keys, const coeb_keypoint* keys_un, int n, const void* depth, int kind,
+                          int stride_bytes, float factor, float mbf, float* uright, float* depth_out) {
+    DepthView D;
+    D.data = depth; D.kind = depth ? kind : 0; D.stride_bytes = stride_bytes; D.factor = factor;
+    stereo_from_rgbd(keys, keys_un, n, D, mbf, uright, depth_out);
+}
+
+// Number of floats in [lo, hi) (bit patterns, stepped by `step`) whose restated logf differs from the C library's.
+long orc_logf_mismatches(uint32_t lo, uint32_t hi, uint32_t step) {
+    long bad = 0;
+    for (uint64_t b = lo; b < hi; b += step) {
+        const uint32_t bits = (uint32_t)b;
+        float x;
+        std::memcpy(&x, &bits, 4);
+        const float a = std::log(x), m = glibc_logf(x);
+        bad += std::memcmp(&a, &m, 4) != 0;
+    }
+    return bad;
+}
+
+int orc_search_local_points(orc_frame* f, int n, const float* xyz, const float* normal, const float* min_dist,
+                            const float* max_dist, const uint8_t* desc, const uint8_t* skip, const uint8_t* has_obs,
+                            const float* Tcw, const float* Ow, float cos_limit, float th, float nnratio, int* kp_match,
+                            uint8_t* in_view, float* proj) {
+    LocalMapSoA M;
+    M.n = n; M.xyz = xyz; M.normal = normal; M.min_dist = min_dist; M.max_dist = max_dist; M.desc = desc;
+    return search_local_points(f->v, M, skip, has_obs, Tcw, Ow, cos_limit, th, nnratio, kp_match, in_view, proj);
 }
 
 }  // extern "C"

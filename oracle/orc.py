@@ -304,3 +304,45 @@ def knn2(q, t, nnratio, nthreads=1):
     secs = lib().orc_knn2_mt(len(q), _p(q), len(t), _p(t), C.c_float(nnratio), _p(idx), _p(d1), _p(d2),
                              int(nthreads))
     return idx, d1, d2, secs
+
+
+def undistort_keypoints(kps, cam, dist5):
+    """Frame::UndistortKeyPoints: dist5 = (k1, k2, p1, p2, k3) or None."""
+    kps = np.ascontiguousarray(kps, dtype=KP_DTYPE)
+    out = np.empty_like(kps)
+    d = None if dist5 is None else _f32(dist5).reshape(5)
+    lib().orc_undistort_keypoints(_p(kps), len(kps), C.byref(cam), _p(d), _p(out))
+    return out
+
+
+def stereo_from_rgbd(kps, kps_un, depth, mbf, factor=1.0):
+    """Frame::ComputeStereoFromRGBD: depth is a float32 map, or a uint16 map scaled by `factor` (convertTo)."""
+    kps = np.ascontiguousarray(kps, dtype=KP_DTYPE)
+    kps_un = np.ascontiguousarray(kps_un, dtype=KP_DTYPE)
+    n = len(kps)
+    ur, dp = np.empty(n, np.float32), np.empty(n, np.float32)
+    if depth is None:
+        kind, dptr, stride = 0, None, 0
+    else:
+        depth = np.ascontiguousarray(depth)
+        assert depth.dtype in (np.float32, np.uint16)
+        kind, dptr, stride = (1 if depth.dtype == np.float32 else 2), _p(depth), depth.strides[0]
+    lib().orc_stereo_from_rgbd(_p(kps), _p(kps_un), n, dptr, kind, stride, C.c_float(factor), C.c_float(mbf), _p(ur), _p(dp))
+    return ur, dp
+
+
+def search_local_points(frame, lm, skip, has_obs, Tcw, Ow, th, nnratio, kp_match, cos_limit=0.5):
+    """Tracking::SearchLocalPoints (isInFrustum + SearchByProjection). lm: dict of arrays (xyz, normal, min_dist,
+    max_dist, desc). Returns (nmatches, kp_match, in_view, proj[n,5] = u, v, ur, viewCos, level)."""
+    kp_match = _i32(kp_match).copy()
+    a = dict(xyz=_f32(lm["xyz"]), normal=_f32(lm["normal"]), min_dist=_f32(lm["min_dist"]), max_dist=_f32(lm["max_dist"]),
+             desc=_u8(lm["desc"]))
+    n = len(a["min_dist"])
+    skip, has_obs = _u8(skip), _u8(has_obs)
+    tc, ow = _f32(Tcw).reshape(12), _f32(Ow).reshape(3)
+    in_view = np.zeros(n, np.uint8)
+    proj = np.zeros((n, 5), np.float32)
+    nm = lib().orc_search_local_points(frame.h, n, _p(a["xyz"]), _p(a["normal"]), _p(a["min_dist"]), _p(a["max_dist"]),
+                                       _p(a["desc"]), _p(skip), _p(has_obs), _p(tc), _p(ow), C.c_float(cos_limit),
+                                       C.c_float(th), C.c_float(nnratio), _p(kp_match), _p(in_view), _p(proj))
+    return nm, kp_match, in_view, proj

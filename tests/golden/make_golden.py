@@ -78,9 +78,34 @@ def matching():
                         n_last=np.int32(n3), kp_match_last=km3, knn_idx=idx, knn_d1=d1, knn_d2=d2)
 
 
+def frame_tail():
+    """Real-OpenCV outputs for the arithmetic of the Frame constructor tail / isInFrustum: undistortPoints with the TUM1
+    calibration, cv::gemm on 3x3 . 3x1 + 3x1 (mRcw * P + mtcw) and cv::norm of a 3-vector."""
+    import cv2
+    rng = np.random.default_rng(9)
+    n = 2000
+    pts = np.zeros((n, 2), np.float32)   # same draw order as tests/test_frame_tail_cpu.py::_random_keys(2000, 9)
+    pts[:, 0] = rng.uniform(0, 639, n)
+    pts[:, 1] = rng.uniform(0, 479, n)
+    K = np.array([[517.306408, 0, 318.643040], [0, 516.469215, 255.313989], [0, 0, 1]], np.float32)
+    D = np.array([0.262383, -0.953104, -0.005358, 0.002628, 1.163314], np.float32)
+    und = cv2.undistortPoints(pts.reshape(-1, 1, 2), K, D, None, K).reshape(-1, 2)
+    rng = np.random.default_rng(10)
+    m = 500
+    R = rng.standard_normal((m, 3, 3)).astype(np.float32)
+    P = (rng.standard_normal((m, 3)) * 5).astype(np.float32)
+    t = rng.standard_normal((m, 3)).astype(np.float32)
+    out = np.stack([cv2.gemm(R[i], P[i].reshape(3, 1), 1.0, t[i].reshape(3, 1), 1.0).reshape(3) for i in range(m)])
+    v = (rng.standard_normal((m, 3)) * 3).astype(np.float32)
+    nrm = np.array([np.float32(cv2.norm(v[i].reshape(3, 1))) for i in range(m)], np.float32)
+    np.savez_compressed(os.path.join(HERE, "frame_tail.npz"), pts=pts, undist=und, gemm_R=R, gemm_P=P, gemm_t=t, gemm_out=out,
+                        norm_v=v, norm_out=nrm)
+
+
 if __name__ == "__main__":
     primitives()
     extraction()
     matching()
+    frame_tail()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))
