@@ -489,6 +489,51 @@ def bench_matching(cb, dev, batch, o_kps, o_desc, o_cnt, ex, args):
         pv[:] = prev
         L.coeb_match_init(m.h, f.h, f2.h, P(pv), P(m12), 100, C.c_float(0.9), 1, C.byref(nm))
     out["search_for_initialization_us"] = _median_us(call_m4, 50)
+    # ---- tracking-thread chain: extract -> Frame tail on the device -> SearchLocalPoints on a resident 5k map ---------
+    gray0 = np.ascontiguousarray(batch["gray"][0])
+    nb0, nt0 = int(batch["nbox"][0]), int(batch["ntm"][0])
+    b0, t0, fl0 = batch["boxes"][0], batch["tm"][0], batch["blur"][0]
+    ex1 = cb.Extractor(NFEAT, 1.2, NLEVELS, 20, 7, device=dev)
+    cap1 = ex1.default_cap()
+    kb1, db1, n1 = np.empty(cap1, cb.KP_DTYPE), np.empty((cap1, 32), np.uint8), C.c_int()
+    depth_pin, depth_owner = cb.pinned_array((H, W), np.uint16)
+    depth_pin[:] = synth.make_depth(0, W, H)
+    dimg = cb.DepthImage(depth_pin.ctypes.data, 2, depth_pin.strides[0], float(np.float32(1.0) / np.float32(5000.0)), 0, W, H)
+    cam = cb.Camera(*cam_args)
+    Tcw, Ow = synth.make_pose(0)
+    lm, skip, has_obs = synth.make_local_map(kps, desc, scale, Tcw, seed=0)
+    dev_map = m.local_map(lm)
+    tcw, ow = f32(Tcw).reshape(12), f32(Ow).reshape(3)
+    kun, ur1, dp1 = np.empty(cap1, cb.KP_DTYPE), np.empty(cap1, np.float32), np.empty(cap1, np.float32)
+    inview = np.empty(dev_map.n, np.uint8)
+    fh = C.c_void_p()
+    nfr = C.c_int()
+
+    def call_extract():
+        L.coeb_extract(ex1.h, P(gray0), W, H, W, P(b0), nb0, P(t0), nt0, P(fl0), nb0, P(kb1), P(db1), cap1, C.byref(n1))
+
+    def call_tail():
+        if fh.value:
+            L.coeb_frame_destroy(fh)
+        L.coeb_frame_from_extractor(m.h, ex1.h, 0, n1.value, C.byref(cam), None, C.byref(dimg), P(kun), P(ur1), P(dp1), C.byref(nfr), C.byref(fh))
+
+    def call_local():
+        km[:] = state
+        L.coeb_search_local_points(m.h, fh, dev_map.h, P(skip), P(has_obs), P(tcw), P(ow), C.c_float(0.5), C.c_float(3.0), C.c_float(0.8),
+                                   P(km), P(inview), None, C.byref(nm))
+
+    def call_chain():
+        call_extract(); call_tail(); call_local()
+    for _ in range(5):
+        call_chain()
+    assert n1.value == len(kps) and nfr.value == len(kps)
+    out["frame_tail_from_extractor_us"] = _median_us(call_tail, 50)
+    out["search_local_points_map5k_us"] = _median_us(call_local, 50)
+    out["track_frame_chain_us"] = _median_us(call_chain, 50)
+    out["track_frame_chain_note"] = ("blocking C calls, host buffers: coeb_extract (640x480 + boxes/T_M in, keypoints/descriptors out) -> "
+                                     "coeb_frame_from_extractor (raw uint16 depth in, mvKeysUn/mvuRight/mvDepth out) -> coeb_search_local_points "
+                                     "(5000-point resident local map; flags in, matches + visibility out)")
+    n_local_gpu, km_local_gpu, inview_gpu = int(nm.value), km.copy(), inview.copy()
     # kNN 4000 x 100k, device resident
     q, t = synth.make_knn_sets(4000, 100000, seed=3)
     dq, dt = torch.from_numpy(q).cuda(dev), torch.from_numpy(t).cuda(dev)
@@ -524,6 +569,17 @@ def bench_matching(cb, dev, batch, o_kps, o_desc, o_cnt, ex, args):
         _, _, _, secs = orc.knn2(q[:1000], t, 0.7, nthreads=th)
         out["cpu_knn2_4000x100k_ms_extrapolated"] = 4e3 * secs
         out["cpu_threads"] = th
+        kun_c = orc.undistort_keypoints(kps, orc.Camera(*cam_args), None)
+        ur_c, dp_c = orc.stereo_from_rgbd(kps, kun_c, np.asarray(depth_pin), cam_args[4], np.float32(1.0) / np.float32(5000.0))
+        fl = orc.Frame(kun_c, desc, orc.Camera(*cam_args), scale, ur_c)
+        out["cpu_frame_tail_us"] = _median_us(lambda: (orc.stereo_from_rgbd(kps, kun_c, np.asarray(depth_pin), cam_args[4], 2e-4),
+                                                       orc.Frame(kun_c, desc, orc.Camera(*cam_args), scale, ur_c)), 10)
+        out["cpu_search_local_points_map5k_us"] = _median_us(lambda: orc.search_local_points(fl, lm, skip, has_obs, Tcw, Ow, 3.0, 0.8, state), 10)
+        n_lc, km_lc, iv_lc, _ = orc.search_local_points(fl, lm, skip, has_obs, Tcw, Ow, 3.0, 0.8, state)
+        out["local_points_bit_exact_vs_cpu"] = bool(n_lc == n_local_gpu and np.array_equal(km_lc, km_local_gpu) and np.array_equal(iv_lc, inview_gpu)
+                                                    and ur_c.tobytes() == ur1[:len(kps)].tobytes() and dp_c.tobytes() == dp1[:len(kps)].tobytes())
+        out["local_points_in_view"] = int(iv_lc.sum())
+        out["local_points_matches"] = int(n_lc)
         n_g, km_g = m.match_projection(f, mp, 3.0, 0.8, state)
         n_c, km_c = orc.match_projection(fc, mp, 3.0, 0.8, state)
         out["bit_exact_vs_cpu"] = bool(n_g == n_c and np.array_equal(km_g, km_c))
