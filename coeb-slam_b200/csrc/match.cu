@@ -914,6 +914,91 @@ __global__ void __launch_bounds__(128) frustum_collect_kernel(FrameDev F, LocalM
     C.count[i] = cnt;
 }
 
+// ---- SearchByBoW (src/ORBmatcher.cc:158-288 and :522-655): matching restricted to features of the same vocabulary node --
+// The node lists (DBoW2::FeatureVector) arrive as CSR; the host intersects the two sorted node-id arrays and hands over
+// one {start1, end1, start2, end2} record per common node. A feature belongs to exactly one node, so the loop-carried
+// state of the reference (a feature of F2 matched by an earlier query is skipped) never crosses a node: one warp owns a
+// node and walks its queries in list order, exactly like the reference; the 32 lanes share the candidate loop.
+struct BowArgs {
+    int n_common;
+    const int4* nodes;             // {start1, end1, start2, end2} into items1 / items2
+    const int *items1, *items2;
+    const uint8_t *valid1, *valid2;   // valid2 may be nullptr (Frame overload)
+    float nnratio;
+    int strict_low;
+};
+
+__global__ void __launch_bounds__(128) bow_node_kernel(FrameDev F1, FrameDev F2, BowArgs a, int* match12, int* matched2) {
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= a.n_common) return;
+    const int4 nd = a.nodes[w];
+    for (int p1 = nd.x; p1 < nd.y; p1++) {
+        const int idx1 = a.items1[p1];
+        if (!a.valid1[idx1]) continue;   // warp-uniform
+        const uint32_t* d1 = F1.desc + 8 * (size_t)idx1;
+        // lane-local scan of candidates lane, lane+32, ... in list order: strict '<' keeps the earliest position
+        int b1 = 256, pos1 = 0x7fffffff, i2best = -1, b2 = 256;
+        for (int p2 = nd.z + lane; p2 < nd.w; p2 += 32) {
+            const int idx2 = a.items2[p2];
+            if (matched2[idx2] || (a.valid2 && !a.valid2[idx2])) continue;
+            const int dist = hamming256(d1, F2.desc + 8 * (size_t)idx2);
+            if (dist < b1) { b2 = b1; b1 = dist; pos1 = p2; i2best = idx2; }
+            else if (dist < b2) b2 = dist;
+        }
+        // warp merge: best = lexicographic min of (dist, list position); second = smallest of the remaining values
+        int gb = b1, gp = pos1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const int ob = __shfl_xor_sync(0xffffffffu, gb, o), op = __shfl_xor_sync(0xffffffffu, gp, o);
+            if (ob < gb || (ob == gb && op < gp)) { gb = ob; gp = op; }
+        }
+        const bool winner = (pos1 == gp) && (gp != 0x7fffffff);
+        int second = winner ? b2 : b1;   // the winner lane contributes its own runner-up, every other lane its best
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) second = min(second, __shfl_xor_sync(0xffffffffu, second, o));
+        const unsigned wm = __ballot_sync(0xffffffffu, winner);
+        const int gi = __shfl_sync(0xffffffffu, i2best, wm ? __ffs(wm) - 1 : 0);
+        const bool low = a.strict_low ? gb < COEB_TH_LOW : gb <= COEB_TH_LOW;
+        if (wm && low && (float)gb < a.nnratio * (float)second) {
+            if (lane == 0) { match12[idx1] = gi; matched2[gi] = 1; }
+            __syncwarp();   // the claim is visible to the next query's candidate loop (same warp)
+        }
+    }
+}
+
+// Rotation-consistency check of SearchByBoW (:275-293, :632-652) + the match count. One CTA.
+__global__ void __launch_bounds__(1024) bow_finish_kernel(FrameDev F1, FrameDev F2, int check_ori, int* match12, int* out_info) {
+    __shared__ int s_hist[COEB_HISTO_LENGTH];
+    __shared__ int s_keep[3], s_count;
+    const int tid = threadIdx.x, T = blockDim.x;
+    if (tid < COEB_HISTO_LENGTH) s_hist[tid] = 0;
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    if (check_ori) {
+        for (int i = tid; i < F1.n; i += T) {
+            const int j = match12[i];
+            if (j >= 0) atomicAdd(&s_hist[rot_bin(F1.angle[i], F2.angle[j])], 1);
+        }
+        __syncthreads();
+        if (tid == 0) three_maxima(s_hist, COEB_HISTO_LENGTH, s_keep[0], s_keep[1], s_keep[2]);
+        __syncthreads();
+    }
+    int mine = 0;
+    for (int i = tid; i < F1.n; i += T) {
+        const int j = match12[i];
+        if (j < 0) continue;
+        if (check_ori) {
+            const int b = rot_bin(F1.angle[i], F2.angle[j]);
+            if (b != s_keep[0] && b != s_keep[1] && b != s_keep[2]) { match12[i] = -1; continue; }
+        }
+        mine++;
+    }
+    if (mine) atomicAdd(&s_count, mine);
+    __syncthreads();
+    if (tid == 0) out_info[0] = s_count;
+}
+
 }  // namespace coeb
 
 // =====================================================================================================================
@@ -1638,6 +1723,80 @@ int coeb_search_local_points(coeb_matcher* m, coeb_frame* F, coeb_local_map* lm,
     if (in_view_out) std::memcpy(in_view_out, m->out.h + al(K * 4) + 256, N);
     if (proj_out) std::memcpy(proj_out, m->out.h + al(K * 4) + 256 + al(N), N * 20);
     if (nmatches_out) *nmatches_out = ((const int*)(m->out.h + al(K * 4)))[0];
+    return COEB_OK;
+}
+
+// ---- SearchByBoW ------------------------------------------------------------------------------------------------------------
+namespace {
+// A DBoW2::FeatureVector as CSR must have ascending unique node ids, monotone starts and every feature index at most once.
+int check_featvec(const char* which, int n_feat, int nn, const int* node, const int* start, const int* items, std::vector<uint8_t>& seen) {
+    if (nn < 0 || (nn > 0 && (!node || !start || !items))) return fail(COEB_ERR_INVALID_ARG, "%s: null feature vector", which);
+    if (nn == 0) return COEB_OK;
+    if (start[0] != 0) return fail(COEB_ERR_INVALID_ARG, "%s: start[0] != 0", which);
+    seen.assign((size_t)std::max(n_feat, 1), 0);
+    for (int k = 0; k < nn; k++) {
+        if (k && node[k] <= node[k - 1]) return fail(COEB_ERR_INVALID_ARG, "%s: node ids not ascending at %d", which, k);
+        if (start[k + 1] < start[k]) return fail(COEB_ERR_INVALID_ARG, "%s: starts not monotone at %d", which, k);
+        for (int p = start[k]; p < start[k + 1]; p++) {
+            const int i = items[p];
+            if (i < 0 || i >= n_feat) return fail(COEB_ERR_INVALID_ARG, "%s: feature index %d out of range", which, i);
+            if (seen[i]) return fail(COEB_ERR_INVALID_ARG, "%s: feature %d listed under two nodes", which, i);
+            seen[i] = 1;
+        }
+    }
+    return COEB_OK;
+}
+}  // namespace
+
+int coeb_match_bow(coeb_matcher* m, coeb_frame* f1, coeb_frame* f2, const uint8_t* valid1, const uint8_t* valid2, int nn1,
+                   const int* node1, const int* start1, const int* items1, int nn2, const int* node2, const int* start2,
+                   const int* items2, float nnratio, int check_ori, int strict_low, int* match12, int* nmatches_out) {
+    if (!m || !f1 || !f2 || !match12) return fail(COEB_ERR_INVALID_ARG, "bad argument");
+    if (nmatches_out) *nmatches_out = 0;
+    for (int i = 0; i < f1->n; i++) match12[i] = -1;
+    if (f1->n == 0 || f2->n == 0) return COEB_OK;
+    if (!valid1) return fail(COEB_ERR_INVALID_ARG, "null valid1");
+    std::vector<uint8_t> seen;
+    int st;
+    if ((st = check_featvec("feature vector 1", f1->n, nn1, node1, start1, items1, seen)) != COEB_OK) return st;
+    if ((st = check_featvec("feature vector 2", f2->n, nn2, node2, start2, items2, seen)) != COEB_OK) return st;
+    // the `while (KFit != KFend && Fit != Fend)` merge with lower_bound (:183-262): the nodes present in both vectors
+    std::vector<int4> common;
+    for (int a = 0, b = 0; a < nn1 && b < nn2;) {
+        if (node1[a] == node2[b]) {
+            if (start1[a + 1] > start1[a] && start2[b + 1] > start2[b]) common.push_back(make_int4(start1[a], start1[a + 1], start2[b], start2[b + 1]));
+            a++; b++;
+        } else if (node1[a] < node2[b]) a = (int)(std::lower_bound(node1 + a, node1 + nn1, node2[b]) - node1);
+        else b = (int)(std::lower_bound(node2 + b, node2 + nn2, node1[a]) - node2);
+    }
+    if (common.empty()) return COEB_OK;
+    CUDA_TRY(cudaSetDevice(m->device));
+    const size_t N1 = f1->n, N2 = f2->n, NC = common.size(), I1 = start1[nn1], I2 = start2[nn2];
+    if ((st = m->in.reserve(al(NC * 16) + al(I1 * 4) + al(I2 * 4) + al(N1) + al(N2))) != COEB_OK) return st;
+    if ((st = m->out.reserve(al(N1 * 4) + 256)) != COEB_OK) return st;
+    if ((st = grow(&m->d_scratch, &m->scratch_bytes, al(N2 * 4))) != COEB_OK) return st;
+    Packer p(m->in);
+    BowArgs a{};
+    a.n_common = (int)NC;
+    a.nodes = p.place(common.data(), NC);
+    a.items1 = p.place(items1, I1);
+    a.items2 = p.place(items2, I2);
+    a.valid1 = p.place(valid1, N1);
+    a.valid2 = valid2 ? p.place(valid2, N2) : nullptr;
+    a.nnratio = nnratio;
+    a.strict_low = strict_low;
+    if ((st = push_inputs(m, p)) != COEB_OK) return st;
+    int* d_m12 = (int*)m->out.d;
+    int* d_info = (int*)(m->out.d + al(N1 * 4));
+    int* d_matched2 = (int*)m->d_scratch;
+    CUDA_TRY(cudaMemsetAsync(d_m12, 0xFF, N1 * 4, m->stream));
+    CUDA_TRY(cudaMemsetAsync(d_matched2, 0, N2 * 4, m->stream));
+    bow_node_kernel<<<(unsigned)((NC * 32 + 127) / 128), 128, 0, m->stream>>>(f1->dev, f2->dev, a, d_m12, d_matched2);
+    bow_finish_kernel<<<1, 1024, 0, m->stream>>>(f1->dev, f2->dev, check_ori, d_m12, d_info);
+    CUDA_TRY(cudaGetLastError());
+    if ((st = pull_outputs(m, al(N1 * 4) + 4)) != COEB_OK) return st;
+    std::memcpy(match12, m->out.h, N1 * 4);
+    if (nmatches_out) *nmatches_out = ((const int*)(m->out.h + al(N1 * 4)))[0];
     return COEB_OK;
 }
 

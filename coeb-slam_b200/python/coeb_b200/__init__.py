@@ -296,6 +296,18 @@ class Matcher:
                                               _p(in_view), _p(proj), C.byref(n)))
         return n.value, kp_match, in_view, proj
 
+    def match_bow(self, f1, f2, valid1, valid2, fv1, fv2, nnratio, check_ori=True, strict_low=False):
+        """ORBmatcher::SearchByBoW; fv = (node, start, items) CSR of a DBoW2 FeatureVector. Returns (n, match12)."""
+        valid1 = _u8(valid1)
+        valid2 = None if valid2 is None else _u8(valid2)
+        n1, s1, i1 = (_i32(a) for a in fv1)
+        n2, s2, i2 = (_i32(a) for a in fv2)
+        m12 = np.empty(f1.n, np.int32)
+        n = C.c_int()
+        _check(lib().coeb_match_bow(self.h, f1.h, f2.h, _p(valid1), _p(valid2), len(n1), _p(n1), _p(s1), _p(i1), len(n2), _p(n2),
+                                    _p(s2), _p(i2), C.c_float(nnratio), int(check_ori), int(strict_low), _p(m12), C.byref(n)))
+        return n.value, m12
+
     def match_projection(self, frame, mp, th, nnratio, kp_match):
         kp_match = _i32(kp_match).copy()
         a = dict(track_in_view=_u8(mp["track_in_view"]), bad=_u8(mp["bad"]), has_obs=_u8(mp["has_obs"]),

@@ -332,3 +332,22 @@ def make_depth(seed=0, w=640, h=480, factor=5000.0):
     holes = _upsample_bilinear(rng.random((h // 16 + 2, w // 16 + 2)), h, w) < 0.3
     d[holes] = 0
     return np.ascontiguousarray(d)
+
+
+def make_feature_vector(desc, n_nodes=100, seed=0):
+    """A stand-in for DBoW2's FeatureVector (vocabulary->transform(..., levelsup=4)): every descriptor is assigned to the
+    nearest of `n_nodes` fixed random 256-bit centres (Hamming), which is what a vocabulary-tree node at that level is.
+    Returns the CSR triple (node ids ascending, start, items in ascending feature index = DBoW2's push order)."""
+    rng = np.random.default_rng(seed + 733)   # the 'vocabulary' depends on the seed only
+    centres = rng.integers(0, 256, size=(n_nodes, 32), dtype=np.uint8)
+    d = np.unpackbits(desc[:, None, :] ^ centres[None, :, :], axis=2).sum(axis=2)
+    node_of = d.argmin(axis=1)
+    nodes, start, items = [], [0], []
+    for k in range(n_nodes):
+        idx = np.nonzero(node_of == k)[0]
+        if len(idx) == 0:
+            continue   # a FeatureVector only holds the nodes that occur
+        nodes.append(7 * k + 3)   # arbitrary ascending ids
+        items.extend(idx.tolist())
+        start.append(len(items))
+    return np.array(nodes, np.int32), np.array(start, np.int32), np.array(items, np.int32)

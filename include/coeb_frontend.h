@@ -247,6 +247,20 @@ int coeb_match_lastframe(coeb_matcher* m, coeb_frame* cur, int n, const uint8_t*
 int coeb_match_init(coeb_matcher* m, coeb_frame* f1, coeb_frame* f2, float* prev_matched, int* matches12,
                     int window_size, float nnratio, int check_ori, int* nmatches_out);
 
+/* ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vpMapPointMatches) (src/ORBmatcher.cc:158-288; strict_low = 0,
+ * valid2 = NULL) and ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vpMatches12) (:522-655; strict_low = 1).
+ * The DBoW2::FeatureVector of each side (mFeatVec, produced by the reference's vocabulary, which stays the reference's)
+ * is passed flattened: nn nodes with ascending ids `node`, node k owning items[start[k] .. start[k+1]) = feature
+ * indices in DBoW2's push order. f1 holds the query side (the keyframe), f2 the searched side.
+ *   valid1 : f1.n bytes, MapPoint exists and !isBad() (:190-196, :558-562)
+ *   valid2 : f2.n bytes or NULL (:575-581; a Frame has no such filter)
+ *   match12: f1.n ints out, matched feature of f2 or -1. For the Frame overload the caller writes
+ *            vpMapPointMatches[match12[i]] = vpMapPointsKF[i].
+ * Returns the match count after the rotation-histogram check (check_ori = mbCheckOrientation). */
+int coeb_match_bow(coeb_matcher* m, coeb_frame* f1, coeb_frame* f2, const uint8_t* valid1, const uint8_t* valid2, int nn1,
+                   const int* node1, const int* start1, const int* items1, int nn2, const int* node2, const int* start2,
+                   const int* items2, float nnratio, int check_ori, int strict_low, int* match12, int* nmatches_out);
+
 /* Frame::ComputeStereoMatches (src/Frame.cc:644-818). Keypoints/descriptors are host arrays; the two
  * pyramids are taken from the extractors that produced them (their last call, frame 0).
  * uright_out / depth_out: N floats (mvuRight, mvDepth; -1 = none). */

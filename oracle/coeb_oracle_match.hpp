@@ -406,6 +406,77 @@ static inline int compute_stereo_matches(int N, const coeb_keypoint* keysL, cons
     return kept;
 }
 
+// DBoW2::FeatureVector flattened: `nn` vocabulary nodes in ascending id order (std::map iteration order), node k owning
+// items[start[k] .. start[k+1]) = indices of the frame's features, in the order DBoW2 pushed them.
+struct FeatVecCSR {
+    int nn = 0;
+    const int* node = nullptr;    // [nn] ascending, unique
+    const int* start = nullptr;   // [nn + 1]
+    const int* items = nullptr;   // [start[nn]]
+    int lower_bound(int from, int id) const {
+        return (int)(std::lower_bound(node + from, node + nn, id) - node);
+    }
+};
+
+// ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vpMapPointMatches) (src/ORBmatcher.cc:158-288) and
+// ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vpMatches12) (:522-655) as one restatement.
+//   F1 = the keyframe whose features are the queries, valid1[i] = its MapPoint exists and is not bad (:190-196, :558-562);
+//   F2 = the frame / keyframe searched; valid2 = nullptr for a Frame (every feature is a candidate), else MapPoint exists
+//        and is not bad (:575-581); a feature of F2 already matched by an earlier query of the call is skipped (:210, :577);
+//   strict_low: the Frame overload accepts bestDist1 <= TH_LOW (:229), the KeyFrame overload bestDist1 < TH_LOW (:601).
+// match12[i1] = matched feature of F2 or -1. For the Frame overload the caller writes vpMapPointMatches[match12[i1]] =
+// vpMapPointsKF[i1]; its rotation histogram holds bestIdxF (:246), which removes exactly the same pairs.
+static inline int search_by_bow(const FrameView& F1, const FrameView& F2, const uint8_t* valid1, const uint8_t* valid2,
+                                const FeatVecCSR& V1, const FeatVecCSR& V2, float nnratio, bool checkOri, bool strict_low,
+                                int* match12) {
+    for (int i = 0; i < F1.n; i++) match12[i] = -1;
+    std::vector<uint8_t> matched2(F2.n, 0);
+    std::vector<int> rotHist[COEB_HISTO_LENGTH];
+    int nmatches = 0;
+    int it1 = 0, it2 = 0;
+    while (it1 != V1.nn && it2 != V2.nn) {
+        if (V1.node[it1] == V2.node[it2]) {
+            for (int p1 = V1.start[it1]; p1 < V1.start[it1 + 1]; p1++) {
+                const int idx1 = V1.items[p1];
+                if (!valid1[idx1]) continue;
+                const uint8_t* d1 = F1.desc + (size_t)idx1 * 32;
+                int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+                for (int p2 = V2.start[it2]; p2 < V2.start[it2 + 1]; p2++) {
+                    const int idx2 = V2.items[p2];
+                    if (matched2[idx2] || (valid2 && !valid2[idx2])) continue;
+                    const int dist = hamming256(d1, F2.desc + (size_t)idx2 * 32);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = idx2; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+                if (strict_low ? bestDist1 < COEB_TH_LOW : bestDist1 <= COEB_TH_LOW) {
+                    if ((float)bestDist1 < nnratio * (float)bestDist2) {
+                        match12[idx1] = bestIdx2;
+                        matched2[bestIdx2] = 1;
+                        if (checkOri) rotHist[rot_bin(F1.kps[idx1].angle, F2.kps[bestIdx2].angle)].push_back(idx1);
+                        nmatches++;
+                    }
+                }
+            }
+            it1++;
+            it2++;
+        } else if (V1.node[it1] < V2.node[it2]) {
+            it1 = V1.lower_bound(it1, V2.node[it2]);
+        } else {
+            it2 = V2.lower_bound(it2, V1.node[it1]);
+        }
+    }
+    if (checkOri) {
+        int sizes[COEB_HISTO_LENGTH], ind1, ind2, ind3;
+        for (int i = 0; i < COEB_HISTO_LENGTH; i++) sizes[i] = (int)rotHist[i].size();
+        three_maxima(sizes, COEB_HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < COEB_HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx1 : rotHist[i]) { match12[idx1] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
+}
+
 // Brute-force k=2 nearest neighbour + ratio test (BASELINE.json config 5). Not a reference
 // function; semantics borrowed from the SearchByBoW inner loop (src/ORBmatcher.cc:201-231) applied
 // to the whole train set: strict '<' updates, first index wins ties, accept if best <= TH_LOW and

@@ -346,3 +346,15 @@ def search_local_points(frame, lm, skip, has_obs, Tcw, Ow, th, nnratio, kp_match
                                        _p(a["desc"]), _p(skip), _p(has_obs), _p(tc), _p(ow), C.c_float(cos_limit),
                                        C.c_float(th), C.c_float(nnratio), _p(kp_match), _p(in_view), _p(proj))
     return nm, kp_match, in_view, proj
+
+
+def match_bow(f1, f2, valid1, valid2, fv1, fv2, nnratio, check_ori=True, strict_low=False):
+    """ORBmatcher::SearchByBoW. fv = (node[nn], start[nn+1], items) CSR of the DBoW2 FeatureVector. Returns (n, match12)."""
+    valid1 = _u8(valid1)
+    valid2 = None if valid2 is None else _u8(valid2)
+    n1, s1, i1 = (_i32(a) for a in fv1)
+    n2, s2, i2 = (_i32(a) for a in fv2)
+    m12 = np.empty(f1.n, np.int32)
+    n = lib().orc_match_bow(f1.h, f2.h, _p(valid1), _p(valid2), len(n1), _p(n1), _p(s1), _p(i1), len(n2), _p(n2), _p(s2), _p(i2),
+                            C.c_float(nnratio), int(check_ori), int(strict_low), _p(m12))
+    return n, m12
