@@ -967,6 +967,64 @@ __global__ void __launch_bounds__(128) bow_node_kernel(FrameDev F1, FrameDev F2,
     }
 }
 
+// ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:657-824): same node walk without loop-carried state (the
+// `vbMatched2[bestIdx2] = true` of the reference is commented out, :765). `dist > bestDist` skips, so among the
+// candidates that pass the geometric tests the smallest distance wins and, on a tie, the LAST one in list order.
+struct TriArgs {
+    float F12[9];
+    float ex, ey;
+    int only_stereo;
+};
+
+__device__ __forceinline__ bool check_dist_epipolar_line(float x1, float y1, float x2, float y2, const float* F12, float sigma2) {   // :140-156
+    const float a = __fadd_rn(__fadd_rn(__fmul_rn(x1, F12[0]), __fmul_rn(y1, F12[3])), F12[6]);
+    const float b = __fadd_rn(__fadd_rn(__fmul_rn(x1, F12[1]), __fmul_rn(y1, F12[4])), F12[7]);
+    const float c = __fadd_rn(__fadd_rn(__fmul_rn(x1, F12[2]), __fmul_rn(y1, F12[5])), F12[8]);
+    const float num = __fadd_rn(__fadd_rn(__fmul_rn(a, x2), __fmul_rn(b, y2)), c);
+    const float den = __fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b));
+    if (den == 0.f) return false;
+    const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+    return (double)dsqr < __dmul_rn(3.84, (double)sigma2);
+}
+
+__global__ void __launch_bounds__(128) triangulation_node_kernel(FrameDev F1, FrameDev F2, BowArgs a, TriArgs t, int* match12) {
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= a.n_common) return;
+    const int4 nd = a.nodes[w];
+    for (int p1 = nd.x; p1 < nd.y; p1++) {
+        const int idx1 = a.items1[p1];
+        if (!a.valid1[idx1]) continue;   // pMP1 exists (:697-701)
+        const bool stereo1 = F1.uright && F1.uright[idx1] >= 0.f;
+        if (t.only_stereo && !stereo1) continue;
+        const uint32_t* d1 = F1.desc + 8 * (size_t)idx1;
+        const float x1 = F1.x[idx1], y1 = F1.y[idx1];
+        int best = COEB_TH_LOW, pos = -1, i2best = -1;
+        for (int p2 = nd.z + lane; p2 < nd.w; p2 += 32) {
+            const int idx2 = a.items2[p2];
+            if (!a.valid2[idx2]) continue;
+            const bool stereo2 = F2.uright && F2.uright[idx2] >= 0.f;
+            if (t.only_stereo && !stereo2) continue;
+            const int dist = hamming256(d1, F2.desc + 8 * (size_t)idx2);
+            if (dist > COEB_TH_LOW || dist > best) continue;
+            const float x2 = F2.x[idx2], y2 = F2.y[idx2], sc = F2.scale[F2.octave[idx2]];
+            if (!stereo1 && !stereo2) {
+                const float dxe = __fsub_rn(t.ex, x2), dye = __fsub_rn(t.ey, y2);
+                if (__fadd_rn(__fmul_rn(dxe, dxe), __fmul_rn(dye, dye)) < __fmul_rn(100.f, sc)) continue;
+            }
+            if (check_dist_epipolar_line(x1, y1, x2, y2, t.F12, __fmul_rn(sc, sc))) { best = dist; pos = p2; i2best = idx2; }
+        }
+        // warp merge: smallest distance, then the largest list position
+        int gb = pos >= 0 ? best : 0x7fffffff, gp = pos;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const int ob = __shfl_xor_sync(0xffffffffu, gb, o), op = __shfl_xor_sync(0xffffffffu, gp, o);
+            if (ob < gb || (ob == gb && op > gp)) { gb = ob; gp = op; }
+        }
+        if (gp >= 0 && pos == gp) match12[idx1] = i2best;   // exactly one lane
+    }
+}
+
 // Rotation-consistency check of SearchByBoW (:275-293, :632-652) + the match count. One CTA.
 __global__ void __launch_bounds__(1024) bow_finish_kernel(FrameDev F1, FrameDev F2, int check_ori, int* match12, int* out_info) {
     __shared__ int s_hist[COEB_HISTO_LENGTH];
@@ -1748,26 +1806,25 @@ int check_featvec(const char* which, int n_feat, int nn, const int* node, const 
 }
 }  // namespace
 
-int coeb_match_bow(coeb_matcher* m, coeb_frame* f1, coeb_frame* f2, const uint8_t* valid1, const uint8_t* valid2, int nn1,
-                   const int* node1, const int* start1, const int* items1, int nn2, const int* node2, const int* start2,
-                   const int* items2, float nnratio, int check_ori, int strict_low, int* match12, int* nmatches_out) {
-    if (!m || !f1 || !f2 || !match12) return fail(COEB_ERR_INVALID_ARG, "bad argument");
-    if (nmatches_out) *nmatches_out = 0;
-    for (int i = 0; i < f1->n; i++) match12[i] = -1;
-    if (f1->n == 0 || f2->n == 0) return COEB_OK;
-    if (!valid1) return fail(COEB_ERR_INVALID_ARG, "null valid1");
+// Validates the two feature vectors, intersects their node lists (the `while (KFit != KFend && Fit != Fend)` merge with
+// lower_bound, :183-262) and stages nodes, item lists and the per-feature flags. Returns COEB_OK with a.n_common == 0 when
+// nothing can match.
+static int stage_bow(coeb_matcher* m, coeb_frame* f1, coeb_frame* f2, const uint8_t* valid1, const uint8_t* valid2, int nn1,
+                     const int* node1, const int* start1, const int* items1, int nn2, const int* node2, const int* start2,
+                     const int* items2, BowArgs* out) {
+    BowArgs a{};
+    *out = a;
     std::vector<uint8_t> seen;
     int st;
     if ((st = check_featvec("feature vector 1", f1->n, nn1, node1, start1, items1, seen)) != COEB_OK) return st;
     if ((st = check_featvec("feature vector 2", f2->n, nn2, node2, start2, items2, seen)) != COEB_OK) return st;
-    // the `while (KFit != KFend && Fit != Fend)` merge with lower_bound (:183-262): the nodes present in both vectors
     std::vector<int4> common;
-    for (int a = 0, b = 0; a < nn1 && b < nn2;) {
-        if (node1[a] == node2[b]) {
-            if (start1[a + 1] > start1[a] && start2[b + 1] > start2[b]) common.push_back(make_int4(start1[a], start1[a + 1], start2[b], start2[b + 1]));
-            a++; b++;
-        } else if (node1[a] < node2[b]) a = (int)(std::lower_bound(node1 + a, node1 + nn1, node2[b]) - node1);
-        else b = (int)(std::lower_bound(node2 + b, node2 + nn2, node1[a]) - node2);
+    for (int i = 0, j = 0; i < nn1 && j < nn2;) {
+        if (node1[i] == node2[j]) {
+            if (start1[i + 1] > start1[i] && start2[j + 1] > start2[j]) common.push_back(make_int4(start1[i], start1[i + 1], start2[j], start2[j + 1]));
+            i++; j++;
+        } else if (node1[i] < node2[j]) i = (int)(std::lower_bound(node1 + i, node1 + nn1, node2[j]) - node1);
+        else j = (int)(std::lower_bound(node2 + j, node2 + nn2, node1[i]) - node2);
     }
     if (common.empty()) return COEB_OK;
     CUDA_TRY(cudaSetDevice(m->device));
@@ -1776,22 +1833,66 @@ int coeb_match_bow(coeb_matcher* m, coeb_frame* f1, coeb_frame* f2, const uint8_
     if ((st = m->out.reserve(al(N1 * 4) + 256)) != COEB_OK) return st;
     if ((st = grow(&m->d_scratch, &m->scratch_bytes, al(N2 * 4))) != COEB_OK) return st;
     Packer p(m->in);
-    BowArgs a{};
     a.n_common = (int)NC;
     a.nodes = p.place(common.data(), NC);
     a.items1 = p.place(items1, I1);
     a.items2 = p.place(items2, I2);
     a.valid1 = p.place(valid1, N1);
     a.valid2 = valid2 ? p.place(valid2, N2) : nullptr;
+    if ((st = push_inputs(m, p)) != COEB_OK) return st;
+    *out = a;
+    return COEB_OK;
+}
+
+int coeb_match_bow(coeb_matcher* m, coeb_frame* f1, coeb_frame* f2, const uint8_t* valid1, const uint8_t* valid2, int nn1,
+                   const int* node1, const int* start1, const int* items1, int nn2, const int* node2, const int* start2,
+                   const int* items2, float nnratio, int check_ori, int strict_low, int* match12, int* nmatches_out) {
+    if (!m || !f1 || !f2 || !match12) return fail(COEB_ERR_INVALID_ARG, "bad argument");
+    if (nmatches_out) *nmatches_out = 0;
+    for (int i = 0; i < f1->n; i++) match12[i] = -1;
+    if (f1->n == 0 || f2->n == 0) return COEB_OK;
+    if (!valid1) return fail(COEB_ERR_INVALID_ARG, "null valid1");
+    BowArgs a{};
+    int st = stage_bow(m, f1, f2, valid1, valid2, nn1, node1, start1, items1, nn2, node2, start2, items2, &a);
+    if (st != COEB_OK || a.n_common == 0) return st;
     a.nnratio = nnratio;
     a.strict_low = strict_low;
-    if ((st = push_inputs(m, p)) != COEB_OK) return st;
+    const size_t N1 = f1->n, N2 = f2->n;
     int* d_m12 = (int*)m->out.d;
     int* d_info = (int*)(m->out.d + al(N1 * 4));
     int* d_matched2 = (int*)m->d_scratch;
     CUDA_TRY(cudaMemsetAsync(d_m12, 0xFF, N1 * 4, m->stream));
     CUDA_TRY(cudaMemsetAsync(d_matched2, 0, N2 * 4, m->stream));
-    bow_node_kernel<<<(unsigned)((NC * 32 + 127) / 128), 128, 0, m->stream>>>(f1->dev, f2->dev, a, d_m12, d_matched2);
+    bow_node_kernel<<<(unsigned)(((size_t)a.n_common * 32 + 127) / 128), 128, 0, m->stream>>>(f1->dev, f2->dev, a, d_m12, d_matched2);
+    bow_finish_kernel<<<1, 1024, 0, m->stream>>>(f1->dev, f2->dev, check_ori, d_m12, d_info);
+    CUDA_TRY(cudaGetLastError());
+    if ((st = pull_outputs(m, al(N1 * 4) + 4)) != COEB_OK) return st;
+    std::memcpy(match12, m->out.h, N1 * 4);
+    if (nmatches_out) *nmatches_out = ((const int*)(m->out.h + al(N1 * 4)))[0];
+    return COEB_OK;
+}
+
+int coeb_match_triangulation(coeb_matcher* m, coeb_frame* f1, coeb_frame* f2, const uint8_t* free1, const uint8_t* free2, int nn1,
+                             const int* node1, const int* start1, const int* items1, int nn2, const int* node2, const int* start2,
+                             const int* items2, const float* F12, const float* epipole_xy, int only_stereo, int check_ori,
+                             int* match12, int* nmatches_out) {
+    if (!m || !f1 || !f2 || !match12 || !F12 || !epipole_xy) return fail(COEB_ERR_INVALID_ARG, "bad argument");
+    if (nmatches_out) *nmatches_out = 0;
+    for (int i = 0; i < f1->n; i++) match12[i] = -1;
+    if (f1->n == 0 || f2->n == 0) return COEB_OK;
+    if (!free1 || !free2) return fail(COEB_ERR_INVALID_ARG, "null free1 / free2");
+    BowArgs a{};
+    int st = stage_bow(m, f1, f2, free1, free2, nn1, node1, start1, items1, nn2, node2, start2, items2, &a);
+    if (st != COEB_OK || a.n_common == 0) return st;
+    TriArgs t{};
+    for (int i = 0; i < 9; i++) t.F12[i] = F12[i];
+    t.ex = epipole_xy[0]; t.ey = epipole_xy[1];
+    t.only_stereo = only_stereo;
+    const size_t N1 = f1->n;
+    int* d_m12 = (int*)m->out.d;
+    int* d_info = (int*)(m->out.d + al(N1 * 4));
+    CUDA_TRY(cudaMemsetAsync(d_m12, 0xFF, N1 * 4, m->stream));
+    triangulation_node_kernel<<<(unsigned)(((size_t)a.n_common * 32 + 127) / 128), 128, 0, m->stream>>>(f1->dev, f2->dev, a, t, d_m12);
     bow_finish_kernel<<<1, 1024, 0, m->stream>>>(f1->dev, f2->dev, check_ori, d_m12, d_info);
     CUDA_TRY(cudaGetLastError());
     if ((st = pull_outputs(m, al(N1 * 4) + 4)) != COEB_OK) return st;

@@ -308,6 +308,18 @@ class Matcher:
                                     _p(s2), _p(i2), C.c_float(nnratio), int(check_ori), int(strict_low), _p(m12), C.byref(n)))
         return n.value, m12
 
+    def match_triangulation(self, f1, f2, free1, free2, fv1, fv2, F12, epipole, only_stereo=False, check_ori=True):
+        """ORBmatcher::SearchForTriangulation. Returns (n, match12)."""
+        free1, free2 = _u8(free1), _u8(free2)
+        n1, s1, i1 = (_i32(a) for a in fv1)
+        n2, s2, i2 = (_i32(a) for a in fv2)
+        F, e = _f32(F12).reshape(9), _f32(epipole).reshape(2)
+        m12 = np.empty(f1.n, np.int32)
+        n = C.c_int()
+        _check(lib().coeb_match_triangulation(self.h, f1.h, f2.h, _p(free1), _p(free2), len(n1), _p(n1), _p(s1), _p(i1), len(n2), _p(n2),
+                                              _p(s2), _p(i2), _p(F), _p(e), int(only_stereo), int(check_ori), _p(m12), C.byref(n)))
+        return n.value, m12
+
     def match_projection(self, frame, mp, th, nnratio, kp_match):
         kp_match = _i32(kp_match).copy()
         a = dict(track_in_view=_u8(mp["track_in_view"]), bad=_u8(mp["bad"]), has_obs=_u8(mp["has_obs"]),

@@ -261,6 +261,18 @@ int coeb_match_bow(coeb_matcher* m, coeb_frame* f1, coeb_frame* f2, const uint8_
                    const int* node1, const int* start1, const int* items1, int nn2, const int* node2, const int* start2,
                    const int* items2, float nnratio, int check_ori, int strict_low, int* match12, int* nmatches_out);
 
+/* ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo) (src/ORBmatcher.cc:657-824), with
+ * CheckDistEpipolarLine (:140-156). Feature vectors as in coeb_match_bow; the frames must carry mvuRight when the
+ * keyframes are stereo / RGB-D (a frame without it counts as monocular).
+ *   free1 / free2 : n bytes each, the feature has NO MapPoint yet (:697-701, :722-726)
+ *   F12           : 3x3 row-major fundamental matrix;  epipole_xy : (ex, ey) of :663-670, which the caller computes with
+ *                   the reference's own cv::Mat expressions (R2w * Cw + t2w, projected)
+ *   match12       : f1.n ints out, vMatches12 (:685); the caller builds vMatchedPairs from the entries >= 0 (:812-819). */
+int coeb_match_triangulation(coeb_matcher* m, coeb_frame* f1, coeb_frame* f2, const uint8_t* free1, const uint8_t* free2,
+                             int nn1, const int* node1, const int* start1, const int* items1, int nn2, const int* node2,
+                             const int* start2, const int* items2, const float* F12, const float* epipole_xy,
+                             int only_stereo, int check_ori, int* match12, int* nmatches_out);
+
 /* Frame::ComputeStereoMatches (src/Frame.cc:644-818). Keypoints/descriptors are host arrays; the two
  * pyramids are taken from the extractors that produced them (their last call, frame 0).
  * uright_out / depth_out: N floats (mvuRight, mvDepth; -1 = none). */

@@ -286,6 +286,16 @@ int orc_match_bow(orc_frame* f1, orc_frame* f2, const uint8_t* valid1, const uin
     return search_by_bow(f1->v, f2->v, valid1, valid2, V1, V2, nnratio, check_ori != 0, strict_low != 0, match12);
 }
 
+int orc_match_triangulation(orc_frame* f1, orc_frame* f2, const uint8_t* free1, const uint8_t* free2, int nn1, const int* node1,
+                            const int* start1, const int* items1, int nn2, const int* node2, const int* start2,
+                            const int* items2, const float* F12, float ex, float ey, int only_stereo, int check_ori,
+                            int* match12) {
+    FeatVecCSR V1, V2;
+    V1.nn = nn1; V1.node = node1; V1.start = start1; V1.items = items1;
+    V2.nn = nn2; V2.node = node2; V2.start = start2; V2.items = items2;
+    return search_for_triangulation(f1->v, f2->v, free1, free2, V1, V2, F12, ex, ey, only_stereo != 0, check_ori != 0, match12);
+}
+
 // Number of floats in [lo, hi) (bit patterns, stepped by `step`) whose restated logf differs from the C library's.
 long orc_logf_mismatches(uint32_t lo, uint32_t hi, uint32_t step) {
     long bad = 0;

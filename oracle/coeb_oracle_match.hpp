@@ -477,6 +477,84 @@ static inline int search_by_bow(const FrameView& F1, const FrameView& F2, const 
     return nmatches;
 }
 
+// ORBmatcher::CheckDistEpipolarLine (src/ORBmatcher.cc:140-156): fp32 left to right, the final comparison in double
+// (3.84 is a double literal). sigma2 = pKF2->mvLevelSigma2[kp2.octave].
+static inline bool check_dist_epipolar_line(const coeb_keypoint& kp1, const coeb_keypoint& kp2, const float* F12, float sigma2) {
+    const float a = kp1.x * F12[0] + kp1.y * F12[3] + F12[6];
+    const float b = kp1.x * F12[1] + kp1.y * F12[4] + F12[7];
+    const float c = kp1.x * F12[2] + kp1.y * F12[5] + F12[8];
+    const float num = a * kp2.x + b * kp2.y + c;
+    const float den = a * a + b * b;
+    if (den == 0) return false;
+    const float dsqr = num * num / den;
+    return (double)dsqr < 3.84 * (double)sigma2;
+}
+
+// ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:657-824). free1 / free2: the keyframe's feature has no MapPoint
+// (:697-701, :722-726); F12 3x3 row-major; (ex, ey) the epipole in the second image (:663-670, computed by the caller with
+// the reference's own cv::Mat expressions); the `vbMatched2[bestIdx2] = true` line is commented out in the reference
+// (:765), so queries do not interact. Ties: `dist > bestDist` skips, so an equal distance met later replaces the match.
+static inline int search_for_triangulation(const FrameView& F1, const FrameView& F2, const uint8_t* free1, const uint8_t* free2,
+                                           const FeatVecCSR& V1, const FeatVecCSR& V2, const float* F12, float ex, float ey,
+                                           bool bOnlyStereo, bool checkOri, int* match12) {
+    for (int i = 0; i < F1.n; i++) match12[i] = -1;
+    std::vector<int> rotHist[COEB_HISTO_LENGTH];
+    int nmatches = 0;
+    int it1 = 0, it2 = 0;
+    while (it1 != V1.nn && it2 != V2.nn) {
+        if (V1.node[it1] == V2.node[it2]) {
+            for (int p1 = V1.start[it1]; p1 < V1.start[it1 + 1]; p1++) {
+                const int idx1 = V1.items[p1];
+                if (!free1[idx1]) continue;
+                const bool bStereo1 = F1.uright && F1.uright[idx1] >= 0;
+                if (bOnlyStereo && !bStereo1) continue;
+                const coeb_keypoint& kp1 = F1.kps[idx1];
+                const uint8_t* d1 = F1.desc + (size_t)idx1 * 32;
+                int bestDist = COEB_TH_LOW, bestIdx2 = -1;
+                for (int p2 = V2.start[it2]; p2 < V2.start[it2 + 1]; p2++) {
+                    const int idx2 = V2.items[p2];
+                    if (!free2[idx2]) continue;
+                    const bool bStereo2 = F2.uright && F2.uright[idx2] >= 0;
+                    if (bOnlyStereo && !bStereo2) continue;
+                    const int dist = hamming256(d1, F2.desc + (size_t)idx2 * 32);
+                    if (dist > COEB_TH_LOW || dist > bestDist) continue;
+                    const coeb_keypoint& kp2 = F2.kps[idx2];
+                    if (!bStereo1 && !bStereo2) {
+                        const float distex = ex - kp2.x, distey = ey - kp2.y;
+                        if (distex * distex + distey * distey < 100 * F2.scale[kp2.octave]) continue;
+                    }
+                    const float s = F2.scale[kp2.octave];
+                    if (check_dist_epipolar_line(kp1, kp2, F12, s * s)) {   // mvLevelSigma2[i] = mvScaleFactor[i]^2 (src/ORBextractor.cc:427)
+                        bestIdx2 = idx2;
+                        bestDist = dist;
+                    }
+                }
+                if (bestIdx2 >= 0) {
+                    match12[idx1] = bestIdx2;
+                    nmatches++;
+                    if (checkOri) rotHist[rot_bin(kp1.angle, F2.kps[bestIdx2].angle)].push_back(idx1);
+                }
+            }
+            it1++;
+            it2++;
+        } else if (V1.node[it1] < V2.node[it2]) {
+            it1 = V1.lower_bound(it1, V2.node[it2]);
+        } else {
+            it2 = V2.lower_bound(it2, V1.node[it1]);
+        }
+    }
+    if (checkOri) {
+        int sizes[COEB_HISTO_LENGTH], ind1, ind2, ind3;
+        for (int i = 0; i < COEB_HISTO_LENGTH; i++) sizes[i] = (int)rotHist[i].size();
+        three_maxima(sizes, COEB_HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < COEB_HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx1 : rotHist[i]) { match12[idx1] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
+}
+
 // Brute-force k=2 nearest neighbour + ratio test (BASELINE.json config 5). Not a reference
 // function; semantics borrowed from the SearchByBoW inner loop (src/ORBmatcher.cc:201-231) applied
 // to the whole train set: strict '<' updates, first index wins ties, accept if best <= TH_LOW and

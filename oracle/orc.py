@@ -358,3 +358,15 @@ def match_bow(f1, f2, valid1, valid2, fv1, fv2, nnratio, check_ori=True, strict_
     n = lib().orc_match_bow(f1.h, f2.h, _p(valid1), _p(valid2), len(n1), _p(n1), _p(s1), _p(i1), len(n2), _p(n2), _p(s2), _p(i2),
                             C.c_float(nnratio), int(check_ori), int(strict_low), _p(m12))
     return n, m12
+
+
+def match_triangulation(f1, f2, free1, free2, fv1, fv2, F12, epipole, only_stereo=False, check_ori=True):
+    """ORBmatcher::SearchForTriangulation. Returns (n, match12)."""
+    free1, free2 = _u8(free1), _u8(free2)
+    n1, s1, i1 = (_i32(a) for a in fv1)
+    n2, s2, i2 = (_i32(a) for a in fv2)
+    F = _f32(F12).reshape(9)
+    m12 = np.empty(f1.n, np.int32)
+    n = lib().orc_match_triangulation(f1.h, f2.h, _p(free1), _p(free2), len(n1), _p(n1), _p(s1), _p(i1), len(n2), _p(n2), _p(s2), _p(i2),
+                                      _p(F), C.c_float(epipole[0]), C.c_float(epipole[1]), int(only_stereo), int(check_ori), _p(m12))
+    return n, m12

@@ -80,3 +80,47 @@ def test_search_by_bow_disjoint_and_partial_vocabularies(gpu, pair):
     dup[1] = dup[0]
     with pytest.raises(gpu.CoebError):
         m.match_bow(fg1, fg2, valid1, None, (n1, s1, dup), fv2, 0.9)
+
+
+def _shift_fundamental(dx, dy):
+    """F12 of two views related by a pure image shift (dx, dy): the epipolar line of x1 is the line through x1 along the shift."""
+    return np.array([[0, 0, dy], [0, 0, -dx], [-dy, dx, 0]], np.float32)
+
+
+@pytest.mark.parametrize("only_stereo,ori,epipole,with_uright", [(False, True, (1e7, -1e7), False), (False, True, (320.0, 240.0), True),
+                                                                 (True, True, (320.0, 240.0), True), (False, False, (100.0, 50.0), False)])
+def test_search_for_triangulation_matches_oracle(gpu, pair, only_stereo, ori, epipole, with_uright):
+    rng = np.random.default_rng(21)
+    ur1 = ur2 = None
+    if with_uright:
+        ur1 = np.where(rng.random(len(pair["k1"])) < 0.6, pair["k1"]["x"] - np.float32(8), np.float32(-1)).astype(np.float32)
+        ur2 = np.where(rng.random(len(pair["k2"])) < 0.6, pair["k2"]["x"] - np.float32(8), np.float32(-1)).astype(np.float32)
+    m = gpu.Matcher()
+    fg1 = m.frame(pair["k1"], pair["d1"], gpu.Camera(*CAM), pair["scale"], ur1)
+    fg2 = m.frame(pair["k2"], pair["d2"], gpu.Camera(*CAM), pair["scale"], ur2)
+    fc1 = orc.Frame(pair["k1"], pair["d1"], orc.Camera(*CAM), pair["scale"], ur1)
+    fc2 = orc.Frame(pair["k2"], pair["d2"], orc.Camera(*CAM), pair["scale"], ur2)
+    free1 = (rng.random(fc1.n) < 0.7).astype(np.uint8)
+    free2 = (rng.random(fc2.n) < 0.7).astype(np.uint8)
+    fv1 = synth.make_feature_vector(pair["d1"], 40, seed=5)
+    fv2 = synth.make_feature_vector(pair["d2"], 40, seed=5)
+    F12 = _shift_fundamental(6.0, -4.0)
+    ng, mg = m.match_triangulation(fg1, fg2, free1, free2, fv1, fv2, F12, epipole, only_stereo, ori)
+    nc, mc = orc.match_triangulation(fc1, fc2, free1, free2, fv1, fv2, F12, epipole, only_stereo, ori)
+    assert ng == nc and np.array_equal(mg, mc)
+    assert nc > 20
+    ok = mg >= 0
+    assert free1[ok].all() and free2[mg[ok]].all()
+    if only_stereo:
+        assert (ur1[ok] >= 0).all() and (ur2[mg[ok]] >= 0).all()
+    # duplicated descriptors on the searched side: equal distances, the LAST candidate in list order must win on both sides
+    k2d = np.concatenate([pair["k2"], pair["k2"]])
+    d2d = np.concatenate([pair["d2"], pair["d2"]])
+    fg2d = m.frame(k2d, d2d, gpu.Camera(*CAM), pair["scale"], None if ur2 is None else np.concatenate([ur2, ur2]))
+    fc2d = orc.Frame(k2d, d2d, orc.Camera(*CAM), pair["scale"], None if ur2 is None else np.concatenate([ur2, ur2]))
+    fv2d = synth.make_feature_vector(d2d, 40, seed=5)
+    free2d = np.concatenate([free2, free2])
+    ng, mg = m.match_triangulation(fg1, fg2d, free1, free2d, fv1, fv2d, F12, epipole, only_stereo, ori)
+    nc, mc = orc.match_triangulation(fc1, fc2d, free1, free2d, fv1, fv2d, F12, epipole, only_stereo, ori)
+    assert ng == nc and np.array_equal(mg, mc)
+    assert (mc[mc >= 0] >= len(pair["k2"])).all(), "ties must resolve to the later duplicate"
