@@ -85,6 +85,9 @@ struct coeb_extractor {
     cudaStream_t pipe_stream[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t pipe_done[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t pipe_ready = nullptr;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;     // dedicated H2D / D2H streams of the pipelined host entry point
+    cudaEvent_t copy_out_done = nullptr;
+    std::vector<cudaEvent_t> chunk_in, chunk_done;           // per sub-batch: input resident / kernels finished
     // blur runs beside FAST + octree on a side stream (both only need the pyramid); one lane per launching stream
     struct Lane { cudaStream_t main; cudaStream_t aux; cudaEvent_t fork, join; };
     std::vector<Lane> lanes;
@@ -398,6 +401,20 @@ int ensure_pipe_streams(coeb_extractor* ex) {
         CUDA_TRY(cudaEventCreateWithFlags(&ex->pipe_done[i], cudaEventDisableTiming));
     }
     CUDA_TRY(cudaEventCreateWithFlags(&ex->pipe_ready, cudaEventDisableTiming));
+    CUDA_TRY(cudaStreamCreateWithFlags(&ex->copy_in, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&ex->copy_out, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&ex->copy_out_done, cudaEventDisableTiming));
+    return COEB_OK;
+}
+
+int ensure_chunk_events(coeb_extractor* ex, int n) {
+    while ((int)ex->chunk_in.size() < n) {
+        cudaEvent_t a = nullptr, b = nullptr;
+        CUDA_TRY(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        ex->chunk_in.push_back(a);
+        ex->chunk_done.push_back(b);
+    }
     return COEB_OK;
 }
 
@@ -474,6 +491,11 @@ void coeb_extractor_destroy(coeb_extractor* ex) {
         if (ex->pipe_done[i]) cudaEventDestroy(ex->pipe_done[i]);
     }
     if (ex->pipe_ready) cudaEventDestroy(ex->pipe_ready);
+    if (ex->copy_in) cudaStreamDestroy(ex->copy_in);
+    if (ex->copy_out) cudaStreamDestroy(ex->copy_out);
+    if (ex->copy_out_done) cudaEventDestroy(ex->copy_out_done);
+    for (auto e : ex->chunk_in) cudaEventDestroy(e);
+    for (auto e : ex->chunk_done) cudaEventDestroy(e);
     cudaStreamDestroy(ex->own_stream);
     delete ex;
 }
@@ -726,58 +748,97 @@ int coeb_extract_batch_host(coeb_extractor* ex, int B, const uint8_t* gray, int 
     int* hstatus = status_out;
     if (!hstatus) { status_local.resize(B); hstatus = status_local.data(); }
 
-    // Sub-batches of kPipeChunk frames round-robin over kPipeStreams streams: the H2D copy of chunk c+1 and the D2H
-    // copy of chunk c-1 overlap the kernels of chunk c (the arenas are frame-major, so a chunk is a pointer offset).
-    static const int pipe_chunk = [] { const char* e = getenv("COEB_PIPE_CHUNK"); int v = e ? atoi(e) : 0; return v > 0 ? v : kPipeChunk; }();
-    const int chunk = B <= 2 * pipe_chunk ? B : pipe_chunk;
+    // Sub-batches of kPipeChunk frames: all H2D copies go back to back on one copy stream, the kernels of sub-batch c run on
+    // compute stream c % kPipeStreams once its input has landed, and the D2H copies follow on a second copy stream. The H2D
+    // engine never waits for a kernel (the arenas are frame-major, so a sub-batch is a pointer offset and no buffer is reused
+    // inside a call).
+    // 64-frame sub-batches from 256 frames on (a 64-frame launch fills the GPU better than a 32-frame one: 134k against 127k
+    // frames/s device-resident), 32-frame ones below; COEB_PIPE_CHUNK overrides (development).
+    static const int pipe_chunk_env = [] { const char* e = getenv("COEB_PIPE_CHUNK"); int v = e ? atoi(e) : 0; return v > 0 ? v : 0; }();
+    const int pipe_chunk = pipe_chunk_env ? pipe_chunk_env : (B >= 256 ? 2 * kPipeChunk : kPipeChunk);
+    const int chunk = B <= 2 * kPipeChunk || B <= pipe_chunk ? B : pipe_chunk;
     const int nchunks = (B + chunk - 1) / chunk;
     const bool piped = nchunks > 1;
     ex->last_passes = nchunks;
     if (piped) {
-        st = ensure_pipe_streams(ex);
-        if (st != COEB_OK) return st;
+        if ((st = ensure_pipe_streams(ex)) != COEB_OK) return st;
+        if ((st = ensure_chunk_events(ex, nchunks)) != COEB_OK) return st;
     }
-    if (piped) {
-        CUDA_TRY(cudaEventRecord(ex->pipe_ready, s));
-        for (int i = 0; i < kPipeStreams; i++) CUDA_TRY(cudaStreamWaitEvent(ex->pipe_stream[i], ex->pipe_ready, 0));
+    static const bool trace = getenv("COEB_PIPE_TRACE") != nullptr;   // development: per-chunk device timeline on stderr
+    std::vector<cudaEvent_t> tev;
+    if (trace) {
+        tev.resize(1 + 3 * (size_t)nchunks);
+        for (auto& e : tev) cudaEventCreate(&e);
+        cudaEventRecord(tev[0], s);
     }
-    for (int c = 0; c < nchunks; c++) {
-        cudaStream_t ps = piped ? ex->pipe_stream[c % kPipeStreams] : s;
-        const int f0 = c * chunk, n = std::min(chunk, B - f0);
-        if (frame_stride == (size_t)stride * height && stride == pitch && stride == width) {
+    auto upload = [&](int f0, int n, cudaStream_t cs) -> cudaError_t {
+        if (frame_stride == (size_t)stride * height && stride == pitch && stride == width)
             // tightly packed frames whose width is already the arena pitch: one linear DMA (2D copies go row by row)
-            CUDA_TRY(cudaMemcpyAsync(ex->d_in_gray + fstride * f0, gray + frame_stride * f0, fstride * n, cudaMemcpyHostToDevice, ps));
-        } else if (frame_stride == (size_t)stride * height) {
-            CUDA_TRY(cudaMemcpy2DAsync(ex->d_in_gray + fstride * f0, pitch, gray + frame_stride * f0, stride, width, (size_t)height * n,
-                                       cudaMemcpyHostToDevice, ps));
-        } else {
-            for (int i = f0; i < f0 + n; i++)
-                CUDA_TRY(cudaMemcpy2DAsync(ex->d_in_gray + fstride * i, pitch, gray + frame_stride * i, stride, width, height,
-                                           cudaMemcpyHostToDevice, ps));
+            return cudaMemcpyAsync(ex->d_in_gray + fstride * f0, gray + frame_stride * f0, fstride * n, cudaMemcpyHostToDevice, cs);
+        if (frame_stride == (size_t)stride * height)
+            return cudaMemcpy2DAsync(ex->d_in_gray + fstride * f0, pitch, gray + frame_stride * f0, stride, width, (size_t)height * n,
+                                     cudaMemcpyHostToDevice, cs);
+        for (int i = f0; i < f0 + n; i++) {
+            cudaError_t e = cudaMemcpy2DAsync(ex->d_in_gray + fstride * i, pitch, gray + frame_stride * i, stride, width, height,
+                                              cudaMemcpyHostToDevice, cs);
+            if (e != cudaSuccess) return e;
         }
-        if (ex->profiling) {
-            st = enqueue(ex, sub_view(ex->geom, v, f0, n, ex->pyr_bytes_per_frame), ps, !piped);
-        } else {
-            // one graph launch instead of ~20 stream operations; the staging buffers and arenas are the handle's own, so a
-            // (sub-)view recurs call after call
-            st = launch_graphed(ex, piped ? sub_view(ex->geom, v, f0, n, ex->pyr_bytes_per_frame) : v, ps);
-        }
+        return cudaSuccess;
+    };
+    auto download = [&](int f0, int n, cudaStream_t cs) -> cudaError_t {
+        cudaError_t e = cudaMemcpyAsync(counts_out + f0, ex->d_out_count + f0, sizeof(int) * n, cudaMemcpyDeviceToHost, cs);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(hstatus + f0, ex->d_out_status + f0, sizeof(int) * n, cudaMemcpyDeviceToHost, cs);
+        if (e == cudaSuccess && kps_out)
+            e = cudaMemcpyAsync(kps_out + (size_t)f0 * cap, ex->d_out_kps + (size_t)f0 * cap, sizeof(coeb_keypoint) * n * cap, cudaMemcpyDeviceToHost, cs);
+        if (e == cudaSuccess && desc_out)
+            e = cudaMemcpyAsync(desc_out + (size_t)f0 * cap * 32, ex->d_out_desc + (size_t)f0 * cap * 32, (size_t)32 * n * cap, cudaMemcpyDeviceToHost, cs);
+        return e;
+    };
+    if (!piped) {
+        CUDA_TRY(upload(0, B, s));
+        if (trace) cudaEventRecord(tev[1], s);
+        st = ex->profiling ? enqueue(ex, v, s, true) : launch_graphed(ex, v, s);   // one graph launch instead of ~20 stream operations
         if (st != COEB_OK) return st;
-        CUDA_TRY(cudaMemcpyAsync(counts_out + f0, ex->d_out_count + f0, sizeof(int) * n, cudaMemcpyDeviceToHost, ps));
-        CUDA_TRY(cudaMemcpyAsync(hstatus + f0, ex->d_out_status + f0, sizeof(int) * n, cudaMemcpyDeviceToHost, ps));
-        if (kps_out)
-            CUDA_TRY(cudaMemcpyAsync(kps_out + (size_t)f0 * cap, ex->d_out_kps + (size_t)f0 * cap, sizeof(coeb_keypoint) * n * cap,
-                                     cudaMemcpyDeviceToHost, ps));
-        if (desc_out)
-            CUDA_TRY(cudaMemcpyAsync(desc_out + (size_t)f0 * cap * 32, ex->d_out_desc + (size_t)f0 * cap * 32, (size_t)32 * n * cap,
-                                     cudaMemcpyDeviceToHost, ps));
-    }
-    if (piped)
-        for (int i = 0; i < kPipeStreams; i++) {
-            CUDA_TRY(cudaEventRecord(ex->pipe_done[i], ex->pipe_stream[i]));
-            CUDA_TRY(cudaStreamWaitEvent(s, ex->pipe_done[i], 0));
+        if (trace) cudaEventRecord(tev[2], s);
+        CUDA_TRY(download(0, B, s));
+        if (trace) cudaEventRecord(tev[3], s);
+    } else {
+        CUDA_TRY(cudaEventRecord(ex->pipe_ready, s));   // the box / T_M copies above, and whatever the caller queued before
+        CUDA_TRY(cudaStreamWaitEvent(ex->copy_in, ex->pipe_ready, 0));
+        for (int c = 0; c < nchunks; c++) {
+            const int f0 = c * chunk, n = std::min(chunk, B - f0);
+            CUDA_TRY(upload(f0, n, ex->copy_in));
+            CUDA_TRY(cudaEventRecord(ex->chunk_in[c], ex->copy_in));
+            if (trace) cudaEventRecord(tev[1 + 3 * c], ex->copy_in);
         }
+        for (int c = 0; c < nchunks; c++) {
+            cudaStream_t ps = ex->pipe_stream[c % kPipeStreams];
+            const int f0 = c * chunk, n = std::min(chunk, B - f0);
+            CUDA_TRY(cudaStreamWaitEvent(ps, ex->chunk_in[c], 0));
+            const BatchView sv = sub_view(ex->geom, v, f0, n, ex->pyr_bytes_per_frame);
+            // the staging buffers and arenas are the handle's own, so a sub-view recurs call after call: graph replay
+            st = ex->profiling ? enqueue(ex, sv, ps, false) : launch_graphed(ex, sv, ps);
+            if (st != COEB_OK) return st;
+            CUDA_TRY(cudaEventRecord(ex->chunk_done[c], ps));
+            if (trace) cudaEventRecord(tev[2 + 3 * c], ps);
+            CUDA_TRY(cudaStreamWaitEvent(ex->copy_out, ex->chunk_done[c], 0));
+            CUDA_TRY(download(f0, n, ex->copy_out));
+            if (trace) cudaEventRecord(tev[3 + 3 * c], ex->copy_out);
+        }
+        CUDA_TRY(cudaEventRecord(ex->copy_out_done, ex->copy_out));
+        CUDA_TRY(cudaStreamWaitEvent(s, ex->copy_out_done, 0));
+    }
     CUDA_TRY(cudaStreamSynchronize(s));
+    if (trace) {
+        for (int c = 0; c < nchunks; c++) {
+            float a = 0, b = 0, d = 0;
+            cudaEventElapsedTime(&a, tev[0], tev[1 + 3 * c]);
+            cudaEventElapsedTime(&b, tev[0], tev[2 + 3 * c]);
+            cudaEventElapsedTime(&d, tev[0], tev[3 + 3 * c]);
+            fprintf(stderr, "[coeb pipe] chunk %d: h2d done %.3f ms, kernels done %.3f ms, d2h done %.3f ms\n", c, a, b, d);
+        }
+        for (auto& e : tev) cudaEventDestroy(e);
+    }
     int worst = COEB_OK;
     for (int i = 0; i < B; i++)
         if (hstatus[i] != COEB_OK && worst == COEB_OK) {

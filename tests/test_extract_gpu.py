@@ -202,3 +202,26 @@ def test_large_host_batch_takes_the_pipelined_path(gpu):
         nb, nt = batch["nbox"][i], batch["ntm"][i]
         kb, db = c.extract(batch["gray"][i], batch["boxes"][i, :nb], batch["tm"][i, :nt], batch["blur"][i, :nb])
         assert counts[i] == len(kb) and kps[i, :counts[i]].tobytes() == kb.tobytes() and np.array_equal(desc[i, :counts[i]], db), i
+
+
+def test_host_batch_of_260_frames_uses_64_frame_sub_batches_with_a_ragged_tail(gpu):
+    B = 260   # 4 x 64 + 4: copy stream, three compute streams, download stream
+    batch = synth.make_batch(B, base_seed=700, unique=6)
+    g = gpu.Extractor()
+    kps, desc, counts, status = g.extract_batch_host(batch["gray"], batch["boxes"], batch["nbox"], batch["tm"], batch["ntm"], batch["blur"])
+    assert (status == 0).all()
+    # same frames through single-frame calls of another handle: the sub-batch boundaries must not show
+    g1 = gpu.Extractor()
+    c = orc.Extractor()
+    for i in (0, 63, 64, 127, 128, 191, 192, 255, 256, 259):
+        nb, nt = batch["nbox"][i], batch["ntm"][i]
+        args = (batch["gray"][i], batch["boxes"][i, :nb], batch["tm"][i, :nt], batch["blur"][i, :nb])
+        k1, d1 = g1.extract(*args)
+        kb, db = c.extract(*args)
+        assert counts[i] == len(kb) and kps[i, :counts[i]].tobytes() == kb.tobytes() and np.array_equal(desc[i, :counts[i]], db), i
+        assert k1.tobytes() == kb.tobytes() and np.array_equal(d1, db)
+    # and a second call on the same handle replays the captured graphs
+    kps2, desc2, counts2, _ = g.extract_batch_host(batch["gray"], batch["boxes"], batch["nbox"], batch["tm"], batch["ntm"], batch["blur"])
+    assert np.array_equal(counts, counts2)
+    for i in range(0, B, 13):
+        assert kps[i, :counts[i]].tobytes() == kps2[i, :counts[i]].tobytes() and np.array_equal(desc[i, :counts[i]], desc2[i, :counts[i]])
