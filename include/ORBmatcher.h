@@ -4,9 +4,13 @@
  * include/ORBmatcher.h:41-69,87-89 for
  *     DescriptorDistance, SearchByProjection(Frame&, vector<MapPoint*>&, th),
  *     SearchByProjection(Frame& cur, const Frame& last, th, bMono), SearchForInitialization(...)
- * plus ComputeStereoMatches as a free function (the reference keeps it in Frame, src/Frame.cc:644-818).
- * The BoW / Fuse / Sim3 / triangulation overloads need DBoW2 and KeyFrame graph state and stay the
- * reference's.
+ * plus ComputeStereoMatches as a free function (the reference keeps it in Frame, src/Frame.cc:644-818), and for the
+ * vocabulary-guided overloads SearchByBoW(KeyFrame*, Frame&, ...), SearchByBoW(KeyFrame*, KeyFrame*, ...) and
+ * SearchForTriangulation (:158-288, :522-655, :657-824): the DBoW2 FeatureVectors stay the reference's (they come out of
+ * its vocabulary) and are flattened to CSR here. Free functions at the end cover the steps either side of the path:
+ * FrameTailFromExtractor (UndistortKeyPoints + ComputeStereoFromRGBD + AssignFeaturesToGrid on the device) and
+ * SearchLocalPoints (isInFrustum + SearchByProjection against a device-resident local map).
+ * Fuse / SearchBySim3 / the KeyFrame SearchByProjection overloads stay the reference's.
  *
  * The member functions are templates over the reference's Frame / MapPoint types, so this header has no
  * dependency on them: it only touches the members the reference functions touch (cited inline). The
@@ -22,6 +26,7 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "ORBextractor.h"
@@ -69,6 +74,26 @@ struct DeviceFrame {
     DeviceFrame(const DeviceFrame&) = delete;
     DeviceFrame& operator=(const DeviceFrame&) = delete;
 };
+
+/* DBoW2::FeatureVector (std::map<NodeId, std::vector<unsigned int>>, iterated in ascending node id) -> CSR. */
+struct FeatVecCSR {
+    std::vector<int> node, start, items;
+    template <class FeatVecT>
+    explicit FeatVecCSR(const FeatVecT& fv) {
+        start.push_back(0);
+        for (auto it = fv.begin(); it != fv.end(); ++it) {
+            node.push_back((int)it->first);
+            for (auto idx : it->second) items.push_back((int)idx);
+            start.push_back((int)items.size());
+        }
+    }
+    int nn() const { return (int)node.size(); }
+};
+
+#ifdef COEB_WITH_OPENCV
+inline void mat33(const cv::Mat& M, float out[9]) { for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) out[3 * r + c] = M.at<float>(r, c); }
+#endif
+template <class A> inline void mat33(const A& M, float out[9]) { for (int i = 0; i < 9; i++) out[i] = M[i]; }
 
 }  // namespace coeb_adapt
 
@@ -168,6 +193,79 @@ public:
         return nmatches;
     }
 
+    /* SearchByBoW(KeyFrame* pKF, Frame &F, vector<MapPoint*> &vpMapPointMatches) -- :158-288 (Tracking::TrackReferenceKeyFrame,
+     * Relocalization). */
+    template <class KeyFrameT, class FrameT, class MapPointT>
+    int SearchByBoW(KeyFrameT* pKF, FrameT& F, std::vector<MapPointT*>& vpMapPointMatches) {
+        const std::vector<MapPointT*> vpMapPointsKF = pKF->GetMapPointMatches();
+        vpMapPointMatches.assign(F.N, static_cast<MapPointT*>(nullptr));
+        const int n1 = (int)vpMapPointsKF.size();
+        std::vector<uint8_t> valid1(n1);
+        for (int i = 0; i < n1; i++) valid1[i] = vpMapPointsKF[i] && !vpMapPointsKF[i]->isBad();
+        const coeb_adapt::FeatVecCSR v1(pKF->mFeatVec), v2(F.mFeatVec);
+        coeb_adapt::DeviceFrame<KeyFrameT> d1(*pKF);
+        coeb_adapt::DeviceFrame<FrameT> d2(F);
+        std::vector<int> m12(n1, -1);
+        int nmatches = 0;
+        coeb_adapt::check(coeb_match_bow(coeb_adapt::matcher(), d1.f, d2.f, valid1.data(), nullptr, v1.nn(), v1.node.data(), v1.start.data(),
+                                         v1.items.data(), v2.nn(), v2.node.data(), v2.start.data(), v2.items.data(), mfNNratio,
+                                         mbCheckOrientation ? 1 : 0, /*strict_low*/ 0, m12.data(), &nmatches));
+        for (int i = 0; i < n1; i++)
+            if (m12[i] >= 0) vpMapPointMatches[m12[i]] = vpMapPointsKF[i];
+        return nmatches;
+    }
+
+    /* SearchByBoW(KeyFrame *pKF1, KeyFrame* pKF2, vector<MapPoint*> &vpMatches12) -- :522-655 (LoopClosing::ComputeSim3). */
+    template <class KeyFrameT, class MapPointT>
+    int SearchByBoW(KeyFrameT* pKF1, KeyFrameT* pKF2, std::vector<MapPointT*>& vpMatches12) {
+        const std::vector<MapPointT*> vp1 = pKF1->GetMapPointMatches(), vp2 = pKF2->GetMapPointMatches();
+        vpMatches12.assign(vp1.size(), static_cast<MapPointT*>(nullptr));
+        std::vector<uint8_t> valid1(vp1.size()), valid2(vp2.size());
+        for (size_t i = 0; i < vp1.size(); i++) valid1[i] = vp1[i] && !vp1[i]->isBad();
+        for (size_t i = 0; i < vp2.size(); i++) valid2[i] = vp2[i] && !vp2[i]->isBad();
+        const coeb_adapt::FeatVecCSR v1(pKF1->mFeatVec), v2(pKF2->mFeatVec);
+        coeb_adapt::DeviceFrame<KeyFrameT> d1(*pKF1), d2(*pKF2);
+        std::vector<int> m12(vp1.size(), -1);
+        int nmatches = 0;
+        coeb_adapt::check(coeb_match_bow(coeb_adapt::matcher(), d1.f, d2.f, valid1.data(), valid2.data(), v1.nn(), v1.node.data(),
+                                         v1.start.data(), v1.items.data(), v2.nn(), v2.node.data(), v2.start.data(), v2.items.data(),
+                                         mfNNratio, mbCheckOrientation ? 1 : 0, /*strict_low*/ 1, m12.data(), &nmatches));
+        for (size_t i = 0; i < vp1.size(); i++)
+            if (m12[i] >= 0) vpMatches12[i] = vp2[m12[i]];
+        return nmatches;
+    }
+
+    /* SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo) -- :657-824 (LocalMapping::CreateNewMapPoints). The
+     * epipole (:663-670) is evaluated here like the reference's cv::Mat expression R2w * Cw + t2w (fp32, left to right). */
+    template <class KeyFrameT, class MatT>
+    int SearchForTriangulation(KeyFrameT* pKF1, KeyFrameT* pKF2, const MatT& F12, std::vector<std::pair<size_t, size_t> >& vMatchedPairs,
+                               const bool bOnlyStereo) {
+        float Cw[3], R2w[9], t2w[3], Fm[9], C2[3];
+        coeb_adapt::xyz3(pKF1->GetCameraCenter(), Cw);
+        coeb_adapt::mat33(pKF2->GetRotation(), R2w);
+        coeb_adapt::xyz3(pKF2->GetTranslation(), t2w);
+        coeb_adapt::mat33(F12, Fm);
+        for (int r = 0; r < 3; r++) C2[r] = R2w[3 * r] * Cw[0] + R2w[3 * r + 1] * Cw[1] + R2w[3 * r + 2] * Cw[2] + t2w[r];
+        const float invz = 1.0f / C2[2];
+        const float epipole[2] = {pKF2->fx * C2[0] * invz + pKF2->cx, pKF2->fy * C2[1] * invz + pKF2->cy};
+        const int n1 = pKF1->N, n2 = pKF2->N;
+        std::vector<uint8_t> free1(n1), free2(n2);
+        for (int i = 0; i < n1; i++) free1[i] = !pKF1->GetMapPoint(i);
+        for (int i = 0; i < n2; i++) free2[i] = !pKF2->GetMapPoint(i);
+        const coeb_adapt::FeatVecCSR v1(pKF1->mFeatVec), v2(pKF2->mFeatVec);
+        coeb_adapt::DeviceFrame<KeyFrameT> d1(*pKF1), d2(*pKF2);
+        std::vector<int> m12(n1, -1);
+        int nmatches = 0;
+        coeb_adapt::check(coeb_match_triangulation(coeb_adapt::matcher(), d1.f, d2.f, free1.data(), free2.data(), v1.nn(), v1.node.data(),
+                                                   v1.start.data(), v1.items.data(), v2.nn(), v2.node.data(), v2.start.data(), v2.items.data(),
+                                                   Fm, epipole, bOnlyStereo ? 1 : 0, mbCheckOrientation ? 1 : 0, m12.data(), &nmatches));
+        vMatchedPairs.clear();
+        vMatchedPairs.reserve(nmatches);
+        for (int i = 0; i < n1; i++)
+            if (m12[i] >= 0) vMatchedPairs.push_back(std::make_pair((size_t)i, (size_t)m12[i]));
+        return nmatches;
+    }
+
     static const int TH_LOW = COEB_TH_LOW;
     static const int TH_HIGH = COEB_TH_HIGH;
     static const int HISTO_LENGTH = COEB_HISTO_LENGTH;
@@ -192,6 +290,83 @@ inline void ComputeStereoMatches(FrameT& F) {
                                         reinterpret_cast<const coeb_keypoint*>(F.mvKeys.data()), dl.data(), Nr,
                                         reinterpret_cast<const coeb_keypoint*>(F.mvKeysRight.data()), dr.data(), F.mbf, F.mb,
                                         F.mvuRight.data(), F.mvDepth.data(), &nmatched));
+}
+
+/* Tail of the RGB-D Frame constructor (src/Frame.cc:213-240) on the device, from the extractor call that has just filled
+ * F.mvKeys / F.mDescriptors (src/Frame.cc:416): writes F.mvKeysUn (UndistortKeyPoints, :579-609), F.mvuRight / F.mvDepth
+ * (ComputeStereoFromRGBD, :820-842) and returns the device-resident frame (grid built, AssignFeaturesToGrid :396-411) that
+ * the coeb_match_* / coeb_search_local_points entry points take; the caller owns it (coeb_frame_destroy). dist5 = mDistCoef
+ * as {k1, k2, p1, p2, k3}; depth as Tracking::GrabImageRGBD holds it (raw CV_16U + mDepthMapFactor, or CV_32F). */
+template <class FrameT>
+inline coeb_frame* FrameTailFromExtractor(FrameT& F, const float* dist5, const coeb_depth_image* depth) {
+    const int N = (int)F.mvKeys.size();
+    coeb_camera cam;
+    cam.fx = F.fx; cam.fy = F.fy; cam.cx = F.cx; cam.cy = F.cy; cam.bf = F.mbf; cam.b = F.mb;
+    cam.min_x = F.mnMinX; cam.max_x = F.mnMaxX; cam.min_y = F.mnMinY; cam.max_y = F.mnMaxY;
+    F.mvKeysUn.resize(N);
+    F.mvuRight.assign(N, -1.0f);
+    F.mvDepth.assign(N, -1.0f);
+    coeb_frame* f = nullptr;
+    int n = 0;
+    coeb_adapt::check(coeb_frame_from_extractor(coeb_adapt::matcher(), F.mpORBextractorLeft->handle(), 0, N, &cam, dist5, depth,
+                                                reinterpret_cast<coeb_keypoint*>(F.mvKeysUn.data()), F.mvuRight.data(), F.mvDepth.data(), &n, &f));
+    return f;
+}
+
+/* Tracking::SearchLocalPoints (src/Tracking.cc:1222-1272) against a device-resident local map built from
+ * mvpLocalMapPoints by MakeLocalMap (rebuild it when Tracking::UpdateLocalPoints changes the vector). dF is the current
+ * frame on the device (FrameTailFromExtractor or coeb_adapt::DeviceFrame). Returns the matcher's count; the MapPoint
+ * bookkeeping of the reference's loops (IncreaseVisible, mnLastFrameSeen, mbTrackInView) is applied here. */
+template <class MapPointT>
+inline coeb_local_map* MakeLocalMap(const std::vector<MapPointT*>& vpLocalMapPoints) {
+    const size_t n = vpLocalMapPoints.size();
+    std::vector<float> xyz(3 * n), nrm(3 * n), dmin(n), dmax(n);
+    std::vector<unsigned char> desc(32 * n);
+    for (size_t i = 0; i < n; i++) {
+        MapPointT* p = vpLocalMapPoints[i];
+        coeb_adapt::xyz3(p->GetWorldPos(), &xyz[3 * i]);
+        coeb_adapt::xyz3(p->GetNormal(), &nrm[3 * i]);
+        dmin[i] = p->GetMinDistance();   // mfMinDistance / mfMaxDistance themselves (protected in include/MapPoint.h: add the two
+        dmax[i] = p->GetMaxDistance();   // one-line getters; the 0.8 / 1.2 factors of src/MapPoint.cc:373-383 are applied on the device)
+        std::memcpy(&desc[32 * i], coeb_adapt::desc_row(p->GetDescriptor(), 0), 32);
+    }
+    coeb_local_map* lm = nullptr;
+    coeb_adapt::check(coeb_local_map_create(coeb_adapt::matcher(), (int)n, xyz.data(), nrm.data(), dmin.data(), dmax.data(), desc.data(), &lm));
+    return lm;
+}
+
+template <class FrameT, class MapPointT>
+inline int SearchLocalPoints(FrameT& F, coeb_frame* dF, coeb_local_map* lm, const std::vector<MapPointT*>& vpLocalMapPoints, float th,
+                             float nnratio = 0.8f) {
+    // first loop (:1225-1241): points already matched in this frame are not searched again
+    for (auto& pMP : F.mvpMapPoints)
+        if (pMP) {
+            if (pMP->isBad()) pMP = nullptr;
+            else { pMP->IncreaseVisible(); pMP->mnLastFrameSeen = F.mnId; pMP->mbTrackInView = false; }
+        }
+    const int n = (int)vpLocalMapPoints.size(), K = (int)F.mvpMapPoints.size();
+    std::vector<uint8_t> skip(n), obs(n), in_view(n);
+    for (int i = 0; i < n; i++) {
+        MapPointT* p = vpLocalMapPoints[i];
+        skip[i] = p->mnLastFrameSeen == F.mnId || p->isBad();   // :1249-1252
+        obs[i] = p->Observations() > 0;
+    }
+    std::vector<int> state(K);
+    for (int k = 0; k < K; k++) state[k] = !F.mvpMapPoints[k] ? -1 : (F.mvpMapPoints[k]->Observations() > 0 ? -2 : -3);
+    float Tcw[12], Ow[3];
+    coeb_adapt::pose34(F.mTcw, Tcw);
+    coeb_adapt::xyz3(F.mOw, Ow);
+    int nmatches = 0;
+    coeb_adapt::check(coeb_search_local_points(coeb_adapt::matcher(), dF, lm, skip.data(), obs.data(), Tcw, Ow, 0.5f, th, nnratio, state.data(),
+                                               in_view.data(), nullptr, &nmatches));
+    for (int i = 0; i < n; i++) {
+        if (skip[i]) continue;
+        vpLocalMapPoints[i]->mbTrackInView = in_view[i] != 0;   // Frame::isInFrustum (:447, :492)
+        if (in_view[i]) vpLocalMapPoints[i]->IncreaseVisible();  // :1254-1258
+    }
+    for (int k = 0; k < K; k++)
+        if (state[k] >= 0) F.mvpMapPoints[k] = vpLocalMapPoints[state[k]];
+    return nmatches;
 }
 
 }  // namespace ORB_SLAM2

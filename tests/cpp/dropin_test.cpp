@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <map>
 #include <vector>
 
 #include "../../include/ORBextractor.h"
@@ -29,6 +30,18 @@ int orc_match_lastframe(orc_frame* cur, int n, const uint8_t* valid, const uint8
 int orc_match_init(orc_frame* f1, orc_frame* f2, float* prev_matched, int* matches12, int window, float nnratio, int check_ori);
 int orc_stereo_match(orc_extractor* exL, orc_extractor* exR, int N, const coeb_keypoint* keysL, const uint8_t* descL, int Nr,
                      const coeb_keypoint* keysR, const uint8_t* descR, float mbf, float mb, float* uright, float* depth);
+int orc_match_bow(orc_frame* f1, orc_frame* f2, const uint8_t* valid1, const uint8_t* valid2, int nn1, const int* node1, const int* start1,
+                  const int* items1, int nn2, const int* node2, const int* start2, const int* items2, float nnratio, int check_ori,
+                  int strict_low, int* match12);
+int orc_match_triangulation(orc_frame* f1, orc_frame* f2, const uint8_t* free1, const uint8_t* free2, int nn1, const int* node1,
+                            const int* start1, const int* items1, int nn2, const int* node2, const int* start2, const int* items2,
+                            const float* F12, float ex, float ey, int only_stereo, int check_ori, int* match12);
+void orc_undistort_keypoints(const coeb_keypoint* keys, int n, const coeb_camera* cam, const float* dist5, coeb_keypoint* keys_un);
+void orc_stereo_from_rgbd(const coeb_keypoint* keys, const coeb_keypoint* keys_un, int n, const void* depth, int kind, int stride_bytes,
+                          float factor, float mbf, float* uright, float* depth_out);
+int orc_search_local_points(orc_frame* f, int n, const float* xyz, const float* normal, const float* min_dist, const float* max_dist,
+                            const uint8_t* desc, const uint8_t* skip, const uint8_t* has_obs, const float* Tcw, const float* Ow,
+                            float cos_limit, float th, float nnratio, int* kp_match, uint8_t* in_view, float* proj);
 }
 
 using coeb_cv::KeyPoint;
@@ -64,11 +77,17 @@ struct MapPoint {
     int nObs = 1, mnTrackScaleLevel = 0;
     float mTrackProjX = 0, mTrackProjY = 0, mTrackProjXR = 0, mTrackViewCos = 1;
     Mat desc;
-    float pos[3] = {0, 0, 1};
+    float pos[3] = {0, 0, 1}, normal[3] = {0, 0, -1}, mfMinDistance = 0.1f, mfMaxDistance = 10.f;
+    long mnLastFrameSeen = -1;
+    int nVisible = 0;
     bool isBad() { return bad; }
     int Observations() { return nObs; }
     const Mat& GetDescriptor() { return desc; }
     const float* GetWorldPos() { return pos; }
+    const float* GetNormal() { return normal; }
+    float GetMinDistance() { return mfMinDistance; }
+    float GetMaxDistance() { return mfMaxDistance; }
+    void IncreaseVisible() { nVisible++; }
 };
 
 struct Frame {
@@ -80,9 +99,34 @@ struct Frame {
     std::vector<bool> mvbOutlier;
     float fx = 535.4f, fy = 539.2f, cx = 320.1f, cy = 247.6f, mbf = 40.f, mb = 40.f / 535.4f;
     float mnMinX = 0, mnMaxX = 640, mnMinY = 0, mnMaxY = 480;
-    float mTcw[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    float mTcw[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0}, mOw[3] = {0, 0, 0};
+    long mnId = 7;
+    std::map<unsigned, std::vector<unsigned> > mFeatVec;   // DBoW2::FeatureVector
     ORB_SLAM2::ORBextractor *mpORBextractorLeft = nullptr, *mpORBextractorRight = nullptr;
+    // KeyFrame-only members used by SearchByBoW / SearchForTriangulation (a KeyFrame is built from a Frame, src/KeyFrame.cc:31-58)
+    float Rcw[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, tcw[3] = {0, 0, 0};
+    std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
+    MapPoint* GetMapPoint(int i) { return mvpMapPoints[i]; }
+    const float* GetCameraCenter() { return mOw; }
+    const float* GetRotation() { return Rcw; }
+    const float* GetTranslation() { return tcw; }
 };
+
+// stand-in vocabulary: node = index of the nearest of 64 pseudo-random 256-bit centres
+static void make_featvec(Frame& F) {
+    static std::vector<uint8_t> centres;
+    if (centres.empty()) { uint32_t save = g_rng; g_rng = 4242; centres.resize(64 * 32); for (auto& b : centres) b = (uint8_t)rnd(); g_rng = save; }
+    F.mFeatVec.clear();
+    for (int i = 0; i < F.N; i++) {
+        int best = 0, bd = 999;
+        for (int c = 0; c < 64; c++) {
+            int d = 0;
+            for (int b = 0; b < 32; b++) d += __builtin_popcount((unsigned)(F.mDescriptors.ptr(i)[b] ^ centres[c * 32 + b]));
+            if (d < bd) { bd = d; best = c; }
+        }
+        F.mFeatVec[(unsigned)(5 * best + 1)].push_back((unsigned)i);
+    }
+}
 
 static int g_fail = 0;
 #define EXPECT(cond, ...) do { if (!(cond)) { g_fail++; std::printf("FAIL %s:%d: ", __FILE__, __LINE__); std::printf(__VA_ARGS__); std::printf("\n"); } } while (0)
@@ -270,6 +314,151 @@ int main() {
         EXPECT(std::memcmp(prev.data(), prev_ref.data(), sizeof(float) * 2 * cur.N) == 0, "vbPrevMatched differs");
         orc_frame_destroy(oc);
         orc_frame_destroy(o2);
+    }
+
+    // ---- vocabulary-guided matchers + the steps either side of the path ----
+    {
+        std::vector<std::vector<float> > nobox; std::vector<Point2f> notm; std::vector<int> noblur;
+        Frame K1, K2;
+        std::vector<uint8_t> img2((size_t)w * h);
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++) img2[(size_t)y * w + x] = img[(size_t)std::min(std::max(y + 3, 0), h - 1) * w + std::min(std::max(x - 7, 0), w - 1)];
+        fill_frame(K1, ex, img, w, h, nobox, notm, noblur);
+        fill_frame(K2, ex, img2, w, h, nobox, notm, noblur);
+        make_featvec(K1); make_featvec(K2);
+        std::vector<MapPoint> mp1(K1.N), mp2(K2.N);
+        for (int i = 0; i < K1.N; i++) { mp1[i].bad = (rnd() % 17) == 0; K1.mvpMapPoints[i] = (rnd() % 6) ? &mp1[i] : nullptr; }
+        for (int i = 0; i < K2.N; i++) { mp2[i].bad = (rnd() % 19) == 0; K2.mvpMapPoints[i] = (rnd() % 5) ? &mp2[i] : nullptr; }
+        coeb_camera c1 = cam_of(K1), c2 = cam_of(K2);
+        orc_frame* o1 = orc_frame_create(reinterpret_cast<coeb_keypoint*>(K1.mvKeysUn.data()), K1.mDescriptors.ptr(0), K1.N, K1.mvuRight.data(), &c1, K1.mvScaleFactors.data(), 8);
+        orc_frame* o2 = orc_frame_create(reinterpret_cast<coeb_keypoint*>(K2.mvKeysUn.data()), K2.mDescriptors.ptr(0), K2.N, K2.mvuRight.data(), &c2, K2.mvScaleFactors.data(), 8);
+        coeb_adapt::FeatVecCSR v1(K1.mFeatVec), v2(K2.mFeatVec);
+        std::vector<uint8_t> valid1(K1.N), valid2(K2.N), free1(K1.N), free2(K2.N);
+        for (int i = 0; i < K1.N; i++) { valid1[i] = K1.mvpMapPoints[i] && !K1.mvpMapPoints[i]->bad; free1[i] = !K1.mvpMapPoints[i]; }
+        for (int i = 0; i < K2.N; i++) { valid2[i] = K2.mvpMapPoints[i] && !K2.mvpMapPoints[i]->bad; free2[i] = !K2.mvpMapPoints[i]; }
+        std::vector<int> m12(K1.N);
+        ORB_SLAM2::ORBmatcher bow(0.7f, true);
+        // SearchByBoW(KeyFrame*, Frame&) (src/Tracking.cc:830-833): K2 plays the current frame
+        {
+            const int nref = orc_match_bow(o1, o2, valid1.data(), nullptr, v1.nn(), v1.node.data(), v1.start.data(), v1.items.data(), v2.nn(), v2.node.data(),
+                                           v2.start.data(), v2.items.data(), 0.7f, 1, 0, m12.data());
+            std::vector<MapPoint*> got;
+            const int ngot = bow.SearchByBoW(&K1, K2, got);
+            EXPECT(ngot == nref && nref > 20, "SearchByBoW(KF, F): %d vs oracle %d", ngot, nref);
+            std::vector<MapPoint*> want(K2.N, nullptr);
+            for (int i = 0; i < K1.N; i++) if (m12[i] >= 0) want[m12[i]] = K1.mvpMapPoints[i];
+            EXPECT(got == want, "SearchByBoW(KF, F): vpMapPointMatches differs");
+        }
+        // SearchByBoW(KeyFrame*, KeyFrame*) (src/LoopClosing.cc:240-260)
+        {
+            const int nref = orc_match_bow(o1, o2, valid1.data(), valid2.data(), v1.nn(), v1.node.data(), v1.start.data(), v1.items.data(), v2.nn(),
+                                           v2.node.data(), v2.start.data(), v2.items.data(), 0.7f, 1, 1, m12.data());
+            std::vector<MapPoint*> got;
+            const int ngot = bow.SearchByBoW(&K1, &K2, got);
+            EXPECT(ngot == nref && nref > 10, "SearchByBoW(KF, KF): %d vs oracle %d", ngot, nref);
+            int bad_ptr = 0;
+            for (int i = 0; i < K1.N; i++) bad_ptr += got[i] != (m12[i] >= 0 ? K2.mvpMapPoints[m12[i]] : nullptr);
+            EXPECT(bad_ptr == 0, "SearchByBoW(KF, KF): %d vpMatches12 entries differ", bad_ptr);
+        }
+        // SearchForTriangulation (src/LocalMapping.cc:252-260); K2 is K1 shifted by (7, -3) px: F12 of a pure image shift
+        {
+            const float F12[9] = {0, 0, -3.f, 0, 0, -7.f, 3.f, 7.f, 0};
+            K1.mOw[0] = 0.3f; K1.mOw[1] = -0.1f; K1.mOw[2] = 0.05f;
+            K2.tcw[0] = 0.1f; K2.tcw[1] = 0.02f; K2.tcw[2] = 0.5f;
+            float C2[3];
+            for (int r = 0; r < 3; r++) C2[r] = K2.Rcw[3 * r] * K1.mOw[0] + K2.Rcw[3 * r + 1] * K1.mOw[1] + K2.Rcw[3 * r + 2] * K1.mOw[2] + K2.tcw[r];
+            const float invz = 1.0f / C2[2], exx = K2.fx * C2[0] * invz + K2.cx, eyy = K2.fy * C2[1] * invz + K2.cy;
+            const int nref = orc_match_triangulation(o1, o2, free1.data(), free2.data(), v1.nn(), v1.node.data(), v1.start.data(), v1.items.data(), v2.nn(),
+                                                     v2.node.data(), v2.start.data(), v2.items.data(), F12, exx, eyy, 0, 1, m12.data());
+            std::vector<std::pair<size_t, size_t> > pairs;
+            const int ngot = bow.SearchForTriangulation(&K1, &K2, F12, pairs, false);
+            EXPECT(ngot == nref && nref > 3, "SearchForTriangulation: %d vs oracle %d", ngot, nref);
+            size_t q = 0; int bad_pair = 0;
+            for (int i = 0; i < K1.N; i++) if (m12[i] >= 0) { bad_pair += q >= pairs.size() || pairs[q].first != (size_t)i || pairs[q].second != (size_t)m12[i]; q++; }
+            EXPECT(bad_pair == 0 && q == pairs.size(), "SearchForTriangulation: vMatchedPairs differs");
+        }
+        orc_frame_destroy(o1);
+        orc_frame_destroy(o2);
+
+        // Frame constructor tail on the device (src/Frame.cc:213-240) with the TUM1 distortion and a raw 16-bit depth map
+        Frame T;
+        T.fx = 517.306408f; T.fy = 516.469215f; T.cx = 318.643040f; T.cy = 255.313989f; T.mb = T.mbf / T.fx;
+        T.mpORBextractorLeft = &ex;
+        fill_frame(T, ex, img, w, h, nobox, notm, noblur);
+        const float dist5[5] = {0.262383f, -0.953104f, -0.005358f, 0.002628f, 1.163314f};
+        std::vector<uint16_t> depth((size_t)w * h);
+        for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) depth[(size_t)y * w + x] = ((x / 16 + y / 16) % 7 == 0) ? 0 : (uint16_t)(4000 + 37 * ((x / 8) % 50) + 91 * ((y / 8) % 40));
+        coeb_depth_image di;
+        di.data = depth.data(); di.kind = 2; di.stride_bytes = w * 2; di.factor = 1.0f / 5000.0f; di.on_device = 0; di.width = w; di.height = h;
+        coeb_frame* dT = ORB_SLAM2::FrameTailFromExtractor(T, dist5, &di);
+        coeb_camera ct = cam_of(T);
+        std::vector<coeb_keypoint> un(T.N);
+        std::vector<float> ur(T.N), dp(T.N);
+        orc_undistort_keypoints(reinterpret_cast<coeb_keypoint*>(T.mvKeys.data()), T.N, &ct, dist5, un.data());
+        orc_stereo_from_rgbd(reinterpret_cast<coeb_keypoint*>(T.mvKeys.data()), un.data(), T.N, depth.data(), 2, w * 2, di.factor, T.mbf, ur.data(), dp.data());
+        EXPECT(std::memcmp(un.data(), T.mvKeysUn.data(), sizeof(coeb_keypoint) * T.N) == 0, "mvKeysUn differs");
+        EXPECT(std::memcmp(ur.data(), T.mvuRight.data(), 4 * T.N) == 0 && std::memcmp(dp.data(), T.mvDepth.data(), 4 * T.N) == 0, "mvuRight / mvDepth (RGB-D) differ");
+        int withd = 0;
+        for (int i = 0; i < T.N; i++) withd += T.mvDepth[i] > 0;
+        EXPECT(withd > T.N / 2 && withd < T.N, "depth coverage %d of %d", withd, T.N);
+
+        // Tracking::SearchLocalPoints against a resident local map (src/Tracking.cc:1222-1272)
+        const int NL = 2500;
+        std::vector<MapPoint> lmp(NL);
+        std::vector<MapPoint*> vl(NL);
+        const float a = 0.02f;
+        const float R[9] = {std::cos(a), 0, std::sin(a), 0, 1, 0, -std::sin(a), 0, std::cos(a)}, t[3] = {0.05f, -0.02f, 0.04f};
+        for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) T.mTcw[4 * r + c] = R[3 * r + c]; T.mTcw[4 * r + 3] = t[r]; }
+        for (int c = 0; c < 3; c++) T.mOw[c] = -(R[c] * t[0] + R[3 + c] * t[1] + R[6 + c] * t[2]);
+        for (int i = 0; i < NL; i++) {
+            MapPoint& m = lmp[i];
+            const int k = rnd() % T.N;
+            const bool truth = (rnd() % 3) != 0;
+            const float u = truth ? T.mvKeysUn[k].pt.x + (rndf() - 0.5f) * 6.f : rndf() * 800.f - 80.f;
+            const float v = truth ? T.mvKeysUn[k].pt.y + (rndf() - 0.5f) * 6.f : rndf() * 600.f - 60.f;
+            const float z = (0.7f + 5.f * rndf()) * ((!truth && (rnd() % 9) == 0) ? -1.f : 1.f);
+            const float pc[3] = {(u - T.cx) * z / T.fx - t[0], (v - T.cy) * z / T.fy - t[1], z - t[2]};
+            for (int c = 0; c < 3; c++) m.pos[c] = R[c] * pc[0] + R[3 + c] * pc[1] + R[6 + c] * pc[2];
+            float po[3], dist = 0;
+            for (int c = 0; c < 3; c++) { po[c] = m.pos[c] - T.mOw[c]; dist += po[c] * po[c]; }
+            dist = std::sqrt(dist);
+            float nn = 0;
+            for (int c = 0; c < 3; c++) { m.normal[c] = po[c] / dist + (rndf() - 0.5f) * (truth ? 0.4f : 2.5f); nn += m.normal[c] * m.normal[c]; }
+            for (int c = 0; c < 3; c++) m.normal[c] /= std::sqrt(nn);
+            const int lvl = std::min(T.mvKeysUn[k].octave + (int)(rnd() & 1), 7);
+            m.mfMaxDistance = dist * std::pow(1.2f, lvl - 0.5f) * ((!truth && (rnd() % 11) == 0) ? 30.f : 1.f);
+            m.mfMinDistance = m.mfMaxDistance / T.mvScaleFactors[7];
+            m.desc.create(1, 32);
+            std::memcpy(m.desc.ptr(0), T.mDescriptors.ptr(k), 32);
+            for (int b = 0, nb = truth ? rnd() % 30 : 120; b < nb; b++) { int bit = rnd() % 256; m.desc.ptr(0)[bit >> 3] ^= (uint8_t)(1 << (bit & 7)); }
+            m.bad = (rnd() % 40) == 0;
+            m.nObs = (rnd() % 30) == 0 ? 0 : 2;
+            m.mnLastFrameSeen = (rnd() % 25) == 0 ? T.mnId : -1;
+            vl[i] = &m;
+        }
+        std::vector<float> xyz(3 * NL), nrm(3 * NL), dmin(NL), dmax(NL);
+        std::vector<uint8_t> ldesc(32 * NL), skip(NL), obs(NL), inview(NL);
+        for (int i = 0; i < NL; i++) {
+            std::memcpy(&xyz[3 * i], lmp[i].pos, 12); std::memcpy(&nrm[3 * i], lmp[i].normal, 12);
+            dmin[i] = lmp[i].mfMinDistance; dmax[i] = lmp[i].mfMaxDistance;
+            std::memcpy(&ldesc[32 * i], lmp[i].desc.ptr(0), 32);
+            skip[i] = lmp[i].mnLastFrameSeen == T.mnId || lmp[i].bad; obs[i] = lmp[i].nObs > 0;
+        }
+        orc_frame* ot = orc_frame_create(un.data(), T.mDescriptors.ptr(0), T.N, ur.data(), &ct, T.mvScaleFactors.data(), 8);
+        std::vector<int> state(T.N, -1);
+        const int nref = orc_search_local_points(ot, NL, xyz.data(), nrm.data(), dmin.data(), dmax.data(), ldesc.data(), skip.data(), obs.data(), T.mTcw, T.mOw,
+                                                 0.5f, 3.f, 0.8f, state.data(), inview.data(), nullptr);
+        coeb_local_map* lm = ORB_SLAM2::MakeLocalMap(vl);
+        const int ngot = ORB_SLAM2::SearchLocalPoints(T, dT, lm, vl, 3.f);
+        EXPECT(ngot == nref && nref > 100, "SearchLocalPoints: %d vs oracle %d", ngot, nref);
+        int bad_ptr = 0, bad_view = 0, nview = 0;
+        for (int k = 0; k < T.N; k++) bad_ptr += T.mvpMapPoints[k] != (state[k] >= 0 ? vl[state[k]] : nullptr);
+        for (int i = 0; i < NL; i++) { if (!skip[i]) { bad_view += (lmp[i].mbTrackInView != (inview[i] != 0)) || (lmp[i].nVisible != (int)inview[i]); nview += inview[i]; } }
+        EXPECT(bad_ptr == 0, "SearchLocalPoints: %d mvpMapPoints entries differ", bad_ptr);
+        EXPECT(bad_view == 0 && nview > 300 && nview < NL, "SearchLocalPoints: visibility bookkeeping (%d wrong, %d in view)", bad_view, nview);
+        coeb_local_map_destroy(lm);
+        coeb_frame_destroy(dT);
+        orc_frame_destroy(ot);
     }
 
     // ---- DescriptorDistance ----
