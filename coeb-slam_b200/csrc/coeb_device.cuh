@@ -10,6 +10,7 @@
 //   level keys    : per (frame, level) up to key_cap selected keypoints {x,y (level coords), response,
 //                   angle}, list order, after culling; plus one counter per (frame, level).
 #pragma once
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -185,6 +186,39 @@ __device__ inline int block_exclusive_scan(int* data, int n, int* s_warp) {
     return total;
 }
 
+#endif
+
+// One TMA descriptor per pyramid level: the level's [B][h][pitch] block as a 3-D byte tensor whose box is one staged tile
+// (box_w x box_h bytes of one frame). Bytes outside the tensor read as 0.
+struct TmaMaps { CUtensorMap m[COEB_MAX_LEVELS]; };
+// false if the driver entry point is missing, an address / stride is not 16-byte aligned or an encode fails: the kernels
+// then stage with plain vector loads.
+bool encode_level_maps(const Geometry& g, const BatchView& v, int box_w, int box_h, TmaMaps* out);
+bool tma_enabled();   // COEB_TMA=0 switches the TMA staging off (development)
+
+#ifdef __CUDACC__
+// Single-use mbarrier + one TMA box load, issued by one thread; every thread of the CTA then calls tma_wait() after a
+// __syncthreads() that follows the issue (which makes the initialised barrier visible).
+__device__ __forceinline__ void tma_issue_box(uint32_t mbar, uint32_t dst, const CUtensorMap* map, int x, int y, int z, int bytes) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_wait(uint32_t mbar) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TMA_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+        "@p bra TMA_DONE;\n"
+        "bra TMA_WAIT;\n"
+        "TMA_DONE:\n"
+        "}\n" ::"r"(mbar)
+        : "memory");
+}
 #endif
 
 // kernel launchers (each enqueues on `stream`, no synchronisation)

@@ -26,6 +26,8 @@
 //   2   cell-aware NMS over A > iniTh, local maxima appended to the level's list, one count per FAST cell.
 // Fallback kernel: persistent CTAs scan the cell counters; a cell with count 0 is recomputed alone (plain scalar code,
 // it is rare) and its local maxima above minTh are appended to the same list.
+#include <cstdlib>
+
 #include "coeb_device.cuh"
 
 namespace coeb {
@@ -108,9 +110,11 @@ __device__ __forceinline__ int cell_of(int x, int size, int rcp, int last) {
     return (x >= kEdge && x < size - kEdge) ? min((int)(((unsigned)(x - kEdge) * (unsigned)rcp) >> 20), last) : -1;
 }
 
+template <bool kTma>
 __global__ void __launch_bounds__(kFtThreads, COEB_FT_MINB) fast_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v,
-                                                             const int4* __restrict__ tiles) {
-    __shared__ __align__(16) uint8_t smem[kFastSmem];
+                                                             const int4* __restrict__ tiles, const __grid_constant__ TmaMaps maps) {
+    __shared__ __align__(128) uint8_t smem[kFastSmem];
+    __shared__ __align__(8) unsigned long long s_mbar;
     uint32_t* const s_img = reinterpret_cast<uint32_t*>(smem + oImg);
     uint8_t* const s_A = smem + oA;
     unsigned short* const s_queue = reinterpret_cast<unsigned short*>(smem + oQueue);
@@ -130,7 +134,12 @@ __global__ void __launch_bounds__(kFtThreads, COEB_FT_MINB) fast_kernel(const __
     // ---- stage the tile: rows ty0-4 .. ty0+kFtH+3, 96 bytes from x = tx0-16 as six 16-byte loads per row. Rows below the
     //      image and columns beyond the row pitch are clamped: only pixels outside the detection domain (whose strength is
     //      never used) can see them, as can the padding bytes between w and the pitch.
-    {
+    const uint32_t a_mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+    if (kTma) {
+        // one thread hands the whole 96 x 72 byte box to the TMA engine (bytes outside the level read as 0, which only
+        // out-of-domain pixels can see); the CTA zeroes its other arrays meanwhile and waits on the mbarrier below
+        if (tid == 0) tma_issue_box(a_mbar, (uint32_t)__cvta_generic_to_shared(s_img), &maps.m[level], tx0 - 16, ty0 - 4, frame, kImgRows * kImgPitch);
+    } else {
         const int pitch = level_pitch(g, v, level);
         const int q = tid & 7, r0 = tid >> 3;
         const uint8_t* __restrict__ src = level_ptr(g, v, level, frame) + min(tx0 - 16 + 16 * q, pitch - 16);
@@ -154,6 +163,7 @@ __global__ void __launch_bounds__(kFtThreads, COEB_FT_MINB) fast_kernel(const __
     }
     if (tid < 4) s_ctr[tid] = 0;
     __syncthreads();
+    if (kTma) tma_wait(a_mbar);
 
     // detection domain [19, w-19) x [19, h-19) in tile coordinates, cut to the A tile [-2, kFtW+2) x [-1, kFtH+1)
     const int xlo = max(kEdge - tx0, -2), xspan = max(min(L.w - kEdge - tx0, kFtW + 2) - xlo, 0);
@@ -445,10 +455,42 @@ int build_fast_tiles(const Geometry& g, int4* out) {
     return total;
 }
 
+bool tma_enabled() {
+    static const bool on = [] { const char* e = getenv("COEB_TMA"); return !e || atoi(e) != 0; }();
+    return on;
+}
+
+bool encode_level_maps(const Geometry& g, const BatchView& v, int box_w, int box_h, TmaMaps* out) {
+    typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeTiled encode = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) fn = nullptr;
+        return (EncodeTiled)fn;
+    }();
+    if (!encode) return false;
+    for (int l = 0; l < g.nlevels; l++) {
+        const cuuint64_t pitch = (cuuint64_t)level_pitch(g, v, l);
+        const cuuint64_t fstride = l == 0 ? v.l0_stride : g.lv[l].img_stride;
+        const cuuint64_t dims[3] = {pitch, (cuuint64_t)g.lv[l].h, (cuuint64_t)v.B};
+        const cuuint64_t strides[2] = {pitch, fstride};
+        const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1u}, estr[3] = {1u, 1u, 1u};
+        void* base = const_cast<uint8_t*>(level_ptr(g, v, l, 0));
+        if (((uintptr_t)base | pitch | fstride) & 15) return false;
+        if (encode(&out->m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    return true;
+}
+
 void launch_fast(const Geometry& g, const BatchView& v, cudaStream_t stream) {
     cudaMemsetAsync(v.lmax_count, 0, sizeof(int) * (size_t)v.B * g.nlevels, stream);
     cudaMemsetAsync(v.cell_count, 0, sizeof(int) * (size_t)v.B * g.cells_per_frame, stream);
-    fast_kernel<<<dim3(g.fast_tiles_per_frame, v.B), kFtThreads, 0, stream>>>(g, v, v.fast_tiles);
+    TmaMaps maps;
+    if (tma_enabled() && encode_level_maps(g, v, kImgPitch, kImgRows, &maps)) fast_kernel<true><<<dim3(g.fast_tiles_per_frame, v.B), kFtThreads, 0, stream>>>(g, v, v.fast_tiles, maps);
+    else fast_kernel<false><<<dim3(g.fast_tiles_per_frame, v.B), kFtThreads, 0, stream>>>(g, v, v.fast_tiles, maps);
     const int cells = v.B * g.cells_per_frame;
     cudaMemsetAsync(v.empty_count, 0, sizeof(int), stream);
     fast_empty_cells_kernel<<<(cells + 255) / 256, 256, 0, stream>>>(g, v);

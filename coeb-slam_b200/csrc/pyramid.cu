@@ -167,9 +167,11 @@ struct BlurTaps {
     __device__ __forceinline__ uint32_t h3(uint32_t w0, uint32_t wp) const { return __dp4a(w0, c_blur_taps[8], __dp4a(wp, c_blur_taps[9], 0u)); }
 };
 
+template <bool kTma>
 __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v,
-                                                            const int4* __restrict__ tiles) {
-    __shared__ __align__(16) uint32_t s_in[kBlurRows * kBlurInWords];
+                                                            const int4* __restrict__ tiles, const __grid_constant__ TmaMaps maps) {
+    __shared__ __align__(128) uint32_t s_in[kBlurRows * kBlurInWords];
+    __shared__ __align__(8) unsigned long long s_mbar;
     __shared__ __align__(16) uint32_t s_v[kBlurPairRows * kBlurVPitch];   // [pair row][x]: H(row 2m) | H(row 2m+1) << 16
     const int frame = blockIdx.y;
     const int4 ti = __ldg(&tiles[blockIdx.x]);   // {level, tx0, ty0, -}
@@ -177,8 +179,24 @@ __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const __grid_constan
     const LevelGeom& L = g.lv[level];
     const int tid = threadIdx.x;
 
-    // stage rows ty0-3 .. ty0+34 (reflected by index), 96 bytes from x = tx0-16 as six 16-byte loads per row
-    {
+    // stage rows ty0-3 .. ty0+34, 96 bytes from x = tx0-16
+    if (kTma) {
+        // one TMA box (out-of-image bytes read as 0); the rows above / below the image are then filled by reflection from the
+        // staged rows themselves (BORDER_REFLECT_101), before the column patches below see them
+        const uint32_t a_mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+        if (tid == 0) tma_issue_box(a_mbar, (uint32_t)__cvta_generic_to_shared(s_in), &maps.m[level], tx0 - 16, ty0 - 3, frame, kBlurRows * kBlurInWords * 4);
+        __syncthreads();
+        tma_wait(a_mbar);
+        if (ty0 < 3 || ty0 + kBlurRows - 3 > L.h) {   // uniform: the tile sees rows outside the image
+            for (int i = tid; i < kBlurRows * kBlurInWords; i += kBlurThreads) {
+                const int r = i / kBlurInWords, wv = i - r * kBlurInWords;
+                const int y = ty0 - 3 + r;
+                const int yy = y < 0 ? -y : (y >= L.h ? 2 * L.h - 2 - y : y);
+                const int rr = yy - ty0 + 3;
+                if (yy != y && rr >= 0 && rr < kBlurRows) s_in[r * kBlurInWords + wv] = s_in[rr * kBlurInWords + wv];   // source rows are in-image rows
+            }
+        }
+    } else {   // six 16-byte loads per row, rows reflected by index
         const uint8_t* __restrict__ src = level_ptr(g, v, level, frame);
         const int spitch = level_pitch(g, v, level);
         const int q = tid & 7, r0 = tid >> 3;
@@ -280,7 +298,11 @@ int build_blur_tiles(const Geometry& g, int4* out) {
 }
 
 void launch_blur(const Geometry& g, const BatchView& v, cudaStream_t stream) {
-    blur_kernel<<<dim3(g.blur_tiles_per_frame, v.B), kBlurThreads, 0, stream>>>(g, v, v.blur_tiles);
+    TmaMaps maps;
+    if (tma_enabled() && encode_level_maps(g, v, kBlurInWords * 4, kBlurRows, &maps))
+        blur_kernel<true><<<dim3(g.blur_tiles_per_frame, v.B), kBlurThreads, 0, stream>>>(g, v, v.blur_tiles, maps);
+    else
+        blur_kernel<false><<<dim3(g.blur_tiles_per_frame, v.B), kBlurThreads, 0, stream>>>(g, v, v.blur_tiles, maps);
 }
 
 // ------------------------------------------------------------------------------------------------
