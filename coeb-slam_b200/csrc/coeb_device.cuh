@@ -193,7 +193,7 @@ __device__ inline int block_exclusive_scan(int* data, int n, int* s_warp) {
 struct TmaMaps { CUtensorMap m[COEB_MAX_LEVELS]; };
 // false if the driver entry point is missing, an address / stride is not 16-byte aligned or an encode fails: the kernels
 // then stage with plain vector loads.
-bool encode_level_maps(const Geometry& g, const BatchView& v, int box_w, int box_h, TmaMaps* out);
+bool encode_level_maps(const Geometry& g, const BatchView& v, int box_w, int box_h, TmaMaps* out, bool blurred = false);
 bool tma_enabled();   // COEB_TMA=0 switches the TMA staging off (development)
 
 #ifdef __CUDACC__
@@ -206,6 +206,29 @@ __device__ __forceinline__ void tma_issue_box(uint32_t mbar, uint32_t dst, const
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                  ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(mbar)
                  : "memory");
+}
+// Re-usable form: initialise once (then __syncthreads / __syncwarp), arm + load per use, wait on the use's parity (0, 1, 0, ...).
+__device__ __forceinline__ void tma_bar_init(uint32_t mbar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_box(uint32_t mbar, uint32_t dst, const CUtensorMap* map, int x, int y, int z, int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_wait_parity(uint32_t mbar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TMA_WAITP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra TMA_DONEP;\n"
+        "bra TMA_WAITP;\n"
+        "TMA_DONEP:\n"
+        "}\n" ::"r"(mbar), "r"(parity)
+        : "memory");
 }
 __device__ __forceinline__ void tma_wait(uint32_t mbar) {
     asm volatile(

@@ -188,6 +188,186 @@ __global__ void __launch_bounds__(256, COEB_DESC_MINB) describe_kernel(const __g
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// TMA variant: same grid, same three phases, but a keypoint's pixels arrive as TMA boxes in shared memory instead of
+// per-lane global gathers. A box must start on a 16-byte boundary of its row (measured: any other start raises an illegal
+// instruction), so it begins at the patch's first column rounded down to 16 and is 16 bytes wider than the patch:
+//   orientation: box 48 x 31 bytes around (x-15, y-15) of the level; lane r owns patch row r: nine shared words from the
+//                patch's first word, funnel-shifted to the first column, and 16 IDP.4A against per-lane constant weight
+//                words (computed once per CTA from umax);
+//   descriptor : box 64 x 37 bytes around (x-18, y-18) of the blurred level (the steered pattern stays within 18 px of the
+//                centre: |(x, y)| <= 13 * sqrt(2)); the 512 samples are byte loads from shared memory.
+// Every warp double-buffers its boxes: the next keypoint's box is in flight while the current one is reduced.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kRawBoxW = 48, kRawBoxH = kPatch;            // 1488 bytes
+constexpr int kBlurBoxW = 64, kBlurBoxH = 37, kBlurR = 18;  // 2368 bytes
+constexpr int kBoxSlot = 2432;                              // bytes per buffer slot (128-byte multiple, holds either box)
+static_assert(kDescChunk <= 256, "one thread per keypoint computes cos / sin");
+
+__global__ void __launch_bounds__(256, COEB_DESC_MINB) describe_tma_kernel(const __grid_constant__ TmaMaps raw_maps, const __grid_constant__ TmaMaps blur_maps,
+                                                                          const __grid_constant__ Geometry g, const __grid_constant__ BatchView v) {
+    __shared__ __align__(128) uint8_t s_box[8][2][kBoxSlot];
+    __shared__ __align__(8) unsigned long long s_bar[8][2];
+    __shared__ float s_pat[1024];         // pattern as floats, transposed: [4*bit + component][lane]
+    __shared__ float2 s_cs[kDescChunk];
+    __shared__ float s_angle[kDescChunk];
+    const int level = blockIdx.x, frame = blockIdx.y;
+    const LevelGeom& L = g.lv[level];
+    const int tid = threadIdx.x;
+
+    const int* kc = v.key_count + frame * g.nlevels;
+    int offset = 0, total = 0;
+    for (int l = 0; l < g.nlevels; l++) {
+        const int c = kc[l];
+        if (l < level) offset += c;
+        total += c;
+    }
+    const int n = kc[level];
+    const int status = v.status[frame];
+    const int chunk0 = blockIdx.z * kDescChunk;
+    if (level == 0 && blockIdx.z == 0 && tid == 0) {
+        int cnt = total;
+        if (status != COEB_OK) cnt = 0;
+        else if (total > g.out_cap) { v.status[frame] = COEB_ERR_CAPACITY; }
+        v.out_count[frame] = cnt;
+    }
+    if (chunk0 >= n || status != COEB_OK || total > g.out_cap) return;   // uniform
+    const int lane = tid & 31, wid = tid >> 5;
+    const uint32_t a_bar0 = (uint32_t)__cvta_generic_to_shared(&s_bar[wid][0]), a_bar1 = (uint32_t)__cvta_generic_to_shared(&s_bar[wid][1]);
+    const uint32_t a_box0 = (uint32_t)__cvta_generic_to_shared(&s_box[wid][0][0]), a_box1 = (uint32_t)__cvta_generic_to_shared(&s_box[wid][1][0]);
+    if (lane == 0) { tma_bar_init(a_bar0); tma_bar_init(a_bar1); }
+    for (int i = tid; i < 1024; i += 256) s_pat[(i & 31) * 32 + (i >> 5)] = (float)c_pattern[i];
+
+    LevelKey* keys = v.keys + (size_t)frame * g.keys_per_frame + L.key_base;
+    coeb_keypoint* okp = v.out_kps + (size_t)frame * g.out_cap + offset;
+    uint8_t* odesc = v.out_desc + ((size_t)frame * g.out_cap + offset) * 32;
+    const float factorPI = (float)(3.14159265358979323846 / 180.0);
+    const int nend = min(n, chunk0 + kDescChunk);
+    const int m = nend - chunk0;   // <= kDescChunk keypoints, warp w takes j = w, w + 8, ...
+
+    // per-lane constants of patch row r = lane (v = r - 15): weight words (u + 32 inside the circular patch, else 0) and
+    // 0/1 mask words for the row sum; byte b of the row is column u = b - 15, byte 31 is padding
+    uint32_t wq[8], mq[8];
+    {
+        const int vv = lane - kHalfPatch;
+        const int um = lane < kPatch ? g.umax[abs(vv)] : -1;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            uint32_t wgt = 0u, msk = 0u;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const int u = 4 * q + b - kHalfPatch;
+                if (abs(u) <= um && 4 * q + b < kPatch) { wgt |= (uint32_t)(u + 32) << (8 * b); msk |= 1u << (8 * b); }
+            }
+            wq[q] = wgt; mq[q] = msk;
+        }
+    }
+    __syncthreads();   // barriers initialised, pattern staged
+    uint32_t par0 = 0u, par1 = 0u;
+
+    // ---- phase 1: IC_Angle ----
+    {
+        const CUtensorMap* map = &raw_maps.m[level];
+        if (lane == 0 && wid < m) {
+            const LevelKey k = keys[chunk0 + wid];
+            tma_load_box(a_bar0, a_box0, map, ((int)k.x - kHalfPatch) & ~15, (int)k.y - kHalfPatch, frame, kRawBoxW * kRawBoxH);
+        }
+        int it = 0;
+        for (int j = wid; j < m; j += 8, it++) {
+            const int slot = it & 1;
+            if (lane == 0 && j + 8 < m) {
+                const LevelKey k = keys[chunk0 + j + 8];
+                tma_load_box(slot ? a_bar0 : a_bar1, slot ? a_box0 : a_box1, map, ((int)k.x - kHalfPatch) & ~15, (int)k.y - kHalfPatch, frame, kRawBoxW * kRawBoxH);
+            }
+            if (slot) { tma_wait_parity(a_bar1, par1); par1 ^= 1u; } else { tma_wait_parity(a_bar0, par0); par0 ^= 1u; }
+            const int ax = ((int)keys[chunk0 + j].x - kHalfPatch) & 15;   // patch's first column inside the box
+            const uint32_t* row = reinterpret_cast<const uint32_t*>(&s_box[wid][slot][(lane < kPatch ? lane : 0) * kRawBoxW]) + (ax >> 2);
+            const int sh = 8 * (ax & 3);
+            uint32_t m10b = 0u, sum = 0u;
+            uint32_t prev = row[0];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const uint32_t next = row[q + 1];
+                const uint32_t w = __funnelshift_r(prev, next, sh);   // bytes ax + 4q .. ax + 4q + 3 of the row
+                m10b = __dp4a(w, wq[q], m10b);
+                sum = __dp4a(w, mq[q], sum);
+                prev = next;
+            }
+            int m10 = (int)m10b - 32 * (int)sum;
+            int m01 = (lane - kHalfPatch) * (int)sum;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+                m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+            }
+            if (lane == 0) {
+                const float ang = fast_atan2_deg((float)m01, (float)m10);
+                s_angle[j] = ang;
+                keys[chunk0 + j].angle = ang;
+            }
+            __syncwarp();   // every lane is done with this slot before it is refilled
+        }
+    }
+    __syncthreads();
+    if (tid < m) {
+        const float angle = __fmul_rn(s_angle[tid], factorPI);
+        s_cs[tid] = make_float2((float)cos((double)angle), (float)sin((double)angle));
+    }
+    __syncthreads();
+
+    // ---- phase 2: steered rBRIEF on the blurred level ----
+    {
+        const CUtensorMap* map = &blur_maps.m[level];
+        int it = 0;
+        const int first_slot = 0;
+        // the slots continue to alternate from 0: both barriers have completed an even or odd number of phases, tracked in par0 / par1
+        if (lane == 0 && wid < m) {
+            const LevelKey k = keys[chunk0 + wid];
+            tma_load_box(a_bar0, a_box0, map, (__float2int_rn(k.x) - kBlurR) & ~15, __float2int_rn(k.y) - kBlurR, frame, kBlurBoxW * kBlurBoxH);
+        }
+        (void)first_slot;
+        for (int j = wid; j < m; j += 8, it++) {
+            const int slot = it & 1;
+            const int i = chunk0 + j;
+            const LevelKey k = keys[i];
+            if (lane == 0 && j + 8 < m) {
+                const LevelKey kn = keys[i + 8];
+                tma_load_box(slot ? a_bar0 : a_bar1, slot ? a_box0 : a_box1, map, (__float2int_rn(kn.x) - kBlurR) & ~15, __float2int_rn(kn.y) - kBlurR, frame,
+                             kBlurBoxW * kBlurBoxH);
+            }
+            const float a = s_cs[j].x, b = s_cs[j].y;
+            if (slot) { tma_wait_parity(a_bar1, par1); par1 ^= 1u; } else { tma_wait_parity(a_bar0, par0); par0 ^= 1u; }
+            const uint8_t* center = &s_box[wid][slot][kBlurR * kBlurBoxW + kBlurR + ((__float2int_rn(k.x) - kBlurR) & 15)];
+            int val = 0;
+#pragma unroll
+            for (int bit = 0; bit < 8; bit++) {
+                const float x0 = s_pat[(4 * bit) * 32 + lane], y0 = s_pat[(4 * bit + 1) * 32 + lane];
+                const float x1 = s_pat[(4 * bit + 2) * 32 + lane], y1 = s_pat[(4 * bit + 3) * 32 + lane];
+                const int r0 = round_even(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+                const int c0 = round_even(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+                const int r1 = round_even(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+                const int c1 = round_even(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+                const int t0 = center[r0 * kBlurBoxW + c0];
+                const int t1 = center[r1 * kBlurBoxW + c1];
+                val |= (t0 < t1) << bit;
+            }
+            odesc[(size_t)i * 32 + lane] = (uint8_t)val;
+            if (lane == 0) {
+                coeb_keypoint o;
+                o.x = level != 0 ? __fmul_rn(k.x, L.scale) : k.x;
+                o.y = level != 0 ? __fmul_rn(k.y, L.scale) : k.y;
+                o.size = (float)L.scaled_patch;
+                o.angle = s_angle[j];
+                o.response = k.response;
+                o.octave = level;
+                o.class_id = -1;
+                okp[i] = o;
+            }
+            __syncwarp();
+        }
+    }
+}
+
 // 0xFF for every byte of aligned word q of a patch row |v| that lies inside the circular patch, for the four alignments
 // of the patch's first column (byte j of word q is column u = 4q + j - al - 15).
 void build_ic_masks(const Geometry& g, uint32_t* out) {
@@ -206,7 +386,12 @@ void build_ic_masks(const Geometry& g, uint32_t* out) {
 void launch_describe(const Geometry& g, const BatchView& v, cudaStream_t stream) {
     int max_keys = 1;
     for (int l = 0; l < g.nlevels; l++) max_keys = std::max(max_keys, g.lv[l].key_cap);
-    describe_kernel<<<dim3(g.nlevels, v.B, (max_keys + kDescChunk - 1) / kDescChunk), 256, 0, stream>>>(g, v);
+    const dim3 grid(g.nlevels, v.B, (max_keys + kDescChunk - 1) / kDescChunk);
+    TmaMaps raw_maps, blur_maps;
+    if (tma_enabled() && encode_level_maps(g, v, kRawBoxW, kRawBoxH, &raw_maps) && encode_level_maps(g, v, kBlurBoxW, kBlurBoxH, &blur_maps, true))
+        describe_tma_kernel<<<grid, 256, 0, stream>>>(raw_maps, blur_maps, g, v);   // descriptors first: within the first 4 KB of parameter space
+    else
+        describe_kernel<<<grid, 256, 0, stream>>>(g, v);
 }
 
 }  // namespace coeb

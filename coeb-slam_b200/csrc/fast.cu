@@ -460,7 +460,7 @@ bool tma_enabled() {
     return on;
 }
 
-bool encode_level_maps(const Geometry& g, const BatchView& v, int box_w, int box_h, TmaMaps* out) {
+bool encode_level_maps(const Geometry& g, const BatchView& v, int box_w, int box_h, TmaMaps* out, bool blurred) {
     typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
     static EncodeTiled encode = [] {
@@ -471,12 +471,12 @@ bool encode_level_maps(const Geometry& g, const BatchView& v, int box_w, int box
     }();
     if (!encode) return false;
     for (int l = 0; l < g.nlevels; l++) {
-        const cuuint64_t pitch = (cuuint64_t)level_pitch(g, v, l);
-        const cuuint64_t fstride = l == 0 ? v.l0_stride : g.lv[l].img_stride;
+        const cuuint64_t pitch = blurred ? (cuuint64_t)g.lv[l].pitch : (cuuint64_t)level_pitch(g, v, l);
+        const cuuint64_t fstride = (l == 0 && !blurred) ? v.l0_stride : g.lv[l].img_stride;
         const cuuint64_t dims[3] = {pitch, (cuuint64_t)g.lv[l].h, (cuuint64_t)v.B};
         const cuuint64_t strides[2] = {pitch, fstride};
         const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1u}, estr[3] = {1u, 1u, 1u};
-        void* base = const_cast<uint8_t*>(level_ptr(g, v, l, 0));
+        void* base = blurred ? (void*)blur_ptr(g, v, l, 0) : (void*)const_cast<uint8_t*>(level_ptr(g, v, l, 0));
         if (((uintptr_t)base | pitch | fstride) & 15) return false;
         if (encode(&out->m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
