@@ -40,20 +40,20 @@ def stage_bytes(n_kp, n_cand):
         "pyramid": float((SIGMA_P - p7) + (SIGMA_P - p0)),      # read resize sources + write L1..L7
         "blur": float(2 * SIGMA_P),                               # read + write every level
         "fast": float(SIGMA_P + 4 * n_cand),                      # read every level + candidate words out
-        "select": float(n_kp * 749 + 4 * n_cand + 16 * n_kp),     # IC patches + candidates in + level keys out
-        "describe": float(n_kp * (512 + 60 + 16)),                # pattern samples + 28 B kp + 32 B desc (+ keys in)
+        "select": float(4 * n_cand + 16 * n_kp),                  # candidates in + level keys out
+        "describe": float(n_kp * (749 + 512 + 60 + 16)),          # IC patches + pattern samples + 28 B kp + 32 B desc (+ keys in)
     }
 
 
 STAGE_KERNELS = {"classify": ["classify_kernel"], "pyramid": ["resize_kernel"], "blur": ["blur_kernel"],
-                 "fast": ["fast_kernel", "fast_fallback_kernel"], "select": ["select_kernel"], "describe": ["describe_kernel"]}
+                 "fast": ["fast_kernel", "fast_fallback_kernel"], "select": ["select_kernel"], "describe": ["describe_tma_kernel"]}
 
 
 def profiled_traffic(stage):
     """dram__bytes_read.sum + dram__bytes_write.sum per step of the stage's kernels, from the committed `ncu --set full`
-    capture of this same command (profiles/r01g_traffic.json); None if the capture is missing."""
+    capture of this same command (profiles/r01k_traffic.json); None if the capture is missing."""
     try:
-        k = json.load(open(os.path.join(ROOT, "profiles", "r01g_traffic.json")))["kernels"]
+        k = json.load(open(os.path.join(ROOT, "profiles", "r01k_traffic.json")))["kernels"]
         return float(sum(k[n]["dram_bytes"] for n in STAGE_KERNELS[stage])), {n: k[n]["alu_pipe_pct"] for n in STAGE_KERNELS[stage]}
     except Exception:
         return None, None
@@ -405,6 +405,12 @@ def run_b200(args):
     achieved = sb[dom] * B / (stage_ms[dom] * 1e-3) / 1e9
     traffic, alu_pct = profiled_traffic(dom)
     pipeline_bytes = 6049674.0
+    per_stage = {}
+    for st_name, ms in stage_ms.items():   # every stage against the same roofline: algorithmic GB/s and the DRAM GB/s ncu saw for its kernels
+        t_bytes, t_alu = profiled_traffic(st_name)
+        per_stage[st_name] = {"algorithmic_gbs": sb.get(st_name, 0.0) * B / (ms * 1e-3) / 1e9 if ms > 0 else None,
+                              "frac": sb.get(st_name, 0.0) * B / (ms * 1e-3) / 1e9 / peak if ms > 0 else None,
+                              "dram_gbs_ncu": (t_bytes / (ms * 1e-3) / 1e9) if (t_bytes and ms > 0) else None, "alu_pipe_pct_ncu": t_alu}
     line = {
         "metric": "frames/s ORB extract+dyn-filter (640x480,1k kps)", "value": value, "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -416,11 +422,11 @@ def run_b200(args):
                 "in_flight": "2 batches: one handle per host thread, blocking coeb_extract_batch_host calls, alternating steps"},
         "gpu_launches": args.steps * launches_per_step,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "traffic_source": "profiles/r01g_traffic.json (ncu --set full, per 256-frame step)",
+                     "frac": achieved / peak, "traffic": traffic, "traffic_source": "profiles/r01k_traffic.json (ncu --set full, per 256-frame step)",
                      "alu_pipe_pct_ncu": alu_pct,
                      "note": "the stage is integer-ALU bound (packed 16-bit min/max), not HBM bound: see DESIGN.md section 5",
                      "algorithmic_bytes_per_launch": sb[dom] * B,
-                     "stage_ms": stage_ms,
+                     "stage_ms": stage_ms, "stages": per_stage,
                      "pipeline": {"bytes_per_frame": pipeline_bytes, "achieved_gbs": pipeline_bytes * value / world / 1e9,
                                   "frac": pipeline_bytes * value / world / 1e9 / peak}},
         "cpu_baseline": cpu, "clocks": clocks, "latency": lat, "match": match,
