@@ -79,13 +79,20 @@ class ClockSampler:
             self.path = f.name
             q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
                  "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-                 "clocks_event_reasons.sw_power_cap")
+                 "clocks_event_reasons.sw_power_cap,timestamp")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q,
                                           "--format=csv,noheader,nounits", "-lms", "20"], stdout=f, stderr=subprocess.DEVNULL)
+            # nvidia-smi needs a moment to come up (longer on an 8-GPU box): wait for its first line so that it is
+            # already looping when the short timed region starts
+            t = time.time()
+            while time.time() - t < 5.0 and os.path.getsize(self.path) == 0:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t_start=None, t_end=None):
+        """Samples whose timestamp lies inside [t_start, t_end] (the timed region); if the region was shorter than the
+        sampling period and caught none, the samples taken since the warm-up (same load) are used and `window` says so."""
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if not self.proc:
             return out
@@ -95,7 +102,23 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         try:
-            rows = [r.split(",") for r in open(self.path).read().strip().splitlines() if r.strip()]
+            rows = [[c.strip() for c in r.split(",")] for r in open(self.path).read().strip().splitlines() if r.strip()]
+            rows = [r for r in rows if len(r) >= 8]
+            out["window"] = "timed region"
+            if t_start is not None:
+                import datetime
+                def ts(r):
+                    try:
+                        return datetime.datetime.strptime(r[7], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    except Exception:
+                        return None
+                inside = [r for r in rows if ts(r) is not None and t_start <= ts(r) <= t_end]
+                if inside:
+                    rows = inside
+                else:
+                    under_load = [r for r in rows if ts(r) is not None and ts(r) >= t_start - 0.5]
+                    rows = under_load or rows[-2:]
+                    out["window"] = "no sample fell inside the %.0f ms timed region: nearest samples under the same load (warm-up / stage pass)" % (1e3 * (t_end - t_start))
             sm = [float(r[0]) for r in rows]
             out["sm_mhz"] = float(np.median(sm)) if sm else None
             out["sm_max_mhz"] = float(rows[0][1]) if rows else None
@@ -192,6 +215,28 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # CUDA arm
 # ------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(torch, dev):
+    """Multi-GPU runs: keep this rank's threads (and so the first touch of its pinned staging buffers) on the NUMA node the GPU
+    hangs off, so that 8 ranks do not pull their host->device traffic across the socket link. Returns the node or None."""
+    try:
+        p = torch.cuda.get_device_properties(dev)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def run_b200(args):
     import torch
     import coeb_b200 as cb
@@ -202,6 +247,7 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device; the CUDA arm has no CPU fallback (use --impl reference for the CPU arm)")
     dev = local % torch.cuda.device_count()
     torch.cuda.set_device(dev)
+    numa_node = bind_to_gpu_numa_node(torch, dev) if world > 1 else None
     B = FRAMES_PER_GPU
     # seeds 0..255 are the frame ids within a shard, the rank is added x1000
     batch = synth.make_batch(B, base_seed=rank * 1000, w=W, h=H, unique=args.unique)
@@ -234,12 +280,13 @@ def run_b200(args):
 
     # ---- device-resident throughput ("value"); per-stage times for the roofline come from a second pass ------------
     ex.set_profiling(bool(args.stage_sync))
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
     sampler = ClockSampler(dev)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    t_clk0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stage_acc = {k: 0.0 for k in ex.STAGES}
     stage_events = []
@@ -252,8 +299,13 @@ def run_b200(args):
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
+    t_clk1 = time.time()
     launches_per_step = ex.launches_per_call()   # of the device-resident call just timed
-    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0 and t_clk1 - t_clk0 < 0.06:   # a region shorter than a few sampling periods: keep the GPU under the same load a little longer
+        for _ in range(args.steps):
+            step_device()
+        torch.cuda.synchronize()
+    clocks = sampler.stop(t_clk0, t_clk1) if rank == 0 else None
     counts = d_counts.cpu().numpy()
     status = d_status.cpu().numpy()
     assert (status == 0).all(), "device reported per-frame failures: %s" % status[status != 0][:8]
@@ -419,7 +471,8 @@ def run_b200(args):
                        mean_keypoints=n_kp),
         "e2e": {"value": e2e_frames / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "wall_frames_per_s": e2e_frames / (e2e_wall_ms * 1e-3),
-                "in_flight": "2 batches: one handle per host thread, blocking coeb_extract_batch_host calls, alternating steps"},
+                "in_flight": "2 batches: one handle per host thread, blocking coeb_extract_batch_host calls, alternating steps",
+                "numa_node_of_rank0": numa_node},
         "gpu_launches": args.steps * launches_per_step,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "traffic_source": "profiles/r01k_traffic.json (ncu --set full, per 256-frame step)",

@@ -75,11 +75,11 @@ struct coeb_extractor {
     DynState* d_dyn = nullptr;
     // staging for the host entry points
     uint8_t* d_in_gray = nullptr; size_t in_gray_bytes = 0; int in_pitch = 0;
-    float *d_in_boxes = nullptr, *d_in_tm = nullptr;
-    int *d_in_nbox = nullptr, *d_in_ntm = nullptr, *d_in_blur = nullptr;
-    size_t in_dyn_cap[5] = {0, 0, 0, 0, 0};
+    char *h_dynin = nullptr, *d_dynin = nullptr; size_t dyn_cap = 0;   // boxes | nbox | blur flags | T_M | ntm of a call: one pinned block, one copy
+    char* d_out_block = nullptr;                                    // counts | status | keypoints | descriptors: one allocation
     coeb_keypoint* d_out_kps = nullptr; uint8_t* d_out_desc = nullptr; int *d_out_count = nullptr, *d_out_status = nullptr;
     size_t out_cap_elems = 0; int out_cap_B = 0;
+    char* h_out1 = nullptr; size_t h_out1_cap = 0;                  // pinned landing block of single-frame calls (one D2H copy)
     BatchView last_view{};
     // copy/compute pipelining of the host entry point
     cudaStream_t pipe_stream[3] = {nullptr, nullptr, nullptr};
@@ -89,7 +89,7 @@ struct coeb_extractor {
     cudaEvent_t copy_out_done = nullptr;
     std::vector<cudaEvent_t> chunk_in, chunk_done;           // per sub-batch: input resident / kernels finished
     // blur runs beside FAST + octree on a side stream (both only need the pyramid); one lane per launching stream
-    struct Lane { cudaStream_t main; cudaStream_t aux; cudaEvent_t fork, join; };
+    struct Lane { cudaStream_t main; cudaStream_t aux; cudaEvent_t fork, join, fork0, cls; };
     std::vector<Lane> lanes;
     // CUDA graphs of the kernel sequence for small non-pipelined host calls (single-frame latency path)
     struct GraphEntry { BatchView view; int w, h, cap, chunk; cudaGraphExec_t exec; };
@@ -321,10 +321,12 @@ int ensure_buf(T** p, size_t* cap, size_t n) {
 coeb_extractor::Lane* lane_for(coeb_extractor* ex, cudaStream_t s) {
     for (auto& l : ex->lanes)
         if (l.main == s) return &l;
-    coeb_extractor::Lane l{s, nullptr, nullptr, nullptr};
+    coeb_extractor::Lane l{s, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (cudaStreamCreateWithFlags(&l.aux, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&l.fork0, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&l.cls, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     ex->lanes.push_back(l);
     return &ex->lanes.back();
 }
@@ -333,13 +335,17 @@ int enqueue(coeb_extractor* ex, const BatchView& v, cudaStream_t s, bool prof) {
     const Geometry& g = ex->geom;
     coeb_extractor::Lane* lane = prof ? nullptr : lane_for(ex, s);
     if (lane) {
-        // classify, pyramid | fork: blur on the side stream, FAST + octree on the main one | join | describe
-        launch_classify(g, v, s);
+        // side stream: classify beside the pyramid, then blur beside FAST + octree | main: pyramid, FAST, octree | join | describe
+        CUDA_TRY(cudaEventRecord(lane->fork0, s));
+        CUDA_TRY(cudaStreamWaitEvent(lane->aux, lane->fork0, 0));
+        launch_classify(g, v, lane->aux);
+        CUDA_TRY(cudaEventRecord(lane->cls, lane->aux));
         launch_pyramid(g, v, s);
         CUDA_TRY(cudaEventRecord(lane->fork, s));
         CUDA_TRY(cudaStreamWaitEvent(lane->aux, lane->fork, 0));
         launch_blur(g, v, lane->aux);
         CUDA_TRY(cudaEventRecord(lane->join, lane->aux));
+        CUDA_TRY(cudaStreamWaitEvent(s, lane->cls, 0));   // FAST reads the per-frame threshold decision
         launch_fast(g, v, s);
         launch_select(g, v, s);
         CUDA_TRY(cudaStreamWaitEvent(s, lane->join, 0));
@@ -481,10 +487,11 @@ void coeb_extractor_destroy(coeb_extractor* ex) {
     free_arenas(ex);
     cudaFree(ex->d_tabs);
     cudaFree(ex->d_fast_tiles);
-    cudaFree(ex->d_in_gray); cudaFree(ex->d_in_boxes); cudaFree(ex->d_in_tm); cudaFree(ex->d_in_nbox); cudaFree(ex->d_in_ntm);
-    cudaFree(ex->d_in_blur); cudaFree(ex->d_out_kps); cudaFree(ex->d_out_desc); cudaFree(ex->d_out_count); cudaFree(ex->d_out_status);
+    cudaFree(ex->d_in_gray); cudaFree(ex->d_dynin); cudaFree(ex->d_out_block);
+    if (ex->h_dynin) cudaFreeHost(ex->h_dynin);
+    if (ex->h_out1) cudaFreeHost(ex->h_out1);
     for (auto& e : ex->graphs) cudaGraphExecDestroy(e.exec);
-    for (auto& l : ex->lanes) { cudaStreamDestroy(l.aux); cudaEventDestroy(l.fork); cudaEventDestroy(l.join); }
+    for (auto& l : ex->lanes) { cudaStreamDestroy(l.aux); cudaEventDestroy(l.fork); cudaEventDestroy(l.join); cudaEventDestroy(l.fork0); cudaEventDestroy(l.cls); }
     for (int i = 0; i < 7; i++) if (ex->ev[i]) cudaEventDestroy(ex->ev[i]);
     for (int i = 0; i < 3; i++) {
         if (ex->pipe_stream[i]) cudaStreamDestroy(ex->pipe_stream[i]);
@@ -712,29 +719,43 @@ int coeb_extract_batch_host(coeb_extractor* ex, int B, const uint8_t* gray, int 
     if (st != COEB_OK) return st;
     const float *dboxes = nullptr, *dtm = nullptr;
     const int *dnbox = nullptr, *dntm = nullptr, *dblur = nullptr;
-    if (nbox) {  // the per-frame box / T_M arrays are tiny: one copy up front
-        if ((st = ensure_buf(&ex->d_in_boxes, &ex->in_dyn_cap[0], (size_t)B * max_box * 4)) != COEB_OK) return st;
-        if ((st = ensure_buf(&ex->d_in_nbox, &ex->in_dyn_cap[1], (size_t)B)) != COEB_OK) return st;
-        if ((st = ensure_buf(&ex->d_in_blur, &ex->in_dyn_cap[2], (size_t)B * max_box)) != COEB_OK) return st;
-        CUDA_TRY(cudaMemcpyAsync(ex->d_in_boxes, boxes, sizeof(float) * B * max_box * 4, cudaMemcpyHostToDevice, s));
-        CUDA_TRY(cudaMemcpyAsync(ex->d_in_nbox, nbox, sizeof(int) * B, cudaMemcpyHostToDevice, s));
-        CUDA_TRY(cudaMemcpyAsync(ex->d_in_blur, blur_flag, sizeof(int) * B * max_box, cudaMemcpyHostToDevice, s));
-        dboxes = ex->d_in_boxes; dnbox = ex->d_in_nbox; dblur = ex->d_in_blur;
-    }
-    if (ntm) {
-        if ((st = ensure_buf(&ex->d_in_tm, &ex->in_dyn_cap[3], (size_t)B * max_tm * 2)) != COEB_OK) return st;
-        if ((st = ensure_buf(&ex->d_in_ntm, &ex->in_dyn_cap[4], (size_t)B)) != COEB_OK) return st;
-        CUDA_TRY(cudaMemcpyAsync(ex->d_in_tm, tm, sizeof(float) * B * max_tm * 2, cudaMemcpyHostToDevice, s));
-        CUDA_TRY(cudaMemcpyAsync(ex->d_in_ntm, ntm, sizeof(int) * B, cudaMemcpyHostToDevice, s));
-        dtm = ex->d_in_tm; dntm = ex->d_in_ntm;
+    if (nbox || ntm) {   // the per-frame box / T_M arrays are tiny: packed into one pinned block, one copy up front
+        auto a256 = [](size_t b) { return (b + 255) & ~(size_t)255; };
+        const size_t o_boxes = 0, o_nbox = o_boxes + a256(nbox ? sizeof(float) * B * max_box * 4 : 0), o_blur = o_nbox + a256(nbox ? sizeof(int) * B : 0);
+        const size_t o_tm = o_blur + a256(nbox ? sizeof(int) * B * max_box : 0), o_ntm = o_tm + a256(ntm ? sizeof(float) * B * max_tm * 2 : 0);
+        const size_t total = o_ntm + a256(ntm ? sizeof(int) * B : 0);
+        if (total > ex->dyn_cap) {
+            if (ex->h_dynin) cudaFreeHost(ex->h_dynin);
+            cudaFree(ex->d_dynin);
+            ex->h_dynin = ex->d_dynin = nullptr; ex->dyn_cap = 0;
+            CUDA_TRY(cudaHostAlloc((void**)&ex->h_dynin, total, cudaHostAllocDefault));
+            CUDA_TRY(cudaMalloc((void**)&ex->d_dynin, total));
+            ex->dyn_cap = total;
+        }
+        if (nbox) {
+            std::memcpy(ex->h_dynin + o_boxes, boxes, sizeof(float) * B * max_box * 4);
+            std::memcpy(ex->h_dynin + o_nbox, nbox, sizeof(int) * B);
+            std::memcpy(ex->h_dynin + o_blur, blur_flag, sizeof(int) * B * max_box);
+            dboxes = (const float*)(ex->d_dynin + o_boxes); dnbox = (const int*)(ex->d_dynin + o_nbox); dblur = (const int*)(ex->d_dynin + o_blur);
+        }
+        if (ntm) {
+            std::memcpy(ex->h_dynin + o_tm, tm, sizeof(float) * B * max_tm * 2);
+            std::memcpy(ex->h_dynin + o_ntm, ntm, sizeof(int) * B);
+            dtm = (const float*)(ex->d_dynin + o_tm); dntm = (const int*)(ex->d_dynin + o_ntm);
+        }
+        CUDA_TRY(cudaMemcpyAsync(ex->d_dynin, ex->h_dynin, total, cudaMemcpyHostToDevice, s));
     }
     if ((size_t)B * cap > ex->out_cap_elems || B > ex->out_cap_B) {
-        cudaFree(ex->d_out_kps); cudaFree(ex->d_out_desc); cudaFree(ex->d_out_count); cudaFree(ex->d_out_status);
-        ex->d_out_kps = nullptr; ex->d_out_desc = nullptr; ex->d_out_count = ex->d_out_status = nullptr;
-        CUDA_TRY(cudaMalloc(&ex->d_out_kps, (size_t)B * cap * sizeof(coeb_keypoint)));
-        CUDA_TRY(cudaMalloc(&ex->d_out_desc, (size_t)B * cap * 32));
-        CUDA_TRY(cudaMalloc(&ex->d_out_count, (size_t)B * sizeof(int)));
-        CUDA_TRY(cudaMalloc(&ex->d_out_status, (size_t)B * sizeof(int)));
+        cudaFree(ex->d_out_block);
+        ex->d_out_block = nullptr; ex->d_out_kps = nullptr; ex->d_out_desc = nullptr; ex->d_out_count = ex->d_out_status = nullptr;
+        // counts | status | keypoints | descriptors in one block: a single-frame call downloads it with one copy
+        const size_t o_kps = ((size_t)2 * B * sizeof(int) + 255) & ~(size_t)255;
+        const size_t o_desc = o_kps + (((size_t)B * cap * sizeof(coeb_keypoint) + 255) & ~(size_t)255);
+        CUDA_TRY(cudaMalloc((void**)&ex->d_out_block, o_desc + (size_t)B * cap * 32));
+        ex->d_out_count = (int*)ex->d_out_block;
+        ex->d_out_status = ex->d_out_count + B;
+        ex->d_out_kps = (coeb_keypoint*)(ex->d_out_block + o_kps);
+        ex->d_out_desc = (uint8_t*)(ex->d_out_block + o_desc);
         ex->out_cap_elems = (size_t)B * cap;
         ex->out_cap_B = B;
     }
@@ -794,13 +815,26 @@ int coeb_extract_batch_host(coeb_extractor* ex, int B, const uint8_t* gray, int 
             e = cudaMemcpyAsync(desc_out + (size_t)f0 * cap * 32, ex->d_out_desc + (size_t)f0 * cap * 32, (size_t)32 * n * cap, cudaMemcpyDeviceToHost, cs);
         return e;
     };
+    bool landed = false;   // single frame: the whole output block came back with one copy into pinned memory
     if (!piped) {
         CUDA_TRY(upload(0, B, s));
         if (trace) cudaEventRecord(tev[1], s);
         st = ex->profiling ? enqueue(ex, v, s, true) : launch_graphed(ex, v, s);   // one graph launch instead of ~20 stream operations
         if (st != COEB_OK) return st;
         if (trace) cudaEventRecord(tev[2], s);
-        CUDA_TRY(download(0, B, s));
+        if (B == 1 && ex->out_cap_B == 1 && ex->out_cap_elems == (size_t)cap) {
+            const size_t bytes = (size_t)((char*)ex->d_out_desc - ex->d_out_block) + (size_t)cap * 32;
+            if (bytes > ex->h_out1_cap) {
+                if (ex->h_out1) cudaFreeHost(ex->h_out1);
+                ex->h_out1 = nullptr; ex->h_out1_cap = 0;
+                CUDA_TRY(cudaHostAlloc((void**)&ex->h_out1, bytes, cudaHostAllocDefault));
+                ex->h_out1_cap = bytes;
+            }
+            CUDA_TRY(cudaMemcpyAsync(ex->h_out1, ex->d_out_block, bytes, cudaMemcpyDeviceToHost, s));
+            landed = true;
+        } else {
+            CUDA_TRY(download(0, B, s));
+        }
         if (trace) cudaEventRecord(tev[3], s);
     } else {
         CUDA_TRY(cudaEventRecord(ex->pipe_ready, s));   // the box / T_M copies above, and whatever the caller queued before
@@ -838,6 +872,14 @@ int coeb_extract_batch_host(coeb_extractor* ex, int B, const uint8_t* gray, int 
             fprintf(stderr, "[coeb pipe] chunk %d: h2d done %.3f ms, kernels done %.3f ms, d2h done %.3f ms\n", c, a, b, d);
         }
         for (auto& e : tev) cudaEventDestroy(e);
+    }
+    if (landed) {   // only the keypoints that exist are copied on to the caller's arrays
+        const int n = ((const int*)ex->h_out1)[0];
+        counts_out[0] = n;
+        hstatus[0] = ((const int*)ex->h_out1)[1];
+        const int m = std::min(std::max(n, 0), cap);
+        if (kps_out) std::memcpy(kps_out, ex->h_out1 + ((char*)ex->d_out_kps - ex->d_out_block), sizeof(coeb_keypoint) * m);
+        if (desc_out) std::memcpy(desc_out, ex->h_out1 + ((char*)ex->d_out_desc - ex->d_out_block), (size_t)32 * m);
     }
     int worst = COEB_OK;
     for (int i = 0; i < B; i++)
