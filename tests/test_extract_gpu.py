@@ -225,3 +225,34 @@ def test_host_batch_of_260_frames_uses_64_frame_sub_batches_with_a_ragged_tail(g
     assert np.array_equal(counts, counts2)
     for i in range(0, B, 13):
         assert kps[i, :counts[i]].tobytes() == kps2[i, :counts[i]].tobytes() and np.array_equal(desc[i, :counts[i]], desc2[i, :counts[i]])
+
+
+def test_plain_load_twins_of_the_tma_kernels(gpu):
+    """COEB_TMA=0 selects the vector-load staging the TMA kernels fall back to (unaligned views, missing driver entry point):
+    the switch is read once per process, so the check runs in a child process and compares with the oracle there."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path[:0] = %r\n"
+        "import coeb_b200 as cb, orc\n"
+        "from coeb_b200 import synth\n"
+        "for seed in (0, 3):\n"
+        "    gray = synth.make_frame(seed)\n"
+        "    boxes, tm, blur = synth.make_dynamic(seed, force_area=(seed == 3))\n"
+        "    kg, dg = cb.Extractor().extract(gray, boxes, tm, blur)\n"
+        "    kc, dc = orc.Extractor().extract(gray, boxes, tm, blur)\n"
+        "    assert kg.tobytes() == kc.tobytes() and np.array_equal(dg, dc), seed\n"
+        "b = synth.make_batch(70, base_seed=900, unique=5)\n"
+        "ex = cb.Extractor()\n"
+        "k, d, c, s = ex.extract_batch_host(b['gray'], b['boxes'], b['nbox'], b['tm'], b['ntm'], b['blur'])\n"
+        "o = orc.Extractor()\n"
+        "for i in (0, 33, 69):\n"
+        "    nb, nt = b['nbox'][i], b['ntm'][i]\n"
+        "    kb, db = o.extract(b['gray'][i], b['boxes'][i, :nb], b['tm'][i, :nt], b['blur'][i, :nb])\n"
+        "    assert c[i] == len(kb) and k[i, :c[i]].tobytes() == kb.tobytes() and np.array_equal(d[i, :c[i]], db), i\n"
+        "print('plain-load path ok')\n") % ([p for p in sys.path if p],)
+    env = dict(os.environ, COEB_TMA="0")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0 and "plain-load path ok" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
