@@ -78,6 +78,67 @@ __device__ __forceinline__ void for_each_in_area(const FrameDev& f, float x, flo
     }
 }
 
+// Warp-cooperative form of the same walk. The window's columns are contiguous item ranges (cells are stored ix-major), so
+// the raw items of the window are numbered column by column with a warp scan, 32 of them are tested per trip (level and
+// distance filters of GetFeaturesInArea, then accept(idx) for the caller's own static filters) and the survivors are
+// ranked with a ballot: emit(pos, idx) sees pos = rank of idx among the survivors in the reference's traversal order.
+// All 32 lanes must call with the same arguments; returns the number of survivors.
+template <class Accept, class Emit>
+__device__ __forceinline__ int warp_for_each_in_area(const FrameDev& f, float x, float y, float r, int minLevel, int maxLevel, Accept&& accept,
+                                                     Emit&& emit) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int nMinCellX = max(0, (int)floorf((x - f.min_x - r) * f.gw_inv));
+    if (nMinCellX >= COEB_GRID_COLS) return 0;
+    const int nMaxCellX = min(COEB_GRID_COLS - 1, (int)ceilf((x - f.min_x + r) * f.gw_inv));
+    if (nMaxCellX < 0) return 0;
+    const int nMinCellY = max(0, (int)floorf((y - f.min_y - r) * f.gh_inv));
+    if (nMinCellY >= COEB_GRID_ROWS) return 0;
+    const int nMaxCellY = min(COEB_GRID_ROWS - 1, (int)ceilf((y - f.min_y + r) * f.gh_inv));
+    if (nMaxCellY < 0) return 0;
+    const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+    const unsigned lt = (1u << lane) - 1u;
+    int cnt = 0;
+    for (int c0 = nMinCellX; c0 <= nMaxCellX; c0 += 32) {   // one trip unless the window is wider than 32 columns
+        const int ix = c0 + lane;
+        int lo = 0, hi = 0;
+        if (ix <= nMaxCellX) { lo = f.cell_start[ix * COEB_GRID_ROWS + nMinCellY]; hi = f.cell_start[ix * COEB_GRID_ROWS + nMaxCellY + 1]; }
+        const int n = hi - lo;
+        int incl = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(full, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int total = __shfl_sync(full, incl, 31);
+        const int ncol = min(32, nMaxCellX - c0 + 1);
+        for (int base = 0; base < total; base += 32) {
+            const int t = base + lane;
+            int col = 0;   // column of raw item t = number of columns that end at or before it
+            for (int c = 0; c < ncol; c++) col += t >= __shfl_sync(full, incl, c);
+            col = min(col, 31);
+            const int ex = __shfl_sync(full, incl - n, col), l0 = __shfl_sync(full, lo, col);
+            bool ok = t < total;
+            int idx = -1;
+            if (ok) {
+                idx = f.cell_items[l0 + (t - ex)];
+                if (bCheckLevels) {
+                    const int o = f.octave[idx];
+                    if (o < minLevel || (maxLevel >= 0 && o > maxLevel)) ok = false;
+                }
+                if (ok) {
+                    const float dx = f.x[idx] - x, dy = f.y[idx] - y;
+                    ok = fabsf(dx) < r && fabsf(dy) < r && accept(idx);
+                }
+            }
+            const unsigned m = __ballot_sync(full, ok);
+            if (ok) emit(cnt + __popc(m & lt), idx);
+            cnt += __popc(m);
+        }
+    }
+    return cnt;
+}
+
 // ---- grid build (Frame::AssignFeaturesToGrid, src/Frame.cc:396-411) -------------------------------------
 // One CTA. Cells ix-major; items ascending by keypoint index (the reference pushes in index order).
 __global__ void __launch_bounds__(1024) grid_build_kernel(FrameDev f, int* cell_start, int* cell_items, int* kp_cell) {
@@ -145,7 +206,16 @@ struct CandLists {
     int2* items;   // [n][cap]: x = idx | octave << 24, y = distance
     int* count;    // [n] candidates found (may exceed cap: overflow)
     int cap;
+    int* active;   // [n] queries with at least one candidate, in no particular order
+    int* meta;     // [0] number of active queries, [1] some list overflowed its capacity (both zeroed before the collect kernel)
 };
+
+// Lane 0 of the collecting warp records the query's candidate count.
+__device__ __forceinline__ void cand_finish(const CandLists& C, int i, int cnt) {
+    C.count[i] = cnt;
+    if (cnt > 0) C.active[atomicAdd(&C.meta[0], 1)] = i;
+    if (cnt > C.cap) C.meta[1] = 1;
+}
 
 // ---- M2: SearchByProjection(Frame&, vector<MapPoint*>&, th) (src/ORBmatcher.cc:45-129) -------------------
 struct MapDev {
@@ -175,16 +245,46 @@ __device__ __forceinline__ void m2_visit(const FrameDev& F, const MapDev& M, flo
     });
 }
 
-__global__ void __launch_bounds__(128) m2_collect_kernel(FrameDev F, MapDev M, float th, const int* kp_state, CandLists C) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= M.n) return;
+// Static part of query i of SearchByProjection(F, MapPoints): window and filters that do not depend on other queries.
+struct M2Query { float x, y, rs, pxr; int lvl; const uint32_t* d; };
+__device__ __forceinline__ bool m2_query(const FrameDev& F, const MapDev& M, float th, int i, M2Query& q) {
+    if (!M.track_in_view[i] || M.bad[i]) return false;
+    q.lvl = M.level[i];
+    float r = ((double)M.view_cos[i] > 0.998) ? 2.5f : 4.0f;  // RadiusByViewingCos (:131-137)
+    if (th != 1.0f) r *= th;                                   // bFactor (:49, :65-66)
+    q.rs = r * F.scale[q.lvl];
+    q.d = M.desc + 8 * (size_t)i;
+    q.pxr = M.proj_xr[i];
+    q.x = M.proj_x[i]; q.y = M.proj_y[i];
+    return true;
+}
+// One warp per map point: the window's keypoints are tested 32 at a time, the survivors written in traversal order.
+__device__ __forceinline__ void m2_collect_warp(const FrameDev& F, const MapDev& M, float th, const int* __restrict__ kp_state, const CandLists& C, int i) {
+    M2Query q;
     int cnt = 0;
-    int2* out = C.items + (size_t)i * C.cap;
-    m2_visit(F, M, th, kp_state, i, [&](int idx, int dist, int oct) {
-        if (cnt < C.cap) out[cnt] = make_int2(idx | (oct << 24), dist);
-        cnt++;
-    });
-    C.count[i] = cnt;
+    if (m2_query(F, M, th, i, q)) {
+        int2* out = C.items + (size_t)i * C.cap;
+        cnt = warp_for_each_in_area(
+            F, q.x, q.y, q.rs, q.lvl - 1, q.lvl,
+            [&](int idx) {
+                if (kp_state[idx] == -2) return false;                 // already holds a MapPoint with observations (:87-89)
+                if (F.uright) {
+                    const float ur = F.uright[idx];
+                    if (ur > 0 && fabsf(q.pxr - ur) > q.rs) return false;   // :91-96
+                }
+                return true;
+            },
+            [&](int pos, int idx) {
+                if (pos < C.cap) out[pos] = make_int2(idx | (F.octave[idx] << 24), hamming256(q.d, F.desc + 8 * (size_t)idx));
+            });
+    }
+    if ((threadIdx.x & 31) == 0) cand_finish(C, i, cnt);
+}
+
+__global__ void __launch_bounds__(256) m2_collect_kernel(FrameDev F, MapDev M, float th, const int* kp_state, CandLists C) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= M.n) return;
+    m2_collect_warp(F, M, th, kp_state, C, i);
 }
 
 // One CTA iterates to the fixed point. res[i] = keypoint claimed by map point i or -1.
@@ -194,22 +294,26 @@ __global__ void __launch_bounds__(1024) m2_resolve_kernel(FrameDev F, MapDev M, 
                                                           int* kp_match /*out, pre-filled with kp_state*/, int* res, int* claim_min, int* out_info) {
     __shared__ int s_changed, s_count;
     const int tid = threadIdx.x, T = blockDim.x;
-    if (kLists) {   // a list overflowed: report and let the host rerun the window-walking variant
-        int over = 0;
-        for (int i = tid; i < M.n; i += T) over |= C.count[i] > C.cap;
-        if (__syncthreads_or(over)) { if (tid == 0) { out_info[0] = 0; out_info[1] = 0; out_info[2] = 1; } return; }
+    if (kLists && C.meta[1]) {   // a list overflowed: report and let the host rerun the window-walking variant
+        if (tid == 0) { out_info[0] = 0; out_info[1] = 0; out_info[2] = 1; }
+        return;
     }
-    for (int i = tid; i < M.n; i += T) res[i] = -1;
+    // Only queries with candidates can match; with lists they were compacted by the collect kernel (in no particular
+    // order: the evaluation of a query depends on the others through claim_min only).
+    const int na = kLists ? C.meta[0] : M.n;
+    auto query = [&](int a) { return kLists ? C.active[a] : a; };
+    for (int a = tid; a < na; a += T) res[query(a)] = -1;
     for (int round = 0; round <= M.n; round++) {
         for (int k = tid; k < F.n; k += T) claim_min[k] = kInf;
         if (tid == 0) s_changed = 0;
         __syncthreads();
-        for (int i = tid; i < M.n; i += T) {
-            const int k = res[i];
+        for (int a = tid; a < na; a += T) {
+            const int i = query(a), k = res[i];
             if (k >= 0 && M.has_obs[i]) atomicMin(&claim_min[k], i);
         }
         __syncthreads();
-        for (int i = tid; i < M.n; i += T) {
+        for (int a = tid; a < na; a += T) {
+            const int i = query(a);
             int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
             auto consider = [&](int idx, int dist, int oct) {
                 if (claim_min[idx] < i) return;   // claimed earlier in this call by a MapPoint with observations (:87-89, :123)
@@ -237,8 +341,10 @@ __global__ void __launch_bounds__(1024) m2_resolve_kernel(FrameDev F, MapDev M, 
     for (int k = tid; k < F.n; k += T) claim_min[k] = -1;  // reuse as "last claimant"
     __syncthreads();
     int mine = 0;
-    for (int i = tid; i < M.n; i += T)
+    for (int a = tid; a < na; a += T) {
+        const int i = query(a);
         if (res[i] >= 0) { atomicMax(&claim_min[res[i]], i); mine++; }
+    }
     if (mine) atomicAdd(&s_count, mine);
     __syncthreads();
     for (int k = tid; k < F.n; k += T)
@@ -312,16 +418,52 @@ __device__ __forceinline__ void m3_visit(const FrameDev& C, const LastDev& L, fl
     });
 }
 
-__global__ void __launch_bounds__(128) m3_collect_kernel(FrameDev Cf, LastDev L, float th, const int* kp_state, CandLists C) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// Static part of query i of SearchByProjection(cur, last): projection, window and level range (:1356-1391).
+struct M3Query { float u, v, radius, ur_proj; int minL, maxL; const uint32_t* d; };
+__device__ __forceinline__ bool m3_query(const FrameDev& C, const LastDev& L, float th, int i, M3Query& q) {
+    if (!L.valid[i]) return false;
+    const float X = L.xyz[3 * i], Y = L.xyz[3 * i + 1], Z = L.xyz[3 * i + 2];
+    const float xc = L.T[0] * X + L.T[1] * Y + L.T[2] * Z + L.T[3];
+    const float yc = L.T[4] * X + L.T[5] * Y + L.T[6] * Z + L.T[7];
+    const float zc = L.T[8] * X + L.T[9] * Y + L.T[10] * Z + L.T[11];
+    const float invzc = (float)(1.0 / (double)zc);
+    if (invzc < 0) return false;
+    q.u = C.fx * xc * invzc + C.cx;
+    q.v = C.fy * yc * invzc + C.cy;
+    if (q.u < C.min_x || q.u > C.max_x) return false;
+    if (q.v < C.min_y || q.v > C.max_y) return false;
+    const int oct = L.octave[i];
+    q.radius = th * C.scale[oct];
+    if (L.forward) { q.minL = oct; q.maxL = -1; }
+    else if (L.backward) { q.minL = 0; q.maxL = oct; }
+    else { q.minL = oct - 1; q.maxL = oct + 1; }
+    q.d = L.desc + 8 * (size_t)i;
+    q.ur_proj = q.u - C.bf * invzc;
+    return true;
+}
+
+__global__ void __launch_bounds__(256) m3_collect_kernel(FrameDev Cf, LastDev L, float th, const int* kp_state, CandLists C) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per last-frame point
     if (i >= L.n) return;
+    M3Query q;
     int cnt = 0;
-    int2* out = C.items + (size_t)i * C.cap;
-    m3_visit(Cf, L, th, kp_state, i, [&](int idx, int dist, int) {
-        if (cnt < C.cap) out[cnt] = make_int2(idx, dist);
-        cnt++;
-    });
-    C.count[i] = cnt;
+    if (m3_query(Cf, L, th, i, q)) {
+        int2* out = C.items + (size_t)i * C.cap;
+        cnt = warp_for_each_in_area(
+            Cf, q.u, q.v, q.radius, q.minL, q.maxL,
+            [&](int i2) {
+                if (kp_state[i2] == -2) return false;
+                if (Cf.uright) {
+                    const float ur = Cf.uright[i2];
+                    if (ur > 0 && fabsf(q.ur_proj - ur) > q.radius) return false;   // :1408-1414
+                }
+                return true;
+            },
+            [&](int pos, int i2) {
+                if (pos < C.cap) out[pos] = make_int2(i2, hamming256(q.d, Cf.desc + 8 * (size_t)i2));
+            });
+    }
+    if ((threadIdx.x & 31) == 0) cand_finish(C, i, cnt);
 }
 
 template <bool kLists>
@@ -331,22 +473,24 @@ __global__ void __launch_bounds__(1024) m3_resolve_kernel(FrameDev C, LastDev L,
     __shared__ int s_hist[COEB_HISTO_LENGTH];
     __shared__ int s_ind[3];
     const int tid = threadIdx.x, T = blockDim.x;
-    if (kLists) {
-        int over = 0;
-        for (int i = tid; i < L.n; i += T) over |= Cl.count[i] > Cl.cap;
-        if (__syncthreads_or(over)) { if (tid == 0) { out_info[0] = 0; out_info[1] = 0; out_info[2] = 1; } return; }
+    if (kLists && Cl.meta[1]) {
+        if (tid == 0) { out_info[0] = 0; out_info[1] = 0; out_info[2] = 1; }
+        return;
     }
-    for (int i = tid; i < L.n; i += T) res[i] = -1;
+    const int na = kLists ? Cl.meta[0] : L.n;   // queries with candidates (compacted by the collect kernel, any order)
+    auto query = [&](int a) { return kLists ? Cl.active[a] : a; };
+    for (int a = tid; a < na; a += T) res[query(a)] = -1;
     for (int round = 0; round <= L.n; round++) {
         for (int k = tid; k < C.n; k += T) claim_min[k] = kInf;
         if (tid == 0) s_changed = 0;
         __syncthreads();
-        for (int i = tid; i < L.n; i += T) {
-            const int k = res[i];
+        for (int a = tid; a < na; a += T) {
+            const int i = query(a), k = res[i];
             if (k >= 0 && L.has_obs[i]) atomicMin(&claim_min[k], i);
         }
         __syncthreads();
-        for (int i = tid; i < L.n; i += T) {
+        for (int a = tid; a < na; a += T) {
+            const int i = query(a);
             int bestDist = 256, bestIdx2 = -1;
             auto consider = [&](int i2, int dist, int) {
                 if (claim_min[i2] < i) return;                           // :1404-1406 with :1429
@@ -372,12 +516,14 @@ __global__ void __launch_bounds__(1024) m3_resolve_kernel(FrameDev C, LastDev L,
     for (int k = tid; k < C.n; k += T) claim_min[k] = -1;
     __syncthreads();
     int mine = 0;
-    for (int i = tid; i < L.n; i += T)
+    for (int a = tid; a < na; a += T) {
+        const int i = query(a);
         if (res[i] >= 0) {
             atomicMax(&claim_min[res[i]], i);
             mine++;
             if (check_ori) atomicAdd(&s_hist[rot_bin(L.angle[i], C.angle[res[i]])], 1);
         }
+    }
     if (mine) atomicAdd(&s_count, mine);
     __syncthreads();
     for (int k = tid; k < C.n; k += T)
@@ -390,11 +536,13 @@ __global__ void __launch_bounds__(1024) m3_resolve_kernel(FrameDev C, LastDev L,
     __syncthreads();
     if (check_ori) {  // rotation consistency (:1449-1468): entries of the losing bins are cleared, each decrements
         int removed = 0;
-        for (int i = tid; i < L.n; i += T)
+        for (int a = tid; a < na; a += T) {
+            const int i = query(a);
             if (res[i] >= 0) {
                 const int bin = rot_bin(L.angle[i], C.angle[res[i]]);
                 if (bin != s_ind[0] && bin != s_ind[1] && bin != s_ind[2]) { kp_match[res[i]] = -1; removed++; }
             }
+        }
         if (removed) atomicSub(&s_count, removed);
     }
     __syncthreads();
@@ -410,16 +558,20 @@ __device__ __forceinline__ void m4_visit(const FrameDev& F1, const FrameDev& F2,
                      [&](int i2) { fn(i2, hamming256(d1, F2.desc + 8 * (size_t)i2), 0); });
 }
 
-__global__ void __launch_bounds__(128) m4_collect_kernel(FrameDev F1, FrameDev F2, const float* prev_in, float window, CandLists C) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) m4_collect_kernel(FrameDev F1, FrameDev F2, const float* prev_in, float window, CandLists C) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per keypoint of F1
     if (i >= F1.n) return;
     int cnt = 0;
-    int2* out = C.items + (size_t)i * C.cap;
-    m4_visit(F1, F2, prev_in, window, i, [&](int idx, int dist, int) {
-        if (cnt < C.cap) out[cnt] = make_int2(idx, dist);
-        cnt++;
-    });
-    C.count[i] = cnt;
+    if (F1.octave[i] <= 0) {   // level1 > 0 -> continue (:421-423)
+        const uint32_t* d1 = F1.desc + 8 * (size_t)i;
+        int2* out = C.items + (size_t)i * C.cap;
+        cnt = warp_for_each_in_area(
+            F2, prev_in[2 * i], prev_in[2 * i + 1], window, 0, 0, [](int) { return true; },
+            [&](int pos, int i2) {
+                if (pos < C.cap) out[pos] = make_int2(i2, hamming256(d1, F2.desc + 8 * (size_t)i2));
+            });
+    }
+    if ((threadIdx.x & 31) == 0) cand_finish(C, i, cnt);
 }
 
 // res[i1] = claimed F2 keypoint or -1, rdist[i1] = its distance. vMatchedDistance seen by query i1 at keypoint k is
@@ -433,10 +585,9 @@ __global__ void __launch_bounds__(1024) m4_resolve_kernel(FrameDev F1, FrameDev 
     __shared__ int s_ind[3];
     __shared__ int s_warp[33];
     const int tid = threadIdx.x, T = blockDim.x;
-    if (kLists) {
-        int over = 0;
-        for (int i = tid; i < F1.n; i += T) over |= C.count[i] > C.cap;
-        if (__syncthreads_or(over)) { if (tid == 0) { out_info[0] = 0; out_info[1] = 0; out_info[2] = 1; } return; }
+    if (kLists && C.meta[1]) {
+        if (tid == 0) { out_info[0] = 0; out_info[1] = 0; out_info[2] = 1; }
+        return;
     }
     for (int i = tid; i < F1.n; i += T) { res[i] = -1; rdist[i] = kInf; }
     for (int round = 0; round <= F1.n; round++) {
@@ -859,10 +1010,11 @@ struct MapFields {   // the MapPoint members isInFrustum writes, as device array
 // Frame::isInFrustum (src/Frame.cc:445-501) + the candidate collection of SearchByProjection for the same map point.
 // fp32 projection left to right without FMA (cv::gemm on 3x3 . 3x1, pinned in tests/test_oracle_vs_cv2.py); cv::norm and
 // Mat::dot accumulate in double.
-__global__ void __launch_bounds__(128) frustum_collect_kernel(FrameDev F, LocalMapDev LM, PoseArgs P, const uint8_t* __restrict__ skip,
+__global__ void __launch_bounds__(256) frustum_collect_kernel(FrameDev F, LocalMapDev LM, PoseArgs P, const uint8_t* __restrict__ skip,
                                                               MapFields out, MapDev M, float th, const int* kp_state, CandLists C, float* proj_out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per map point: every lane evaluates the (cheap) frustum test
     if (i >= LM.n) return;
+    const bool writer = (threadIdx.x & 31) == 0;
     bool in = false;
     float u = 0.f, v = 0.f, ur = 0.f, viewCos = 0.f;
     int lvl = 0;
@@ -899,19 +1051,13 @@ __global__ void __launch_bounds__(128) frustum_collect_kernel(FrameDev F, LocalM
         }
     }
     if (!in) { u = v = ur = viewCos = 0.f; lvl = 0; }
-    out.track_in_view[i] = in ? 1 : 0;
-    out.proj_x[i] = u; out.proj_y[i] = v; out.proj_xr[i] = ur; out.view_cos[i] = viewCos; out.level[i] = lvl;
-    if (proj_out) { float* q = proj_out + 5 * (size_t)i; q[0] = u; q[1] = v; q[2] = ur; q[3] = viewCos; q[4] = (float)lvl; }
-    // candidate collection of SearchByProjection for this map point (same thread: it reads back its own stores)
-    int cnt = 0;
-    if (in) {
-        int2* lst = C.items + (size_t)i * C.cap;
-        m2_visit(F, M, th, kp_state, i, [&](int idx, int dist, int oct) {
-            if (cnt < C.cap) lst[cnt] = make_int2(idx | (oct << 24), dist);
-            cnt++;
-        });
+    if (writer) {
+        out.track_in_view[i] = in ? 1 : 0;
+        out.proj_x[i] = u; out.proj_y[i] = v; out.proj_xr[i] = ur; out.view_cos[i] = viewCos; out.level[i] = lvl;
+        if (proj_out) { float* q = proj_out + 5 * (size_t)i; q[0] = u; q[1] = v; q[2] = ur; q[3] = viewCos; q[4] = (float)lvl; }
     }
-    C.count[i] = cnt;
+    __syncwarp();   // the collection below reads the fields back through M (same warp)
+    m2_collect_warp(F, M, th, kp_state, C, i);
 }
 
 // ---- SearchByBoW (src/ORBmatcher.cc:158-288 and :522-655): matching restricted to features of the same vocabulary node --
@@ -1167,6 +1313,18 @@ int push_inputs(coeb_matcher* m, const Packer& p) {
     if (p.off) CUDA_TRY(cudaMemcpyAsync(m->in.d, m->in.h, p.off, cudaMemcpyHostToDevice, m->stream));
     return COEB_OK;
 }
+// Candidate lists of n queries inside a scratch block: counts | active | meta | items. Returns the bytes used.
+size_t lists_bytes(size_t n, int cap) { return 2 * al(n * 4) + al(8) + al(n * cap * 8); }
+CandLists carve_lists(char* sc, size_t n, int cap) {
+    CandLists C{};
+    C.count = (int*)sc; sc += al(n * 4);
+    C.active = (int*)sc; sc += al(n * 4);
+    C.meta = (int*)sc; sc += al(8);
+    C.items = (int2*)sc;
+    C.cap = cap;
+    return C;
+}
+
 int pull_outputs(coeb_matcher* m, size_t bytes) {
     if (bytes) CUDA_TRY(cudaMemcpyAsync(m->out.h, m->out.d, bytes, cudaMemcpyDeviceToHost, m->stream));
     CUDA_TRY(cudaStreamSynchronize(m->stream));
@@ -1330,7 +1488,7 @@ int coeb_match_projection(coeb_matcher* m, coeb_frame* F, int n, const uint8_t* 
     if ((st = m->in.reserve(3 * al(N) + 5 * al(N * 4) + al(N * 32) + al(K * 4))) != COEB_OK) return st;
     if ((st = m->out.reserve(al(K * 4) + 256)) != COEB_OK) return st;
     const int cap = 32;   // candidates kept per map point; a fuller window falls back to the window-walking kernel
-    if ((st = grow(&m->d_scratch, &m->scratch_bytes, al(N * 4) + al(K * 4) + al(N * 4) + al(N * cap * 8))) != COEB_OK) return st;
+    if ((st = grow(&m->d_scratch, &m->scratch_bytes, al(N * 4) + al(K * 4) + lists_bytes(N, cap))) != COEB_OK) return st;
     Packer p(m->in);
     MapDev M{};
     M.n = n;
@@ -1344,9 +1502,10 @@ int coeb_match_projection(coeb_matcher* m, coeb_frame* F, int n, const uint8_t* 
     int* d_info = (int*)(m->out.d + al(K * 4));
     int* d_res = (int*)m->d_scratch;
     int* d_claim = (int*)((char*)m->d_scratch + al(N * 4));
-    CandLists C{(int2*)((char*)m->d_scratch + 2 * al(N * 4) + al(K * 4)), (int*)((char*)m->d_scratch + al(N * 4) + al(K * 4)), cap};
+    const CandLists C = carve_lists((char*)m->d_scratch + al(N * 4) + al(K * 4), N, cap);
+    CUDA_TRY(cudaMemsetAsync(C.meta, 0, 8, m->stream));
     CUDA_TRY(cudaMemcpyAsync(d_kpm, d_state, K * 4, cudaMemcpyDeviceToDevice, m->stream));
-    m2_collect_kernel<<<(n + 127) / 128, 128, 0, m->stream>>>(F->dev, M, th, d_state, C);
+    m2_collect_kernel<<<(n + 7) / 8, 256, 0, m->stream>>>(F->dev, M, th, d_state, C);
     m2_resolve_kernel<true><<<1, 1024, 0, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info);
     CUDA_TRY(cudaGetLastError());
     if ((st = pull_outputs(m, al(K * 4) + 12)) != COEB_OK) return st;
@@ -1377,7 +1536,7 @@ int coeb_match_lastframe(coeb_matcher* m, coeb_frame* cur, int n, const uint8_t*
     if ((st = m->in.reserve(2 * al(N) + al(N * 12) + 2 * al(N * 4) + al(N * 32) + al(K * 4))) != COEB_OK) return st;
     if ((st = m->out.reserve(al(K * 4) + 256)) != COEB_OK) return st;
     const int cap = 64;
-    if ((st = grow(&m->d_scratch, &m->scratch_bytes, al(N * 4) + al(K * 4) + al(N * 4) + al(N * cap * 8))) != COEB_OK) return st;
+    if ((st = grow(&m->d_scratch, &m->scratch_bytes, al(N * 4) + al(K * 4) + lists_bytes(N, cap))) != COEB_OK) return st;
     Packer p(m->in);
     LastDev L{};
     L.n = n;
@@ -1396,9 +1555,10 @@ int coeb_match_lastframe(coeb_matcher* m, coeb_frame* cur, int n, const uint8_t*
     int* d_info = (int*)(m->out.d + al(K * 4));
     int* d_res = (int*)m->d_scratch;
     int* d_claim = (int*)((char*)m->d_scratch + al(N * 4));
-    CandLists C{(int2*)((char*)m->d_scratch + 2 * al(N * 4) + al(K * 4)), (int*)((char*)m->d_scratch + al(N * 4) + al(K * 4)), cap};
+    const CandLists C = carve_lists((char*)m->d_scratch + al(N * 4) + al(K * 4), N, cap);
+    CUDA_TRY(cudaMemsetAsync(C.meta, 0, 8, m->stream));
     CUDA_TRY(cudaMemcpyAsync(d_kpm, d_state, K * 4, cudaMemcpyDeviceToDevice, m->stream));
-    m3_collect_kernel<<<(n + 127) / 128, 128, 0, m->stream>>>(cur->dev, L, th, d_state, C);
+    m3_collect_kernel<<<(n + 7) / 8, 256, 0, m->stream>>>(cur->dev, L, th, d_state, C);
     m3_resolve_kernel<true><<<1, 1024, 0, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info);
     CUDA_TRY(cudaGetLastError());
     if ((st = pull_outputs(m, al(K * 4) + 12)) != COEB_OK) return st;
@@ -1425,7 +1585,7 @@ int coeb_match_init(coeb_matcher* m, coeb_frame* f1, coeb_frame* f2, float* prev
     if ((st = m->in.reserve(al(N1 * 8))) != COEB_OK) return st;
     if ((st = m->out.reserve(al(N1 * 4) + al(N1 * 8) + 256)) != COEB_OK) return st;
     const int cap = 256;
-    if ((st = grow(&m->d_scratch, &m->scratch_bytes, 2 * al(N1 * 4) + 2 * al((N2 + 1) * 4) + al(N1 * 8) + al(N1 * 4) + al(N1 * cap * 8))) != COEB_OK) return st;
+    if ((st = grow(&m->d_scratch, &m->scratch_bytes, 2 * al(N1 * 4) + 2 * al((N2 + 1) * 4) + al(N1 * 8) + lists_bytes(N1, cap))) != COEB_OK) return st;
     Packer p(m->in);
     const float* d_prev = p.place(prev_matched, N1 * 2);
     if ((st = push_inputs(m, p)) != COEB_OK) return st;
@@ -1435,12 +1595,12 @@ int coeb_match_init(coeb_matcher* m, coeb_frame* f1, coeb_frame* f2, float* prev
     int* d_cls = (int*)sc; sc += al((N2 + 1) * 4);
     int* d_clf = (int*)sc; sc += al((N2 + 1) * 4);
     int2* d_items = (int2*)sc; sc += al(N1 * 8);
-    CandLists C{nullptr, (int*)sc, cap}; sc += al(N1 * 4);
-    C.items = (int2*)sc;
+    const CandLists C = carve_lists(sc, N1, cap);
+    CUDA_TRY(cudaMemsetAsync(C.meta, 0, 8, m->stream));
     int* d_m12 = (int*)m->out.d;
     float* d_prev_out = (float*)(m->out.d + al(N1 * 4));
     int* d_info = (int*)(m->out.d + al(N1 * 4) + al(N1 * 8));
-    m4_collect_kernel<<<(f1->n + 127) / 128, 128, 0, m->stream>>>(f1->dev, f2->dev, d_prev, (float)window_size, C);
+    m4_collect_kernel<<<(f1->n + 7) / 8, 256, 0, m->stream>>>(f1->dev, f2->dev, d_prev, (float)window_size, C);
     m4_resolve_kernel<true><<<1, 1024, 0, m->stream>>>(f1->dev, f2->dev, d_prev, (float)window_size, nnratio, check_ori, C, d_res, d_rdist, d_cls,
                                                        d_clf, d_items, d_m12, d_prev_out, d_info);
     CUDA_TRY(cudaGetLastError());
@@ -1734,7 +1894,7 @@ int coeb_search_local_points(coeb_matcher* m, coeb_frame* F, coeb_local_map* lm,
     if ((st = m->out.reserve(out_bytes)) != COEB_OK) return st;
     const int cap = 32;
     // scratch: res, claim, list counts, lists | MapPoint fields written by the frustum pass
-    const size_t sc_bytes = al(N * 4) + al(K * 4) + al(N * 4) + al(N * cap * 8) + 5 * al(N * 4) + 2 * al(N);
+    const size_t sc_bytes = al(N * 4) + al(K * 4) + lists_bytes(N, cap) + 5 * al(N * 4) + 2 * al(N);
     if ((st = grow(&m->d_scratch, &m->scratch_bytes, sc_bytes)) != COEB_OK) return st;
     Packer p(m->in);
     const uint8_t* d_skip = p.place(skip, N);
@@ -1744,8 +1904,7 @@ int coeb_search_local_points(coeb_matcher* m, coeb_frame* F, coeb_local_map* lm,
     char* sc = (char*)m->d_scratch;
     int* d_res = (int*)sc; sc += al(N * 4);
     int* d_claim = (int*)sc; sc += al(K * 4);
-    CandLists C{nullptr, (int*)sc, cap}; sc += al(N * 4);
-    C.items = (int2*)sc; sc += al(N * cap * 8);
+    const CandLists C = carve_lists(sc, N, cap); sc += lists_bytes(N, cap);
     MapFields mf{};
     mf.proj_x = (float*)sc; sc += al(N * 4);
     mf.proj_y = (float*)sc; sc += al(N * 4);
@@ -1766,8 +1925,9 @@ int coeb_search_local_points(coeb_matcher* m, coeb_frame* F, coeb_local_map* lm,
     P.cos_limit = viewing_cos_limit;
     P.nlevels = F->nlevels;
     CUDA_TRY(cudaMemsetAsync(d_zero, 0, N, m->stream));
+    CUDA_TRY(cudaMemsetAsync(C.meta, 0, 8, m->stream));
     if (F->n) CUDA_TRY(cudaMemcpyAsync(d_kpm, d_state, (size_t)F->n * 4, cudaMemcpyDeviceToDevice, m->stream));
-    frustum_collect_kernel<<<(n + 127) / 128, 128, 0, m->stream>>>(F->dev, lm->dev, P, d_skip, mf, M, th, d_state, C, d_proj);
+    frustum_collect_kernel<<<(n + 7) / 8, 256, 0, m->stream>>>(F->dev, lm->dev, P, d_skip, mf, M, th, d_state, C, d_proj);
     m2_resolve_kernel<true><<<1, 1024, 0, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info);
     CUDA_TRY(cudaGetLastError());
     if ((st = pull_outputs(m, out_bytes)) != COEB_OK) return st;
