@@ -626,13 +626,18 @@ static int launch_graphed(coeb_extractor* ex, const BatchView& v, cudaStream_t s
     int st = enqueue_chunked(ex, v, s, chunk);
     cudaError_t e = cudaStreamEndCapture(s, &graph);
     if (st != COEB_OK || e != cudaSuccess || !graph) {
+        if (getenv("COEB_DEBUG_GRAPH")) fprintf(stderr, "[coeb] graph capture failed: st=%d, %s\n", st, cudaGetErrorString(e));
         if (graph) cudaGraphDestroy(graph);
         cudaGetLastError();
         return enqueue_chunked(ex, v, s, chunk);   // capture not possible here: plain launches
     }
     e = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
-    if (e != cudaSuccess) { cudaGetLastError(); return enqueue_chunked(ex, v, s, chunk); }
+    if (e != cudaSuccess) {
+        if (getenv("COEB_DEBUG_GRAPH")) fprintf(stderr, "[coeb] graph instantiate failed: %s\n", cudaGetErrorString(e));
+        cudaGetLastError();
+        return enqueue_chunked(ex, v, s, chunk);
+    }
     if (ex->graphs.size() >= 32) { cudaGraphExecDestroy(ex->graphs.front().exec); ex->graphs.erase(ex->graphs.begin()); }
     coeb_extractor::GraphEntry ge;
     ge.view = v; ge.w = g.w0; ge.h = g.h0; ge.cap = g.out_cap; ge.chunk = chunk; ge.exec = exec;
