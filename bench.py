@@ -443,9 +443,57 @@ def run_b200(args):
         # the CPU sample doubles as a parity check of the timed GPU run
         same = all(ccounts[i] == o_cnt[i] and ckps[i, :ccounts[i]].tobytes() == o_kps[i, :o_cnt[i]].tobytes()
                    and cdesc[i, :ccounts[i]].tobytes() == o_desc[i, :o_cnt[i]].tobytes() for i in range(sample))
+        # single-thread per-frame latency with the per-stage breakdown: 4 warm-up frames, then 24 frames
+        oex = orc.Extractor(NFEAT, 1.2, NLEVELS, 20, 7)
+        st_lat = []
+        for i in range(28):
+            nb, nt = int(batch["nbox"][i]), int(batch["ntm"][i])
+            t = time.perf_counter()
+            oex.extract(batch["gray"][i], batch["boxes"][i, :nb], batch["tm"][i, :nt], batch["blur"][i, :nb])
+            if i >= 4:
+                st_lat.append(time.perf_counter() - t)
+        stage_t, nfr = oex.stage_times()
+        # secondary, OpenCV-backed number: the cv2 calls the reference makes per frame (resize chain, one cv::FAST per 30 px cell with
+        # the minTh retry, one GaussianBlur per level) driven like src/ORBextractor.cc drives them, single thread; its octree,
+        # orientation and descriptor loops are the reference's own C++ and are not included, so this is a lower bound of its CPU path
+        cv_prims_ms = None
+        try:
+            import cv2
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            from oracle_cv2 import ExtractorA
+            cv2.setNumThreads(1)
+            xa = ExtractorA(NFEAT, 1.2, NLEVELS)
+            det_ini, det_min = cv2.FastFeatureDetector_create(20, True), cv2.FastFeatureDetector_create(7, True)
+            tt = []
+            for i in range(10):
+                t = time.perf_counter()
+                for im in xa.pyramid(batch["gray"][i]):
+                    hh, ww = im.shape
+                    nC, nR = int((ww - 32 + 6) / 30), int((hh - 32 + 6) / 30)
+                    wC, hC = -(-(ww - 32 + 6) // nC), -(-(hh - 32 + 6) // nR)
+                    for ci in range(nR):
+                        y0 = 16 + ci * hC
+                        if y0 >= hh - 16 - 3:
+                            continue
+                        for cj in range(nC):
+                            x0 = 16 + cj * wC
+                            if x0 >= ww - 16 - 6:
+                                continue
+                            roi = im[y0:min(y0 + hC + 6, hh - 16), x0:min(x0 + wC + 6, ww - 16)]
+                            if not det_ini.detect(roi):
+                                det_min.detect(roi)
+                    cv2.GaussianBlur(im, (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101)
+                if i >= 2:
+                    tt.append(time.perf_counter() - t)
+            cv_prims_ms = 1e3 * float(np.median(tt))
+        except Exception:
+            pass
         cpu = {"value": sample / secs, "unit": "frames/s", "cores": threads, "kind": "port",
                "sample": "first %d frames of the rank-0 shard, one oracle extractor per thread, %d threads" % (sample, threads),
-               "bit_exact_vs_gpu": bool(same)}
+               "bit_exact_vs_gpu": bool(same),
+               "single_thread_ms_per_frame_median": 1e3 * float(np.median(st_lat)),
+               "single_thread_stage_ms_per_frame": {k: 1e3 * v / max(nfr, 1) for k, v in stage_t.items()},
+               "opencv_primitives_only_ms_per_frame": cv_prims_ms}
 
     if rank != 0:
         return 0

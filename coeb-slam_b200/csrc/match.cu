@@ -1454,6 +1454,17 @@ int coeb_frame_features_in_area(coeb_frame* f, float x, float y, float r, int mi
     return *n_out > cap ? fail(COEB_ERR_CAPACITY, "need %d entries", *n_out) : COEB_OK;
 }
 
+int coeb_hamming256(const void* a, const void* b) {
+    int dist = 0;
+    for (int i = 0; i < 8; i++) {
+        uint32_t x, y;
+        std::memcpy(&x, (const char*)a + 4 * i, 4);
+        std::memcpy(&y, (const char*)b + 4 * i, 4);
+        dist += __builtin_popcount(x ^ y);
+    }
+    return dist;
+}
+
 int coeb_hamming256_batch(coeb_matcher* m, const uint8_t* a, const uint8_t* b, int n, int* dist_out) {
     if (!m || !a || !b || !dist_out || n < 0) return fail(COEB_ERR_INVALID_ARG, "bad argument");
     if (n == 0) return COEB_OK;

@@ -196,6 +196,11 @@ int coeb_frame_from_extractor(coeb_matcher* m, coeb_extractor* ex, int frame_ind
 int coeb_frame_features_in_area(coeb_frame* f, float x, float y, float r, int min_level, int max_level, int* idx_out,
                                 int cap, int* n_out);
 
+/* ORBmatcher::DescriptorDistance for ONE pair (src/ORBmatcher.cc:1648-1664), host pointers to two 32-byte rows. The reference
+ * calls it for single pairs from host loops (src/Frame.cc:719, src/MapPoint.cc:281): eight popcounts on the calling thread, no
+ * device work, no handle. Batches go through coeb_hamming256_batch. */
+int coeb_hamming256(const void* a, const void* b);
+
 /* ORBmatcher::DescriptorDistance for n pairs (src/ORBmatcher.cc:1648-1664). Host pointers, n x 32 bytes each. */
 int coeb_hamming256_batch(coeb_matcher* m, const uint8_t* a, const uint8_t* b, int n, int* dist_out);
 
