@@ -94,14 +94,17 @@ __device__ __forceinline__ uint32_t corner_strength2(uint32_t c, const uint32_t 
 }
 
 // Can either pixel packed in `c` be a corner at the threshold? Every 9-arc holds two neighbouring compass points
-// (ring 0, 4, 8, 12), so the arc strength is bounded by max_k min(d_k, d_k+4) (mirrored for dark arcs).
-// thb / tdb = 256 + th / 256 - th per lane.
-__device__ __forceinline__ bool compass_bound2(uint32_t c, uint32_t r0, uint32_t r4, uint32_t r8, uint32_t r12, uint32_t thb, uint32_t tdb) {
-    const uint32_t cb = c + 0x01000100u;
-    const uint32_t d0 = cb - r0, d4 = cb - r4, d8 = cb - r8, d12 = cb - r12;
-    const uint32_t bb = __vimax3_s16x2(__vimax3_s16x2(__vmins2(d0, d4), __vmins2(d4, d8), __vmins2(d8, d12)), __vmins2(d12, d0), thb);
-    const uint32_t bd = __vimin3_s16x2(__vimin3_s16x2(__vmaxs2(d0, d4), __vmaxs2(d4, d8), __vmaxs2(d8, d12)), __vmaxs2(d12, d0), tdb);
-    return (bb != thb) | (bd != tdb);
+// (ring 0, 4, 8, 12), so a bright corner needs d_k > th on two neighbouring compass points (mirrored for dark arcs).
+// "Some neighbouring pair passes" is the complement of "{0, 8} both fail or {4, 12} both fail" (the vertex covers of the
+// 4-cycle), so with one fail bit per compass point the test is two AND/OR steps per polarity. The fail bit is bit 14 of
+// r_k + (0x4000 + th - c) per 16-bit lane (set iff r_k >= c - th, i.e. d_k <= th; lanes stay in (0x3f00, 0x4200), no carries),
+// and of (0x4000 + th + c) - r_k for dark arcs: the eight additions run on the multiply pipe (IMAD), six logic operations and
+// one compare on the ALU pipe FAST is bound by (the min/max form of the same bound took fifteen). tb = 0x40004000 + th * 0x10001.
+__device__ __forceinline__ bool compass_bound2(uint32_t c, uint32_t r0, uint32_t r4, uint32_t r8, uint32_t r12, uint32_t tb) {
+    const uint32_t kb = tb - c, kd = tb + c;
+    const uint32_t fb = ((r0 + kb) & (r8 + kb)) | ((r4 + kb) & (r12 + kb));   // bit 14: no bright pair of neighbours
+    const uint32_t fd = ((kd - r0) & (kd - r8)) | ((kd - r4) & (kd - r12));   // bit 14: no dark pair of neighbours
+    return (~(fb & fd) & 0x40004000u) != 0u;
 }
 
 // FAST cell of a level coordinate (minBorder-relative detection coordinates, src/ORBextractor.cc:813-828); -1 outside the
@@ -173,7 +176,7 @@ __global__ void __launch_bounds__(kFtThreads, COEB_FT_MINB) fast_kernel(const __
     //      A warp takes 16 groups of rows y and y+2 (24-word row pitch: the two half-warps hit disjoint banks); the 1 px
     //      ring the NMS needs around the tile is one more pass of single pairs.
     {
-        const uint32_t th2 = (uint32_t)thIni * 0x00010001u, thb = 0x01000100u + th2, tdb = 0x01000100u - th2;
+        const uint32_t tb = 0x40004000u + (uint32_t)thIni * 0x00010001u;
         const int gxi = lane & 15, px = 4 * gxi;
         const int ay0 = 4 * (tid >> 6) + ((tid >> 5) & 1) + ((lane >> 4) << 1);   // + 16 per iteration
         const bool x01 = (unsigned)(px + 1 - xlo) < (unsigned)(xspan + 1), x23 = (unsigned)(px + 3 - xlo) < (unsigned)(xspan + 1);
@@ -185,8 +188,8 @@ __global__ void __launch_bounds__(kFtThreads, COEB_FT_MINB) fast_kernel(const __
             const uint32_t S0 = row[3 * kImgWords], S8 = row[-3 * kImgWords];
             const uint32_t S4 = __funnelshift_r(c, row[1], 24), S12 = __funnelshift_r(row[-1], c, 8);
             const bool yok = (unsigned)(ay0 + 16 * it - ylo) < (unsigned)yspan;
-            const bool f01 = compass_bound2(pair_lo(c), pair_lo(S0), pair_lo(S4), pair_lo(S8), pair_lo(S12), thb, tdb) & yok & x01;
-            const bool f23 = compass_bound2(pair_hi(c), pair_hi(S0), pair_hi(S4), pair_hi(S8), pair_hi(S12), thb, tdb) & yok & x23;
+            const bool f01 = compass_bound2(pair_lo(c), pair_lo(S0), pair_lo(S4), pair_lo(S8), pair_lo(S12), tb) & yok & x01;
+            const bool f23 = compass_bound2(pair_hi(c), pair_hi(S0), pair_hi(S4), pair_hi(S8), pair_hi(S12), tb) & yok & x23;
             flags |= ((unsigned)f01 << (2 * it)) | ((unsigned)f23 << (2 * it + 1));
         }
         // ring pairs: rows -1 and kFtH over x = -2 .. kFtW+1, columns (-2,-1) and (kFtW, kFtW+1) over the tile rows
@@ -203,7 +206,7 @@ __global__ void __launch_bounds__(kFtThreads, COEB_FT_MINB) fast_kernel(const __
             const uint32_t S4 = __funnelshift_r(c, rr[1], 24), S12 = __funnelshift_r(rr[-1], c, 8);
             const bool ok = (unsigned)(ray - ylo) < (unsigned)yspan && (unsigned)(2 * rpi + 1 - xlo) < (unsigned)(xspan + 1);
             const bool f = compass_bound2(__byte_perm(c, 0u, sel), __byte_perm(rr[3 * kImgWords], 0u, sel), __byte_perm(S4, 0u, sel),
-                                          __byte_perm(rr[-3 * kImgWords], 0u, sel), __byte_perm(S12, 0u, sel), thb, tdb) & ok;
+                                          __byte_perm(rr[-3 * kImgWords], 0u, sel), __byte_perm(S12, 0u, sel), tb) & ok;
             re = ((ray + 1) << 6) | (rpi + 1);
             flags |= (unsigned)f << (2 * kPairIters);
         }
