@@ -400,11 +400,12 @@ __global__ void __launch_bounds__(128) fast_fallback_kernel(const __grid_constan
             for (int x = lane; x < dw; x += 32) {
                 const uint8_t* p = &s_img[(y + 3) * kRoiPitch + ax + (x + 3)];
                 const int cc = p[0];
-                {   // compass bound (see fast_kernel 1a): in flat cells almost every pixel stops here
-                    const int e0 = cc - (int)p[off[0]], e4 = cc - (int)p[off[4]], e8 = cc - (int)p[off[8]], e12 = cc - (int)p[off[12]];
-                    const int ub = max(max(min(e0, e4), min(e4, e8)), max(min(e8, e12), min(e12, e0)));
-                    const int ud = min(min(max(e0, e4), max(e4, e8)), min(max(e8, e12), max(e12, e0)));
-                    if (ub <= thMin && -ud <= thMin) continue;   // s_A stays 0
+                {   // compass bound as fail bits (see compass_bound2): bit 14 of r + (0x4000 + th - c) is set iff d <= th
+                    const int r0 = p[off[0]], r4 = p[off[4]], r8 = p[off[8]], r12 = p[off[12]];
+                    const int kb = 0x4000 + thMin - cc, kd = 0x4000 + thMin + cc;
+                    const int fb = ((r0 + kb) & (r8 + kb)) | ((r4 + kb) & (r12 + kb));
+                    const int fd = ((kd - r0) & (kd - r8)) | ((kd - r4) & (kd - r12));
+                    if (fb & fd & 0x4000) continue;   // neither polarity has two neighbouring compass points beyond minTh: s_A stays 0
                 }
                 int d[16];
 #pragma unroll

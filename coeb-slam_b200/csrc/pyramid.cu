@@ -23,13 +23,14 @@ namespace coeb {
 // cut out of two aligned source words with one PRMT whose selector depends only on the column (computed once per
 // thread), and h = a0*S[sx] + a1*S[sx+1] is one IDP.2A with the table's packed (a0, a1) halfwords as they are. Output
 // pixels 0,1 and 2,3 of a thread each share one pair of source words per source row.
+constexpr int kRzGroups = 16, kRzRowsPerBlock = 16;   // block = 16 four-pixel groups x 16 rows
 template <int kResizeRows>
 __global__ void __launch_bounds__(256) resize_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v,
                                                      int level) {
     const LevelGeom& D = g.lv[level];
     const LevelGeom& S = g.lv[level - 1];
     const int frame = blockIdx.z;
-    const int dx0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int dx0 = (blockIdx.x * kRzGroups + threadIdx.x) * 4;   // a warp covers 2 rows x 64 pixels: less of it hangs over the row's end than with 1 x 128
     if (dx0 >= D.w) return;
     const uint8_t* __restrict__ src = level_ptr(g, v, level - 1, frame);
     const int spitch = level_pitch(g, v, level - 1);
@@ -53,11 +54,12 @@ __global__ void __launch_bounds__(256) resize_kernel(const __grid_constant__ Geo
     uint8_t* out = dst + dx0;
 #pragma unroll
     for (int j = 0; j < kResizeRows; j++) {
-        const int dy = blockIdx.y * (8 * kResizeRows) + threadIdx.y + 8 * j;
+        const int dy = blockIdx.y * (kRzRowsPerBlock * kResizeRows) + threadIdx.y + kRzRowsPerBlock * j;
         if (dy >= D.h) break;
         const int2 ye = __ldg(&yt[dy]);
         const int sy0 = ye.x & 0xFFFF, sy1 = (int)((uint32_t)ye.x >> 16);   // clamped on the host
-        const uint32_t b0 = ye.y & 0xFFFF, b1 = (uint32_t)ye.y >> 16;
+        // (b * x) >> 16 == umulhi(b << 16, x): one multiply-high on the multiply pipe instead of a multiply and a shift
+        const uint32_t b0s = (uint32_t)ye.y << 16, b1s = (uint32_t)ye.y & 0xFFFF0000u;
         uint32_t o[4];
 #pragma unroll
         for (int u = 0; u < 2; u++) {
@@ -68,7 +70,7 @@ __global__ void __launch_bounds__(256) resize_kernel(const __grid_constant__ Geo
             for (int i = 2 * u; i < 2 * u + 2; i++) {
                 const uint32_t h0 = __dp2a_lo(wgt[i], __byte_perm(t0, t1, sel[i]), 0u);
                 const uint32_t h1 = __dp2a_lo(wgt[i], __byte_perm(q0, q1, sel[i]), 0u);
-                o[i] = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2u) >> 2;   // <= 255 by construction
+                o[i] = (__umulhi(b0s, h0 >> 4) + __umulhi(b1s, h1 >> 4) + 2u) >> 2;   // each product truncated on its own; <= 255 by construction
             }
         }
         // pitch is a multiple of 64: padding absorbs the tail
@@ -111,14 +113,16 @@ void launch_pyramid(const Geometry& g, const BatchView& v, cudaStream_t stream) 
     for (int l = 1; l < g.nlevels; l++) {
         dim3 block(32, 8);
         const int tiles_x = (g.lv[l].w + 127) / 128;
+        const dim3 rz_block(kRzGroups, kRzRowsPerBlock);
+        const int rz_x = (g.lv[l].w + 4 * kRzGroups - 1) / (4 * kRzGroups);
         // consecutive output columns are at most 2 source columns apart up to a 2:1 reduction: the paired-word path applies
         const bool paired = 2LL * g.lv[l].w >= g.lv[l - 1].w && g.lv[l - 1].w >= 8;
         if (!paired) {
             resize_generic_kernel<<<dim3(tiles_x, (g.lv[l].h + 7) / 8, v.B), block, 0, stream>>>(g, v, l);
-        } else if ((long long)tiles_x * ((g.lv[l].h + 31) / 32) * v.B >= 2 * 148) {
-            resize_kernel<4><<<dim3(tiles_x, (g.lv[l].h + 31) / 32, v.B), block, 0, stream>>>(g, v, l);
+        } else if ((long long)rz_x * ((g.lv[l].h + 4 * kRzRowsPerBlock - 1) / (4 * kRzRowsPerBlock)) * v.B >= 2 * 148) {
+            resize_kernel<4><<<dim3(rz_x, (g.lv[l].h + 4 * kRzRowsPerBlock - 1) / (4 * kRzRowsPerBlock), v.B), rz_block, 0, stream>>>(g, v, l);
         } else {
-            resize_kernel<1><<<dim3(tiles_x, (g.lv[l].h + 7) / 8, v.B), block, 0, stream>>>(g, v, l);
+            resize_kernel<1><<<dim3(rz_x, (g.lv[l].h + kRzRowsPerBlock - 1) / kRzRowsPerBlock, v.B), rz_block, 0, stream>>>(g, v, l);
         }
     }
 }
