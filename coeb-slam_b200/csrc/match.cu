@@ -139,6 +139,33 @@ __device__ __forceinline__ int warp_for_each_in_area(const FrameDev& f, float x,
     return cnt;
 }
 
+// glibc 2.39 logf (sysdeps/ieee754/flt-32/e_logf.c: 16-entry table, degree-3 polynomial in double), restated so that
+// MapPoint::PredictScale's `ceil(log(ratio) / mfLogScaleFactor)` (src/MapPoint.cc:402-417, float overloads) is the same
+// float on the device as on the reference's host; the oracle carries the same restatement and pins it against libm.
+__constant__ double kLogfTab[16][2] = {
+    {0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2}, {0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2},
+    {0x1.49539f0f010bp+0, -0x1.01eae7f513a67p-2},  {0x1.3c995b0b80385p+0, -0x1.b31d8a68224e9p-3},
+    {0x1.30d190c8864a5p+0, -0x1.6574f0ac07758p-3}, {0x1.25e227b0b8eap+0, -0x1.1aa2bc79c81p-3},
+    {0x1.1bb4a4a1a343fp+0, -0x1.a4e76ce8c0e5ep-4}, {0x1.12358f08ae5bap+0, -0x1.1973c5a611cccp-4},
+    {0x1.0953f419900a7p+0, -0x1.252f438e10c1ep-5}, {0x1p+0, 0x0p+0},
+    {0x1.e608cfd9a47acp-1, 0x1.aa5aa5df25984p-5},  {0x1.ca4b31f026aap-1, 0x1.c5e53aa362eb4p-4},
+    {0x1.b2036576afce6p-1, 0x1.526e57720db08p-3},  {0x1.9c2d163a1aa2dp-1, 0x1.bc2860d22477p-3},
+    {0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2},  {0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2}};
+
+__device__ __forceinline__ float glibc_logf(float x) {   // normal positive x only (the caller guarantees it)
+    const uint32_t ix = __float_as_uint(x);
+    if (ix == 0x3f800000u) return 0.f;
+    const uint32_t tmp = ix - 0x3f330000u;
+    const int i = (tmp >> 19) & 15;
+    const int k = (int)tmp >> 23;
+    const double z = (double)__uint_as_float(ix - (tmp & 0xff800000u));
+    const double r = z * kLogfTab[i][0] - 1, y0 = kLogfTab[i][1] + (double)k * 0x1.62e42fefa39efp-1, r2 = r * r;
+    double y = 0x1.5575b0be00b6ap-2 * r + -0x1.ffffef20a4123p-2;
+    y = -0x1.00ea348b88334p-2 * r2 + y;
+    y = y * r2 + (y0 + r);
+    return (float)y;
+}
+
 // ---- grid build (Frame::AssignFeaturesToGrid, src/Frame.cc:396-411) -------------------------------------
 // One CTA. Cells ix-major; items ascending by keypoint index (the reference pushes in index order).
 __global__ void __launch_bounds__(1024) grid_build_kernel(FrameDev f, int* cell_start, int* cell_items, int* kp_cell) {
@@ -385,40 +412,16 @@ struct LastDev {
     const uint32_t* desc;
     float T[12];       // Tcw of the current frame, 3x4 row-major
     int forward, backward;
+    int max_accept;    // TH_HIGH for the frame-to-frame overload, ORBdist for the relocalisation overload
+    // relocalisation overload (src/ORBmatcher.cc:1473-1600): the level comes from MapPoint::PredictScale, points behind the camera are
+    // not rejected, every claim blocks, no stereo test
+    int reloc, nlevels;
+    const float *min_dist, *max_dist;
+    float Ow[3];
 };
 
-template <class Fn>
-__device__ __forceinline__ void m3_visit(const FrameDev& C, const LastDev& L, float th, const int* __restrict__ kp_state, int i, Fn&& fn) {
-    if (!L.valid[i]) return;
-    const float X = L.xyz[3 * i], Y = L.xyz[3 * i + 1], Z = L.xyz[3 * i + 2];
-    // x3Dc = Rcw*x3Dw + tcw (:1362), fp32 left to right (no FMA: the file is built with -fmad=false)
-    const float xc = L.T[0] * X + L.T[1] * Y + L.T[2] * Z + L.T[3];
-    const float yc = L.T[4] * X + L.T[5] * Y + L.T[6] * Z + L.T[7];
-    const float zc = L.T[8] * X + L.T[9] * Y + L.T[10] * Z + L.T[11];
-    const float invzc = (float)(1.0 / (double)zc);
-    if (invzc < 0) return;
-    const float u = C.fx * xc * invzc + C.cx, v = C.fy * yc * invzc + C.cy;
-    if (u < C.min_x || u > C.max_x) return;
-    if (v < C.min_y || v > C.max_y) return;
-    const int oct = L.octave[i];
-    const float radius = th * C.scale[oct];
-    int minL, maxL;
-    if (L.forward) { minL = oct; maxL = -1; }           // :1386-1391
-    else if (L.backward) { minL = 0; maxL = oct; }
-    else { minL = oct - 1; maxL = oct + 1; }
-    const uint32_t* d = L.desc + 8 * (size_t)i;
-    const float ur_proj = u - C.bf * invzc;
-    for_each_in_area(C, u, v, radius, minL, maxL, [&](int i2) {
-        if (kp_state[i2] == -2) return;
-        if (C.uright) {
-            const float ur = C.uright[i2];
-            if (ur > 0) { const float er = fabsf(ur_proj - ur); if (er > radius) return; }   // :1408-1414
-        }
-        fn(i2, hamming256(d, C.desc + 8 * (size_t)i2), 0);
-    });
-}
-
-// Static part of query i of SearchByProjection(cur, last): projection, window and level range (:1356-1391).
+// Static part of query i of SearchByProjection(cur, last) (:1356-1391) and of the relocalisation overload (:1490-1530):
+// projection, window and level range. fp32 left to right (no FMA: the file is built with -fmad=false).
 struct M3Query { float u, v, radius, ur_proj; int minL, maxL; const uint32_t* d; };
 __device__ __forceinline__ bool m3_query(const FrameDev& C, const LastDev& L, float th, int i, M3Query& q) {
     if (!L.valid[i]) return false;
@@ -427,19 +430,51 @@ __device__ __forceinline__ bool m3_query(const FrameDev& C, const LastDev& L, fl
     const float yc = L.T[4] * X + L.T[5] * Y + L.T[6] * Z + L.T[7];
     const float zc = L.T[8] * X + L.T[9] * Y + L.T[10] * Z + L.T[11];
     const float invzc = (float)(1.0 / (double)zc);
-    if (invzc < 0) return false;
+    if (!L.reloc && invzc < 0) return false;   // :1368-1369; the relocalisation overload has no such test
     q.u = C.fx * xc * invzc + C.cx;
     q.v = C.fy * yc * invzc + C.cy;
     if (q.u < C.min_x || q.u > C.max_x) return false;
     if (q.v < C.min_y || q.v > C.max_y) return false;
-    const int oct = L.octave[i];
+    int oct;
+    if (L.reloc) {
+        const float ox = X - L.Ow[0], oy = Y - L.Ow[1], oz = Z - L.Ow[2];
+        const double s2 = __dadd_rn(__dadd_rn(__dmul_rn((double)ox, (double)ox), __dmul_rn((double)oy, (double)oy)), __dmul_rn((double)oz, (double)oz));
+        const float dist3D = (float)sqrt(s2);   // cv::norm: double accumulation
+        if (dist3D < 0.8f * L.min_dist[i] || dist3D > 1.2f * L.max_dist[i]) return false;   // :1514-1519
+        const float ratio = L.max_dist[i] / dist3D;   // MapPoint::PredictScale (src/MapPoint.cc:402-417)
+        int nScale = 0;
+        if (ratio >= 1.17549435e-38f && ratio <= 3.402823466e+38f) nScale = (int)ceilf(glibc_logf(ratio) / (L.nlevels > 1 ? glibc_logf(C.scale[1]) : 1.f));
+        oct = nScale < 0 ? 0 : (nScale >= L.nlevels ? L.nlevels - 1 : nScale);
+    } else {
+        oct = L.octave[i];
+    }
     q.radius = th * C.scale[oct];
-    if (L.forward) { q.minL = oct; q.maxL = -1; }
+    if (L.forward) { q.minL = oct; q.maxL = -1; }           // :1386-1391
     else if (L.backward) { q.minL = 0; q.maxL = oct; }
     else { q.minL = oct - 1; q.maxL = oct + 1; }
     q.d = L.desc + 8 * (size_t)i;
     q.ur_proj = q.u - C.bf * invzc;
     return true;
+}
+// Per-candidate static filter of both overloads: a keypoint that already holds a MapPoint (with observations for the
+// frame-to-frame overload: kp_state -2; the caller of the relocalisation overload encodes every non-null entry as -2), and the
+// stereo consistency test (:1408-1414, frame-to-frame only).
+__device__ __forceinline__ bool m3_accept(const FrameDev& C, const LastDev& L, const M3Query& q, const int* __restrict__ kp_state, int i2) {
+    if (kp_state[i2] == -2) return false;
+    if (!L.reloc && C.uright) {
+        const float ur = C.uright[i2];
+        if (ur > 0 && fabsf(q.ur_proj - ur) > q.radius) return false;
+    }
+    return true;
+}
+
+template <class Fn>
+__device__ __forceinline__ void m3_visit(const FrameDev& C, const LastDev& L, float th, const int* __restrict__ kp_state, int i, Fn&& fn) {
+    M3Query q;
+    if (!m3_query(C, L, th, i, q)) return;
+    for_each_in_area(C, q.u, q.v, q.radius, q.minL, q.maxL, [&](int i2) {
+        if (m3_accept(C, L, q, kp_state, i2)) fn(i2, hamming256(q.d, C.desc + 8 * (size_t)i2), 0);
+    });
 }
 
 __global__ void __launch_bounds__(256) m3_collect_kernel(FrameDev Cf, LastDev L, float th, const int* kp_state, CandLists C) {
@@ -451,14 +486,7 @@ __global__ void __launch_bounds__(256) m3_collect_kernel(FrameDev Cf, LastDev L,
         int2* out = C.items + (size_t)i * C.cap;
         cnt = warp_for_each_in_area(
             Cf, q.u, q.v, q.radius, q.minL, q.maxL,
-            [&](int i2) {
-                if (kp_state[i2] == -2) return false;
-                if (Cf.uright) {
-                    const float ur = Cf.uright[i2];
-                    if (ur > 0 && fabsf(q.ur_proj - ur) > q.radius) return false;   // :1408-1414
-                }
-                return true;
-            },
+            [&](int i2) { return m3_accept(Cf, L, q, kp_state, i2); },
             [&](int pos, int i2) {
                 if (pos < C.cap) out[pos] = make_int2(i2, hamming256(q.d, Cf.desc + 8 * (size_t)i2));
             });
@@ -503,7 +531,7 @@ __global__ void __launch_bounds__(1024) m3_resolve_kernel(FrameDev C, LastDev L,
             } else {
                 m3_visit(C, L, th, kp_state, i, consider);
             }
-            const int out = bestDist <= COEB_TH_HIGH ? bestIdx2 : -1;
+            const int out = bestDist <= L.max_accept ? bestIdx2 : -1;
             if (out != res[i]) { res[i] = out; s_changed = 1; }
         }
         __syncthreads();
@@ -968,33 +996,6 @@ __global__ void __launch_bounds__(128) frame_tail_kernel(TailArgs a) {
     }
     a.x[i] = kp.x; a.y[i] = kp.y; a.angle[i] = kp.angle; a.octave[i] = kp.octave; a.uright[i] = ur;
     a.keys_un[i] = kp; a.depth_out[i] = dp;
-}
-
-// glibc 2.39 logf (sysdeps/ieee754/flt-32/e_logf.c: 16-entry table, degree-3 polynomial in double), restated so that
-// MapPoint::PredictScale's `ceil(log(ratio) / mfLogScaleFactor)` (src/MapPoint.cc:402-417, float overloads) is the same
-// float on the device as on the reference's host; the oracle carries the same restatement and pins it against libm.
-__constant__ double kLogfTab[16][2] = {
-    {0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2}, {0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2},
-    {0x1.49539f0f010bp+0, -0x1.01eae7f513a67p-2},  {0x1.3c995b0b80385p+0, -0x1.b31d8a68224e9p-3},
-    {0x1.30d190c8864a5p+0, -0x1.6574f0ac07758p-3}, {0x1.25e227b0b8eap+0, -0x1.1aa2bc79c81p-3},
-    {0x1.1bb4a4a1a343fp+0, -0x1.a4e76ce8c0e5ep-4}, {0x1.12358f08ae5bap+0, -0x1.1973c5a611cccp-4},
-    {0x1.0953f419900a7p+0, -0x1.252f438e10c1ep-5}, {0x1p+0, 0x0p+0},
-    {0x1.e608cfd9a47acp-1, 0x1.aa5aa5df25984p-5},  {0x1.ca4b31f026aap-1, 0x1.c5e53aa362eb4p-4},
-    {0x1.b2036576afce6p-1, 0x1.526e57720db08p-3},  {0x1.9c2d163a1aa2dp-1, 0x1.bc2860d22477p-3},
-    {0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2},  {0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2}};
-
-__device__ __forceinline__ float glibc_logf(float x) {   // normal positive x only (the caller guarantees it)
-    const uint32_t ix = __float_as_uint(x);
-    if (ix == 0x3f800000u) return 0.f;
-    const uint32_t tmp = ix - 0x3f330000u;
-    const int i = (tmp >> 19) & 15;
-    const int k = (int)tmp >> 23;
-    const double z = (double)__uint_as_float(ix - (tmp & 0xff800000u));
-    const double r = z * kLogfTab[i][0] - 1, y0 = kLogfTab[i][1] + (double)k * 0x1.62e42fefa39efp-1, r2 = r * r;
-    double y = 0x1.5575b0be00b6ap-2 * r + -0x1.ffffef20a4123p-2;
-    y = -0x1.00ea348b88334p-2 * r2 + y;
-    y = y * r2 + (y0 + r);
-    return (float)y;
 }
 
 struct LocalMapDev {
@@ -1562,6 +1563,7 @@ int coeb_match_lastframe(coeb_matcher* m, coeb_frame* cur, int n, const uint8_t*
     const float tz = Tcw_last[8] * twc[0] + Tcw_last[9] * twc[1] + Tcw_last[10] * twc[2] + Tcw_last[11];
     L.forward = (tz > cur->dev.b && !mono) ? 1 : 0;
     L.backward = (-tz > cur->dev.b && !mono) ? 1 : 0;
+    L.max_accept = COEB_TH_HIGH;   // :1425
     int* d_kpm = (int*)m->out.d;
     int* d_info = (int*)(m->out.d + al(K * 4));
     int* d_res = (int*)m->d_scratch;
@@ -2069,6 +2071,66 @@ int coeb_match_triangulation(coeb_matcher* m, coeb_frame* f1, coeb_frame* f2, co
     if ((st = pull_outputs(m, al(N1 * 4) + 4)) != COEB_OK) return st;
     std::memcpy(match12, m->out.h, N1 * 4);
     if (nmatches_out) *nmatches_out = ((const int*)(m->out.h + al(N1 * 4)))[0];
+    return COEB_OK;
+}
+
+// ---- relocalisation overload of SearchByProjection ---------------------------------------------------------------------------
+int coeb_match_reloc(coeb_matcher* m, coeb_frame* cur, int n, const uint8_t* valid, const float* xyz, const float* min_dist,
+                     const float* max_dist, const float* angle, const uint8_t* desc, const float* Tcw, const float* Ow, float th,
+                     int orb_dist, int check_ori, int* kp_match, int* nmatches_out) {
+    if (!m || !cur || n < 0 || !kp_match || !Tcw || !Ow) return fail(COEB_ERR_INVALID_ARG, "bad argument");
+    if (nmatches_out) *nmatches_out = 0;
+    if (n == 0 || cur->n == 0) return COEB_OK;
+    if (!valid || !xyz || !min_dist || !max_dist || !angle || !desc) return fail(COEB_ERR_INVALID_ARG, "null keyframe array");
+    CUDA_TRY(cudaSetDevice(m->device));
+    const size_t N = n, K = cur->n;
+    int st;
+    if ((st = m->in.reserve(2 * al(N) + al(N * 12) + 3 * al(N * 4) + al(N * 32) + al(K * 4))) != COEB_OK) return st;
+    if ((st = m->out.reserve(al(K * 4) + 256)) != COEB_OK) return st;
+    const int cap = 64;
+    if ((st = grow(&m->d_scratch, &m->scratch_bytes, al(N * 4) + al(K * 4) + lists_bytes(N, cap))) != COEB_OK) return st;
+    Packer p(m->in);
+    LastDev L{};
+    L.n = n;
+    L.valid = p.place(valid, N);
+    uint8_t* d_ones = p.room<uint8_t>(N);   // every successful query claims its keypoint (:1546-1547): has_obs = 1
+    std::memset(p.host_at(d_ones), 1, N);
+    L.has_obs = d_ones;
+    L.xyz = p.place(xyz, N * 3);
+    L.min_dist = p.place(min_dist, N); L.max_dist = p.place(max_dist, N);
+    L.angle = p.place(angle, N); L.desc = (const uint32_t*)p.place(desc, N * 32);
+    L.octave = nullptr;
+    // every non-null entry of CurrentFrame.mvpMapPoints blocks: -3 ("holds a MapPoint without observations") counts like -2
+    int* h_state = p.host_at(p.room<int>(K));
+    const int* d_state = (const int*)((char*)m->in.d + ((char*)h_state - m->in.h));
+    for (size_t k = 0; k < K; k++) h_state[k] = kp_match[k] == -1 ? -1 : -2;
+    if ((st = push_inputs(m, p)) != COEB_OK) return st;
+    for (int i = 0; i < 12; i++) L.T[i] = Tcw[i];
+    for (int i = 0; i < 3; i++) L.Ow[i] = Ow[i];
+    L.forward = L.backward = 0;   // levels nPredictedLevel - 1 .. + 1 (:1528)
+    L.reloc = 1; L.nlevels = cur->nlevels; L.max_accept = orb_dist;
+    int* d_kpm = (int*)m->out.d;
+    int* d_info = (int*)(m->out.d + al(K * 4));
+    int* d_res = (int*)m->d_scratch;
+    int* d_claim = (int*)((char*)m->d_scratch + al(N * 4));
+    const CandLists C = carve_lists((char*)m->d_scratch + al(N * 4) + al(K * 4), N, cap);
+    CUDA_TRY(cudaMemsetAsync(C.meta, 0, 8, m->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_kpm, d_state, K * 4, cudaMemcpyDeviceToDevice, m->stream));
+    m3_collect_kernel<<<(n + 7) / 8, 256, 0, m->stream>>>(cur->dev, L, th, d_state, C);
+    m3_resolve_kernel<true><<<1, 1024, 0, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info);
+    CUDA_TRY(cudaGetLastError());
+    if ((st = pull_outputs(m, al(K * 4) + 12)) != COEB_OK) return st;
+    if (((const int*)(m->out.h + al(K * 4)))[2]) {
+        CUDA_TRY(cudaMemcpyAsync(d_kpm, d_state, K * 4, cudaMemcpyDeviceToDevice, m->stream));
+        m3_resolve_kernel<false><<<1, 1024, 0, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info);
+        CUDA_TRY(cudaGetLastError());
+        if ((st = pull_outputs(m, al(K * 4) + 12)) != COEB_OK) return st;
+    }
+    // entries that were occupied keep the caller's own encoding; free ones take the result (>= 0 assigned, -1 still free)
+    const int* h = (const int*)m->out.h;
+    for (size_t k = 0; k < K; k++)
+        if (kp_match[k] == -1) kp_match[k] = h[k];
+    if (nmatches_out) *nmatches_out = ((const int*)(m->out.h + al(K * 4)))[0];
     return COEB_OK;
 }
 

@@ -320,6 +320,18 @@ class Matcher:
                                               _p(s2), _p(i2), _p(F), _p(e), int(only_stereo), int(check_ori), _p(m12), C.byref(n)))
         return n.value, m12
 
+    def match_reloc(self, cur, kf, Tcw, Ow, th, orb_dist, check_ori, kp_match):
+        """Relocalisation SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist). Returns (n, kp_match)."""
+        kp_match = _i32(kp_match).copy()
+        a = dict(valid=_u8(kf["valid"]), xyz=_f32(kf["xyz"]), min_dist=_f32(kf["min_dist"]), max_dist=_f32(kf["max_dist"]),
+                 angle=_f32(kf["angle"]), desc=_u8(kf["desc"]))
+        tc, ow = _f32(Tcw).reshape(12), _f32(Ow).reshape(3)
+        n = C.c_int()
+        _check(lib().coeb_match_reloc(self.h, cur.h, len(a["valid"]), _p(a["valid"]), _p(a["xyz"]), _p(a["min_dist"]), _p(a["max_dist"]),
+                                      _p(a["angle"]), _p(a["desc"]), _p(tc), _p(ow), C.c_float(th), int(orb_dist), int(check_ori),
+                                      _p(kp_match), C.byref(n)))
+        return n.value, kp_match
+
     def match_projection(self, frame, mp, th, nnratio, kp_match):
         kp_match = _i32(kp_match).copy()
         a = dict(track_in_view=_u8(mp["track_in_view"]), bad=_u8(mp["bad"]), has_obs=_u8(mp["has_obs"]),

@@ -10,7 +10,8 @@
  * its vocabulary) and are flattened to CSR here. Free functions at the end cover the steps either side of the path:
  * FrameTailFromExtractor (UndistortKeyPoints + ComputeStereoFromRGBD + AssignFeaturesToGrid on the device) and
  * SearchLocalPoints (isInFrustum + SearchByProjection against a device-resident local map).
- * Fuse / SearchBySim3 / the KeyFrame SearchByProjection overloads stay the reference's.
+ * The relocalisation overload SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist) (:1473-1600) is covered too.
+ * Fuse / SearchBySim3 / the loop-closing SearchByProjection(KeyFrame*, Scw, ...) stay the reference's.
  *
  * The member functions are templates over the reference's Frame / MapPoint types, so this header has no
  * dependency on them: it only touches the members the reference functions touch (cited inline). The
@@ -177,6 +178,38 @@ public:
             if (state[k] >= 0) CurrentFrame.mvpMapPoints[k] = LastFrame.mvpMapPoints[state[k]];
             else if (state[k] == -1) CurrentFrame.mvpMapPoints[k] = nullptr;   /* cleared by the rotation check (:1463) */
         }
+        return nmatches;
+    }
+
+    /* SearchByProjection(Frame &CurrentFrame, KeyFrame* pKF, const set<MapPoint*> &sAlreadyFound, const float th, const int ORBdist)
+     * -- :1473-1600 (Tracking::Relocalization). MapPoint needs the GetMinDistance() / GetMaxDistance() getters (see MakeLocalMap). */
+    template <class FrameT, class KeyFrameT, class SetT>
+    int SearchByProjection(FrameT& CurrentFrame, KeyFrameT* pKF, const SetT& sAlreadyFound, const float th, const int ORBdist) {
+        const auto vpMPs = pKF->GetMapPointMatches();
+        const int n = (int)vpMPs.size(), K = (int)CurrentFrame.mvpMapPoints.size();
+        std::vector<uint8_t> valid(n), desc((size_t)n * 32);
+        std::vector<float> xyz((size_t)n * 3), dmin(n), dmax(n), ang(n);
+        for (int i = 0; i < n; i++) {
+            auto* p = vpMPs[i];
+            valid[i] = p && !p->isBad() && !sAlreadyFound.count(p);
+            ang[i] = pKF->mvKeysUn[i].angle;
+            if (valid[i]) {
+                coeb_adapt::xyz3(p->GetWorldPos(), &xyz[(size_t)i * 3]);
+                dmin[i] = p->GetMinDistance(); dmax[i] = p->GetMaxDistance();
+                std::memcpy(&desc[(size_t)i * 32], coeb_adapt::desc_row(p->GetDescriptor(), 0), 32);
+            }
+        }
+        float Tc[12], Ow[3];
+        coeb_adapt::pose34(CurrentFrame.mTcw, Tc);
+        coeb_adapt::xyz3(CurrentFrame.mOw, Ow);   // -Rcw^T tcw, the expression of :1479
+        std::vector<int> state(K);
+        for (int k = 0; k < K; k++) state[k] = CurrentFrame.mvpMapPoints[k] ? -2 : -1;
+        coeb_adapt::DeviceFrame<FrameT> dC(CurrentFrame);
+        int nmatches = 0;
+        coeb_adapt::check(coeb_match_reloc(coeb_adapt::matcher(), dC.f, n, valid.data(), xyz.data(), dmin.data(), dmax.data(), ang.data(), desc.data(),
+                                           Tc, Ow, th, ORBdist, mbCheckOrientation ? 1 : 0, state.data(), &nmatches));
+        for (int k = 0; k < K; k++)
+            if (state[k] >= 0) CurrentFrame.mvpMapPoints[k] = vpMPs[state[k]];
         return nmatches;
     }
 

@@ -247,6 +247,18 @@ int coeb_match_lastframe(coeb_matcher* m, coeb_frame* cur, int n, const uint8_t*
                          const float* Tcw_cur, const float* Tcw_last, float th, int mono, int check_ori,
                          int* kp_match, int* nmatches_out);
 
+/* ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, th, ORBdist)
+ * (src/ORBmatcher.cc:1473-1600), the guided search of Tracking::Relocalization. Per keyframe map point i:
+ *   valid (pMP && !isBad() && !sAlreadyFound.count(pMP)), xyz (GetWorldPos), min_dist / max_dist (mfMinDistance / mfMaxDistance),
+ *   angle (pKF->mvKeysUn[i].angle), desc (GetDescriptor()).
+ * Tcw: CurrentFrame.mTcw, 3x4 row-major; Ow: -Rcw^T tcw (:1479, equal to CurrentFrame.mOw).
+ * kp_match (in/out, cur.n ints): -1 = CurrentFrame.mvpMapPoints[k] is NULL, any other negative value = it holds a MapPoint
+ * (every non-null entry blocks, :1546-1547; such entries come back unchanged); on return >= 0 is the keyframe map point
+ * assigned by this call. orb_dist is the ORBdist acceptance threshold. */
+int coeb_match_reloc(coeb_matcher* m, coeb_frame* cur, int n, const uint8_t* valid, const float* xyz, const float* min_dist,
+                     const float* max_dist, const float* angle, const uint8_t* desc, const float* Tcw, const float* Ow, float th,
+                     int orb_dist, int check_ori, int* kp_match, int* nmatches_out);
+
 /* ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize)
  * (src/ORBmatcher.cc:405-520). prev_matched: F1.n x 2 floats in/out; matches12: F1.n ints out. */
 int coeb_match_init(coeb_matcher* m, coeb_frame* f1, coeb_frame* f2, float* prev_matched, int* matches12,

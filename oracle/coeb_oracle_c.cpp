@@ -296,6 +296,12 @@ int orc_match_triangulation(orc_frame* f1, orc_frame* f2, const uint8_t* free1, 
     return search_for_triangulation(f1->v, f2->v, free1, free2, V1, V2, F12, ex, ey, only_stereo != 0, check_ori != 0, match12);
 }
 
+int orc_match_reloc(orc_frame* cur, int n, const uint8_t* valid, const float* xyz, const float* min_dist, const float* max_dist,
+                    const float* angle, const uint8_t* desc, const float* Tcw, const float* Ow, float th, int orb_dist, int check_ori,
+                    int* kp_match) {
+    return search_by_projection_reloc(cur->v, n, valid, xyz, min_dist, max_dist, angle, desc, Tcw, Ow, th, orb_dist, check_ori != 0, kp_match);
+}
+
 // Number of floats in [lo, hi) (bit patterns, stepped by `step`) whose restated logf differs from the C library's.
 long orc_logf_mismatches(uint32_t lo, uint32_t hi, uint32_t step) {
     long bad = 0;

@@ -195,4 +195,68 @@ static inline int search_local_points(const FrameView& F, const LocalMapSoA& M, 
     return search_by_projection_map(F, mp, th, nnratio, kp_match);
 }
 
+// ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, th, ORBdist)
+// (src/ORBmatcher.cc:1473-1600; Tracking::Relocalization). Per keyframe map point i: valid = pMP && !isBad() &&
+// !sAlreadyFound.count(pMP); xyz = GetWorldPos(); min/max_dist = mfMinDistance / mfMaxDistance; angle = pKF->mvKeysUn[i].angle;
+// desc = GetDescriptor(). Tcw = CurrentFrame.mTcw (3x4), Ow = -Rcw^T tcw as the reference evaluates it (:1479).
+// kp_match encodes CurrentFrame.mvpMapPoints: -1 empty, any other negative value = holds a MapPoint (every non-null entry blocks,
+// :1546-1547); on return >= 0 is the keyframe map point assigned by this call. Note that, unlike the frame-to-frame overload,
+// the reference does not reject points behind the camera here (no invzc < 0 test).
+static inline int search_by_projection_reloc(const FrameView& C, int n, const uint8_t* valid, const float* xyz, const float* min_dist,
+                                             const float* max_dist, const float* angle, const uint8_t* desc, const float* Tcw,
+                                             const float* Ow, float th, int ORBdist, bool checkOri, int* kp_match) {
+    int nmatches = 0;
+    std::vector<int> rotHist[COEB_HISTO_LENGTH];
+    const float logScale = C.nlevels > 1 ? glibc_logf(C.scale[1]) : 1.f;
+    std::vector<int> vIndices2;
+    for (int i = 0; i < n; i++) {
+        if (!valid[i]) continue;
+        const float* P = xyz + 3 * (size_t)i;
+        const float xc = Tcw[0] * P[0] + Tcw[1] * P[1] + Tcw[2] * P[2] + Tcw[3];
+        const float yc = Tcw[4] * P[0] + Tcw[5] * P[1] + Tcw[6] * P[2] + Tcw[7];
+        const float zc = Tcw[8] * P[0] + Tcw[9] * P[1] + Tcw[10] * P[2] + Tcw[11];
+        const float invzc = (float)(1.0 / (double)zc);
+        const float u = C.cam.fx * xc * invzc + C.cam.cx;
+        const float v = C.cam.fy * yc * invzc + C.cam.cy;
+        if (u < C.cam.min_x || u > C.cam.max_x) continue;
+        if (v < C.cam.min_y || v > C.cam.max_y) continue;
+        const float PO[3] = {P[0] - Ow[0], P[1] - Ow[1], P[2] - Ow[2]};
+        double s = 0;
+        for (int k = 0; k < 3; k++) s += (double)PO[k] * (double)PO[k];
+        const float dist3D = (float)std::sqrt(s);
+        const float maxDistance = 1.2f * max_dist[i], minDistance = 0.8f * min_dist[i];
+        if (dist3D < minDistance || dist3D > maxDistance) continue;
+        const float ratio = max_dist[i] / dist3D;   // MapPoint::PredictScale (src/MapPoint.cc:402-417)
+        int nPredictedLevel = 0;
+        if (ratio >= FLT_MIN && ratio <= FLT_MAX) nPredictedLevel = (int)std::ceil(glibc_logf(ratio) / logScale);
+        if (nPredictedLevel < 0) nPredictedLevel = 0;
+        else if (nPredictedLevel >= C.nlevels) nPredictedLevel = C.nlevels - 1;
+        const float radius = th * C.scale[nPredictedLevel];
+        C.features_in_area(u, v, radius, nPredictedLevel - 1, nPredictedLevel + 1, vIndices2);
+        if (vIndices2.empty()) continue;
+        const uint8_t* dMP = desc + (size_t)i * 32;
+        int bestDist = 256, bestIdx2 = -1;
+        for (int i2 : vIndices2) {
+            if (kp_match[i2] != KP_FREE) continue;
+            const int dist = hamming256(dMP, C.desc + (size_t)i2 * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= ORBdist) {
+            kp_match[bestIdx2] = i;
+            nmatches++;
+            if (checkOri) rotHist[rot_bin(angle[i], C.kps[bestIdx2].angle)].push_back(bestIdx2);
+        }
+    }
+    if (checkOri) {
+        int sizes[COEB_HISTO_LENGTH], ind1, ind2, ind3;
+        for (int i = 0; i < COEB_HISTO_LENGTH; i++) sizes[i] = (int)rotHist[i].size();
+        three_maxima(sizes, COEB_HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < COEB_HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int k : rotHist[i]) { kp_match[k] = KP_FREE; nmatches--; }
+        }
+    }
+    return nmatches;
+}
+
 }  // namespace orc

@@ -370,3 +370,15 @@ def match_triangulation(f1, f2, free1, free2, fv1, fv2, F12, epipole, only_stere
     n = lib().orc_match_triangulation(f1.h, f2.h, _p(free1), _p(free2), len(n1), _p(n1), _p(s1), _p(i1), len(n2), _p(n2), _p(s2), _p(i2),
                                       _p(F), C.c_float(epipole[0]), C.c_float(epipole[1]), int(only_stereo), int(check_ori), _p(m12))
     return n, m12
+
+
+def match_reloc(cur, kf, Tcw, Ow, th, orb_dist, check_ori, kp_match):
+    """Relocalisation SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist). kf: dict of arrays (valid, xyz,
+    min_dist, max_dist, angle, desc). Returns (nmatches, kp_match)."""
+    kp_match = _i32(kp_match).copy()
+    a = dict(valid=_u8(kf["valid"]), xyz=_f32(kf["xyz"]), min_dist=_f32(kf["min_dist"]), max_dist=_f32(kf["max_dist"]),
+             angle=_f32(kf["angle"]), desc=_u8(kf["desc"]))
+    tc, ow = _f32(Tcw).reshape(12), _f32(Ow).reshape(3)
+    n = lib().orc_match_reloc(cur.h, len(a["valid"]), _p(a["valid"]), _p(a["xyz"]), _p(a["min_dist"]), _p(a["max_dist"]),
+                              _p(a["angle"]), _p(a["desc"]), _p(tc), _p(ow), C.c_float(th), int(orb_dist), int(check_ori), _p(kp_match))
+    return n, kp_match

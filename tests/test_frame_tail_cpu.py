@@ -155,3 +155,74 @@ def test_search_local_points_oracle_against_numpy_and_flat_matcher():
               view_cos=proj[:, 3], level=proj[:, 4].astype(np.int32), desc=lm["desc"])
     nm2, kpm2 = orc.match_projection(F, mp, 3.0, 0.8, state)
     assert nm2 == nm and np.array_equal(kpm, kpm2)
+
+
+def test_relocalisation_oracle_against_python_transcription():
+    """src/ORBmatcher.cc:1473-1600 transcribed with numpy scalars; windows through the (separately pinned) grid query."""
+    f32 = np.float32
+    ex = orc.Extractor()
+    kps, desc = ex.extract(synth.make_frame(210))
+    scale = ex.tables()["scale"]
+    cam_args = (535.4, 539.2, 320.1, 247.6, 40.0, 40.0 / 535.4, 0.0, 640.0, 0.0, 480.0)
+    cam = orc.Camera(*cam_args)
+    F = orc.Frame(kps, desc, cam, scale, None)
+    Tcw, Ow = synth.make_pose(5)
+    lm, skip, _ = synth.make_local_map(kps, desc, scale, Tcw, seed=5, n_map=1200, n_true=600)
+    rng = np.random.default_rng(5)
+    valid = (1 - skip).astype(np.uint8)
+    angle = rng.uniform(0, 360, len(skip)).astype(np.float32)
+    state = rng.choice([-1, -1, -1, -2, -3], size=len(kps)).astype(np.int32)
+    kf = dict(valid=valid, xyz=lm["xyz"], min_dist=lm["min_dist"], max_dist=lm["max_dist"], angle=angle, desc=lm["desc"])
+    th, orb_dist = f32(10.0), 100
+    n, km = orc.match_reloc(F, kf, Tcw, Ow, th, orb_dist, True, state)
+
+    T = Tcw.reshape(3, 4).astype(np.float32)
+    logs = np.log(np.float64(scale[1]))
+    km2 = state.copy()
+    hist = [[] for _ in range(30)]
+    n2 = 0
+    for i in range(len(valid)):
+        if not valid[i]:
+            continue
+        P = lm["xyz"][i]
+        pc = [f32(f32(f32(f32(T[r, 0] * P[0]) + f32(T[r, 1] * P[1])) + f32(T[r, 2] * P[2])) + T[r, 3]) for r in range(3)]
+        with np.errstate(divide="ignore"):
+            invz = f32(np.float64(1.0) / np.float64(pc[2]))
+        u = f32(f32(f32(f32(cam.fx) * pc[0]) * invz) + f32(cam.cx))
+        v = f32(f32(f32(f32(cam.fy) * pc[1]) * invz) + f32(cam.cy))
+        if u < cam.min_x or u > cam.max_x or v < cam.min_y or v > cam.max_y:   # no test on the sign of z in this overload
+            continue
+        po = (P - Ow).astype(np.float32)
+        d3 = f32(np.sqrt((po.astype(np.float64) ** 2).sum()))
+        if d3 < f32(0.8) * lm["min_dist"][i] or d3 > f32(1.2) * lm["max_dist"][i]:
+            continue
+        lvl = int(np.clip(np.ceil(np.log(np.float64(lm["max_dist"][i] / d3)) / logs), 0, len(scale) - 1))
+        win = F.features_in_area(u, v, f32(th * scale[lvl]), lvl - 1, lvl + 1)
+        best, bi = 256, -1
+        for i2 in win:
+            if km2[i2] != -1:
+                continue
+            dist = int(np.unpackbits(lm["desc"][i] ^ desc[i2]).sum())
+            if dist < best:
+                best, bi = dist, int(i2)
+        if best <= orb_dist:
+            km2[bi] = i
+            n2 += 1
+            rot = f32(angle[i]) - f32(kps["angle"][bi])
+            if rot < 0:
+                rot = f32(rot + f32(360.0))
+            b = int(np.floor(float(f32(rot * f32(1.0 / 30))) + 0.5))
+            hist[0 if b == 30 else b].append(bi)
+    sizes = [len(h) for h in hist]
+    order = sorted(range(30), key=lambda k: (-sizes[k], k))
+    keep = [order[0]] if sizes[order[0]] > 0 else []
+    if keep and sizes[order[1]] > 0 and not f32(sizes[order[1]]) < f32(0.1) * f32(sizes[order[0]]):
+        keep.append(order[1])
+        if sizes[order[2]] > 0 and not f32(sizes[order[2]]) < f32(0.1) * f32(sizes[order[0]]):
+            keep.append(order[2])
+    for b in range(30):
+        if b not in keep:
+            for k in hist[b]:
+                km2[k] = -1
+                n2 -= 1
+    assert n == n2 and np.array_equal(km, km2) and n > 20

@@ -136,3 +136,28 @@ def test_search_local_points_edge_cases(gpu):
     empty = {k: a[:0] for k, a in lm.items()}
     ng, kg, vg, _ = m.search_local_points(fg, m.local_map(empty), skip[:0], has_obs[:0], Tcw, Ow, 3.0, 0.8, state)
     assert ng == 0 and len(vg) == 0 and np.array_equal(kg, state)
+
+
+@pytest.mark.parametrize("th,orb_dist,ori,seed", [(10.0, 100, True, 1), (3.0, 64, True, 2), (10.0, 100, False, 3), (60.0, 100, True, 4)])
+def test_relocalisation_search_by_projection_matches_oracle(gpu, th, orb_dist, ori, seed):
+    """SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist) of Tracking::Relocalization: every non-null entry of
+    mvpMapPoints blocks, points behind the camera are NOT rejected (the reference has no such test), the level comes from
+    PredictScale. th = 60 makes windows wide enough to overflow the 64-entry candidate lists (window-walking fallback)."""
+    g, c, kps, desc = _extract_both(gpu, 200 + seed, dynamic=False)
+    scale = c.tables()["scale"]
+    m = gpu.Matcher()
+    fg = m.frame(kps, desc, gpu.Camera(*TUM3_CAM), scale, None)
+    fc = orc.Frame(kps, desc, orc.Camera(*TUM3_CAM), scale, None)
+    Tcw, Ow = synth.make_pose(seed)
+    lm, skip, _ = synth.make_local_map(kps, desc, scale, Tcw, seed=seed, n_map=1500, n_true=700)
+    rng = np.random.default_rng(seed)
+    kf = dict(valid=(1 - skip).astype(np.uint8), xyz=lm["xyz"], min_dist=lm["min_dist"], max_dist=lm["max_dist"],
+              angle=rng.uniform(0, 360, len(skip)).astype(np.float32), desc=lm["desc"])
+    state = rng.choice([-1, -1, -1, -1, -2, -3], size=len(kps)).astype(np.int32)
+    ng, kg = m.match_reloc(fg, kf, Tcw, Ow, th, orb_dist, ori, state)
+    nc, kc = orc.match_reloc(fc, kf, Tcw, Ow, th, orb_dist, ori, state)
+    assert ng == nc and np.array_equal(kg, kc)
+    assert nc > (5 if ori else 100)
+    assert np.array_equal(kg[state != -1], state[state != -1]), "occupied entries must come back untouched"
+    got = kg[kg >= 0]
+    assert len(np.unique(got)) == len(got), "a keyframe map point was assigned twice"
