@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <map>
+#include <set>
 #include <vector>
 
 #include "../../include/ORBextractor.h"
@@ -39,6 +40,9 @@ int orc_match_triangulation(orc_frame* f1, orc_frame* f2, const uint8_t* free1, 
 void orc_undistort_keypoints(const coeb_keypoint* keys, int n, const coeb_camera* cam, const float* dist5, coeb_keypoint* keys_un);
 void orc_stereo_from_rgbd(const coeb_keypoint* keys, const coeb_keypoint* keys_un, int n, const void* depth, int kind, int stride_bytes,
                           float factor, float mbf, float* uright, float* depth_out);
+int orc_match_reloc(orc_frame* cur, int n, const uint8_t* valid, const float* xyz, const float* min_dist, const float* max_dist,
+                    const float* angle, const uint8_t* desc, const float* Tcw, const float* Ow, float th, int orb_dist, int check_ori,
+                    int* kp_match);
 int orc_search_local_points(orc_frame* f, int n, const float* xyz, const float* normal, const float* min_dist, const float* max_dist,
                             const uint8_t* desc, const uint8_t* skip, const uint8_t* has_obs, const float* Tcw, const float* Ow,
                             float cos_limit, float th, float nnratio, int* kp_match, uint8_t* in_view, float* proj);
@@ -456,6 +460,38 @@ int main() {
         for (int i = 0; i < NL; i++) { if (!skip[i]) { bad_view += (lmp[i].mbTrackInView != (inview[i] != 0)) || (lmp[i].nVisible != (int)inview[i]); nview += inview[i]; } }
         EXPECT(bad_ptr == 0, "SearchLocalPoints: %d mvpMapPoints entries differ", bad_ptr);
         EXPECT(bad_view == 0 && nview > 300 && nview < NL, "SearchLocalPoints: visibility bookkeeping (%d wrong, %d in view)", bad_view, nview);
+        // ---- relocalisation SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist) (src/Tracking.cc:1436-1545) ----
+        {
+            Frame KFr;   // plays the candidate keyframe: its map points are the local-map points above, one per keypoint slot
+            KFr.N = 1200;
+            KFr.mvKeysUn.resize(KFr.N);
+            KFr.mvpMapPoints.assign(KFr.N, nullptr);
+            std::set<MapPoint*> already;
+            for (int i = 0; i < KFr.N; i++) {
+                KFr.mvKeysUn[i].angle = 360.f * rndf();
+                if (rnd() % 9) KFr.mvpMapPoints[i] = &lmp[i];
+                if ((rnd() % 13) == 0) already.insert(&lmp[i]);
+            }
+            for (int k = 0; k < T.N; k++) T.mvpMapPoints[k] = (k % 6 == 0) ? &lmp[NL - 1 - (k % 50)] : nullptr;   // occupied entries block
+            std::vector<uint8_t> rvalid(KFr.N);
+            std::vector<float> rang(KFr.N);
+            for (int i = 0; i < KFr.N; i++) {
+                MapPoint* p = KFr.mvpMapPoints[i];
+                rvalid[i] = p && !p->bad && !already.count(p);
+                rang[i] = KFr.mvKeysUn[i].angle;
+            }
+            std::vector<int> rstate(T.N);
+            std::vector<MapPoint*> before = T.mvpMapPoints;
+            for (int k = 0; k < T.N; k++) rstate[k] = T.mvpMapPoints[k] ? -2 : -1;
+            const int rref = orc_match_reloc(ot, KFr.N, rvalid.data(), xyz.data(), dmin.data(), dmax.data(), rang.data(), ldesc.data(), T.mTcw, T.mOw, 10.f,
+                                             100, 1, rstate.data());
+            ORB_SLAM2::ORBmatcher rm(0.75f, true);
+            const int rgot = rm.SearchByProjection(T, &KFr, already, 10.f, 100);
+            EXPECT(rgot == rref && rref > 3, "SearchByProjection(reloc): %d vs oracle %d", rgot, rref);
+            int bad_ptr = 0;
+            for (int k = 0; k < T.N; k++) bad_ptr += T.mvpMapPoints[k] != (rstate[k] >= 0 ? KFr.mvpMapPoints[rstate[k]] : before[k]);
+            EXPECT(bad_ptr == 0, "SearchByProjection(reloc): %d mvpMapPoints entries differ", bad_ptr);
+        }
         coeb_local_map_destroy(lm);
         coeb_frame_destroy(dT);
         orc_frame_destroy(ot);
