@@ -27,6 +27,7 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -56,11 +57,21 @@ inline void check(int st) {
     if (st != COEB_OK) throw std::runtime_error(std::string("coeb: ") + coeb_last_error());
 }
 
-/* RAII upload of the Frame fields the matchers read (mvKeysUn, mDescriptors, mvuRight, bounds, scale factors). */
+/* Does the Frame type carry a device-resident twin (a `coeb_frame* mpDeviceFrame` member, filled by FrameTailFromExtractor)? */
+template <class T, class = void> struct has_device_frame : std::false_type {};
+template <class T> struct has_device_frame<T, std::void_t<decltype(std::declval<const T&>().mpDeviceFrame)>> : std::true_type {};
+
+/* The Frame fields the matchers read (mvKeysUn, mDescriptors, mvuRight, bounds, scale factors) on the device. A Frame that
+ * already owns a device frame (member mpDeviceFrame, see FrameTailFromExtractor) is used as it is: no upload, no grid build;
+ * otherwise the fields are uploaded for the duration of the call (RAII). */
 template <class FrameT>
 struct DeviceFrame {
     coeb_frame* f = nullptr;
+    bool owned = true;
     explicit DeviceFrame(const FrameT& F) {
+        if constexpr (has_device_frame<FrameT>::value) {
+            if (F.mpDeviceFrame) { f = F.mpDeviceFrame; owned = false; return; }
+        }
         const int n = (int)F.mvKeysUn.size();
         std::vector<unsigned char> desc((size_t)n * 32);
         for (int i = 0; i < n; i++) std::memcpy(&desc[(size_t)i * 32], desc_row(F.mDescriptors, i), 32);
@@ -71,7 +82,7 @@ struct DeviceFrame {
                                 F.mvuRight.empty() ? nullptr : F.mvuRight.data(), &cam, F.mvScaleFactors.data(),
                                 (int)F.mvScaleFactors.size(), &f));
     }
-    ~DeviceFrame() { coeb_frame_destroy(f); }
+    ~DeviceFrame() { if (owned) coeb_frame_destroy(f); }
     DeviceFrame(const DeviceFrame&) = delete;
     DeviceFrame& operator=(const DeviceFrame&) = delete;
 };

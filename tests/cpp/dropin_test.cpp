@@ -107,6 +107,7 @@ struct Frame {
     long mnId = 7;
     std::map<unsigned, std::vector<unsigned> > mFeatVec;   // DBoW2::FeatureVector
     ORB_SLAM2::ORBextractor *mpORBextractorLeft = nullptr, *mpORBextractorRight = nullptr;
+    coeb_frame* mpDeviceFrame = nullptr;   // device twin kept by the Frame; the adapters use it when set
     // KeyFrame-only members used by SearchByBoW / SearchForTriangulation (a KeyFrame is built from a Frame, src/KeyFrame.cc:31-58)
     float Rcw[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, tcw[3] = {0, 0, 0};
     std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
@@ -395,6 +396,7 @@ int main() {
         coeb_depth_image di;
         di.data = depth.data(); di.kind = 2; di.stride_bytes = w * 2; di.factor = 1.0f / 5000.0f; di.on_device = 0; di.width = w; di.height = h;
         coeb_frame* dT = ORB_SLAM2::FrameTailFromExtractor(T, dist5, &di);
+        T.mpDeviceFrame = dT;   // later matcher calls on T reuse it instead of uploading the frame again
         coeb_camera ct = cam_of(T);
         std::vector<coeb_keypoint> un(T.N);
         std::vector<float> ur(T.N), dp(T.N);
@@ -493,6 +495,7 @@ int main() {
             EXPECT(bad_ptr == 0, "SearchByProjection(reloc): %d mvpMapPoints entries differ", bad_ptr);
         }
         coeb_local_map_destroy(lm);
+        T.mpDeviceFrame = nullptr;
         coeb_frame_destroy(dT);
         orc_frame_destroy(ot);
     }
