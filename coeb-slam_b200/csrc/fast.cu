@@ -295,10 +295,10 @@ __global__ void __launch_bounds__(kFtThreads, COEB_FT_MINB) fast_kernel(const __
         const int A = a[0];
         const int n_l = a[-1], n_r = a[1], n_ul = a[-kAW - 1], n_u = a[-kAW], n_ur = a[-kAW + 1], n_dl = a[kAW - 1], n_d = a[kAW], n_dr = a[kAW + 1];
         bool keep = A > max(max(max(n_l, n_r), max(n_ul, n_u)), max(max(n_ur, n_dl), max(n_d, n_dr)));
-        if (!keep) {
+        if (!keep && ((((eL | eR) >> px) | ((eU | eD) >> py)) & 1ull)) {   // suppressed, but the pixel touches a cell boundary
             // a larger neighbour only counts if it belongs to the same cell (each cell is an independent cv::FAST call)
             const bool sl = !((eL >> px) & 1ull), sr = !((eR >> px) & 1ull), su = !((eU >> py) & 1ull), sd = !((eD >> py) & 1ull);
-            if (!(sl && sr && su && sd)) {
+            {
                 int m = 0;
                 if (sl) m = max(m, n_l);
                 if (sr) m = max(m, n_r);
