@@ -641,6 +641,30 @@ def bench_matching(cb, dev, batch, o_kps, o_desc, o_cnt, ex, args):
                                      "coeb_frame_from_extractor (raw uint16 depth in, mvKeysUn/mvuRight/mvDepth out) -> coeb_search_local_points "
                                      "(5000-point resident local map; flags in, matches + visibility out)")
     n_local_gpu, km_local_gpu, inview_gpu = int(nm.value), km.copy(), inview.copy()
+    # ---- BASELINE.json configs[3] (KITTI-shaped stereo pair, nFeatures 2000) and the extraction of configs[4] (1080p, 4000) ----
+    sw, sh = 1241, 376
+    left = synth.make_frame(300, sw, sh)
+    right = synth.make_stereo_right(left, seed=300)
+    exL, exR = cb.Extractor(2000, 1.2, NLEVELS, 20, 7, device=dev), cb.Extractor(2000, 1.2, NLEVELS, 20, 7, device=dev)
+    for _ in range(3):
+        kl, dl = exL.extract(left)
+        kr, dr = exR.extract(right)
+    bf_s, b_s = 386.1448, 386.1448 / 718.856
+
+    def stereo_frame():
+        a = exL.extract(left)
+        b = exR.extract(right)
+        return m.stereo_match(exL, exR, a[0], a[1], b[0], b[1], bf_s, b_s)
+    n_st, ur_st, dp_st = stereo_frame()
+    out["stereo_1241x376_extract_pair_us"] = _median_us(lambda: (exL.extract(left), exR.extract(right)), 20)
+    out["stereo_1241x376_compute_stereo_matches_us"] = _median_us(lambda: m.stereo_match(exL, exR, kl, dl, kr, dr, bf_s, b_s), 20)
+    out["stereo_1241x376_points_with_depth"] = int(n_st)
+    big = synth.make_frame(500, 1920, 1080)
+    exB = cb.Extractor(4000, 1.2, NLEVELS, 20, 7, device=dev)
+    for _ in range(3):
+        kb, db = exB.extract(big)
+    out["extract_1920x1080_nf4000_us"] = _median_us(lambda: exB.extract(big), 20)
+    out["extract_1920x1080_keypoints"] = int(len(kb))
     # kNN 4000 x 100k, device resident
     q, t = synth.make_knn_sets(4000, 100000, seed=3)
     dq, dt = torch.from_numpy(q).cuda(dev), torch.from_numpy(t).cuda(dev)
@@ -687,6 +711,12 @@ def bench_matching(cb, dev, batch, o_kps, o_desc, o_cnt, ex, args):
                                                     and ur_c.tobytes() == ur1[:len(kps)].tobytes() and dp_c.tobytes() == dp1[:len(kps)].tobytes())
         out["local_points_in_view"] = int(iv_lc.sum())
         out["local_points_matches"] = int(n_lc)
+        oL, oR = orc.Extractor(2000, 1.2, NLEVELS, 20, 7), orc.Extractor(2000, 1.2, NLEVELS, 20, 7)
+        okl, odl = oL.extract(left)
+        okr, odr = oR.extract(right)
+        out["cpu_stereo_1241x376_compute_stereo_matches_us"] = _median_us(lambda: orc.stereo_match(oL, oR, okl, odl, okr, odr, bf_s, b_s), 5)
+        n_sc, ur_sc, dp_sc = orc.stereo_match(oL, oR, okl, odl, okr, odr, bf_s, b_s)
+        out["stereo_bit_exact_vs_cpu"] = bool(n_sc == n_st and ur_sc.tobytes() == ur_st.tobytes() and dp_sc.tobytes() == dp_st.tobytes())
         n_g, km_g = m.match_projection(f, mp, 3.0, 0.8, state)
         n_c, km_c = orc.match_projection(fc, mp, 3.0, 0.8, state)
         out["bit_exact_vs_cpu"] = bool(n_g == n_c and np.array_equal(km_g, km_c))

@@ -75,6 +75,7 @@ struct coeb_extractor {
     DynState* d_dyn = nullptr;
     // staging for the host entry points
     uint8_t* d_in_gray = nullptr; size_t in_gray_bytes = 0; int in_pitch = 0;
+    uint8_t* d_in_linear = nullptr; size_t in_linear_bytes = 0;   // landing buffer for tightly packed frames whose width is not the arena pitch
     char *h_dynin = nullptr, *d_dynin = nullptr; size_t dyn_cap = 0;   // boxes | nbox | blur flags | T_M | ntm of a call: one pinned block, one copy
     char* d_out_block = nullptr;                                    // counts | status | keypoints | descriptors: one allocation
     coeb_keypoint* d_out_kps = nullptr; uint8_t* d_out_desc = nullptr; int *d_out_count = nullptr, *d_out_status = nullptr;
@@ -487,7 +488,7 @@ void coeb_extractor_destroy(coeb_extractor* ex) {
     free_arenas(ex);
     cudaFree(ex->d_tabs);
     cudaFree(ex->d_fast_tiles);
-    cudaFree(ex->d_in_gray); cudaFree(ex->d_dynin); cudaFree(ex->d_out_block);
+    cudaFree(ex->d_in_gray); cudaFree(ex->d_in_linear); cudaFree(ex->d_dynin); cudaFree(ex->d_out_block);
     if (ex->h_dynin) cudaFreeHost(ex->h_dynin);
     if (ex->h_out1) cudaFreeHost(ex->h_out1);
     for (auto& e : ex->graphs) cudaGraphExecDestroy(e.exec);
@@ -722,6 +723,9 @@ int coeb_extract_batch_host(coeb_extractor* ex, int B, const uint8_t* gray, int 
     const size_t fstride = (size_t)pitch * height;
     st = ensure_buf(&ex->d_in_gray, &ex->in_gray_bytes, fstride * B);
     if (st != COEB_OK) return st;
+    if (frame_stride == (size_t)stride * height && !(stride == pitch && stride == width)) {
+        if ((st = ensure_buf(&ex->d_in_linear, &ex->in_linear_bytes, frame_stride * B)) != COEB_OK) return st;
+    }
     const float *dboxes = nullptr, *dtm = nullptr;
     const int *dnbox = nullptr, *dntm = nullptr, *dblur = nullptr;
     if (nbox || ntm) {   // the per-frame box / T_M arrays are tiny: packed into one pinned block, one copy up front
@@ -801,6 +805,14 @@ int coeb_extract_batch_host(coeb_extractor* ex, int B, const uint8_t* gray, int 
         if (frame_stride == (size_t)stride * height && stride == pitch && stride == width)
             // tightly packed frames whose width is already the arena pitch: one linear DMA (2D copies go row by row)
             return cudaMemcpyAsync(ex->d_in_gray + fstride * f0, gray + frame_stride * f0, fstride * n, cudaMemcpyHostToDevice, cs);
+        if (frame_stride == (size_t)stride * height && ex->d_in_linear) {
+            // contiguous rows of another pitch (e.g. 1241-pixel KITTI rows): one linear DMA into a landing buffer, then a device-side
+            // 2-D copy into the pitch-aligned arena (a host-to-device 2-D copy goes row by row and is several times slower)
+            cudaError_t e = cudaMemcpyAsync(ex->d_in_linear + frame_stride * f0, gray + frame_stride * f0, frame_stride * n, cudaMemcpyHostToDevice, cs);
+            if (e != cudaSuccess) return e;
+            return cudaMemcpy2DAsync(ex->d_in_gray + fstride * f0, pitch, ex->d_in_linear + frame_stride * f0, stride, width, (size_t)height * n,
+                                     cudaMemcpyDeviceToDevice, cs);
+        }
         if (frame_stride == (size_t)stride * height)
             return cudaMemcpy2DAsync(ex->d_in_gray + fstride * f0, pitch, gray + frame_stride * f0, stride, width, (size_t)height * n,
                                      cudaMemcpyHostToDevice, cs);
