@@ -205,7 +205,8 @@ constexpr int kBoxSlot = 2432;                              // bytes per buffer 
 static_assert(kDescChunk <= 256, "one thread per keypoint computes cos / sin");
 
 __global__ void __launch_bounds__(256, COEB_DESC_MINB) describe_tma_kernel(const __grid_constant__ TmaMaps raw_maps, const __grid_constant__ TmaMaps blur_maps,
-                                                                          const __grid_constant__ Geometry g, const __grid_constant__ BatchView v) {
+                                                                          const __grid_constant__ Geometry g, const __grid_constant__ BatchView v,
+                                                                          const int chunk /* keypoints per CTA, <= kDescChunk */) {
     __shared__ __align__(128) uint8_t s_box[8][2][kBoxSlot];
     __shared__ __align__(8) unsigned long long s_bar[8][2];
     __shared__ float s_pat[1024];         // pattern as floats, transposed: [4*bit + component][lane]
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(256, COEB_DESC_MINB) describe_tma_kernel(const
     }
     const int n = kc[level];
     const int status = v.status[frame];
-    const int chunk0 = blockIdx.z * kDescChunk;
+    const int chunk0 = blockIdx.z * chunk;
     if (level == 0 && blockIdx.z == 0 && tid == 0) {
         int cnt = total;
         if (status != COEB_OK) cnt = 0;
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__(256, COEB_DESC_MINB) describe_tma_kernel(const
     coeb_keypoint* okp = v.out_kps + (size_t)frame * g.out_cap + offset;
     uint8_t* odesc = v.out_desc + ((size_t)frame * g.out_cap + offset) * 32;
     const float factorPI = (float)(3.14159265358979323846 / 180.0);
-    const int nend = min(n, chunk0 + kDescChunk);
+    const int nend = min(n, chunk0 + chunk);
     const int m = nend - chunk0;   // <= kDescChunk keypoints, warp w takes j = w, w + 8, ...
 
     // per-lane constants of patch row r = lane (v = r - 15): weight words (u + 32 inside the circular patch, else 0) and
@@ -388,10 +389,15 @@ void launch_describe(const Geometry& g, const BatchView& v, cudaStream_t stream)
     for (int l = 0; l < g.nlevels; l++) max_keys = std::max(max_keys, g.lv[l].key_cap);
     const dim3 grid(g.nlevels, v.B, (max_keys + kDescChunk - 1) / kDescChunk);
     TmaMaps raw_maps, blur_maps;
-    if (tma_enabled() && encode_level_maps(g, v, kRawBoxW, kRawBoxH, &raw_maps) && encode_level_maps(g, v, kBlurBoxW, kBlurBoxH, &blur_maps, true))
-        describe_tma_kernel<<<grid, 256, 0, stream>>>(raw_maps, blur_maps, g, v);   // descriptors first: within the first 4 KB of parameter space
-    else
+    if (tma_enabled() && encode_level_maps(g, v, kRawBoxW, kRawBoxH, &raw_maps) && encode_level_maps(g, v, kBlurBoxW, kBlurBoxH, &blur_maps, true)) {
+        // a few frames (the tracking thread's single-frame call): 16 keypoints per CTA, i.e. 2 per warp, so that the level's
+        // keypoints spread over four times as many SMs; batches keep 64 per CTA
+        const int chunk = v.B <= 4 ? 16 : kDescChunk;
+        describe_tma_kernel<<<dim3(g.nlevels, v.B, (max_keys + chunk - 1) / chunk), 256, 0, stream>>>(raw_maps, blur_maps, g, v, chunk);
+    }
+    else {
         describe_kernel<<<grid, 256, 0, stream>>>(g, v);
+    }
 }
 
 }  // namespace coeb
