@@ -165,6 +165,7 @@ __global__ void __launch_bounds__(kSelThreads, 3) select_kernel(const __grid_con
                 if (cur[i].count > 1) { s_P[s_scanA[i]] = (unsigned short)i; s_slot[i] = (unsigned short)s_scanA[i]; }
                 else s_slot[i] = 0xFFFF;
             }
+            for (int i = tid; i < 4 * nP; i += T) s_cc[i] = 0;   // tentative child counts, zeroed in the same phase
         } else {
             // careful phase: previous round's multi-key children, largest first, later-created first on ties (:688-692)
             nP = nE;
@@ -180,13 +181,12 @@ __global__ void __launch_bounds__(kSelThreads, 3) select_kernel(const __grid_con
                 s_P[rank] = s_E[e];
                 s_slot[s_E[e]] = (unsigned short)rank;
             }
+            for (int i = tid; i < 4 * nP; i += T) s_cc[i] = 0;
         }
         __syncthreads();
         if (nP == 0) break;  // nothing left to split: list size cannot change (:676)
 
         // tentative children of every node in P
-        for (int i = tid; i < 4 * nP; i += T) s_cc[i] = 0;
-        __syncthreads();
         for (int k = tid; k < nkeys; k += T) {
             const int nd = knode[k];
             const int p = s_slot[nd];
@@ -222,16 +222,21 @@ __global__ void __launch_bounds__(kSelThreads, 3) select_kernel(const __grid_con
             __syncthreads();
         }
 
-        // creation sequence: for p in processing order, children q = 0..3 that hold keys
-        for (int i = tid; i < 4 * nProc; i += T) s_scanA[i] = s_cc[i] > 0;
-        __syncthreads();
-        const int totalNew = block_exclusive_scan(s_scanA, 4 * nProc, s_warp);
+        // creation sequence: for p in processing order, children q = 0..3 that hold keys. One packed scan gives both the creation
+        // index of every child (low half) and its rank among the multi-key children (high half): the latter are next round's
+        // expandable list, in creation order.
+        for (int i = tid; i < 4 * nProc; i += T) {
+            const int c = s_cc[i];
+            s_scanA[i] = (c > 0) | ((c > 1) << 16);
+        }
         // surviving old nodes keep their relative order behind the new ones
         for (int i = tid; i < nList; i += T) {
             const int p = s_slot[i];
             s_scanB[i] = !(p != 0xFFFF && p < nProc);
         }
         __syncthreads();
+        const int totals = block_exclusive_scan(s_scanA, 4 * nProc, s_warp);
+        const int totalNew = totals & 0xFFFF, nE2 = totals >> 16;
         const int nKeep = block_exclusive_scan(s_scanB, nList, s_warp);
         const int newSize = totalNew + nKeep;
         if (newSize > LC) {  // cannot happen for max_nodes >= max(N + 3, 4 * nIni); fail loudly
@@ -258,27 +263,12 @@ __global__ void __launch_bounds__(kSelThreads, 3) select_kernel(const __grid_con
                 c.y0 = (q & 2) ? ym : n.y0;
                 c.y1 = (q & 2) ? n.y1 : ym;
                 c.count = cnt;
-                const int pos = totalNew - 1 - s_scanA[i];  // push_front in creation order
+                const int pos = totalNew - 1 - (s_scanA[i] & 0xFFFF);  // push_front in creation order
                 nxt[pos] = c;
                 s_childpos[i] = (unsigned short)pos;
+                if (cnt > 1) s_E2[s_scanA[i] >> 16] = (unsigned short)pos;   // next round's expandable list
             }
         }
-        __syncthreads();
-        // next round's expandable list: multi-key children in creation order
-        // creation index c = s_scanA[i] for children with keys; flag multi-key ones, indexed by creation index
-        int* s_flag = s_scanB;  // size LC >= totalNew
-        for (int i = tid; i < totalNew; i += T) s_flag[i] = 0;
-        __syncthreads();
-        for (int i = tid; i < 4 * nProc; i += T)
-            if (s_cc[i] > 1) s_flag[s_scanA[i]] = 1;
-        __syncthreads();
-        // s_E2[rank among multi-key children] = list position of that child
-        // (position of creation index c is totalNew-1-c)
-        for (int i = tid; i < totalNew; i += T) s_cc[i] = s_flag[i];  // s_cc is free now (4*LC >= totalNew)
-        __syncthreads();
-        const int nE2 = block_exclusive_scan(s_cc, totalNew, s_warp);
-        for (int i = tid; i < totalNew; i += T)
-            if (s_flag[i]) s_E2[s_cc[i]] = (unsigned short)(totalNew - 1 - i);
         __syncthreads();
 
         // move the keys
