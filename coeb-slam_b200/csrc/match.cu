@@ -316,11 +316,16 @@ __global__ void __launch_bounds__(256) m2_collect_kernel(FrameDev F, MapDev M, f
 
 // One CTA iterates to the fixed point. res[i] = keypoint claimed by map point i or -1.
 // claim_min[idx] = smallest i (with Observations()>0) that currently claims idx.
+// The claim table (one int per keypoint of the frame) lives in shared memory when it fits: dynamic shared memory = F.n ints, else 0
+// and the global scratch array is used.
+extern __shared__ int s_claim_dyn[];
 template <bool kLists>
 __global__ void __launch_bounds__(1024) m2_resolve_kernel(FrameDev F, MapDev M, float th, float nnratio, const int* kp_state, CandLists C,
-                                                          int* kp_match /*out, pre-filled with kp_state*/, int* res, int* claim_min, int* out_info) {
+                                                          int* kp_match /*out, pre-filled with kp_state*/, int* res, int* claim_glob, int* out_info,
+                                                          int claim_in_smem) {
     __shared__ int s_changed, s_count;
     const int tid = threadIdx.x, T = blockDim.x;
+    int* const claim_min = claim_in_smem ? s_claim_dyn : claim_glob;
     if (kLists && C.meta[1]) {   // a list overflowed: report and let the host rerun the window-walking variant
         if (tid == 0) { out_info[0] = 0; out_info[1] = 0; out_info[2] = 1; }
         return;
@@ -496,11 +501,12 @@ __global__ void __launch_bounds__(256) m3_collect_kernel(FrameDev Cf, LastDev L,
 
 template <bool kLists>
 __global__ void __launch_bounds__(1024) m3_resolve_kernel(FrameDev C, LastDev L, float th, int check_ori, const int* kp_state, CandLists Cl,
-                                                          int* kp_match, int* res, int* claim_min, int* out_info) {
+                                                          int* kp_match, int* res, int* claim_glob, int* out_info, int claim_in_smem) {
     __shared__ int s_changed, s_count;
     __shared__ int s_hist[COEB_HISTO_LENGTH];
     __shared__ int s_ind[3];
     const int tid = threadIdx.x, T = blockDim.x;
+    int* const claim_min = claim_in_smem ? s_claim_dyn : claim_glob;
     if (kLists && Cl.meta[1]) {
         if (tid == 0) { out_info[0] = 0; out_info[1] = 0; out_info[2] = 1; }
         return;
@@ -971,7 +977,7 @@ struct TailArgs {
     const void* depth; int depth_kind, depth_stride, depth_w, depth_h; float depth_factor;
     // frame block
     float *x, *y, *angle; int* octave; float* uright; uint32_t* desc_out;
-    coeb_keypoint* keys_un; float* depth_out;
+    coeb_keypoint* keys_un; float* depth_out; float* uright_dl;   // download block: mvKeysUn | mvuRight | mvDepth, contiguous
 };
 
 // UndistortKeyPoints + ComputeStereoFromRGBD (src/Frame.cc:579-609, 820-842): one thread per keypoint writes the SoA
@@ -995,7 +1001,7 @@ __global__ void __launch_bounds__(128) frame_tail_kernel(TailArgs a) {
         if (d > 0) { dp = d; ur = __fsub_rn(kp.x, __fdiv_rn(a.bf, d)); }
     }
     a.x[i] = kp.x; a.y[i] = kp.y; a.angle[i] = kp.angle; a.octave[i] = kp.octave; a.uright[i] = ur;
-    a.keys_un[i] = kp; a.depth_out[i] = dp;
+    a.keys_un[i] = kp; a.depth_out[i] = dp; a.uright_dl[i] = ur;
 }
 
 struct LocalMapDev {
@@ -1500,6 +1506,7 @@ int coeb_match_projection(coeb_matcher* m, coeb_frame* F, int n, const uint8_t* 
     if ((st = m->in.reserve(3 * al(N) + 5 * al(N * 4) + al(N * 32) + al(K * 4))) != COEB_OK) return st;
     if ((st = m->out.reserve(al(K * 4) + 256)) != COEB_OK) return st;
     const int cap = 32;   // candidates kept per map point; a fuller window falls back to the window-walking kernel
+    const size_t claim_smem = (size_t)F->n * 4 <= 40 * 1024 ? (size_t)F->n * 4 : 0;   // claim table in shared memory when it fits
     if ((st = grow(&m->d_scratch, &m->scratch_bytes, al(N * 4) + al(K * 4) + lists_bytes(N, cap))) != COEB_OK) return st;
     Packer p(m->in);
     MapDev M{};
@@ -1518,12 +1525,12 @@ int coeb_match_projection(coeb_matcher* m, coeb_frame* F, int n, const uint8_t* 
     CUDA_TRY(cudaMemsetAsync(C.meta, 0, 8, m->stream));
     CUDA_TRY(cudaMemcpyAsync(d_kpm, d_state, K * 4, cudaMemcpyDeviceToDevice, m->stream));
     m2_collect_kernel<<<(n + 7) / 8, 256, 0, m->stream>>>(F->dev, M, th, d_state, C);
-    m2_resolve_kernel<true><<<1, 1024, 0, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info);
+    m2_resolve_kernel<true><<<1, 1024, claim_smem, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0);
     CUDA_TRY(cudaGetLastError());
     if ((st = pull_outputs(m, al(K * 4) + 12)) != COEB_OK) return st;
     if (((const int*)(m->out.h + al(K * 4)))[2]) {   // a candidate list overflowed: exact window-walking variant
         CUDA_TRY(cudaMemcpyAsync(d_kpm, d_state, K * 4, cudaMemcpyDeviceToDevice, m->stream));
-        m2_resolve_kernel<false><<<1, 1024, 0, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info);
+        m2_resolve_kernel<false><<<1, 1024, claim_smem, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0);
         CUDA_TRY(cudaGetLastError());
         if ((st = pull_outputs(m, al(K * 4) + 12)) != COEB_OK) return st;
     }
@@ -1548,6 +1555,7 @@ int coeb_match_lastframe(coeb_matcher* m, coeb_frame* cur, int n, const uint8_t*
     if ((st = m->in.reserve(2 * al(N) + al(N * 12) + 2 * al(N * 4) + al(N * 32) + al(K * 4))) != COEB_OK) return st;
     if ((st = m->out.reserve(al(K * 4) + 256)) != COEB_OK) return st;
     const int cap = 64;
+    const size_t claim_smem = K * 4 <= 40 * 1024 ? K * 4 : 0;   // claim table in shared memory when it fits
     if ((st = grow(&m->d_scratch, &m->scratch_bytes, al(N * 4) + al(K * 4) + lists_bytes(N, cap))) != COEB_OK) return st;
     Packer p(m->in);
     LastDev L{};
@@ -1572,12 +1580,12 @@ int coeb_match_lastframe(coeb_matcher* m, coeb_frame* cur, int n, const uint8_t*
     CUDA_TRY(cudaMemsetAsync(C.meta, 0, 8, m->stream));
     CUDA_TRY(cudaMemcpyAsync(d_kpm, d_state, K * 4, cudaMemcpyDeviceToDevice, m->stream));
     m3_collect_kernel<<<(n + 7) / 8, 256, 0, m->stream>>>(cur->dev, L, th, d_state, C);
-    m3_resolve_kernel<true><<<1, 1024, 0, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info);
+    m3_resolve_kernel<true><<<1, 1024, claim_smem, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0);
     CUDA_TRY(cudaGetLastError());
     if ((st = pull_outputs(m, al(K * 4) + 12)) != COEB_OK) return st;
     if (((const int*)(m->out.h + al(K * 4)))[2]) {
         CUDA_TRY(cudaMemcpyAsync(d_kpm, d_state, K * 4, cudaMemcpyDeviceToDevice, m->stream));
-        m3_resolve_kernel<false><<<1, 1024, 0, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info);
+        m3_resolve_kernel<false><<<1, 1024, claim_smem, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0);
         CUDA_TRY(cudaGetLastError());
         if ((st = pull_outputs(m, al(K * 4) + 12)) != COEB_OK) return st;
     }
@@ -1798,6 +1806,7 @@ int coeb_frame_from_extractor(coeb_matcher* m, coeb_extractor* ex, int frame_ind
     int* d_cell_start = (int*)carve((kGridCells + 1) * 4); int* d_cell_items = (int*)carve(nn * 4); int* d_kp_cell = (int*)carve(nn * 4);
     a.keys_un = (coeb_keypoint*)carve(nn * sizeof(coeb_keypoint));
     float* d_uright_copy = (float*)carve(nn * 4);
+    a.uright_dl = d_uright_copy;
     a.depth_out = (float*)carve(nn * 4);
     const size_t dl_bytes = (size_t)((char*)a.depth_out - (char*)a.keys_un) + nn * 4;
 
@@ -1831,9 +1840,7 @@ int coeb_frame_from_extractor(coeb_matcher* m, coeb_extractor* ex, int frame_ind
     if (e != cudaSuccess) return bail(fail(COEB_ERR_CUDA, "frame tail launch failed: %s", cudaGetErrorString(e)));
     const bool want = n > 0 && (keys_un_out || uright_out || depth_out);
     if (want) {
-        // uright lives in the SoA part; a copy next to keys_un / depth makes the download one block
-        if ((e = cudaMemcpyAsync(d_uright_copy, a.uright, nn * 4, cudaMemcpyDeviceToDevice, s)) != cudaSuccess)
-            return bail(fail(COEB_ERR_CUDA, "%s", cudaGetErrorString(e)));
+        // the kernel wrote uright twice (SoA part and next to keys_un / depth), so the download is one block
         if ((st = m->out.reserve(dl_bytes)) != COEB_OK) return bail(st);
         if ((e = cudaMemcpyAsync(m->out.h, a.keys_un, dl_bytes, cudaMemcpyDeviceToHost, s)) != cudaSuccess)
             return bail(fail(COEB_ERR_CUDA, "%s", cudaGetErrorString(e)));
@@ -1906,6 +1913,7 @@ int coeb_search_local_points(coeb_matcher* m, coeb_frame* F, coeb_local_map* lm,
     const size_t out_bytes = al(K * 4) + 256 + al(N) + (proj_out ? al(N * 20) : 0);
     if ((st = m->out.reserve(out_bytes)) != COEB_OK) return st;
     const int cap = 32;
+    const size_t claim_smem = (size_t)F->n * 4 <= 40 * 1024 ? (size_t)F->n * 4 : 0;
     // scratch: res, claim, list counts, lists | MapPoint fields written by the frustum pass
     const size_t sc_bytes = al(N * 4) + al(K * 4) + lists_bytes(N, cap) + 5 * al(N * 4) + 2 * al(N);
     if ((st = grow(&m->d_scratch, &m->scratch_bytes, sc_bytes)) != COEB_OK) return st;
@@ -1941,12 +1949,12 @@ int coeb_search_local_points(coeb_matcher* m, coeb_frame* F, coeb_local_map* lm,
     CUDA_TRY(cudaMemsetAsync(C.meta, 0, 8, m->stream));
     if (F->n) CUDA_TRY(cudaMemcpyAsync(d_kpm, d_state, (size_t)F->n * 4, cudaMemcpyDeviceToDevice, m->stream));
     frustum_collect_kernel<<<(n + 7) / 8, 256, 0, m->stream>>>(F->dev, lm->dev, P, d_skip, mf, M, th, d_state, C, d_proj);
-    m2_resolve_kernel<true><<<1, 1024, 0, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info);
+    m2_resolve_kernel<true><<<1, 1024, claim_smem, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0);
     CUDA_TRY(cudaGetLastError());
     if ((st = pull_outputs(m, out_bytes)) != COEB_OK) return st;
     if (((const int*)(m->out.h + al(K * 4)))[2]) {   // a candidate list overflowed: exact window-walking variant
         if (F->n) CUDA_TRY(cudaMemcpyAsync(d_kpm, d_state, (size_t)F->n * 4, cudaMemcpyDeviceToDevice, m->stream));
-        m2_resolve_kernel<false><<<1, 1024, 0, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info);
+        m2_resolve_kernel<false><<<1, 1024, claim_smem, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0);
         CUDA_TRY(cudaGetLastError());
         if ((st = pull_outputs(m, al(K * 4) + 12)) != COEB_OK) return st;
     }
@@ -2088,6 +2096,7 @@ int coeb_match_reloc(coeb_matcher* m, coeb_frame* cur, int n, const uint8_t* val
     if ((st = m->in.reserve(2 * al(N) + al(N * 12) + 3 * al(N * 4) + al(N * 32) + al(K * 4))) != COEB_OK) return st;
     if ((st = m->out.reserve(al(K * 4) + 256)) != COEB_OK) return st;
     const int cap = 64;
+    const size_t claim_smem = K * 4 <= 40 * 1024 ? K * 4 : 0;   // claim table in shared memory when it fits
     if ((st = grow(&m->d_scratch, &m->scratch_bytes, al(N * 4) + al(K * 4) + lists_bytes(N, cap))) != COEB_OK) return st;
     Packer p(m->in);
     LastDev L{};
@@ -2117,12 +2126,12 @@ int coeb_match_reloc(coeb_matcher* m, coeb_frame* cur, int n, const uint8_t* val
     CUDA_TRY(cudaMemsetAsync(C.meta, 0, 8, m->stream));
     CUDA_TRY(cudaMemcpyAsync(d_kpm, d_state, K * 4, cudaMemcpyDeviceToDevice, m->stream));
     m3_collect_kernel<<<(n + 7) / 8, 256, 0, m->stream>>>(cur->dev, L, th, d_state, C);
-    m3_resolve_kernel<true><<<1, 1024, 0, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info);
+    m3_resolve_kernel<true><<<1, 1024, claim_smem, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0);
     CUDA_TRY(cudaGetLastError());
     if ((st = pull_outputs(m, al(K * 4) + 12)) != COEB_OK) return st;
     if (((const int*)(m->out.h + al(K * 4)))[2]) {
         CUDA_TRY(cudaMemcpyAsync(d_kpm, d_state, K * 4, cudaMemcpyDeviceToDevice, m->stream));
-        m3_resolve_kernel<false><<<1, 1024, 0, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info);
+        m3_resolve_kernel<false><<<1, 1024, claim_smem, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0);
         CUDA_TRY(cudaGetLastError());
         if ((st = pull_outputs(m, al(K * 4) + 12)) != COEB_OK) return st;
     }
