@@ -256,3 +256,33 @@ def test_plain_load_twins_of_the_tma_kernels(gpu):
     env = dict(os.environ, COEB_TMA="0")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0 and "plain-load path ok" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
+
+
+def test_create_destroy_cycles_do_not_leak_device_memory(gpu):
+    """COEB's frame-loss logic re-creates the extractor (`new ORBextractor(nFeatures + 500, ...)`, src/Tracking.cc:434-465) and the
+    drop-in matchers create and destroy device frames per call: handles must give their device memory back."""
+    import torch
+    gray = synth.make_frame(5)
+    kps0 = None
+
+    def cycle():
+        nonlocal kps0
+        ex = gpu.Extractor(1500)
+        k, d = ex.extract(gray)
+        if kps0 is None:
+            kps0 = k.tobytes()
+        assert k.tobytes() == kps0
+        m = gpu.Matcher()
+        f = m.frame(k, d, gpu.Camera(535.4, 539.2, 320.1, 247.6, 40.0, 0.0747, 0.0, 640.0, 0.0, 480.0), ex.tables()["scale"])
+        f.close()
+        m.close()
+        ex.close()
+    for _ in range(3):
+        cycle()
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    for _ in range(40):
+        cycle()
+    torch.cuda.synchronize()
+    free1 = torch.cuda.mem_get_info()[0]
+    assert free0 - free1 < 8 << 20, "device memory shrank by %.1f MB over 40 create/destroy cycles" % ((free0 - free1) / 2 ** 20)
