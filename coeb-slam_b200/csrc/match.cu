@@ -1067,6 +1067,74 @@ __global__ void __launch_bounds__(256) frustum_collect_kernel(FrameDev F, LocalM
     m2_collect_warp(F, M, th, kp_state, C, i);
 }
 
+// ---- search half of ORBmatcher::Fuse(KeyFrame*, vpMapPoints, th) (src/ORBmatcher.cc:826-961) ---------------------------------
+// One warp per map point: projection and the visibility tests (every lane, the arithmetic is a few dozen operations), then the
+// window walk with the level and chi-square filters, Hamming distances lane-parallel and an argmin over (distance, traversal
+// position). No query reads what another one writes: the reference's Replace / AddObservation side effects are the caller's.
+__global__ void __launch_bounds__(256) fuse_search_kernel(FrameDev F, LocalMapDev LM, PoseArgs P, const uint8_t* __restrict__ valid, float th, int* best_out) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= LM.n) return;
+    const int lane = threadIdx.x & 31;
+    int result = -1;
+    if (valid[i]) {
+        const float X0 = LM.xyz[3 * i], Y0 = LM.xyz[3 * i + 1], Z0 = LM.xyz[3 * i + 2];
+        const float* T = P.T;
+        const float X = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[0], X0), __fmul_rn(T[1], Y0)), __fmul_rn(T[2], Z0)), T[3]);
+        const float Y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[4], X0), __fmul_rn(T[5], Y0)), __fmul_rn(T[6], Z0)), T[7]);
+        const float Z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[8], X0), __fmul_rn(T[9], Y0)), __fmul_rn(T[10], Z0)), T[11]);
+        bool ok = !(Z < 0.0f);
+        const float invz = __fdiv_rn(1.0f, Z);
+        const float u = __fadd_rn(__fmul_rn(F.fx, __fmul_rn(X, invz)), F.cx), v = __fadd_rn(__fmul_rn(F.fy, __fmul_rn(Y, invz)), F.cy);
+        ok = ok && (u >= F.min_x && u < F.max_x && v >= F.min_y && v < F.max_y);   // KeyFrame::IsInImage
+        const float ur = __fsub_rn(u, __fmul_rn(F.bf, invz));
+        const float ox = __fsub_rn(X0, P.Ow[0]), oy = __fsub_rn(Y0, P.Ow[1]), oz = __fsub_rn(Z0, P.Ow[2]);
+        const double s2 = __dadd_rn(__dadd_rn(__dmul_rn((double)ox, (double)ox), __dmul_rn((double)oy, (double)oy)), __dmul_rn((double)oz, (double)oz));
+        const float dist3D = (float)sqrt(s2);
+        ok = ok && !(dist3D < __fmul_rn(0.8f, LM.min_dist[i]) || dist3D > __fmul_rn(1.2f, LM.max_dist[i]));
+        const double dot = __dadd_rn(__dadd_rn(__dmul_rn((double)ox, (double)LM.normal[3 * i]), __dmul_rn((double)oy, (double)LM.normal[3 * i + 1])),
+                                     __dmul_rn((double)oz, (double)LM.normal[3 * i + 2]));
+        ok = ok && !(dot < __dmul_rn(0.5, (double)dist3D));
+        if (ok) {
+            const float ratio = __fdiv_rn(LM.max_dist[i], dist3D);
+            int lvl = 0;
+            if (ratio >= 1.17549435e-38f && ratio <= 3.402823466e+38f) lvl = (int)ceilf(__fdiv_rn(glibc_logf(ratio), P.nlevels > 1 ? glibc_logf(F.scale[1]) : 1.f));
+            lvl = lvl < 0 ? 0 : (lvl >= P.nlevels ? P.nlevels - 1 : lvl);
+            const float radius = __fmul_rn(th, F.scale[lvl]);
+            const uint32_t* d = LM.desc + 8 * (size_t)i;
+            int key = kInf, myidx = -1;   // lane-local best: (distance << 16 | traversal position)
+            warp_for_each_in_area(
+                F, u, v, radius, -1, -1,
+                [&](int idx) {
+                    const int kl = F.octave[idx];
+                    if (kl < lvl - 1 || kl > lvl) return false;
+                    const float sc = F.scale[kl];
+                    const float inv = __fdiv_rn(1.0f, __fmul_rn(sc, sc));
+                    const float ex = __fsub_rn(u, F.x[idx]), ey = __fsub_rn(v, F.y[idx]);
+                    const float kr = F.uright ? F.uright[idx] : -1.f;
+                    if (kr >= 0) {
+                        const float er = __fsub_rn(ur, kr);
+                        const float e2 = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(er, er));
+                        return !((double)__fmul_rn(e2, inv) > 7.8);
+                    }
+                    const float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+                    return !((double)__fmul_rn(e2, inv) > 5.99);
+                },
+                [&](int pos, int idx) {
+                    const int dist = hamming256(d, F.desc + 8 * (size_t)idx);
+                    const int k = (dist << 16) | min(pos, 0xFFFF);
+                    if (dist < 256 && k < key) { key = k; myidx = idx; }
+                });
+            const int best = __reduce_min_sync(0xffffffffu, key);
+            const unsigned who = __ballot_sync(0xffffffffu, key == best && key != kInf);
+            if (who) {
+                const int idx = __shfl_sync(0xffffffffu, myidx, __ffs(who) - 1);
+                if ((best >> 16) <= COEB_TH_LOW) result = idx;
+            }
+        }
+    }
+    if (lane == 0) best_out[i] = result;
+}
+
 // ---- SearchByBoW (src/ORBmatcher.cc:158-288 and :522-655): matching restricted to features of the same vocabulary node --
 // The node lists (DBoW2::FeatureVector) arrive as CSR; the host intersects the two sorted node-id arrays and hands over
 // one {start1, end1, start2, end2} record per common node. A feature belongs to exactly one node, so the loop-carried
@@ -2140,6 +2208,34 @@ int coeb_match_reloc(coeb_matcher* m, coeb_frame* cur, int n, const uint8_t* val
     for (size_t k = 0; k < K; k++)
         if (kp_match[k] == -1) kp_match[k] = h[k];
     if (nmatches_out) *nmatches_out = ((const int*)(m->out.h + al(K * 4)))[0];
+    return COEB_OK;
+}
+
+// ---- search half of Fuse ------------------------------------------------------------------------------------------------------
+int coeb_fuse_search(coeb_matcher* m, coeb_frame* kf, coeb_local_map* lm, const uint8_t* valid, const float* Tcw, const float* Ow, float th,
+                     int* best_idx, int* nfused_out) {
+    if (!m || !kf || !lm || !Tcw || !Ow || !best_idx) return fail(COEB_ERR_INVALID_ARG, "bad argument");
+    if (nfused_out) *nfused_out = 0;
+    const int n = lm->n;
+    if (n == 0) return COEB_OK;
+    if (!valid) return fail(COEB_ERR_INVALID_ARG, "null valid");
+    if (kf->n == 0) { for (int i = 0; i < n; i++) best_idx[i] = -1; return COEB_OK; }
+    CUDA_TRY(cudaSetDevice(m->device));
+    const size_t N = n;
+    int st;
+    if ((st = m->in.reserve(al(N))) != COEB_OK || (st = m->out.reserve(al(N * 4))) != COEB_OK) return st;
+    Packer p(m->in);
+    const uint8_t* d_valid = p.place(valid, N);
+    if ((st = push_inputs(m, p)) != COEB_OK) return st;
+    PoseArgs P{};
+    for (int i = 0; i < 12; i++) P.T[i] = Tcw[i];
+    for (int i = 0; i < 3; i++) P.Ow[i] = Ow[i];
+    P.nlevels = kf->nlevels;
+    fuse_search_kernel<<<(n + 7) / 8, 256, 0, m->stream>>>(kf->dev, lm->dev, P, d_valid, th, (int*)m->out.d);
+    CUDA_TRY(cudaGetLastError());
+    if ((st = pull_outputs(m, N * 4)) != COEB_OK) return st;
+    std::memcpy(best_idx, m->out.h, N * 4);
+    if (nfused_out) { int c = 0; for (int i = 0; i < n; i++) c += best_idx[i] >= 0; *nfused_out = c; }
     return COEB_OK;
 }
 

@@ -10,8 +10,9 @@
  * its vocabulary) and are flattened to CSR here. Free functions at the end cover the steps either side of the path:
  * FrameTailFromExtractor (UndistortKeyPoints + ComputeStereoFromRGBD + AssignFeaturesToGrid on the device) and
  * SearchLocalPoints (isInFrustum + SearchByProjection against a device-resident local map).
- * The relocalisation overload SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist) (:1473-1600) is covered too.
- * Fuse / SearchBySim3 / the loop-closing SearchByProjection(KeyFrame*, Scw, ...) stay the reference's.
+ * The relocalisation overload SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist) (:1473-1600) and
+ * Fuse(KeyFrame*, vpMapPoints, th) (:826-961) are covered too. The Sim3 functions of loop closing (SearchBySim3, Fuse with Scw,
+ * SearchByProjection(KeyFrame*, Scw, ...)) stay the reference's.
  *
  * The member functions are templates over the reference's Frame / MapPoint types, so this header has no
  * dependency on them: it only touches the members the reference functions touch (cited inline). The
@@ -110,6 +111,8 @@ template <class A> inline void mat33(const A& M, float out[9]) { for (int i = 0;
 }  // namespace coeb_adapt
 
 namespace ORB_SLAM2 {
+
+template <class MapPointT> inline coeb_local_map* MakeLocalMap(const std::vector<MapPointT*>& vpLocalMapPoints);
 
 class ORBmatcher {
 public:
@@ -308,6 +311,51 @@ public:
         for (int i = 0; i < n1; i++)
             if (m12[i] >= 0) vMatchedPairs.push_back(std::make_pair((size_t)i, (size_t)m12[i]));
         return nmatches;
+    }
+
+    /* Fuse(KeyFrame* pKF, const vector<MapPoint*> &vpMapPoints, const float th=3.0) -- :826-961 (LocalMapping::SearchInNeighbors).
+     * The search runs on the device for all map points at once; the MapPoint side effects are then applied in list order exactly
+     * as the reference's loop does (:938-957): nothing they change is read by the search. */
+    template <class KeyFrameT, class MapPointT>
+    int Fuse(KeyFrameT* pKF, const std::vector<MapPointT*>& vpMapPoints, const float th = 3.0) {
+        const int n = (int)vpMapPoints.size();
+        std::vector<uint8_t> valid(n);
+        std::vector<MapPointT*> pts(n);
+        MapPointT* any = nullptr;
+        for (int i = 0; i < n; i++) {
+            MapPointT* p = vpMapPoints[i];
+            valid[i] = p && !p->isBad() && !p->IsInKeyFrame(pKF);
+            if (valid[i] && !any) any = p;
+        }
+        if (!any) return 0;
+        for (int i = 0; i < n; i++) pts[i] = valid[i] ? vpMapPoints[i] : any;   // invalid slots only need well-formed fields
+        coeb_local_map* lm = MakeLocalMap(pts);
+        float T[12], R[9], t[3], Ow[3];
+        coeb_adapt::mat33(pKF->GetRotation(), R);
+        coeb_adapt::xyz3(pKF->GetTranslation(), t);
+        coeb_adapt::xyz3(pKF->GetCameraCenter(), Ow);
+        for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) T[4 * r + c] = R[3 * r + c]; T[4 * r + 3] = t[r]; }
+        coeb_adapt::DeviceFrame<KeyFrameT> dK(*pKF);
+        std::vector<int> best(n, -1);
+        int nFused = 0;
+        const int st = coeb_fuse_search(coeb_adapt::matcher(), dK.f, lm, valid.data(), T, Ow, th, best.data(), &nFused);
+        coeb_local_map_destroy(lm);
+        coeb_adapt::check(st);
+        for (int i = 0; i < n; i++) {
+            if (best[i] < 0) continue;
+            MapPointT* pMP = vpMapPoints[i];
+            MapPointT* pMPinKF = pKF->GetMapPoint(best[i]);
+            if (pMPinKF) {
+                if (!pMPinKF->isBad()) {
+                    if (pMPinKF->Observations() > pMP->Observations()) pMP->Replace(pMPinKF);
+                    else pMPinKF->Replace(pMP);
+                }
+            } else {
+                pMP->AddObservation(pKF, best[i]);
+                pKF->AddMapPoint(pMP, best[i]);
+            }
+        }
+        return nFused;
     }
 
     static const int TH_LOW = COEB_TH_LOW;

@@ -238,6 +238,16 @@ int coeb_search_local_points(coeb_matcher* m, coeb_frame* F, coeb_local_map* lm,
                              const uint8_t* has_obs, const float* Tcw, const float* Ow, float viewing_cos_limit, float th,
                              float nnratio, int* kp_match, uint8_t* in_view_out, float* proj_out, int* nmatches_out);
 
+/* Search half of ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, th) (src/ORBmatcher.cc:826-961;
+ * LocalMapping::SearchInNeighbors): for every map point of `lm` the keypoint of the keyframe `kf` it would be fused into
+ * (projection, IsInImage, distance range, 60-degree viewing cone, PredictScale, window of radius th * scale, level and
+ * chi-square filters (5.99 mono / 7.8 stereo), best Hamming distance <= TH_LOW), or -1. The MapPoint side effects of the
+ * reference loop (Replace / AddObservation / AddMapPoint, :938-957) depend only on these indices and stay with the caller,
+ * applied in list order.  valid: n bytes, pMP && !isBad() && !IsInKeyFrame(pKF).  Tcw: [GetRotation() | GetTranslation()],
+ * Ow: GetCameraCenter().  best_idx: n ints out; *nfused_out = nFused. */
+int coeb_fuse_search(coeb_matcher* m, coeb_frame* kf, coeb_local_map* lm, const uint8_t* valid, const float* Tcw, const float* Ow,
+                     float th, int* best_idx, int* nfused_out);
+
 /* ORBmatcher::SearchByProjection(Frame& cur, const Frame& last, th, bMono) (src/ORBmatcher.cc:1329-1471).
  * Per last-frame keypoint i: valid (mvpMapPoints[i] && !mvbOutlier[i]), has_obs, xyz (GetWorldPos),
  * octave (LastFrame.mvKeys[i].octave), angle (LastFrame.mvKeysUn[i].angle), desc (pMP->GetDescriptor()).

@@ -302,6 +302,13 @@ int orc_match_reloc(orc_frame* cur, int n, const uint8_t* valid, const float* xy
     return search_by_projection_reloc(cur->v, n, valid, xyz, min_dist, max_dist, angle, desc, Tcw, Ow, th, orb_dist, check_ori != 0, kp_match);
 }
 
+int orc_fuse_search(orc_frame* f, int n, const float* xyz, const float* normal, const float* min_dist, const float* max_dist,
+                    const uint8_t* desc, const uint8_t* valid, const float* Tcw, const float* Ow, float th, int* best_idx) {
+    LocalMapSoA M;
+    M.n = n; M.xyz = xyz; M.normal = normal; M.min_dist = min_dist; M.max_dist = max_dist; M.desc = desc;
+    return fuse_search(f->v, M, valid, Tcw, Ow, th, best_idx);
+}
+
 // Number of floats in [lo, hi) (bit patterns, stepped by `step`) whose restated logf differs from the C library's.
 long orc_logf_mismatches(uint32_t lo, uint32_t hi, uint32_t step) {
     long bad = 0;

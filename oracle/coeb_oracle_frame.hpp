@@ -259,4 +259,70 @@ static inline int search_by_projection_reloc(const FrameView& C, int n, const ui
     return nmatches;
 }
 
+// The search half of ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, th) (src/ORBmatcher.cc:826-961;
+// LocalMapping::SearchInNeighbors): for every map point the keypoint of the keyframe it would be fused into (bestIdx with
+// bestDist <= TH_LOW), or -1. The pointer-graph half (Replace / AddObservation / AddMapPoint, :938-957) stays with the caller and is
+// applied in list order from these indices: the search itself reads nothing those calls change.
+// valid[i] = pMP && !pMP->isBad() && !pMP->IsInKeyFrame(pKF). F is the keyframe (mvKeysUn, mvuRight, bounds, scale factors).
+static inline int fuse_search(const FrameView& F, const LocalMapSoA& M, const uint8_t* valid, const float* Tcw, const float* Ow, float th,
+                              int* best_idx) {
+    int nFused = 0;
+    const float logScale = F.nlevels > 1 ? glibc_logf(F.scale[1]) : 1.f;
+    std::vector<int> vIndices;
+    for (int i = 0; i < M.n; i++) {
+        best_idx[i] = -1;
+        if (!valid[i]) continue;
+        const float* P = M.xyz + 3 * (size_t)i;
+        const float X = Tcw[0] * P[0] + Tcw[1] * P[1] + Tcw[2] * P[2] + Tcw[3];
+        const float Y = Tcw[4] * P[0] + Tcw[5] * P[1] + Tcw[6] * P[2] + Tcw[7];
+        const float Z = Tcw[8] * P[0] + Tcw[9] * P[1] + Tcw[10] * P[2] + Tcw[11];
+        if (Z < 0.0f) continue;
+        const float invz = 1 / Z;
+        const float x = X * invz, y = Y * invz;
+        const float u = F.cam.fx * x + F.cam.cx, v = F.cam.fy * y + F.cam.cy;
+        if (!(u >= F.cam.min_x && u < F.cam.max_x && v >= F.cam.min_y && v < F.cam.max_y)) continue;   // KeyFrame::IsInImage
+        const float ur = u - F.cam.bf * invz;
+        const float maxDistance = 1.2f * M.max_dist[i], minDistance = 0.8f * M.min_dist[i];
+        const float PO[3] = {P[0] - Ow[0], P[1] - Ow[1], P[2] - Ow[2]};
+        double s = 0;
+        for (int k = 0; k < 3; k++) s += (double)PO[k] * (double)PO[k];
+        const float dist3D = (float)std::sqrt(s);
+        if (dist3D < minDistance || dist3D > maxDistance) continue;
+        const float* Pn = M.normal + 3 * (size_t)i;
+        double dot = 0;
+        for (int k = 0; k < 3; k++) dot += (double)PO[k] * (double)Pn[k];
+        if (dot < 0.5 * (double)dist3D) continue;   // viewing angle below 60 degrees (:884)
+        const float ratio = M.max_dist[i] / dist3D;
+        int nPredictedLevel = 0;
+        if (ratio >= FLT_MIN && ratio <= FLT_MAX) nPredictedLevel = (int)std::ceil(glibc_logf(ratio) / logScale);
+        if (nPredictedLevel < 0) nPredictedLevel = 0;
+        else if (nPredictedLevel >= F.nlevels) nPredictedLevel = F.nlevels - 1;
+        const float radius = th * F.scale[nPredictedLevel];
+        F.features_in_area(u, v, radius, -1, -1, vIndices);
+        if (vIndices.empty()) continue;
+        const uint8_t* dMP = M.desc + (size_t)i * 32;
+        int bestDist = 256, bestIdx = -1;
+        for (int idx : vIndices) {
+            const coeb_keypoint& kp = F.kps[idx];
+            const int kpLevel = kp.octave;
+            if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
+            const float sc = F.scale[kpLevel];
+            const float invSigma2 = 1.0f / (sc * sc);   // mvInvLevelSigma2 (src/ORBextractor.cc:427-428, 434-435)
+            const float ex = u - kp.x, ey = v - kp.y;
+            if (F.uright && F.uright[idx] >= 0) {
+                const float er = ur - F.uright[idx];
+                const float e2 = ex * ex + ey * ey + er * er;
+                if ((double)(e2 * invSigma2) > 7.8) continue;
+            } else {
+                const float e2 = ex * ex + ey * ey;
+                if ((double)(e2 * invSigma2) > 5.99) continue;
+            }
+            const int dist = hamming256(dMP, F.desc + (size_t)idx * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+        }
+        if (bestDist <= COEB_TH_LOW) { best_idx[i] = bestIdx; nFused++; }
+    }
+    return nFused;
+}
+
 }  // namespace orc

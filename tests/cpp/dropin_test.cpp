@@ -43,6 +43,8 @@ void orc_stereo_from_rgbd(const coeb_keypoint* keys, const coeb_keypoint* keys_u
 int orc_match_reloc(orc_frame* cur, int n, const uint8_t* valid, const float* xyz, const float* min_dist, const float* max_dist,
                     const float* angle, const uint8_t* desc, const float* Tcw, const float* Ow, float th, int orb_dist, int check_ori,
                     int* kp_match);
+int orc_fuse_search(orc_frame* f, int n, const float* xyz, const float* normal, const float* min_dist, const float* max_dist,
+                    const uint8_t* desc, const uint8_t* valid, const float* Tcw, const float* Ow, float th, int* best_idx);
 int orc_search_local_points(orc_frame* f, int n, const float* xyz, const float* normal, const float* min_dist, const float* max_dist,
                             const uint8_t* desc, const uint8_t* skip, const uint8_t* has_obs, const float* Tcw, const float* Ow,
                             float cos_limit, float th, float nnratio, int* kp_match, uint8_t* in_view, float* proj);
@@ -92,6 +94,11 @@ struct MapPoint {
     float GetMinDistance() { return mfMinDistance; }
     float GetMaxDistance() { return mfMaxDistance; }
     void IncreaseVisible() { nVisible++; }
+    // Fuse side effects (src/MapPoint.cc): recorded, not simulated
+    const void* inKF = nullptr; int obsIdx = -1; MapPoint* replacedBy = nullptr;
+    bool IsInKeyFrame(const void* kf) { return inKF == kf; }
+    void AddObservation(const void* kf, int idx) { inKF = kf; obsIdx = idx; nObs++; }
+    void Replace(MapPoint* other) { replacedBy = other; bad = true; }
 };
 
 struct Frame {
@@ -112,6 +119,7 @@ struct Frame {
     float Rcw[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, tcw[3] = {0, 0, 0};
     std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
     MapPoint* GetMapPoint(int i) { return mvpMapPoints[i]; }
+    void AddMapPoint(MapPoint* p, int i) { mvpMapPoints[i] = p; }
     const float* GetCameraCenter() { return mOw; }
     const float* GetRotation() { return Rcw; }
     const float* GetTranslation() { return tcw; }
@@ -493,6 +501,38 @@ int main() {
             int bad_ptr = 0;
             for (int k = 0; k < T.N; k++) bad_ptr += T.mvpMapPoints[k] != (rstate[k] >= 0 ? KFr.mvpMapPoints[rstate[k]] : before[k]);
             EXPECT(bad_ptr == 0, "SearchByProjection(reloc): %d mvpMapPoints entries differ", bad_ptr);
+        }
+        // ---- Fuse(KeyFrame*, vpMapPoints, th) (src/LocalMapping.cc:484-515): search on the device, side effects on the host ----
+        {
+            for (int k = 0; k < T.N; k++) T.mvpMapPoints[k] = (k % 4 == 0) ? &lmp[NL - 1 - (k % 60)] : nullptr;
+            for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) T.Rcw[3 * r + c] = T.mTcw[4 * r + c]; T.tcw[r] = T.mTcw[4 * r + 3]; }
+            std::vector<uint8_t> fvalid(NL);
+            for (int i = 0; i < NL; i++) { lmp[i].inKF = (i % 17 == 0) ? (const void*)&T : nullptr; lmp[i].replacedBy = nullptr; fvalid[i] = !lmp[i].bad && lmp[i].inKF != (const void*)&T; }
+            std::vector<int> fbest(NL);
+            const int fref = orc_fuse_search(ot, NL, xyz.data(), nrm.data(), dmin.data(), dmax.data(), ldesc.data(), fvalid.data(), T.mTcw, T.mOw, 3.f, fbest.data());
+            std::vector<MapPoint*> beforeKF = T.mvpMapPoints;
+            std::vector<MapPoint> snapshot = lmp;
+            ORB_SLAM2::ORBmatcher fm;
+            const int fgot = fm.Fuse(&T, vl, 3.f);
+            EXPECT(fgot == fref && fref > 100, "Fuse: %d vs oracle %d", fgot, fref);
+            std::vector<MapPoint> after = lmp;
+            std::vector<MapPoint*> afterKF = T.mvpMapPoints;
+            // the reference's loop (:938-957) replayed from the oracle's indices on the restored state
+            lmp = snapshot;
+            T.mvpMapPoints = beforeKF;
+            for (int i = 0; i < NL; i++) {
+                if (fbest[i] < 0) continue;
+                MapPoint* pMP = vl[i];
+                MapPoint* in = T.GetMapPoint(fbest[i]);
+                if (in) {
+                    if (!in->isBad()) { if (in->Observations() > pMP->Observations()) pMP->Replace(in); else in->Replace(pMP); }
+                } else { pMP->AddObservation(&T, fbest[i]); T.AddMapPoint(pMP, fbest[i]); }
+            }
+            int wrong = 0;
+            for (int i = 0; i < NL; i++)
+                wrong += after[i].bad != lmp[i].bad || after[i].replacedBy != lmp[i].replacedBy || after[i].obsIdx != lmp[i].obsIdx || after[i].nObs != lmp[i].nObs;
+            for (int k = 0; k < T.N; k++) wrong += afterKF[k] != T.mvpMapPoints[k];
+            EXPECT(wrong == 0, "Fuse: %d map points with unexpected side effects", wrong);
         }
         coeb_local_map_destroy(lm);
         T.mpDeviceFrame = nullptr;

@@ -161,3 +161,23 @@ def test_relocalisation_search_by_projection_matches_oracle(gpu, th, orb_dist, o
     assert np.array_equal(kg[state != -1], state[state != -1]), "occupied entries must come back untouched"
     got = kg[kg >= 0]
     assert len(np.unique(got)) == len(got), "a keyframe map point was assigned twice"
+
+
+@pytest.mark.parametrize("th,seed,stereo", [(3.0, 1, True), (3.0, 2, False), (1.0, 3, True), (25.0, 4, True)])
+def test_fuse_search_matches_oracle(gpu, th, seed, stereo):
+    """Search half of ORBmatcher::Fuse(KeyFrame*, vpMapPoints, th): the keypoint every map point would be fused into."""
+    g, c, kps, desc = _extract_both(gpu, 300 + seed, dynamic=False)
+    scale = c.tables()["scale"]
+    rng = np.random.default_rng(seed)
+    uright = np.where(rng.random(len(kps)) < 0.5, kps["x"] - np.float32(40.0) / rng.uniform(0.5, 5.0, len(kps)).astype(np.float32),
+                      np.float32(-1)).astype(np.float32) if stereo else None
+    m = gpu.Matcher()
+    fg = m.frame(kps, desc, gpu.Camera(*TUM3_CAM), scale, uright)
+    fc = orc.Frame(kps, desc, orc.Camera(*TUM3_CAM), scale, uright)
+    Tcw, Ow = synth.make_pose(seed)
+    lm, skip, _ = synth.make_local_map(kps, desc, scale, Tcw, seed=seed, n_map=3000, n_true=min(900, len(kps)))
+    valid = (1 - skip).astype(np.uint8)
+    ng, bg = m.fuse_search(fg, m.local_map(lm), valid, Tcw, Ow, th)
+    nc, bc = orc.fuse_search(fc, lm, valid, Tcw, Ow, th)
+    assert ng == nc and np.array_equal(bg, bc)
+    assert nc > 50 and (bc[valid == 0] == -1).all()
