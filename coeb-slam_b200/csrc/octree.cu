@@ -22,7 +22,13 @@
 
 namespace coeb {
 
-constexpr int kSelThreads = 384;
+#ifndef COEB_SEL_THREADS
+#define COEB_SEL_THREADS 384
+#endif
+#ifndef COEB_SEL_MINB
+#define COEB_SEL_MINB 3
+#endif
+constexpr int kSelThreads = COEB_SEL_THREADS;
 constexpr int kKeyCache = 4096;   // candidates per (level, frame) kept in shared memory (4 + 2 bytes each)
 constexpr unsigned long long kOrdMask = 0xFFFFFFFFFFFFull;  // 48-bit candidate-order field
 
@@ -43,7 +49,7 @@ __device__ __forceinline__ unsigned long long order_key(const LevelGeom& L, int 
 
 extern __shared__ unsigned char s_dyn_raw[];
 
-__global__ void __launch_bounds__(kSelThreads, 3) select_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v) {
+__global__ void __launch_bounds__(kSelThreads, COEB_SEL_MINB) select_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v) {
     const int level = blockIdx.x, frame = blockIdx.y;
     const LevelGeom& L = g.lv[level];
     const DynState& dyn = v.dyn[frame];
