@@ -1071,7 +1071,8 @@ __global__ void __launch_bounds__(256) frustum_collect_kernel(FrameDev F, LocalM
 // One warp per map point: projection and the visibility tests (every lane, the arithmetic is a few dozen operations), then the
 // window walk with the level and chi-square filters, Hamming distances lane-parallel and an argmin over (distance, traversal
 // position). No query reads what another one writes: the reference's Replace / AddObservation side effects are the caller's.
-__global__ void __launch_bounds__(256) fuse_search_kernel(FrameDev F, LocalMapDev LM, PoseArgs P, const uint8_t* __restrict__ valid, float th, int* best_out) {
+__global__ void __launch_bounds__(256) fuse_search_kernel(FrameDev F, LocalMapDev LM, PoseArgs P, const uint8_t* __restrict__ valid, float th, int chi2_tests,
+                                                          int* best_out) {
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (i >= LM.n) return;
     const int lane = threadIdx.x & 31;
@@ -1107,6 +1108,7 @@ __global__ void __launch_bounds__(256) fuse_search_kernel(FrameDev F, LocalMapDe
                 [&](int idx) {
                     const int kl = F.octave[idx];
                     if (kl < lvl - 1 || kl > lvl) return false;
+                    if (!chi2_tests) return true;   // Fuse(pKF, Scw, ...) of loop closing has no reprojection-error test
                     const float sc = F.scale[kl];
                     const float inv = __fdiv_rn(1.0f, __fmul_rn(sc, sc));
                     const float ex = __fsub_rn(u, F.x[idx]), ey = __fsub_rn(v, F.y[idx]);
@@ -2213,7 +2215,7 @@ int coeb_match_reloc(coeb_matcher* m, coeb_frame* cur, int n, const uint8_t* val
 
 // ---- search half of Fuse ------------------------------------------------------------------------------------------------------
 int coeb_fuse_search(coeb_matcher* m, coeb_frame* kf, coeb_local_map* lm, const uint8_t* valid, const float* Tcw, const float* Ow, float th,
-                     int* best_idx, int* nfused_out) {
+                     int chi2_tests, int* best_idx, int* nfused_out) {
     if (!m || !kf || !lm || !Tcw || !Ow || !best_idx) return fail(COEB_ERR_INVALID_ARG, "bad argument");
     if (nfused_out) *nfused_out = 0;
     const int n = lm->n;
@@ -2231,7 +2233,7 @@ int coeb_fuse_search(coeb_matcher* m, coeb_frame* kf, coeb_local_map* lm, const 
     for (int i = 0; i < 12; i++) P.T[i] = Tcw[i];
     for (int i = 0; i < 3; i++) P.Ow[i] = Ow[i];
     P.nlevels = kf->nlevels;
-    fuse_search_kernel<<<(n + 7) / 8, 256, 0, m->stream>>>(kf->dev, lm->dev, P, d_valid, th, (int*)m->out.d);
+    fuse_search_kernel<<<(n + 7) / 8, 256, 0, m->stream>>>(kf->dev, lm->dev, P, d_valid, th, chi2_tests, (int*)m->out.d);
     CUDA_TRY(cudaGetLastError());
     if ((st = pull_outputs(m, N * 4)) != COEB_OK) return st;
     std::memcpy(best_idx, m->out.h, N * 4);

@@ -332,13 +332,13 @@ class Matcher:
                                       _p(kp_match), C.byref(n)))
         return n.value, kp_match
 
-    def fuse_search(self, frame, local_map, valid, Tcw, Ow, th):
+    def fuse_search(self, frame, local_map, valid, Tcw, Ow, th, chi2_tests=True):
         """Search half of ORBmatcher::Fuse(KeyFrame*, vpMapPoints, th). Returns (nFused, best_idx[n])."""
         valid = _u8(valid)
         tc, ow = _f32(Tcw).reshape(12), _f32(Ow).reshape(3)
         best = np.empty(local_map.n, np.int32)
         n = C.c_int()
-        _check(lib().coeb_fuse_search(self.h, frame.h, local_map.h, _p(valid), _p(tc), _p(ow), C.c_float(th), _p(best), C.byref(n)))
+        _check(lib().coeb_fuse_search(self.h, frame.h, local_map.h, _p(valid), _p(tc), _p(ow), C.c_float(th), int(chi2_tests), _p(best), C.byref(n)))
         return n.value, best
 
     def match_projection(self, frame, mp, th, nnratio, kp_match):

@@ -338,7 +338,7 @@ public:
         coeb_adapt::DeviceFrame<KeyFrameT> dK(*pKF);
         std::vector<int> best(n, -1);
         int nFused = 0;
-        const int st = coeb_fuse_search(coeb_adapt::matcher(), dK.f, lm, valid.data(), T, Ow, th, best.data(), &nFused);
+        const int st = coeb_fuse_search(coeb_adapt::matcher(), dK.f, lm, valid.data(), T, Ow, th, /*chi2_tests*/ 1, best.data(), &nFused);
         coeb_local_map_destroy(lm);
         coeb_adapt::check(st);
         for (int i = 0; i < n; i++) {

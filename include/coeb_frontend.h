@@ -244,9 +244,12 @@ int coeb_search_local_points(coeb_matcher* m, coeb_frame* F, coeb_local_map* lm,
  * chi-square filters (5.99 mono / 7.8 stereo), best Hamming distance <= TH_LOW), or -1. The MapPoint side effects of the
  * reference loop (Replace / AddObservation / AddMapPoint, :938-957) depend only on these indices and stay with the caller,
  * applied in list order.  valid: n bytes, pMP && !isBad() && !IsInKeyFrame(pKF).  Tcw: [GetRotation() | GetTranslation()],
- * Ow: GetCameraCenter().  best_idx: n ints out; *nfused_out = nFused. */
+ * Ow: GetCameraCenter().  best_idx: n ints out; *nfused_out = nFused.
+ * chi2_tests = 0 gives the search of the loop-closing overload Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) (:963-1093): the same
+ * projection and filters without the reprojection-error test, with [Rcw | tcw] and Ow from the decomposed Sim3 (:973-977, the
+ * caller's cv::Mat expressions) and valid = !isBad() && !spAlreadyFound.count(pMP). */
 int coeb_fuse_search(coeb_matcher* m, coeb_frame* kf, coeb_local_map* lm, const uint8_t* valid, const float* Tcw, const float* Ow,
-                     float th, int* best_idx, int* nfused_out);
+                     float th, int chi2_tests, int* best_idx, int* nfused_out);
 
 /* ORBmatcher::SearchByProjection(Frame& cur, const Frame& last, th, bMono) (src/ORBmatcher.cc:1329-1471).
  * Per last-frame keypoint i: valid (mvpMapPoints[i] && !mvbOutlier[i]), has_obs, xyz (GetWorldPos),

@@ -303,10 +303,10 @@ int orc_match_reloc(orc_frame* cur, int n, const uint8_t* valid, const float* xy
 }
 
 int orc_fuse_search(orc_frame* f, int n, const float* xyz, const float* normal, const float* min_dist, const float* max_dist,
-                    const uint8_t* desc, const uint8_t* valid, const float* Tcw, const float* Ow, float th, int* best_idx) {
+                    const uint8_t* desc, const uint8_t* valid, const float* Tcw, const float* Ow, float th, int chi2_tests, int* best_idx) {
     LocalMapSoA M;
     M.n = n; M.xyz = xyz; M.normal = normal; M.min_dist = min_dist; M.max_dist = max_dist; M.desc = desc;
-    return fuse_search(f->v, M, valid, Tcw, Ow, th, best_idx);
+    return fuse_search(f->v, M, valid, Tcw, Ow, th, chi2_tests != 0, best_idx);
 }
 
 // Number of floats in [lo, hi) (bit patterns, stepped by `step`) whose restated logf differs from the C library's.

@@ -264,8 +264,11 @@ static inline int search_by_projection_reloc(const FrameView& C, int n, const ui
 // bestDist <= TH_LOW), or -1. The pointer-graph half (Replace / AddObservation / AddMapPoint, :938-957) stays with the caller and is
 // applied in list order from these indices: the search itself reads nothing those calls change.
 // valid[i] = pMP && !pMP->isBad() && !pMP->IsInKeyFrame(pKF). F is the keyframe (mvKeysUn, mvuRight, bounds, scale factors).
+// chi2_tests = false gives the search of Fuse(KeyFrame* pKF, cv::Mat Scw, vpPoints, th, vpReplacePoint) (:963-1093): same projection
+// and filters with [Rcw | tcw] and Ow taken from the decomposed Sim3 (:973-977), valid = !isBad() && !spAlreadyFound.count(pMP), and no
+// reprojection-error test.
 static inline int fuse_search(const FrameView& F, const LocalMapSoA& M, const uint8_t* valid, const float* Tcw, const float* Ow, float th,
-                              int* best_idx) {
+                              bool chi2_tests, int* best_idx) {
     int nFused = 0;
     const float logScale = F.nlevels > 1 ? glibc_logf(F.scale[1]) : 1.f;
     std::vector<int> vIndices;
@@ -309,7 +312,9 @@ static inline int fuse_search(const FrameView& F, const LocalMapSoA& M, const ui
             const float sc = F.scale[kpLevel];
             const float invSigma2 = 1.0f / (sc * sc);   // mvInvLevelSigma2 (src/ORBextractor.cc:427-428, 434-435)
             const float ex = u - kp.x, ey = v - kp.y;
-            if (F.uright && F.uright[idx] >= 0) {
+            if (!chi2_tests) {
+                // Fuse(pKF, Scw, ...) of loop closing (:963-1093) has no reprojection-error test
+            } else if (F.uright && F.uright[idx] >= 0) {
                 const float er = ur - F.uright[idx];
                 const float e2 = ex * ex + ey * ey + er * er;
                 if ((double)(e2 * invSigma2) > 7.8) continue;

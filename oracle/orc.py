@@ -384,7 +384,7 @@ def match_reloc(cur, kf, Tcw, Ow, th, orb_dist, check_ori, kp_match):
     return n, kp_match
 
 
-def fuse_search(frame, lm, valid, Tcw, Ow, th):
+def fuse_search(frame, lm, valid, Tcw, Ow, th, chi2_tests=True):
     """Search half of ORBmatcher::Fuse(KeyFrame*, vpMapPoints, th). Returns (nFused, best_idx[n])."""
     a = dict(xyz=_f32(lm["xyz"]), normal=_f32(lm["normal"]), min_dist=_f32(lm["min_dist"]), max_dist=_f32(lm["max_dist"]), desc=_u8(lm["desc"]))
     n = len(a["min_dist"])
@@ -392,5 +392,5 @@ def fuse_search(frame, lm, valid, Tcw, Ow, th):
     tc, ow = _f32(Tcw).reshape(12), _f32(Ow).reshape(3)
     best = np.empty(n, np.int32)
     nf = lib().orc_fuse_search(frame.h, n, _p(a["xyz"]), _p(a["normal"]), _p(a["min_dist"]), _p(a["max_dist"]), _p(a["desc"]), _p(valid),
-                               _p(tc), _p(ow), C.c_float(th), _p(best))
+                               _p(tc), _p(ow), C.c_float(th), int(chi2_tests), _p(best))
     return nf, best

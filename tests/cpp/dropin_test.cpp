@@ -44,7 +44,7 @@ int orc_match_reloc(orc_frame* cur, int n, const uint8_t* valid, const float* xy
                     const float* angle, const uint8_t* desc, const float* Tcw, const float* Ow, float th, int orb_dist, int check_ori,
                     int* kp_match);
 int orc_fuse_search(orc_frame* f, int n, const float* xyz, const float* normal, const float* min_dist, const float* max_dist,
-                    const uint8_t* desc, const uint8_t* valid, const float* Tcw, const float* Ow, float th, int* best_idx);
+                    const uint8_t* desc, const uint8_t* valid, const float* Tcw, const float* Ow, float th, int chi2_tests, int* best_idx);
 int orc_search_local_points(orc_frame* f, int n, const float* xyz, const float* normal, const float* min_dist, const float* max_dist,
                             const uint8_t* desc, const uint8_t* skip, const uint8_t* has_obs, const float* Tcw, const float* Ow,
                             float cos_limit, float th, float nnratio, int* kp_match, uint8_t* in_view, float* proj);
@@ -509,7 +509,7 @@ int main() {
             std::vector<uint8_t> fvalid(NL);
             for (int i = 0; i < NL; i++) { lmp[i].inKF = (i % 17 == 0) ? (const void*)&T : nullptr; lmp[i].replacedBy = nullptr; fvalid[i] = !lmp[i].bad && lmp[i].inKF != (const void*)&T; }
             std::vector<int> fbest(NL);
-            const int fref = orc_fuse_search(ot, NL, xyz.data(), nrm.data(), dmin.data(), dmax.data(), ldesc.data(), fvalid.data(), T.mTcw, T.mOw, 3.f, fbest.data());
+            const int fref = orc_fuse_search(ot, NL, xyz.data(), nrm.data(), dmin.data(), dmax.data(), ldesc.data(), fvalid.data(), T.mTcw, T.mOw, 3.f, 1, fbest.data());
             std::vector<MapPoint*> beforeKF = T.mvpMapPoints;
             std::vector<MapPoint> snapshot = lmp;
             ORB_SLAM2::ORBmatcher fm;

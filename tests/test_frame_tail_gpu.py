@@ -163,8 +163,9 @@ def test_relocalisation_search_by_projection_matches_oracle(gpu, th, orb_dist, o
     assert len(np.unique(got)) == len(got), "a keyframe map point was assigned twice"
 
 
-@pytest.mark.parametrize("th,seed,stereo", [(3.0, 1, True), (3.0, 2, False), (1.0, 3, True), (25.0, 4, True)])
-def test_fuse_search_matches_oracle(gpu, th, seed, stereo):
+@pytest.mark.parametrize("th,seed,stereo,chi2", [(3.0, 1, True, True), (3.0, 2, False, True), (1.0, 3, True, True), (25.0, 4, True, True),
+                                                 (4.0, 5, True, False), (10.0, 6, False, False)])
+def test_fuse_search_matches_oracle(gpu, th, seed, stereo, chi2):
     """Search half of ORBmatcher::Fuse(KeyFrame*, vpMapPoints, th): the keypoint every map point would be fused into."""
     g, c, kps, desc = _extract_both(gpu, 300 + seed, dynamic=False)
     scale = c.tables()["scale"]
@@ -177,7 +178,7 @@ def test_fuse_search_matches_oracle(gpu, th, seed, stereo):
     Tcw, Ow = synth.make_pose(seed)
     lm, skip, _ = synth.make_local_map(kps, desc, scale, Tcw, seed=seed, n_map=3000, n_true=min(900, len(kps)))
     valid = (1 - skip).astype(np.uint8)
-    ng, bg = m.fuse_search(fg, m.local_map(lm), valid, Tcw, Ow, th)
-    nc, bc = orc.fuse_search(fc, lm, valid, Tcw, Ow, th)
+    ng, bg = m.fuse_search(fg, m.local_map(lm), valid, Tcw, Ow, th, chi2)
+    nc, bc = orc.fuse_search(fc, lm, valid, Tcw, Ow, th, chi2)
     assert ng == nc and np.array_equal(bg, bc)
     assert nc > 50 and (bc[valid == 0] == -1).all()
