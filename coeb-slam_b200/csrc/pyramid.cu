@@ -159,6 +159,8 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 // uniform registers on every trip of the loop).
 __constant__ uint32_t c_blur_taps[10] = {0x30221200u, 0x12223038u, 0x22120000u, 0x22303830u, 0x00000012u,
                                          0x12000000u, 0x30383022u, 0x00001222u, 0x38302212u, 0x00122230u};
+__constant__ uint32_t c_blur_vtaps[8] = {18u | (34u << 8), 48u | (56u << 8), 48u | (34u << 8), 18u,
+                                          18u << 8,         34u | (48u << 8), 56u | (48u << 8), 34u | (18u << 8)};
 struct BlurTaps {
     __device__ __forceinline__ uint32_t h0(uint32_t wm, uint32_t w0) const { return __dp4a(wm, c_blur_taps[0], __dp4a(w0, c_blur_taps[1], 0u)); }
     __device__ __forceinline__ uint32_t h1(uint32_t wm, uint32_t w0, uint32_t wp) const {
@@ -191,12 +193,14 @@ __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const __grid_constan
         __syncthreads();
         tma_wait(a_mbar);
         if (ty0 < 3 || ty0 + kBlurRows - 3 > L.h) {   // uniform: the tile sees rows outside the image
-            for (int i = tid; i < kBlurRows * kBlurInWords; i += kBlurThreads) {
-                const int r = i / kBlurInWords, wv = i - r * kBlurInWords;
-                const int y = ty0 - 3 + r;
-                const int yy = y < 0 ? -y : (y >= L.h ? 2 * L.h - 2 - y : y);
+            // only the three rows just above (y = -3..-1) and just below (y = h..h+2) the image are ever read by an in-image output
+            for (int i = tid; i < 6 * kBlurInWords; i += kBlurThreads) {
+                const int k = i / kBlurInWords, wv = i - k * kBlurInWords;
+                const int y = k < 3 ? k - 3 : L.h + (k - 3);
+                const int r = y - ty0 + 3;
+                const int yy = y < 0 ? -y : 2 * L.h - 2 - y;
                 const int rr = yy - ty0 + 3;
-                if (yy != y && rr >= 0 && rr < kBlurRows) s_in[r * kBlurInWords + wv] = s_in[rr * kBlurInWords + wv];   // source rows are in-image rows
+                if (r >= 0 && r < kBlurRows && rr >= 0 && rr < kBlurRows) s_in[r * kBlurInWords + wv] = s_in[rr * kBlurInWords + wv];   // source rows are in-image rows
             }
         }
     } else {   // six 16-byte loads per row, rows reflected by index
@@ -264,8 +268,9 @@ __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const __grid_constan
             uint8_t* dst = blur_ptr(g, v, level, frame) + (size_t)(ty0 + 4 * strip) * L.pitch + x;
             // taps over rows r..r+6 as (lo, hi) weights of four row pairs: an even row starts on a pair, an odd row one
             // halfword later
-            constexpr uint32_t E0 = 18u | (34u << 8), E1 = 48u | (56u << 8), E2 = 48u | (34u << 8), E3 = 18u;
-            constexpr uint32_t O0 = 18u << 8, O1 = 34u | (48u << 8), O2 = 56u | (48u << 8), O3 = 34u | (18u << 8);
+            // (kept in constant memory like the H taps: as immediates they are re-materialised in uniform registers per use)
+            const uint32_t E0 = c_blur_vtaps[0], E1 = c_blur_vtaps[1], E2 = c_blur_vtaps[2], E3 = c_blur_vtaps[3];
+            const uint32_t O0 = c_blur_vtaps[4], O1 = c_blur_vtaps[5], O2 = c_blur_vtaps[6], O3 = c_blur_vtaps[7];
             const int rows = min(4, L.h - (ty0 + 4 * strip));   // rows of this strip inside the image (may be <= 0)
 #pragma unroll
             for (int r = 0; r < 4; r++) {
