@@ -212,6 +212,7 @@ __global__ void __launch_bounds__(256, COEB_DESC_MINB) describe_tma_kernel(const
     __shared__ float s_pat[1024];         // pattern as floats, transposed: [4*bit + component][lane]
     __shared__ float2 s_cs[kDescChunk];
     __shared__ float s_angle[kDescChunk];
+    __shared__ LevelKey s_key[kDescChunk];   // the chunk's keypoints, fetched once (every warp reads each of its keypoints three times)
     const int level = blockIdx.x, frame = blockIdx.y;
     const LevelGeom& L = g.lv[level];
     const int tid = threadIdx.x;
@@ -263,25 +264,26 @@ __global__ void __launch_bounds__(256, COEB_DESC_MINB) describe_tma_kernel(const
             wq[q] = wgt; mq[q] = msk;
         }
     }
-    __syncthreads();   // barriers initialised, pattern staged
+    if (tid < m) s_key[tid] = keys[chunk0 + tid];
+    __syncthreads();   // barriers initialised, pattern and keypoints staged
     uint32_t par0 = 0u, par1 = 0u;
 
     // ---- phase 1: IC_Angle ----
     {
         const CUtensorMap* map = &raw_maps.m[level];
         if (lane == 0 && wid < m) {
-            const LevelKey k = keys[chunk0 + wid];
+            const LevelKey k = s_key[wid];
             tma_load_box(a_bar0, a_box0, map, ((int)k.x - kHalfPatch) & ~15, (int)k.y - kHalfPatch, frame, kRawBoxW * kRawBoxH);
         }
         int it = 0;
         for (int j = wid; j < m; j += 8, it++) {
             const int slot = it & 1;
             if (lane == 0 && j + 8 < m) {
-                const LevelKey k = keys[chunk0 + j + 8];
+                const LevelKey k = s_key[j + 8];
                 tma_load_box(slot ? a_bar0 : a_bar1, slot ? a_box0 : a_box1, map, ((int)k.x - kHalfPatch) & ~15, (int)k.y - kHalfPatch, frame, kRawBoxW * kRawBoxH);
             }
             if (slot) { tma_wait_parity(a_bar1, par1); par1 ^= 1u; } else { tma_wait_parity(a_bar0, par0); par0 ^= 1u; }
-            const int ax = ((int)keys[chunk0 + j].x - kHalfPatch) & 15;   // patch's first column inside the box
+            const int ax = ((int)s_key[j].x - kHalfPatch) & 15;   // patch's first column inside the box
             const uint32_t* row = reinterpret_cast<const uint32_t*>(&s_box[wid][slot][(lane < kPatch ? lane : 0) * kRawBoxW]) + (ax >> 2);
             const int sh = 8 * (ax & 3);
             uint32_t m10b = 0u, sum = 0u;
@@ -323,16 +325,16 @@ __global__ void __launch_bounds__(256, COEB_DESC_MINB) describe_tma_kernel(const
         const int first_slot = 0;
         // the slots continue to alternate from 0: both barriers have completed an even or odd number of phases, tracked in par0 / par1
         if (lane == 0 && wid < m) {
-            const LevelKey k = keys[chunk0 + wid];
+            const LevelKey k = s_key[wid];
             tma_load_box(a_bar0, a_box0, map, (__float2int_rn(k.x) - kBlurR) & ~15, __float2int_rn(k.y) - kBlurR, frame, kBlurBoxW * kBlurBoxH);
         }
         (void)first_slot;
         for (int j = wid; j < m; j += 8, it++) {
             const int slot = it & 1;
             const int i = chunk0 + j;
-            const LevelKey k = keys[i];
+            const LevelKey k = s_key[j];
             if (lane == 0 && j + 8 < m) {
-                const LevelKey kn = keys[i + 8];
+                const LevelKey kn = s_key[j + 8];
                 tma_load_box(slot ? a_bar0 : a_bar1, slot ? a_box0 : a_box1, map, (__float2int_rn(kn.x) - kBlurR) & ~15, __float2int_rn(kn.y) - kBlurR, frame,
                              kBlurBoxW * kBlurBoxH);
             }

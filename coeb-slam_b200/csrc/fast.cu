@@ -365,7 +365,8 @@ __global__ void __launch_bounds__(128) fast_fallback_kernel(const __grid_constan
     __shared__ __align__(4) uint8_t s_img[kMaxRoi * kRoiPitch];
     __shared__ uint8_t s_A[(kMaxRoi - 4) * (kMaxRoi - 4)];
     __shared__ uint32_t s_list[(kMaxRoi - 6) * (kMaxRoi - 6) / 2];
-    __shared__ int s_n, s_base;
+    uint16_t* const s_queue = reinterpret_cast<uint16_t*>(s_list);   // pass A -> pass B survivors; dead before the NMS pass fills s_list
+    __shared__ int s_n, s_base, s_qn;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_empty = *v.empty_count;
     for (int e = blockIdx.x; e < n_empty; e += gridDim.x) {
@@ -392,35 +393,58 @@ __global__ void __launch_bounds__(128) fast_fallback_kernel(const __grid_constan
             reinterpret_cast<uint32_t*>(s_img)[y * (kRoiPitch / 4) + wi] = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)y * pitch) + wi);
         }
         for (int i = tid; i < aw * (dh + 2); i += 128) s_A[i] = 0;
-        if (tid == 0) s_n = 0;
+        if (tid == 0) { s_n = 0; s_qn = 0; }
         __syncthreads();
         constexpr int P = kRoiPitch;
         const int off[16] = {3 * P, 3 * P + 1, 2 * P + 2, P + 3, 3, -P + 3, -2 * P + 2, -3 * P + 1, -3 * P, -3 * P - 1, -2 * P - 2, -P - 3, -3, P - 3, 2 * P - 2, 3 * P - 1};
-        for (int y = warp; y < dh; y += 4)
-            for (int x = lane; x < dw; x += 32) {
+        // pass A: the compass bound on every pixel; survivors go to a queue so that the exact score below runs on full warps
+        const int npx = dw * dh;
+        const uint32_t rcp = ((1u << 20) + dw - 1) / dw;   // i / dw == (i * rcp) >> 20 for i < npx (dw, dh <= 66)
+        for (int i0 = 0; i0 < npx; i0 += 128) {
+            const int i = i0 + tid;
+            bool pass = false;
+            uint32_t yx = 0;
+            if (i < npx) {
+                const int y = (int)(((uint32_t)i * rcp) >> 20), x = i - y * dw;
+                yx = (uint32_t)(y << 8 | x);
                 const uint8_t* p = &s_img[(y + 3) * kRoiPitch + ax + (x + 3)];
                 const int cc = p[0];
-                {   // compass bound as fail bits (see compass_bound2): bit 14 of r + (0x4000 + th - c) is set iff d <= th
-                    const int r0 = p[off[0]], r4 = p[off[4]], r8 = p[off[8]], r12 = p[off[12]];
-                    const int kb = 0x4000 + thMin - cc, kd = 0x4000 + thMin + cc;
-                    const int fb = ((r0 + kb) & (r8 + kb)) | ((r4 + kb) & (r12 + kb));
-                    const int fd = ((kd - r0) & (kd - r8)) | ((kd - r4) & (kd - r12));
-                    if (fb & fd & 0x4000) continue;   // neither polarity has two neighbouring compass points beyond minTh: s_A stays 0
-                }
-                int d[16];
-#pragma unroll
-                for (int k = 0; k < 16; k++) d[k] = cc - (int)p[off[k]];
-                int mn[16], mx[16];
-#pragma unroll
-                for (int k = 0; k < 16; k++) { mn[k] = min(d[k], min(d[(k + 1) & 15], d[(k + 2) & 15])); mx[k] = max(d[k], max(d[(k + 1) & 15], d[(k + 2) & 15])); }
-                int best_b = -256, best_d = 256;
-#pragma unroll
-                for (int k = 0; k < 16; k++) {
-                    best_b = max(best_b, min(mn[k], min(mn[(k + 3) & 15], mn[(k + 6) & 15])));
-                    best_d = min(best_d, max(mx[k], max(mx[(k + 3) & 15], mx[(k + 6) & 15])));
-                }
-                s_A[(y + 1) * aw + (x + 1)] = (uint8_t)max(max(best_b, -best_d), 0);
+                // compass bound as fail bits (see compass_bound2): bit 14 of r + (0x4000 + th - c) is set iff d <= th
+                const int r0 = p[off[0]], r4 = p[off[4]], r8 = p[off[8]], r12 = p[off[12]];
+                const int kb = 0x4000 + thMin - cc, kd = 0x4000 + thMin + cc;
+                const int fb = ((r0 + kb) & (r8 + kb)) | ((r4 + kb) & (r12 + kb));
+                const int fd = ((kd - r0) & (kd - r8)) | ((kd - r4) & (kd - r12));
+                pass = !(fb & fd & 0x4000);   // otherwise neither polarity has two neighbouring compass points beyond minTh: s_A stays 0
             }
+            const unsigned bm = __ballot_sync(0xffffffffu, pass);
+            if (bm) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_qn, __popc(bm));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (pass) s_queue[base + __popc(bm & ((1u << lane) - 1))] = (uint16_t)yx;
+            }
+        }
+        __syncthreads();
+        // pass B: exact FAST-9 score of the survivors
+        const int nq = s_qn;
+        for (int q = tid; q < nq; q += 128) {
+            const int yx = s_queue[q], y = yx >> 8, x = yx & 255;
+            const uint8_t* p = &s_img[(y + 3) * kRoiPitch + ax + (x + 3)];
+            const int cc = p[0];
+            int d[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) d[k] = cc - (int)p[off[k]];
+            int mn[16], mx[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) { mn[k] = min(d[k], min(d[(k + 1) & 15], d[(k + 2) & 15])); mx[k] = max(d[k], max(d[(k + 1) & 15], d[(k + 2) & 15])); }
+            int best_b = -256, best_d = 256;
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                best_b = max(best_b, min(mn[k], min(mn[(k + 3) & 15], mn[(k + 6) & 15])));
+                best_d = min(best_d, max(mx[k], max(mx[(k + 3) & 15], mx[(k + 6) & 15])));
+            }
+            s_A[(y + 1) * aw + (x + 1)] = (uint8_t)max(max(best_b, -best_d), 0);
+        }
         __syncthreads();
         for (int y = warp; y < dh; y += 4)
             for (int x = lane; x < dw; x += 32) {
