@@ -213,7 +213,8 @@ __global__ void __launch_bounds__(256, COEB_DESC_MINB) describe_tma_kernel(const
     __shared__ float2 s_cs[kDescChunk];
     __shared__ float s_angle[kDescChunk];
     __shared__ LevelKey s_key[kDescChunk];   // the chunk's keypoints, fetched once (every warp reads each of its keypoints three times)
-    const int level = blockIdx.x, frame = blockIdx.y;
+    // chunk index fastest: the CTAs that read one level of one frame run together, so overlapping boxes hit in L2
+    const int level = blockIdx.y, frame = blockIdx.z;
     const LevelGeom& L = g.lv[level];
     const int tid = threadIdx.x;
 
@@ -226,8 +227,8 @@ __global__ void __launch_bounds__(256, COEB_DESC_MINB) describe_tma_kernel(const
     }
     const int n = kc[level];
     const int status = v.status[frame];
-    const int chunk0 = blockIdx.z * chunk;
-    if (level == 0 && blockIdx.z == 0 && tid == 0) {
+    const int chunk0 = blockIdx.x * chunk;
+    if (level == 0 && blockIdx.x == 0 && tid == 0) {
         int cnt = total;
         if (status != COEB_OK) cnt = 0;
         else if (total > g.out_cap) { v.status[frame] = COEB_ERR_CAPACITY; }
@@ -395,7 +396,7 @@ void launch_describe(const Geometry& g, const BatchView& v, cudaStream_t stream)
         // a few frames (the tracking thread's single-frame call): 16 keypoints per CTA, i.e. 2 per warp, so that the level's
         // keypoints spread over four times as many SMs; batches keep 64 per CTA
         const int chunk = v.B <= 4 ? 16 : kDescChunk;
-        describe_tma_kernel<<<dim3(g.nlevels, v.B, (max_keys + chunk - 1) / chunk), 256, 0, stream>>>(raw_maps, blur_maps, g, v, chunk);
+        describe_tma_kernel<<<dim3((max_keys + chunk - 1) / chunk, g.nlevels, v.B), 256, 0, stream>>>(raw_maps, blur_maps, g, v, chunk);
     }
     else {
         describe_kernel<<<grid, 256, 0, stream>>>(g, v);
