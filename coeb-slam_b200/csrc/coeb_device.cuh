@@ -146,9 +146,11 @@ __device__ inline bool is_moving(const DynState& d, float ptx, float pty, int le
 
 #ifdef __CUDACC__
 // In-place exclusive prefix sum of data[0..n) (shared or global memory) by the whole CTA; returns the total.
-// All threads must call; s_warp is a 33-int shared scratch array.
+// All threads must call; s_warp is a 33-int shared scratch array. kT = the CTA size when it is known at compile time (the
+// chunk size then is a multiply-shift instead of a division by blockDim.x).
+template <int kT = 0>
 __device__ inline int block_exclusive_scan(int* data, int n, int* s_warp) {
-    const int T = blockDim.x, tid = threadIdx.x;
+    const int T = kT ? kT : (int)blockDim.x, tid = threadIdx.x;
     const int chunk = (n + T - 1) / T;
     const int lo = min(tid * chunk, n), hi = min(lo + chunk, n);
     int sum = 0;

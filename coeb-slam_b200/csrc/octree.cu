@@ -32,33 +32,39 @@ constexpr int kSelThreads = COEB_SEL_THREADS;
 constexpr int kKeyCache = 4096;   // candidates per (level, frame) kept in shared memory (4 + 2 bytes each)
 constexpr unsigned long long kOrdMask = 0xFFFFFFFFFFFFull;  // 48-bit candidate-order field
 
-struct QNode {
+struct __align__(16) QNode {
     unsigned short x0, x1, y0, y1;
+    unsigned short xm, ym;   // split lines: x0 + ceil((x1 - x0) / 2), likewise y (src/ORBextractor.cc:491-492)
     int count;
 };
+__device__ __forceinline__ void set_split(QNode& n) {
+    n.xm = (unsigned short)(n.x0 + ((n.x1 - n.x0 + 1) >> 1));
+    n.ym = (unsigned short)(n.y0 + ((n.y1 - n.y0 + 1) >> 1));
+}
 
 // Candidate order of the reference's vToDistributeKeys: cells row-major, raster inside a cell
 // (src/ORBextractor.cc:811-848). A cell detects x in [j*wCell+3, (j+1)*wCell+3) (minBorder-relative),
 // the last cell of a row/column absorbing the clamped remainder, so (x, y) identifies the cell.
 __device__ __forceinline__ unsigned long long order_key(const LevelGeom& L, int x, int y, int lastI, int lastJ) {
-    const int j = min((x - 3) / L.wCell, lastJ), i = min((y - 3) / L.hCell, lastI);
+    const int j = min((int)(((unsigned)(x - 3) * (unsigned)L.rcpW) >> 20), lastJ), i = min((int)(((unsigned)(y - 3) * (unsigned)L.rcpH) >> 20), lastI);
     const unsigned long long ord = ((((unsigned long long)i << 12 | (unsigned long long)j) << 12 | (unsigned long long)y) << 12) |
                                    (unsigned long long)x;
     return ord;  // < 2^48
 }
 
-extern __shared__ unsigned char s_dyn_raw[];
+extern __shared__ __align__(16) unsigned char s_dyn_raw[];
 
 __global__ void __launch_bounds__(kSelThreads, COEB_SEL_MINB) select_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v) {
     const int level = blockIdx.x, frame = blockIdx.y;
     const LevelGeom& L = g.lv[level];
     const DynState& dyn = v.dyn[frame];
-    const int tid = threadIdx.x, T = blockDim.x;
+    constexpr int T = kSelThreads;
+    const int tid = threadIdx.x;
     const int LC = g.max_nodes;
 
     // ---- shared memory carve-up -----------------------------------------------------------------
     unsigned char* sp = s_dyn_raw;
-    unsigned long long* s_best = reinterpret_cast<unsigned long long*>(sp); sp += sizeof(unsigned long long) * LC;
+    unsigned long long* s_best = reinterpret_cast<unsigned long long*>(sp); sp += (sizeof(unsigned long long) * LC + 15) & ~(size_t)15;   // QNode is 16-byte aligned
     QNode* s_nodeA = reinterpret_cast<QNode*>(sp); sp += sizeof(QNode) * LC;
     QNode* s_nodeB = reinterpret_cast<QNode*>(sp); sp += sizeof(QNode) * LC;
     int* s_cc = reinterpret_cast<int*>(sp); sp += sizeof(int) * 4 * LC;      // tentative child counts [slot][4]
@@ -100,7 +106,8 @@ __global__ void __launch_bounds__(kSelThreads, COEB_SEL_MINB) select_kernel(cons
         for (int k = tid; k < nl; k += T) {
             const uint32_t key = lm[k];
             const int x = key & 0xFFF, y = (key >> 12) & 0xFFF, A = (int)(key >> 24) + 1;
-            const int j = min((x - 3) / L.wCell, lastJ), i = min((y - 3) / L.hCell, lastI);
+            // cell of the candidate, as in fast.cu cell_of (exact multiply-shift quotient, checked on the host)
+            const int j = min((int)(((unsigned)(x - 3) * (unsigned)L.rcpW) >> 20), lastJ), i = min((int)(((unsigned)(y - 3) * (unsigned)L.rcpH) >> 20), lastI);
             const int th = cellcnt[i * L.nCols + j] > 0 ? thIni : thMin;
             if (A > th && !(dyn.area_flag && is_moving(dyn, (float)x, (float)y, level, L.scale, g.w0, g.h0)))
             {
@@ -133,6 +140,7 @@ __global__ void __launch_bounds__(kSelThreads, COEB_SEL_MINB) select_kernel(cons
         n.x1 = (unsigned short)(int)__fmul_rn(hX, (float)(i + 1));
         n.y0 = 0;
         n.y1 = (unsigned short)H;
+        set_split(n);
         n.count = 0;
         nxt[i] = n;
     }
@@ -147,7 +155,7 @@ __global__ void __launch_bounds__(kSelThreads, COEB_SEL_MINB) select_kernel(cons
     __syncthreads();
     for (int i = tid; i < nIni; i += T) s_scanA[i] = nxt[i].count > 0;
     __syncthreads();
-    int nList = block_exclusive_scan(s_scanA, nIni, s_warp);
+    int nList = block_exclusive_scan<kSelThreads>(s_scanA, nIni, s_warp);
     for (int i = tid; i < nIni; i += T)
         if (nxt[i].count > 0) cur[s_scanA[i]] = nxt[i];
     __syncthreads();
@@ -166,7 +174,7 @@ __global__ void __launch_bounds__(kSelThreads, COEB_SEL_MINB) select_kernel(cons
             // full pass: every multi-key node, in list order (:613-672)
             for (int i = tid; i < nList; i += T) s_scanA[i] = cur[i].count > 1;
             __syncthreads();
-            nP = block_exclusive_scan(s_scanA, nList, s_warp);
+            nP = block_exclusive_scan<kSelThreads>(s_scanA, nList, s_warp);
             for (int i = tid; i < nList; i += T) {
                 if (cur[i].count > 1) { s_P[s_scanA[i]] = (unsigned short)i; s_slot[i] = (unsigned short)s_scanA[i]; }
                 else s_slot[i] = 0xFFFF;
@@ -198,7 +206,7 @@ __global__ void __launch_bounds__(kSelThreads, COEB_SEL_MINB) select_kernel(cons
             const int p = s_slot[nd];
             if (p != 0xFFFF) {
                 const QNode n = cur[nd];
-                const int xm = n.x0 + ((n.x1 - n.x0 + 1) >> 1), ym = n.y0 + ((n.y1 - n.y0 + 1) >> 1);  // ceil(w/2) (:491-492)
+                const int xm = n.xm, ym = n.ym;
                 const uint32_t key = keys[k];
                 const int x = key & 0xFFF, y = (key >> 12) & 0xFFF;
                 const int q = (x < xm ? 0 : 1) + (y < ym ? 0 : 2);
@@ -215,7 +223,7 @@ __global__ void __launch_bounds__(kSelThreads, COEB_SEL_MINB) select_kernel(cons
                 s_scanA[p] = (c[0] > 0) + (c[1] > 0) + (c[2] > 0) + (c[3] > 0) - 1;
             }
             __syncthreads();
-            block_exclusive_scan(s_scanA, nP, s_warp);
+            block_exclusive_scan<kSelThreads>(s_scanA, nP, s_warp);
             if (tid == 0) s_misc[0] = nP;
             __syncthreads();
             for (int p = tid; p < nP; p += T) {
@@ -241,9 +249,9 @@ __global__ void __launch_bounds__(kSelThreads, COEB_SEL_MINB) select_kernel(cons
             s_scanB[i] = !(p != 0xFFFF && p < nProc);
         }
         __syncthreads();
-        const int totals = block_exclusive_scan(s_scanA, 4 * nProc, s_warp);
+        const int totals = block_exclusive_scan<kSelThreads>(s_scanA, 4 * nProc, s_warp);
         const int totalNew = totals & 0xFFFF, nE2 = totals >> 16;
-        const int nKeep = block_exclusive_scan(s_scanB, nList, s_warp);
+        const int nKeep = block_exclusive_scan<kSelThreads>(s_scanB, nList, s_warp);
         const int newSize = totalNew + nKeep;
         if (newSize > LC) {  // cannot happen for max_nodes >= max(N + 3, 4 * nIni); fail loudly
             if (tid == 0) { *key_count = 0; atomicMin(&v.status[frame], (int)COEB_ERR_CAPACITY); }
@@ -262,12 +270,13 @@ __global__ void __launch_bounds__(kSelThreads, COEB_SEL_MINB) select_kernel(cons
             if (cnt > 0) {
                 const int p = i >> 2, q = i & 3;
                 const QNode n = cur[s_P[p]];
-                const int xm = n.x0 + ((n.x1 - n.x0 + 1) >> 1), ym = n.y0 + ((n.y1 - n.y0 + 1) >> 1);
+                const int xm = n.xm, ym = n.ym;
                 QNode c;
                 c.x0 = (q & 1) ? xm : n.x0;
                 c.x1 = (q & 1) ? n.x1 : xm;
                 c.y0 = (q & 2) ? ym : n.y0;
                 c.y1 = (q & 2) ? n.y1 : ym;
+                set_split(c);
                 c.count = cnt;
                 const int pos = totalNew - 1 - (s_scanA[i] & 0xFFFF);  // push_front in creation order
                 nxt[pos] = c;
@@ -283,7 +292,7 @@ __global__ void __launch_bounds__(kSelThreads, COEB_SEL_MINB) select_kernel(cons
             const int p = s_slot[nd];
             if (p != 0xFFFF && p < nProc) {
                 const QNode n = cur[nd];
-                const int xm = n.x0 + ((n.x1 - n.x0 + 1) >> 1), ym = n.y0 + ((n.y1 - n.y0 + 1) >> 1);
+                const int xm = n.xm, ym = n.ym;
                 const uint32_t key = keys[k];
                 const int x = key & 0xFFF, y = (key >> 12) & 0xFFF;
                 const int q = (x < xm ? 0 : 1) + (y < ym ? 0 : 2);
@@ -326,7 +335,7 @@ __global__ void __launch_bounds__(kSelThreads, COEB_SEL_MINB) select_kernel(cons
         s_scanA[i] = keep;
     }
     __syncthreads();
-    const int nOut = block_exclusive_scan(s_scanA, nList, s_warp);
+    const int nOut = block_exclusive_scan<kSelThreads>(s_scanA, nList, s_warp);
     LevelKey* out = v.keys + (size_t)frame * g.keys_per_frame + L.key_base;
     if (nOut > L.key_cap) {
         if (tid == 0) { *key_count = 0; atomicMin(&v.status[frame], (int)COEB_ERR_CAPACITY); }
@@ -350,7 +359,7 @@ __global__ void __launch_bounds__(kSelThreads, COEB_SEL_MINB) select_kernel(cons
 }
 
 size_t select_smem_bytes(int LC) {
-    return (size_t)LC * (sizeof(unsigned long long) + 2 * sizeof(QNode) + 4 * 4 + 4 * 4 + 4 + 4 * 2 + 2 * 5) + 16 + (size_t)kKeyCache * 6;
+    return (size_t)LC * (sizeof(unsigned long long) + 2 * sizeof(QNode) + 4 * 4 + 4 * 4 + 4 + 4 * 2 + 2 * 5) + 32 + (size_t)kKeyCache * 6;
 }
 
 void launch_select(const Geometry& g, const BatchView& v, cudaStream_t stream) {
