@@ -52,6 +52,44 @@ __device__ __forceinline__ unsigned long long order_key(const LevelGeom& L, int 
     return ord;  // < 2^48
 }
 
+// Two independent in-place exclusive prefix sums (a[0..na), b[0..nb)) sharing their three barriers. Returns a's total, b's in *tb.
+__device__ __forceinline__ int block_exclusive_scan2(int* a, int na, int* b, int nb, int* s_wa, int* s_wb, int* tb) {
+    constexpr int T = kSelThreads;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int ca = (na + T - 1) / T, cb = (nb + T - 1) / T;
+    const int loa = min(tid * ca, na), hia = min(loa + ca, na), lob = min(tid * cb, nb), hib = min(lob + cb, nb);
+    int sa = 0, sb = 0;
+    for (int i = loa; i < hia; i++) sa += a[i];
+    for (int i = lob; i < hib; i++) sb += b[i];
+    int ia = sa, ib = sb;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int ta = __shfl_up_sync(0xffffffffu, ia, o), t2 = __shfl_up_sync(0xffffffffu, ib, o);
+        if (lane >= o) { ia += ta; ib += t2; }
+    }
+    if (lane == 31) { s_wa[wid] = ia; s_wb[wid] = ib; }
+    __syncthreads();
+    if (wid == 0) {
+        const int va = lane < (T >> 5) ? s_wa[lane] : 0, vb = lane < (T >> 5) ? s_wb[lane] : 0;
+        int wa = va, wb = vb;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int ta = __shfl_up_sync(0xffffffffu, wa, o), t2 = __shfl_up_sync(0xffffffffu, wb, o);
+            if (lane >= o) { wa += ta; wb += t2; }
+        }
+        s_wa[lane] = wa - va; s_wb[lane] = wb - vb;
+        if (lane == 31) { s_wa[32] = wa; s_wb[32] = wb; }
+    }
+    __syncthreads();
+    int ra = s_wa[wid] + ia - sa, rb = s_wb[wid] + ib - sb;
+    for (int i = loa; i < hia; i++) { const int t = a[i]; a[i] = ra; ra += t; }
+    for (int i = lob; i < hib; i++) { const int t = b[i]; b[i] = rb; rb += t; }
+    const int total = s_wa[32];
+    *tb = s_wb[32];
+    __syncthreads();
+    return total;
+}
+
 extern __shared__ __align__(16) unsigned char s_dyn_raw[];
 
 __global__ void __launch_bounds__(kSelThreads, COEB_SEL_MINB) select_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v) {
@@ -79,7 +117,7 @@ __global__ void __launch_bounds__(kSelThreads, COEB_SEL_MINB) select_kernel(cons
     sp = s_dyn_raw + ((sp - s_dyn_raw + 15) & ~(size_t)15);
     uint32_t* s_keys = reinterpret_cast<uint32_t*>(sp); sp += sizeof(uint32_t) * kKeyCache;          // candidate cache
     unsigned short* s_knode = reinterpret_cast<unsigned short*>(sp); sp += sizeof(unsigned short) * kKeyCache;
-    __shared__ int s_warp[33];
+    __shared__ int s_warp[33], s_warp2[33];
     __shared__ int s_misc[8];
 
     int* key_count = v.key_count + frame * g.nlevels + level;
@@ -211,6 +249,7 @@ __global__ void __launch_bounds__(kSelThreads, COEB_SEL_MINB) select_kernel(cons
                 const int x = key & 0xFFF, y = (key >> 12) & 0xFFF;
                 const int q = (x < xm ? 0 : 1) + (y < ym ? 0 : 2);
                 atomicAdd(&s_cc[4 * p + q], 1);
+                knode[k] = (unsigned short)(nd | (q << 14));   // the quadrant rides in the two top bits until the keys move below
             }
         }
         __syncthreads();
@@ -249,9 +288,9 @@ __global__ void __launch_bounds__(kSelThreads, COEB_SEL_MINB) select_kernel(cons
             s_scanB[i] = !(p != 0xFFFF && p < nProc);
         }
         __syncthreads();
-        const int totals = block_exclusive_scan<kSelThreads>(s_scanA, 4 * nProc, s_warp);
+        int nKeep;
+        const int totals = block_exclusive_scan2(s_scanA, 4 * nProc, s_scanB, nList, s_warp, s_warp2, &nKeep);
         const int totalNew = totals & 0xFFFF, nE2 = totals >> 16;
-        const int nKeep = block_exclusive_scan<kSelThreads>(s_scanB, nList, s_warp);
         const int newSize = totalNew + nKeep;
         if (newSize > LC) {  // cannot happen for max_nodes >= max(N + 3, 4 * nIni); fail loudly
             if (tid == 0) { *key_count = 0; atomicMin(&v.status[frame], (int)COEB_ERR_CAPACITY); }
@@ -288,18 +327,10 @@ __global__ void __launch_bounds__(kSelThreads, COEB_SEL_MINB) select_kernel(cons
 
         // move the keys
         for (int k = tid; k < nkeys; k += T) {
-            const int nd = knode[k];
+            const int kn = knode[k];
+            const int nd = kn & 0x3FFF, q = kn >> 14;
             const int p = s_slot[nd];
-            if (p != 0xFFFF && p < nProc) {
-                const QNode n = cur[nd];
-                const int xm = n.xm, ym = n.ym;
-                const uint32_t key = keys[k];
-                const int x = key & 0xFFF, y = (key >> 12) & 0xFFF;
-                const int q = (x < xm ? 0 : 1) + (y < ym ? 0 : 2);
-                knode[k] = s_childpos[4 * p + q];
-            } else {
-                knode[k] = s_oldpos[nd];
-            }
+            knode[k] = (p != 0xFFFF && p < nProc) ? s_childpos[4 * p + q] : s_oldpos[nd];
         }
         __syncthreads();
         { QNode* t = cur; cur = nxt; nxt = t; }
