@@ -52,15 +52,18 @@ __device__ __forceinline__ unsigned long long order_key(const LevelGeom& L, int 
     return ord;  // < 2^48
 }
 
-// Two independent in-place exclusive prefix sums (a[0..na), b[0..nb)) sharing their three barriers. Returns a's total, b's in *tb.
-__device__ __forceinline__ int block_exclusive_scan2(int* a, int na, int* b, int nb, int* s_wa, int* s_wb, int* tb) {
+// Two independent exclusive prefix sums sharing their three barriers: a[i] = sum of fa(j), j < i, for i in [0, na), likewise b / fb.
+// The inputs are computed on the fly (fa / fb read data that is stable since the last barrier), so no flag pass and no barrier
+// precede the scan. Returns a's total, b's in *tb.
+template <class FA, class FB>
+__device__ __forceinline__ int block_exclusive_scan2(int* a, int na, FA fa, int* b, int nb, FB fb, int* s_wa, int* s_wb, int* tb) {
     constexpr int T = kSelThreads;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int ca = (na + T - 1) / T, cb = (nb + T - 1) / T;
     const int loa = min(tid * ca, na), hia = min(loa + ca, na), lob = min(tid * cb, nb), hib = min(lob + cb, nb);
     int sa = 0, sb = 0;
-    for (int i = loa; i < hia; i++) sa += a[i];
-    for (int i = lob; i < hib; i++) sb += b[i];
+    for (int i = loa; i < hia; i++) { const int t = fa(i); a[i] = t; sa += t; }
+    for (int i = lob; i < hib; i++) { const int t = fb(i); b[i] = t; sb += t; }
     int ia = sa, ib = sb;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -210,9 +213,8 @@ __global__ void __launch_bounds__(kSelThreads, COEB_SEL_MINB) select_kernel(cons
         int nP;
         if (!careful) {
             // full pass: every multi-key node, in list order (:613-672)
-            for (int i = tid; i < nList; i += T) s_scanA[i] = cur[i].count > 1;
-            __syncthreads();
-            nP = block_exclusive_scan<kSelThreads>(s_scanA, nList, s_warp);
+            int unused;
+            nP = block_exclusive_scan2(s_scanA, nList, [&](int i) { return (int)(cur[i].count > 1); }, s_scanB, 0, [](int) { return 0; }, s_warp, s_warp2, &unused);
             for (int i = tid; i < nList; i += T) {
                 if (cur[i].count > 1) { s_P[s_scanA[i]] = (unsigned short)i; s_slot[i] = (unsigned short)s_scanA[i]; }
                 else s_slot[i] = 0xFFFF;
@@ -278,18 +280,11 @@ __global__ void __launch_bounds__(kSelThreads, COEB_SEL_MINB) select_kernel(cons
         // creation sequence: for p in processing order, children q = 0..3 that hold keys. One packed scan gives both the creation
         // index of every child (low half) and its rank among the multi-key children (high half): the latter are next round's
         // expandable list, in creation order.
-        for (int i = tid; i < 4 * nProc; i += T) {
-            const int c = s_cc[i];
-            s_scanA[i] = (c > 0) | ((c > 1) << 16);
-        }
-        // surviving old nodes keep their relative order behind the new ones
-        for (int i = tid; i < nList; i += T) {
-            const int p = s_slot[i];
-            s_scanB[i] = !(p != 0xFFFF && p < nProc);
-        }
-        __syncthreads();
+        // (second scan) surviving old nodes keep their relative order behind the new ones
         int nKeep;
-        const int totals = block_exclusive_scan2(s_scanA, 4 * nProc, s_scanB, nList, s_warp, s_warp2, &nKeep);
+        const int totals = block_exclusive_scan2(
+            s_scanA, 4 * nProc, [&](int i) { const int c = s_cc[i]; return (c > 0) | ((c > 1) << 16); },
+            s_scanB, nList, [&](int i) { const int p = s_slot[i]; return (int)!(p != 0xFFFF && p < nProc); }, s_warp, s_warp2, &nKeep);
         const int totalNew = totals & 0xFFFF, nE2 = totals >> 16;
         const int newSize = totalNew + nKeep;
         if (newSize > LC) {  // cannot happen for max_nodes >= max(N + 3, 4 * nIni); fail loudly
