@@ -307,11 +307,9 @@ __global__ void __launch_bounds__(kFtThreads, COEB_FT_MINB) fast_kernel(const __
                 keep = A > m;
             }
         }
-        if (keep) {
+        if (keep) {   // few lanes get here: only the list entry is made now, the cell counts wait for the dense copy-out loop below
             const int x = tx0 + px, y = ty0 + py;   // level coordinates; emitted minBorder-relative (:844-845)
-            const int cj = cell_of(x, L.w, L.rcpW, L.lastJ), ci = cell_of(y, L.h, L.rcpH, L.lastI);
             s_list[smem_add(a_ctr + 8, 1)] = (uint32_t)(x - kMinBorder) | ((uint32_t)(y - kMinBorder) << 12) | ((uint32_t)(A - 1) << 24);
-            atomicAdd(&cellcnt[ci * L.nCols + cj], 1);
         }
     }
     __syncthreads();
@@ -322,7 +320,12 @@ __global__ void __launch_bounds__(kFtThreads, COEB_FT_MINB) fast_kernel(const __
     const int base = s_ctr[3];
     uint32_t* out = v.lmax + (size_t)frame * g.cand_per_frame + L.cand_base + base;
     const int room = L.cand_cap - base;
-    for (int i = tid; i < n && i < room; i += kFtThreads) out[i] = s_list[i];
+    for (int i = tid; i < n; i += kFtThreads) {
+        const uint32_t key = s_list[i];
+        const int x = (int)(key & 0xFFFu) + kMinBorder, y = (int)((key >> 12) & 0xFFFu) + kMinBorder;
+        atomicAdd(&cellcnt[cell_of(y, L.h, L.rcpH, L.lastI) * L.nCols + cell_of(x, L.w, L.rcpW, L.lastJ)], 1);
+        if (i < room) out[i] = key;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
