@@ -96,7 +96,7 @@ __device__ __forceinline__ int block_exclusive_scan2(int* a, int na, FA fa, int*
 extern __shared__ __align__(16) unsigned char s_dyn_raw[];
 
 __global__ void __launch_bounds__(kSelThreads, COEB_SEL_MINB) select_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v) {
-    const int level = blockIdx.x, frame = blockIdx.y;
+    const int level = blockIdx.y, frame = blockIdx.x;   // level-major launch order: the long CTAs (level 0) start first, the short ones fill the tail
     const LevelGeom& L = g.lv[level];
     const DynState& dyn = v.dyn[frame];
     constexpr int T = kSelThreads;
@@ -395,7 +395,7 @@ void launch_select(const Geometry& g, const BatchView& v, cudaStream_t stream) {
         cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
-    select_kernel<<<dim3(g.nlevels, v.B), kSelThreads, smem, stream>>>(g, v);
+    select_kernel<<<dim3(v.B, g.nlevels), kSelThreads, smem, stream>>>(g, v);
 }
 
 }  // namespace coeb
