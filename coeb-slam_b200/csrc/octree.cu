@@ -55,9 +55,8 @@ __device__ __forceinline__ unsigned long long order_key(const LevelGeom& L, int 
 // Two independent exclusive prefix sums sharing their three barriers: a[i] = sum of fa(j), j < i, for i in [0, na), likewise b / fb.
 // The inputs are computed on the fly (fa / fb read data that is stable since the last barrier), so no flag pass and no barrier
 // precede the scan. Returns a's total, b's in *tb.
-template <class FA, class FB>
+template <int T, class FA, class FB>
 __device__ __forceinline__ int block_exclusive_scan2(int* a, int na, FA fa, int* b, int nb, FB fb, int* s_wa, int* s_wb, int* tb) {
-    constexpr int T = kSelThreads;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int ca = (na + T - 1) / T, cb = (nb + T - 1) / T;
     const int loa = min(tid * ca, na), hia = min(loa + ca, na), lob = min(tid * cb, nb), hib = min(lob + cb, nb);
@@ -95,11 +94,14 @@ __device__ __forceinline__ int block_exclusive_scan2(int* a, int na, FA fa, int*
 
 extern __shared__ __align__(16) unsigned char s_dyn_raw[];
 
-__global__ void __launch_bounds__(kSelThreads, COEB_SEL_MINB) select_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v) {
+// T = CTA size (compile-time, so that the scans' chunking is a multiply-shift). For a single frame a level is one CTA and the longest
+// one (level 0) sets the latency: 384, 512, 768 and 1024 threads were measured there and make no difference (151.5-152.3 us per
+// call): the passes are chains of barriers and shared-memory round trips, not thread-count bound.
+template <int T, int kMinBlocks>
+__global__ void __launch_bounds__(T, kMinBlocks) select_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v) {
     const int level = blockIdx.y, frame = blockIdx.x;   // level-major launch order: the long CTAs (level 0) start first, the short ones fill the tail
     const LevelGeom& L = g.lv[level];
     const DynState& dyn = v.dyn[frame];
-    constexpr int T = kSelThreads;
     const int tid = threadIdx.x;
     const int LC = g.max_nodes;
 
@@ -196,7 +198,7 @@ __global__ void __launch_bounds__(kSelThreads, COEB_SEL_MINB) select_kernel(cons
     __syncthreads();
     for (int i = tid; i < nIni; i += T) s_scanA[i] = nxt[i].count > 0;
     __syncthreads();
-    int nList = block_exclusive_scan<kSelThreads>(s_scanA, nIni, s_warp);
+    int nList = block_exclusive_scan<T>(s_scanA, nIni, s_warp);
     for (int i = tid; i < nIni; i += T)
         if (nxt[i].count > 0) cur[s_scanA[i]] = nxt[i];
     __syncthreads();
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(kSelThreads, COEB_SEL_MINB) select_kernel(cons
         if (!careful) {
             // full pass: every multi-key node, in list order (:613-672)
             int unused;
-            nP = block_exclusive_scan2(s_scanA, nList, [&](int i) { return (int)(cur[i].count > 1); }, s_scanB, 0, [](int) { return 0; }, s_warp, s_warp2, &unused);
+            nP = block_exclusive_scan2<T>(s_scanA, nList, [&](int i) { return (int)(cur[i].count > 1); }, s_scanB, 0, [](int) { return 0; }, s_warp, s_warp2, &unused);
             for (int i = tid; i < nList; i += T) {
                 if (cur[i].count > 1) { s_P[s_scanA[i]] = (unsigned short)i; s_slot[i] = (unsigned short)s_scanA[i]; }
                 else s_slot[i] = 0xFFFF;
@@ -264,7 +266,7 @@ __global__ void __launch_bounds__(kSelThreads, COEB_SEL_MINB) select_kernel(cons
                 s_scanA[p] = (c[0] > 0) + (c[1] > 0) + (c[2] > 0) + (c[3] > 0) - 1;
             }
             __syncthreads();
-            block_exclusive_scan<kSelThreads>(s_scanA, nP, s_warp);
+            block_exclusive_scan<T>(s_scanA, nP, s_warp);
             if (tid == 0) s_misc[0] = nP;
             __syncthreads();
             for (int p = tid; p < nP; p += T) {
@@ -282,7 +284,7 @@ __global__ void __launch_bounds__(kSelThreads, COEB_SEL_MINB) select_kernel(cons
         // expandable list, in creation order.
         // (second scan) surviving old nodes keep their relative order behind the new ones
         int nKeep;
-        const int totals = block_exclusive_scan2(
+        const int totals = block_exclusive_scan2<T>(
             s_scanA, 4 * nProc, [&](int i) { const int c = s_cc[i]; return (c > 0) | ((c > 1) << 16); },
             s_scanB, nList, [&](int i) { const int p = s_slot[i]; return (int)!(p != 0xFFFF && p < nProc); }, s_warp, s_warp2, &nKeep);
         const int totalNew = totals & 0xFFFF, nE2 = totals >> 16;
@@ -361,7 +363,7 @@ __global__ void __launch_bounds__(kSelThreads, COEB_SEL_MINB) select_kernel(cons
         s_scanA[i] = keep;
     }
     __syncthreads();
-    const int nOut = block_exclusive_scan<kSelThreads>(s_scanA, nList, s_warp);
+    const int nOut = block_exclusive_scan<T>(s_scanA, nList, s_warp);
     LevelKey* out = v.keys + (size_t)frame * g.keys_per_frame + L.key_base;
     if (nOut > L.key_cap) {
         if (tid == 0) { *key_count = 0; atomicMin(&v.status[frame], (int)COEB_ERR_CAPACITY); }
@@ -390,12 +392,16 @@ size_t select_smem_bytes(int LC) {
 
 void launch_select(const Geometry& g, const BatchView& v, cudaStream_t stream) {
     const size_t smem = select_smem_bytes(g.max_nodes);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
+    // the opt-in shared-memory size is a per-device function attribute: one handle per GPU may live in the same process
+    static size_t configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t& done = configured[dev & 63];
+    if (smem > done) {
+        cudaFuncSetAttribute(select_kernel<kSelThreads, COEB_SEL_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        done = smem;
     }
-    select_kernel<<<dim3(v.B, g.nlevels), kSelThreads, smem, stream>>>(g, v);
+    select_kernel<kSelThreads, COEB_SEL_MINB><<<dim3(v.B, g.nlevels), kSelThreads, smem, stream>>>(g, v);
 }
 
 }  // namespace coeb
