@@ -428,25 +428,20 @@ __global__ void __launch_bounds__(128) fast_fallback_kernel(const __grid_constan
             }
         }
         __syncthreads();
-        // pass B: exact FAST-9 score of the survivors
+        // pass B: exact FAST-9 score of the survivors, two queue entries per thread in the packed 16-bit form of the main kernel
+        // (the two pixels of a "pair" are unrelated here: their ring bytes are packed with one multiply-add each)
         const int nq = s_qn;
-        for (int q = tid; q < nq; q += 128) {
-            const int yx = s_queue[q], y = yx >> 8, x = yx & 255;
-            const uint8_t* p = &s_img[(y + 3) * kRoiPitch + ax + (x + 3)];
-            const int cc = p[0];
-            int d[16];
+        for (int q = 2 * tid; q < nq; q += 256) {
+            const int yxa = s_queue[q], yxb = s_queue[min(q + 1, nq - 1)];
+            const int ya = yxa >> 8, xa = yxa & 255, yb = yxb >> 8, xb = yxb & 255;
+            const uint8_t* pa = &s_img[(ya + 3) * kRoiPitch + ax + (xa + 3)];
+            const uint8_t* pb = &s_img[(yb + 3) * kRoiPitch + ax + (xb + 3)];
+            uint32_t r[16];
 #pragma unroll
-            for (int k = 0; k < 16; k++) d[k] = cc - (int)p[off[k]];
-            int mn[16], mx[16];
-#pragma unroll
-            for (int k = 0; k < 16; k++) { mn[k] = min(d[k], min(d[(k + 1) & 15], d[(k + 2) & 15])); mx[k] = max(d[k], max(d[(k + 1) & 15], d[(k + 2) & 15])); }
-            int best_b = -256, best_d = 256;
-#pragma unroll
-            for (int k = 0; k < 16; k++) {
-                best_b = max(best_b, min(mn[k], min(mn[(k + 3) & 15], mn[(k + 6) & 15])));
-                best_d = min(best_d, max(mx[k], max(mx[(k + 3) & 15], mx[(k + 6) & 15])));
-            }
-            s_A[(y + 1) * aw + (x + 1)] = (uint8_t)max(max(best_b, -best_d), 0);
+            for (int k = 0; k < 16; k++) r[k] = (uint32_t)pb[off[k]] * 65536u + (uint32_t)pa[off[k]];
+            const uint32_t a2 = corner_strength2((uint32_t)pb[0] * 65536u + (uint32_t)pa[0], r);
+            s_A[(ya + 1) * aw + (xa + 1)] = (uint8_t)(a2 & 0xFFFFu);
+            s_A[(yb + 1) * aw + (xb + 1)] = (uint8_t)(a2 >> 16);   // q + 1 == nq: the same pixel, the same value
         }
         __syncthreads();
         for (int y = warp; y < dh; y += 4)
