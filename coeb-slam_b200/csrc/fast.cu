@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(kFtThreads, COEB_FT_MINB) fast_kernel(const __
     unsigned short* const s_cq = reinterpret_cast<unsigned short*>(smem + oCq);
     uint32_t* const s_list = reinterpret_cast<uint32_t*>(smem + oList);
     uint32_t* const s_edge = reinterpret_cast<uint32_t*>(smem + oEdge);
-    int* const s_ctr = reinterpret_cast<int*>(smem + oCtr);   // 0 nq, 1 nc, 2 n, 3 base
+    int* const s_ctr = reinterpret_cast<int*>(smem + oCtr);   // 0 nq, 1 nc, 2 n, 3 base, 4 n2
     const uint32_t a_ctr = (uint32_t)__cvta_generic_to_shared(s_ctr);
 
     const int frame = blockIdx.y;
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(kFtThreads, COEB_FT_MINB) fast_kernel(const __
         const unsigned mr = __ballot_sync(0xffffffffu, cell_of(x + 1, size, rcp, last) != c);
         if (lane == 0) { s_edge[(tid >> 5) & 1 | (rows ? 4 : 0)] = ml; s_edge[((tid >> 5) & 1 | (rows ? 4 : 0)) + 2] = mr; }
     }
-    if (tid < 4) s_ctr[tid] = 0;
+    if (tid < 5) s_ctr[tid] = 0;
     __syncthreads();
     if (kTma) tma_wait(a_mbar);
 
@@ -283,33 +283,50 @@ __global__ void __launch_bounds__(kFtThreads, COEB_FT_MINB) fast_kernel(const __
     }
     __syncthreads();
 
-    // ---- 2: cell-aware NMS at iniTh; local maxima are emitted, each FAST cell counts its own ----
+    // ---- 2: cell-aware NMS at iniTh. 2a tests every candidate against its 8 neighbours on full warps; the few that are kept, and
+    //      the suppressed ones that touch a cell boundary (a larger neighbour only counts inside the same cell: each cell is an
+    //      independent cv::FAST call), go to a second queue, so that the boundary test and the emission (2b) run on full warps too.
+    //      The queue lives in the staged tile, which is dead after 1b.
     const int nc = s_ctr[1];
     const unsigned long long eL = *reinterpret_cast<const unsigned long long*>(s_edge), eR = *reinterpret_cast<const unsigned long long*>(s_edge + 2);
     const unsigned long long eU = *reinterpret_cast<const unsigned long long*>(s_edge + 4), eD = *reinterpret_cast<const unsigned long long*>(s_edge + 6);
     int* cellcnt = v.cell_count + (size_t)frame * g.cells_per_frame + L.cell_base;
+    unsigned short* const s_q2 = reinterpret_cast<unsigned short*>(smem + oImg);
+    constexpr int kQ2Cap = kImgRows * kImgPitch / 2;
+    auto emit = [&](int px, int py, int A) {   // level coordinates; emitted minBorder-relative (:844-845)
+        s_list[smem_add(a_ctr + 8, 1)] = (uint32_t)(tx0 + px - kMinBorder) | ((uint32_t)(ty0 + py - kMinBorder) << 12) | ((uint32_t)(A - 1) << 24);
+    };
+    auto keep_in_cell = [&](int px, int py) {   // the NMS of a pixel that touches a cell boundary: neighbours of other cells do not count
+        const uint8_t* a = &s_A[(py + 1) * kAW + px + 4];
+        const bool sl = !((eL >> px) & 1ull), sr = !((eR >> px) & 1ull), su = !((eU >> py) & 1ull), sd = !((eD >> py) & 1ull);
+        int m = 0;
+        if (sl) m = max(m, (int)a[-1]);
+        if (sr) m = max(m, (int)a[1]);
+        if (su) { m = max(m, (int)a[-kAW]); if (sl) m = max(m, (int)a[-kAW - 1]); if (sr) m = max(m, (int)a[-kAW + 1]); }
+        if (sd) { m = max(m, (int)a[kAW]); if (sl) m = max(m, (int)a[kAW - 1]); if (sr) m = max(m, (int)a[kAW + 1]); }
+        return (int)a[0] > m;
+    };
     for (int i = tid; i < nc; i += kFtThreads) {
         const int e = s_cq[i];
         const int py = e >> 6, px = e & 63;
         const uint8_t* a = &s_A[(py + 1) * kAW + px + 4];
         const int A = a[0];
         const int n_l = a[-1], n_r = a[1], n_ul = a[-kAW - 1], n_u = a[-kAW], n_ur = a[-kAW + 1], n_dl = a[kAW - 1], n_d = a[kAW], n_dr = a[kAW + 1];
-        bool keep = A > max(max(max(n_l, n_r), max(n_ul, n_u)), max(max(n_ur, n_dl), max(n_d, n_dr)));
-        if (!keep && ((((eL | eR) >> px) | ((eU | eD) >> py)) & 1ull)) {   // suppressed, but the pixel touches a cell boundary
-            // a larger neighbour only counts if it belongs to the same cell (each cell is an independent cv::FAST call)
-            const bool sl = !((eL >> px) & 1ull), sr = !((eR >> px) & 1ull), su = !((eU >> py) & 1ull), sd = !((eD >> py) & 1ull);
-            {
-                int m = 0;
-                if (sl) m = max(m, n_l);
-                if (sr) m = max(m, n_r);
-                if (su) { m = max(m, n_u); if (sl) m = max(m, n_ul); if (sr) m = max(m, n_ur); }
-                if (sd) { m = max(m, n_d); if (sl) m = max(m, n_dl); if (sr) m = max(m, n_dr); }
-                keep = A > m;
-            }
+        const bool keep = A > max(max(max(n_l, n_r), max(n_ul, n_u)), max(max(n_ur, n_dl), max(n_d, n_dr)));
+        const bool edge = !keep && ((((eL | eR) >> px) | ((eU | eD) >> py)) & 1ull);
+        if (keep || edge) {
+            const int pos = smem_add(a_ctr + 16, 1);
+            if (pos < kQ2Cap) s_q2[pos] = (unsigned short)(e | (edge ? 0x8000 : 0));
+            else if (keep || keep_in_cell(px, py)) emit(px, py, A);   // more entries than a tile can plausibly produce: handled in place
         }
-        if (keep) {   // few lanes get here: only the list entry is made now, the cell counts wait for the dense copy-out loop below
-            const int x = tx0 + px, y = ty0 + py;   // level coordinates; emitted minBorder-relative (:844-845)
-            s_list[smem_add(a_ctr + 8, 1)] = (uint32_t)(x - kMinBorder) | ((uint32_t)(y - kMinBorder) << 12) | ((uint32_t)(A - 1) << 24);
+    }
+    __syncthreads();
+    {
+        const int n2 = min(s_ctr[4], kQ2Cap);
+        for (int i = tid; i < n2; i += kFtThreads) {
+            const int e = s_q2[i];
+            const int py = (e >> 6) & 63, px = e & 63;
+            if (!(e & 0x8000) || keep_in_cell(px, py)) emit(px, py, s_A[(py + 1) * kAW + px + 4]);
         }
     }
     __syncthreads();
