@@ -51,9 +51,9 @@ STAGE_KERNELS = {"classify": ["classify_kernel"], "pyramid": ["resize_kernel"], 
 
 def profiled_traffic(stage):
     """dram__bytes_read.sum + dram__bytes_write.sum per step of the stage's kernels, from the committed `ncu --set full`
-    capture of this same command (profiles/r01q_traffic.json); None if the capture is missing."""
+    capture of this same command (profiles/r01r_traffic.json); None if the capture is missing."""
     try:
-        k = json.load(open(os.path.join(ROOT, "profiles", "r01q_traffic.json")))["kernels"]
+        k = json.load(open(os.path.join(ROOT, "profiles", "r01r_traffic.json")))["kernels"]
         return float(sum(k[n]["dram_bytes"] for n in STAGE_KERNELS[stage])), {n: k[n]["alu_pipe_pct"] for n in STAGE_KERNELS[stage]}
     except Exception:
         return None, None
@@ -523,7 +523,7 @@ def run_b200(args):
                 "numa_node_of_rank0": numa_node},
         "gpu_launches": args.steps * launches_per_step,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "traffic_source": "profiles/r01q_traffic.json (ncu --set full, per 256-frame step)",
+                     "frac": achieved / peak, "traffic": traffic, "traffic_source": "profiles/r01r_traffic.json (ncu --set full, per 256-frame step)",
                      "alu_pipe_pct_ncu": alu_pct,
                      "note": "the stage is integer-ALU bound (packed 16-bit min/max), not HBM bound: see DESIGN.md section 5",
                      "algorithmic_bytes_per_launch": sb[dom] * B,
