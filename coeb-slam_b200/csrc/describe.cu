@@ -323,13 +323,11 @@ __global__ void __launch_bounds__(256, COEB_DESC_MINB) describe_tma_kernel(const
     {
         const CUtensorMap* map = &blur_maps.m[level];
         int it = 0;
-        const int first_slot = 0;
         // the slots continue to alternate from 0: both barriers have completed an even or odd number of phases, tracked in par0 / par1
         if (lane == 0 && wid < m) {
             const LevelKey k = s_key[wid];
             tma_load_box(a_bar0, a_box0, map, (__float2int_rn(k.x) - kBlurR) & ~15, __float2int_rn(k.y) - kBlurR, frame, kBlurBoxW * kBlurBoxH);
         }
-        (void)first_slot;
         for (int j = wid; j < m; j += 8, it++) {
             const int slot = it & 1;
             const int i = chunk0 + j;
