@@ -12,7 +12,7 @@
 
 namespace coeb {
 
-__constant__ signed char c_pattern[1024] = {
+__constant__ __align__(4) signed char c_pattern[1024] = {
 #include "../../include/coeb_orb_pattern.inc"
 };
 
@@ -209,7 +209,6 @@ __global__ void __launch_bounds__(256, COEB_DESC_MINB) describe_tma_kernel(const
                                                                           const int chunk /* keypoints per CTA, <= kDescChunk */) {
     __shared__ __align__(128) uint8_t s_box[8][2][kBoxSlot];
     __shared__ __align__(8) unsigned long long s_bar[8][2];
-    __shared__ float s_pat[1024];         // pattern as floats, transposed: [4*bit + component][lane]
     __shared__ float2 s_cs[kDescChunk];
     __shared__ float s_angle[kDescChunk];
     __shared__ LevelKey s_key[kDescChunk];   // the chunk's keypoints, fetched once (every warp reads each of its keypoints three times)
@@ -239,7 +238,6 @@ __global__ void __launch_bounds__(256, COEB_DESC_MINB) describe_tma_kernel(const
     const uint32_t a_bar0 = (uint32_t)__cvta_generic_to_shared(&s_bar[wid][0]), a_bar1 = (uint32_t)__cvta_generic_to_shared(&s_bar[wid][1]);
     const uint32_t a_box0 = (uint32_t)__cvta_generic_to_shared(&s_box[wid][0][0]), a_box1 = (uint32_t)__cvta_generic_to_shared(&s_box[wid][1][0]);
     if (lane == 0) { tma_bar_init(a_bar0); tma_bar_init(a_bar1); }
-    for (int i = tid; i < 1024; i += 256) s_pat[(i & 31) * 32 + (i >> 5)] = (float)c_pattern[i];
 
     LevelKey* keys = v.keys + (size_t)frame * g.keys_per_frame + L.key_base;
     coeb_keypoint* okp = v.out_kps + (size_t)frame * g.out_cap + offset;
@@ -266,7 +264,13 @@ __global__ void __launch_bounds__(256, COEB_DESC_MINB) describe_tma_kernel(const
         }
     }
     if (tid < m) s_key[tid] = keys[chunk0 + tid];
-    __syncthreads();   // barriers initialised, pattern and keypoints staged
+    // the lane's 32 pattern coordinates (descriptor byte `lane`: pairs 8*lane .. 8*lane+7) as 8 words of biased bytes
+    // (x0, y0, x1, y1) + 128: a byte becomes its float by one PRMT into the mantissa of 2^23 and one subtraction, instead of a
+    // shared-memory load per coordinate (the stage is bound by shared-memory traffic, the ALU / FMA pipes are idle)
+    uint32_t pw[8];
+#pragma unroll
+    for (int bit = 0; bit < 8; bit++) pw[bit] = *reinterpret_cast<const uint32_t*>(&c_pattern[lane * 32 + 4 * bit]) ^ 0x80808080u;
+    __syncthreads();   // barriers initialised, keypoints staged
     uint32_t par0 = 0u, par1 = 0u;
 
     // ---- phase 1: IC_Angle ----
@@ -343,8 +347,11 @@ __global__ void __launch_bounds__(256, COEB_DESC_MINB) describe_tma_kernel(const
             int val = 0;
 #pragma unroll
             for (int bit = 0; bit < 8; bit++) {
-                const float x0 = s_pat[(4 * bit) * 32 + lane], y0 = s_pat[(4 * bit + 1) * 32 + lane];
-                const float x1 = s_pat[(4 * bit + 2) * 32 + lane], y1 = s_pat[(4 * bit + 3) * 32 + lane];
+                const float kBias = 8388736.f;   // 2^23 + 128
+                const float x0 = __fsub_rn(__uint_as_float(__byte_perm(pw[bit], 0x4B000000u, 0x7650)), kBias);
+                const float y0 = __fsub_rn(__uint_as_float(__byte_perm(pw[bit], 0x4B000000u, 0x7651)), kBias);
+                const float x1 = __fsub_rn(__uint_as_float(__byte_perm(pw[bit], 0x4B000000u, 0x7652)), kBias);
+                const float y1 = __fsub_rn(__uint_as_float(__byte_perm(pw[bit], 0x4B000000u, 0x7653)), kBias);
                 const int r0 = round_even(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
                 const int c0 = round_even(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
                 const int r1 = round_even(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
