@@ -82,3 +82,17 @@ def test_stage_byte_model_matches_survey_total():
     assert bench.SIGMA_P == 950532
     assert int(sb["pyramid"]) == 643332 + 926546 and int(sb["blur"]) == 1901064 and int(sb["fast"]) == 950532
     assert int(total) + 0 == 6049674 - 307200 + 0 or int(total) + 307200 == 6049674
+
+
+def test_documents_only_cite_profile_files_that_exist():
+    """DESIGN.md / README.md / profiles/README.md / bench.py name captures under profiles/: every named file must be committed."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    have = set(os.listdir(os.path.join(root, "profiles")))
+    missing = []
+    for doc in ("DESIGN.md", "README.md", os.path.join("profiles", "README.md"), "bench.py"):
+        text = open(os.path.join(root, doc)).read()
+        for name in re.findall(r"\b(r\d\d[a-z]_[A-Za-z0-9_]+\.(?:json|csv|txt))\b", text):
+            if name not in have:
+                missing.append((doc, name))
+    assert not missing, missing
