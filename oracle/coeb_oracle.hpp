@@ -385,6 +385,13 @@ static inline void quad_divide(const QuadNode& p, const std::vector<Cand>& c, Qu
     for (int q = 0; q < 4; q++) ch[q].no_more = ch[q].keys.size() == 1;
 }
 
+// How often the heap-address tie-break of :691 can matter (read by tests/test_ref_parity_cpu.py through
+// orc_octree_tie_stats): a careful-phase round whose sorted list holds equal sizes among the entries it expands
+// ("order tie": the children are pushed in another order, so the output ORDER may differ) or whose >= N cut-off falls
+// inside a run of equal sizes ("cut tie": another node is expanded, so the output SET may differ).
+struct OctreeTieStats { long calls = 0, careful_rounds = 0, rounds_with_order_tie = 0, rounds_with_cut_tie = 0; };
+inline thread_local OctreeTieStats g_tie_stats;   // one instance across the translation units that include this header
+
 // Returns indices (into cands) of the retained key of each final node, in final list order.
 //
 // Tie-break rule (documented deviation from a non-deterministic reference): the reference sorts
@@ -435,6 +442,7 @@ static inline std::vector<int> octree_distribute(const std::vector<Cand>& cands,
         }
     };
 
+    g_tie_stats.calls++;
     bool finish = false;
     while (!finish) {
         int prevSize = (int)nodes.size();
@@ -460,12 +468,22 @@ static inline std::vector<int> octree_distribute(const std::vector<Cand>& cands,
                           [](const std::pair<SizeSeq, QuadNode*>& a, const std::pair<SizeSeq, QuadNode*>& b) {
                               return a.first < b.first;
                           });
+                int j_stop = -1;
                 for (int j = (int)prev.size() - 1; j >= 0; j--) {
                     QuadNode ch[4];
                     quad_divide(*prev[j].second, cands, ch);
                     push_children(ch);
                     nodes.erase(prev[j].second->self);
-                    if ((int)nodes.size() >= N) break;
+                    if ((int)nodes.size() >= N) { j_stop = j; break; }
+                }
+                {   // tie statistics only; no effect on the result
+                    g_tie_stats.careful_rounds++;
+                    const int first = j_stop < 0 ? 0 : j_stop;
+                    bool order_tie = false;
+                    for (int j = (int)prev.size() - 1; j > first; j--)
+                        if (prev[j].first.first == prev[j - 1].first.first) { order_tie = true; break; }
+                    if (order_tie) g_tie_stats.rounds_with_order_tie++;
+                    if (j_stop > 0 && prev[j_stop].first.first == prev[j_stop - 1].first.first) g_tie_stats.rounds_with_cut_tie++;
                 }
                 if ((int)nodes.size() >= N || (int)nodes.size() == prevSize) finish = true;
             }

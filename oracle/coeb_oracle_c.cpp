@@ -55,6 +55,12 @@ int orc_octree(const float* cand_xyr, int n, int minX, int maxX, int minY, int m
     return (int)sel.size();
 }
 
+// out4 = {octree calls, careful-phase rounds, rounds with an order tie, rounds with a cut tie} of this thread since the last reset
+void orc_octree_tie_stats(long* out4, int reset) {
+    if (out4) { out4[0] = g_tie_stats.calls; out4[1] = g_tie_stats.careful_rounds; out4[2] = g_tie_stats.rounds_with_order_tie; out4[3] = g_tie_stats.rounds_with_cut_tie; }
+    if (reset) g_tie_stats = OctreeTieStats();
+}
+
 // ---- extractor -----------------------------------------------------------------------------
 struct orc_extractor {
     Extractor ex;

@@ -129,6 +129,13 @@ def octree(cand_xyr, minX, maxX, minY, maxY, N):
     return out[:n].copy()
 
 
+def octree_tie_stats(reset=False):
+    """(octree calls, careful-phase rounds, rounds with an order tie, rounds with a cut tie) on this thread; see coeb_oracle.hpp."""
+    out = (C.c_long * 4)()
+    lib().orc_octree_tie_stats(out, int(reset))
+    return dict(calls=out[0], careful_rounds=out[1], order_tie_rounds=out[2], cut_tie_rounds=out[3])
+
+
 def hamming256(a, b):
     return int(lib().orc_hamming256(_p(_u8(a)), _p(_u8(b))))
 
