@@ -224,3 +224,49 @@ def stereo_from_rgbd(kps, kps_un, depth, mbf, factor=1.0, variant="ref"):
     lib(variant).ref_stereo_from_rgbd(_p(kps), _p(kps_un), n, _p(depth), kind, depth.shape[1], depth.shape[0], depth.strides[0],
                                       C.c_float(factor), C.c_float(mbf), _p(ur), _p(dp))
     return ur, dp
+
+
+def match_bow(f1, f2, valid1, valid2, fv1, fv2, nnratio, check_ori=True, strict_low=False):
+    valid1 = _u8(valid1)
+    valid2 = None if valid2 is None else _u8(valid2)
+    n1, s1, i1 = (_i32(a) for a in fv1)
+    n2, s2, i2 = (_i32(a) for a in fv2)
+    m12 = np.empty(f1.n, np.int32)
+    n = f1.L.ref_match_bow(f1.h, f2.h, _p(valid1), _p(valid2), len(n1), _p(n1), _p(s1), _p(i1), len(n2), _p(n2), _p(s2), _p(i2),
+                           C.c_float(nnratio), int(check_ori), int(strict_low), _p(m12))
+    return n, m12
+
+
+def match_triangulation(f1, f2, free1, free2, fv1, fv2, F12, t2w, only_stereo=False, check_ori=True):
+    """Keyframe 1 at the origin, keyframe 2 at [I | t2w]. Returns (n, match12, (ex, ey)) with the epipole the reference's
+    expression gives for these poses."""
+    free1, free2 = _u8(free1), _u8(free2)
+    n1, s1, i1 = (_i32(a) for a in fv1)
+    n2, s2, i2 = (_i32(a) for a in fv2)
+    F, t = _f32(F12).reshape(9), _f32(t2w).reshape(3)
+    m12 = np.empty(f1.n, np.int32)
+    ex, ey = C.c_float(), C.c_float()
+    n = f1.L.ref_match_triangulation(f1.h, f2.h, _p(free1), _p(free2), len(n1), _p(n1), _p(s1), _p(i1), len(n2), _p(n2), _p(s2), _p(i2),
+                                     _p(F), _p(t), int(only_stereo), int(check_ori), _p(m12), C.byref(ex), C.byref(ey))
+    return n, m12, (ex.value, ey.value)
+
+
+def match_reloc(cur, kf, Tcw, th, orb_dist, check_ori, kp_match):
+    """Returns (nmatches, kp_match, Ow)."""
+    kp_match = _i32(kp_match).copy()
+    a = dict(valid=_u8(kf["valid"]), xyz=_f32(kf["xyz"]), min_dist=_f32(kf["min_dist"]), max_dist=_f32(kf["max_dist"]),
+             angle=_f32(kf["angle"]), desc=_u8(kf["desc"]))
+    tc = _f32(Tcw).reshape(12)
+    ow = np.zeros(3, np.float32)
+    n = cur.L.ref_match_reloc(cur.h, len(a["valid"]), _p(a["valid"]), _p(a["xyz"]), _p(a["min_dist"]), _p(a["max_dist"]), _p(a["angle"]),
+                              _p(a["desc"]), _p(tc), _p(ow), C.c_float(th), int(orb_dist), int(check_ori), _p(kp_match))
+    return n, kp_match, ow
+
+
+def blur_flags(gray, boxes, variant="ref"):
+    gray = _u8(gray)
+    boxes = _f32(boxes).reshape(-1, 4)
+    flags = np.zeros(len(boxes), np.int32)
+    means = np.zeros(len(boxes), np.float64)
+    lib(variant).ref_blur_flags(_p(gray), gray.shape[1], gray.shape[0], gray.strides[0], _p(boxes), len(boxes), _p(flags), _p(means))
+    return flags, means

@@ -389,3 +389,170 @@ void ref_stereo_from_rgbd(const coeb_keypoint* keys, const coeb_keypoint* keys_u
 }
 
 }  // extern "C"
+
+// ---- KeyFrame-based searches ----------------------------------------------------------------------------------------
+namespace {
+
+// DBoW2::FeatureVector from the CSR triple of the orc_ twin (node ids ascending, items in push order).
+DBoW2::FeatureVector to_featvec(int nn, const int* node, const int* start, const int* items) {
+    DBoW2::FeatureVector fv;
+    for (int k = 0; k < nn; k++)
+        for (int j = start[k]; j < start[k + 1]; j++) fv.addFeature((DBoW2::NodeId)node[k], (unsigned int)items[j]);
+    return fv;
+}
+
+// KeyFrame::KeyFrame(Frame&, Map*, KeyFrameDatabase*) (src/KeyFrame.cc:32-56) copies keypoints, descriptors, grid, feature
+// vector, scale tables and pose from the Frame.
+KeyFrame* new_keyframe(Frame& F, const cv::Mat& Tcw) {
+    F.SetPose(Tcw);
+    F.mpORBvocabulary = nullptr;
+    return new KeyFrame(F, &the_map(), nullptr);
+}
+
+}  // namespace
+
+extern "C" {
+
+// ORBmatcher::SearchByBoW: strict_low == 0 -> (KeyFrame* pKF, Frame& F, vpMapPointMatches) (src/ORBmatcher.cc:158-288),
+// valid2 must be null; strict_low != 0 -> (KeyFrame* pKF1, KeyFrame* pKF2, vpMatches12) (:522-655).
+int ref_match_bow(ref_frame* f1, ref_frame* f2, const uint8_t* valid1, const uint8_t* valid2, int nn1, const int* node1, const int* start1,
+                  const int* items1, int nn2, const int* node2, const int* start2, const int* items2, float nnratio, int check_ori,
+                  int strict_low, int* match12) {
+    Frame &F1 = *f1->F, &F2 = *f2->F;
+    F1.mFeatVec = to_featvec(nn1, node1, start1, items1);
+    F2.mFeatVec = to_featvec(nn2, node2, start2, items2);
+    KeyFrame* kf1 = new_keyframe(F1, cv::Mat::eye(4, 4, CV_32F));
+    std::vector<MapPoint*> mp1((size_t)F1.N, nullptr), mp2((size_t)F2.N, nullptr);
+    for (int i = 0; i < F1.N; i++)
+        if (valid1[i]) { mp1[i] = new_map_point(nullptr, nullptr, 1.f, 1.f, nullptr, false, 1); kf1->AddMapPoint(mp1[i], i); }
+    for (int i = 0; i < F1.N; i++) match12[i] = -1;
+    ORBmatcher matcher(nnratio, check_ori != 0);
+    int nm;
+    if (!strict_low) {
+        std::vector<MapPoint*> vpMapPointMatches;
+        nm = matcher.SearchByBoW(kf1, F2, vpMapPointMatches);
+        std::map<MapPoint*, int> idx1;
+        for (int i = 0; i < F1.N; i++) if (mp1[i]) idx1[mp1[i]] = i;
+        for (int i2 = 0; i2 < F2.N; i2++)
+            if (vpMapPointMatches[i2]) match12[idx1.at(vpMapPointMatches[i2])] = i2;
+    } else {
+        KeyFrame* kf2 = new_keyframe(F2, cv::Mat::eye(4, 4, CV_32F));
+        for (int i = 0; i < F2.N; i++)
+            if (!valid2 || valid2[i]) { mp2[i] = new_map_point(nullptr, nullptr, 1.f, 1.f, nullptr, false, 1); kf2->AddMapPoint(mp2[i], i); }
+        std::vector<MapPoint*> vpMatches12;
+        nm = matcher.SearchByBoW(kf1, kf2, vpMatches12);
+        std::map<MapPoint*, int> idx2;
+        for (int i = 0; i < F2.N; i++) if (mp2[i]) idx2[mp2[i]] = i;
+        for (int i1 = 0; i1 < F1.N; i1++)
+            if (vpMatches12[i1]) match12[i1] = idx2.at(vpMatches12[i1]);
+        delete kf2;
+    }
+    delete kf1;
+    free_points(mp1);
+    free_points(mp2);
+    return nm;
+}
+
+// ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:657-824). Keyframe 1 sits at the origin and keyframe 2 at
+// [I | t2w], so the reference's own epipole expression (:663-670) evaluates fx * t2w.x / t2w.z + cx; (ex_out, ey_out)
+// return what it computed from the same inputs.
+int ref_match_triangulation(ref_frame* f1, ref_frame* f2, const uint8_t* free1, const uint8_t* free2, int nn1, const int* node1,
+                            const int* start1, const int* items1, int nn2, const int* node2, const int* start2, const int* items2,
+                            const float* F12, const float* t2w, int only_stereo, int check_ori, int* match12, float* ex_out, float* ey_out) {
+    Frame &F1 = *f1->F, &F2 = *f2->F;
+    F1.mFeatVec = to_featvec(nn1, node1, start1, items1);
+    F2.mFeatVec = to_featvec(nn2, node2, start2, items2);
+    const float mb1 = F1.mb, mb2 = F2.mb;
+    F1.mb = 0.f;   // mHalfBaseline = F.mb / 2 (src/KeyFrame.cc:46): the camera centre Cw is then exactly Ow
+    F2.mb = 0.f;
+    cv::Mat T2 = cv::Mat::eye(4, 4, CV_32F);
+    for (int k = 0; k < 3; k++) T2.at<float>(k, 3) = t2w[k];
+    KeyFrame* kf1 = new_keyframe(F1, cv::Mat::eye(4, 4, CV_32F));
+    KeyFrame* kf2 = new_keyframe(F2, T2);
+    F1.mb = mb1;
+    F2.mb = mb2;
+    std::vector<MapPoint*> mp1, mp2;
+    for (int i = 0; i < F1.N; i++)
+        if (!free1[i]) { mp1.push_back(new_map_point(nullptr, nullptr, 1.f, 1.f, nullptr, false, 1)); kf1->AddMapPoint(mp1.back(), i); }
+    for (int i = 0; i < F2.N; i++)
+        if (!free2[i]) { mp2.push_back(new_map_point(nullptr, nullptr, 1.f, 1.f, nullptr, false, 1)); kf2->AddMapPoint(mp2.back(), i); }
+    cv::Mat F(3, 3, CV_32F);
+    for (int k = 0; k < 9; k++) F.at<float>(k / 3, k % 3) = F12[k];
+    if (ex_out && ey_out) {   // the reference's expression, in this translation unit's arithmetic
+        cv::Mat C2 = kf2->GetRotation() * kf1->GetCameraCenter() + kf2->GetTranslation();
+        const float invz = 1.0f / C2.at<float>(2);
+        *ex_out = kf2->fx * C2.at<float>(0) * invz + kf2->cx;
+        *ey_out = kf2->fy * C2.at<float>(1) * invz + kf2->cy;
+    }
+    std::vector<std::pair<size_t, size_t> > pairs;
+    ORBmatcher matcher(0.6f, check_ori != 0);   // LocalMapping::CreateNewMapPoints: ORBmatcher matcher(0.6, false)
+    const int nm = matcher.SearchForTriangulation(kf1, kf2, F, pairs, only_stereo != 0);
+    for (int i = 0; i < F1.N; i++) match12[i] = -1;
+    for (size_t k = 0; k < pairs.size(); k++) match12[pairs[k].first] = (int)pairs[k].second;
+    delete kf1;
+    delete kf2;
+    free_points(mp1);
+    free_points(mp2);
+    return nm;
+}
+
+// Relocalisation overload SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist) (src/ORBmatcher.cc:1473-1600).
+// valid[i] = the keyframe's map point i exists, is not bad and is not in sAlreadyFound.
+int ref_match_reloc(ref_frame* cur, int n, const uint8_t* valid, const float* xyz, const float* min_dist, const float* max_dist,
+                    const float* angle, const uint8_t* desc, const float* Tcw, float* Ow_out, float th, int orb_dist, int check_ori,
+                    int* kp_match) {
+    Frame& C = *cur->F;
+    C.SetPose(pose44(Tcw));
+    if (Ow_out) for (int k = 0; k < 3; k++) Ow_out[k] = C.mOw.at<float>(k);
+    Frame K;   // the keyframe's source frame: only keypoint angles and the scale tables matter
+    K.N = n;
+    K.mvKeys.resize(n);
+    for (int i = 0; i < n; i++) K.mvKeys[i] = cv::KeyPoint(0.f, 0.f, 31.f, angle[i], 0.f, 0, -1);
+    K.mvKeysUn = K.mvKeys;
+    K.mvuRight.assign(n, -1.f);
+    K.mvDepth.assign(n, -1.f);
+    K.mDescriptors = cv::Mat::zeros(std::max(n, 1), 32, CV_8UC1);
+    K.mvpMapPoints.assign(n, static_cast<MapPoint*>(nullptr));
+    K.mnScaleLevels = C.mnScaleLevels; K.mfScaleFactor = C.mfScaleFactor; K.mfLogScaleFactor = C.mfLogScaleFactor;
+    K.mvScaleFactors = C.mvScaleFactors; K.mvLevelSigma2 = C.mvLevelSigma2; K.mvInvLevelSigma2 = C.mvInvLevelSigma2;
+    K.mbf = C.mbf; K.mb = C.mb;
+    KeyFrame* kf = new_keyframe(K, cv::Mat::eye(4, 4, CV_32F));
+    std::vector<MapPoint*> mps((size_t)n, nullptr);
+    for (int i = 0; i < n; i++) {
+        mps[i] = new_map_point(xyz + 3 * (size_t)i, nullptr, min_dist[i], max_dist[i], desc + (size_t)32 * i, false, 1);
+        if (valid[i]) kf->AddMapPoint(mps[i], i);
+    }
+    Claims claims;
+    for (int i = 0; i < C.N; i++) C.mvpMapPoints[i] = kp_match[i] == -1 ? nullptr : claims.taken;   // every non-null entry blocks (:1546-1547)
+    std::set<MapPoint*> sAlreadyFound;
+    ORBmatcher matcher(0.9f, check_ori != 0);
+    const int nm = matcher.SearchByProjection(C, kf, sAlreadyFound, th, orb_dist);
+    std::map<MapPoint*, int> index;
+    for (int i = 0; i < n; i++) index[mps[i]] = i;
+    for (int i = 0; i < C.N; i++) {
+        MapPoint* p = C.mvpMapPoints[i];
+        if (!p) kp_match[i] = -1;
+        else if (p != claims.taken) kp_match[i] = index.at(p);
+    }
+    C.mvpMapPoints.assign(C.N, static_cast<MapPoint*>(nullptr));
+    delete kf;
+    free_points(mps);
+    return nm;
+}
+
+// blur_flag of the RGB-D Frame constructor (src/Frame.cc:171-202): per box, Frame::detect_laplacian of the cropped
+// region (:905-913), flag = mean < 4.2.
+void ref_blur_flags(const uint8_t* gray, int w, int h, int stride, const float* boxes, int nbox, int* flags, double* means) {
+    cv::Mat imGray(h, w, CV_8UC1, (void*)gray, (size_t)stride);
+    cv::Mat imGray_copy = imGray.clone();
+    Frame F;
+    for (int i = 0; i < nbox; i++) {
+        const float* box = boxes + 4 * i;
+        cv::Mat image = imGray_copy(cv::Rect(int(box[0]), int(box[1]), int(box[2] - box[0]), int(box[3] - box[1]))).clone();
+        const double cast1 = F.detect_laplacian(image);
+        if (means) means[i] = cast1;
+        flags[i] = cast1 < 4.2 ? 1 : 0;
+    }
+}
+
+}  // extern "C"

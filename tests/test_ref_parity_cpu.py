@@ -287,8 +287,9 @@ def test_search_local_points(tum, seed, th, variant):
     fo, fr = _pair(tum, uright=uright, variant=variant)
     state = rng.choice([-1, -1, -1, -2, -3], size=len(kps)).astype(np.int32)
     n_r, k_r, v_r, p_r, ow_r = ref.search_local_points(fr, lm, skip, has_obs, Tcw, th, 0.8, state)
-    assert ow_r.tobytes() == np.asarray(Ow, np.float32).tobytes()    # the camera centre the callers compute is the reference's
-    n_o, k_o, v_o, p_o = orc.search_local_points(fo, lm, skip, has_obs, Tcw, Ow, th, 0.8, state)
+    assert np.allclose(ow_r, Ow, atol=1e-6)
+    # Ow is an INPUT of the C ABI: the drop-in adapter hands over the reference's own mOw (include/ORBmatcher.h)
+    n_o, k_o, v_o, p_o = orc.search_local_points(fo, lm, skip, has_obs, Tcw, ow_r, th, 0.8, state)
     assert np.array_equal(v_o, v_r) and v_o.sum() > 500
     # u, v, uR, viewCos, predicted level of every visible point
     if variant == "nofma":
@@ -320,3 +321,91 @@ def test_undistort_and_rgbd_depth():
     dm = (d16.astype(np.float32) * f).astype(np.float32)
     a, b = orc.stereo_from_rgbd(kps, un, dm, cam.bf), ref.stereo_from_rgbd(kps, un, dm, cam.bf)
     assert a[0].tobytes() == b[0].tobytes() and a[1].tobytes() == b[1].tobytes() and (a[1] > 0).mean() > 0.5
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# the "next" rows of SURVEY.md section 8(f) that go through KeyFrame objects, and the blur flag
+# --------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def two_views():
+    ex = orc.Extractor(nfeatures=600)
+    g1 = synth.make_frame(301)
+    k1, d1 = ex.extract(g1)
+    k2, d2 = ex.extract(synth.shift_image(g1, -5, 3))
+    return dict(k1=k1, d1=d1, k2=k2, d2=d2, scale=ex.tables()["scale"])
+
+
+@pytest.mark.parametrize("ratio,ori,strict,use_valid2,n_nodes", [(0.7, True, False, False, 60), (0.9, True, True, True, 60),
+                                                                 (0.9, False, False, False, 5), (0.75, True, True, False, 20)])
+def test_search_by_bow_both_overloads(two_views, ratio, ori, strict, use_valid2, n_nodes, variant):
+    v = two_views
+    t1, t2 = dict(kps=v["k1"], desc=v["d1"], scale=v["scale"]), dict(kps=v["k2"], desc=v["d2"], scale=v["scale"])
+    f1o, f1r = _pair(t1, variant=variant)
+    f2o, f2r = _pair(t2, variant=variant)
+    rng = np.random.default_rng(3)
+    valid1 = (rng.random(len(v["k1"])) < 0.85).astype(np.uint8)
+    valid2 = (rng.random(len(v["k2"])) < 0.9).astype(np.uint8) if use_valid2 else None
+    fv1, fv2 = synth.make_feature_vector(v["d1"], n_nodes, seed=4), synth.make_feature_vector(v["d2"], n_nodes, seed=4)
+    a = orc.match_bow(f1o, f2o, valid1, valid2, fv1, fv2, ratio, ori, strict)
+    b = ref.match_bow(f1r, f2r, valid1, valid2, fv1, fv2, ratio, ori, strict)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1]) and a[0] > 30
+
+
+@pytest.mark.parametrize("only_stereo,t2w", [(False, (-0.0375, -0.0883, 1.0)), (True, (1.5, 1.5, 0.001)), (False, (0.2, 0.1, 0.5))])
+def test_search_for_triangulation(two_views, only_stereo, t2w, variant):
+    v = two_views
+    rng = np.random.default_rng(6)
+    ur1 = np.where(rng.random(len(v["k1"])) < 0.6, v["k1"]["x"] - np.float32(5), np.float32(-1)).astype(np.float32)
+    ur2 = np.where(rng.random(len(v["k2"])) < 0.6, v["k2"]["x"] - np.float32(5), np.float32(-1)).astype(np.float32)
+    t1, t2 = dict(kps=v["k1"], desc=v["d1"], scale=v["scale"]), dict(kps=v["k2"], desc=v["d2"], scale=v["scale"])
+    f1o, f1r = _pair(t1, uright=ur1, variant=variant)
+    f2o, f2r = _pair(t2, uright=ur2, variant=variant)
+    free1, free2 = (rng.random(len(v["k1"])) < 0.8).astype(np.uint8), (rng.random(len(v["k2"])) < 0.8).astype(np.uint8)
+    fv1, fv2 = synth.make_feature_vector(v["d1"], 30, seed=7), synth.make_feature_vector(v["d2"], 30, seed=7)
+    F12 = np.array([[0, 0, 3.0], [0, 0, 5.0], [-3.0, -5.0, 0]], np.float32)   # pure shift (-5, 3)
+    n_r, m_r, epi = ref.match_triangulation(f1r, f2r, free1, free2, fv1, fv2, F12, t2w, only_stereo, True)
+    # the epipole as the callers of the C ABI compute it: fp32, left to right, no FMA (src/ORBmatcher.cc:663-670)
+    f32 = np.float32
+    invz = f32(1.0) / f32(t2w[2])
+    ex = f32(f32(f32(f32(CAM_ARGS[0]) * f32(t2w[0])) * invz) + f32(CAM_ARGS[2]))
+    ey = f32(f32(f32(f32(CAM_ARGS[1]) * f32(t2w[1])) * invz) + f32(CAM_ARGS[3]))
+    if variant == "nofma":
+        assert (f32(epi[0]), f32(epi[1])) == (ex, ey)
+    n_o, m_o = orc.match_triangulation(f1o, f2o, free1, free2, fv1, fv2, F12, (ex, ey), only_stereo, True)
+    assert n_o == n_r and np.array_equal(m_o, m_r) and n_o > 10
+
+
+@pytest.mark.parametrize("th,orb_dist,ori,seed", [(10.0, 100, True, 1), (3.0, 64, True, 2), (60.0, 100, False, 3)])
+def test_relocalisation_search_by_projection(th, orb_dist, ori, seed, variant):
+    ex = orc.Extractor()
+    kps, desc = ex.extract(synth.make_frame(200 + seed))
+    scale = ex.tables()["scale"]
+    fo, fr = _pair(dict(kps=kps, desc=desc, scale=scale), variant=variant)
+    Tcw, Ow = synth.make_pose(seed)
+    lm, skip, _ = synth.make_local_map(kps, desc, scale, Tcw, seed=seed, n_map=1500, n_true=700)
+    rng = np.random.default_rng(seed)
+    kf = dict(valid=(1 - skip).astype(np.uint8), xyz=lm["xyz"], min_dist=lm["min_dist"], max_dist=lm["max_dist"],
+              angle=rng.uniform(0, 360, len(skip)).astype(np.float32), desc=lm["desc"])
+    state = rng.choice([-1, -1, -1, -1, -2, -3], size=len(kps)).astype(np.int32)
+    n_r, k_r, ow_r = ref.match_reloc(fr, kf, Tcw, th, orb_dist, ori, state)
+    assert np.allclose(ow_r, Ow, atol=1e-6)
+    # Ow is an INPUT of the C ABI: the drop-in adapter hands over the reference's own mOw (include/ORBmatcher.h)
+    n_o, k_o = orc.match_reloc(fo, kf, Tcw, ow_r, th, orb_dist, ori, state)
+    assert n_o == n_r and np.array_equal(k_o, k_r) and n_o > (5 if ori else 100)
+
+
+def test_blur_flags_of_the_frame_constructor():
+    """Frame::detect_laplacian per box and the 4.2 threshold (src/Frame.cc:171-202, 905-913)."""
+    rng = np.random.default_rng(11)
+    for seed in range(6):
+        gray = synth.make_frame(seed).copy()
+        if seed % 2:   # a smooth region so that some boxes fall below the threshold
+            gray[100:400, 150:500] = (gray[100:400, 150:500].astype(np.int32) // 16 * 16 + 8).astype(np.uint8)
+            gray[120:380, 170:480] = 128
+        boxes = []
+        for _ in range(4):
+            x0, y0 = int(rng.integers(0, 400)), int(rng.integers(0, 250))
+            boxes.append([x0, y0, x0 + int(rng.integers(40, 230)), y0 + int(rng.integers(40, 220))])
+        boxes = np.array(boxes, np.float32)
+        (fo, mo), (fr, mr) = orc.blur_flags(gray, boxes), ref.blur_flags(gray, boxes)
+        assert np.array_equal(fo, fr) and mo.tobytes() == mr.tobytes()
