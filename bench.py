@@ -7,7 +7,7 @@ sharded across ranks with no collective (weak scaling). A "step" is one pass of 
 rank's 256-frame shard.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]           # CUDA arm (default N=1)
-  python bench.py --impl reference ...                           # the reference's CPU algorithm (oracle port)
+  python bench.py --impl reference ...                           # the reference's own CPU extractor (oracle/_ref), all host threads
 
 Prints ONE JSON line on rank 0. torch is used only for device buffers, the timing events on the launch
 stream and the (gloo) barrier / max-over-ranks; the hot path is libcoeb_frontend.so.
@@ -26,6 +26,7 @@ sys.path[:0] = [os.path.join(ROOT, "coeb-slam_b200", "python")]
 
 import numpy as np  # noqa: E402
 
+METRIC = "frames/s ORB extract+dyn-filter (640x480,1k kps)"
 W, H, NFEAT, NLEVELS = 640, 480, 1000, 8
 FRAMES_PER_GPU = 256
 LEVELS = [(640, 480), (533, 400), (444, 333), (370, 278), (309, 231), (257, 193), (214, 161), (179, 134)]
@@ -49,14 +50,31 @@ STAGE_KERNELS = {"classify": ["classify_kernel"], "pyramid": ["resize_kernel"], 
                  "fast": ["fast_kernel", "fast_fallback_kernel"], "select": ["select_kernel"], "describe": ["describe_tma_kernel"]}
 
 
+def newest_traffic_capture():
+    """Path of the newest committed `ncu --set full` traffic summary (profiles/rNNx_traffic.json: round number, then letter)."""
+    import glob
+    import re
+    best = None
+    for f in glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")):
+        m = re.match(r"r(\d+)([a-z]*)_traffic\.json$", os.path.basename(f))
+        if m and (best is None or (int(m.group(1)), m.group(2)) > best[0]):
+            best = ((int(m.group(1)), m.group(2)), f)
+    return best[1] if best else None
+
+
 def profiled_traffic(stage):
-    """dram__bytes_read.sum + dram__bytes_write.sum per step of the stage's kernels, from the committed `ncu --set full`
-    capture of this same command (profiles/r01r_traffic.json); None if the capture is missing."""
+    """dram__bytes_read.sum + dram__bytes_write.sum per step of the stage's kernels, from the newest committed `ncu --set full`
+    capture of this same command; (None, None, None) if there is none. Kernels a later build no longer launches are skipped."""
     try:
-        k = json.load(open(os.path.join(ROOT, "profiles", "r01r_traffic.json")))["kernels"]
-        return float(sum(k[n]["dram_bytes"] for n in STAGE_KERNELS[stage])), {n: k[n]["alu_pipe_pct"] for n in STAGE_KERNELS[stage]}
+        path = newest_traffic_capture()
+        k = json.load(open(path))["kernels"]
+        names = [n for n in STAGE_KERNELS[stage] if n in k]
+        if not names:
+            return None, None, None
+        return (float(sum(k[n]["dram_bytes"] for n in names)), {n: k[n]["alu_pipe_pct"] for n in names},
+                "profiles/" + os.path.basename(path) + " (ncu --set full, per 256-frame step)")
     except Exception:
-        return None, None
+        return None, None, None
 
 
 def measured_peak_gbs():
@@ -170,28 +188,44 @@ def base_config(n_gpus):
     return {"workload": "configs[1]: batched ORB extract + dynamic filter, %d synthetic 640x480 frames per GPU, "
                         "nFeatures=1000, 8 levels x1.2, FAST 20/7, YOLO boxes + T_M per frame" % FRAMES_PER_GPU,
             "frames_per_gpu": FRAMES_PER_GPU, "width": W, "height": H, "nfeatures": NFEAT, "nlevels": NLEVELS,
-            "sharding": "independent frame shards, no collective", "n_gpus": n_gpus}
+            "sharding": "independent frame shards, no collective", "n_gpus": n_gpus,
+            "l2": "per step the inputs + pyramid arenas (~0.6 GB per shard) exceed the 126 MB L2; no explicit flush"}
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm: the reference's CPU algorithm (oracle port; the reference itself cannot be built
-# here: no OpenCV C++ headers, DBoW2/g2o absent -- DESIGN.md section 7)
+# reference arm: the reference's OWN CPU implementation (oracle/_ref: src/ORBextractor.cc compiled unchanged against
+# the test-only OpenCV shim), one extractor per host thread, all host threads. Falls back to the
+# oracle port (kind "port") only if the prebuilt oracle/_ref library did not travel with the snapshot.
 # ------------------------------------------------------------------------------------------------
+def cpu_arm():
+    """(module, kind, description) of the CPU implementation timed beside the GPU: oracle/_ref if present, else the port."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orc
+    try:
+        import ref
+        if ref.available():
+            ref.lib("ref")
+            return ref, orc, "reference", "oracle/_ref: reference src/ORBextractor.cc unchanged (-O3 -march=x86-64-v3), OpenCV primitives from the cv2-pinned shim"
+    except Exception as e:   # noqa: BLE001 -- a missing prebuilt library must not kill the bench line
+        sys.stderr.write("bench.py: oracle/_ref unavailable (%s); timing the oracle port instead\n" % e)
+    return orc, orc, "port", "oracle port (oracle/libcoeb_oracle.so)"
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import orc
+    impl, orc, kind, what = cpu_arm()
     from coeb_b200 import synth
     threads = orc.hardware_threads()
     sample = int(args.ref_frames)
-    batch = synth.make_batch(sample, base_seed=0, w=W, h=H, unique=min(sample, 32))
+    # the first `sample` frames of the rank-0 shard of the CUDA arm (same seeds, same boxes / T_M / blur flags)
+    batch = synth.make_batch(FRAMES_PER_GPU, base_seed=0, w=W, h=H, unique=args.unique)
+    sub = {k: np.ascontiguousarray(batch[k][:sample]) for k in batch}
     params = orc.OrbParams(NFEAT, 1.2, NLEVELS, 20, 7)
 
     def step():
-        secs, counts, _, _ = orc.extract_batch_mt(params, batch["gray"], batch["boxes"], batch["nbox"], batch["tm"],
-                                                  batch["ntm"], batch["blur"], threads)
+        secs, counts, _, _ = impl.extract_batch_mt(params, sub["gray"], sub["boxes"], sub["nbox"], sub["tm"], sub["ntm"], sub["blur"], threads)
         return secs, counts
     for _ in range(max(args.warmup, 1)):
         step()
@@ -200,12 +234,13 @@ def run_reference(args):
         s, counts = step()
         t += s
     fps = sample * args.steps / t
-    line = {"impl": "reference", "metric": "frames/s ORB extract+dyn-filter (640x480,1k kps)", "value": fps, "unit": "frames/s",
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": base_config(args.gpus),
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-                             "sample": "%d frames of the same workload per step, one oracle extractor per thread" % sample},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
+                             "sample": "each step = the first %d frames of the rank-0 shard (of %d), one extractor per thread, %d threads; %s"
+                                       % (sample, FRAMES_PER_GPU, threads, what)},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "mean_keypoints": float(np.mean(counts))}
     print(json.dumps(line))
@@ -325,7 +360,7 @@ def run_b200(args):
 
     if args.skip_e2e:
         if rank == 0:
-            print(json.dumps({"metric": "frames/s ORB extract+dyn-filter (640x480,1k kps)", "value": value, "unit": "frames/s",
+            print(json.dumps({"metric": METRIC, "value": value, "unit": "frames/s",
                               "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
                               "stage_ms": stage_ms, "note": "--skip-e2e profiling run, not a bench line"}))
         return 0
@@ -432,17 +467,30 @@ def run_b200(args):
     # ---- CPU baseline beside it (rank 0, N=1 only) --------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        sys.path.insert(0, os.path.join(ROOT, "oracle"))
-        import orc
+        impl, orc, cpu_kind, cpu_what = cpu_arm()
         threads = orc.hardware_threads()
         sample = int(args.cpu_frames)
         params = orc.OrbParams(NFEAT, 1.2, NLEVELS, 20, 7)
         sub = {k: np.ascontiguousarray(batch[k][:sample]) for k in batch}
-        secs, ccounts, ckps, cdesc = orc.extract_batch_mt(params, sub["gray"], sub["boxes"], sub["nbox"], sub["tm"], sub["ntm"],
-                                                          sub["blur"], threads, cap=cap, want_outputs=True)
-        # the CPU sample doubles as a parity check of the timed GPU run
-        same = all(ccounts[i] == o_cnt[i] and ckps[i, :ccounts[i]].tobytes() == o_kps[i, :o_cnt[i]].tobytes()
-                   and cdesc[i, :ccounts[i]].tobytes() == o_desc[i, :o_cnt[i]].tobytes() for i in range(sample))
+        impl.extract_batch_mt(params, sub["gray"][:threads], sub["boxes"][:threads], sub["nbox"][:threads], sub["tm"][:threads],
+                              sub["ntm"][:threads], sub["blur"][:threads], threads)   # warm-up: first touch of every thread's buffers
+        secs, _, _, _ = impl.extract_batch_mt(params, sub["gray"], sub["boxes"], sub["nbox"], sub["tm"], sub["ntm"], sub["blur"], threads)
+
+        # the CPU sample doubles as a parity check of the timed GPU run: against the oracle port and, when it travelled with the
+        # snapshot, against the monotonic-heap build of the reference itself (the plain build's octree tie order depends on glibc's
+        # allocation history, tests/test_ref_parity_cpu.py)
+        def same_as_gpu(mod, **kw):
+            _, cc, ck, cd = mod.extract_batch_mt(params, sub["gray"], sub["boxes"], sub["nbox"], sub["tm"], sub["ntm"], sub["blur"], threads,
+                                                 cap=cap, want_outputs=True, **kw)
+            return bool(all(cc[i] == o_cnt[i] and ck[i, :cc[i]].tobytes() == o_kps[i, :o_cnt[i]].tobytes()
+                            and cd[i, :cc[i]].tobytes() == o_desc[i, :o_cnt[i]].tobytes() for i in range(sample)))
+        same = same_as_gpu(orc)
+        same_ref = None
+        if cpu_kind == "reference":
+            try:
+                same_ref = same_as_gpu(impl, variant="mono")
+            except Exception:
+                same_ref = None
         # single-thread per-frame latency with the per-stage breakdown: 4 warm-up frames, then 24 frames
         oex = orc.Extractor(NFEAT, 1.2, NLEVELS, 20, 7)
         st_lat = []
@@ -488,9 +536,10 @@ def run_b200(args):
             cv_prims_ms = 1e3 * float(np.median(tt))
         except Exception:
             pass
-        cpu = {"value": sample / secs, "unit": "frames/s", "cores": threads, "kind": "port",
-               "sample": "first %d frames of the rank-0 shard, one oracle extractor per thread, %d threads" % (sample, threads),
-               "bit_exact_vs_gpu": bool(same),
+        cpu = {"value": sample / secs, "unit": "frames/s", "cores": threads, "kind": cpu_kind,
+               "sample": "first %d frames of the rank-0 shard, one extractor per thread, %d threads; %s" % (sample, threads, cpu_what),
+               "bit_exact_vs_gpu": bool(same) if same_ref is None else bool(same and same_ref),
+               "gpu_equals_oracle_port": bool(same), "gpu_equals_reference_monotonic_heap": same_ref,
                "single_thread_ms_per_frame_median": 1e3 * float(np.median(st_lat)),
                "single_thread_stage_ms_per_frame": {k: 1e3 * v / max(nfr, 1) for k, v in stage_t.items()},
                "opencv_primitives_only_ms_per_frame": cv_prims_ms}
@@ -498,32 +547,32 @@ def run_b200(args):
     if rank != 0:
         return 0
     n_kp = float(np.mean(counts))
-    n_cand = float(args.cand_estimate)
+    # FAST candidates per frame, measured: the lists the timed run handed to the octree (frames 0..7 of the shard, all levels)
+    n_cand = float(np.mean([sum(len(ex.level_candidates(l, frame=f)) for l in range(NLEVELS)) for f in range(8)]))
     sb = stage_bytes(n_kp, n_cand)
     dom = max(stage_ms, key=lambda k: stage_ms[k])
     peak, peak_kind = measured_peak_gbs()
     achieved = sb[dom] * B / (stage_ms[dom] * 1e-3) / 1e9
-    traffic, alu_pct = profiled_traffic(dom)
+    traffic, alu_pct, traffic_src = profiled_traffic(dom)
     pipeline_bytes = 6049674.0
     per_stage = {}
     for st_name, ms in stage_ms.items():   # every stage against the same roofline: algorithmic GB/s and the DRAM GB/s ncu saw for its kernels
-        t_bytes, t_alu = profiled_traffic(st_name)
+        t_bytes, t_alu, _ = profiled_traffic(st_name)
         per_stage[st_name] = {"algorithmic_gbs": sb.get(st_name, 0.0) * B / (ms * 1e-3) / 1e9 if ms > 0 else None,
                               "frac": sb.get(st_name, 0.0) * B / (ms * 1e-3) / 1e9 / peak if ms > 0 else None,
                               "dram_gbs_ncu": (t_bytes / (ms * 1e-3) / 1e9) if (t_bytes and ms > 0) else None, "alu_pipe_pct_ncu": t_alu}
     line = {
-        "metric": "frames/s ORB extract+dyn-filter (640x480,1k kps)", "value": value, "unit": "frames/s", "n_gpus": world,
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": dict(base_config(world), l2="inputs + pyramid arenas (~0.6 GB per shard) exceed the 126 MB L2; no explicit flush",
-                       mean_keypoints=n_kp),
+        "config": base_config(world), "mean_keypoints": n_kp,
         "e2e": {"value": e2e_frames / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "wall_frames_per_s": e2e_frames / (e2e_wall_ms * 1e-3),
                 "in_flight": "2 batches: one handle per host thread, blocking coeb_extract_batch_host calls, alternating steps",
                 "numa_node_of_rank0": numa_node},
         "gpu_launches": args.steps * launches_per_step,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "traffic_source": "profiles/r01r_traffic.json (ncu --set full, per 256-frame step)",
+                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "candidates_per_frame_measured": n_cand,
                      "alu_pipe_pct_ncu": alu_pct,
                      "note": "the stage is integer-ALU bound (packed 16-bit min/max), not HBM bound: see DESIGN.md section 5",
                      "algorithmic_bytes_per_launch": sb[dom] * B,
@@ -552,8 +601,11 @@ def bench_matching(cb, dev, batch, o_kps, o_desc, o_cnt, ex, args):
     import torch
     from coeb_b200 import synth
     out = {}
-    kps = np.ascontiguousarray(o_kps[0, :o_cnt[0]])
-    desc = np.ascontiguousarray(o_desc[0, :o_cnt[0]])
+    # configs[2] is quoted on ~1000 keypoints: take the frames of the shard that carry no person box (nothing culled)
+    nobox = [i for i in range(len(o_cnt)) if int(batch["nbox"][i]) == 0]
+    fa, fb = nobox[0], nobox[1]
+    kps = np.ascontiguousarray(o_kps[fa, :o_cnt[fa]])
+    desc = np.ascontiguousarray(o_desc[fa, :o_cnt[fa]])
     scale = ex.tables()["scale"]
     cam_args = (535.4, 539.2, 320.1, 247.6, 40.0, 40.0 / 535.4, 0.0, 640.0, 0.0, 480.0)
     m = cb.Matcher(device=dev)
@@ -586,8 +638,8 @@ def bench_matching(cb, dev, batch, o_kps, o_desc, o_cnt, ex, args):
         L.coeb_match_lastframe(m.h, f.h, len(a3[0]), *[P(a) for a in a3], P(tc), P(tl), C.c_float(15.0), 0, 1, P(km), C.byref(nm))
     out["search_by_projection_map5k_us"] = _median_us(call_m2, 50)
     out["search_by_projection_lastframe_us"] = _median_us(call_m3, 50)
-    k2 = np.ascontiguousarray(o_kps[1, :o_cnt[1]])
-    d2 = np.ascontiguousarray(o_desc[1, :o_cnt[1]])
+    k2 = np.ascontiguousarray(o_kps[fb, :o_cnt[fb]])
+    d2 = np.ascontiguousarray(o_desc[fb, :o_cnt[fb]])
     f2 = m.frame(k2, d2, cb.Camera(*cam_args), scale, None)
     prev = np.stack([kps["x"], kps["y"]], axis=1).astype(np.float32)
     pv, m12 = prev.copy(), np.empty(len(kps), np.int32)
@@ -597,9 +649,9 @@ def bench_matching(cb, dev, batch, o_kps, o_desc, o_cnt, ex, args):
         L.coeb_match_init(m.h, f.h, f2.h, P(pv), P(m12), 100, C.c_float(0.9), 1, C.byref(nm))
     out["search_for_initialization_us"] = _median_us(call_m4, 50)
     # ---- tracking-thread chain: extract -> Frame tail on the device -> SearchLocalPoints on a resident 5k map ---------
-    gray0 = np.ascontiguousarray(batch["gray"][0])
-    nb0, nt0 = int(batch["nbox"][0]), int(batch["ntm"][0])
-    b0, t0, fl0 = batch["boxes"][0], batch["tm"][0], batch["blur"][0]
+    gray0 = np.ascontiguousarray(batch["gray"][fa])
+    nb0, nt0 = int(batch["nbox"][fa]), int(batch["ntm"][fa])
+    b0, t0, fl0 = batch["boxes"][fa], batch["tm"][fa], batch["blur"][fa]
     ex1 = cb.Extractor(NFEAT, 1.2, NLEVELS, 20, 7, device=dev)
     cap1 = ex1.default_cap()
     kb1, db1, n1 = np.empty(cap1, cb.KP_DTYPE), np.empty((cap1, 32), np.uint8), C.c_int()
@@ -726,14 +778,13 @@ def bench_matching(cb, dev, batch, o_kps, o_desc, o_cnt, ex, args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--unique", type=int, default=64, help="distinct generated images per shard (the rest are shifted copies)")
-    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--e2e-steps", type=int, default=60)
     ap.add_argument("--cpu-frames", type=int, default=128, help="frames of the shard timed on the host cores (CPU baseline)")
-    ap.add_argument("--ref-frames", type=int, default=64, help="--impl reference: frames per step")
-    ap.add_argument("--cand-estimate", type=float, default=16000.0, help="FAST candidates per frame used for algorithmic bytes")
+    ap.add_argument("--ref-frames", type=int, default=FRAMES_PER_GPU, help="--impl reference: frames per step (default: the whole 256-frame shard)")
     ap.add_argument("--stage-sync", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-match", action="store_true")

@@ -276,7 +276,15 @@ int build_geometry(coeb_extractor* ex, int w, int h) {
     return COEB_OK;
 }
 
+// A captured graph names device pointers (arenas, staging, output block): every (re)allocation of one of them drops the cache,
+// so that a stale graph can never replay writes into freed memory.
+static void drop_graphs(coeb_extractor* ex) {
+    for (auto& e : ex->graphs) cudaGraphExecDestroy(e.exec);
+    ex->graphs.clear();
+}
+
 void free_arenas(coeb_extractor* ex) {
+    drop_graphs(ex);
     cudaFree(ex->d_lmax); cudaFree(ex->d_lmax_count); cudaFree(ex->d_cell_count); cudaFree(ex->d_empty_cells); cudaFree(ex->d_empty_count);
     ex->d_lmax = nullptr; ex->d_lmax_count = ex->d_cell_count = ex->d_empty_cells = ex->d_empty_count = nullptr;
     cudaFree(ex->d_pyr); cudaFree(ex->d_blur); cudaFree(ex->d_cand); cudaFree(ex->d_knode); cudaFree(ex->d_cand_count);
@@ -721,6 +729,7 @@ int coeb_extract_batch_host(coeb_extractor* ex, int B, const uint8_t* gray, int 
     // device staging: level 0 goes into a pitch-aligned buffer; outputs into [B][cap] arrays
     const int pitch = (width + 63) & ~63;
     const size_t fstride = (size_t)pitch * height;
+    if (fstride * B > ex->in_gray_bytes) drop_graphs(ex);
     st = ensure_buf(&ex->d_in_gray, &ex->in_gray_bytes, fstride * B);
     if (st != COEB_OK) return st;
     if (frame_stride == (size_t)stride * height && !(stride == pitch && stride == width)) {
@@ -734,6 +743,7 @@ int coeb_extract_batch_host(coeb_extractor* ex, int B, const uint8_t* gray, int 
         const size_t o_tm = o_blur + a256(nbox ? sizeof(int) * B * max_box : 0), o_ntm = o_tm + a256(ntm ? sizeof(float) * B * max_tm * 2 : 0);
         const size_t total = o_ntm + a256(ntm ? sizeof(int) * B : 0);
         if (total > ex->dyn_cap) {
+            drop_graphs(ex);
             if (ex->h_dynin) cudaFreeHost(ex->h_dynin);
             cudaFree(ex->d_dynin);
             ex->h_dynin = ex->d_dynin = nullptr; ex->dyn_cap = 0;
@@ -755,6 +765,7 @@ int coeb_extract_batch_host(coeb_extractor* ex, int B, const uint8_t* gray, int 
         CUDA_TRY(cudaMemcpyAsync(ex->d_dynin, ex->h_dynin, total, cudaMemcpyHostToDevice, s));
     }
     if ((size_t)B * cap > ex->out_cap_elems || B > ex->out_cap_B) {
+        drop_graphs(ex);
         cudaFree(ex->d_out_block);
         ex->d_out_block = nullptr; ex->d_out_kps = nullptr; ex->d_out_desc = nullptr; ex->d_out_count = ex->d_out_status = nullptr;
         // counts | status | keypoints | descriptors in one block: a single-frame call downloads it with one copy
@@ -868,7 +879,8 @@ int coeb_extract_batch_host(coeb_extractor* ex, int B, const uint8_t* gray, int 
             CUDA_TRY(cudaStreamWaitEvent(ps, ex->chunk_in[c], 0));
             const BatchView sv = sub_view(ex->geom, v, f0, n, ex->pyr_bytes_per_frame);
             // the staging buffers and arenas are the handle's own, so a sub-view recurs call after call: graph replay
-            st = ex->profiling ? enqueue(ex, sv, ps, false) : launch_graphed(ex, sv, ps);
+            // (a call with more sub-batches than the cache holds would re-capture every one of them each time: plain launches)
+            st = (ex->profiling || nchunks > 24) ? enqueue(ex, sv, ps, false) : launch_graphed(ex, sv, ps);
             if (st != COEB_OK) return st;
             CUDA_TRY(cudaEventRecord(ex->chunk_done[c], ps));
             if (trace) cudaEventRecord(tev[2 + 3 * c], ps);
@@ -894,9 +906,10 @@ int coeb_extract_batch_host(coeb_extractor* ex, int B, const uint8_t* gray, int 
         const int n = ((const int*)ex->h_out1)[0];
         counts_out[0] = n;
         hstatus[0] = ((const int*)ex->h_out1)[1];
-        const int m = std::min(std::max(n, 0), cap);
-        if (kps_out) std::memcpy(kps_out, ex->h_out1 + ((char*)ex->d_out_kps - ex->d_out_block), sizeof(coeb_keypoint) * m);
-        if (desc_out) std::memcpy(desc_out, ex->h_out1 + ((char*)ex->d_out_desc - ex->d_out_block), (size_t)32 * m);
+        // on COEB_ERR_CAPACITY the device wrote no keypoint (only the required count): nothing to copy
+        const int m = hstatus[0] == COEB_OK ? std::min(std::max(n, 0), cap) : 0;
+        if (kps_out && m) std::memcpy(kps_out, ex->h_out1 + ((char*)ex->d_out_kps - ex->d_out_block), sizeof(coeb_keypoint) * m);
+        if (desc_out && m) std::memcpy(desc_out, ex->h_out1 + ((char*)ex->d_out_desc - ex->d_out_block), (size_t)32 * m);
     }
     int worst = COEB_OK;
     for (int i = 0; i < B; i++)
@@ -909,6 +922,20 @@ int coeb_extract_batch_host(coeb_extractor* ex, int B, const uint8_t* gray, int 
     return worst;
 }
 
+int coeb_extractor_max_keypoints(const coeb_extractor* ex, int width, int height, int* max_out) {
+    if (!ex || !max_out || width < 1 || height < 1) return fail(COEB_ERR_INVALID_ARG, "bad argument");
+    int total = 0;
+    for (int l = 0; l < ex->params.nlevels; l++) {   // same level geometry as build_geometry()
+        const int lw = round_half_even((float)width * ex->inv_scale[l]), lh = round_half_even((float)height * ex->inv_scale[l]);
+        const int bw = lw - kEdge + 3 - kMinBorder, bh = lh - kEdge + 3 - kMinBorder;
+        if (bw < 1 || bh < 1) return fail(COEB_ERR_UNSUPPORTED, "level %d (%dx%d) is smaller than the FAST border", l, lw, lh);
+        const int n_ini = (int)std::round((float)bw / (float)bh);
+        total += std::max(ex->per_level[l] + 3, 4 * n_ini);
+    }
+    *max_out = total;
+    return COEB_OK;
+}
+
 int coeb_extract(coeb_extractor* ex, const uint8_t* gray, int width, int height, int stride, const float* boxes_xyxy,
                  int nbox, const float* tm_xy, int ntm, const int* blur_flag, int nblur, coeb_keypoint* kps_out,
                  uint8_t* desc_out, int cap, int* n_out) {
@@ -917,6 +944,7 @@ int coeb_extract(coeb_extractor* ex, const uint8_t* gray, int width, int height,
     if (!gray || width <= 0 || height <= 0) return COEB_OK;  // `if (_image.empty()) return;` (src/ORBextractor.cc:1096)
     if (nbox < 0 || ntm < 0 || nblur < 0) return fail(COEB_ERR_INVALID_ARG, "negative count");
     if (nbox > COEB_MAX_BOXES) return fail(COEB_ERR_INVALID_ARG, "at most %d boxes per frame", COEB_MAX_BOXES);
+    if ((nbox > 0 && !boxes_xyxy) || (ntm > 0 && !tm_xy) || (nblur > 0 && !blur_flag)) return fail(COEB_ERR_INVALID_ARG, "a count is positive but its array is null");
     // Fixed-shape staging (COEB_MAX_BOXES boxes, T_M capacity rounded up to 64) so that every call of this handle has the
     // same device view and replays the same CUDA graph. blur_flag is indexed by box id in the reference (:1168);
     // missing entries count as 0.

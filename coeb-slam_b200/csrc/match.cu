@@ -20,6 +20,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <mutex>
+#include <set>
 #include <vector>
 
 #include "../../include/coeb_frontend.h"
@@ -1349,11 +1351,11 @@ struct coeb_matcher {
     void* d_in = nullptr; size_t in_bytes = 0;        // kNN partials
     void* d_depth = nullptr; size_t depth_bytes = 0;  // uploaded depth map of coeb_frame_from_extractor
     cudaEvent_t ev_ex = nullptr;                       // orders the matcher's stream after an extractor's
-    std::vector<std::pair<size_t, void*>> frame_pool;  // device blocks of destroyed frames, reused by the next ones
 };
 
 struct coeb_frame {
-    coeb_matcher* m = nullptr;
+    coeb_matcher* m = nullptr;   // the matcher that built the frame; only dereferenced while it is registered as alive
+    int device = 0;
     int n = 0, nlevels = 0;
     void* block = nullptr;
     size_t block_bytes = 0;
@@ -1362,6 +1364,7 @@ struct coeb_frame {
 
 struct coeb_local_map {
     coeb_matcher* m = nullptr;
+    int device = 0;
     int n = 0;
     void* block = nullptr;
     coeb::LocalMapDev dev{};
@@ -1375,6 +1378,59 @@ extern "C" int coeb_extractor_tables(const coeb_extractor* ex, int* nlevels, flo
 extern "C" int coeb_extractor_device_stream(coeb_extractor* ex, int* device, void** stream);
 
 namespace {
+
+// Frames outlive the call that made them and, in ORB-SLAM, the thread: a Frame / KeyFrame that owns a device twin is handed from
+// Tracking to LocalMapping and LoopClosing and destroyed there, while the matcher is thread-local to Tracking. So the pool of
+// recycled frame blocks and the set of live matchers are process-wide and locked; coeb_frame_destroy never touches the matcher.
+struct FrameBlocks {
+    std::mutex mu;
+    std::vector<std::pair<size_t, void*>> pool[16];   // per device: blocks of destroyed frames, reused by the next ones
+    std::set<const coeb_matcher*> alive;
+    int matchers_on[16] = {0};
+    void* take(int device, size_t need, size_t* bytes) {
+        std::lock_guard<std::mutex> g(mu);
+        auto& v = pool[device & 15];
+        for (size_t i = 0; i < v.size(); i++)
+            if (v[i].first >= need) {
+                void* p = v[i].second;
+                *bytes = v[i].first;
+                v.erase(v.begin() + i);
+                return p;
+            }
+        return nullptr;
+    }
+    void give(int device, size_t bytes, void* p) {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            auto& v = pool[device & 15];
+            if (matchers_on[device & 15] > 0 && v.size() < 8) { v.push_back({bytes, p}); return; }
+        }
+        int cur = -1;
+        cudaGetDevice(&cur);
+        cudaSetDevice(device);
+        cudaFree(p);
+        if (cur >= 0) cudaSetDevice(cur);
+    }
+    void matcher_created(const coeb_matcher* m, int device) {
+        std::lock_guard<std::mutex> g(mu);
+        alive.insert(m);
+        matchers_on[device & 15]++;
+    }
+    void matcher_destroyed(const coeb_matcher* m, int device) {   // the caller has made `device` current
+        std::vector<std::pair<size_t, void*>> drop;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            alive.erase(m);
+            if (--matchers_on[device & 15] <= 0) drop.swap(pool[device & 15]);
+        }
+        for (auto& b : drop) cudaFree(b.second);
+    }
+    bool is_alive(const coeb_matcher* m) {
+        std::lock_guard<std::mutex> g(mu);
+        return alive.count(m) != 0;
+    }
+};
+FrameBlocks g_frames;
 
 int grow(void** p, size_t* cap, size_t bytes) {
     if (bytes <= *cap && *p) return COEB_OK;
@@ -1421,6 +1477,7 @@ int coeb_matcher_create(int device, coeb_matcher** out) {
     m->device = device;
     if (cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete m; return fail(COEB_ERR_CUDA, "cudaStreamCreate failed"); }
     m->stream = m->own_stream;
+    g_frames.matcher_created(m, device);
     *out = m;
     return COEB_OK;
 }
@@ -1435,7 +1492,7 @@ void coeb_matcher_destroy(coeb_matcher* m) {
     cudaFree(m->d_in);
     cudaFree(m->d_depth);
     if (m->ev_ex) cudaEventDestroy(m->ev_ex);
-    for (auto& b : m->frame_pool) cudaFree(b.second);
+    g_frames.matcher_destroyed(m, m->device);
     cudaStreamDestroy(m->own_stream);
     delete m;
 }
@@ -1455,14 +1512,8 @@ int coeb_frame_create(coeb_matcher* m, const coeb_keypoint* kps, const uint8_t* 
     // one device block per frame: x, y, angle, octave, uright, desc, cell_start, cell_items, kp_cell
     const size_t need = 5 * al(nn * 4) + al(nn * 32) + al((kGridCells + 1) * 4) + 2 * al(nn * 4);
     coeb_frame* f = new coeb_frame();
-    f->m = m; f->n = n; f->nlevels = nlevels;
-    for (size_t i = 0; i < m->frame_pool.size(); i++)
-        if (m->frame_pool[i].first >= need) {
-            f->block_bytes = m->frame_pool[i].first;
-            f->block = m->frame_pool[i].second;
-            m->frame_pool.erase(m->frame_pool.begin() + i);
-            break;
-        }
+    f->m = m; f->device = m->device; f->n = n; f->nlevels = nlevels;
+    f->block = g_frames.take(m->device, need, &f->block_bytes);
     if (!f->block) {
         const size_t want = std::max<size_t>(need + need / 4, 1 << 17);
         if (cudaMalloc(&f->block, want) != cudaSuccess) { delete f; return fail(COEB_ERR_CUDA, "cudaMalloc(%zu) failed", want); }
@@ -1505,16 +1556,14 @@ int coeb_frame_create(coeb_matcher* m, const coeb_keypoint* kps, const uint8_t* 
 
 void coeb_frame_destroy(coeb_frame* f) {
     if (!f) return;
-    if (f->block) {
-        if (f->m->frame_pool.size() < 8) f->m->frame_pool.push_back({f->block_bytes, f->block});
-        else { cudaSetDevice(f->m->device); cudaFree(f->block); }
-    }
+    if (f->block) g_frames.give(f->device, f->block_bytes, f->block);   // any thread; the owning matcher may be gone
     delete f;
 }
 
 int coeb_frame_features_in_area(coeb_frame* f, float x, float y, float r, int min_level, int max_level, int* idx_out, int cap,
                                 int* n_out) {
     if (!f || !n_out || cap < 0) return fail(COEB_ERR_INVALID_ARG, "bad argument");
+    if (!g_frames.is_alive(f->m)) return fail(COEB_ERR_INVALID_ARG, "the matcher that built this frame has been destroyed");
     coeb_matcher* m = f->m;
     CUDA_TRY(cudaSetDevice(m->device));
     int st = m->out.reserve((size_t)(cap + 1) * 4 + 256);
@@ -1850,14 +1899,8 @@ int coeb_frame_from_extractor(coeb_matcher* m, coeb_extractor* ex, int frame_ind
     // are contiguous so that the host copy is one transfer
     const size_t need = 5 * al(nn * 4) + al(nn * 32) + al((kGridCells + 1) * 4) + 2 * al(nn * 4) + al(nn * sizeof(coeb_keypoint)) + 2 * al(nn * 4);
     coeb_frame* f = new coeb_frame();
-    f->m = m; f->n = n; f->nlevels = nlevels;
-    for (size_t i = 0; i < m->frame_pool.size(); i++)
-        if (m->frame_pool[i].first >= need) {
-            f->block_bytes = m->frame_pool[i].first;
-            f->block = m->frame_pool[i].second;
-            m->frame_pool.erase(m->frame_pool.begin() + i);
-            break;
-        }
+    f->m = m; f->device = m->device; f->n = n; f->nlevels = nlevels;
+    f->block = g_frames.take(m->device, need, &f->block_bytes);
     if (!f->block) {
         const size_t want = std::max<size_t>(need + need / 4, 1 << 17);
         if (cudaMalloc(&f->block, want) != cudaSuccess) { delete f; return fail(COEB_ERR_CUDA, "cudaMalloc(%zu) failed", want); }
@@ -1938,7 +1981,7 @@ int coeb_local_map_create(coeb_matcher* m, int n, const float* xyz, const float*
     int st = m->in.reserve(bytes);
     if (st != COEB_OK) return st;
     coeb_local_map* lm = new coeb_local_map();
-    lm->m = m; lm->n = n;
+    lm->m = m; lm->device = m->device; lm->n = n;
     if (cudaMalloc(&lm->block, bytes) != cudaSuccess) { delete lm; return fail(COEB_ERR_CUDA, "cudaMalloc(%zu) failed", bytes); }
     size_t off = 0;
     auto put = [&](const void* src, size_t elem_bytes) {   // stages one array, returns its device address
@@ -1962,7 +2005,7 @@ int coeb_local_map_create(coeb_matcher* m, int n, const float* xyz, const float*
 
 void coeb_local_map_destroy(coeb_local_map* lm) {
     if (!lm) return;
-    cudaSetDevice(lm->m->device);
+    cudaSetDevice(lm->device);
     cudaFree(lm->block);
     delete lm;
 }

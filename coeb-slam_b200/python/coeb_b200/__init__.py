@@ -105,8 +105,11 @@ class Extractor:
         except Exception:
             pass
 
-    def default_cap(self):
-        return self.nfeatures + 4 * self.nlevels + 32
+    def default_cap(self, w=640, h=480):
+        """Upper bound of the keypoints one w x h frame can yield (coeb_extractor_max_keypoints), rounded up to a multiple of 8."""
+        n = C.c_int()
+        _check(lib().coeb_extractor_max_keypoints(self.h, int(w), int(h), C.byref(n)))
+        return (n.value + 7) & ~7
 
     def set_stream(self, stream_ptr):
         _check(lib().coeb_extractor_set_stream(self.h, C.c_void_p(int(stream_ptr) if stream_ptr else 0)))
@@ -142,7 +145,7 @@ class Extractor:
         boxes = _c(boxes if boxes is not None else np.zeros((0, 4)), np.float32).reshape(-1, 4)
         tm = _c(tm if tm is not None else np.zeros((0, 2)), np.float32).reshape(-1, 2)
         blur = _c(blur_flag if blur_flag is not None else np.zeros(len(boxes)), np.int32)
-        cap = cap or self.default_cap()
+        cap = cap or self.default_cap(w, h)
         kps = np.empty(cap, KP_DTYPE)
         desc = np.empty((cap, 32), np.uint8)
         n = C.c_int(0)
@@ -155,7 +158,7 @@ class Extractor:
         """gray [B,h,w] u8 (host). Returns (kps [B,cap], desc [B,cap,32], counts [B], status [B])."""
         assert gray.dtype == np.uint8 and gray.ndim == 3 and gray.flags.c_contiguous
         B, h, w = gray.shape
-        cap = cap or self.default_cap()
+        cap = cap or self.default_cap(w, h)
         if out is None:
             out = (np.empty((B, cap), KP_DTYPE), np.empty((B, cap, 32), np.uint8), np.empty(B, np.int32),
                    np.empty(B, np.int32))

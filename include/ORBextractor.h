@@ -145,7 +145,8 @@ private:
         if (image.empty()) return;
         const unsigned char* pix = image.data; const int w = image.cols, h = image.rows; const int stride = (int)image.step;
 #endif
-        const int cap = nfeatures_ + 4 * nlevels_ + 32;      /* the octree may return a few more than nfeatures */
+        int cap = 0;                                         /* the octree may return more than nfeatures: ask the library for the bound */
+        check(coeb_extractor_max_keypoints(ex_, w, h, &cap));
         kp_buf_.resize(cap);
         desc_buf_.resize((size_t)cap * 32);
         int n = 0;

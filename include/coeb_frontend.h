@@ -96,6 +96,12 @@ int coeb_extract_batch_device(coeb_extractor* ex, int B, const uint8_t* gray, in
 int coeb_extractor_device_outputs(coeb_extractor* ex, int frame, const coeb_keypoint** d_kps, const uint8_t** d_desc,
                                   const int** d_count, int* cap);
 
+/* Upper bound of the keypoints one width x height frame can yield, for sizing `cap`: per level max(N_l + 3, 4 * nIni_l).
+ * DistributeOctTree stops once it holds N_l nodes but its last expansion may overshoot by three, and its first round splits
+ * every one of the nIni_l = round(w/h) root nodes whatever N_l is (src/ORBextractor.cc:546-676), so nfeatures alone is not a
+ * bound (small nfeatures, wide images). */
+int coeb_extractor_max_keypoints(const coeb_extractor* ex, int width, int height, int* max_out);
+
 /* Kernel launches the last coeb_extract_batch_* call enqueued (for benchmark accounting; large batches run as several
  * sub-batches, each with its own launches). */
 int coeb_extractor_launches_per_call(const coeb_extractor* ex);
