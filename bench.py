@@ -21,8 +21,13 @@ import tempfile
 import threading
 import time
 
+# one rank per GPU and two lane threads per rank: library thread pools (OpenMP / MKL behind numpy and torch) would oversubscribe the
+# host cores of a many-GPU box, so they are held to one thread before anything imports them
+for _v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+    os.environ.setdefault(_v, "1")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
-sys.path[:0] = [os.path.join(ROOT, "coeb-slam_b200", "python")]
+sys.path[:0] = [os.path.join(ROOT, "coeb-slam_b200", "python"), os.path.join(ROOT, "tools")]
 
 import numpy as np  # noqa: E402
 
@@ -283,6 +288,15 @@ def run_b200(args):
     dev = local % torch.cuda.device_count()
     torch.cuda.set_device(dev)
     numa_node = bind_to_gpu_numa_node(torch, dev) if world > 1 else None
+    torch.set_num_threads(1)
+    # each rank keeps to its own slice of the host cores (after the NUMA restriction above), and inside the slice the two lane
+    # threads of the end-to-end region get a core each: eight ranks on a 32-vCPU box otherwise migrate over each other
+    my_cores = sorted(os.sched_getaffinity(0))
+    if world > 1 and len(my_cores) >= 2 * world:
+        ranks_here = [r for r in range(world)]   # one node: LOCAL_RANK == RANK
+        k = len(my_cores) // len(ranks_here)
+        my_cores = my_cores[local * k:(local + 1) * k]
+        os.sched_setaffinity(0, set(my_cores))
     B = FRAMES_PER_GPU
     # seeds 0..255 are the frame ids within a shard, the rank is added x1000
     batch = synth.make_batch(B, base_seed=rank * 1000, w=W, h=H, unique=args.unique)
@@ -402,6 +416,11 @@ def run_b200(args):
 
     def run_lane(lane, n):
         torch.cuda.set_device(dev)
+        if len(my_cores) >= 3:
+            try:
+                os.sched_setaffinity(0, {my_cores[lane % len(my_cores)]})   # pid 0 = the calling thread
+            except OSError:
+                pass
         for _ in range(n):
             step_host(lane)
 
@@ -429,6 +448,12 @@ def run_b200(args):
     assert o_kps.tobytes() == outs_b[0].tobytes() and o_desc.tobytes() == outs_b[1].tobytes(), "the two in-flight lanes disagree"
     h2d = sum(int(pin[k].nbytes) for k in pin)
     d2h = int(o_kps.nbytes + o_desc.nbytes + o_cnt.nbytes + o_st.nbytes)
+    # the copy ceiling of this box at this N: plain pinned cudaMemcpyAsync of one step's frames on every rank at once, with the
+    # result copies running the other way (tools/h2d_probe.py)
+    import h2d_probe
+    barrier()
+    probe_secs, probe_all = h2d_probe.measure(torch, dev, int(pin["gray"].nbytes), 10, dist, also_d2h_bytes=d2h)
+    probe_gbs = world * int(pin["gray"].nbytes) * 10 / max(probe_all or [probe_secs]) / 1e9
 
     # ---- single-frame latency (the tracking thread consumes one frame at a time) -------------------
     lat = None
@@ -569,6 +594,10 @@ def run_b200(args):
         "e2e": {"value": e2e_frames / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "wall_frames_per_s": e2e_frames / (e2e_wall_ms * 1e-3),
                 "in_flight": "2 batches: one handle per host thread, blocking coeb_extract_batch_host calls, alternating steps",
+                "copy_ceiling_GBps": probe_gbs, "frac_of_copy_ceiling": (e2e_frames / (e2e_ms * 1e-3)) * (h2d / B) / 1e9 / probe_gbs,
+                "copy_ceiling_note": "tools/h2d_probe.py run in-line: pinned cudaMemcpyAsync of one step's frames on all %d GPUs at once, "
+                                     "D2H of the result size the other way" % world,
+                "host_cores_of_rank0": len(my_cores),
                 "numa_node_of_rank0": numa_node},
         "gpu_launches": args.steps * launches_per_step,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",

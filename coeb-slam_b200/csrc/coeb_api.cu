@@ -764,7 +764,9 @@ int coeb_extract_batch_host(coeb_extractor* ex, int B, const uint8_t* gray, int 
         }
         CUDA_TRY(cudaMemcpyAsync(ex->d_dynin, ex->h_dynin, total, cudaMemcpyHostToDevice, s));
     }
-    if ((size_t)B * cap > ex->out_cap_elems || B > ex->out_cap_B) {
+    // a single-frame call always comes back as one block through pinned memory (only the rows that exist are then copied on to
+    // the caller), so its block is laid out for exactly (1, cap)
+    if ((size_t)B * cap > ex->out_cap_elems || B > ex->out_cap_B || (B == 1 && (ex->out_cap_B != 1 || ex->out_cap_elems != (size_t)cap))) {
         drop_graphs(ex);
         cudaFree(ex->d_out_block);
         ex->d_out_block = nullptr; ex->d_out_kps = nullptr; ex->d_out_desc = nullptr; ex->d_out_count = ex->d_out_status = nullptr;

@@ -62,9 +62,44 @@ typedef Mat& OutputArray;
 }  // namespace coeb_cv
 #endif
 
+/* The two places where cv::Mat and the stand-in differ in spelling (an 8-bit single-channel matrix), so that every other line of
+ * the adapters is the same text in both modes. */
+namespace coeb_adapt {
+#ifdef COEB_WITH_OPENCV
+#ifndef CV_Assert
+#define CV_Assert(expr) do { if (!(expr)) throw std::runtime_error("assertion failed: " #expr); } while (0)
+#endif
+inline void create_u8(cv::Mat& m, int rows, int cols) { m.create(rows, cols, CV_8UC1); }
+inline cv::Mat wrap_u8(int rows, int cols, unsigned char* data, size_t step) { return cv::Mat(rows, cols, CV_8UC1, data, step); }
+#else
+inline void create_u8(coeb_cv::Mat& m, int rows, int cols) { m.create(rows, cols); }
+inline coeb_cv::Mat wrap_u8(int rows, int cols, unsigned char* data, size_t step) { return coeb_cv::Mat(rows, cols, data, step); }
+#endif
+}  // namespace coeb_adapt
+
 namespace ORB_SLAM2 {
 
 static_assert(sizeof(coeb_cv::KeyPoint) == sizeof(coeb_keypoint), "cv::KeyPoint must be the 28-byte POD the C ABI returns");
+
+class ORBextractor;
+
+/* `mvImagePyramid` of the reference is a public std::vector<cv::Mat> that Frame::ComputeStereoMatches reads
+ * (src/Frame.cc:651, 741, 753, 758). Here the levels live in HBM, so the member is a view that fetches a level from the
+ * device the first time it is indexed after an extraction: reference code that says `mvImagePyramid[l]` compiles unchanged and
+ * sees the right pixels (at the price of one copy per level touched); coeb_stereo_match reads the levels where they are. */
+class LazyPyramid {
+public:
+    explicit LazyPyramid(ORBextractor* owner) : owner_(owner) {}
+    size_t size() const { return mats_.size(); }
+    bool empty() const { return mats_.empty(); }
+    void resize(size_t n) { mats_.resize(n); fresh_.assign(n, false); }
+    inline coeb_cv::Mat& operator[](size_t level);
+    void invalidate() { fresh_.assign(mats_.size(), false); }
+private:
+    ORBextractor* owner_;
+    std::vector<coeb_cv::Mat> mats_;
+    std::vector<bool> fresh_;
+};
 
 class ORBextractor {
 public:
@@ -72,7 +107,7 @@ public:
 
     /* reference: include/ORBextractor.h:50-51, src/ORBextractor.cc:418-477. `device` selects the GPU. */
     ORBextractor(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST, int device = 0)
-        : ex_(nullptr), nlevels_(nlevels), scaleFactor_(scaleFactor), nfeatures_(nfeatures) {
+        : mvImagePyramid(this), ex_(nullptr), nlevels_(nlevels), scaleFactor_(scaleFactor), nfeatures_(nfeatures), extracted_(false) {
         coeb_orb_params p;
         p.nfeatures = nfeatures; p.scale_factor = scaleFactor; p.nlevels = nlevels; p.ini_th_fast = iniThFAST; p.min_th_fast = minThFAST;
         check(coeb_extractor_create(&p, device, &ex_));
@@ -114,18 +149,17 @@ public:
     std::vector<float> GetScaleSigmaSquares() { return mvLevelSigma2; }
     std::vector<float> GetInverseScaleSigmaSquares() { return mvInvLevelSigma2; }
 
-    /* The reference exposes the pyramid as a public member read by Frame::ComputeStereoMatches (src/Frame.cc:651,741,753).
-     * The levels live in HBM; coeb_stereo_match reads them there (pass handle()). Call SyncPyramidToHost() only if host
-     * code really needs the pixels: it copies every level into mvImagePyramid. */
-    std::vector<coeb_cv::Mat> mvImagePyramid;
-    void SyncPyramidToHost() {
-        for (int l = 0; l < nlevels_; l++) {
-            int w = 0, h = 0;
-            check(coeb_pyramid_level(ex_, 0, l, 0, nullptr, &w, &h, nullptr));
-            mvImagePyramid[l].create(h, w);
-            check(coeb_pyramid_level_copy(ex_, 0, l, 0, mvImagePyramid[l].ptr(0)));
-        }
+    /* include/ORBextractor.h:99 of the reference; see LazyPyramid above. */
+    LazyPyramid mvImagePyramid;
+    /* Copies one level of the last extraction into `m` (w x h, 8-bit); throws if nothing has been extracted yet. */
+    void FetchLevel(int level, coeb_cv::Mat& m) {
+        if (!extracted_) throw std::runtime_error("ORBextractor::mvImagePyramid read before the first extraction");
+        int w = 0, h = 0;
+        check(coeb_pyramid_level(ex_, 0, level, 0, nullptr, &w, &h, nullptr));
+        coeb_adapt::create_u8(m, h, w);
+        check(coeb_pyramid_level_copy(ex_, 0, level, 0, m.ptr(0)));
     }
+    void SyncPyramidToHost() { for (int l = 0; l < nlevels_; l++) (void)mvImagePyramid[l]; }
 
     coeb_extractor* handle() { return ex_; }
 
@@ -151,6 +185,8 @@ private:
         desc_buf_.resize((size_t)cap * 32);
         int n = 0;
         check(coeb_extract(ex_, pix, w, h, stride, boxes, nbox, tm, ntm, blur, nblur, kp_buf_.data(), desc_buf_.data(), cap, &n));
+        extracted_ = true;
+        mvImagePyramid.invalidate();                         /* the reference rebuilds the pyramid on every call (:1351) */
         keypoints.resize(n);
         if (n) std::memcpy(static_cast<void*>(keypoints.data()), kp_buf_.data(), sizeof(coeb_keypoint) * n);
 #ifdef COEB_WITH_OPENCV
@@ -169,10 +205,20 @@ private:
     int nlevels_;
     float scaleFactor_;
     int nfeatures_;
+    bool extracted_;
     std::vector<float> mvScaleFactor, mvInvScaleFactor, mvLevelSigma2, mvInvLevelSigma2;
     std::vector<coeb_keypoint> kp_buf_;
     std::vector<unsigned char> desc_buf_;
 };
+
+inline coeb_cv::Mat& LazyPyramid::operator[](size_t level) {
+    if (level >= mats_.size()) throw std::out_of_range("ORBextractor::mvImagePyramid: level out of range");
+    if (!fresh_[level]) {
+        owner_->FetchLevel((int)level, mats_[level]);
+        fresh_[level] = true;
+    }
+    return mats_[level];
+}
 
 }  // namespace ORB_SLAM2
 

@@ -43,8 +43,9 @@ inline void pose34(const cv::Mat& Tcw, float out[12]) {
     for (int r = 0; r < 3; r++) for (int c = 0; c < 4; c++) out[4 * r + c] = Tcw.at<float>(r, c);
 }
 inline void xyz3(const cv::Mat& p, float out[3]) { out[0] = p.at<float>(0); out[1] = p.at<float>(1); out[2] = p.at<float>(2); }
-#endif
+#else
 inline const unsigned char* desc_row(const coeb_cv::Mat& m, int i) { return m.ptr(i); }
+#endif
 template <class A> inline void pose34(const A& Tcw, float out[12]) { for (int i = 0; i < 12; i++) out[i] = Tcw[i]; }
 template <class A> inline void xyz3(const A& p, float out[3]) { out[0] = p[0]; out[1] = p[1]; out[2] = p[2]; }
 

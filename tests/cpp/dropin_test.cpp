@@ -15,6 +15,7 @@
 extern "C" {
 struct orc_extractor;
 struct orc_frame;
+int orc_level_image(orc_extractor* e, int level, int which, uint8_t* dst);
 orc_extractor* orc_extractor_create(const coeb_orb_params* p);
 void orc_extractor_destroy(orc_extractor* e);
 int orc_extract(orc_extractor* e, const uint8_t* gray, int w, int h, int stride, const float* boxes, int nbox, const float* tm, int ntm,
@@ -152,7 +153,7 @@ static coeb_camera cam_of(const Frame& F) {
 
 static void fill_frame(Frame& F, ORB_SLAM2::ORBextractor& ex, const std::vector<uint8_t>& img, int w, int h,
                        std::vector<std::vector<float> >& box, std::vector<Point2f>& tm, std::vector<int>& blur) {
-    Mat gray(h, w, const_cast<uint8_t*>(img.data()), (size_t)w), none, mask_result;
+    Mat gray = coeb_adapt::wrap_u8(h, w, const_cast<uint8_t*>(img.data()), (size_t)w), none, mask_result;
     ex(gray, none, none, none, F.mvKeys, F.mDescriptors, box, tm, mask_result, blur);   // src/Frame.cc:416
     F.N = (int)F.mvKeys.size();
     F.mvKeysUn = F.mvKeys;                                                                // k1 == 0 (src/Frame.cc:581-585)
@@ -187,14 +188,22 @@ int main() {
     EXPECT(on == F.N && std::memcmp(F.mDescriptors.ptr(0), odesc.data(), (size_t)32 * on) == 0, "descriptors differ");
     // classic 4-argument form == COEB form without boxes
     {
-        std::vector<KeyPoint> k4; Mat d4, gray(h, w, img.data(), (size_t)w), none;
+        std::vector<KeyPoint> k4; Mat d4, gray = coeb_adapt::wrap_u8(h, w, img.data(), (size_t)w), none;
         ex(gray, none, k4, d4);
         int n4 = 0;
         orc_extract(oex, img.data(), w, h, w, nullptr, 0, nullptr, 0, nullptr, 0, okp.data(), odesc.data(), 4096, &n4);
         EXPECT(n4 == (int)k4.size() && std::memcmp(k4.data(), okp.data(), sizeof(coeb_keypoint) * n4) == 0, "4-arg operator() differs");
         EXPECT(ex.GetLevels() == 8 && ex.GetScaleFactors().size() == 8 && std::fabs(ex.GetScaleFactor() - 1.2f) < 1e-6f, "getters");
-        ex.SyncPyramidToHost();
-        EXPECT(ex.mvImagePyramid[1].cols == 533 && ex.mvImagePyramid[7].rows == 134, "pyramid geometry");
+        // the public pyramid member fetches a level the first time it is read after an extraction (src/Frame.cc:651, 741 read it)
+        EXPECT(ex.mvImagePyramid.size() == 8 && ex.mvImagePyramid[1].cols == 533 && ex.mvImagePyramid[7].rows == 134, "pyramid geometry");
+        EXPECT(std::memcmp(ex.mvImagePyramid[0].ptr(100), img.data() + 100 * w, w) == 0, "level 0 of the lazy pyramid is not the input image");
+        {
+            std::vector<uint8_t> lvl(533 * 400);
+            orc_level_image(oex, 1, 0, lvl.data());
+            bool same = true;
+            for (int y = 0; y < 400; y++) same = same && std::memcmp(ex.mvImagePyramid[1].ptr(y), lvl.data() + (size_t)y * 533, 533) == 0;
+            EXPECT(same, "level 1 of the lazy pyramid differs from the oracle");
+        }
         // empty image: silent return, outputs untouched (src/ORBextractor.cc:1096-1097)
         Mat empty; size_t before = k4.size();
         ex(empty, none, k4, d4);
@@ -219,7 +228,7 @@ int main() {
     for (int i = 0; i < NM; i++) {
         MapPoint& m = mps[i];
         const int k = rnd() % F.N;
-        m.desc.create(1, 32);
+        coeb_adapt::create_u8(m.desc, 1, 32);
         std::memcpy(m.desc.ptr(0), F.mDescriptors.ptr(k), 32);
         for (int b = 0, nb = rnd() % 30; b < nb; b++) { int bit = rnd() % 256; m.desc.ptr(0)[bit >> 3] ^= (uint8_t)(1 << (bit & 7)); }
         m.mTrackProjX = F.mvKeysUn[k].pt.x + (rndf() - 0.5f) * 8.f;
@@ -277,7 +286,7 @@ int main() {
             const float z = 0.8f + 5.f * rndf();
             const float pc[3] = {(cur.mvKeysUn[k].pt.x - cur.cx) * z / cur.fx - t[0], (cur.mvKeysUn[k].pt.y - cur.cy) * z / cur.fy - t[1], z - t[2]};
             for (int c = 0; c < 3; c++) m.pos[c] = R[c] * pc[0] + R[3 + c] * pc[1] + R[6 + c] * pc[2];   // R^T (pc - t)
-            m.desc.create(1, 32);
+            coeb_adapt::create_u8(m.desc, 1, 32);
             std::memcpy(m.desc.ptr(0), cur.mDescriptors.ptr(k), 32);
             for (int b = 0, nb = rnd() % 25; b < nb; b++) { int bit = rnd() % 256; m.desc.ptr(0)[bit >> 3] ^= (uint8_t)(1 << (bit & 7)); }
             m.nObs = (rnd() % 25) == 0 ? 0 : 3;
@@ -442,7 +451,7 @@ int main() {
             const int lvl = std::min(T.mvKeysUn[k].octave + (int)(rnd() & 1), 7);
             m.mfMaxDistance = dist * std::pow(1.2f, lvl - 0.5f) * ((!truth && (rnd() % 11) == 0) ? 30.f : 1.f);
             m.mfMinDistance = m.mfMaxDistance / T.mvScaleFactors[7];
-            m.desc.create(1, 32);
+            coeb_adapt::create_u8(m.desc, 1, 32);
             std::memcpy(m.desc.ptr(0), T.mDescriptors.ptr(k), 32);
             for (int b = 0, nb = truth ? rnd() % 30 : 120; b < nb; b++) { int bit = rnd() % 256; m.desc.ptr(0)[bit >> 3] ^= (uint8_t)(1 << (bit & 7)); }
             m.bad = (rnd() % 40) == 0;
@@ -558,7 +567,7 @@ int main() {
         Frame S;
         S.mpORBextractorLeft = &exL; S.mpORBextractorRight = &exR;
         S.mbf = 386.1448f; S.mb = 386.1448f / 718.856f;
-        Mat gl(sh, sw, L.data(), (size_t)sw), gr(sh, sw, Rr.data(), (size_t)sw), none;
+        Mat gl = coeb_adapt::wrap_u8(sh, sw, L.data(), (size_t)sw), gr = coeb_adapt::wrap_u8(sh, sw, Rr.data(), (size_t)sw), none;
         exL(gl, none, S.mvKeys, S.mDescriptors);
         exR(gr, none, S.mvKeysRight, S.mDescriptorsRight);
         std::vector<coeb_keypoint> kl(8192), kr(8192);
