@@ -24,8 +24,8 @@
 //       plain 32-bit subtract cannot borrow across lanes; the sliding 9-window min / max is two min3 (max3) stages:
 //       m3[k] = min3(d[k], d[k+1], d[k+2]); m9[k] = min3(m3[k], m3[k+3], m3[k+6]).
 //   2   cell-aware NMS over A > iniTh, local maxima appended to the level's list, one count per FAST cell.
-// Fallback kernel: persistent CTAs scan the cell counters; a cell with count 0 is recomputed alone (plain scalar code,
-// it is rare) and its local maxima above minTh are appended to the same list.
+// Fallback kernel: the cells whose counter stayed 0 are listed and recomputed alone at minTh, one warp per cell, in the same
+// packed two-pixel form; their local maxima are appended to the same list.
 #include <cstdlib>
 
 #include "coeb_device.cuh"
@@ -381,15 +381,50 @@ __global__ void __launch_bounds__(256) fast_empty_cells_kernel(const __grid_cons
     }
 }
 
-__global__ void __launch_bounds__(128) fast_fallback_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v) {
-    __shared__ __align__(4) uint8_t s_img[kMaxRoi * kRoiPitch];
-    __shared__ uint8_t s_A[(kMaxRoi - 4) * (kMaxRoi - 4)];
-    __shared__ uint32_t s_list[(kMaxRoi - 6) * (kMaxRoi - 6) / 2];
-    uint16_t* const s_queue = reinterpret_cast<uint16_t*>(s_list);   // pass A -> pass B survivors; dead before the NMS pass fills s_list
-    __shared__ int s_n, s_base, s_qn;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// One WARP per empty cell, no block barrier: the cell's ROI is staged as aligned words, the compass bound runs in the packed
+// two-pixel form of the main kernel on four pixels per lane and step, the few survivors are scored exactly (same code path as
+// 1b above) and the pixels above minTh are remembered, so that the cell-local 3x3 NMS only visits those. The per-warp shared
+// region is sized on the host from the largest cell of the geometry (a 640x480 pyramid needs 4.6 KB per warp, so that an SM
+// holds 40 such warps; the compile-time maximum would be 12 KB): the kernel is bound by load and shared-memory latency.
+constexpr int kFbWarps = 8;
+constexpr int kFbQueue = 192;             // survivor queue entries per warp, flushed before a step could overflow it
+constexpr int kFbList = 96;               // staged local maxima per warp, flushed to the level's list when nearly full
+constexpr int kFbCand = 160;              // remembered pixels above minTh per warp; more than that: the NMS scans the whole map
+struct FbLayout {
+    int pw;        // staged row pitch in words: 1 pad + data words (3 lead-in + widest ROI + 3) + 1 pad
+    int rows;      // tallest ROI
+    int aw;        // strength map row pitch in bytes (multiple of 16)
+    int arows;     // detection rows + a zero row above and below
+    int img_bytes; // staged ROI, rounded up to 16
+    int bytes;     // per-warp region
+};
+__host__ __device__ inline FbLayout fb_layout(const Geometry& g) {
+    int wc = 0, hc = 0;
+    for (int l = 0; l < g.nlevels; l++) { wc = max(wc, g.lv[l].wCell); hc = max(hc, g.lv[l].hCell); }
+    FbLayout f;
+    f.pw = ((3 + wc + 6 + 3) >> 2) + 2;
+    f.rows = hc + 6;
+    f.aw = (wc + 8 + 15) & ~15;
+    f.arows = hc + 2;
+    f.img_bytes = (f.rows * f.pw * 4 + 15) & ~15;
+    f.bytes = (f.img_bytes + f.arows * f.aw + 2 * kFbQueue + 4 * kFbList + 2 * kFbCand + 15) & ~15;
+    return f;
+}
+
+__global__ void __launch_bounds__(32 * kFbWarps) fast_fallback_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v,
+                                                                      const __grid_constant__ FbLayout F) {
+    extern __shared__ __align__(16) uint8_t fb_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t* const region = fb_smem + (size_t)warp * F.bytes;
+    uint32_t* const s_img = reinterpret_cast<uint32_t*>(region);
+    uint8_t* const s_A = region + F.img_bytes;
+    unsigned short* const s_queue = reinterpret_cast<unsigned short*>(s_A + F.arows * F.aw);
+    uint32_t* const s_list = reinterpret_cast<uint32_t*>(s_queue + kFbQueue);
+    unsigned short* const s_cand = reinterpret_cast<unsigned short*>(s_list + kFbList);
+    const int PW = F.pw, AW = F.aw;
+    const unsigned lt = (1u << lane) - 1u;
     const int n_empty = *v.empty_count;
-    for (int e = blockIdx.x; e < n_empty; e += gridDim.x) {
+    for (int e = blockIdx.x * kFbWarps + warp; e < n_empty; e += gridDim.x * kFbWarps) {
         const int c = v.empty_cells[e];
         const int frame = c / g.cells_per_frame, cf = c - frame * g.cells_per_frame;
         int level = 0;
@@ -399,89 +434,146 @@ __global__ void __launch_bounds__(128) fast_fallback_kernel(const __grid_constan
         const int ci = cell / L.nCols, cj = cell - ci * L.nCols;
         // cell ROI (src/ORBextractor.cc:813-828), level coordinates
         const int iniX = kMinBorder + cj * L.wCell, iniY = kMinBorder + ci * L.hCell;
-        const int maxX = min(iniX + L.wCell + 6, L.maxBX), maxY = min(iniY + L.hCell + 6, L.maxBY);
-        const int rw = maxX - iniX, rh = maxY - iniY;
+        const int rw = min(iniX + L.wCell + 6, L.maxBX) - iniX, rh = min(iniY + L.hCell + 6, L.maxBY) - iniY;
         const int dw = rw - 6, dh = rh - 6;          // detection area: ROI rows/cols [3, dim-3)
-        const int aw = dw + 2;                       // s_A row pitch (1 px zero border each side)
         const int thMin = v.dyn[frame].area_flag ? 10 : 7;
         const int pitch = level_pitch(g, v, level);
         const int ax = iniX & 3, nw = (ax + rw + 3) >> 2;   // aligned words per ROI row (the ROI ends 16 px before the row does)
         const uint8_t* __restrict__ img = level_ptr(g, v, level, frame) + (size_t)iniY * pitch + (iniX - ax);
-        __syncthreads();   // previous cell's shared data fully consumed
-        for (int i = tid; i < rh * nw; i += 128) {
-            const int y = i / nw, wi = i - y * nw;
-            reinterpret_cast<uint32_t*>(s_img)[y * (kRoiPitch / 4) + wi] = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)y * pitch) + wi);
-        }
-        for (int i = tid; i < aw * (dh + 2); i += 128) s_A[i] = 0;
-        if (tid == 0) { s_n = 0; s_qn = 0; }
-        __syncthreads();
-        constexpr int P = kRoiPitch;
-        const int off[16] = {3 * P, 3 * P + 1, 2 * P + 2, P + 3, 3, -P + 3, -2 * P + 2, -3 * P + 1, -3 * P, -3 * P - 1, -2 * P - 2, -P - 3, -3, P - 3, 2 * P - 2, 3 * P - 1};
-        // pass A: the compass bound on every pixel; survivors go to a queue so that the exact score below runs on full warps
-        const int npx = dw * dh;
-        const uint32_t rcp = ((1u << 20) + dw - 1) / dw;   // i / dw == (i * rcp) >> 20 for i < npx (dw, dh <= 66)
-        for (int i0 = 0; i0 < npx; i0 += 128) {
-            const int i = i0 + tid;
-            bool pass = false;
-            uint32_t yx = 0;
-            if (i < npx) {
-                const int y = (int)(((uint32_t)i * rcp) >> 20), x = i - y * dw;
-                yx = (uint32_t)(y << 8 | x);
-                const uint8_t* p = &s_img[(y + 3) * kRoiPitch + ax + (x + 3)];
-                const int cc = p[0];
-                // compass bound as fail bits (see compass_bound2): bit 14 of r + (0x4000 + th - c) is set iff d <= th
-                const int r0 = p[off[0]], r4 = p[off[4]], r8 = p[off[8]], r12 = p[off[12]];
-                const int kb = 0x4000 + thMin - cc, kd = 0x4000 + thMin + cc;
-                const int fb = ((r0 + kb) & (r8 + kb)) | ((r4 + kb) & (r12 + kb));
-                const int fd = ((kd - r0) & (kd - r8)) | ((kd - r4) & (kd - r12));
-                pass = !(fb & fd & 0x4000);   // otherwise neither polarity has two neighbouring compass points beyond minTh: s_A stays 0
+        const int aoff = 4 + ((ax + 1) & 1);        // strength map column of detection x = 0: keeps a pixel pair 2-byte aligned
+        __syncwarp();   // the previous cell's shared data is fully consumed
+        {
+            const uint32_t rcp = ((1u << 16) + nw - 1) / nw;   // i / nw == (i * rcp) >> 16 for i < 72 * 20
+            for (int i = lane; i < rh * nw; i += 32) {
+                const int y = (int)(((uint32_t)i * rcp) >> 16), wi = i - y * nw;
+                s_img[y * PW + 1 + wi] = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)y * pitch) + wi);
             }
-            const unsigned bm = __ballot_sync(0xffffffffu, pass);
-            if (bm) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&s_qn, __popc(bm));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (pass) s_queue[base + __popc(bm & ((1u << lane) - 1))] = (uint16_t)yx;
-            }
+            for (int i = lane; i < (dh + 2) * AW / 16; i += 32) reinterpret_cast<uint4*>(s_A)[i] = make_uint4(0u, 0u, 0u, 0u);
         }
-        __syncthreads();
-        // pass B: exact FAST-9 score of the survivors, two queue entries per thread in the packed 16-bit form of the main kernel
-        // (the two pixels of a "pair" are unrelated here: their ring bytes are packed with one multiply-add each)
-        const int nq = s_qn;
-        for (int q = 2 * tid; q < nq; q += 256) {
-            const int yxa = s_queue[q], yxb = s_queue[min(q + 1, nq - 1)];
-            const int ya = yxa >> 8, xa = yxa & 255, yb = yxb >> 8, xb = yxb & 255;
-            const uint8_t* pa = &s_img[(ya + 3) * kRoiPitch + ax + (xa + 3)];
-            const uint8_t* pb = &s_img[(yb + 3) * kRoiPitch + ax + (xb + 3)];
-            uint32_t r[16];
+        __syncwarp();
+        int n_out = 0, n_cand = 0;   // staged local maxima, remembered pixels above minTh (warp-uniform)
+        auto flush_list = [&]() {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(v.lmax_count + frame * g.nlevels + level, n_out);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            uint32_t* out = v.lmax + (size_t)frame * g.cand_per_frame + L.cand_base;
+            for (int i = lane; i < n_out; i += 32)
+                if (base + i < L.cand_cap) out[base + i] = s_list[i];
+            n_out = 0;
+            __syncwarp();
+        };
+        // exact strength of the queued pairs -> strength map (pixels outside the detection columns are blanked)
+        auto score_queue = [&](int nq) {
+            for (int q0 = 0; q0 < nq; q0 += 32) {
+                const int q = q0 + lane;
+                bool c0 = false, c1 = false;
+                int id = 0;
+                if (q < nq) {
+                    const int ent = s_queue[q];
+                    const int y = ent >> 6, p = ent & 63;            // staged row, pair index (first pixel = staged column 2p)
+                    const uint32_t* row = &s_img[y * PW + 1 + (p >> 1)];
+                    const uint32_t *r3 = row + 3 * PW, *rm3 = row - 3 * PW, *r2 = row + 2 * PW, *rm2 = row - 2 * PW, *r1 = row + PW, *rm1 = row - PW;
+                    uint32_t S[16];
+                    S[0] = r3[0];                                   S[1] = __funnelshift_r(r3[0], r3[1], 8);
+                    S[2] = __funnelshift_r(r2[0], r2[1], 16);       S[3] = __funnelshift_r(r1[0], r1[1], 24);
+                    S[4] = __funnelshift_r(row[0], row[1], 24);     S[5] = __funnelshift_r(rm1[0], rm1[1], 24);
+                    S[6] = __funnelshift_r(rm2[0], rm2[1], 16);     S[7] = __funnelshift_r(rm3[0], rm3[1], 8);
+                    S[8] = rm3[0];                                  S[9] = __funnelshift_r(rm3[-1], rm3[0], 24);
+                    S[10] = __funnelshift_r(rm2[-1], rm2[0], 16);   S[11] = __funnelshift_r(rm1[-1], rm1[0], 8);
+                    S[12] = __funnelshift_r(row[-1], row[0], 8);    S[13] = __funnelshift_r(r1[-1], r1[0], 8);
+                    S[14] = __funnelshift_r(r2[-1], r2[0], 16);     S[15] = __funnelshift_r(r3[-1], r3[0], 24);
+                    const uint32_t sel = (p & 1) ? 0x4342u : 0x4140u;
+                    uint32_t r[16];
 #pragma unroll
-            for (int k = 0; k < 16; k++) r[k] = (uint32_t)pb[off[k]] * 65536u + (uint32_t)pa[off[k]];
-            const uint32_t a2 = corner_strength2((uint32_t)pb[0] * 65536u + (uint32_t)pa[0], r);
-            s_A[(ya + 1) * aw + (xa + 1)] = (uint8_t)(a2 & 0xFFFFu);
-            s_A[(yb + 1) * aw + (xb + 1)] = (uint8_t)(a2 >> 16);   // q + 1 == nq: the same pixel, the same value
-        }
-        __syncthreads();
-        for (int y = warp; y < dh; y += 4)
-            for (int x = lane; x < dw; x += 32) {
-                const uint8_t* a = &s_A[(y + 1) * aw + (x + 1)];
-                const int A = a[0];
-                if (A > thMin) {
-                    const int nb = max(max(max(a[-1], a[1]), max(a[-aw - 1], a[-aw])), max(max(a[-aw + 1], a[aw - 1]), max(a[aw], a[aw + 1])));
-                    if (A > nb) {
-                        const int px = x + 3 + cj * L.wCell, py = y + 3 + ci * L.hCell;  // minBorder-relative (:844-845)
-                        s_list[atomicAdd(&s_n, 1)] = (uint32_t)px | ((uint32_t)py << 12) | ((uint32_t)(A - 1) << 24);
-                    }
+                    for (int k = 0; k < 16; k++) r[k] = __byte_perm(S[k], 0u, sel);
+                    const uint32_t a2 = corner_strength2(__byte_perm(row[0], 0u, sel), r);
+                    const int dx = 2 * p - ax - 3;                   // detection column of the pair's first pixel
+                    const uint32_t lo = (unsigned)dx < (unsigned)dw ? (a2 & 0xFFu) : 0u;
+                    const uint32_t hi = (unsigned)(dx + 1) < (unsigned)dw ? (a2 >> 16) : 0u;
+                    id = (y - 3) * AW + dx + aoff;                   // byte offset inside the map, without the zero row
+                    *reinterpret_cast<unsigned short*>(&s_A[id + AW]) = (unsigned short)(lo | (hi << 8));
+                    c0 = (int)lo > thMin;
+                    c1 = (int)hi > thMin;
+                }
+                const unsigned m0 = __ballot_sync(0xffffffffu, c0), m1 = __ballot_sync(0xffffffffu, c1);
+                const int add = __popc(m0) + __popc(m1);
+                if (n_cand + add <= kFbCand) {
+                    if (c0) s_cand[n_cand + __popc(m0 & lt)] = (unsigned short)id;
+                    if (c1) s_cand[n_cand + __popc(m0) + __popc(m1 & lt)] = (unsigned short)(id + 1);
+                    n_cand += add;
+                } else {
+                    n_cand = kFbCand + 1;   // too many to remember: the NMS scans the map
                 }
             }
-        __syncthreads();
-        const int n = s_n;
-        if (n > 0) {
-            if (tid == 0) s_base = atomicAdd(v.lmax_count + frame * g.nlevels + level, n);
-            __syncthreads();
-            uint32_t* out = v.lmax + (size_t)frame * g.cand_per_frame + L.cand_base + s_base;
-            const int room = L.cand_cap - s_base;
-            for (int i = tid; i < n && i < room; i += 128) out[i] = s_list[i];
+            __syncwarp();
+        };
+        // pass A: compass bound at minTh on every pixel pair of the detection area
+        {
+            const uint32_t tb = 0x40004000u + (uint32_t)thMin * 0x00010001u;
+            const int g0 = (ax + 3) >> 2, ng = ((ax + 3 + dw - 1) >> 2) - g0 + 1;   // aligned 4-pixel groups that touch the detection columns
+            const uint32_t rcpg = ((1u << 16) + ng - 1) / ng;
+            const int total = dh * ng;
+            int nq = 0;   // warp-uniform
+            for (int i0 = 0; i0 < total; i0 += 32) {
+                const int i = i0 + lane;
+                bool f01 = false, f23 = false;
+                int ent = 0;
+                if (i < total) {
+                    const int yy = (int)(((uint32_t)i * rcpg) >> 16), gi = g0 + (i - yy * ng);
+                    const int y = yy + 3;
+                    const uint32_t* row = &s_img[y * PW + 1 + gi];
+                    const uint32_t cw = row[0];
+                    const uint32_t S0 = row[3 * PW], S8 = row[-3 * PW];
+                    const uint32_t S4 = __funnelshift_r(cw, row[1], 24), S12 = __funnelshift_r(row[-1], cw, 8);
+                    const int dx = 4 * gi - ax - 3;   // detection column of the group's first pixel
+                    const bool x01 = (unsigned)(dx + 1) < (unsigned)(dw + 1), x23 = (unsigned)(dx + 3) < (unsigned)(dw + 1);   // either pixel of the pair inside
+                    f01 = x01 && compass_bound2(pair_lo(cw), pair_lo(S0), pair_lo(S4), pair_lo(S8), pair_lo(S12), tb);
+                    f23 = x23 && compass_bound2(pair_hi(cw), pair_hi(S0), pair_hi(S4), pair_hi(S8), pair_hi(S12), tb);
+                    ent = (y << 6) | (2 * gi);
+                }
+                const unsigned m0 = __ballot_sync(0xffffffffu, f01), m1 = __ballot_sync(0xffffffffu, f23);
+                if (f01) s_queue[nq + __popc(m0 & lt)] = (unsigned short)ent;
+                nq += __popc(m0);
+                if (f23) s_queue[nq + __popc(m1 & lt)] = (unsigned short)(ent + 1);
+                nq += __popc(m1);
+                if (nq > kFbQueue - 64) {   // the next step may add 64 entries
+                    __syncwarp();
+                    score_queue(nq);
+                    nq = 0;
+                }
+            }
+            __syncwarp();
+            score_queue(nq);
         }
+        // cell-local NMS (each cell is an independent cv::FAST call) of the pixels above minTh
+        auto nms_emit = [&](bool have, int id) {   // id: byte offset of the pixel inside the map without the zero row
+            bool keep = false;
+            int A = 0;
+            if (have) {
+                const uint8_t* a = &s_A[id + AW];
+                A = a[0];
+                if (A > thMin) {
+                    const int nb = max(max(max(a[-1], a[1]), max(a[-AW - 1], a[-AW])), max(max(a[-AW + 1], a[AW - 1]), max(a[AW], a[AW + 1])));
+                    keep = A > nb;
+                }
+            }
+            const unsigned mk = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+                const int dy = id / AW, col = id - dy * AW;
+                const int px = (col - aoff) + 3 + cj * L.wCell, py = dy + 3 + ci * L.hCell;   // minBorder-relative (:844-845)
+                s_list[n_out + __popc(mk & lt)] = (uint32_t)px | ((uint32_t)py << 12) | ((uint32_t)(A - 1) << 24);
+            }
+            n_out += __popc(mk);
+            if (n_out > kFbList - 32) { __syncwarp(); flush_list(); }
+        };
+        if (n_cand <= kFbCand) {
+            for (int i0 = 0; i0 < n_cand; i0 += 32) nms_emit(i0 + lane < n_cand, i0 + lane < n_cand ? (int)s_cand[i0 + lane] : 0);
+        } else {
+            const int total = dh * AW;
+            for (int i0 = 0; i0 < total; i0 += 32) nms_emit(i0 + lane < total, i0 + lane);
+        }
+        __syncwarp();
+        if (n_out > 0) flush_list();
     }
 }
 
@@ -537,7 +629,19 @@ void launch_fast(const Geometry& g, const BatchView& v, cudaStream_t stream) {
     const int cells = v.B * g.cells_per_frame;
     cudaMemsetAsync(v.empty_count, 0, sizeof(int), stream);
     fast_empty_cells_kernel<<<(cells + 255) / 256, 256, 0, stream>>>(g, v);
-    fast_fallback_kernel<<<std::min(cells, 148 * 8), 128, 0, stream>>>(g, v);
+    {
+        const FbLayout F = fb_layout(g);
+        const size_t smem = (size_t)F.bytes * kFbWarps;
+        static size_t configured[64] = {};   // opt-in shared-memory size: a per-device function attribute
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (smem > configured[dev & 63]) {
+            cudaFuncSetAttribute(fast_fallback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            configured[dev & 63] = smem;
+        }
+        const int ctas_per_sm = std::max(1, std::min(8, (int)((200u << 10) / smem)));
+        fast_fallback_kernel<<<148 * ctas_per_sm, 32 * kFbWarps, smem, stream>>>(g, v, F);
+    }
 }
 
 }  // namespace coeb
