@@ -372,6 +372,11 @@ def run_b200(args):
     frames_total = reduce_sum(dist, float(B * args.steps))
     value = frames_total / (ms_total * 1e-3)
 
+    if args.match_only:   # profiling runs of the matcher kernels: one untimed host-path extraction for the inputs, then the matching section
+        if rank == 0:
+            kps_h, desc_h, cnt_h, st_h = ex.extract_batch_host(batch["gray"], batch["boxes"], batch["nbox"], batch["tm"], batch["ntm"], batch["blur"], cap=cap)
+            print(json.dumps({"match": bench_matching(cb, dev, batch, kps_h, desc_h, cnt_h, ex, args), "note": "--match-only profiling run, not a bench line"}))
+        return 0
     if args.skip_e2e:
         if rank == 0:
             print(json.dumps({"metric": METRIC, "value": value, "unit": "frames/s",
@@ -818,6 +823,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-match", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: device-resident part only")
+    ap.add_argument("--match-only", action="store_true", help="profiling runs: the matching section only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

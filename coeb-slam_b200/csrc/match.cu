@@ -19,6 +19,7 @@
 // natural outcome of the per-thread sequential scan.
 #include <algorithm>
 #include <cmath>
+#include <chrono>
 #include <cstring>
 #include <mutex>
 #include <set>
@@ -237,6 +238,7 @@ struct CandLists {
     int cap;
     int* active;   // [n] queries with at least one candidate, in no particular order
     int* meta;     // [0] number of active queries, [1] some list overflowed its capacity (both zeroed before the collect kernel)
+    int* top;      // [n] list positions of the two smallest (distance, position) entries: best | second << 16 (0xFFFF = none); M2 only
 };
 
 // Lane 0 of the collecting warp records the query's candidate count.
@@ -244,6 +246,21 @@ __device__ __forceinline__ void cand_finish(const CandLists& C, int i, int cnt) 
     C.count[i] = cnt;
     if (cnt > 0) C.active[atomicAdd(&C.meta[0], 1)] = i;
     if (cnt > C.cap) C.meta[1] = 1;
+}
+
+// Sequential walk of one candidate list by one thread, eight entries in flight: the entries are independent loads, but a loop
+// that tests each one before fetching the next pays one memory round trip per entry (a 32-entry list cost ~10 us per round
+// of the resolve kernels, which was most of their time).
+template <class Fn>
+__device__ __forceinline__ void walk_list(const int2* __restrict__ it, int n, Fn&& fn) {
+    for (int c0 = 0; c0 < n; c0 += 8) {
+        int2 e[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) e[u] = it[min(c0 + u, n - 1)];
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+            if (c0 + u < n) fn(e[u]);
+    }
 }
 
 // ---- M2: SearchByProjection(Frame&, vector<MapPoint*>&, th) (src/ORBmatcher.cc:45-129) -------------------
@@ -291,6 +308,7 @@ __device__ __forceinline__ bool m2_query(const FrameDev& F, const MapDev& M, flo
 __device__ __forceinline__ void m2_collect_warp(const FrameDev& F, const MapDev& M, float th, const int* __restrict__ kp_state, const CandLists& C, int i) {
     M2Query q;
     int cnt = 0;
+    unsigned k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;   // this lane's two smallest distance << 16 | list position
     if (m2_query(F, M, th, i, q)) {
         int2* out = C.items + (size_t)i * C.cap;
         cnt = warp_for_each_in_area(
@@ -304,10 +322,26 @@ __device__ __forceinline__ void m2_collect_warp(const FrameDev& F, const MapDev&
                 return true;
             },
             [&](int pos, int idx) {
-                if (pos < C.cap) out[pos] = make_int2(idx | (F.octave[idx] << 24), hamming256(q.d, F.desc + 8 * (size_t)idx));
+                if (pos < C.cap) {
+                    const int dist = hamming256(q.d, F.desc + 8 * (size_t)idx);
+                    out[pos] = make_int2(idx | (F.octave[idx] << 24), dist);
+                    const unsigned key = ((unsigned)dist << 16) | (unsigned)pos;
+                    if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
+                }
             });
     }
-    if ((threadIdx.x & 31) == 0) cand_finish(C, i, cnt);
+    // The sequential best / second-best bookkeeping of :100-113 ends with the two smallest entries in (distance, traversal position)
+    // order, whatever the order of arrival: the resolve kernel starts from them and only walks a list when a claim removes one.
+    unsigned b1 = k1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) b1 = min(b1, __shfl_xor_sync(0xffffffffu, b1, o));
+    unsigned b2 = (k1 == b1) ? k2 : k1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) b2 = min(b2, __shfl_xor_sync(0xffffffffu, b2, o));
+    if ((threadIdx.x & 31) == 0) {
+        if (C.top) C.top[i] = (int)((b1 & 0xFFFFu) | ((b2 == 0xFFFFFFFFu ? 0xFFFFu : (b2 & 0xFFFFu)) << 16));
+        cand_finish(C, i, cnt);
+    }
 }
 
 __global__ void __launch_bounds__(256) m2_collect_kernel(FrameDev F, MapDev M, float th, const int* kp_state, CandLists C) {
@@ -320,12 +354,14 @@ __global__ void __launch_bounds__(256) m2_collect_kernel(FrameDev F, MapDev M, f
 // claim_min[idx] = smallest i (with Observations()>0) that currently claims idx.
 // The claim table (one int per keypoint of the frame) lives in shared memory when it fits: dynamic shared memory = F.n ints, else 0
 // and the global scratch array is used.
-extern __shared__ int s_claim_dyn[];
+extern __shared__ __align__(16) int s_claim_dyn[];
 template <bool kLists>
-__global__ void __launch_bounds__(1024) m2_resolve_kernel(FrameDev F, MapDev M, float th, float nnratio, const int* kp_state, CandLists C,
-                                                          int* kp_match /*out, pre-filled with kp_state*/, int* res, int* claim_glob, int* out_info,
-                                                          int claim_in_smem) {
-    __shared__ int s_changed, s_count;
+__global__ void __launch_bounds__(1024, 1) m2_resolve_kernel(FrameDev F, MapDev M, float th, float nnratio, const int* kp_state, CandLists C,
+                                                          int* kp_match /*out: every entry written*/, int* res, int* claim_glob, int* out_info,
+                                                          int claim_in_smem, int cache_cap /*active queries the dynamic shared memory can hold*/) {
+    __shared__ int s_changed, s_count, s_nslow;
+    constexpr int kSlowCap = 1024;
+    __shared__ int s_slow[kSlowCap];
     const int tid = threadIdx.x, T = blockDim.x;
     int* const claim_min = claim_in_smem ? s_claim_dyn : claim_glob;
     if (kLists && C.meta[1]) {   // a list overflowed: report and let the host rerun the window-walking variant
@@ -336,6 +372,135 @@ __global__ void __launch_bounds__(1024) m2_resolve_kernel(FrameDev F, MapDev M, 
     // order: the evaluation of a query depends on the others through claim_min only).
     const int na = kLists ? C.meta[0] : M.n;
     auto query = [&](int a) { return kLists ? C.active[a] : a; };
+    if (kLists && na <= cache_cap) {
+        // Cached path: the active queries and, for each, the two list entries that decide the outcome when no claim touches them
+        // (C.top) are copied to shared memory once, so that a round of the fixed-point iteration reads shared memory only and the loops
+        // stay rolled (the kernel runs on one SM: an unrolled register version was bound by instruction fetch). A query one of whose
+        // two entries is claimed by an earlier map point is queued and its list re-examined by a whole warp.
+        int* const qi = s_claim_dyn + (claim_in_smem ? F.n : 0);
+        int* const qres = qi + cache_cap;
+        int2* const q1 = reinterpret_cast<int2*>(qres + cache_cap + (((claim_in_smem ? F.n : 0) + 2 * cache_cap) & 1));   // 8-byte aligned
+        int2* const q2 = q1 + cache_cap;
+        unsigned char* const qcnt = reinterpret_cast<unsigned char*>(q2 + cache_cap);   // list lengths (at most C.cap <= 64)
+        const int lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+        for (int a = tid; a < na; a += T) {
+            const int i = C.active[a];
+            const int2* it = C.items + (size_t)i * C.cap;
+            const unsigned tp = (unsigned)C.top[i];
+            const int2 e1 = it[tp & 0xFFFFu];
+            int2 e2 = make_int2(-1, 256);
+            if ((tp >> 16) != 0xFFFFu) { e2 = it[tp >> 16]; if (e2.y >= 256) e2 = make_int2(-1, 256); }   // (a distance of 256 never enters, :100)
+            qi[a] = M.has_obs[i] ? i : (i | (int)0x40000000);   // bit 30: Observations() == 0, its claims do not block (:87-89)
+            qres[a] = -1;
+            q1[a] = e1;
+            q2[a] = e2;
+            qcnt[a] = (unsigned char)min(C.count[i], 255);
+        }
+        auto decide = [&](int bestDist, int bestLevel, int bestIdx, int bestDist2, int bestLevel2) {
+            return (bestDist <= COEB_TH_HIGH && !(bestLevel == bestLevel2 && (float)bestDist > nnratio * (float)bestDist2)) ? bestIdx : -1;
+        };
+        for (int round = 0; round <= M.n; round++) {
+            for (int k = tid; k < F.n; k += T) claim_min[k] = kInf;
+            if (tid == 0) { s_changed = 0; s_nslow = 0; }
+            __syncthreads();
+            for (int a = tid; a < na; a += T) {
+                const int r = qres[a], iq = qi[a];
+                if (r >= 0 && !(iq & 0x40000000)) atomicMin(&claim_min[r], iq);
+            }
+            __syncthreads();
+            bool changed_here = false;
+            for (int a = tid; a < na; a += T) {
+                const int i = qi[a] & 0x3FFFFFFF;
+                const int2 e1 = q1[a], e2 = q2[a];
+                int out;
+                if (e1.y > COEB_TH_HIGH) {
+                    out = -1;   // exclusions can only raise the best distance
+                } else if (claim_min[e1.x & 0xFFFFFF] >= i && (e2.x < 0 || claim_min[e2.x & 0xFFFFFF] >= i)) {
+                    out = decide(e1.y, e1.x >> 24, e1.x & 0xFFFFFF, e2.y, e2.x < 0 ? -1 : (e2.x >> 24));   // every other exclusion leaves these two in place
+                } else {
+                    const int k = atomicAdd(&s_nslow, 1);
+                    if (k < kSlowCap) { s_slow[k] = a; continue; }
+                    int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;   // queue full: walked in place
+                    walk_list(C.items + (size_t)i * C.cap, C.count[i], [&](const int2 e) {
+                        const int idx = e.x & 0xFFFFFF, dist = e.y, oct = e.x >> 24;
+                        if (claim_min[idx] < i) return;   // claimed earlier in this call by a MapPoint with observations (:87-89, :123)
+                        if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = oct; bestIdx = idx; }
+                        else if (dist < bestDist2) { bestLevel2 = oct; bestDist2 = dist; }
+                    });
+                    out = decide(bestDist, bestLevel, bestIdx, bestDist2, bestLevel2);
+                }
+                if (out != qres[a]) { qres[a] = out; changed_here = true; }
+            }
+            __syncthreads();
+            {   // one warp per queued query: its entries are tested side by side and the two smallest (distance, position) keys among
+                // those no earlier map point claims are found with two warp reductions. A lane holds entries lane and lane + 32 (lists have
+                // at most 64 entries); the lists of a warp's next query are already in flight while the current one is reduced.
+                const int ns = min(s_nslow, kSlowCap);
+                auto fetch = [&](int k, int& i, int& n, int2& ea, int2& eb) {
+                    i = -1; n = 0; ea = eb = make_int2(0, 256);
+                    if (k < ns) {
+                        const int a = s_slow[k];
+                        i = qi[a] & 0x3FFFFFFF;
+                        n = qcnt[a];
+                        const int2* it = C.items + (size_t)i * C.cap;
+                        if (lane < n) ea = it[lane];
+                        if (lane + 32 < n) eb = it[lane + 32];
+                    }
+                };
+                int i, n, i_nx, n_nx;
+                int2 ea, eb, ea_nx, eb_nx;
+                fetch(warp, i, n, ea, eb);
+                for (int k = warp; k < ns; k += nwarps) {
+                    fetch(k + nwarps, i_nx, n_nx, ea_nx, eb_nx);
+                    const bool oka = lane < n && ea.y < 256 && claim_min[ea.x & 0xFFFFFF] >= i;
+                    const bool okb = lane + 32 < n && eb.y < 256 && claim_min[eb.x & 0xFFFFFF] >= i;
+                    const unsigned ka = oka ? (((unsigned)ea.y << 16) | (unsigned)lane) : 0xFFFFFFFFu;
+                    const unsigned kb = okb ? (((unsigned)eb.y << 16) | (unsigned)(lane + 32)) : 0xFFFFFFFFu;
+                    const unsigned k1 = min(ka, kb), k2 = max(ka, kb);
+                    unsigned b1 = k1;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) b1 = min(b1, __shfl_xor_sync(0xffffffffu, b1, o));
+                    unsigned b2 = (k1 == b1) ? k2 : k1;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) b2 = min(b2, __shfl_xor_sync(0xffffffffu, b2, o));
+                    // the winners' entries come from the lanes that hold them
+                    const int l1 = (int)(b1 & 31u), l2 = (int)(b2 & 31u);
+                    const int x1a = __shfl_sync(0xffffffffu, ea.x, l1), x1b = __shfl_sync(0xffffffffu, eb.x, l1);
+                    const int x2a = __shfl_sync(0xffffffffu, ea.x, l2), x2b = __shfl_sync(0xffffffffu, eb.x, l2);
+                    if (lane == 0) {
+                        int out = -1;
+                        if (b1 != 0xFFFFFFFFu) {
+                            const int x1 = (b1 & 32u) ? x1b : x1a;
+                            int d2 = 256, lv2 = -1;
+                            if (b2 != 0xFFFFFFFFu) { d2 = (int)(b2 >> 16); lv2 = ((b2 & 32u) ? x2b : x2a) >> 24; }
+                            out = decide((int)(b1 >> 16), x1 >> 24, x1 & 0xFFFFFF, d2, lv2);
+                        }
+                        const int a = s_slow[k];
+                        if (out != qres[a]) { qres[a] = out; s_changed = 1; }
+                    }
+                    i = i_nx; n = n_nx; ea = ea_nx; eb = eb_nx;
+                }
+            }
+            if (changed_here) s_changed = 1;
+            __syncthreads();
+            const int changed = s_changed;
+            __syncthreads();
+            if (!changed) { if (tid == 0) out_info[1] = round + 1; break; }
+        }
+        // F.mvpMapPoints[bestIdx] = pMP in query order: the last writer wins; every success counts (:123-124)
+        if (tid == 0) s_count = 0;
+        for (int k = tid; k < F.n; k += T) claim_min[k] = -1;  // reuse as "last claimant"
+        __syncthreads();
+        int mine = 0;
+        for (int a = tid; a < na; a += T)
+            if (qres[a] >= 0) { atomicMax(&claim_min[qres[a]], qi[a] & 0x3FFFFFFF); mine++; }
+        if (mine) atomicAdd(&s_count, mine);
+        __syncthreads();
+        for (int k = tid; k < F.n; k += T)
+            kp_match[k] = claim_min[k] >= 0 ? claim_min[k] : kp_state[k];   // untouched entries keep the caller's state
+        if (tid == 0) { out_info[0] = s_count; out_info[2] = 0; }
+        return;
+    }
     for (int a = tid; a < na; a += T) res[query(a)] = -1;
     for (int round = 0; round <= M.n; round++) {
         for (int k = tid; k < F.n; k += T) claim_min[k] = kInf;
@@ -355,9 +520,7 @@ __global__ void __launch_bounds__(1024) m2_resolve_kernel(FrameDev F, MapDev M, 
                 else if (dist < bestDist2) { bestLevel2 = oct; bestDist2 = dist; }
             };
             if (kLists) {
-                const int2* it = C.items + (size_t)i * C.cap;
-                const int n = C.count[i];
-                for (int c = 0; c < n; c++) { const int2 e = it[c]; consider(e.x & 0xFFFFFF, e.y, e.x >> 24); }
+                walk_list(C.items + (size_t)i * C.cap, C.count[i], [&](const int2 e) { consider(e.x & 0xFFFFFF, e.y, e.x >> 24); });
             } else {
                 m2_visit(F, M, th, kp_state, i, consider);
             }
@@ -382,7 +545,7 @@ __global__ void __launch_bounds__(1024) m2_resolve_kernel(FrameDev F, MapDev M, 
     if (mine) atomicAdd(&s_count, mine);
     __syncthreads();
     for (int k = tid; k < F.n; k += T)
-        if (claim_min[k] >= 0) kp_match[k] = claim_min[k];
+        kp_match[k] = claim_min[k] >= 0 ? claim_min[k] : kp_state[k];   // untouched entries keep the caller's state
     if (tid == 0) { out_info[0] = s_count; out_info[2] = 0; }
 }
 
@@ -489,20 +652,30 @@ __global__ void __launch_bounds__(256) m3_collect_kernel(FrameDev Cf, LastDev L,
     if (i >= L.n) return;
     M3Query q;
     int cnt = 0;
+    unsigned k1 = 0xFFFFFFFFu;   // this lane's smallest distance << 16 | list position
     if (m3_query(Cf, L, th, i, q)) {
         int2* out = C.items + (size_t)i * C.cap;
         cnt = warp_for_each_in_area(
             Cf, q.u, q.v, q.radius, q.minL, q.maxL,
             [&](int i2) { return m3_accept(Cf, L, q, kp_state, i2); },
             [&](int pos, int i2) {
-                if (pos < C.cap) out[pos] = make_int2(i2, hamming256(q.d, Cf.desc + 8 * (size_t)i2));
+                if (pos < C.cap) {
+                    const int dist = hamming256(q.d, Cf.desc + 8 * (size_t)i2);
+                    out[pos] = make_int2(i2, dist);
+                    k1 = min(k1, ((unsigned)dist << 16) | (unsigned)pos);
+                }
             });
     }
-    if ((threadIdx.x & 31) == 0) cand_finish(C, i, cnt);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) k1 = min(k1, __shfl_xor_sync(0xffffffffu, k1, o));   // strict '<' of :1421-1425: first of the smallest
+    if ((threadIdx.x & 31) == 0) {
+        if (C.top) C.top[i] = (int)(k1 & 0xFFFFu);
+        cand_finish(C, i, cnt);
+    }
 }
 
 template <bool kLists>
-__global__ void __launch_bounds__(1024) m3_resolve_kernel(FrameDev C, LastDev L, float th, int check_ori, const int* kp_state, CandLists Cl,
+__global__ void __launch_bounds__(512, 1) m3_resolve_kernel(FrameDev C, LastDev L, float th, int check_ori, const int* kp_state, CandLists Cl,
                                                           int* kp_match, int* res, int* claim_glob, int* out_info, int claim_in_smem) {
     __shared__ int s_changed, s_count;
     __shared__ int s_hist[COEB_HISTO_LENGTH];
@@ -515,6 +688,91 @@ __global__ void __launch_bounds__(1024) m3_resolve_kernel(FrameDev C, LastDev L,
     }
     const int na = kLists ? Cl.meta[0] : L.n;   // queries with candidates (compacted by the collect kernel, any order)
     auto query = [&](int a) { return kLists ? Cl.active[a] : a; };
+    constexpr int Q = 10;
+    if (kLists && na <= Q * T) {
+        // Register path (see m2_resolve_kernel): a thread owns up to Q active queries and keeps the list entry that wins when no claim
+        // touches it, so a round of the fixed-point iteration reads shared memory only.
+        int qi[Q], qres[Q];
+        int2 q1[Q];
+        bool qobs[Q];
+#pragma unroll
+        for (int j = 0; j < Q; j++) {
+            const int a = tid + j * T;
+            qi[j] = -1; qres[j] = -1; qobs[j] = false; q1[j] = make_int2(0, 256);
+            if (a < na) {
+                const int i = Cl.active[a];
+                qi[j] = i;
+                q1[j] = Cl.items[(size_t)i * Cl.cap + Cl.top[i]];
+                qobs[j] = L.has_obs[i] != 0;
+            }
+        }
+        for (int round = 0; round <= L.n; round++) {
+            for (int k = tid; k < C.n; k += T) claim_min[k] = kInf;
+            if (tid == 0) s_changed = 0;
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < Q; j++)
+                if (qres[j] >= 0 && qobs[j]) atomicMin(&claim_min[qres[j]], qi[j]);
+            __syncthreads();
+            bool changed_here = false;
+#pragma unroll
+            for (int j = 0; j < Q; j++) {
+                const int i = qi[j];
+                if (i < 0) continue;
+                int bestDist = 256, bestIdx2 = -1;
+                if (claim_min[q1[j].x] >= i) {
+                    if (q1[j].y < 256) { bestDist = q1[j].y; bestIdx2 = q1[j].x; }
+                } else {
+                    walk_list(Cl.items + (size_t)i * Cl.cap, Cl.count[i], [&](const int2 e) {
+                        if (claim_min[e.x] < i) return;                          // :1404-1406 with :1429
+                        if (e.y < bestDist) { bestDist = e.y; bestIdx2 = e.x; }
+                    });
+                }
+                const int out = bestDist <= L.max_accept ? bestIdx2 : -1;
+                if (out != qres[j]) { qres[j] = out; changed_here = true; }
+            }
+            if (changed_here) s_changed = 1;
+            __syncthreads();
+            const int changed = s_changed;
+            __syncthreads();
+            if (!changed) { if (tid == 0) out_info[1] = round + 1; break; }
+        }
+        if (tid == 0) s_count = 0;
+        for (int k = tid; k < COEB_HISTO_LENGTH; k += T) s_hist[k] = 0;
+        for (int k = tid; k < C.n; k += T) claim_min[k] = -1;
+        __syncthreads();
+        int mine = 0;
+        int qbin[Q];
+#pragma unroll
+        for (int j = 0; j < Q; j++) {
+            qbin[j] = -1;
+            if (qres[j] >= 0) {
+                atomicMax(&claim_min[qres[j]], qi[j]);
+                mine++;
+                if (check_ori) { qbin[j] = rot_bin(L.angle[qi[j]], C.angle[qres[j]]); atomicAdd(&s_hist[qbin[j]], 1); }
+            }
+        }
+        if (mine) atomicAdd(&s_count, mine);
+        __syncthreads();
+        for (int k = tid; k < C.n; k += T)
+            kp_match[k] = claim_min[k] >= 0 ? claim_min[k] : kp_state[k];   // untouched entries keep the caller's state
+        if (tid == 0 && check_ori) {
+            int a, b, c;
+            three_maxima(s_hist, COEB_HISTO_LENGTH, a, b, c);
+            s_ind[0] = a; s_ind[1] = b; s_ind[2] = c;
+        }
+        __syncthreads();
+        if (check_ori) {  // rotation consistency (:1449-1468): entries of the losing bins are cleared, each decrements
+            int removed = 0;
+#pragma unroll
+            for (int j = 0; j < Q; j++)
+                if (qres[j] >= 0 && qbin[j] != s_ind[0] && qbin[j] != s_ind[1] && qbin[j] != s_ind[2]) { kp_match[qres[j]] = -1; removed++; }
+            if (removed) atomicSub(&s_count, removed);
+        }
+        __syncthreads();
+        if (tid == 0) { out_info[0] = s_count; out_info[2] = 0; }
+        return;
+    }
     for (int a = tid; a < na; a += T) res[query(a)] = -1;
     for (int round = 0; round <= L.n; round++) {
         for (int k = tid; k < C.n; k += T) claim_min[k] = kInf;
@@ -533,9 +791,7 @@ __global__ void __launch_bounds__(1024) m3_resolve_kernel(FrameDev C, LastDev L,
                 if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
             };
             if (kLists) {
-                const int2* it = Cl.items + (size_t)i * Cl.cap;
-                const int n = Cl.count[i];
-                for (int c = 0; c < n; c++) { const int2 e = it[c]; consider(e.x, e.y, 0); }
+                walk_list(Cl.items + (size_t)i * Cl.cap, Cl.count[i], [&](const int2 e) { consider(e.x, e.y, 0); });
             } else {
                 m3_visit(C, L, th, kp_state, i, consider);
             }
@@ -563,7 +819,7 @@ __global__ void __launch_bounds__(1024) m3_resolve_kernel(FrameDev C, LastDev L,
     if (mine) atomicAdd(&s_count, mine);
     __syncthreads();
     for (int k = tid; k < C.n; k += T)
-        if (claim_min[k] >= 0) kp_match[k] = claim_min[k];
+        kp_match[k] = claim_min[k] >= 0 ? claim_min[k] : kp_state[k];   // untouched entries keep the caller's state
     if (tid == 0 && check_ori) {
         int a, b, c;
         three_maxima(s_hist, COEB_HISTO_LENGTH, a, b, c);
@@ -652,9 +908,7 @@ __global__ void __launch_bounds__(1024) m4_resolve_kernel(FrameDev F1, FrameDev 
                 else if (dist < bestDist2) bestDist2 = dist;
             };
             if (kLists) {
-                const int2* it = C.items + (size_t)i1 * C.cap;
-                const int n = C.count[i1];
-                for (int c = 0; c < n; c++) { const int2 e = it[c]; consider(e.x, e.y, 0); }
+                walk_list(C.items + (size_t)i1 * C.cap, C.count[i1], [&](const int2 e) { consider(e.x, e.y, 0); });
             } else {
                 m4_visit(F1, F2, prev_in, window, i1, consider);
             }
@@ -1442,17 +1696,31 @@ int grow(void** p, size_t* cap, size_t bytes) {
     return COEB_OK;
 }
 
+// Dynamic shared memory of a resolve kernel: the claim table (when it fits) followed by the cached active queries
+// (bytes_per_query each; see the cached path of m2_resolve_kernel). Returns the byte count, sets *cache_cap.
+size_t resolve_smem(size_t claim_bytes, int n_queries, int bytes_per_query, int* cache_cap) {
+    const size_t budget = 200 * 1024, fixed = claim_bytes + 16;
+    const size_t room = budget > fixed ? budget - fixed : 0;
+    *cache_cap = (int)std::min<size_t>((size_t)std::max(n_queries, 0), room / bytes_per_query) & ~1;
+    return fixed + (size_t)*cache_cap * bytes_per_query;
+}
+template <class K>
+void allow_smem(K kernel, size_t bytes) {   // opt-in above 48 KB: a per-device function attribute
+    if (bytes > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+}
+
 int push_inputs(coeb_matcher* m, const Packer& p) {
     if (p.off) CUDA_TRY(cudaMemcpyAsync(m->in.d, m->in.h, p.off, cudaMemcpyHostToDevice, m->stream));
     return COEB_OK;
 }
 // Candidate lists of n queries inside a scratch block: counts | active | meta | items. Returns the bytes used.
-size_t lists_bytes(size_t n, int cap) { return 2 * al(n * 4) + al(8) + al(n * cap * 8); }
+size_t lists_bytes(size_t n, int cap) { return 3 * al(n * 4) + al(8) + al(n * cap * 8); }
 CandLists carve_lists(char* sc, size_t n, int cap) {
     CandLists C{};
     C.count = (int*)sc; sc += al(n * 4);
     C.active = (int*)sc; sc += al(n * 4);
     C.meta = (int*)sc; sc += al(8);
+    C.top = (int*)sc; sc += al(n * 4);
     C.items = (int2*)sc;
     C.cap = cap;
     return C;
@@ -1620,12 +1888,14 @@ int coeb_match_projection(coeb_matcher* m, coeb_frame* F, int n, const uint8_t* 
     for (int i = 0; i < n; i++)
         if (track_in_view[i] && !bad[i] && (level[i] < 0 || level[i] >= F->nlevels)) return fail(COEB_ERR_INVALID_ARG, "map point %d: level %d", i, level[i]);
     CUDA_TRY(cudaSetDevice(m->device));
+    const bool trace = getenv("COEB_MATCH_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
     const size_t N = n, K = F->n;
     int st;
     if ((st = m->in.reserve(3 * al(N) + 5 * al(N * 4) + al(N * 32) + al(K * 4))) != COEB_OK) return st;
     if ((st = m->out.reserve(al(K * 4) + 256)) != COEB_OK) return st;
     const int cap = 32;   // candidates kept per map point; a fuller window falls back to the window-walking kernel
-    const size_t claim_smem = (size_t)F->n * 4 <= 40 * 1024 ? (size_t)F->n * 4 : 0;   // claim table in shared memory when it fits
+    const size_t claim_smem = (size_t)F->n * 4 <= 32 * 1024 ? (size_t)F->n * 4 : 0;   // claim table in shared memory when it fits
     if ((st = grow(&m->d_scratch, &m->scratch_bytes, al(N * 4) + al(K * 4) + lists_bytes(N, cap))) != COEB_OK) return st;
     Packer p(m->in);
     MapDev M{};
@@ -1635,6 +1905,7 @@ int coeb_match_projection(coeb_matcher* m, coeb_frame* F, int n, const uint8_t* 
     M.level = p.place(level, N);
     M.desc = (const uint32_t*)p.place(desc, N * 32);
     const int* d_state = p.place(kp_match, K);
+    const auto t_packed = std::chrono::steady_clock::now();
     if ((st = push_inputs(m, p)) != COEB_OK) return st;
     int* d_kpm = (int*)m->out.d;                       // [K] then info[2]
     int* d_info = (int*)(m->out.d + al(K * 4));
@@ -1642,19 +1913,26 @@ int coeb_match_projection(coeb_matcher* m, coeb_frame* F, int n, const uint8_t* 
     int* d_claim = (int*)((char*)m->d_scratch + al(N * 4));
     const CandLists C = carve_lists((char*)m->d_scratch + al(N * 4) + al(K * 4), N, cap);
     CUDA_TRY(cudaMemsetAsync(C.meta, 0, 8, m->stream));
-    CUDA_TRY(cudaMemcpyAsync(d_kpm, d_state, K * 4, cudaMemcpyDeviceToDevice, m->stream));
     m2_collect_kernel<<<(n + 7) / 8, 256, 0, m->stream>>>(F->dev, M, th, d_state, C);
-    m2_resolve_kernel<true><<<1, 1024, claim_smem, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0);
+    { int cc = 0; const size_t sm = resolve_smem(claim_smem, M.n + 1, 25, &cc); allow_smem(m2_resolve_kernel<true>, sm);
+      m2_resolve_kernel<true><<<1, 1024, sm, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0, cc); }
     CUDA_TRY(cudaGetLastError());
+    const auto t_queued = std::chrono::steady_clock::now();
     if ((st = pull_outputs(m, al(K * 4) + 12)) != COEB_OK) return st;
+    if (trace) {
+        const auto t_done = std::chrono::steady_clock::now();
+        auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+        fprintf(stderr, "[coeb match] SearchByProjection(map) host timeline: validate + pack %.1f us, enqueue %.1f us, wait %.1f us\n", us(t_begin, t_packed), us(t_packed, t_queued), us(t_queued, t_done));
+    }
     if (((const int*)(m->out.h + al(K * 4)))[2]) {   // a candidate list overflowed: exact window-walking variant
-        CUDA_TRY(cudaMemcpyAsync(d_kpm, d_state, K * 4, cudaMemcpyDeviceToDevice, m->stream));
-        m2_resolve_kernel<false><<<1, 1024, claim_smem, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0);
+        { int cc = 0; const size_t sm = resolve_smem(claim_smem, M.n + 1, 25, &cc); allow_smem(m2_resolve_kernel<false>, sm);
+      m2_resolve_kernel<false><<<1, 1024, sm, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0, cc); }
         CUDA_TRY(cudaGetLastError());
         if ((st = pull_outputs(m, al(K * 4) + 12)) != COEB_OK) return st;
     }
     std::memcpy(kp_match, m->out.h, K * 4);
     if (nmatches_out) *nmatches_out = ((const int*)(m->out.h + al(K * 4)))[0];
+    if (getenv("COEB_MATCH_TRACE")) fprintf(stderr, "[coeb match] SearchByProjection(map): %d map points, %d keypoints, %d fixed-point rounds\n", n, F->n, ((const int*)(m->out.h + al(K * 4)))[1]);
     return COEB_OK;
 }
 
@@ -1674,7 +1952,7 @@ int coeb_match_lastframe(coeb_matcher* m, coeb_frame* cur, int n, const uint8_t*
     if ((st = m->in.reserve(2 * al(N) + al(N * 12) + 2 * al(N * 4) + al(N * 32) + al(K * 4))) != COEB_OK) return st;
     if ((st = m->out.reserve(al(K * 4) + 256)) != COEB_OK) return st;
     const int cap = 64;
-    const size_t claim_smem = K * 4 <= 40 * 1024 ? K * 4 : 0;   // claim table in shared memory when it fits
+    const size_t claim_smem = K * 4 <= 32 * 1024 ? K * 4 : 0;   // claim table in shared memory when it fits
     if ((st = grow(&m->d_scratch, &m->scratch_bytes, al(N * 4) + al(K * 4) + lists_bytes(N, cap))) != COEB_OK) return st;
     Packer p(m->in);
     LastDev L{};
@@ -1697,14 +1975,12 @@ int coeb_match_lastframe(coeb_matcher* m, coeb_frame* cur, int n, const uint8_t*
     int* d_claim = (int*)((char*)m->d_scratch + al(N * 4));
     const CandLists C = carve_lists((char*)m->d_scratch + al(N * 4) + al(K * 4), N, cap);
     CUDA_TRY(cudaMemsetAsync(C.meta, 0, 8, m->stream));
-    CUDA_TRY(cudaMemcpyAsync(d_kpm, d_state, K * 4, cudaMemcpyDeviceToDevice, m->stream));
     m3_collect_kernel<<<(n + 7) / 8, 256, 0, m->stream>>>(cur->dev, L, th, d_state, C);
-    m3_resolve_kernel<true><<<1, 1024, claim_smem, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0);
+    m3_resolve_kernel<true><<<1, 512, claim_smem, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0);
     CUDA_TRY(cudaGetLastError());
     if ((st = pull_outputs(m, al(K * 4) + 12)) != COEB_OK) return st;
     if (((const int*)(m->out.h + al(K * 4)))[2]) {
-        CUDA_TRY(cudaMemcpyAsync(d_kpm, d_state, K * 4, cudaMemcpyDeviceToDevice, m->stream));
-        m3_resolve_kernel<false><<<1, 1024, claim_smem, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0);
+        m3_resolve_kernel<false><<<1, 512, claim_smem, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0);
         CUDA_TRY(cudaGetLastError());
         if ((st = pull_outputs(m, al(K * 4) + 12)) != COEB_OK) return st;
     }
@@ -2026,7 +2302,7 @@ int coeb_search_local_points(coeb_matcher* m, coeb_frame* F, coeb_local_map* lm,
     const size_t out_bytes = al(K * 4) + 256 + al(N) + (proj_out ? al(N * 20) : 0);
     if ((st = m->out.reserve(out_bytes)) != COEB_OK) return st;
     const int cap = 32;
-    const size_t claim_smem = (size_t)F->n * 4 <= 40 * 1024 ? (size_t)F->n * 4 : 0;
+    const size_t claim_smem = (size_t)F->n * 4 <= 32 * 1024 ? (size_t)F->n * 4 : 0;
     // scratch: res, claim, list counts, lists | MapPoint fields written by the frustum pass
     const size_t sc_bytes = al(N * 4) + al(K * 4) + lists_bytes(N, cap) + 5 * al(N * 4) + 2 * al(N);
     if ((st = grow(&m->d_scratch, &m->scratch_bytes, sc_bytes)) != COEB_OK) return st;
@@ -2060,14 +2336,14 @@ int coeb_search_local_points(coeb_matcher* m, coeb_frame* F, coeb_local_map* lm,
     P.nlevels = F->nlevels;
     CUDA_TRY(cudaMemsetAsync(d_zero, 0, N, m->stream));
     CUDA_TRY(cudaMemsetAsync(C.meta, 0, 8, m->stream));
-    if (F->n) CUDA_TRY(cudaMemcpyAsync(d_kpm, d_state, (size_t)F->n * 4, cudaMemcpyDeviceToDevice, m->stream));
     frustum_collect_kernel<<<(n + 7) / 8, 256, 0, m->stream>>>(F->dev, lm->dev, P, d_skip, mf, M, th, d_state, C, d_proj);
-    m2_resolve_kernel<true><<<1, 1024, claim_smem, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0);
+    { int cc = 0; const size_t sm = resolve_smem(claim_smem, M.n + 1, 25, &cc); allow_smem(m2_resolve_kernel<true>, sm);
+      m2_resolve_kernel<true><<<1, 1024, sm, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0, cc); }
     CUDA_TRY(cudaGetLastError());
     if ((st = pull_outputs(m, out_bytes)) != COEB_OK) return st;
     if (((const int*)(m->out.h + al(K * 4)))[2]) {   // a candidate list overflowed: exact window-walking variant
-        if (F->n) CUDA_TRY(cudaMemcpyAsync(d_kpm, d_state, (size_t)F->n * 4, cudaMemcpyDeviceToDevice, m->stream));
-        m2_resolve_kernel<false><<<1, 1024, claim_smem, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0);
+        { int cc = 0; const size_t sm = resolve_smem(claim_smem, M.n + 1, 25, &cc); allow_smem(m2_resolve_kernel<false>, sm);
+      m2_resolve_kernel<false><<<1, 1024, sm, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0, cc); }
         CUDA_TRY(cudaGetLastError());
         if ((st = pull_outputs(m, al(K * 4) + 12)) != COEB_OK) return st;
     }
@@ -2209,7 +2485,7 @@ int coeb_match_reloc(coeb_matcher* m, coeb_frame* cur, int n, const uint8_t* val
     if ((st = m->in.reserve(2 * al(N) + al(N * 12) + 3 * al(N * 4) + al(N * 32) + al(K * 4))) != COEB_OK) return st;
     if ((st = m->out.reserve(al(K * 4) + 256)) != COEB_OK) return st;
     const int cap = 64;
-    const size_t claim_smem = K * 4 <= 40 * 1024 ? K * 4 : 0;   // claim table in shared memory when it fits
+    const size_t claim_smem = K * 4 <= 32 * 1024 ? K * 4 : 0;   // claim table in shared memory when it fits
     if ((st = grow(&m->d_scratch, &m->scratch_bytes, al(N * 4) + al(K * 4) + lists_bytes(N, cap))) != COEB_OK) return st;
     Packer p(m->in);
     LastDev L{};
@@ -2237,14 +2513,12 @@ int coeb_match_reloc(coeb_matcher* m, coeb_frame* cur, int n, const uint8_t* val
     int* d_claim = (int*)((char*)m->d_scratch + al(N * 4));
     const CandLists C = carve_lists((char*)m->d_scratch + al(N * 4) + al(K * 4), N, cap);
     CUDA_TRY(cudaMemsetAsync(C.meta, 0, 8, m->stream));
-    CUDA_TRY(cudaMemcpyAsync(d_kpm, d_state, K * 4, cudaMemcpyDeviceToDevice, m->stream));
     m3_collect_kernel<<<(n + 7) / 8, 256, 0, m->stream>>>(cur->dev, L, th, d_state, C);
-    m3_resolve_kernel<true><<<1, 1024, claim_smem, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0);
+    m3_resolve_kernel<true><<<1, 512, claim_smem, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0);
     CUDA_TRY(cudaGetLastError());
     if ((st = pull_outputs(m, al(K * 4) + 12)) != COEB_OK) return st;
     if (((const int*)(m->out.h + al(K * 4)))[2]) {
-        CUDA_TRY(cudaMemcpyAsync(d_kpm, d_state, K * 4, cudaMemcpyDeviceToDevice, m->stream));
-        m3_resolve_kernel<false><<<1, 1024, claim_smem, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0);
+        m3_resolve_kernel<false><<<1, 512, claim_smem, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0);
         CUDA_TRY(cudaGetLastError());
         if ((st = pull_outputs(m, al(K * 4) + 12)) != COEB_OK) return st;
     }
