@@ -774,6 +774,27 @@ def bench_matching(cb, dev, batch, o_kps, o_desc, o_cnt, ex, args):
     # POPC issues at 16 lanes/clk/SM on CC 10.0 (CUDA programming guide, arithmetic instruction throughput table)
     out["knn2_int_pipe_frac_at_max_clock"] = popc / (knn_ms * 1e-3) / (n_sm * 16 * 1.965e9)
     m.set_stream(0)
+    # ---- Frame::ProcessMovingObject (src/Frame.cc:311-393): the producer of T_M, one frame pair per blocking call ----
+    try:
+        from coeb_b200 import motion as cmotion
+        mo = cmotion.Motion(device=dev)
+        mp_prev, mp_cur, _ = synth.make_motion_pair(0)
+        for _ in range(3):
+            tm_g, tr_g = mo.process(mp_prev, mp_cur)
+        out["process_moving_object_us"] = _median_us(lambda: mo.process(mp_prev, mp_cur), 20)
+        out["process_moving_object_points"] = int(tr_g["n_points"])
+        out["process_moving_object_tm"] = int(len(tm_g))
+        if not args.no_cpu:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import pmo
+            import cv2
+            cv2.setNumThreads(1)
+            out["cpu_process_moving_object_us_cv2_1thread"] = _median_us(lambda: pmo.process_moving_object(mp_prev, mp_cur), 5)
+            cv2.setNumThreads(0)
+            out["cpu_process_moving_object_us_cv2_all_threads"] = _median_us(lambda: pmo.process_moving_object(mp_prev, mp_cur), 5)
+        mo.close()
+    except Exception as e:   # noqa: BLE001
+        out["process_moving_object_error"] = str(e)[:200]
     if not args.no_cpu:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import orc

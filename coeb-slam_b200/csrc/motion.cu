@@ -1,0 +1,815 @@
+// motion.cu -- Frame::ProcessMovingObject (reference src/Frame.cc:311-393), SURVEY.md section 8(f) row 1: the producer of T_M,
+// the "moving" points the extractor's box classification consumes (src/ORBextractor.cc:1101-1195).
+//
+// The reference body is six OpenCV calls and two loops of its own:
+//   goodFeaturesToTrack(prev, 1000, 0.01, 8, noArray, 3, useHarris, 0.04)        :333   -> harris_response / harris_candidates kernels,
+//                                                                                           sort + minimum-distance pass on the host
+//   cornerSubPix(prev, pts, (10,10), (-1,-1), (ITER|EPS, 20, 0.03))              :334   -> corner_subpix_kernel (one warp per corner)
+//   calcOpticalFlowPyrLK(prev, cur, pts, next, state, err, (22,22), 5, (20,.01)) :335   -> pyr_down / scharr kernels, lk_kernel (one warp per point,
+//                                                                                           all pyramid levels in one launch)
+//   5-px border test, 3x3 SAD test (limit 2120)                                  :336-364 -> tail of lk_kernel
+//   findFundamentalMat(F_pre, F_next, mask, FM_RANSAC, 0.1, 0.99)                :370   -> host (normalised 8-point inside RANSAC, own generator)
+//   epipolar distance > 1 -> T_M                                                 :372-385 -> epipolar_kernel (double precision, the reference's expression)
+//
+// The arithmetic of the OpenCV calls is OpenCV's (third party, pinned to 4.13.0). It is restated here operation by operation
+// (integer pyramid, integer Scharr derivatives and Q14 bilinear weights of the LK tracker are exact; the float parts follow the
+// scalar code paths without FMA), but OpenCV's own float paths are SIMD builds with fused multiply-adds and another summation
+// order, and its RANSAC draws from its own generator: parity for this row is by tolerance (tests/test_motion_gpu.py).
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "../../include/coeb_frontend.h"
+#include "coeb_device.cuh"
+#include "coeb_host.hpp"
+
+namespace coeb {
+
+constexpr int kMoMaxLevels = 8;
+constexpr int kMoMaxPts = 4096;
+constexpr int kMoMaxCand = 1 << 17;
+
+__device__ __forceinline__ int refl101(int i, int n) {   // one reflection: valid for -n < i < 2n - 1 (n >= 2)
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * n - 2 - i;
+    return i;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// cv::cornerHarris(src, dst, blockSize 3, ksize 3, k) on CV_8U: Sobel derivatives scaled by 1 / (4 * 3 * 255), products,
+// unnormalised 3x3 box sums (accumulated in double by OpenCV's box filter for float input), a*c - b*b - k*(a+c)^2 in double.
+// Borders: BORDER_REFLECT_101 for the Sobel pass and for the box sums.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kHtW = 32, kHtH = 8;
+__global__ void __launch_bounds__(kHtW * kHtH) harris_response_kernel(const uint8_t* __restrict__ img, int w, int h, int pitch, double k, float s1, float s2,
+                                                                      float* __restrict__ resp, unsigned* __restrict__ max_bits) {
+    __shared__ float s_dx[(kHtH + 2) * (kHtW + 2)], s_dy[(kHtH + 2) * (kHtW + 2)];
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * kHtW + tx;
+    const int x0 = blockIdx.x * kHtW, y0 = blockIdx.y * kHtH;
+    // The derivative at a position outside the image is the derivative at its mirror image (the box filter reflects the
+    // derivative planes), so the 1-px frame of the tile is filled through the mirrored CENTRE coordinates.
+    // derivative planes for the tile with a 1-px frame: each entry is evaluated at its own (mirrored) centre
+    for (int i = tid; i < (kHtH + 2) * (kHtW + 2); i += kHtW * kHtH) {
+        const int ly = i / (kHtW + 2), lx = i - ly * (kHtW + 2);
+        const int cx = refl101(min(max(x0 + lx - 1, -1), w), w), cy = refl101(min(max(y0 + ly - 1, -1), h), h);
+        const int xm = refl101(cx - 1, w), xp = refl101(cx + 1, w), ym = refl101(cy - 1, h), yp = refl101(cy + 1, h);
+        const uint8_t *r0 = img + (size_t)ym * pitch, *r1 = img + (size_t)cy * pitch, *r2 = img + (size_t)yp * pitch;
+        // dx: row filter [-1 0 1] (exact), column filter s*[1 2 1]: (2s)*r(y) + s*(r(y+1) + r(y-1))
+        const float d0 = (float)((int)r0[xp] - (int)r0[xm]), d1 = (float)((int)r1[xp] - (int)r1[xm]), d2 = (float)((int)r2[xp] - (int)r2[xm]);
+        s_dx[i] = __fadd_rn(__fmul_rn(s2, d1), __fmul_rn(s1, __fadd_rn(d2, d0)));
+        // dy: row filter s*[1 2 1]: p(x)*(2s) + (p(x-1) + p(x+1))*s, column filter [-1 0 1] (exact difference of the two rows)
+        const float t0 = __fadd_rn(__fmul_rn((float)r0[cx], s2), __fmul_rn((float)((int)r0[xm] + (int)r0[xp]), s1));
+        const float t2 = __fadd_rn(__fmul_rn((float)r2[cx], s2), __fmul_rn((float)((int)r2[xm] + (int)r2[xp]), s1));
+        s_dy[i] = __fsub_rn(t2, t0);
+    }
+    __syncthreads();
+    const int x = x0 + tx, y = y0 + ty;
+    if (x >= w || y >= h) return;
+    double a = 0, b = 0, c = 0;
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const float dx = s_dx[(ty + j) * (kHtW + 2) + tx + i], dy = s_dy[(ty + j) * (kHtW + 2) + tx + i];
+            a += (double)__fmul_rn(dx, dx);
+            b += (double)__fmul_rn(dx, dy);
+            c += (double)__fmul_rn(dy, dy);
+        }
+    const float fa = (float)a, fb = (float)b, fc = (float)c;   // the box filter stores floats
+    const float r = (float)((double)fa * fc - (double)fb * fb - k * ((double)fa + fc) * ((double)fa + fc));
+    resp[(size_t)y * w + x] = r;
+    if (r > 0.f) atomicMax(max_bits, __float_as_uint(r));   // positive floats order like their bit patterns
+}
+
+// goodFeaturesToTrack: threshold(eig, max * quality, THRESH_TOZERO), dilate 3x3, keep interior pixels with val != 0 && val == dilated.
+__global__ void __launch_bounds__(256) harris_candidates_kernel(const float* __restrict__ resp, int w, int h, const unsigned* __restrict__ max_bits, float quality,
+                                                                float2* __restrict__ cand, int* __restrict__ n_cand, int cap) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x < 1 || y < 1 || x >= w - 1 || y >= h - 1) return;
+    const float thresh = (float)((double)__uint_as_float(*max_bits) * (double)quality);
+    const float v = resp[(size_t)y * w + x];
+    if (!(v > thresh)) return;
+    float m = v;
+#pragma unroll
+    for (int j = -1; j <= 1; j++)
+#pragma unroll
+        for (int i = -1; i <= 1; i++) {
+            const float n = resp[(size_t)(y + j) * w + x + i];
+            if (n > thresh) m = fmaxf(m, n);
+        }
+    if (v == m) {
+        const int pos = atomicAdd(n_cand, 1);
+        if (pos < cap) cand[pos] = make_float2(v, __int_as_float(y * w + x));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// cv::cornerSubPix(src, corners, win (hw, hw), zeroZone (-1,-1), criteria): one warp per corner. Each iteration samples a
+// (2hw+3)^2 patch around the current estimate (cv::getRectSubPix: float bilinear weights, replicated border) and solves the
+// 2x2 gradient-weighted system in double.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kSpMaxWin = 23;   // 2 * 10 + 3
+__global__ void __launch_bounds__(128) corner_subpix_kernel(const uint8_t* __restrict__ img, int w, int h, int pitch, float2* __restrict__ pts, int n, int hw,
+                                                            int max_iters, double eps2, const float* __restrict__ mask) {
+    __shared__ float s_patch[4][kSpMaxWin * kSpMaxWin];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int p = blockIdx.x * 4 + wid;
+    if (p >= n) return;
+    float* patch = s_patch[wid];
+    const int win = 2 * hw + 1, pw = win + 2;
+    const float2 cT = pts[p];
+    float2 cI = cT;
+    int iter = 0;
+    double err = 0;
+    do {
+        // getRectSubPix(src, (pw, pw), cI, patch, CV_32F)
+        const float cxf = cI.x - (float)(pw - 1) * 0.5f, cyf = cI.y - (float)(pw - 1) * 0.5f;
+        const int ipx = (int)floorf(cxf), ipy = (int)floorf(cyf);
+        const float a = cxf - (float)ipx, b = cyf - (float)ipy;
+        const float a11 = __fmul_rn(1.f - a, 1.f - b), a12 = __fmul_rn(a, 1.f - b), a21 = __fmul_rn(1.f - a, b), a22 = __fmul_rn(a, b);
+        for (int i = lane; i < pw * pw; i += 32) {
+            const int py = i / pw, px = i - py * pw;
+            const int x0 = min(max(ipx + px, 0), w - 1), x1 = min(max(ipx + px + 1, 0), w - 1);
+            const int y0 = min(max(ipy + py, 0), h - 1), y1 = min(max(ipy + py + 1, 0), h - 1);
+            const float v00 = img[(size_t)y0 * pitch + x0], v01 = img[(size_t)y0 * pitch + x1], v10 = img[(size_t)y1 * pitch + x0], v11 = img[(size_t)y1 * pitch + x1];
+            patch[i] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v00, a11), __fmul_rn(v01, a12)), __fmul_rn(v10, a21)), __fmul_rn(v11, a22));
+        }
+        __syncwarp();
+        double sa = 0, sb = 0, sc = 0, sbb1 = 0, sbb2 = 0;
+        for (int i = lane; i < win * win; i += 32) {
+            const int yy = i / win, xx = i - yy * win;
+            const float* sp = patch + (yy + 1) * pw + (xx + 1);
+            const double m = mask[i];
+            const double tgx = (double)__fsub_rn(sp[1], sp[-1]), tgy = (double)__fsub_rn(sp[pw], sp[-pw]);
+            const double gxx = tgx * tgx * m, gxy = tgx * tgy * m, gyy = tgy * tgy * m;
+            const double px = xx - hw, py = yy - hw;
+            sa += gxx; sb += gxy; sc += gyy;
+            sbb1 += gxx * px + gxy * py;
+            sbb2 += gxy * px + gyy * py;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sa += __shfl_xor_sync(0xffffffffu, sa, o); sb += __shfl_xor_sync(0xffffffffu, sb, o); sc += __shfl_xor_sync(0xffffffffu, sc, o);
+            sbb1 += __shfl_xor_sync(0xffffffffu, sbb1, o); sbb2 += __shfl_xor_sync(0xffffffffu, sbb2, o);
+        }
+        __syncwarp();
+        const double det = sa * sc - sb * sb;
+        if (fabs(det) <= DBL_EPSILON * DBL_EPSILON) break;
+        const double scale = 1.0 / det;
+        float2 cI2;
+        cI2.x = (float)((double)cI.x + sc * scale * sbb1 - sb * scale * sbb2);
+        cI2.y = (float)((double)cI.y - sb * scale * sbb1 + sa * scale * sbb2);
+        err = ((double)cI2.x - cI.x) * ((double)cI2.x - cI.x) + ((double)cI2.y - cI.y) * ((double)cI2.y - cI.y);
+        cI = cI2;
+        if (cI.x < 0 || cI.x >= (float)w || cI.y < 0 || cI.y >= (float)h) break;
+    } while (++iter < max_iters && err > eps2);
+    // poor convergence: the initial point stays
+    if (fabsf(cI.x - cT.x) > (float)hw || fabsf(cI.y - cT.y) > (float)hw) cI = cT;
+    if (lane == 0) pts[p] = cI;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// cv::pyrDown (8-bit): 5x5 binomial [1 4 6 4 1] x [1 4 6 4 1], (sum + 128) >> 8, BORDER_REFLECT_101; size ((w+1)/2, (h+1)/2).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pyr_down_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch, uint8_t* __restrict__ dst, int dw, int dh, int dpitch) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= dw || y >= dh) return;
+    const int wgt[5] = {1, 4, 6, 4, 1};
+    int sum = 0;
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+        const uint8_t* row = src + (size_t)refl101(2 * y + j - 2, sh) * spitch;
+        int rs = 0;
+#pragma unroll
+        for (int i = 0; i < 5; i++) rs += wgt[i] * row[refl101(2 * x + i - 2, sw)];
+        sum += wgt[j] * rs;
+    }
+    dst[(size_t)y * dpitch + x] = (uint8_t)((sum + 128) >> 8);
+}
+
+// calcScharrDeriv (video/lkpyramid.cpp): Ix = [3 10 3]^T x [-1 0 1], Iy = [-1 0 1]^T x [3 10 3], int16, reflected borders.
+__global__ void __launch_bounds__(256) scharr_kernel(const uint8_t* __restrict__ src, int w, int h, int pitch, short2* __restrict__ d) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= w || y >= h) return;
+    const int xm = refl101(x - 1, w), xp = refl101(x + 1, w);
+    const uint8_t *r0 = src + (size_t)refl101(y - 1, h) * pitch, *r1 = src + (size_t)y * pitch, *r2 = src + (size_t)refl101(y + 1, h) * pitch;
+    auto t0 = [&](int xx) { return ((int)r0[xx] + (int)r2[xx]) * 3 + (int)r1[xx] * 10; };   // vertical smoothing
+    auto t1 = [&](int xx) { return (int)r2[xx] - (int)r0[xx]; };                             // vertical difference
+    const int ix = t0(xp) - t0(xm);
+    const int iy = (t1(xp) + t1(xm)) * 3 + t1(x) * 10;
+    d[(size_t)y * w + x] = make_short2((short)ix, (short)iy);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// LKTrackerInvoker (video/lkpyramid.cpp) for every pyramid level, coarsest first, one warp per point. The image windows read
+// the level through BORDER_REFLECT_101 (the reference pyramid carries a winSize border), the derivative window reads zeros
+// outside the level (BORDER_CONSTANT). Bilinear weights are Q14 integers, the patch and its derivatives are int16, the sums
+// are float: exactly the reference's types.
+// ---------------------------------------------------------------------------------------------------------------------
+struct LkLevels {
+    int nlevels;                       // levels actually built (maxLevel + 1)
+    int w[kMoMaxLevels], h[kMoMaxLevels], pitch[kMoMaxLevels];
+    const uint8_t* prev[kMoMaxLevels];
+    const uint8_t* cur[kMoMaxLevels];
+    const short2* deriv[kMoMaxLevels];
+};
+constexpr int kLkMaxWin = 32;
+constexpr int kLkWarps = 4;
+
+__global__ void __launch_bounds__(32 * kLkWarps) lk_kernel(const __grid_constant__ LkLevels L, const float2* __restrict__ prev_pts, int n, int win, int max_iters,
+                                                           float eps2, float min_eig_thr, float2* __restrict__ next_pts, uint8_t* __restrict__ status,
+                                                           int edge, float sad_limit) {
+    __shared__ short s_I[kLkWarps][kLkMaxWin * kLkMaxWin], s_Ix[kLkWarps][kLkMaxWin * kLkMaxWin], s_Iy[kLkWarps][kLkMaxWin * kLkMaxWin];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int p = blockIdx.x * kLkWarps + wid;
+    if (p >= n) return;
+    short *Ib = s_I[wid], *Ixb = s_Ix[wid], *Iyb = s_Iy[wid];
+    const float2 pt0 = prev_pts[p];
+    const float half = (float)(win - 1) * 0.5f;
+    const float FLT_SCALE = 1.f / (1 << 20);
+    float2 nextPt = make_float2(0.f, 0.f);
+    bool st = true;
+    for (int level = L.nlevels - 1; level >= 0; level--) {
+        const int w = L.w[level], h = L.h[level], pitch = L.pitch[level];
+        const uint8_t *I = L.prev[level], *J = L.cur[level];
+        const short2* D = L.deriv[level];
+        const float sc = (float)(1. / (double)(1 << level));
+        float2 prevPt = make_float2(__fmul_rn(pt0.x, sc), __fmul_rn(pt0.y, sc));
+        if (level == L.nlevels - 1) nextPt = prevPt;
+        else nextPt = make_float2(__fmul_rn(nextPt.x, 2.f), __fmul_rn(nextPt.y, 2.f));
+        prevPt.x = __fsub_rn(prevPt.x, half); prevPt.y = __fsub_rn(prevPt.y, half);
+        const int ipx = (int)floorf(prevPt.x), ipy = (int)floorf(prevPt.y);
+        if (ipx < -win || ipx >= w || ipy < -win || ipy >= h) {
+            if (level == 0) st = false;
+            continue;
+        }
+        float a = __fsub_rn(prevPt.x, (float)ipx), b = __fsub_rn(prevPt.y, (float)ipy);
+        int iw00 = __float2int_rn(__fmul_rn(__fmul_rn(1.f - a, 1.f - b), 16384.f));
+        int iw01 = __float2int_rn(__fmul_rn(__fmul_rn(a, 1.f - b), 16384.f));
+        int iw10 = __float2int_rn(__fmul_rn(__fmul_rn(1.f - a, b), 16384.f));
+        int iw11 = 16384 - iw00 - iw01 - iw10;
+        float A11 = 0, A12 = 0, A22 = 0;
+        for (int i = lane; i < win * win; i += 32) {
+            const int y = i / win, x = i - y * win;
+            const int gx0 = ipx + x, gy0 = ipy + y;
+            const int x0 = refl101(gx0, w), x1 = refl101(gx0 + 1, w), y0 = refl101(gy0, h), y1 = refl101(gy0 + 1, h);
+            const int ival = ((int)I[(size_t)y0 * pitch + x0] * iw00 + (int)I[(size_t)y0 * pitch + x1] * iw01 + (int)I[(size_t)y1 * pitch + x0] * iw10 +
+                              (int)I[(size_t)y1 * pitch + x1] * iw11 + (1 << 8)) >> 9;
+            auto dv = [&](int gx, int gy) { return ((unsigned)gx < (unsigned)w && (unsigned)gy < (unsigned)h) ? D[(size_t)gy * w + gx] : make_short2(0, 0); };
+            const short2 d00 = dv(gx0, gy0), d01 = dv(gx0 + 1, gy0), d10 = dv(gx0, gy0 + 1), d11 = dv(gx0 + 1, gy0 + 1);
+            const int ixval = ((int)d00.x * iw00 + (int)d01.x * iw01 + (int)d10.x * iw10 + (int)d11.x * iw11 + (1 << 13)) >> 14;
+            const int iyval = ((int)d00.y * iw00 + (int)d01.y * iw01 + (int)d10.y * iw10 + (int)d11.y * iw11 + (1 << 13)) >> 14;
+            Ib[i] = (short)ival; Ixb[i] = (short)ixval; Iyb[i] = (short)iyval;
+            A11 += (float)(ixval * ixval); A12 += (float)(ixval * iyval); A22 += (float)(iyval * iyval);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            A11 += __shfl_xor_sync(0xffffffffu, A11, o); A12 += __shfl_xor_sync(0xffffffffu, A12, o); A22 += __shfl_xor_sync(0xffffffffu, A22, o);
+        }
+        __syncwarp();
+        A11 *= FLT_SCALE; A12 *= FLT_SCALE; A22 *= FLT_SCALE;
+        float Dt = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+        const float dA = __fsub_rn(A11, A22);
+        const float minEig = (A22 + A11 - sqrtf(__fadd_rn(__fmul_rn(dA, dA), __fmul_rn(4.f, __fmul_rn(A12, A12))))) / (float)(2 * win * win);
+        if (minEig < min_eig_thr || Dt < FLT_EPSILON) {
+            if (level == 0) st = false;
+            continue;
+        }
+        Dt = 1.f / Dt;
+        nextPt.x = __fsub_rn(nextPt.x, half); nextPt.y = __fsub_rn(nextPt.y, half);
+        float2 prevDelta = make_float2(0.f, 0.f);
+        float2 result = make_float2(__fadd_rn(nextPt.x, half), __fadd_rn(nextPt.y, half));
+        for (int j = 0; j < max_iters; j++) {
+            const int inx = (int)floorf(nextPt.x), iny = (int)floorf(nextPt.y);
+            if (inx < -win || inx >= w || iny < -win || iny >= h) {
+                if (level == 0) st = false;
+                break;
+            }
+            a = __fsub_rn(nextPt.x, (float)inx); b = __fsub_rn(nextPt.y, (float)iny);
+            iw00 = __float2int_rn(__fmul_rn(__fmul_rn(1.f - a, 1.f - b), 16384.f));
+            iw01 = __float2int_rn(__fmul_rn(__fmul_rn(a, 1.f - b), 16384.f));
+            iw10 = __float2int_rn(__fmul_rn(__fmul_rn(1.f - a, b), 16384.f));
+            iw11 = 16384 - iw00 - iw01 - iw10;
+            float b1 = 0, b2 = 0;
+            for (int i = lane; i < win * win; i += 32) {
+                const int y = i / win, x = i - y * win;
+                const int x0 = refl101(inx + x, w), x1 = refl101(inx + x + 1, w), y0 = refl101(iny + y, h), y1 = refl101(iny + y + 1, h);
+                const int jv = ((int)J[(size_t)y0 * pitch + x0] * iw00 + (int)J[(size_t)y0 * pitch + x1] * iw01 + (int)J[(size_t)y1 * pitch + x0] * iw10 +
+                                (int)J[(size_t)y1 * pitch + x1] * iw11 + (1 << 8)) >> 9;
+                const int diff = jv - (int)Ib[i];
+                b1 += (float)(diff * (int)Ixb[i]);
+                b2 += (float)(diff * (int)Iyb[i]);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { b1 += __shfl_xor_sync(0xffffffffu, b1, o); b2 += __shfl_xor_sync(0xffffffffu, b2, o); }
+            b1 *= FLT_SCALE; b2 *= FLT_SCALE;
+            const float2 delta = make_float2(__fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), Dt), __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), Dt));
+            nextPt.x = __fadd_rn(nextPt.x, delta.x); nextPt.y = __fadd_rn(nextPt.y, delta.y);
+            result = make_float2(__fadd_rn(nextPt.x, half), __fadd_rn(nextPt.y, half));
+            if ((double)delta.x * delta.x + (double)delta.y * delta.y <= (double)eps2) break;
+            if (j > 0 && fabsf(delta.x + prevDelta.x) < 0.01f && fabsf(delta.y + prevDelta.y) < 0.01f) {
+                result.x = __fsub_rn(result.x, __fmul_rn(delta.x, 0.5f)); result.y = __fsub_rn(result.y, __fmul_rn(delta.y, 0.5f));
+                break;
+            }
+            prevDelta = delta;
+        }
+        nextPt = result;
+        __syncwarp();
+    }
+    if (lane == 0) {
+        next_pts[p] = nextPt;
+        // src/Frame.cc:336-364: 5-px border test on the truncated coordinates, then the 3x3 sum of absolute differences
+        if (st && edge >= 0) {
+            const int w = L.w[0], h = L.h[0], pitch = L.pitch[0];
+            const int x1 = (int)pt0.x, y1 = (int)pt0.y, x2 = (int)nextPt.x, y2 = (int)nextPt.y;
+            if (x1 < edge || x1 >= w - edge || x2 < edge || x2 >= w - edge || y1 < edge || y1 >= h - edge || y2 < edge || y2 >= h - edge) {
+                st = false;
+            } else {
+                int sad = 0;
+                for (int j = -1; j <= 1; j++)
+                    for (int i = -1; i <= 1; i++) sad += abs((int)L.prev[0][(size_t)(y1 + j) * pitch + x1 + i] - (int)L.cur[0][(size_t)(y2 + j) * pitch + x2 + i]);
+                if ((float)sad > sad_limit) st = false;
+            }
+        }
+        status[p] = st ? 1 : 0;
+    }
+}
+
+// src/Frame.cc:372-385: the epipolar distance of every tracked point, in double, with the reference's expression.
+__global__ void epipolar_kernel(const float2* __restrict__ pre, const float2* __restrict__ nxt, const uint8_t* __restrict__ status, int n, const double* __restrict__ F,
+                                double limit, uint8_t* __restrict__ moving, double* __restrict__ dist) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t mv = 0;
+    double dd = -1.0;
+    if (status[i]) {
+        const double px = pre[i].x, py = pre[i].y;
+        const double A = __dadd_rn(__dadd_rn(__dmul_rn(F[0], px), __dmul_rn(F[1], py)), F[2]);
+        const double B = __dadd_rn(__dadd_rn(__dmul_rn(F[3], px), __dmul_rn(F[4], py)), F[5]);
+        const double C = __dadd_rn(__dadd_rn(__dmul_rn(F[6], px), __dmul_rn(F[7], py)), F[8]);
+        dd = fabs(__dadd_rn(__dadd_rn(__dmul_rn(A, (double)nxt[i].x), __dmul_rn(B, (double)nxt[i].y)), C)) / sqrt(__dadd_rn(__dmul_rn(A, A), __dmul_rn(B, B)));
+        mv = !(dd <= limit);
+    }
+    moving[i] = mv;
+    if (dist) dist[i] = dd;
+}
+
+}  // namespace coeb
+
+using namespace coeb;
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------------
+struct coeb_motion {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int w = 0, h = 0, pitch = 0, nlevels = 0;
+    int lw[kMoMaxLevels] = {0}, lh[kMoMaxLevels] = {0}, lp[kMoMaxLevels] = {0};
+    uint8_t* d_pyr[2][kMoMaxLevels] = {{nullptr}};   // [0] previous frame, [1] current frame
+    short2* d_deriv[kMoMaxLevels] = {nullptr};
+    float* d_resp = nullptr;
+    unsigned* d_max = nullptr;      // [0] max response bits, [1] candidate count
+    float2* d_cand = nullptr;
+    float2 *d_pre = nullptr, *d_next = nullptr;
+    uint8_t *d_status = nullptr, *d_moving = nullptr;
+    double *d_F = nullptr, *d_dist = nullptr;
+    float* d_mask = nullptr; int mask_hw = 0;
+    char* h_pin = nullptr; size_t pin_bytes = 0;
+    std::vector<float2> cand_host;
+};
+
+namespace {
+
+void motion_free_images(coeb_motion* m) {
+    for (int f = 0; f < 2; f++)
+        for (int l = 0; l < kMoMaxLevels; l++) { cudaFree(m->d_pyr[f][l]); m->d_pyr[f][l] = nullptr; }
+    for (int l = 0; l < kMoMaxLevels; l++) { cudaFree(m->d_deriv[l]); m->d_deriv[l] = nullptr; }
+    cudaFree(m->d_resp); m->d_resp = nullptr;
+    m->w = m->h = 0;
+}
+
+// (Re)allocates the per-size buffers. Pyramid levels as cv::buildOpticalFlowPyramid lays them out: ((w+1)/2, (h+1)/2) per level,
+// stopping before a level that is not larger than the tracking window.
+int motion_prepare(coeb_motion* m, int w, int h, int win, int max_level) {
+    int nl = 1, cw = w, ch = h;
+    int lw[kMoMaxLevels], lh[kMoMaxLevels];
+    lw[0] = w; lh[0] = h;
+    while (nl <= max_level && nl < kMoMaxLevels) {
+        const int nw = (cw + 1) / 2, nh = (ch + 1) / 2;
+        if (nw <= win || nh <= win) break;
+        lw[nl] = nw; lh[nl] = nh; cw = nw; ch = nh; nl++;
+    }
+    bool same = m->w == w && m->h == h && m->nlevels == nl;
+    if (same) return COEB_OK;
+    motion_free_images(m);
+    m->w = w; m->h = h; m->nlevels = nl; m->pitch = (w + 63) & ~63;
+    for (int l = 0; l < nl; l++) {
+        m->lw[l] = lw[l]; m->lh[l] = lh[l]; m->lp[l] = (lw[l] + 63) & ~63;
+        for (int f = 0; f < 2; f++) CUDA_TRY(cudaMalloc(&m->d_pyr[f][l], (size_t)m->lp[l] * lh[l]));
+        CUDA_TRY(cudaMalloc(&m->d_deriv[l], sizeof(short2) * (size_t)lw[l] * lh[l]));
+    }
+    CUDA_TRY(cudaMalloc(&m->d_resp, sizeof(float) * (size_t)w * h));
+    return COEB_OK;
+}
+
+int motion_pin(coeb_motion* m, size_t bytes) {
+    if (bytes <= m->pin_bytes) return COEB_OK;
+    if (m->h_pin) cudaFreeHost(m->h_pin);
+    m->h_pin = nullptr; m->pin_bytes = 0;
+    CUDA_TRY(cudaHostAlloc((void**)&m->h_pin, bytes, cudaHostAllocDefault));
+    m->pin_bytes = bytes;
+    return COEB_OK;
+}
+
+int upload_level0(coeb_motion* m, int which, const uint8_t* gray, int stride) {
+    CUDA_TRY(cudaMemcpy2DAsync(m->d_pyr[which][0], m->lp[0], gray, stride, m->w, m->h, cudaMemcpyHostToDevice, m->stream));
+    return COEB_OK;
+}
+
+void build_pyramid(coeb_motion* m, int which) {
+    for (int l = 1; l < m->nlevels; l++)
+        pyr_down_kernel<<<dim3((m->lw[l] + 31) / 32, (m->lh[l] + 7) / 8), 256, 0, m->stream>>>(m->d_pyr[which][l - 1], m->lw[l - 1], m->lh[l - 1], m->lp[l - 1],
+                                                                                           m->d_pyr[which][l], m->lw[l], m->lh[l], m->lp[l]);
+}
+
+int ensure_mask(coeb_motion* m, int hw) {
+    if (m->d_mask && m->mask_hw == hw) return COEB_OK;
+    cudaFree(m->d_mask); m->d_mask = nullptr;
+    const int win = 2 * hw + 1;
+    std::vector<float> mask((size_t)win * win);
+    for (int i = 0; i < win; i++) {   // cornersubpix.cpp: float arguments, float exp
+        const float y = (float)(i - hw) / hw;
+        const float vy = std::exp(-y * y);
+        for (int j = 0; j < win; j++) {
+            const float x = (float)(j - hw) / hw;
+            mask[(size_t)i * win + j] = (float)(vy * std::exp(-x * x));
+        }
+    }
+    CUDA_TRY(cudaMalloc(&m->d_mask, mask.size() * sizeof(float)));
+    CUDA_TRY(cudaMemcpy(m->d_mask, mask.data(), mask.size() * sizeof(float), cudaMemcpyHostToDevice));
+    m->mask_hw = hw;
+    return COEB_OK;
+}
+
+// goodFeaturesToTrack after the response: candidates sorted by (value descending, raster position descending -- the pointer
+// tie-break of greaterThanPtr), then the minimum-distance pass over a grid of cell size round(minDistance).
+int select_corners(std::vector<float2>& cand, int w, int h, int max_corners, double min_distance, float* xy_out, int cap) {
+    std::sort(cand.begin(), cand.end(), [](const float2& a, const float2& b) {
+        if (a.x != b.x) return a.x > b.x;
+        int ia, ib;
+        std::memcpy(&ia, &a.y, 4); std::memcpy(&ib, &b.y, 4);
+        return ia > ib;
+    });
+    int n = 0;
+    if (min_distance >= 1) {
+        const int cell = (int)std::lrint(min_distance);
+        const int gw = (w + cell - 1) / cell, gh = (h + cell - 1) / cell;
+        std::vector<std::vector<float2> > grid((size_t)gw * gh);
+        const double md2 = min_distance * min_distance;
+        for (size_t i = 0; i < cand.size(); i++) {
+            int idx;
+            std::memcpy(&idx, &cand[i].y, 4);
+            const int y = idx / w, x = idx - y * w;
+            bool good = true;
+            const int xc = x / cell, yc = y / cell;
+            const int x1 = std::max(0, xc - 1), y1 = std::max(0, yc - 1), x2 = std::min(gw - 1, xc + 1), y2 = std::min(gh - 1, yc + 1);
+            for (int yy = y1; yy <= y2 && good; yy++)
+                for (int xx = x1; xx <= x2 && good; xx++)
+                    for (const float2& q : grid[(size_t)yy * gw + xx]) {
+                        const float dx = (float)x - q.x, dy = (float)y - q.y;
+                        if (dx * dx + dy * dy < md2) { good = false; break; }
+                    }
+            if (good) {
+                grid[(size_t)yc * gw + xc].push_back(make_float2((float)x, (float)y));
+                if (n < cap) { xy_out[2 * n] = (float)x; xy_out[2 * n + 1] = (float)y; }
+                n++;
+                if (max_corners > 0 && n == max_corners) break;
+            }
+        }
+    } else {
+        for (size_t i = 0; i < cand.size(); i++) {
+            int idx;
+            std::memcpy(&idx, &cand[i].y, 4);
+            if (n < cap) { xy_out[2 * n] = (float)(idx % w); xy_out[2 * n + 1] = (float)(idx / w); }
+            n++;
+            if (max_corners > 0 && n == max_corners) break;
+        }
+    }
+    return n;
+}
+
+// ---- fundamental matrix: normalised 8-point inside RANSAC (host, double) -------------------------------------------------
+// Smallest-eigenvalue eigenvector of a symmetric n x n matrix by cyclic Jacobi rotations.
+void jacobi_eigen(double* A, int n, double* V, double* ev) {
+    for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) V[i * n + j] = i == j;
+    for (int sweep = 0; sweep < 60; sweep++) {
+        double off = 0;
+        for (int i = 0; i < n; i++) for (int j = i + 1; j < n; j++) off += A[i * n + j] * A[i * n + j];
+        if (off < 1e-30) break;
+        for (int p = 0; p < n; p++)
+            for (int q = p + 1; q < n; q++) {
+                if (std::fabs(A[p * n + q]) < 1e-300) continue;
+                const double theta = (A[q * n + q] - A[p * n + p]) / (2 * A[p * n + q]);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1));
+                const double c = 1 / std::sqrt(t * t + 1), s = t * c;
+                for (int k = 0; k < n; k++) { const double akp = A[k * n + p], akq = A[k * n + q]; A[k * n + p] = c * akp - s * akq; A[k * n + q] = s * akp + c * akq; }
+                for (int k = 0; k < n; k++) { const double apk = A[p * n + k], aqk = A[q * n + k]; A[p * n + k] = c * apk - s * aqk; A[q * n + k] = s * apk + c * aqk; }
+                for (int k = 0; k < n; k++) { const double vkp = V[k * n + p], vkq = V[k * n + q]; V[k * n + p] = c * vkp - s * vkq; V[k * n + q] = s * vkp + c * vkq; }
+            }
+    }
+    for (int i = 0; i < n; i++) ev[i] = A[i * n + i];
+}
+
+// 8-point algorithm on the points idx[0..cnt): Hartley normalisation, least-squares null vector, rank-2 projection. false if degenerate.
+bool eight_point(const float* p1, const float* p2, const int* idx, int cnt, double F[9]) {
+    double m1x = 0, m1y = 0, m2x = 0, m2y = 0;
+    for (int k = 0; k < cnt; k++) { const int i = idx[k]; m1x += p1[2 * i]; m1y += p1[2 * i + 1]; m2x += p2[2 * i]; m2y += p2[2 * i + 1]; }
+    m1x /= cnt; m1y /= cnt; m2x /= cnt; m2y /= cnt;
+    double s1 = 0, s2 = 0;
+    for (int k = 0; k < cnt; k++) {
+        const int i = idx[k];
+        s1 += std::sqrt((p1[2 * i] - m1x) * (p1[2 * i] - m1x) + (p1[2 * i + 1] - m1y) * (p1[2 * i + 1] - m1y));
+        s2 += std::sqrt((p2[2 * i] - m2x) * (p2[2 * i] - m2x) + (p2[2 * i + 1] - m2y) * (p2[2 * i + 1] - m2y));
+    }
+    if (s1 < 1e-12 || s2 < 1e-12) return false;
+    s1 = std::sqrt(2.0) * cnt / s1; s2 = std::sqrt(2.0) * cnt / s2;
+    double A[81] = {0};
+    for (int k = 0; k < cnt; k++) {
+        const int i = idx[k];
+        const double x1 = (p1[2 * i] - m1x) * s1, y1 = (p1[2 * i + 1] - m1y) * s1, x2 = (p2[2 * i] - m2x) * s2, y2 = (p2[2 * i + 1] - m2y) * s2;
+        const double r[9] = {x2 * x1, x2 * y1, x2, y2 * x1, y2 * y1, y2, x1, y1, 1};
+        for (int a = 0; a < 9; a++) for (int b = 0; b < 9; b++) A[a * 9 + b] += r[a] * r[b];
+    }
+    double V[81], ev[9];
+    jacobi_eigen(A, 9, V, ev);
+    int mi = 0;
+    for (int i = 1; i < 9; i++) if (ev[i] < ev[mi]) mi = i;
+    double F0[9];
+    for (int i = 0; i < 9; i++) F0[i] = V[i * 9 + mi];
+    // rank 2: F0 = U S V^T, zero the smallest singular value. Through the eigen decomposition of F0^T F0.
+    double G[9] = {0}, Vg[9], eg[3];
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) for (int k = 0; k < 3; k++) G[a * 3 + b] += F0[k * 3 + a] * F0[k * 3 + b];
+    jacobi_eigen(G, 3, Vg, eg);
+    int sm = 0;
+    for (int i = 1; i < 3; i++) if (eg[i] < eg[sm]) sm = i;
+    // F2 = F0 (I - v v^T) with v the right singular vector of the smallest singular value
+    double v[3] = {Vg[0 * 3 + sm], Vg[1 * 3 + sm], Vg[2 * 3 + sm]}, F2[9];
+    for (int a = 0; a < 3; a++) {
+        const double d = F0[a * 3] * v[0] + F0[a * 3 + 1] * v[1] + F0[a * 3 + 2] * v[2];
+        for (int b = 0; b < 3; b++) F2[a * 3 + b] = F0[a * 3 + b] - d * v[b];
+    }
+    // denormalise: F = T2^T F2 T1, T = [s 0 -s m; 0 s -s m; 0 0 1]
+    const double T1[9] = {s1, 0, -s1 * m1x, 0, s1, -s1 * m1y, 0, 0, 1}, T2[9] = {s2, 0, -s2 * m2x, 0, s2, -s2 * m2y, 0, 0, 1};
+    double tmp[9] = {0};
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) for (int k = 0; k < 3; k++) tmp[a * 3 + b] += T2[k * 3 + a] * F2[k * 3 + b];
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) { F[a * 3 + b] = 0; for (int k = 0; k < 3; k++) F[a * 3 + b] += tmp[a * 3 + k] * T1[k * 3 + b]; }
+    if (std::fabs(F[8]) > FLT_EPSILON) { const double inv = 1.0 / F[8]; for (int i = 0; i < 9; i++) F[i] *= inv; }   // cv scales so that F(2,2) = 1
+    return true;
+}
+
+// OpenCV's error of a correspondence under F: the larger of the two squared point-to-epipolar-line distances.
+inline double fm_error(const double F[9], const float* p1, const float* p2, int i) {
+    const double x1 = p1[2 * i], y1 = p1[2 * i + 1], x2 = p2[2 * i], y2 = p2[2 * i + 1];
+    double a = F[0] * x1 + F[1] * y1 + F[2], b = F[3] * x1 + F[4] * y1 + F[5], c = F[6] * x1 + F[7] * y1 + F[8];
+    const double s2 = 1. / (a * a + b * b), d2 = x2 * a + y2 * b + c;
+    a = F[0] * x2 + F[3] * y2 + F[6]; b = F[1] * x2 + F[4] * y2 + F[7]; c = F[2] * x2 + F[5] * y2 + F[8];
+    const double s1 = 1. / (a * a + b * b), d1 = x1 * a + y1 * b + c;
+    return std::max(d1 * d1 * s1, d2 * d2 * s2);
+}
+
+}  // namespace
+
+extern "C" {
+
+int coeb_motion_create(int device, coeb_motion** out) {
+    if (!out) return fail(COEB_ERR_INVALID_ARG, "null argument");
+    int st = check_device(device);
+    if (st != COEB_OK) return st;
+    CUDA_TRY(cudaSetDevice(device));
+    coeb_motion* m = new coeb_motion();
+    m->device = device;
+    if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) { delete m; return fail(COEB_ERR_CUDA, "cudaStreamCreate failed"); }
+    cudaError_t e = cudaMalloc(&m->d_max, 16);
+    if (e == cudaSuccess) e = cudaMalloc(&m->d_cand, sizeof(float2) * kMoMaxCand);
+    if (e == cudaSuccess) e = cudaMalloc(&m->d_pre, sizeof(float2) * kMoMaxPts);
+    if (e == cudaSuccess) e = cudaMalloc(&m->d_next, sizeof(float2) * kMoMaxPts);
+    if (e == cudaSuccess) e = cudaMalloc(&m->d_status, kMoMaxPts);
+    if (e == cudaSuccess) e = cudaMalloc(&m->d_moving, kMoMaxPts);
+    if (e == cudaSuccess) e = cudaMalloc(&m->d_F, 9 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&m->d_dist, kMoMaxPts * sizeof(double));
+    if (e != cudaSuccess) { coeb_motion_destroy(m); return fail(COEB_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e)); }
+    *out = m;
+    return COEB_OK;
+}
+
+void coeb_motion_destroy(coeb_motion* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    motion_free_images(m);
+    cudaFree(m->d_max); cudaFree(m->d_cand); cudaFree(m->d_pre); cudaFree(m->d_next); cudaFree(m->d_status); cudaFree(m->d_moving); cudaFree(m->d_F);
+    cudaFree(m->d_dist); cudaFree(m->d_mask);
+    if (m->h_pin) cudaFreeHost(m->h_pin);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+}
+
+int coeb_motion_good_features(coeb_motion* m, const uint8_t* gray, int width, int height, int stride, int max_corners, double quality, double min_distance,
+                              double harris_k, float* xy_out, int cap, int* n_out) {
+    if (!m || !gray || !xy_out || !n_out || width < 8 || height < 8 || stride < width || cap < 0) return fail(COEB_ERR_INVALID_ARG, "bad argument");
+    *n_out = 0;
+    CUDA_TRY(cudaSetDevice(m->device));
+    int st = motion_prepare(m, width, height, 22, 5);
+    if (st != COEB_OK) return st;
+    if ((st = upload_level0(m, 0, gray, stride)) != COEB_OK) return st;
+    CUDA_TRY(cudaMemsetAsync(m->d_max, 0, 16, m->stream));
+    // Sobel scale of cornerHarris for 8-bit input: 1 / (2^(ksize-1) * blockSize * 255); the kernel taps are float(1*scale), float(2*scale)
+    const double scale = 1.0 / ((double)(1 << 2) * 3 * 255.0);
+    harris_response_kernel<<<dim3((width + kHtW - 1) / kHtW, (height + kHtH - 1) / kHtH), dim3(kHtW, kHtH), 0, m->stream>>>(
+        m->d_pyr[0][0], width, height, m->lp[0], harris_k, (float)(1.0 * scale), (float)(2.0 * scale), m->d_resp, m->d_max);
+    harris_candidates_kernel<<<dim3((width + 31) / 32, (height + 7) / 8), 256, 0, m->stream>>>(m->d_resp, width, height, m->d_max, (float)quality, m->d_cand,
+                                                                                            (int*)(m->d_max + 1), kMoMaxCand);
+    CUDA_TRY(cudaGetLastError());
+    unsigned info[2];
+    CUDA_TRY(cudaMemcpyAsync(info, m->d_max, 8, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    const int nc = std::min<int>((int)info[1], kMoMaxCand);
+    if ((int)info[1] > kMoMaxCand) return fail(COEB_ERR_CAPACITY, "%u corner candidates (at most %d)", info[1], kMoMaxCand);
+    m->cand_host.resize(nc);
+    if (nc) CUDA_TRY(cudaMemcpy(m->cand_host.data(), m->d_cand, sizeof(float2) * nc, cudaMemcpyDeviceToHost));
+    const int n = select_corners(m->cand_host, width, height, max_corners, min_distance, xy_out, cap);
+    *n_out = n;
+    return n > cap ? COEB_ERR_CAPACITY : COEB_OK;
+}
+
+int coeb_motion_corner_subpix(coeb_motion* m, const uint8_t* gray, int width, int height, int stride, float* xy_inout, int n, int half_win, int max_iters,
+                              double eps) {
+    if (!m || !gray || (n > 0 && !xy_inout) || n < 0 || n > kMoMaxPts || half_win < 1 || 2 * half_win + 3 > kSpMaxWin) return fail(COEB_ERR_INVALID_ARG, "bad argument");
+    if (n == 0) return COEB_OK;
+    CUDA_TRY(cudaSetDevice(m->device));
+    int st = motion_prepare(m, width, height, 22, 5);
+    if (st != COEB_OK) return st;
+    if ((st = ensure_mask(m, half_win)) != COEB_OK) return st;
+    if ((st = upload_level0(m, 0, gray, stride)) != COEB_OK) return st;
+    CUDA_TRY(cudaMemcpyAsync(m->d_pre, xy_inout, sizeof(float2) * n, cudaMemcpyHostToDevice, m->stream));
+    const double e = std::max(eps, 0.0);
+    corner_subpix_kernel<<<(n + 3) / 4, 128, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, half_win, std::max(max_iters, 1), e * e, m->d_mask);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(xy_inout, m->d_pre, sizeof(float2) * n, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    return COEB_OK;
+}
+
+static int run_lk(coeb_motion* m, int n, int win, int max_iters, double eps, double min_eig, int edge, float sad_limit) {
+    build_pyramid(m, 0);
+    build_pyramid(m, 1);
+    LkLevels L{};
+    L.nlevels = m->nlevels;
+    for (int l = 0; l < m->nlevels; l++) {
+        scharr_kernel<<<dim3((m->lw[l] + 31) / 32, (m->lh[l] + 7) / 8), 256, 0, m->stream>>>(m->d_pyr[0][l], m->lw[l], m->lh[l], m->lp[l], m->d_deriv[l]);
+        L.w[l] = m->lw[l]; L.h[l] = m->lh[l]; L.pitch[l] = m->lp[l];
+        L.prev[l] = m->d_pyr[0][l]; L.cur[l] = m->d_pyr[1][l]; L.deriv[l] = m->d_deriv[l];
+    }
+    lk_kernel<<<(n + kLkWarps - 1) / kLkWarps, 32 * kLkWarps, 0, m->stream>>>(L, m->d_pre, n, win, max_iters, (float)(eps * eps), (float)min_eig, m->d_next, m->d_status, edge,
+                                                                        sad_limit);
+    CUDA_TRY(cudaGetLastError());
+    return COEB_OK;
+}
+
+int coeb_motion_lk(coeb_motion* m, const uint8_t* prev_gray, const uint8_t* cur_gray, int width, int height, int stride, const float* prev_xy, int n, int win,
+                   int max_level, int max_iters, double eps, double min_eig_threshold, float* next_xy, uint8_t* status) {
+    if (!m || !prev_gray || !cur_gray || n < 0 || n > kMoMaxPts || (n > 0 && (!prev_xy || !next_xy || !status)) || win < 3 || win > kLkMaxWin || max_level < 0)
+        return fail(COEB_ERR_INVALID_ARG, "bad argument");
+    if (n == 0) return COEB_OK;
+    CUDA_TRY(cudaSetDevice(m->device));
+    m->w = 0;   // the level layout depends on (win, max_level): lay it out again
+    int st = motion_prepare(m, width, height, win, max_level);
+    if (st != COEB_OK) return st;
+    if ((st = upload_level0(m, 0, prev_gray, stride)) != COEB_OK) return st;
+    if ((st = upload_level0(m, 1, cur_gray, stride)) != COEB_OK) return st;
+    CUDA_TRY(cudaMemcpyAsync(m->d_pre, prev_xy, sizeof(float2) * n, cudaMemcpyHostToDevice, m->stream));
+    if ((st = run_lk(m, n, win, std::max(max_iters, 1), eps, min_eig_threshold, -1, 0.f)) != COEB_OK) return st;
+    CUDA_TRY(cudaMemcpyAsync(next_xy, m->d_next, sizeof(float2) * n, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaMemcpyAsync(status, m->d_status, n, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    return COEB_OK;
+}
+
+int coeb_fundamental_ransac(const float* p1_xy, const float* p2_xy, int n, double threshold, double confidence, int max_iters, unsigned seed, double F_out[9],
+                            uint8_t* inlier_mask, int* n_inliers) {
+    if (!p1_xy || !p2_xy || !F_out || n < 0) return fail(COEB_ERR_INVALID_ARG, "bad argument");
+    if (n_inliers) *n_inliers = 0;
+    if (n < 8) return fail(COEB_ERR_INVALID_ARG, "the fundamental matrix needs at least 8 correspondences (got %d)", n);
+    const double thr2 = threshold * threshold;
+    uint64_t rng = 0x9E3779B97F4A7C15ull ^ ((uint64_t)seed * 0xD1342543DE82EF95ull + 1);
+    auto next = [&]() { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return (uint32_t)(rng >> 32); };
+    std::vector<uint8_t> best_mask(n, 0), mask(n);
+    int best = 0, iters = std::max(max_iters, 1);
+    double Fb[9] = {0}, F[9];
+    for (int it = 0; it < iters; it++) {
+        int idx[8];
+        for (int k = 0; k < 8;) {   // 8 distinct indices
+            const int c = (int)(next() % (uint32_t)n);
+            bool dup = false;
+            for (int j = 0; j < k; j++) dup |= idx[j] == c;
+            if (!dup) idx[k++] = c;
+        }
+        if (!eight_point(p1_xy, p2_xy, idx, 8, F)) continue;
+        int cnt = 0;
+        for (int i = 0; i < n; i++) { mask[i] = fm_error(F, p1_xy, p2_xy, i) <= thr2; cnt += mask[i]; }
+        if (cnt > best) {
+            best = cnt; best_mask = mask; std::memcpy(Fb, F, sizeof(F));
+            // cv::RANSACUpdateNumIters: log(1 - confidence) / log(1 - inlier_ratio^8)
+            const double ep = 1.0 - (double)cnt / n, num = std::log(std::max(1.0 - confidence, DBL_MIN)), den = std::log(std::max(1.0 - std::pow(1.0 - ep, 8), DBL_MIN));
+            if (den < 0 && -num < (double)iters * -den) iters = std::max(it + 1, (int)std::lrint(num / den));
+        }
+    }
+    if (best < 8) return fail(COEB_ERR_UNSUPPORTED, "RANSAC found no model with 8 inliers");
+    std::vector<int> in;
+    for (int i = 0; i < n; i++) if (best_mask[i]) in.push_back(i);
+    if (!eight_point(p1_xy, p2_xy, in.data(), (int)in.size(), F)) std::memcpy(F, Fb, sizeof(F));   // final fit on the consensus set
+    std::memcpy(F_out, F, sizeof(F));
+    if (inlier_mask) std::memcpy(inlier_mask, best_mask.data(), n);
+    if (n_inliers) *n_inliers = best;
+    return COEB_OK;
+}
+
+int coeb_epipolar_outliers(coeb_motion* m, const float* pre_xy, const float* next_xy, const uint8_t* status, int n, const double F[9], double limit,
+                           uint8_t* moving_out, double* dist_out) {
+    if (!m || n < 0 || n > kMoMaxPts || (n > 0 && (!pre_xy || !next_xy || !status || !moving_out)) || !F) return fail(COEB_ERR_INVALID_ARG, "bad argument");
+    if (n == 0) return COEB_OK;
+    CUDA_TRY(cudaSetDevice(m->device));
+    CUDA_TRY(cudaMemcpyAsync(m->d_pre, pre_xy, sizeof(float2) * n, cudaMemcpyHostToDevice, m->stream));
+    CUDA_TRY(cudaMemcpyAsync(m->d_next, next_xy, sizeof(float2) * n, cudaMemcpyHostToDevice, m->stream));
+    CUDA_TRY(cudaMemcpyAsync(m->d_status, status, n, cudaMemcpyHostToDevice, m->stream));
+    CUDA_TRY(cudaMemcpyAsync(m->d_F, F, 9 * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+    epipolar_kernel<<<(n + 127) / 128, 128, 0, m->stream>>>(m->d_pre, m->d_next, m->d_status, n, m->d_F, limit, m->d_moving, m->d_dist);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(moving_out, m->d_moving, n, cudaMemcpyDeviceToHost, m->stream));
+    if (dist_out) CUDA_TRY(cudaMemcpyAsync(dist_out, m->d_dist, sizeof(double) * n, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    return COEB_OK;
+}
+
+int coeb_process_moving_object(coeb_motion* m, const uint8_t* prev_gray, const uint8_t* cur_gray, int width, int height, int stride, float* tm_xy_out, int cap,
+                               int* n_tm_out, coeb_motion_trace* trace) {
+    if (!m || !prev_gray || !cur_gray || !n_tm_out || cap < 0 || (cap > 0 && !tm_xy_out)) return fail(COEB_ERR_INVALID_ARG, "bad argument");
+    *n_tm_out = 0;
+    if (trace) { trace->n_points = trace->n_tracked = trace->n_inliers = 0; trace->have_F = 0; }
+    CUDA_TRY(cudaSetDevice(m->device));
+    // goodFeaturesToTrack + cornerSubPix on the previous frame (:333-334)
+    std::vector<float> pre(2 * 1000);
+    int n = 0;
+    int st = coeb_motion_good_features(m, prev_gray, width, height, stride, 1000, 0.01, 8.0, 0.04, pre.data(), 1000, &n);
+    if (st != COEB_OK) return st;
+    if (trace) trace->n_points = n;
+    if (n == 0) return COEB_OK;
+    if ((st = ensure_mask(m, 10)) != COEB_OK) return st;
+    CUDA_TRY(cudaMemcpyAsync(m->d_pre, pre.data(), sizeof(float2) * n, cudaMemcpyHostToDevice, m->stream));   // level 0 of the previous frame is resident
+    corner_subpix_kernel<<<(n + 3) / 4, 128, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, 10, 20, 0.03 * 0.03, m->d_mask);
+    // calcOpticalFlowPyrLK + border / SAD tests (:335-364)
+    if ((st = upload_level0(m, 1, cur_gray, stride)) != COEB_OK) return st;
+    if ((st = run_lk(m, n, 22, 20, 0.01, 1e-4, /*limit_edge_corner*/ 5, /*limit_of_check*/ 2120.f)) != COEB_OK) return st;
+    std::vector<float> nxt(2 * (size_t)n);
+    std::vector<uint8_t> state(n);
+    CUDA_TRY(cudaMemcpyAsync(pre.data(), m->d_pre, sizeof(float2) * n, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaMemcpyAsync(nxt.data(), m->d_next, sizeof(float2) * n, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaMemcpyAsync(state.data(), m->d_status, n, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    // findFundamentalMat(F_prepoint, F_nextpoint, FM_RANSAC, 0.1, 0.99) on the surviving pairs (:353-370)
+    std::vector<float> f1, f2;
+    for (int i = 0; i < n; i++)
+        if (state[i]) { f1.push_back(pre[2 * i]); f1.push_back(pre[2 * i + 1]); f2.push_back(nxt[2 * i]); f2.push_back(nxt[2 * i + 1]); }
+    const int nf = (int)f1.size() / 2;
+    if (trace) {
+        trace->n_tracked = nf;
+        const int c = std::min(n, COEB_MOTION_TRACE_POINTS);
+        std::memcpy(trace->pre_xy, pre.data(), sizeof(float) * 2 * c);
+        std::memcpy(trace->next_xy, nxt.data(), sizeof(float) * 2 * c);
+        std::memcpy(trace->state, state.data(), c);
+    }
+    double F[9];
+    int ninl = 0;
+    if (nf < 8 || coeb_fundamental_ransac(f1.data(), f2.data(), nf, 0.1, 0.99, 1000, 12345u, F, nullptr, &ninl) != COEB_OK) return COEB_OK;   // no model: no T_M
+    if (trace) { trace->n_inliers = ninl; trace->have_F = 1; std::memcpy(trace->F, F, sizeof(F)); }
+    // epipolar distance > 1 -> T_M, in point order (:372-385); the points are still resident
+    CUDA_TRY(cudaMemcpyAsync(m->d_F, F, sizeof(F), cudaMemcpyHostToDevice, m->stream));
+    epipolar_kernel<<<(n + 127) / 128, 128, 0, m->stream>>>(m->d_pre, m->d_next, m->d_status, n, m->d_F, 1.0, m->d_moving, nullptr);
+    CUDA_TRY(cudaGetLastError());
+    std::vector<uint8_t> mv(n);
+    CUDA_TRY(cudaMemcpyAsync(mv.data(), m->d_moving, n, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    int k = 0;
+    for (int i = 0; i < n; i++)
+        if (mv[i]) {
+            if (k < cap) { tm_xy_out[2 * k] = nxt[2 * i]; tm_xy_out[2 * k + 1] = nxt[2 * i + 1]; }
+            k++;
+        }
+    *n_tm_out = k;
+    return k > cap ? COEB_ERR_CAPACITY : COEB_OK;
+}
+
+}  // extern "C"

@@ -351,3 +351,59 @@ def make_feature_vector(desc, n_nodes=100, seed=0):
         items.extend(idx.tolist())
         start.append(len(items))
     return np.array(nodes, np.int32), np.array(start, np.int32), np.array(items, np.int32)
+
+
+def warp_affine(gray, A, t):
+    """Bilinear resampling of `gray` under x_src = A @ x_dst + t (2x2 matrix, 2-vector), edges replicated, rounded to uint8."""
+    h, w = gray.shape
+    ys, xs = np.mgrid[0:h, 0:w].astype(np.float64)
+    sx = A[0][0] * xs + A[0][1] * ys + t[0]
+    sy = A[1][0] * xs + A[1][1] * ys + t[1]
+    sx = np.clip(sx, 0, w - 1.001)
+    sy = np.clip(sy, 0, h - 1.001)
+    x0, y0 = np.floor(sx).astype(np.int64), np.floor(sy).astype(np.int64)
+    fx, fy = sx - x0, sy - y0
+    g = gray.astype(np.float64)
+    v = (g[y0, x0] * (1 - fx) * (1 - fy) + g[y0, x0 + 1] * fx * (1 - fy) + g[y0 + 1, x0] * (1 - fx) * fy + g[y0 + 1, x0 + 1] * fx * fy)
+    return np.clip(np.rint(v), 0, 255).astype(np.uint8)
+
+
+def warp_flow(gray, fx, fy):
+    """cur(x, y) = gray(x - fx(x, y), y - fy(x, y)), bilinear, edges replicated, rounded to uint8."""
+    h, w = gray.shape
+    ys, xs = np.mgrid[0:h, 0:w].astype(np.float64)
+    sx = np.clip(xs - fx, 0, w - 1.001)
+    sy = np.clip(ys - fy, 0, h - 1.001)
+    x0, y0 = np.floor(sx).astype(np.int64), np.floor(sy).astype(np.int64)
+    ax, ay = sx - x0, sy - y0
+    g = gray.astype(np.float64)
+    v = g[y0, x0] * (1 - ax) * (1 - ay) + g[y0, x0 + 1] * ax * (1 - ay) + g[y0 + 1, x0] * (1 - ax) * ay + g[y0 + 1, x0 + 1] * ax * ay
+    return np.clip(np.rint(v), 0, 255).astype(np.uint8)
+
+
+def make_motion_pair(seed, w=640, h=480, moving=True):
+    """Two consecutive frames for Frame::ProcessMovingObject: a translating camera in front of a scene with smoothly varying
+    depth (motion parallax, so that the epipolar geometry is well determined), one or two rectangular 'objects' that move on
+    their own against it, and pixel noise that differs between the frames. Returns (prev, cur, boxes[n, 4] of the moving
+    objects in the current frame)."""
+    rng = np.random.default_rng(seed + 9001)
+    prev = make_frame(seed + 500, w, h)
+    depth = 2.0 + 3.0 * _upsample_bilinear(rng.random((5, 6)), h, w)             # metres
+    f, cx, cy = 520.0, w / 2.0, h / 2.0
+    t = np.array([rng.uniform(0.015, 0.03) * rng.choice([-1, 1]), rng.uniform(-0.008, 0.008), rng.uniform(-0.03, 0.03)])
+    ys, xs = np.mgrid[0:h, 0:w].astype(np.float64)
+    flow_x = (f * t[0] - (xs - cx) * t[2]) / depth
+    flow_y = (f * t[1] - (ys - cy) * t[2]) / depth
+    cur = warp_flow(prev, flow_x, flow_y)
+    boxes = []
+    if moving:
+        for _ in range(int(rng.integers(1, 3))):
+            bw, bh = int(rng.integers(90, 200)), int(rng.integers(120, 260))
+            x0, y0 = int(rng.integers(20, w - bw - 20)), int(rng.integers(20, h - bh - 20))
+            d = np.array([rng.uniform(-3, 3), rng.uniform(6, 11) * rng.choice([-1, 1])])   # mostly across the epipolar lines
+            obj = warp_flow(prev, np.full((h, w), d[0]), np.full((h, w), d[1]))
+            cur[y0:y0 + bh, x0:x0 + bw] = obj[y0:y0 + bh, x0:x0 + bw]
+            boxes.append([x0, y0, x0 + bw, y0 + bh])
+    noise = rng.normal(0, 1.5, cur.shape)
+    cur = np.clip(np.rint(cur.astype(np.float64) + noise), 0, 255).astype(np.uint8)
+    return prev, cur, np.array(boxes, np.float32).reshape(-1, 4)

@@ -327,6 +327,48 @@ int coeb_knn2(coeb_matcher* m, const uint8_t* query, int nq, const uint8_t* trai
 int coeb_knn2_device(coeb_matcher* m, const uint8_t* d_query, int nq, const uint8_t* d_train, int nt, float nnratio,
                      int* d_best_idx, int* d_d1, int* d_d2);
 
+/* ---- Frame::ProcessMovingObject (src/Frame.cc:311-393): the producer of T_M ---------------------------------------------------
+ * The reference body is goodFeaturesToTrack -> cornerSubPix -> calcOpticalFlowPyrLK -> its own border / SAD tests ->
+ * findFundamentalMat(RANSAC) -> its own epipolar-distance test. The arithmetic of those OpenCV calls is not the reference's;
+ * parity for these entry points is by the tolerances stated in DESIGN.md section 2 and tests/test_motion_gpu.py, not bit-exact. */
+typedef struct coeb_motion coeb_motion;
+int coeb_motion_create(int device, coeb_motion** out);
+void coeb_motion_destroy(coeb_motion* m);
+
+#define COEB_MOTION_TRACE_POINTS 1000
+/* Intermediates of one coeb_process_moving_object call (for tests and diagnostics): prepoint / nextpoint / state of
+ * src/Frame.cc:32-35 after the SAD test, and the fundamental matrix of :370. */
+typedef struct coeb_motion_trace {
+    int32_t n_points, n_tracked, n_inliers, have_F;
+    float pre_xy[2 * COEB_MOTION_TRACE_POINTS], next_xy[2 * COEB_MOTION_TRACE_POINTS];
+    uint8_t state[COEB_MOTION_TRACE_POINTS];
+    double F[9];
+} coeb_motion_trace;
+
+/* The whole function: prev_gray is imGrayPre, cur_gray the frame being constructed (8-bit, same size). tm_xy_out receives
+ * T_M (nextpoint of every tracked point whose epipolar distance exceeds 1, in point order), at most cap pairs. */
+int coeb_process_moving_object(coeb_motion* m, const uint8_t* prev_gray, const uint8_t* cur_gray, int width, int height, int stride,
+                               float* tm_xy_out, int cap, int* n_tm_out, coeb_motion_trace* trace /* may be NULL */);
+
+/* The stages, callable on their own (host arrays in and out):
+ * cv::goodFeaturesToTrack(gray, corners, max_corners, quality, min_distance, noArray(), 3, true, harris_k)       (:333) */
+int coeb_motion_good_features(coeb_motion* m, const uint8_t* gray, int width, int height, int stride, int max_corners, double quality,
+                              double min_distance, double harris_k, float* xy_out, int cap, int* n_out);
+/* cv::cornerSubPix(gray, corners, Size(half_win, half_win), Size(-1,-1), TermCriteria(ITER|EPS, max_iters, eps))    (:334) */
+int coeb_motion_corner_subpix(coeb_motion* m, const uint8_t* gray, int width, int height, int stride, float* xy_inout, int n, int half_win,
+                              int max_iters, double eps);
+/* cv::calcOpticalFlowPyrLK(prev, cur, prev_xy, next_xy, status, err, Size(win, win), max_level,
+ *                          TermCriteria(ITER|EPS, max_iters, eps), 0, min_eig_threshold)                             (:335) */
+int coeb_motion_lk(coeb_motion* m, const uint8_t* prev_gray, const uint8_t* cur_gray, int width, int height, int stride, const float* prev_xy,
+                   int n, int win, int max_level, int max_iters, double eps, double min_eig_threshold, float* next_xy, uint8_t* status);
+/* cv::findFundamentalMat(p1, p2, FM_RANSAC, threshold, confidence) -- host code: normalised 8-point inside RANSAC with its own
+ * generator (seed), final fit on the consensus set, F scaled so that F[8] = 1.                                        (:370) */
+int coeb_fundamental_ransac(const float* p1_xy, const float* p2_xy, int n, double threshold, double confidence, int max_iters,
+                            unsigned seed, double F_out[9], uint8_t* inlier_mask /* may be NULL */, int* n_inliers /* may be NULL */);
+/* The epipolar test of :372-385 for every point with status != 0: moving_out[i] = distance > limit. */
+int coeb_epipolar_outliers(coeb_motion* m, const float* pre_xy, const float* next_xy, const uint8_t* status, int n, const double F[9],
+                           double limit, uint8_t* moving_out, double* dist_out /* may be NULL */);
+
 #ifdef __cplusplus
 }
 #endif
