@@ -771,8 +771,12 @@ def bench_matching(cb, dev, batch, o_kps, o_desc, o_cnt, ex, args):
     n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
     out["knn2_4000x100k_ms"] = knn_ms
     out["knn2_popc_per_s"] = popc / (knn_ms * 1e-3)
-    # POPC issues at 16 lanes/clk/SM on CC 10.0 (CUDA programming guide, arithmetic instruction throughput table)
-    out["knn2_int_pipe_frac_at_max_clock"] = popc / (knn_ms * 1e-3) / (n_sm * 16 * 1.965e9)
+    # POPC issues at 16 lanes/clk/SM on CC 10.0 (XU pipe). The figure above counts the ALGORITHMIC 8 POPC per pair; the kernel folds
+    # seven of the eight difference words with carry-save adders first and executes 5 POPC per pair (ncu: XU pipe 91.6 % before the
+    # folding, profiles/r02a_match_pipes.json), so the algorithmic rate may exceed the pipe's peak
+    out["knn2_popc_executed_per_pair"] = 5
+    out["knn2_algorithmic_popc_rate_over_xu_peak"] = popc / (knn_ms * 1e-3) / (n_sm * 16 * 1.965e9)
+    out["knn2_xu_pipe_frac_at_max_clock"] = (popc * 5 / 8) / (knn_ms * 1e-3) / (n_sm * 16 * 1.965e9)
     m.set_stream(0)
     # ---- Frame::ProcessMovingObject (src/Frame.cc:311-393): the producer of T_M, one frame pair per blocking call ----
     try:

@@ -1137,6 +1137,30 @@ constexpr int kKnnQ = 2;         // queries per thread
 constexpr int kKnnThreads = 128;
 constexpr int kKnnTile = 256;    // train descriptors per shared-memory stage
 
+// Hamming distance of two 256-bit descriptors with five population counts instead of eight. POPC issues on the XU pipe at a
+// quarter of the integer-ALU rate (ncu: the plain 8-POPC loop ran the XU pipe at 91.6 % with the ALU pipe half idle), so three
+// carry-save adders (two LOP3 each: parity 0x96, majority 0xE8) fold seven of the eight difference words into two "ones" words and
+// three "twos" words first: distance = popc(s3) + popc(w7) + 2 * (popc(c1) + popc(c2) + popc(c3)). Exact, like the plain sum.
+__device__ __forceinline__ uint32_t lop3_xor3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t lop3_maj(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ int hamming256_csa(const uint4& qa, const uint4& qb, const uint4& ta, const uint4& tb) {
+    const uint32_t w0 = qa.x ^ ta.x, w1 = qa.y ^ ta.y, w2 = qa.z ^ ta.z, w3 = qa.w ^ ta.w;
+    const uint32_t w4 = qb.x ^ tb.x, w5 = qb.y ^ tb.y, w6 = qb.z ^ tb.z, w7 = qb.w ^ tb.w;
+    const uint32_t s1 = lop3_xor3(w0, w1, w2), c1 = lop3_maj(w0, w1, w2);
+    const uint32_t s2 = lop3_xor3(w3, w4, w5), c2 = lop3_maj(w3, w4, w5);
+    const uint32_t s3 = lop3_xor3(s1, s2, w6), c3 = lop3_maj(s1, s2, w6);
+    // (folding further, down to four population counts, makes the ALU pipe the bound: 0.70 ms against 0.61 ms for this form)
+    return (__popc(s3) + __popc(w7)) + 2 * (__popc(c1) + __popc(c2) + __popc(c3));
+}
+
 __global__ void __launch_bounds__(kKnnThreads) knn2_partial_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __restrict__ t, int nt,
                                                                     int chunk, int* p_d1, int* p_idx, int* p_d2) {
     __shared__ uint4 s_t[kKnnTile * 2];
@@ -1162,8 +1186,7 @@ __global__ void __launch_bounds__(kKnnThreads) knn2_partial_kernel(const uint32_
             const uint4 ta = s_t[2 * j], tb = s_t[2 * j + 1];
 #pragma unroll
             for (int k = 0; k < kKnnQ; k++) {
-                const int dist = __popc(qa[k].x ^ ta.x) + __popc(qa[k].y ^ ta.y) + __popc(qa[k].z ^ ta.z) + __popc(qa[k].w ^ ta.w) +
-                                 __popc(qb[k].x ^ tb.x) + __popc(qb[k].y ^ tb.y) + __popc(qb[k].z ^ tb.z) + __popc(qb[k].w ^ tb.w);
+                const int dist = hamming256_csa(qa[k], qb[k], ta, tb);
                 if (dist < d1[k]) { d2[k] = d1[k]; d1[k] = dist; bi[k] = base + j; }
                 else if (dist < d2[k]) d2[k] = dist;
             }
