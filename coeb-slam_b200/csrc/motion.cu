@@ -17,6 +17,9 @@
 // order, and its RANSAC draws from its own generator: parity for this row is by tolerance (tests/test_motion_gpu.py).
 #include <algorithm>
 #include <cfloat>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -457,12 +460,23 @@ int ensure_mask(coeb_motion* m, int hw) {
 // goodFeaturesToTrack after the response: candidates sorted by (value descending, raster position descending -- the pointer
 // tie-break of greaterThanPtr), then the minimum-distance pass over a grid of cell size round(minDistance).
 int select_corners(std::vector<float2>& cand, int w, int h, int max_corners, double min_distance, float* xy_out, int cap) {
-    std::sort(cand.begin(), cand.end(), [](const float2& a, const float2& b) {
-        if (a.x != b.x) return a.x > b.x;
-        int ia, ib;
-        std::memcpy(&ia, &a.y, 4); std::memcpy(&ib, &b.y, 4);
-        return ia > ib;
-    });
+    // positive floats order like their bit patterns: one 64-bit key (value bits, raster position) per candidate, sorted descending
+    static_assert(sizeof(float2) == sizeof(unsigned long long), "a candidate is one 64-bit key");
+    {
+        unsigned long long* key = reinterpret_cast<unsigned long long*>(cand.data());
+        for (size_t i = 0; i < cand.size(); i++) {
+            unsigned vb, ib;
+            std::memcpy(&vb, &cand[i].x, 4); std::memcpy(&ib, &cand[i].y, 4);
+            key[i] = ((unsigned long long)vb << 32) | ib;
+        }
+        std::sort(key, key + cand.size(), [](unsigned long long a, unsigned long long b) { return a > b; });
+        for (size_t i = 0; i < cand.size(); i++) {
+            const unsigned vb = (unsigned)(key[i] >> 32), ib = (unsigned)key[i];
+            float2 c;
+            std::memcpy(&c.x, &vb, 4); std::memcpy(&c.y, &ib, 4);
+            cand[i] = c;
+        }
+    }
     int n = 0;
     if (min_distance >= 1) {
         const int cell = (int)std::lrint(min_distance);
@@ -567,6 +581,70 @@ bool eight_point(const float* p1, const float* p2, const int* idx, int cnt, doub
     for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) for (int k = 0; k < 3; k++) tmp[a * 3 + b] += T2[k * 3 + a] * F2[k * 3 + b];
     for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) { F[a * 3 + b] = 0; for (int k = 0; k < 3; k++) F[a * 3 + b] += tmp[a * 3 + k] * T1[k * 3 + b]; }
     if (std::fabs(F[8]) > FLT_EPSILON) { const double inv = 1.0 / F[8]; for (int i = 0; i < 9; i++) F[i] *= inv; }   // cv scales so that F(2,2) = 1
+    return true;
+}
+
+// The null vector of the 8 x 9 epipolar system of exactly eight correspondences by Gaussian elimination with partial pivoting
+// (the minimal-sample hypotheses of RANSAC; the least-squares fit above is kept for the final estimate on the consensus set),
+// followed by the same rank-2 projection. Points are Hartley-normalised first. false if the sample is degenerate.
+bool eight_point_minimal(const float* p1, const float* p2, const int* idx, double F[9]) {
+    double m1x = 0, m1y = 0, m2x = 0, m2y = 0;
+    for (int k = 0; k < 8; k++) { const int i = idx[k]; m1x += p1[2 * i]; m1y += p1[2 * i + 1]; m2x += p2[2 * i]; m2y += p2[2 * i + 1]; }
+    m1x /= 8; m1y /= 8; m2x /= 8; m2y /= 8;
+    double s1 = 0, s2 = 0;
+    for (int k = 0; k < 8; k++) {
+        const int i = idx[k];
+        s1 += std::sqrt((p1[2 * i] - m1x) * (p1[2 * i] - m1x) + (p1[2 * i + 1] - m1y) * (p1[2 * i + 1] - m1y));
+        s2 += std::sqrt((p2[2 * i] - m2x) * (p2[2 * i] - m2x) + (p2[2 * i + 1] - m2y) * (p2[2 * i + 1] - m2y));
+    }
+    if (s1 < 1e-12 || s2 < 1e-12) return false;
+    s1 = std::sqrt(2.0) * 8 / s1; s2 = std::sqrt(2.0) * 8 / s2;
+    double A[8][9];
+    for (int k = 0; k < 8; k++) {
+        const int i = idx[k];
+        const double x1 = (p1[2 * i] - m1x) * s1, y1 = (p1[2 * i + 1] - m1y) * s1, x2 = (p2[2 * i] - m2x) * s2, y2 = (p2[2 * i + 1] - m2y) * s2;
+        const double r[9] = {x2 * x1, x2 * y1, x2, y2 * x1, y2 * y1, y2, x1, y1, 1};
+        for (int a = 0; a < 9; a++) A[k][a] = r[a];
+    }
+    // reduced row echelon form with column pivoting bookkeeping: the one free column gives the null vector
+    int piv_col[8];
+    bool used[9] = {false};
+    for (int r = 0; r < 8; r++) {
+        int br = r, bc = -1;
+        double best = 0;
+        for (int rr = r; rr < 8; rr++)
+            for (int c = 0; c < 9; c++)
+                if (!used[c] && std::fabs(A[rr][c]) > best) { best = std::fabs(A[rr][c]); br = rr; bc = c; }
+        if (bc < 0 || best < 1e-10) return false;
+        if (br != r) for (int c = 0; c < 9; c++) std::swap(A[r][c], A[br][c]);
+        used[bc] = true; piv_col[r] = bc;
+        const double inv = 1.0 / A[r][bc];
+        for (int c = 0; c < 9; c++) A[r][c] *= inv;
+        for (int rr = 0; rr < 8; rr++)
+            if (rr != r && A[rr][bc] != 0.0) {
+                const double f = A[rr][bc];
+                for (int c = 0; c < 9; c++) A[rr][c] -= f * A[r][c];
+            }
+    }
+    int free_col = 0;
+    while (used[free_col]) free_col++;
+    double F0[9];
+    F0[free_col] = 1.0;
+    for (int r = 0; r < 8; r++) F0[piv_col[r]] = -A[r][free_col];
+    double G[9] = {0}, Vg[9], eg[3];
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) for (int k = 0; k < 3; k++) G[a * 3 + b] += F0[k * 3 + a] * F0[k * 3 + b];
+    jacobi_eigen(G, 3, Vg, eg);
+    int sm = 0;
+    for (int i = 1; i < 3; i++) if (eg[i] < eg[sm]) sm = i;
+    double v[3] = {Vg[0 * 3 + sm], Vg[1 * 3 + sm], Vg[2 * 3 + sm]}, F2[9];
+    for (int a = 0; a < 3; a++) {
+        const double d = F0[a * 3] * v[0] + F0[a * 3 + 1] * v[1] + F0[a * 3 + 2] * v[2];
+        for (int b = 0; b < 3; b++) F2[a * 3 + b] = F0[a * 3 + b] - d * v[b];
+    }
+    const double T1[9] = {s1, 0, -s1 * m1x, 0, s1, -s1 * m1y, 0, 0, 1}, T2[9] = {s2, 0, -s2 * m2x, 0, s2, -s2 * m2y, 0, 0, 1};
+    double tmp[9] = {0};
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) for (int k = 0; k < 3; k++) tmp[a * 3 + b] += T2[k * 3 + a] * F2[k * 3 + b];
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) { F[a * 3 + b] = 0; for (int k = 0; k < 3; k++) F[a * 3 + b] += tmp[a * 3 + k] * T1[k * 3 + b]; }
     return true;
 }
 
@@ -717,7 +795,7 @@ int coeb_fundamental_ransac(const float* p1_xy, const float* p2_xy, int n, doubl
             for (int j = 0; j < k; j++) dup |= idx[j] == c;
             if (!dup) idx[k++] = c;
         }
-        if (!eight_point(p1_xy, p2_xy, idx, 8, F)) continue;
+        if (!eight_point_minimal(p1_xy, p2_xy, idx, F)) continue;
         int cnt = 0;
         for (int i = 0; i < n; i++) { mask[i] = fm_error(F, p1_xy, p2_xy, i) <= thr2; cnt += mask[i]; }
         if (cnt > best) {
@@ -760,6 +838,10 @@ int coeb_process_moving_object(coeb_motion* m, const uint8_t* prev_gray, const u
     *n_tm_out = 0;
     if (trace) { trace->n_points = trace->n_tracked = trace->n_inliers = 0; trace->have_F = 0; }
     CUDA_TRY(cudaSetDevice(m->device));
+    const bool timeline = getenv("COEB_MOTION_TRACE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+    const auto t0 = now();
     // goodFeaturesToTrack + cornerSubPix on the previous frame (:333-334)
     std::vector<float> pre(2 * 1000);
     int n = 0;
@@ -767,6 +849,7 @@ int coeb_process_moving_object(coeb_motion* m, const uint8_t* prev_gray, const u
     if (st != COEB_OK) return st;
     if (trace) trace->n_points = n;
     if (n == 0) return COEB_OK;
+    const auto t1 = now();
     if ((st = ensure_mask(m, 10)) != COEB_OK) return st;
     CUDA_TRY(cudaMemcpyAsync(m->d_pre, pre.data(), sizeof(float2) * n, cudaMemcpyHostToDevice, m->stream));   // level 0 of the previous frame is resident
     corner_subpix_kernel<<<(n + 3) / 4, 128, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, 10, 20, 0.03 * 0.03, m->d_mask);
@@ -779,6 +862,7 @@ int coeb_process_moving_object(coeb_motion* m, const uint8_t* prev_gray, const u
     CUDA_TRY(cudaMemcpyAsync(nxt.data(), m->d_next, sizeof(float2) * n, cudaMemcpyDeviceToHost, m->stream));
     CUDA_TRY(cudaMemcpyAsync(state.data(), m->d_status, n, cudaMemcpyDeviceToHost, m->stream));
     CUDA_TRY(cudaStreamSynchronize(m->stream));
+    const auto t2 = now();
     // findFundamentalMat(F_prepoint, F_nextpoint, FM_RANSAC, 0.1, 0.99) on the surviving pairs (:353-370)
     std::vector<float> f1, f2;
     for (int i = 0; i < n; i++)
@@ -795,6 +879,7 @@ int coeb_process_moving_object(coeb_motion* m, const uint8_t* prev_gray, const u
     int ninl = 0;
     if (nf < 8 || coeb_fundamental_ransac(f1.data(), f2.data(), nf, 0.1, 0.99, 1000, 12345u, F, nullptr, &ninl) != COEB_OK) return COEB_OK;   // no model: no T_M
     if (trace) { trace->n_inliers = ninl; trace->have_F = 1; std::memcpy(trace->F, F, sizeof(F)); }
+    const auto t3 = now();
     // epipolar distance > 1 -> T_M, in point order (:372-385); the points are still resident
     CUDA_TRY(cudaMemcpyAsync(m->d_F, F, sizeof(F), cudaMemcpyHostToDevice, m->stream));
     epipolar_kernel<<<(n + 127) / 128, 128, 0, m->stream>>>(m->d_pre, m->d_next, m->d_status, n, m->d_F, 1.0, m->d_moving, nullptr);
@@ -809,6 +894,9 @@ int coeb_process_moving_object(coeb_motion* m, const uint8_t* prev_gray, const u
             k++;
         }
     *n_tm_out = k;
+    if (timeline)
+        fprintf(stderr, "[coeb motion] corners (upload, Harris, candidates, sort, min-distance) %.0f us, subpix + pyramids + LK %.0f us, RANSAC %.0f us (%d of %d inliers), epipolar %.0f us\n",
+                us(t0, t1), us(t1, t2), us(t2, t3), ninl, nf, us(t3, now()));
     return k > cap ? COEB_ERR_CAPACITY : COEB_OK;
 }
 

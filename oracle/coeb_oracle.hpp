@@ -4,11 +4,15 @@
 // product library (coeb-slam_b200/). Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline
 // legs may use it, and there only as the checker / the timed CPU arm.
 //
-// PARITY STATUS: "parity unpinned by the reference". The reference ships no tests, golden vectors
-// or known-answer fixtures and cannot be compiled here (no OpenCV C++ headers,
-// DBoW2/g2o absent). The OpenCV primitives it calls are therefore restated to their integer models
-// and pinned against the installed OpenCV 4.13.0 (python cv2) in tests/test_oracle_vs_cv2.py;
-// the control flow follows the cited reference lines.
+// PARITY STATUS: pinned to the reference itself. The reference ships no tests, golden vectors or
+// known-answer fixtures, but its hot-path sources (src/ORBextractor.cc,
+// ORBmatcher.cc, Frame.cc, MapPoint.cc, KeyFrame.cc, Map.cc) compile unchanged against the test-only
+// OpenCV stand-in of oracle/ref_shim/ into oracle/_ref (recipe: `make -C oracle _ref`), and
+// tests/test_ref_parity_cpu.py requires this restatement to equal them bit for bit (extraction
+// against the monotonic-heap build, because the reference's octree tie order depends on heap
+// addresses). The OpenCV primitives the reference calls are restated here as
+// integer models and pinned against the installed OpenCV 4.13.0 (python cv2) in
+// tests/test_oracle_vs_cv2.py; the shim uses these same models.
 //
 // Every function cites the reference file:line it restates (paths relative to /root/reference).
 #pragma once
