@@ -343,6 +343,32 @@ coeb_extractor::Lane* lane_for(coeb_extractor* ex, cudaStream_t s) {
 int enqueue(coeb_extractor* ex, const BatchView& v, cudaStream_t s, bool prof) {
     const Geometry& g = ex->geom;
     coeb_extractor::Lane* lane = prof ? nullptr : lane_for(ex, s);
+    if (lane && v.B <= 4 && !getenv("COEB_NO_L0_OVERLAP")) {
+        // Small batches (the tracking thread's single frame): the seven dependent resize launches are a latency chain that uses a
+        // fraction of the GPU, and level 0 -- a third of the FAST tiles -- does not depend on it. Side stream: classify, FAST on the
+        // level-0 tiles, then (once the pyramid is there) the blur | main: pyramid chain, FAST on levels 1.., fallback, octree |
+        // join | describe.
+        const int n0 = fast_tiles_of_level0(g);
+        CUDA_TRY(cudaEventRecord(lane->fork0, s));
+        CUDA_TRY(cudaStreamWaitEvent(lane->aux, lane->fork0, 0));
+        launch_classify(g, v, lane->aux);
+        launch_fast_reset(g, v, lane->aux);
+        launch_fast_tiles(g, v, lane->aux, 0, n0);
+        CUDA_TRY(cudaEventRecord(lane->cls, lane->aux));     // classification, counters and the level-0 candidates are in place
+        launch_pyramid(g, v, s);
+        CUDA_TRY(cudaEventRecord(lane->fork, s));
+        CUDA_TRY(cudaStreamWaitEvent(lane->aux, lane->fork, 0));
+        launch_blur(g, v, lane->aux);
+        CUDA_TRY(cudaEventRecord(lane->join, lane->aux));
+        CUDA_TRY(cudaStreamWaitEvent(s, lane->cls, 0));
+        launch_fast_tiles(g, v, s, n0, g.fast_tiles_per_frame - n0);
+        launch_fast_tail(g, v, s);
+        launch_select(g, v, s);
+        CUDA_TRY(cudaStreamWaitEvent(s, lane->join, 0));
+        launch_describe(g, v, s);
+        CUDA_TRY(cudaGetLastError());
+        return COEB_OK;
+    }
     if (lane) {
         // side stream: classify beside the pyramid, then blur beside FAST + octree | main: pyramid, FAST, octree | join | describe
         CUDA_TRY(cudaEventRecord(lane->fork0, s));

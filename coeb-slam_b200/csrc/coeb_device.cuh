@@ -251,6 +251,10 @@ void launch_classify(const Geometry& g, const BatchView& v, cudaStream_t stream)
 void launch_pyramid(const Geometry& g, const BatchView& v, cudaStream_t stream);
 void launch_blur(const Geometry& g, const BatchView& v, cudaStream_t stream);
 void launch_fast(const Geometry& g, const BatchView& v, cudaStream_t stream);
+int fast_tiles_of_level0(const Geometry& g);
+void launch_fast_reset(const Geometry& g, const BatchView& v, cudaStream_t stream);
+void launch_fast_tiles(const Geometry& g, const BatchView& v, cudaStream_t stream, int first, int count);
+void launch_fast_tail(const Geometry& g, const BatchView& v, cudaStream_t stream);
 // Host-side FAST tile table of one frame (level, tx0, ty0 per 64x30 tile), uploaded once per geometry.
 int build_fast_tiles(const Geometry& g, int4* out_or_null);
 int build_blur_tiles(const Geometry& g, int4* out_or_null);

@@ -620,12 +620,29 @@ bool encode_level_maps(const Geometry& g, const BatchView& v, int box_w, int box
     return true;
 }
 
-void launch_fast(const Geometry& g, const BatchView& v, cudaStream_t stream) {
+// The FAST stage in three pieces, so that a small batch can run the level-0 tiles (which need no resize) beside the pyramid chain:
+//   launch_fast_reset  zeroes the per-level and per-cell counters;
+//   launch_fast_tiles  runs the main kernel on tiles [first, first + count) of the level-major tile table;
+//   launch_fast_tail   lists the cells that stayed empty and redoes them at minTh.
+int fast_tiles_of_level0(const Geometry& g) {
+    const int tiles_x = std::max(1, (g.lv[0].w - kEdge - kMinBorder + kFtW - 1) / kFtW);
+    const int tiles_y = std::max(1, (g.lv[0].h - kEdge - kMinBorder + kFtH - 1) / kFtH);
+    return tiles_x * tiles_y;
+}
+
+void launch_fast_reset(const Geometry& g, const BatchView& v, cudaStream_t stream) {
     cudaMemsetAsync(v.lmax_count, 0, sizeof(int) * (size_t)v.B * g.nlevels, stream);
     cudaMemsetAsync(v.cell_count, 0, sizeof(int) * (size_t)v.B * g.cells_per_frame, stream);
+}
+
+void launch_fast_tiles(const Geometry& g, const BatchView& v, cudaStream_t stream, int first, int count) {
+    if (count <= 0) return;
     TmaMaps maps;
-    if (tma_enabled() && encode_level_maps(g, v, kImgPitch, kImgRows, &maps)) fast_kernel<true><<<dim3(g.fast_tiles_per_frame, v.B), kFtThreads, 0, stream>>>(g, v, v.fast_tiles, maps);
-    else fast_kernel<false><<<dim3(g.fast_tiles_per_frame, v.B), kFtThreads, 0, stream>>>(g, v, v.fast_tiles, maps);
+    if (tma_enabled() && encode_level_maps(g, v, kImgPitch, kImgRows, &maps)) fast_kernel<true><<<dim3(count, v.B), kFtThreads, 0, stream>>>(g, v, v.fast_tiles + first, maps);
+    else fast_kernel<false><<<dim3(count, v.B), kFtThreads, 0, stream>>>(g, v, v.fast_tiles + first, maps);
+}
+
+void launch_fast_tail(const Geometry& g, const BatchView& v, cudaStream_t stream) {
     const int cells = v.B * g.cells_per_frame;
     cudaMemsetAsync(v.empty_count, 0, sizeof(int), stream);
     fast_empty_cells_kernel<<<(cells + 255) / 256, 256, 0, stream>>>(g, v);
@@ -642,6 +659,12 @@ void launch_fast(const Geometry& g, const BatchView& v, cudaStream_t stream) {
         const int ctas_per_sm = std::max(1, std::min(8, (int)((200u << 10) / smem)));
         fast_fallback_kernel<<<148 * ctas_per_sm, 32 * kFbWarps, smem, stream>>>(g, v, F);
     }
+}
+
+void launch_fast(const Geometry& g, const BatchView& v, cudaStream_t stream) {
+    launch_fast_reset(g, v, stream);
+    launch_fast_tiles(g, v, stream, 0, g.fast_tiles_per_frame);
+    launch_fast_tail(g, v, stream);
 }
 
 }  // namespace coeb
