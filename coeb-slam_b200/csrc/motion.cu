@@ -108,20 +108,66 @@ __global__ void __launch_bounds__(256) harris_candidates_kernel(const float* __r
     }
 }
 
+// goodFeaturesToTrack sorts the candidates by (response descending, address descending): both orders are the order of the 64-bit
+// key response-bits << 32 | raster index (responses are positive floats). One CTA sorts up to kSortCap keys in shared memory
+// (bitonic network); longer lists are sorted on the host.
+constexpr int kSortCap = 8192;
+__global__ void __launch_bounds__(1024) sort_candidates_kernel(float2* __restrict__ cand, const int* __restrict__ n_cand) {
+    extern __shared__ unsigned long long s_key[];
+    const int n = *n_cand;
+    if (n > kSortCap || n < 2) return;
+    int m = 2;
+    while (m < n) m <<= 1;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        unsigned long long k = 0ull;   // padding sorts last in descending order
+        if (i < n) { const float2 c = cand[i]; k = ((unsigned long long)__float_as_uint(c.x) << 32) | (unsigned)__float_as_int(c.y); }
+        s_key[i] = k;
+    }
+    __syncthreads();
+    for (int size = 2; size <= m; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = threadIdx.x; t < (m >> 1); t += blockDim.x) {
+                const int i = 2 * t - (t & (stride - 1)), j = i + stride;
+                const bool desc = (i & size) == 0;
+                const unsigned long long a = s_key[i], b = s_key[j];
+                if ((a < b) == desc) { s_key[i] = b; s_key[j] = a; }
+            }
+            __syncthreads();
+        }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned long long k = s_key[i];
+        cand[i] = make_float2(__uint_as_float((unsigned)(k >> 32)), __int_as_float((int)(unsigned)k));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // cv::cornerSubPix(src, corners, win (hw, hw), zeroZone (-1,-1), criteria): one warp per corner. Each iteration samples a
 // (2hw+3)^2 patch around the current estimate (cv::getRectSubPix: float bilinear weights, replicated border) and solves the
 // 2x2 gradient-weighted system in double.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kSpMaxWin = 23;   // 2 * 10 + 3
-__global__ void __launch_bounds__(128) corner_subpix_kernel(const uint8_t* __restrict__ img, int w, int h, int pitch, float2* __restrict__ pts, int n, int hw,
+template <int HW>
+__global__ void __launch_bounds__(128) corner_subpix_kernel(const uint8_t* __restrict__ img, int w, int h, int pitch, float2* __restrict__ pts, int n,
                                                             int max_iters, double eps2, const float* __restrict__ mask) {
-    __shared__ float s_patch[4][kSpMaxWin * kSpMaxWin];
+    constexpr int hw = HW, win = 2 * HW + 1, pw = win + 2;
+    constexpr int NP = (pw * pw + 31) / 32, NG = (win * win + 31) / 32;   // patch samples / gradient terms per lane
+    __shared__ float s_patch[4][pw * pw];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int p = blockIdx.x * 4 + wid;
     if (p >= n) return;
     float* patch = s_patch[wid];
-    const int win = 2 * hw + 1, pw = win + 2;
+    // this lane's share of the window, fixed over the iterations: sample offsets, and for the gradient terms the patch index
+    // and the Gaussian weight
+    int soff[NP], gidx[NG];
+    float gm[NG];
+#pragma unroll
+    for (int k = 0; k < NP; k++) { const int i = lane + 32 * k, py = i / pw; soff[k] = py * pitch + (i - py * pw); }
+#pragma unroll
+    for (int k = 0; k < NG; k++) {
+        const int i = lane + 32 * k, yy = i / win, xx = i - yy * win;
+        gidx[k] = (yy + 1) * pw + (xx + 1);
+        gm[k] = i < win * win ? mask[i] : 0.f;
+    }
     const float2 cT = pts[p];
     float2 cI = cT;
     int iter = 0;
@@ -132,25 +178,41 @@ __global__ void __launch_bounds__(128) corner_subpix_kernel(const uint8_t* __res
         const int ipx = (int)floorf(cxf), ipy = (int)floorf(cyf);
         const float a = cxf - (float)ipx, b = cyf - (float)ipy;
         const float a11 = __fmul_rn(1.f - a, 1.f - b), a12 = __fmul_rn(a, 1.f - b), a21 = __fmul_rn(1.f - a, b), a22 = __fmul_rn(a, b);
-        for (int i = lane; i < pw * pw; i += 32) {
-            const int py = i / pw, px = i - py * pw;
-            const int x0 = min(max(ipx + px, 0), w - 1), x1 = min(max(ipx + px + 1, 0), w - 1);
-            const int y0 = min(max(ipy + py, 0), h - 1), y1 = min(max(ipy + py + 1, 0), h - 1);
-            const float v00 = img[(size_t)y0 * pitch + x0], v01 = img[(size_t)y0 * pitch + x1], v10 = img[(size_t)y1 * pitch + x0], v11 = img[(size_t)y1 * pitch + x1];
-            patch[i] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v00, a11), __fmul_rn(v01, a12)), __fmul_rn(v10, a21)), __fmul_rn(v11, a22));
+        if (ipx >= 0 && ipy >= 0 && ipx + pw + 1 <= w && ipy + pw + 1 <= h) {   // the patch lies inside the image
+            const uint8_t* base = img + (size_t)ipy * pitch + ipx;
+#pragma unroll
+            for (int k = 0; k < NP; k++) {
+                const int i = lane + 32 * k;
+                if (i < pw * pw) {
+                    const uint8_t* q = base + soff[k];
+                    patch[i] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn((float)q[0], a11), __fmul_rn((float)q[1], a12)), __fmul_rn((float)q[pitch], a21)), __fmul_rn((float)q[pitch + 1], a22));
+                }
+            }
+        } else {
+            for (int i = lane; i < pw * pw; i += 32) {
+                const int py = i / pw, px = i - py * pw;
+                const int x0 = min(max(ipx + px, 0), w - 1), x1 = min(max(ipx + px + 1, 0), w - 1);
+                const int y0 = min(max(ipy + py, 0), h - 1), y1 = min(max(ipy + py + 1, 0), h - 1);
+                const float v00 = img[(size_t)y0 * pitch + x0], v01 = img[(size_t)y0 * pitch + x1], v10 = img[(size_t)y1 * pitch + x0], v11 = img[(size_t)y1 * pitch + x1];
+                patch[i] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v00, a11), __fmul_rn(v01, a12)), __fmul_rn(v10, a21)), __fmul_rn(v11, a22));
+            }
         }
         __syncwarp();
         double sa = 0, sb = 0, sc = 0, sbb1 = 0, sbb2 = 0;
-        for (int i = lane; i < win * win; i += 32) {
-            const int yy = i / win, xx = i - yy * win;
-            const float* sp = patch + (yy + 1) * pw + (xx + 1);
-            const double m = mask[i];
-            const double tgx = (double)__fsub_rn(sp[1], sp[-1]), tgy = (double)__fsub_rn(sp[pw], sp[-pw]);
-            const double gxx = tgx * tgx * m, gxy = tgx * tgy * m, gyy = tgy * tgy * m;
-            const double px = xx - hw, py = yy - hw;
-            sa += gxx; sb += gxy; sc += gyy;
-            sbb1 += gxx * px + gxy * py;
-            sbb2 += gxy * px + gyy * py;
+#pragma unroll
+        for (int k = 0; k < NG; k++) {
+            const int i = lane + 32 * k;
+            if (i < win * win) {
+                const float* sp = patch + gidx[k];
+                const int yy = i / win, xx = i - yy * win;
+                const double m = gm[k];
+                const double tgx = (double)__fsub_rn(sp[1], sp[-1]), tgy = (double)__fsub_rn(sp[pw], sp[-pw]);
+                const double gxx = tgx * tgx * m, gxy = tgx * tgy * m, gyy = tgy * tgy * m;
+                const double px = xx - hw, py = yy - hw;
+                sa += gxx; sb += gxy; sc += gyy;
+                sbb1 += gxx * px + gxy * py;
+                sbb2 += gxy * px + gyy * py;
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -340,6 +402,167 @@ __global__ void __launch_bounds__(32 * kLkWarps) lk_kernel(const __grid_constant
     }
 }
 
+// The same tracker for a compile-time window (the reference's 22 x 22): the patch of the first image and its derivatives stay in
+// registers (NS = ceil(WIN^2 / 32) pixels per lane), and a window that lies inside the level is read through per-lane offsets
+// computed once per level, without the per-pixel reflection and index arithmetic of the general kernel above. Same operations in
+// the same order per lane, so both kernels give the same floats.
+template <int WIN>
+__global__ void __launch_bounds__(32 * kLkWarps) lk_kernel_w(const __grid_constant__ LkLevels L, const float2* __restrict__ prev_pts, int n, int max_iters,
+                                                           float eps2, float min_eig_thr, float2* __restrict__ next_pts, uint8_t* __restrict__ status,
+                                                           int edge, float sad_limit) {
+    constexpr int win = WIN, NS = (WIN * WIN + 31) / 32;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int p = blockIdx.x * kLkWarps + wid;
+    if (p >= n) return;
+    int Ib[NS], Ixb[NS], Iyb[NS], off[NS];   // this lane's pixels i = lane + 32 k of the window: patch value, derivatives, y * pitch + x
+    const float2 pt0 = prev_pts[p];
+    const float half = (float)(win - 1) * 0.5f;
+    const float FLT_SCALE = 1.f / (1 << 20);
+    float2 nextPt = make_float2(0.f, 0.f);
+    bool st = true;
+    for (int level = L.nlevels - 1; level >= 0; level--) {
+        const int w = L.w[level], h = L.h[level], pitch = L.pitch[level];
+        const uint8_t *I = L.prev[level], *J = L.cur[level];
+        const short2* D = L.deriv[level];
+#pragma unroll
+        for (int k = 0; k < NS; k++) { const int i = lane + 32 * k, y = i / WIN; off[k] = y * pitch + (i - y * WIN); }
+        const float sc = (float)(1. / (double)(1 << level));
+        float2 prevPt = make_float2(__fmul_rn(pt0.x, sc), __fmul_rn(pt0.y, sc));
+        if (level == L.nlevels - 1) nextPt = prevPt;
+        else nextPt = make_float2(__fmul_rn(nextPt.x, 2.f), __fmul_rn(nextPt.y, 2.f));
+        prevPt.x = __fsub_rn(prevPt.x, half); prevPt.y = __fsub_rn(prevPt.y, half);
+        const int ipx = (int)floorf(prevPt.x), ipy = (int)floorf(prevPt.y);
+        if (ipx < -win || ipx >= w || ipy < -win || ipy >= h) {
+            if (level == 0) st = false;
+            continue;
+        }
+        float a = __fsub_rn(prevPt.x, (float)ipx), b = __fsub_rn(prevPt.y, (float)ipy);
+        int iw00 = __float2int_rn(__fmul_rn(__fmul_rn(1.f - a, 1.f - b), 16384.f));
+        int iw01 = __float2int_rn(__fmul_rn(__fmul_rn(a, 1.f - b), 16384.f));
+        int iw10 = __float2int_rn(__fmul_rn(__fmul_rn(1.f - a, b), 16384.f));
+        int iw11 = 16384 - iw00 - iw01 - iw10;
+        float A11 = 0, A12 = 0, A22 = 0;
+        const bool insideI = ipx >= 0 && ipy >= 0 && ipx + WIN + 1 <= w && ipy + WIN + 1 <= h;
+#pragma unroll
+        for (int k = 0; k < NS; k++) {
+            const int i = lane + 32 * k;
+            Ib[k] = Ixb[k] = Iyb[k] = 0;
+            if (i < WIN * WIN) {
+                int ival, ixval, iyval;
+                if (insideI) {
+                    const uint8_t* q = I + (size_t)ipy * pitch + ipx + off[k];
+                    ival = ((int)q[0] * iw00 + (int)q[1] * iw01 + (int)q[pitch] * iw10 + (int)q[pitch + 1] * iw11 + (1 << 8)) >> 9;
+                    const int y = i / WIN, x = i - y * WIN;
+                    const short2* dq = D + (size_t)(ipy + y) * w + ipx + x;
+                    const short2 d00 = dq[0], d01 = dq[1], d10 = dq[w], d11 = dq[w + 1];
+                    ixval = ((int)d00.x * iw00 + (int)d01.x * iw01 + (int)d10.x * iw10 + (int)d11.x * iw11 + (1 << 13)) >> 14;
+                    iyval = ((int)d00.y * iw00 + (int)d01.y * iw01 + (int)d10.y * iw10 + (int)d11.y * iw11 + (1 << 13)) >> 14;
+                } else {
+                    const int y = i / WIN, x = i - y * WIN;
+                    const int gx0 = ipx + x, gy0 = ipy + y;
+                    const int x0 = refl101(gx0, w), x1 = refl101(gx0 + 1, w), y0 = refl101(gy0, h), y1 = refl101(gy0 + 1, h);
+                    ival = ((int)I[(size_t)y0 * pitch + x0] * iw00 + (int)I[(size_t)y0 * pitch + x1] * iw01 + (int)I[(size_t)y1 * pitch + x0] * iw10 +
+                            (int)I[(size_t)y1 * pitch + x1] * iw11 + (1 << 8)) >> 9;
+                    auto dv = [&](int gx, int gy) { return ((unsigned)gx < (unsigned)w && (unsigned)gy < (unsigned)h) ? D[(size_t)gy * w + gx] : make_short2(0, 0); };
+                    const short2 d00 = dv(gx0, gy0), d01 = dv(gx0 + 1, gy0), d10 = dv(gx0, gy0 + 1), d11 = dv(gx0 + 1, gy0 + 1);
+                    ixval = ((int)d00.x * iw00 + (int)d01.x * iw01 + (int)d10.x * iw10 + (int)d11.x * iw11 + (1 << 13)) >> 14;
+                    iyval = ((int)d00.y * iw00 + (int)d01.y * iw01 + (int)d10.y * iw10 + (int)d11.y * iw11 + (1 << 13)) >> 14;
+                }
+                ival = (int)(short)ival; ixval = (int)(short)ixval; iyval = (int)(short)iyval;   // the reference stores int16
+                Ib[k] = ival; Ixb[k] = ixval; Iyb[k] = iyval;
+                A11 += (float)(ixval * ixval); A12 += (float)(ixval * iyval); A22 += (float)(iyval * iyval);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            A11 += __shfl_xor_sync(0xffffffffu, A11, o); A12 += __shfl_xor_sync(0xffffffffu, A12, o); A22 += __shfl_xor_sync(0xffffffffu, A22, o);
+        }
+        A11 *= FLT_SCALE; A12 *= FLT_SCALE; A22 *= FLT_SCALE;
+        float Dt = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+        const float dA = __fsub_rn(A11, A22);
+        const float minEig = (A22 + A11 - sqrtf(__fadd_rn(__fmul_rn(dA, dA), __fmul_rn(4.f, __fmul_rn(A12, A12))))) / (float)(2 * win * win);
+        if (minEig < min_eig_thr || Dt < FLT_EPSILON) {
+            if (level == 0) st = false;
+            continue;
+        }
+        Dt = 1.f / Dt;
+        nextPt.x = __fsub_rn(nextPt.x, half); nextPt.y = __fsub_rn(nextPt.y, half);
+        float2 prevDelta = make_float2(0.f, 0.f);
+        float2 result = make_float2(__fadd_rn(nextPt.x, half), __fadd_rn(nextPt.y, half));
+        for (int j = 0; j < max_iters; j++) {
+            const int inx = (int)floorf(nextPt.x), iny = (int)floorf(nextPt.y);
+            if (inx < -win || inx >= w || iny < -win || iny >= h) {
+                if (level == 0) st = false;
+                break;
+            }
+            a = __fsub_rn(nextPt.x, (float)inx); b = __fsub_rn(nextPt.y, (float)iny);
+            iw00 = __float2int_rn(__fmul_rn(__fmul_rn(1.f - a, 1.f - b), 16384.f));
+            iw01 = __float2int_rn(__fmul_rn(__fmul_rn(a, 1.f - b), 16384.f));
+            iw10 = __float2int_rn(__fmul_rn(__fmul_rn(1.f - a, b), 16384.f));
+            iw11 = 16384 - iw00 - iw01 - iw10;
+            float b1 = 0, b2 = 0;
+            const bool insideJ = inx >= 0 && iny >= 0 && inx + WIN + 1 <= w && iny + WIN + 1 <= h;
+            if (insideJ) {
+                const uint8_t* base = J + (size_t)iny * pitch + inx;
+#pragma unroll
+                for (int k = 0; k < NS; k++)
+                    if (lane + 32 * k < WIN * WIN) {
+                        const uint8_t* q = base + off[k];
+                        const int jv = ((int)q[0] * iw00 + (int)q[1] * iw01 + (int)q[pitch] * iw10 + (int)q[pitch + 1] * iw11 + (1 << 8)) >> 9;
+                        const int diff = jv - Ib[k];
+                        b1 += (float)(diff * Ixb[k]);
+                        b2 += (float)(diff * Iyb[k]);
+                    }
+            } else {
+#pragma unroll
+                for (int k = 0; k < NS; k++) {
+                    const int i = lane + 32 * k;
+                    if (i < WIN * WIN) {
+                        const int y = i / WIN, x = i - y * WIN;
+                        const int x0 = refl101(inx + x, w), x1 = refl101(inx + x + 1, w), y0 = refl101(iny + y, h), y1 = refl101(iny + y + 1, h);
+                        const int jv = ((int)J[(size_t)y0 * pitch + x0] * iw00 + (int)J[(size_t)y0 * pitch + x1] * iw01 + (int)J[(size_t)y1 * pitch + x0] * iw10 +
+                                        (int)J[(size_t)y1 * pitch + x1] * iw11 + (1 << 8)) >> 9;
+                        const int diff = jv - Ib[k];
+                        b1 += (float)(diff * Ixb[k]);
+                        b2 += (float)(diff * Iyb[k]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { b1 += __shfl_xor_sync(0xffffffffu, b1, o); b2 += __shfl_xor_sync(0xffffffffu, b2, o); }
+            b1 *= FLT_SCALE; b2 *= FLT_SCALE;
+            const float2 delta = make_float2(__fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), Dt), __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), Dt));
+            nextPt.x = __fadd_rn(nextPt.x, delta.x); nextPt.y = __fadd_rn(nextPt.y, delta.y);
+            result = make_float2(__fadd_rn(nextPt.x, half), __fadd_rn(nextPt.y, half));
+            if ((double)delta.x * delta.x + (double)delta.y * delta.y <= (double)eps2) break;
+            if (j > 0 && fabsf(delta.x + prevDelta.x) < 0.01f && fabsf(delta.y + prevDelta.y) < 0.01f) {
+                result.x = __fsub_rn(result.x, __fmul_rn(delta.x, 0.5f)); result.y = __fsub_rn(result.y, __fmul_rn(delta.y, 0.5f));
+                break;
+            }
+            prevDelta = delta;
+        }
+        nextPt = result;
+        __syncwarp();
+    }
+    if (lane == 0) {
+        next_pts[p] = nextPt;
+        // src/Frame.cc:336-364: 5-px border test on the truncated coordinates, then the 3x3 sum of absolute differences
+        if (st && edge >= 0) {
+            const int w = L.w[0], h = L.h[0], pitch = L.pitch[0];
+            const int x1 = (int)pt0.x, y1 = (int)pt0.y, x2 = (int)nextPt.x, y2 = (int)nextPt.y;
+            if (x1 < edge || x1 >= w - edge || x2 < edge || x2 >= w - edge || y1 < edge || y1 >= h - edge || y2 < edge || y2 >= h - edge) {
+                st = false;
+            } else {
+                int sad = 0;
+                for (int j = -1; j <= 1; j++)
+                    for (int i = -1; i <= 1; i++) sad += abs((int)L.prev[0][(size_t)(y1 + j) * pitch + x1 + i] - (int)L.cur[0][(size_t)(y2 + j) * pitch + x2 + i]);
+                if ((float)sad > sad_limit) st = false;
+            }
+        }
+        status[p] = st ? 1 : 0;
+    }
+}
+
 // src/Frame.cc:372-385: the epipolar distance of every tracked point, in double, with the reference's expression.
 __global__ void epipolar_kernel(const float2* __restrict__ pre, const float2* __restrict__ nxt, const uint8_t* __restrict__ status, int n, const double* __restrict__ F,
                                 double limit, uint8_t* __restrict__ moving, double* __restrict__ dist) {
@@ -459,10 +682,10 @@ int ensure_mask(coeb_motion* m, int hw) {
 
 // goodFeaturesToTrack after the response: candidates sorted by (value descending, raster position descending -- the pointer
 // tie-break of greaterThanPtr), then the minimum-distance pass over a grid of cell size round(minDistance).
-int select_corners(std::vector<float2>& cand, int w, int h, int max_corners, double min_distance, float* xy_out, int cap) {
+int select_corners(std::vector<float2>& cand, bool sorted, int w, int h, int max_corners, double min_distance, float* xy_out, int cap) {
     // positive floats order like their bit patterns: one 64-bit key (value bits, raster position) per candidate, sorted descending
     static_assert(sizeof(float2) == sizeof(unsigned long long), "a candidate is one 64-bit key");
-    {
+    if (!sorted) {
         unsigned long long* key = reinterpret_cast<unsigned long long*>(cand.data());
         for (size_t i = 0; i < cand.size(); i++) {
             unsigned vb, ib;
@@ -710,15 +933,26 @@ int coeb_motion_good_features(coeb_motion* m, const uint8_t* gray, int width, in
         m->d_pyr[0][0], width, height, m->lp[0], harris_k, (float)(1.0 * scale), (float)(2.0 * scale), m->d_resp, m->d_max);
     harris_candidates_kernel<<<dim3((width + 31) / 32, (height + 7) / 8), 256, 0, m->stream>>>(m->d_resp, width, height, m->d_max, (float)quality, m->d_cand,
                                                                                             (int*)(m->d_max + 1), kMoMaxCand);
+    {
+        static bool configured[64] = {};
+        if (!configured[m->device & 63]) { cudaFuncSetAttribute(sort_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8); configured[m->device & 63] = true; }
+        sort_candidates_kernel<<<1, 1024, kSortCap * 8, m->stream>>>(m->d_cand, (const int*)(m->d_max + 1));
+    }
     CUDA_TRY(cudaGetLastError());
-    unsigned info[2];
-    CUDA_TRY(cudaMemcpyAsync(info, m->d_max, 8, cudaMemcpyDeviceToHost, m->stream));
+    // the count and the first kSortCap candidates come back in one transfer (the count sits right in front of the list)
+    int st2 = motion_pin(m, 16 + sizeof(float2) * kSortCap);
+    if (st2 != COEB_OK) return st2;
+    CUDA_TRY(cudaMemcpyAsync(m->h_pin, m->d_max, 16, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaMemcpyAsync(m->h_pin + 16, m->d_cand, sizeof(float2) * kSortCap, cudaMemcpyDeviceToHost, m->stream));
     CUDA_TRY(cudaStreamSynchronize(m->stream));
-    const int nc = std::min<int>((int)info[1], kMoMaxCand);
+    const unsigned* info = reinterpret_cast<const unsigned*>(m->h_pin);
     if ((int)info[1] > kMoMaxCand) return fail(COEB_ERR_CAPACITY, "%u corner candidates (at most %d)", info[1], kMoMaxCand);
+    const int nc = (int)info[1];
     m->cand_host.resize(nc);
-    if (nc) CUDA_TRY(cudaMemcpy(m->cand_host.data(), m->d_cand, sizeof(float2) * nc, cudaMemcpyDeviceToHost));
-    const int n = select_corners(m->cand_host, width, height, max_corners, min_distance, xy_out, cap);
+    const bool sorted = nc <= kSortCap;
+    if (sorted) { if (nc) std::memcpy(m->cand_host.data(), m->h_pin + 16, sizeof(float2) * nc); }
+    else CUDA_TRY(cudaMemcpy(m->cand_host.data(), m->d_cand, sizeof(float2) * nc, cudaMemcpyDeviceToHost));
+    const int n = select_corners(m->cand_host, sorted, width, height, max_corners, min_distance, xy_out, cap);
     *n_out = n;
     return n > cap ? COEB_ERR_CAPACITY : COEB_OK;
 }
@@ -734,7 +968,12 @@ int coeb_motion_corner_subpix(coeb_motion* m, const uint8_t* gray, int width, in
     if ((st = upload_level0(m, 0, gray, stride)) != COEB_OK) return st;
     CUDA_TRY(cudaMemcpyAsync(m->d_pre, xy_inout, sizeof(float2) * n, cudaMemcpyHostToDevice, m->stream));
     const double e = std::max(eps, 0.0);
-    corner_subpix_kernel<<<(n + 3) / 4, 128, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, half_win, std::max(max_iters, 1), e * e, m->d_mask);
+    switch (half_win) {   // the window is a compile-time size: its per-lane offsets and weights live in registers
+        case 10: corner_subpix_kernel<10><<<(n + 3) / 4, 128, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, std::max(max_iters, 1), e * e, m->d_mask); break;
+        case 5: corner_subpix_kernel<5><<<(n + 3) / 4, 128, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, std::max(max_iters, 1), e * e, m->d_mask); break;
+        case 3: corner_subpix_kernel<3><<<(n + 3) / 4, 128, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, std::max(max_iters, 1), e * e, m->d_mask); break;
+        default: return fail(COEB_ERR_UNSUPPORTED, "cornerSubPix half window %d (built for 3, 5 and 10)", half_win);
+    }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(xy_inout, m->d_pre, sizeof(float2) * n, cudaMemcpyDeviceToHost, m->stream));
     CUDA_TRY(cudaStreamSynchronize(m->stream));
@@ -751,8 +990,12 @@ static int run_lk(coeb_motion* m, int n, int win, int max_iters, double eps, dou
         L.w[l] = m->lw[l]; L.h[l] = m->lh[l]; L.pitch[l] = m->lp[l];
         L.prev[l] = m->d_pyr[0][l]; L.cur[l] = m->d_pyr[1][l]; L.deriv[l] = m->d_deriv[l];
     }
-    lk_kernel<<<(n + kLkWarps - 1) / kLkWarps, 32 * kLkWarps, 0, m->stream>>>(L, m->d_pre, n, win, max_iters, (float)(eps * eps), (float)min_eig, m->d_next, m->d_status, edge,
-                                                                        sad_limit);
+    if (win == 22)
+        lk_kernel_w<22><<<(n + kLkWarps - 1) / kLkWarps, 32 * kLkWarps, 0, m->stream>>>(L, m->d_pre, n, max_iters, (float)(eps * eps), (float)min_eig, m->d_next, m->d_status, edge,
+                                                                                  sad_limit);
+    else
+        lk_kernel<<<(n + kLkWarps - 1) / kLkWarps, 32 * kLkWarps, 0, m->stream>>>(L, m->d_pre, n, win, max_iters, (float)(eps * eps), (float)min_eig, m->d_next, m->d_status, edge,
+                                                                            sad_limit);
     CUDA_TRY(cudaGetLastError());
     return COEB_OK;
 }
@@ -852,7 +1095,7 @@ int coeb_process_moving_object(coeb_motion* m, const uint8_t* prev_gray, const u
     const auto t1 = now();
     if ((st = ensure_mask(m, 10)) != COEB_OK) return st;
     CUDA_TRY(cudaMemcpyAsync(m->d_pre, pre.data(), sizeof(float2) * n, cudaMemcpyHostToDevice, m->stream));   // level 0 of the previous frame is resident
-    corner_subpix_kernel<<<(n + 3) / 4, 128, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, 10, 20, 0.03 * 0.03, m->d_mask);
+    corner_subpix_kernel<10><<<(n + 3) / 4, 128, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, 20, 0.03 * 0.03, m->d_mask);
     // calcOpticalFlowPyrLK + border / SAD tests (:335-364)
     if ((st = upload_level0(m, 1, cur_gray, stride)) != COEB_OK) return st;
     if ((st = run_lk(m, n, 22, 20, 0.01, 1e-4, /*limit_edge_corner*/ 5, /*limit_of_check*/ 2120.f)) != COEB_OK) return st;

@@ -87,6 +87,21 @@ def test_lk_against_cv2(mo, seed):
     assert both.sum() > 300 and (d <= 0.05).mean() >= 0.97, (int(both.sum()), float((d <= 0.05).mean()), float(np.percentile(d, 99)))
 
 
+@pytest.mark.parametrize("win,max_level", [(15, 3), (31, 2)])
+def test_lk_other_windows_use_the_general_kernel(mo, win, max_level):
+    """The reference's 22 x 22 window runs a kernel specialised at compile time; every other size runs the general one."""
+    prev, cur, _ = synth.make_motion_pair(5)
+    pts = pmo.corner_subpix(prev, pmo.good_features(prev))
+    ref, st_ref, _ = cv2.calcOpticalFlowPyrLK(prev, cur, pts.reshape(-1, 1, 2), None, winSize=(win, win), maxLevel=max_level,
+                                              criteria=(cv2.TERM_CRITERIA_MAX_ITER | cv2.TERM_CRITERIA_EPS, 20, 0.01))
+    ref, st_ref = ref.reshape(-1, 2), st_ref.reshape(-1)
+    got, st_got = mo.lk(prev, cur, pts, win=win, max_level=max_level)
+    assert (st_ref == st_got).mean() >= 0.98
+    both = (st_ref != 0) & (st_got != 0)
+    d = np.abs(got - ref)[both].max(axis=1)
+    assert both.sum() > 300 and (d <= 0.05).mean() >= 0.96, (int(both.sum()), float((d <= 0.05).mean()))
+
+
 def test_lk_exact_shift_is_recovered(mo):
     prev = synth.make_frame(901)
     cur = synth.shift_image(prev, 7, -5)
