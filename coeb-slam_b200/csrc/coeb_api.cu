@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -61,6 +62,7 @@ struct coeb_extractor {
     std::vector<int2> h_tabs;
     int2* d_tabs = nullptr;
     int4* d_fast_tiles = nullptr;
+    PyrRegionLevel* d_pyr_regions = nullptr; int n_pyr_regions = 0, pyr_regions_smem = 0;   // small-batch pyramid (one launch)
     size_t pyr_bytes_per_frame = 0;
     // arenas
     int cap_B = 0;
@@ -80,7 +82,8 @@ struct coeb_extractor {
     char* d_out_block = nullptr;                                    // counts | status | keypoints | descriptors: one allocation
     coeb_keypoint* d_out_kps = nullptr; uint8_t* d_out_desc = nullptr; int *d_out_count = nullptr, *d_out_status = nullptr;
     size_t out_cap_elems = 0; int out_cap_B = 0;
-    char* h_out1 = nullptr; size_t h_out1_cap = 0;                  // pinned landing block of single-frame calls (one D2H copy)
+    char* h_out1 = nullptr; size_t h_out1_cap = 0;                  // mapped pinned block of single-frame calls: the descriptor stage writes the results into it
+    uint8_t* h_in1 = nullptr; size_t h_in1_cap = 0;                 // pinned staging of a single pageable frame (pitch layout)
     BatchView last_view{};
     // copy/compute pipelining of the host entry point
     cudaStream_t pipe_stream[3] = {nullptr, nullptr, nullptr};
@@ -90,13 +93,14 @@ struct coeb_extractor {
     cudaEvent_t copy_out_done = nullptr;
     std::vector<cudaEvent_t> chunk_in, chunk_done;           // per sub-batch: input resident / kernels finished
     // blur runs beside FAST + octree on a side stream (both only need the pyramid); one lane per launching stream
-    struct Lane { cudaStream_t main; cudaStream_t aux; cudaEvent_t fork, join, fork0, cls; };
+    struct Lane { cudaStream_t main; cudaStream_t aux; cudaEvent_t fork, join, fork0, cls; cudaStream_t aux2; cudaEvent_t sel0; };
     std::vector<Lane> lanes;
     // CUDA graphs of the kernel sequence for small non-pipelined host calls (single-frame latency path)
     struct GraphEntry { BatchView view; int w, h, cap, chunk; cudaGraphExec_t exec; };
     std::vector<GraphEntry> graphs;
     int graph_warm = 0;
     int last_passes = 1;   // sub-batches the last batch call was split into (launch accounting)
+    unsigned long long* d_trace = nullptr;   // COEB_KERNEL_TRACE=1 with a -DCOEB_KERNEL_TRACE build: per-kernel start / end stamps
     // optional per-stage CUDA events (benchmark accounting)
     bool profiling = false;
     cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -269,6 +273,15 @@ int build_geometry(coeb_extractor* ex, int w, int h) {
         CUDA_TRY(cudaMalloc(&ex->d_tabs, ex->h_tabs.size() * sizeof(int2)));
         CUDA_TRY(cudaMemcpy(ex->d_tabs, ex->h_tabs.data(), ex->h_tabs.size() * sizeof(int2), cudaMemcpyHostToDevice));
     }
+    if (ex->d_pyr_regions) cudaFree(ex->d_pyr_regions);
+    ex->d_pyr_regions = nullptr;
+    ex->n_pyr_regions = build_pyramid_regions(g, ex->h_tabs.data(), nullptr, &ex->pyr_regions_smem);
+    if (ex->n_pyr_regions > 0) {
+        std::vector<PyrRegionLevel> regions((size_t)ex->n_pyr_regions * nl);
+        build_pyramid_regions(g, ex->h_tabs.data(), regions.data(), &ex->pyr_regions_smem);
+        CUDA_TRY(cudaMalloc(&ex->d_pyr_regions, regions.size() * sizeof(PyrRegionLevel)));
+        CUDA_TRY(cudaMemcpy(ex->d_pyr_regions, regions.data(), regions.size() * sizeof(PyrRegionLevel), cudaMemcpyHostToDevice));
+    }
     ex->geom_valid = true;
     ex->cap_B = 0;  // arenas must be re-laid out for the new geometry
     for (auto& e : ex->graphs) cudaGraphExecDestroy(e.exec);
@@ -330,9 +343,11 @@ int ensure_buf(T** p, size_t* cap, size_t n) {
 coeb_extractor::Lane* lane_for(coeb_extractor* ex, cudaStream_t s) {
     for (auto& l : ex->lanes)
         if (l.main == s) return &l;
-    coeb_extractor::Lane l{s, nullptr, nullptr, nullptr, nullptr, nullptr};
+    coeb_extractor::Lane l{s, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (cudaStreamCreateWithFlags(&l.aux, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming) != cudaSuccess ||
+    if (cudaStreamCreateWithFlags(&l.aux2, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&l.sel0, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&l.fork0, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&l.cls, cudaEventDisableTiming) != cudaSuccess) return nullptr;
@@ -344,26 +359,33 @@ int enqueue(coeb_extractor* ex, const BatchView& v, cudaStream_t s, bool prof) {
     const Geometry& g = ex->geom;
     coeb_extractor::Lane* lane = prof ? nullptr : lane_for(ex, s);
     if (lane && v.B <= 4 && !getenv("COEB_NO_L0_OVERLAP")) {
-        // Small batches (the tracking thread's single frame): the seven dependent resize launches are a latency chain that uses a
-        // fraction of the GPU, and level 0 -- a third of the FAST tiles -- does not depend on it. Side stream: classify, FAST on the
-        // level-0 tiles, then (once the pyramid is there) the blur | main: pyramid chain, FAST on levels 1.., fallback, octree |
-        // join | describe.
+        // Small batches (the tracking thread's single frame) are latency, not work: every kernel is a few microseconds whatever its
+        // size, so the call is as long as its longest chain of dependent launches. Level 0 needs no resize and owns the longest
+        // octree, so it runs end to end on a side stream beside everything else:
+        //   aux : classify, counters | FAST level 0 -> minTh fallback level 0 -> octree level 0
+        //   main: pyramid (one launch: pyramid_regions_kernel) -> FAST levels 1.. -> fallback -> octree levels 1..
+        //   aux2: blur (once the pyramid is there)
+        //   join -> describe
+        static const bool no_regions = getenv("COEB_NO_PYR_REGIONS") != nullptr;
         const int n0 = fast_tiles_of_level0(g);
         CUDA_TRY(cudaEventRecord(lane->fork0, s));
         CUDA_TRY(cudaStreamWaitEvent(lane->aux, lane->fork0, 0));
         launch_classify(g, v, lane->aux);
-        launch_fast_reset(g, v, lane->aux);
+        CUDA_TRY(cudaEventRecord(lane->cls, lane->aux));     // classification and zeroed counters are in place
         launch_fast_tiles(g, v, lane->aux, 0, n0);
-        CUDA_TRY(cudaEventRecord(lane->cls, lane->aux));     // classification, counters and the level-0 candidates are in place
-        launch_pyramid(g, v, s);
-        CUDA_TRY(cudaEventRecord(lane->fork, s));
-        CUDA_TRY(cudaStreamWaitEvent(lane->aux, lane->fork, 0));
-        launch_blur(g, v, lane->aux);
-        CUDA_TRY(cudaEventRecord(lane->join, lane->aux));
+        launch_fast_tail_levels(g, v, lane->aux, 0, 1);
+        launch_select(g, v, lane->aux, 0, 1);
+        CUDA_TRY(cudaEventRecord(lane->sel0, lane->aux));
+        if (no_regions || !launch_pyramid_regions(g, v, s)) launch_pyramid(g, v, s);
         CUDA_TRY(cudaStreamWaitEvent(s, lane->cls, 0));
         launch_fast_tiles(g, v, s, n0, g.fast_tiles_per_frame - n0);
-        launch_fast_tail(g, v, s);
-        launch_select(g, v, s);
+        CUDA_TRY(cudaEventRecord(lane->fork, s));
+        CUDA_TRY(cudaStreamWaitEvent(lane->aux2, lane->fork, 0));
+        launch_blur(g, v, lane->aux2);   // after the FAST tiles: measured, a blur that runs beside them more than doubles their time
+        CUDA_TRY(cudaEventRecord(lane->join, lane->aux2));
+        launch_fast_tail_levels(g, v, s, 1, g.nlevels);
+        launch_select(g, v, s, 1, g.nlevels);
+        CUDA_TRY(cudaStreamWaitEvent(s, lane->sel0, 0));
         CUDA_TRY(cudaStreamWaitEvent(s, lane->join, 0));
         launch_describe(g, v, s);
         CUDA_TRY(cudaGetLastError());
@@ -506,6 +528,7 @@ int coeb_extractor_create(const coeb_orb_params* params, int device, coeb_extrac
     ex->params = *params;
     ex->device = device;
     build_tables(ex);
+    if (getenv("COEB_KERNEL_TRACE")) cudaMalloc(&ex->d_trace, 32 * sizeof(unsigned long long));
     if (cudaStreamCreateWithFlags(&ex->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete ex;
         return fail(COEB_ERR_CUDA, "cudaStreamCreate failed");
@@ -522,11 +545,14 @@ void coeb_extractor_destroy(coeb_extractor* ex) {
     free_arenas(ex);
     cudaFree(ex->d_tabs);
     cudaFree(ex->d_fast_tiles);
+    cudaFree(ex->d_pyr_regions);
+    cudaFree(ex->d_trace);
     cudaFree(ex->d_in_gray); cudaFree(ex->d_in_linear); cudaFree(ex->d_dynin); cudaFree(ex->d_out_block);
     if (ex->h_dynin) cudaFreeHost(ex->h_dynin);
     if (ex->h_out1) cudaFreeHost(ex->h_out1);
+    if (ex->h_in1) cudaFreeHost(ex->h_in1);
     for (auto& e : ex->graphs) cudaGraphExecDestroy(e.exec);
-    for (auto& l : ex->lanes) { cudaStreamDestroy(l.aux); cudaEventDestroy(l.fork); cudaEventDestroy(l.join); cudaEventDestroy(l.fork0); cudaEventDestroy(l.cls); }
+    for (auto& l : ex->lanes) { cudaStreamDestroy(l.aux); cudaStreamDestroy(l.aux2); cudaEventDestroy(l.sel0); cudaEventDestroy(l.fork); cudaEventDestroy(l.join); cudaEventDestroy(l.fork0); cudaEventDestroy(l.cls); }
     for (int i = 0; i < 7; i++) if (ex->ev[i]) cudaEventDestroy(ex->ev[i]);
     for (int i = 0; i < 3; i++) {
         if (ex->pipe_stream[i]) cudaStreamDestroy(ex->pipe_stream[i]);
@@ -622,7 +648,8 @@ static bool same_view(const BatchView& a, const BatchView& b) {
     return a.B == b.B && a.l0 == b.l0 && a.l0_pitch == b.l0_pitch && a.l0_stride == b.l0_stride && a.pyr == b.pyr && a.blur == b.blur &&
            a.tabs == b.tabs && a.cand == b.cand && a.keys == b.keys && a.dyn == b.dyn && a.boxes == b.boxes && a.nbox == b.nbox &&
            a.max_box == b.max_box && a.tm == b.tm && a.ntm == b.ntm && a.max_tm == b.max_tm && a.blur_flag == b.blur_flag &&
-           a.out_kps == b.out_kps && a.out_desc == b.out_desc && a.out_count == b.out_count && a.status == b.status;
+           a.out_kps == b.out_kps && a.out_desc == b.out_desc && a.out_count == b.out_count && a.status == b.status &&
+           a.mirror_hdr == b.mirror_hdr && a.mirror_kps == b.mirror_kps && a.mirror_desc == b.mirror_desc && a.pyr_regions == b.pyr_regions;
 }
 
 // Large resident batches run as sub-batches round-robin over the pipeline streams: kernel tails of one sub-batch overlap
@@ -701,12 +728,14 @@ static int prepare_view(coeb_extractor* ex, int B, const uint8_t* gray, int widt
     v.l0 = gray; v.l0_pitch = stride; v.l0_stride = frame_stride;
     v.pyr = ex->d_pyr; v.blur = ex->d_blur; v.tabs = ex->d_tabs; v.fast_tiles = ex->d_fast_tiles; v.blur_tiles = ex->d_fast_tiles + ex->geom.fast_tiles_per_frame;
     v.ic_mask = reinterpret_cast<const uint32_t*>(v.blur_tiles + ex->geom.blur_tiles_per_frame);
+    v.pyr_regions = ex->d_pyr_regions; v.n_pyr_regions = ex->n_pyr_regions; v.pyr_regions_smem = ex->pyr_regions_smem;
     v.cand = ex->d_cand; v.cand_count = ex->d_cand_count; v.keys = ex->d_keys; v.key_count = ex->d_key_count;
     v.dyn = ex->d_dyn; v.knode = ex->d_knode;
     v.lmax = ex->d_lmax; v.lmax_count = ex->d_lmax_count; v.cell_count = ex->d_cell_count;
     v.empty_cells = ex->d_empty_cells; v.empty_count = ex->d_empty_count;
     v.boxes = boxes; v.nbox = nbox; v.max_box = max_box; v.tm = tm; v.ntm = ntm; v.max_tm = max_tm; v.blur_flag = blur_flag;
     v.out_kps = kps_out; v.out_desc = desc_out; v.out_count = counts_out; v.status = status_out;
+    v.trace = ex->d_trace;
     *out = v;
     return COEB_OK;
 }
@@ -742,6 +771,10 @@ int coeb_extract_batch_host(coeb_extractor* ex, int B, const uint8_t* gray, int 
                             size_t frame_stride, const float* boxes, const int* nbox, int max_box, const float* tm,
                             const int* ntm, int max_tm, const int* blur_flag, coeb_keypoint* kps_out,
                             uint8_t* desc_out, int* counts_out, int* status_out, int cap) {
+    static const bool host_trace = getenv("COEB_HOST_TRACE") != nullptr;   // development: host-side timeline of the call on stderr
+    double ht[8] = {0};
+    auto stamp = [&](int i) { if (host_trace) ht[i] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    stamp(0);
     int st = validate_common(ex, B, gray, width, height, stride, cap);
     if (st != COEB_OK) return st;
     if (!counts_out) return fail(COEB_ERR_INVALID_ARG, "null counts_out");
@@ -811,6 +844,21 @@ int coeb_extract_batch_host(coeb_extractor* ex, int B, const uint8_t* gray, int 
     st = prepare_view(ex, B, ex->d_in_gray, width, height, pitch, fstride, dboxes, dnbox, max_box, dtm, dntm, max_tm, dblur, ex->d_out_kps,
                       ex->d_out_desc, ex->d_out_count, ex->d_out_status, cap, &v);
     if (st != COEB_OK) return st;
+    // single frame: the results land in mapped pinned memory straight from the descriptor stage, no copy node
+    const bool mirrored = B == 1 && ex->out_cap_B == 1 && ex->out_cap_elems == (size_t)cap && !getenv("COEB_NO_MIRROR");
+    if (mirrored) {
+        const size_t bytes = (size_t)((char*)ex->d_out_desc - ex->d_out_block) + (size_t)cap * 32;
+        if (bytes > ex->h_out1_cap) {
+            drop_graphs(ex);
+            if (ex->h_out1) cudaFreeHost(ex->h_out1);
+            ex->h_out1 = nullptr; ex->h_out1_cap = 0;
+            CUDA_TRY(cudaHostAlloc((void**)&ex->h_out1, bytes, cudaHostAllocMapped));
+            ex->h_out1_cap = bytes;
+        }
+        v.mirror_hdr = (int*)ex->h_out1;
+        v.mirror_kps = (coeb_keypoint*)(ex->h_out1 + ((char*)ex->d_out_kps - ex->d_out_block));
+        v.mirror_desc = (uint8_t*)(ex->h_out1 + ((char*)ex->d_out_desc - ex->d_out_block));
+    }
     ex->last_view = v;
     ex->last_B = B;
     std::vector<int> status_local;
@@ -841,6 +889,33 @@ int coeb_extract_batch_host(coeb_extractor* ex, int B, const uint8_t* gray, int 
         cudaEventRecord(tev[0], s);
     }
     auto upload = [&](int f0, int n, cudaStream_t cs) -> cudaError_t {
+        if (B == 1 && fstride <= (size_t)(8u << 20) && !getenv("COEB_NO_STAGE")) {
+            // A single frame in pageable memory: cudaMemcpyAsync would stage it inside the driver and block for the whole copy
+            // (~25 us for 300 KB). Staging it here, in two halves, lets the second half's memcpy and the graph launch overlap the DMA,
+            // and lays rows of any stride out in the arena pitch on the way (no device-side re-pitch).
+            cudaPointerAttributes pa;
+            if (cudaPointerGetAttributes(&pa, gray) != cudaSuccess) { cudaGetLastError(); pa.type = cudaMemoryTypeUnregistered; }
+            if (pa.type == cudaMemoryTypeUnregistered) {
+                if (fstride > ex->h_in1_cap) {
+                    if (ex->h_in1) cudaFreeHost(ex->h_in1);
+                    ex->h_in1 = nullptr; ex->h_in1_cap = 0;
+                    if (cudaHostAlloc((void**)&ex->h_in1, fstride, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); ex->h_in1 = nullptr; }
+                    else ex->h_in1_cap = fstride;
+                }
+                if (ex->h_in1) {
+                    const int half = (height + 1) / 2;
+                    for (int part = 0; part < 2; part++) {
+                        const int y0 = part * half, y1 = std::min(height, y0 + half);
+                        if (y1 <= y0) break;
+                        if (stride == pitch) std::memcpy(ex->h_in1 + (size_t)y0 * pitch, gray + (size_t)y0 * stride, (size_t)(y1 - y0) * pitch);
+                        else for (int y = y0; y < y1; y++) std::memcpy(ex->h_in1 + (size_t)y * pitch, gray + (size_t)y * stride, width);
+                        cudaError_t e = cudaMemcpyAsync(ex->d_in_gray + (size_t)y0 * pitch, ex->h_in1 + (size_t)y0 * pitch, (size_t)(y1 - y0) * pitch, cudaMemcpyHostToDevice, cs);
+                        if (e != cudaSuccess) return e;
+                    }
+                    return cudaSuccess;
+                }
+            }
+        }
         if (frame_stride == (size_t)stride * height && stride == pitch && stride == width)
             // tightly packed frames whose width is already the arena pitch: one linear DMA (2D copies go row by row)
             return cudaMemcpyAsync(ex->d_in_gray + fstride * f0, gray + frame_stride * f0, fstride * n, cudaMemcpyHostToDevice, cs);
@@ -871,26 +946,23 @@ int coeb_extract_batch_host(coeb_extractor* ex, int B, const uint8_t* gray, int 
             e = cudaMemcpyAsync(desc_out + (size_t)f0 * cap * 32, ex->d_out_desc + (size_t)f0 * cap * 32, (size_t)32 * n * cap, cudaMemcpyDeviceToHost, cs);
         return e;
     };
-    bool landed = false;   // single frame: the whole output block came back with one copy into pinned memory
+    bool landed = false;   // single frame: the descriptor stage wrote the whole output block into mapped pinned memory
     if (!piped) {
+        stamp(1);
         CUDA_TRY(upload(0, B, s));
+        stamp(2);
         if (trace) cudaEventRecord(tev[1], s);
+        if (ex->d_trace) {   // development: stamps reset before the kernels (min slots all ones, max slots zero)
+            unsigned long long init[32];
+            for (int i = 0; i < 32; i++) init[i] = (i & 1) || i >= 24 ? 0ull : ~0ull;
+            CUDA_TRY(cudaMemcpyAsync(ex->d_trace, init, sizeof(init), cudaMemcpyHostToDevice, s));
+        }
         st = ex->profiling ? enqueue(ex, v, s, true) : launch_graphed(ex, v, s);   // one graph launch instead of ~20 stream operations
         if (st != COEB_OK) return st;
         if (trace) cudaEventRecord(tev[2], s);
-        if (B == 1 && ex->out_cap_B == 1 && ex->out_cap_elems == (size_t)cap) {
-            const size_t bytes = (size_t)((char*)ex->d_out_desc - ex->d_out_block) + (size_t)cap * 32;
-            if (bytes > ex->h_out1_cap) {
-                if (ex->h_out1) cudaFreeHost(ex->h_out1);
-                ex->h_out1 = nullptr; ex->h_out1_cap = 0;
-                CUDA_TRY(cudaHostAlloc((void**)&ex->h_out1, bytes, cudaHostAllocDefault));
-                ex->h_out1_cap = bytes;
-            }
-            CUDA_TRY(cudaMemcpyAsync(ex->h_out1, ex->d_out_block, bytes, cudaMemcpyDeviceToHost, s));
-            landed = true;
-        } else {
-            CUDA_TRY(download(0, B, s));
-        }
+        stamp(3);
+        if (mirrored) landed = true;
+        else CUDA_TRY(download(0, B, s));
         if (trace) cudaEventRecord(tev[3], s);
     } else {
         CUDA_TRY(cudaEventRecord(ex->pipe_ready, s));   // the box / T_M copies above, and whatever the caller queued before
@@ -920,6 +992,7 @@ int coeb_extract_batch_host(coeb_extractor* ex, int B, const uint8_t* gray, int 
         CUDA_TRY(cudaStreamWaitEvent(s, ex->copy_out_done, 0));
     }
     CUDA_TRY(cudaStreamSynchronize(s));
+    stamp(4);
     if (trace) {
         for (int c = 0; c < nchunks; c++) {
             float a = 0, b = 0, d = 0;
@@ -930,6 +1003,20 @@ int coeb_extract_batch_host(coeb_extractor* ex, int B, const uint8_t* gray, int 
         }
         for (auto& e : tev) cudaEventDestroy(e);
     }
+    if (ex->d_trace && !piped) {
+        static const char* names[16] = {"classify", "fast L0", "fast L1..", "fallback L0", "fallback L1..", "octree L0", "octree L1..", "pyramid regions",
+                                        "resize chain", "blur", "describe", "empty-cell list", "", "", "", ""};
+        unsigned long long t[32];
+        cudaMemcpy(t, ex->d_trace, sizeof(t), cudaMemcpyDeviceToHost);
+        unsigned long long t0 = ~0ull;
+        for (int i = 0; i < 12; i++) if (t[2 * i + 1]) t0 = std::min(t0, t[2 * i]);
+        fprintf(stderr, "[coeb kernels]");
+        for (int i = 0; i < 12; i++)
+            if (t[2 * i + 1]) fprintf(stderr, " %s %.1f-%.1f |", names[i], (double)(t[2 * i] - t0) * 1e-3, (double)(t[2 * i + 1] - t0) * 1e-3);
+        fprintf(stderr, " marks (octree L0: gathered, roots, rounds[%d], best):", (int)t[31]);
+        for (int i = 24; i < 31; i++) if (t[i]) fprintf(stderr, " %.1f", (double)(t[i] - t0) * 1e-3);
+        fprintf(stderr, "\n");
+    }
     if (landed) {   // only the keypoints that exist are copied on to the caller's arrays
         const int n = ((const int*)ex->h_out1)[0];
         counts_out[0] = n;
@@ -939,6 +1026,10 @@ int coeb_extract_batch_host(coeb_extractor* ex, int B, const uint8_t* gray, int 
         if (kps_out && m) std::memcpy(kps_out, ex->h_out1 + ((char*)ex->d_out_kps - ex->d_out_block), sizeof(coeb_keypoint) * m);
         if (desc_out && m) std::memcpy(desc_out, ex->h_out1 + ((char*)ex->d_out_desc - ex->d_out_block), (size_t)32 * m);
     }
+    stamp(5);
+    if (host_trace && !piped)
+        fprintf(stderr, "[coeb host] set-up %.1f us | upload enqueued %.1f | kernels enqueued %.1f | synchronised %.1f | results copied %.1f\n", ht[1] - ht[0], ht[2] - ht[0],
+                ht[3] - ht[0], ht[4] - ht[0], ht[5] - ht[0]);
     int worst = COEB_OK;
     for (int i = 0; i < B; i++)
         if (hstatus[i] != COEB_OK && worst == COEB_OK) {

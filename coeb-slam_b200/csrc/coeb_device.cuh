@@ -81,6 +81,15 @@ struct TileMap {
     int tiles_x[COEB_MAX_LEVELS];
 };
 
+// Small-batch pyramid (pyramid.cu, pyramid_regions_kernel): one CTA owns a rectangle of EVERY level and computes the whole chain
+// for it in shared memory. Per (region, level): the rectangle it computes (owned + the halo the next level's rectangle reads, x
+// bounds multiples of 4), the rectangle it owns (written to global memory), and where the computed rectangle lives in shared memory.
+struct PyrRegionLevel {
+    short cx0, cy0, cx1, cy1;
+    short ox0, oy0, ox1, oy1;
+    int soff, pitch;
+};
+
 // Device pointers of one batch launch.
 struct BatchView {
     int B;
@@ -93,6 +102,8 @@ struct BatchView {
     const int4* fast_tiles;            // FAST tile table {level, tx0, ty0, 0}, one entry per tile of one frame
     const int4* blur_tiles;            // blur tile table, same layout
     const uint32_t* ic_mask;           // [4 alignments][16 |v|][9 words]: 0xFF per patch byte inside the circular IC_Angle patch
+    const PyrRegionLevel* pyr_regions; // [n_pyr_regions][nlevels] small-batch pyramid regions (null: resize chain only)
+    int n_pyr_regions, pyr_regions_smem;
     uint32_t* cand;                    // [B][cand_per_frame]
     int* cand_count;                   // [B][nlevels]
     LevelKey* keys;                    // [B][keys_per_frame]
@@ -113,6 +124,10 @@ struct BatchView {
     uint8_t* out_desc;                 // [B][out_cap][32]
     int* out_count;                    // [B]
     int* status;                       // [B] per-frame coeb_status
+    // single-frame host calls: the descriptor stage also writes its results straight into mapped pinned host memory (a device-to-
+    // host copy node costs ~10 us of latency, the posted writes of 60 KB cost none); null otherwise. hdr = {count, final status}
+    int* mirror_hdr; coeb_keypoint* mirror_kps; uint8_t* mirror_desc;
+    unsigned long long* trace;         // development (-DCOEB_KERNEL_TRACE builds, COEB_KERNEL_TRACE=1): [16][2] first start / last end per kernel, %globaltimer ns
 };
 
 __host__ __device__ inline const uint8_t* level_ptr(const Geometry& g, const BatchView& v, int level, int frame) {
@@ -145,6 +160,30 @@ __device__ inline bool is_moving(const DynState& d, float ptx, float pty, int le
 }
 
 #ifdef __CUDACC__
+// Development timeline of one call as the GPU ran it (graph replay included), for the latency path where ncu's serialised,
+// cold-cache launch list misleads: every kernel notes the start of its first CTA and the end of its last one in v.trace.
+// Compiled in only with -DCOEB_KERNEL_TRACE (tools/build_trace.sh); ids: 0 classify, 1/2 FAST level 0 / levels 1.., 3/4 minTh
+// fallback, 5/6 octree, 7 pyramid (regions), 8 resize chain, 9 blur, 10 describe, 11 empty-cell list.
+#ifdef COEB_KERNEL_TRACE
+struct KernelTrace {
+    unsigned long long* slot;
+    unsigned long long t0;
+    __device__ __forceinline__ static unsigned long long now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+    __device__ __forceinline__ KernelTrace(unsigned long long* trace, int id) : slot(trace ? trace + 2 * id : nullptr), t0(0) {
+        if (slot && threadIdx.x == 0 && threadIdx.y == 0) t0 = now();
+    }
+    __device__ __forceinline__ ~KernelTrace() {
+        if (slot && threadIdx.x == 0 && threadIdx.y == 0) { atomicMin(slot, t0); atomicMax(slot + 1, now()); }
+    }
+};
+#define COEB_TRACE(v, id) KernelTrace coeb_kernel_trace_((v).trace, (id))
+// phase marks inside one chosen CTA: slots 24..31 hold absolute stamps (0: not reached)
+#define COEB_TRACE_MARK(v, cond, slot) do { if ((v).trace && (cond) && threadIdx.x == 0) (v).trace[24 + (slot)] = KernelTrace::now(); } while (0)
+#else
+#define COEB_TRACE(v, id)
+#define COEB_TRACE_MARK(v, cond, slot)
+#endif
+
 // In-place exclusive prefix sum of data[0..n) (shared or global memory) by the whole CTA; returns the total.
 // All threads must call; s_warp is a 33-int shared scratch array. kT = the CTA size when it is known at compile time (the
 // chunk size then is a multiply-shift instead of a division by blockDim.x).
@@ -249,18 +288,24 @@ __device__ __forceinline__ void tma_wait(uint32_t mbar) {
 // kernel launchers (each enqueues on `stream`, no synchronisation)
 void launch_classify(const Geometry& g, const BatchView& v, cudaStream_t stream);
 void launch_pyramid(const Geometry& g, const BatchView& v, cudaStream_t stream);
+// Region table of the small-batch pyramid from the host copy of the resize tables; returns the region count (0: not applicable)
+// and the dynamic shared memory one CTA needs.
+int build_pyramid_regions(const Geometry& g, const int2* h_tabs, PyrRegionLevel* out_or_null, int* smem_bytes);
+bool launch_pyramid_regions(const Geometry& g, const BatchView& v, cudaStream_t stream);   // false: no region table, nothing launched
 void launch_blur(const Geometry& g, const BatchView& v, cudaStream_t stream);
 void launch_fast(const Geometry& g, const BatchView& v, cudaStream_t stream);
 int fast_tiles_of_level0(const Geometry& g);
-void launch_fast_reset(const Geometry& g, const BatchView& v, cudaStream_t stream);
 void launch_fast_tiles(const Geometry& g, const BatchView& v, cudaStream_t stream, int first, int count);
 void launch_fast_tail(const Geometry& g, const BatchView& v, cudaStream_t stream);
+// Small batches: the minTh fallback of the cells of levels [level_lo, level_hi), one warp per cell, each warp testing its own
+// cell's counter (no list kernel in between).
+void launch_fast_tail_levels(const Geometry& g, const BatchView& v, cudaStream_t stream, int level_lo, int level_hi);
 // Host-side FAST tile table of one frame (level, tx0, ty0 per 64x30 tile), uploaded once per geometry.
 int build_fast_tiles(const Geometry& g, int4* out_or_null);
 int build_blur_tiles(const Geometry& g, int4* out_or_null);
 constexpr int kIcMaskWords = 4 * 16 * 9;
 void build_ic_masks(const Geometry& g, uint32_t* out);
-void launch_select(const Geometry& g, const BatchView& v, cudaStream_t stream);
+void launch_select(const Geometry& g, const BatchView& v, cudaStream_t stream, int level_lo = 0, int level_hi = -1);   // levels [lo, hi), default all
 void launch_describe(const Geometry& g, const BatchView& v, cudaStream_t stream);
 
 }  // namespace coeb

@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(256, COEB_DESC_MINB) describe_kernel(const __g
         if (status != COEB_OK) cnt = 0;
         else if (total > g.out_cap) { v.status[frame] = COEB_ERR_CAPACITY; }
         v.out_count[frame] = cnt;
+        if (v.mirror_hdr) { v.mirror_hdr[0] = cnt; v.mirror_hdr[1] = status != COEB_OK ? status : (total > g.out_cap ? (int)COEB_ERR_CAPACITY : (int)COEB_OK); }
     }
     if (chunk0 >= n || status != COEB_OK || total > g.out_cap) return;   // uniform; most chunks of the coarse levels are empty
     for (int i = tid; i < 1024; i += 256) s_pat[(i & 31) * 32 + (i >> 5)] = (float)c_pattern[i];   // byte `i>>5` uses ints [32*(i>>5), +32)
@@ -173,6 +174,7 @@ __global__ void __launch_bounds__(256, COEB_DESC_MINB) describe_kernel(const __g
                 val |= (t0 < t1) << bit;
             }
             odesc[(size_t)i * 32 + lane] = (uint8_t)val;
+            if (v.mirror_desc) v.mirror_desc[(size_t)(offset + i) * 32 + lane] = (uint8_t)val;
             if (lane == 0) {
                 coeb_keypoint o;
                 o.x = level != 0 ? __fmul_rn(k.x, L.scale) : k.x;   // keypoint->pt *= scale (:1327-1334)
@@ -183,6 +185,7 @@ __global__ void __launch_bounds__(256, COEB_DESC_MINB) describe_kernel(const __g
                 o.octave = level;
                 o.class_id = -1;
                 okp[i] = o;
+                if (v.mirror_kps) v.mirror_kps[offset + i] = o;
             }
         }
     }
@@ -204,9 +207,12 @@ constexpr int kBlurBoxW = 64, kBlurBoxH = 37, kBlurR = 18;  // 2368 bytes
 constexpr int kBoxSlot = 2432;                              // bytes per buffer slot (128-byte multiple, holds either box)
 static_assert(kDescChunk <= 256, "one thread per keypoint computes cos / sin");
 
+// kMirror: single-frame host calls, results also go to mapped pinned host memory (BatchView::mirror_*)
+template <bool kMirror>
 __global__ void __launch_bounds__(256, COEB_DESC_MINB) describe_tma_kernel(const __grid_constant__ TmaMaps raw_maps, const __grid_constant__ TmaMaps blur_maps,
                                                                           const __grid_constant__ Geometry g, const __grid_constant__ BatchView v,
                                                                           const int chunk /* keypoints per CTA, <= kDescChunk */) {
+    COEB_TRACE(v, 10);
     __shared__ __align__(128) uint8_t s_box[8][2][kBoxSlot];
     __shared__ __align__(8) unsigned long long s_bar[8][2];
     __shared__ float2 s_cs[kDescChunk];
@@ -232,6 +238,7 @@ __global__ void __launch_bounds__(256, COEB_DESC_MINB) describe_tma_kernel(const
         if (status != COEB_OK) cnt = 0;
         else if (total > g.out_cap) { v.status[frame] = COEB_ERR_CAPACITY; }
         v.out_count[frame] = cnt;
+        if (kMirror && v.mirror_hdr) { v.mirror_hdr[0] = cnt; v.mirror_hdr[1] = status != COEB_OK ? status : (total > g.out_cap ? (int)COEB_ERR_CAPACITY : (int)COEB_OK); }
     }
     if (chunk0 >= n || status != COEB_OK || total > g.out_cap) return;   // uniform
     const int lane = tid & 31, wid = tid >> 5;
@@ -361,6 +368,7 @@ __global__ void __launch_bounds__(256, COEB_DESC_MINB) describe_tma_kernel(const
                 val |= (t0 < t1) << bit;
             }
             odesc[(size_t)i * 32 + lane] = (uint8_t)val;
+            if (kMirror && v.mirror_desc) v.mirror_desc[(size_t)(offset + i) * 32 + lane] = (uint8_t)val;
             if (lane == 0) {
                 coeb_keypoint o;
                 o.x = level != 0 ? __fmul_rn(k.x, L.scale) : k.x;
@@ -371,6 +379,7 @@ __global__ void __launch_bounds__(256, COEB_DESC_MINB) describe_tma_kernel(const
                 o.octave = level;
                 o.class_id = -1;
                 okp[i] = o;
+                if (kMirror && v.mirror_kps) v.mirror_kps[offset + i] = o;
             }
             __syncwarp();
         }
@@ -401,7 +410,8 @@ void launch_describe(const Geometry& g, const BatchView& v, cudaStream_t stream)
         // a few frames (the tracking thread's single-frame call): 16 keypoints per CTA, i.e. 2 per warp, so that the level's
         // keypoints spread over four times as many SMs; batches keep 64 per CTA
         const int chunk = v.B <= 4 ? 16 : kDescChunk;
-        describe_tma_kernel<<<dim3((max_keys + chunk - 1) / chunk, g.nlevels, v.B), 256, 0, stream>>>(raw_maps, blur_maps, g, v, chunk);
+        if (v.mirror_hdr) describe_tma_kernel<true><<<dim3((max_keys + chunk - 1) / chunk, g.nlevels, v.B), 256, 0, stream>>>(raw_maps, blur_maps, g, v, chunk);
+        else describe_tma_kernel<false><<<dim3((max_keys + chunk - 1) / chunk, g.nlevels, v.B), 256, 0, stream>>>(raw_maps, blur_maps, g, v, chunk);
     }
     else {
         describe_kernel<<<grid, 256, 0, stream>>>(g, v);

@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(kFtThreads, COEB_FT_MINB) fast_kernel(const __
     const int level = ti.x, tx0 = ti.y, ty0 = ti.z;
     const LevelGeom& L = g.lv[level];
     const int tid = threadIdx.x, lane = tid & 31;
+    COEB_TRACE(v, tiles[0].x == 0 ? 1 : 2);
     const int thIni = v.dyn[frame].area_flag ? 30 : 20;   // threshold override, src/ORBextractor.cc:775-784
 
     // ---- stage the tile: rows ty0-4 .. ty0+kFtH+3, 96 bytes from x = tx0-16 as six 16-byte loads per row. Rows below the
@@ -355,6 +356,7 @@ constexpr int kRoiPitch = kMaxRoi + 4;   // staged with aligned word loads: up t
 
 // Lists the FAST cells that exist (src/ORBextractor.cc:816-826) and produced nothing at iniTh. One thread per cell.
 __global__ void __launch_bounds__(256) fast_empty_cells_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v) {
+    COEB_TRACE(v, 11);
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const int total = v.B * g.cells_per_frame;
     bool empty = false;
@@ -411,9 +413,14 @@ __host__ __device__ inline FbLayout fb_layout(const Geometry& g) {
     return f;
 }
 
+// kDirect (small batches): no list of empty cells; the warps cover every cell of levels [cell_lo, cell_hi) of every frame and each
+// one tests its own cell's counter (and the geometry conditions of fast_empty_cells_kernel), which takes the list kernel and one
+// dependent global load off the latency path.
+template <bool kDirect>
 __global__ void __launch_bounds__(32 * kFbWarps) fast_fallback_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v,
-                                                                      const __grid_constant__ FbLayout F) {
+                                                                      const __grid_constant__ FbLayout F, const int cell_lo, const int cell_hi) {
     extern __shared__ __align__(16) uint8_t fb_smem[];
+    COEB_TRACE(v, kDirect && cell_lo > 0 ? 4 : 3);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t* const region = fb_smem + (size_t)warp * F.bytes;
     uint32_t* const s_img = reinterpret_cast<uint32_t*>(region);
@@ -423,9 +430,16 @@ __global__ void __launch_bounds__(32 * kFbWarps) fast_fallback_kernel(const __gr
     unsigned short* const s_cand = reinterpret_cast<unsigned short*>(s_list + kFbList);
     const int PW = F.pw, AW = F.aw;
     const unsigned lt = (1u << lane) - 1u;
-    const int n_empty = *v.empty_count;
+    const int n_empty = kDirect ? v.B * (cell_hi - cell_lo) : *v.empty_count;
     for (int e = blockIdx.x * kFbWarps + warp; e < n_empty; e += gridDim.x * kFbWarps) {
-        const int c = v.empty_cells[e];
+        int c;
+        if (kDirect) {
+            const int f = e / (cell_hi - cell_lo);
+            c = f * g.cells_per_frame + cell_lo + (e - f * (cell_hi - cell_lo));
+            if (v.cell_count[c] != 0) continue;
+        } else {
+            c = v.empty_cells[e];
+        }
         const int frame = c / g.cells_per_frame, cf = c - frame * g.cells_per_frame;
         int level = 0;
         while (level + 1 < g.nlevels && cf >= g.lv[level + 1].cell_base) level++;
@@ -434,7 +448,9 @@ __global__ void __launch_bounds__(32 * kFbWarps) fast_fallback_kernel(const __gr
         const int ci = cell / L.nCols, cj = cell - ci * L.nCols;
         // cell ROI (src/ORBextractor.cc:813-828), level coordinates
         const int iniX = kMinBorder + cj * L.wCell, iniY = kMinBorder + ci * L.hCell;
+        if (kDirect && (iniY >= L.maxBY - 3 || iniX >= L.maxBX - 6)) continue;   // cells the reference skips (:816-826)
         const int rw = min(iniX + L.wCell + 6, L.maxBX) - iniX, rh = min(iniY + L.hCell + 6, L.maxBY) - iniY;
+        if (kDirect && (rw < 7 || rh < 7)) continue;
         const int dw = rw - 6, dh = rh - 6;          // detection area: ROI rows/cols [3, dim-3)
         const int thMin = v.dyn[frame].area_flag ? 10 : 7;
         const int pitch = level_pitch(g, v, level);
@@ -621,18 +637,13 @@ bool encode_level_maps(const Geometry& g, const BatchView& v, int box_w, int box
 }
 
 // The FAST stage in three pieces, so that a small batch can run the level-0 tiles (which need no resize) beside the pyramid chain:
-//   launch_fast_reset  zeroes the per-level and per-cell counters;
+//   (classify_kernel, which always runs first, zeroes the per-level and per-cell counters)
 //   launch_fast_tiles  runs the main kernel on tiles [first, first + count) of the level-major tile table;
 //   launch_fast_tail   lists the cells that stayed empty and redoes them at minTh.
 int fast_tiles_of_level0(const Geometry& g) {
     const int tiles_x = std::max(1, (g.lv[0].w - kEdge - kMinBorder + kFtW - 1) / kFtW);
     const int tiles_y = std::max(1, (g.lv[0].h - kEdge - kMinBorder + kFtH - 1) / kFtH);
     return tiles_x * tiles_y;
-}
-
-void launch_fast_reset(const Geometry& g, const BatchView& v, cudaStream_t stream) {
-    cudaMemsetAsync(v.lmax_count, 0, sizeof(int) * (size_t)v.B * g.nlevels, stream);
-    cudaMemsetAsync(v.cell_count, 0, sizeof(int) * (size_t)v.B * g.cells_per_frame, stream);
 }
 
 void launch_fast_tiles(const Geometry& g, const BatchView& v, cudaStream_t stream, int first, int count) {
@@ -642,27 +653,39 @@ void launch_fast_tiles(const Geometry& g, const BatchView& v, cudaStream_t strea
     else fast_kernel<false><<<dim3(count, v.B), kFtThreads, 0, stream>>>(g, v, v.fast_tiles + first, maps);
 }
 
+static size_t fallback_smem(const FbLayout& F) {
+    const size_t smem = (size_t)F.bytes * kFbWarps;
+    static size_t configured[64] = {};   // opt-in shared-memory size: a per-device function attribute
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > configured[dev & 63]) {
+        cudaFuncSetAttribute(fast_fallback_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(fast_fallback_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured[dev & 63] = smem;
+    }
+    return smem;
+}
+
 void launch_fast_tail(const Geometry& g, const BatchView& v, cudaStream_t stream) {
     const int cells = v.B * g.cells_per_frame;
     cudaMemsetAsync(v.empty_count, 0, sizeof(int), stream);
     fast_empty_cells_kernel<<<(cells + 255) / 256, 256, 0, stream>>>(g, v);
-    {
-        const FbLayout F = fb_layout(g);
-        const size_t smem = (size_t)F.bytes * kFbWarps;
-        static size_t configured[64] = {};   // opt-in shared-memory size: a per-device function attribute
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (smem > configured[dev & 63]) {
-            cudaFuncSetAttribute(fast_fallback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            configured[dev & 63] = smem;
-        }
-        const int ctas_per_sm = std::max(1, std::min(8, (int)((200u << 10) / smem)));
-        fast_fallback_kernel<<<148 * ctas_per_sm, 32 * kFbWarps, smem, stream>>>(g, v, F);
-    }
+    const FbLayout F = fb_layout(g);
+    const size_t smem = fallback_smem(F);
+    const int ctas_per_sm = std::max(1, std::min(8, (int)((200u << 10) / smem)));
+    fast_fallback_kernel<false><<<148 * ctas_per_sm, 32 * kFbWarps, smem, stream>>>(g, v, F, 0, 0);
+}
+
+void launch_fast_tail_levels(const Geometry& g, const BatchView& v, cudaStream_t stream, int level_lo, int level_hi) {
+    if (level_hi <= level_lo) return;
+    const int cell_lo = g.lv[level_lo].cell_base, cell_hi = level_hi < g.nlevels ? g.lv[level_hi].cell_base : g.cells_per_frame;
+    const FbLayout F = fb_layout(g);
+    const size_t smem = fallback_smem(F);
+    const int warps = v.B * (cell_hi - cell_lo);
+    fast_fallback_kernel<true><<<(warps + kFbWarps - 1) / kFbWarps, 32 * kFbWarps, smem, stream>>>(g, v, F, cell_lo, cell_hi);
 }
 
 void launch_fast(const Geometry& g, const BatchView& v, cudaStream_t stream) {
-    launch_fast_reset(g, v, stream);
     launch_fast_tiles(g, v, stream, 0, g.fast_tiles_per_frame);
     launch_fast_tail(g, v, stream);
 }

@@ -28,6 +28,12 @@ namespace coeb {
 #ifndef COEB_SEL_MINB
 #define COEB_SEL_MINB 3
 #endif
+#ifndef COEB_SEL_GU
+#define COEB_SEL_GU 4   // candidates per thread in flight in the gather phase
+#endif
+#ifndef COEB_SEL_KU
+#define COEB_SEL_KU 2   // keys per thread in flight in the two key passes of a round
+#endif
 constexpr int kSelThreads = COEB_SEL_THREADS;
 constexpr int kKeyCache = 4096;   // candidates per (level, frame) kept in shared memory (4 + 2 bytes each)
 constexpr unsigned long long kOrdMask = 0xFFFFFFFFFFFFull;  // 48-bit candidate-order field
@@ -52,44 +58,32 @@ __device__ __forceinline__ unsigned long long order_key(const LevelGeom& L, int 
     return ord;  // < 2^48
 }
 
-// Two independent exclusive prefix sums sharing their three barriers: a[i] = sum of fa(j), j < i, for i in [0, na), likewise b / fb.
-// The inputs are computed on the fly (fa / fb read data that is stable since the last barrier), so no flag pass and no barrier
-// precede the scan. Returns a's total, b's in *tb.
-template <int T, class FA, class FB>
-__device__ __forceinline__ int block_exclusive_scan2(int* a, int na, FA fa, int* b, int nb, FB fb, int* s_wa, int* s_wb, int* tb) {
+// Exclusive prefix COUNT of a predicate over i in [0, n): one element per thread and trip, ONE barrier per trip and no shuffle chain
+// (the rounds below are chains of barriers and dependent shared-memory round trips, not work): every warp ballots, lane 0 publishes
+// the warp's count, and after the barrier every thread adds up the counts of the warps before its own. emit(i, pos, flag) runs for
+// every i < n. s_cnt is a double buffer ([2][T / 32]) whose parity the caller carries from call to call. Returns the total.
+template <int T, class F, class E>
+__device__ __forceinline__ int block_flag_scan(int n, F flag, E emit, int (*s_cnt)[T / 32], int& par) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int ca = (na + T - 1) / T, cb = (nb + T - 1) / T;
-    const int loa = min(tid * ca, na), hia = min(loa + ca, na), lob = min(tid * cb, nb), hib = min(lob + cb, nb);
-    int sa = 0, sb = 0;
-    for (int i = loa; i < hia; i++) { const int t = fa(i); a[i] = t; sa += t; }
-    for (int i = lob; i < hib; i++) { const int t = fb(i); b[i] = t; sb += t; }
-    int ia = sa, ib = sb;
+    int run = 0;
+    for (int i0 = 0; i0 < n; i0 += T) {
+        const int i = i0 + tid;
+        const bool f = i < n && flag(i);
+        const unsigned b = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) s_cnt[par][wid] = __popc(b);
+        __syncthreads();
+        int pre = 0, tot = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int ta = __shfl_up_sync(0xffffffffu, ia, o), t2 = __shfl_up_sync(0xffffffffu, ib, o);
-        if (lane >= o) { ia += ta; ib += t2; }
-    }
-    if (lane == 31) { s_wa[wid] = ia; s_wb[wid] = ib; }
-    __syncthreads();
-    if (wid == 0) {
-        const int va = lane < (T >> 5) ? s_wa[lane] : 0, vb = lane < (T >> 5) ? s_wb[lane] : 0;
-        int wa = va, wb = vb;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int ta = __shfl_up_sync(0xffffffffu, wa, o), t2 = __shfl_up_sync(0xffffffffu, wb, o);
-            if (lane >= o) { wa += ta; wb += t2; }
+        for (int w = 0; w < T / 32; w++) {
+            const int c = s_cnt[par][w];
+            tot += c;
+            if (w < wid) pre += c;
         }
-        s_wa[lane] = wa - va; s_wb[lane] = wb - vb;
-        if (lane == 31) { s_wa[32] = wa; s_wb[32] = wb; }
+        par ^= 1;
+        if (i < n) emit(i, run + pre + __popc(b & ((1u << lane) - 1u)), f);
+        run += tot;
     }
-    __syncthreads();
-    int ra = s_wa[wid] + ia - sa, rb = s_wb[wid] + ib - sb;
-    for (int i = loa; i < hia; i++) { const int t = a[i]; a[i] = ra; ra += t; }
-    for (int i = lob; i < hib; i++) { const int t = b[i]; b[i] = rb; rb += t; }
-    const int total = s_wa[32];
-    *tb = s_wb[32];
-    __syncthreads();
-    return total;
+    return run;
 }
 
 extern __shared__ __align__(16) unsigned char s_dyn_raw[];
@@ -98,8 +92,9 @@ extern __shared__ __align__(16) unsigned char s_dyn_raw[];
 // one (level 0) sets the latency: 384, 512, 768 and 1024 threads were measured there and make no difference (151.5-152.3 us per
 // call): the passes are chains of barriers and shared-memory round trips, not thread-count bound.
 template <int T, int kMinBlocks>
-__global__ void __launch_bounds__(T, kMinBlocks) select_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v) {
-    const int level = blockIdx.y, frame = blockIdx.x;   // level-major launch order: the long CTAs (level 0) start first, the short ones fill the tail
+__global__ void __launch_bounds__(T, kMinBlocks) select_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v, const int level_lo) {
+    const int level = level_lo + blockIdx.y, frame = blockIdx.x;   // level-major launch order: the long CTAs (level 0) start first, the short ones fill the tail
+    COEB_TRACE(v, level_lo > 0 ? 6 : 5);
     const LevelGeom& L = g.lv[level];
     const DynState& dyn = v.dyn[frame];
     const int tid = threadIdx.x;
@@ -122,7 +117,9 @@ __global__ void __launch_bounds__(T, kMinBlocks) select_kernel(const __grid_cons
     sp = s_dyn_raw + ((sp - s_dyn_raw + 15) & ~(size_t)15);
     uint32_t* s_keys = reinterpret_cast<uint32_t*>(sp); sp += sizeof(uint32_t) * kKeyCache;          // candidate cache
     unsigned short* s_knode = reinterpret_cast<unsigned short*>(sp); sp += sizeof(unsigned short) * kKeyCache;
-    __shared__ int s_warp[33], s_warp2[33];
+    __shared__ int s_warp[33];
+    __shared__ int s_cnt[2][T / 32];   // block_flag_scan's double buffer
+    int par = 0;
     __shared__ int s_misc[8];
 
     int* key_count = v.key_count + frame * g.nlevels + level;
@@ -146,22 +143,37 @@ __global__ void __launch_bounds__(T, kMinBlocks) select_kernel(const __grid_cons
         const int thIni = dyn.area_flag ? 30 : 20, thMin = dyn.area_flag ? 10 : 7;   // :775-784
         if (tid == 0) s_misc[1] = 0;
         __syncthreads();
-        for (int k = tid; k < nl; k += T) {
-            const uint32_t key = lm[k];
-            const int x = key & 0xFFF, y = (key >> 12) & 0xFFF, A = (int)(key >> 24) + 1;
-            // cell of the candidate, as in fast.cu cell_of (exact multiply-shift quotient, checked on the host)
-            const int j = min((int)(((unsigned)(x - 3) * (unsigned)L.rcpW) >> 20), lastJ), i = min((int)(((unsigned)(y - 3) * (unsigned)L.rcpH) >> 20), lastI);
-            const int th = cellcnt[i * L.nCols + j] > 0 ? thIni : thMin;
-            if (A > th && !(dyn.area_flag && is_moving(dyn, (float)x, (float)y, level, L.scale, g.w0, g.h0)))
-            {
-                const int pos = atomicAdd(&s_misc[1], 1);
-                gkeys[pos] = key;
-                if (cached) s_keys[pos] = key;
+        // Two dependent global loads per candidate (the candidate, then its cell's counter): eight candidates per thread are in
+        // flight together, so a level costs a few round trips instead of one per candidate and thread.
+        constexpr int kU = COEB_SEL_GU;
+        for (int k0 = tid; k0 < nl; k0 += kU * T) {
+            uint32_t key[kU];
+            int cnt[kU];
+#pragma unroll
+            for (int u = 0; u < kU; u++) key[u] = k0 + u * T < nl ? __ldg(&lm[k0 + u * T]) : 0u;
+#pragma unroll
+            for (int u = 0; u < kU; u++) {
+                const int x = key[u] & 0xFFF, y = (key[u] >> 12) & 0xFFF;
+                // cell of the candidate, as in fast.cu cell_of (exact multiply-shift quotient, checked on the host)
+                const int j = min((int)(((unsigned)(x - 3) * (unsigned)L.rcpW) >> 20), lastJ), i = min((int)(((unsigned)(y - 3) * (unsigned)L.rcpH) >> 20), lastI);
+                cnt[u] = k0 + u * T < nl ? cellcnt[i * L.nCols + j] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < kU; u++) {
+                if (k0 + u * T >= nl) break;
+                const int x = key[u] & 0xFFF, y = (key[u] >> 12) & 0xFFF, A = (int)(key[u] >> 24) + 1;
+                const int th = cnt[u] > 0 ? thIni : thMin;
+                if (A > th && !(dyn.area_flag && is_moving(dyn, (float)x, (float)y, level, L.scale, g.w0, g.h0))) {
+                    const int pos = atomicAdd(&s_misc[1], 1);
+                    gkeys[pos] = key[u];
+                    if (cached) s_keys[pos] = key[u];
+                }
             }
         }
         __syncthreads();
     }
     const int nkeys = s_misc[1];
+    COEB_TRACE_MARK(v, level == 0 && frame == 0, 0);   // gathered
     if (tid == 0) v.cand_count[frame * g.nlevels + level] = nkeys;
     if (nkeys == 0 || dyn.bad_box) {
         if (tid == 0) *key_count = 0;
@@ -188,12 +200,17 @@ __global__ void __launch_bounds__(T, kMinBlocks) select_kernel(const __grid_cons
         nxt[i] = n;
     }
     __syncthreads();
-    for (int k = tid; k < nkeys; k += T) {
-        const int x = keys[k] & 0xFFF;
-        int r = (int)__fdiv_rn((float)x, hX);
-        r = min(max(r, 0), nIni - 1);
-        knode[k] = (unsigned short)r;
-        atomicAdd(&nxt[r].count, 1);
+    if (nIni == 1) {   // one root (every image that is not wider than 3:2): all keys are its keys, no counting
+        for (int k = tid; k < nkeys; k += T) knode[k] = 0;
+        if (tid == 0) nxt[0].count = nkeys;
+    } else {
+        for (int k = tid; k < nkeys; k += T) {
+            const int x = keys[k] & 0xFFF;
+            int r = (int)__fdiv_rn((float)x, hX);
+            r = min(max(r, 0), nIni - 1);
+            knode[k] = (unsigned short)r;
+            atomicAdd(&nxt[r].count, 1);
+        }
     }
     __syncthreads();
     for (int i = tid; i < nIni; i += T) s_scanA[i] = nxt[i].count > 0;
@@ -207,6 +224,7 @@ __global__ void __launch_bounds__(T, kMinBlocks) select_kernel(const __grid_cons
     }
     __syncthreads();
 
+    COEB_TRACE_MARK(v, level == 0 && frame == 0, 1);   // roots
     // ---- rounds (:601-745) -------------------------------------------------------------------------
     bool careful = false;
     int nE = 0;  // expandable nodes created in the previous round, creation order, in s_E
@@ -215,12 +233,13 @@ __global__ void __launch_bounds__(T, kMinBlocks) select_kernel(const __grid_cons
         int nP;
         if (!careful) {
             // full pass: every multi-key node, in list order (:613-672)
-            int unused;
-            nP = block_exclusive_scan2<T>(s_scanA, nList, [&](int i) { return (int)(cur[i].count > 1); }, s_scanB, 0, [](int) { return 0; }, s_warp, s_warp2, &unused);
-            for (int i = tid; i < nList; i += T) {
-                if (cur[i].count > 1) { s_P[s_scanA[i]] = (unsigned short)i; s_slot[i] = (unsigned short)s_scanA[i]; }
-                else s_slot[i] = 0xFFFF;
-            }
+            nP = block_flag_scan<T>(
+                nList, [&](int i) { return cur[i].count > 1; },
+                [&](int i, int pos, bool f) {
+                    if (f) { s_P[pos] = (unsigned short)i; s_slot[i] = (unsigned short)pos; }
+                    else s_slot[i] = 0xFFFF;
+                },
+                s_cnt, par);
             for (int i = tid; i < 4 * nP; i += T) s_cc[i] = 0;   // tentative child counts, zeroed in the same phase
         } else {
             // careful phase: previous round's multi-key children, largest first, later-created first on ties (:688-692)
@@ -242,18 +261,29 @@ __global__ void __launch_bounds__(T, kMinBlocks) select_kernel(const __grid_cons
         __syncthreads();
         if (nP == 0) break;  // nothing left to split: list size cannot change (:676)
 
-        // tentative children of every node in P
-        for (int k = tid; k < nkeys; k += T) {
-            const int nd = knode[k];
-            const int p = s_slot[nd];
-            if (p != 0xFFFF) {
-                const QNode n = cur[nd];
-                const int xm = n.xm, ym = n.ym;
-                const uint32_t key = keys[k];
-                const int x = key & 0xFFF, y = (key >> 12) & 0xFFF;
-                const int q = (x < xm ? 0 : 1) + (y < ym ? 0 : 2);
-                atomicAdd(&s_cc[4 * p + q], 1);
-                knode[k] = (unsigned short)(nd | (q << 14));   // the quadrant rides in the two top bits until the keys move below
+        // tentative children of every node in P. A key's step is a chain of dependent shared-memory loads (node id -> slot -> split
+        // lines); four keys per thread are in flight together so that the chains overlap.
+        constexpr int kKU = COEB_SEL_KU;
+        for (int k0 = tid; k0 < nkeys; k0 += kKU * T) {
+            int nd[kKU], ps[kKU];
+            uint32_t key[kKU], xy[kKU];
+#pragma unroll
+            for (int u = 0; u < kKU; u++) nd[u] = k0 + u * T < nkeys ? (int)knode[k0 + u * T] : -1;
+#pragma unroll
+            for (int u = 0; u < kKU; u++) {
+                ps[u] = nd[u] >= 0 ? (int)s_slot[nd[u]] : 0xFFFF;
+                key[u] = nd[u] >= 0 ? keys[k0 + u * T] : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < kKU; u++) xy[u] = ps[u] != 0xFFFF ? reinterpret_cast<const uint32_t*>(&cur[nd[u]])[2] : 0u;   // xm | ym << 16
+#pragma unroll
+            for (int u = 0; u < kKU; u++) {
+                if (ps[u] != 0xFFFF) {
+                    const int x = key[u] & 0xFFF, y = (key[u] >> 12) & 0xFFF;
+                    const int q = (x < (int)(xy[u] & 0xFFFFu) ? 0 : 1) + (y < (int)(xy[u] >> 16) ? 0 : 2);
+                    atomicAdd(&s_cc[4 * ps[u] + q], 1);
+                    knode[k0 + u * T] = (unsigned short)(nd[u] | (q << 14));   // the quadrant rides in the two top bits until the keys move below
+                }
             }
         }
         __syncthreads();
@@ -279,65 +309,115 @@ __global__ void __launch_bounds__(T, kMinBlocks) select_kernel(const __grid_cons
             __syncthreads();
         }
 
-        // creation sequence: for p in processing order, children q = 0..3 that hold keys. One packed scan gives both the creation
-        // index of every child (low half) and its rank among the multi-key children (high half): the latter are next round's
-        // expandable list, in creation order.
-        // (second scan) surviving old nodes keep their relative order behind the new ones
-        int nKeep;
-        const int totals = block_exclusive_scan2<T>(
-            s_scanA, 4 * nProc, [&](int i) { const int c = s_cc[i]; return (c > 0) | ((c > 1) << 16); },
-            s_scanB, nList, [&](int i) { const int p = s_slot[i]; return (int)!(p != 0xFFFF && p < nProc); }, s_warp, s_warp2, &nKeep);
-        const int totalNew = totals & 0xFFFF, nE2 = totals >> 16;
+        // Creation sequence: for p in processing order, children q = 0..3 that hold keys; the multi-key ones among them are next
+        // round's expandable list, in creation order; the surviving old nodes keep their relative order behind the new ones. All
+        // three are prefix counts of flags, taken together with ballots (thread t of a trip owns processed node t and list entry t)
+        // and one barrier per trip: child (p, q)'s creation index is the children of the nodes before p plus p's own earlier ones.
+        const int lane = tid & 31, wid = tid >> 5;
+        const unsigned lt = (1u << lane) - 1u;
+        int totalNew = 0, nE2 = 0, nKeep = 0;
+        for (int i0 = 0; i0 < max(nProc, nList); i0 += T) {
+            const int p = i0 + tid;
+            int4 cc = make_int4(0, 0, 0, 0);
+            if (p < nProc) cc = *reinterpret_cast<const int4*>(&s_cc[4 * p]);
+            bool keep = false;
+            if (p < nList) { const int sl = s_slot[p]; keep = !(sl != 0xFFFF && sl < nProc); }
+            const unsigned b0 = __ballot_sync(0xffffffffu, cc.x > 0), b1 = __ballot_sync(0xffffffffu, cc.y > 0);
+            const unsigned b2 = __ballot_sync(0xffffffffu, cc.z > 0), b3 = __ballot_sync(0xffffffffu, cc.w > 0);
+            const unsigned e0 = __ballot_sync(0xffffffffu, cc.x > 1), e1 = __ballot_sync(0xffffffffu, cc.y > 1);
+            const unsigned e2 = __ballot_sync(0xffffffffu, cc.z > 1), e3 = __ballot_sync(0xffffffffu, cc.w > 1);
+            const unsigned bk = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0)   // <= 128 children, <= 128 expandable, <= 32 kept per warp: 10 bits each
+                s_cnt[par][wid] = (__popc(b0) + __popc(b1) + __popc(b2) + __popc(b3)) | ((__popc(e0) + __popc(e1) + __popc(e2) + __popc(e3)) << 10) | (__popc(bk) << 20);
+            __syncthreads();
+            int preC = 0, preE = 0, preK = 0, totC = 0, totE = 0, totK = 0;
+#pragma unroll
+            for (int w = 0; w < T / 32; w++) {
+                const int c = s_cnt[par][w];
+                totC += c & 0x3FF; totE += (c >> 10) & 0x3FF; totK += c >> 20;
+                if (w < wid) { preC += c & 0x3FF; preE += (c >> 10) & 0x3FF; preK += c >> 20; }
+            }
+            par ^= 1;
+            if (p < nProc)
+                s_scanA[p] = (totalNew + preC + __popc(b0 & lt) + __popc(b1 & lt) + __popc(b2 & lt) + __popc(b3 & lt)) |
+                             ((nE2 + preE + __popc(e0 & lt) + __popc(e1 & lt) + __popc(e2 & lt) + __popc(e3 & lt)) << 16);
+            if (p < nList && keep) s_scanB[p] = nKeep + preK + __popc(bk & lt);
+            totalNew += totC; nE2 += totE; nKeep += totK;
+        }
         const int newSize = totalNew + nKeep;
         if (newSize > LC) {  // cannot happen for max_nodes >= max(N + 3, 4 * nIni); fail loudly
             if (tid == 0) { *key_count = 0; atomicMin(&v.status[frame], (int)COEB_ERR_CAPACITY); }
             return;
         }
-        for (int i = tid; i < nList; i += T) {
-            const int p = s_slot[i];
-            if (!(p != 0xFFFF && p < nProc)) {
-                const int pos = totalNew + s_scanB[i];
-                s_oldpos[i] = (unsigned short)pos;
-                nxt[pos] = cur[i];
+        // same thread <-> same p as above: what it reads from s_scanA / s_scanB it wrote itself
+        for (int i0 = 0; i0 < max(nProc, nList); i0 += T) {
+            const int p = i0 + tid;
+            if (p < nList) {
+                const int sl = s_slot[p];
+                if (!(sl != 0xFFFF && sl < nProc)) {
+                    const int pos = totalNew + s_scanB[p];
+                    s_oldpos[p] = (unsigned short)pos;
+                    nxt[pos] = cur[p];
+                }
             }
-        }
-        for (int i = tid; i < 4 * nProc; i += T) {
-            const int cnt = s_cc[i];
-            if (cnt > 0) {
-                const int p = i >> 2, q = i & 3;
+            if (p < nProc) {
+                const int4 cc = *reinterpret_cast<const int4*>(&s_cc[4 * p]);
+                const int cnts[4] = {cc.x, cc.y, cc.z, cc.w};
+                int ci = s_scanA[p] & 0xFFFF, ei = s_scanA[p] >> 16;
                 const QNode n = cur[s_P[p]];
                 const int xm = n.xm, ym = n.ym;
-                QNode c;
-                c.x0 = (q & 1) ? xm : n.x0;
-                c.x1 = (q & 1) ? n.x1 : xm;
-                c.y0 = (q & 2) ? ym : n.y0;
-                c.y1 = (q & 2) ? n.y1 : ym;
-                set_split(c);
-                c.count = cnt;
-                const int pos = totalNew - 1 - (s_scanA[i] & 0xFFFF);  // push_front in creation order
-                nxt[pos] = c;
-                s_childpos[i] = (unsigned short)pos;
-                if (cnt > 1) s_E2[s_scanA[i] >> 16] = (unsigned short)pos;   // next round's expandable list
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int cnt = cnts[q];
+                    if (cnt > 0) {
+                        QNode c;
+                        c.x0 = (q & 1) ? xm : n.x0;
+                        c.x1 = (q & 1) ? n.x1 : xm;
+                        c.y0 = (q & 2) ? ym : n.y0;
+                        c.y1 = (q & 2) ? n.y1 : ym;
+                        set_split(c);
+                        c.count = cnt;
+                        const int pos = totalNew - 1 - ci;  // push_front in creation order
+                        nxt[pos] = c;
+                        s_childpos[4 * p + q] = (unsigned short)pos;
+                        if (cnt > 1) s_E2[ei++] = (unsigned short)pos;   // next round's expandable list
+                        ci++;
+                    }
+                }
             }
         }
         __syncthreads();
 
-        // move the keys
-        for (int k = tid; k < nkeys; k += T) {
-            const int kn = knode[k];
-            const int nd = kn & 0x3FFF, q = kn >> 14;
-            const int p = s_slot[nd];
-            knode[k] = (p != 0xFFFF && p < nProc) ? s_childpos[4 * p + q] : s_oldpos[nd];
+        // move the keys (same batching)
+        for (int k0 = tid; k0 < nkeys; k0 += kKU * T) {
+            int kn[kKU], ps[kKU], to[kKU];
+#pragma unroll
+            for (int u = 0; u < kKU; u++) kn[u] = k0 + u * T < nkeys ? (int)knode[k0 + u * T] : -1;
+#pragma unroll
+            for (int u = 0; u < kKU; u++) ps[u] = kn[u] >= 0 ? (int)s_slot[kn[u] & 0x3FFF] : 0xFFFF;
+#pragma unroll
+            for (int u = 0; u < kKU; u++) {
+                const int nd = kn[u] & 0x3FFF, q = kn[u] >> 14;
+                to[u] = kn[u] < 0 ? 0 : (ps[u] != 0xFFFF && ps[u] < nProc) ? (int)s_childpos[4 * ps[u] + q] : (int)s_oldpos[nd];
+            }
+#pragma unroll
+            for (int u = 0; u < kKU; u++)
+                if (kn[u] >= 0) knode[k0 + u * T] = (unsigned short)to[u];
         }
         __syncthreads();
         { QNode* t = cur; cur = nxt; nxt = t; }
         { unsigned short* t = s_E; s_E = s_E2; s_E2 = t; }
         nE = nE2;
         nList = newSize;
+#ifdef COEB_KERNEL_TRACE
+        if (v.trace && level == 0 && frame == 0 && tid == 0) v.trace[31] = (unsigned long long)(round + 1);   // rounds done
+        if (round < 3) COEB_TRACE_MARK(v, level == 0 && frame == 0, 4 + round);
+#endif
         if (nList >= N || nList == prevSize) break;               // :676, :741
         if (!careful && nList + 3 * nE > N) careful = true;        // :680
     }
 
+    COEB_TRACE_MARK(v, level == 0 && frame == 0, 2);   // rounds
     // ---- best key per node (:748-766) -------------------------------------------------------------
     for (int i = tid; i < nList; i += T) s_best[i] = 0ull;
     __syncthreads();
@@ -352,45 +432,44 @@ __global__ void __launch_bounds__(T, kMinBlocks) select_kernel(const __grid_cons
     }
     __syncthreads();
 
+    COEB_TRACE_MARK(v, level == 0 && frame == 0, 3);   // best key
     // ---- fix-up (:877-890), orientation (:902-903), post cull (:1204-1207), ordered compaction -----
     // s_scanA: keep flag / position; keys are written level-relative + 16.
-    for (int i = tid; i < nList; i += T) {
-        const unsigned long long ord = kOrdMask - (s_best[i] & kOrdMask);
-        const int x = (int)(ord & 0xFFF), y = (int)((ord >> 12) & 0xFFF);
-        const float fx = (float)(x + kMinBorder), fy = (float)(y + kMinBorder);
-        int keep = 1;
-        if (!dyn.area_flag && level < 8 && is_moving(dyn, fx, fy, level, L.scale, g.w0, g.h0)) keep = 0;
-        s_scanA[i] = keep;
-    }
-    __syncthreads();
-    const int nOut = block_exclusive_scan<T>(s_scanA, nList, s_warp);
+    // orientation (:902-903) is computed by describe_kernel, which has the keypoint-parallel shape for it
     LevelKey* out = v.keys + (size_t)frame * g.keys_per_frame + L.key_base;
+    const int nOut = block_flag_scan<T>(
+        nList,
+        [&](int i) {
+            const unsigned long long ord = kOrdMask - (s_best[i] & kOrdMask);
+            const int x = (int)(ord & 0xFFF), y = (int)((ord >> 12) & 0xFFF);
+            return !(!dyn.area_flag && level < 8 && is_moving(dyn, (float)(x + kMinBorder), (float)(y + kMinBorder), level, L.scale, g.w0, g.h0));
+        },
+        [&](int i, int pos, bool keep) {
+            if (!keep || pos >= L.key_cap) return;   // beyond the capacity: reported below, nothing is written out of bounds
+            const unsigned long long best = s_best[i];
+            const unsigned long long ord = kOrdMask - (best & kOrdMask);
+            LevelKey k;
+            k.x = (float)((int)(ord & 0xFFF) + kMinBorder);
+            k.y = (float)((int)((ord >> 12) & 0xFFF) + kMinBorder);
+            k.response = (float)(int)(best >> 48);
+            k.angle = 0.f;
+            out[pos] = k;
+        },
+        s_cnt, par);
     if (nOut > L.key_cap) {
         if (tid == 0) { *key_count = 0; atomicMin(&v.status[frame], (int)COEB_ERR_CAPACITY); }
         return;
     }
     if (tid == 0) *key_count = nOut;
-
-    // orientation (:902-903) is computed by describe_kernel, which has the keypoint-parallel shape for it
-    for (int i = tid; i < nList; i += T) {
-        const bool keep = (i + 1 < nList ? s_scanA[i + 1] : nOut) != s_scanA[i];
-        if (!keep) continue;
-        const unsigned long long best = s_best[i];
-        const unsigned long long ord = kOrdMask - (best & kOrdMask);
-        LevelKey k;
-        k.x = (float)((int)(ord & 0xFFF) + kMinBorder);
-        k.y = (float)((int)((ord >> 12) & 0xFFF) + kMinBorder);
-        k.response = (float)(int)(best >> 48);
-        k.angle = 0.f;
-        out[s_scanA[i]] = k;
-    }
 }
 
 size_t select_smem_bytes(int LC) {
     return (size_t)LC * (sizeof(unsigned long long) + 2 * sizeof(QNode) + 4 * 4 + 4 * 4 + 4 + 4 * 2 + 2 * 5) + 32 + (size_t)kKeyCache * 6;
 }
 
-void launch_select(const Geometry& g, const BatchView& v, cudaStream_t stream) {
+void launch_select(const Geometry& g, const BatchView& v, cudaStream_t stream, int level_lo, int level_hi) {
+    if (level_hi < 0) level_hi = g.nlevels;
+    if (level_hi <= level_lo) return;
     const size_t smem = select_smem_bytes(g.max_nodes);
     // the opt-in shared-memory size is a per-device function attribute: one handle per GPU may live in the same process
     static size_t configured[64] = {};
@@ -401,7 +480,7 @@ void launch_select(const Geometry& g, const BatchView& v, cudaStream_t stream) {
         cudaFuncSetAttribute(select_kernel<kSelThreads, COEB_SEL_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         done = smem;
     }
-    select_kernel<kSelThreads, COEB_SEL_MINB><<<dim3(v.B, g.nlevels), kSelThreads, smem, stream>>>(g, v);
+    select_kernel<kSelThreads, COEB_SEL_MINB><<<dim3(v.B, level_hi - level_lo), kSelThreads, smem, stream>>>(g, v, level_lo);
 }
 
 }  // namespace coeb

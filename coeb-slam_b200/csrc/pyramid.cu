@@ -27,6 +27,7 @@ constexpr int kRzGroups = 16, kRzRowsPerBlock = 16;   // block = 16 four-pixel g
 template <int kResizeRows>
 __global__ void __launch_bounds__(256) resize_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v,
                                                      int level) {
+    COEB_TRACE(v, 8);
     const LevelGeom& D = g.lv[level];
     const LevelGeom& S = g.lv[level - 1];
     const int frame = blockIdx.z;
@@ -127,6 +128,183 @@ void launch_pyramid(const Geometry& g, const BatchView& v, cudaStream_t stream) 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Small batches (the tracking thread's single frame): the chain above is seven dependent launches of ~4 us each, whatever the level
+// size, i.e. latency and not work. Here ONE launch builds the whole pyramid: the image is cut into regions, a CTA owns the same
+// relative rectangle of every level and computes the chain for it in shared memory, level after level, with the same tables and the
+// same arithmetic. A level-l rectangle reads a slightly larger rectangle of level l-1 than the CTA owns there, so the computed
+// rectangles carry a halo that grows towards level 1 (about 15 px) and neighbouring CTAs compute those pixels twice (identical
+// values; only the owner writes them to global memory). The rectangles come from the host (build_pyramid_regions), which walks the
+// very tables the kernel uses, so every source pixel a CTA reads is inside the rectangle it computed one level up.
+// ------------------------------------------------------------------------------------------------
+#ifndef COEB_PR_THREADS
+#define COEB_PR_THREADS 1024
+#endif
+#ifndef COEB_PR_CELL
+#define COEB_PR_CELL 60
+#endif
+constexpr int kPrThreads = COEB_PR_THREADS;
+
+__global__ void __launch_bounds__(kPrThreads) pyramid_regions_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v) {
+    COEB_TRACE(v, 7);
+    extern __shared__ __align__(16) uint8_t pr_smem[];
+    __shared__ PyrRegionLevel R[COEB_MAX_LEVELS];
+    const int frame = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int kWarps = kPrThreads / 32;
+    static_assert(sizeof(PyrRegionLevel) == 24, "copied as six words");
+    // Global round trips are what this kernel's time is made of, so there are two: the region's rectangles, then -- all loads in
+    // flight together -- the table slices of every level it touches and the level-0 rectangle. The level loop below only waits on
+    // shared memory. Slices live behind the image rectangles (int2 units from s_tab): per level the columns [cx0, cx1) clamped to
+    // the last column, then the rows [cy0, cy1).
+    if (threadIdx.x < 6 * g.nlevels) reinterpret_cast<int*>(R)[threadIdx.x] = __ldg(reinterpret_cast<const int*>(v.pyr_regions + (size_t)blockIdx.x * g.nlevels) + threadIdx.x);
+    __syncthreads();
+    int2* const s_tab = reinterpret_cast<int2*>(pr_smem + R[g.nlevels - 1].soff + ((R[g.nlevels - 1].pitch * (R[g.nlevels - 1].cy1 - R[g.nlevels - 1].cy0) + 15) & ~15));
+    {
+        int total = 0;
+        for (int l = 1; l < g.nlevels; l++) total += (R[l].cx1 - R[l].cx0) + (R[l].cy1 - R[l].cy0);
+        for (int i = threadIdx.x; i < total; i += kPrThreads) {
+            int l = 1, j = i;
+            for (; l < g.nlevels - 1; l++) {
+                const int n = (R[l].cx1 - R[l].cx0) + (R[l].cy1 - R[l].cy0);
+                if (j < n) break;
+                j -= n;
+            }
+            const LevelGeom& D = g.lv[l];
+            const int2* __restrict__ xt = v.tabs + D.tab_base;
+            const int cw = R[l].cx1 - R[l].cx0;
+            s_tab[i] = j < cw ? __ldg(&xt[min(R[l].cx0 + j, D.w - 1)]) : __ldg(&xt[D.w + R[l].cy0 + (j - cw)]);   // tail -> row padding, like the chain
+        }
+    }
+    {   // level 0: the rectangle the chain reads, as aligned words (base, pitch and cx0 are multiples of 4)
+        const PyrRegionLevel r = R[0];
+        const int wq = (r.cx1 - r.cx0) >> 2, ch = r.cy1 - r.cy0;
+        const int pitch = level_pitch(g, v, 0);
+        const uint8_t* __restrict__ src = level_ptr(g, v, 0, frame) + r.cx0;
+        const uint32_t rcp = ((1u << 16) + wq - 1) / wq;   // exact for wq * ch < 2^15 (checked on the host)
+#pragma unroll 4
+        for (int i = threadIdx.x; i < wq * ch; i += kPrThreads) {
+            const int y = (int)(((uint32_t)i * rcp) >> 16), q = i - y * wq;
+            reinterpret_cast<uint32_t*>(pr_smem + r.soff + y * r.pitch)[q] = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)(r.cy0 + y) * pitch) + q);
+        }
+    }
+    int toff = 0;
+    for (int l = 1; l < g.nlevels; l++) {
+        __syncthreads();
+        const PyrRegionLevel d = R[l], s = R[l - 1];
+        const LevelGeom& D = g.lv[l];
+        const int cw = d.cx1 - d.cx0, ch = d.cy1 - d.cy0, gq = cw >> 2;
+        const int2* xs = s_tab + toff;
+        const int2* ys = xs + cw;
+        toff += cw + ch;
+        const int sw1 = g.lv[l - 1].w - 1;
+        const uint8_t* S = pr_smem + s.soff - s.cy0 * s.pitch - s.cx0;   // indexed by absolute level coordinates
+        uint8_t* O = pr_smem + d.soff;
+        uint8_t* dst = v.pyr + D.img_base + (unsigned long long)frame * D.img_stride;
+        // (row, 4-pixel group) tasks spread over all threads: a level is a handful of dependent shared-memory round trips
+        const uint32_t rcp = ((1u << 16) + gq - 1) / gq;   // i / gq == (i * rcp) >> 16 for i < 2^16 / gq * ... (checked on the host: gq * ch < 32768)
+        for (int i = threadIdx.x; i < gq * ch; i += kPrThreads) {
+            const int y = (int)(((uint32_t)i * rcp) >> 16), q = i - y * gq;
+            const int dx0 = d.cx0 + 4 * q, dy = d.cy0 + y;
+            const int2 ye = ys[y];
+            const uint8_t* r0 = S + (ye.x & 0xFFFF) * s.pitch;
+            const uint8_t* r1 = S + (int)((uint32_t)ye.x >> 16) * s.pitch;
+            const uint32_t b0 = (uint32_t)ye.y & 0xFFFFu, b1 = (uint32_t)ye.y >> 16;
+            uint32_t packed = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int2 xe = xs[4 * q + k];
+                const int sx = xe.x, sx1 = min(xe.x + 1, sw1);
+                const uint32_t a0 = (uint32_t)xe.y & 0xFFFFu, a1 = (uint32_t)xe.y >> 16;
+                const uint32_t h0 = r0[sx] * a0 + r0[sx1] * a1;
+                const uint32_t h1 = r1[sx] * a0 + r1[sx1] * a1;
+                packed |= ((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2u) >> 2) << (8 * k);
+            }
+            *reinterpret_cast<uint32_t*>(O + y * d.pitch + 4 * q) = packed;
+            if (dx0 >= d.ox0 && dx0 < d.ox1 && dy >= d.oy0 && dy < d.oy1) *reinterpret_cast<uint32_t*>(dst + (size_t)dy * D.pitch + dx0) = packed;
+        }
+    }
+}
+
+// Region table: regions x levels. x bounds of owned and computed rectangles are multiples of 4 (the last one rounded up into the
+// row padding, which the chain's last 4-pixel group writes as well). Returns 0 when the image is too small to cut.
+int build_pyramid_regions(const Geometry& g, const int2* tabs, PyrRegionLevel* out, int* smem_bytes) {
+    const int nl = g.nlevels;
+    *smem_bytes = 0;
+    if (nl < 2) return 0;
+    const LevelGeom& T = g.lv[nl - 1];
+    const int RX = std::max(1, std::min(std::min(16, (g.w0 + COEB_PR_CELL / 2) / COEB_PR_CELL), T.w / 8));
+    const int RY = std::max(1, std::min(std::min(16, (g.h0 + COEB_PR_CELL / 2) / COEB_PR_CELL), T.h / 4));
+    auto up4 = [](int x) { return (x + 3) & ~3; };
+    int worst = 0;
+    for (int j = 0; j < RY; j++)
+        for (int i = 0; i < RX; i++) {
+            PyrRegionLevel r[COEB_MAX_LEVELS];
+            for (int l = 0; l < nl; l++) {
+                const LevelGeom& L = g.lv[l];
+                r[l].ox0 = (short)(((long long)i * L.w / RX) & ~3LL);
+                r[l].ox1 = (short)(i + 1 == RX ? up4(L.w) : (((long long)(i + 1) * L.w / RX) & ~3LL));
+                r[l].oy0 = (short)((long long)j * L.h / RY);
+                r[l].oy1 = (short)((long long)(j + 1) * L.h / RY);
+                if (r[l].ox1 <= r[l].ox0 || r[l].oy1 <= r[l].oy0) return 0;
+            }
+            r[nl - 1].cx0 = r[nl - 1].ox0; r[nl - 1].cx1 = r[nl - 1].ox1; r[nl - 1].cy0 = r[nl - 1].oy0; r[nl - 1].cy1 = r[nl - 1].oy1;
+            for (int l = nl - 1; l >= 1; l--) {
+                const LevelGeom& D = g.lv[l];
+                const LevelGeom& S = g.lv[l - 1];
+                const int2* xt = tabs + D.tab_base;
+                const int2* yt = xt + D.w;
+                const int xa = r[l].cx0, xb = std::min((int)r[l].cx1, D.w) - 1;   // columns whose table entries are read
+                int nx0 = xt[xa].x, nx1 = std::min(xt[xb].x + 1, S.w - 1);
+                for (int x = xa; x <= xb; x++) { nx0 = std::min(nx0, xt[x].x); nx1 = std::max(nx1, std::min(xt[x].x + 1, S.w - 1)); }
+                int ny0 = S.h, ny1 = 0;
+                for (int y = r[l].cy0; y < r[l].cy1; y++) {
+                    const int s0 = yt[y].x & 0xFFFF, s1 = (int)((unsigned)yt[y].x >> 16);
+                    ny0 = std::min(ny0, std::min(s0, s1));
+                    ny1 = std::max(ny1, std::max(s0, s1));
+                }
+                r[l - 1].cx0 = (short)(std::min((int)r[l - 1].ox0, nx0) & ~3);
+                r[l - 1].cx1 = (short)up4(std::max((int)r[l - 1].ox1, nx1 + 1));
+                r[l - 1].cy0 = (short)std::min((int)r[l - 1].oy0, ny0);
+                r[l - 1].cy1 = (short)std::max((int)r[l - 1].oy1, ny1 + 1);
+            }
+            int off = 0, tab = 0;
+            for (int l = 0; l < nl; l++) {
+                r[l].pitch = r[l].cx1 - r[l].cx0;
+                r[l].soff = off;
+                off += (r[l].pitch * (r[l].cy1 - r[l].cy0) + 15) & ~15;
+                if (l > 0) tab += r[l].pitch + (r[l].cy1 - r[l].cy0);   // the table slices follow the rectangles
+                // the kernel turns a task index into (row, group) with a 16-bit reciprocal: exact while rows * groups < 2^15
+                const int gq = r[l].pitch >> 2, ch = r[l].cy1 - r[l].cy0;
+                {
+                    if ((long long)gq * ch >= 32768) return 0;
+                    const unsigned rcp = ((1u << 16) + gq - 1) / gq;
+                    for (int t = 0; t < gq * ch; t++)
+                        if ((int)(((unsigned)t * rcp) >> 16) != t / gq) return 0;
+                }
+            }
+            off += tab * (int)sizeof(int2);
+            worst = std::max(worst, off);
+            if (out) std::copy(r, r + nl, out + (size_t)(j * RX + i) * nl);
+        }
+    if (worst > 200 * 1024) return 0;
+    *smem_bytes = worst;
+    return RX * RY;
+}
+
+bool launch_pyramid_regions(const Geometry& g, const BatchView& v, cudaStream_t stream) {
+    if (!v.pyr_regions || v.n_pyr_regions <= 0 || (((uintptr_t)level_ptr(g, v, 0, 0) | (uintptr_t)level_pitch(g, v, 0) | (uintptr_t)v.l0_stride) & 3)) return false;
+    static int configured[64] = {};   // opt-in shared-memory size: a per-device function attribute
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (v.pyr_regions_smem > configured[dev & 63]) {
+        cudaFuncSetAttribute(pyramid_regions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v.pyr_regions_smem);
+        configured[dev & 63] = v.pyr_regions_smem;
+    }
+    pyramid_regions_kernel<<<dim3(v.n_pyr_regions, v.B), kPrThreads, v.pyr_regions_smem, stream>>>(g, v);
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Gaussian 7x7 sigma=2, OpenCV bit-exact fixed point: Q8 kernel {18,34,48,56,48,34,18};
 // horizontal pass -> Q8.8 (uint16), vertical pass -> Q16.16, (v + 32768) >> 16. BORDER_REFLECT_101
 // on the level itself (the reference blurs a clone of the ROI, so the pyramid border is not seen).
@@ -184,6 +362,7 @@ __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const __grid_constan
     const LevelGeom& L = g.lv[level];
     const int tid = threadIdx.x;
 
+    COEB_TRACE(v, 9);
     // stage rows ty0-3 .. ty0+34, 96 bytes from x = tx0-16
     if (kTma) {
         // one TMA box (out-of-image bytes read as 0); the rows above / below the image are then filled by reflection from the
@@ -323,9 +502,13 @@ void launch_blur(const Geometry& g, const BatchView& v, cudaStream_t stream) {
 // reference zero-fills in its 480x640 mask; area accumulates in box order (fp32).
 // ------------------------------------------------------------------------------------------------
 __global__ void classify_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v) {
+    COEB_TRACE(v, 0);
     const int frame = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
     const int lane = threadIdx.x & 31;
     if (frame >= v.B) return;
+    // the FAST stage's counters of this frame start at zero (a memset node costs a small batch 3-4 us of its latency chain)
+    for (int i = lane; i < g.nlevels; i += 32) v.lmax_count[frame * g.nlevels + i] = 0;
+    for (int i = lane; i < g.cells_per_frame; i += 32) v.cell_count[(size_t)frame * g.cells_per_frame + i] = 0;
     DynState* out = &v.dyn[frame];
     const int nbox = v.nbox ? v.nbox[frame] : 0;
     const int ntm = v.ntm ? v.ntm[frame] : 0;
