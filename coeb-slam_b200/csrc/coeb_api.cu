@@ -100,6 +100,7 @@ struct coeb_extractor {
     std::vector<GraphEntry> graphs;
     int graph_warm = 0;
     int last_passes = 1;   // sub-batches the last batch call was split into (launch accounting)
+    int last_pass_launches = 0;   // kernels one pass launched (set by enqueue)
     unsigned long long* d_trace = nullptr;   // COEB_KERNEL_TRACE=1 with a -DCOEB_KERNEL_TRACE build: per-kernel start / end stamps
     // optional per-stage CUDA events (benchmark accounting)
     bool profiling = false;
@@ -376,7 +377,8 @@ int enqueue(coeb_extractor* ex, const BatchView& v, cudaStream_t s, bool prof) {
         launch_fast_tail_levels(g, v, lane->aux, 0, 1);
         launch_select(g, v, lane->aux, 0, 1);
         CUDA_TRY(cudaEventRecord(lane->sel0, lane->aux));
-        if (no_regions || !launch_pyramid_regions(g, v, s)) launch_pyramid(g, v, s);
+        ex->last_pass_launches = 1 + 1 + 1 + 2 + 2 + 2 + 1;
+        if (no_regions || !launch_pyramid_regions(g, v, s)) { launch_pyramid(g, v, s); ex->last_pass_launches += g.nlevels - 2; }
         CUDA_TRY(cudaStreamWaitEvent(s, lane->cls, 0));
         launch_fast_tiles(g, v, s, n0, g.fast_tiles_per_frame - n0);
         CUDA_TRY(cudaEventRecord(lane->fork, s));
@@ -391,6 +393,7 @@ int enqueue(coeb_extractor* ex, const BatchView& v, cudaStream_t s, bool prof) {
         CUDA_TRY(cudaGetLastError());
         return COEB_OK;
     }
+    ex->last_pass_launches = 1 + (g.nlevels - 1) + 1 + 3 + 1 + 1;
     if (lane) {
         // side stream: classify beside the pyramid, then blur beside FAST + octree | main: pyramid, FAST, octree | join | describe
         CUDA_TRY(cudaEventRecord(lane->fork0, s));
@@ -621,8 +624,10 @@ int coeb_extractor_device_outputs(coeb_extractor* ex, int frame, const coeb_keyp
 
 int coeb_extractor_launches_per_call(const coeb_extractor* ex) {
     if (!ex) return 0;
-    // classify + (nlevels-1) resizes + blur + FAST + empty-cell list + FAST fallback + select + describe (the two counter memsets are not kernels of ours)
-    return (1 + (ex->params.nlevels - 1) + 1 + 3 + 1 + 1) * ex->last_passes;
+    // batches: classify + (nlevels-1) resizes + blur + FAST + empty-cell list + FAST fallback + select + describe;
+    // small batches: classify + pyramid (1 launch, or the chain) + blur + 2 FAST + 2 fallback + 2 select + describe
+    const int per_pass = ex->last_pass_launches ? ex->last_pass_launches : 1 + (ex->params.nlevels - 1) + 1 + 3 + 1 + 1;
+    return per_pass * ex->last_passes;
 }
 
 int coeb_extractor_set_profiling(coeb_extractor* ex, int on) {

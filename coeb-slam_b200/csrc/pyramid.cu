@@ -180,10 +180,10 @@ __global__ void __launch_bounds__(kPrThreads) pyramid_regions_kernel(const __gri
         const int wq = (r.cx1 - r.cx0) >> 2, ch = r.cy1 - r.cy0;
         const int pitch = level_pitch(g, v, 0);
         const uint8_t* __restrict__ src = level_ptr(g, v, 0, frame) + r.cx0;
-        const uint32_t rcp = ((1u << 16) + wq - 1) / wq;   // exact for wq * ch < 2^15 (checked on the host)
+        const uint32_t rcp = 0xFFFFFFFFu / (uint32_t)wq + 1u;   // i / wq == umulhi(i, rcp) for wq >= 2 and every i here (checked on the host)
 #pragma unroll 4
         for (int i = threadIdx.x; i < wq * ch; i += kPrThreads) {
-            const int y = (int)(((uint32_t)i * rcp) >> 16), q = i - y * wq;
+            const int y = wq > 1 ? (int)__umulhi((uint32_t)i, rcp) : i, q = i - y * wq;
             reinterpret_cast<uint32_t*>(pr_smem + r.soff + y * r.pitch)[q] = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)(r.cy0 + y) * pitch) + q);
         }
     }
@@ -201,9 +201,9 @@ __global__ void __launch_bounds__(kPrThreads) pyramid_regions_kernel(const __gri
         uint8_t* O = pr_smem + d.soff;
         uint8_t* dst = v.pyr + D.img_base + (unsigned long long)frame * D.img_stride;
         // (row, 4-pixel group) tasks spread over all threads: a level is a handful of dependent shared-memory round trips
-        const uint32_t rcp = ((1u << 16) + gq - 1) / gq;   // i / gq == (i * rcp) >> 16 for i < 2^16 / gq * ... (checked on the host: gq * ch < 32768)
+        const uint32_t rcp = 0xFFFFFFFFu / (uint32_t)gq + 1u;   // i / gq == umulhi(i, rcp), as above
         for (int i = threadIdx.x; i < gq * ch; i += kPrThreads) {
-            const int y = (int)(((uint32_t)i * rcp) >> 16), q = i - y * gq;
+            const int y = gq > 1 ? (int)__umulhi((uint32_t)i, rcp) : i, q = i - y * gq;
             const int dx0 = d.cx0 + 4 * q, dy = d.cy0 + y;
             const int2 ye = ys[y];
             const uint8_t* r0 = S + (ye.x & 0xFFFF) * s.pitch;
@@ -273,13 +273,12 @@ int build_pyramid_regions(const Geometry& g, const int2* tabs, PyrRegionLevel* o
                 r[l].soff = off;
                 off += (r[l].pitch * (r[l].cy1 - r[l].cy0) + 15) & ~15;
                 if (l > 0) tab += r[l].pitch + (r[l].cy1 - r[l].cy0);   // the table slices follow the rectangles
-                // the kernel turns a task index into (row, group) with a 16-bit reciprocal: exact while rows * groups < 2^15
+                // the kernel turns a task index into (row, group) with a 32-bit reciprocal and a multiply-high
                 const int gq = r[l].pitch >> 2, ch = r[l].cy1 - r[l].cy0;
-                {
-                    if ((long long)gq * ch >= 32768) return 0;
-                    const unsigned rcp = ((1u << 16) + gq - 1) / gq;
+                if (gq > 1) {
+                    const unsigned rcp = 0xFFFFFFFFu / (unsigned)gq + 1u;
                     for (int t = 0; t < gq * ch; t++)
-                        if ((int)(((unsigned)t * rcp) >> 16) != t / gq) return 0;
+                        if ((int)(((unsigned long long)t * rcp) >> 32) != t / gq) return 0;
                 }
             }
             off += tab * (int)sizeof(int2);

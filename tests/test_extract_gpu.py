@@ -286,3 +286,26 @@ def test_create_destroy_cycles_do_not_leak_device_memory(gpu):
     torch.cuda.synchronize()
     free1 = torch.cuda.mem_get_info()[0]
     assert free0 - free1 < 8 << 20, "device memory shrank by %.1f MB over 40 create/destroy cycles" % ((free0 - free1) / 2 ** 20)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h", [(640, 480), (1241, 376), (333, 257), (1920, 1080)])
+def test_small_batch_path_equals_the_batch_path(gpu, w, h):
+    """Up to four frames take the latency path (level 0 end to end on a side stream, the whole pyramid in ONE launch whose CTAs
+    compute a region of every level in shared memory, per-cell fallback, results mirrored into mapped pinned memory); larger
+    batches take the resize chain. Both must produce the same pyramid, bit for bit, and the same keypoints and descriptors."""
+    ex = gpu.Extractor(1000, 1.2, 8, 20, 7)
+    frames = np.stack([synth.make_frame(40 + i, w, h) for i in range(6)])
+    one_k, one_d = ex.extract(frames[0])
+    small = ex.launches_per_call()
+    one_levels = [ex.level_image(l) for l in range(8)]
+    one_blur = [ex.level_image(l, blurred=True) for l in range(8)]
+    kps, desc, counts, status = ex.extract_batch_host(frames)
+    assert ex.launches_per_call() == 1 + 7 + 1 + 3 + 1 + 1
+    assert small == 10, "the single-frame call did not take the one-launch pyramid"
+    assert (status == 0).all() and counts[0] == len(one_k)
+    for l in range(8):
+        assert np.array_equal(one_levels[l], ex.level_image(l, frame=0)), "pyramid level %d" % l
+        assert np.array_equal(one_blur[l], ex.level_image(l, frame=0, blurred=True)), "blurred level %d" % l
+    assert kps[0, :counts[0]].tobytes() == one_k.tobytes() and np.array_equal(desc[0, :counts[0]], one_d)
+    ex.close()
