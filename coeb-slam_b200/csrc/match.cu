@@ -237,7 +237,8 @@ struct CandLists {
     int* count;    // [n] candidates found (may exceed cap: overflow)
     int cap;
     int* active;   // [n] queries with at least one candidate, in no particular order
-    int* meta;     // [0] number of active queries, [1] some list overflowed its capacity (both zeroed before the collect kernel)
+    int* meta;     // [0] number of active queries, [1] some list overflowed its capacity. Zero before the collect kernel: a fixed
+                   // per-matcher word pair that the (single-CTA) resolve kernel clears again once it has read it -- no memset node per call
     int* top;      // [n] list positions of the two smallest (distance, position) entries: best | second << 16 (0xFFFF = none); M2 only
 };
 
@@ -364,13 +365,18 @@ __global__ void __launch_bounds__(1024, 1) m2_resolve_kernel(FrameDev F, MapDev 
     __shared__ int s_slow[kSlowCap];
     const int tid = threadIdx.x, T = blockDim.x;
     int* const claim_min = claim_in_smem ? s_claim_dyn : claim_glob;
-    if (kLists && C.meta[1]) {   // a list overflowed: report and let the host rerun the window-walking variant
+    const int na = kLists ? C.meta[0] : M.n;
+    const bool overflow = kLists && C.meta[1];
+    if (kLists) {   // every thread has read the two words: cleared for the next call's collect kernel
+        __syncthreads();
+        if (tid == 0) { C.meta[0] = 0; C.meta[1] = 0; }
+    }
+    if (overflow) {   // a list overflowed: report and let the host rerun the window-walking variant
         if (tid == 0) { out_info[0] = 0; out_info[1] = 0; out_info[2] = 1; }
         return;
     }
     // Only queries with candidates can match; with lists they were compacted by the collect kernel (in no particular
     // order: the evaluation of a query depends on the others through claim_min only).
-    const int na = kLists ? C.meta[0] : M.n;
     auto query = [&](int a) { return kLists ? C.active[a] : a; };
     if (kLists && na <= cache_cap) {
         // Cached path: the active queries and, for each, the two list entries that decide the outcome when no claim touches them
@@ -682,11 +688,16 @@ __global__ void __launch_bounds__(512, 1) m3_resolve_kernel(FrameDev C, LastDev 
     __shared__ int s_ind[3];
     const int tid = threadIdx.x, T = blockDim.x;
     int* const claim_min = claim_in_smem ? s_claim_dyn : claim_glob;
-    if (kLists && Cl.meta[1]) {
+    const int na = kLists ? Cl.meta[0] : L.n;   // queries with candidates (compacted by the collect kernel, any order)
+    const bool overflow = kLists && Cl.meta[1];
+    if (kLists) {   // cleared for the next call's collect kernel (see CandLists::meta)
+        __syncthreads();
+        if (tid == 0) { Cl.meta[0] = 0; Cl.meta[1] = 0; }
+    }
+    if (overflow) {
         if (tid == 0) { out_info[0] = 0; out_info[1] = 0; out_info[2] = 1; }
         return;
     }
-    const int na = kLists ? Cl.meta[0] : L.n;   // queries with candidates (compacted by the collect kernel, any order)
     auto query = [&](int a) { return kLists ? Cl.active[a] : a; };
     constexpr int Q = 10;
     if (kLists && na <= Q * T) {
@@ -877,7 +888,12 @@ __global__ void __launch_bounds__(1024) m4_resolve_kernel(FrameDev F1, FrameDev 
     __shared__ int s_ind[3];
     __shared__ int s_warp[33];
     const int tid = threadIdx.x, T = blockDim.x;
-    if (kLists && C.meta[1]) {
+    const bool overflow = kLists && C.meta[1];
+    if (kLists) {   // cleared for the next call's collect kernel (see CandLists::meta)
+        __syncthreads();
+        if (tid == 0) { C.meta[0] = 0; C.meta[1] = 0; }
+    }
+    if (overflow) {
         if (tid == 0) { out_info[0] = 0; out_info[1] = 0; out_info[2] = 1; }
         return;
     }
@@ -1291,6 +1307,7 @@ struct LocalMapDev {
 struct PoseArgs { float T[12]; float Ow[3]; float cos_limit; int nlevels; };
 struct MapFields {   // the MapPoint members isInFrustum writes, as device arrays (they are MapDev's inputs)
     uint8_t* track_in_view; float *proj_x, *proj_y, *proj_xr, *view_cos; int* level;
+    uint8_t* track_in_view_host;   // second copy of the visibility flags in mapped host memory (the caller's mbTrackInView), may be null
 };
 
 // Frame::isInFrustum (src/Frame.cc:445-501) + the candidate collection of SearchByProjection for the same map point.
@@ -1339,6 +1356,7 @@ __global__ void __launch_bounds__(256) frustum_collect_kernel(FrameDev F, LocalM
     if (!in) { u = v = ur = viewCos = 0.f; lvl = 0; }
     if (writer) {
         out.track_in_view[i] = in ? 1 : 0;
+        if (out.track_in_view_host) out.track_in_view_host[i] = in ? 1 : 0;
         out.proj_x[i] = u; out.proj_y[i] = v; out.proj_xr[i] = ur; out.view_cos[i] = viewCos; out.level[i] = lvl;
         if (proj_out) { float* q = proj_out + 5 * (size_t)i; q[0] = u; q[1] = v; q[2] = ur; q[3] = viewCos; q[4] = (float)lvl; }
     }
@@ -1589,9 +1607,22 @@ struct Stage {
         cap = want;
         return COEB_OK;
     }
+    // Results the kernels write exactly once (match tables, counts) go straight into mapped pinned host memory (d == h): the
+    // posted writes cost the call nothing, a device-to-host copy behind the last kernel costs it 8-10 us.
+    int reserve_mapped(size_t bytes) {
+        if (bytes <= cap) return COEB_OK;
+        size_t want = std::max<size_t>(bytes + bytes / 2, 1 << 16);
+        if (h) cudaFreeHost(h);
+        h = d = nullptr;
+        cap = 0;
+        CUDA_TRY(cudaHostAlloc((void**)&h, want, cudaHostAllocMapped));
+        d = h;
+        cap = want;
+        return COEB_OK;
+    }
     void release() {
         if (h) cudaFreeHost(h);
-        if (d) cudaFree(d);
+        if (d && d != h) cudaFree(d);
         h = d = nullptr;
         cap = 0;
     }
@@ -1624,6 +1655,9 @@ struct coeb_matcher {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     Stage in, out;                                   // inputs (H2D) and results (D2H)
+    Stage outm;                                      // results written once by the last kernel: mapped pinned memory, no copy
+    int* d_meta = nullptr;                           // CandLists::meta: zero between calls (the resolve kernels clear it again)
+    uint8_t* d_zero = nullptr; size_t zero_bytes = 0;   // all-zero flags (isBad() of a resident local map)
     void* d_scratch = nullptr; size_t scratch_bytes = 0;
     void* d_in = nullptr; size_t in_bytes = 0;        // kNN partials
     void* d_depth = nullptr; size_t depth_bytes = 0;  // uploaded depth map of coeb_frame_from_extractor
@@ -1738,15 +1772,20 @@ int push_inputs(coeb_matcher* m, const Packer& p) {
 }
 // Candidate lists of n queries inside a scratch block: counts | active | meta | items. Returns the bytes used.
 size_t lists_bytes(size_t n, int cap) { return 3 * al(n * 4) + al(8) + al(n * cap * 8); }
-CandLists carve_lists(char* sc, size_t n, int cap) {
+CandLists carve_lists(char* sc, size_t n, int cap, int* meta) {
     CandLists C{};
     C.count = (int*)sc; sc += al(n * 4);
     C.active = (int*)sc; sc += al(n * 4);
-    C.meta = (int*)sc; sc += al(8);
+    C.meta = meta; sc += al(8);
     C.top = (int*)sc; sc += al(n * 4);
     C.items = (int2*)sc;
     C.cap = cap;
     return C;
+}
+
+int sync_outputs(coeb_matcher* m) {   // results in m->outm: the kernels wrote them into host memory themselves
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    return COEB_OK;
 }
 
 int pull_outputs(coeb_matcher* m, size_t bytes) {
@@ -1768,6 +1807,11 @@ int coeb_matcher_create(int device, coeb_matcher** out) {
     m->device = device;
     if (cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete m; return fail(COEB_ERR_CUDA, "cudaStreamCreate failed"); }
     m->stream = m->own_stream;
+    if (cudaMalloc((void**)&m->d_meta, 256) != cudaSuccess || cudaMemset(m->d_meta, 0, 256) != cudaSuccess) {
+        cudaStreamDestroy(m->own_stream);
+        delete m;
+        return fail(COEB_ERR_CUDA, "matcher scratch allocation failed");
+    }
     g_frames.matcher_created(m, device);
     *out = m;
     return COEB_OK;
@@ -1779,6 +1823,9 @@ void coeb_matcher_destroy(coeb_matcher* m) {
     cudaStreamSynchronize(m->stream);
     m->in.release();
     m->out.release();
+    m->outm.release();
+    cudaFree(m->d_meta);
+    cudaFree(m->d_zero);
     cudaFree(m->d_scratch);
     cudaFree(m->d_in);
     cudaFree(m->d_depth);
@@ -1916,7 +1963,7 @@ int coeb_match_projection(coeb_matcher* m, coeb_frame* F, int n, const uint8_t* 
     const size_t N = n, K = F->n;
     int st;
     if ((st = m->in.reserve(3 * al(N) + 5 * al(N * 4) + al(N * 32) + al(K * 4))) != COEB_OK) return st;
-    if ((st = m->out.reserve(al(K * 4) + 256)) != COEB_OK) return st;
+    if ((st = m->outm.reserve_mapped(al(K * 4) + 256)) != COEB_OK) return st;
     const int cap = 32;   // candidates kept per map point; a fuller window falls back to the window-walking kernel
     const size_t claim_smem = (size_t)F->n * 4 <= 32 * 1024 ? (size_t)F->n * 4 : 0;   // claim table in shared memory when it fits
     if ((st = grow(&m->d_scratch, &m->scratch_bytes, al(N * 4) + al(K * 4) + lists_bytes(N, cap))) != COEB_OK) return st;
@@ -1930,32 +1977,31 @@ int coeb_match_projection(coeb_matcher* m, coeb_frame* F, int n, const uint8_t* 
     const int* d_state = p.place(kp_match, K);
     const auto t_packed = std::chrono::steady_clock::now();
     if ((st = push_inputs(m, p)) != COEB_OK) return st;
-    int* d_kpm = (int*)m->out.d;                       // [K] then info[2]
-    int* d_info = (int*)(m->out.d + al(K * 4));
+    int* d_kpm = (int*)m->outm.d;                       // [K] then info[2]
+    int* d_info = (int*)(m->outm.d + al(K * 4));
     int* d_res = (int*)m->d_scratch;
     int* d_claim = (int*)((char*)m->d_scratch + al(N * 4));
-    const CandLists C = carve_lists((char*)m->d_scratch + al(N * 4) + al(K * 4), N, cap);
-    CUDA_TRY(cudaMemsetAsync(C.meta, 0, 8, m->stream));
+    const CandLists C = carve_lists((char*)m->d_scratch + al(N * 4) + al(K * 4), N, cap, m->d_meta);
     m2_collect_kernel<<<(n + 7) / 8, 256, 0, m->stream>>>(F->dev, M, th, d_state, C);
     { int cc = 0; const size_t sm = resolve_smem(claim_smem, M.n + 1, 25, &cc); allow_smem(m2_resolve_kernel<true>, sm);
       m2_resolve_kernel<true><<<1, 1024, sm, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0, cc); }
     CUDA_TRY(cudaGetLastError());
     const auto t_queued = std::chrono::steady_clock::now();
-    if ((st = pull_outputs(m, al(K * 4) + 12)) != COEB_OK) return st;
+    if ((st = sync_outputs(m)) != COEB_OK) return st;
     if (trace) {
         const auto t_done = std::chrono::steady_clock::now();
         auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
         fprintf(stderr, "[coeb match] SearchByProjection(map) host timeline: validate + pack %.1f us, enqueue %.1f us, wait %.1f us\n", us(t_begin, t_packed), us(t_packed, t_queued), us(t_queued, t_done));
     }
-    if (((const int*)(m->out.h + al(K * 4)))[2]) {   // a candidate list overflowed: exact window-walking variant
+    if (((const int*)(m->outm.h + al(K * 4)))[2]) {   // a candidate list overflowed: exact window-walking variant
         { int cc = 0; const size_t sm = resolve_smem(claim_smem, M.n + 1, 25, &cc); allow_smem(m2_resolve_kernel<false>, sm);
       m2_resolve_kernel<false><<<1, 1024, sm, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0, cc); }
         CUDA_TRY(cudaGetLastError());
-        if ((st = pull_outputs(m, al(K * 4) + 12)) != COEB_OK) return st;
+        if ((st = sync_outputs(m)) != COEB_OK) return st;
     }
-    std::memcpy(kp_match, m->out.h, K * 4);
-    if (nmatches_out) *nmatches_out = ((const int*)(m->out.h + al(K * 4)))[0];
-    if (getenv("COEB_MATCH_TRACE")) fprintf(stderr, "[coeb match] SearchByProjection(map): %d map points, %d keypoints, %d fixed-point rounds\n", n, F->n, ((const int*)(m->out.h + al(K * 4)))[1]);
+    std::memcpy(kp_match, m->outm.h, K * 4);
+    if (nmatches_out) *nmatches_out = ((const int*)(m->outm.h + al(K * 4)))[0];
+    if (getenv("COEB_MATCH_TRACE")) fprintf(stderr, "[coeb match] SearchByProjection(map): %d map points, %d keypoints, %d fixed-point rounds\n", n, F->n, ((const int*)(m->outm.h + al(K * 4)))[1]);
     return COEB_OK;
 }
 
@@ -1973,7 +2019,7 @@ int coeb_match_lastframe(coeb_matcher* m, coeb_frame* cur, int n, const uint8_t*
     const size_t N = n, K = cur->n;
     int st;
     if ((st = m->in.reserve(2 * al(N) + al(N * 12) + 2 * al(N * 4) + al(N * 32) + al(K * 4))) != COEB_OK) return st;
-    if ((st = m->out.reserve(al(K * 4) + 256)) != COEB_OK) return st;
+    if ((st = m->outm.reserve_mapped(al(K * 4) + 256)) != COEB_OK) return st;
     const int cap = 64;
     const size_t claim_smem = K * 4 <= 32 * 1024 ? K * 4 : 0;   // claim table in shared memory when it fits
     if ((st = grow(&m->d_scratch, &m->scratch_bytes, al(N * 4) + al(K * 4) + lists_bytes(N, cap))) != COEB_OK) return st;
@@ -1992,23 +2038,22 @@ int coeb_match_lastframe(coeb_matcher* m, coeb_frame* cur, int n, const uint8_t*
     L.forward = (tz > cur->dev.b && !mono) ? 1 : 0;
     L.backward = (-tz > cur->dev.b && !mono) ? 1 : 0;
     L.max_accept = COEB_TH_HIGH;   // :1425
-    int* d_kpm = (int*)m->out.d;
-    int* d_info = (int*)(m->out.d + al(K * 4));
+    int* d_kpm = (int*)m->outm.d;
+    int* d_info = (int*)(m->outm.d + al(K * 4));
     int* d_res = (int*)m->d_scratch;
     int* d_claim = (int*)((char*)m->d_scratch + al(N * 4));
-    const CandLists C = carve_lists((char*)m->d_scratch + al(N * 4) + al(K * 4), N, cap);
-    CUDA_TRY(cudaMemsetAsync(C.meta, 0, 8, m->stream));
+    const CandLists C = carve_lists((char*)m->d_scratch + al(N * 4) + al(K * 4), N, cap, m->d_meta);
     m3_collect_kernel<<<(n + 7) / 8, 256, 0, m->stream>>>(cur->dev, L, th, d_state, C);
     m3_resolve_kernel<true><<<1, 512, claim_smem, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0);
     CUDA_TRY(cudaGetLastError());
-    if ((st = pull_outputs(m, al(K * 4) + 12)) != COEB_OK) return st;
-    if (((const int*)(m->out.h + al(K * 4)))[2]) {
+    if ((st = sync_outputs(m)) != COEB_OK) return st;
+    if (((const int*)(m->outm.h + al(K * 4)))[2]) {
         m3_resolve_kernel<false><<<1, 512, claim_smem, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0);
         CUDA_TRY(cudaGetLastError());
-        if ((st = pull_outputs(m, al(K * 4) + 12)) != COEB_OK) return st;
+        if ((st = sync_outputs(m)) != COEB_OK) return st;
     }
-    std::memcpy(kp_match, m->out.h, K * 4);
-    if (nmatches_out) *nmatches_out = ((const int*)(m->out.h + al(K * 4)))[0];
+    std::memcpy(kp_match, m->outm.h, K * 4);
+    if (nmatches_out) *nmatches_out = ((const int*)(m->outm.h + al(K * 4)))[0];
     return COEB_OK;
 }
 
@@ -2034,8 +2079,7 @@ int coeb_match_init(coeb_matcher* m, coeb_frame* f1, coeb_frame* f2, float* prev
     int* d_cls = (int*)sc; sc += al((N2 + 1) * 4);
     int* d_clf = (int*)sc; sc += al((N2 + 1) * 4);
     int2* d_items = (int2*)sc; sc += al(N1 * 8);
-    const CandLists C = carve_lists(sc, N1, cap);
-    CUDA_TRY(cudaMemsetAsync(C.meta, 0, 8, m->stream));
+    const CandLists C = carve_lists(sc, N1, cap, m->d_meta);
     int* d_m12 = (int*)m->out.d;
     float* d_prev_out = (float*)(m->out.d + al(N1 * 4));
     int* d_info = (int*)(m->out.d + al(N1 * 4) + al(N1 * 8));
@@ -2323,11 +2367,18 @@ int coeb_search_local_points(coeb_matcher* m, coeb_frame* F, coeb_local_map* lm,
     int st;
     if ((st = m->in.reserve(2 * al(N) + al(K * 4))) != COEB_OK) return st;
     const size_t out_bytes = al(K * 4) + 256 + al(N) + (proj_out ? al(N * 20) : 0);
-    if ((st = m->out.reserve(out_bytes)) != COEB_OK) return st;
+    if ((st = m->outm.reserve_mapped(out_bytes)) != COEB_OK) return st;
     const int cap = 32;
     const size_t claim_smem = (size_t)F->n * 4 <= 32 * 1024 ? (size_t)F->n * 4 : 0;
     // scratch: res, claim, list counts, lists | MapPoint fields written by the frustum pass
     const size_t sc_bytes = al(N * 4) + al(K * 4) + lists_bytes(N, cap) + 5 * al(N * 4) + 2 * al(N);
+    if (N > m->zero_bytes) {   // all-zero isBad() flags: written once, when the buffer grows
+        cudaFree(m->d_zero);
+        m->d_zero = nullptr; m->zero_bytes = 0;
+        CUDA_TRY(cudaMalloc((void**)&m->d_zero, al(N + N / 2)));
+        CUDA_TRY(cudaMemsetAsync(m->d_zero, 0, al(N + N / 2), m->stream));
+        m->zero_bytes = al(N + N / 2);
+    }
     if ((st = grow(&m->d_scratch, &m->scratch_bytes, sc_bytes)) != COEB_OK) return st;
     Packer p(m->in);
     const uint8_t* d_skip = p.place(skip, N);
@@ -2337,18 +2388,19 @@ int coeb_search_local_points(coeb_matcher* m, coeb_frame* F, coeb_local_map* lm,
     char* sc = (char*)m->d_scratch;
     int* d_res = (int*)sc; sc += al(N * 4);
     int* d_claim = (int*)sc; sc += al(K * 4);
-    const CandLists C = carve_lists(sc, N, cap); sc += lists_bytes(N, cap);
+    const CandLists C = carve_lists(sc, N, cap, m->d_meta); sc += lists_bytes(N, cap);
     MapFields mf{};
     mf.proj_x = (float*)sc; sc += al(N * 4);
     mf.proj_y = (float*)sc; sc += al(N * 4);
     mf.proj_xr = (float*)sc; sc += al(N * 4);
     mf.view_cos = (float*)sc; sc += al(N * 4);
     mf.level = (int*)sc; sc += al(N * 4);
-    uint8_t* d_zero = (uint8_t*)sc; sc += al(N);   // isBad(): bad points arrive as skip
-    int* d_kpm = (int*)m->out.d;
-    int* d_info = (int*)(m->out.d + al(K * 4));
-    mf.track_in_view = (uint8_t*)(m->out.d + al(K * 4) + 256);
-    float* d_proj = proj_out ? (float*)(m->out.d + al(K * 4) + 256 + al(N)) : nullptr;
+    uint8_t* d_zero = m->d_zero;                   // isBad(): bad points arrive as skip
+    mf.track_in_view = (uint8_t*)sc; sc += al(N);  // device copy: the collection reads it back
+    int* d_kpm = (int*)m->outm.d;
+    int* d_info = (int*)(m->outm.d + al(K * 4));
+    mf.track_in_view_host = (uint8_t*)(m->outm.d + al(K * 4) + 256);
+    float* d_proj = proj_out ? (float*)(m->outm.d + al(K * 4) + 256 + al(N)) : nullptr;
     MapDev M{};
     M.n = n; M.track_in_view = mf.track_in_view; M.bad = d_zero; M.has_obs = d_obs;
     M.proj_x = mf.proj_x; M.proj_y = mf.proj_y; M.proj_xr = mf.proj_xr; M.view_cos = mf.view_cos; M.level = mf.level; M.desc = lm->dev.desc;
@@ -2357,23 +2409,21 @@ int coeb_search_local_points(coeb_matcher* m, coeb_frame* F, coeb_local_map* lm,
     for (int i = 0; i < 3; i++) P.Ow[i] = Ow[i];
     P.cos_limit = viewing_cos_limit;
     P.nlevels = F->nlevels;
-    CUDA_TRY(cudaMemsetAsync(d_zero, 0, N, m->stream));
-    CUDA_TRY(cudaMemsetAsync(C.meta, 0, 8, m->stream));
     frustum_collect_kernel<<<(n + 7) / 8, 256, 0, m->stream>>>(F->dev, lm->dev, P, d_skip, mf, M, th, d_state, C, d_proj);
     { int cc = 0; const size_t sm = resolve_smem(claim_smem, M.n + 1, 25, &cc); allow_smem(m2_resolve_kernel<true>, sm);
       m2_resolve_kernel<true><<<1, 1024, sm, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0, cc); }
     CUDA_TRY(cudaGetLastError());
-    if ((st = pull_outputs(m, out_bytes)) != COEB_OK) return st;
-    if (((const int*)(m->out.h + al(K * 4)))[2]) {   // a candidate list overflowed: exact window-walking variant
+    if ((st = sync_outputs(m)) != COEB_OK) return st;
+    if (((const int*)(m->outm.h + al(K * 4)))[2]) {   // a candidate list overflowed: exact window-walking variant
         { int cc = 0; const size_t sm = resolve_smem(claim_smem, M.n + 1, 25, &cc); allow_smem(m2_resolve_kernel<false>, sm);
       m2_resolve_kernel<false><<<1, 1024, sm, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0, cc); }
         CUDA_TRY(cudaGetLastError());
-        if ((st = pull_outputs(m, al(K * 4) + 12)) != COEB_OK) return st;
+        if ((st = sync_outputs(m)) != COEB_OK) return st;
     }
-    if (F->n) std::memcpy(kp_match, m->out.h, (size_t)F->n * 4);
-    if (in_view_out) std::memcpy(in_view_out, m->out.h + al(K * 4) + 256, N);
-    if (proj_out) std::memcpy(proj_out, m->out.h + al(K * 4) + 256 + al(N), N * 20);
-    if (nmatches_out) *nmatches_out = ((const int*)(m->out.h + al(K * 4)))[0];
+    if (F->n) std::memcpy(kp_match, m->outm.h, (size_t)F->n * 4);
+    if (in_view_out) std::memcpy(in_view_out, m->outm.h + al(K * 4) + 256, N);
+    if (proj_out) std::memcpy(proj_out, m->outm.h + al(K * 4) + 256 + al(N), N * 20);
+    if (nmatches_out) *nmatches_out = ((const int*)(m->outm.h + al(K * 4)))[0];
     return COEB_OK;
 }
 
@@ -2506,7 +2556,7 @@ int coeb_match_reloc(coeb_matcher* m, coeb_frame* cur, int n, const uint8_t* val
     const size_t N = n, K = cur->n;
     int st;
     if ((st = m->in.reserve(2 * al(N) + al(N * 12) + 3 * al(N * 4) + al(N * 32) + al(K * 4))) != COEB_OK) return st;
-    if ((st = m->out.reserve(al(K * 4) + 256)) != COEB_OK) return st;
+    if ((st = m->outm.reserve_mapped(al(K * 4) + 256)) != COEB_OK) return st;
     const int cap = 64;
     const size_t claim_smem = K * 4 <= 32 * 1024 ? K * 4 : 0;   // claim table in shared memory when it fits
     if ((st = grow(&m->d_scratch, &m->scratch_bytes, al(N * 4) + al(K * 4) + lists_bytes(N, cap))) != COEB_OK) return st;
@@ -2530,26 +2580,25 @@ int coeb_match_reloc(coeb_matcher* m, coeb_frame* cur, int n, const uint8_t* val
     for (int i = 0; i < 3; i++) L.Ow[i] = Ow[i];
     L.forward = L.backward = 0;   // levels nPredictedLevel - 1 .. + 1 (:1528)
     L.reloc = 1; L.nlevels = cur->nlevels; L.max_accept = orb_dist;
-    int* d_kpm = (int*)m->out.d;
-    int* d_info = (int*)(m->out.d + al(K * 4));
+    int* d_kpm = (int*)m->outm.d;
+    int* d_info = (int*)(m->outm.d + al(K * 4));
     int* d_res = (int*)m->d_scratch;
     int* d_claim = (int*)((char*)m->d_scratch + al(N * 4));
-    const CandLists C = carve_lists((char*)m->d_scratch + al(N * 4) + al(K * 4), N, cap);
-    CUDA_TRY(cudaMemsetAsync(C.meta, 0, 8, m->stream));
+    const CandLists C = carve_lists((char*)m->d_scratch + al(N * 4) + al(K * 4), N, cap, m->d_meta);
     m3_collect_kernel<<<(n + 7) / 8, 256, 0, m->stream>>>(cur->dev, L, th, d_state, C);
     m3_resolve_kernel<true><<<1, 512, claim_smem, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0);
     CUDA_TRY(cudaGetLastError());
-    if ((st = pull_outputs(m, al(K * 4) + 12)) != COEB_OK) return st;
-    if (((const int*)(m->out.h + al(K * 4)))[2]) {
+    if ((st = sync_outputs(m)) != COEB_OK) return st;
+    if (((const int*)(m->outm.h + al(K * 4)))[2]) {
         m3_resolve_kernel<false><<<1, 512, claim_smem, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0);
         CUDA_TRY(cudaGetLastError());
-        if ((st = pull_outputs(m, al(K * 4) + 12)) != COEB_OK) return st;
+        if ((st = sync_outputs(m)) != COEB_OK) return st;
     }
     // entries that were occupied keep the caller's own encoding; free ones take the result (>= 0 assigned, -1 still free)
-    const int* h = (const int*)m->out.h;
+    const int* h = (const int*)m->outm.h;
     for (size_t k = 0; k < K; k++)
         if (kp_match[k] == -1) kp_match[k] = h[k];
-    if (nmatches_out) *nmatches_out = ((const int*)(m->out.h + al(K * 4)))[0];
+    if (nmatches_out) *nmatches_out = ((const int*)(m->outm.h + al(K * 4)))[0];
     return COEB_OK;
 }
 
