@@ -263,10 +263,11 @@ int build_geometry(coeb_extractor* ex, int w, int h) {
         g.fast_tiles_per_frame = build_fast_tiles(g, nullptr);
         g.blur_tiles_per_frame = build_blur_tiles(g, nullptr);
         // FAST tiles, then blur tiles, then the IC_Angle patch masks
-        std::vector<int4> tiles(g.fast_tiles_per_frame + g.blur_tiles_per_frame + kIcMaskWords / 4);
+        const size_t fast_int4 = (size_t)kFastTileInt4 * g.fast_tiles_per_frame;
+        std::vector<int4> tiles(fast_int4 + g.blur_tiles_per_frame + kIcMaskWords / 4);
         build_fast_tiles(g, tiles.data());
-        build_blur_tiles(g, tiles.data() + g.fast_tiles_per_frame);
-        build_ic_masks(g, reinterpret_cast<uint32_t*>(tiles.data() + g.fast_tiles_per_frame + g.blur_tiles_per_frame));
+        build_blur_tiles(g, tiles.data() + fast_int4);
+        build_ic_masks(g, reinterpret_cast<uint32_t*>(tiles.data() + fast_int4 + g.blur_tiles_per_frame));
         CUDA_TRY(cudaMalloc(&ex->d_fast_tiles, tiles.size() * sizeof(int4)));
         CUDA_TRY(cudaMemcpy(ex->d_fast_tiles, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice));
     }
@@ -731,7 +732,7 @@ static int prepare_view(coeb_extractor* ex, int B, const uint8_t* gray, int widt
     BatchView v{};
     v.B = B;
     v.l0 = gray; v.l0_pitch = stride; v.l0_stride = frame_stride;
-    v.pyr = ex->d_pyr; v.blur = ex->d_blur; v.tabs = ex->d_tabs; v.fast_tiles = ex->d_fast_tiles; v.blur_tiles = ex->d_fast_tiles + ex->geom.fast_tiles_per_frame;
+    v.pyr = ex->d_pyr; v.blur = ex->d_blur; v.tabs = ex->d_tabs; v.fast_tiles = ex->d_fast_tiles; v.blur_tiles = ex->d_fast_tiles + (size_t)kFastTileInt4 * ex->geom.fast_tiles_per_frame;
     v.ic_mask = reinterpret_cast<const uint32_t*>(v.blur_tiles + ex->geom.blur_tiles_per_frame);
     v.pyr_regions = ex->d_pyr_regions; v.n_pyr_regions = ex->n_pyr_regions; v.pyr_regions_smem = ex->pyr_regions_smem;
     v.cand = ex->d_cand; v.cand_count = ex->d_cand_count; v.keys = ex->d_keys; v.key_count = ex->d_key_count;

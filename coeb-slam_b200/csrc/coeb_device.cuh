@@ -25,6 +25,7 @@ constexpr int kHalfPatch = 15;   // HALF_PATCH_SIZE, :75
 constexpr int kPatch = 31;       // PATCH_SIZE, :74
 constexpr int kMinBorder = 16;   // EDGE_THRESHOLD - 3, :795
 constexpr int kCellW = 30;       // W, :789
+constexpr int kFastTileInt4 = 3; // int4 entries per tile of the FAST tile table (fast.cu build_fast_tiles)
 
 struct LevelGeom {
     int w, h, pitch;             // level image size and row pitch (bytes)
@@ -99,7 +100,7 @@ struct BatchView {
     uint8_t* pyr;                      // pyramid arena (levels >= 1; level 0 too unless aliased)
     uint8_t* blur;                     // blurred arena
     const int2* tabs;                  // resize tables
-    const int4* fast_tiles;            // FAST tile table {level, tx0, ty0, 0}, one entry per tile of one frame
+    const int4* fast_tiles;            // FAST tile table, kFastTileInt4 entries per tile of one frame: {level, tx0, ty0, 0} and the tile's cell-boundary masks
     const int4* blur_tiles;            // blur tile table, same layout
     const uint32_t* ic_mask;           // [4 alignments][16 |v|][9 words]: 0xFF per patch byte inside the circular IC_Angle patch
     const PyrRegionLevel* pyr_regions; // [n_pyr_regions][nlevels] small-batch pyramid regions (null: resize chain only)

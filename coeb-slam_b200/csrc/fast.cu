@@ -54,8 +54,7 @@ constexpr int oA = oImg + kImgRows * kImgPitch;
 constexpr int oQueue = oA + kARows * kAW;                 // ushort[kPairCap]     pixel pairs that pass the compass bound
 constexpr int oCq = (oQueue + 2 * kPairCap + 15) & ~15;   // ushort[kFtW*kFtH]    pixels with A > iniTh (NMS candidates)
 constexpr int oList = oCq + 2 * kFtW * kFtH;              // uint32[kFtW*kFtH/2]  emitted local maxima
-constexpr int oEdge = oList + 2 * kFtW * kFtH;            // uint32[8]: cell-boundary masks (columns L/R, rows U/D), 64 bit each
-constexpr int oCtr = oEdge + 32;                          // int[8]: nq, nc, n, base
+constexpr int oCtr = oList + 2 * kFtW * kFtH;             // int[8]: nq, nc, n, base
 constexpr int kFastSmem = oCtr + 32;
 static_assert(oA % 16 == 0 && oQueue % 16 == 0 && (kARows * kAW) % 16 == 0, "16-byte stores");
 
@@ -123,12 +122,11 @@ __global__ void __launch_bounds__(kFtThreads, COEB_FT_MINB) fast_kernel(const __
     unsigned short* const s_queue = reinterpret_cast<unsigned short*>(smem + oQueue);
     unsigned short* const s_cq = reinterpret_cast<unsigned short*>(smem + oCq);
     uint32_t* const s_list = reinterpret_cast<uint32_t*>(smem + oList);
-    uint32_t* const s_edge = reinterpret_cast<uint32_t*>(smem + oEdge);
     int* const s_ctr = reinterpret_cast<int*>(smem + oCtr);   // 0 nq, 1 nc, 2 n, 3 base, 4 n2
     const uint32_t a_ctr = (uint32_t)__cvta_generic_to_shared(s_ctr);
 
     const int frame = blockIdx.y;
-    const int4 ti = __ldg(&tiles[blockIdx.x]);   // {level, tx0, ty0, -} built on the host: no per-thread div/mod or level search
+    const int4 ti = __ldg(&tiles[kFastTileInt4 * blockIdx.x]);   // {level, tx0, ty0, -} built on the host: no per-thread div/mod or level search
     const int level = ti.x, tx0 = ti.y, ty0 = ti.z;
     const LevelGeom& L = g.lv[level];
     const int tid = threadIdx.x, lane = tid & 31;
@@ -154,17 +152,6 @@ __global__ void __launch_bounds__(kFtThreads, COEB_FT_MINB) fast_kernel(const __
         }
     }
     for (int i = tid; i < kARows * kAW / 16; i += kFtThreads) reinterpret_cast<uint4*>(s_A)[i] = make_uint4(0u, 0u, 0u, 0u);
-    // cell-boundary masks: bit i of word pair 0/1 = the left/right neighbour of column tx0+i lies in another FAST cell (or
-    // outside the detection domain) and so cannot suppress it; word pairs 2/3 = same for the rows above/below
-    if (tid < 128) {
-        const bool rows = tid >= 64;
-        const int i = tid & 63;
-        const int x = (rows ? ty0 : tx0) + i, size = rows ? L.h : L.w, rcp = rows ? L.rcpH : L.rcpW, last = rows ? L.lastI : L.lastJ;
-        const int c = cell_of(x, size, rcp, last);
-        const unsigned ml = __ballot_sync(0xffffffffu, cell_of(x - 1, size, rcp, last) != c);
-        const unsigned mr = __ballot_sync(0xffffffffu, cell_of(x + 1, size, rcp, last) != c);
-        if (lane == 0) { s_edge[(tid >> 5) & 1 | (rows ? 4 : 0)] = ml; s_edge[((tid >> 5) & 1 | (rows ? 4 : 0)) + 2] = mr; }
-    }
     if (tid < 5) s_ctr[tid] = 0;
     __syncthreads();
     if (kTma) tma_wait(a_mbar);
@@ -289,8 +276,11 @@ __global__ void __launch_bounds__(kFtThreads, COEB_FT_MINB) fast_kernel(const __
     //      independent cv::FAST call), go to a second queue, so that the boundary test and the emission (2b) run on full warps too.
     //      The queue lives in the staged tile, which is dead after 1b.
     const int nc = s_ctr[1];
-    const unsigned long long eL = *reinterpret_cast<const unsigned long long*>(s_edge), eR = *reinterpret_cast<const unsigned long long*>(s_edge + 2);
-    const unsigned long long eU = *reinterpret_cast<const unsigned long long*>(s_edge + 4), eD = *reinterpret_cast<const unsigned long long*>(s_edge + 6);
+    // cell-boundary masks of the tile (host-built, build_fast_tiles): bit i of eL / eR = the left / right neighbour of column tx0+i lies
+    // in another FAST cell (or outside the detection domain) and so cannot suppress it; eU / eD the same for the rows above / below
+    const int4 ex_ = __ldg(&tiles[kFastTileInt4 * blockIdx.x + 1]), ey_ = __ldg(&tiles[kFastTileInt4 * blockIdx.x + 2]);
+    const unsigned long long eL = (unsigned)ex_.x | ((unsigned long long)(unsigned)ex_.y << 32), eR = (unsigned)ex_.z | ((unsigned long long)(unsigned)ex_.w << 32);
+    const unsigned long long eU = (unsigned)ey_.x | ((unsigned long long)(unsigned)ey_.y << 32), eD = (unsigned)ey_.z | ((unsigned long long)(unsigned)ey_.w << 32);
     int* cellcnt = v.cell_count + (size_t)frame * g.cells_per_frame + L.cell_base;
     unsigned short* const s_q2 = reinterpret_cast<unsigned short*>(smem + oImg);
     constexpr int kQ2Cap = kImgRows * kImgPitch / 2;
@@ -594,14 +584,35 @@ __global__ void __launch_bounds__(32 * kFbWarps) fast_fallback_kernel(const __gr
 }
 
 // Tiles cover the detection domain x in [19, w-19), y in [19, h-19) of every level, starting at the 4-aligned x = 16.
+static int cell_of_host(int x, int size, int rcp, int last) {   // cell_of() above
+    return (x >= kEdge && x < size - kEdge) ? std::min((int)(((unsigned)(x - kEdge) * (unsigned)rcp) >> 20), last) : -1;
+}
+
+// kFastTileInt4 entries per tile: {level, tx0, ty0, 0}, then the tile's cell-boundary masks {eL, eR}, {eU, eD} as 64-bit pairs (the
+// kernel used to derive them with 128 threads, three divisions each and four ballots per tile: ~4 % of its instructions).
 int build_fast_tiles(const Geometry& g, int4* out) {
     int total = 0;
     for (int l = 0; l < g.nlevels; l++) {
-        const int tiles_x = std::max(1, (g.lv[l].w - kEdge - kMinBorder + kFtW - 1) / kFtW);
-        const int tiles_y = std::max(1, (g.lv[l].h - kEdge - kMinBorder + kFtH - 1) / kFtH);
+        const LevelGeom& L = g.lv[l];
+        const int tiles_x = std::max(1, (L.w - kEdge - kMinBorder + kFtW - 1) / kFtW);
+        const int tiles_y = std::max(1, (L.h - kEdge - kMinBorder + kFtH - 1) / kFtH);
         for (int ty = 0; ty < tiles_y; ty++)
-            for (int tx = 0; tx < tiles_x; tx++, total++)
-                if (out) out[total] = make_int4(l, kMinBorder + tx * kFtW, kMinBorder + ty * kFtH, 0);
+            for (int tx = 0; tx < tiles_x; tx++, total++) {
+                if (!out) continue;
+                const int tx0 = kMinBorder + tx * kFtW, ty0 = kMinBorder + ty * kFtH;
+                unsigned long long e[4] = {0, 0, 0, 0};   // L, R, U, D
+                for (int i = 0; i < 64; i++) {
+                    const int cx = cell_of_host(tx0 + i, L.w, L.rcpW, L.lastJ), cy = cell_of_host(ty0 + i, L.h, L.rcpH, L.lastI);
+                    if (cell_of_host(tx0 + i - 1, L.w, L.rcpW, L.lastJ) != cx) e[0] |= 1ull << i;
+                    if (cell_of_host(tx0 + i + 1, L.w, L.rcpW, L.lastJ) != cx) e[1] |= 1ull << i;
+                    if (cell_of_host(ty0 + i - 1, L.h, L.rcpH, L.lastI) != cy) e[2] |= 1ull << i;
+                    if (cell_of_host(ty0 + i + 1, L.h, L.rcpH, L.lastI) != cy) e[3] |= 1ull << i;
+                }
+                int4* t = out + (size_t)kFastTileInt4 * total;
+                t[0] = make_int4(l, tx0, ty0, 0);
+                t[1] = make_int4((int)(unsigned)e[0], (int)(unsigned)(e[0] >> 32), (int)(unsigned)e[1], (int)(unsigned)(e[1] >> 32));
+                t[2] = make_int4((int)(unsigned)e[2], (int)(unsigned)(e[2] >> 32), (int)(unsigned)e[3], (int)(unsigned)(e[3] >> 32));
+            }
     }
     return total;
 }
@@ -649,8 +660,8 @@ int fast_tiles_of_level0(const Geometry& g) {
 void launch_fast_tiles(const Geometry& g, const BatchView& v, cudaStream_t stream, int first, int count) {
     if (count <= 0) return;
     TmaMaps maps;
-    if (tma_enabled() && encode_level_maps(g, v, kImgPitch, kImgRows, &maps)) fast_kernel<true><<<dim3(count, v.B), kFtThreads, 0, stream>>>(g, v, v.fast_tiles + first, maps);
-    else fast_kernel<false><<<dim3(count, v.B), kFtThreads, 0, stream>>>(g, v, v.fast_tiles + first, maps);
+    if (tma_enabled() && encode_level_maps(g, v, kImgPitch, kImgRows, &maps)) fast_kernel<true><<<dim3(count, v.B), kFtThreads, 0, stream>>>(g, v, v.fast_tiles + (size_t)kFastTileInt4 * first, maps);
+    else fast_kernel<false><<<dim3(count, v.B), kFtThreads, 0, stream>>>(g, v, v.fast_tiles + (size_t)kFastTileInt4 * first, maps);
 }
 
 static size_t fallback_smem(const FbLayout& F) {
