@@ -327,16 +327,21 @@ __global__ void __launch_bounds__(T, kMinBlocks) select_kernel(const __grid_cons
             const unsigned e0 = __ballot_sync(0xffffffffu, cc.x > 1), e1 = __ballot_sync(0xffffffffu, cc.y > 1);
             const unsigned e2 = __ballot_sync(0xffffffffu, cc.z > 1), e3 = __ballot_sync(0xffffffffu, cc.w > 1);
             const unsigned bk = __ballot_sync(0xffffffffu, keep);
-            if (lane == 0)   // <= 128 children, <= 128 expandable, <= 32 kept per warp: 10 bits each
-                s_cnt[par][wid] = (__popc(b0) + __popc(b1) + __popc(b2) + __popc(b3)) | ((__popc(e0) + __popc(e1) + __popc(e2) + __popc(e3)) << 10) | (__popc(bk) << 20);
+            // children | expandable << 11 | kept << 22: the CTA-wide sums stay inside their fields (<= 4 T, <= 4 T, <= T with T <= 512),
+            // so the packed words are added as they are
+            static_assert(T <= 512, "field widths of the packed prefix counts");
+            if (lane == 0)
+                s_cnt[par][wid] = (__popc(b0) + __popc(b1) + __popc(b2) + __popc(b3)) | ((__popc(e0) + __popc(e1) + __popc(e2) + __popc(e3)) << 11) | (__popc(bk) << 22);
             __syncthreads();
-            int preC = 0, preE = 0, preK = 0, totC = 0, totE = 0, totK = 0;
+            unsigned pre = 0, tot = 0;
 #pragma unroll
             for (int w = 0; w < T / 32; w++) {
-                const int c = s_cnt[par][w];
-                totC += c & 0x3FF; totE += (c >> 10) & 0x3FF; totK += c >> 20;
-                if (w < wid) { preC += c & 0x3FF; preE += (c >> 10) & 0x3FF; preK += c >> 20; }
+                const unsigned c = (unsigned)s_cnt[par][w];
+                tot += c;
+                if (w < wid) pre += c;
             }
+            const int preC = pre & 0x7FF, preE = (pre >> 11) & 0x7FF, preK = pre >> 22;
+            const int totC = tot & 0x7FF, totE = (tot >> 11) & 0x7FF, totK = tot >> 22;
             par ^= 1;
             if (p < nProc)
                 s_scanA[p] = (totalNew + preC + __popc(b0 & lt) + __popc(b1 & lt) + __popc(b2 & lt) + __popc(b3 & lt)) |
