@@ -2290,24 +2290,27 @@ int coeb_frame_from_extractor(coeb_matcher* m, coeb_extractor* ex, int frame_ind
     d.gh_inv = (float)COEB_GRID_ROWS / (cam->max_y - cam->min_y);
     d.fx = cam->fx; d.fy = cam->fy; d.cx = cam->cx; d.cy = cam->cy; d.bf = cam->bf; d.b = cam->b;
     for (int i = 0; i < COEB_MAX_LEVELS; i++) d.scale[i] = i < nlevels ? scale[i] : 0.f;
+    // the AoS copies the caller asked for (mvKeysUn, mvuRight, mvDepth) are written by the kernel straight into mapped pinned host
+    // memory, in the layout of the frame block's own copies: no device-to-host copy behind the kernels
+    const bool want = n > 0 && (keys_un_out || uright_out || depth_out);
+    const size_t off_ur = (size_t)((char*)d_uright_copy - (char*)a.keys_un), off_dp = (size_t)((char*)a.depth_out - (char*)a.keys_un);
+    if (want) {
+        if ((st = m->outm.reserve_mapped(dl_bytes)) != COEB_OK) return bail(st);
+        a.keys_un = (coeb_keypoint*)m->outm.d;
+        a.uright_dl = (float*)(m->outm.d + off_ur);
+        a.depth_out = (float*)(m->outm.d + off_dp);
+    }
     if (n > 0) frame_tail_kernel<<<(n + 127) / 128, 128, 0, s>>>(a);
     grid_build_kernel<<<1, 1024, 0, s>>>(d, d_cell_start, d_cell_items, d_kp_cell);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return bail(fail(COEB_ERR_CUDA, "frame tail launch failed: %s", cudaGetErrorString(e)));
-    const bool want = n > 0 && (keys_un_out || uright_out || depth_out);
-    if (want) {
-        // the kernel wrote uright twice (SoA part and next to keys_un / depth), so the download is one block
-        if ((st = m->out.reserve(dl_bytes)) != COEB_OK) return bail(st);
-        if ((e = cudaMemcpyAsync(m->out.h, a.keys_un, dl_bytes, cudaMemcpyDeviceToHost, s)) != cudaSuccess)
-            return bail(fail(COEB_ERR_CUDA, "%s", cudaGetErrorString(e)));
-    }
     // blocking like every Frame-building call: the caller may reuse its depth buffer and the extractor
     if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return bail(fail(COEB_ERR_CUDA, "frame tail failed: %s", cudaGetErrorString(e)));
     if (want) {
-        const char* h = m->out.h;
+        const char* h = m->outm.h;
         if (keys_un_out) std::memcpy(keys_un_out, h, (size_t)n * sizeof(coeb_keypoint));
-        if (uright_out) std::memcpy(uright_out, h + ((char*)d_uright_copy - (char*)a.keys_un), (size_t)n * 4);
-        if (depth_out) std::memcpy(depth_out, h + ((char*)a.depth_out - (char*)a.keys_un), (size_t)n * 4);
+        if (uright_out) std::memcpy(uright_out, h + off_ur, (size_t)n * 4);
+        if (depth_out) std::memcpy(depth_out, h + off_dp, (size_t)n * 4);
     }
     if (n_out) *n_out = n;
     *out = f;

@@ -309,3 +309,23 @@ def test_small_batch_path_equals_the_batch_path(gpu, w, h):
         assert np.array_equal(one_blur[l], ex.level_image(l, frame=0, blurred=True)), "blurred level %d" % l
     assert kps[0, :counts[0]].tobytes() == one_k.tobytes() and np.array_equal(desc[0, :counts[0]], one_d)
     ex.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B", [2, 3, 4])
+def test_batches_of_two_to_four_frames_take_the_latency_path(gpu, B):
+    """2-4 frames run like a single one (side-stream level 0, one-launch pyramid with one grid row per frame, per-cell fallback):
+    every stage of every frame against the oracle, dynamic boxes and the area_flag thresholds included."""
+    batch = synth.make_batch(B, base_seed=3)   # seed 3 takes the area_flag path
+    g = gpu.Extractor()
+    kps, desc, counts, status = g.extract_batch_host(batch["gray"], batch["boxes"], batch["nbox"], batch["tm"], batch["ntm"], batch["blur"])
+    assert (status == 0).all() and g.launches_per_call() == 10
+    c = orc.Extractor()
+    flags = 0
+    for i in range(B):
+        nb, nt = batch["nbox"][i], batch["ntm"][i]
+        compare_frame(g, c, batch["gray"][i], batch["boxes"][i, :nb], batch["tm"][i, :nt], batch["blur"][i, :nb],
+                      stages=True, frame=i, kps=kps[i, :counts[i]], desc=desc[i, :counts[i]])
+        flags += c.dyn_info()["area_flag"]
+    assert flags >= 1
+    g.close()
