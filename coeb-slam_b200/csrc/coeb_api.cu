@@ -623,6 +623,18 @@ int coeb_extractor_device_outputs(coeb_extractor* ex, int frame, const coeb_keyp
     return COEB_OK;
 }
 
+int coeb_extractor_host_outputs(coeb_extractor* ex, int frame, const coeb_keypoint** h_kps, int* count) {
+    if (!ex || !h_kps) return fail(COEB_ERR_INVALID_ARG, "bad argument");
+    *h_kps = nullptr;
+    if (count) *count = 0;
+    if (!ex->geom_valid || frame != 0 || ex->last_B != 1 || !ex->last_view.mirror_hdr || !ex->h_out1) return COEB_OK;
+    const int* hdr = (const int*)ex->h_out1;
+    if (hdr[1] != COEB_OK) return COEB_OK;
+    *h_kps = ex->last_view.mirror_kps;
+    if (count) *count = hdr[0];
+    return COEB_OK;
+}
+
 int coeb_extractor_launches_per_call(const coeb_extractor* ex) {
     if (!ex) return 0;
     // batches: classify + (nlevels-1) resizes + blur + FAST + empty-cell list + FAST fallback + select + describe;

@@ -1269,7 +1269,7 @@ struct TailArgs {
     float fx, fy, cx, cy, bf;
     float dist[5];
     int undistort;
-    const void* depth; int depth_kind, depth_stride, depth_w, depth_h; float depth_factor;
+    const void* depth; int depth_kind, depth_stride, depth_w, depth_h; float depth_factor;   // kind 3 / 4: one float per keypoint, gathered on the host (4: raw uint16 value, factor still to apply)
     // frame block
     float *x, *y, *angle; int* octave; float* uright; uint32_t* desc_out;
     coeb_keypoint* keys_un; float* depth_out; float* uright_dl;   // download block: mvKeysUn | mvuRight | mvDepth, contiguous
@@ -1289,7 +1289,10 @@ __global__ void __launch_bounds__(128) frame_tail_kernel(TailArgs a) {
     if (a.depth_kind) {
         const int row = (int)v, col = (int)u;   // imDepth.at<float>(v, u): float -> int truncation
         float d = 0.f;
-        if ((unsigned)row < (unsigned)a.depth_h && (unsigned)col < (unsigned)a.depth_w) {
+        if (a.depth_kind >= 3) {
+            const float g = ((const float*)a.depth)[i];
+            d = a.depth_kind == 3 ? g : __fmul_rn(g, a.depth_factor);
+        } else if ((unsigned)row < (unsigned)a.depth_h && (unsigned)col < (unsigned)a.depth_w) {
             const char* p = (const char*)a.depth + (size_t)row * a.depth_stride;
             d = a.depth_kind == 1 ? ((const float*)p)[col] : __fmul_rn((float)((const unsigned short*)p)[col], a.depth_factor);
         }
@@ -2270,7 +2273,31 @@ int coeb_frame_from_extractor(coeb_matcher* m, coeb_extractor* ex, int frame_ind
     a.depth_kind = kind;
     if (kind) {
         a.depth_w = depth->width; a.depth_h = depth->height; a.depth_factor = depth->factor;
+        const coeb_keypoint* h_kps = nullptr;
+        int h_n = 0;
+        if (!depth->on_device && n > 0 && !getenv("COEB_NO_DEPTH_GATHER")) coeb_extractor_host_outputs(ex, frame_index, &h_kps, &h_n);
         if (depth->on_device) { a.depth = depth->data; a.depth_stride = depth->stride_bytes; }
+        else if (h_kps && h_n == n) {
+            // The extractor left its keypoints in host memory (single-frame call): the ~1000 depth values ComputeStereoFromRGBD reads
+            // are gathered here and uploaded as 4 KB instead of the whole depth map (0.6 MB: 11 us from pinned memory, ~40 us from a
+            // pageable cv::Mat). Same truncation and the same bounds test as the kernel's own gather.
+            if ((st = m->in.reserve(al((size_t)n * 4))) != COEB_OK) return bail(st);
+            float* g = (float*)m->in.h;
+            const char* img = (const char*)depth->data;
+            for (int i = 0; i < n; i++) {
+                const int row = (int)h_kps[i].y, col = (int)h_kps[i].x;
+                float val = 0.f;
+                if ((unsigned)row < (unsigned)depth->height && (unsigned)col < (unsigned)depth->width) {
+                    const char* p = img + (size_t)row * depth->stride_bytes;
+                    val = kind == 1 ? ((const float*)p)[col] : (float)((const unsigned short*)p)[col];
+                }
+                g[i] = val;
+            }
+            cudaError_t e = cudaMemcpyAsync(m->in.d, m->in.h, (size_t)n * 4, cudaMemcpyHostToDevice, s);
+            if (e != cudaSuccess) return bail(fail(COEB_ERR_CUDA, "depth upload failed: %s", cudaGetErrorString(e)));
+            a.depth = m->in.d; a.depth_stride = 0;
+            a.depth_kind = kind == 1 ? 3 : 4;
+        }
         else {
             const size_t row = (size_t)depth->width * (kind == 1 ? 4 : 2);
             const size_t pitch = (row + 15) & ~(size_t)15;

@@ -96,6 +96,12 @@ int coeb_extract_batch_device(coeb_extractor* ex, int B, const uint8_t* gray, in
 int coeb_extractor_device_outputs(coeb_extractor* ex, int frame, const coeb_keypoint** d_kps, const uint8_t** d_desc,
                                   const int** d_count, int* cap);
 
+/* Host-side copy of the same keypoints when the last call was a single-frame host call (coeb_extract, or coeb_extract_batch_host
+ * with one frame): the descriptor stage writes its results into pinned host memory as well, and consumers that only need a few
+ * values per keypoint from a host image (coeb_frame_from_extractor gathers the depth of ~1000 pixels instead of uploading the
+ * depth map) read them there. *h_kps == NULL when the last call left no host copy. Valid until the next call on the handle. */
+int coeb_extractor_host_outputs(coeb_extractor* ex, int frame, const coeb_keypoint** h_kps, int* count);
+
 /* Upper bound of the keypoints one width x height frame can yield, for sizing `cap`: per level max(N_l + 3, 4 * nIni_l).
  * DistributeOctTree stops once it holds N_l nodes but its last expansion may overshoot by three, and its first round splits
  * every one of the nIni_l = round(w/h) root nodes whatever N_l is (src/ORBextractor.cc:546-676), so nfeatures alone is not a
