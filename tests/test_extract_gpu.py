@@ -329,3 +329,30 @@ def test_batches_of_two_to_four_frames_take_the_latency_path(gpu, B):
         flags += c.dyn_info()["area_flag"]
     assert flags >= 1
     g.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("switches", [("COEB_NO_L0_OVERLAP",), ("COEB_NO_PYR_REGIONS",), ("COEB_NO_MIRROR", "COEB_NO_STAGE")])
+def test_single_frame_fast_paths_can_be_switched_off(gpu, switches):
+    """The latency path of a single-frame call is made of independent shortcuts (level 0 on a side stream, one-launch pyramid,
+    results mirrored into mapped memory, staged upload); each has a development switch that restores the plain path. Same results
+    either way (child process: some switches are read once)."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path[:0] = %r\n"
+        "import coeb_b200 as cb, orc\n"
+        "from coeb_b200 import synth\n"
+        "ex, o = cb.Extractor(), orc.Extractor()\n"
+        "for seed in (0, 3, 5, 0):\n"
+        "    gray = synth.make_frame(seed)\n"
+        "    boxes, tm, blur = synth.make_dynamic(seed, force_area=(seed == 3))\n"
+        "    kg, dg = ex.extract(gray, boxes, tm, blur)\n"
+        "    kc, dc = o.extract(gray, boxes, tm, blur)\n"
+        "    assert kg.tobytes() == kc.tobytes() and np.array_equal(dg, dc), seed\n"
+        "print('switched path ok')\n") % ([p for p in sys.path if p],)
+    env = dict(os.environ, **{k: "1" for k in switches})
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0 and "switched path ok" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
