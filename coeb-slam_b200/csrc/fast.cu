@@ -53,8 +53,12 @@ constexpr int oImg = 0;
 constexpr int oA = oImg + kImgRows * kImgPitch;
 constexpr int oQueue = oA + kARows * kAW;                 // ushort[kPairCap]     pixel pairs that pass the compass bound
 constexpr int oCq = (oQueue + 2 * kPairCap + 15) & ~15;   // ushort[kFtW*kFtH]    pixels with A > iniTh (NMS candidates)
-constexpr int oList = oCq + 2 * kFtW * kFtH;              // uint32[kFtW*kFtH/2]  emitted local maxima
-constexpr int oCtr = oList + 2 * kFtW * kFtH;             // int[8]: nq, nc, n, base
+// Local maxima a tile can emit: a cell keeps at most one pixel of every 2x2 block (strict 3x3 maxima inside the cell), and 64 pixels
+// touch at most four cells (cells are >= 30 px), so at most (32 + 2)^2 = 1156 per tile.
+constexpr int kListCap = 1280;
+static_assert(kFtW == 64 && kFtH <= 64 && kListCap >= (kFtW / 2 + 2) * (kFtH / 2 + 2), "local-maximum bound of a tile");
+constexpr int oList = oCq + 2 * kFtW * kFtH;              // uint32[kListCap]  emitted local maxima
+constexpr int oCtr = oList + 4 * kListCap;                // int[8]: nq, nc, n, base
 constexpr int kFastSmem = oCtr + 32;
 static_assert(oA % 16 == 0 && oQueue % 16 == 0 && (kARows * kAW) % 16 == 0, "16-byte stores");
 
