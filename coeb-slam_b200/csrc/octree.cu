@@ -37,6 +37,7 @@ namespace coeb {
 constexpr int kSelThreads = COEB_SEL_THREADS;
 constexpr int kKeyCache = 4096;   // candidates per (level, frame) kept in shared memory (4 + 2 bytes each)
 constexpr unsigned long long kOrdMask = 0xFFFFFFFFFFFFull;  // 48-bit candidate-order field
+constexpr uint32_t kNoSplit = 0xFFFFFFFFu;                  // s_split entry of a node that is not split this round (split lines are < 0xFFFF)
 
 struct __align__(16) QNode {
     unsigned short x0, x1, y0, y1;
@@ -105,11 +106,11 @@ __global__ void __launch_bounds__(T, kMinBlocks) select_kernel(const __grid_cons
     unsigned long long* s_best = reinterpret_cast<unsigned long long*>(sp); sp += (sizeof(unsigned long long) * LC + 15) & ~(size_t)15;   // QNode is 16-byte aligned
     QNode* s_nodeA = reinterpret_cast<QNode*>(sp); sp += sizeof(QNode) * LC;
     QNode* s_nodeB = reinterpret_cast<QNode*>(sp); sp += sizeof(QNode) * LC;
-    int* s_cc = reinterpret_cast<int*>(sp); sp += sizeof(int) * 4 * LC;      // tentative child counts [slot][4]
+    int* s_cc = reinterpret_cast<int*>(sp); sp += sizeof(int) * 4 * LC;      // tentative child counts [node id][4]
     int* s_scanA = reinterpret_cast<int*>(sp); sp += sizeof(int) * 4 * LC;   // scratch for scans (up to 4*LC entries)
+    unsigned short* s_newpos = reinterpret_cast<unsigned short*>(sp); sp += sizeof(unsigned short) * 4 * LC;   // [node id][quadrant] -> list position after the round (8-byte aligned rows)
     int* s_scanB = reinterpret_cast<int*>(sp); sp += sizeof(int) * LC;
-    unsigned short* s_childpos = reinterpret_cast<unsigned short*>(sp); sp += sizeof(unsigned short) * 4 * LC;
-    unsigned short* s_oldpos = reinterpret_cast<unsigned short*>(sp); sp += sizeof(unsigned short) * LC;
+    uint32_t* s_split = reinterpret_cast<uint32_t*>(sp); sp += sizeof(uint32_t) * LC;   // node id -> xm | ym << 16 if the node is split this round, else kNoSplit
     unsigned short* s_slot = reinterpret_cast<unsigned short*>(sp); sp += sizeof(unsigned short) * LC;
     unsigned short* s_P = reinterpret_cast<unsigned short*>(sp); sp += sizeof(unsigned short) * LC;
     unsigned short* s_E = reinterpret_cast<unsigned short*>(sp); sp += sizeof(unsigned short) * LC;
@@ -236,52 +237,56 @@ __global__ void __launch_bounds__(T, kMinBlocks) select_kernel(const __grid_cons
             nP = block_flag_scan<T>(
                 nList, [&](int i) { return cur[i].count > 1; },
                 [&](int i, int pos, bool f) {
-                    if (f) { s_P[pos] = (unsigned short)i; s_slot[i] = (unsigned short)pos; }
-                    else s_slot[i] = 0xFFFF;
+                    if (f) {
+                        s_P[pos] = (unsigned short)i; s_slot[i] = (unsigned short)pos;
+                        s_split[i] = reinterpret_cast<const uint32_t*>(&cur[i])[2];   // xm | ym << 16
+                        *reinterpret_cast<int4*>(&s_cc[4 * i]) = make_int4(0, 0, 0, 0);   // tentative child counts, zeroed in the same phase
+                    } else {
+                        s_slot[i] = 0xFFFF; s_split[i] = kNoSplit;
+                    }
                 },
                 s_cnt, par);
-            for (int i = tid; i < 4 * nP; i += T) s_cc[i] = 0;   // tentative child counts, zeroed in the same phase
         } else {
             // careful phase: previous round's multi-key children, largest first, later-created first on ties (:688-692)
             nP = nE;
-            for (int i = tid; i < nList; i += T) s_slot[i] = 0xFFFF;
+            for (int i = tid; i < nList; i += T) { s_slot[i] = 0xFFFF; s_split[i] = kNoSplit; }
             __syncthreads();
             for (int e = tid; e < nE; e += T) {
-                const int ce = cur[s_E[e]].count;
+                const int nd = s_E[e];
+                const int ce = cur[nd].count;
                 int rank = 0;
                 for (int f = 0; f < nE; f++) {
                     const int cf = cur[s_E[f]].count;
                     rank += (cf > ce) || (cf == ce && f > e);
                 }
-                s_P[rank] = s_E[e];
-                s_slot[s_E[e]] = (unsigned short)rank;
+                s_P[rank] = (unsigned short)nd;
+                s_slot[nd] = (unsigned short)rank;
+                s_split[nd] = reinterpret_cast<const uint32_t*>(&cur[nd])[2];
+                *reinterpret_cast<int4*>(&s_cc[4 * nd]) = make_int4(0, 0, 0, 0);
             }
-            for (int i = tid; i < 4 * nP; i += T) s_cc[i] = 0;
         }
         __syncthreads();
         if (nP == 0) break;  // nothing left to split: list size cannot change (:676)
 
-        // tentative children of every node in P. A key's step is a chain of dependent shared-memory loads (node id -> slot -> split
-        // lines); four keys per thread are in flight together so that the chains overlap.
+        // tentative children of every node in P: node id -> split lines (or "not split") -> quadrant; a few keys per thread are in
+        // flight together so that the chains of dependent shared-memory loads overlap
         constexpr int kKU = COEB_SEL_KU;
         for (int k0 = tid; k0 < nkeys; k0 += kKU * T) {
-            int nd[kKU], ps[kKU];
+            int nd[kKU];
             uint32_t key[kKU], xy[kKU];
 #pragma unroll
             for (int u = 0; u < kKU; u++) nd[u] = k0 + u * T < nkeys ? (int)knode[k0 + u * T] : -1;
 #pragma unroll
             for (int u = 0; u < kKU; u++) {
-                ps[u] = nd[u] >= 0 ? (int)s_slot[nd[u]] : 0xFFFF;
+                xy[u] = nd[u] >= 0 ? s_split[nd[u]] : kNoSplit;
                 key[u] = nd[u] >= 0 ? keys[k0 + u * T] : 0u;
             }
 #pragma unroll
-            for (int u = 0; u < kKU; u++) xy[u] = ps[u] != 0xFFFF ? reinterpret_cast<const uint32_t*>(&cur[nd[u]])[2] : 0u;   // xm | ym << 16
-#pragma unroll
             for (int u = 0; u < kKU; u++) {
-                if (ps[u] != 0xFFFF) {
+                if (xy[u] != kNoSplit) {
                     const int x = key[u] & 0xFFF, y = (key[u] >> 12) & 0xFFF;
                     const int q = (x < (int)(xy[u] & 0xFFFFu) ? 0 : 1) + (y < (int)(xy[u] >> 16) ? 0 : 2);
-                    atomicAdd(&s_cc[4 * ps[u] + q], 1);
+                    atomicAdd(&s_cc[4 * nd[u] + q], 1);
                     knode[k0 + u * T] = (unsigned short)(nd[u] | (q << 14));   // the quadrant rides in the two top bits until the keys move below
                 }
             }
@@ -292,7 +297,7 @@ __global__ void __launch_bounds__(T, kMinBlocks) select_kernel(const __grid_cons
         int nProc = nP;
         if (careful) {
             for (int p = tid; p < nP; p += T) {
-                const int* c = &s_cc[4 * p];
+                const int* c = &s_cc[4 * s_P[p]];
                 s_scanA[p] = (c[0] > 0) + (c[1] > 0) + (c[2] > 0) + (c[3] > 0) - 1;
             }
             __syncthreads();
@@ -300,7 +305,7 @@ __global__ void __launch_bounds__(T, kMinBlocks) select_kernel(const __grid_cons
             if (tid == 0) s_misc[0] = nP;
             __syncthreads();
             for (int p = tid; p < nP; p += T) {
-                const int* c = &s_cc[4 * p];
+                const int* c = &s_cc[4 * s_P[p]];
                 const int after = nList + s_scanA[p] + (c[0] > 0) + (c[1] > 0) + (c[2] > 0) + (c[3] > 0) - 1;
                 if (after >= N) atomicMin(&s_misc[0], p + 1);  // break after the first split reaching N (:737-738)
             }
@@ -319,7 +324,7 @@ __global__ void __launch_bounds__(T, kMinBlocks) select_kernel(const __grid_cons
         for (int i0 = 0; i0 < max(nProc, nList); i0 += T) {
             const int p = i0 + tid;
             int4 cc = make_int4(0, 0, 0, 0);
-            if (p < nProc) cc = *reinterpret_cast<const int4*>(&s_cc[4 * p]);
+            if (p < nProc) cc = *reinterpret_cast<const int4*>(&s_cc[4 * s_P[p]]);
             bool keep = false;
             if (p < nList) { const int sl = s_slot[p]; keep = !(sl != 0xFFFF && sl < nProc); }
             const unsigned b0 = __ballot_sync(0xffffffffu, cc.x > 0), b1 = __ballot_sync(0xffffffffu, cc.y > 0);
@@ -360,16 +365,19 @@ __global__ void __launch_bounds__(T, kMinBlocks) select_kernel(const __grid_cons
             if (p < nList) {
                 const int sl = s_slot[p];
                 if (!(sl != 0xFFFF && sl < nProc)) {
-                    const int pos = totalNew + s_scanB[p];
-                    s_oldpos[p] = (unsigned short)pos;
+                    const uint32_t pos = (uint32_t)(totalNew + s_scanB[p]);
+                    // all four quadrants: the keys of a node that was a candidate of the careful phase but is not split after all
+                    // already carry a quadrant
+                    *reinterpret_cast<uint2*>(&s_newpos[4 * p]) = make_uint2(pos | (pos << 16), pos | (pos << 16));
                     nxt[pos] = cur[p];
                 }
             }
             if (p < nProc) {
-                const int4 cc = *reinterpret_cast<const int4*>(&s_cc[4 * p]);
+                const int ndp = s_P[p];
+                const int4 cc = *reinterpret_cast<const int4*>(&s_cc[4 * ndp]);
                 const int cnts[4] = {cc.x, cc.y, cc.z, cc.w};
                 int ci = s_scanA[p] & 0xFFFF, ei = s_scanA[p] >> 16;
-                const QNode n = cur[s_P[p]];
+                const QNode n = cur[ndp];
                 const int xm = n.xm, ym = n.ym;
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
@@ -384,7 +392,7 @@ __global__ void __launch_bounds__(T, kMinBlocks) select_kernel(const __grid_cons
                         c.count = cnt;
                         const int pos = totalNew - 1 - ci;  // push_front in creation order
                         nxt[pos] = c;
-                        s_childpos[4 * p + q] = (unsigned short)pos;
+                        s_newpos[4 * ndp + q] = (unsigned short)pos;
                         if (cnt > 1) s_E2[ei++] = (unsigned short)pos;   // next round's expandable list
                         ci++;
                     }
@@ -393,18 +401,13 @@ __global__ void __launch_bounds__(T, kMinBlocks) select_kernel(const __grid_cons
         }
         __syncthreads();
 
-        // move the keys (same batching)
+        // move the keys: (node id, quadrant) -> position in the new list, one table look-up
         for (int k0 = tid; k0 < nkeys; k0 += kKU * T) {
-            int kn[kKU], ps[kKU], to[kKU];
+            int kn[kKU], to[kKU];
 #pragma unroll
             for (int u = 0; u < kKU; u++) kn[u] = k0 + u * T < nkeys ? (int)knode[k0 + u * T] : -1;
 #pragma unroll
-            for (int u = 0; u < kKU; u++) ps[u] = kn[u] >= 0 ? (int)s_slot[kn[u] & 0x3FFF] : 0xFFFF;
-#pragma unroll
-            for (int u = 0; u < kKU; u++) {
-                const int nd = kn[u] & 0x3FFF, q = kn[u] >> 14;
-                to[u] = kn[u] < 0 ? 0 : (ps[u] != 0xFFFF && ps[u] < nProc) ? (int)s_childpos[4 * ps[u] + q] : (int)s_oldpos[nd];
-            }
+            for (int u = 0; u < kKU; u++) to[u] = kn[u] >= 0 ? (int)s_newpos[((kn[u] & 0x3FFF) << 2) | (kn[u] >> 14)] : 0;
 #pragma unroll
             for (int u = 0; u < kKU; u++)
                 if (kn[u] >= 0) knode[k0 + u * T] = (unsigned short)to[u];
@@ -469,7 +472,7 @@ __global__ void __launch_bounds__(T, kMinBlocks) select_kernel(const __grid_cons
 }
 
 size_t select_smem_bytes(int LC) {
-    return (size_t)LC * (sizeof(unsigned long long) + 2 * sizeof(QNode) + 4 * 4 + 4 * 4 + 4 + 4 * 2 + 2 * 5) + 32 + (size_t)kKeyCache * 6;
+    return (size_t)LC * (sizeof(unsigned long long) + 2 * sizeof(QNode) + 4 * 4 + 4 * 4 + 4 * 2 + 4 + 4 + 2 * 4) + 48 + (size_t)kKeyCache * 6;
 }
 
 void launch_select(const Geometry& g, const BatchView& v, cudaStream_t stream, int level_lo, int level_hi) {
