@@ -22,11 +22,17 @@
 
 namespace coeb {
 
+// CTA size / resident CTAs per SM. Batches: 256 x 4 (measured after the ballot scans and the node-indexed tables: stage 0.103 ms
+// per 256 frames against 0.129 with 384 x 3, 0.107 with 192 x 5, 0.109 with 128 x 6, 0.170 with 512 x 2, and the step follows:
+// 1.355 against 1.381 ms). A single frame is one CTA per level and pure latency: 384 threads give 105.6 us per call, 256 give 110.3.
 #ifndef COEB_SEL_THREADS
-#define COEB_SEL_THREADS 384
+#define COEB_SEL_THREADS 256
 #endif
 #ifndef COEB_SEL_MINB
-#define COEB_SEL_MINB 3
+#define COEB_SEL_MINB 4
+#endif
+#ifndef COEB_SEL_THREADS_SMALL
+#define COEB_SEL_THREADS_SMALL 384
 #endif
 #ifndef COEB_SEL_GU
 #define COEB_SEL_GU 4   // candidates per thread in flight in the gather phase
@@ -89,9 +95,7 @@ __device__ __forceinline__ int block_flag_scan(int n, F flag, E emit, int (*s_cn
 
 extern __shared__ __align__(16) unsigned char s_dyn_raw[];
 
-// T = CTA size (compile-time, so that the scans' chunking is a multiply-shift). For a single frame a level is one CTA and the longest
-// one (level 0) sets the latency: 384, 512, 768 and 1024 threads were measured there and make no difference (151.5-152.3 us per
-// call): the passes are chains of barriers and shared-memory round trips, not thread-count bound.
+// T = CTA size (compile-time: the scans' warp loops unroll); see COEB_SEL_THREADS above for the two sizes in use.
 template <int T, int kMinBlocks>
 __global__ void __launch_bounds__(T, kMinBlocks) select_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v, const int level_lo) {
     const int level = level_lo + blockIdx.y, frame = blockIdx.x;   // level-major launch order: the long CTAs (level 0) start first, the short ones fill the tail
@@ -486,9 +490,11 @@ void launch_select(const Geometry& g, const BatchView& v, cudaStream_t stream, i
     size_t& done = configured[dev & 63];
     if (smem > done) {
         cudaFuncSetAttribute(select_kernel<kSelThreads, COEB_SEL_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(select_kernel<COEB_SEL_THREADS_SMALL, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         done = smem;
     }
-    select_kernel<kSelThreads, COEB_SEL_MINB><<<dim3(v.B, level_hi - level_lo), kSelThreads, smem, stream>>>(g, v, level_lo);
+    if (v.B <= 4) select_kernel<COEB_SEL_THREADS_SMALL, 3><<<dim3(v.B, level_hi - level_lo), COEB_SEL_THREADS_SMALL, smem, stream>>>(g, v, level_lo);
+    else select_kernel<kSelThreads, COEB_SEL_MINB><<<dim3(v.B, level_hi - level_lo), kSelThreads, smem, stream>>>(g, v, level_lo);
 }
 
 }  // namespace coeb
