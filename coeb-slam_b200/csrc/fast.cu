@@ -382,7 +382,10 @@ __global__ void __launch_bounds__(256) fast_empty_cells_kernel(const __grid_cons
 // 1b above) and the pixels above minTh are remembered, so that the cell-local 3x3 NMS only visits those. The per-warp shared
 // region is sized on the host from the largest cell of the geometry (a 640x480 pyramid needs 4.6 KB per warp, so that an SM
 // holds 40 such warps; the compile-time maximum would be 12 KB): the kernel is bound by load and shared-memory latency.
-constexpr int kFbWarps = 8;
+#ifndef COEB_FB_WARPS
+#define COEB_FB_WARPS 8
+#endif
+constexpr int kFbWarps = COEB_FB_WARPS;
 constexpr int kFbQueue = 192;             // survivor queue entries per warp, flushed before a step could overflow it
 constexpr int kFbList = 96;               // staged local maxima per warp, flushed to the level's list when nearly full
 constexpr int kFbCand = 160;              // remembered pixels above minTh per warp; more than that: the NMS scans the whole map

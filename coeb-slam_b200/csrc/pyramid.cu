@@ -24,8 +24,11 @@ namespace coeb {
 // thread), and h = a0*S[sx] + a1*S[sx+1] is one IDP.2A with the table's packed (a0, a1) halfwords as they are. Output
 // pixels 0,1 and 2,3 of a thread each share one pair of source words per source row.
 constexpr int kRzGroups = 16, kRzRowsPerBlock = 16;   // block = 16 four-pixel groups x 16 rows
+#ifndef COEB_RZ_MINB
+#define COEB_RZ_MINB 8   // 32 registers, full occupancy: pyramid 0.236 -> 0.230 ms (the kernel waits on loads)
+#endif
 template <int kResizeRows>
-__global__ void __launch_bounds__(256) resize_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v,
+__global__ void __launch_bounds__(256, COEB_RZ_MINB) resize_kernel(const __grid_constant__ Geometry g, const __grid_constant__ BatchView v,
                                                      int level) {
     COEB_TRACE(v, 8);
     const LevelGeom& D = g.lv[level];
