@@ -169,9 +169,27 @@ __device__ __forceinline__ float glibc_logf(float x) {   // normal positive x on
     return (float)y;
 }
 
+#ifdef COEB_KERNEL_TRACE
+// Development timeline (tools/build_trace.sh builds): first-CTA start / last-CTA end of the matcher kernels of one call, %globaltimer ns.
+// ids: 0 frame tail, 1 grid build, 2 frustum + collect, 3 m2 collect, 4 m2 resolve (marks 8..15 inside it), 5 m3 collect, 6 m3 resolve
+__device__ unsigned long long g_mtrace[32];
+struct MatchTrace {
+    int id; unsigned long long t0;
+    __device__ __forceinline__ static unsigned long long now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+    __device__ __forceinline__ MatchTrace(int i) : id(i), t0(0) { if (threadIdx.x == 0 && threadIdx.y == 0) t0 = now(); }
+    __device__ __forceinline__ ~MatchTrace() { if (threadIdx.x == 0 && threadIdx.y == 0) { atomicMin(&g_mtrace[2 * id], t0); atomicMax(&g_mtrace[2 * id + 1], now()); } }
+};
+#define COEB_MTRACE(id) MatchTrace coeb_match_trace_(id)
+#define COEB_MMARK(slot) do { if (threadIdx.x == 0) g_mtrace[16 + (slot)] = MatchTrace::now(); } while (0)
+#else
+#define COEB_MTRACE(id)
+#define COEB_MMARK(slot)
+#endif
+
 // ---- grid build (Frame::AssignFeaturesToGrid, src/Frame.cc:396-411) -------------------------------------
 // One CTA. Cells ix-major; items ascending by keypoint index (the reference pushes in index order).
 __global__ void __launch_bounds__(1024) grid_build_kernel(FrameDev f, int* cell_start, int* cell_items, int* kp_cell) {
+    COEB_MTRACE(1);
     __shared__ int s_cnt[kGridCells + 1];
     __shared__ int s_warp[33];
     const int tid = threadIdx.x, T = blockDim.x;
@@ -346,6 +364,7 @@ __device__ __forceinline__ void m2_collect_warp(const FrameDev& F, const MapDev&
 }
 
 __global__ void __launch_bounds__(256) m2_collect_kernel(FrameDev F, MapDev M, float th, const int* kp_state, CandLists C) {
+    COEB_MTRACE(3);
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (i >= M.n) return;
     m2_collect_warp(F, M, th, kp_state, C, i);
@@ -360,6 +379,7 @@ template <bool kLists>
 __global__ void __launch_bounds__(1024, 1) m2_resolve_kernel(FrameDev F, MapDev M, float th, float nnratio, const int* kp_state, CandLists C,
                                                           int* kp_match /*out: every entry written*/, int* res, int* claim_glob, int* out_info,
                                                           int claim_in_smem, int cache_cap /*active queries the dynamic shared memory can hold*/) {
+    COEB_MTRACE(4);
     __shared__ int s_changed, s_count, s_nslow;
     constexpr int kSlowCap = 1024;
     __shared__ int s_slow[kSlowCap];
@@ -405,7 +425,9 @@ __global__ void __launch_bounds__(1024, 1) m2_resolve_kernel(FrameDev F, MapDev 
         auto decide = [&](int bestDist, int bestLevel, int bestIdx, int bestDist2, int bestLevel2) {
             return (bestDist <= COEB_TH_HIGH && !(bestLevel == bestLevel2 && (float)bestDist > nnratio * (float)bestDist2)) ? bestIdx : -1;
         };
+        COEB_MMARK(0);   // active queries cached
         for (int round = 0; round <= M.n; round++) {
+            if (round < 6) COEB_MMARK(1 + round);
             for (int k = tid; k < F.n; k += T) claim_min[k] = kInf;
             if (tid == 0) { s_changed = 0; s_nslow = 0; }
             __syncthreads();
@@ -1278,6 +1300,7 @@ struct TailArgs {
 // UndistortKeyPoints + ComputeStereoFromRGBD (src/Frame.cc:579-609, 820-842): one thread per keypoint writes the SoA
 // the matchers read and the AoS the host downloads; the descriptor rows are copied as words.
 __global__ void __launch_bounds__(128) frame_tail_kernel(TailArgs a) {
+    COEB_MTRACE(0);
     const int n = a.n;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     for (int w = i; w < n * 8; w += gridDim.x * blockDim.x) a.desc_out[w] = a.desc[w];
@@ -1318,6 +1341,7 @@ struct MapFields {   // the MapPoint members isInFrustum writes, as device array
 // Mat::dot accumulate in double.
 __global__ void __launch_bounds__(256) frustum_collect_kernel(FrameDev F, LocalMapDev LM, PoseArgs P, const uint8_t* __restrict__ skip,
                                                               MapFields out, MapDev M, float th, const int* kp_state, CandLists C, float* proj_out) {
+    COEB_MTRACE(2);
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per map point: every lane evaluates the (cheap) frustum test
     if (i >= LM.n) return;
     const bool writer = (threadIdx.x & 31) == 0;
@@ -2383,6 +2407,27 @@ void coeb_local_map_destroy(coeb_local_map* lm) {
     delete lm;
 }
 
+#ifdef COEB_KERNEL_TRACE
+static void print_mtrace(const char* what) {
+    if (!getenv("COEB_KERNEL_TRACE")) return;
+    static const char* names[8] = {"frame tail", "grid build", "frustum+collect", "m2 collect", "m2 resolve", "m3 collect", "m3 resolve", ""};
+    unsigned long long t[32];
+    cudaMemcpyFromSymbol(t, g_mtrace, sizeof(t));
+    unsigned long long t0 = ~0ull;
+    for (int i = 0; i < 8; i++) if (t[2 * i + 1]) t0 = std::min(t0, t[2 * i]);
+    fprintf(stderr, "[coeb match kernels] %s:", what);
+    for (int i = 0; i < 8; i++) if (t[2 * i + 1]) fprintf(stderr, " %s %.1f-%.1f |", names[i], (double)(t[2 * i] - t0) * 1e-3, (double)(t[2 * i + 1] - t0) * 1e-3);
+    fprintf(stderr, " marks:");
+    for (int i = 16; i < 32; i++) if (t[i]) fprintf(stderr, " %.1f", (double)(t[i] - t0) * 1e-3);
+    fprintf(stderr, "\n");
+    unsigned long long init[32];
+    for (int i = 0; i < 32; i++) init[i] = (i < 16 && !(i & 1)) ? ~0ull : 0ull;
+    cudaMemcpyToSymbol(g_mtrace, init, sizeof(init));
+}
+#else
+static void print_mtrace(const char*) {}
+#endif
+
 int coeb_search_local_points(coeb_matcher* m, coeb_frame* F, coeb_local_map* lm, const uint8_t* skip, const uint8_t* has_obs,
                              const float* Tcw, const float* Ow, float viewing_cos_limit, float th, float nnratio, int* kp_match,
                              uint8_t* in_view_out, float* proj_out, int* nmatches_out) {
@@ -2454,6 +2499,7 @@ int coeb_search_local_points(coeb_matcher* m, coeb_frame* F, coeb_local_map* lm,
     if (in_view_out) std::memcpy(in_view_out, m->outm.h + al(K * 4) + 256, N);
     if (proj_out) std::memcpy(proj_out, m->outm.h + al(K * 4) + 256 + al(N), N * 20);
     if (nmatches_out) *nmatches_out = ((const int*)(m->outm.h + al(K * 4)))[0];
+    print_mtrace("SearchLocalPoints");
     return COEB_OK;
 }
 

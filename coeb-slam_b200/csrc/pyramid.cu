@@ -152,8 +152,6 @@ __global__ void __launch_bounds__(kPrThreads) pyramid_regions_kernel(const __gri
     extern __shared__ __align__(16) uint8_t pr_smem[];
     __shared__ PyrRegionLevel R[COEB_MAX_LEVELS];
     const int frame = blockIdx.y;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int kWarps = kPrThreads / 32;
     static_assert(sizeof(PyrRegionLevel) == 24, "copied as six words");
     // Global round trips are what this kernel's time is made of, so there are two: the region's rectangles, then -- all loads in
     // flight together -- the table slices of every level it touches and the level-0 rectangle. The level loop below only waits on
