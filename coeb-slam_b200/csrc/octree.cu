@@ -13,7 +13,11 @@
 //     every key finds its child independently and children are counted with shared-memory atomics;
 //   * node ids ARE list positions. A round (full or careful) turns the list L into
 //         reverse(children created this round, in creation order) ++ (L minus the split nodes)
-//     (children are push_front'ed as created, :630-667 / :698-733), which is two prefix sums;
+//     (children are push_front'ed as created, :630-667 / :698-733), which is prefix COUNTS of flags: taken with warp ballots,
+//     the three counts of a round packed into one word per warp, one barrier per scan (block_flag_scan and the round body);
+//   * per round a key makes two table look-ups: node id -> split lines (s_split, or "not split") gives its quadrant, then
+//     (node id, quadrant) -> position in the new list (s_newpos). Both tables are indexed by node id, written by the few threads
+//     that own nodes; the passes over the keys carry no slot indirection and no branch;
 //   * the careful phase's sort of (size, pointer) pairs (:691) uses the creation index as the second
 //     key (documented tie-break, identical to the CPU oracle) and is done by rank counting;
 //   * the per-node "best response, first key wins" (:748-766) is a 64-bit atomicMax on
