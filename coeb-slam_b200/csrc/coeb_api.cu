@@ -925,7 +925,8 @@ int coeb_extract_batch_host(coeb_extractor* ex, int B, const uint8_t* gray, int 
                     for (int part = 0; part < 2; part++) {
                         const int y0 = part * half, y1 = std::min(height, y0 + half);
                         if (y1 <= y0) break;
-                        if (stride == pitch) std::memcpy(ex->h_in1 + (size_t)y0 * pitch, gray + (size_t)y0 * stride, (size_t)(y1 - y0) * pitch);
+                        // (the caller's last row may end after `width` bytes: its padding is not read)
+                        if (stride == pitch) std::memcpy(ex->h_in1 + (size_t)y0 * pitch, gray + (size_t)y0 * stride, (size_t)(y1 - y0 - 1) * pitch + width);
                         else for (int y = y0; y < y1; y++) std::memcpy(ex->h_in1 + (size_t)y * pitch, gray + (size_t)y * stride, width);
                         cudaError_t e = cudaMemcpyAsync(ex->d_in_gray + (size_t)y0 * pitch, ex->h_in1 + (size_t)y0 * pitch, (size_t)(y1 - y0) * pitch, cudaMemcpyHostToDevice, cs);
                         if (e != cudaSuccess) return e;

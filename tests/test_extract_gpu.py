@@ -356,3 +356,26 @@ def test_single_frame_fast_paths_can_be_switched_off(gpu, switches):
     env = dict(os.environ, **{k: "1" for k in switches})
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0 and "switched path ok" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,stride", [(640, 704), (600, 640), (333, 400)])
+def test_single_frame_with_a_row_stride(gpu, w, stride):
+    """A cv::Mat ROI or an aligned allocation hands over rows that are `stride` bytes apart; the single-frame call stages them
+    into the arena pitch on the host. The buffer ends right after the last row's pixels (no trailing padding to read)."""
+    import ctypes as C
+    h = 257 if w == 333 else 480
+    img = synth.make_frame(77, w, h)
+    flat = np.zeros(stride * (h - 1) + w, np.uint8)   # exactly as long as the last pixel
+    rows = np.lib.stride_tricks.as_strided(flat, shape=(h, w), strides=(stride, 1))
+    rows[:] = img
+    ex = gpu.Extractor(800, 1.2, 8, 20, 7)
+    cap = ex.default_cap(w, h)
+    kps, desc, n = np.empty(cap, gpu.KP_DTYPE), np.empty((cap, 32), np.uint8), C.c_int()
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    for _ in range(3):   # eager calls, then the replayed graph
+        st = gpu.lib().coeb_extract(ex.h, P(flat), w, h, stride, None, 0, None, 0, None, 0, P(kps), P(desc), cap, C.byref(n))
+        assert st == 0
+        kc, dc = orc.Extractor(800, 1.2, 8, 20, 7).extract(img)
+        assert n.value == len(kc) and kps[:n.value].tobytes() == kc.tobytes() and np.array_equal(desc[:n.value], dc)
+    ex.close()
