@@ -388,6 +388,10 @@ __global__ void __launch_bounds__(256) fast_empty_cells_kernel(const __grid_cons
 constexpr int kFbWarps = COEB_FB_WARPS;
 constexpr int kFbQueue = 192;             // survivor queue entries per warp, flushed before a step could overflow it
 constexpr int kFbList = 96;               // staged local maxima per warp, flushed to the level's list when nearly full
+#ifndef COEB_FB_STRIPS
+#define COEB_FB_STRIPS 2
+#endif
+constexpr int kFbStrips = COEB_FB_STRIPS;   // small batches: horizontal strips per cell, one warp each
 constexpr int kFbCand = 160;              // remembered pixels above minTh per warp; more than that: the NMS scans the whole map
 struct FbLayout {
     int pw;        // staged row pitch in words: 1 pad + data words (3 lead-in + widest ROI + 3) + 1 pad
@@ -427,12 +431,18 @@ __global__ void __launch_bounds__(32 * kFbWarps) fast_fallback_kernel(const __gr
     unsigned short* const s_cand = reinterpret_cast<unsigned short*>(s_list + kFbList);
     const int PW = F.pw, AW = F.aw;
     const unsigned lt = (1u << lane) - 1u;
-    const int n_empty = kDirect ? v.B * (cell_hi - cell_lo) : *v.empty_count;
+    // kDirect also cuts a cell into kFbStrips horizontal strips, one warp each: a single frame has a few hundred empty cells and
+    // 148 SMs, and one warp's compass pass and exact scores of a whole 30 x 30 cell at minTh were 6.5 of the kernel's 10 us. A strip
+    // computes one more row above and below (the 3x3 NMS of its own rows reads them) and emits its own rows only; the warps never meet.
+    constexpr int kStrips = kDirect ? kFbStrips : 1;
+    const int n_empty = kDirect ? v.B * (cell_hi - cell_lo) * kStrips : *v.empty_count;
     for (int e = blockIdx.x * kFbWarps + warp; e < n_empty; e += gridDim.x * kFbWarps) {
-        int c;
+        int c, strip = 0;
         if (kDirect) {
-            const int f = e / (cell_hi - cell_lo);
-            c = f * g.cells_per_frame + cell_lo + (e - f * (cell_hi - cell_lo));
+            const int per_frame = (cell_hi - cell_lo) * kStrips;
+            const int f = e / per_frame, rem = e - f * per_frame;
+            strip = rem % kStrips;
+            c = f * g.cells_per_frame + cell_lo + rem / kStrips;
             if (v.cell_count[c] != 0) continue;
         } else {
             c = v.empty_cells[e];
@@ -444,10 +454,23 @@ __global__ void __launch_bounds__(32 * kFbWarps) fast_fallback_kernel(const __gr
         const int cell = cf - L.cell_base;
         const int ci = cell / L.nCols, cj = cell - ci * L.nCols;
         // cell ROI (src/ORBextractor.cc:813-828), level coordinates
-        const int iniX = kMinBorder + cj * L.wCell, iniY = kMinBorder + ci * L.hCell;
+        const int iniX = kMinBorder + cj * L.wCell;
+        int iniY = kMinBorder + ci * L.hCell;
         if (kDirect && (iniY >= L.maxBY - 3 || iniX >= L.maxBX - 6)) continue;   // cells the reference skips (:816-826)
-        const int rw = min(iniX + L.wCell + 6, L.maxBX) - iniX, rh = min(iniY + L.hCell + 6, L.maxBY) - iniY;
+        const int rw = min(iniX + L.wCell + 6, L.maxBX) - iniX;
+        int rh = min(iniY + L.hCell + 6, L.maxBY) - iniY;
         if (kDirect && (rw < 7 || rh < 7)) continue;
+        // rows of the cell's detection area this warp emits [y0, y1) and computes [cy0, cy0 + dh): the whole cell unless kDirect
+        int y0 = 0, y1 = rh - 6, cy0 = 0;
+        if (kStrips > 1) {
+            const int dh_cell = rh - 6;
+            y0 = strip * dh_cell / kStrips; y1 = (strip + 1) * dh_cell / kStrips;
+            if (y1 <= y0) continue;
+            cy0 = max(0, y0 - 1);
+            const int cy1 = min(dh_cell, y1 + 1);
+            iniY += cy0;               // the strip is staged and scored like a short cell of its own
+            rh = cy1 - cy0 + 6;
+        }
         const int dw = rw - 6, dh = rh - 6;          // detection area: ROI rows/cols [3, dim-3)
         const int thMin = v.dyn[frame].area_flag ? 10 : 7;
         const int pitch = level_pitch(g, v, level);
@@ -570,10 +593,11 @@ __global__ void __launch_bounds__(32 * kFbWarps) fast_fallback_kernel(const __gr
                     keep = A > nb;
                 }
             }
+            if (kStrips > 1 && keep) { const int row = id / AW + cy0; keep = row >= y0 && row < y1; }   // halo rows belong to the neighbouring strip
             const unsigned mk = __ballot_sync(0xffffffffu, keep);
             if (keep) {
                 const int dy = id / AW, col = id - dy * AW;
-                const int px = (col - aoff) + 3 + cj * L.wCell, py = dy + 3 + ci * L.hCell;   // minBorder-relative (:844-845)
+                const int px = (col - aoff) + 3 + cj * L.wCell, py = dy + cy0 + 3 + ci * L.hCell;   // minBorder-relative (:844-845)
                 s_list[n_out + __popc(mk & lt)] = (uint32_t)px | ((uint32_t)py << 12) | ((uint32_t)(A - 1) << 24);
             }
             n_out += __popc(mk);
@@ -699,7 +723,7 @@ void launch_fast_tail_levels(const Geometry& g, const BatchView& v, cudaStream_t
     const int cell_lo = g.lv[level_lo].cell_base, cell_hi = level_hi < g.nlevels ? g.lv[level_hi].cell_base : g.cells_per_frame;
     const FbLayout F = fb_layout(g);
     const size_t smem = fallback_smem(F);
-    const int warps = v.B * (cell_hi - cell_lo);
+    const int warps = v.B * (cell_hi - cell_lo) * kFbStrips;
     fast_fallback_kernel<true><<<(warps + kFbWarps - 1) / kFbWarps, 32 * kFbWarps, smem, stream>>>(g, v, F, cell_lo, cell_hi);
 }
 
