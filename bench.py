@@ -397,23 +397,27 @@ def run_b200(args):
     o_st, p4 = cb.pinned_array((B,), np.int32)
     owners += [p1, p2, p3, p4]
 
-    # Two batches in flight: one handle (own streams, arenas and staging) per host thread, alternating steps, so the H2D
-    # copy of one batch overlaps the kernels and the D2H copy of the other (each call is blocking; ctypes drops the GIL).
+    # Several batches in flight (--e2e-lanes, default 3): one handle (own streams, arenas and staging) per host thread, so the H2D
+    # copy of one batch overlaps the kernels and the D2H copy of the others (each call is blocking; ctypes drops the GIL). Two lanes
+    # already run at the copy ceiling on a quiet host (172.0 k frames/s, three: 172.1 k, four: 169.7 k; 8 GPUs: 476.0 k / 475.1 k);
+    # the third keeps the copy engine fed when a host thread is late (one run on a noisy box fell to 132 k with two).
     import threading
     lanes = [(ex, pin, (o_kps, o_desc, o_cnt, o_st))]
-    ex_b = cb.Extractor(NFEAT, 1.2, NLEVELS, 20, 7, device=dev)
-    pin_b = {}
-    for k in pin:
-        arr, own = cb.pinned_array(pin[k].shape, pin[k].dtype)
-        arr[...] = pin[k]
-        pin_b[k] = arr
-        owners.append(own)
-    outs_b = []
-    for shape, dt in (((B, cap), cb.KP_DTYPE), ((B, cap, 32), np.uint8), ((B,), np.int32), ((B,), np.int32)):
-        arr, own = cb.pinned_array(shape, dt)
-        outs_b.append(arr)
-        owners.append(own)
-    lanes.append((ex_b, pin_b, tuple(outs_b)))
+    n_lanes = max(2, int(args.e2e_lanes))
+    for _ in range(n_lanes - 1):
+        ex_b = cb.Extractor(NFEAT, 1.2, NLEVELS, 20, 7, device=dev)
+        pin_b = {}
+        for k in pin:
+            arr, own = cb.pinned_array(pin[k].shape, pin[k].dtype)
+            arr[...] = pin[k]
+            pin_b[k] = arr
+            owners.append(own)
+        outs_b = []
+        for shape, dt in (((B, cap), cb.KP_DTYPE), ((B, cap, 32), np.uint8), ((B,), np.int32), ((B,), np.int32)):
+            arr, own = cb.pinned_array(shape, dt)
+            outs_b.append(arr)
+            owners.append(own)
+        lanes.append((ex_b, pin_b, tuple(outs_b)))
 
     def step_host(lane):
         e, pn, out = lanes[lane]
@@ -430,15 +434,16 @@ def run_b200(args):
             step_host(lane)
 
     for _ in range(max(1, min(args.warmup, 3))):
-        step_host(0)
-        step_host(1)
+        for ln in range(n_lanes):
+            step_host(ln)
     barrier()
     h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2e_steps = max(2, min(args.steps, args.e2e_steps))
-    e2e_steps -= e2e_steps % 2
+    e2e_steps -= e2e_steps % n_lanes
+    e2e_steps = max(e2e_steps, n_lanes)
     t0 = time.perf_counter()
     h0.record(stream)
-    workers = [threading.Thread(target=run_lane, args=(i, e2e_steps // 2)) for i in range(2)]
+    workers = [threading.Thread(target=run_lane, args=(i, e2e_steps // n_lanes)) for i in range(n_lanes)]
     for w in workers:
         w.start()
     for w in workers:
@@ -449,8 +454,9 @@ def run_b200(args):
     e2e_ms = reduce_max(dist, h0.elapsed_time(h1))  # device time between the bracketing events, max over ranks
     e2e_wall_ms = reduce_max(dist, wall * 1e3)
     e2e_frames = reduce_sum(dist, float(B * e2e_steps))
-    assert np.array_equal(o_cnt, counts) and np.array_equal(outs_b[2], counts), "host-path and device-path keypoint counts differ"
-    assert o_kps.tobytes() == outs_b[0].tobytes() and o_desc.tobytes() == outs_b[1].tobytes(), "the two in-flight lanes disagree"
+    for _, _, ob in lanes[1:]:
+        assert np.array_equal(o_cnt, counts) and np.array_equal(ob[2], counts), "host-path and device-path keypoint counts differ"
+        assert o_kps.tobytes() == ob[0].tobytes() and o_desc.tobytes() == ob[1].tobytes(), "the in-flight lanes disagree"
     h2d = sum(int(pin[k].nbytes) for k in pin)
     d2h = int(o_kps.nbytes + o_desc.nbytes + o_cnt.nbytes + o_st.nbytes)
     # the copy ceiling of this box at this N: plain pinned cudaMemcpyAsync of one step's frames on every rank at once, with the
@@ -605,7 +611,7 @@ def run_b200(args):
         "config": base_config(world), "mean_keypoints": n_kp,
         "e2e": {"value": e2e_frames / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "wall_frames_per_s": e2e_frames / (e2e_wall_ms * 1e-3),
-                "in_flight": "2 batches: one handle per host thread, blocking coeb_extract_batch_host calls, alternating steps",
+                "in_flight": "%d batches: one handle per host thread, blocking coeb_extract_batch_host calls, alternating steps" % n_lanes,
                 "copy_ceiling_GBps": probe_gbs, "frac_of_copy_ceiling": (e2e_frames / (e2e_ms * 1e-3)) * (h2d / B) / 1e9 / probe_gbs,
                 "copy_ceiling_note": "tools/h2d_probe.py run in-line: pinned cudaMemcpyAsync of one step's frames on all %d GPUs at once, "
                                      "D2H of the result size the other way" % world,
@@ -861,6 +867,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--unique", type=int, default=64, help="distinct generated images per shard (the rest are shifted copies)")
     ap.add_argument("--e2e-steps", type=int, default=60)
+    ap.add_argument("--e2e-lanes", type=int, default=3, help="batches in flight in the end-to-end region (one handle and host thread each)")
     ap.add_argument("--cpu-frames", type=int, default=128, help="frames of the shard timed on the host cores (CPU baseline)")
     ap.add_argument("--ref-frames", type=int, default=FRAMES_PER_GPU, help="--impl reference: frames per step (default: the whole 256-frame shard)")
     ap.add_argument("--stage-sync", action="store_true")
