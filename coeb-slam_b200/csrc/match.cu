@@ -181,9 +181,12 @@ struct MatchTrace {
 };
 #define COEB_MTRACE(id) MatchTrace coeb_match_trace_(id)
 #define COEB_MMARK(slot) do { if (threadIdx.x == 0) g_mtrace[16 + (slot)] = MatchTrace::now(); } while (0)
+__device__ int g_mstat[16];   // resolve kernel: [0] active queries, [1 + round] queries whose deciding entries were claimed (slow path)
+#define COEB_MSTAT(slot, val) do { if (threadIdx.x == 0 && (slot) < 16) g_mstat[slot] = (val); } while (0)
 #else
 #define COEB_MTRACE(id)
 #define COEB_MMARK(slot)
+#define COEB_MSTAT(slot, val)
 #endif
 
 // ---- grid build (Frame::AssignFeaturesToGrid, src/Frame.cc:396-411) -------------------------------------
@@ -258,7 +261,11 @@ struct CandLists {
     int* meta;     // [0] number of active queries, [1] some list overflowed its capacity. Zero before the collect kernel: a fixed
                    // per-matcher word pair that the (single-CTA) resolve kernel clears again once it has read it -- no memset node per call
     int* top;      // [n] list positions of the two smallest (distance, position) entries: best | second << 16 (0xFFFF = none); M2 only
+    int4* rec;     // [n] M2 only, indexed like `active`: {query | kNoObsBit, best entry .x, second entry .x or -1, best distance | second
+                   // distance << 9 | min(count, 255) << 18}: everything the resolve kernel caches per query, as one coalesced 16-byte load
+                   // (fetched through active -> top / count / has_obs -> items, ~5 scattered sectors per query, one SM needed 4 us per 1000 queries)
 };
+constexpr int kNoObsBit = 0x40000000;   // query ids in the resolve kernels: Observations() == 0, its claims do not block (:87-89)
 
 // Lane 0 of the collecting warp records the query's candidate count.
 __device__ __forceinline__ void cand_finish(const CandLists& C, int i, int cnt) {
@@ -281,6 +288,12 @@ __device__ __forceinline__ void walk_list(const int2* __restrict__ it, int n, Fn
             if (c0 + u < n) fn(e[u]);
     }
 }
+
+// Programmatic dependent launch (sm_90+): a collect kernel lets the dependent resolve kernel be scheduled as soon as every CTA of
+// the collect grid has started; the resolve kernel waits (for completion and visibility of the whole collect grid) before it reads.
+// Both are no-ops for launches without the programmatic-serialisation attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---- M2: SearchByProjection(Frame&, vector<MapPoint*>&, th) (src/ORBmatcher.cc:45-129) -------------------
 struct MapDev {
@@ -324,11 +337,13 @@ __device__ __forceinline__ bool m2_query(const FrameDev& F, const MapDev& M, flo
     return true;
 }
 // One warp per map point: the window's keypoints are tested 32 at a time, the survivors written in traversal order.
-__device__ __forceinline__ void m2_collect_warp(const FrameDev& F, const MapDev& M, float th, const int* __restrict__ kp_state, const CandLists& C, int i) {
-    M2Query q;
+// `valid` / `q`: the query's static part (m2_query), `obs`: Observations() > 0.
+__device__ __forceinline__ void m2_collect_query(const FrameDev& F, const int* __restrict__ kp_state, const CandLists& C, int i, bool valid, const M2Query& q,
+                                                 bool obs) {
     int cnt = 0;
     unsigned k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;   // this lane's two smallest distance << 16 | list position
-    if (m2_query(F, M, th, i, q)) {
+    int k1x = -1, k2x = -1;                        // ... and their entries' .x (keypoint | octave << 24)
+    if (valid) {
         int2* out = C.items + (size_t)i * C.cap;
         cnt = warp_for_each_in_area(
             F, q.x, q.y, q.rs, q.lvl - 1, q.lvl,
@@ -343,9 +358,10 @@ __device__ __forceinline__ void m2_collect_warp(const FrameDev& F, const MapDev&
             [&](int pos, int idx) {
                 if (pos < C.cap) {
                     const int dist = hamming256(q.d, F.desc + 8 * (size_t)idx);
-                    out[pos] = make_int2(idx | (F.octave[idx] << 24), dist);
+                    const int ex = idx | (F.octave[idx] << 24);
+                    out[pos] = make_int2(ex, dist);
                     const unsigned key = ((unsigned)dist << 16) | (unsigned)pos;
-                    if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
+                    if (key < k1) { k2 = k1; k2x = k1x; k1 = key; k1x = ex; } else if (key < k2) { k2 = key; k2x = ex; }
                 }
             });
     }
@@ -354,17 +370,41 @@ __device__ __forceinline__ void m2_collect_warp(const FrameDev& F, const MapDev&
     unsigned b1 = k1;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) b1 = min(b1, __shfl_xor_sync(0xffffffffu, b1, o));
-    unsigned b2 = (k1 == b1) ? k2 : k1;
+    const unsigned c2 = (k1 == b1) ? k2 : k1;
+    const int c2x = (k1 == b1) ? k2x : k1x;
+    unsigned b2 = c2;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) b2 = min(b2, __shfl_xor_sync(0xffffffffu, b2, o));
+    // keys carry their list position, so each winner sits in exactly one lane
+    const int x1 = __shfl_sync(0xffffffffu, k1x, __ffs(__ballot_sync(0xffffffffu, k1 == b1)) - 1);
+    const int x2 = __shfl_sync(0xffffffffu, c2x, __ffs(__ballot_sync(0xffffffffu, c2 == b2)) - 1);
     if ((threadIdx.x & 31) == 0) {
         if (C.top) C.top[i] = (int)((b1 & 0xFFFFu) | ((b2 == 0xFFFFFFFFu ? 0xFFFFu : (b2 & 0xFFFFu)) << 16));
-        cand_finish(C, i, cnt);
+        C.count[i] = cnt;
+        // A query whose smallest distance exceeds TH_HIGH can never match, whatever the other queries claim (exclusions only raise
+        // its best distance, :115), and so never claims either: it is not handed to the resolve kernel at all. (On the benchmark's
+        // map four of five queries with candidates are of this kind, and the resolve kernel's warps ran 5.6 live lanes of 32.)
+        if (cnt > 0 && (b1 >> 16) <= (unsigned)COEB_TH_HIGH) {
+            const int a = atomicAdd(&C.meta[0], 1);
+            C.active[a] = i;
+            if (C.rec) {
+                const int d1 = (int)min(b1 >> 16, 256u), d2 = (int)min(b2 >> 16, 256u);   // (no key: 0xFFFF -> 256, "none")
+                C.rec[a] = make_int4(obs ? i : (i | kNoObsBit), x1, d2 < 256 ? x2 : -1, d1 | (d2 << 9) | (min(cnt, 255) << 18));
+            }
+        }
+        if (cnt > C.cap) C.meta[1] = 1;
     }
+}
+__device__ __forceinline__ void m2_collect_warp(const FrameDev& F, const MapDev& M, float th, const int* __restrict__ kp_state, const CandLists& C, int i) {
+    M2Query q;
+    const bool obs = M.has_obs[i] != 0;
+    const bool valid = m2_query(F, M, th, i, q);
+    m2_collect_query(F, kp_state, C, i, valid, q, obs);
 }
 
 __global__ void __launch_bounds__(256) m2_collect_kernel(FrameDev F, MapDev M, float th, const int* kp_state, CandLists C) {
     COEB_MTRACE(3);
+    pdl_launch_dependents();   // the resolve kernel may take its SM and run its prologue now; it waits for this grid before reading
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (i >= M.n) return;
     m2_collect_warp(F, M, th, kp_state, C, i);
@@ -375,16 +415,19 @@ __global__ void __launch_bounds__(256) m2_collect_kernel(FrameDev F, MapDev M, f
 // The claim table (one int per keypoint of the frame) lives in shared memory when it fits: dynamic shared memory = F.n ints, else 0
 // and the global scratch array is used.
 extern __shared__ __align__(16) int s_claim_dyn[];
-template <bool kLists>
+// kSmem (the claim table's address space) is a template argument: behind a run-time choice of pointer every access to the table is a
+// GENERIC load / store / atomic (ATOM.E.MIN on a shared-memory address), several times the cost of LDS / ATOMS.
+template <bool kLists, bool kSmem>
 __global__ void __launch_bounds__(1024, 1) m2_resolve_kernel(FrameDev F, MapDev M, float th, float nnratio, const int* kp_state, CandLists C,
                                                           int* kp_match /*out: every entry written*/, int* res, int* claim_glob, int* out_info,
-                                                          int claim_in_smem, int cache_cap /*active queries the dynamic shared memory can hold*/) {
+                                                          int cache_cap /*active queries the dynamic shared memory can hold*/) {
+    constexpr bool claim_in_smem = kSmem;
     COEB_MTRACE(4);
     __shared__ int s_changed, s_count, s_nslow;
     constexpr int kSlowCap = 1024;
     __shared__ int s_slow[kSlowCap];
     const int tid = threadIdx.x, T = blockDim.x;
-    int* const claim_min = claim_in_smem ? s_claim_dyn : claim_glob;
+    int* const claim_min = kSmem ? s_claim_dyn : claim_glob;
     const int na = kLists ? C.meta[0] : M.n;
     const bool overflow = kLists && C.meta[1];
     if (kLists) {   // every thread has read the two words: cleared for the next call's collect kernel
@@ -426,6 +469,7 @@ __global__ void __launch_bounds__(1024, 1) m2_resolve_kernel(FrameDev F, MapDev 
             return (bestDist <= COEB_TH_HIGH && !(bestLevel == bestLevel2 && (float)bestDist > nnratio * (float)bestDist2)) ? bestIdx : -1;
         };
         COEB_MMARK(0);   // active queries cached
+        COEB_MSTAT(0, na);
         for (int round = 0; round <= M.n; round++) {
             if (round < 6) COEB_MMARK(1 + round);
             for (int k = tid; k < F.n; k += T) claim_min[k] = kInf;
@@ -464,6 +508,7 @@ __global__ void __launch_bounds__(1024, 1) m2_resolve_kernel(FrameDev F, MapDev 
                 // those no earlier map point claims are found with two warp reductions. A lane holds entries lane and lane + 32 (lists have
                 // at most 64 entries); the lists of a warp's next query are already in flight while the current one is reduced.
                 const int ns = min(s_nslow, kSlowCap);
+                COEB_MSTAT(1 + round, s_nslow);
                 auto fetch = [&](int k, int& i, int& n, int2& ea, int2& eb) {
                     i = -1; n = 0; ea = eb = make_int2(0, 256);
                     if (k < ns) {
@@ -575,6 +620,224 @@ __global__ void __launch_bounds__(1024, 1) m2_resolve_kernel(FrameDev F, MapDev 
     for (int k = tid; k < F.n; k += T)
         kp_match[k] = claim_min[k] >= 0 ? claim_min[k] : kp_state[k];   // untouched entries keep the caller's state
     if (tid == 0) { out_info[0] = s_count; out_info[2] = 0; }
+}
+
+// Cached form of the fixed-point iteration above for maps whose active queries all fit in shared memory (the host checks that
+// M.n <= cache_cap before choosing it), re-cut for the latency of ONE call (SearchLocalPoints runs once per tracked frame). The
+// kernel is one CTA on one SM, and what bounds it there is that SM's issue rate (32 warps, 4 instructions per clock), not latency:
+//   * launched with programmatic stream serialisation: the CTA is resident and has initialised its tables while the collect
+//     kernel still runs (griddepcontrol.wait orders every read of the collect kernel's output);
+//   * round 0 (no claims yet: every query decides from its two smallest entries) is fused into the caching pass;
+//   * three claim tables rotate (read X = claims of R_t, write Y = claims of R_t+1 as each query decides, reset Z), so a round
+//     is two barriers instead of five: decide | claimed queries | __syncthreads_or(changed);
+//   * a query whose deciding entries were claimed once stays queued (its evaluation there is exact whether or not the claim
+//     persists), so its queue position is stable: a list of up to kSl entries (nearly all of them: a window holds a handful of
+//     keypoints) is copied to shared memory once and walked by ONE thread per round in the reference's order -- a warp per
+//     query spent ~100 instructions per query and round on reductions over mostly empty lanes, 3 of a round's 4.3 us.
+//     Longer lists keep the warp-per-query form.
+constexpr int kSl = 8;   // entries of a short list
+template <bool kSmem>
+__global__ void __launch_bounds__(1024, 1) m2_resolve_cached_kernel(int Fn, int Mn, float nnratio, const int* __restrict__ kp_state, CandLists C,
+                                                                 int* kp_match, int* claim_glob, int* out_info, int cache_cap, int slow_cap,
+                                                                 const uint4* __restrict__ flags_dev, uint4* flags_host, int flags_vec) {
+    constexpr bool claim_in_smem = kSmem;
+    COEB_MTRACE(4);
+    constexpr int kLongCap = 256, kSlowBit = 0x20000000, kIdMask = 0x1FFFFFFF;
+    __shared__ int s_nslow, s_nlong, s_count;
+    __shared__ int s_slow[1024], s_long[kLongCap];
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+    int* const tab = kSmem ? s_claim_dyn : claim_glob;   // three claim tables of Fn ints
+    const int tab_ints = claim_in_smem ? 3 * Fn : 0;
+    int* const qi = s_claim_dyn + tab_ints;
+    int* const qres = qi + cache_cap;
+    int2* const q1 = reinterpret_cast<int2*>(qres + cache_cap + ((tab_ints + 2 * cache_cap) & 1));   // 8-byte aligned
+    int2* const q2 = q1 + cache_cap;
+    unsigned char* const qcnt = reinterpret_cast<unsigned char*>(q2 + cache_cap);   // list lengths (at most C.cap <= 64)
+    int2* const sl = reinterpret_cast<int2*>(qcnt + ((cache_cap + 7) & ~7));        // [kSl][slow_cap]: entry u of queued query k
+    slow_cap = min(slow_cap, 1024);
+    for (int k = tid; k < 3 * Fn; k += T) tab[k] = kInf;
+    if (tid == 0) { s_nslow = 0; s_nlong = 0; }
+    COEB_MMARK(12);
+    pdl_wait();   // the collect kernel has finished and its lists are visible
+    COEB_MMARK(13);
+    // SearchLocalPoints: the visibility flags the collect kernel left in device memory travel to the caller's (mapped) array from
+    // here, as 16-byte posted writes that overlap the rounds below. Written by the collect kernel itself they were 5000 one-byte
+    // writes across PCIe that its completion, and so this kernel's start, waited 3-4 us for.
+    for (int k = tid; k < flags_vec; k += T) flags_host[k] = flags_dev[k];
+    const int na = C.meta[0];
+    const bool overflow = C.meta[1] != 0 || na > cache_cap;
+    __syncthreads();   // every thread has read the two words: cleared for the next call's collect kernel
+    COEB_MMARK(14);
+    if (tid == 0) { C.meta[0] = 0; C.meta[1] = 0; }
+    if (overflow) {   // a list overflowed: report and let the host rerun the window-walking variant
+        if (tid == 0) { out_info[0] = 0; out_info[1] = 0; out_info[2] = 1; }
+        return;
+    }
+    auto decide = [&](int bestDist, int bestLevel, int bestIdx, int bestDist2, int bestLevel2) {
+        return (bestDist <= COEB_TH_HIGH && !(bestLevel == bestLevel2 && (float)bestDist > nnratio * (float)bestDist2)) ? bestIdx : -1;
+    };
+    // caching pass + round 0: R_1 = F(nothing claimed); its claims go to table 0
+    for (int a = tid; a < na; a += T) {
+        const int4 r = C.rec[a];
+        const int iq = r.x, d2 = (r.w >> 9) & 511;
+        const int2 e1 = make_int2(r.y, r.w & 511);
+        const int2 e2 = (r.z < 0 || d2 >= 256) ? make_int2(-1, 256) : make_int2(r.z, d2);   // (a distance of 256 never enters, :100)
+        const int out = e1.y <= COEB_TH_HIGH ? decide(e1.y, e1.x >> 24, e1.x & 0xFFFFFF, e2.y, e2.x < 0 ? -1 : (e2.x >> 24)) : -1;
+        qi[a] = iq;
+        qres[a] = out;
+        q1[a] = e1;
+        q2[a] = e2;
+        qcnt[a] = (unsigned char)(r.w >> 18);
+        if (out >= 0 && !(iq & kNoObsBit)) atomicMin(&tab[out], iq & kIdMask);
+    }
+    COEB_MMARK(0);   // active queries cached, round 0 done
+    COEB_MSTAT(0, na);
+#ifdef COEB_KERNEL_TRACE
+    const long long trace_c0 = clock64();
+#endif
+    __syncthreads();
+    int ns_loaded = 0, round = 1;
+    for (;; round++) {
+        if (round < 7) COEB_MMARK(round);
+        const int* const X = tab + ((round - 1) % 3) * Fn;
+        int* const Y = tab + (round % 3) * Fn;
+        int* const Z = tab + ((round + 1) % 3) * Fn;
+        bool changed_here = false;
+        auto settle = [&](int a, int iq, int out) {   // R_t+1 of query a, and its claim on behalf of the next round
+            if (out != qres[a]) { qres[a] = out; changed_here = true; }
+            if (out >= 0 && !(iq & kNoObsBit)) atomicMin(&Y[out], iq & kIdMask);
+        };
+        for (int k = tid; k < Fn; k += T) Z[k] = kInf;   // read last in the previous round, written next in the following one
+        if (round == 2) COEB_MMARK(8);
+        for (int a = tid; a < na; a += T) {
+            const int iq = qi[a];
+            if (iq & kSlowBit) continue;
+            const int2 e1 = q1[a];
+            if (e1.y > COEB_TH_HIGH) continue;   // exclusions can only raise the best distance: stays -1
+            const int i = iq & kIdMask;
+            const int2 e2 = q2[a];
+            int out;
+            const int c1 = X[e1.x & 0xFFFFFF], c2 = X[max(e2.x, 0) & 0xFFFFFF];   // both look-ups in flight
+            if (c1 >= i && (e2.x < 0 || c2 >= i)) {
+                out = decide(e1.y, e1.x >> 24, e1.x & 0xFFFFFF, e2.y, e2.x < 0 ? -1 : (e2.x >> 24));   // every other exclusion leaves these two in place
+            } else {
+                if ((int)qcnt[a] <= kSl) {
+                    const int k = atomicAdd(&s_nslow, 1);
+                    if (k < slow_cap) { s_slow[k] = a; qi[a] = iq | kSlowBit; continue; }
+                } else {
+                    const int k = atomicAdd(&s_nlong, 1);
+                    if (k < kLongCap) { s_long[k] = a; qi[a] = iq | kSlowBit; continue; }
+                }
+                int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;   // queue full: walked in place
+                walk_list(C.items + (size_t)i * C.cap, C.count[i], [&](const int2 e) {
+                    const int idx = e.x & 0xFFFFFF, dist = e.y, oct = e.x >> 24;
+                    if (X[idx] < i) return;   // claimed earlier in this call by a MapPoint with observations (:87-89, :123)
+                    if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = oct; bestIdx = idx; }
+                    else if (dist < bestDist2) { bestLevel2 = oct; bestDist2 = dist; }
+                });
+                out = decide(bestDist, bestLevel, bestIdx, bestDist2, bestLevel2);
+            }
+            settle(a, iq, out);
+        }
+        if (round == 2) COEB_MMARK(9);
+        __syncthreads();
+        if (round == 2) COEB_MMARK(10);
+        const int ns = min(s_nslow, slow_cap), nl = min(s_nlong, kLongCap);
+        COEB_MSTAT(round, s_nslow + s_nlong);
+        // short lists: one thread per queued query walks its entries in list order, exactly the loop of :84-113
+        for (int k = tid; k < ns; k += T) {
+            const int a = s_slow[k];
+            const int iq = qi[a], i = iq & kIdMask, n = qcnt[a];
+            int2 e[kSl];
+            if (k >= ns_loaded) {   // queued in this round: fetch the list (all entries in flight) and keep it
+                const int2* it = C.items + (size_t)i * C.cap;
+#pragma unroll
+                for (int u = 0; u < kSl; u++) e[u] = it[min(u, n - 1)];
+#pragma unroll
+                for (int u = 0; u < kSl; u++) sl[u * slow_cap + k] = e[u];
+            } else {
+#pragma unroll
+                for (int u = 0; u < kSl; u++) e[u] = sl[u * slow_cap + k];
+            }
+            // the walk of :84-113 without branches (the claim look-ups are independent loads, the bookkeeping a chain of selects; the
+            // branchy form cost a dependent look-up and two branch resolutions per entry, and 24 of the 32 warps wait for this loop)
+            int claim[kSl];
+#pragma unroll
+            for (int u = 0; u < kSl; u++) claim[u] = X[e[u].x & 0xFFFFFF];
+            int bestDist = 256, bestX = -1, bestDist2 = 256, bestLevel2 = -1;   // bestX: keypoint | level << 24 of the best entry
+#pragma unroll
+            for (int u = 0; u < kSl; u++) {
+                const int dist = (u < n && claim[u] >= i) ? e[u].y : 256;   // an entry that is skipped behaves like distance 256: never enters
+                const bool lt1 = dist < bestDist, lt2 = dist < bestDist2;
+                bestLevel2 = lt1 ? (bestX >> 24) : (lt2 ? (e[u].x >> 24) : bestLevel2);
+                bestDist2 = lt1 ? bestDist : (lt2 ? dist : bestDist2);
+                bestX = lt1 ? e[u].x : bestX;
+                bestDist = lt1 ? dist : bestDist;
+            }
+            settle(a, iq, decide(bestDist, bestX >> 24, bestX < 0 ? -1 : (bestX & 0xFFFFFF), bestDist2, bestLevel2));
+        }
+        ns_loaded = ns;
+        if (round == 2) COEB_MMARK(11);
+        if (nl > 0) {   // long lists: one warp per queued query; its entries are tested side by side and the two smallest (distance, position)
+                        // keys among those no earlier map point claims are found with two warp reductions. A lane holds entries lane and lane + 32.
+            auto fetch = [&](int k, int& a, int2& ea, int2& eb) {   // the next query's list is in flight while the current one is reduced
+                a = 0; ea = eb = make_int2(0, 256);
+                if (k < nl) {
+                    a = s_long[k];
+                    const int n = qcnt[a];
+                    const int2* it = C.items + (size_t)(qi[a] & kIdMask) * C.cap;
+                    if (lane < n) ea = it[lane];
+                    if (lane + 32 < n) eb = it[lane + 32];
+                }
+            };
+            int a, a_nx;
+            int2 ea, eb, ea_nx, eb_nx;
+            fetch(warp, a, ea, eb);
+            for (int k = warp; k < nl; k += nwarps) {
+                fetch(k + nwarps, a_nx, ea_nx, eb_nx);
+                const int iq = qi[a], i = iq & kIdMask, n = qcnt[a];
+                const bool oka = lane < n && ea.y < 256 && X[ea.x & 0xFFFFFF] >= i;
+                const bool okb = lane + 32 < n && eb.y < 256 && X[eb.x & 0xFFFFFF] >= i;
+                const unsigned ka = oka ? (((unsigned)ea.y << 16) | (unsigned)lane) : 0xFFFFFFFFu;
+                const unsigned kb = okb ? (((unsigned)eb.y << 16) | (unsigned)(lane + 32)) : 0xFFFFFFFFu;
+                const unsigned k1 = min(ka, kb), k2 = max(ka, kb);
+                const unsigned b1 = __reduce_min_sync(0xffffffffu, k1);
+                const unsigned b2 = __reduce_min_sync(0xffffffffu, (k1 == b1) ? k2 : k1);
+                const int l1 = (int)(b1 & 31u), l2 = (int)(b2 & 31u);   // the winners' entries come from the lanes that hold them
+                const int x1a = __shfl_sync(0xffffffffu, ea.x, l1), x1b = __shfl_sync(0xffffffffu, eb.x, l1);
+                const int x2a = __shfl_sync(0xffffffffu, ea.x, l2), x2b = __shfl_sync(0xffffffffu, eb.x, l2);
+                if (lane == 0) {
+                    int out = -1;
+                    if (b1 != 0xFFFFFFFFu) {
+                        const int x1 = (b1 & 32u) ? x1b : x1a;
+                        int d2 = 256, lv2 = -1;
+                        if (b2 != 0xFFFFFFFFu) { d2 = (int)(b2 >> 16); lv2 = ((b2 & 32u) ? x2b : x2a) >> 24; }
+                        out = decide((int)(b1 >> 16), x1 >> 24, x1 & 0xFFFFFF, d2, lv2);
+                    }
+                    settle(a, iq, out);
+                }
+                a = a_nx; ea = ea_nx; eb = eb_nx;
+            }
+        }
+        if (round == 2) COEB_MMARK(15);
+        if (!__syncthreads_or(changed_here) || round > Mn) break;
+    }
+#ifdef COEB_KERNEL_TRACE
+    COEB_MMARK(7);   // rounds done
+    COEB_MSTAT(12, (int)(clock64() - trace_c0));   // SM cycles between mark 0 and mark 7
+#endif
+    // F.mvpMapPoints[bestIdx] = pMP in query order: the last writer wins; every success counts (:123-124)
+    if (tid == 0) s_count = 0;
+    for (int k = tid; k < Fn; k += T) tab[k] = -1;   // "last claimant"
+    __syncthreads();
+    int mine = 0;
+    for (int a = tid; a < na; a += T)
+        if (qres[a] >= 0) { atomicMax(&tab[qres[a]], qi[a] & kIdMask); mine++; }
+    if (mine) atomicAdd(&s_count, mine);
+    __syncthreads();
+    for (int k = tid; k < Fn; k += T)
+        kp_match[k] = tab[k] >= 0 ? tab[k] : kp_state[k];   // untouched entries keep the caller's state
+    if (tid == 0) { out_info[0] = s_count; out_info[1] = round + 1; out_info[2] = 0; }
 }
 
 // ---- M5: ComputeThreeMaxima (src/ORBmatcher.cc:1602-1643) ------------------------------------------------------
@@ -702,14 +965,15 @@ __global__ void __launch_bounds__(256) m3_collect_kernel(FrameDev Cf, LastDev L,
     }
 }
 
-template <bool kLists>
+template <bool kLists, bool kSmem>
 __global__ void __launch_bounds__(512, 1) m3_resolve_kernel(FrameDev C, LastDev L, float th, int check_ori, const int* kp_state, CandLists Cl,
-                                                          int* kp_match, int* res, int* claim_glob, int* out_info, int claim_in_smem) {
+                                                          int* kp_match, int* res, int* claim_glob, int* out_info) {
+    constexpr bool claim_in_smem = kSmem;
     __shared__ int s_changed, s_count;
     __shared__ int s_hist[COEB_HISTO_LENGTH];
     __shared__ int s_ind[3];
     const int tid = threadIdx.x, T = blockDim.x;
-    int* const claim_min = claim_in_smem ? s_claim_dyn : claim_glob;
+    int* const claim_min = kSmem ? s_claim_dyn : claim_glob;
     const int na = kLists ? Cl.meta[0] : L.n;   // queries with candidates (compacted by the collect kernel, any order)
     const bool overflow = kLists && Cl.meta[1];
     if (kLists) {   // cleared for the next call's collect kernel (see CandLists::meta)
@@ -1342,6 +1606,7 @@ struct MapFields {   // the MapPoint members isInFrustum writes, as device array
 __global__ void __launch_bounds__(256) frustum_collect_kernel(FrameDev F, LocalMapDev LM, PoseArgs P, const uint8_t* __restrict__ skip,
                                                               MapFields out, MapDev M, float th, const int* kp_state, CandLists C, float* proj_out) {
     COEB_MTRACE(2);
+    pdl_launch_dependents();   // see m2_collect_kernel
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per map point: every lane evaluates the (cheap) frustum test
     if (i >= LM.n) return;
     const bool writer = (threadIdx.x & 31) == 0;
@@ -1349,8 +1614,13 @@ __global__ void __launch_bounds__(256) frustum_collect_kernel(FrameDev F, LocalM
     float u = 0.f, v = 0.f, ur = 0.f, viewCos = 0.f;
     int lvl = 0;
     const float log_scale = P.nlevels > 1 ? glibc_logf(F.scale[1]) : 1.f;   // mfLogScaleFactor = log(mfScaleFactor) (src/Frame.cc:151)
-    if (!skip[i]) {
-        const float X = LM.xyz[3 * i], Y = LM.xyz[3 * i + 1], Z = LM.xyz[3 * i + 2];
+    // every field of the map point is fetched up front (one round trip to L2 instead of one per nested test of isInFrustum: the kernel
+    // is a chain of such round trips under 5000 resident warps)
+    const bool skipped = skip[i] != 0, obs = M.has_obs[i] != 0;
+    const float X = LM.xyz[3 * i], Y = LM.xyz[3 * i + 1], Z = LM.xyz[3 * i + 2];
+    const float max_dist = LM.max_dist[i], min_dist = LM.min_dist[i];
+    const float nx = LM.normal[3 * i], ny = LM.normal[3 * i + 1], nz = LM.normal[3 * i + 2];
+    if (!skipped) {
         const float* T = P.T;
         const float PcX = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[0], X), __fmul_rn(T[1], Y)), __fmul_rn(T[2], Z)), T[3]);
         const float PcY = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[4], X), __fmul_rn(T[5], Y)), __fmul_rn(T[6], Z)), T[7]);
@@ -1360,16 +1630,15 @@ __global__ void __launch_bounds__(256) frustum_collect_kernel(FrameDev F, LocalM
             u = __fadd_rn(__fmul_rn(__fmul_rn(F.fx, PcX), invz), F.cx);
             v = __fadd_rn(__fmul_rn(__fmul_rn(F.fy, PcY), invz), F.cy);
             if (!(u < F.min_x || u > F.max_x) && !(v < F.min_y || v > F.max_y)) {
-                const float maxD = __fmul_rn(1.2f, LM.max_dist[i]), minD = __fmul_rn(0.8f, LM.min_dist[i]);
+                const float maxD = __fmul_rn(1.2f, max_dist), minD = __fmul_rn(0.8f, min_dist);
                 const float ox = __fsub_rn(X, P.Ow[0]), oy = __fsub_rn(Y, P.Ow[1]), oz = __fsub_rn(Z, P.Ow[2]);
                 const double s = __dadd_rn(__dadd_rn(__dmul_rn((double)ox, (double)ox), __dmul_rn((double)oy, (double)oy)), __dmul_rn((double)oz, (double)oz));
                 const float dist = (float)sqrt(s);
                 if (!(dist < minD || dist > maxD)) {
-                    const float nx = LM.normal[3 * i], ny = LM.normal[3 * i + 1], nz = LM.normal[3 * i + 2];
                     const double dot = __dadd_rn(__dadd_rn(__dmul_rn((double)ox, (double)nx), __dmul_rn((double)oy, (double)ny)), __dmul_rn((double)oz, (double)nz));
                     viewCos = (float)(dot / (double)dist);
                     if (!(viewCos < P.cos_limit)) {
-                        const float ratio = __fdiv_rn(LM.max_dist[i], dist);
+                        const float ratio = __fdiv_rn(max_dist, dist);
                         int nScale = 0;
                         if (ratio >= 1.17549435e-38f && ratio <= 3.402823466e+38f) nScale = (int)ceilf(__fdiv_rn(glibc_logf(ratio), log_scale));
                         lvl = nScale < 0 ? 0 : (nScale >= P.nlevels ? P.nlevels - 1 : nScale);
@@ -1387,8 +1656,16 @@ __global__ void __launch_bounds__(256) frustum_collect_kernel(FrameDev F, LocalM
         out.proj_x[i] = u; out.proj_y[i] = v; out.proj_xr[i] = ur; out.view_cos[i] = viewCos; out.level[i] = lvl;
         if (proj_out) { float* q = proj_out + 5 * (size_t)i; q[0] = u; q[1] = v; q[2] = ur; q[3] = viewCos; q[4] = (float)lvl; }
     }
-    __syncwarp();   // the collection below reads the fields back through M (same warp)
-    m2_collect_warp(F, M, th, kp_state, C, i);
+    // the collection of SearchByProjection for this map point, from the registers (m2_query's arithmetic on the values just written;
+    // isBad() points arrive as `skip`)
+    M2Query q;
+    q.lvl = lvl;
+    float r = ((double)viewCos > 0.998) ? 2.5f : 4.0f;   // RadiusByViewingCos (:131-137)
+    if (th != 1.0f) r *= th;                              // bFactor (:49, :65-66)
+    q.rs = r * F.scale[lvl];
+    q.d = LM.desc + 8 * (size_t)i;
+    q.pxr = ur; q.x = u; q.y = v;
+    m2_collect_query(F, kp_state, C, i, in, q, obs);
 }
 
 // ---- search half of ORBmatcher::Fuse(KeyFrame*, vpMapPoints, th) (src/ORBmatcher.cc:826-961) ---------------------------------
@@ -1798,18 +2075,74 @@ int push_inputs(coeb_matcher* m, const Packer& p) {
     return COEB_OK;
 }
 // Candidate lists of n queries inside a scratch block: counts | active | meta | items. Returns the bytes used.
-size_t lists_bytes(size_t n, int cap) { return 3 * al(n * 4) + al(8) + al(n * cap * 8); }
+size_t lists_bytes(size_t n, int cap) { return 3 * al(n * 4) + al(8) + al(n * 16) + al(n * cap * 8); }
 CandLists carve_lists(char* sc, size_t n, int cap, int* meta) {
     CandLists C{};
     C.count = (int*)sc; sc += al(n * 4);
     C.active = (int*)sc; sc += al(n * 4);
     C.meta = meta; sc += al(8);
     C.top = (int*)sc; sc += al(n * 4);
+    C.rec = (int4*)sc; sc += al(n * 16);
     C.items = (int2*)sc;
     C.cap = cap;
     return C;
 }
 
+// The fixed-point resolve of SearchByProjection(F, MapPoints) behind a collect kernel already enqueued on m->stream. Maps whose
+// queries all fit in shared memory (about 7000 map points) take m2_resolve_cached_kernel, launched programmatically dependent on the
+// collect kernel; larger ones the general kernel. d_claim holds 3 * K ints.
+bool m2_cached_fits(const coeb_frame* F, int n_map) {
+    static const bool general = getenv("COEB_M2_GENERAL") != nullptr;   // development switch: always the general kernel
+    const size_t claim3 = (size_t)F->n * 12 <= 48 * 1024 ? (size_t)F->n * 12 : 0;
+    int cc = 0;
+    resolve_smem(claim3, n_map + 1, 25, &cc);
+    return cc >= n_map && !general;
+}
+// flags_dev / flags_host (optional, 16-byte aligned, flags_bytes rounded up to 16): copied device -> mapped host memory by the cached
+// kernel; only passed when m2_cached_fits() says that kernel runs.
+int launch_m2_resolve(coeb_matcher* m, const coeb_frame* F, const MapDev& M, float th, float nnratio, const int* d_state, const CandLists& C, int* d_kpm,
+                      int* d_res, int* d_claim, int* d_info, const uint8_t* flags_dev = nullptr, uint8_t* flags_host = nullptr, size_t flags_bytes = 0) {
+    static bool big_smem[64][2] = {};   // opt-in above 48 KB of dynamic shared memory: a per-device function attribute, set once
+    const int dv = m->device & 63;
+    const size_t claim3 = (size_t)F->n * 12 <= 48 * 1024 ? (size_t)F->n * 12 : 0;
+    int cc = 0;
+    const size_t sm3 = resolve_smem(claim3, M.n + 1, 25, &cc);
+    if (m2_cached_fits(F, M.n)) {
+        const uint4* fd = reinterpret_cast<const uint4*>(flags_dev);
+        uint4* fh = reinterpret_cast<uint4*>(flags_host);
+        const int fv = flags_dev && flags_host ? (int)((flags_bytes + 15) / 16) : 0;
+        if (!big_smem[dv][0]) {
+            CUDA_TRY(cudaFuncSetAttribute(m2_resolve_cached_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+            CUDA_TRY(cudaFuncSetAttribute(m2_resolve_cached_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+            big_smem[dv][0] = true;
+        }
+        cudaLaunchConfig_t cfg = {};
+        // the shared-memory copies of the short lists of queued queries (kSl entries each) take what is left of the budget
+        const size_t lists_at = (sm3 + 7 + 8) & ~(size_t)7, budget = 204 * 1024;
+        const int slow_cap = (int)std::min<size_t>(1024, budget > lists_at ? (budget - lists_at) / (kSl * 8) : 0) & ~31;
+        cfg.gridDim = dim3(1); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = lists_at + (size_t)slow_cap * kSl * 8; cfg.stream = m->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (claim3) CUDA_TRY(cudaLaunchKernelEx(&cfg, m2_resolve_cached_kernel<true>, F->n, M.n, nnratio, d_state, C, d_kpm, d_claim, d_info, cc, slow_cap, fd, fh, fv));
+        else CUDA_TRY(cudaLaunchKernelEx(&cfg, m2_resolve_cached_kernel<false>, F->n, M.n, nnratio, d_state, C, d_kpm, d_claim, d_info, cc, slow_cap, fd, fh, fv));
+        return COEB_OK;
+    }
+    const size_t claim_smem = (size_t)F->n * 4 <= 32 * 1024 ? (size_t)F->n * 4 : 0;   // claim table in shared memory when it fits
+    const size_t sm = resolve_smem(claim_smem, M.n + 1, 25, &cc);
+    if (!big_smem[dv][1]) {
+        CUDA_TRY(cudaFuncSetAttribute(m2_resolve_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(m2_resolve_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+        big_smem[dv][1] = true;
+    }
+    if (claim_smem) m2_resolve_kernel<true, true><<<1, 1024, sm, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info, cc);
+    else m2_resolve_kernel<true, false><<<1, 1024, sm, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info, cc);
+    CUDA_TRY(cudaGetLastError());
+    return COEB_OK;
+}
+
+void print_mtrace(const char* what);
 int sync_outputs(coeb_matcher* m) {   // results in m->outm: the kernels wrote them into host memory themselves
     CUDA_TRY(cudaStreamSynchronize(m->stream));
     return COEB_OK;
@@ -1993,7 +2326,7 @@ int coeb_match_projection(coeb_matcher* m, coeb_frame* F, int n, const uint8_t* 
     if ((st = m->outm.reserve_mapped(al(K * 4) + 256)) != COEB_OK) return st;
     const int cap = 32;   // candidates kept per map point; a fuller window falls back to the window-walking kernel
     const size_t claim_smem = (size_t)F->n * 4 <= 32 * 1024 ? (size_t)F->n * 4 : 0;   // claim table in shared memory when it fits
-    if ((st = grow(&m->d_scratch, &m->scratch_bytes, al(N * 4) + al(K * 4) + lists_bytes(N, cap))) != COEB_OK) return st;
+    if ((st = grow(&m->d_scratch, &m->scratch_bytes, al(N * 4) + al(K * 12) + lists_bytes(N, cap))) != COEB_OK) return st;
     Packer p(m->in);
     MapDev M{};
     M.n = n;
@@ -2008,11 +2341,10 @@ int coeb_match_projection(coeb_matcher* m, coeb_frame* F, int n, const uint8_t* 
     int* d_info = (int*)(m->outm.d + al(K * 4));
     int* d_res = (int*)m->d_scratch;
     int* d_claim = (int*)((char*)m->d_scratch + al(N * 4));
-    const CandLists C = carve_lists((char*)m->d_scratch + al(N * 4) + al(K * 4), N, cap, m->d_meta);
+    const CandLists C = carve_lists((char*)m->d_scratch + al(N * 4) + al(K * 12), N, cap, m->d_meta);
     m2_collect_kernel<<<(n + 7) / 8, 256, 0, m->stream>>>(F->dev, M, th, d_state, C);
-    { int cc = 0; const size_t sm = resolve_smem(claim_smem, M.n + 1, 25, &cc); allow_smem(m2_resolve_kernel<true>, sm);
-      m2_resolve_kernel<true><<<1, 1024, sm, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0, cc); }
     CUDA_TRY(cudaGetLastError());
+    if ((st = launch_m2_resolve(m, F, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info)) != COEB_OK) return st;
     const auto t_queued = std::chrono::steady_clock::now();
     if ((st = sync_outputs(m)) != COEB_OK) return st;
     if (trace) {
@@ -2021,13 +2353,14 @@ int coeb_match_projection(coeb_matcher* m, coeb_frame* F, int n, const uint8_t* 
         fprintf(stderr, "[coeb match] SearchByProjection(map) host timeline: validate + pack %.1f us, enqueue %.1f us, wait %.1f us\n", us(t_begin, t_packed), us(t_packed, t_queued), us(t_queued, t_done));
     }
     if (((const int*)(m->outm.h + al(K * 4)))[2]) {   // a candidate list overflowed: exact window-walking variant
-        { int cc = 0; const size_t sm = resolve_smem(claim_smem, M.n + 1, 25, &cc); allow_smem(m2_resolve_kernel<false>, sm);
-      m2_resolve_kernel<false><<<1, 1024, sm, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0, cc); }
+        if (claim_smem) m2_resolve_kernel<false, true><<<1, 1024, claim_smem + 16, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info, 0);
+        else m2_resolve_kernel<false, false><<<1, 1024, 16, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info, 0);
         CUDA_TRY(cudaGetLastError());
         if ((st = sync_outputs(m)) != COEB_OK) return st;
     }
     std::memcpy(kp_match, m->outm.h, K * 4);
     if (nmatches_out) *nmatches_out = ((const int*)(m->outm.h + al(K * 4)))[0];
+    print_mtrace("SearchByProjection(map)");
     if (getenv("COEB_MATCH_TRACE")) fprintf(stderr, "[coeb match] SearchByProjection(map): %d map points, %d keypoints, %d fixed-point rounds\n", n, F->n, ((const int*)(m->outm.h + al(K * 4)))[1]);
     return COEB_OK;
 }
@@ -2049,7 +2382,7 @@ int coeb_match_lastframe(coeb_matcher* m, coeb_frame* cur, int n, const uint8_t*
     if ((st = m->outm.reserve_mapped(al(K * 4) + 256)) != COEB_OK) return st;
     const int cap = 64;
     const size_t claim_smem = K * 4 <= 32 * 1024 ? K * 4 : 0;   // claim table in shared memory when it fits
-    if ((st = grow(&m->d_scratch, &m->scratch_bytes, al(N * 4) + al(K * 4) + lists_bytes(N, cap))) != COEB_OK) return st;
+    if ((st = grow(&m->d_scratch, &m->scratch_bytes, al(N * 4) + al(K * 12) + lists_bytes(N, cap))) != COEB_OK) return st;
     Packer p(m->in);
     LastDev L{};
     L.n = n;
@@ -2071,11 +2404,13 @@ int coeb_match_lastframe(coeb_matcher* m, coeb_frame* cur, int n, const uint8_t*
     int* d_claim = (int*)((char*)m->d_scratch + al(N * 4));
     const CandLists C = carve_lists((char*)m->d_scratch + al(N * 4) + al(K * 4), N, cap, m->d_meta);
     m3_collect_kernel<<<(n + 7) / 8, 256, 0, m->stream>>>(cur->dev, L, th, d_state, C);
-    m3_resolve_kernel<true><<<1, 512, claim_smem, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0);
+    if (claim_smem) m3_resolve_kernel<true, true><<<1, 512, claim_smem, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info);
+    else m3_resolve_kernel<true, false><<<1, 512, 0, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info);
     CUDA_TRY(cudaGetLastError());
     if ((st = sync_outputs(m)) != COEB_OK) return st;
     if (((const int*)(m->outm.h + al(K * 4)))[2]) {
-        m3_resolve_kernel<false><<<1, 512, claim_smem, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0);
+        if (claim_smem) m3_resolve_kernel<false, true><<<1, 512, claim_smem, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info);
+    else m3_resolve_kernel<false, false><<<1, 512, 0, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info);
         CUDA_TRY(cudaGetLastError());
         if ((st = sync_outputs(m)) != COEB_OK) return st;
     }
@@ -2408,7 +2743,9 @@ void coeb_local_map_destroy(coeb_local_map* lm) {
 }
 
 #ifdef COEB_KERNEL_TRACE
-static void print_mtrace(const char* what) {
+extern "C++" {
+namespace {
+void print_mtrace(const char* what) {
     if (!getenv("COEB_KERNEL_TRACE")) return;
     static const char* names[8] = {"frame tail", "grid build", "frustum+collect", "m2 collect", "m2 resolve", "m3 collect", "m3 resolve", ""};
     unsigned long long t[32];
@@ -2419,13 +2756,22 @@ static void print_mtrace(const char* what) {
     for (int i = 0; i < 8; i++) if (t[2 * i + 1]) fprintf(stderr, " %s %.1f-%.1f |", names[i], (double)(t[2 * i] - t0) * 1e-3, (double)(t[2 * i + 1] - t0) * 1e-3);
     fprintf(stderr, " marks:");
     for (int i = 16; i < 32; i++) if (t[i]) fprintf(stderr, " %.1f", (double)(t[i] - t0) * 1e-3);
+    int ms[16];
+    cudaMemcpyFromSymbol(ms, g_mstat, sizeof(ms));
+    fprintf(stderr, " | active %d, slow per round:", ms[0]);
+    for (int i = 1; i < 12 && ms[i] >= 0; i++) fprintf(stderr, " %d", ms[i]);
+    if (ms[12] > 0 && t[16] && t[23]) fprintf(stderr, " | rounds: %d SM cycles in %.1f us = %.0f MHz", ms[12], (double)(t[23] - t[16]) * 1e-3, ms[12] / ((double)(t[23] - t[16]) * 1e-3));
     fprintf(stderr, "\n");
+    for (int i = 0; i < 16; i++) ms[i] = -1;
+    cudaMemcpyToSymbol(g_mstat, ms, sizeof(ms));
     unsigned long long init[32];
     for (int i = 0; i < 32; i++) init[i] = (i < 16 && !(i & 1)) ? ~0ull : 0ull;
     cudaMemcpyToSymbol(g_mtrace, init, sizeof(init));
 }
+}  // namespace
+}  // extern "C++"
 #else
-static void print_mtrace(const char*) {}
+extern "C++" { namespace { void print_mtrace(const char*) {} } }
 #endif
 
 int coeb_search_local_points(coeb_matcher* m, coeb_frame* F, coeb_local_map* lm, const uint8_t* skip, const uint8_t* has_obs,
@@ -2446,7 +2792,7 @@ int coeb_search_local_points(coeb_matcher* m, coeb_frame* F, coeb_local_map* lm,
     const int cap = 32;
     const size_t claim_smem = (size_t)F->n * 4 <= 32 * 1024 ? (size_t)F->n * 4 : 0;
     // scratch: res, claim, list counts, lists | MapPoint fields written by the frustum pass
-    const size_t sc_bytes = al(N * 4) + al(K * 4) + lists_bytes(N, cap) + 5 * al(N * 4) + 2 * al(N);
+    const size_t sc_bytes = al(N * 4) + al(K * 12) + lists_bytes(N, cap) + 5 * al(N * 4) + 2 * al(N);
     if (N > m->zero_bytes) {   // all-zero isBad() flags: written once, when the buffer grows
         cudaFree(m->d_zero);
         m->d_zero = nullptr; m->zero_bytes = 0;
@@ -2462,7 +2808,7 @@ int coeb_search_local_points(coeb_matcher* m, coeb_frame* F, coeb_local_map* lm,
     if ((st = push_inputs(m, p)) != COEB_OK) return st;
     char* sc = (char*)m->d_scratch;
     int* d_res = (int*)sc; sc += al(N * 4);
-    int* d_claim = (int*)sc; sc += al(K * 4);
+    int* d_claim = (int*)sc; sc += al(K * 12);
     const CandLists C = carve_lists(sc, N, cap, m->d_meta); sc += lists_bytes(N, cap);
     MapFields mf{};
     mf.proj_x = (float*)sc; sc += al(N * 4);
@@ -2474,7 +2820,9 @@ int coeb_search_local_points(coeb_matcher* m, coeb_frame* F, coeb_local_map* lm,
     mf.track_in_view = (uint8_t*)sc; sc += al(N);  // device copy: the collection reads it back
     int* d_kpm = (int*)m->outm.d;
     int* d_info = (int*)(m->outm.d + al(K * 4));
-    mf.track_in_view_host = (uint8_t*)(m->outm.d + al(K * 4) + 256);
+    uint8_t* const flags_host = (uint8_t*)(m->outm.d + al(K * 4) + 256);
+    const bool cached = m2_cached_fits(F, n);      // the cached resolve kernel forwards the flags to the host (see there)
+    mf.track_in_view_host = cached ? nullptr : flags_host;
     float* d_proj = proj_out ? (float*)(m->outm.d + al(K * 4) + 256 + al(N)) : nullptr;
     MapDev M{};
     M.n = n; M.track_in_view = mf.track_in_view; M.bad = d_zero; M.has_obs = d_obs;
@@ -2485,13 +2833,12 @@ int coeb_search_local_points(coeb_matcher* m, coeb_frame* F, coeb_local_map* lm,
     P.cos_limit = viewing_cos_limit;
     P.nlevels = F->nlevels;
     frustum_collect_kernel<<<(n + 7) / 8, 256, 0, m->stream>>>(F->dev, lm->dev, P, d_skip, mf, M, th, d_state, C, d_proj);
-    { int cc = 0; const size_t sm = resolve_smem(claim_smem, M.n + 1, 25, &cc); allow_smem(m2_resolve_kernel<true>, sm);
-      m2_resolve_kernel<true><<<1, 1024, sm, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0, cc); }
     CUDA_TRY(cudaGetLastError());
+    if ((st = launch_m2_resolve(m, F, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info, cached ? mf.track_in_view : nullptr, flags_host, N)) != COEB_OK) return st;
     if ((st = sync_outputs(m)) != COEB_OK) return st;
     if (((const int*)(m->outm.h + al(K * 4)))[2]) {   // a candidate list overflowed: exact window-walking variant
-        { int cc = 0; const size_t sm = resolve_smem(claim_smem, M.n + 1, 25, &cc); allow_smem(m2_resolve_kernel<false>, sm);
-      m2_resolve_kernel<false><<<1, 1024, sm, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0, cc); }
+        if (claim_smem) m2_resolve_kernel<false, true><<<1, 1024, claim_smem + 16, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info, 0);
+        else m2_resolve_kernel<false, false><<<1, 1024, 16, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info, 0);
         CUDA_TRY(cudaGetLastError());
         if ((st = sync_outputs(m)) != COEB_OK) return st;
     }
@@ -2635,7 +2982,7 @@ int coeb_match_reloc(coeb_matcher* m, coeb_frame* cur, int n, const uint8_t* val
     if ((st = m->outm.reserve_mapped(al(K * 4) + 256)) != COEB_OK) return st;
     const int cap = 64;
     const size_t claim_smem = K * 4 <= 32 * 1024 ? K * 4 : 0;   // claim table in shared memory when it fits
-    if ((st = grow(&m->d_scratch, &m->scratch_bytes, al(N * 4) + al(K * 4) + lists_bytes(N, cap))) != COEB_OK) return st;
+    if ((st = grow(&m->d_scratch, &m->scratch_bytes, al(N * 4) + al(K * 12) + lists_bytes(N, cap))) != COEB_OK) return st;
     Packer p(m->in);
     LastDev L{};
     L.n = n;
@@ -2662,11 +3009,13 @@ int coeb_match_reloc(coeb_matcher* m, coeb_frame* cur, int n, const uint8_t* val
     int* d_claim = (int*)((char*)m->d_scratch + al(N * 4));
     const CandLists C = carve_lists((char*)m->d_scratch + al(N * 4) + al(K * 4), N, cap, m->d_meta);
     m3_collect_kernel<<<(n + 7) / 8, 256, 0, m->stream>>>(cur->dev, L, th, d_state, C);
-    m3_resolve_kernel<true><<<1, 512, claim_smem, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0);
+    if (claim_smem) m3_resolve_kernel<true, true><<<1, 512, claim_smem, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info);
+    else m3_resolve_kernel<true, false><<<1, 512, 0, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info);
     CUDA_TRY(cudaGetLastError());
     if ((st = sync_outputs(m)) != COEB_OK) return st;
     if (((const int*)(m->outm.h + al(K * 4)))[2]) {
-        m3_resolve_kernel<false><<<1, 512, claim_smem, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info, claim_smem != 0);
+        if (claim_smem) m3_resolve_kernel<false, true><<<1, 512, claim_smem, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info);
+    else m3_resolve_kernel<false, false><<<1, 512, 0, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info);
         CUDA_TRY(cudaGetLastError());
         if ((st = sync_outputs(m)) != COEB_OK) return st;
     }
