@@ -1563,12 +1563,7 @@ struct TailArgs {
 
 // UndistortKeyPoints + ComputeStereoFromRGBD (src/Frame.cc:579-609, 820-842): one thread per keypoint writes the SoA
 // the matchers read and the AoS the host downloads; the descriptor rows are copied as words.
-__global__ void __launch_bounds__(128) frame_tail_kernel(TailArgs a) {
-    COEB_MTRACE(0);
-    const int n = a.n;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    for (int w = i; w < n * 8; w += gridDim.x * blockDim.x) a.desc_out[w] = a.desc[w];
-    if (i >= n) return;
+__device__ __forceinline__ void frame_tail_point(const TailArgs& a, int i, float& xu, float& yu) {
     coeb_keypoint kp = a.kps[i];
     const float u = kp.x, v = kp.y;
     if (a.undistort) undistort_point(u, v, a.fx, a.fy, a.cx, a.cy, a.dist, kp.x, kp.y);
@@ -1587,6 +1582,71 @@ __global__ void __launch_bounds__(128) frame_tail_kernel(TailArgs a) {
     }
     a.x[i] = kp.x; a.y[i] = kp.y; a.angle[i] = kp.angle; a.octave[i] = kp.octave; a.uright[i] = ur;
     a.keys_un[i] = kp; a.depth_out[i] = dp; a.uright_dl[i] = ur;
+    xu = kp.x; yu = kp.y;
+}
+__global__ void __launch_bounds__(128) frame_tail_kernel(TailArgs a) {
+    COEB_MTRACE(0);
+    const int n = a.n;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int w = i; w < n * 8; w += gridDim.x * blockDim.x) a.desc_out[w] = a.desc[w];
+    if (i >= n) return;
+    float xu, yu;
+    frame_tail_point(a, i, xu, yu);
+}
+
+// Both steps in ONE single-CTA launch for frames of up to kTailGridMax keypoints (a tracked frame has 1000-2000): the per-keypoint
+// tail, then Frame::AssignFeaturesToGrid from the undistorted coordinates still in registers, with the cell table, the fill cursors
+// and the item list in shared memory. As two launches the grid kernel started 7 us after the 3-us tail kernel (whose writes into the
+// caller's mapped arrays have to reach the host first) and then spent 9 us on global round trips.
+constexpr int kTailGridMax = 2048;
+__global__ void __launch_bounds__(1024, 1) frame_tail_grid_kernel(TailArgs a, FrameDev f, int* __restrict__ cell_start, int* __restrict__ cell_items) {
+    COEB_MTRACE(0);
+    __shared__ int s_start[kGridCells + 1], s_fill[kGridCells];
+    __shared__ short s_cell[kTailGridMax], s_items[kTailGridMax];
+    __shared__ int s_warp[33];
+    const int tid = threadIdx.x, T = blockDim.x, n = a.n;
+    for (int i = tid; i <= kGridCells; i += T) s_start[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += T) {
+        float xu, yu;
+        frame_tail_point(a, i, xu, yu);
+        // PosInGrid: round() half away from zero (src/Frame.cc:560-561)
+        const int px = (int)roundf((xu - f.min_x) * f.gw_inv), py = (int)roundf((yu - f.min_y) * f.gh_inv);
+        int c = -1;
+        if (!(px < 0 || px >= COEB_GRID_COLS || py < 0 || py >= COEB_GRID_ROWS)) {
+            c = px * COEB_GRID_ROWS + py;
+            atomicAdd(&s_start[c], 1);
+        }
+        s_cell[i] = (short)c;
+    }
+    for (int w = tid; w < n * 8; w += T) a.desc_out[w] = a.desc[w];
+    __syncthreads();
+    const int total = block_exclusive_scan(s_start, kGridCells, s_warp);
+    if (tid == 0) s_start[kGridCells] = total;
+    __syncthreads();
+    for (int i = tid; i <= kGridCells; i += T) {
+        const int v = s_start[i];
+        cell_start[i] = v;
+        if (i < kGridCells) s_fill[i] = v;
+    }
+    __syncthreads();
+    // fill with atomic slots, then sort each (tiny) cell: items end up ascending by keypoint index, the order in which the reference pushes them
+    for (int i = tid; i < n; i += T) {
+        const int c = s_cell[i];
+        if (c >= 0) s_items[atomicAdd(&s_fill[c], 1)] = (short)i;
+    }
+    __syncthreads();
+    for (int c = tid; c < kGridCells; c += T) {
+        const int lo = s_start[c], hi = s_start[c + 1];
+        for (int i = lo + 1; i < hi; i++) {
+            const short v = s_items[i];
+            int j = i - 1;
+            while (j >= lo && s_items[j] > v) { s_items[j + 1] = s_items[j]; j--; }
+            s_items[j + 1] = v;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < total; i += T) cell_items[i] = s_items[i];
 }
 
 struct LocalMapDev {
@@ -1960,6 +2020,7 @@ struct coeb_matcher {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     Stage in, out;                                   // inputs (H2D) and results (D2H)
     Stage outm;                                      // results written once by the last kernel: mapped pinned memory, no copy
+    Stage inm;                                       // small inputs read once by the first kernel: mapped pinned memory, no copy
     int* d_meta = nullptr;                           // CandLists::meta: zero between calls (the resolve kernels clear it again)
     uint8_t* d_zero = nullptr; size_t zero_bytes = 0;   // all-zero flags (isBad() of a resident local map)
     void* d_scratch = nullptr; size_t scratch_bytes = 0;
@@ -2184,6 +2245,7 @@ void coeb_matcher_destroy(coeb_matcher* m) {
     m->in.release();
     m->out.release();
     m->outm.release();
+    m->inm.release();
     cudaFree(m->d_meta);
     cudaFree(m->d_zero);
     cudaFree(m->d_scratch);
@@ -2640,8 +2702,10 @@ int coeb_frame_from_extractor(coeb_matcher* m, coeb_extractor* ex, int frame_ind
             // The extractor left its keypoints in host memory (single-frame call): the ~1000 depth values ComputeStereoFromRGBD reads
             // are gathered here and uploaded as 4 KB instead of the whole depth map (0.6 MB: 11 us from pinned memory, ~40 us from a
             // pageable cv::Mat). Same truncation and the same bounds test as the kernel's own gather.
-            if ((st = m->in.reserve(al((size_t)n * 4))) != COEB_OK) return bail(st);
-            float* g = (float*)m->in.h;
+            // The values sit in mapped pinned memory and the kernel reads them across PCIe itself (32 coalesced 128-byte reads): a
+            // host-to-device copy node in front of the kernel costs the call more than the transfer.
+            if ((st = m->inm.reserve_mapped(al((size_t)n * 4))) != COEB_OK) return bail(st);
+            float* g = (float*)m->inm.h;
             const char* img = (const char*)depth->data;
             for (int i = 0; i < n; i++) {
                 const int row = (int)h_kps[i].y, col = (int)h_kps[i].x;
@@ -2652,9 +2716,7 @@ int coeb_frame_from_extractor(coeb_matcher* m, coeb_extractor* ex, int frame_ind
                 }
                 g[i] = val;
             }
-            cudaError_t e = cudaMemcpyAsync(m->in.d, m->in.h, (size_t)n * 4, cudaMemcpyHostToDevice, s);
-            if (e != cudaSuccess) return bail(fail(COEB_ERR_CUDA, "depth upload failed: %s", cudaGetErrorString(e)));
-            a.depth = m->in.d; a.depth_stride = 0;
+            a.depth = m->inm.d; a.depth_stride = 0;
             a.depth_kind = kind == 1 ? 3 : 4;
         }
         else {
@@ -2686,8 +2748,13 @@ int coeb_frame_from_extractor(coeb_matcher* m, coeb_extractor* ex, int frame_ind
         a.uright_dl = (float*)(m->outm.d + off_ur);
         a.depth_out = (float*)(m->outm.d + off_dp);
     }
-    if (n > 0) frame_tail_kernel<<<(n + 127) / 128, 128, 0, s>>>(a);
-    grid_build_kernel<<<1, 1024, 0, s>>>(d, d_cell_start, d_cell_items, d_kp_cell);
+    static const bool two_launches = getenv("COEB_TAIL_TWO_LAUNCHES") != nullptr;   // development switch
+    if (n <= kTailGridMax && !two_launches) {
+        frame_tail_grid_kernel<<<1, 1024, 0, s>>>(a, d, d_cell_start, d_cell_items);
+    } else {
+        if (n > 0) frame_tail_kernel<<<(n + 127) / 128, 128, 0, s>>>(a);
+        grid_build_kernel<<<1, 1024, 0, s>>>(d, d_cell_start, d_cell_items, d_kp_cell);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return bail(fail(COEB_ERR_CUDA, "frame tail launch failed: %s", cudaGetErrorString(e)));
     // blocking like every Frame-building call: the caller may reuse its depth buffer and the extractor
