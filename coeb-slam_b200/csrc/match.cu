@@ -939,6 +939,7 @@ __device__ __forceinline__ void m3_visit(const FrameDev& C, const LastDev& L, fl
 }
 
 __global__ void __launch_bounds__(256) m3_collect_kernel(FrameDev Cf, LastDev L, float th, const int* kp_state, CandLists C) {
+    COEB_MTRACE(5);
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per last-frame point
     if (i >= L.n) return;
     M3Query q;
@@ -968,6 +969,7 @@ __global__ void __launch_bounds__(256) m3_collect_kernel(FrameDev Cf, LastDev L,
 template <bool kLists, bool kSmem>
 __global__ void __launch_bounds__(512, 1) m3_resolve_kernel(FrameDev C, LastDev L, float th, int check_ori, const int* kp_state, CandLists Cl,
                                                           int* kp_match, int* res, int* claim_glob, int* out_info) {
+    COEB_MTRACE(6);
     constexpr bool claim_in_smem = kSmem;
     __shared__ int s_changed, s_count;
     __shared__ int s_hist[COEB_HISTO_LENGTH];
@@ -1148,6 +1150,7 @@ __device__ __forceinline__ void m4_visit(const FrameDev& F1, const FrameDev& F2,
 }
 
 __global__ void __launch_bounds__(256) m4_collect_kernel(FrameDev F1, FrameDev F2, const float* prev_in, float window, CandLists C) {
+    COEB_MTRACE(5);
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per keypoint of F1
     if (i >= F1.n) return;
     int cnt = 0;
@@ -1169,6 +1172,7 @@ template <bool kLists>
 __global__ void __launch_bounds__(1024) m4_resolve_kernel(FrameDev F1, FrameDev F2, const float* prev_in, float window, float nnratio,
                                                           int check_ori, CandLists C, int* res, int* rdist, int* cl_start, int* cl_fill,
                                                           int2* cl_items, int* matches12, float* prev_out, int* out_info) {
+    COEB_MTRACE(6);
     __shared__ int s_changed, s_count;
     __shared__ int s_hist[COEB_HISTO_LENGTH];
     __shared__ int s_ind[3];
@@ -2478,6 +2482,7 @@ int coeb_match_lastframe(coeb_matcher* m, coeb_frame* cur, int n, const uint8_t*
     }
     std::memcpy(kp_match, m->outm.h, K * 4);
     if (nmatches_out) *nmatches_out = ((const int*)(m->outm.h + al(K * 4)))[0];
+    print_mtrace("SearchByProjection(last frame)");
     return COEB_OK;
 }
 
@@ -2521,6 +2526,7 @@ int coeb_match_init(coeb_matcher* m, coeb_frame* f1, coeb_frame* f2, float* prev
     std::memcpy(matches12, m->out.h, N1 * 4);
     std::memcpy(prev_matched, m->out.h + al(N1 * 4), N1 * 8);
     if (nmatches_out) *nmatches_out = ((const int*)(m->out.h + al(N1 * 4) + al(N1 * 8)))[0];
+    print_mtrace("SearchForInitialization");
     return COEB_OK;
 }
 
@@ -2814,7 +2820,7 @@ extern "C++" {
 namespace {
 void print_mtrace(const char* what) {
     if (!getenv("COEB_KERNEL_TRACE")) return;
-    static const char* names[8] = {"frame tail", "grid build", "frustum+collect", "m2 collect", "m2 resolve", "m3 collect", "m3 resolve", ""};
+    static const char* names[8] = {"frame tail", "grid build", "frustum+collect", "m2 collect", "m2 resolve", "m3/m4 collect", "m3/m4 resolve", ""};
     unsigned long long t[32];
     cudaMemcpyFromSymbol(t, g_mtrace, sizeof(t));
     unsigned long long t0 = ~0ull;

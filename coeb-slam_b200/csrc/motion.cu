@@ -605,11 +605,20 @@ struct coeb_motion {
     float* d_mask = nullptr; int mask_hw = 0;
     char* h_pin = nullptr; size_t pin_bytes = 0;
     std::vector<float2> cand_host;
+    // coeb_process_moving_object: the current frame's upload, both pyramids and the derivative images run on a side stream beside the
+    // corner stage (which ends in a host round trip); `side` describes the work good_features() enqueues there before it synchronises
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_prev = nullptr, ev_side = nullptr;
+    uint8_t* h_frame[2] = {nullptr, nullptr}; size_t frame_bytes = 0;   // pinned staging of the two (pageable) frames, dense rows
+    cudaGraphExec_t side_graph = nullptr;                               // the side stream's work: fixed addresses, one launch
+    struct { const uint8_t* cur_gray = nullptr; int stride = 0; bool done = false; } side;
 };
 
 namespace {
 
+void drop_side_graph(coeb_motion* m);
 void motion_free_images(coeb_motion* m) {
+    drop_side_graph(m);
     for (int f = 0; f < 2; f++)
         for (int l = 0; l < kMoMaxLevels; l++) { cudaFree(m->d_pyr[f][l]); m->d_pyr[f][l] = nullptr; }
     for (int l = 0; l < kMoMaxLevels; l++) { cudaFree(m->d_deriv[l]); m->d_deriv[l] = nullptr; }
@@ -650,15 +659,70 @@ int motion_pin(coeb_motion* m, size_t bytes) {
     return COEB_OK;
 }
 
-int upload_level0(coeb_motion* m, int which, const uint8_t* gray, int stride) {
-    CUDA_TRY(cudaMemcpy2DAsync(m->d_pyr[which][0], m->lp[0], gray, stride, m->w, m->h, cudaMemcpyHostToDevice, m->stream));
+void drop_side_graph(coeb_motion* m) {
+    if (m->side_graph) { cudaGraphExecDestroy(m->side_graph); m->side_graph = nullptr; }
+}
+
+// The caller's frame is pageable as a rule (a cv::Mat): copied into pinned memory here (~10 us for 640x480) it travels by DMA while
+// the host goes on; handed to cudaMemcpy2DAsync directly the driver stages it itself and the call blocks for ~35 us.
+int stage_frame(coeb_motion* m, int which, const uint8_t* gray, int stride) {
+    const size_t need = (size_t)m->w * m->h;
+    if (need > m->frame_bytes) {
+        drop_side_graph(m);
+        for (int f = 0; f < 2; f++) { if (m->h_frame[f]) cudaFreeHost(m->h_frame[f]); m->h_frame[f] = nullptr; }
+        m->frame_bytes = 0;
+        for (int f = 0; f < 2; f++) CUDA_TRY(cudaHostAlloc((void**)&m->h_frame[f], need, cudaHostAllocDefault));
+        m->frame_bytes = need;
+    }
+    if (stride == m->w) std::memcpy(m->h_frame[which], gray, need);
+    else for (int y = 0; y < m->h; y++) std::memcpy(m->h_frame[which] + (size_t)y * m->w, gray + (size_t)y * stride, m->w);
     return COEB_OK;
 }
 
-void build_pyramid(coeb_motion* m, int which) {
+int upload_level0(coeb_motion* m, int which, const uint8_t* gray, int stride, cudaStream_t stream = nullptr) {
+    int st = stage_frame(m, which, gray, stride);
+    if (st != COEB_OK) return st;
+    CUDA_TRY(cudaMemcpy2DAsync(m->d_pyr[which][0], m->lp[0], m->h_frame[which], m->w, m->w, m->h, cudaMemcpyHostToDevice, stream ? stream : m->stream));
+    return COEB_OK;
+}
+
+void build_pyramid(coeb_motion* m, int which, cudaStream_t stream = nullptr) {
+    if (!stream) stream = m->stream;
     for (int l = 1; l < m->nlevels; l++)
-        pyr_down_kernel<<<dim3((m->lw[l] + 31) / 32, (m->lh[l] + 7) / 8), 256, 0, m->stream>>>(m->d_pyr[which][l - 1], m->lw[l - 1], m->lh[l - 1], m->lp[l - 1],
-                                                                                           m->d_pyr[which][l], m->lw[l], m->lh[l], m->lp[l]);
+        pyr_down_kernel<<<dim3((m->lw[l] + 31) / 32, (m->lh[l] + 7) / 8), 256, 0, stream>>>(m->d_pyr[which][l - 1], m->lw[l - 1], m->lh[l - 1], m->lp[l - 1],
+                                                                                        m->d_pyr[which][l], m->lw[l], m->lh[l], m->lp[l]);
+}
+
+void derivative_images(coeb_motion* m, cudaStream_t stream) {
+    for (int l = 0; l < m->nlevels; l++)
+        scharr_kernel<<<dim3((m->lw[l] + 31) / 32, (m->lh[l] + 7) / 8), 256, 0, stream>>>(m->d_pyr[0][l], m->lw[l], m->lh[l], m->lp[l], m->d_deriv[l]);
+}
+
+// Called by good_features() between its last launch and its synchronisation, when coeb_process_moving_object asked for it: everything
+// calcOpticalFlowPyrLK needs besides the points (current frame, both pyramids, Scharr images of the previous one) is enqueued on the
+// side stream, so the staging of the pageable current frame overlaps the Harris kernels and the kernels overlap the host's
+// minimum-distance pass. The LK launch waits for ev_side.
+int enqueue_side_work(coeb_motion* m) {
+    if (!m->side.cur_gray) return COEB_OK;
+    int st = stage_frame(m, 1, m->side.cur_gray, m->side.stride);
+    if (st != COEB_OK) return st;
+    CUDA_TRY(cudaStreamWaitEvent(m->stream2, m->ev_prev, 0));   // level 0 of the previous frame has landed
+    if (!m->side_graph) {   // every address is fixed until the buffers are laid out again: captured once, replayed as one launch
+        cudaGraph_t g = nullptr;
+        CUDA_TRY(cudaStreamBeginCapture(m->stream2, cudaStreamCaptureModeThreadLocal));
+        cudaMemcpy2DAsync(m->d_pyr[1][0], m->lp[0], m->h_frame[1], m->w, m->w, m->h, cudaMemcpyHostToDevice, m->stream2);
+        build_pyramid(m, 0, m->stream2);
+        derivative_images(m, m->stream2);
+        build_pyramid(m, 1, m->stream2);
+        cudaError_t e = cudaStreamEndCapture(m->stream2, &g);
+        if (e == cudaSuccess) e = cudaGraphInstantiate(&m->side_graph, g, 0);
+        if (g) cudaGraphDestroy(g);
+        if (e != cudaSuccess) { m->side_graph = nullptr; return fail(COEB_ERR_CUDA, "side-stream graph: %s", cudaGetErrorString(e)); }
+    }
+    CUDA_TRY(cudaGraphLaunch(m->side_graph, m->stream2));
+    CUDA_TRY(cudaEventRecord(m->ev_side, m->stream2));
+    m->side.done = true;
+    return COEB_OK;
 }
 
 int ensure_mask(coeb_motion* m, int hw) {
@@ -742,10 +806,12 @@ int select_corners(std::vector<float2>& cand, bool sorted, int w, int h, int max
 // Smallest-eigenvalue eigenvector of a symmetric n x n matrix by cyclic Jacobi rotations.
 void jacobi_eigen(double* A, int n, double* V, double* ev) {
     for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) V[i * n + j] = i == j;
+    double diag2 = 0;
+    for (int i = 0; i < n; i++) diag2 += A[i * n + i] * A[i * n + i];
     for (int sweep = 0; sweep < 60; sweep++) {
         double off = 0;
         for (int i = 0; i < n; i++) for (int j = i + 1; j < n; j++) off += A[i * n + j] * A[i * n + j];
-        if (off < 1e-30) break;
+        if (off < 1e-30 || off < 1e-28 * diag2) break;   // converged to ~1e-14 of the matrix scale (the convergence is quadratic: one more sweep squares it)
         for (int p = 0; p < n; p++)
             for (int q = p + 1; q < n; q++) {
                 if (std::fabs(A[p * n + q]) < 1e-300) continue;
@@ -871,15 +937,41 @@ bool eight_point_minimal(const float* p1, const float* p2, const int* idx, doubl
     return true;
 }
 
-// OpenCV's error of a correspondence under F: the larger of the two squared point-to-epipolar-line distances.
-inline double fm_error(const double F[9], const float* p1, const float* p2, int i) {
-    const double x1 = p1[2 * i], y1 = p1[2 * i + 1], x2 = p2[2 * i], y2 = p2[2 * i + 1];
-    double a = F[0] * x1 + F[1] * y1 + F[2], b = F[3] * x1 + F[4] * y1 + F[5], c = F[6] * x1 + F[7] * y1 + F[8];
-    const double s2 = 1. / (a * a + b * b), d2 = x2 * a + y2 * b + c;
-    a = F[0] * x2 + F[3] * y2 + F[6]; b = F[1] * x2 + F[4] * y2 + F[7]; c = F[2] * x2 + F[5] * y2 + F[8];
-    const double s1 = 1. / (a * a + b * b), d1 = x1 * a + y1 * b + c;
-    return std::max(d1 * d1 * s1, d2 * d2 * s2);
+// OpenCV's error of a correspondence under F is the larger of the two squared point-to-epipolar-line distances,
+//   max( (x2.F x1)^2 / |(F x1)_xy|^2 , (x1.F^T x2)^2 / |(F^T x2)_xy|^2 ),
+// and a correspondence is an inlier when it is <= threshold^2. RANSAC only needs that decision, so the count below compares
+// d^2 <= thr2 * (a^2 + b^2) for both lines: no division, no branch, structure-of-arrays doubles -- a loop the host compiler turns
+// into packed arithmetic (the AVX2 + FMA clone is picked at run time when the CPU has both). The scoring of ~30 hypotheses over ~600 tracks
+// was two thirds of the 190 us this step took.
+#define COEB_FM_COUNT_BODY                                                                                              \
+    int cnt = 0;                                                                                                        \
+    for (int i = 0; i < n; i++) {                                                                                       \
+        const double a = F[0] * x1[i] + F[1] * y1[i] + F[2], b = F[3] * x1[i] + F[4] * y1[i] + F[5], c = F[6] * x1[i] + F[7] * y1[i] + F[8]; \
+        const double d = x2[i] * a + y2[i] * b + c;   /* x2 . F x1 == x1 . F^T x2: one residual serves both lines */    \
+        const double at = F[0] * x2[i] + F[3] * y2[i] + F[6], bt = F[1] * x2[i] + F[4] * y2[i] + F[7];                  \
+        const double dd = d * d;                                                                                        \
+        const unsigned char in = (unsigned char)((dd <= thr2 * (a * a + b * b)) & (dd <= thr2 * (at * at + bt * bt)));  \
+        mask[i] = in;                                                                                                   \
+        cnt += in;                                                                                                      \
+    }                                                                                                                   \
+    return cnt;
+int fm_count_inliers_base(const double* F, const double* x1, const double* y1, const double* x2, const double* y2, int n, double thr2, unsigned char* mask) {
+    COEB_FM_COUNT_BODY
 }
+#if defined(__x86_64__) && defined(__GNUC__)
+__attribute__((target("avx2,fma"))) int fm_count_inliers_avx2(const double* F, const double* x1, const double* y1, const double* x2, const double* y2, int n,
+                                                          double thr2, unsigned char* mask) {
+    COEB_FM_COUNT_BODY
+}
+int fm_count_inliers(const double* F, const double* x1, const double* y1, const double* x2, const double* y2, int n, double thr2, unsigned char* mask) {
+    static const bool avx2 = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("fma");
+    return avx2 ? fm_count_inliers_avx2(F, x1, y1, x2, y2, n, thr2, mask) : fm_count_inliers_base(F, x1, y1, x2, y2, n, thr2, mask);
+}
+#else
+int fm_count_inliers(const double* F, const double* x1, const double* y1, const double* x2, const double* y2, int n, double thr2, unsigned char* mask) {
+    return fm_count_inliers_base(F, x1, y1, x2, y2, n, thr2, mask);
+}
+#endif
 
 }  // namespace
 
@@ -893,6 +985,11 @@ int coeb_motion_create(int device, coeb_motion** out) {
     coeb_motion* m = new coeb_motion();
     m->device = device;
     if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) { delete m; return fail(COEB_ERR_CUDA, "cudaStreamCreate failed"); }
+    if (cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&m->ev_prev, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->ev_side, cudaEventDisableTiming) != cudaSuccess) {
+        coeb_motion_destroy(m);
+        return fail(COEB_ERR_CUDA, "side stream / event creation failed");
+    }
     cudaError_t e = cudaMalloc(&m->d_max, 16);
     if (e == cudaSuccess) e = cudaMalloc(&m->d_cand, sizeof(float2) * kMoMaxCand);
     if (e == cudaSuccess) e = cudaMalloc(&m->d_pre, sizeof(float2) * kMoMaxPts);
@@ -910,10 +1007,14 @@ void coeb_motion_destroy(coeb_motion* m) {
     if (!m) return;
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
+    if (m->stream2) { cudaStreamSynchronize(m->stream2); cudaStreamDestroy(m->stream2); }
+    if (m->ev_prev) cudaEventDestroy(m->ev_prev);
+    if (m->ev_side) cudaEventDestroy(m->ev_side);
     motion_free_images(m);
     cudaFree(m->d_max); cudaFree(m->d_cand); cudaFree(m->d_pre); cudaFree(m->d_next); cudaFree(m->d_status); cudaFree(m->d_moving); cudaFree(m->d_F);
     cudaFree(m->d_dist); cudaFree(m->d_mask);
     if (m->h_pin) cudaFreeHost(m->h_pin);
+    for (int f = 0; f < 2; f++) if (m->h_frame[f]) cudaFreeHost(m->h_frame[f]);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
 }
@@ -926,6 +1027,7 @@ int coeb_motion_good_features(coeb_motion* m, const uint8_t* gray, int width, in
     int st = motion_prepare(m, width, height, 22, 5);
     if (st != COEB_OK) return st;
     if ((st = upload_level0(m, 0, gray, stride)) != COEB_OK) return st;
+    if (m->side.cur_gray) CUDA_TRY(cudaEventRecord(m->ev_prev, m->stream));
     CUDA_TRY(cudaMemsetAsync(m->d_max, 0, 16, m->stream));
     // Sobel scale of cornerHarris for 8-bit input: 1 / (2^(ksize-1) * blockSize * 255); the kernel taps are float(1*scale), float(2*scale)
     const double scale = 1.0 / ((double)(1 << 2) * 3 * 255.0);
@@ -944,6 +1046,7 @@ int coeb_motion_good_features(coeb_motion* m, const uint8_t* gray, int width, in
     if (st2 != COEB_OK) return st2;
     CUDA_TRY(cudaMemcpyAsync(m->h_pin, m->d_max, 16, cudaMemcpyDeviceToHost, m->stream));
     CUDA_TRY(cudaMemcpyAsync(m->h_pin + 16, m->d_cand, sizeof(float2) * kSortCap, cudaMemcpyDeviceToHost, m->stream));
+    if ((st2 = enqueue_side_work(m)) != COEB_OK) return st2;
     CUDA_TRY(cudaStreamSynchronize(m->stream));
     const unsigned* info = reinterpret_cast<const unsigned*>(m->h_pin);
     if ((int)info[1] > kMoMaxCand) return fail(COEB_ERR_CAPACITY, "%u corner candidates (at most %d)", info[1], kMoMaxCand);
@@ -980,13 +1083,17 @@ int coeb_motion_corner_subpix(coeb_motion* m, const uint8_t* gray, int width, in
     return COEB_OK;
 }
 
-static int run_lk(coeb_motion* m, int n, int win, int max_iters, double eps, double min_eig, int edge, float sad_limit) {
-    build_pyramid(m, 0);
-    build_pyramid(m, 1);
+static int run_lk(coeb_motion* m, int n, int win, int max_iters, double eps, double min_eig, int edge, float sad_limit, bool images_on_side_stream = false) {
+    if (images_on_side_stream) {
+        CUDA_TRY(cudaStreamWaitEvent(m->stream, m->ev_side, 0));
+    } else {
+        build_pyramid(m, 0);
+        build_pyramid(m, 1);
+        derivative_images(m, m->stream);
+    }
     LkLevels L{};
     L.nlevels = m->nlevels;
     for (int l = 0; l < m->nlevels; l++) {
-        scharr_kernel<<<dim3((m->lw[l] + 31) / 32, (m->lh[l] + 7) / 8), 256, 0, m->stream>>>(m->d_pyr[0][l], m->lw[l], m->lh[l], m->lp[l], m->d_deriv[l]);
         L.w[l] = m->lw[l]; L.h[l] = m->lh[l]; L.pitch[l] = m->lp[l];
         L.prev[l] = m->d_pyr[0][l]; L.cur[l] = m->d_pyr[1][l]; L.deriv[l] = m->d_deriv[l];
     }
@@ -1028,6 +1135,9 @@ int coeb_fundamental_ransac(const float* p1_xy, const float* p2_xy, int n, doubl
     uint64_t rng = 0x9E3779B97F4A7C15ull ^ ((uint64_t)seed * 0xD1342543DE82EF95ull + 1);
     auto next = [&]() { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return (uint32_t)(rng >> 32); };
     std::vector<uint8_t> best_mask(n, 0), mask(n);
+    std::vector<double> soa(4 * (size_t)n);
+    double *sx1 = soa.data(), *sy1 = sx1 + n, *sx2 = sy1 + n, *sy2 = sx2 + n;
+    for (int i = 0; i < n; i++) { sx1[i] = p1_xy[2 * i]; sy1[i] = p1_xy[2 * i + 1]; sx2[i] = p2_xy[2 * i]; sy2[i] = p2_xy[2 * i + 1]; }
     int best = 0, iters = std::max(max_iters, 1);
     double Fb[9] = {0}, F[9];
     for (int it = 0; it < iters; it++) {
@@ -1039,10 +1149,9 @@ int coeb_fundamental_ransac(const float* p1_xy, const float* p2_xy, int n, doubl
             if (!dup) idx[k++] = c;
         }
         if (!eight_point_minimal(p1_xy, p2_xy, idx, F)) continue;
-        int cnt = 0;
-        for (int i = 0; i < n; i++) { mask[i] = fm_error(F, p1_xy, p2_xy, i) <= thr2; cnt += mask[i]; }
+        const int cnt = fm_count_inliers(F, sx1, sy1, sx2, sy2, n, thr2, mask.data());
         if (cnt > best) {
-            best = cnt; best_mask = mask; std::memcpy(Fb, F, sizeof(F));
+            best = cnt; best_mask.swap(mask); std::memcpy(Fb, F, sizeof(F));
             // cv::RANSACUpdateNumIters: log(1 - confidence) / log(1 - inlier_ratio^8)
             const double ep = 1.0 - (double)cnt / n, num = std::log(std::max(1.0 - confidence, DBL_MIN)), den = std::log(std::max(1.0 - std::pow(1.0 - ep, 8), DBL_MIN));
             if (den < 0 && -num < (double)iters * -den) iters = std::max(it + 1, (int)std::lrint(num / den));
@@ -1088,7 +1197,12 @@ int coeb_process_moving_object(coeb_motion* m, const uint8_t* prev_gray, const u
     // goodFeaturesToTrack + cornerSubPix on the previous frame (:333-334)
     std::vector<float> pre(2 * 1000);
     int n = 0;
+    static const bool one_stream = getenv("COEB_MOTION_ONE_STREAM") != nullptr;   // development switch
+    m->side.cur_gray = one_stream ? nullptr : cur_gray; m->side.stride = stride; m->side.done = false;
     int st = coeb_motion_good_features(m, prev_gray, width, height, stride, 1000, 0.01, 8.0, 0.04, pre.data(), 1000, &n);
+    m->side.cur_gray = nullptr;
+    const bool side_done = m->side.done;
+    if (st != COEB_OK || n == 0) { if (side_done) cudaStreamSynchronize(m->stream2); }   // nothing follows: the side stream must not outlive the call
     if (st != COEB_OK) return st;
     if (trace) trace->n_points = n;
     if (n == 0) return COEB_OK;
@@ -1097,8 +1211,8 @@ int coeb_process_moving_object(coeb_motion* m, const uint8_t* prev_gray, const u
     CUDA_TRY(cudaMemcpyAsync(m->d_pre, pre.data(), sizeof(float2) * n, cudaMemcpyHostToDevice, m->stream));   // level 0 of the previous frame is resident
     corner_subpix_kernel<10><<<(n + 3) / 4, 128, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, 20, 0.03 * 0.03, m->d_mask);
     // calcOpticalFlowPyrLK + border / SAD tests (:335-364)
-    if ((st = upload_level0(m, 1, cur_gray, stride)) != COEB_OK) return st;
-    if ((st = run_lk(m, n, 22, 20, 0.01, 1e-4, /*limit_edge_corner*/ 5, /*limit_of_check*/ 2120.f)) != COEB_OK) return st;
+    if (!side_done && (st = upload_level0(m, 1, cur_gray, stride)) != COEB_OK) return st;
+    if ((st = run_lk(m, n, 22, 20, 0.01, 1e-4, /*limit_edge_corner*/ 5, /*limit_of_check*/ 2120.f, side_done)) != COEB_OK) return st;
     std::vector<float> nxt(2 * (size_t)n);
     std::vector<uint8_t> state(n);
     CUDA_TRY(cudaMemcpyAsync(pre.data(), m->d_pre, sizeof(float2) * n, cudaMemcpyDeviceToHost, m->stream));

@@ -87,6 +87,23 @@ class Motion:
                      state=np.array(tr.state[:k], np.uint8), F=np.array(tr.F[:], np.float64).reshape(3, 3) if tr.have_F else None)
         return tm[:n.value].copy(), trace
 
+    def prepared_process(self, prev, cur, cap=1000):
+        """The C call with its ctypes arguments built once (what a C++ caller pays): returns a zero-argument callable that runs
+        coeb_process_moving_object on the two frames and returns the number of T_M points (results stay in the prepared buffers)."""
+        prev, cur = _gray(prev), _gray(cur)
+        assert prev.shape == cur.shape
+        tm = np.zeros((cap, 2), np.float32)
+        n = C.c_int()
+        fn = lib().coeb_process_moving_object
+        a = (self.h, _p(prev), _p(cur), prev.shape[1], prev.shape[0], prev.strides[0], _p(tm), cap, C.byref(n), None)
+        keep = (prev, cur, tm, n)
+
+        def call():
+            _check(fn(*a))
+            return n.value
+        call.keep = keep
+        return call
+
 
 def fundamental_ransac(p1, p2, threshold=0.1, confidence=0.99, max_iters=1000, seed=12345):
     """Host code of the library (no device needed). Returns (F [3,3], inlier mask)."""
