@@ -636,10 +636,16 @@ __global__ void __launch_bounds__(1024, 1) m2_resolve_kernel(FrameDev F, MapDev 
 //     query spent ~100 instructions per query and round on reductions over mostly empty lanes, 3 of a round's 4.3 us.
 //     Longer lists keep the warp-per-query form.
 constexpr int kSl = 8;   // entries of a short list
-template <bool kSmem>
-__global__ void __launch_bounds__(1024, 1) m2_resolve_cached_kernel(int Fn, int Mn, float nnratio, const int* __restrict__ kp_state, CandLists C,
+// kMode 2: SearchByProjection(F, MapPoints) -- best and second best with the level / ratio test (:115-121).
+// kMode 3: SearchByProjection(cur, last) and its relocalisation overload -- the best unclaimed candidate within `accept` (:1421-1429),
+//          then the rotation-consistency histogram over the accepted matches (:1431-1468); records carry no second entry.
+__device__ __forceinline__ int rot_bin(float a1, float a2);
+__device__ void three_maxima(const int* histo, int L, int& ind1, int& ind2, int& ind3);
+struct RotArgs { int check_ori; const float* q_angle; const float* k_angle; };   // kMode 3: angles of the queries / of the frame's keypoints
+template <bool kSmem, int kMode>
+__global__ void __launch_bounds__(1024, 1) m2_resolve_cached_kernel(int Fn, int Mn, float nnratio, int accept, const int* __restrict__ kp_state, CandLists C,
                                                                  int* kp_match, int* claim_glob, int* out_info, int cache_cap, int slow_cap,
-                                                                 const uint4* __restrict__ flags_dev, uint4* flags_host, int flags_vec) {
+                                                                 const uint4* __restrict__ flags_dev, uint4* flags_host, int flags_vec, RotArgs rot) {
     constexpr bool claim_in_smem = kSmem;
     COEB_MTRACE(4);
     constexpr int kLongCap = 256, kSlowBit = 0x20000000, kIdMask = 0x1FFFFFFF;
@@ -674,7 +680,8 @@ __global__ void __launch_bounds__(1024, 1) m2_resolve_cached_kernel(int Fn, int 
         return;
     }
     auto decide = [&](int bestDist, int bestLevel, int bestIdx, int bestDist2, int bestLevel2) {
-        return (bestDist <= COEB_TH_HIGH && !(bestLevel == bestLevel2 && (float)bestDist > nnratio * (float)bestDist2)) ? bestIdx : -1;
+        if (kMode == 3) return bestDist <= accept ? bestIdx : -1;
+        return (bestDist <= accept && !(bestLevel == bestLevel2 && (float)bestDist > nnratio * (float)bestDist2)) ? bestIdx : -1;
     };
     // caching pass + round 0: R_1 = F(nothing claimed); its claims go to table 0
     for (int a = tid; a < na; a += T) {
@@ -682,7 +689,7 @@ __global__ void __launch_bounds__(1024, 1) m2_resolve_cached_kernel(int Fn, int 
         const int iq = r.x, d2 = (r.w >> 9) & 511;
         const int2 e1 = make_int2(r.y, r.w & 511);
         const int2 e2 = (r.z < 0 || d2 >= 256) ? make_int2(-1, 256) : make_int2(r.z, d2);   // (a distance of 256 never enters, :100)
-        const int out = e1.y <= COEB_TH_HIGH ? decide(e1.y, e1.x >> 24, e1.x & 0xFFFFFF, e2.y, e2.x < 0 ? -1 : (e2.x >> 24)) : -1;
+        const int out = e1.y <= accept ? decide(e1.y, e1.x >> 24, e1.x & 0xFFFFFF, e2.y, e2.x < 0 ? -1 : (e2.x >> 24)) : -1;
         qi[a] = iq;
         qres[a] = out;
         q1[a] = e1;
@@ -713,7 +720,7 @@ __global__ void __launch_bounds__(1024, 1) m2_resolve_cached_kernel(int Fn, int 
             const int iq = qi[a];
             if (iq & kSlowBit) continue;
             const int2 e1 = q1[a];
-            if (e1.y > COEB_TH_HIGH) continue;   // exclusions can only raise the best distance: stays -1
+            if (e1.y > accept) continue;   // exclusions can only raise the best distance: stays -1
             const int i = iq & kIdMask;
             const int2 e2 = q2[a];
             int out;
@@ -826,17 +833,41 @@ __global__ void __launch_bounds__(1024, 1) m2_resolve_cached_kernel(int Fn, int 
     COEB_MMARK(7);   // rounds done
     COEB_MSTAT(12, (int)(clock64() - trace_c0));   // SM cycles between mark 0 and mark 7
 #endif
-    // F.mvpMapPoints[bestIdx] = pMP in query order: the last writer wins; every success counts (:123-124)
+    // F.mvpMapPoints[bestIdx] = pMP in query order: the last writer wins; every success counts (:123-124, :1429-1430)
+    __shared__ int s_hist[COEB_HISTO_LENGTH];
+    __shared__ int s_ind[3];
     if (tid == 0) s_count = 0;
+    if (kMode == 3) for (int k = tid; k < COEB_HISTO_LENGTH; k += T) s_hist[k] = 0;
     for (int k = tid; k < Fn; k += T) tab[k] = -1;   // "last claimant"
     __syncthreads();
     int mine = 0;
     for (int a = tid; a < na; a += T)
-        if (qres[a] >= 0) { atomicMax(&tab[qres[a]], qi[a] & kIdMask); mine++; }
+        if (qres[a] >= 0) {
+            const int i = qi[a] & kIdMask;
+            atomicMax(&tab[qres[a]], i);
+            mine++;
+            if (kMode == 3 && rot.check_ori) atomicAdd(&s_hist[rot_bin(rot.q_angle[i], rot.k_angle[qres[a]])], 1);
+        }
     if (mine) atomicAdd(&s_count, mine);
     __syncthreads();
     for (int k = tid; k < Fn; k += T)
         kp_match[k] = tab[k] >= 0 ? tab[k] : kp_state[k];   // untouched entries keep the caller's state
+    if (kMode == 3 && rot.check_ori) {   // rotation consistency (:1449-1468): entries of the losing bins are cleared, each decrements
+        if (tid == 0) {
+            int a, b, c;
+            three_maxima(s_hist, COEB_HISTO_LENGTH, a, b, c);
+            s_ind[0] = a; s_ind[1] = b; s_ind[2] = c;
+        }
+        __syncthreads();   // (also orders the kp_match writes above before the clearing writes below)
+        int removed = 0;
+        for (int a = tid; a < na; a += T)
+            if (qres[a] >= 0) {
+                const int bin = rot_bin(rot.q_angle[qi[a] & kIdMask], rot.k_angle[qres[a]]);
+                if (bin != s_ind[0] && bin != s_ind[1] && bin != s_ind[2]) { kp_match[qres[a]] = -1; removed++; }
+            }
+        if (removed) atomicSub(&s_count, removed);
+        __syncthreads();
+    }
     if (tid == 0) { out_info[0] = s_count; out_info[1] = round + 1; out_info[2] = 0; }
 }
 
@@ -940,11 +971,14 @@ __device__ __forceinline__ void m3_visit(const FrameDev& C, const LastDev& L, fl
 
 __global__ void __launch_bounds__(256) m3_collect_kernel(FrameDev Cf, LastDev L, float th, const int* kp_state, CandLists C) {
     COEB_MTRACE(5);
+    pdl_launch_dependents();   // see m2_collect_kernel
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per last-frame point
     if (i >= L.n) return;
     M3Query q;
     int cnt = 0;
     unsigned k1 = 0xFFFFFFFFu;   // this lane's smallest distance << 16 | list position
+    int k1x = -1;                // ... and its keypoint
+    const bool obs = L.has_obs[i] != 0;
     if (m3_query(Cf, L, th, i, q)) {
         int2* out = C.items + (size_t)i * C.cap;
         cnt = warp_for_each_in_area(
@@ -954,15 +988,25 @@ __global__ void __launch_bounds__(256) m3_collect_kernel(FrameDev Cf, LastDev L,
                 if (pos < C.cap) {
                     const int dist = hamming256(q.d, Cf.desc + 8 * (size_t)i2);
                     out[pos] = make_int2(i2, dist);
-                    k1 = min(k1, ((unsigned)dist << 16) | (unsigned)pos);
+                    const unsigned key = ((unsigned)dist << 16) | (unsigned)pos;
+                    if (key < k1) { k1 = key; k1x = i2; }
                 }
             });
     }
+    unsigned b1 = k1;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) k1 = min(k1, __shfl_xor_sync(0xffffffffu, k1, o));   // strict '<' of :1421-1425: first of the smallest
+    for (int o = 16; o > 0; o >>= 1) b1 = min(b1, __shfl_xor_sync(0xffffffffu, b1, o));   // strict '<' of :1421-1425: first of the smallest
+    const int x1 = __shfl_sync(0xffffffffu, k1x, __ffs(__ballot_sync(0xffffffffu, k1 == b1)) - 1);   // (the key carries its position: one holder)
     if ((threadIdx.x & 31) == 0) {
-        if (C.top) C.top[i] = (int)(k1 & 0xFFFFu);
-        cand_finish(C, i, cnt);
+        if (C.top) C.top[i] = (int)(b1 & 0xFFFFu);
+        C.count[i] = cnt;
+        // a query whose smallest distance exceeds the acceptance bound can never match or claim (exclusions only raise it): not handed on
+        if (cnt > 0 && (b1 >> 16) <= (unsigned)L.max_accept) {
+            const int a = atomicAdd(&C.meta[0], 1);
+            C.active[a] = i;
+            if (C.rec) C.rec[a] = make_int4(obs ? i : (i | kNoObsBit), x1, -1, (int)(b1 >> 16) | (256 << 9) | (min(cnt, 255) << 18));
+        }
+        if (cnt > C.cap) C.meta[1] = 1;
     }
 }
 
@@ -2165,35 +2209,44 @@ bool m2_cached_fits(const coeb_frame* F, int n_map) {
 }
 // flags_dev / flags_host (optional, 16-byte aligned, flags_bytes rounded up to 16): copied device -> mapped host memory by the cached
 // kernel; only passed when m2_cached_fits() says that kernel runs.
-int launch_m2_resolve(coeb_matcher* m, const coeb_frame* F, const MapDev& M, float th, float nnratio, const int* d_state, const CandLists& C, int* d_kpm,
-                      int* d_res, int* d_claim, int* d_info, const uint8_t* flags_dev = nullptr, uint8_t* flags_host = nullptr, size_t flags_bytes = 0) {
-    static bool big_smem[64][2] = {};   // opt-in above 48 KB of dynamic shared memory: a per-device function attribute, set once
+// Launches the cached resolve kernel (kMode 2 or 3) programmatically dependent on the collect kernel enqueued before it.
+// The caller has checked m2_cached_fits(F, n_queries).
+template <int kMode>
+int launch_cached_resolve(coeb_matcher* m, const coeb_frame* F, int n_queries, float nnratio, int accept, const int* d_state, const CandLists& C, int* d_kpm,
+                          int* d_claim, int* d_info, const uint8_t* flags_dev, uint8_t* flags_host, size_t flags_bytes, const RotArgs& rot) {
+    static bool big_smem[64] = {};   // opt-in above 48 KB of dynamic shared memory: a per-device function attribute, set once
     const int dv = m->device & 63;
     const size_t claim3 = (size_t)F->n * 12 <= 48 * 1024 ? (size_t)F->n * 12 : 0;
     int cc = 0;
-    const size_t sm3 = resolve_smem(claim3, M.n + 1, 25, &cc);
-    if (m2_cached_fits(F, M.n)) {
-        const uint4* fd = reinterpret_cast<const uint4*>(flags_dev);
-        uint4* fh = reinterpret_cast<uint4*>(flags_host);
-        const int fv = flags_dev && flags_host ? (int)((flags_bytes + 15) / 16) : 0;
-        if (!big_smem[dv][0]) {
-            CUDA_TRY(cudaFuncSetAttribute(m2_resolve_cached_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
-            CUDA_TRY(cudaFuncSetAttribute(m2_resolve_cached_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
-            big_smem[dv][0] = true;
-        }
-        cudaLaunchConfig_t cfg = {};
-        // the shared-memory copies of the short lists of queued queries (kSl entries each) take what is left of the budget
-        const size_t lists_at = (sm3 + 7 + 8) & ~(size_t)7, budget = 204 * 1024;
-        const int slow_cap = (int)std::min<size_t>(1024, budget > lists_at ? (budget - lists_at) / (kSl * 8) : 0) & ~31;
-        cfg.gridDim = dim3(1); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = lists_at + (size_t)slow_cap * kSl * 8; cfg.stream = m->stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        if (claim3) CUDA_TRY(cudaLaunchKernelEx(&cfg, m2_resolve_cached_kernel<true>, F->n, M.n, nnratio, d_state, C, d_kpm, d_claim, d_info, cc, slow_cap, fd, fh, fv));
-        else CUDA_TRY(cudaLaunchKernelEx(&cfg, m2_resolve_cached_kernel<false>, F->n, M.n, nnratio, d_state, C, d_kpm, d_claim, d_info, cc, slow_cap, fd, fh, fv));
-        return COEB_OK;
+    const size_t sm3 = resolve_smem(claim3, n_queries + 1, 25, &cc);
+    const uint4* fd = reinterpret_cast<const uint4*>(flags_dev);
+    uint4* fh = reinterpret_cast<uint4*>(flags_host);
+    const int fv = flags_dev && flags_host ? (int)((flags_bytes + 15) / 16) : 0;
+    if (!big_smem[dv]) {
+        CUDA_TRY(cudaFuncSetAttribute(m2_resolve_cached_kernel<true, kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(m2_resolve_cached_kernel<false, kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+        big_smem[dv] = true;
     }
+    cudaLaunchConfig_t cfg = {};
+    // the shared-memory copies of the short lists of queued queries (kSl entries each) take what is left of the budget
+    const size_t lists_at = (sm3 + 7 + 8) & ~(size_t)7, budget = 204 * 1024;
+    const int slow_cap = (int)std::min<size_t>(1024, budget > lists_at ? (budget - lists_at) / (kSl * 8) : 0) & ~31;
+    cfg.gridDim = dim3(1); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = lists_at + (size_t)slow_cap * kSl * 8; cfg.stream = m->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (claim3) CUDA_TRY(cudaLaunchKernelEx(&cfg, m2_resolve_cached_kernel<true, kMode>, F->n, n_queries, nnratio, accept, d_state, C, d_kpm, d_claim, d_info, cc, slow_cap, fd, fh, fv, rot));
+    else CUDA_TRY(cudaLaunchKernelEx(&cfg, m2_resolve_cached_kernel<false, kMode>, F->n, n_queries, nnratio, accept, d_state, C, d_kpm, d_claim, d_info, cc, slow_cap, fd, fh, fv, rot));
+    return COEB_OK;
+}
+
+int launch_m2_resolve(coeb_matcher* m, const coeb_frame* F, const MapDev& M, float th, float nnratio, const int* d_state, const CandLists& C, int* d_kpm,
+                      int* d_res, int* d_claim, int* d_info, const uint8_t* flags_dev = nullptr, uint8_t* flags_host = nullptr, size_t flags_bytes = 0) {
+    static bool big_smem[64][2] = {};
+    const int dv = m->device & 63;
+    int cc = 0;
+    if (m2_cached_fits(F, M.n)) return launch_cached_resolve<2>(m, F, M.n, nnratio, COEB_TH_HIGH, d_state, C, d_kpm, d_claim, d_info, flags_dev, flags_host, flags_bytes, RotArgs{});
     const size_t claim_smem = (size_t)F->n * 4 <= 32 * 1024 ? (size_t)F->n * 4 : 0;   // claim table in shared memory when it fits
     const size_t sm = resolve_smem(claim_smem, M.n + 1, 25, &cc);
     if (!big_smem[dv][1]) {
@@ -2468,9 +2521,14 @@ int coeb_match_lastframe(coeb_matcher* m, coeb_frame* cur, int n, const uint8_t*
     int* d_info = (int*)(m->outm.d + al(K * 4));
     int* d_res = (int*)m->d_scratch;
     int* d_claim = (int*)((char*)m->d_scratch + al(N * 4));
-    const CandLists C = carve_lists((char*)m->d_scratch + al(N * 4) + al(K * 4), N, cap, m->d_meta);
+    const CandLists C = carve_lists((char*)m->d_scratch + al(N * 4) + al(K * 12), N, cap, m->d_meta);
     m3_collect_kernel<<<(n + 7) / 8, 256, 0, m->stream>>>(cur->dev, L, th, d_state, C);
-    if (claim_smem) m3_resolve_kernel<true, true><<<1, 512, claim_smem, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info);
+    CUDA_TRY(cudaGetLastError());
+    if (m2_cached_fits(cur, n)) {   // the latency form of the fixed-point iteration (m2_resolve_cached_kernel, kMode 3)
+        RotArgs rot{check_ori, L.angle, cur->dev.angle};
+        if ((st = launch_cached_resolve<3>(m, cur, n, 0.f, L.max_accept, d_state, C, d_kpm, d_claim, d_info, nullptr, nullptr, 0, rot)) != COEB_OK) return st;
+    }
+    else if (claim_smem) m3_resolve_kernel<true, true><<<1, 512, claim_smem, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info);
     else m3_resolve_kernel<true, false><<<1, 512, 0, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info);
     CUDA_TRY(cudaGetLastError());
     if ((st = sync_outputs(m)) != COEB_OK) return st;
@@ -3080,9 +3138,14 @@ int coeb_match_reloc(coeb_matcher* m, coeb_frame* cur, int n, const uint8_t* val
     int* d_info = (int*)(m->outm.d + al(K * 4));
     int* d_res = (int*)m->d_scratch;
     int* d_claim = (int*)((char*)m->d_scratch + al(N * 4));
-    const CandLists C = carve_lists((char*)m->d_scratch + al(N * 4) + al(K * 4), N, cap, m->d_meta);
+    const CandLists C = carve_lists((char*)m->d_scratch + al(N * 4) + al(K * 12), N, cap, m->d_meta);
     m3_collect_kernel<<<(n + 7) / 8, 256, 0, m->stream>>>(cur->dev, L, th, d_state, C);
-    if (claim_smem) m3_resolve_kernel<true, true><<<1, 512, claim_smem, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info);
+    CUDA_TRY(cudaGetLastError());
+    if (m2_cached_fits(cur, n)) {   // the latency form of the fixed-point iteration (m2_resolve_cached_kernel, kMode 3)
+        RotArgs rot{check_ori, L.angle, cur->dev.angle};
+        if ((st = launch_cached_resolve<3>(m, cur, n, 0.f, L.max_accept, d_state, C, d_kpm, d_claim, d_info, nullptr, nullptr, 0, rot)) != COEB_OK) return st;
+    }
+    else if (claim_smem) m3_resolve_kernel<true, true><<<1, 512, claim_smem, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info);
     else m3_resolve_kernel<true, false><<<1, 512, 0, m->stream>>>(cur->dev, L, th, check_ori, d_state, C, d_kpm, d_res, d_claim, d_info);
     CUDA_TRY(cudaGetLastError());
     if ((st = sync_outputs(m)) != COEB_OK) return st;
