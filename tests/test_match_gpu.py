@@ -216,3 +216,25 @@ def test_wide_windows_take_the_overflow_fallback(gpu, tum):
     n_c, m_c, p_c = orc.match_init(f1c, f2c, prev, 400, 0.9, True)
     n_g, m_g, p_g = m.match_init(f1g, f2g, prev, 400, 0.9, True)
     assert n_c == n_g and np.array_equal(m_c, m_g) and np.array_equal(p_c, p_g)
+
+
+@pytest.mark.parametrize("n_map,th", [(5000, 1.0), (5000, 3.0), (9000, 1.0)])
+def test_dense_frames_and_large_maps(gpu, tum, n_map, th):
+    """The latency form of the resolve kernel keeps its claim tables in shared memory up to 4096 keypoints and caches up to ~7000
+    queries; a denser frame (tables in global memory, long candidate lists) and a larger map (general kernel) must equal the
+    oracle as well."""
+    ex = orc.Extractor()
+    parts = [ex.extract(synth.make_frame(300 + s)) for s in range(6)]
+    kps, desc = np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+    assert len(kps) > 4200
+    mp, uright = synth.make_map_points(kps, desc, tum["scale"], seed=n_map, n_map=n_map, n_true=2500)
+    m, fg, fc = _frames(gpu, tum, kps=kps, desc=desc, uright=uright)
+    rng = np.random.default_rng(n_map)
+    state = rng.choice([-1, -1, -1, -2], size=len(kps)).astype(np.int32)
+    n_c, km_c = orc.match_projection(fc, mp, th, 0.8, state)
+    n_g, km_g = m.match_projection(fg, mp, th, 0.8, state)
+    assert n_c == n_g and np.array_equal(km_c, km_g) and n_c > 300
+    last, Tc, Tl = synth.make_last_frame(kps, desc, seed=n_map + 1)
+    n_c, km_c = orc.match_lastframe(fc, last, Tc, Tl, 7.0 * th, False, True, state)
+    n_g, km_g = m.match_lastframe(fg, last, Tc, Tl, 7.0 * th, False, True, state)
+    assert n_c == n_g and np.array_equal(km_c, km_g) and n_c > 300
