@@ -768,8 +768,48 @@ int select_corners(std::vector<float2>& cand, bool sorted, int w, int h, int max
     if (min_distance >= 1) {
         const int cell = (int)std::lrint(min_distance);
         const int gw = (w + cell - 1) / cell, gh = (h + cell - 1) / cell;
-        std::vector<std::vector<float2> > grid((size_t)gw * gh);
         const double md2 = min_distance * min_distance;
+        // Flat grid: accepted corners are >= minDistance apart, so a cell of that size holds a handful; kSlots each, counts in one byte
+        // array (a vector per cell cost this pass 4800 constructions and a heap allocation per occupied cell: 70 us of the call).
+        // Should a cell ever fill up, the pass starts over with the general container below.
+        constexpr int kSlots = 6;
+        static thread_local std::vector<unsigned char> cnt;
+        static thread_local std::vector<short> slot;
+        cnt.assign((size_t)gw * gh, 0);
+        if (slot.size() < (size_t)gw * gh * kSlots * 2) slot.resize((size_t)gw * gh * kSlots * 2);
+        bool overflow = false;
+        const unsigned rcp_w = w < 65536 ? (unsigned)(((1ull << 32) + w - 1) / w) : 0;   // idx / w by multiply-shift (exact for idx < 2^32 / w ... checked below)
+        for (size_t i = 0; i < cand.size() && !overflow; i++) {
+            int idx;
+            std::memcpy(&idx, &cand[i].y, 4);
+            int y = rcp_w ? (int)(((unsigned long long)(unsigned)idx * rcp_w) >> 32) : idx / w;
+            int x = idx - y * w;
+            if (x < 0 || x >= w) { y = idx / w; x = idx - y * w; }   // the reciprocal may be one off at the far end: redo exactly
+            const int xc = x / cell, yc = y / cell;
+            const int x1 = std::max(0, xc - 1), y1 = std::max(0, yc - 1), x2 = std::min(gw - 1, xc + 1), y2 = std::min(gh - 1, yc + 1);
+            bool good = true;
+            for (int yy = y1; yy <= y2 && good; yy++)
+                for (int xx = x1; xx <= x2 && good; xx++) {
+                    const size_t c = (size_t)yy * gw + xx;
+                    const short* q = &slot[c * kSlots * 2];
+                    for (int k = 0; k < cnt[c]; k++) {
+                        const float dx = (float)(x - q[2 * k]), dy = (float)(y - q[2 * k + 1]);
+                        if (dx * dx + dy * dy < md2) { good = false; break; }
+                    }
+                }
+            if (good) {
+                const size_t c = (size_t)yc * gw + xc;
+                if (cnt[c] == kSlots) { overflow = true; break; }
+                slot[(c * kSlots + cnt[c]) * 2] = (short)x; slot[(c * kSlots + cnt[c]) * 2 + 1] = (short)y;
+                cnt[c]++;
+                if (n < cap) { xy_out[2 * n] = (float)x; xy_out[2 * n + 1] = (float)y; }
+                n++;
+                if (max_corners > 0 && n == max_corners) break;
+            }
+        }
+        if (!overflow) return n;
+        n = 0;
+        std::vector<std::vector<float2> > grid((size_t)gw * gh);
         for (size_t i = 0; i < cand.size(); i++) {
             int idx;
             std::memcpy(&idx, &cand[i].y, 4);
@@ -1019,8 +1059,13 @@ void coeb_motion_destroy(coeb_motion* m) {
     delete m;
 }
 
+// COEB_MOTION_TRACE: host time marks inside good_features() (us since its entry): 0 frame staged + upload enqueued, 1 kernels and
+// result copies enqueued, 2 side-stream work enqueued, 3 synchronised, 4 minimum-distance pass done
+static thread_local double g_gf_mark[5];
 int coeb_motion_good_features(coeb_motion* m, const uint8_t* gray, int width, int height, int stride, int max_corners, double quality, double min_distance,
                               double harris_k, float* xy_out, int cap, int* n_out) {
+    const auto gf_t0 = std::chrono::steady_clock::now();
+    auto gf_mark = [&](int k) { g_gf_mark[k] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - gf_t0).count(); };
     if (!m || !gray || !xy_out || !n_out || width < 8 || height < 8 || stride < width || cap < 0) return fail(COEB_ERR_INVALID_ARG, "bad argument");
     *n_out = 0;
     CUDA_TRY(cudaSetDevice(m->device));
@@ -1028,6 +1073,7 @@ int coeb_motion_good_features(coeb_motion* m, const uint8_t* gray, int width, in
     if (st != COEB_OK) return st;
     if ((st = upload_level0(m, 0, gray, stride)) != COEB_OK) return st;
     if (m->side.cur_gray) CUDA_TRY(cudaEventRecord(m->ev_prev, m->stream));
+    gf_mark(0);
     CUDA_TRY(cudaMemsetAsync(m->d_max, 0, 16, m->stream));
     // Sobel scale of cornerHarris for 8-bit input: 1 / (2^(ksize-1) * blockSize * 255); the kernel taps are float(1*scale), float(2*scale)
     const double scale = 1.0 / ((double)(1 << 2) * 3 * 255.0);
@@ -1046,8 +1092,11 @@ int coeb_motion_good_features(coeb_motion* m, const uint8_t* gray, int width, in
     if (st2 != COEB_OK) return st2;
     CUDA_TRY(cudaMemcpyAsync(m->h_pin, m->d_max, 16, cudaMemcpyDeviceToHost, m->stream));
     CUDA_TRY(cudaMemcpyAsync(m->h_pin + 16, m->d_cand, sizeof(float2) * kSortCap, cudaMemcpyDeviceToHost, m->stream));
+    gf_mark(1);
     if ((st2 = enqueue_side_work(m)) != COEB_OK) return st2;
+    gf_mark(2);
     CUDA_TRY(cudaStreamSynchronize(m->stream));
+    gf_mark(3);
     const unsigned* info = reinterpret_cast<const unsigned*>(m->h_pin);
     if ((int)info[1] > kMoMaxCand) return fail(COEB_ERR_CAPACITY, "%u corner candidates (at most %d)", info[1], kMoMaxCand);
     const int nc = (int)info[1];
@@ -1056,6 +1105,7 @@ int coeb_motion_good_features(coeb_motion* m, const uint8_t* gray, int width, in
     if (sorted) { if (nc) std::memcpy(m->cand_host.data(), m->h_pin + 16, sizeof(float2) * nc); }
     else CUDA_TRY(cudaMemcpy(m->cand_host.data(), m->d_cand, sizeof(float2) * nc, cudaMemcpyDeviceToHost));
     const int n = select_corners(m->cand_host, sorted, width, height, max_corners, min_distance, xy_out, cap);
+    gf_mark(4);
     *n_out = n;
     return n > cap ? COEB_ERR_CAPACITY : COEB_OK;
 }
@@ -1252,8 +1302,9 @@ int coeb_process_moving_object(coeb_motion* m, const uint8_t* prev_gray, const u
         }
     *n_tm_out = k;
     if (timeline)
-        fprintf(stderr, "[coeb motion] corners (upload, Harris, candidates, sort, min-distance) %.0f us, subpix + pyramids + LK %.0f us, RANSAC %.0f us (%d of %d inliers), epipolar %.0f us\n",
-                us(t0, t1), us(t1, t2), us(t2, t3), ninl, nf, us(t3, now()));
+        fprintf(stderr, "[coeb motion] corners (upload, Harris, candidates, sort, min-distance) %.0f us [staged %.0f, enqueued %.0f, side work %.0f, synchronised %.0f, selected %.0f], "
+                        "subpix + pyramids + LK %.0f us, RANSAC %.0f us (%d of %d inliers), epipolar %.0f us\n",
+                us(t0, t1), g_gf_mark[0], g_gf_mark[1], g_gf_mark[2], g_gf_mark[3], g_gf_mark[4], us(t1, t2), us(t2, t3), ninl, nf, us(t3, now()));
     return k > cap ? COEB_ERR_CAPACITY : COEB_OK;
 }
 
