@@ -235,6 +235,104 @@ __global__ void __launch_bounds__(128) corner_subpix_kernel(const uint8_t* __res
     if (lane == 0) pts[p] = cI;
 }
 
+// The same iteration with one CTA (kPtWarps warps) per corner: a frame has ~600 corners and the device 148 SMs, so one warp per corner left
+// four warps per SM, each walking 17 patch samples and 14 gradient terms per lane and iteration with nothing to hide their latency
+// behind (57 us for 591 corners). With the window spread over 128 threads an iteration is 5 samples and 4 terms per thread, one block
+// barrier for the patch and one for the five sums (per-warp partials in shared memory, added in warp order by every thread, so all threads
+// hold the same doubles and take the same branches).
+constexpr int kPtWarps = 4;   // measured: 8 warps per point are slower again (subpix + LK 146 us against 122 us, 187 us with one)
+template <int HW>
+__global__ void __launch_bounds__(32 * kPtWarps) corner_subpix_cta_kernel(const uint8_t* __restrict__ img, int w, int h, int pitch, float2* __restrict__ pts, int n,
+                                                                         int max_iters, double eps2, const float* __restrict__ mask) {
+    constexpr int hw = HW, win = 2 * HW + 1, pw = win + 2, T = 32 * kPtWarps;
+    constexpr int NP = (pw * pw + T - 1) / T, NG = (win * win + T - 1) / T;   // patch samples / gradient terms per thread
+    __shared__ float patch[pw * pw];
+    __shared__ double s_red[2][kPtWarps][5];
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const int p = blockIdx.x;
+    if (p >= n) return;
+    int soff[NP], gidx[NG];
+    float gm[NG];
+#pragma unroll
+    for (int k = 0; k < NP; k++) { const int i = t + T * k, py = i / pw; soff[k] = py * pitch + (i - py * pw); }
+#pragma unroll
+    for (int k = 0; k < NG; k++) {
+        const int i = t + T * k, yy = i / win, xx = i - yy * win;
+        gidx[k] = (yy + 1) * pw + (xx + 1);
+        gm[k] = i < win * win ? mask[i] : 0.f;
+    }
+    const float2 cT = pts[p];
+    float2 cI = cT;
+    int iter = 0, par = 0;
+    double err = 0;
+    do {
+        // getRectSubPix(src, (pw, pw), cI, patch, CV_32F)
+        const float cxf = cI.x - (float)(pw - 1) * 0.5f, cyf = cI.y - (float)(pw - 1) * 0.5f;
+        const int ipx = (int)floorf(cxf), ipy = (int)floorf(cyf);
+        const float a = cxf - (float)ipx, b = cyf - (float)ipy;
+        const float a11 = __fmul_rn(1.f - a, 1.f - b), a12 = __fmul_rn(a, 1.f - b), a21 = __fmul_rn(1.f - a, b), a22 = __fmul_rn(a, b);
+        if (ipx >= 0 && ipy >= 0 && ipx + pw + 1 <= w && ipy + pw + 1 <= h) {   // the patch lies inside the image
+            const uint8_t* base = img + (size_t)ipy * pitch + ipx;
+#pragma unroll
+            for (int k = 0; k < NP; k++) {
+                const int i = t + T * k;
+                if (i < pw * pw) {
+                    const uint8_t* q = base + soff[k];
+                    patch[i] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn((float)q[0], a11), __fmul_rn((float)q[1], a12)), __fmul_rn((float)q[pitch], a21)), __fmul_rn((float)q[pitch + 1], a22));
+                }
+            }
+        } else {
+            for (int i = t; i < pw * pw; i += T) {
+                const int py = i / pw, px = i - py * pw;
+                const int x0 = min(max(ipx + px, 0), w - 1), x1 = min(max(ipx + px + 1, 0), w - 1);
+                const int y0 = min(max(ipy + py, 0), h - 1), y1 = min(max(ipy + py + 1, 0), h - 1);
+                const float v00 = img[(size_t)y0 * pitch + x0], v01 = img[(size_t)y0 * pitch + x1], v10 = img[(size_t)y1 * pitch + x0], v11 = img[(size_t)y1 * pitch + x1];
+                patch[i] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v00, a11), __fmul_rn(v01, a12)), __fmul_rn(v10, a21)), __fmul_rn(v11, a22));
+            }
+        }
+        __syncthreads();
+        double sa = 0, sb = 0, sc = 0, sbb1 = 0, sbb2 = 0;
+#pragma unroll
+        for (int k = 0; k < NG; k++) {
+            const int i = t + T * k;
+            if (i < win * win) {
+                const float* sp = patch + gidx[k];
+                const int yy = i / win, xx = i - yy * win;
+                const double m = gm[k];
+                const double tgx = (double)__fsub_rn(sp[1], sp[-1]), tgy = (double)__fsub_rn(sp[pw], sp[-pw]);
+                const double gxx = tgx * tgx * m, gxy = tgx * tgy * m, gyy = tgy * tgy * m;
+                const double px = xx - hw, py = yy - hw;
+                sa += gxx; sb += gxy; sc += gyy;
+                sbb1 += gxx * px + gxy * py;
+                sbb2 += gxy * px + gyy * py;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sa += __shfl_xor_sync(0xffffffffu, sa, o); sb += __shfl_xor_sync(0xffffffffu, sb, o); sc += __shfl_xor_sync(0xffffffffu, sc, o);
+            sbb1 += __shfl_xor_sync(0xffffffffu, sbb1, o); sbb2 += __shfl_xor_sync(0xffffffffu, sbb2, o);
+        }
+        if (lane == 0) { double* r = s_red[par][wid]; r[0] = sa; r[1] = sb; r[2] = sc; r[3] = sbb1; r[4] = sbb2; }
+        __syncthreads();   // (also: every thread has read the patch before the next iteration overwrites it)
+        sa = sb = sc = sbb1 = sbb2 = 0;
+#pragma unroll
+        for (int g = 0; g < kPtWarps; g++) { const double* r = s_red[par][g]; sa += r[0]; sb += r[1]; sc += r[2]; sbb1 += r[3]; sbb2 += r[4]; }
+        par ^= 1;
+        const double det = sa * sc - sb * sb;
+        if (fabs(det) <= DBL_EPSILON * DBL_EPSILON) break;
+        const double scale = 1.0 / det;
+        float2 cI2;
+        cI2.x = (float)((double)cI.x + sc * scale * sbb1 - sb * scale * sbb2);
+        cI2.y = (float)((double)cI.y - sb * scale * sbb1 + sa * scale * sbb2);
+        err = ((double)cI2.x - cI.x) * ((double)cI2.x - cI.x) + ((double)cI2.y - cI.y) * ((double)cI2.y - cI.y);
+        cI = cI2;
+        if (cI.x < 0 || cI.x >= (float)w || cI.y < 0 || cI.y >= (float)h) break;
+    } while (++iter < max_iters && err > eps2);
+    // poor convergence: the initial point stays
+    if (fabsf(cI.x - cT.x) > (float)hw || fabsf(cI.y - cT.y) > (float)hw) cI = cT;
+    if (t == 0) pts[p] = cI;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // cv::pyrDown (8-bit): 5x5 binomial [1 4 6 4 1] x [1 4 6 4 1], (sum + 128) >> 8, BORDER_REFLECT_101; size ((w+1)/2, (h+1)/2).
 // ---------------------------------------------------------------------------------------------------------------------
@@ -545,6 +643,175 @@ __global__ void __launch_bounds__(32 * kLkWarps) lk_kernel_w(const __grid_consta
         __syncwarp();
     }
     if (lane == 0) {
+        next_pts[p] = nextPt;
+        // src/Frame.cc:336-364: 5-px border test on the truncated coordinates, then the 3x3 sum of absolute differences
+        if (st && edge >= 0) {
+            const int w = L.w[0], h = L.h[0], pitch = L.pitch[0];
+            const int x1 = (int)pt0.x, y1 = (int)pt0.y, x2 = (int)nextPt.x, y2 = (int)nextPt.y;
+            if (x1 < edge || x1 >= w - edge || x2 < edge || x2 >= w - edge || y1 < edge || y1 >= h - edge || y2 < edge || y2 >= h - edge) {
+                st = false;
+            } else {
+                int sad = 0;
+                for (int j = -1; j <= 1; j++)
+                    for (int i = -1; i <= 1; i++) sad += abs((int)L.prev[0][(size_t)(y1 + j) * pitch + x1 + i] - (int)L.cur[0][(size_t)(y2 + j) * pitch + x2 + i]);
+                if ((float)sad > sad_limit) st = false;
+            }
+        }
+        status[p] = st ? 1 : 0;
+    }
+}
+
+// lk_kernel_w with one CTA (kPtWarps warps) per point, for the same reason as corner_subpix_cta_kernel: 591 points as 591 warps were four
+// warps per SM, 16 window pixels per lane and iteration (83 us). Here a thread owns 4 pixels of the 22 x 22 window; the sums of a level
+// (A11, A12, A22) and of an iteration (b1, b2) are warp-reduced, exchanged through shared memory and added in warp order by every thread,
+// so the point's state is identical in all 128 threads and every branch is uniform.
+__device__ __forceinline__ void cta_sum3(float& a, float& b, float& c, float (*s_red)[kPtWarps][3], int& par) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { s_red[par][wid][0] = a; s_red[par][wid][1] = b; s_red[par][wid][2] = c; }
+    __syncthreads();
+    a = b = c = 0.f;
+#pragma unroll
+    for (int g = 0; g < kPtWarps; g++) { a += s_red[par][g][0]; b += s_red[par][g][1]; c += s_red[par][g][2]; }
+    par ^= 1;   // the next exchange uses the other buffer: one barrier per exchange is enough
+}
+
+template <int WIN>
+__global__ void __launch_bounds__(32 * kPtWarps) lk_cta_kernel(const __grid_constant__ LkLevels L, const float2* __restrict__ prev_pts, int n, int max_iters,
+                                                              float eps2, float min_eig_thr, float2* __restrict__ next_pts, uint8_t* __restrict__ status,
+                                                              int edge, float sad_limit) {
+    constexpr int win = WIN, T = 32 * kPtWarps, NS = (WIN * WIN + T - 1) / T;
+    __shared__ float s_red[2][kPtWarps][3];
+    const int t = threadIdx.x;
+    const int p = blockIdx.x;
+    if (p >= n) return;
+    int par = 0;
+    int Ib[NS], Ixb[NS], Iyb[NS], off[NS];   // this thread's pixels i = t + T k of the window: patch value, derivatives, y * pitch + x
+    const float2 pt0 = prev_pts[p];
+    const float half = (float)(win - 1) * 0.5f;
+    const float FLT_SCALE = 1.f / (1 << 20);
+    float2 nextPt = make_float2(0.f, 0.f);
+    bool st = true;
+    for (int level = L.nlevels - 1; level >= 0; level--) {
+        const int w = L.w[level], h = L.h[level], pitch = L.pitch[level];
+        const uint8_t *I = L.prev[level], *J = L.cur[level];
+        const short2* D = L.deriv[level];
+#pragma unroll
+        for (int k = 0; k < NS; k++) { const int i = t + T * k, y = i / WIN; off[k] = y * pitch + (i - y * WIN); }
+        const float sc = (float)(1. / (double)(1 << level));
+        float2 prevPt = make_float2(__fmul_rn(pt0.x, sc), __fmul_rn(pt0.y, sc));
+        if (level == L.nlevels - 1) nextPt = prevPt;
+        else nextPt = make_float2(__fmul_rn(nextPt.x, 2.f), __fmul_rn(nextPt.y, 2.f));
+        prevPt.x = __fsub_rn(prevPt.x, half); prevPt.y = __fsub_rn(prevPt.y, half);
+        const int ipx = (int)floorf(prevPt.x), ipy = (int)floorf(prevPt.y);
+        if (ipx < -win || ipx >= w || ipy < -win || ipy >= h) {
+            if (level == 0) st = false;
+            continue;
+        }
+        float a = __fsub_rn(prevPt.x, (float)ipx), b = __fsub_rn(prevPt.y, (float)ipy);
+        int iw00 = __float2int_rn(__fmul_rn(__fmul_rn(1.f - a, 1.f - b), 16384.f));
+        int iw01 = __float2int_rn(__fmul_rn(__fmul_rn(a, 1.f - b), 16384.f));
+        int iw10 = __float2int_rn(__fmul_rn(__fmul_rn(1.f - a, b), 16384.f));
+        int iw11 = 16384 - iw00 - iw01 - iw10;
+        float A11 = 0, A12 = 0, A22 = 0;
+        const bool insideI = ipx >= 0 && ipy >= 0 && ipx + WIN + 1 <= w && ipy + WIN + 1 <= h;
+#pragma unroll
+        for (int k = 0; k < NS; k++) {
+            const int i = t + T * k;
+            Ib[k] = Ixb[k] = Iyb[k] = 0;
+            if (i < WIN * WIN) {
+                int ival, ixval, iyval;
+                const int y = i / WIN, x = i - y * WIN;
+                if (insideI) {
+                    const uint8_t* q = I + (size_t)ipy * pitch + ipx + off[k];
+                    ival = ((int)q[0] * iw00 + (int)q[1] * iw01 + (int)q[pitch] * iw10 + (int)q[pitch + 1] * iw11 + (1 << 8)) >> 9;
+                    const short2* dq = D + (size_t)(ipy + y) * w + ipx + x;
+                    const short2 d00 = dq[0], d01 = dq[1], d10 = dq[w], d11 = dq[w + 1];
+                    ixval = ((int)d00.x * iw00 + (int)d01.x * iw01 + (int)d10.x * iw10 + (int)d11.x * iw11 + (1 << 13)) >> 14;
+                    iyval = ((int)d00.y * iw00 + (int)d01.y * iw01 + (int)d10.y * iw10 + (int)d11.y * iw11 + (1 << 13)) >> 14;
+                } else {
+                    const int gx0 = ipx + x, gy0 = ipy + y;
+                    const int x0 = refl101(gx0, w), x1 = refl101(gx0 + 1, w), y0 = refl101(gy0, h), y1 = refl101(gy0 + 1, h);
+                    ival = ((int)I[(size_t)y0 * pitch + x0] * iw00 + (int)I[(size_t)y0 * pitch + x1] * iw01 + (int)I[(size_t)y1 * pitch + x0] * iw10 +
+                            (int)I[(size_t)y1 * pitch + x1] * iw11 + (1 << 8)) >> 9;
+                    auto dv = [&](int gx, int gy) { return ((unsigned)gx < (unsigned)w && (unsigned)gy < (unsigned)h) ? D[(size_t)gy * w + gx] : make_short2(0, 0); };
+                    const short2 d00 = dv(gx0, gy0), d01 = dv(gx0 + 1, gy0), d10 = dv(gx0, gy0 + 1), d11 = dv(gx0 + 1, gy0 + 1);
+                    ixval = ((int)d00.x * iw00 + (int)d01.x * iw01 + (int)d10.x * iw10 + (int)d11.x * iw11 + (1 << 13)) >> 14;
+                    iyval = ((int)d00.y * iw00 + (int)d01.y * iw01 + (int)d10.y * iw10 + (int)d11.y * iw11 + (1 << 13)) >> 14;
+                }
+                ival = (int)(short)ival; ixval = (int)(short)ixval; iyval = (int)(short)iyval;   // the reference stores int16
+                Ib[k] = ival; Ixb[k] = ixval; Iyb[k] = iyval;
+                A11 += (float)(ixval * ixval); A12 += (float)(ixval * iyval); A22 += (float)(iyval * iyval);
+            }
+        }
+        cta_sum3(A11, A12, A22, s_red, par);
+        A11 *= FLT_SCALE; A12 *= FLT_SCALE; A22 *= FLT_SCALE;
+        float Dt = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+        const float dA = __fsub_rn(A11, A22);
+        const float minEig = (A22 + A11 - sqrtf(__fadd_rn(__fmul_rn(dA, dA), __fmul_rn(4.f, __fmul_rn(A12, A12))))) / (float)(2 * win * win);
+        if (minEig < min_eig_thr || Dt < FLT_EPSILON) {
+            if (level == 0) st = false;
+            continue;
+        }
+        Dt = 1.f / Dt;
+        nextPt.x = __fsub_rn(nextPt.x, half); nextPt.y = __fsub_rn(nextPt.y, half);
+        float2 prevDelta = make_float2(0.f, 0.f);
+        float2 result = make_float2(__fadd_rn(nextPt.x, half), __fadd_rn(nextPt.y, half));
+        for (int j = 0; j < max_iters; j++) {
+            const int inx = (int)floorf(nextPt.x), iny = (int)floorf(nextPt.y);
+            if (inx < -win || inx >= w || iny < -win || iny >= h) {
+                if (level == 0) st = false;
+                break;
+            }
+            a = __fsub_rn(nextPt.x, (float)inx); b = __fsub_rn(nextPt.y, (float)iny);
+            iw00 = __float2int_rn(__fmul_rn(__fmul_rn(1.f - a, 1.f - b), 16384.f));
+            iw01 = __float2int_rn(__fmul_rn(__fmul_rn(a, 1.f - b), 16384.f));
+            iw10 = __float2int_rn(__fmul_rn(__fmul_rn(1.f - a, b), 16384.f));
+            iw11 = 16384 - iw00 - iw01 - iw10;
+            float b1 = 0, b2 = 0, unused = 0;
+            const bool insideJ = inx >= 0 && iny >= 0 && inx + WIN + 1 <= w && iny + WIN + 1 <= h;
+            if (insideJ) {
+                const uint8_t* base = J + (size_t)iny * pitch + inx;
+#pragma unroll
+                for (int k = 0; k < NS; k++)
+                    if (t + T * k < WIN * WIN) {
+                        const uint8_t* q = base + off[k];
+                        const int jv = ((int)q[0] * iw00 + (int)q[1] * iw01 + (int)q[pitch] * iw10 + (int)q[pitch + 1] * iw11 + (1 << 8)) >> 9;
+                        const int diff = jv - Ib[k];
+                        b1 += (float)(diff * Ixb[k]);
+                        b2 += (float)(diff * Iyb[k]);
+                    }
+            } else {
+#pragma unroll
+                for (int k = 0; k < NS; k++) {
+                    const int i = t + T * k;
+                    if (i < WIN * WIN) {
+                        const int y = i / WIN, x = i - y * WIN;
+                        const int x0 = refl101(inx + x, w), x1 = refl101(inx + x + 1, w), y0 = refl101(iny + y, h), y1 = refl101(iny + y + 1, h);
+                        const int jv = ((int)J[(size_t)y0 * pitch + x0] * iw00 + (int)J[(size_t)y0 * pitch + x1] * iw01 + (int)J[(size_t)y1 * pitch + x0] * iw10 +
+                                        (int)J[(size_t)y1 * pitch + x1] * iw11 + (1 << 8)) >> 9;
+                        const int diff = jv - Ib[k];
+                        b1 += (float)(diff * Ixb[k]);
+                        b2 += (float)(diff * Iyb[k]);
+                    }
+                }
+            }
+            cta_sum3(b1, b2, unused, s_red, par);
+            b1 *= FLT_SCALE; b2 *= FLT_SCALE;
+            const float2 delta = make_float2(__fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), Dt), __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), Dt));
+            nextPt.x = __fadd_rn(nextPt.x, delta.x); nextPt.y = __fadd_rn(nextPt.y, delta.y);
+            result = make_float2(__fadd_rn(nextPt.x, half), __fadd_rn(nextPt.y, half));
+            if ((double)delta.x * delta.x + (double)delta.y * delta.y <= (double)eps2) break;
+            if (j > 0 && fabsf(delta.x + prevDelta.x) < 0.01f && fabsf(delta.y + prevDelta.y) < 0.01f) {
+                result.x = __fsub_rn(result.x, __fmul_rn(delta.x, 0.5f)); result.y = __fsub_rn(result.y, __fmul_rn(delta.y, 0.5f));
+                break;
+            }
+            prevDelta = delta;
+        }
+        nextPt = result;
+    }
+    if (t == 0) {
         next_pts[p] = nextPt;
         // src/Frame.cc:336-364: 5-px border test on the truncated coordinates, then the 3x3 sum of absolute differences
         if (st && edge >= 0) {
@@ -1122,7 +1389,10 @@ int coeb_motion_corner_subpix(coeb_motion* m, const uint8_t* gray, int width, in
     CUDA_TRY(cudaMemcpyAsync(m->d_pre, xy_inout, sizeof(float2) * n, cudaMemcpyHostToDevice, m->stream));
     const double e = std::max(eps, 0.0);
     switch (half_win) {   // the window is a compile-time size: its per-lane offsets and weights live in registers
-        case 10: corner_subpix_kernel<10><<<(n + 3) / 4, 128, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, std::max(max_iters, 1), e * e, m->d_mask); break;
+        case 10:
+            if (getenv("COEB_MOTION_WARP_PER_POINT")) corner_subpix_kernel<10><<<(n + 3) / 4, 128, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, std::max(max_iters, 1), e * e, m->d_mask);
+            else corner_subpix_cta_kernel<10><<<n, 32 * kPtWarps, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, std::max(max_iters, 1), e * e, m->d_mask);
+            break;
         case 5: corner_subpix_kernel<5><<<(n + 3) / 4, 128, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, std::max(max_iters, 1), e * e, m->d_mask); break;
         case 3: corner_subpix_kernel<3><<<(n + 3) / 4, 128, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, std::max(max_iters, 1), e * e, m->d_mask); break;
         default: return fail(COEB_ERR_UNSUPPORTED, "cornerSubPix half window %d (built for 3, 5 and 10)", half_win);
@@ -1147,7 +1417,10 @@ static int run_lk(coeb_motion* m, int n, int win, int max_iters, double eps, dou
         L.w[l] = m->lw[l]; L.h[l] = m->lh[l]; L.pitch[l] = m->lp[l];
         L.prev[l] = m->d_pyr[0][l]; L.cur[l] = m->d_pyr[1][l]; L.deriv[l] = m->d_deriv[l];
     }
-    if (win == 22)
+    static const bool warp_per_point = getenv("COEB_MOTION_WARP_PER_POINT") != nullptr;   // development switch: the one-warp-per-point kernels
+    if (win == 22 && !warp_per_point)
+        lk_cta_kernel<22><<<n, 32 * kPtWarps, 0, m->stream>>>(L, m->d_pre, n, max_iters, (float)(eps * eps), (float)min_eig, m->d_next, m->d_status, edge, sad_limit);
+    else if (win == 22)
         lk_kernel_w<22><<<(n + kLkWarps - 1) / kLkWarps, 32 * kLkWarps, 0, m->stream>>>(L, m->d_pre, n, max_iters, (float)(eps * eps), (float)min_eig, m->d_next, m->d_status, edge,
                                                                                   sad_limit);
     else
@@ -1259,7 +1532,11 @@ int coeb_process_moving_object(coeb_motion* m, const uint8_t* prev_gray, const u
     const auto t1 = now();
     if ((st = ensure_mask(m, 10)) != COEB_OK) return st;
     CUDA_TRY(cudaMemcpyAsync(m->d_pre, pre.data(), sizeof(float2) * n, cudaMemcpyHostToDevice, m->stream));   // level 0 of the previous frame is resident
-    corner_subpix_kernel<10><<<(n + 3) / 4, 128, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, 20, 0.03 * 0.03, m->d_mask);
+    {
+        static const bool warp_per_point = getenv("COEB_MOTION_WARP_PER_POINT") != nullptr;
+        if (warp_per_point) corner_subpix_kernel<10><<<(n + 3) / 4, 128, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, 20, 0.03 * 0.03, m->d_mask);
+        else corner_subpix_cta_kernel<10><<<n, 32 * kPtWarps, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, 20, 0.03 * 0.03, m->d_mask);
+    }
     // calcOpticalFlowPyrLK + border / SAD tests (:335-364)
     if (!side_done && (st = upload_level0(m, 1, cur_gray, stride)) != COEB_OK) return st;
     if ((st = run_lk(m, n, 22, 20, 0.01, 1e-4, /*limit_edge_corner*/ 5, /*limit_of_check*/ 2120.f, side_done)) != COEB_OK) return st;
