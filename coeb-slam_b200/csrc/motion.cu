@@ -112,9 +112,18 @@ __global__ void __launch_bounds__(256) harris_candidates_kernel(const float* __r
 // key response-bits << 32 | raster index (responses are positive floats). One CTA sorts up to kSortCap keys in shared memory
 // (bitonic network); longer lists are sorted on the host.
 constexpr int kSortCap = 8192;
-__global__ void __launch_bounds__(1024) sort_candidates_kernel(float2* __restrict__ cand, const int* __restrict__ n_cand) {
+// The sorted list and the {max response bits, count} words go straight into the caller's mapped pinned block (`host`: 16 bytes of
+// info, then the candidates): no device-to-host copy nodes behind the kernel. Lists the kernel does not sort (n > kSortCap) are fetched
+// from `cand` by the host.
+// The kernel is the last reader of the two words and clears them for the next call's Harris kernels (no memset node per call).
+__global__ void __launch_bounds__(1024) sort_candidates_kernel(float2* __restrict__ cand, unsigned* __restrict__ info, char* __restrict__ host) {
     extern __shared__ unsigned long long s_key[];
-    const int n = *n_cand;
+    const int n = (int)info[1];
+    if (threadIdx.x < 4) reinterpret_cast<unsigned*>(host)[threadIdx.x] = info[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x < 4) info[threadIdx.x] = 0u;
+    float2* const out = reinterpret_cast<float2*>(host + 16);
+    if (n == 1 && threadIdx.x == 0) out[0] = cand[0];
     if (n > kSortCap || n < 2) return;
     int m = 2;
     while (m < n) m <<= 1;
@@ -132,11 +141,14 @@ __global__ void __launch_bounds__(1024) sort_candidates_kernel(float2* __restric
                 const unsigned long long a = s_key[i], b = s_key[j];
                 if ((a < b) == desc) { s_key[i] = b; s_key[j] = a; }
             }
-            __syncthreads();
+            // A warp's 32 pairs of one pass span 64 consecutive keys, and for strides <= 32 they stay inside those 64: the stages of such a
+            // run only need the warp to agree (63 of the 91 stages of 8192 keys: 21.8 -> ~11 us); a block barrier closes the run.
+            if (stride > 32 || (stride == 1 && size >= 64)) __syncthreads();
+            else __syncwarp();
         }
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const unsigned long long k = s_key[i];
-        cand[i] = make_float2(__uint_as_float((unsigned)(k >> 32)), __int_as_float((int)(unsigned)k));
+        out[i] = make_float2(__uint_as_float((unsigned)(k >> 32)), __int_as_float((int)(unsigned)k));
     }
 }
 
@@ -243,7 +255,8 @@ __global__ void __launch_bounds__(128) corner_subpix_kernel(const uint8_t* __res
 constexpr int kPtWarps = 4;   // measured: 8 warps per point are slower again (subpix + LK 146 us against 122 us, 187 us with one)
 template <int HW>
 __global__ void __launch_bounds__(32 * kPtWarps) corner_subpix_cta_kernel(const uint8_t* __restrict__ img, int w, int h, int pitch, float2* __restrict__ pts, int n,
-                                                                         int max_iters, double eps2, const float* __restrict__ mask) {
+                                                                         int max_iters, double eps2, const float* __restrict__ mask, float2* __restrict__ pts_host,
+                                                                         const float2* __restrict__ pts_in /* initial corners, if not pts (mapped host memory) */) {
     constexpr int hw = HW, win = 2 * HW + 1, pw = win + 2, T = 32 * kPtWarps;
     constexpr int NP = (pw * pw + T - 1) / T, NG = (win * win + T - 1) / T;   // patch samples / gradient terms per thread
     __shared__ float patch[pw * pw];
@@ -261,7 +274,7 @@ __global__ void __launch_bounds__(32 * kPtWarps) corner_subpix_cta_kernel(const 
         gidx[k] = (yy + 1) * pw + (xx + 1);
         gm[k] = i < win * win ? mask[i] : 0.f;
     }
-    const float2 cT = pts[p];
+    const float2 cT = pts_in ? pts_in[p] : pts[p];
     float2 cI = cT;
     int iter = 0, par = 0;
     double err = 0;
@@ -330,7 +343,10 @@ __global__ void __launch_bounds__(32 * kPtWarps) corner_subpix_cta_kernel(const 
     } while (++iter < max_iters && err > eps2);
     // poor convergence: the initial point stays
     if (fabsf(cI.x - cT.x) > (float)hw || fabsf(cI.y - cT.y) > (float)hw) cI = cT;
-    if (t == 0) pts[p] = cI;
+    if (t == 0) {
+        pts[p] = cI;
+        if (pts_host) pts_host[p] = cI;   // mapped pinned copy for the caller: no device-to-host copy node
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -680,7 +696,7 @@ __device__ __forceinline__ void cta_sum3(float& a, float& b, float& c, float (*s
 template <int WIN>
 __global__ void __launch_bounds__(32 * kPtWarps) lk_cta_kernel(const __grid_constant__ LkLevels L, const float2* __restrict__ prev_pts, int n, int max_iters,
                                                               float eps2, float min_eig_thr, float2* __restrict__ next_pts, uint8_t* __restrict__ status,
-                                                              int edge, float sad_limit) {
+                                                              int edge, float sad_limit, float2* __restrict__ next_host, uint8_t* __restrict__ status_host) {
     constexpr int win = WIN, T = 32 * kPtWarps, NS = (WIN * WIN + T - 1) / T;
     __shared__ float s_red[2][kPtWarps][3];
     const int t = threadIdx.x;
@@ -813,6 +829,7 @@ __global__ void __launch_bounds__(32 * kPtWarps) lk_cta_kernel(const __grid_cons
     }
     if (t == 0) {
         next_pts[p] = nextPt;
+        if (next_host) next_host[p] = nextPt;
         // src/Frame.cc:336-364: 5-px border test on the truncated coordinates, then the 3x3 sum of absolute differences
         if (st && edge >= 0) {
             const int w = L.w[0], h = L.h[0], pitch = L.pitch[0];
@@ -827,6 +844,7 @@ __global__ void __launch_bounds__(32 * kPtWarps) lk_cta_kernel(const __grid_cons
             }
         }
         status[p] = st ? 1 : 0;
+        if (status_host) status_host[p] = st ? 1 : 0;
     }
 }
 
@@ -865,12 +883,14 @@ struct coeb_motion {
     short2* d_deriv[kMoMaxLevels] = {nullptr};
     float* d_resp = nullptr;
     unsigned* d_max = nullptr;      // [0] max response bits, [1] candidate count
+    bool info_dirty = true;         // d_max has to be cleared before the next Harris pass (the sort kernel normally does it)
     float2* d_cand = nullptr;
     float2 *d_pre = nullptr, *d_next = nullptr;
     uint8_t *d_status = nullptr, *d_moving = nullptr;
     double *d_F = nullptr, *d_dist = nullptr;
     float* d_mask = nullptr; int mask_hw = 0;
     char* h_pin = nullptr; size_t pin_bytes = 0;
+    char* h_out = nullptr;          // mapped pinned block the point kernels mirror their outputs into (coeb_process_moving_object)
     std::vector<float2> cand_host;
     // coeb_process_moving_object: the current frame's upload, both pyramids and the derivative images run on a side stream beside the
     // corner stage (which ends in a host round trip); `side` describes the work good_features() enqueues there before it synchronises
@@ -921,7 +941,7 @@ int motion_pin(coeb_motion* m, size_t bytes) {
     if (bytes <= m->pin_bytes) return COEB_OK;
     if (m->h_pin) cudaFreeHost(m->h_pin);
     m->h_pin = nullptr; m->pin_bytes = 0;
-    CUDA_TRY(cudaHostAlloc((void**)&m->h_pin, bytes, cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc((void**)&m->h_pin, bytes, cudaHostAllocMapped));   // (the sort kernel writes into it)
     m->pin_bytes = bytes;
     return COEB_OK;
 }
@@ -1321,6 +1341,7 @@ void coeb_motion_destroy(coeb_motion* m) {
     cudaFree(m->d_max); cudaFree(m->d_cand); cudaFree(m->d_pre); cudaFree(m->d_next); cudaFree(m->d_status); cudaFree(m->d_moving); cudaFree(m->d_F);
     cudaFree(m->d_dist); cudaFree(m->d_mask);
     if (m->h_pin) cudaFreeHost(m->h_pin);
+    if (m->h_out) cudaFreeHost(m->h_out);
     for (int f = 0; f < 2; f++) if (m->h_frame[f]) cudaFreeHost(m->h_frame[f]);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
@@ -1341,24 +1362,24 @@ int coeb_motion_good_features(coeb_motion* m, const uint8_t* gray, int width, in
     if ((st = upload_level0(m, 0, gray, stride)) != COEB_OK) return st;
     if (m->side.cur_gray) CUDA_TRY(cudaEventRecord(m->ev_prev, m->stream));
     gf_mark(0);
-    CUDA_TRY(cudaMemsetAsync(m->d_max, 0, 16, m->stream));
+    if (m->info_dirty) CUDA_TRY(cudaMemsetAsync(m->d_max, 0, 16, m->stream));   // first call, or a call that failed before its sort kernel
+    m->info_dirty = true;
     // Sobel scale of cornerHarris for 8-bit input: 1 / (2^(ksize-1) * blockSize * 255); the kernel taps are float(1*scale), float(2*scale)
     const double scale = 1.0 / ((double)(1 << 2) * 3 * 255.0);
     harris_response_kernel<<<dim3((width + kHtW - 1) / kHtW, (height + kHtH - 1) / kHtH), dim3(kHtW, kHtH), 0, m->stream>>>(
         m->d_pyr[0][0], width, height, m->lp[0], harris_k, (float)(1.0 * scale), (float)(2.0 * scale), m->d_resp, m->d_max);
     harris_candidates_kernel<<<dim3((width + 31) / 32, (height + 7) / 8), 256, 0, m->stream>>>(m->d_resp, width, height, m->d_max, (float)quality, m->d_cand,
                                                                                             (int*)(m->d_max + 1), kMoMaxCand);
+    // the count and the first kSortCap candidates arrive in the mapped pinned block (the count sits right in front of the list)
+    int st2 = motion_pin(m, 16 + sizeof(float2) * kSortCap);
+    if (st2 != COEB_OK) return st2;
     {
         static bool configured[64] = {};
         if (!configured[m->device & 63]) { cudaFuncSetAttribute(sort_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8); configured[m->device & 63] = true; }
-        sort_candidates_kernel<<<1, 1024, kSortCap * 8, m->stream>>>(m->d_cand, (const int*)(m->d_max + 1));
+        sort_candidates_kernel<<<1, 1024, kSortCap * 8, m->stream>>>(m->d_cand, m->d_max, m->h_pin);
     }
     CUDA_TRY(cudaGetLastError());
-    // the count and the first kSortCap candidates come back in one transfer (the count sits right in front of the list)
-    int st2 = motion_pin(m, 16 + sizeof(float2) * kSortCap);
-    if (st2 != COEB_OK) return st2;
-    CUDA_TRY(cudaMemcpyAsync(m->h_pin, m->d_max, 16, cudaMemcpyDeviceToHost, m->stream));
-    CUDA_TRY(cudaMemcpyAsync(m->h_pin + 16, m->d_cand, sizeof(float2) * kSortCap, cudaMemcpyDeviceToHost, m->stream));
+    m->info_dirty = false;   // the sort kernel leaves the words cleared
     gf_mark(1);
     if ((st2 = enqueue_side_work(m)) != COEB_OK) return st2;
     gf_mark(2);
@@ -1391,7 +1412,7 @@ int coeb_motion_corner_subpix(coeb_motion* m, const uint8_t* gray, int width, in
     switch (half_win) {   // the window is a compile-time size: its per-lane offsets and weights live in registers
         case 10:
             if (getenv("COEB_MOTION_WARP_PER_POINT")) corner_subpix_kernel<10><<<(n + 3) / 4, 128, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, std::max(max_iters, 1), e * e, m->d_mask);
-            else corner_subpix_cta_kernel<10><<<n, 32 * kPtWarps, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, std::max(max_iters, 1), e * e, m->d_mask);
+            else corner_subpix_cta_kernel<10><<<n, 32 * kPtWarps, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, std::max(max_iters, 1), e * e, m->d_mask, nullptr, nullptr);
             break;
         case 5: corner_subpix_kernel<5><<<(n + 3) / 4, 128, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, std::max(max_iters, 1), e * e, m->d_mask); break;
         case 3: corner_subpix_kernel<3><<<(n + 3) / 4, 128, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, std::max(max_iters, 1), e * e, m->d_mask); break;
@@ -1403,7 +1424,9 @@ int coeb_motion_corner_subpix(coeb_motion* m, const uint8_t* gray, int width, in
     return COEB_OK;
 }
 
-static int run_lk(coeb_motion* m, int n, int win, int max_iters, double eps, double min_eig, int edge, float sad_limit, bool images_on_side_stream = false) {
+static int run_lk(coeb_motion* m, int n, int win, int max_iters, double eps, double min_eig, int edge, float sad_limit, bool images_on_side_stream = false,
+                  float2* next_host = nullptr, uint8_t* status_host = nullptr, bool* mirrored = nullptr) {
+    if (mirrored) *mirrored = false;
     if (images_on_side_stream) {
         CUDA_TRY(cudaStreamWaitEvent(m->stream, m->ev_side, 0));
     } else {
@@ -1419,7 +1442,11 @@ static int run_lk(coeb_motion* m, int n, int win, int max_iters, double eps, dou
     }
     static const bool warp_per_point = getenv("COEB_MOTION_WARP_PER_POINT") != nullptr;   // development switch: the one-warp-per-point kernels
     if (win == 22 && !warp_per_point)
-        lk_cta_kernel<22><<<n, 32 * kPtWarps, 0, m->stream>>>(L, m->d_pre, n, max_iters, (float)(eps * eps), (float)min_eig, m->d_next, m->d_status, edge, sad_limit);
+    {
+        lk_cta_kernel<22><<<n, 32 * kPtWarps, 0, m->stream>>>(L, m->d_pre, n, max_iters, (float)(eps * eps), (float)min_eig, m->d_next, m->d_status, edge, sad_limit, next_host,
+                                                              status_host);
+        if (mirrored) *mirrored = next_host && status_host;
+    }
     else if (win == 22)
         lk_kernel_w<22><<<(n + kLkWarps - 1) / kLkWarps, 32 * kLkWarps, 0, m->stream>>>(L, m->d_pre, n, max_iters, (float)(eps * eps), (float)min_eig, m->d_next, m->d_status, edge,
                                                                                   sad_limit);
@@ -1531,21 +1558,35 @@ int coeb_process_moving_object(coeb_motion* m, const uint8_t* prev_gray, const u
     if (n == 0) return COEB_OK;
     const auto t1 = now();
     if ((st = ensure_mask(m, 10)) != COEB_OK) return st;
-    CUDA_TRY(cudaMemcpyAsync(m->d_pre, pre.data(), sizeof(float2) * n, cudaMemcpyHostToDevice, m->stream));   // level 0 of the previous frame is resident
+    // refined corners, tracked positions and states are written by the kernels into this mapped pinned block as well
+    if (!m->h_out) CUDA_TRY(cudaHostAlloc((void**)&m->h_out, (size_t)kMoMaxPts * 25, cudaHostAllocMapped));
+    float2* const h_pre = reinterpret_cast<float2*>(m->h_out);
+    float2* const h_next = h_pre + kMoMaxPts;
+    uint8_t* const h_state = reinterpret_cast<uint8_t*>(h_next + kMoMaxPts);
+    bool pre_mirrored = false, lk_mirrored = false;
+    static const bool warp_per_point_ = getenv("COEB_MOTION_WARP_PER_POINT") != nullptr;
+    float2* const h_in = reinterpret_cast<float2*>(h_state + kMoMaxPts);   // the selected corners: read by the sub-pixel kernel across PCIe (8 bytes per CTA), no upload node
+    if (warp_per_point_) CUDA_TRY(cudaMemcpyAsync(m->d_pre, pre.data(), sizeof(float2) * n, cudaMemcpyHostToDevice, m->stream));   // level 0 of the previous frame is resident
+    else std::memcpy(h_in, pre.data(), sizeof(float2) * n);
     {
         static const bool warp_per_point = getenv("COEB_MOTION_WARP_PER_POINT") != nullptr;
         if (warp_per_point) corner_subpix_kernel<10><<<(n + 3) / 4, 128, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, 20, 0.03 * 0.03, m->d_mask);
-        else corner_subpix_cta_kernel<10><<<n, 32 * kPtWarps, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, 20, 0.03 * 0.03, m->d_mask);
+        else corner_subpix_cta_kernel<10><<<n, 32 * kPtWarps, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, 20, 0.03 * 0.03, m->d_mask, h_pre, h_in);
+        pre_mirrored = !warp_per_point;
     }
     // calcOpticalFlowPyrLK + border / SAD tests (:335-364)
     if (!side_done && (st = upload_level0(m, 1, cur_gray, stride)) != COEB_OK) return st;
-    if ((st = run_lk(m, n, 22, 20, 0.01, 1e-4, /*limit_edge_corner*/ 5, /*limit_of_check*/ 2120.f, side_done)) != COEB_OK) return st;
+    if ((st = run_lk(m, n, 22, 20, 0.01, 1e-4, /*limit_edge_corner*/ 5, /*limit_of_check*/ 2120.f, side_done, h_next, h_state, &lk_mirrored)) != COEB_OK) return st;
     std::vector<float> nxt(2 * (size_t)n);
     std::vector<uint8_t> state(n);
-    CUDA_TRY(cudaMemcpyAsync(pre.data(), m->d_pre, sizeof(float2) * n, cudaMemcpyDeviceToHost, m->stream));
-    CUDA_TRY(cudaMemcpyAsync(nxt.data(), m->d_next, sizeof(float2) * n, cudaMemcpyDeviceToHost, m->stream));
-    CUDA_TRY(cudaMemcpyAsync(state.data(), m->d_status, n, cudaMemcpyDeviceToHost, m->stream));
+    if (!pre_mirrored) CUDA_TRY(cudaMemcpyAsync(pre.data(), m->d_pre, sizeof(float2) * n, cudaMemcpyDeviceToHost, m->stream));
+    if (!lk_mirrored) {
+        CUDA_TRY(cudaMemcpyAsync(nxt.data(), m->d_next, sizeof(float2) * n, cudaMemcpyDeviceToHost, m->stream));
+        CUDA_TRY(cudaMemcpyAsync(state.data(), m->d_status, n, cudaMemcpyDeviceToHost, m->stream));
+    }
     CUDA_TRY(cudaStreamSynchronize(m->stream));
+    if (pre_mirrored) std::memcpy(pre.data(), h_pre, sizeof(float2) * n);
+    if (lk_mirrored) { std::memcpy(nxt.data(), h_next, sizeof(float2) * n); std::memcpy(state.data(), h_state, n); }
     const auto t2 = now();
     // findFundamentalMat(F_prepoint, F_nextpoint, FM_RANSAC, 0.1, 0.99) on the surviving pairs (:353-370)
     std::vector<float> f1, f2;
@@ -1564,13 +1605,29 @@ int coeb_process_moving_object(coeb_motion* m, const uint8_t* prev_gray, const u
     if (nf < 8 || coeb_fundamental_ransac(f1.data(), f2.data(), nf, 0.1, 0.99, 1000, 12345u, F, nullptr, &ninl) != COEB_OK) return COEB_OK;   // no model: no T_M
     if (trace) { trace->n_inliers = ninl; trace->have_F = 1; std::memcpy(trace->F, F, sizeof(F)); }
     const auto t3 = now();
-    // epipolar distance > 1 -> T_M, in point order (:372-385); the points are still resident
-    CUDA_TRY(cudaMemcpyAsync(m->d_F, F, sizeof(F), cudaMemcpyHostToDevice, m->stream));
-    epipolar_kernel<<<(n + 127) / 128, 128, 0, m->stream>>>(m->d_pre, m->d_next, m->d_status, n, m->d_F, 1.0, m->d_moving, nullptr);
-    CUDA_TRY(cudaGetLastError());
-    std::vector<uint8_t> mv(n);
-    CUDA_TRY(cudaMemcpyAsync(mv.data(), m->d_moving, n, cudaMemcpyDeviceToHost, m->stream));
-    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    // epipolar distance > 1 -> T_M, in point order (:372-385). The tracks are on the host already (the RANSAC ran on them) and there are
+    // a few hundred of them: the test runs here, in the operation order of epipolar_kernel (IEEE double, no contraction: same decisions),
+    // instead of costing the call another upload, launch, download and synchronisation (22 us).
+    static const bool device_epipolar = getenv("COEB_MOTION_DEVICE_EPIPOLAR") != nullptr;   // development switch
+    std::vector<uint8_t> mv(n, 0);
+    if (device_epipolar) {
+        CUDA_TRY(cudaMemcpyAsync(m->d_F, F, sizeof(F), cudaMemcpyHostToDevice, m->stream));
+        epipolar_kernel<<<(n + 127) / 128, 128, 0, m->stream>>>(m->d_pre, m->d_next, m->d_status, n, m->d_F, 1.0, m->d_moving, nullptr);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(mv.data(), m->d_moving, n, cudaMemcpyDeviceToHost, m->stream));
+        CUDA_TRY(cudaStreamSynchronize(m->stream));
+    } else {
+        for (int i = 0; i < n; i++) {
+            if (!state[i]) continue;
+            const volatile double px = pre[2 * i], py = pre[2 * i + 1], qx = nxt[2 * i], qy = nxt[2 * i + 1];
+            const volatile double A = (F[0] * px + F[1] * py) + F[2];
+            const volatile double B = (F[3] * px + F[4] * py) + F[5];
+            const volatile double C = (F[6] * px + F[7] * py) + F[8];
+            const volatile double num = std::fabs((A * qx + B * qy) + C), den = std::sqrt(A * A + B * B);
+            const double dd = num / den;
+            mv[i] = !(dd <= 1.0);
+        }
+    }
     int k = 0;
     for (int i = 0; i < n; i++)
         if (mv[i]) {
