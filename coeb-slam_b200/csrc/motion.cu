@@ -1153,6 +1153,38 @@ void jacobi_eigen(double* A, int n, double* V, double* ev) {
     for (int i = 0; i < n; i++) ev[i] = A[i * n + i];
 }
 
+// Unit eigenvector of the smallest eigenvalue of a symmetric positive semi-definite 3 x 3 matrix in closed form (trigonometric
+// eigenvalues, then the largest cross product of two rows of G - lambda I): the right singular vector the rank-2 projection of the
+// minimal-sample hypotheses removes. The Jacobi sweeps this replaces were a third of a hypothesis (0.47 of 1.35 us, ~40 per call).
+// false if the matrix is (numerically) a multiple of the identity.
+bool smallest_eigvec3(const double* G, double v[3]) {
+    const double p1 = G[1] * G[1] + G[2] * G[2] + G[5] * G[5];
+    const double q = (G[0] + G[4] + G[8]) / 3.0;
+    const double d0 = G[0] - q, d1 = G[4] - q, d2 = G[8] - q;
+    const double p2 = d0 * d0 + d1 * d1 + d2 * d2 + 2.0 * p1;
+    if (!(p2 > 0.0)) return false;
+    const double p = std::sqrt(p2 / 6.0), ip = 1.0 / p;
+    const double b00 = d0 * ip, b11 = d1 * ip, b22 = d2 * ip, b01 = G[1] * ip, b02 = G[2] * ip, b12 = G[5] * ip;
+    double r = 0.5 * (b00 * (b11 * b22 - b12 * b12) - b01 * (b01 * b22 - b12 * b02) + b02 * (b01 * b12 - b11 * b02));
+    r = r < -1.0 ? -1.0 : (r > 1.0 ? 1.0 : r);
+    const double phi = std::acos(r) / 3.0;
+    const double lam = q + 2.0 * p * std::cos(phi + 2.0943951023931953);   // + 2 pi / 3: the smallest of the three
+    const double r0[3] = {G[0] - lam, G[1], G[2]}, r1[3] = {G[3], G[4] - lam, G[5]}, r2[3] = {G[6], G[7], G[8] - lam};
+    const double c[3][3] = {{r0[1] * r1[2] - r0[2] * r1[1], r0[2] * r1[0] - r0[0] * r1[2], r0[0] * r1[1] - r0[1] * r1[0]},
+                            {r0[1] * r2[2] - r0[2] * r2[1], r0[2] * r2[0] - r0[0] * r2[2], r0[0] * r2[1] - r0[1] * r2[0]},
+                            {r1[1] * r2[2] - r1[2] * r2[1], r1[2] * r2[0] - r1[0] * r2[2], r1[0] * r2[1] - r1[1] * r2[0]}};
+    int best = 0;
+    double nb = -1.0;
+    for (int i = 0; i < 3; i++) {
+        const double n2 = c[i][0] * c[i][0] + c[i][1] * c[i][1] + c[i][2] * c[i][2];
+        if (n2 > nb) { nb = n2; best = i; }
+    }
+    if (!(nb > 0.0)) return false;
+    const double inv = 1.0 / std::sqrt(nb);
+    v[0] = c[best][0] * inv; v[1] = c[best][1] * inv; v[2] = c[best][2] * inv;
+    return true;
+}
+
 // 8-point algorithm on the points idx[0..cnt): Hartley normalisation, least-squares null vector, rank-2 projection. false if degenerate.
 bool eight_point(const float* p1, const float* p2, const int* idx, int cnt, double F[9]) {
     double m1x = 0, m1y = 0, m2x = 0, m2y = 0;
@@ -1171,8 +1203,9 @@ bool eight_point(const float* p1, const float* p2, const int* idx, int cnt, doub
         const int i = idx[k];
         const double x1 = (p1[2 * i] - m1x) * s1, y1 = (p1[2 * i + 1] - m1y) * s1, x2 = (p2[2 * i] - m2x) * s2, y2 = (p2[2 * i + 1] - m2y) * s2;
         const double r[9] = {x2 * x1, x2 * y1, x2, y2 * x1, y2 * y1, y2, x1, y1, 1};
-        for (int a = 0; a < 9; a++) for (int b = 0; b < 9; b++) A[a * 9 + b] += r[a] * r[b];
+        for (int a = 0; a < 9; a++) for (int b = a; b < 9; b++) A[a * 9 + b] += r[a] * r[b];   // upper triangle, mirrored below
     }
+    for (int a = 0; a < 9; a++) for (int b = 0; b < a; b++) A[a * 9 + b] = A[b * 9 + a];
     double V[81], ev[9];
     jacobi_eigen(A, 9, V, ev);
     int mi = 0;
@@ -1247,12 +1280,15 @@ bool eight_point_minimal(const float* p1, const float* p2, const int* idx, doubl
     double F0[9];
     F0[free_col] = 1.0;
     for (int r = 0; r < 8; r++) F0[piv_col[r]] = -A[r][free_col];
-    double G[9] = {0}, Vg[9], eg[3];
+    double G[9] = {0}, v[3], F2[9];
     for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) for (int k = 0; k < 3; k++) G[a * 3 + b] += F0[k * 3 + a] * F0[k * 3 + b];
-    jacobi_eigen(G, 3, Vg, eg);
-    int sm = 0;
-    for (int i = 1; i < 3; i++) if (eg[i] < eg[sm]) sm = i;
-    double v[3] = {Vg[0 * 3 + sm], Vg[1 * 3 + sm], Vg[2 * 3 + sm]}, F2[9];
+    if (!smallest_eigvec3(G, v)) {   // (a multiple of the identity: any direction serves; keep the general routine for it)
+        double Vg[9], eg[3];
+        jacobi_eigen(G, 3, Vg, eg);
+        int sm = 0;
+        for (int i = 1; i < 3; i++) if (eg[i] < eg[sm]) sm = i;
+        v[0] = Vg[0 * 3 + sm]; v[1] = Vg[1 * 3 + sm]; v[2] = Vg[2 * 3 + sm];
+    }
     for (int a = 0; a < 3; a++) {
         const double d = F0[a * 3] * v[0] + F0[a * 3 + 1] * v[1] + F0[a * 3 + 2] * v[2];
         for (int b = 0; b < 3; b++) F2[a * 3 + b] = F0[a * 3 + b] - d * v[b];
