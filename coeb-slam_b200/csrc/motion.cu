@@ -2,14 +2,15 @@
 // the "moving" points the extractor's box classification consumes (src/ORBextractor.cc:1101-1195).
 //
 // The reference body is six OpenCV calls and two loops of its own:
-//   goodFeaturesToTrack(prev, 1000, 0.01, 8, noArray, 3, useHarris, 0.04)        :333   -> harris_response / harris_candidates kernels,
-//                                                                                           sort + minimum-distance pass on the host
-//   cornerSubPix(prev, pts, (10,10), (-1,-1), (ITER|EPS, 20, 0.03))              :334   -> corner_subpix_kernel (one warp per corner)
-//   calcOpticalFlowPyrLK(prev, cur, pts, next, state, err, (22,22), 5, (20,.01)) :335   -> pyr_down / scharr kernels, lk_kernel (one warp per point,
-//                                                                                           all pyramid levels in one launch)
-//   5-px border test, 3x3 SAD test (limit 2120)                                  :336-364 -> tail of lk_kernel
+//   goodFeaturesToTrack(prev, 1000, 0.01, 8, noArray, 3, useHarris, 0.04)        :333   -> harris_response / harris_candidates / sort_candidates kernels,
+//                                                                                           minimum-distance pass on the host
+//   cornerSubPix(prev, pts, (10,10), (-1,-1), (ITER|EPS, 20, 0.03))              :334   -> corner_subpix_cta_kernel (one CTA of four warps per corner)
+//   calcOpticalFlowPyrLK(prev, cur, pts, next, state, err, (22,22), 5, (20,.01)) :335   -> pyr_down / scharr kernels (one captured graph on a side stream),
+//                                                                                           lk_cta_kernel (one CTA per point, all pyramid levels in one launch)
+//   5-px border test, 3x3 SAD test (limit 2120)                                  :336-364 -> tail of the LK kernel
 //   findFundamentalMat(F_pre, F_next, mask, FM_RANSAC, 0.1, 0.99)                :370   -> host (normalised 8-point inside RANSAC, own generator)
-//   epipolar distance > 1 -> T_M                                                 :372-385 -> epipolar_kernel (double precision, the reference's expression)
+//   epipolar distance > 1 -> T_M                                                 :372-385 -> on the host tracks inside coeb_process_moving_object, epipolar_kernel
+//                                                                                           behind coeb_epipolar_outliers (double precision, the reference's expression)
 //
 // The arithmetic of the OpenCV calls is OpenCV's (third party, pinned to 4.13.0). It is restated here operation by operation
 // (integer pyramid, integer Scharr derivatives and Q14 bilinear weights of the LK tracker are exact; the float parts follow the
