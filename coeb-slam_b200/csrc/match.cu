@@ -11,7 +11,10 @@
 // query i is a function F(i, results of queries j < i). The kernels evaluate all queries in
 // parallel and iterate R <- F(R) to a fixed point; any fixed point equals the sequential result
 // (induction on i), and the iteration reaches it after at most n rounds (round t fixes queries < t);
-// in practice 2-4 rounds, since conflicts are rare and local.
+// in practice 2-4 rounds, since conflicts are rare and local. The iteration runs in ONE CTA; m2_resolve_cached_kernel is its
+// form cut for the latency of a single call (records written by the collect kernels, rotating claim tables, a programmatic
+// dependent launch; SearchByProjection, SearchLocalPoints, the frame-to-frame search and its relocalisation overload), the
+// m2 / m3 / m4 resolve kernels the general ones (large maps, SearchForInitialization, the window-walking fallback).
 //
 // Tie-breaks follow the grid traversal order of GetFeaturesInArea (ix outer, iy inner, insertion
 // order inside a cell): the device grid stores cells ix-major, items in ascending keypoint index, so
@@ -2174,10 +2177,6 @@ size_t resolve_smem(size_t claim_bytes, int n_queries, int bytes_per_query, int*
     *cache_cap = (int)std::min<size_t>((size_t)std::max(n_queries, 0), room / bytes_per_query) & ~1;
     return fixed + (size_t)*cache_cap * bytes_per_query;
 }
-template <class K>
-void allow_smem(K kernel, size_t bytes) {   // opt-in above 48 KB: a per-device function attribute
-    if (bytes > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
-}
 
 int push_inputs(coeb_matcher* m, const Packer& p) {
     if (p.off) CUDA_TRY(cudaMemcpyAsync(m->in.d, m->in.h, p.off, cudaMemcpyHostToDevice, m->stream));
@@ -2243,16 +2242,16 @@ int launch_cached_resolve(coeb_matcher* m, const coeb_frame* F, int n_queries, f
 
 int launch_m2_resolve(coeb_matcher* m, const coeb_frame* F, const MapDev& M, float th, float nnratio, const int* d_state, const CandLists& C, int* d_kpm,
                       int* d_res, int* d_claim, int* d_info, const uint8_t* flags_dev = nullptr, uint8_t* flags_host = nullptr, size_t flags_bytes = 0) {
-    static bool big_smem[64][2] = {};
+    if (m2_cached_fits(F, M.n)) return launch_cached_resolve<2>(m, F, M.n, nnratio, COEB_TH_HIGH, d_state, C, d_kpm, d_claim, d_info, flags_dev, flags_host, flags_bytes, RotArgs{});
+    static bool big_smem[64] = {};   // opt-in above 48 KB of dynamic shared memory: a per-device function attribute, set once
     const int dv = m->device & 63;
     int cc = 0;
-    if (m2_cached_fits(F, M.n)) return launch_cached_resolve<2>(m, F, M.n, nnratio, COEB_TH_HIGH, d_state, C, d_kpm, d_claim, d_info, flags_dev, flags_host, flags_bytes, RotArgs{});
     const size_t claim_smem = (size_t)F->n * 4 <= 32 * 1024 ? (size_t)F->n * 4 : 0;   // claim table in shared memory when it fits
     const size_t sm = resolve_smem(claim_smem, M.n + 1, 25, &cc);
-    if (!big_smem[dv][1]) {
+    if (!big_smem[dv]) {
         CUDA_TRY(cudaFuncSetAttribute(m2_resolve_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
         CUDA_TRY(cudaFuncSetAttribute(m2_resolve_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
-        big_smem[dv][1] = true;
+        big_smem[dv] = true;
     }
     if (claim_smem) m2_resolve_kernel<true, true><<<1, 1024, sm, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info, cc);
     else m2_resolve_kernel<true, false><<<1, 1024, sm, m->stream>>>(F->dev, M, th, nnratio, d_state, C, d_kpm, d_res, d_claim, d_info, cc);

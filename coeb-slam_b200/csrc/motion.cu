@@ -1339,6 +1339,12 @@ int fm_count_inliers(const double* F, const double* x1, const double* y1, const 
 
 }  // namespace
 
+// Development switch (read once): the one-warp-per-point cornerSubPix / LK kernels instead of the CTA-per-point ones.
+static bool motion_warp_per_point() {
+    static const bool on = getenv("COEB_MOTION_WARP_PER_POINT") != nullptr;
+    return on;
+}
+
 extern "C" {
 
 int coeb_motion_create(int device, coeb_motion** out) {
@@ -1448,7 +1454,7 @@ int coeb_motion_corner_subpix(coeb_motion* m, const uint8_t* gray, int width, in
     const double e = std::max(eps, 0.0);
     switch (half_win) {   // the window is a compile-time size: its per-lane offsets and weights live in registers
         case 10:
-            if (getenv("COEB_MOTION_WARP_PER_POINT")) corner_subpix_kernel<10><<<(n + 3) / 4, 128, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, std::max(max_iters, 1), e * e, m->d_mask);
+            if (motion_warp_per_point()) corner_subpix_kernel<10><<<(n + 3) / 4, 128, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, std::max(max_iters, 1), e * e, m->d_mask);
             else corner_subpix_cta_kernel<10><<<n, 32 * kPtWarps, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, std::max(max_iters, 1), e * e, m->d_mask, nullptr, nullptr);
             break;
         case 5: corner_subpix_kernel<5><<<(n + 3) / 4, 128, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, std::max(max_iters, 1), e * e, m->d_mask); break;
@@ -1477,7 +1483,7 @@ static int run_lk(coeb_motion* m, int n, int win, int max_iters, double eps, dou
         L.w[l] = m->lw[l]; L.h[l] = m->lh[l]; L.pitch[l] = m->lp[l];
         L.prev[l] = m->d_pyr[0][l]; L.cur[l] = m->d_pyr[1][l]; L.deriv[l] = m->d_deriv[l];
     }
-    static const bool warp_per_point = getenv("COEB_MOTION_WARP_PER_POINT") != nullptr;   // development switch: the one-warp-per-point kernels
+    const bool warp_per_point = motion_warp_per_point();
     if (win == 22 && !warp_per_point)
     {
         lk_cta_kernel<22><<<n, 32 * kPtWarps, 0, m->stream>>>(L, m->d_pre, n, max_iters, (float)(eps * eps), (float)min_eig, m->d_next, m->d_status, edge, sad_limit, next_host,
@@ -1601,12 +1607,12 @@ int coeb_process_moving_object(coeb_motion* m, const uint8_t* prev_gray, const u
     float2* const h_next = h_pre + kMoMaxPts;
     uint8_t* const h_state = reinterpret_cast<uint8_t*>(h_next + kMoMaxPts);
     bool pre_mirrored = false, lk_mirrored = false;
-    static const bool warp_per_point_ = getenv("COEB_MOTION_WARP_PER_POINT") != nullptr;
+    const bool warp_per_point_ = motion_warp_per_point();
     float2* const h_in = reinterpret_cast<float2*>(h_state + kMoMaxPts);   // the selected corners: read by the sub-pixel kernel across PCIe (8 bytes per CTA), no upload node
     if (warp_per_point_) CUDA_TRY(cudaMemcpyAsync(m->d_pre, pre.data(), sizeof(float2) * n, cudaMemcpyHostToDevice, m->stream));   // level 0 of the previous frame is resident
     else std::memcpy(h_in, pre.data(), sizeof(float2) * n);
     {
-        static const bool warp_per_point = getenv("COEB_MOTION_WARP_PER_POINT") != nullptr;
+        const bool warp_per_point = motion_warp_per_point();
         if (warp_per_point) corner_subpix_kernel<10><<<(n + 3) / 4, 128, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, 20, 0.03 * 0.03, m->d_mask);
         else corner_subpix_cta_kernel<10><<<n, 32 * kPtWarps, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, 20, 0.03 * 0.03, m->d_mask, h_pre, h_in);
         pre_mirrored = !warp_per_point;
