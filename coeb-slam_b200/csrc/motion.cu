@@ -2,8 +2,8 @@
 // the "moving" points the extractor's box classification consumes (src/ORBextractor.cc:1101-1195).
 //
 // The reference body is six OpenCV calls and two loops of its own:
-//   goodFeaturesToTrack(prev, 1000, 0.01, 8, noArray, 3, useHarris, 0.04)        :333   -> harris_response / harris_candidates / sort_candidates kernels,
-//                                                                                           minimum-distance pass on the host
+//   goodFeaturesToTrack(prev, 1000, 0.01, 8, noArray, 3, useHarris, 0.04)        :333   -> harris_response / harris_candidates / sort_candidates kernels; the
+//                                                                                           minimum-distance pass in the sort kernel's CTA (whole call) or on the host
 //   cornerSubPix(prev, pts, (10,10), (-1,-1), (ITER|EPS, 20, 0.03))              :334   -> corner_subpix_cta_kernel (one CTA of four warps per corner)
 //   calcOpticalFlowPyrLK(prev, cur, pts, next, state, err, (22,22), 5, (20,.01)) :335   -> pyr_down / scharr kernels (one captured graph on a side stream),
 //                                                                                           lk_cta_kernel (one CTA per point, all pyramid levels in one launch)
@@ -117,18 +117,55 @@ constexpr int kSortCap = 8192;
 // info, then the candidates): no device-to-host copy nodes behind the kernel. Lists the kernel does not sort (n > kSortCap) are fetched
 // from `cand` by the host.
 // The kernel is the last reader of the two words and clears them for the next call's Harris kernels (no memset node per call).
-__global__ void __launch_bounds__(1024) sort_candidates_kernel(float2* __restrict__ cand, unsigned* __restrict__ info, char* __restrict__ host) {
-    extern __shared__ unsigned long long s_key[];
+//
+// With sel.enabled the same CTA goes on to goodFeaturesToTrack's minimum-distance pass (imgproc/featureselect.cpp: candidates in sorted
+// order; one is accepted unless an ALREADY ACCEPTED one lies closer than minDistance; stop at maxCorners), so that the corners never
+// visit the host and cornerSubPix / LK can be enqueued behind this kernel without a synchronisation. The pass is sequential as written;
+// here accepted(i) = no accepted j < i within the distance is iterated to its (unique: the dependencies run from earlier to later
+// candidates only) fixed point, 1024 candidates at a time in sorted order: everything before the current chunk is final, so a
+// candidate is either killed by a final earlier one or depends on the few close candidates of its own chunk (listed once in shared
+// memory); in-place updates, a chunk is done when one sweep changes nothing. The chunks stop once maxCorners are accepted.
+constexpr int kSelMaxCells = 4800, kSelNb = 12, kSelAccSlots = 4, kSelChunkSlots = 8;
+// shared-memory layout of the pass (bytes; it aliases the sorted keys, which are turned into positions first)
+constexpr int oSelPos = 0;                                             // unsigned[kSortCap]: x | y << 16 of candidate i (sorted order)
+constexpr int oSelA = oSelPos + kSortCap * 4;                          // uchar[1024]: accepted flag of the chunk's candidates
+constexpr int oSelAccCnt = oSelA + 1024;                               // int[cells]: accepted corners per cell (all chunks so far)
+constexpr int oSelAccSlot = oSelAccCnt + 4 * kSelMaxCells;             // ushort[cells][kSelAccSlots]: their candidate numbers
+constexpr int oSelChCnt = oSelAccSlot + 2 * kSelMaxCells * kSelAccSlots;   // int[cells]: live candidates of the current chunk per cell
+constexpr int oSelChSlot = oSelChCnt + 4 * kSelMaxCells;               // ushort[cells][kSelChunkSlots]: their thread numbers
+constexpr int oSelNb = oSelChSlot + 2 * kSelMaxCells * kSelChunkSlots; // ushort[1024][kSelNb]: close live predecessors of a thread's candidate
+constexpr int oSelWarp = oSelNb + 1024 * kSelNb * 2;                   // int[40]: scan scratch, accepted so far, overflow flag
+constexpr int kSelSmem = oSelWarp + 160;
+static_assert(kSelSmem >= kSortCap * 8 && kSelSmem <= 227 * 1024, "the selection arrays alias the sorted keys and fit one SM");
+struct SelectArgs {
+    int enabled, w, cell, gw, gh, max_corners, d2max;   // d2max: largest integer squared distance that is < minDistance^2
+    float2 *out_dev, *out_host;   // accepted corners in order (device for cornerSubPix, mapped host copy for the caller)
+    int *n_dev, *n_host;          // their number; -1: not selected here (too many candidates, or a grid that does not fit): host pass
+};
+__global__ void __launch_bounds__(1024) sort_candidates_kernel(float2* __restrict__ cand, unsigned* __restrict__ info, char* __restrict__ host, const SelectArgs sel) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    unsigned long long* const s_key = reinterpret_cast<unsigned long long*>(s_raw);
+    const int tid = threadIdx.x, T = blockDim.x;
     const int n = (int)info[1];
-    if (threadIdx.x < 4) reinterpret_cast<unsigned*>(host)[threadIdx.x] = info[threadIdx.x];
+    if (tid < 4) reinterpret_cast<unsigned*>(host)[tid] = info[tid];
     __syncthreads();
-    if (threadIdx.x < 4) info[threadIdx.x] = 0u;
+    if (tid < 4) info[tid] = 0u;
     float2* const out = reinterpret_cast<float2*>(host + 16);
-    if (n == 1 && threadIdx.x == 0) out[0] = cand[0];
+    const bool select_here = sel.enabled && n <= kSortCap && sel.gw * sel.gh <= kSelMaxCells;
+    if (sel.enabled && !select_here && tid == 0) { *sel.n_dev = -8; *sel.n_host = -8; }
+    if (n == 0 && select_here && tid == 0) { *sel.n_dev = 0; *sel.n_host = 0; }
+    if (n == 1 && tid == 0) {
+        out[0] = cand[0];
+        if (select_here) {
+            const int idx = __float_as_int(cand[0].y), y = idx / sel.w;
+            const float2 c = make_float2((float)(idx - y * sel.w), (float)y);
+            sel.out_dev[0] = c; sel.out_host[0] = c; *sel.n_dev = 1; *sel.n_host = 1;
+        }
+    }
     if (n > kSortCap || n < 2) return;
     int m = 2;
     while (m < n) m <<= 1;
-    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    for (int i = tid; i < m; i += T) {
         unsigned long long k = 0ull;   // padding sorts last in descending order
         if (i < n) { const float2 c = cand[i]; k = ((unsigned long long)__float_as_uint(c.x) << 32) | (unsigned)__float_as_int(c.y); }
         s_key[i] = k;
@@ -136,20 +173,156 @@ __global__ void __launch_bounds__(1024) sort_candidates_kernel(float2* __restric
     __syncthreads();
     for (int size = 2; size <= m; size <<= 1)
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int t = threadIdx.x; t < (m >> 1); t += blockDim.x) {
+            for (int t = tid; t < (m >> 1); t += T) {
                 const int i = 2 * t - (t & (stride - 1)), j = i + stride;
                 const bool desc = (i & size) == 0;
                 const unsigned long long a = s_key[i], b = s_key[j];
                 if ((a < b) == desc) { s_key[i] = b; s_key[j] = a; }
             }
             // A warp's 32 pairs of one pass span 64 consecutive keys, and for strides <= 32 they stay inside those 64: the stages of such a
-            // run only need the warp to agree (63 of the 91 stages of 8192 keys: 21.8 -> ~11 us); a block barrier closes the run.
+            // run only need the warp to agree (63 of the 91 stages of 8192 keys: 21.8 -> 19 us); a block barrier closes the run.
             if (stride > 32 || (stride == 1 && size >= 64)) __syncthreads();
             else __syncwarp();
         }
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const unsigned long long k = s_key[i];
-        out[i] = make_float2(__uint_as_float((unsigned)(k >> 32)), __int_as_float((int)(unsigned)k));
+    if (!select_here) {
+        for (int i = tid; i < n; i += T) {
+            const unsigned long long k = s_key[i];
+            out[i] = make_float2(__uint_as_float((unsigned)(k >> 32)), __int_as_float((int)(unsigned)k));
+        }
+        return;
+    }
+    // ---- minimum-distance pass ----
+    unsigned* const pos = reinterpret_cast<unsigned*>(s_raw + oSelPos);
+    unsigned char* const acc = s_raw + oSelA;
+    int* const acc_cnt = reinterpret_cast<int*>(s_raw + oSelAccCnt);
+    unsigned short* const acc_slot = reinterpret_cast<unsigned short*>(s_raw + oSelAccSlot);
+    int* const ch_cnt = reinterpret_cast<int*>(s_raw + oSelChCnt);
+    unsigned short* const ch_slot = reinterpret_cast<unsigned short*>(s_raw + oSelChSlot);
+    unsigned short* const nbl = reinterpret_cast<unsigned short*>(s_raw + oSelNb) + tid * kSelNb;
+    int* const s_warp = reinterpret_cast<int*>(s_raw + oSelWarp);   // [0..32] warp totals, [33] chunk total, [34] accepted so far, [35] a cell list overflowed
+    const int ncell = sel.gw * sel.gh, cell = sel.cell;
+    unsigned mine[kSortCap / 1024];
+#pragma unroll
+    for (int k = 0; k < kSortCap / 1024; k++) {
+        const int i = tid + k * 1024;
+        unsigned v = 0u;
+        if (i < n) { const int idx = (int)(unsigned)s_key[i], y = idx / sel.w; v = (unsigned)(idx - y * sel.w) | ((unsigned)y << 16); }
+        mine[k] = v;
+    }
+    __syncthreads();   // every key has been read: its storage is reused from here on
+#pragma unroll
+    for (int k = 0; k < kSortCap / 1024; k++) { const int i = tid + k * 1024; if (i < n) pos[i] = mine[k]; }
+    for (int c = tid; c < ncell; c += T) { acc_cnt[c] = 0; ch_cnt[c] = 0; }
+    if (tid < 2) s_warp[34 + tid] = 0;
+    __syncthreads();
+    const int lane = tid & 31, wid = tid >> 5;
+    for (int base = 0; base < n; base += T) {
+        if (s_warp[34] >= sel.max_corners || s_warp[35]) break;   // uniform: both written before the last barrier of the previous chunk
+        const int i = base + tid;
+        const bool valid = i < n;
+        // 1. killed by a corner accepted in an earlier chunk? (the reference's own test: a few accepted corners per cell)
+        bool live = valid;
+        int xi = 0, yi = 0, cx0 = 0, cx1 = -1, cy0 = 0, cy1 = -1, mycell = 0;
+        if (valid) {
+            const unsigned p = pos[i];
+            xi = (int)(p & 0xFFFFu); yi = (int)(p >> 16);
+            const int xc = xi / cell, yc = yi / cell;
+            mycell = yc * sel.gw + xc;
+            cx0 = max(0, xc - 1); cx1 = min(sel.gw - 1, xc + 1); cy0 = max(0, yc - 1); cy1 = min(sel.gh - 1, yc + 1);
+            for (int yy = cy0; yy <= cy1 && live; yy++)
+                for (int xx = cx0; xx <= cx1 && live; xx++) {
+                    const int c = yy * sel.gw + xx;
+                    const int cnt = min(acc_cnt[c], kSelAccSlots);
+                    for (int k = 0; k < cnt; k++) {
+                        const unsigned q = pos[acc_slot[c * kSelAccSlots + k]];
+                        const int dx = xi - (int)(q & 0xFFFFu), dy = yi - (int)(q >> 16);
+                        if (dx * dx + dy * dy <= sel.d2max) { live = false; break; }
+                    }
+                }
+            // 2. the live candidates of this chunk are listed by cell
+            if (live) {
+                const int slot = atomicAdd(&ch_cnt[mycell], 1);
+                if (slot < kSelChunkSlots) ch_slot[mycell * kSelChunkSlots + slot] = (unsigned short)tid;
+                else atomicOr(&s_warp[35], 1);
+            }
+        }
+        acc[tid] = live ? 1 : 0;
+        __syncthreads();
+        // 3. close live predecessors inside the chunk
+        int nnb = 0;
+        if (live) {
+            for (int yy = cy0; yy <= cy1; yy++)
+                for (int xx = cx0; xx <= cx1; xx++) {
+                    const int c = yy * sel.gw + xx;
+                    const int cnt = min(ch_cnt[c], kSelChunkSlots);
+                    for (int k = 0; k < cnt; k++) {
+                        const int tj = ch_slot[c * kSelChunkSlots + k];
+                        if (tj >= tid) continue;
+                        const unsigned q = pos[base + tj];
+                        const int dx = xi - (int)(q & 0xFFFFu), dy = yi - (int)(q >> 16);
+                        if (dx * dx + dy * dy > sel.d2max) continue;
+                        if (nnb < kSelNb) nbl[nnb] = (unsigned short)tj;
+                        nnb = min(nnb + 1, kSelNb + 1);   // kSelNb + 1: more than the list holds, the cells are walked again in every sweep
+                    }
+                }
+        }
+        // 4. accepted(i) = no accepted close predecessor, iterated in place until a sweep changes nothing
+        bool a = live;
+        for (;;) {
+            bool changed = false;
+            if (live) {
+                bool now = true;
+                if (nnb <= kSelNb) {
+                    for (int k = 0; k < nnb; k++) if (acc[nbl[k]]) { now = false; break; }
+                } else {
+                    for (int yy = cy0; yy <= cy1 && now; yy++)
+                        for (int xx = cx0; xx <= cx1 && now; xx++) {
+                            const int c = yy * sel.gw + xx;
+                            const int cnt = min(ch_cnt[c], kSelChunkSlots);
+                            for (int k = 0; k < cnt; k++) {
+                                const int tj = ch_slot[c * kSelChunkSlots + k];
+                                if (tj >= tid || !acc[tj]) continue;
+                                const unsigned q = pos[base + tj];
+                                const int dx = xi - (int)(q & 0xFFFFu), dy = yi - (int)(q >> 16);
+                                if (dx * dx + dy * dy <= sel.d2max) { now = false; break; }
+                            }
+                        }
+                }
+                if (now != a) { a = now; acc[tid] = now ? 1 : 0; changed = true; }
+            }
+            if (!__syncthreads_or(changed)) break;
+        }
+        // 5. the accepted ones join the accepted grid and are emitted in sorted order
+        if (a) {
+            const int slot = atomicAdd(&acc_cnt[mycell], 1);
+            if (slot < kSelAccSlots) acc_slot[mycell * kSelAccSlots + slot] = (unsigned short)i;
+            else atomicOr(&s_warp[35], 4);
+        }
+        if (live) ch_cnt[mycell] = 0;   // (every listed candidate clears its cell: ready for the next chunk)
+        const unsigned bal = __ballot_sync(0xffffffffu, a);
+        if (lane == 0) s_warp[wid] = __popc(bal);
+        __syncthreads();
+        if (wid == 0) {
+            const int v = s_warp[lane];
+            int inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t2 = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t2; }
+            s_warp[lane] = inc - v;               // exclusive prefix of the warp totals
+            if (lane == 31) s_warp[33] = inc;     // chunk total
+        }
+        __syncthreads();
+        const int before = s_warp[34];
+        if (a) {
+            const int rank = before + s_warp[wid] + __popc(bal & ((1u << lane) - 1u));
+            if (rank < sel.max_corners) { const float2 c = make_float2((float)xi, (float)yi); sel.out_dev[rank] = c; sel.out_host[rank] = c; }
+        }
+        __syncthreads();
+        if (tid == 0) s_warp[34] = before + s_warp[33];
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const int k = s_warp[35] ? -s_warp[35] : min(s_warp[34], sel.max_corners);   // (negative: which list overflowed, 1 chunk cell | 4 accepted cell; 8: not attempted)   // a cell list overflowed (never seen: accepted corners are minDistance apart): host pass
+        *sel.n_dev = k; *sel.n_host = k;
     }
 }
 
@@ -257,8 +430,10 @@ constexpr int kPtWarps = 4;   // measured: 8 warps per point are slower again (s
 template <int HW>
 __global__ void __launch_bounds__(32 * kPtWarps) corner_subpix_cta_kernel(const uint8_t* __restrict__ img, int w, int h, int pitch, float2* __restrict__ pts, int n,
                                                                          int max_iters, double eps2, const float* __restrict__ mask, float2* __restrict__ pts_host,
-                                                                         const float2* __restrict__ pts_in /* initial corners, if not pts (mapped host memory) */) {
+                                                                         const float2* __restrict__ pts_in /* initial corners, if not pts (mapped host memory) */,
+                                                                         const int* __restrict__ n_ptr /* the number of corners, if only the device knows it yet */) {
     constexpr int hw = HW, win = 2 * HW + 1, pw = win + 2, T = 32 * kPtWarps;
+    if (n_ptr) n = *n_ptr;
     constexpr int NP = (pw * pw + T - 1) / T, NG = (win * win + T - 1) / T;   // patch samples / gradient terms per thread
     __shared__ float patch[pw * pw];
     __shared__ double s_red[2][kPtWarps][5];
@@ -697,8 +872,10 @@ __device__ __forceinline__ void cta_sum3(float& a, float& b, float& c, float (*s
 template <int WIN>
 __global__ void __launch_bounds__(32 * kPtWarps) lk_cta_kernel(const __grid_constant__ LkLevels L, const float2* __restrict__ prev_pts, int n, int max_iters,
                                                               float eps2, float min_eig_thr, float2* __restrict__ next_pts, uint8_t* __restrict__ status,
-                                                              int edge, float sad_limit, float2* __restrict__ next_host, uint8_t* __restrict__ status_host) {
+                                                              int edge, float sad_limit, float2* __restrict__ next_host, uint8_t* __restrict__ status_host,
+                                                              const int* __restrict__ n_ptr) {
     constexpr int win = WIN, T = 32 * kPtWarps, NS = (WIN * WIN + T - 1) / T;
+    if (n_ptr) n = *n_ptr;
     __shared__ float s_red[2][kPtWarps][3];
     const int t = threadIdx.x;
     const int p = blockIdx.x;
@@ -875,6 +1052,9 @@ using namespace coeb;
 // ---------------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------------
+// Mapped pinned block of coeb_process_moving_object (h_out): refined corners | tracked positions | states | selected corners | count
+constexpr size_t kOutPre = 0, kOutNext = kOutPre + sizeof(float2) * kMoMaxPts, kOutState = kOutNext + sizeof(float2) * kMoMaxPts,
+                 kOutSelected = kOutState + kMoMaxPts, kOutCount = kOutSelected + sizeof(float2) * kMoMaxPts, kOutBytes = kOutCount + 16;
 struct coeb_motion {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -885,6 +1065,7 @@ struct coeb_motion {
     float* d_resp = nullptr;
     unsigned* d_max = nullptr;      // [0] max response bits, [1] candidate count
     bool info_dirty = true;         // d_max has to be cleared before the next Harris pass (the sort kernel normally does it)
+    bool force_host_select = false; // coeb_process_moving_object's second attempt after the device declined the minimum-distance pass
     float2* d_cand = nullptr;
     float2 *d_pre = nullptr, *d_next = nullptr;
     uint8_t *d_status = nullptr, *d_moving = nullptr;
@@ -899,7 +1080,7 @@ struct coeb_motion {
     cudaEvent_t ev_prev = nullptr, ev_side = nullptr;
     uint8_t* h_frame[2] = {nullptr, nullptr}; size_t frame_bytes = 0;   // pinned staging of the two (pageable) frames, dense rows
     cudaGraphExec_t side_graph = nullptr;                               // the side stream's work: fixed addresses, one launch
-    struct { const uint8_t* cur_gray = nullptr; int stride = 0; bool done = false; } side;
+    struct { const uint8_t* cur_gray = nullptr; int stride = 0; bool done = false; bool select_on_device = false; } side;
 };
 
 namespace {
@@ -1416,16 +1597,26 @@ int coeb_motion_good_features(coeb_motion* m, const uint8_t* gray, int width, in
     // the count and the first kSortCap candidates arrive in the mapped pinned block (the count sits right in front of the list)
     int st2 = motion_pin(m, 16 + sizeof(float2) * kSortCap);
     if (st2 != COEB_OK) return st2;
+    SelectArgs sel{};
+    if (m->side.select_on_device && m->h_out && min_distance >= 1 && width < 65536 && height < 65536) {   // coeb_process_moving_object: the minimum-distance pass stays on the device
+        sel.enabled = 1; sel.w = width; sel.cell = (int)std::lrint(min_distance);
+        sel.gw = (width + sel.cell - 1) / sel.cell; sel.gh = (height + sel.cell - 1) / sel.cell;
+        sel.max_corners = std::min(max_corners > 0 ? max_corners : kMoMaxPts, std::min(cap, kMoMaxPts));
+        sel.d2max = (int)std::ceil(min_distance * min_distance) - 1;
+        sel.out_dev = m->d_pre; sel.out_host = reinterpret_cast<float2*>(m->h_out + kOutSelected);
+        sel.n_dev = reinterpret_cast<int*>(m->d_max + 2); sel.n_host = reinterpret_cast<int*>(m->h_out + kOutCount);
+    }
     {
         static bool configured[64] = {};
-        if (!configured[m->device & 63]) { cudaFuncSetAttribute(sort_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8); configured[m->device & 63] = true; }
-        sort_candidates_kernel<<<1, 1024, kSortCap * 8, m->stream>>>(m->d_cand, m->d_max, m->h_pin);
+        if (!configured[m->device & 63]) { cudaFuncSetAttribute(sort_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelSmem); configured[m->device & 63] = true; }
+        sort_candidates_kernel<<<1, 1024, sel.enabled ? kSelSmem : kSortCap * 8, m->stream>>>(m->d_cand, m->d_max, m->h_pin, sel);
     }
     CUDA_TRY(cudaGetLastError());
     m->info_dirty = false;   // the sort kernel leaves the words cleared
     gf_mark(1);
     if ((st2 = enqueue_side_work(m)) != COEB_OK) return st2;
     gf_mark(2);
+    if (sel.enabled) { *n_out = -1; return COEB_OK; }   // the caller goes on enqueueing; the count is in the mapped block after its synchronisation
     CUDA_TRY(cudaStreamSynchronize(m->stream));
     gf_mark(3);
     const unsigned* info = reinterpret_cast<const unsigned*>(m->h_pin);
@@ -1455,7 +1646,7 @@ int coeb_motion_corner_subpix(coeb_motion* m, const uint8_t* gray, int width, in
     switch (half_win) {   // the window is a compile-time size: its per-lane offsets and weights live in registers
         case 10:
             if (motion_warp_per_point()) corner_subpix_kernel<10><<<(n + 3) / 4, 128, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, std::max(max_iters, 1), e * e, m->d_mask);
-            else corner_subpix_cta_kernel<10><<<n, 32 * kPtWarps, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, std::max(max_iters, 1), e * e, m->d_mask, nullptr, nullptr);
+            else corner_subpix_cta_kernel<10><<<n, 32 * kPtWarps, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, std::max(max_iters, 1), e * e, m->d_mask, nullptr, nullptr, nullptr);
             break;
         case 5: corner_subpix_kernel<5><<<(n + 3) / 4, 128, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, std::max(max_iters, 1), e * e, m->d_mask); break;
         case 3: corner_subpix_kernel<3><<<(n + 3) / 4, 128, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, std::max(max_iters, 1), e * e, m->d_mask); break;
@@ -1468,7 +1659,7 @@ int coeb_motion_corner_subpix(coeb_motion* m, const uint8_t* gray, int width, in
 }
 
 static int run_lk(coeb_motion* m, int n, int win, int max_iters, double eps, double min_eig, int edge, float sad_limit, bool images_on_side_stream = false,
-                  float2* next_host = nullptr, uint8_t* status_host = nullptr, bool* mirrored = nullptr) {
+                  float2* next_host = nullptr, uint8_t* status_host = nullptr, bool* mirrored = nullptr, const int* n_ptr = nullptr) {
     if (mirrored) *mirrored = false;
     if (images_on_side_stream) {
         CUDA_TRY(cudaStreamWaitEvent(m->stream, m->ev_side, 0));
@@ -1487,7 +1678,7 @@ static int run_lk(coeb_motion* m, int n, int win, int max_iters, double eps, dou
     if (win == 22 && !warp_per_point)
     {
         lk_cta_kernel<22><<<n, 32 * kPtWarps, 0, m->stream>>>(L, m->d_pre, n, max_iters, (float)(eps * eps), (float)min_eig, m->d_next, m->d_status, edge, sad_limit, next_host,
-                                                              status_host);
+                                                              status_host, n_ptr);
         if (mirrored) *mirrored = next_host && status_host;
     }
     else if (win == 22)
@@ -1591,45 +1782,66 @@ int coeb_process_moving_object(coeb_motion* m, const uint8_t* prev_gray, const u
     std::vector<float> pre(2 * 1000);
     int n = 0;
     static const bool one_stream = getenv("COEB_MOTION_ONE_STREAM") != nullptr;   // development switch
+    // refined corners, tracked positions and states are written by the kernels into this mapped pinned block as well
+    if (!m->h_out) CUDA_TRY(cudaHostAlloc((void**)&m->h_out, kOutBytes, cudaHostAllocMapped));
+    float2* const h_pre = reinterpret_cast<float2*>(m->h_out + kOutPre);
+    float2* const h_next = reinterpret_cast<float2*>(m->h_out + kOutNext);
+    uint8_t* const h_state = reinterpret_cast<uint8_t*>(m->h_out + kOutState);
+    float2* const h_in = reinterpret_cast<float2*>(m->h_out + kOutSelected);   // the selected corners
+    const bool warp_per_point = motion_warp_per_point();
+    // The minimum-distance pass normally runs on the device, behind the sort (SelectArgs): the corners never visit the host and the call
+    // synchronises once, after LK. COEB_MOTION_HOST_SELECT (read per call, so that a test can run both) keeps the host pass.
+    m->side.select_on_device = !warp_per_point && !m->force_host_select && getenv("COEB_MOTION_HOST_SELECT") == nullptr;
     m->side.cur_gray = one_stream ? nullptr : cur_gray; m->side.stride = stride; m->side.done = false;
     int st = coeb_motion_good_features(m, prev_gray, width, height, stride, 1000, 0.01, 8.0, 0.04, pre.data(), 1000, &n);
     m->side.cur_gray = nullptr;
+    m->side.select_on_device = false;
     const bool side_done = m->side.done;
+    const bool dev_sel = st == COEB_OK && n == -1;   // the corners and their number are on the device (and on their way into h_out)
     if (st != COEB_OK || n == 0) { if (side_done) cudaStreamSynchronize(m->stream2); }   // nothing follows: the side stream must not outlive the call
     if (st != COEB_OK) return st;
-    if (trace) trace->n_points = n;
     if (n == 0) return COEB_OK;
     const auto t1 = now();
     if ((st = ensure_mask(m, 10)) != COEB_OK) return st;
-    // refined corners, tracked positions and states are written by the kernels into this mapped pinned block as well
-    if (!m->h_out) CUDA_TRY(cudaHostAlloc((void**)&m->h_out, (size_t)kMoMaxPts * 25, cudaHostAllocMapped));
-    float2* const h_pre = reinterpret_cast<float2*>(m->h_out);
-    float2* const h_next = h_pre + kMoMaxPts;
-    uint8_t* const h_state = reinterpret_cast<uint8_t*>(h_next + kMoMaxPts);
     bool pre_mirrored = false, lk_mirrored = false;
-    const bool warp_per_point_ = motion_warp_per_point();
-    float2* const h_in = reinterpret_cast<float2*>(h_state + kMoMaxPts);   // the selected corners: read by the sub-pixel kernel across PCIe (8 bytes per CTA), no upload node
-    if (warp_per_point_) CUDA_TRY(cudaMemcpyAsync(m->d_pre, pre.data(), sizeof(float2) * n, cudaMemcpyHostToDevice, m->stream));   // level 0 of the previous frame is resident
-    else std::memcpy(h_in, pre.data(), sizeof(float2) * n);
-    {
-        const bool warp_per_point = motion_warp_per_point();
-        if (warp_per_point) corner_subpix_kernel<10><<<(n + 3) / 4, 128, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, 20, 0.03 * 0.03, m->d_mask);
-        else corner_subpix_cta_kernel<10><<<n, 32 * kPtWarps, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, 20, 0.03 * 0.03, m->d_mask, h_pre, h_in);
-        pre_mirrored = !warp_per_point;
+    const int n_launch = dev_sel ? 1000 : n;                                      // CTAs beyond the device's count leave at once
+    const int* const n_ptr = dev_sel ? reinterpret_cast<const int*>(m->d_max + 2) : nullptr;
+    if (!dev_sel) {
+        if (warp_per_point) CUDA_TRY(cudaMemcpyAsync(m->d_pre, pre.data(), sizeof(float2) * n, cudaMemcpyHostToDevice, m->stream));   // level 0 of the previous frame is resident
+        else std::memcpy(h_in, pre.data(), sizeof(float2) * n);   // read by the sub-pixel kernel across PCIe (8 bytes per CTA), no upload node
     }
+    if (warp_per_point) corner_subpix_kernel<10><<<(n + 3) / 4, 128, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n, 20, 0.03 * 0.03, m->d_mask);
+    else corner_subpix_cta_kernel<10><<<n_launch, 32 * kPtWarps, 0, m->stream>>>(m->d_pyr[0][0], width, height, m->lp[0], m->d_pre, n_launch, 20, 0.03 * 0.03, m->d_mask, h_pre,
+                                                                                 dev_sel ? nullptr : h_in, n_ptr);
+    pre_mirrored = !warp_per_point;
     // calcOpticalFlowPyrLK + border / SAD tests (:335-364)
     if (!side_done && (st = upload_level0(m, 1, cur_gray, stride)) != COEB_OK) return st;
-    if ((st = run_lk(m, n, 22, 20, 0.01, 1e-4, /*limit_edge_corner*/ 5, /*limit_of_check*/ 2120.f, side_done, h_next, h_state, &lk_mirrored)) != COEB_OK) return st;
-    std::vector<float> nxt(2 * (size_t)n);
-    std::vector<uint8_t> state(n);
-    if (!pre_mirrored) CUDA_TRY(cudaMemcpyAsync(pre.data(), m->d_pre, sizeof(float2) * n, cudaMemcpyDeviceToHost, m->stream));
+    if ((st = run_lk(m, n_launch, 22, 20, 0.01, 1e-4, /*limit_edge_corner*/ 5, /*limit_of_check*/ 2120.f, side_done, h_next, h_state, &lk_mirrored, n_ptr)) != COEB_OK) return st;
+    if (!dev_sel) {
+        if (!pre_mirrored) CUDA_TRY(cudaMemcpyAsync(pre.data(), m->d_pre, sizeof(float2) * n, cudaMemcpyDeviceToHost, m->stream));
+    }
+    std::vector<float> nxt;
+    std::vector<uint8_t> state;
     if (!lk_mirrored) {
+        nxt.resize(2 * (size_t)n); state.resize(n);
         CUDA_TRY(cudaMemcpyAsync(nxt.data(), m->d_next, sizeof(float2) * n, cudaMemcpyDeviceToHost, m->stream));
         CUDA_TRY(cudaMemcpyAsync(state.data(), m->d_status, n, cudaMemcpyDeviceToHost, m->stream));
     }
     CUDA_TRY(cudaStreamSynchronize(m->stream));
+    if (dev_sel) {
+        n = *reinterpret_cast<const int*>(m->h_out + kOutCount);
+        if (n < 0 && timeline) fprintf(stderr, "[coeb motion] device selection declined (code %d): host pass\n", -n);
+        if (n < 0) {   // the device left the selection to the host (more candidates than it sorts, or a grid that does not fit): once more, the host way
+            m->force_host_select = true;
+            st = coeb_process_moving_object(m, prev_gray, cur_gray, width, height, stride, tm_xy_out, cap, n_tm_out, trace);
+            m->force_host_select = false;
+            return st;
+        }
+        if (n == 0) return COEB_OK;
+    }
+    if (trace) trace->n_points = n;
     if (pre_mirrored) std::memcpy(pre.data(), h_pre, sizeof(float2) * n);
-    if (lk_mirrored) { std::memcpy(nxt.data(), h_next, sizeof(float2) * n); std::memcpy(state.data(), h_state, n); }
+    if (lk_mirrored) { nxt.resize(2 * (size_t)n); state.resize(n); std::memcpy(nxt.data(), h_next, sizeof(float2) * n); std::memcpy(state.data(), h_state, n); }
     const auto t2 = now();
     // findFundamentalMat(F_prepoint, F_nextpoint, FM_RANSAC, 0.1, 0.99) on the surviving pairs (:353-370)
     std::vector<float> f1, f2;

@@ -151,3 +151,24 @@ def test_whole_function_against_oracle(mo, seed):
     # and most of them lie on the objects that actually moved
     inside = sum(any(b[0] - 4 <= x < b[2] + 4 and b[1] - 4 <= y < b[3] + 4 for b in boxes) for x, y in tm)
     assert inside >= 0.6 * len(tm)
+
+
+@pytest.mark.parametrize("seed", SEEDS[:4])
+def test_device_minimum_distance_pass_equals_the_host_pass(mo, seed):
+    """coeb_process_moving_object selects the corners on the device (fixed-point form of goodFeaturesToTrack's sequential
+    minimum-distance pass, behind the sort); COEB_MOTION_HOST_SELECT keeps the host pass. Same corners in the same order,
+    hence identical tracks, states and T_M."""
+    prev, cur, _ = synth.make_motion_pair(seed)
+    os.environ.pop("COEB_MOTION_HOST_SELECT", None)
+    tm_d, tr_d = mo.process(prev, cur)
+    os.environ["COEB_MOTION_HOST_SELECT"] = "1"
+    try:
+        tm_h, tr_h = mo.process(prev, cur)
+    finally:
+        os.environ.pop("COEB_MOTION_HOST_SELECT", None)
+    assert tr_d["n_points"] == tr_h["n_points"] > 300
+    assert np.array_equal(tr_d["prepoint"], tr_h["prepoint"]) and np.array_equal(tr_d["nextpoint"], tr_h["nextpoint"])
+    assert np.array_equal(tr_d["state"], tr_h["state"]) and np.array_equal(tm_d, tm_h)
+    # and the corners are goodFeaturesToTrack's: the public entry point (host pass) returns the same list before refinement
+    pts = mo.good_features(prev)
+    assert len(pts) == tr_d["n_points"]
