@@ -1440,45 +1440,77 @@ __global__ void __launch_bounds__(256) stereo_match_kernel(StereoDev S, float* u
 }
 
 // Outlier cut (:804-817): median = SAD at sorted position size/2; entries with SAD >= 1.5*1.4*median are removed.
-__global__ void __launch_bounds__(1024) stereo_outlier_kernel(int N, float* uright, float* depth, const int* sad, int* out_info) {
-    __shared__ int s_cnt, s_lo, s_hi;
+// The final mvuRight / mvDepth and the count also go into mapped pinned memory (`*_host`): no device-to-host copy node behind the kernel.
+__global__ void __launch_bounds__(1024) stereo_outlier_kernel(int N, float* uright, float* depth, const int* sad, int* out_info, float* uright_host, float* depth_host,
+                                                              int* info_host) {
+    __shared__ int s_cnt, s_hi, s_sel[2];
+    __shared__ int s_hist[256];
     const int tid = threadIdx.x, T = blockDim.x;
     if (tid == 0) s_cnt = 0;
+    if (tid < 256) s_hist[tid] = 0;
     __syncthreads();
+    // the median SAD by a two-level histogram (SADs are below 121 * 510 < 2^16: high byte, then low byte inside the bin that holds the
+    // rank): three passes over the values instead of the 16 of a bisection on the value range
     int mine = 0;
-    for (int i = tid; i < N; i += T) mine += sad[i] >= 0;
+    for (int i = tid; i < N; i += T) {
+        const int v = sad[i];
+        if (v >= 0) { mine++; atomicAdd(&s_hist[v >> 8], 1); }
+    }
     if (mine) atomicAdd(&s_cnt, mine);
     __syncthreads();
     const int M = s_cnt;
-    if (M == 0) { if (tid == 0) out_info[0] = 0; return; }
-    const int target = M / 2;  // 0-based rank in ascending order
-    // smallest v with #(sad <= v) >= target + 1, by bisection on the value range
-    int lo = 0, hi = 121 * 510;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        __syncthreads();
-        if (tid == 0) s_lo = 0;
-        __syncthreads();
-        int c = 0;
-        for (int i = tid; i < N; i += T) c += (sad[i] >= 0 && sad[i] <= mid);
-        if (c) atomicAdd(&s_lo, c);
-        __syncthreads();
-        if (s_lo >= target + 1) hi = mid; else lo = mid + 1;
+    if (M == 0) {
+        for (int i = tid; i < N; i += T) { uright_host[i] = uright[i]; depth_host[i] = depth[i]; }
+        if (tid == 0) { out_info[0] = 0; info_host[0] = 0; }
+        return;
     }
-    const float median = (float)lo;
-    const float thDist = 1.5f * 1.4f * median;
+    // bin that holds ascending rank r (0-based) of the histogram, and the rank inside it: warp 0, eight bins per lane
+    auto locate = [&](int r) {
+        if (tid < 32) {
+            int h[8], sum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { h[k] = s_hist[8 * tid + k]; sum += h[k]; }
+            int inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t2 = __shfl_up_sync(0xffffffffu, inc, o); if (tid >= o) inc += t2; }
+            int c = inc - sum;
+            if (r >= c && r < inc) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    if (r < c + h[k]) { s_sel[0] = 8 * tid + k; s_sel[1] = r - c; break; }
+                    c += h[k];
+                }
+            }
+        }
+    };
+    locate(M / 2);   // sorted position size / 2 (:806)
     __syncthreads();
+    const int hi_bin = s_sel[0], r2 = s_sel[1];
+    __syncthreads();
+    if (tid < 256) s_hist[tid] = 0;
     if (tid == 0) s_hi = 0;
     __syncthreads();
+    for (int i = tid; i < N; i += T) {
+        const int v = sad[i];
+        if (v >= 0 && (v >> 8) == hi_bin) atomicAdd(&s_hist[v & 255], 1);
+    }
+    __syncthreads();
+    locate(r2);
+    __syncthreads();
+    const float median = (float)((hi_bin << 8) | s_sel[0]);
+    const float thDist = 1.5f * 1.4f * median;
     int kept = 0;
-    for (int i = tid; i < N; i += T)
+    for (int i = tid; i < N; i += T) {
+        float u = uright[i], d = depth[i];
         if (sad[i] >= 0) {
             if ((float)sad[i] < thDist) kept++;
-            else { uright[i] = -1.f; depth[i] = -1.f; }
+            else { u = -1.f; d = -1.f; uright[i] = u; depth[i] = d; }
         }
+        uright_host[i] = u; depth_host[i] = d;
+    }
     if (kept) atomicAdd(&s_hi, kept);
     __syncthreads();
-    if (tid == 0) out_info[0] = s_hi;
+    if (tid == 0) { out_info[0] = s_hi; info_host[0] = s_hi; }
 }
 
 // ---- config 5: brute-force k=2 Hamming search + ratio test -----------------------------------------------------------
@@ -2631,12 +2663,13 @@ int coeb_stereo_match(coeb_matcher* m, coeb_extractor* left, coeb_extractor* rig
     int* dinfo = (int*)(m->out.d + 2 * al(NL * 4));
     int* dsad = (int*)m->d_scratch;
     stereo_match_kernel<<<(N + 7) / 8, 256, 0, m->stream>>>(S, dur, ddp, dsad);
-    stereo_outlier_kernel<<<1, 1024, 0, m->stream>>>(N, dur, ddp, dsad, dinfo);
+    if ((st = m->outm.reserve_mapped(2 * al(NL * 4) + 256)) != COEB_OK) return st;
+    stereo_outlier_kernel<<<1, 1024, 0, m->stream>>>(N, dur, ddp, dsad, dinfo, (float*)m->outm.d, (float*)(m->outm.d + al(NL * 4)), (int*)(m->outm.d + 2 * al(NL * 4)));
     CUDA_TRY(cudaGetLastError());
-    if ((st = pull_outputs(m, 2 * al(NL * 4) + 8)) != COEB_OK) return st;
-    std::memcpy(uright_out, m->out.h, NL * 4);
-    std::memcpy(depth_out, m->out.h + al(NL * 4), NL * 4);
-    if (nmatched_out) *nmatched_out = ((const int*)(m->out.h + 2 * al(NL * 4)))[0];
+    if ((st = sync_outputs(m)) != COEB_OK) return st;
+    std::memcpy(uright_out, m->outm.h, NL * 4);
+    std::memcpy(depth_out, m->outm.h + al(NL * 4), NL * 4);
+    if (nmatched_out) *nmatched_out = ((const int*)(m->outm.h + 2 * al(NL * 4)))[0];
     return COEB_OK;
 }
 
