@@ -1218,7 +1218,8 @@ __global__ void __launch_bounds__(256) m4_collect_kernel(FrameDev F1, FrameDev F
 template <bool kLists>
 __global__ void __launch_bounds__(1024) m4_resolve_kernel(FrameDev F1, FrameDev F2, const float* prev_in, float window, float nnratio,
                                                           int check_ori, CandLists C, int* res, int* rdist, int* cl_start, int* cl_fill,
-                                                          int2* cl_items, int* matches12, float* prev_out, int* out_info) {
+                                                          int2* cl_items, int* matches12, float* prev_out, int* out_info, int* m12_host) {
+    // (prev_out and out_info may be mapped pinned memory: written once; matches12 is read back and stays on the device, m12_host is its copy)
     COEB_MTRACE(6);
     __shared__ int s_changed, s_count;
     __shared__ int s_hist[COEB_HISTO_LENGTH];
@@ -1312,6 +1313,7 @@ __global__ void __launch_bounds__(1024) m4_resolve_kernel(FrameDev F1, FrameDev 
     __syncthreads();
     for (int i = tid; i < F1.n; i += T) {  // update prev matched (:515-517)
         const int k = matches12[i];
+        m12_host[i] = k;
         prev_out[2 * i] = k >= 0 ? F2.x[k] : prev_in[2 * i];
         prev_out[2 * i + 1] = k >= 0 ? F2.y[k] : prev_in[2 * i + 1];
     }
@@ -2585,7 +2587,8 @@ int coeb_match_init(coeb_matcher* m, coeb_frame* f1, coeb_frame* f2, float* prev
     const size_t N1 = f1->n, N2 = f2->n;
     int st;
     if ((st = m->in.reserve(al(N1 * 8))) != COEB_OK) return st;
-    if ((st = m->out.reserve(al(N1 * 4) + al(N1 * 8) + 256)) != COEB_OK) return st;
+    if ((st = m->out.reserve(al(N1 * 4))) != COEB_OK) return st;
+    if ((st = m->outm.reserve_mapped(al(N1 * 4) + al(N1 * 8) + 256)) != COEB_OK) return st;
     const int cap = 256;
     if ((st = grow(&m->d_scratch, &m->scratch_bytes, 2 * al(N1 * 4) + 2 * al((N2 + 1) * 4) + al(N1 * 8) + lists_bytes(N1, cap))) != COEB_OK) return st;
     Packer p(m->in);
@@ -2598,23 +2601,24 @@ int coeb_match_init(coeb_matcher* m, coeb_frame* f1, coeb_frame* f2, float* prev
     int* d_clf = (int*)sc; sc += al((N2 + 1) * 4);
     int2* d_items = (int2*)sc; sc += al(N1 * 8);
     const CandLists C = carve_lists(sc, N1, cap, m->d_meta);
-    int* d_m12 = (int*)m->out.d;
-    float* d_prev_out = (float*)(m->out.d + al(N1 * 4));
-    int* d_info = (int*)(m->out.d + al(N1 * 4) + al(N1 * 8));
+    int* d_m12 = (int*)m->out.d;                                  // read back by the kernel: device; its final state is mirrored below
+    int* h_m12 = (int*)m->outm.d;                                 // results, written once: mapped pinned memory, no copy node
+    float* d_prev_out = (float*)(m->outm.d + al(N1 * 4));
+    int* d_info = (int*)(m->outm.d + al(N1 * 4) + al(N1 * 8));
     m4_collect_kernel<<<(f1->n + 7) / 8, 256, 0, m->stream>>>(f1->dev, f2->dev, d_prev, (float)window_size, C);
     m4_resolve_kernel<true><<<1, 1024, 0, m->stream>>>(f1->dev, f2->dev, d_prev, (float)window_size, nnratio, check_ori, C, d_res, d_rdist, d_cls,
-                                                       d_clf, d_items, d_m12, d_prev_out, d_info);
+                                                       d_clf, d_items, d_m12, d_prev_out, d_info, h_m12);
     CUDA_TRY(cudaGetLastError());
-    if ((st = pull_outputs(m, al(N1 * 4) + al(N1 * 8) + 12)) != COEB_OK) return st;
-    if (((const int*)(m->out.h + al(N1 * 4) + al(N1 * 8)))[2]) {
+    if ((st = sync_outputs(m)) != COEB_OK) return st;
+    if (((const int*)(m->outm.h + al(N1 * 4) + al(N1 * 8)))[2]) {
         m4_resolve_kernel<false><<<1, 1024, 0, m->stream>>>(f1->dev, f2->dev, d_prev, (float)window_size, nnratio, check_ori, C, d_res, d_rdist,
-                                                            d_cls, d_clf, d_items, d_m12, d_prev_out, d_info);
+                                                            d_cls, d_clf, d_items, d_m12, d_prev_out, d_info, h_m12);
         CUDA_TRY(cudaGetLastError());
-        if ((st = pull_outputs(m, al(N1 * 4) + al(N1 * 8) + 12)) != COEB_OK) return st;
+        if ((st = sync_outputs(m)) != COEB_OK) return st;
     }
-    std::memcpy(matches12, m->out.h, N1 * 4);
-    std::memcpy(prev_matched, m->out.h + al(N1 * 4), N1 * 8);
-    if (nmatches_out) *nmatches_out = ((const int*)(m->out.h + al(N1 * 4) + al(N1 * 8)))[0];
+    std::memcpy(matches12, m->outm.h, N1 * 4);
+    std::memcpy(prev_matched, m->outm.h + al(N1 * 4), N1 * 8);
+    if (nmatches_out) *nmatches_out = ((const int*)(m->outm.h + al(N1 * 4) + al(N1 * 8)))[0];
     print_mtrace("SearchForInitialization");
     return COEB_OK;
 }
