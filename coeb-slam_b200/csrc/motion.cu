@@ -1659,7 +1659,9 @@ int coeb_motion_good_features(coeb_motion* m, const uint8_t* gray, int width, in
     int st2 = motion_pin(m, 16 + sizeof(float2) * kSortCap);
     if (st2 != COEB_OK) return st2;
     SelectArgs sel{};
-    if (m->side.select_on_device && m->h_out && min_distance >= 1 && width < 65536 && height < 65536) {   // coeb_process_moving_object: the minimum-distance pass stays on the device
+    const int sel_cell = min_distance >= 1 ? (int)std::lrint(min_distance) : 1;
+    const bool sel_fits = ((width + sel_cell - 1) / sel_cell) * ((height + sel_cell - 1) / sel_cell) <= kSelMaxCells;   // else the host pass, decided here: no wasted attempt
+    if (m->side.select_on_device && m->h_out && min_distance >= 1 && width < 65536 && height < 65536 && sel_fits) {   // coeb_process_moving_object: the minimum-distance pass stays on the device
         sel.enabled = 1; sel.w = width; sel.cell = (int)std::lrint(min_distance);
         sel.gw = (width + sel.cell - 1) / sel.cell; sel.gh = (height + sel.cell - 1) / sel.cell;
         sel.max_corners = std::min(max_corners > 0 ? max_corners : kMoMaxPts, std::min(cap, kMoMaxPts));

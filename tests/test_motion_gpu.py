@@ -172,3 +172,19 @@ def test_device_minimum_distance_pass_equals_the_host_pass(mo, seed):
     # and the corners are goodFeaturesToTrack's: the public entry point (host pass) returns the same list before refinement
     pts = mo.good_features(prev)
     assert len(pts) == tr_d["n_points"]
+
+
+def test_larger_frames_keep_the_host_minimum_distance_pass(mo):
+    """The device pass holds a grid of 4800 minimum-distance cells (640x480 at 8 px); a larger frame is decided on the host before
+    anything is launched, takes the host pass and must give what the forced host pass gives."""
+    prev, cur, boxes = synth.make_motion_pair(3, w=960, h=540)
+    tm_a, tr_a = mo.process(prev, cur)
+    os.environ["COEB_MOTION_HOST_SELECT"] = "1"
+    try:
+        tm_b, tr_b = mo.process(prev, cur)
+    finally:
+        os.environ.pop("COEB_MOTION_HOST_SELECT", None)
+    assert tr_a["n_points"] == tr_b["n_points"] > 300 and np.array_equal(tm_a, tm_b) and np.array_equal(tr_a["state"], tr_b["state"])
+    assert tr_a["F"] is not None and len(tm_a) > 0
+    inside = sum(any(b[0] - 4 <= x < b[2] + 4 and b[1] - 4 <= y < b[3] + 4 for b in boxes) for x, y in tm_a)
+    assert inside >= 0.5 * len(tm_a)
