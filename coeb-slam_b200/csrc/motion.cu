@@ -1490,6 +1490,35 @@ bool eight_point_minimal(const float* p1, const float* p2, const int* idx, doubl
         const double r[9] = {x2 * x1, x2 * y1, x2, y2 * x1, y2 * y1, y2, x1, y1, 1};
         for (int a = 0; a < 9; a++) A[k][a] = r[a];
     }
+    double F0[9];
+    // Fast path: elimination with row pivoting on the first eight columns and the last one free (F0[8] = 1), a third of the operations of
+    // the fully pivoted form below, which takes over when a pivot says that this choice of free column is a bad one (F0[8] ~ 0).
+    bool solved = true;
+    {
+        double B[8][9];
+        std::memcpy(B, A, sizeof(B));
+        for (int c = 0; c < 8 && solved; c++) {
+            int pr = c;
+            double best = std::fabs(B[c][c]);
+            for (int rr = c + 1; rr < 8; rr++) if (std::fabs(B[rr][c]) > best) { best = std::fabs(B[rr][c]); pr = rr; }
+            if (best < 1e-7) { solved = false; break; }
+            if (pr != c) for (int cc = c; cc < 9; cc++) std::swap(B[c][cc], B[pr][cc]);
+            const double inv = 1.0 / B[c][c];
+            for (int rr = c + 1; rr < 8; rr++) {
+                const double f = B[rr][c] * inv;
+                for (int cc = c + 1; cc < 9; cc++) B[rr][cc] -= f * B[c][cc];
+            }
+        }
+        if (solved) {
+            F0[8] = 1.0;
+            for (int c = 7; c >= 0; c--) {
+                double t = B[c][8];
+                for (int cc = c + 1; cc < 8; cc++) t += B[c][cc] * F0[cc];
+                F0[c] = -t / B[c][c];
+            }
+        }
+    }
+    if (!solved) {
     // reduced row echelon form with column pivoting bookkeeping: the one free column gives the null vector
     int piv_col[8];
     bool used[9] = {false};
@@ -1512,9 +1541,9 @@ bool eight_point_minimal(const float* p1, const float* p2, const int* idx, doubl
     }
     int free_col = 0;
     while (used[free_col]) free_col++;
-    double F0[9];
     F0[free_col] = 1.0;
     for (int r = 0; r < 8; r++) F0[piv_col[r]] = -A[r][free_col];
+    }
     double G[9] = {0}, v[3], F2[9];
     for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) for (int k = 0; k < 3; k++) G[a * 3 + b] += F0[k * 3 + a] * F0[k * 3 + b];
     if (!smallest_eigvec3(G, v)) {   // (a multiple of the identity: any direction serves; keep the general routine for it)
