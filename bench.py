@@ -813,6 +813,19 @@ def bench_matching(cb, dev, batch, o_kps, o_desc, o_cnt, ex, args):
         pmo_call = mo.prepared_process(mp_prev, mp_cur)   # ctypes arguments marshalled outside the clock, as for the other calls
         assert pmo_call() == len(tm_g)
         out["process_moving_object_us"] = _median_us(pmo_call, 20)
+        # the same as the reference runs it: imGrayPre is the previous call's frame, resident on the device (coeb_process_moving_object_next)
+        # (frames fed alternately; the clock brackets the calls that pair (mp_prev -> mp_cur), the pair the two-frame figure above is for)
+        seq_call = mo.prepared_process_next([mp_prev, mp_cur])
+        for _ in range(4):
+            seq_call()
+        ts = []
+        for _ in range(20):
+            seq_call()                      # mp_prev arrives (pairs mp_cur -> mp_prev: not timed)
+            t = time.perf_counter()
+            n_seq = seq_call()              # mp_cur arrives
+            ts.append(time.perf_counter() - t)
+        assert n_seq == len(tm_g)
+        out["process_moving_object_next_us"] = 1e6 * float(np.median(ts))
         out["process_moving_object_points"] = int(tr_g["n_points"])
         out["process_moving_object_tm"] = int(len(tm_g))
         if not args.no_cpu:

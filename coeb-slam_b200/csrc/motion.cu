@@ -134,8 +134,10 @@ constexpr int oSelAccSlot = oSelAccCnt + 4 * kSelMaxCells;             // ushort
 constexpr int oSelChCnt = oSelAccSlot + 2 * kSelMaxCells * kSelAccSlots;   // int[cells]: live candidates of the current chunk per cell
 constexpr int oSelChSlot = oSelChCnt + 4 * kSelMaxCells;               // ushort[cells][kSelChunkSlots]: their thread numbers
 constexpr int oSelNb = oSelChSlot + 2 * kSelMaxCells * kSelChunkSlots; // ushort[1024][kSelNb]: close live predecessors of a thread's candidate
-constexpr int oSelWarp = oSelNb + 1024 * kSelNb * 2;                   // int[40]: scan scratch, accepted so far, overflow flag
-constexpr int kSelSmem = oSelWarp + 160;
+constexpr int oSelWarp = oSelNb + 1024 * kSelNb * 2;                   // int[40]: scan scratch, accepted so far, overflow flag, spill count
+constexpr int kSelSpill = 256;
+constexpr int oSelSpill = oSelWarp + 160;                              // ushort[kSelSpill]: live candidates of the chunk whose cell list was full
+constexpr int kSelSmem = oSelSpill + 2 * kSelSpill;
 static_assert(kSelSmem >= kSortCap * 8 && kSelSmem <= 227 * 1024, "the selection arrays alias the sorted keys and fit one SM");
 struct SelectArgs {
     int enabled, w, cell, gw, gh, max_corners, d2max;   // d2max: largest integer squared distance that is < minDistance^2
@@ -199,7 +201,8 @@ __global__ void __launch_bounds__(1024) sort_candidates_kernel(float2* __restric
     int* const ch_cnt = reinterpret_cast<int*>(s_raw + oSelChCnt);
     unsigned short* const ch_slot = reinterpret_cast<unsigned short*>(s_raw + oSelChSlot);
     unsigned short* const nbl = reinterpret_cast<unsigned short*>(s_raw + oSelNb) + tid * kSelNb;
-    int* const s_warp = reinterpret_cast<int*>(s_raw + oSelWarp);   // [0..32] warp totals, [33] chunk total, [34] accepted so far, [35] a cell list overflowed
+    int* const s_warp = reinterpret_cast<int*>(s_raw + oSelWarp);   // [0..32] warp totals, [33] chunk total, [34] accepted so far, [35] a list overflowed for good, [36] spilled candidates
+    unsigned short* const spill = reinterpret_cast<unsigned short*>(s_raw + oSelSpill);
     const int ncell = sel.gw * sel.gh, cell = sel.cell;
     unsigned mine[kSortCap / 1024];
 #pragma unroll
@@ -213,7 +216,7 @@ __global__ void __launch_bounds__(1024) sort_candidates_kernel(float2* __restric
 #pragma unroll
     for (int k = 0; k < kSortCap / 1024; k++) { const int i = tid + k * 1024; if (i < n) pos[i] = mine[k]; }
     for (int c = tid; c < ncell; c += T) { acc_cnt[c] = 0; ch_cnt[c] = 0; }
-    if (tid < 2) s_warp[34 + tid] = 0;
+    if (tid < 3) s_warp[34 + tid] = 0;
     __syncthreads();
     const int lane = tid & 31, wid = tid >> 5;
     for (int base = 0; base < n; base += T) {
@@ -243,18 +246,24 @@ __global__ void __launch_bounds__(1024) sort_candidates_kernel(float2* __restric
             if (live) {
                 const int slot = atomicAdd(&ch_cnt[mycell], 1);
                 if (slot < kSelChunkSlots) ch_slot[mycell * kSelChunkSlots + slot] = (unsigned short)tid;
-                else atomicOr(&s_warp[35], 1);
+                else {   // a crowded cell (many strong local maxima side by side): the candidate goes to a chunk-wide list every live candidate also walks
+                    const int k = atomicAdd(&s_warp[36], 1);
+                    if (k < kSelSpill) spill[k] = (unsigned short)tid; else atomicOr(&s_warp[35], 1);
+                }
             }
         }
         acc[tid] = live ? 1 : 0;
         __syncthreads();
         // 3. close live predecessors inside the chunk
         int nnb = 0;
+        bool near_spill = false;   // one of the nine cells was full: only then can a spilled candidate be close
         if (live) {
             for (int yy = cy0; yy <= cy1; yy++)
                 for (int xx = cx0; xx <= cx1; xx++) {
                     const int c = yy * sel.gw + xx;
-                    const int cnt = min(ch_cnt[c], kSelChunkSlots);
+                    const int raw = ch_cnt[c];
+                    near_spill |= raw > kSelChunkSlots;
+                    const int cnt = min(raw, kSelChunkSlots);
                     for (int k = 0; k < cnt; k++) {
                         const int tj = ch_slot[c * kSelChunkSlots + k];
                         if (tj >= tid) continue;
@@ -265,6 +274,16 @@ __global__ void __launch_bounds__(1024) sort_candidates_kernel(float2* __restric
                         nnb = min(nnb + 1, kSelNb + 1);   // kSelNb + 1: more than the list holds, the cells are walked again in every sweep
                     }
                 }
+            const int nsp = near_spill ? min(s_warp[36], kSelSpill) : 0;
+            for (int k = 0; k < nsp; k++) {
+                const int tj = spill[k];
+                if (tj >= tid) continue;
+                const unsigned q = pos[base + tj];
+                const int dx = xi - (int)(q & 0xFFFFu), dy = yi - (int)(q >> 16);
+                if (dx * dx + dy * dy > sel.d2max) continue;
+                if (nnb < kSelNb) nbl[nnb] = (unsigned short)tj;
+                nnb = min(nnb + 1, kSelNb + 1);
+            }
         }
         // 4. accepted(i) = no accepted close predecessor, iterated in place until a sweep changes nothing
         bool a = live;
@@ -287,6 +306,14 @@ __global__ void __launch_bounds__(1024) sort_candidates_kernel(float2* __restric
                                 if (dx * dx + dy * dy <= sel.d2max) { now = false; break; }
                             }
                         }
+                    const int nsp = near_spill ? min(s_warp[36], kSelSpill) : 0;
+                    for (int k = 0; k < nsp && now; k++) {
+                        const int tj = spill[k];
+                        if (tj >= tid || !acc[tj]) continue;
+                        const unsigned q = pos[base + tj];
+                        const int dx = xi - (int)(q & 0xFFFFu), dy = yi - (int)(q >> 16);
+                        if (dx * dx + dy * dy <= sel.d2max) now = false;
+                    }
                 }
                 if (now != a) { a = now; acc[tid] = now ? 1 : 0; changed = true; }
             }
@@ -317,11 +344,11 @@ __global__ void __launch_bounds__(1024) sort_candidates_kernel(float2* __restric
             if (rank < sel.max_corners) { const float2 c = make_float2((float)xi, (float)yi); sel.out_dev[rank] = c; sel.out_host[rank] = c; }
         }
         __syncthreads();
-        if (tid == 0) s_warp[34] = before + s_warp[33];
+        if (tid == 0) { s_warp[34] = before + s_warp[33]; s_warp[36] = 0; }
         __syncthreads();
     }
     if (tid == 0) {
-        const int k = s_warp[35] ? -s_warp[35] : min(s_warp[34], sel.max_corners);   // (negative: which list overflowed, 1 chunk cell | 4 accepted cell; 8: not attempted)   // a cell list overflowed (never seen: accepted corners are minDistance apart): host pass
+        const int k = s_warp[35] ? -s_warp[35] : min(s_warp[34], sel.max_corners);   // (negative: which list overflowed for good, 1 spill list | 4 accepted cell; 8: not attempted)   // a cell list overflowed (never seen: accepted corners are minDistance apart): host pass
         *sel.n_dev = k; *sel.n_host = k;
     }
 }
@@ -1079,8 +1106,14 @@ struct coeb_motion {
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_prev = nullptr, ev_side = nullptr;
     uint8_t* h_frame[2] = {nullptr, nullptr}; size_t frame_bytes = 0;   // pinned staging of the two (pageable) frames, dense rows
-    cudaGraphExec_t side_graph = nullptr;                               // the side stream's work: fixed addresses, one launch
-    struct { const uint8_t* cur_gray = nullptr; int stride = 0; bool done = false; bool select_on_device = false; } side;
+    // the side stream's work as captured graphs (fixed addresses, one launch): [0..1] for a call that uploads both frames, [2..3] for a
+    // sequence call (the previous frame is resident, its pyramid built); two of each because the two pyramid buffers swap roles from call
+    // to call, keyed by the level-0 address of the "previous" buffer at capture time
+    cudaGraphExec_t side_graph[4] = {nullptr, nullptr, nullptr, nullptr};
+    const void* side_graph_key[4] = {nullptr, nullptr, nullptr, nullptr};
+    // coeb_process_moving_object_next: the current frame of the last call stays in d_pyr[1] with its pyramid
+    bool cur_resident = false; int res_w = 0, res_h = 0;
+    struct { const uint8_t* cur_gray = nullptr; int stride = 0; bool done = false; bool select_on_device = false; bool prev_resident = false; } side;
 };
 
 namespace {
@@ -1129,7 +1162,11 @@ int motion_pin(coeb_motion* m, size_t bytes) {
 }
 
 void drop_side_graph(coeb_motion* m) {
-    if (m->side_graph) { cudaGraphExecDestroy(m->side_graph); m->side_graph = nullptr; }
+    for (int k = 0; k < 4; k++) {
+        if (m->side_graph[k]) cudaGraphExecDestroy(m->side_graph[k]);
+        m->side_graph[k] = nullptr; m->side_graph_key[k] = nullptr;
+    }
+    m->cur_resident = false;   // (called whenever the image buffers are laid out again)
 }
 
 // The caller's frame is pageable as a rule (a cv::Mat): copied into pinned memory here (~10 us for 640x480) it travels by DMA while
@@ -1176,19 +1213,25 @@ int enqueue_side_work(coeb_motion* m) {
     int st = stage_frame(m, 1, m->side.cur_gray, m->side.stride);
     if (st != COEB_OK) return st;
     CUDA_TRY(cudaStreamWaitEvent(m->stream2, m->ev_prev, 0));   // level 0 of the previous frame has landed
-    if (!m->side_graph) {   // every address is fixed until the buffers are laid out again: captured once, replayed as one launch
+    const int base = m->side.prev_resident ? 2 : 0;
+    int slot = -1;
+    for (int k = base; k < base + 2; k++) if (m->side_graph[k] && m->side_graph_key[k] == m->d_pyr[0][0]) slot = k;
+    if (slot < 0) {   // every address is fixed until the buffers are laid out again: captured once per role assignment, replayed as one launch
+        slot = m->side_graph[base] ? base + 1 : base;
+        if (m->side_graph[slot]) { cudaGraphExecDestroy(m->side_graph[slot]); m->side_graph[slot] = nullptr; }
         cudaGraph_t g = nullptr;
         CUDA_TRY(cudaStreamBeginCapture(m->stream2, cudaStreamCaptureModeThreadLocal));
         cudaMemcpy2DAsync(m->d_pyr[1][0], m->lp[0], m->h_frame[1], m->w, m->w, m->h, cudaMemcpyHostToDevice, m->stream2);
-        build_pyramid(m, 0, m->stream2);
+        if (!m->side.prev_resident) build_pyramid(m, 0, m->stream2);   // a resident previous frame was the current one of the last call: its pyramid exists
         derivative_images(m, m->stream2);
         build_pyramid(m, 1, m->stream2);
         cudaError_t e = cudaStreamEndCapture(m->stream2, &g);
-        if (e == cudaSuccess) e = cudaGraphInstantiate(&m->side_graph, g, 0);
+        if (e == cudaSuccess) e = cudaGraphInstantiate(&m->side_graph[slot], g, 0);
         if (g) cudaGraphDestroy(g);
-        if (e != cudaSuccess) { m->side_graph = nullptr; return fail(COEB_ERR_CUDA, "side-stream graph: %s", cudaGetErrorString(e)); }
+        if (e != cudaSuccess) { m->side_graph[slot] = nullptr; return fail(COEB_ERR_CUDA, "side-stream graph: %s", cudaGetErrorString(e)); }
+        m->side_graph_key[slot] = m->d_pyr[0][0];
     }
-    CUDA_TRY(cudaGraphLaunch(m->side_graph, m->stream2));
+    CUDA_TRY(cudaGraphLaunch(m->side_graph[slot], m->stream2));
     CUDA_TRY(cudaEventRecord(m->ev_side, m->stream2));
     m->side.done = true;
     return COEB_OK;
@@ -1673,7 +1716,7 @@ int coeb_motion_good_features(coeb_motion* m, const uint8_t* gray, int width, in
     CUDA_TRY(cudaSetDevice(m->device));
     int st = motion_prepare(m, width, height, 22, 5);
     if (st != COEB_OK) return st;
-    if ((st = upload_level0(m, 0, gray, stride)) != COEB_OK) return st;
+    if (!m->side.prev_resident && (st = upload_level0(m, 0, gray, stride)) != COEB_OK) return st;
     if (m->side.cur_gray) CUDA_TRY(cudaEventRecord(m->ev_prev, m->stream));
     gf_mark(0);
     if (m->info_dirty) CUDA_TRY(cudaMemsetAsync(m->d_max, 0, 16, m->stream));   // first call, or a call that failed before its sort kernel
@@ -1860,12 +1903,17 @@ int coeb_epipolar_outliers(coeb_motion* m, const float* pre_xy, const float* nex
     return COEB_OK;
 }
 
-int coeb_process_moving_object(coeb_motion* m, const uint8_t* prev_gray, const uint8_t* cur_gray, int width, int height, int stride, float* tm_xy_out, int cap,
-                               int* n_tm_out, coeb_motion_trace* trace) {
-    if (!m || !prev_gray || !cur_gray || !n_tm_out || cap < 0 || (cap > 0 && !tm_xy_out)) return fail(COEB_ERR_INVALID_ARG, "bad argument");
+// prev_resident: the previous frame is the current frame of the last call, still on the device with its pyramid (d_pyr[1]): the two
+// pyramid buffers swap roles (unless `swapped` says a first attempt of this call already did) and nothing of it is uploaded or rebuilt.
+static int process_impl(coeb_motion* m, const uint8_t* prev_gray, const uint8_t* cur_gray, int width, int height, int stride, float* tm_xy_out, int cap,
+                        int* n_tm_out, coeb_motion_trace* trace, bool prev_resident, bool swapped) {
     *n_tm_out = 0;
     if (trace) { trace->n_points = trace->n_tracked = trace->n_inliers = 0; trace->have_F = 0; }
     CUDA_TRY(cudaSetDevice(m->device));
+    if (prev_resident && !swapped)
+        for (int l = 0; l < kMoMaxLevels; l++) std::swap(m->d_pyr[0][l], m->d_pyr[1][l]);
+    m->cur_resident = false;   // until this call has left its current frame and pyramid behind
+    if (prev_resident) prev_gray = cur_gray;   // (never read: good_features skips the upload)
     const bool timeline = getenv("COEB_MOTION_TRACE") != nullptr;
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
@@ -1885,14 +1933,16 @@ int coeb_process_moving_object(coeb_motion* m, const uint8_t* prev_gray, const u
     // synchronises once, after LK. COEB_MOTION_HOST_SELECT (read per call, so that a test can run both) keeps the host pass.
     m->side.select_on_device = !warp_per_point && !m->force_host_select && getenv("COEB_MOTION_HOST_SELECT") == nullptr;
     m->side.cur_gray = one_stream ? nullptr : cur_gray; m->side.stride = stride; m->side.done = false;
+    m->side.prev_resident = prev_resident;
     int st = coeb_motion_good_features(m, prev_gray, width, height, stride, 1000, 0.01, 8.0, 0.04, pre.data(), 1000, &n);
     m->side.cur_gray = nullptr;
     m->side.select_on_device = false;
+    m->side.prev_resident = false;
     const bool side_done = m->side.done;
     const bool dev_sel = st == COEB_OK && n == -1;   // the corners and their number are on the device (and on their way into h_out)
     if (st != COEB_OK || n == 0) { if (side_done) cudaStreamSynchronize(m->stream2); }   // nothing follows: the side stream must not outlive the call
     if (st != COEB_OK) return st;
-    if (n == 0) return COEB_OK;
+    if (n == 0) { m->cur_resident = side_done; m->res_w = width; m->res_h = height; return COEB_OK; }
     const auto t1 = now();
     if ((st = ensure_mask(m, 10)) != COEB_OK) return st;
     bool pre_mirrored = false, lk_mirrored = false;
@@ -1920,12 +1970,13 @@ int coeb_process_moving_object(coeb_motion* m, const uint8_t* prev_gray, const u
         CUDA_TRY(cudaMemcpyAsync(state.data(), m->d_status, n, cudaMemcpyDeviceToHost, m->stream));
     }
     CUDA_TRY(cudaStreamSynchronize(m->stream));
+    m->cur_resident = true; m->res_w = width; m->res_h = height;   // LK has run: the current frame and its pyramid are in d_pyr[1]
     if (dev_sel) {
         n = *reinterpret_cast<const int*>(m->h_out + kOutCount);
         if (n < 0 && timeline) fprintf(stderr, "[coeb motion] device selection declined (code %d): host pass\n", -n);
         if (n < 0) {   // the device left the selection to the host (more candidates than it sorts, or a grid that does not fit): once more, the host way
             m->force_host_select = true;
-            st = coeb_process_moving_object(m, prev_gray, cur_gray, width, height, stride, tm_xy_out, cap, n_tm_out, trace);
+            st = process_impl(m, prev_gray, cur_gray, width, height, stride, tm_xy_out, cap, n_tm_out, trace, prev_resident, /*swapped*/ true);
             m->force_host_select = false;
             return st;
         }
@@ -1987,6 +2038,32 @@ int coeb_process_moving_object(coeb_motion* m, const uint8_t* prev_gray, const u
                         "subpix + pyramids + LK %.0f us, RANSAC %.0f us (%d of %d inliers), epipolar %.0f us\n",
                 us(t0, t1), g_gf_mark[0], g_gf_mark[1], g_gf_mark[2], g_gf_mark[3], g_gf_mark[4], us(t1, t2), us(t2, t3), ninl, nf, us(t3, now()));
     return k > cap ? COEB_ERR_CAPACITY : COEB_OK;
+}
+
+int coeb_process_moving_object(coeb_motion* m, const uint8_t* prev_gray, const uint8_t* cur_gray, int width, int height, int stride, float* tm_xy_out, int cap,
+                               int* n_tm_out, coeb_motion_trace* trace) {
+    if (!m || !prev_gray || !cur_gray || !n_tm_out || cap < 0 || (cap > 0 && !tm_xy_out)) return fail(COEB_ERR_INVALID_ARG, "bad argument");
+    return process_impl(m, prev_gray, cur_gray, width, height, stride, tm_xy_out, cap, n_tm_out, trace, false, false);
+}
+
+int coeb_process_moving_object_next(coeb_motion* m, const uint8_t* cur_gray, int width, int height, int stride, float* tm_xy_out, int cap, int* n_tm_out,
+                                    coeb_motion_trace* trace) {
+    if (!m || !cur_gray || !n_tm_out || cap < 0 || (cap > 0 && !tm_xy_out) || width < 8 || height < 8 || stride < width) return fail(COEB_ERR_INVALID_ARG, "bad argument");
+    if (m->cur_resident && m->res_w == width && m->res_h == height)
+        return process_impl(m, nullptr, cur_gray, width, height, stride, tm_xy_out, cap, n_tm_out, trace, /*prev_resident*/ true, false);
+    // first frame of a sequence (`if (imGrayPre.data)` fails, src/Frame.cc:164): nothing to compare with; the frame and its pyramid stay on the device
+    *n_tm_out = 0;
+    if (trace) { trace->n_points = trace->n_tracked = trace->n_inliers = 0; trace->have_F = 0; }
+    CUDA_TRY(cudaSetDevice(m->device));
+    m->cur_resident = false;
+    int st = motion_prepare(m, width, height, 22, 5);
+    if (st != COEB_OK) return st;
+    if ((st = upload_level0(m, 1, cur_gray, stride)) != COEB_OK) return st;
+    build_pyramid(m, 1);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    m->cur_resident = true; m->res_w = width; m->res_h = height;
+    return COEB_OK;
 }
 
 }  // extern "C"

@@ -87,6 +87,37 @@ class Motion:
                      state=np.array(tr.state[:k], np.uint8), F=np.array(tr.F[:], np.float64).reshape(3, 3) if tr.have_F else None)
         return tm[:n.value].copy(), trace
 
+    def process_next(self, cur, cap=1000):
+        """Sequence form (coeb_process_moving_object_next): the previous frame is the current frame of the last process / process_next
+        call, resident on the device. Returns (T_M [n,2], trace dict); the first call of a sequence returns no points."""
+        cur = _gray(cur)
+        tm = np.zeros((cap, 2), np.float32)
+        n = C.c_int()
+        tr = MotionTrace()
+        _check(lib().coeb_process_moving_object_next(self.h, _p(cur), cur.shape[1], cur.shape[0], cur.strides[0], _p(tm), cap, C.byref(n), C.byref(tr)))
+        k = min(tr.n_points, TRACE_POINTS)
+        trace = dict(n_points=tr.n_points, n_tracked=tr.n_tracked, n_inliers=tr.n_inliers,
+                     prepoint=np.array(tr.pre_xy[:2 * k], np.float32).reshape(-1, 2), nextpoint=np.array(tr.next_xy[:2 * k], np.float32).reshape(-1, 2),
+                     state=np.array(tr.state[:k], np.uint8), F=np.array(tr.F[:], np.float64).reshape(3, 3) if tr.have_F else None)
+        return tm[:n.value].copy(), trace
+
+    def prepared_process_next(self, frames, cap=1000):
+        """The sequence call with its ctypes arguments built once: returns a zero-argument callable that feeds the frames round robin
+        (each call pairs the previous call's frame with the next one) and returns the number of T_M points."""
+        frames = [_gray(f) for f in frames]
+        tm = np.zeros((cap, 2), np.float32)
+        n = C.c_int()
+        fn = lib().coeb_process_moving_object_next
+        args = [(self.h, _p(f), f.shape[1], f.shape[0], f.strides[0], _p(tm), cap, C.byref(n), None) for f in frames]
+        state = {"i": 0}
+
+        def call():
+            _check(fn(*args[state["i"]]))
+            state["i"] = (state["i"] + 1) % len(args)
+            return n.value
+        call.keep = (frames, tm, n)
+        return call
+
     def prepared_process(self, prev, cur, cap=1000):
         """The C call with its ctypes arguments built once (what a C++ caller pays): returns a zero-argument callable that runs
         coeb_process_moving_object on the two frames and returns the number of T_M points (results stay in the prepared buffers)."""

@@ -356,6 +356,13 @@ typedef struct coeb_motion_trace {
 int coeb_process_moving_object(coeb_motion* m, const uint8_t* prev_gray, const uint8_t* cur_gray, int width, int height, int stride,
                                float* tm_xy_out, int cap, int* n_tm_out, coeb_motion_trace* trace /* may be NULL */);
 
+/* The same for a sequence, as the reference runs it (imGrayPre is the frame of the previous call, src/Frame.cc:164-209): the previous frame is
+ * the current frame of the last coeb_process_moving_object / coeb_process_moving_object_next call on this handle, still on the device with
+ * its pyramid, so only cur_gray travels. The first call of a sequence (or the first after a change of size) keeps the frame and returns no
+ * T_M, like the reference's first frame. Results are identical to coeb_process_moving_object(previous frame, cur_gray). */
+int coeb_process_moving_object_next(coeb_motion* m, const uint8_t* cur_gray, int width, int height, int stride, float* tm_xy_out, int cap,
+                                    int* n_tm_out, coeb_motion_trace* trace /* may be NULL */);
+
 /* The stages, callable on their own (host arrays in and out):
  * cv::goodFeaturesToTrack(gray, corners, max_corners, quality, min_distance, noArray(), 3, true, harris_k)       (:333) */
 int coeb_motion_good_features(coeb_motion* m, const uint8_t* gray, int width, int height, int stride, int max_corners, double quality,

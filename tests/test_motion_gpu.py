@@ -36,6 +36,12 @@ def mo():
     return motion.Motion()
 
 
+@pytest.fixture(scope="module")
+def gpu_motion_factory(mo):
+    from coeb_b200 import motion
+    return motion.Motion
+
+
 SEEDS = list(range(8))
 
 
@@ -188,3 +194,27 @@ def test_larger_frames_keep_the_host_minimum_distance_pass(mo):
     assert tr_a["F"] is not None and len(tm_a) > 0
     inside = sum(any(b[0] - 4 <= x < b[2] + 4 and b[1] - 4 <= y < b[3] + 4 for b in boxes) for x, y in tm_a)
     assert inside >= 0.5 * len(tm_a)
+
+
+@pytest.mark.parametrize("seed", SEEDS[:3])
+def test_sequence_call_equals_the_two_frame_call(mo, gpu_motion_factory, seed):
+    """coeb_process_moving_object_next keeps the last call's current frame and pyramid on the device as the next call's previous frame
+    (the reference's imGrayPre): the first call of a sequence returns nothing, every later one what the two-frame call returns for
+    (previous frame, this frame) -- bit for bit, whichever of the two pyramid buffers holds which frame."""
+    a, b, _ = synth.make_motion_pair(seed)
+    c = synth.shift_image(b, 3, -2)
+    ref_ab, tr_ab = mo.process(a, b)
+    ref_bc, tr_bc = mo.process(b, c)
+    ref_ca, tr_ca = mo.process(c, a)
+    seq = gpu_motion_factory()
+    tm0, tr0 = seq.process_next(a)
+    assert len(tm0) == 0 and tr0["n_points"] == 0
+    for frame, ref, tr_ref in ((b, ref_ab, tr_ab), (c, ref_bc, tr_bc), (a, ref_ca, tr_ca)):
+        tm, tr = seq.process_next(frame)
+        assert tr["n_points"] == tr_ref["n_points"] and np.array_equal(tr["prepoint"], tr_ref["prepoint"]) and np.array_equal(tr["nextpoint"], tr_ref["nextpoint"])
+        assert np.array_equal(tr["state"], tr_ref["state"]) and np.array_equal(tm, ref)
+    # a two-frame call leaves its current frame behind as well
+    tm_m, _ = seq.process(a, b)
+    tm_n, _ = seq.process_next(c)
+    assert np.array_equal(tm_m, ref_ab) and np.array_equal(tm_n, ref_bc)
+    seq.close()

@@ -5,7 +5,8 @@ sys.path[:0] = ['coeb-slam_b200/python']
 from coeb_b200 import synth, motion
 mo = motion.Motion()
 prev, cur, _ = synth.make_motion_pair(0)
-call = mo.prepared_process(prev, cur)
+seq = len(sys.argv) > 2 and sys.argv[2] == "seq"   # the sequence form: frames fed round robin, the previous one resident on the device
+call = mo.prepared_process_next([prev, cur]) if seq else mo.prepared_process(prev, cur)
 for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 4):
     n = call()
 print("ok", n)
