@@ -768,6 +768,19 @@ def bench_matching(cb, dev, batch, o_kps, o_desc, o_cnt, ex, args):
         return m.stereo_match(exL, exR, a[0], a[1], b[0], b[1], bf_s, b_s)
     n_st, ur_st, dp_st = stereo_frame()
     out["stereo_1241x376_extract_pair_us"] = _median_us(lambda: (exL.extract(left), exR.extract(right)), 20)
+    # the same pair as ONE two-frame call of one extractor (left / right extractors with equal parameters, as ORB-SLAM constructs them);
+    # coeb_stereo_match_frames then takes frames 0 and 1 of it
+    ex2 = cb.Extractor(2000, 1.2, NLEVELS, 20, 7, device=dev)
+    pair = np.ascontiguousarray(np.stack([left, right]))
+    cap2 = ex2.default_cap(sw, sh)
+    out2 = (np.empty((2, cap2), cb.KP_DTYPE), np.empty((2, cap2, 32), np.uint8), np.empty(2, np.int32), np.empty(2, np.int32))
+    for _ in range(3):
+        ex2.extract_batch_host(pair, out=out2)
+    assert out2[2][0] == len(kl) and out2[2][1] == len(kr) and np.array_equal(out2[1][0, :len(kl)], dl)
+    out["stereo_1241x376_extract_pair_one_call_us"] = _median_us(lambda: ex2.extract_batch_host(pair, out=out2), 20)
+    n_st2, ur_st2, _ = m.stereo_match_frames(ex2, 0, ex2, 1, kl, dl, kr, dr, bf_s, b_s)
+    out["stereo_one_call_equals_two_calls"] = bool(n_st2 == n_st and np.array_equal(ur_st2, ur_st))
+    ex2.close()
     out["stereo_1241x376_compute_stereo_matches_us"] = _median_us(lambda: m.stereo_match(exL, exR, kl, dl, kr, dr, bf_s, b_s), 20)
     out["stereo_1241x376_points_with_depth"] = int(n_st)
     big = synth.make_frame(500, 1920, 1080)

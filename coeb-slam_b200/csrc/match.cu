@@ -2626,7 +2626,13 @@ int coeb_match_init(coeb_matcher* m, coeb_frame* f1, coeb_frame* f2, float* prev
 int coeb_stereo_match(coeb_matcher* m, coeb_extractor* left, coeb_extractor* right, int N, const coeb_keypoint* keys_left,
                       const uint8_t* desc_left, int Nr, const coeb_keypoint* keys_right, const uint8_t* desc_right, float bf,
                       float b, float* uright_out, float* depth_out, int* nmatched_out) {
-    if (!m || !left || !right || N < 0 || Nr < 0 || !uright_out || !depth_out) return fail(COEB_ERR_INVALID_ARG, "bad argument");
+    return coeb_stereo_match_frames(m, left, 0, right, 0, N, keys_left, desc_left, Nr, keys_right, desc_right, bf, b, uright_out, depth_out, nmatched_out);
+}
+
+int coeb_stereo_match_frames(coeb_matcher* m, coeb_extractor* left, int frame_left, coeb_extractor* right, int frame_right, int N,
+                             const coeb_keypoint* keys_left, const uint8_t* desc_left, int Nr, const coeb_keypoint* keys_right,
+                             const uint8_t* desc_right, float bf, float b, float* uright_out, float* depth_out, int* nmatched_out) {
+    if (!m || !left || !right || N < 0 || Nr < 0 || !uright_out || !depth_out || frame_left < 0 || frame_right < 0) return fail(COEB_ERR_INVALID_ARG, "bad argument");
     if (nmatched_out) *nmatched_out = 0;
     for (int i = 0; i < N; i++) { uright_out[i] = -1.f; depth_out[i] = -1.f; }
     if (N == 0 || Nr == 0) return COEB_OK;
@@ -2637,8 +2643,8 @@ int coeb_stereo_match(coeb_matcher* m, coeb_extractor* left, coeb_extractor* rig
     if (st != COEB_OK) return st;
     for (int l = 0; l < nl; l++) {
         int w2 = 0, h2 = 0;
-        if ((st = coeb_pyramid_level(left, 0, l, 0, &S.pyrL[l], &S.lw[l], &S.lh[l], &S.pitchL[l])) != COEB_OK) return st;
-        if ((st = coeb_pyramid_level(right, 0, l, 0, &S.pyrR[l], &w2, &h2, &S.pitchR[l])) != COEB_OK) return st;
+        if ((st = coeb_pyramid_level(left, frame_left, l, 0, &S.pyrL[l], &S.lw[l], &S.lh[l], &S.pitchL[l])) != COEB_OK) return st;
+        if ((st = coeb_pyramid_level(right, frame_right, l, 0, &S.pyrR[l], &w2, &h2, &S.pitchR[l])) != COEB_OK) return st;
         if (w2 != S.lw[l] || h2 != S.lh[l]) return fail(COEB_ERR_INVALID_ARG, "left/right pyramids differ in size at level %d", l);
     }
     for (int i = 0; i < N; i++) if (keys_left[i].octave < 0 || keys_left[i].octave >= nl) return fail(COEB_ERR_INVALID_ARG, "left keypoint %d: octave", i);

@@ -386,6 +386,18 @@ class Matcher:
                                        _p(descR), C.c_float(bf), C.c_float(b), _p(ur), _p(dp), C.byref(n)))
         return n.value, ur, dp
 
+    def stereo_match_frames(self, exL, frame_left, exR, frame_right, kpsL, descL, kpsR, descR, bf, b):
+        """ComputeStereoMatches on the pyramids of (exL, frame_left) and (exR, frame_right): e.g. frames 0 and 1 of one two-frame call."""
+        kpsL = np.ascontiguousarray(kpsL, dtype=KP_DTYPE)
+        kpsR = np.ascontiguousarray(kpsR, dtype=KP_DTYPE)
+        descL, descR = _u8(descL), _u8(descR)
+        ur = np.empty(len(kpsL), np.float32)
+        dp = np.empty(len(kpsL), np.float32)
+        n = C.c_int()
+        _check(lib().coeb_stereo_match_frames(self.h, exL.h, int(frame_left), exR.h, int(frame_right), len(kpsL), _p(kpsL), _p(descL), len(kpsR), _p(kpsR),
+                                              _p(descR), C.c_float(bf), C.c_float(b), _p(ur), _p(dp), C.byref(n)))
+        return n.value, ur, dp
+
     def knn2(self, q, t, nnratio):
         q, t = _u8(q).reshape(-1, 32), _u8(t).reshape(-1, 32)
         idx, d1, d2 = (np.empty(len(q), np.int32) for _ in range(3))

@@ -161,6 +161,14 @@ def test_stereo_matches_kitti_shape(gpu):
     assert np.array_equal(ur_c, ur_g)
     assert np.array_equal(dp_c, dp_g)
     assert n_c > 100
+    # the pair as ONE two-frame call of one extractor, matched as frames 0 and 1 of it: same keypoints, same matches
+    g2 = gpu.Extractor(nfeatures=nf)
+    k2, d2, c2, s2 = g2.extract_batch_host(np.ascontiguousarray(np.stack([left, right])))
+    assert (s2 == 0).all() and c2[0] == len(kl) and c2[1] == len(kr)
+    assert k2[0, :c2[0]].tobytes() == kl.tobytes() and k2[1, :c2[1]].tobytes() == kr.tobytes()
+    assert np.array_equal(d2[0, :c2[0]], dl) and np.array_equal(d2[1, :c2[1]], dr)
+    n_2, ur_2, dp_2 = gpu.Matcher().stereo_match_frames(g2, 0, g2, 1, kl, dl, kr, dr, bf, b)
+    assert n_2 == n_c and np.array_equal(ur_2, ur_c) and np.array_equal(dp_2, dp_c)
 
 
 def test_knn2_small_exact_and_ties(gpu):
