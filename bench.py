@@ -834,9 +834,9 @@ def bench_matching(cb, dev, batch, o_kps, o_desc, o_cnt, ex, args):
         ts = []
         for _ in range(20):
             seq_call()                      # mp_prev arrives (pairs mp_cur -> mp_prev: not timed)
-            t = time.perf_counter()
+            t_seq = time.perf_counter()
             n_seq = seq_call()              # mp_cur arrives
-            ts.append(time.perf_counter() - t)
+            ts.append(time.perf_counter() - t_seq)
         assert n_seq == len(tm_g)
         out["process_moving_object_next_us"] = 1e6 * float(np.median(ts))
         out["process_moving_object_points"] = int(tr_g["n_points"])
