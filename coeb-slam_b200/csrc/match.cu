@@ -235,6 +235,54 @@ __global__ void __launch_bounds__(1024) grid_build_kernel(FrameDev f, int* cell_
     }
 }
 
+// The same grid for frames of up to kGridSmemMax keypoints with the cell table, the fill cursors and the item list in shared memory
+// (one pass over the coordinates, no global round trips between the steps; see frame_tail_grid_kernel for the RGB-D constructor's form).
+constexpr int kGridSmemMax = 2048;
+__global__ void __launch_bounds__(1024, 1) grid_build_smem_kernel(FrameDev f, int* __restrict__ cell_start, int* __restrict__ cell_items) {
+    __shared__ int s_start[kGridCells + 1], s_fill[kGridCells];
+    __shared__ short s_cell[kGridSmemMax], s_items[kGridSmemMax];
+    __shared__ int s_warp[33];
+    const int tid = threadIdx.x, T = blockDim.x, n = f.n;
+    for (int i = tid; i <= kGridCells; i += T) s_start[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += T) {
+        // PosInGrid: round() half away from zero (src/Frame.cc:560-561)
+        const int px = (int)roundf((f.x[i] - f.min_x) * f.gw_inv), py = (int)roundf((f.y[i] - f.min_y) * f.gh_inv);
+        int c = -1;
+        if (!(px < 0 || px >= COEB_GRID_COLS || py < 0 || py >= COEB_GRID_ROWS)) {
+            c = px * COEB_GRID_ROWS + py;
+            atomicAdd(&s_start[c], 1);
+        }
+        s_cell[i] = (short)c;
+    }
+    __syncthreads();
+    const int total = block_exclusive_scan(s_start, kGridCells, s_warp);
+    if (tid == 0) s_start[kGridCells] = total;
+    __syncthreads();
+    for (int i = tid; i <= kGridCells; i += T) {
+        const int v = s_start[i];
+        cell_start[i] = v;
+        if (i < kGridCells) s_fill[i] = v;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += T) {
+        const int c = s_cell[i];
+        if (c >= 0) s_items[atomicAdd(&s_fill[c], 1)] = (short)i;
+    }
+    __syncthreads();
+    for (int c = tid; c < kGridCells; c += T) {   // items of a cell in ascending keypoint index, the order in which the reference pushes them
+        const int lo = s_start[c], hi = s_start[c + 1];
+        for (int i = lo + 1; i < hi; i++) {
+            const short v = s_items[i];
+            int j = i - 1;
+            while (j >= lo && s_items[j] > v) { s_items[j + 1] = s_items[j]; j--; }
+            s_items[j + 1] = v;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < total; i += T) cell_items[i] = s_items[i];
+}
+
 __global__ void features_in_area_kernel(FrameDev f, float x, float y, float r, int minLevel, int maxLevel, int* out, int cap, int* n_out) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     int n = 0;
@@ -2396,7 +2444,8 @@ int coeb_frame_create(coeb_matcher* m, const coeb_keypoint* kps, const uint8_t* 
     d.gh_inv = (float)COEB_GRID_ROWS / (cam->max_y - cam->min_y);
     d.fx = cam->fx; d.fy = cam->fy; d.cx = cam->cx; d.cy = cam->cy; d.bf = cam->bf; d.b = cam->b;
     for (int i = 0; i < COEB_MAX_LEVELS; i++) d.scale[i] = i < nlevels ? scale_factors[i] : 0.f;
-    grid_build_kernel<<<1, 1024, 0, s>>>(d, d_cell_start, d_cell_items, d_kp_cell);
+    if (n <= kGridSmemMax) grid_build_smem_kernel<<<1, 1024, 0, s>>>(d, d_cell_start, d_cell_items);
+    else grid_build_kernel<<<1, 1024, 0, s>>>(d, d_cell_start, d_cell_items, d_kp_cell);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);  // the pinned staging block is reused by the next call
     if (e != cudaSuccess) { coeb_frame_destroy(f); return fail(COEB_ERR_CUDA, "frame upload / grid build failed: %s", cudaGetErrorString(e)); }
