@@ -98,3 +98,31 @@ def test_fundamental_ransac_recovers_a_known_geometry():
     _, d_own = pmo.epipolar_outliers(F2, g["prepoint"], g["nextpoint"], g["state"])
     far = keep & (g["dist"] > 2.5)
     assert far.sum() > 20 and (d_own[far] > 1).mean() > 0.9 and (d_own[keep & (g["dist"] < 0.3)] <= 1).mean() > 0.95
+
+
+def test_fundamental_ransac_degenerate_and_translation_inputs():
+    """Host code of the product library: fewer than eight points and identical points fail loudly (no model, no crash); a pure
+    sideways translation (epipoles at infinity) is recovered like any other geometry."""
+    from coeb_b200 import motion
+    import coeb_b200
+    rng = np.random.default_rng(11)
+    with pytest.raises(coeb_b200.CoebError):
+        motion.fundamental_ransac(rng.uniform(0, 600, (7, 2)).astype(np.float32), rng.uniform(0, 600, (7, 2)).astype(np.float32))
+    same = np.tile(np.array([[100.0, 50.0]], np.float32), (40, 1))
+    with pytest.raises(coeb_b200.CoebError):
+        motion.fundamental_ransac(same, same)
+    X = np.concatenate([rng.uniform(-3, 3, (300, 2)), rng.uniform(4, 12, (300, 1))], axis=1)
+    K = np.array([[520.0, 0, 320], [0, 520, 240], [0, 0, 1]])
+    x1 = (K @ X.T).T
+    x1 = x1[:, :2] / x1[:, 2:]
+    x2 = (K @ (X + np.array([0.3, 0.0, 0.0])).T).T
+    x2 = x2[:, :2] / x2[:, 2:]
+    bad = rng.random(300) < 0.25
+    x2[bad] += rng.uniform(-30, 30, (int(bad.sum()), 2))
+    F, mask = motion.fundamental_ransac(x1.astype(np.float32), x2.astype(np.float32), 0.1, 0.99, 2000, 3)
+    assert mask[~bad].mean() > 0.95 and mask[bad].mean() < 0.1
+    h1 = np.concatenate([x1, np.ones((300, 1))], axis=1)
+    h2 = np.concatenate([x2, np.ones((300, 1))], axis=1)
+    l2 = (F @ h1.T).T
+    d = np.abs((h2 * l2).sum(axis=1)) / np.hypot(l2[:, 0], l2[:, 1])
+    assert d[~bad].max() < 0.05
