@@ -742,6 +742,9 @@ def bench_matching(cb, dev, batch, o_kps, o_desc, o_cnt, ex, args):
 
     def call_chain():
         call_extract(); call_tail(); call_local()
+
+    def call_chain_head():
+        call_extract(); call_tail()
     for _ in range(5):
         call_chain()
     assert n1.value == len(kps) and nfr.value == len(kps)
@@ -839,6 +842,17 @@ def bench_matching(cb, dev, batch, o_kps, o_desc, o_cnt, ex, args):
             ts.append(time.perf_counter() - t_seq)
         assert n_seq == len(tm_g)
         out["process_moving_object_next_us"] = 1e6 * float(np.median(ts))
+        # one frame of the COEB front end as the tracking thread runs it, five blocking C calls back to back: ProcessMovingObject (sequence
+        # form) -> extract + dynamic filter -> Frame tail -> SearchByProjection(cur, last) -> SearchLocalPoints
+        ts = []
+        for _ in range(20):
+            seq_call()
+            t_seq = time.perf_counter()
+            seq_call(); call_chain_head(); call_m3(); call_local()
+            ts.append(time.perf_counter() - t_seq)
+        out["coeb_frame_front_end_us"] = 1e6 * float(np.median(ts))
+        out["coeb_frame_front_end_note"] = ("coeb_process_moving_object_next -> coeb_extract -> coeb_frame_from_extractor -> coeb_match_lastframe -> "
+                                            "coeb_search_local_points, host buffers in and out, one 640x480 frame")
         out["process_moving_object_points"] = int(tr_g["n_points"])
         out["process_moving_object_tm"] = int(len(tm_g))
         if not args.no_cpu:
