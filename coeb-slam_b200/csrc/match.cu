@@ -2516,8 +2516,14 @@ int coeb_match_projection(coeb_matcher* m, coeb_frame* F, int n, const uint8_t* 
     if (n == 0 || F->n == 0) return COEB_OK;
     if (!track_in_view || !bad || !has_obs || !proj_x || !proj_y || !proj_xr || !level || !view_cos || !desc)
         return fail(COEB_ERR_INVALID_ARG, "null map-point array");
-    for (int i = 0; i < n; i++)
-        if (track_in_view[i] && !bad[i] && (level[i] < 0 || level[i] >= F->nlevels)) return fail(COEB_ERR_INVALID_ARG, "map point %d: level %d", i, level[i]);
+    {   // (one branch-free pass the compiler vectorises; the offending point is looked up only if there is one)
+        const unsigned nl = (unsigned)F->nlevels;
+        unsigned any = 0;
+        for (int i = 0; i < n; i++) any |= (unsigned)(track_in_view[i] != 0) & (unsigned)(bad[i] == 0) & (unsigned)((unsigned)level[i] >= nl);
+        if (any)
+            for (int i = 0; i < n; i++)
+                if (track_in_view[i] && !bad[i] && (level[i] < 0 || level[i] >= F->nlevels)) return fail(COEB_ERR_INVALID_ARG, "map point %d: level %d", i, level[i]);
+    }
     CUDA_TRY(cudaSetDevice(m->device));
     const bool trace = getenv("COEB_MATCH_TRACE") != nullptr;
     const auto t_begin = std::chrono::steady_clock::now();
