@@ -125,19 +125,28 @@ constexpr int kSortCap = 8192;
 // candidates only) fixed point, 1024 candidates at a time in sorted order: everything before the current chunk is final, so a
 // candidate is either killed by a final earlier one or depends on the few close candidates of its own chunk (listed once in shared
 // memory); in-place updates, a chunk is done when one sweep changes nothing. The chunks stop once maxCorners are accepted.
-constexpr int kSelMaxCells = 4800, kSelNb = 12, kSelAccSlots = 4, kSelChunkSlots = 8;
-// shared-memory layout of the pass (bytes; it aliases the sorted keys, which are turned into positions first)
+constexpr int kSelMaxCells = 4800, kSelNb = 12, kSelAccSlots = 4, kSelChunkSlots = 12;
+// shared-memory layout of the pass (bytes; it aliases the sorted keys, which are turned into positions first). The per-cell counters are
+// bytes, four to a word (atomicAdd on the word; a cell holds at most 64 pixels), which is what lets the chunk lists have 12 slots per cell:
+// with 8, strong corners packed along one edge overflowed them on some frames and the spill list below made the pass three times longer.
 constexpr int oSelPos = 0;                                             // unsigned[kSortCap]: x | y << 16 of candidate i (sorted order)
 constexpr int oSelA = oSelPos + kSortCap * 4;                          // uchar[1024]: accepted flag of the chunk's candidates
-constexpr int oSelAccCnt = oSelA + 1024;                               // int[cells]: accepted corners per cell (all chunks so far)
-constexpr int oSelAccSlot = oSelAccCnt + 4 * kSelMaxCells;             // ushort[cells][kSelAccSlots]: their candidate numbers
-constexpr int oSelChCnt = oSelAccSlot + 2 * kSelMaxCells * kSelAccSlots;   // int[cells]: live candidates of the current chunk per cell
-constexpr int oSelChSlot = oSelChCnt + 4 * kSelMaxCells;               // ushort[cells][kSelChunkSlots]: their thread numbers
+constexpr int oSelAccCnt = oSelA + 1024;                               // uchar[cells]: accepted corners per cell (all chunks so far)
+constexpr int oSelAccSlot = oSelAccCnt + kSelMaxCells;                 // ushort[cells][kSelAccSlots]: their candidate numbers
+constexpr int oSelChCnt = oSelAccSlot + 2 * kSelMaxCells * kSelAccSlots;   // uchar[cells]: live candidates of the current chunk per cell
+constexpr int oSelChSlot = oSelChCnt + kSelMaxCells;                   // ushort[cells][kSelChunkSlots]: their thread numbers
 constexpr int oSelNb = oSelChSlot + 2 * kSelMaxCells * kSelChunkSlots; // ushort[1024][kSelNb]: close live predecessors of a thread's candidate
 constexpr int oSelWarp = oSelNb + 1024 * kSelNb * 2;                   // int[40]: scan scratch, accepted so far, overflow flag, spill count
 constexpr int kSelSpill = 256;
 constexpr int oSelSpill = oSelWarp + 160;                              // ushort[kSelSpill]: live candidates of the chunk whose cell list was full
-constexpr int kSelSmem = oSelSpill + 2 * kSelSpill;
+constexpr int kSelPool = 4096;
+constexpr int oSelPool = oSelSpill + 2 * kSelSpill;                    // ushort[kSelPool]: close live predecessors beyond the kSelNb of a thread's own list
+constexpr int kSelSmem = oSelPool + 2 * kSelPool;
+static_assert(oSelAccCnt % 4 == 0 && oSelChCnt % 4 == 0 && kSelMaxCells % 4 == 0, "byte counters are updated through their words");
+// byte counter c of a packed array: add one (returns the old count) / read / clear
+__device__ __forceinline__ int cnt8_inc(unsigned* w, int c) { const int sh = 8 * (c & 3); return (int)((atomicAdd(&w[c >> 2], 1u << sh) >> sh) & 0xFFu); }
+__device__ __forceinline__ int cnt8_get(const unsigned* w, int c) { return (int)((w[c >> 2] >> (8 * (c & 3))) & 0xFFu); }
+__device__ __forceinline__ void cnt8_clear(unsigned* w, int c) { atomicAnd(&w[c >> 2], ~(0xFFu << (8 * (c & 3)))); }
 static_assert(kSelSmem >= kSortCap * 8 && kSelSmem <= 227 * 1024, "the selection arrays alias the sorted keys and fit one SM");
 struct SelectArgs {
     int enabled, w, cell, gw, gh, max_corners, d2max;   // d2max: largest integer squared distance that is < minDistance^2
@@ -196,13 +205,14 @@ __global__ void __launch_bounds__(1024) sort_candidates_kernel(float2* __restric
     // ---- minimum-distance pass ----
     unsigned* const pos = reinterpret_cast<unsigned*>(s_raw + oSelPos);
     unsigned char* const acc = s_raw + oSelA;
-    int* const acc_cnt = reinterpret_cast<int*>(s_raw + oSelAccCnt);
+    unsigned* const acc_cnt = reinterpret_cast<unsigned*>(s_raw + oSelAccCnt);
     unsigned short* const acc_slot = reinterpret_cast<unsigned short*>(s_raw + oSelAccSlot);
-    int* const ch_cnt = reinterpret_cast<int*>(s_raw + oSelChCnt);
+    unsigned* const ch_cnt = reinterpret_cast<unsigned*>(s_raw + oSelChCnt);
     unsigned short* const ch_slot = reinterpret_cast<unsigned short*>(s_raw + oSelChSlot);
     unsigned short* const nbl = reinterpret_cast<unsigned short*>(s_raw + oSelNb) + tid * kSelNb;
-    int* const s_warp = reinterpret_cast<int*>(s_raw + oSelWarp);   // [0..32] warp totals, [33] chunk total, [34] accepted so far, [35] a list overflowed for good, [36] spilled candidates
+    int* const s_warp = reinterpret_cast<int*>(s_raw + oSelWarp);   // [0..32] warp totals, [33] chunk total, [34] accepted so far, [35] a list overflowed for good, [36] spilled candidates, [37] pool entries handed out
     unsigned short* const spill = reinterpret_cast<unsigned short*>(s_raw + oSelSpill);
+    unsigned short* const pool = reinterpret_cast<unsigned short*>(s_raw + oSelPool);
     const int ncell = sel.gw * sel.gh, cell = sel.cell;
     unsigned mine[kSortCap / 1024];
 #pragma unroll
@@ -215,8 +225,8 @@ __global__ void __launch_bounds__(1024) sort_candidates_kernel(float2* __restric
     __syncthreads();   // every key has been read: its storage is reused from here on
 #pragma unroll
     for (int k = 0; k < kSortCap / 1024; k++) { const int i = tid + k * 1024; if (i < n) pos[i] = mine[k]; }
-    for (int c = tid; c < ncell; c += T) { acc_cnt[c] = 0; ch_cnt[c] = 0; }
-    if (tid < 3) s_warp[34 + tid] = 0;
+    for (int c = tid; c < (ncell + 3) / 4; c += T) { acc_cnt[c] = 0u; ch_cnt[c] = 0u; }
+    if (tid < 4) s_warp[34 + tid] = 0;
     __syncthreads();
     const int lane = tid & 31, wid = tid >> 5;
     for (int base = 0; base < n; base += T) {
@@ -235,7 +245,7 @@ __global__ void __launch_bounds__(1024) sort_candidates_kernel(float2* __restric
             for (int yy = cy0; yy <= cy1 && live; yy++)
                 for (int xx = cx0; xx <= cx1 && live; xx++) {
                     const int c = yy * sel.gw + xx;
-                    const int cnt = min(acc_cnt[c], kSelAccSlots);
+                    const int cnt = min(cnt8_get(acc_cnt, c), kSelAccSlots);
                     for (int k = 0; k < cnt; k++) {
                         const unsigned q = pos[acc_slot[c * kSelAccSlots + k]];
                         const int dx = xi - (int)(q & 0xFFFFu), dy = yi - (int)(q >> 16);
@@ -244,7 +254,7 @@ __global__ void __launch_bounds__(1024) sort_candidates_kernel(float2* __restric
                 }
             // 2. the live candidates of this chunk are listed by cell
             if (live) {
-                const int slot = atomicAdd(&ch_cnt[mycell], 1);
+                const int slot = cnt8_inc(ch_cnt, mycell);
                 if (slot < kSelChunkSlots) ch_slot[mycell * kSelChunkSlots + slot] = (unsigned short)tid;
                 else {   // a crowded cell (many strong local maxima side by side): the candidate goes to a chunk-wide list every live candidate also walks
                     const int k = atomicAdd(&s_warp[36], 1);
@@ -254,50 +264,67 @@ __global__ void __launch_bounds__(1024) sort_candidates_kernel(float2* __restric
         }
         acc[tid] = live ? 1 : 0;
         __syncthreads();
-        // 3. close live predecessors inside the chunk
-        int nnb = 0;
+        // 3. close live predecessors inside the chunk: the first kSelNb in the thread's own list, the rest (dense clusters of strong corners:
+        // up to ~50 local maxima lie within minDistance of one) in a slice of a pool shared by the chunk, filled by a second identical walk
+        int nnb = 0, pool_off = -1;
         bool near_spill = false;   // one of the nine cells was full: only then can a spilled candidate be close
         if (live) {
-            for (int yy = cy0; yy <= cy1; yy++)
-                for (int xx = cx0; xx <= cx1; xx++) {
-                    const int c = yy * sel.gw + xx;
-                    const int raw = ch_cnt[c];
-                    near_spill |= raw > kSelChunkSlots;
-                    const int cnt = min(raw, kSelChunkSlots);
-                    for (int k = 0; k < cnt; k++) {
-                        const int tj = ch_slot[c * kSelChunkSlots + k];
-                        if (tj >= tid) continue;
-                        const unsigned q = pos[base + tj];
-                        const int dx = xi - (int)(q & 0xFFFFu), dy = yi - (int)(q >> 16);
-                        if (dx * dx + dy * dy > sel.d2max) continue;
-                        if (nnb < kSelNb) nbl[nnb] = (unsigned short)tj;
-                        nnb = min(nnb + 1, kSelNb + 1);   // kSelNb + 1: more than the list holds, the cells are walked again in every sweep
+            auto walk = [&](auto&& emit) {
+                for (int yy = cy0; yy <= cy1; yy++)
+                    for (int xx = cx0; xx <= cx1; xx++) {
+                        const int c = yy * sel.gw + xx;
+                        const int raw = cnt8_get(ch_cnt, c);
+                        near_spill |= raw > kSelChunkSlots;
+                        const int cnt = min(raw, kSelChunkSlots);
+                        for (int k = 0; k < cnt; k++) {
+                            const int tj = ch_slot[c * kSelChunkSlots + k];
+                            if (tj >= tid) continue;
+                            const unsigned q = pos[base + tj];
+                            const int dx = xi - (int)(q & 0xFFFFu), dy = yi - (int)(q >> 16);
+                            if (dx * dx + dy * dy <= sel.d2max) emit(tj);
+                        }
                     }
+                const int nsp = near_spill ? min(s_warp[36], kSelSpill) : 0;
+                for (int k = 0; k < nsp; k++) {
+                    const int tj = spill[k];
+                    if (tj >= tid) continue;
+                    const unsigned q = pos[base + tj];
+                    const int dx = xi - (int)(q & 0xFFFFu), dy = yi - (int)(q >> 16);
+                    if (dx * dx + dy * dy <= sel.d2max) emit(tj);
                 }
-            const int nsp = near_spill ? min(s_warp[36], kSelSpill) : 0;
-            for (int k = 0; k < nsp; k++) {
-                const int tj = spill[k];
-                if (tj >= tid) continue;
-                const unsigned q = pos[base + tj];
-                const int dx = xi - (int)(q & 0xFFFFu), dy = yi - (int)(q >> 16);
-                if (dx * dx + dy * dy > sel.d2max) continue;
-                if (nnb < kSelNb) nbl[nnb] = (unsigned short)tj;
-                nnb = min(nnb + 1, kSelNb + 1);
+            };
+            walk([&](int tj) { if (nnb < kSelNb) nbl[nnb] = (unsigned short)tj; nnb++; });
+            if (nnb > kSelNb) {
+                const int extra = nnb - kSelNb, off = atomicAdd(&s_warp[37], extra);
+                if (off + extra <= kSelPool) {   // (else: the cells are walked again in every sweep)
+                    pool_off = off;
+                    int idx = 0;
+                    walk([&](int tj) { if (idx >= kSelNb) pool[off + idx - kSelNb] = (unsigned short)tj; idx++; });
+                }
             }
         }
         // 4. accepted(i) = no accepted close predecessor, iterated in place until a sweep changes nothing
         bool a = live;
+#ifdef COEB_SEL_DEBUG
+        int dbg_sweeps = 0;
+        const int dbg_live = __syncthreads_count(live), dbg_over = __syncthreads_count(nnb > kSelNb && pool_off < 0), dbg_nsp = __syncthreads_count(near_spill);
+#endif
         for (;;) {
+#ifdef COEB_SEL_DEBUG
+            dbg_sweeps++;
+#endif
             bool changed = false;
             if (live) {
                 bool now = true;
-                if (nnb <= kSelNb) {
-                    for (int k = 0; k < nnb; k++) if (acc[nbl[k]]) { now = false; break; }
+                if (nnb <= kSelNb || pool_off >= 0) {
+                    const int n1 = min(nnb, kSelNb);
+                    for (int k = 0; k < n1; k++) if (acc[nbl[k]]) { now = false; break; }
+                    for (int k = 0; k < nnb - kSelNb && now; k++) if (acc[pool[pool_off + k]]) now = false;
                 } else {
                     for (int yy = cy0; yy <= cy1 && now; yy++)
                         for (int xx = cx0; xx <= cx1 && now; xx++) {
                             const int c = yy * sel.gw + xx;
-                            const int cnt = min(ch_cnt[c], kSelChunkSlots);
+                            const int cnt = min(cnt8_get(ch_cnt, c), kSelChunkSlots);
                             for (int k = 0; k < cnt; k++) {
                                 const int tj = ch_slot[c * kSelChunkSlots + k];
                                 if (tj >= tid || !acc[tj]) continue;
@@ -319,13 +346,16 @@ __global__ void __launch_bounds__(1024) sort_candidates_kernel(float2* __restric
             }
             if (!__syncthreads_or(changed)) break;
         }
+#ifdef COEB_SEL_DEBUG
+        if (tid == 0) printf("[sel] n %d base %d live %d sweeps %d over-list %d near-spill %d spilled %d accepted-before %d\n", n, base, dbg_live, dbg_sweeps, dbg_over, dbg_nsp, s_warp[36], s_warp[34]);
+#endif
         // 5. the accepted ones join the accepted grid and are emitted in sorted order
         if (a) {
-            const int slot = atomicAdd(&acc_cnt[mycell], 1);
+            const int slot = cnt8_inc(acc_cnt, mycell);
             if (slot < kSelAccSlots) acc_slot[mycell * kSelAccSlots + slot] = (unsigned short)i;
             else atomicOr(&s_warp[35], 4);
         }
-        if (live) ch_cnt[mycell] = 0;   // (every listed candidate clears its cell: ready for the next chunk)
+        if (live) cnt8_clear(ch_cnt, mycell);   // (every listed candidate clears its cell: ready for the next chunk)
         const unsigned bal = __ballot_sync(0xffffffffu, a);
         if (lane == 0) s_warp[wid] = __popc(bal);
         __syncthreads();
@@ -344,7 +374,7 @@ __global__ void __launch_bounds__(1024) sort_candidates_kernel(float2* __restric
             if (rank < sel.max_corners) { const float2 c = make_float2((float)xi, (float)yi); sel.out_dev[rank] = c; sel.out_host[rank] = c; }
         }
         __syncthreads();
-        if (tid == 0) { s_warp[34] = before + s_warp[33]; s_warp[36] = 0; }
+        if (tid == 0) { s_warp[34] = before + s_warp[33]; s_warp[36] = 0; s_warp[37] = 0; }
         __syncthreads();
     }
     if (tid == 0) {
