@@ -142,6 +142,7 @@ constexpr int oSelSpill = oSelWarp + 160;                              // ushort
 constexpr int kSelPool = 4096;
 constexpr int oSelPool = oSelSpill + 2 * kSelSpill;                    // ushort[kSelPool]: close live predecessors beyond the kSelNb of a thread's own list
 constexpr int kSelSmem = oSelPool + 2 * kSelPool;
+static_assert(oSelAccSlot % 8 == 0 && kSelAccSlots == 4 && oSelChSlot % 8 == 0 && oSelNb % 8 == 0 && kSelChunkSlots % 4 == 0 && kSelNb % 4 == 0, "slot rows and neighbour lists are read four entries (one uint2) at a time");
 static_assert(oSelAccCnt % 4 == 0 && oSelChCnt % 4 == 0 && kSelMaxCells % 4 == 0, "byte counters are updated through their words");
 // byte counter c of a packed array: add one (returns the old count) / read / clear
 __device__ __forceinline__ int cnt8_inc(unsigned* w, int c) { const int sh = 8 * (c & 3); return (int)((atomicAdd(&w[c >> 2], 1u << sh) >> sh) & 0xFFu); }
@@ -246,10 +247,16 @@ __global__ void __launch_bounds__(1024) sort_candidates_kernel(float2* __restric
                 for (int xx = cx0; xx <= cx1 && live; xx++) {
                     const int c = yy * sel.gw + xx;
                     const int cnt = min(cnt8_get(acc_cnt, c), kSelAccSlots);
-                    for (int k = 0; k < cnt; k++) {
-                        const unsigned q = pos[acc_slot[c * kSelAccSlots + k]];
-                        const int dx = xi - (int)(q & 0xFFFFu), dy = yi - (int)(q >> 16);
-                        if (dx * dx + dy * dy <= sel.d2max) { live = false; break; }
+                    if (cnt == 0) continue;
+                    const uint2 w = *reinterpret_cast<const uint2*>(acc_slot + c * kSelAccSlots);   // the cell's four slots in one load
+                    const unsigned j[4] = {w.x & 0xFFFFu, w.x >> 16, w.y & 0xFFFFu, w.y >> 16};
+                    unsigned q[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) q[u] = pos[u < cnt ? (j[u] & (kSortCap - 1)) : 0];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int dx = xi - (int)(q[u] & 0xFFFFu), dy = yi - (int)(q[u] >> 16);
+                        if (u < cnt && dx * dx + dy * dy <= sel.d2max) live = false;
                     }
                 }
             // 2. the live candidates of this chunk are listed by cell
@@ -276,12 +283,19 @@ __global__ void __launch_bounds__(1024) sort_candidates_kernel(float2* __restric
                         const int raw = cnt8_get(ch_cnt, c);
                         near_spill |= raw > kSelChunkSlots;
                         const int cnt = min(raw, kSelChunkSlots);
-                        for (int k = 0; k < cnt; k++) {
-                            const int tj = ch_slot[c * kSelChunkSlots + k];
-                            if (tj >= tid) continue;
-                            const unsigned q = pos[base + tj];
-                            const int dx = xi - (int)(q & 0xFFFFu), dy = yi - (int)(q >> 16);
-                            if (dx * dx + dy * dy <= sel.d2max) emit(tj);
+                        const uint2* const row = reinterpret_cast<const uint2*>(ch_slot + c * kSelChunkSlots);
+                        for (int k0 = 0; k0 < cnt; k0 += 4) {   // four slots at a time: one load, four independent position reads (in slot order)
+                            const uint2 w = row[k0 >> 2];
+                            const int tj[4] = {(int)(w.x & 0xFFFFu), (int)(w.x >> 16), (int)(w.y & 0xFFFFu), (int)(w.y >> 16)};
+                            bool ok[4];
+                            unsigned q[4];
+#pragma unroll
+                            for (int u = 0; u < 4; u++) { ok[u] = k0 + u < cnt && tj[u] < tid; q[u] = pos[base + (ok[u] ? tj[u] : 0)]; }
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const int dx = xi - (int)(q[u] & 0xFFFFu), dy = yi - (int)(q[u] >> 16);
+                                if (ok[u] && dx * dx + dy * dy <= sel.d2max) emit(tj[u]);
+                            }
                         }
                     }
                 const int nsp = near_spill ? min(s_warp[36], kSelSpill) : 0;
@@ -318,7 +332,14 @@ __global__ void __launch_bounds__(1024) sort_candidates_kernel(float2* __restric
                 bool now = true;
                 if (nnb <= kSelNb || pool_off >= 0) {
                     const int n1 = min(nnb, kSelNb);
-                    for (int k = 0; k < n1; k++) if (acc[nbl[k]]) { now = false; break; }
+                    const uint2* const nrow = reinterpret_cast<const uint2*>(nbl);
+                    unsigned hit = 0u;
+                    for (int k0 = 0; k0 < n1; k0 += 4) {   // (entries past n1 are stale: masked into range, their flags ignored)
+                        const uint2 w = nrow[k0 >> 2];
+                        const unsigned a0 = acc[w.x & 1023u], a1 = acc[(w.x >> 16) & 1023u], a2 = acc[w.y & 1023u], a3 = acc[(w.y >> 16) & 1023u];
+                        hit |= a0 | (k0 + 1 < n1 ? a1 : 0u) | (k0 + 2 < n1 ? a2 : 0u) | (k0 + 3 < n1 ? a3 : 0u);
+                    }
+                    now = hit == 0u;
                     for (int k = 0; k < nnb - kSelNb && now; k++) if (acc[pool[pool_off + k]]) now = false;
                 } else {
                     for (int yy = cy0; yy <= cy1 && now; yy++)
