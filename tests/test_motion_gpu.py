@@ -180,6 +180,46 @@ def test_device_minimum_distance_pass_equals_the_host_pass(mo, seed):
     assert len(pts) == tr_d["n_points"]
 
 
+def _device_and_host_selection(mo, a, b):
+    os.environ.pop("COEB_MOTION_HOST_SELECT", None)
+    tm_d, tr_d = mo.process(a, b)
+    os.environ["COEB_MOTION_HOST_SELECT"] = "1"
+    try:
+        tm_h, tr_h = mo.process(a, b)
+    finally:
+        os.environ.pop("COEB_MOTION_HOST_SELECT", None)
+    return tm_d, tr_d, tm_h, tr_h
+
+
+@pytest.mark.parametrize("seed", SEEDS[:4])
+def test_device_minimum_distance_pass_on_clustered_corners(mo, seed):
+    """The same comparison with the pair swapped: the second frames of the synthetic pairs carry the moved objects' edges and the
+    pixel noise, so their strong corners sit in clusters (seed 0: 71 candidates of the first chunk with more than 12 close
+    predecessors, a cell with 13 live candidates): the pooled neighbour lists and the chunk-wide spill list decide them."""
+    prev, cur, _ = synth.make_motion_pair(seed)
+    tm_d, tr_d, tm_h, tr_h = _device_and_host_selection(mo, cur, prev)
+    assert tr_d["n_points"] == tr_h["n_points"] > 300
+    assert np.array_equal(tr_d["prepoint"], tr_h["prepoint"]) and np.array_equal(tr_d["nextpoint"], tr_h["nextpoint"])
+    assert np.array_equal(tr_d["state"], tr_h["state"]) and np.array_equal(tm_d, tm_h)
+
+
+def test_plateaus_of_equal_response_hand_over_to_the_host_pass(mo):
+    """Two noise-free 2-px checkerboards: every pixel of a patch is a maximum of its 3x3 neighbourhood (plateaus of exactly equal
+    Harris response), 64 candidates per minimum-distance cell and ~100 close predecessors each. No list of the device pass holds
+    that; the kernel reports it and the call repeats the selection on the host. Same result as the forced host pass."""
+    rng = np.random.default_rng(5)
+    prev = np.full((480, 640), 128, np.uint8)
+    yy, xx = np.mgrid[0:40, 0:40]
+    for _ in range(2):
+        x0, y0 = int(rng.integers(40, 560)), int(rng.integers(40, 400))
+        prev[y0:y0 + 40, x0:x0 + 40] = ((((yy // 2) + (xx // 2)) & 1) * 160 + 40).astype(np.uint8)
+    cur = np.roll(prev, 2, axis=1)
+    tm_d, tr_d, tm_h, tr_h = _device_and_host_selection(mo, prev, cur)
+    assert tr_d["n_points"] == tr_h["n_points"] >= 16
+    assert np.array_equal(tr_d["prepoint"], tr_h["prepoint"]) and np.array_equal(tr_d["nextpoint"], tr_h["nextpoint"])
+    assert np.array_equal(tr_d["state"], tr_h["state"]) and np.array_equal(tm_d, tm_h)
+
+
 def test_larger_frames_keep_the_host_minimum_distance_pass(mo):
     """The device pass holds a grid of 4800 minimum-distance cells (640x480 at 8 px); a larger frame is decided on the host before
     anything is launched, takes the host pass and must give what the forced host pass gives."""
