@@ -154,6 +154,66 @@ struct SelectArgs {
     float2 *out_dev, *out_host;   // accepted corners in order (device for cornerSubPix, mapped host copy for the caller)
     int *n_dev, *n_host;          // their number; -1: not selected here (too many candidates, or a grid that does not fit): host pass
 };
+// Bitonic sort (descending) of the n candidate keys (response bits << 32 | pixel index; padded with zeros to m, a power of two) by one CTA of
+// 1024 threads, result in s_key[0..m). A thread holds K = m / 1024 consecutive keys in registers: the stages with a stride below K are
+// compare-exchanges inside the thread, those below 32 K are warp shuffles, and only the few strides that cross warps go through shared
+// memory (15 of the 66 stages of 2048 keys; the all-shared form was bound by its four 8-byte shared-memory accesses per pair and stage).
+template <int K>
+__device__ __forceinline__ void sort_keys_desc(unsigned long long* __restrict__ s_key, const float2* __restrict__ cand, int n, int m, int tid) {
+    unsigned long long k[K];
+#pragma unroll
+    for (int r = 0; r < K; r++) {
+        const int e = tid * K + r;
+        unsigned long long v = 0ull;   // padding sorts last
+        if (e < n) { const float2 c = cand[e]; v = ((unsigned long long)__float_as_uint(c.x) << 32) | (unsigned)__float_as_int(c.y); }
+        k[r] = v;
+    }
+    for (int size = 2; size <= m; size <<= 1) {
+        int stride = size >> 1;
+        if (stride >= 32 * K) {   // strides that cross warps: through shared memory
+#pragma unroll
+            for (int r = 0; r < K; r++) s_key[tid * K + r] = k[r];
+            __syncthreads();
+            for (; stride >= 32 * K; stride >>= 1) {
+                for (int t = tid; t < (m >> 1); t += 1024) {
+                    const int i = 2 * t - (t & (stride - 1)), j = i + stride;
+                    const bool desc = (i & size) == 0;
+                    const unsigned long long a = s_key[i], b = s_key[j];
+                    if ((a < b) == desc) { s_key[i] = b; s_key[j] = a; }
+                }
+                __syncthreads();
+            }
+#pragma unroll
+            for (int r = 0; r < K; r++) k[r] = s_key[tid * K + r];
+        }
+        for (; stride >= K; stride >>= 1) {   // strides inside the warp: the partner key sits in lane ^ (stride / K), same register
+            const int lx = stride / K;
+            const bool upper = (tid & lx) != 0;
+#pragma unroll
+            for (int r = 0; r < K; r++) {
+                const bool desc = ((tid * K + r) & size) == 0;
+                const unsigned long long o = __shfl_xor_sync(0xffffffffu, k[r], lx);
+                const unsigned long long mx = k[r] > o ? k[r] : o, mn = k[r] > o ? o : k[r];
+                k[r] = (desc != upper) ? mx : mn;
+            }
+        }
+#pragma unroll
+        for (int st = K / 2; st >= 1; st >>= 1) {   // strides inside the thread
+            if (st > (size >> 1)) continue;
+#pragma unroll
+            for (int r = 0; r < K; r++) {
+                if (r & st) continue;
+                const bool desc = ((tid * K + r) & size) == 0;
+                const unsigned long long a = k[r], b = k[r | st];
+                if ((a < b) == desc) { k[r] = b; k[r | st] = a; }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < K; r++) s_key[tid * K + r] = k[r];
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(1024) sort_candidates_kernel(float2* __restrict__ cand, unsigned* __restrict__ info, char* __restrict__ host, const SelectArgs sel) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     unsigned long long* const s_key = reinterpret_cast<unsigned long long*>(s_raw);
@@ -177,25 +237,10 @@ __global__ void __launch_bounds__(1024) sort_candidates_kernel(float2* __restric
     if (n > kSortCap || n < 2) return;
     int m = 2;
     while (m < n) m <<= 1;
-    for (int i = tid; i < m; i += T) {
-        unsigned long long k = 0ull;   // padding sorts last in descending order
-        if (i < n) { const float2 c = cand[i]; k = ((unsigned long long)__float_as_uint(c.x) << 32) | (unsigned)__float_as_int(c.y); }
-        s_key[i] = k;
-    }
-    __syncthreads();
-    for (int size = 2; size <= m; size <<= 1)
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int t = tid; t < (m >> 1); t += T) {
-                const int i = 2 * t - (t & (stride - 1)), j = i + stride;
-                const bool desc = (i & size) == 0;
-                const unsigned long long a = s_key[i], b = s_key[j];
-                if ((a < b) == desc) { s_key[i] = b; s_key[j] = a; }
-            }
-            // A warp's 32 pairs of one pass span 64 consecutive keys, and for strides <= 32 they stay inside those 64: the stages of such a
-            // run only need the warp to agree (63 of the 91 stages of 8192 keys: 21.8 -> 19 us); a block barrier closes the run.
-            if (stride > 32 || (stride == 1 && size >= 64)) __syncthreads();
-            else __syncwarp();
-        }
+    if (m <= 1024) sort_keys_desc<1>(s_key, cand, n, m, tid);
+    else if (m == 2048) sort_keys_desc<2>(s_key, cand, n, m, tid);
+    else if (m == 4096) sort_keys_desc<4>(s_key, cand, n, m, tid);
+    else sort_keys_desc<8>(s_key, cand, n, m, tid);
     if (!select_here) {
         for (int i = tid; i < n; i += T) {
             const unsigned long long k = s_key[i];
