@@ -193,8 +193,7 @@ __device__ __forceinline__ void sort_keys_desc(unsigned long long* __restrict__ 
             for (int r = 0; r < K; r++) {
                 const bool desc = ((tid * K + r) & size) == 0;
                 const unsigned long long o = __shfl_xor_sync(0xffffffffu, k[r], lx);
-                const unsigned long long mx = k[r] > o ? k[r] : o, mn = k[r] > o ? o : k[r];
-                k[r] = (desc != upper) ? mx : mn;
+                k[r] = ((k[r] > o) == (desc != upper)) ? k[r] : o;   // keeps the larger key where the pair's larger one belongs
             }
         }
 #pragma unroll
@@ -219,6 +218,9 @@ __global__ void __launch_bounds__(1024) sort_candidates_kernel(float2* __restric
     unsigned long long* const s_key = reinterpret_cast<unsigned long long*>(s_raw);
     const int tid = threadIdx.x, T = blockDim.x;
     const int n = (int)info[1];
+#ifdef COEB_SEL_DEBUG   // development build (tools/build_variant.sh NAME motion.cu -DCOEB_SEL_DEBUG=1): one line per phase and chunk with SM cycles and list statistics
+    const long long dbg_t0 = clock64();
+#endif
     if (tid < 4) reinterpret_cast<unsigned*>(host)[tid] = info[tid];
     __syncthreads();
     if (tid < 4) info[tid] = 0u;
@@ -241,6 +243,9 @@ __global__ void __launch_bounds__(1024) sort_candidates_kernel(float2* __restric
     else if (m == 2048) sort_keys_desc<2>(s_key, cand, n, m, tid);
     else if (m == 4096) sort_keys_desc<4>(s_key, cand, n, m, tid);
     else sort_keys_desc<8>(s_key, cand, n, m, tid);
+#ifdef COEB_SEL_DEBUG
+    const long long dbg_t1 = clock64();
+#endif
     if (!select_here) {
         for (int i = tid; i < n; i += T) {
             const unsigned long long k = s_key[i];
@@ -275,7 +280,13 @@ __global__ void __launch_bounds__(1024) sort_candidates_kernel(float2* __restric
     if (tid < 4) s_warp[34 + tid] = 0;
     __syncthreads();
     const int lane = tid & 31, wid = tid >> 5;
+#ifdef COEB_SEL_DEBUG
+    if (tid == 0) printf("[sel] cycles: sort %lld, prepare %lld\n", dbg_t1 - dbg_t0, clock64() - dbg_t1);
+#endif
     for (int base = 0; base < n; base += T) {
+#ifdef COEB_SEL_DEBUG
+        const long long dbg_c0 = clock64();
+#endif
         if (s_warp[34] >= sel.max_corners || s_warp[35]) break;   // uniform: both written before the last barrier of the previous chunk
         const int i = base + tid;
         const bool valid = i < n;
@@ -316,6 +327,9 @@ __global__ void __launch_bounds__(1024) sort_candidates_kernel(float2* __restric
         }
         acc[tid] = live ? 1 : 0;
         __syncthreads();
+#ifdef COEB_SEL_DEBUG
+        const long long dbg_c1 = clock64();
+#endif
         // 3. close live predecessors inside the chunk: the first kSelNb in the thread's own list, the rest (dense clusters of strong corners:
         // up to ~50 local maxima lie within minDistance of one) in a slice of a pool shared by the chunk, filled by a second identical walk
         int nnb = 0, pool_off = -1;
@@ -366,6 +380,7 @@ __global__ void __launch_bounds__(1024) sort_candidates_kernel(float2* __restric
         bool a = live;
 #ifdef COEB_SEL_DEBUG
         int dbg_sweeps = 0;
+        const long long dbg_c2 = (__syncthreads(), clock64());
         const int dbg_live = __syncthreads_count(live), dbg_over = __syncthreads_count(nnb > kSelNb && pool_off < 0), dbg_nsp = __syncthreads_count(near_spill);
 #endif
         for (;;) {
@@ -413,7 +428,7 @@ __global__ void __launch_bounds__(1024) sort_candidates_kernel(float2* __restric
             if (!__syncthreads_or(changed)) break;
         }
 #ifdef COEB_SEL_DEBUG
-        if (tid == 0) printf("[sel] n %d base %d live %d sweeps %d over-list %d near-spill %d spilled %d accepted-before %d\n", n, base, dbg_live, dbg_sweeps, dbg_over, dbg_nsp, s_warp[36], s_warp[34]);
+        if (tid == 0) printf("[sel] n %d base %d live %d sweeps %d over-list %d near-spill %d spilled %d accepted-before %d | cycles: accepted grid + listing %lld, walk %lld, sweeps %lld\n", n, base, dbg_live, dbg_sweeps, dbg_over, dbg_nsp, s_warp[36], s_warp[34], dbg_c1 - dbg_c0, dbg_c2 - dbg_c1, clock64() - dbg_c2);
 #endif
         // 5. the accepted ones join the accepted grid and are emitted in sorted order
         if (a) {
