@@ -1752,8 +1752,15 @@ __attribute__((target("avx2,fma"))) int fm_count_inliers_avx2(const double* F, c
                                                           double thr2, unsigned char* mask, int best) {
     COEB_FM_COUNT_BODY
 }
+__attribute__((target("avx512f,avx512vl,avx512bw,avx512dq,fma,prefer-vector-width=512"))) int fm_count_inliers_avx512(const double* F, const double* x1, const double* y1, const double* x2,
+                                                                                                               const double* y2, int n, double thr2, unsigned char* mask, int best) {
+    COEB_FM_COUNT_BODY
+}
 int fm_count_inliers(const double* F, const double* x1, const double* y1, const double* x2, const double* y2, int n, double thr2, unsigned char* mask, int best) {
     static const bool avx2 = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("fma");
+    static const bool avx512 = avx2 && __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512vl") && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512dq") &&
+                               getenv("COEB_MOTION_NO_AVX512") == nullptr;   // (development switch: the 256-bit clone)
+    if (avx512) return fm_count_inliers_avx512(F, x1, y1, x2, y2, n, thr2, mask, best);
     return avx2 ? fm_count_inliers_avx2(F, x1, y1, x2, y2, n, thr2, mask, best) : fm_count_inliers_base(F, x1, y1, x2, y2, n, thr2, mask, best);
 }
 #else
