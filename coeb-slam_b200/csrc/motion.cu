@@ -1572,6 +1572,40 @@ bool smallest_eigvec_inverse_iteration(const double* A, int n, double* v) {
     return false;
 }
 
+// The 9 x 9 normal matrix of the final fit, sum over the consensus set of r r^T with r the epipolar row of a normalised correspondence, as whole
+// rows: every entry is the same sum of the same products in the same (point) order as the upper-triangle loop in eight_point (a product does not
+// depend on the order of its factors; multiplies and adds are separate instructions here: explicit intrinsics, no FMA in the target), so the matrix
+// is the same to the last bit, but a row of twelve (nine and three zeros) is three 4-wide multiplies and adds where the triangle was 45 scalar
+// pairs. false: this CPU has no AVX2, the caller runs the scalar loop.
+#if defined(__x86_64__) && defined(__GNUC__)
+__attribute__((target("avx2"))) bool normal_matrix_rows_avx2(const float* p1, const float* p2, const int* idx, int cnt, double m1x, double m1y, double m2x, double m2y, double s1, double s2,
+                                                             double A[81]) {
+    typedef double v4 __attribute__((vector_size(32)));
+    v4 acc[9][3];
+    for (int a = 0; a < 9; a++) for (int q = 0; q < 3; q++) acc[a][q] = v4{0, 0, 0, 0};
+    for (int k = 0; k < cnt; k++) {
+        const int i = idx[k];
+        const double x1 = (p1[2 * i] - m1x) * s1, y1 = (p1[2 * i + 1] - m1y) * s1, x2 = (p2[2 * i] - m2x) * s2, y2 = (p2[2 * i + 1] - m2y) * s2;
+        const double r[9] = {x2 * x1, x2 * y1, x2, y2 * x1, y2 * y1, y2, x1, y1, 1};
+        const v4 r0 = {r[0], r[1], r[2], r[3]}, r1 = {r[4], r[5], r[6], r[7]}, r2 = {r[8], 0, 0, 0};
+#pragma GCC unroll 9
+        for (int a = 0; a < 9; a++) {
+            const v4 ra = {r[a], r[a], r[a], r[a]};
+            const v4 t0 = ra * r0, t1 = ra * r1, t2 = ra * r2;   // (no FMA in this target: the sums below round like the scalar loop's)
+            acc[a][0] += t0; acc[a][1] += t1; acc[a][2] += t2;
+        }
+    }
+    for (int a = 0; a < 9; a++) for (int b = 0; b < 9; b++) A[a * 9 + b] = acc[a][b >> 2][b & 3];
+    return true;
+}
+bool normal_matrix_rows(const float* p1, const float* p2, const int* idx, int cnt, double m1x, double m1y, double m2x, double m2y, double s1, double s2, double A[81]) {
+    static const bool avx2 = __builtin_cpu_supports("avx2") && getenv("COEB_MOTION_SCALAR_FIT") == nullptr;   // (development switch: the scalar triangle loop)
+    return avx2 && normal_matrix_rows_avx2(p1, p2, idx, cnt, m1x, m1y, m2x, m2y, s1, s2, A);
+}
+#else
+bool normal_matrix_rows(const float*, const float*, const int*, int, double, double, double, double, double, double, double*) { return false; }
+#endif
+
 // 8-point algorithm on the points idx[0..cnt): Hartley normalisation, least-squares null vector, rank-2 projection. false if degenerate.
 bool eight_point(const float* p1, const float* p2, const int* idx, int cnt, double F[9]) {
     double m1x = 0, m1y = 0, m2x = 0, m2y = 0;
@@ -1586,13 +1620,15 @@ bool eight_point(const float* p1, const float* p2, const int* idx, int cnt, doub
     if (s1 < 1e-12 || s2 < 1e-12) return false;
     s1 = std::sqrt(2.0) * cnt / s1; s2 = std::sqrt(2.0) * cnt / s2;
     double A[81] = {0};
-    for (int k = 0; k < cnt; k++) {
-        const int i = idx[k];
-        const double x1 = (p1[2 * i] - m1x) * s1, y1 = (p1[2 * i + 1] - m1y) * s1, x2 = (p2[2 * i] - m2x) * s2, y2 = (p2[2 * i + 1] - m2y) * s2;
-        const double r[9] = {x2 * x1, x2 * y1, x2, y2 * x1, y2 * y1, y2, x1, y1, 1};
-        for (int a = 0; a < 9; a++) for (int b = a; b < 9; b++) A[a * 9 + b] += r[a] * r[b];   // upper triangle, mirrored below
+    if (!normal_matrix_rows(p1, p2, idx, cnt, m1x, m1y, m2x, m2y, s1, s2, A)) {
+        for (int k = 0; k < cnt; k++) {
+            const int i = idx[k];
+            const double x1 = (p1[2 * i] - m1x) * s1, y1 = (p1[2 * i + 1] - m1y) * s1, x2 = (p2[2 * i] - m2x) * s2, y2 = (p2[2 * i + 1] - m2y) * s2;
+            const double r[9] = {x2 * x1, x2 * y1, x2, y2 * x1, y2 * y1, y2, x1, y1, 1};
+            for (int a = 0; a < 9; a++) for (int b = a; b < 9; b++) A[a * 9 + b] += r[a] * r[b];   // upper triangle, mirrored below
+        }
+        for (int a = 0; a < 9; a++) for (int b = 0; b < a; b++) A[a * 9 + b] = A[b * 9 + a];
     }
-    for (int a = 0; a < 9; a++) for (int b = 0; b < a; b++) A[a * 9 + b] = A[b * 9 + a];
     double F0[9];
     if (!smallest_eigvec_inverse_iteration(A, 9, F0)) {
         double V[81], ev[9];

@@ -131,14 +131,16 @@ def test_fundamental_ransac_degenerate_and_translation_inputs():
 def test_fundamental_ransac_vector_clones_agree():
     """The hypothesis scoring of coeb_fundamental_ransac has one clone per vector width (picked once per process from the CPU's flags;
     COEB_MOTION_NO_AVX512 keeps the 256-bit one where the 512-bit one would run): the same expression element by element, so the
-    consensus set and F must be the same to the last bit. Two processes, one per clone, on the golden tracks."""
+    consensus set and F must be the same to the last bit; so must F with the final fit's normal matrix accumulated as whole rows
+    (COEB_MOTION_SCALAR_FIT keeps the scalar loop). One process per variant, on the golden tracks."""
     import subprocess
     code = ("import sys, zlib, numpy as np; sys.path.insert(0, %r); from coeb_b200 import motion; g = np.load(%r); keep = g['state'] != 0; "
             "F, m = motion.fundamental_ransac(g['prepoint'][keep], g['nextpoint'][keep], 0.1, 0.99, 1000, 12345); "
             "print(zlib.crc32(F.tobytes()), zlib.crc32(m.tobytes()), int(m.sum()))") % (os.path.join(ROOT, "coeb-slam_b200", "python"), os.path.join(G, "motion_seed0.npz"))
     outs = []
-    for extra in ({}, {"COEB_MOTION_NO_AVX512": "1"}):
-        env = dict(os.environ, **extra)
-        env.pop("COEB_MOTION_NO_AVX512", None) if not extra else None
+    for extra in ({}, {"COEB_MOTION_NO_AVX512": "1"}, {"COEB_MOTION_SCALAR_FIT": "1"}):
+        env = {k: v for k, v in os.environ.items() if k not in ("COEB_MOTION_NO_AVX512", "COEB_MOTION_SCALAR_FIT")}
+        env.update(extra)
         outs.append(subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout.split())
-    assert outs[0] == outs[1] and int(outs[0][2]) > 100
+    # (the third process accumulates the final fit's normal matrix with the scalar upper-triangle loop instead of whole 4-wide rows)
+    assert outs[0] == outs[1] == outs[2] and int(outs[0][2]) > 100
