@@ -2,7 +2,7 @@
 // matchers: the tail of the RGB-D Frame constructor (UndistortKeyPoints, ComputeStereoFromRGBD) and the
 // visibility test in front of SearchByProjection (Frame::isInFrustum + MapPoint::PredictScale, as driven by
 // Tracking::SearchLocalPoints). TEST INFRASTRUCTURE ONLY (see coeb_oracle.hpp for the rules and for the
-// "parity unpinned" statement).
+// parity status: pinned to the reference itself through oracle/_ref).
 //
 // OpenCV arithmetic on this path, each model checked against cv2 4.13 in tests/test_oracle_vs_cv2.py:
 //   cv::undistortPoints(src, dst, K, D, noArray(), K): double precision, 5 fixed-point iterations, no EPS test;

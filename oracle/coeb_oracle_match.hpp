@@ -1,6 +1,6 @@
 // coeb_oracle_match.hpp -- CPU restatement of the keypoint grid, the Hamming matchers and the stereo
 // matcher of the reference. TEST INFRASTRUCTURE ONLY (see coeb_oracle.hpp for the rules and for the
-// "parity unpinned" statement). Pointer-graph state (MapPoint*, Frame members) is flattened into the
+// parity status: pinned to the reference itself through oracle/_ref). Pointer-graph state (MapPoint*, Frame members) is flattened into the
 // structure-of-arrays inputs that the C ABI (include/coeb_frontend.h) also takes.
 #pragma once
 #include "coeb_oracle.hpp"
